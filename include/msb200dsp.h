@@ -1,0 +1,275 @@
+/*
+ * msb200dsp.h — C ABI of libmsb200dsp.so: mediastreamer2's per-tick DSP hot path on NVIDIA B200 (sm_100a).
+ *
+ * Plain C: pointers and sizes only, no CUDA / torch types. Device pointers cross the ABI as `void *`.
+ * Every object is a BANK: the same reference filter instantiated for `n` independent call streams (or rooms, or
+ * video streams) whose per-stream state lives in HBM in structure-of-arrays layout. One call = one MSTicker tick
+ * (or one block / frame) of every stream in the bank = one or two kernel launches.
+ *
+ * The reference calls `MSFilterDesc.process(MSFilter*)` once per stream per tick on the ticker thread
+ * (/root/reference/src/base/msticker.c:244-259). Each `msb200_<filter>_process*` below is the batched equivalent of
+ * the cited process() body; `plugin/` wraps them back into MSFilterDesc objects with the reference's ids, names and
+ * method tables.
+ *
+ * Error convention: functions return 0 on success, a negative MSB200_E* code otherwise; msb200_last_error() gives a
+ * thread-local message. There is NO CPU fallback: without a CUDA device every create/process call fails with
+ * MSB200_ENODEV.
+ *
+ * Two flavours of every process call:
+ *   _process      host buffers (pageable or pinned): H2D copy + kernel(s) + D2H copy + stream sync ("e2e" path,
+ *                 what an MSFilter.process() wrapper calls)
+ *   _process_dev  device buffers, asynchronous on the context's stream (chaining filters without leaving HBM)
+ */
+#ifndef MSB200DSP_H
+#define MSB200DSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSB200_API __attribute__((visibility("default")))
+
+#define MSB200_OK 0
+#define MSB200_EINVAL (-1) /* bad argument (the reference's methods return -1 likewise, src/base/msfilter.c:196) */
+#define MSB200_ENODEV (-2) /* no CUDA device / driver: nothing runs, by design */
+#define MSB200_ECUDA (-3)  /* a CUDA runtime call failed; see msb200_last_error() */
+#define MSB200_ENOMEM (-4)
+#define MSB200_ESTATE (-5) /* call not valid in the object's current state */
+
+typedef struct msb200_ctx msb200_ctx;
+
+/* ---------------------------------------------------------------------------------------------------- context */
+MSB200_API int msb200_version(void);
+MSB200_API const char *msb200_last_error(void);
+/* One context per (process, GPU): owns a CUDA stream, timing events and a pinned staging arena. */
+MSB200_API int msb200_ctx_create(int device_ordinal, msb200_ctx **out);
+MSB200_API void msb200_ctx_destroy(msb200_ctx *ctx);
+MSB200_API int msb200_ctx_sync(msb200_ctx *ctx);
+/* Kernel launches issued through this context since creation (bench.py reports it as gpu_launches). */
+MSB200_API uint64_t msb200_ctx_launch_count(msb200_ctx *ctx);
+/* Raw device memory helpers so that a plain-C (or ctypes) caller can keep buffers resident in HBM. */
+MSB200_API int msb200_dev_alloc(msb200_ctx *ctx, size_t bytes, void **dev_ptr);
+MSB200_API int msb200_dev_free(msb200_ctx *ctx, void *dev_ptr);
+MSB200_API int msb200_host_alloc_pinned(msb200_ctx *ctx, size_t bytes, void **host_ptr);
+MSB200_API int msb200_host_free_pinned(msb200_ctx *ctx, void *host_ptr);
+MSB200_API int msb200_memcpy_h2d(msb200_ctx *ctx, void *dev, const void *host, size_t bytes);
+MSB200_API int msb200_memcpy_d2h(msb200_ctx *ctx, void *host, const void *dev, size_t bytes);
+MSB200_API int msb200_memset_dev(msb200_ctx *ctx, void *dev, int value, size_t bytes);
+/* Device-side stopwatch on the context's stream (CUDA events): start, run work, stop -> milliseconds. */
+MSB200_API int msb200_timer_start(msb200_ctx *ctx);
+MSB200_API int msb200_timer_stop_ms(msb200_ctx *ctx, float *ms);
+/* Write `bytes` of scratch (> L2) so the next timed launch starts from HBM, not from the 126 MB L2. */
+MSB200_API int msb200_flush_l2(msb200_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------------- MSAudioMixer
+ * Replaces mixer_process() /root/reference/src/audiofilters/audiomixer.c:288-346 (accumulate :33-38, saturate
+ * :40-44, apply_gain :46-51, channel_process_in :78-90, channel_process_out :113-130) for `n_rooms` mixers of
+ * `n_pins` pins each. The per-pin bufferizer / bypass / flow-control decisions (:92-111, :244-286) depend on
+ * ticker->time and stay on the host (plugin/); what arrives here is, per pin, either one tick of samples
+ * (present=1) or nothing (present=0 -> contributes zeros, exactly as :88).
+ * Layouts: in  [room][pin][nwords] s16;  present [room][pin] u8;
+ *          out conference mode: [room][pin][nwords] s16 = sat(sum - own) (own = post-gain input if active and present)
+ *              plain mode:      [room][nwords] s16 = sat(sum)
+ * Bit-exact with the reference, including saturation to [-32767, 32767] and `(int)(gain*(float)s)` gain. */
+typedef struct msb200_mixer msb200_mixer;
+MSB200_API int msb200_mixer_create(msb200_ctx *ctx, int n_rooms, int n_pins, int nwords, int conf_mode,
+                                   msb200_mixer **out);
+MSB200_API void msb200_mixer_destroy(msb200_mixer *m);
+MSB200_API int msb200_mixer_set_input_gain(msb200_mixer *m, int room, int pin, float gain); /* MS_AUDIO_MIXER_SET_INPUT_GAIN */
+MSB200_API int msb200_mixer_set_active(msb200_mixer *m, int room, int pin, int active);     /* MS_AUDIO_MIXER_SET_ACTIVE */
+MSB200_API int msb200_mixer_process(msb200_mixer *m, const int16_t *in, const uint8_t *present, int16_t *out);
+MSB200_API int msb200_mixer_process_dev(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out);
+/* Cross-GPU conference: phase 1 writes each room's int32 partial sum of the LOCAL pins to d_sum
+ * [room][nwords] (the caller all-reduces it with ncclSum/ncclInt32 — integer, hence order-independent and
+ * bit-exact), phase 2 emits the local pins' outputs from the reduced sum. */
+MSB200_API int msb200_mixer_partial_dev(msb200_mixer *m, const void *d_in, const void *d_present, void *d_sum_i32);
+MSB200_API int msb200_mixer_finish_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *d_sum_i32,
+                                        void *d_out);
+
+/* ---------------------------------------------------------------------------------------------------- MSVolume
+ * Replaces the light path of volume_process() /root/reference/src/audiofilters/msvolume.c:503-513:
+ * update_energy :388-407, volume_noise_gate_process :240-260, apply_gain :409-445 (Q12 integer gain, truncating
+ * division, saturation to +-32767, optional DC removal). One block of `nsamples` per stream per call, in place.
+ * The float state machine is evaluated in the reference's operation order (no FMA contraction): bit-exact. */
+typedef struct msb200_volume msb200_volume;
+typedef struct msb200_volume_state {
+	float energy, level_pk, instant_energy, gain, static_gain, target_gain, ng_gain, ng_threshold, ng_floorgain;
+	int32_t dc_offset, ng_noise_dur, noise_gate_enabled, remove_dc, sample_rate, fast_upramp;
+} msb200_volume_state;
+MSB200_API int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_volume **out);
+MSB200_API void msb200_volume_destroy(msb200_volume *v);
+MSB200_API int msb200_volume_set_gain(msb200_volume *v, int stream, float gain);           /* MS_VOLUME_SET_GAIN :270-276 */
+MSB200_API int msb200_volume_set_db_gain(msb200_volume *v, int stream, float db);          /* MS_VOLUME_SET_DB_GAIN :262-268 */
+MSB200_API int msb200_volume_enable_noise_gate(msb200_volume *v, int stream, int enabled); /* :352-359 */
+MSB200_API int msb200_volume_set_noise_gate_threshold(msb200_volume *v, int stream, float thr);
+MSB200_API int msb200_volume_set_noise_gate_floorgain(msb200_volume *v, int stream, float g);
+MSB200_API int msb200_volume_remove_dc(msb200_volume *v, int stream, int enabled);
+MSB200_API int msb200_volume_get_state(msb200_volume *v, int stream, msb200_volume_state *st);
+/* io: [stream][nsamples] s16, processed in place */
+MSB200_API int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples);
+MSB200_API int msb200_volume_process_dev(msb200_volume *v, void *d_io, int nsamples, int stride_samples);
+
+/* ---------------------------------------------------------------------------------------------------- MSChannelAdapter
+ * Replaces adapter_process() /root/reference/src/audiofilters/chanadapt.c:99-132 (mono->stereo duplicate,
+ * stereo->mono take-left) and the two-mono-pins -> interleaved-stereo path :68-97. Stateless, bit-exact. */
+#define MSB200_CHAN_MONO_TO_STEREO 0
+#define MSB200_CHAN_STEREO_TO_MONO 1
+#define MSB200_CHAN_2MONO_TO_STEREO 2
+/* mode 0: in [n][frames] -> out [n][frames][2];  mode 1: in [n][frames][2] -> out [n][frames];
+ * mode 2: in = pin0 [n][frames], in2 = pin1 [n][frames] (NULL -> zeros) -> out [n][frames][2] */
+MSB200_API int msb200_chanadapt_process(msb200_ctx *ctx, int mode, int n_streams, int frames, const int16_t *in,
+                                        const int16_t *in2, int16_t *out);
+MSB200_API int msb200_chanadapt_process_dev(msb200_ctx *ctx, int mode, int n_streams, int frames, const void *d_in,
+                                            const void *d_in2, void *d_out);
+
+/* ---------------------------------------------------------------------------------------------------- MSEqualizer
+ * Replaces equalizer_process() /root/reference/src/audiofilters/equalizer.c:279-288 -> ms_fir_mem16()
+ * /root/reference/src/utils/dsptools.c:253-268 (float build): nfft-tap direct-form FIR with a per-stream delay line,
+ * accumulated from tap ord-1 down to 0 in float32 without FMA, output cast to s16 by C truncation — bit-exact given
+ * equal taps. The taps (gain table -> IFFT -> time shift -> Hamming, equalizer.c:215-237) are computed on the host by
+ * msb200_equalizer_set_gain(), mirroring MS_EQUALIZER_SET_GAIN (:147-172). */
+typedef struct msb200_equalizer msb200_equalizer;
+MSB200_API int msb200_equalizer_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block,
+                                       msb200_equalizer **out);
+MSB200_API void msb200_equalizer_destroy(msb200_equalizer *e);
+MSB200_API int msb200_equalizer_nfft(msb200_equalizer *e);
+MSB200_API int msb200_equalizer_set_gain(msb200_equalizer *e, int stream, float frequency, float gain, float width);
+MSB200_API int msb200_equalizer_get_gain(msb200_equalizer *e, int stream, float frequency, float *gain);
+MSB200_API int msb200_equalizer_set_active(msb200_equalizer *e, int stream, int active);
+/* direct tap access (tests, state restore): taps [nfft] float */
+MSB200_API int msb200_equalizer_set_taps(msb200_equalizer *e, int stream, const float *taps);
+MSB200_API int msb200_equalizer_get_taps(msb200_equalizer *e, int stream, float *taps);
+MSB200_API int msb200_equalizer_process(msb200_equalizer *e, int16_t *io, int nsamples);
+MSB200_API int msb200_equalizer_process_dev(msb200_equalizer *e, void *d_io, int nsamples, int stride_samples);
+
+/* ---------------------------------------------------------------------------------------------------- MSResample
+ * Replaces resample_process_ms2() /root/reference/src/audiofilters/msresample.c:122-179, i.e. the call
+ * speex_resampler_process_int(handle, 0, in, &inlen, out, &outlen) (:157) with quality
+ * SPEEX_RESAMPLER_QUALITY_VOIP = 3 (:104). speexdsp is NOT under /root/reference; the algorithm (Kaiser-windowed sinc
+ * polyphase, direct table when den<=8 else cubic-interpolated oversampled table) is restated in oracle/oracle_resample.c.
+ * All streams of a bank share rates and are fed the same number of frames per call; per-stream filter phase is kept.
+ * out must hold msb200_resample_max_out(r, in_frames) frames per stream; *out_frames receives the produced count
+ * (identical for all streams fed in lockstep). Mono or interleaved multi-channel (channel 0..nch-1 independent). */
+typedef struct msb200_resample msb200_resample;
+MSB200_API int msb200_resample_create(msb200_ctx *ctx, int n_streams, int in_rate, int out_rate, int nchannels,
+                                      int max_in_frames, msb200_resample **out);
+MSB200_API void msb200_resample_destroy(msb200_resample *r);
+MSB200_API int msb200_resample_max_out(msb200_resample *r, int in_frames); /* inlen*out/in + 1, msresample.c:151-152 */
+MSB200_API int msb200_resample_reset(msb200_resample *r);
+MSB200_API int msb200_resample_process(msb200_resample *r, const int16_t *in, int in_frames, int16_t *out,
+                                       int out_stride_frames, int *out_frames);
+MSB200_API int msb200_resample_process_dev(msb200_resample *r, const void *d_in, int in_frames, int in_stride_frames,
+                                           void *d_out, int out_stride_frames, int *out_frames);
+
+/* ---------------------------------------------------------------------------------------------------- MSSpeexEC
+ * Replaces the arithmetic of speex_ec_process() /root/reference/src/audiofilters/speexec.c:223-305:
+ * per `framesize` block  speex_echo_cancellation(ec, mic, ref, out) + speex_preprocess_run(den, out)  (:297-298)
+ * configured as speex_ec_preprocess() does (:188-216): framesize = largest pow2 <= 64*rate/8000 (:171-180),
+ * filter length = tail_ms*rate/1000 (:194), SPEEX_ECHO_SET_SAMPLING_RATE, preprocessor bound to the echo state
+ * (:203; denoise on, residual-echo suppression on, AGC/VAD/dereverb off).
+ * speexdsp is NOT under /root/reference; the MDF two-path canceller and the preprocessor are restated in
+ * oracle/oracle_aec.c (parity unpinned by the reference's own tests: SURVEY §8c).
+ * One call processes `nframes` consecutive frames of every stream. Layouts: mic, ref, out [stream][nframes*framesize]. */
+typedef struct msb200_aec msb200_aec;
+typedef struct msb200_aec_info {
+	int32_t frame_size, window_size, M, sample_rate, filter_length;
+	size_t state_bytes_per_stream;
+} msb200_aec_info;
+MSB200_API int msb200_aec_frame_size_for_rate(int sample_rate, int framesize_at_8000); /* adjust_framesize :171-180 */
+MSB200_API int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_length_ms,
+                                 int framesize_at_8000, msb200_aec **out);
+MSB200_API void msb200_aec_destroy(msb200_aec *a);
+MSB200_API int msb200_aec_get_info(msb200_aec *a, msb200_aec_info *info);
+MSB200_API int msb200_aec_reset(msb200_aec *a, int stream); /* stream < 0: all */
+MSB200_API int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes);
+MSB200_API int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes,
+                                      int stride_samples);
+/* MS_ECHO_CANCELLER_GET/SET_STATE_STRING (speexec.c:119-167, 361-374): the adaptive-filter weights of one stream as
+ * an opaque blob (our format: header + W[M][N] float). */
+MSB200_API size_t msb200_aec_state_blob_size(msb200_aec *a);
+MSB200_API int msb200_aec_get_state_blob(msb200_aec *a, int stream, void *blob, size_t size);
+MSB200_API int msb200_aec_set_state_blob(msb200_aec *a, int stream, const void *blob, size_t size);
+/* Debug/parity probes: copies a named internal per-stream vector to host ("W","foreground","X","power","power_1",
+ * "prop","noise","echo_noise","gain2", scalar pack "scalars"). Returns number of floats written or <0. */
+MSB200_API int msb200_aec_probe(msb200_aec *a, int stream, const char *what, float *out, int max_floats);
+
+/* ---------------------------------------------------------------------------------------------------- audio chain
+ * The BASELINE cfg2 pipeline as one resident device-side graph, one call per 10 ms tick for `n_streams` streams:
+ *   ref  [in_rate] -> MSResample -> \
+ *                                    MSSpeexEC(rate, tail) -> MSVolume(gain) -> [optional MSAudioMixer rooms of P]
+ *   mic  [in_rate] -> MSResample -> /
+ * (graph shape: /root/reference/src/voip/audiostream.c:1798-1832; conference: src/voip/audioconference.c:209-257).
+ * The EC re-frames 10 ms ticks into `framesize` blocks exactly as its MSBufferizer does (speexec.c:252-259): the
+ * number of output samples per tick varies (0, 1 or 2 frames); the volume stage runs per EC output block, as the
+ * reference's per-mblk loop does (msvolume.c:505-512); the mixer stage re-frames to 10 ms (audiomixer.c:78-90). */
+typedef struct msb200_chain msb200_chain;
+typedef struct msb200_chain_params {
+	int32_t n_streams;
+	int32_t in_rate;         /* e.g. 16000 */
+	int32_t rate;            /* e.g. 48000 */
+	int32_t tail_length_ms;  /* 250 */
+	int32_t framesize_at_8000; /* 64 */
+	float volume_gain;       /* 0.8 */
+	int32_t mixer_pins;      /* 0 = no mixer stage; else streams are grouped in rooms of this many pins (conference mode) */
+	int32_t use_cuda_graph;  /* capture the per-tick launch sequence (one graph per frame-count) */
+} msb200_chain_params;
+MSB200_API int msb200_chain_create(msb200_ctx *ctx, const msb200_chain_params *p, msb200_chain **out);
+MSB200_API void msb200_chain_destroy(msb200_chain *c);
+/* samples per stream the next tick will produce on the (pre-mixer) EC/volume output, and after the mixer */
+MSB200_API int msb200_chain_next_out_samples(msb200_chain *c);
+MSB200_API int msb200_chain_max_out_samples(msb200_chain *c);
+/* Host path: ref_in/mic_in [stream][in_rate/100] s16 -> out [stream][max_out_samples] s16 (first *out_samples valid).
+ * H2D, all kernels, D2H inside. */
+MSB200_API int msb200_chain_tick(msb200_chain *c, const int16_t *ref_in, const int16_t *mic_in, int16_t *out,
+                                 int *out_samples);
+/* Device path: inputs/outputs already resident; asynchronous. */
+MSB200_API int msb200_chain_tick_dev(msb200_chain *c, const void *d_ref_in, const void *d_mic_in, void *d_out,
+                                     int *out_samples);
+MSB200_API int msb200_chain_launches_per_tick(msb200_chain *c);
+MSB200_API msb200_aec *msb200_chain_aec(msb200_chain *c);
+
+/* ---------------------------------------------------------------------------------------------------- video
+ * Pixel formats: the reference's MSPixFmt values (include/mediastreamer2/msvideo.h:267-280) plus NV12/NV21 appended
+ * (the reference has no such member; SURVEY §8a note). */
+#define MSB200_PIX_YUV420P 0
+#define MSB200_PIX_YUYV 1
+#define MSB200_PIX_RGB24 2
+#define MSB200_PIX_RGB24_REV 3 /* BGR24 bottom-up in the reference's world; here: BGR byte order */
+#define MSB200_PIX_UYVY 5
+#define MSB200_PIX_YUY2 6
+#define MSB200_PIX_RGBA32 7
+#define MSB200_PIX_NV12 100
+#define MSB200_PIX_NV21 101
+
+/* NV12/NV21 -> I420 with rotation {0,90,180,270} and optional nearest 1/2 decimation: bit-exact replacement of
+ * copy_ycbcrbiplanar_to_true_yuv_with_rotation_and_down_scale_by_2() /root/reference/src/voip/msvideo.c:787-919.
+ * (w,h) is the DESTINATION size before rotation, as in the reference. Batched over n_frames frames laid out
+ * back-to-back: src frame = y plane (y_stride*src_h) then cbcr plane (cbcr_stride*src_h/2); dst = tight I420. */
+MSB200_API int msb200_nv12_to_i420(msb200_ctx *ctx, int n_frames, const uint8_t *src, size_t src_frame_bytes,
+                                   size_t cbcr_offset, int rotation, int w, int h, int y_stride, int cbcr_stride,
+                                   int u_first, int down_scale, uint8_t *dst);
+MSB200_API int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void *d_src, size_t src_frame_bytes,
+                                       size_t cbcr_offset, int rotation, int w, int h, int y_stride, int cbcr_stride,
+                                       int u_first, int down_scale, void *d_dst);
+
+/* MSScaler replacement: create_context / context_process / context_free of MSScalerDesc
+ * (include/mediastreamer2/msvideo.h:473-479; backends src/voip/msvideo.c:517-691), used by MSPixConv
+ * (src/videofilters/pixconv.c:62-94) and MSSizeConv (src/videofilters/sizeconv.c:97-184), batched over n_frames.
+ * Arithmetic: the swscale SWS_BILINEAR pipeline the reference's ffmpeg back-end runs (msvideo.c:651-681) restated in
+ * oracle/oracle_video.c and pinned against libswscale 9.1.100 golden frames (tests/golden/). */
+typedef struct msb200_scaler msb200_scaler;
+MSB200_API int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int dst_w, int dst_h,
+                                    int dst_fmt, msb200_scaler **out);
+MSB200_API void msb200_scaler_destroy(msb200_scaler *s);
+MSB200_API size_t msb200_scaler_src_frame_bytes(msb200_scaler *s);
+MSB200_API size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s);
+MSB200_API int msb200_scaler_process(msb200_scaler *s, int n_frames, const uint8_t *src, uint8_t *dst);
+MSB200_API int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSB200DSP_H */

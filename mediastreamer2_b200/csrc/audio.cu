@@ -1,0 +1,721 @@
+// audio.cu — MSAudioMixer, MSVolume, MSChannelAdapter, MSEqualizer, MSResample as batched sm_100a kernels.
+//
+// Every kernel here is HBM/latency bound integer or float32 work: the design rules are coalesced
+// 16-byte accesses, shared-memory staging where a block is re-read, and enough CTAs to cover 148 SMs.
+// Bit-exactness rules: integer paths reproduce the reference's C semantics (truncating casts and
+// divisions, asymmetric +-32767 clamp); float32 state machines and dot products use __fmul_rn/__fadd_rn in the
+// reference's evaluation order so that nvcc never contracts them into FMAs.
+#include "msb200_internal.h"
+
+#include <cmath>
+
+// ======================================================================================================= mixer
+// reference: /root/reference/src/audiofilters/audiomixer.c  (accumulate :33-38, saturate :40-44, apply_gain :46-51,
+// channel_process_in :78-90, channel_process_out :113-130, make_output :210-217)
+
+__device__ __forceinline__ int mix_sat(int s) { // audiomixer.c:40-44 — clamps to [-32767, 32767]
+	return s > 32767 ? 32767 : (s < -32767 ? -32767 : s);
+}
+__device__ __forceinline__ int mix_contrib(int s, float gain) { // :46-51, only when gain != 1.0 (:82)
+	if (gain != 1.0f) return mix_sat(__float2int_rz(__fmul_rn(gain, (float)s)));
+	return s;
+}
+
+struct msb200_mixer {
+	msb200_ctx *ctx;
+	int n_rooms, n_pins, nwords, conf_mode;
+	float *d_gain;     // [room][pin]
+	uint8_t *d_active; // [room][pin]
+	std::vector<float> h_gain;
+	std::vector<uint8_t> h_active;
+	bool dirty;
+	msb200_devbuf in, present, out;
+};
+
+// One thread owns a column of VEC consecutive samples of one room and walks the pins twice: first to build the
+// int32 sums, then to emit sat(sum - own) per pin. The second walk re-reads lines the same thread just touched
+// (L1/L2 hits), so DRAM traffic stays at the algorithmic P*2n in + P*2n out.
+template <int VEC> struct s16vec;
+template <> struct s16vec<8> { typedef int4 type; };
+template <> struct s16vec<4> { typedef int2 type; };
+template <> struct s16vec<2> { typedef int type; };
+template <> struct s16vec<1> { typedef short type; };
+
+template <int VEC> __device__ __forceinline__ void unpack_s16(const typename s16vec<VEC>::type &v, int (&s)[VEC]);
+template <> __device__ __forceinline__ void unpack_s16<8>(const int4 &v, int (&s)[8]) {
+	s[0] = (short)(v.x & 0xffff); s[1] = v.x >> 16; s[2] = (short)(v.y & 0xffff); s[3] = v.y >> 16;
+	s[4] = (short)(v.z & 0xffff); s[5] = v.z >> 16; s[6] = (short)(v.w & 0xffff); s[7] = v.w >> 16;
+}
+template <> __device__ __forceinline__ void unpack_s16<4>(const int2 &v, int (&s)[4]) {
+	s[0] = (short)(v.x & 0xffff); s[1] = v.x >> 16; s[2] = (short)(v.y & 0xffff); s[3] = v.y >> 16;
+}
+template <> __device__ __forceinline__ void unpack_s16<2>(const int &v, int (&s)[2]) {
+	s[0] = (short)(v & 0xffff); s[1] = v >> 16;
+}
+template <> __device__ __forceinline__ void unpack_s16<1>(const short &v, int (&s)[1]) {
+	s[0] = v;
+}
+__device__ __forceinline__ int pack2(int lo, int hi) {
+	return (lo & 0xffff) | (hi << 16);
+}
+template <int VEC> __device__ __forceinline__ typename s16vec<VEC>::type pack_s16(const int (&s)[VEC]);
+template <> __device__ __forceinline__ int4 pack_s16<8>(const int (&s)[8]) {
+	return make_int4(pack2(s[0], s[1]), pack2(s[2], s[3]), pack2(s[4], s[5]), pack2(s[6], s[7]));
+}
+template <> __device__ __forceinline__ int2 pack_s16<4>(const int (&s)[4]) {
+	return make_int2(pack2(s[0], s[1]), pack2(s[2], s[3]));
+}
+template <> __device__ __forceinline__ int pack_s16<2>(const int (&s)[2]) {
+	return pack2(s[0], s[1]);
+}
+template <> __device__ __forceinline__ short pack_s16<1>(const int (&s)[1]) {
+	return (short)s[0];
+}
+
+// mode 0: full (sum + outputs); mode 1: partial sums only -> d_sum; mode 2: outputs from given d_sum
+template <int VEC>
+__global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in, const uint8_t *__restrict__ present,
+                                                    const float *__restrict__ gain, const uint8_t *__restrict__ active,
+                                                    short *__restrict__ out, int *__restrict__ sum_io, int n_rooms,
+                                                    int n_pins, int nwords, int conf_mode, int mode) {
+	typedef typename s16vec<VEC>::type V;
+	const int nvec = nwords / VEC;
+	const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long)n_rooms * nvec) return;
+	const int room = (int)(gid / nvec), col = (int)(gid % nvec);
+	const size_t chan0 = (size_t)room * n_pins;
+	const V *inv = reinterpret_cast<const V *>(in) + chan0 * nvec + col;
+	int sum[VEC];
+#pragma unroll
+	for (int k = 0; k < VEC; ++k) sum[k] = 0;
+	if (mode != 2) {
+#pragma unroll 4
+		for (int p = 0; p < n_pins; ++p) {
+			if (!present[chan0 + p] || !active[chan0 + p]) continue;
+			const float g = gain[chan0 + p];
+			int s[VEC];
+			unpack_s16<VEC>(inv[(size_t)p * nvec], s);
+#pragma unroll
+			for (int k = 0; k < VEC; ++k) sum[k] += mix_contrib(s[k], g);
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < VEC; ++k) sum[k] = sum_io[(size_t)room * nwords + col * VEC + k];
+	}
+	if (mode == 1) {
+#pragma unroll
+		for (int k = 0; k < VEC; ++k) sum_io[(size_t)room * nwords + col * VEC + k] = sum[k];
+		return;
+	}
+	if (!conf_mode) { // make_output :210-217
+		int o[VEC];
+#pragma unroll
+		for (int k = 0; k < VEC; ++k) o[k] = mix_sat(sum[k]);
+		reinterpret_cast<V *>(out)[(size_t)room * nvec + col] = pack_s16<VEC>(o);
+		return;
+	}
+	V *outv = reinterpret_cast<V *>(out) + chan0 * nvec + col;
+#pragma unroll 4
+	for (int p = 0; p < n_pins; ++p) { // channel_process_out :113-130
+		int o[VEC];
+		if (active[chan0 + p] && present[chan0 + p]) {
+			const float g = gain[chan0 + p];
+			int s[VEC];
+			unpack_s16<VEC>(inv[(size_t)p * nvec], s);
+#pragma unroll
+			for (int k = 0; k < VEC; ++k) o[k] = mix_sat(sum[k] - mix_contrib(s[k], g));
+		} else {
+#pragma unroll
+			for (int k = 0; k < VEC; ++k) o[k] = mix_sat(sum[k]);
+		}
+		outv[(size_t)p * nvec] = pack_s16<VEC>(o);
+	}
+}
+
+static int mixer_upload(msb200_mixer *m) {
+	if (!m->dirty) return MSB200_OK;
+	size_t n = (size_t)m->n_rooms * m->n_pins;
+	MSB200_CUDA(cudaMemcpyAsync(m->d_gain, m->h_gain.data(), n * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+	MSB200_CUDA(cudaMemcpyAsync(m->d_active, m->h_active.data(), n, cudaMemcpyHostToDevice, m->ctx->stream));
+	// the host vectors may be modified right after we return: make the copy complete first
+	MSB200_CUDA(cudaStreamSynchronize(m->ctx->stream));
+	m->dirty = false;
+	return MSB200_OK;
+}
+
+static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out, void *d_sum, int mode) {
+	int r = mixer_upload(m);
+	if (r) return r;
+	const int nw = m->nwords;
+	const bool al16 = ((uintptr_t)d_in % 16 == 0) && (d_out == nullptr || (uintptr_t)d_out % 16 == 0);
+	int vec = (nw % 8 == 0 && al16) ? 8 : (nw % 4 == 0 && al16) ? 4 : (nw % 2 == 0 && al16) ? 2 : 1;
+	// prefer more, narrower threads when the grid would not cover the chip (148 SMs x >=4 CTAs of 128)
+	while (vec > 2 && (long)m->n_rooms * (nw / vec) < 148L * 4 * 128) vec /= 2;
+	const long nthreads = (long)m->n_rooms * (nw / vec);
+	const int block = 128, grid = (int)((nthreads + block - 1) / block);
+#define MIX_ARGS                                                                                                       \
+	(const short *)d_in, (const uint8_t *)d_present, m->d_gain, m->d_active, (short *)d_out, (int *)d_sum, m->n_rooms, \
+	    m->n_pins, nw, m->conf_mode, mode
+	switch (vec) {
+		case 8: MSB200_LAUNCH(m->ctx, mixer_kernel<8>, grid, block, 0, MIX_ARGS); break;
+		case 4: MSB200_LAUNCH(m->ctx, mixer_kernel<4>, grid, block, 0, MIX_ARGS); break;
+		case 2: MSB200_LAUNCH(m->ctx, mixer_kernel<2>, grid, block, 0, MIX_ARGS); break;
+		default: MSB200_LAUNCH(m->ctx, mixer_kernel<1>, grid, block, 0, MIX_ARGS); break;
+	}
+#undef MIX_ARGS
+	return MSB200_OK;
+}
+
+extern "C" {
+
+int msb200_mixer_create(msb200_ctx *ctx, int n_rooms, int n_pins, int nwords, int conf_mode, msb200_mixer **out) {
+	MSB200_CHECK_ARG(ctx && out && n_rooms > 0 && n_pins > 0 && n_pins <= 50 /* MIXER_MAX_CHANNELS :29 */ && nwords > 0);
+	msb200_mixer *m = new msb200_mixer();
+	m->ctx = ctx;
+	m->n_rooms = n_rooms;
+	m->n_pins = n_pins;
+	m->nwords = nwords;
+	m->conf_mode = conf_mode;
+	size_t n = (size_t)n_rooms * n_pins;
+	m->h_gain.assign(n, 1.0f);  // channel_init :64-70
+	m->h_active.assign(n, 1);
+	m->dirty = true;
+	MSB200_CUDA(cudaMalloc(&m->d_gain, n * sizeof(float)));
+	MSB200_CUDA(cudaMalloc(&m->d_active, n));
+	*out = m;
+	return MSB200_OK;
+}
+void msb200_mixer_destroy(msb200_mixer *m) {
+	if (!m) return;
+	cudaStreamSynchronize(m->ctx->stream);
+	cudaFree(m->d_gain);
+	cudaFree(m->d_active);
+	m->in.release();
+	m->present.release();
+	m->out.release();
+	delete m;
+}
+int msb200_mixer_set_input_gain(msb200_mixer *m, int room, int pin, float gain) {
+	MSB200_CHECK_ARG(m && room >= 0 && room < m->n_rooms && pin >= 0 && pin < m->n_pins);
+	m->h_gain[(size_t)room * m->n_pins + pin] = gain;
+	m->dirty = true;
+	return MSB200_OK;
+}
+int msb200_mixer_set_active(msb200_mixer *m, int room, int pin, int active) {
+	MSB200_CHECK_ARG(m && room >= 0 && room < m->n_rooms && pin >= 0 && pin < m->n_pins);
+	m->h_active[(size_t)room * m->n_pins + pin] = active ? 1 : 0;
+	m->dirty = true;
+	return MSB200_OK;
+}
+int msb200_mixer_process_dev(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out) {
+	MSB200_CHECK_ARG(m && d_in && d_present && d_out);
+	return mixer_launch(m, d_in, d_present, d_out, nullptr, 0);
+}
+int msb200_mixer_partial_dev(msb200_mixer *m, const void *d_in, const void *d_present, void *d_sum) {
+	MSB200_CHECK_ARG(m && d_in && d_present && d_sum);
+	return mixer_launch(m, d_in, d_present, nullptr, d_sum, 1);
+}
+int msb200_mixer_finish_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *d_sum, void *d_out) {
+	MSB200_CHECK_ARG(m && d_in && d_present && d_sum && d_out);
+	return mixer_launch(m, d_in, d_present, d_out, (void *)d_sum, 2);
+}
+int msb200_mixer_process(msb200_mixer *m, const int16_t *in, const uint8_t *present, int16_t *out) {
+	MSB200_CHECK_ARG(m && in && present && out);
+	size_t nch = (size_t)m->n_rooms * m->n_pins;
+	size_t in_bytes = nch * m->nwords * 2;
+	size_t out_bytes = m->conf_mode ? in_bytes : (size_t)m->n_rooms * m->nwords * 2;
+	int r;
+	if ((r = m->in.reserve(in_bytes)) || (r = m->present.reserve(nch)) || (r = m->out.reserve(out_bytes))) return r;
+	cudaStream_t s = m->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(m->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaMemcpyAsync(m->present.p, present, nch, cudaMemcpyHostToDevice, s));
+	if ((r = mixer_launch(m, m->in.p, m->present.p, m->out.p, nullptr, 0))) return r;
+	MSB200_CUDA(cudaMemcpyAsync(out, m->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+} // extern "C"
+
+// ======================================================================================================= volume
+// reference: /root/reference/src/audiofilters/msvolume.c light path :503-513
+//   update_energy :388-407, volume_noise_gate_process :240-260, apply_gain :409-445, saturate :382-384
+
+struct msb200_volume {
+	msb200_ctx *ctx;
+	int n, rate, max_block;
+	msb200_volume_state *d_state;
+	msb200_devbuf io;
+};
+
+__device__ __forceinline__ int vol_sat(int v) { // :382-384
+	return v > 32767 ? 32767 : (v < -32767 ? -32767 : v);
+}
+
+// One warp per stream. The block is staged in shared memory by coalesced loads; lane 0 reproduces the reference's
+// strictly sequential float32 accumulation (acc += s*s) so `energy` is bit-exact; peak and DC sums are integer and
+// reduced across the warp; then all lanes apply the Q12 gain and store.
+__global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st,
+                                                     int n_streams, int nsamples, int stride) {
+	extern __shared__ short vsm[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int stream = blockIdx.x * (blockDim.x >> 5) + warp;
+	if (stream >= n_streams) return;
+	short *buf = vsm + (size_t)warp * ((nsamples + 1) & ~1);
+	short *g = io + (size_t)stream * stride;
+	int pk = 0, dcsum = 0;
+	for (int i = lane; i < nsamples; i += 32) {
+		int s = g[i];
+		buf[i] = (short)s;
+		int a = s < 0 ? -s : s;
+		pk = a > pk ? a : pk;
+		dcsum += s;
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		int opk = __shfl_xor_sync(0xffffffffu, pk, o);
+		pk = opk > pk ? opk : pk;
+		dcsum += __shfl_xor_sync(0xffffffffu, dcsum, o);
+	}
+	__syncwarp();
+	int intgain = 4096, apply = 0, dc_prev = 0, remove_dc = 0;
+	if (lane == 0) {
+		msb200_volume_state v = st[stream];
+		float acc = 0.f;
+		for (int i = 0; i < nsamples; ++i) {
+			int s = buf[i];
+			acc = __fadd_rn(acc, (float)(s * s));
+		}
+		const float max_e = 32768 * 0.7f;
+		// en = (float)((sqrt(acc / n) + 1) / max_e)  — float division, then double sqrt/add/div (C promotions)
+		float q = __fdiv_rn(acc, (float)nsamples);
+		float en = (float)((sqrt((double)q) + 1.0) / (double)max_e);
+		v.energy = __fadd_rn(__fmul_rn(en, 0.2f), __fmul_rn(v.energy, (1.0f - 0.2f)));
+		v.level_pk = __fdiv_rn((float)pk, max_e);
+		v.instant_energy = en;
+		float tgain = v.static_gain;
+		if (v.noise_gate_enabled) {
+			float t = v.ng_floorgain;
+			if (v.instant_energy > v.ng_threshold) {
+				v.ng_noise_dur = 400;
+				t = 1.0f;
+			} else if (v.ng_noise_dur > 0) {
+				v.ng_noise_dur -= (nsamples * 1000) / v.sample_rate;
+				t = 1.0f;
+			}
+			v.ng_gain = __fadd_rn(__fmul_rn(v.ng_gain, 0.75f), __fmul_rn(t, 0.25f));
+		}
+		if (v.gain < tgain) {
+			if (v.gain < v.ng_floorgain) v.gain = v.ng_floorgain;
+			v.gain = __fmul_rn(v.gain, v.fast_upramp ? (1 + 0.4f * 3) : (1 + 0.4f));
+			if (v.gain > tgain) v.gain = tgain;
+		} else if (v.gain > tgain) {
+			v.gain = __fmul_rn(v.gain, 1 - 0.4f);
+			if (v.gain < tgain) v.gain = tgain;
+			v.fast_upramp = 0;
+		}
+		float gain = __fmul_rn(v.gain, v.ng_gain);
+		intgain = __float2int_rz(__fmul_rn(gain, 4096.f));
+		remove_dc = v.remove_dc;
+		dc_prev = v.dc_offset;
+		apply = remove_dc ? 1 : (gain != 1.0f);
+		if (remove_dc) v.dc_offset = (v.dc_offset * 7 + dcsum * 2 / (nsamples * 2)) / 8;
+		st[stream] = v;
+	}
+	intgain = __shfl_sync(0xffffffffu, intgain, 0);
+	apply = __shfl_sync(0xffffffffu, apply, 0);
+	remove_dc = __shfl_sync(0xffffffffu, remove_dc, 0);
+	dc_prev = __shfl_sync(0xffffffffu, dc_prev, 0);
+	if (!apply) return; // gain == 1: the reference leaves the block untouched (:441)
+	for (int i = lane; i < nsamples; i += 32) {
+		int s = buf[i];
+		if (remove_dc) s -= dc_prev;
+		g[i] = (short)vol_sat((s * intgain) / 4096); // C truncating division
+	}
+}
+
+// stream == -1 applies the setter to every stream of the bank (one round trip)
+static int volume_update_state(msb200_volume *v, int stream, void (*fn)(msb200_volume_state *, float, int), float f, int i) {
+	MSB200_CHECK_ARG(v && stream >= -1 && stream < v->n);
+	const int first = stream < 0 ? 0 : stream, count = stream < 0 ? v->n : 1;
+	std::vector<msb200_volume_state> st((size_t)count);
+	cudaStream_t s = v->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(st.data(), v->d_state + first, sizeof(msb200_volume_state) * (size_t)count, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	for (auto &x : st) fn(&x, f, i);
+	MSB200_CUDA(cudaMemcpyAsync(v->d_state + first, st.data(), sizeof(msb200_volume_state) * (size_t)count, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+extern "C" {
+
+int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_volume **out) {
+	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && sample_rate > 0 && max_block > 0 && max_block <= 8192);
+	msb200_volume *v = new msb200_volume();
+	v->ctx = ctx;
+	v->n = n_streams;
+	v->rate = sample_rate;
+	v->max_block = max_block;
+	std::vector<msb200_volume_state> init((size_t)n_streams);
+	for (auto &s : init) { // volume_init :86-120
+		memset(&s, 0, sizeof(s));
+		s.static_gain = s.gain = s.target_gain = 1.f;
+		s.ng_threshold = 0.1f;
+		s.ng_floorgain = 0.005f;
+		s.ng_gain = 1.f;
+		s.sample_rate = sample_rate;
+	}
+	MSB200_CUDA(cudaMalloc(&v->d_state, sizeof(msb200_volume_state) * (size_t)n_streams));
+	MSB200_CUDA(cudaMemcpy(v->d_state, init.data(), sizeof(msb200_volume_state) * (size_t)n_streams, cudaMemcpyHostToDevice));
+	*out = v;
+	return MSB200_OK;
+}
+void msb200_volume_destroy(msb200_volume *v) {
+	if (!v) return;
+	cudaStreamSynchronize(v->ctx->stream);
+	cudaFree(v->d_state);
+	v->io.release();
+	delete v;
+}
+int msb200_volume_set_gain(msb200_volume *v, int stream, float gain) { // volume_set_gain :270-276
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) { s->gain = s->target_gain = s->static_gain = f; }, gain, 0);
+}
+int msb200_volume_set_db_gain(msb200_volume *v, int stream, float db) { // volume_set_db_gain :262-268 (pow(10, db/10), sic)
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) { s->gain = s->static_gain = (float)pow(10, f / 10); }, db, 0);
+}
+int msb200_volume_enable_noise_gate(msb200_volume *v, int stream, int enabled) { // :352-359
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float, int e) {
+		s->noise_gate_enabled = e ? 1 : 0;
+		if (s->noise_gate_enabled) s->gain = s->target_gain = s->ng_floorgain;
+	}, 0.f, enabled);
+}
+int msb200_volume_set_noise_gate_threshold(msb200_volume *v, int stream, float thr) {
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) { s->ng_threshold = f; }, thr, 0);
+}
+int msb200_volume_set_noise_gate_floorgain(msb200_volume *v, int stream, float g) { // :367-378
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) {
+		s->ng_floorgain = f < 0.005f ? 0.005f : f;
+		if (s->noise_gate_enabled) s->gain = s->target_gain = s->ng_floorgain;
+	}, g, 0);
+}
+int msb200_volume_remove_dc(msb200_volume *v, int stream, int enabled) {
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float, int e) { s->remove_dc = e; }, 0.f, enabled);
+}
+int msb200_volume_get_state(msb200_volume *v, int stream, msb200_volume_state *st) {
+	MSB200_CHECK_ARG(v && st && stream >= 0 && stream < v->n);
+	MSB200_CUDA(cudaMemcpyAsync(st, v->d_state + stream, sizeof(*st), cudaMemcpyDeviceToHost, v->ctx->stream));
+	MSB200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+	return MSB200_OK;
+}
+int msb200_volume_process_dev(msb200_volume *v, void *d_io, int nsamples, int stride) {
+	MSB200_CHECK_ARG(v && d_io && nsamples > 0 && nsamples <= v->max_block && stride >= nsamples);
+	const int warps = 8;
+	size_t smem = (size_t)warps * ((nsamples + 1) & ~1) * sizeof(short);
+	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->n, warps), warps * 32, smem, (short *)d_io, v->d_state, v->n,
+	              nsamples, stride);
+	return MSB200_OK;
+}
+int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples) {
+	MSB200_CHECK_ARG(v && io);
+	size_t bytes = (size_t)v->n * nsamples * 2;
+	int r = v->io.reserve(bytes);
+	if (r) return r;
+	cudaStream_t s = v->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(v->io.p, io, bytes, cudaMemcpyHostToDevice, s));
+	if ((r = msb200_volume_process_dev(v, v->io.p, nsamples, nsamples))) return r;
+	MSB200_CUDA(cudaMemcpyAsync(io, v->io.p, bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+} // extern "C"
+
+// ======================================================================================================= channel adapter
+// reference: /root/reference/src/audiofilters/chanadapt.c:68-131
+
+__global__ void chanadapt_kernel(const short *__restrict__ in, const short *__restrict__ in2, short *__restrict__ out,
+                                 long total, int mode) {
+	long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long step = (long)gridDim.x * blockDim.x;
+	for (; i < total; i += step) {
+		if (mode == MSB200_CHAN_MONO_TO_STEREO) { // :112-120
+			int s = (unsigned short)in[i];
+			reinterpret_cast<int *>(out)[i] = s | (s << 16);
+		} else if (mode == MSB200_CHAN_STEREO_TO_MONO) { // :121-129 (left channel)
+			out[i] = (short)(reinterpret_cast<const int *>(in)[i] & 0xffff);
+		} else { // :78-96 (absent pin -> zeros)
+			int l = in ? (unsigned short)in[i] : 0, r = in2 ? (unsigned short)in2[i] : 0;
+			reinterpret_cast<int *>(out)[i] = l | (r << 16);
+		}
+	}
+}
+
+extern "C" {
+int msb200_chanadapt_process_dev(msb200_ctx *ctx, int mode, int n_streams, int frames, const void *d_in,
+                                 const void *d_in2, void *d_out) {
+	MSB200_CHECK_ARG(ctx && d_out && n_streams > 0 && frames > 0 && mode >= 0 && mode <= 2);
+	MSB200_CHECK_ARG(mode == MSB200_CHAN_2MONO_TO_STEREO || d_in != nullptr);
+	long total = (long)n_streams * frames;
+	int block = 256;
+	long want = (total + block - 1) / block;
+	int grid = (int)(want < (long)ctx->sm_count * 16 ? want : (long)ctx->sm_count * 16);
+	MSB200_LAUNCH(ctx, chanadapt_kernel, grid, block, 0, (const short *)d_in, (const short *)d_in2, (short *)d_out, total, mode);
+	return MSB200_OK;
+}
+int msb200_chanadapt_process(msb200_ctx *ctx, int mode, int n_streams, int frames, const int16_t *in, const int16_t *in2,
+                             int16_t *out) {
+	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && frames > 0 && mode >= 0 && mode <= 2);
+	size_t mono = (size_t)n_streams * frames * 2;
+	size_t in_bytes = mode == MSB200_CHAN_STEREO_TO_MONO ? mono * 2 : mono;
+	size_t out_bytes = mode == MSB200_CHAN_STEREO_TO_MONO ? mono : mono * 2;
+	void *d_in = nullptr, *d_in2 = nullptr, *d_out = nullptr;
+	cudaStream_t s = ctx->stream;
+	MSB200_CUDA(cudaMalloc(&d_out, out_bytes));
+	if (in) {
+		MSB200_CUDA(cudaMalloc(&d_in, in_bytes));
+		MSB200_CUDA(cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
+	}
+	if (in2 && mode == MSB200_CHAN_2MONO_TO_STEREO) {
+		MSB200_CUDA(cudaMalloc(&d_in2, in_bytes));
+		MSB200_CUDA(cudaMemcpyAsync(d_in2, in2, in_bytes, cudaMemcpyHostToDevice, s));
+	}
+	int r = msb200_chanadapt_process_dev(ctx, mode, n_streams, frames, d_in, d_in2, d_out);
+	if (!r) {
+		cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s);
+		cudaStreamSynchronize(s);
+	}
+	cudaFree(d_in);
+	cudaFree(d_in2);
+	cudaFree(d_out);
+	return r;
+}
+} // extern "C"
+
+// ======================================================================================================= equalizer
+// reference: /root/reference/src/audiofilters/equalizer.c:263-288, /root/reference/src/utils/dsptools.c:253-268
+
+struct msb200_equalizer {
+	msb200_ctx *ctx;
+	int n, rate, nfft, max_block;
+	float *d_taps;      // [stream][nfft]
+	float *d_hist;      // [stream][nfft-1] previous inputs, oldest first
+	uint8_t *d_active;  // [stream]
+	std::vector<std::vector<float>> fft_cpx; // host gain tables, packed real spectrum (equalizer.c:49-55)
+	msb200_devbuf io;
+};
+
+// x86 semantics of the C cast (int16_t)float in word16_to_int16 (equalizer.c:251-255): truncate to int32
+// (out-of-range -> 0x80000000), keep the low 16 bits.
+__device__ __forceinline__ short c_cast_f32_s16(float f) {
+	int i;
+	if (!(f > -2147483904.0f && f < 2147483648.0f)) i = (int)0x80000000u;
+	else i = __float2int_rz(f);
+	return (short)(i & 0xffff);
+}
+
+// One CTA per stream, one thread per output sample. x[] = history (ord-1) ++ block in shared memory as float.
+// y[i] = sum_{j=ord-1..0} num[j]*x[i-j], accumulated in exactly that order with separate multiply and add.
+__global__ void __launch_bounds__(512) eq_fir_kernel(short *__restrict__ io, const float *__restrict__ taps,
+                                                     float *__restrict__ hist, const uint8_t *__restrict__ active,
+                                                     int nsamples, int stride, int ord) {
+	extern __shared__ float esm[];
+	float *num = esm;          // [ord]
+	float *x = esm + ord;      // [ord-1 + nsamples]
+	const int stream = blockIdx.x;
+	if (!active[stream]) return;
+	short *g = io + (size_t)stream * stride;
+	float *h = hist + (size_t)stream * (ord - 1);
+	for (int i = threadIdx.x; i < ord; i += blockDim.x) num[i] = taps[(size_t)stream * ord + i];
+	for (int i = threadIdx.x; i < ord - 1; i += blockDim.x) x[i] = h[i];
+	for (int i = threadIdx.x; i < nsamples; i += blockDim.x) x[ord - 1 + i] = (float)g[i];
+	__syncthreads();
+	for (int i = threadIdx.x; i < nsamples; i += blockDim.x) {
+		const float *xi = x + i; // xi[ord-1-j] == x[i-j] in block coordinates
+		float acc = __fmul_rn(xi[0], num[ord - 1]);
+#pragma unroll 8
+		for (int j = ord - 2; j >= 0; --j) acc = __fadd_rn(acc, __fmul_rn(num[j], xi[ord - 1 - j]));
+		g[i] = c_cast_f32_s16(acc);
+	}
+	// new history = last ord-1 inputs
+	for (int i = threadIdx.x; i < ord - 1; i += blockDim.x) h[i] = x[nsamples + i];
+}
+
+static void eq_flatten(std::vector<float> &t, int nfft) { // equalizer_state_flatten :49-55
+	t.assign((size_t)nfft, 0.f);
+	float val = 1.0f / (float)nfft;
+	t[0] = val;
+	for (int i = 1; i < nfft; i += 2) t[(size_t)i] = val;
+}
+static int eq_hz_to_index(int rate, int nfft, int hz) { // :98-111
+	if (hz < 0) return -1;
+	if (hz > rate / 2) hz = rate / 2;
+	int ret = ((hz * nfft) + (rate / 2)) / rate;
+	if (ret == nfft / 2) ret = (nfft / 2) - 1;
+	return ret;
+}
+static int eq_index2hz(int rate, int nfft, int index) { // :113-115
+	return (index * rate + nfft / 2) / nfft;
+}
+static float eq_gainpoint(int f, int freq_0, float sqrt_gain, int freq_bw) { // :131-138
+	float k1 = ((float)(f * f) - (float)(freq_0 * freq_0));
+	k1 *= k1;
+	float k2 = (float)(f * freq_bw);
+	k2 *= k2;
+	return (k1 + k2 * sqrt_gain) / (k1 + k2 / sqrt_gain);
+}
+static void eq_point_set(std::vector<float> &t, int nfft, int i, float gain) { // :140-148
+	int index = 1 + ((i - 1) * 2);
+	if (index >= 0 && index < nfft) t[(size_t)index] = (t[(size_t)index] * (float)(int)(gain * 32768)) / 32768;
+}
+// gain table -> impulse response: ms_ifft (unnormalised packed-real inverse, kiss_fftr.c:261-296) + time_shift
+// (equalizer.c:184-193) + Hamming (:203-213). The inverse transform is evaluated directly in double precision.
+static void eq_design(const std::vector<float> &spec, int n, std::vector<float> &fir) {
+	fir.assign((size_t)n, 0.f);
+	const int half = n / 2;
+	std::vector<double> ct((size_t)n), sn((size_t)n);
+	for (int i = 0; i < n; ++i) {
+		ct[(size_t)i] = cos(2.0 * M_PI * i / n);
+		sn[(size_t)i] = sin(2.0 * M_PI * i / n);
+	}
+	for (int t = 0; t < n; ++t) {
+		double acc = (double)spec[0] + ((t & 1) ? -(double)spec[(size_t)n - 1] : (double)spec[(size_t)n - 1]);
+		for (int k = 1; k < half; ++k) {
+			size_t a = (size_t)(((long)k * t) % n);
+			acc += 2.0 * ((double)spec[(size_t)(2 * k - 1)] * ct[a] - (double)spec[(size_t)(2 * k)] * sn[a]);
+		}
+		fir[(size_t)((t + half) % n)] = (float)acc; // time shift: swap halves
+	}
+	for (int i = 0; i < n; ++i) {
+		float x = (float)((float)i * 2 * M_PI / (float)n);
+		float w = (float)(0.54 - (0.46 * cos(x)));
+		fir[(size_t)i] = w * fir[(size_t)i];
+	}
+}
+static int eq_upload_taps(msb200_equalizer *e, int stream) {
+	std::vector<float> fir;
+	eq_design(e->fft_cpx[(size_t)stream], e->nfft, fir);
+	MSB200_CUDA(cudaMemcpyAsync(e->d_taps + (size_t)stream * e->nfft, fir.data(), sizeof(float) * (size_t)e->nfft,
+	                            cudaMemcpyHostToDevice, e->ctx->stream));
+	MSB200_CUDA(cudaStreamSynchronize(e->ctx->stream));
+	return MSB200_OK;
+}
+
+extern "C" {
+
+int msb200_equalizer_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_equalizer **out) {
+	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && sample_rate > 0 && max_block > 0 && max_block <= 8192);
+	msb200_equalizer *e = new msb200_equalizer();
+	e->ctx = ctx;
+	e->n = n_streams;
+	e->rate = sample_rate;
+	e->nfft = sample_rate < 16000 ? 128 : (sample_rate < 32000 ? 256 : 512); // equalizer_rate_update :57-79
+	e->max_block = max_block;
+	e->fft_cpx.resize((size_t)n_streams);
+	MSB200_CUDA(cudaMalloc(&e->d_taps, sizeof(float) * (size_t)n_streams * e->nfft));
+	MSB200_CUDA(cudaMalloc(&e->d_hist, sizeof(float) * (size_t)n_streams * (e->nfft - 1)));
+	MSB200_CUDA(cudaMalloc(&e->d_active, (size_t)n_streams));
+	MSB200_CUDA(cudaMemset(e->d_hist, 0, sizeof(float) * (size_t)n_streams * (e->nfft - 1)));
+	MSB200_CUDA(cudaMemset(e->d_active, 1, (size_t)n_streams));
+	std::vector<float> flat, fir, all((size_t)n_streams * e->nfft);
+	eq_flatten(flat, e->nfft);
+	eq_design(flat, e->nfft, fir);
+	for (int s = 0; s < n_streams; ++s) {
+		e->fft_cpx[(size_t)s] = flat;
+		memcpy(&all[(size_t)s * e->nfft], fir.data(), sizeof(float) * (size_t)e->nfft);
+	}
+	MSB200_CUDA(cudaMemcpy(e->d_taps, all.data(), sizeof(float) * all.size(), cudaMemcpyHostToDevice));
+	*out = e;
+	return MSB200_OK;
+}
+void msb200_equalizer_destroy(msb200_equalizer *e) {
+	if (!e) return;
+	cudaStreamSynchronize(e->ctx->stream);
+	cudaFree(e->d_taps);
+	cudaFree(e->d_hist);
+	cudaFree(e->d_active);
+	e->io.release();
+	delete e;
+}
+int msb200_equalizer_nfft(msb200_equalizer *e) {
+	return e ? e->nfft : MSB200_EINVAL;
+}
+int msb200_equalizer_set_gain(msb200_equalizer *e, int stream, float frequency, float gain, float width) {
+	MSB200_CHECK_ARG(e && stream >= 0 && stream < e->n);
+	// equalizer_state_set :150-177
+	std::vector<float> &t = e->fft_cpx[(size_t)stream];
+	const int rate = e->rate, nfft = e->nfft;
+	int freq_0 = (int)frequency, freq_bw = (int)width, i, f;
+	int delta_f = eq_index2hz(rate, nfft, 1);
+	float sqrt_gain = (float)sqrt(gain);
+	int mid = eq_hz_to_index(rate, nfft, freq_0);
+	MSB200_CHECK_ARG(mid >= 0);
+	freq_bw -= delta_f / 2;
+	if (freq_bw < delta_f / 2) freq_bw = delta_f / 2;
+	i = mid;
+	eq_point_set(t, nfft, i, gain);
+	do {
+		i++;
+		f = eq_index2hz(rate, nfft, i);
+		gain = eq_gainpoint(f - delta_f, freq_0, sqrt_gain, freq_bw);
+		eq_point_set(t, nfft, i, gain);
+	} while (i < nfft / 2 && (gain > 1.1 || gain < 0.9));
+	i = mid;
+	do {
+		i--;
+		f = eq_index2hz(rate, nfft, i);
+		gain = eq_gainpoint(f + delta_f, freq_0, sqrt_gain, freq_bw);
+		eq_point_set(t, nfft, i, gain);
+	} while (i >= 0 && (gain > 1.1 || gain < 0.9));
+	return eq_upload_taps(e, stream);
+}
+int msb200_equalizer_get_gain(msb200_equalizer *e, int stream, float frequency, float *gain) { // :121-125
+	MSB200_CHECK_ARG(e && gain && stream >= 0 && stream < e->n);
+	int idx = eq_hz_to_index(e->rate, e->nfft, (int)frequency);
+	*gain = idx >= 0 ? e->fft_cpx[(size_t)stream][(size_t)idx * 2] * (float)e->nfft : 0.f;
+	return MSB200_OK;
+}
+int msb200_equalizer_set_active(msb200_equalizer *e, int stream, int active) {
+	MSB200_CHECK_ARG(e && stream >= 0 && stream < e->n);
+	uint8_t a = active ? 1 : 0;
+	MSB200_CUDA(cudaMemcpyAsync(e->d_active + stream, &a, 1, cudaMemcpyHostToDevice, e->ctx->stream));
+	MSB200_CUDA(cudaStreamSynchronize(e->ctx->stream));
+	return MSB200_OK;
+}
+int msb200_equalizer_set_taps(msb200_equalizer *e, int stream, const float *taps) {
+	MSB200_CHECK_ARG(e && taps && stream >= 0 && stream < e->n);
+	MSB200_CUDA(cudaMemcpyAsync(e->d_taps + (size_t)stream * e->nfft, taps, sizeof(float) * (size_t)e->nfft,
+	                            cudaMemcpyHostToDevice, e->ctx->stream));
+	MSB200_CUDA(cudaStreamSynchronize(e->ctx->stream));
+	return MSB200_OK;
+}
+int msb200_equalizer_get_taps(msb200_equalizer *e, int stream, float *taps) {
+	MSB200_CHECK_ARG(e && taps && stream >= 0 && stream < e->n);
+	MSB200_CUDA(cudaMemcpyAsync(taps, e->d_taps + (size_t)stream * e->nfft, sizeof(float) * (size_t)e->nfft,
+	                            cudaMemcpyDeviceToHost, e->ctx->stream));
+	MSB200_CUDA(cudaStreamSynchronize(e->ctx->stream));
+	return MSB200_OK;
+}
+int msb200_equalizer_process_dev(msb200_equalizer *e, void *d_io, int nsamples, int stride) {
+	MSB200_CHECK_ARG(e && d_io && nsamples > 0 && nsamples <= e->max_block && stride >= nsamples);
+	size_t smem = sizeof(float) * (size_t)(e->nfft + e->nfft - 1 + nsamples);
+	int block = nsamples >= 512 ? 512 : ((nsamples + 31) & ~31);
+	if (smem > 48 * 1024) MSB200_CUDA(cudaFuncSetAttribute(eq_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	MSB200_LAUNCH(e->ctx, eq_fir_kernel, e->n, block, smem, (short *)d_io, e->d_taps, e->d_hist, e->d_active, nsamples,
+	              stride, e->nfft);
+	return MSB200_OK;
+}
+int msb200_equalizer_process(msb200_equalizer *e, int16_t *io, int nsamples) {
+	MSB200_CHECK_ARG(e && io);
+	size_t bytes = (size_t)e->n * nsamples * 2;
+	int r = e->io.reserve(bytes);
+	if (r) return r;
+	cudaStream_t s = e->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(e->io.p, io, bytes, cudaMemcpyHostToDevice, s));
+	if ((r = msb200_equalizer_process_dev(e, e->io.p, nsamples, nsamples))) return r;
+	MSB200_CUDA(cudaMemcpyAsync(io, e->io.p, bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,80 @@
+// msb200_internal.h — shared internals of libmsb200dsp.so (not installed; the public ABI is include/msb200dsp.h)
+#pragma once
+#include "msb200dsp.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+struct msb200_ctx {
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+	uint64_t launches = 0;
+	void *flush_buf = nullptr; // > L2, written by msb200_flush_l2
+	size_t flush_bytes = 0;
+};
+
+void msb200_set_error(const char *fmt, ...);
+
+#define MSB200_CUDA(expr)                                                                                              \
+	do {                                                                                                               \
+		cudaError_t _e = (expr);                                                                                       \
+		if (_e != cudaSuccess) {                                                                                       \
+			msb200_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));                    \
+			return MSB200_ECUDA;                                                                                       \
+		}                                                                                                              \
+	} while (0)
+
+#define MSB200_CHECK_ARG(cond)                                                                                         \
+	do {                                                                                                               \
+		if (!(cond)) {                                                                                                 \
+			msb200_set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond);                                \
+			return MSB200_EINVAL;                                                                                      \
+		}                                                                                                              \
+	} while (0)
+
+// every kernel launch goes through this so the launch counter is honest
+#define MSB200_LAUNCH(ctx, kernel, grid, block, smem, ...)                                                             \
+	do {                                                                                                               \
+		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                               \
+		(ctx)->launches++;                                                                                             \
+		cudaError_t _e = cudaGetLastError();                                                                           \
+		if (_e != cudaSuccess) {                                                                                       \
+			msb200_set_error("%s:%d: launch %s -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(_e));           \
+			return MSB200_ECUDA;                                                                                       \
+		}                                                                                                              \
+	} while (0)
+
+static inline int msb200_div_up(int a, int b) {
+	return (a + b - 1) / b;
+}
+
+// device scratch that grows on demand (per object staging of host-path calls)
+struct msb200_devbuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t bytes) {
+		if (bytes <= cap) return MSB200_OK;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		cudaError_t e = cudaMalloc(&p, bytes);
+		if (e != cudaSuccess) {
+			msb200_set_error("cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+			return MSB200_ENOMEM;
+		}
+		cap = bytes;
+		return MSB200_OK;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};

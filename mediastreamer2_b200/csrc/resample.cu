@@ -1,0 +1,284 @@
+// resample.cu — MSResample: batched polyphase sinc resampler (speexdsp quality 3 "VOIP" design).
+//
+// Replaces resample_process_ms2() /root/reference/src/audiofilters/msresample.c:122-179, i.e.
+// speex_resampler_process_int() of the external speexdsp library (restated in oracle/oracle_resample.c — see the
+// provenance note there). Filter design (Kaiser-windowed sinc table) runs once on the host at bank creation; the
+// per-tick work is one kernel: CTA per (stream, channel), thread per output sample, 48-tap (or filt_len-tap)
+// float32 dot product accumulated in the library's sequential order with separate multiply and add.
+#include "msb200_internal.h"
+
+#include <cmath>
+
+// ----------------------------------------------------------------------------------------------- host: filter design
+namespace {
+
+const double kaiser8_table[36] = {
+    0.99537781, 1.00000000, 0.99537781, 0.98162644, 0.95908712, 0.92831446, 0.89005583, 0.84522401, 0.79486424,
+    0.74011713, 0.68217934, 0.62226347, 0.56155915, 0.50119680, 0.44221549, 0.38553619, 0.33194107, 0.28205962,
+    0.23636152, 0.19515633, 0.15859932, 0.12670280, 0.09935205, 0.07632451, 0.05731132, 0.04193980, 0.02979584,
+    0.02044510, 0.01345224, 0.00839739, 0.00481569, 0.00247437, 0.00112393, 0.00042834, 0.00011921, 0.00000000};
+const int kaiser8_oversample = 32;
+
+// window lookup with the library's cubic interpolation (float index arithmetic, double accumulation)
+double window_func(float x) {
+	float y = x * (float)kaiser8_oversample;
+	int ind = (int)floor(y);
+	float frac = y - (float)ind;
+	double c3 = -0.1666666667 * frac + 0.1666666667 * (frac * frac * frac);
+	double c2 = frac + 0.5 * (frac * frac) - 0.5 * (frac * frac * frac);
+	double c0 = -0.3333333333 * frac + 0.5 * (frac * frac) - 0.1666666667 * (frac * frac * frac);
+	double c1 = 1.f - c3 - c2 - c0;
+	return c0 * kaiser8_table[ind] + c1 * kaiser8_table[ind + 1] + c2 * kaiser8_table[ind + 2] + c3 * kaiser8_table[ind + 3];
+}
+float sinc_point(float cutoff, float x, int N) {
+	float xx = x * cutoff;
+	if (fabs(x) < 1e-6) return cutoff;
+	if (fabs(x) > .5 * N) return 0;
+	return (float)(cutoff * sin(M_PI * xx) / (M_PI * xx) * window_func((float)fabs(2. * x / N)));
+}
+uint32_t gcd_u32(uint32_t a, uint32_t b) {
+	while (b) {
+		uint32_t t = a % b;
+		a = b;
+		b = t;
+	}
+	return a;
+}
+
+struct ResampleDesign {
+	uint32_t num, den, filt_len, oversample;
+	int int_advance, frac_advance, use_direct;
+	std::vector<float> table;
+};
+
+// quality 3: base_length 48, oversample 8, downsample_bw 0.895, upsample_bw 0.917, Kaiser-8 window
+void design(uint32_t in_rate, uint32_t out_rate, ResampleDesign &d) {
+	uint32_t g = gcd_u32(in_rate, out_rate);
+	d.num = in_rate / g;
+	d.den = out_rate / g;
+	d.int_advance = (int)(d.num / d.den);
+	d.frac_advance = (int)(d.num % d.den);
+	d.oversample = 8;
+	d.filt_len = 48;
+	float cutoff;
+	if (d.num > d.den) {
+		cutoff = 0.895f * (float)d.den / (float)d.num;
+		d.filt_len = (uint32_t)(((uint64_t)d.filt_len * d.num) / d.den);
+		d.filt_len = ((d.filt_len - 1) & (~0x7u)) + 8;
+		if (2 * d.den < d.num) d.oversample >>= 1;
+		if (4 * d.den < d.num) d.oversample >>= 1;
+		if (8 * d.den < d.num) d.oversample >>= 1;
+		if (16 * d.den < d.num) d.oversample >>= 1;
+		if (d.oversample < 1) d.oversample = 1;
+	} else {
+		cutoff = 0.917f;
+	}
+	d.use_direct = d.filt_len * d.den <= d.filt_len * d.oversample + 8;
+	if (d.use_direct) {
+		d.table.assign((size_t)d.filt_len * d.den, 0.f);
+		for (uint32_t i = 0; i < d.den; i++)
+			for (int32_t j = 0; j < (int32_t)d.filt_len; j++)
+				d.table[(size_t)i * d.filt_len + (size_t)j] =
+				    sinc_point(cutoff, ((float)(j - (int32_t)d.filt_len / 2 + 1) - ((float)i) / (float)d.den), (int)d.filt_len);
+	} else {
+		d.table.assign((size_t)d.filt_len * d.oversample + 8, 0.f);
+		for (int32_t i = -4; i < (int32_t)(d.oversample * d.filt_len + 4); i++)
+			d.table[(size_t)(i + 4)] =
+			    sinc_point(cutoff, ((float)i / (float)d.oversample - (float)(d.filt_len / 2)), (int)d.filt_len);
+	}
+}
+
+} // namespace
+
+// ----------------------------------------------------------------------------------------------- device
+struct ResampleParams {
+	int filt_len, den, oversample, int_advance, frac_advance, use_direct, table_len, nch;
+};
+
+__device__ __forceinline__ short word2int(float x) { // speexdsp arch.h WORD2INT (float build)
+	return (short)(x < -32767.5f ? -32768 : (x > 32766.5f ? 32767 : (int)floorf(.5f + x)));
+}
+
+// grid = (n_streams * nch); hist: [stream][ch][filt_len-1] s16 (exact: the library keeps the same integers as float)
+__global__ void __launch_bounds__(256)
+    resample_kernel(const short *__restrict__ in, int in_frames, int in_stride, short *__restrict__ out, int out_frames,
+                    int out_stride, short *__restrict__ hist, const float *__restrict__ table, ResampleParams p,
+                    int last_sample0, int samp_frac0) {
+	extern __shared__ float rsm[];
+	float *tab = rsm;               // [table_len]
+	float *x = rsm + p.table_len;   // [filt_len-1 + in_frames]
+	const int N = p.filt_len;
+	const int stream = blockIdx.x / p.nch, ch = blockIdx.x % p.nch;
+	const short *gin = in + ((size_t)stream * in_stride) * p.nch + ch;
+	short *gout = out + ((size_t)stream * out_stride) * p.nch + ch;
+	short *h = hist + ((size_t)stream * p.nch + ch) * (N - 1);
+	for (int i = threadIdx.x; i < p.table_len; i += blockDim.x) tab[i] = table[i];
+	for (int i = threadIdx.x; i < N - 1; i += blockDim.x) x[i] = (float)h[i];
+	for (int i = threadIdx.x; i < in_frames; i += blockDim.x) x[N - 1 + i] = (float)gin[(size_t)i * p.nch];
+	__syncthreads();
+	for (int k = threadIdx.x; k < out_frames; k += blockDim.x) {
+		// closed form of the library's (last_sample, samp_frac_num) recurrence after k outputs
+		long t = (long)samp_frac0 + (long)k * p.frac_advance;
+		int last = last_sample0 + k * p.int_advance + (int)(t / p.den);
+		int frac = (int)(t % p.den);
+		const float *iptr = x + last;
+		float y;
+		if (p.use_direct) { // resampler_basic_direct_single
+			const float *sinct = tab + (size_t)frac * N;
+			float sum = 0.f;
+#pragma unroll 8
+			for (int j = 0; j < N; ++j) sum = __fadd_rn(sum, __fmul_rn(sinct[j], iptr[j]));
+			y = sum;
+		} else { // resampler_basic_interpolate_single
+			const int offset = frac * p.oversample / p.den;
+			const float fr = __fdiv_rn((float)((frac * p.oversample) % p.den), (float)p.den);
+			float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+			for (int j = 0; j < N; ++j) {
+				const float c = iptr[j];
+				const float *tp = tab + 4 + (j + 1) * p.oversample - offset;
+				a0 = __fadd_rn(a0, __fmul_rn(c, tp[-2]));
+				a1 = __fadd_rn(a1, __fmul_rn(c, tp[-1]));
+				a2 = __fadd_rn(a2, __fmul_rn(c, tp[0]));
+				a3 = __fadd_rn(a3, __fmul_rn(c, tp[1]));
+			}
+			// cubic_coef(): evaluated left to right in float, interp[2] through double (the literal 1. is a double)
+			float f2 = __fmul_rn(fr, fr), f3 = __fmul_rn(f2, fr);
+			float i0 = __fadd_rn(__fmul_rn(-0.16667f, fr), __fmul_rn(__fmul_rn(__fmul_rn(0.16667f, fr), fr), fr));
+			float i1 = __fsub_rn(__fadd_rn(fr, __fmul_rn(__fmul_rn(0.5f, fr), fr)), __fmul_rn(__fmul_rn(__fmul_rn(0.5f, fr), fr), fr));
+			float i3 = __fsub_rn(__fadd_rn(__fmul_rn(-0.33333f, fr), __fmul_rn(__fmul_rn(0.5f, fr), fr)),
+			                     __fmul_rn(__fmul_rn(__fmul_rn(0.16667f, fr), fr), fr));
+			float i2 = (float)(1. - (double)i0 - (double)i1 - (double)i3);
+			(void)f2; (void)f3;
+			y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(i0, a0), __fmul_rn(i1, a1)), __fmul_rn(i2, a2)), __fmul_rn(i3, a3));
+		}
+		gout[(size_t)k * p.nch] = word2int(y);
+	}
+	__syncthreads();
+	// mem[j] = mem[j + in_frames] for j < N-1
+	for (int i = threadIdx.x; i < N - 1; i += blockDim.x) h[i] = (short)x[i + in_frames];
+}
+
+struct msb200_resample {
+	msb200_ctx *ctx;
+	int n, in_rate, out_rate, nch, max_in;
+	ResampleDesign d;
+	ResampleParams p;
+	float *d_table;
+	short *d_hist;
+	int last_sample, samp_frac; // bank-wide phase (all streams are fed in lockstep)
+	msb200_devbuf in, out;
+};
+
+// how many outputs the library loop produces for `in_frames` inputs from phase (last, frac), capped at out_cap;
+// also returns the phase after the call (speex_resampler_process_native bookkeeping)
+static int resample_count(const ResampleDesign &d, int in_frames, int out_cap, int &last, int &frac) {
+	int out = 0;
+	int l = last, f = frac;
+	// closed form would do; the loop is <= out_cap iterations of integer adds per CALL (not per stream)
+	while (!(l >= in_frames || out >= out_cap)) {
+		out++;
+		l += d.int_advance;
+		f += d.frac_advance;
+		if (f >= (int)d.den) {
+			f -= (int)d.den;
+			l++;
+		}
+	}
+	int consumed = in_frames;
+	if (l < in_frames) consumed = l;
+	last = l - consumed;
+	frac = f;
+	return out;
+}
+
+extern "C" {
+
+int msb200_resample_create(msb200_ctx *ctx, int n_streams, int in_rate, int out_rate, int nchannels, int max_in_frames,
+                           msb200_resample **out) {
+	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && in_rate > 0 && out_rate > 0 && in_rate != out_rate);
+	MSB200_CHECK_ARG(nchannels >= 1 && nchannels <= 8 && max_in_frames > 0 && max_in_frames <= 16384);
+	msb200_resample *r = new msb200_resample();
+	r->ctx = ctx;
+	r->n = n_streams;
+	r->in_rate = in_rate;
+	r->out_rate = out_rate;
+	r->nch = nchannels;
+	r->max_in = max_in_frames;
+	design((uint32_t)in_rate, (uint32_t)out_rate, r->d);
+	r->p.filt_len = (int)r->d.filt_len;
+	r->p.den = (int)r->d.den;
+	r->p.oversample = (int)r->d.oversample;
+	r->p.int_advance = r->d.int_advance;
+	r->p.frac_advance = r->d.frac_advance;
+	r->p.use_direct = r->d.use_direct;
+	r->p.table_len = (int)r->d.table.size();
+	r->p.nch = nchannels;
+	r->last_sample = 0;
+	r->samp_frac = 0;
+	size_t smem = sizeof(float) * ((size_t)r->p.table_len + r->d.filt_len - 1 + (size_t)max_in_frames);
+	if (smem > 200 * 1024) {
+		msb200_set_error("resampler %d->%d with %d frames/call needs %zu B of shared memory", in_rate, out_rate, max_in_frames, smem);
+		delete r;
+		return MSB200_EINVAL;
+	}
+	if (smem > 48 * 1024)
+		MSB200_CUDA(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	size_t hist = (size_t)n_streams * nchannels * (r->d.filt_len - 1);
+	MSB200_CUDA(cudaMalloc(&r->d_table, sizeof(float) * r->d.table.size()));
+	MSB200_CUDA(cudaMalloc(&r->d_hist, sizeof(short) * hist));
+	MSB200_CUDA(cudaMemcpy(r->d_table, r->d.table.data(), sizeof(float) * r->d.table.size(), cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemset(r->d_hist, 0, sizeof(short) * hist));
+	*out = r;
+	return MSB200_OK;
+}
+void msb200_resample_destroy(msb200_resample *r) {
+	if (!r) return;
+	cudaStreamSynchronize(r->ctx->stream);
+	cudaFree(r->d_table);
+	cudaFree(r->d_hist);
+	r->in.release();
+	r->out.release();
+	delete r;
+}
+int msb200_resample_max_out(msb200_resample *r, int in_frames) { // msresample.c:151-152
+	if (!r || in_frames < 0) return MSB200_EINVAL;
+	return (int)(((uint64_t)in_frames * (uint32_t)r->out_rate) / (uint32_t)r->in_rate) + 1;
+}
+int msb200_resample_reset(msb200_resample *r) {
+	MSB200_CHECK_ARG(r);
+	r->last_sample = r->samp_frac = 0;
+	MSB200_CUDA(cudaMemsetAsync(r->d_hist, 0, sizeof(short) * (size_t)r->n * r->nch * (r->d.filt_len - 1), r->ctx->stream));
+	return MSB200_OK;
+}
+int msb200_resample_process_dev(msb200_resample *r, const void *d_in, int in_frames, int in_stride, void *d_out,
+                                int out_stride, int *out_frames) {
+	MSB200_CHECK_ARG(r && d_in && d_out && in_frames > 0 && in_frames <= r->max_in && in_stride >= in_frames);
+	int cap = msb200_resample_max_out(r, in_frames);
+	MSB200_CHECK_ARG(out_stride >= cap);
+	int last0 = r->last_sample, frac0 = r->samp_frac;
+	int n_out = resample_count(r->d, in_frames, cap, r->last_sample, r->samp_frac);
+	if (out_frames) *out_frames = n_out;
+	size_t smem = sizeof(float) * ((size_t)r->p.table_len + r->d.filt_len - 1 + (size_t)in_frames);
+	int block = n_out >= 256 ? 256 : ((n_out + 31) & ~31);
+	if (block < 32) block = 32;
+	MSB200_LAUNCH(r->ctx, resample_kernel, r->n * r->nch, block, smem, (const short *)d_in, in_frames, in_stride,
+	              (short *)d_out, n_out, out_stride, r->d_hist, r->d_table, r->p, last0, frac0);
+	return MSB200_OK;
+}
+int msb200_resample_process(msb200_resample *r, const int16_t *in, int in_frames, int16_t *out, int out_stride,
+                            int *out_frames) {
+	MSB200_CHECK_ARG(r && in && out && in_frames > 0);
+	int cap = msb200_resample_max_out(r, in_frames);
+	MSB200_CHECK_ARG(out_stride >= cap);
+	size_t in_bytes = (size_t)r->n * in_frames * r->nch * 2, out_bytes = (size_t)r->n * out_stride * r->nch * 2;
+	int rc;
+	if ((rc = r->in.reserve(in_bytes)) || (rc = r->out.reserve(out_bytes))) return rc;
+	cudaStream_t s = r->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(r->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+	if ((rc = msb200_resample_process_dev(r, r->in.p, in_frames, in_frames, r->out.p, out_stride, out_frames))) return rc;
+	MSB200_CUDA(cudaMemcpyAsync(out, r->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+} // extern "C"

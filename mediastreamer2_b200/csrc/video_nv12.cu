@@ -1,0 +1,159 @@
+// video_nv12.cu — NV12/NV21 -> I420 (+ rotation 0/90/180/270, + nearest 1/2 decimation), batched over frames.
+//
+// Bit-exact replacement of copy_ycbcrbiplanar_to_true_yuv_with_rotation_and_down_scale_by_2()
+// /root/reference/src/voip/msvideo.c:787-919 (rotate_plane_down_scale_by_2 :734-776). Pure byte movement: the
+// kernel is destination-centric (each thread produces 4 consecutive output bytes so stores are coalesced 32-bit
+// words); the rotation-0 full-size path moves 16 bytes per thread when strides and bases allow it.
+#include "msb200_internal.h"
+
+struct Nv12Params {
+	int rotation, w, h, ys, cs, u_first, f; // (w,h) = destination size; f = decimation factor (1 or 2)
+	size_t src_frame_bytes, cbcr_offset, dst_frame_bytes;
+};
+
+// source offset of destination luma pixel (i,j) — derived from msvideo.c:832-857 (0), :866-872 (180), :734-776 (90/270)
+__device__ __forceinline__ size_t nv12_src_y(const Nv12Params &p, int i, int j) {
+	switch (p.rotation) {
+		case 0: return (size_t)(i * p.f) * p.ys + (size_t)j * p.f;
+		case 180: return (size_t)(p.h - 1 - i) * p.ys * p.f + (size_t)(p.w - 1 - j) * p.f;
+		case 90: return (size_t)(p.w - 1 - j) * p.f * p.ys + (size_t)i * p.f;          // clockwise
+		default: return (size_t)j * p.f * p.ys + (size_t)(p.h - 1 - i) * p.f;          // 270, anticlockwise
+	}
+}
+// source offset (of the Cb byte) for destination chroma pixel (i,j)
+__device__ __forceinline__ size_t nv12_src_c(const Nv12Params &p, int i, int j) {
+	const int uw = p.w / 2, uh = p.h / 2;
+	switch (p.rotation) {
+		case 0: return (size_t)p.cs * i * p.f + (size_t)2 * j * p.f;
+		case 180: return (size_t)p.cs * (uh - 1 - i) * p.f + (size_t)2 * (uw - 1 - j) * p.f;
+		case 90: return (size_t)(uw - 1 - j) * ((size_t)(p.cs / 2) * 2 * p.f) + (size_t)i * 2 * p.f;
+		default: return (size_t)j * ((size_t)(p.cs / 2) * 2 * p.f) + (size_t)(uh - 1 - i) * 2 * p.f;
+	}
+}
+
+// generic path: grid.y = frame, one thread per 4 destination bytes of the frame (luma quads, then U quads, then V quads)
+__global__ void __launch_bounds__(256) nv12_generic_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, Nv12Params p) {
+	const int uw = p.w / 2, uh = p.h / 2;
+	const long yq = ((long)p.w * p.h + 3) / 4, cq = ((long)uw * uh + 3) / 4;
+	const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= yq + 2 * cq) return;
+	const uint8_t *fs = src + (size_t)blockIdx.y * p.src_frame_bytes;
+	uint8_t *fd = dst + (size_t)blockIdx.y * p.dst_frame_bytes;
+	uint8_t v[4];
+	if (q < yq) {
+		const long base = q * 4, total = (long)p.w * p.h;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			long idx = base + k;
+			if (idx < total) v[k] = fs[nv12_src_y(p, (int)(idx / p.w), (int)(idx % p.w))];
+		}
+		uint8_t *o = fd + base;
+		if (base + 3 < total && (((uintptr_t)o) & 3) == 0) *reinterpret_cast<uchar4 *>(o) = make_uchar4(v[0], v[1], v[2], v[3]);
+		else
+			for (int k = 0; k < 4 && base + k < total; ++k) o[k] = v[k];
+		return;
+	}
+	const bool is_v = (q - yq) >= cq;
+	const long base = ((q - yq) - (is_v ? cq : 0)) * 4, total = (long)uw * uh;
+	const uint8_t *cb = fs + p.cbcr_offset + (is_v ? 1 : 0);
+	// uFirstvSecond == FALSE swaps the destination planes (:822-826)
+	const int plane = (is_v ? 1 : 0) ^ (p.u_first ? 0 : 1);
+	uint8_t *o = fd + (size_t)p.w * p.h + (size_t)plane * total + base;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		long idx = base + k;
+		if (idx < total) v[k] = cb[nv12_src_c(p, (int)(idx / uw), (int)(idx % uw))];
+	}
+	if (base + 3 < total && (((uintptr_t)o) & 3) == 0) *reinterpret_cast<uchar4 *>(o) = make_uchar4(v[0], v[1], v[2], v[3]);
+	else
+		for (int k = 0; k < 4 && base + k < total; ++k) o[k] = v[k];
+}
+
+// fast path (rotation 0, no decimation, w % 32 == 0, 16-byte aligned rows): one thread copies 16 luma bytes, or
+// de-interleaves 32 CbCr bytes into 16 U + 16 V.
+__global__ void __launch_bounds__(256) nv12_fast_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, Nv12Params p) {
+	const int uw = p.w / 2, uh = p.h / 2;
+	const int yv = p.w / 16, cv = uw / 16;
+	const long ny = (long)yv * p.h, nc = (long)cv * uh;
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= ny + nc) return;
+	const uint8_t *fs = src + (size_t)blockIdx.y * p.src_frame_bytes;
+	uint8_t *fd = dst + (size_t)blockIdx.y * p.dst_frame_bytes;
+	if (t < ny) {
+		const int row = (int)(t / yv), col = (int)(t % yv);
+		const int4 v = __ldg(reinterpret_cast<const int4 *>(fs + (size_t)row * p.ys) + col);
+		reinterpret_cast<int4 *>(fd + (size_t)row * p.w)[col] = v;
+		return;
+	}
+	const long c = t - ny;
+	const int row = (int)(c / cv), col = (int)(c % cv);
+	const int4 *s = reinterpret_cast<const int4 *>(fs + p.cbcr_offset + (size_t)row * p.cs) + 2 * col;
+	const int4 a = __ldg(s), b = __ldg(s + 1);
+	// bytes: Cb0 Cr0 Cb1 Cr1 ... ; __byte_perm picks even (0x6420-style) / odd bytes of a register pair
+	int4 u, v;
+	u.x = __byte_perm(a.x, a.y, 0x6420); v.x = __byte_perm(a.x, a.y, 0x7531);
+	u.y = __byte_perm(a.z, a.w, 0x6420); v.y = __byte_perm(a.z, a.w, 0x7531);
+	u.z = __byte_perm(b.x, b.y, 0x6420); v.z = __byte_perm(b.x, b.y, 0x7531);
+	u.w = __byte_perm(b.z, b.w, 0x6420); v.w = __byte_perm(b.z, b.w, 0x7531);
+	uint8_t *pu = fd + (size_t)p.w * p.h + (p.u_first ? 0 : (size_t)uw * uh);
+	uint8_t *pv = fd + (size_t)p.w * p.h + (p.u_first ? (size_t)uw * uh : 0);
+	reinterpret_cast<int4 *>(pu + (size_t)row * uw)[col] = u;
+	reinterpret_cast<int4 *>(pv + (size_t)row * uw)[col] = v;
+}
+
+extern "C" {
+
+int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void *d_src, size_t src_frame_bytes, size_t cbcr_offset,
+                            int rotation, int w, int h, int y_stride, int cbcr_stride, int u_first, int down_scale,
+                            void *d_dst) {
+	MSB200_CHECK_ARG(ctx && d_src && d_dst && n_frames > 0 && n_frames <= 65535 && w > 0 && h > 0 && (w % 2) == 0 && (h % 2) == 0);
+	MSB200_CHECK_ARG(rotation == 0 || rotation == 90 || rotation == 180 || rotation == 270);
+	Nv12Params p;
+	p.rotation = rotation;
+	p.w = w;
+	p.h = h;
+	p.ys = y_stride;
+	p.cs = cbcr_stride;
+	p.u_first = u_first;
+	p.f = down_scale ? 2 : 1;
+	p.src_frame_bytes = src_frame_bytes;
+	p.cbcr_offset = cbcr_offset;
+	p.dst_frame_bytes = (size_t)w * h * 3 / 2;
+	const int sw = (rotation % 180 == 0 ? w : h) * p.f, sh = (rotation % 180 == 0 ? h : w) * p.f;
+	MSB200_CHECK_ARG(y_stride >= sw && cbcr_stride >= sw && cbcr_offset >= (size_t)y_stride * (sh - 1) + sw);
+	MSB200_CHECK_ARG(src_frame_bytes >= cbcr_offset + (size_t)cbcr_stride * (sh / 2 - 1) + sw);
+	const bool fast = rotation == 0 && !down_scale && (w % 32) == 0 && (y_stride % 16) == 0 && (cbcr_stride % 16) == 0 &&
+	                  (cbcr_offset % 16) == 0 && (src_frame_bytes % 16) == 0 && ((uintptr_t)d_src % 16) == 0 &&
+	                  ((uintptr_t)d_dst % 16) == 0 && (((size_t)w * h / 4) % 16) == 0;
+	if (fast) {
+		long threads = (long)(w / 16) * h + (long)(w / 32) * (h / 2);
+		dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
+		MSB200_LAUNCH(ctx, nv12_fast_kernel, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, p);
+	} else {
+		long quads = ((long)w * h + 3) / 4 + 2 * (((long)(w / 2) * (h / 2) + 3) / 4);
+		dim3 grid((unsigned)((quads + 255) / 256), (unsigned)n_frames);
+		MSB200_LAUNCH(ctx, nv12_generic_kernel, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, p);
+	}
+	return MSB200_OK;
+}
+
+int msb200_nv12_to_i420(msb200_ctx *ctx, int n_frames, const uint8_t *src, size_t src_frame_bytes, size_t cbcr_offset,
+                        int rotation, int w, int h, int y_stride, int cbcr_stride, int u_first, int down_scale, uint8_t *dst) {
+	MSB200_CHECK_ARG(ctx && src && dst && n_frames > 0);
+	void *d_src = nullptr, *d_dst = nullptr;
+	size_t in_bytes = src_frame_bytes * (size_t)n_frames, out_bytes = (size_t)w * h * 3 / 2 * (size_t)n_frames;
+	MSB200_CUDA(cudaMalloc(&d_src, in_bytes));
+	MSB200_CUDA(cudaMalloc(&d_dst, out_bytes));
+	cudaStream_t s = ctx->stream;
+	int r = MSB200_OK;
+	if (cudaMemcpyAsync(d_src, src, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) r = MSB200_ECUDA;
+	if (!r) r = msb200_nv12_to_i420_dev(ctx, n_frames, d_src, src_frame_bytes, cbcr_offset, rotation, w, h, y_stride, cbcr_stride, u_first, down_scale, d_dst);
+	if (!r && cudaMemcpyAsync(dst, d_dst, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) r = MSB200_ECUDA;
+	if (cudaStreamSynchronize(s) != cudaSuccess && !r) r = MSB200_ECUDA;
+	cudaFree(d_src);
+	cudaFree(d_dst);
+	if (r == MSB200_ECUDA) msb200_set_error("nv12_to_i420: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+	return r;
+}
+
+} // extern "C"

@@ -332,3 +332,10 @@ int ref_nv12_to_i420(const uint8_t *y, const uint8_t *cbcr, int rotation, int w,
 	ms_yuv_buf_allocator_free(alloc);
 	return n;
 }
+
+/* ---------------------------------------------------------------- direct call: ms_fir_mem16 (float build) */
+#include "mediastreamer2/dsptools.h"
+/* src/utils/dsptools.c:253-268 */
+void ref_fir_mem16(const float *x, const float *num, float *y, int N, int ord, float *mem) {
+	ms_fir_mem16((const ms_word16_t *)x, (const ms_coef_t *)num, (ms_word16_t *)y, N, ord, (ms_mem_t *)mem);
+}
