@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native mediastreamer2 DSP hot path.
+
+Workload (BASELINE.json configs[1], "cfg2"): 4096 concurrent 48 kHz mono call streams per GPU through
+MSResample(16k->48k) x2 -> MSSpeexEC(tail 250 ms: frame 256, M 47) -> MSVolume(0.8) at the 10 ms MSTicker tick.
+One "step" = one tick of every stream (resident device chain, libmsb200dsp.so through its C ABI).
+
+  value  whole-job stream-ticks/s with the tick's inputs already resident in HBM (device-pointer entry point)
+  e2e    the same metric through the host-buffer entry point (pinned host PCM in, H2D + kernels + D2H inside)
+  roofline  the echo-canceller kernel: algorithmic bytes / CUDA-event time of its launches inside the timed region
+  cpu_baseline  the oracle's CPU chain on this box's host cores (bounded sample), rank 0, N=1 only
+
+`--impl reference` times the reference-side CPU implementation of the path (the restated speexdsp-based chain: the
+library itself is not in the reference tree, see oracle/oracle_aec.c) with all host threads on the same config.
+
+Multi-GPU (torchrun, one rank per GPU): streams are independent -> sharded 4096 per rank, no data-path collective
+("scaling": "weak"); torch.distributed is used only for the barrier and the max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+STREAMS_PER_GPU = 4096
+IN_RATE, RATE, TAIL_MS, GAIN = 16000, 48000, 250, 0.8
+METRIC = "concurrent 48 kHz streams/sec through resample+AEC+mix @ 10 ms tick; pixconv Mpix/s"
+UNIT = "stream-ticks/s"
+WORKLOAD = ("cfg2: 4096 concurrent 48 kHz mono streams per GPU, MSResample(16k->48k) x2 -> MSSpeexEC(tail 250 ms, "
+            "frame 256, M 47) -> MSVolume(0.8), one 10 ms tick per step")
+# algorithmic HBM bytes of one echo-canceller frame of one stream:
+# X ring read M blocks + write 1, FG read, W read + write; blocks of F float2
+AEC_F, AEC_M = 256, 47
+AEC_BYTES_PER_FRAME = ((AEC_M + 1) + AEC_M + 2 * AEC_M) * AEC_F * 8  # = 387,072 B
+
+
+def synth_inputs(n_streams: int, n_ticks: int):
+    """[ticks][streams][160] far-end and mic PCM. A pool of distinct cfg2 streams, tiled across the batch (the work per
+    stream does not depend on the data; distinct seeds only keep the adaptive filters in a realistic regime)."""
+    from synth import cfg2_stream
+
+    pool = 32
+    ti = IN_RATE // 100
+    base = [cfg2_stream(s, ti * n_ticks, IN_RATE) for s in range(pool)]
+    ref = np.stack([b[0] for b in base]).reshape(pool, n_ticks, ti)
+    mic = np.stack([b[1] for b in base]).reshape(pool, n_ticks, ti)
+    idx = np.arange(n_streams) % pool
+    ref = np.ascontiguousarray(ref[idx].transpose(1, 0, 2))
+    mic = np.ascontiguousarray(mic[idx].transpose(1, 0, 2))
+    return ref, mic
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, name in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak_gbs() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except (ValueError, KeyError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_chain(n_streams: int, n_ticks: int, threads: int):
+    """the oracle's CPU chain on host cores; returns (stream-ticks/s, seconds)"""
+    import _oracle as O
+
+    L = O.oracle()
+    L.orc_chain_bench.restype = C.c_double
+    L.orc_chain_bench.argtypes = [C.c_int] * 6 + [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_long)]
+    ref, mic = synth_inputs(n_streams, n_ticks)  # [ticks][streams][160]
+    ref = np.ascontiguousarray(ref.transpose(1, 0, 2))
+    mic = np.ascontiguousarray(mic.transpose(1, 0, 2))
+    n = C.c_long()
+    dt = L.orc_chain_bench(n_streams, n_ticks, threads, IN_RATE, RATE, TAIL_MS, GAIN, ref.ctypes.data, mic.ctypes.data,
+                           None, C.byref(n))
+    return n_streams * n_ticks / dt, dt
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference-side CPU chain, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step_streams = max(threads * 4, 64)
+    ticks_per_step = 10
+    for _ in range(min(args.warmup, 1)):
+        cpu_chain(per_step_streams, ticks_per_step, threads)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        v, dt = cpu_chain(per_step_streams, ticks_per_step, threads)
+        t_total += dt
+        n_total += per_step_streams * ticks_per_step
+        if t_total > 150:
+            break
+    value = n_total / t_total
+    sample = (f"{per_step_streams} streams x {ticks_per_step} ticks per step, {threads} threads, free-running; "
+              f"restated speexdsp chain (oracle/), the library itself is not in the reference tree")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+
+    from mediastreamer2_b200 import filters as F
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = F.Context(local_rank)
+    S = STREAMS_PER_GPU
+    ti = IN_RATE // 100
+    pool_ticks = 64
+    ref_h, mic_h = synth_inputs(S, pool_ticks)
+    chain = F.AudioChain(ctx, S, IN_RATE, RATE, TAIL_MS, GAIN, 0)
+    max_out = chain.max_out
+    # pinned host staging (e2e path) and resident device copies (device path)
+    ref_pin = ctx.pinned((pool_ticks, S, ti), np.int16)
+    mic_pin = ctx.pinned((pool_ticks, S, ti), np.int16)
+    out_pin = ctx.pinned((S, max_out), np.int16)
+    ref_pin[...] = ref_h
+    mic_pin[...] = mic_h
+    tick_bytes = S * ti * 2
+    d_ref = ctx.dev_alloc(pool_ticks * tick_bytes)
+    d_mic = ctx.dev_alloc(pool_ticks * tick_bytes)
+    d_out = ctx.dev_alloc(S * max_out * 2)
+    ctx.h2d(d_ref, ref_pin)
+    ctx.h2d(d_mic, mic_pin)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(ms: float) -> float:
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_no = 0
+
+    def dev_step():
+        nonlocal step_no
+        k = step_no % pool_ticks
+        n = chain.tick_dev(d_ref + k * tick_bytes, d_mic + k * tick_bytes, d_out)
+        step_no += 1
+        return n
+
+    def host_step():
+        nonlocal step_no
+        k = step_no % pool_ticks
+        _, n = chain.tick(ref_pin[k], mic_pin[k], out_pin)
+        step_no += 1
+        return n
+
+    # ---------------------------------------------------------------- device-resident: `value` + roofline
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    chain.enable_kernel_timing(True)
+    chain.kernel_timing()  # reset
+    l0 = ctx.launches
+    ctx.timer_start()
+    for _ in range(args.steps):
+        dev_step()
+    ms_dev = ctx.timer_stop_ms()
+    launches = ctx.launches - l0
+    aec_ms, aec_launches, aec_frames = chain.kernel_timing()
+    chain.enable_kernel_timing(False)
+    barrier()
+    ms_dev = max_over_ranks(ms_dev)
+    # ---------------------------------------------------------------- end to end through host buffers: `e2e`
+    for _ in range(3):
+        host_step()
+    barrier()
+    out_samples = 0
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        out_samples += host_step()
+    ms_e2e_dev = ctx.timer_stop_ms()
+    ms_e2e = max(ms_e2e_dev, 1000.0 * (time.perf_counter() - t0))  # host-side wall time bounds the device time
+    barrier()
+    clocks = sampler.stop()
+    ms_e2e = max_over_ranks(ms_e2e)
+
+    total_ticks = S * world * args.steps
+    value = total_ticks / (ms_dev / 1000.0)
+    e2e_value = total_ticks / (ms_e2e / 1000.0)
+    peak, peak_src = hbm_peak_gbs()
+    achieved = None
+    if aec_launches and aec_ms > 0:
+        bytes_per_launch = AEC_BYTES_PER_FRAME * (aec_frames / aec_launches) * S
+        achieved = bytes_per_launch / (aec_ms / aec_launches / 1000.0) / 1e9
+    traffic = None
+    tpath = ROOT / "profiles" / "aec_traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+        except ValueError:
+            traffic = None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": S, "realtime_streams_equiv": value / 100.0,
+                   "l2": "per-step working set (AEC state 1.19 GB per 4096 streams) >> 126 MB L2; no flush needed",
+                   "sharding": "streams independent: 4096 per rank, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * tick_bytes,
+                "d2h_bytes_per_step": int(out_samples / args.steps) * S * 2 if args.steps else 0,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "aec_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "bytes_per_frame_per_stream": AEC_BYTES_PER_FRAME,
+                     "kernel_ms_per_launch": (aec_ms / aec_launches) if aec_launches else None,
+                     "kernel_share_of_step": (aec_ms / ms_dev) if ms_dev else None},
+    }
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only, bounded sample)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_streams, n_ticks = max(threads * 4, 64), 20
+        v1, dt1 = cpu_chain(n_streams, n_ticks, threads)
+        reps = max(1, min(10, int(12.0 / max(dt1, 1e-3))))
+        best = v1
+        for _ in range(reps - 1):
+            v, _ = cpu_chain(n_streams, n_ticks, threads)
+            best = max(best, v)
+        line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n_streams} streams x {n_ticks} ticks, {threads} pthreads, best of {reps}; "
+                                          f"oracle chain (restated speexdsp resampler + MDF + preprocessor, in-tree volume)"}
+    # ---------------------------------------------------------------- second headline: pixconv (when built)
+    try:
+        from bench_video import pixconv_bench  # noqa: WPS433
+
+        if rank == 0:
+            line["pixconv"] = pixconv_bench(ctx, peak)
+    except ImportError:
+        pass
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    chain.close()
+    for p in (d_ref, d_mic, d_out):
+        ctx.dev_free(p)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -229,6 +229,11 @@ MSB200_API int msb200_chain_tick(msb200_chain *c, const int16_t *ref_in, const i
 MSB200_API int msb200_chain_tick_dev(msb200_chain *c, const void *d_ref_in, const void *d_mic_in, void *d_out,
                                      int *out_samples);
 MSB200_API int msb200_chain_launches_per_tick(msb200_chain *c);
+/* Per-kernel device timing of the dominant kernel (the echo canceller) with CUDA events recorded on the launching
+ * stream around every AEC launch while enabled; get_ returns the accumulated milliseconds, launches and frames since
+ * the last call and resets the counters (synchronises the stream). Used by bench.py for the roofline figure. */
+MSB200_API int msb200_chain_enable_kernel_timing(msb200_chain *c, int enabled);
+MSB200_API int msb200_chain_get_kernel_timing(msb200_chain *c, float *aec_ms, int *aec_launches, int *aec_frames);
 MSB200_API msb200_aec *msb200_chain_aec(msb200_chain *c);
 
 /* ---------------------------------------------------------------------------------------------------- video

@@ -128,6 +128,8 @@ _SIGS = {
     "msb200_chain_tick_dev": (_I, [_P, _P, _P, _P, _PI]),
     "msb200_chain_launches_per_tick": (_I, [_P]),
     "msb200_chain_aec": (_P, [_P]),
+    "msb200_chain_enable_kernel_timing": (_I, [_P, _I]),
+    "msb200_chain_get_kernel_timing": (_I, [_P, C.POINTER(C.c_float), _PI, _PI]),
     "msb200_nv12_to_i420": (_I, [_P, _I, _P, _SZ, _SZ, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msb200_nv12_to_i420_dev": (_I, [_P, _I, _P, _SZ, _SZ, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msb200_scaler_create": (_I, [_P, _I, _I, _I, _I, _I, _I, _PP]),

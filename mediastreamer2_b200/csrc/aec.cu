@@ -1,0 +1,1181 @@
+// aec.cu — MSSpeexEC arithmetic: MDF two-path echo canceller + preprocessor (denoise / residual-echo suppression),
+// one CTA per call stream, `nframes` consecutive frames per launch.
+//
+// Replaces, per framesize block, speex_echo_cancellation() + speex_preprocess_run() as called from
+// /root/reference/src/audiofilters/speexec.c:297-298 with the configuration of speex_ec_preprocess() :188-216.
+// speexdsp itself is not under /root/reference; the algorithm is restated in oracle/oracle_aec.c (see its header for
+// provenance and "parity unpinned"). This file follows that restatement statement by statement; arithmetic that the
+// oracle does in a fixed order (FFT butterflies, spectral products, filterbank sums, state recurrences) is done in the
+// same order with -fmad=false, so the only deviations are the block-parallel reductions (inner products, Pey/Pyy,
+// |W_j|^2), which sum in tree order instead of sequentially.
+//
+// Data layout in HBM (per stream, contiguous "page" so one CTA streams it linearly; SURVEY §8d: ~0.39 MB/frame):
+//   X   [(M+1)][F] float2   far-end spectra, ring buffer over blocks (slot = (head + j) % (M+1), head shared by the
+//                           bank because all streams advance in lockstep) — replaces speex's per-frame memmove
+//   W   [M][F] float2       background (adaptive) filter
+//   FG  [M][F] float2       foreground filter
+//   small state             window halves, previous error spectrum, power spectra, preprocessor state (~20 KB)
+// Spectra use float2 per bin with bin 0 = (DC, Nyquist): 8-byte aligned, coalesced accesses (256 threads x 8 B = one
+// 2 KB row per block). The hot loop over the M blocks reads X, FG, W once and writes W once per frame.
+#include "msb200_internal.h"
+
+#include <cmath>
+
+#define NB_BANDS 24
+
+struct AecLayout {        // offsets in floats inside one stream's small-state page
+	int xprev, E, last_y, power, power_1, Eh, Yh, prop, wnorm, scal, ints;
+	int inbuf, outbuf, old_ps, noise, echo_noise, zeta, S, Smin, Stmp;
+	int total;
+};
+enum { // scal[] indices
+	SC_DAVG1, SC_DAVG2, SC_DVAR1, SC_DVAR2, SC_PEY, SC_PYY, SC_SUM_ADAPT, SC_LEAK, SC_MEMX, SC_MEMD, SC_MEME,
+	SC_NOTCH0, SC_NOTCH1, SC_COUNT = 16
+};
+enum { IN_ADAPTED, IN_SATURATED, IN_SCREWED, IN_CANCEL_COUNT, IN_NB_ADAPT, IN_MIN_COUNT, IN_COUNT = 8 };
+
+struct AecParams {
+	int F, N, M, L, log2L, rate;
+	float spec_average, beta0, beta_max, notch_radius, preemph;
+	int noise_suppress, echo_suppress, echo_suppress_active;
+	AecLayout lay;
+	size_t x_stride, w_stride; // float2 per stream for X and for W / FG
+	// bank-wide constant tables (device pointers)
+	const float2 *tw;   // [L/2]  (cos, sin)(2 pi j / L)
+	const float2 *spl;  // [L+1]  (cos, sin)(2 pi k / N)
+	const float *window;  // [N] hann
+	const float *pwindow; // [N] preprocessor conj window
+	const int *bank_left; // [F]
+	const float *filter_left, *filter_right; // [F]
+	const int *band_start; // [NB_BANDS+1] first bin whose left band is b
+	const float *prop0;    // [M] initial proportional weights
+};
+
+// ------------------------------------------------------------------------------------------------ block helpers
+// All helpers are called by every thread of the CTA (blockDim.x == F).
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+// deterministic block sum: shuffle tree inside each warp, then warp partials added in warp order. `red` = smem[32]
+__device__ float block_sum(float v, float *red) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	v = warp_sum(v);
+	__syncthreads(); // protect `red` from the previous use
+	if (lane == 0) red[warp] = v;
+	__syncthreads();
+	float s = 0.f;
+	for (int w = 0; w < nw; ++w) s += red[w];
+	return s;
+}
+__device__ int block_any(int pred) {
+	return __syncthreads_or(pred);
+}
+
+// complex radix-2 Stockham FFT of length L over shared memory, one output element per thread per stage.
+// Mirrors oracle/oracle_aec.c:cfft() operation for operation. Returns the buffer holding the result.
+__device__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int L, int sign) {
+	const int o = threadIdx.x;
+	for (int n = L, s = 1; n > 1; n >>= 1, s <<= 1) {
+		const int m = n >> 1;
+		const int q = o & (s - 1), tmp = o / s, r = tmp & 1, p = tmp >> 1;
+		const float2 a = x[q + s * p], b = x[q + s * (p + m)];
+		float2 out;
+		if (!r) {
+			out.x = a.x + b.x;
+			out.y = a.y + b.y;
+		} else {
+			const float2 w = tw[p * s];
+			const float wr = w.x, wi = sign < 0 ? -w.y : w.y;
+			const float dr = a.x - b.x, di = a.y - b.y;
+			out.x = dr * wr - di * wi;
+			out.y = dr * wi + di * wr;
+		}
+		y[o] = out;
+		__syncthreads();
+		float2 *sw = x;
+		x = y;
+		y = sw;
+	}
+	return x;
+}
+
+// real forward FFT (spx_fft semantics: input scaled by 1/N): in[N] real (smem) -> spec[L] float2 (smem, bin0=(DC,Nyq))
+// bufa/bufb: float2[L] scratch. in may alias nothing; spec may alias neither scratch.
+__device__ void rfft(const float *in, float2 *spec, float2 *bufa, float2 *bufb, const AecParams &P, const float2 *tw,
+                     const float2 *spl) {
+	const int k = threadIdx.x, L = P.L;
+	const float scale = (float)(1. / P.N);
+	bufa[k] = make_float2(scale * in[2 * k], scale * in[2 * k + 1]);
+	__syncthreads();
+	const float2 *Z = cfft(bufa, bufb, tw, L, -1);
+	float2 out;
+	if (k == 0) {
+		out.x = Z[0].x + Z[0].y;
+		out.y = Z[0].x - Z[0].y;
+	} else {
+		const float zr = Z[k].x, zi = Z[k].y, yr = Z[L - k].x, yi = -Z[L - k].y;
+		const float er = 0.5f * (zr + yr), ei = 0.5f * (zi + yi);
+		const float dr = 0.5f * (zr - yr), di = 0.5f * (zi - yi);
+		const float c = spl[k].x, s = spl[k].y;
+		out.x = er + (c * di - s * dr);
+		out.y = ei - (s * di + c * dr);
+	}
+	__syncthreads(); // all reads of Z done before spec (which may be reused scratch by the caller later) is written
+	spec[k] = out;
+	__syncthreads();
+}
+
+// real inverse FFT (spx_ifft, unscaled): spec[L] float2 (bin0=(DC,Nyq)) -> out[N] real (smem)
+__device__ void irfft(const float2 *spec, float *out, float2 *bufa, float2 *bufb, const AecParams &P, const float2 *tw,
+                      const float2 *spl) {
+	const int k = threadIdx.x, L = P.L;
+	float2 z;
+	if (k == 0) {
+		z.x = spec[0].x + spec[0].y;
+		z.y = spec[0].x - spec[0].y;
+	} else {
+		const float xr = spec[k].x, xi = spec[k].y;
+		const float yr = spec[L - k].x, yi = -spec[L - k].y;
+		const float er = xr + yr, ei = xi + yi, dr = xr - yr, di = xi - yi;
+		const float c = spl[k].x, s = spl[k].y;
+		const float orr = dr * c - di * s, oi = dr * s + di * c;
+		z.x = er - oi;
+		z.y = ei + orr;
+	}
+	__syncthreads();
+	bufa[k] = z;
+	__syncthreads();
+	const float2 *r = cfft(bufa, bufb, tw, L, +1);
+	const float2 v = r[k];
+	__syncthreads();
+	out[2 * k] = v.x;
+	out[2 * k + 1] = v.y;
+	__syncthreads();
+}
+
+__device__ __forceinline__ short word2int(float x) {
+	return (short)(x < -32767.5f ? -32768 : (x > 32766.5f ? 32767 : (int)floor(.5 + (double)x)));
+}
+
+// per-band sum in the oracle's accumulation order (filterbank_compute_bank32): thread b < NB_BANDS
+__device__ void filterbank_bank32(const float *ps, float *mel, const AecParams &P) {
+	const int b = threadIdx.x;
+	if (b < NB_BANDS) {
+		float acc = 0.f;
+		if (b > 0)
+			for (int i = P.band_start[b - 1]; i < P.band_start[b]; ++i) acc += P.filter_right[i] * ps[i];
+		for (int i = P.band_start[b]; i < P.band_start[b + 1]; ++i) acc += P.filter_left[i] * ps[i];
+		mel[b] = acc;
+	}
+	__syncthreads();
+}
+__device__ __forceinline__ float filterbank_psd16(const float *mel, int i, const AecParams &P) {
+	const int l = P.bank_left[i];
+	float tmp = mel[l] * P.filter_left[i];
+	tmp += mel[l + 1] * P.filter_right[i];
+	return tmp;
+}
+
+__device__ float hypergeom_gain(float xx) {
+	const float table[21] = {0.82157f, 1.02017f, 1.20461f, 1.37534f, 1.53363f, 1.68092f, 1.81865f,
+	                         1.94811f, 2.07038f, 2.18638f, 2.29688f, 2.40255f, 2.50391f, 2.60144f,
+	                         2.69551f, 2.78647f, 2.87458f, 2.96015f, 3.04333f, 3.12431f, 3.20326f};
+	float x = xx;
+	float integer = (float)floor((double)(2 * x));
+	int ind = (int)integer;
+	if (ind < 0) return 1.f;
+	if (ind > 19) return (float)(1 + .1296 / (double)x);
+	float frac = 2 * x - integer;
+	return (float)((double)((1 - frac) * table[ind] + frac * table[ind + 1]) / sqrt((double)(x + .0001f)));
+}
+__device__ __forceinline__ float qcurve(float x) {
+	return 1.f / (1.f + .15f / x);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+// dynamic shared memory map (floats): see carve-up at the top of the kernel body
+__global__ void __launch_bounds__(256)
+    aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
+               int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
+               float *__restrict__ gS, AecParams P, int head0, int in_frame0, int in_ring, int out_stride, int out_frame0,
+               int out_ring) {
+	extern __shared__ float sm[];
+	const int F = P.F, N = P.N, M = P.M, L = P.L;
+	const int t = threadIdx.x;
+	const int stream = blockIdx.x;
+	// ---- shared memory carve-up
+	float2 *tw = reinterpret_cast<float2 *>(sm);           // [L/2]
+	float2 *spl = tw + L / 2;                              // [L+1] (+1 pad)
+	float2 *bufa = spl + L + 2;                            // [L]
+	float2 *bufb = bufa + L;                               // [L]
+	float2 *specA = bufb + L;                              // [L] spectrum scratch A
+	float2 *specB = specA + L;                             // [L] spectrum scratch B
+	float2 *Eprev = specB + L;                             // [L] previous frame's error spectrum
+	float *xw = reinterpret_cast<float *>(Eprev + L);      // [N] far-end window
+	float *ebuf = xw + N;                                  // [N]
+	float *ybuf = ebuf + N;                                // [N]
+	float *input = ybuf + N;                               // [F]
+	float *tmpv = input + F;                               // [N] generic real scratch
+	float *power_1 = tmpv + N;                             // [F+1]
+	float *vec1 = power_1 + F + 1;                         // [F+NB_BANDS+1]
+	float *vec2 = vec1 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
+	float *vec3 = vec2 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
+	float *vec4 = vec3 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
+	float *vec5 = vec4 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
+	float *prop = vec5 + F + NB_BANDS + 1;                 // [M]
+	float *wpart = prop + M;                               // [M][8] per-warp |W_j|^2 partials
+	float *red = wpart + M * 8;                            // [32]
+	float *sc = red + 32;                                  // [SC_COUNT]
+	int *si = reinterpret_cast<int *>(sc + SC_COUNT);      // [IN_COUNT]
+
+	float2 *X = gX + (size_t)stream * P.x_stride;
+	float2 *W = gW + (size_t)stream * P.w_stride;
+	float2 *FG = gFG + (size_t)stream * P.w_stride;
+	float *S = gS + (size_t)stream * P.lay.total;
+	const AecLayout &ly = P.lay;
+	const int nwarps = (F + 31) >> 5, lane = t & 31, warp = t >> 5;
+
+	// ---- load constants and per-stream small state
+	for (int i = t; i < L / 2; i += F) tw[i] = P.tw[i];
+	for (int i = t; i <= L; i += F) spl[i] = P.spl[i];
+	Eprev[t] = reinterpret_cast<float2 *>(S + ly.E)[t];
+	xw[F + t] = S[ly.xprev + t];
+	for (int i = t; i <= F; i += F) power_1[i] = S[ly.power_1 + i];
+	for (int i = t; i < M; i += F) prop[i] = S[ly.prop + i];
+	if (t < SC_COUNT) sc[t] = S[ly.scal + t];
+	if (t < IN_COUNT) si[t] = reinterpret_cast<int *>(S + ly.ints)[t];
+	__syncthreads();
+
+	int head = head0;
+	for (int fr = 0; fr < nframes; ++fr) {
+		// frame addressing: linear, or frame-aligned circular buffers (chain re-framing between 10 ms ticks and frames)
+		const int fin = in_ring > 0 ? (in_frame0 + fr) % in_ring : fr;
+		const int fout = out_ring > 0 ? (out_frame0 + fr) % out_ring : fr;
+		const short *in_mic = mic + (size_t)stream * io_stride + (size_t)fin * F;
+		const short *in_ref = ref + (size_t)stream * io_stride + (size_t)fin * F;
+		short *o16 = out + (size_t)stream * out_stride + (size_t)fout * F;
+		const int mic_i = in_mic[t];
+		const int ref_i = in_ref[t];
+		head = (head + M) % (M + 1); // head - 1 mod (M+1): newest block goes to slot `head`
+		const float ss = .35f / (float)M, ss_1 = 1 - ss;
+
+		// ---- DC notch (serial IIR, filter_dc_notch16) then pre-emphasis on the microphone
+		tmpv[t] = (float)mic_i;
+		__syncthreads();
+		if (t == 0) {
+			const float radius = P.notch_radius;
+			const float den2 = radius * radius + .7f * (1 - radius) * (1 - radius);
+			float m0 = sc[SC_NOTCH0], m1 = sc[SC_NOTCH1];
+			for (int i = 0; i < F; ++i) {
+				const float vin = tmpv[i];
+				const float vout = m0 + vin;
+				m0 = m1 + 2 * (-vin + radius * vout);
+				m1 = vin - den2 * vout;
+				input[i] = radius * vout;
+			}
+			sc[SC_NOTCH0] = m0;
+			sc[SC_NOTCH1] = m1;
+		}
+		__syncthreads();
+		{
+			const float prev = t == 0 ? sc[SC_MEMD] : input[t - 1];
+			const float v = input[t] - P.preemph * prev;
+			const float lastv = input[F - 1];
+			__syncthreads();
+			input[t] = v;
+			if (t == 0) sc[SC_MEMD] = lastv;
+		}
+		// ---- far-end window shift + pre-emphasis
+		{
+			const float old = xw[F + t];
+			tmpv[t] = (float)ref_i;
+			__syncthreads();
+			const float prev = t == 0 ? sc[SC_MEMX] : tmpv[t - 1];
+			xw[t] = old;
+			xw[F + t] = (float)ref_i - P.preemph * prev;
+			__syncthreads();
+			if (t == 0) sc[SC_MEMX] = tmpv[F - 1];
+		}
+		// ---- X_0 = FFT(x) into the ring
+		rfft(xw, specA, bufa, bufb, P, tw, spl);
+		X[(size_t)head * F + t] = specA[t];
+		float Sxx = block_sum(xw[F + t] * xw[F + t], red);
+
+		// ---- adjust proportional adaptation rate (uses |W_j|^2 of the previous frame's final W)
+		if (si[IN_ADAPTED]) {
+			// mdf_adjust_prop: prop_j = sqrt(1 + |W_j|^2); += .1*max; normalise to .99
+			if (t < M) prop[t] = (float)sqrt((double)(1.f + S[ly.wnorm + t]));
+			__syncthreads();
+			if (t == 0) {
+				float max_sum = 1, prop_sum = 1;
+				for (int i = 0; i < M; ++i)
+					if (prop[i] > max_sum) max_sum = prop[i];
+				for (int i = 0; i < M; ++i) {
+					prop[i] += .1f * max_sum;
+					prop_sum += prop[i];
+				}
+				for (int i = 0; i < M; ++i) prop[i] = (.99f * prop[i]) / prop_sum;
+			}
+			__syncthreads();
+		}
+
+		// ---- the pass over the M blocks: foreground output, weight update (+AUMDF constraint), background output
+		const bool do_update = si[IN_SATURATED] == 0;
+		const int cc = si[IN_CANCEL_COUNT] + 1; // st->cancel_count++ at the top of the frame
+		const int constr_j = cc % (M - 1) + 1;
+		float2 yfg = make_float2(0.f, 0.f), ybg = make_float2(0.f, 0.f);
+		const float2 Ep = Eprev[t];
+		const float p1 = power_1[t], p1n = power_1[F]; // p1n only meaningful for thread 0 (Nyquist)
+		float2 xj = specA[t];                          // X_0 (just computed)
+		for (int j = 0; j < M; ++j) {
+			const int slot1 = (head + j + 1) % (M + 1);
+			const float2 xj1 = X[(size_t)slot1 * F + t];
+			const float2 fg = FG[(size_t)j * F + t];
+			float2 w = W[(size_t)j * F + t];
+			// foreground: Y += X_j * FG_j (spectral_mul_accum; bin 0 carries two real products)
+			if (t == 0) {
+				yfg.x += xj.x * fg.x;
+				yfg.y += xj.y * fg.y;
+			} else {
+				yfg.x += (xj.x * fg.x - xj.y * fg.y);
+				yfg.y += (xj.y * fg.x + xj.x * fg.y);
+			}
+			// gradient: W_j += prop_j * power_1 * conj(X_{j+1}) * E  (weighted_spectral_mul_conj)
+			if (do_update) {
+				const float pj = prop[j];
+				if (t == 0) {
+					w.x += (pj * p1) * (xj1.x * Ep.x);
+					w.y += (pj * p1n) * (xj1.y * Ep.y);
+				} else {
+					const float Wg = pj * p1;
+					w.x += Wg * (xj1.x * Ep.x + xj1.y * Ep.y);
+					w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
+				}
+			}
+			// AUMDF: constrain block 0 and one rotating block (IFFT, zero second half, FFT)
+			if (j == 0 || j == constr_j) {
+				specB[t] = w;
+				__syncthreads();
+				irfft(specB, tmpv, bufa, bufb, P, tw, spl);
+				tmpv[F + t] = 0.f;
+				__syncthreads();
+				rfft(tmpv, specB, bufa, bufb, P, tw, spl);
+				w = specB[t];
+			}
+			if (do_update || j == 0 || j == constr_j) W[(size_t)j * F + t] = w;
+			// |W_j|^2 partial for next frame's mdf_adjust_prop
+			{
+				float n2 = w.x * w.x + w.y * w.y;
+				n2 = warp_sum(n2);
+				if (lane == 0) wpart[j * 8 + warp] = n2;
+			}
+			// background: Y += X_j * W_j
+			if (t == 0) {
+				ybg.x += xj.x * w.x;
+				ybg.y += xj.y * w.y;
+			} else {
+				ybg.x += (xj.x * w.x - xj.y * w.y);
+				ybg.y += (xj.y * w.x + xj.x * w.y);
+			}
+			xj = xj1;
+		}
+		__syncthreads();
+		if (t < M) {
+			float s = 0.f;
+			for (int w8 = 0; w8 < nwarps; ++w8) s += wpart[t * 8 + w8];
+			S[ly.wnorm + t] = s;
+		}
+		if (!do_update && t == 0) si[IN_SATURATED]--;
+
+		// ---- foreground error
+		specA[t] = yfg;
+		__syncthreads();
+		irfft(specA, ebuf, bufa, bufb, P, tw, spl);
+		{
+			const float v = input[t] - ebuf[t + F];
+			__syncthreads();
+			ebuf[t] = v;
+		}
+		float Sff = block_sum(ebuf[t] * ebuf[t], red);
+		// ---- background error
+		specA[t] = ybg;
+		__syncthreads();
+		irfft(specA, ybuf, bufa, bufb, P, tw, spl);
+		float dd = ebuf[t + F] - ybuf[t + F];
+		float Dbf = 10 + block_sum(dd * dd, red);
+		ebuf[t] = input[t] - ybuf[t + F];
+		float See = block_sum(ebuf[t] * ebuf[t], red);
+
+		// ---- two-path logic (every thread evaluates the same scalars)
+		float Davg1 = .6f * sc[SC_DAVG1] + .4f * (Sff - See);
+		float Davg2 = .85f * sc[SC_DAVG2] + .15f * (Sff - See);
+		float Dvar1 = .36f * sc[SC_DVAR1] + .16f * Sff * Dbf;
+		float Dvar2 = .7225f * sc[SC_DVAR2] + .0225f * Sff * Dbf;
+		int update_foreground = 0;
+		if ((Sff - See) * fabsf(Sff - See) > (Sff * Dbf)) update_foreground = 1;
+		else if ((Davg1 * fabsf(Davg1)) > (.5f * Dvar1)) update_foreground = 1;
+		else if ((Davg2 * fabsf(Davg2)) > (.25f * Dvar2)) update_foreground = 1;
+		__syncthreads(); // everyone has read sc[] before it is rewritten
+		if (update_foreground) {
+			Davg1 = Davg2 = 0;
+			Dvar1 = Dvar2 = 0;
+			for (int j = 0; j < M; ++j) FG[(size_t)j * F + t] = W[(size_t)j * F + t];
+			ebuf[t + F] = P.window[t + F] * ebuf[t + F] + P.window[t] * ybuf[t + F];
+		} else {
+			int reset_background = 0;
+			if ((-(Sff - See) * fabsf(Sff - See)) > (4.f * (Sff * Dbf))) reset_background = 1;
+			if ((-Davg1 * fabsf(Davg1)) > (4.f * Dvar1)) reset_background = 1;
+			if ((-Davg2 * fabsf(Davg2)) > (4.f * Dvar2)) reset_background = 1;
+			if (reset_background) {
+				for (int j = 0; j < M; ++j) {
+					const float2 w = FG[(size_t)j * F + t];
+					W[(size_t)j * F + t] = w;
+					float n2 = warp_sum(w.x * w.x + w.y * w.y);
+					if (lane == 0) wpart[j * 8 + warp] = n2;
+				}
+				__syncthreads();
+				if (t < M) {
+					float s = 0.f;
+					for (int w8 = 0; w8 < nwarps; ++w8) s += wpart[t * 8 + w8];
+					S[ly.wnorm + t] = s;
+				}
+				ybuf[t + F] = ebuf[t + F];
+				ebuf[t] = input[t] - ybuf[t + F];
+				See = Sff;
+				Davg1 = Davg2 = 0;
+				Dvar1 = Dvar2 = 0;
+			}
+		}
+		if (t == 0) {
+			sc[SC_DAVG1] = Davg1;
+			sc[SC_DAVG2] = Davg2;
+			sc[SC_DVAR1] = Dvar1;
+			sc[SC_DVAR2] = Dvar2;
+		}
+		__syncthreads();
+
+		// ---- output with de-emphasis (serial IIR) and saturation test
+		const int sat = block_any(mic_i <= -32000 || mic_i >= 32000);
+		tmpv[t] = input[t] - ebuf[t + F];
+		__syncthreads();
+		if (t == 0) {
+			float memE = sc[SC_MEME];
+			for (int i = 0; i < F; ++i) {
+				float tmp_out = tmpv[i] + P.preemph * memE;
+				tmpv[i] = tmp_out;
+				memE = tmp_out;
+			}
+			sc[SC_MEME] = memE;
+			if (sat && si[IN_SATURATED] == 0) si[IN_SATURATED] = 1;
+		}
+		__syncthreads();
+		int out_i = word2int(tmpv[t]);
+
+		// ---- error / echo-estimate spectra for the next update
+		{
+			const float ev = ebuf[t];
+			__syncthreads();
+			ebuf[t + F] = ev;
+			ebuf[t] = 0.f;
+			__syncthreads();
+		}
+		float Sey = block_sum(ebuf[t + F] * ybuf[t + F], red);
+		float Syy = block_sum(ybuf[t + F] * ybuf[t + F], red);
+		float Sdd = block_sum(input[t] * input[t], red);
+		rfft(ebuf, Eprev, bufa, bufb, P, tw, spl); // E (kept for the next frame's gradient)
+		ybuf[t] = 0.f;
+		__syncthreads();
+		rfft(ybuf, specB, bufa, bufb, P, tw, spl); // Y
+		// Rf -> vec1, Yf -> vec2, Xf -> vec3 (F+1 bins; bin F is the Nyquist term held by thread 0)
+		{
+			const float2 e = Eprev[t], y = specB[t], x0 = X[(size_t)head * F + t];
+			if (t == 0) {
+				vec1[0] = e.x * e.x; vec1[F] = e.y * e.y;
+				vec2[0] = y.x * y.x; vec2[F] = y.y * y.y;
+				vec3[0] = x0.x * x0.x; vec3[F] = x0.y * x0.y;
+			} else {
+				vec1[t] = e.x * e.x + e.y * e.y;
+				vec2[t] = y.x * y.x + y.y * y.y;
+				vec3[t] = x0.x * x0.x + x0.y * x0.y;
+			}
+		}
+		__syncthreads();
+
+		// ---- sanity checks
+		int screwed = si[IN_SCREWED];
+		bool zero_out = false;
+		if (!(Syy >= 0 && Sxx >= 0 && See >= 0) || !(Sff < N * 1e9 && Syy < N * 1e9 && Sxx < N * 1e9)) {
+			screwed += 50;
+			zero_out = true;
+		} else if (Sff > Sdd + (float)(N * 10000)) {
+			screwed++;
+		} else {
+			screwed = 0;
+		}
+		if (zero_out) out_i = 0;
+		__syncthreads();
+		if (screwed >= 50) {
+			// speex_echo_state_reset(): filters, history and statistics back to their initial values
+			for (int j = 0; j < M; ++j) {
+				W[(size_t)j * F + t] = make_float2(0.f, 0.f);
+				FG[(size_t)j * F + t] = make_float2(0.f, 0.f);
+			}
+			for (int j = 0; j <= M; ++j) X[(size_t)j * F + t] = make_float2(0.f, 0.f);
+			for (int i = t; i <= F; i += F) {
+				S[ly.power + i] = 0;
+				power_1[i] = 1.f;
+				S[ly.Eh + i] = 0;
+				S[ly.Yh + i] = 0;
+			}
+			S[ly.last_y + t] = 0; // first half only, as the library does
+			Eprev[t] = make_float2(0.f, 0.f);
+			xw[t] = 0;
+			xw[F + t] = 0;
+			if (t < M) S[ly.wnorm + t] = 0;
+			__syncthreads();
+			if (t == 0) {
+				si[IN_CANCEL_COUNT] = 0;
+				si[IN_SCREWED] = 0;
+				si[IN_SATURATED] = 0;
+				si[IN_ADAPTED] = 0;
+				sc[SC_NOTCH0] = sc[SC_NOTCH1] = 0;
+				sc[SC_MEMD] = sc[SC_MEME] = sc[SC_MEMX] = 0;
+				sc[SC_SUM_ADAPT] = 0;
+				sc[SC_PEY] = sc[SC_PYY] = 1.f;
+				sc[SC_DAVG1] = sc[SC_DAVG2] = sc[SC_DVAR1] = sc[SC_DVAR2] = 0;
+			}
+			__syncthreads();
+			// the library returns before the adaptation statistics; the preprocessor still runs on `out`
+		} else {
+			if (t == 0) {
+				si[IN_SCREWED] = screwed;
+				si[IN_CANCEL_COUNT] = cc;
+			}
+			See = See > (float)(N * 100) ? See : (float)(N * 100);
+			Sxx += Sxx; // the library accumulates the far-end energy a second time at this point
+			// ---- smoothed far-end power, filtered spectra, leak estimate
+			float pey_part = 0.f, pyy_part = 0.f;
+			for (int j = t; j <= F; j += F) {
+				const float pw = ss_1 * S[ly.power + j] + 1 + ss * vec3[j];
+				S[ly.power + j] = pw;
+				vec4[j] = pw;
+				const float Eh_old = S[ly.Eh + j], Yh_old = S[ly.Yh + j];
+				const float Eh = vec1[j] - Eh_old, Yh = vec2[j] - Yh_old;
+				pey_part += Eh * Yh;
+				pyy_part += Yh * Yh;
+				S[ly.Eh + j] = (1 - P.spec_average) * Eh_old + P.spec_average * vec1[j];
+				S[ly.Yh + j] = (1 - P.spec_average) * Yh_old + P.spec_average * vec2[j];
+			}
+			float Pey = 1.f + block_sum(pey_part, red);
+			float Pyy = 1.f + block_sum(pyy_part, red);
+			Pyy = (float)sqrt((double)Pyy);
+			Pey = Pey / Pyy;
+			float tmp32 = P.beta0 * Syy;
+			if (tmp32 > P.beta_max * See) tmp32 = P.beta_max * See;
+			const float alpha = tmp32 / See, alpha_1 = 1.f - alpha;
+			float sPey = alpha_1 * sc[SC_PEY] + alpha * Pey;
+			float sPyy = alpha_1 * sc[SC_PYY] + alpha * Pyy;
+			if (sPyy < 1.f) sPyy = 1.f;
+			if (sPey < .005f * sPyy) sPey = .005f * sPyy;
+			if (sPey > sPyy) sPey = sPyy;
+			float leak = sPey / sPyy;
+			if (leak > 16383) leak = 32767;
+			float RER = (.0001f * Sxx + 3.f * leak * Syy) / See;
+			if (RER < Sey * Sey / (1 + See * Syy)) RER = Sey * Sey / (1 + See * Syy);
+			if (RER > .5f) RER = .5f;
+			int adapted = si[IN_ADAPTED];
+			float sum_adapt = sc[SC_SUM_ADAPT];
+			if (!adapted && sum_adapt > (float)M && leak * Syy > .03f * Syy) adapted = 1;
+			__syncthreads();
+			if (adapted) {
+				for (int i = t; i <= F; i += F) {
+					float r = leak * vec2[i];
+					const float e = vec1[i] + 1;
+					if (r > .5f * e) r = .5f * e;
+					r = .7f * r + .3f * (RER * e);
+					power_1[i] = r / (e * (vec4[i] + 10));
+				}
+			} else {
+				float adapt_rate = 0;
+				if (Sxx > (float)(N * 1000)) {
+					float tq = .25f * Sxx;
+					if (tq > .25f * See) tq = .25f * See;
+					adapt_rate = tq / See;
+				}
+				for (int i = t; i <= F; i += F) power_1[i] = adapt_rate / (vec4[i] + 10);
+				sum_adapt = sum_adapt + adapt_rate;
+			}
+			if (t == 0) {
+				sc[SC_PEY] = sPey;
+				sc[SC_PYY] = sPyy;
+				sc[SC_LEAK] = leak;
+				sc[SC_SUM_ADAPT] = sum_adapt;
+				si[IN_ADAPTED] = adapted;
+			}
+			// ---- last_y (residual echo input for the preprocessor)
+			{
+				const float second = S[ly.last_y + F + t];
+				S[ly.last_y + t] = second;
+				if (adapted) S[ly.last_y + F + t] = (float)(mic_i - out_i);
+			}
+			__syncthreads();
+		}
+
+		// ========================================================================= speex_preprocess_run
+		{
+			const int Mb = NB_BANDS;
+			int nb_adapt = si[IN_NB_ADAPT] + 1;
+			if (nb_adapt > 20000) nb_adapt = 20000;
+			int min_count = si[IN_MIN_COUNT] + 1;
+			float beta = 1.0f / (float)nb_adapt;
+			if (beta < .03f) beta = .03f;
+			const float beta_1 = 1.f - beta;
+			float *ps = vec1, *echo_noise = vec2, *noise = vec3, *prior = vec4, *gains = vec5;
+			// ---- speex_echo_get_residual: |FFT(window * last_y)|^2 * leak2, truncated to integers
+			tmpv[t] = P.window[t] * S[ly.last_y + t];
+			tmpv[t + F] = P.window[t + F] * S[ly.last_y + F + t];
+			__syncthreads();
+			rfft(tmpv, specB, bufa, bufb, P, tw, spl);
+			const float leak_now = sc[SC_LEAK];
+			const float leak2 = leak_now > .5f ? 1.f : 2 * leak_now;
+			{
+				const float2 y = specB[t];
+				float re = t == 0 ? y.x * y.x : y.x * y.x + y.y * y.y;
+				re = (float)(int)(leak2 * re);
+				// NaN / absurd-value guard on the DC term (residual_echo[0])
+				if (t == 0) red[0] = re;
+				__syncthreads();
+				const float r0 = red[0];
+				if (!(r0 >= 0 && r0 < F * 1e9f)) re = 0;
+				const float a = .6f * S[ly.echo_noise + t];
+				echo_noise[t] = a > re ? a : re;
+				__syncthreads();
+			}
+			filterbank_bank32(echo_noise, echo_noise + F, P);
+			// ---- preprocess_analysis
+			{
+				const float a = S[ly.inbuf + t] * P.pwindow[t];
+				const float b = (float)out_i * P.pwindow[F + t];
+				S[ly.inbuf + t] = (float)out_i;
+				tmpv[t] = a;
+				tmpv[F + t] = b;
+				__syncthreads();
+			}
+			rfft(tmpv, specA, bufa, bufb, P, tw, spl); // ft stays in specA (bin 0 = (ft[0], ft[2N-1]))
+			{
+				const float2 f = specA[t];
+				ps[t] = t == 0 ? f.x * f.x : f.x * f.x + f.y * f.y;
+				__syncthreads();
+			}
+			filterbank_bank32(ps, ps + F, P);
+			// ---- update_noise_prob
+			float Sv;
+			const int min_range = nb_adapt < 100 ? 15 : (nb_adapt < 1000 ? 50 : (nb_adapt < 10000 ? 150 : 300));
+			{
+				const float Sold = S[ly.S + t];
+				if (t == 0) Sv = .8f * Sold + .2f * ps[0];
+				else if (t == F - 1) Sv = .8f * Sold + .2f * ps[F - 1];
+				else Sv = .8f * Sold + .05f * ps[t - 1] + .1f * ps[t] + .05f * ps[t + 1];
+				S[ly.S + t] = Sv;
+				float smin = S[ly.Smin + t], stmp = S[ly.Stmp + t];
+				if (nb_adapt == 1) smin = stmp = 0;
+				if (min_count > min_range) {
+					smin = stmp < Sv ? stmp : Sv;
+					stmp = Sv;
+				} else {
+					smin = smin < Sv ? smin : Sv;
+					stmp = stmp < Sv ? stmp : Sv;
+				}
+				S[ly.Smin + t] = smin;
+				S[ly.Stmp + t] = stmp;
+				const int update_prob = (.4f * Sv > smin) ? 1 : 0;
+				float nz = S[ly.noise + t];
+				if (!update_prob || ps[t] < nz) {
+					const float v = beta_1 * nz + beta * ps[t];
+					nz = v > 0 ? v : 0;
+				}
+				noise[t] = nz;
+				S[ly.noise + t] = nz;
+				__syncthreads();
+			}
+			if (min_count > min_range) min_count = 0;
+			filterbank_bank32(noise, noise + F, P);
+			// ---- SNRs over F + Mb entries (thread t: bin t; threads < Mb also band F + t)
+			float post_me[2], old_ps_me[2];
+			for (int r = 0; r < 2; ++r) {
+				const int i = r == 0 ? t : F + t;
+				if (r == 1 && t >= Mb) break;
+				float old_ps = S[ly.old_ps + i];
+				if (nb_adapt == 1) old_ps = ps[i];
+				const float tot_noise = 1.f + noise[i] + echo_noise[i] + 0.f;
+				float post = ps[i] / tot_noise - 1.f;
+				if (post > 100.f) post = 100.f;
+				const float rr = old_ps / (old_ps + tot_noise);
+				const float gamma = .1f + .89f * (rr * rr);
+				float pr = gamma * (post > 0 ? post : 0) + (1.f - gamma) * (old_ps / tot_noise);
+				if (pr > 100.f) pr = 100.f;
+				prior[i] = pr;
+				post_me[r] = post;
+				old_ps_me[r] = old_ps;
+			}
+			__syncthreads();
+			// ---- zeta
+			{
+				float z = S[ly.zeta + t];
+				if (t == 0) z = .7f * z + .3f * prior[0];
+				else if (t < F - 1) z = .7f * z + .15f * prior[t] + .075f * prior[t - 1] + .075f * prior[t + 1];
+				else z = .7f * z + .3f * prior[t];
+				S[ly.zeta + t] = z;
+				if (t < Mb) {
+					float zb = .7f * S[ly.zeta + F + t] + .3f * prior[F + t];
+					S[ly.zeta + F + t] = zb;
+					gains[F + t] = zb; // stash band zeta for Zframe
+				}
+				__syncthreads();
+			}
+			if (t == 0) {
+				float Zframe = 0;
+				for (int i = 0; i < Mb; ++i) Zframe = Zframe + gains[F + i];
+				red[1] = .1f + .899f * qcurve(Zframe / (float)Mb);
+			}
+			__syncthreads();
+			const float Pframe = red[1];
+			const float effective_echo_suppress =
+			    (1.f - Pframe) * (float)P.echo_suppress + Pframe * (float)P.echo_suppress_active;
+			// ---- Bark-band gains: gain -> tmpv[0..Mb), gain2 -> tmpv[Mb..2Mb), gain_floor -> tmpv[2Mb..3Mb)
+			__syncthreads();
+			if (t < Mb) {
+				const int i = F + t;
+				const float noise_floor = (float)exp((double)(.2302585f * (float)P.noise_suppress));
+				const float echo_floor = (float)exp((double)(.2302585f * effective_echo_suppress));
+				const float gfl = (float)(sqrt((double)(noise_floor * noise[i] + echo_floor * echo_noise[i])) /
+				                          sqrt((double)(1 + noise[i] + echo_noise[i])));
+				const float prior_ratio = prior[i] / (prior[i] + 1.f);
+				const float theta = prior_ratio * (1.f + post_me[1]);
+				const float MM = hypergeom_gain(theta);
+				float g = prior_ratio * MM;
+				if (g > 1.f) g = 1.f;
+				S[ly.old_ps + i] = .2f * old_ps_me[1] + (.8f * (g * g)) * ps[i];
+				const float zb = gains[F + t];
+				const float P1 = .199f + .8f * qcurve(zb);
+				const float q = 1.f - Pframe * P1;
+				const double ee = exp((double)(-theta));
+				const float gain2b = (float)(1 / (1.f + (double)((q / (1.f - q)) * (1 + prior[i])) * ee));
+				tmpv[t] = g;
+				tmpv[Mb + t] = gain2b;
+				tmpv[2 * Mb + t] = gfl;
+			}
+			__syncthreads();
+			// ---- linear-frequency gains
+			{
+				const float gain_b = filterbank_psd16(tmpv, t, P);
+				const float p = filterbank_psd16(tmpv + Mb, t, P);
+				const float gfl = filterbank_psd16(tmpv + 2 * Mb, t, P);
+				const float prior_ratio = prior[t] / (prior[t] + 1.f);
+				const float theta = prior_ratio * (1.f + post_me[0]);
+				const float MM = hypergeom_gain(theta);
+				float g = prior_ratio * MM;
+				if (g > 1.f) g = 1.f;
+				if (.333f * g > gain_b) g = 3.f * gain_b;
+				S[ly.old_ps + t] = .2f * old_ps_me[0] + (.8f * (g * g)) * ps[t];
+				if (g < gfl) g = gfl;
+				const float tq = p * (float)sqrt((double)g) + (1.f - p) * (float)sqrt((double)gfl);
+				gains[t] = tq * tq;
+				S[ly.echo_noise + t] = echo_noise[t];
+				if (t < Mb) S[ly.echo_noise + F + t] = echo_noise[F + t]; // band part is recomputed each frame
+				__syncthreads();
+			}
+			// ---- apply gain, inverse FFT, synthesis window, overlap-add
+			{
+				float2 f = specA[t];
+				if (t == 0) {
+					f.x = gains[0] * f.x;
+					f.y = gains[F - 1] * f.y;
+				} else {
+					f.x = gains[t] * f.x;
+					f.y = gains[t] * f.y;
+				}
+				__syncthreads();
+				specA[t] = f;
+				__syncthreads();
+			}
+			irfft(specA, tmpv, bufa, bufb, P, tw, spl);
+			{
+				const float a = tmpv[t] * P.pwindow[t];
+				const float b = tmpv[F + t] * P.pwindow[F + t];
+				o16[t] = word2int(S[ly.outbuf + t] + a);
+				S[ly.outbuf + t] = b;
+			}
+			if (t == 0) {
+				si[IN_NB_ADAPT] = nb_adapt;
+				si[IN_MIN_COUNT] = min_count;
+			}
+			__syncthreads();
+		}
+	}
+
+	// ---- store per-stream small state kept in shared memory
+	reinterpret_cast<float2 *>(S + ly.E)[t] = Eprev[t];
+	S[ly.xprev + t] = xw[F + t];
+	for (int i = t; i <= F; i += F) S[ly.power_1 + i] = power_1[i];
+	for (int i = t; i < M; i += F) S[ly.prop + i] = prop[i];
+	if (t < SC_COUNT) S[ly.scal + t] = sc[t];
+	if (t < IN_COUNT) reinterpret_cast<int *>(S + ly.ints)[t] = si[t];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct msb200_aec {
+	msb200_ctx *ctx;
+	int n;
+	AecParams P;
+	int head; // ring head shared by all streams
+	size_t smem_bytes;
+	float2 *dX, *dW, *dFG;
+	float *dS;
+	void *d_tables;
+	std::vector<float> init_page;
+	msb200_devbuf mic, ref, out;
+	int tail_ms, filter_length;
+};
+
+static float to_bark(float n) {
+	return 13.1f * (float)atan(.00074f * n) + 2.24f * (float)atan(n * n * 1.85e-8f) + 1e-4f * n;
+}
+
+static size_t aec_smem_floats(int F, int M) {
+	const int N = 2 * F, L = F;
+	size_t f2 = (size_t)(L / 2) + (L + 2) + 5 * (size_t)L; // tw, spl, bufa, bufb, specA, specB, Eprev
+	size_t fl = (size_t)N * 4 + F + (F + 1) + 5 * (size_t)(F + NB_BANDS + 1) + M + (size_t)M * 8 + 32 + SC_COUNT + IN_COUNT;
+	return f2 * 2 + fl;
+}
+
+static int aec_write_init(msb200_aec *a, int first, int count) {
+	// X, W, FG zero; small page = init_page
+	const AecParams &P = a->P;
+	cudaStream_t s = a->ctx->stream;
+	MSB200_CUDA(cudaMemsetAsync(a->dX + (size_t)first * P.x_stride, 0, sizeof(float2) * P.x_stride * (size_t)count, s));
+	MSB200_CUDA(cudaMemsetAsync(a->dW + (size_t)first * P.w_stride, 0, sizeof(float2) * P.w_stride * (size_t)count, s));
+	MSB200_CUDA(cudaMemsetAsync(a->dFG + (size_t)first * P.w_stride, 0, sizeof(float2) * P.w_stride * (size_t)count, s));
+	std::vector<float> pages((size_t)count * P.lay.total);
+	for (int i = 0; i < count; ++i) memcpy(&pages[(size_t)i * P.lay.total], a->init_page.data(), sizeof(float) * (size_t)P.lay.total);
+	MSB200_CUDA(cudaMemcpyAsync(a->dS + (size_t)first * P.lay.total, pages.data(), sizeof(float) * pages.size(), cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+extern "C" {
+
+int msb200_aec_frame_size_for_rate(int sample_rate, int framesize_at_8000) { // adjust_framesize, speexec.c:171-180
+	int newsize = (framesize_at_8000 * sample_rate) / 8000, n = 1, next;
+	while ((next = n << 1) <= newsize) n = next;
+	return n;
+}
+
+int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_length_ms, int framesize_at_8000,
+                      msb200_aec **out) {
+	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && sample_rate >= 8000 && tail_length_ms > 0 && framesize_at_8000 > 0);
+	const int F = msb200_aec_frame_size_for_rate(sample_rate, framesize_at_8000);
+	MSB200_CHECK_ARG(F >= 32 && F <= 256); // one thread per bin; 8 kHz..48 kHz with the reference's framesize 64
+	const int filter_length = (tail_length_ms * sample_rate) / 1000; // speexec.c:194
+	const int N = 2 * F, L = F, M = (filter_length + F - 1) / F;
+	MSB200_CHECK_ARG(M >= 2 && M <= 512);
+	msb200_aec *a = new msb200_aec();
+	a->ctx = ctx;
+	a->n = n_streams;
+	a->tail_ms = tail_length_ms;
+	a->filter_length = filter_length;
+	a->head = 0;
+	AecParams &P = a->P;
+	P.F = F; P.N = N; P.M = M; P.L = L; P.rate = sample_rate;
+	P.log2L = 0;
+	while ((1 << P.log2L) < L) P.log2L++;
+	P.spec_average = (float)F / (float)sample_rate;
+	P.beta0 = (2.0f * (float)F) / (float)sample_rate;
+	P.beta_max = (.5f * (float)F) / (float)sample_rate;
+	P.notch_radius = sample_rate < 12000 ? .9f : (sample_rate < 24000 ? .982f : .992f);
+	P.preemph = .9f;
+	P.noise_suppress = -15; P.echo_suppress = -40; P.echo_suppress_active = -15;
+	// small-state layout
+	AecLayout &ly = P.lay;
+	int o = 0;
+	auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+	ly.xprev = take(F); ly.E = take(N); ly.last_y = take(N); ly.power = take(F + 1); ly.power_1 = take(F + 1);
+	ly.Eh = take(F + 1); ly.Yh = take(F + 1); ly.prop = take(M); ly.wnorm = take(M); ly.scal = take(SC_COUNT);
+	ly.ints = take(IN_COUNT); ly.inbuf = take(F); ly.outbuf = take(F); ly.old_ps = take(F + NB_BANDS);
+	ly.noise = take(F + NB_BANDS); ly.echo_noise = take(F + NB_BANDS); ly.zeta = take(F + NB_BANDS);
+	ly.S = take(F); ly.Smin = take(F); ly.Stmp = take(F);
+	ly.total = o;
+	P.x_stride = (size_t)(M + 1) * F;
+	P.w_stride = (size_t)M * F;
+	// initial page (speex_echo_state_init + speex_preprocess_state_init)
+	a->init_page.assign((size_t)ly.total, 0.f);
+	for (int i = 0; i <= F; ++i) a->init_page[(size_t)ly.power_1 + i] = 1.f;
+	std::vector<float> prop((size_t)M);
+	{
+		float sum, decay = (float)exp(-2.4 / M);
+		prop[0] = .7f;
+		sum = prop[0];
+		for (int i = 1; i < M; i++) {
+			prop[(size_t)i] = prop[(size_t)i - 1] * decay;
+			sum = sum + prop[(size_t)i];
+		}
+		for (int i = M - 1; i >= 0; i--) prop[(size_t)i] = (.8f * prop[(size_t)i]) / sum;
+	}
+	for (int i = 0; i < M; ++i) a->init_page[(size_t)ly.prop + i] = prop[(size_t)i];
+	a->init_page[(size_t)ly.scal + SC_PEY] = 1.f;
+	a->init_page[(size_t)ly.scal + SC_PYY] = 1.f;
+	for (int i = 0; i < F + NB_BANDS; ++i) {
+		a->init_page[(size_t)ly.noise + i] = 1.f;
+		a->init_page[(size_t)ly.old_ps + i] = 1.f;
+	}
+	// constant tables
+	std::vector<float2> tw((size_t)L / 2), spl((size_t)L + 1);
+	for (int j = 0; j < L / 2; ++j) tw[(size_t)j] = make_float2((float)cos(2.0 * M_PI * j / L), (float)sin(2.0 * M_PI * j / L));
+	for (int k = 0; k <= L; ++k) spl[(size_t)k] = make_float2((float)cos(2.0 * M_PI * k / N), (float)sin(2.0 * M_PI * k / N));
+	std::vector<float> window((size_t)N), pwindow((size_t)N);
+	for (int i = 0; i < N; i++) window[(size_t)i] = (float)(.5 - .5 * cos(2 * M_PI * i / N));
+	for (int i = 0; i < N; i++) { // conj_window(2*F)
+		float tmp, x = (4.f * (float)i) / (float)N;
+		int inv = 0;
+		if (x < 1.f) {
+		} else if (x < 2.f) {
+			x = 2.f - x;
+			inv = 1;
+		} else if (x < 3.f) {
+			x = x - 2.f;
+			inv = 1;
+		} else {
+			x = 2.f - x + 2.f;
+		}
+		x = 1.271903f * x;
+		tmp = .5f - .5f * (float)cos(.5 * M_PI * x);
+		tmp = tmp * tmp;
+		if (inv) tmp = 1.f - tmp;
+		pwindow[(size_t)i] = (float)sqrt(tmp);
+	}
+	std::vector<int> bank_left((size_t)F, 0), band_start(NB_BANDS + 1, F);
+	std::vector<float> fl((size_t)F, 0.f), frr((size_t)F, 0.f);
+	{ // filterbank_new(NB_BANDS, rate, F, 1)
+		float df = (float)sample_rate / (2.f * (float)F);
+		float max_mel = to_bark((float)sample_rate / 2);
+		float mel_interval = max_mel / (float)(NB_BANDS - 1);
+		for (int i = 0; i < F; i++) {
+			float curr_freq = (float)i * df;
+			float mel = to_bark(curr_freq);
+			float val;
+			int id1;
+			if (mel > max_mel) break;
+			id1 = (int)(floor(mel / mel_interval));
+			if (id1 > NB_BANDS - 2) {
+				id1 = NB_BANDS - 2;
+				val = 1.f;
+			} else {
+				val = (mel - (float)id1 * mel_interval) / mel_interval;
+			}
+			bank_left[(size_t)i] = id1;
+			fl[(size_t)i] = 1.f - val;
+			frr[(size_t)i] = val;
+		}
+		// band_start[b] = first bin with left band >= b (bins are monotonic in band index)
+		for (int b = NB_BANDS; b >= 0; --b) {
+			int first = F;
+			for (int i = F - 1; i >= 0; --i)
+				if (bank_left[(size_t)i] >= b) first = i;
+			band_start[(size_t)b] = first;
+		}
+	}
+	// one allocation for all tables
+	size_t off = 0;
+	auto place = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+	size_t o_tw = place(sizeof(float2) * tw.size()), o_spl = place(sizeof(float2) * spl.size());
+	size_t o_win = place(sizeof(float) * N), o_pwin = place(sizeof(float) * N), o_bl = place(sizeof(int) * F);
+	size_t o_fl = place(sizeof(float) * F), o_fr = place(sizeof(float) * F), o_bs = place(sizeof(int) * (NB_BANDS + 1));
+	size_t o_prop = place(sizeof(float) * M);
+	MSB200_CUDA(cudaMalloc(&a->d_tables, off));
+	char *base = (char *)a->d_tables;
+	MSB200_CUDA(cudaMemcpy(base + o_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_spl, spl.data(), sizeof(float2) * spl.size(), cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_win, window.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_pwin, pwindow.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_bl, bank_left.data(), sizeof(int) * F, cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_fl, fl.data(), sizeof(float) * F, cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_fr, frr.data(), sizeof(float) * F, cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_bs, band_start.data(), sizeof(int) * (NB_BANDS + 1), cudaMemcpyHostToDevice));
+	MSB200_CUDA(cudaMemcpy(base + o_prop, prop.data(), sizeof(float) * M, cudaMemcpyHostToDevice));
+	P.tw = (const float2 *)(base + o_tw); P.spl = (const float2 *)(base + o_spl);
+	P.window = (const float *)(base + o_win); P.pwindow = (const float *)(base + o_pwin);
+	P.bank_left = (const int *)(base + o_bl); P.filter_left = (const float *)(base + o_fl);
+	P.filter_right = (const float *)(base + o_fr); P.band_start = (const int *)(base + o_bs);
+	P.prop0 = (const float *)(base + o_prop);
+	// state
+	MSB200_CUDA(cudaMalloc(&a->dX, sizeof(float2) * P.x_stride * (size_t)n_streams));
+	MSB200_CUDA(cudaMalloc(&a->dW, sizeof(float2) * P.w_stride * (size_t)n_streams));
+	MSB200_CUDA(cudaMalloc(&a->dFG, sizeof(float2) * P.w_stride * (size_t)n_streams));
+	MSB200_CUDA(cudaMalloc(&a->dS, sizeof(float) * (size_t)ly.total * (size_t)n_streams));
+	int r = aec_write_init(a, 0, n_streams);
+	if (r) return r;
+	a->smem_bytes = aec_smem_floats(F, M) * sizeof(float);
+	if (a->smem_bytes > 48 * 1024)
+		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+	*out = a;
+	return MSB200_OK;
+}
+
+void msb200_aec_destroy(msb200_aec *a) {
+	if (!a) return;
+	cudaStreamSynchronize(a->ctx->stream);
+	cudaFree(a->dX);
+	cudaFree(a->dW);
+	cudaFree(a->dFG);
+	cudaFree(a->dS);
+	cudaFree(a->d_tables);
+	a->mic.release();
+	a->ref.release();
+	a->out.release();
+	delete a;
+}
+
+int msb200_aec_get_info(msb200_aec *a, msb200_aec_info *info) {
+	MSB200_CHECK_ARG(a && info);
+	info->frame_size = a->P.F;
+	info->window_size = a->P.N;
+	info->M = a->P.M;
+	info->sample_rate = a->P.rate;
+	info->filter_length = a->filter_length;
+	info->state_bytes_per_stream = sizeof(float2) * (a->P.x_stride + 2 * a->P.w_stride) + sizeof(float) * (size_t)a->P.lay.total;
+	return MSB200_OK;
+}
+
+int msb200_aec_reset(msb200_aec *a, int stream) {
+	MSB200_CHECK_ARG(a && stream >= -1 && stream < a->n);
+	return stream < 0 ? aec_write_init(a, 0, a->n) : aec_write_init(a, stream, 1);
+}
+
+int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes, int stride) {
+	MSB200_CHECK_ARG(a && nframes > 0 && stride >= nframes * a->P.F);
+	return msb200i_aec_launch(a, d_mic, d_ref, stride, 0, 0, d_out, stride, 0, 0, nframes);
+}
+} // extern "C"
+int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int in_stride, int in_frame0,
+                       int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes) {
+	MSB200_CHECK_ARG(a && d_mic && d_ref && d_out && nframes > 0);
+	MSB200_LAUNCH(a->ctx, aec_kernel, a->n, a->P.F, a->smem_bytes, (const short *)d_mic, (const short *)d_ref,
+	              (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, a->head, in_frame0,
+	              in_ring_frames, out_stride, out_frame0, out_ring_frames);
+	// advance the shared ring head exactly as the kernel did
+	for (int f = 0; f < nframes; ++f) a->head = (a->head + a->P.M) % (a->P.M + 1);
+	return MSB200_OK;
+}
+extern "C" {
+
+int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes) {
+	MSB200_CHECK_ARG(a && mic && ref && out && nframes > 0);
+	size_t bytes = (size_t)a->n * nframes * a->P.F * 2;
+	int r;
+	if ((r = a->mic.reserve(bytes)) || (r = a->ref.reserve(bytes)) || (r = a->out.reserve(bytes))) return r;
+	cudaStream_t s = a->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(a->mic.p, mic, bytes, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaMemcpyAsync(a->ref.p, ref, bytes, cudaMemcpyHostToDevice, s));
+	if ((r = msb200_aec_process_dev(a, a->mic.p, a->ref.p, a->out.p, nframes, nframes * a->P.F))) return r;
+	MSB200_CUDA(cudaMemcpyAsync(out, a->out.p, bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+// blob = {magic, F, M, rate} + W [M][F] float2 + FG [M][F] float2
+size_t msb200_aec_state_blob_size(msb200_aec *a) {
+	return a ? 16 + 2 * sizeof(float2) * a->P.w_stride : 0;
+}
+int msb200_aec_get_state_blob(msb200_aec *a, int stream, void *blob, size_t size) {
+	MSB200_CHECK_ARG(a && blob && stream >= 0 && stream < a->n && size >= msb200_aec_state_blob_size(a));
+	int32_t hdr[4] = {0x4D534145, a->P.F, a->P.M, a->P.rate};
+	memcpy(blob, hdr, 16);
+	size_t wb = sizeof(float2) * a->P.w_stride;
+	cudaStream_t s = a->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync((char *)blob + 16, a->dW + (size_t)stream * a->P.w_stride, wb, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaMemcpyAsync((char *)blob + 16 + wb, a->dFG + (size_t)stream * a->P.w_stride, wb, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+int msb200_aec_set_state_blob(msb200_aec *a, int stream, const void *blob, size_t size) {
+	MSB200_CHECK_ARG(a && blob && stream >= 0 && stream < a->n && size >= msb200_aec_state_blob_size(a));
+	int32_t hdr[4];
+	memcpy(hdr, blob, 16);
+	if (hdr[0] != 0x4D534145 || hdr[1] != a->P.F || hdr[2] != a->P.M || hdr[3] != a->P.rate) {
+		msb200_set_error("AEC state blob does not match this canceller (F/M/rate)");
+		return MSB200_EINVAL;
+	}
+	size_t wb = sizeof(float2) * a->P.w_stride;
+	cudaStream_t s = a->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(a->dW + (size_t)stream * a->P.w_stride, (const char *)blob + 16, wb, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaMemcpyAsync(a->dFG + (size_t)stream * a->P.w_stride, (const char *)blob + 16 + wb, wb, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+// probes return data in the ORACLE's layout (speex packed spectra, X ordered newest block first)
+int msb200_aec_probe(msb200_aec *a, int stream, const char *what, float *out, int max_floats) {
+	MSB200_CHECK_ARG(a && what && out && stream >= 0 && stream < a->n);
+	const AecParams &P = a->P;
+	const int F = P.F, N = P.N, M = P.M;
+	cudaStream_t s = a->ctx->stream;
+	auto unpack_blocks = [&](const float2 *dev, int nblocks, int ring_head) -> int {
+		std::vector<float2> tmp((size_t)nblocks * F);
+		if (cudaMemcpyAsync(tmp.data(), dev, sizeof(float2) * tmp.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess) return MSB200_ECUDA;
+		cudaStreamSynchronize(s);
+		int n = 0;
+		for (int j = 0; j < nblocks; ++j) {
+			const int slot = ring_head < 0 ? j : (ring_head + j) % nblocks;
+			const float2 *b = &tmp[(size_t)slot * F];
+			for (int i = 0; i < N && n < max_floats; ++i, ++n) {
+				float v;
+				if (i == 0) v = b[0].x;
+				else if (i == N - 1) v = b[0].y;
+				else v = (i & 1) ? b[(i + 1) / 2].x : b[i / 2].y;
+				out[n] = v;
+			}
+		}
+		return n;
+	};
+	if (!strcmp(what, "W")) return unpack_blocks(a->dW + (size_t)stream * P.w_stride, M, -1);
+	if (!strcmp(what, "foreground")) return unpack_blocks(a->dFG + (size_t)stream * P.w_stride, M, -1);
+	if (!strcmp(what, "X")) return unpack_blocks(a->dX + (size_t)stream * P.x_stride, M + 1, a->head);
+	std::vector<float> page((size_t)P.lay.total);
+	MSB200_CUDA(cudaMemcpyAsync(page.data(), a->dS + (size_t)stream * P.lay.total, sizeof(float) * page.size(), cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	const AecLayout &ly = P.lay;
+	int off = -1, n = 0;
+	if (!strcmp(what, "power")) off = ly.power, n = F + 1;
+	else if (!strcmp(what, "power_1")) off = ly.power_1, n = F + 1;
+	else if (!strcmp(what, "prop")) off = ly.prop, n = M;
+	else if (!strcmp(what, "last_y")) off = ly.last_y, n = N;
+	else if (!strcmp(what, "noise")) off = ly.noise, n = F + NB_BANDS;
+	else if (!strcmp(what, "echo_noise")) off = ly.echo_noise, n = F + NB_BANDS;
+	else if (!strcmp(what, "old_ps")) off = ly.old_ps, n = F + NB_BANDS;
+	else if (!strcmp(what, "scalars")) {
+		const float *sc = &page[(size_t)ly.scal];
+		const int *si = reinterpret_cast<const int *>(&page[(size_t)ly.ints]);
+		float v[16] = {(float)si[IN_ADAPTED], sc[SC_SUM_ADAPT], sc[SC_LEAK], sc[SC_PEY], sc[SC_PYY], sc[SC_DAVG1],
+		               sc[SC_DAVG2], sc[SC_DVAR1], sc[SC_DVAR2], (float)si[IN_SATURATED], (float)si[IN_SCREWED],
+		               (float)si[IN_CANCEL_COUNT], sc[SC_MEME], sc[SC_MEMD], sc[SC_MEMX], (float)si[IN_NB_ADAPT]};
+		n = max_floats < 16 ? max_floats : 16;
+		memcpy(out, v, sizeof(float) * (size_t)n);
+		return n;
+	} else if (!strcmp(what, "E")) {
+		const float2 *b = reinterpret_cast<const float2 *>(&page[(size_t)ly.E]);
+		for (int i = 0; i < N && n < max_floats; ++i, ++n)
+			out[n] = i == 0 ? b[0].x : (i == N - 1 ? b[0].y : ((i & 1) ? b[(i + 1) / 2].x : b[i / 2].y));
+		return n;
+	} else {
+		msb200_set_error("unknown probe '%s'", what);
+		return MSB200_EINVAL;
+	}
+	if (n > max_floats) n = max_floats;
+	memcpy(out, &page[(size_t)off], sizeof(float) * (size_t)n);
+	return n;
+}
+
+} // extern "C"

@@ -77,14 +77,15 @@ template <int VEC>
 __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in, const uint8_t *__restrict__ present,
                                                     const float *__restrict__ gain, const uint8_t *__restrict__ active,
                                                     short *__restrict__ out, int *__restrict__ sum_io, int n_rooms,
-                                                    int n_pins, int nwords, int conf_mode, int mode) {
+                                                    int n_pins, int nwords, int conf_mode, int mode, long in_pin_vecs) {
 	typedef typename s16vec<VEC>::type V;
 	const int nvec = nwords / VEC;
 	const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (gid >= (long)n_rooms * nvec) return;
 	const int room = (int)(gid / nvec), col = (int)(gid % nvec);
 	const size_t chan0 = (size_t)room * n_pins;
-	const V *inv = reinterpret_cast<const V *>(in) + chan0 * nvec + col;
+	// in_pin_vecs: distance between consecutive pins' blocks in V units (nvec when the input is dense)
+	const V *inv = reinterpret_cast<const V *>(in) + chan0 * in_pin_vecs + col;
 	int sum[VEC];
 #pragma unroll
 	for (int k = 0; k < VEC; ++k) sum[k] = 0;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in
 			if (!present[chan0 + p] || !active[chan0 + p]) continue;
 			const float g = gain[chan0 + p];
 			int s[VEC];
-			unpack_s16<VEC>(inv[(size_t)p * nvec], s);
+			unpack_s16<VEC>(inv[(size_t)p * in_pin_vecs], s);
 #pragma unroll
 			for (int k = 0; k < VEC; ++k) sum[k] += mix_contrib(s[k], g);
 		}
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in
 		if (active[chan0 + p] && present[chan0 + p]) {
 			const float g = gain[chan0 + p];
 			int s[VEC];
-			unpack_s16<VEC>(inv[(size_t)p * nvec], s);
+			unpack_s16<VEC>(inv[(size_t)p * in_pin_vecs], s);
 #pragma unroll
 			for (int k = 0; k < VEC; ++k) o[k] = mix_sat(sum[k] - mix_contrib(s[k], g));
 		} else {
@@ -143,19 +144,22 @@ static int mixer_upload(msb200_mixer *m) {
 	return MSB200_OK;
 }
 
-static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out, void *d_sum, int mode) {
+static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out, void *d_sum, int mode,
+                        long in_pin_stride = 0) {
 	int r = mixer_upload(m);
 	if (r) return r;
 	const int nw = m->nwords;
 	const bool al16 = ((uintptr_t)d_in % 16 == 0) && (d_out == nullptr || (uintptr_t)d_out % 16 == 0);
+	if (in_pin_stride <= 0) in_pin_stride = nw;
 	int vec = (nw % 8 == 0 && al16) ? 8 : (nw % 4 == 0 && al16) ? 4 : (nw % 2 == 0 && al16) ? 2 : 1;
+	while (vec > 1 && in_pin_stride % vec) vec /= 2;
 	// prefer more, narrower threads when the grid would not cover the chip (148 SMs x >=4 CTAs of 128)
 	while (vec > 2 && (long)m->n_rooms * (nw / vec) < 148L * 4 * 128) vec /= 2;
 	const long nthreads = (long)m->n_rooms * (nw / vec);
 	const int block = 128, grid = (int)((nthreads + block - 1) / block);
 #define MIX_ARGS                                                                                                       \
 	(const short *)d_in, (const uint8_t *)d_present, m->d_gain, m->d_active, (short *)d_out, (int *)d_sum, m->n_rooms, \
-	    m->n_pins, nw, m->conf_mode, mode
+	    m->n_pins, nw, m->conf_mode, mode, in_pin_stride / vec
 	switch (vec) {
 		case 8: MSB200_LAUNCH(m->ctx, mixer_kernel<8>, grid, block, 0, MIX_ARGS); break;
 		case 4: MSB200_LAUNCH(m->ctx, mixer_kernel<4>, grid, block, 0, MIX_ARGS); break;
@@ -237,6 +241,11 @@ int msb200_mixer_process(msb200_mixer *m, const int16_t *in, const uint8_t *pres
 
 } // extern "C"
 
+int msb200i_mixer_launch(msb200_mixer *m, const void *d_in, long in_pin_stride, const void *d_present, void *d_out) {
+	MSB200_CHECK_ARG(m && d_in && d_present && d_out);
+	return mixer_launch(m, d_in, d_present, d_out, nullptr, 0, in_pin_stride);
+}
+
 // ======================================================================================================= volume
 // reference: /root/reference/src/audiofilters/msvolume.c light path :503-513
 //   update_energy :388-407, volume_noise_gate_process :240-260, apply_gain :409-445, saturate :382-384
@@ -256,13 +265,19 @@ __device__ __forceinline__ int vol_sat(int v) { // :382-384
 // strictly sequential float32 accumulation (acc += s*s) so `energy` is bit-exact; peak and DC sums are integer and
 // reduced across the warp; then all lanes apply the Q12 gain and store.
 __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st,
-                                                     int n_streams, int nsamples, int stride) {
+                                                     int n_streams, int nsamples, int stride, int nblocks, int block0,
+                                                     int ring_blocks) {
 	extern __shared__ short vsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int stream = blockIdx.x * (blockDim.x >> 5) + warp;
 	if (stream >= n_streams) return;
 	short *buf = vsm + (size_t)warp * ((nsamples + 1) & ~1);
-	short *g = io + (size_t)stream * stride;
+	// nblocks consecutive blocks (the reference processes one mblk at a time, msvolume.c:505-512), optionally laid out
+	// in a block-aligned circular buffer
+	for (int blk = 0; blk < nblocks; ++blk) {
+	const int bpos = ring_blocks > 0 ? (block0 + blk) % ring_blocks : blk;
+	short *g = io + (size_t)stream * stride + (size_t)bpos * nsamples;
+	__syncwarp();
 	int pk = 0, dcsum = 0;
 	for (int i = lane; i < nsamples; i += 32) {
 		int s = g[i];
@@ -326,11 +341,12 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 	apply = __shfl_sync(0xffffffffu, apply, 0);
 	remove_dc = __shfl_sync(0xffffffffu, remove_dc, 0);
 	dc_prev = __shfl_sync(0xffffffffu, dc_prev, 0);
-	if (!apply) return; // gain == 1: the reference leaves the block untouched (:441)
+	if (!apply) continue; // gain == 1: the reference leaves the block untouched (:441)
 	for (int i = lane; i < nsamples; i += 32) {
 		int s = buf[i];
 		if (remove_dc) s -= dc_prev;
 		g[i] = (short)vol_sat((s * intgain) / 4096); // C truncating division
+	}
 	}
 }
 
@@ -409,12 +425,8 @@ int msb200_volume_get_state(msb200_volume *v, int stream, msb200_volume_state *s
 	return MSB200_OK;
 }
 int msb200_volume_process_dev(msb200_volume *v, void *d_io, int nsamples, int stride) {
-	MSB200_CHECK_ARG(v && d_io && nsamples > 0 && nsamples <= v->max_block && stride >= nsamples);
-	const int warps = 8;
-	size_t smem = (size_t)warps * ((nsamples + 1) & ~1) * sizeof(short);
-	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->n, warps), warps * 32, smem, (short *)d_io, v->d_state, v->n,
-	              nsamples, stride);
-	return MSB200_OK;
+	MSB200_CHECK_ARG(stride >= nsamples);
+	return msb200i_volume_launch(v, d_io, nsamples, stride, 1, 0, 0);
 }
 int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples) {
 	MSB200_CHECK_ARG(v && io);
@@ -430,6 +442,15 @@ int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples) {
 }
 
 } // extern "C"
+
+int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride, int nblocks, int block0, int ring_blocks) {
+	MSB200_CHECK_ARG(v && d_io && nsamples > 0 && nsamples <= v->max_block && nblocks > 0);
+	const int warps = 8;
+	size_t smem = (size_t)warps * ((nsamples + 1) & ~1) * sizeof(short);
+	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->n, warps), warps * 32, smem, (short *)d_io, v->d_state, v->n,
+	              nsamples, stride, nblocks, block0, ring_blocks);
+	return MSB200_OK;
+}
 
 // ======================================================================================================= channel adapter
 // reference: /root/reference/src/audiofilters/chanadapt.c:68-131

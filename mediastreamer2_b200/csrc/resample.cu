@@ -103,7 +103,7 @@ __device__ __forceinline__ short word2int(float x) { // speexdsp arch.h WORD2INT
 __global__ void __launch_bounds__(256)
     resample_kernel(const short *__restrict__ in, int in_frames, int in_stride, short *__restrict__ out, int out_frames,
                     int out_stride, short *__restrict__ hist, const float *__restrict__ table, ResampleParams p,
-                    int last_sample0, int samp_frac0) {
+                    int last_sample0, int samp_frac0, int ring_off, int ring_cap) {
 	extern __shared__ float rsm[];
 	float *tab = rsm;               // [table_len]
 	float *x = rsm + p.table_len;   // [filt_len-1 + in_frames]
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(256)
 			(void)f2; (void)f3;
 			y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(i0, a0), __fmul_rn(i1, a1)), __fmul_rn(i2, a2)), __fmul_rn(i3, a3));
 		}
-		gout[(size_t)k * p.nch] = word2int(y);
+		// ring_cap > 0: the output row is a circular buffer of ring_cap frames, written from ring_off (chain re-framing)
+		const int ko = ring_cap > 0 ? (ring_off + k) % ring_cap : k;
+		gout[(size_t)ko * p.nch] = word2int(y);
 	}
 	__syncthreads();
 	// mem[j] = mem[j + in_frames] for j < N-1
@@ -252,9 +254,14 @@ int msb200_resample_reset(msb200_resample *r) {
 }
 int msb200_resample_process_dev(msb200_resample *r, const void *d_in, int in_frames, int in_stride, void *d_out,
                                 int out_stride, int *out_frames) {
+	return msb200i_resample_launch(r, d_in, in_frames, in_stride, d_out, out_stride, 0, 0, out_frames);
+}
+} // extern "C"
+int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames, int in_stride, void *d_out,
+                            int out_stride, int ring_off, int ring_cap, int *out_frames) {
 	MSB200_CHECK_ARG(r && d_in && d_out && in_frames > 0 && in_frames <= r->max_in && in_stride >= in_frames);
 	int cap = msb200_resample_max_out(r, in_frames);
-	MSB200_CHECK_ARG(out_stride >= cap);
+	MSB200_CHECK_ARG(ring_cap > 0 ? out_stride >= ring_cap : out_stride >= cap);
 	int last0 = r->last_sample, frac0 = r->samp_frac;
 	int n_out = resample_count(r->d, in_frames, cap, r->last_sample, r->samp_frac);
 	if (out_frames) *out_frames = n_out;
@@ -262,9 +269,10 @@ int msb200_resample_process_dev(msb200_resample *r, const void *d_in, int in_fra
 	int block = n_out >= 256 ? 256 : ((n_out + 31) & ~31);
 	if (block < 32) block = 32;
 	MSB200_LAUNCH(r->ctx, resample_kernel, r->n * r->nch, block, smem, (const short *)d_in, in_frames, in_stride,
-	              (short *)d_out, n_out, out_stride, r->d_hist, r->d_table, r->p, last0, frac0);
+	              (short *)d_out, n_out, out_stride, r->d_hist, r->d_table, r->p, last0, frac0, ring_off, ring_cap);
 	return MSB200_OK;
 }
+extern "C" {
 int msb200_resample_process(msb200_resample *r, const int16_t *in, int in_frames, int16_t *out, int out_stride,
                             int *out_frames) {
 	MSB200_CHECK_ARG(r && in && out && in_frames > 0);

@@ -318,6 +318,14 @@ class AudioChain:
         check(self.lib.msb200_chain_tick(self.h, _ptr(ref_in), _ptr(mic_in), _ptr(out), C.byref(got)))
         return out, got.value
 
+    def enable_kernel_timing(self, enabled: bool = True):
+        check(self.lib.msb200_chain_enable_kernel_timing(self.h, int(enabled)))
+
+    def kernel_timing(self):
+        ms, nl, nf = C.c_float(), C.c_int(), C.c_int()
+        check(self.lib.msb200_chain_get_kernel_timing(self.h, C.byref(ms), C.byref(nl), C.byref(nf)))
+        return float(ms.value), nl.value, nf.value
+
     def tick_dev(self, d_ref: int, d_mic: int, d_out: int) -> int:
         got = C.c_int()
         check(self.lib.msb200_chain_tick_dev(self.h, C.c_void_p(d_ref), C.c_void_p(d_mic), C.c_void_p(d_out), C.byref(got)))
