@@ -51,6 +51,19 @@ struct AecParams {
 	const float *prop0;    // [M] initial proportional weights
 };
 
+// ------------------------------------------------------------------------------------------------ cp.async (LDGSTS)
+#define AEC_STAGES 4
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+	asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+	asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ block helpers
 // All helpers are called by every thread of the CTA (blockDim.x == F).
 
@@ -74,20 +87,22 @@ __device__ int block_any(int pred) {
 	return __syncthreads_or(pred);
 }
 
-// complex radix-2 Stockham FFT of length L over shared memory, one output element per thread per stage.
-// Mirrors oracle/oracle_aec.c:cfft() operation for operation. Returns the buffer holding the result.
-__device__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int L, int sign) {
+// complex radix-2 Stockham FFT of length L = 1 << LOG2L over shared memory, one output element per thread per stage.
+// Mirrors oracle/oracle_aec.c:cfft() operation for operation (stage loop fully unrolled: all index math is shifts and
+// masks with compile-time constants). Returns the buffer holding the result.
+template <int LOG2L> __device__ __forceinline__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int sign) {
 	const int o = threadIdx.x;
-	for (int n = L, s = 1; n > 1; n >>= 1, s <<= 1) {
-		const int m = n >> 1;
-		const int q = o & (s - 1), tmp = o / s, r = tmp & 1, p = tmp >> 1;
+#pragma unroll
+	for (int st = 0; st < LOG2L; ++st) {
+		const int s = 1 << st, m = 1 << (LOG2L - 1 - st);
+		const int q = o & (s - 1), tmp = o >> st, r = tmp & 1, p = tmp >> 1;
 		const float2 a = x[q + s * p], b = x[q + s * (p + m)];
 		float2 out;
 		if (!r) {
 			out.x = a.x + b.x;
 			out.y = a.y + b.y;
 		} else {
-			const float2 w = tw[p * s];
+			const float2 w = tw[p << st];
 			const float wr = w.x, wi = sign < 0 ? -w.y : w.y;
 			const float dr = a.x - b.x, di = a.y - b.y;
 			out.x = dr * wr - di * wi;
@@ -104,13 +119,14 @@ __device__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int L, int sign)
 
 // real forward FFT (spx_fft semantics: input scaled by 1/N): in[N] real (smem) -> spec[L] float2 (smem, bin0=(DC,Nyq))
 // bufa/bufb: float2[L] scratch. in may alias nothing; spec may alias neither scratch.
+template <int LOG2L>
 __device__ void rfft(const float *in, float2 *spec, float2 *bufa, float2 *bufb, const AecParams &P, const float2 *tw,
                      const float2 *spl) {
-	const int k = threadIdx.x, L = P.L;
+	const int k = threadIdx.x, L = 1 << LOG2L;
 	const float scale = (float)(1. / P.N);
 	bufa[k] = make_float2(scale * in[2 * k], scale * in[2 * k + 1]);
 	__syncthreads();
-	const float2 *Z = cfft(bufa, bufb, tw, L, -1);
+	const float2 *Z = cfft<LOG2L>(bufa, bufb, tw, -1);
 	float2 out;
 	if (k == 0) {
 		out.x = Z[0].x + Z[0].y;
@@ -129,9 +145,10 @@ __device__ void rfft(const float *in, float2 *spec, float2 *bufa, float2 *bufb, 
 }
 
 // real inverse FFT (spx_ifft, unscaled): spec[L] float2 (bin0=(DC,Nyq)) -> out[N] real (smem)
+template <int LOG2L>
 __device__ void irfft(const float2 *spec, float *out, float2 *bufa, float2 *bufb, const AecParams &P, const float2 *tw,
                       const float2 *spl) {
-	const int k = threadIdx.x, L = P.L;
+	const int k = threadIdx.x, L = 1 << LOG2L;
 	float2 z;
 	if (k == 0) {
 		z.x = spec[0].x + spec[0].y;
@@ -148,7 +165,7 @@ __device__ void irfft(const float2 *spec, float *out, float2 *bufa, float2 *bufb
 	__syncthreads();
 	bufa[k] = z;
 	__syncthreads();
-	const float2 *r = cfft(bufa, bufb, tw, L, +1);
+	const float2 *r = cfft<LOG2L>(bufa, bufb, tw, +1);
 	const float2 v = r[k];
 	__syncthreads();
 	out[2 * k] = v.x;
@@ -197,13 +214,15 @@ __device__ __forceinline__ float qcurve(float x) {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 // dynamic shared memory map (floats): see carve-up at the top of the kernel body
-__global__ void __launch_bounds__(256)
+template <int LOG2L>
+__global__ void __launch_bounds__(1 << LOG2L, (768 >> LOG2L))
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
                float *__restrict__ gS, AecParams P, int head0, int in_frame0, int in_ring, int out_stride, int out_frame0,
                int out_ring) {
 	extern __shared__ float sm[];
-	const int F = P.F, N = P.N, M = P.M, L = P.L;
+	constexpr int F = 1 << LOG2L, N = 2 * F, L = F;
+	const int M = P.M;
 	const int t = threadIdx.x;
 	const int stream = blockIdx.x;
 	// ---- shared memory carve-up
@@ -214,7 +233,8 @@ __global__ void __launch_bounds__(256)
 	float2 *specA = bufb + L;                              // [L] spectrum scratch A
 	float2 *specB = specA + L;                             // [L] spectrum scratch B
 	float2 *Eprev = specB + L;                             // [L] previous frame's error spectrum
-	float *xw = reinterpret_cast<float *>(Eprev + L);      // [N] far-end window
+	float2 *pipe = Eprev + L;                              // [AEC_STAGES][3][L] cp.async ring: X_{j+1}, FG_j, W_j
+	float *xw = reinterpret_cast<float *>(pipe + AEC_STAGES * 3 * L); // [N] far-end window
 	float *ebuf = xw + N;                                  // [N]
 	float *ybuf = ebuf + N;                                // [N]
 	float *input = ybuf + N;                               // [F]
@@ -300,7 +320,7 @@ __global__ void __launch_bounds__(256)
 			if (t == 0) sc[SC_MEMX] = tmpv[F - 1];
 		}
 		// ---- X_0 = FFT(x) into the ring
-		rfft(xw, specA, bufa, bufb, P, tw, spl);
+		rfft<LOG2L>(xw, specA, bufa, bufb, P, tw, spl);
 		X[(size_t)head * F + t] = specA[t];
 		float Sxx = block_sum(xw[F + t] * xw[F + t], red);
 
@@ -322,68 +342,104 @@ __global__ void __launch_bounds__(256)
 			__syncthreads();
 		}
 
-		// ---- the pass over the M blocks: foreground output, weight update (+AUMDF constraint), background output
+		// ---- the pass over the M blocks: foreground output, weight update (+AUMDF constraint), background output.
+		// X_{j+1}, FG_j and W_j are streamed HBM -> shared memory with cp.async, AEC_STAGES blocks ahead of their use;
+		// every thread copies and later reads only its own bin, so the pipeline needs no block barrier, only
+		// cp.async.wait_group.
 		const bool do_update = si[IN_SATURATED] == 0;
 		const int cc = si[IN_CANCEL_COUNT] + 1; // st->cancel_count++ at the top of the frame
 		const int constr_j = cc % (M - 1) + 1;
+		// |W_j|^2 is only consumed by mdf_adjust_prop once the filter counts as adapted (or is about to)
+		const bool need_wnorm = si[IN_ADAPTED] || sc[SC_SUM_ADAPT] > (float)M - 1.f;
 		float2 yfg = make_float2(0.f, 0.f), ybg = make_float2(0.f, 0.f);
 		const float2 Ep = Eprev[t];
 		const float p1 = power_1[t], p1n = power_1[F]; // p1n only meaningful for thread 0 (Nyquist)
 		float2 xj = specA[t];                          // X_0 (just computed)
-		for (int j = 0; j < M; ++j) {
-			const int slot1 = (head + j + 1) % (M + 1);
-			const float2 xj1 = X[(size_t)slot1 * F + t];
-			const float2 fg = FG[(size_t)j * F + t];
-			float2 w = W[(size_t)j * F + t];
-			// foreground: Y += X_j * FG_j (spectral_mul_accum; bin 0 carries two real products)
-			if (t == 0) {
-				yfg.x += xj.x * fg.x;
-				yfg.y += xj.y * fg.y;
-			} else {
-				yfg.x += (xj.x * fg.x - xj.y * fg.y);
-				yfg.y += (xj.y * fg.x + xj.x * fg.y);
+		{
+			const float2 *gXt = X + t;
+			const float2 *gFt = FG + t;
+			float2 *gWt = W + t;
+			int slot_pf = head + 1; // ring slot of X_{j+1} for the block being prefetched
+			if (slot_pf > M) slot_pf = 0;
+			auto prefetch = [&](int jj, int stage) {
+				float2 *dst = pipe + (size_t)stage * 3 * F + t;
+				cp_async8(dst, gXt + (size_t)slot_pf * F);
+				cp_async8(dst + F, gFt + (size_t)jj * F);
+				cp_async8(dst + 2 * F, gWt + (size_t)jj * F);
+				slot_pf = slot_pf + 1 > M ? 0 : slot_pf + 1;
+			};
+#pragma unroll
+			for (int pj = 0; pj < AEC_STAGES - 1; ++pj) {
+				if (pj < M) prefetch(pj, pj);
+				cp_async_commit();
 			}
-			// gradient: W_j += prop_j * power_1 * conj(X_{j+1}) * E  (weighted_spectral_mul_conj)
-			if (do_update) {
-				const float pj = prop[j];
-				if (t == 0) {
-					w.x += (pj * p1) * (xj1.x * Ep.x);
-					w.y += (pj * p1n) * (xj1.y * Ep.y);
-				} else {
-					const float Wg = pj * p1;
-					w.x += Wg * (xj1.x * Ep.x + xj1.y * Ep.y);
-					w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
+			int stage = 0;
+			for (int j = 0; j < M; ++j) {
+				{ // keep AEC_STAGES-1 blocks in flight
+					const int jn = j + AEC_STAGES - 1;
+					int st_n = stage + AEC_STAGES - 1;
+					if (st_n >= AEC_STAGES) st_n -= AEC_STAGES;
+					if (jn < M) prefetch(jn, st_n);
+					cp_async_commit();
 				}
+				cp_async_wait<AEC_STAGES - 1>();
+				const float2 *src = pipe + (size_t)stage * 3 * F + t;
+				const float2 xj1 = src[0];
+				const float2 fg = src[F];
+				float2 w = src[2 * F];
+				stage = stage + 1 == AEC_STAGES ? 0 : stage + 1;
+				// foreground: Y += X_j * FG_j (spectral_mul_accum; bin 0 carries two real products)
+				if (t == 0) {
+					yfg.x += xj.x * fg.x;
+					yfg.y += xj.y * fg.y;
+				} else {
+					yfg.x += (xj.x * fg.x - xj.y * fg.y);
+					yfg.y += (xj.y * fg.x + xj.x * fg.y);
+				}
+				// gradient: W_j += prop_j * power_1 * conj(X_{j+1}) * E  (weighted_spectral_mul_conj)
+				if (do_update) {
+					const float pj = prop[j];
+					if (t == 0) {
+						w.x += (pj * p1) * (xj1.x * Ep.x);
+						w.y += (pj * p1n) * (xj1.y * Ep.y);
+					} else {
+						const float Wg = pj * p1;
+						w.x += Wg * (xj1.x * Ep.x + xj1.y * Ep.y);
+						w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
+					}
+				}
+				// AUMDF: constrain block 0 and one rotating block (IFFT, zero second half, FFT)
+				const bool constrained = j == 0 || j == constr_j;
+				if (constrained) {
+					specB[t] = w;
+					__syncthreads();
+					irfft<LOG2L>(specB, tmpv, bufa, bufb, P, tw, spl);
+					tmpv[F + t] = 0.f;
+					__syncthreads();
+					rfft<LOG2L>(tmpv, specB, bufa, bufb, P, tw, spl);
+					w = specB[t];
+				}
+				if (do_update || constrained) gWt[(size_t)j * F] = w;
+				// |W_j|^2 partial for next frame's mdf_adjust_prop
+				if (need_wnorm) {
+					float n2 = w.x * w.x + w.y * w.y;
+					n2 = warp_sum(n2);
+					if (lane == 0) wpart[j * 8 + warp] = n2;
+				}
+				// background: Y += X_j * W_j
+				if (t == 0) {
+					ybg.x += xj.x * w.x;
+					ybg.y += xj.y * w.y;
+				} else {
+					ybg.x += (xj.x * w.x - xj.y * w.y);
+					ybg.y += (xj.y * w.x + xj.x * w.y);
+				}
+				xj = xj1;
 			}
-			// AUMDF: constrain block 0 and one rotating block (IFFT, zero second half, FFT)
-			if (j == 0 || j == constr_j) {
-				specB[t] = w;
-				__syncthreads();
-				irfft(specB, tmpv, bufa, bufb, P, tw, spl);
-				tmpv[F + t] = 0.f;
-				__syncthreads();
-				rfft(tmpv, specB, bufa, bufb, P, tw, spl);
-				w = specB[t];
-			}
-			if (do_update || j == 0 || j == constr_j) W[(size_t)j * F + t] = w;
-			// |W_j|^2 partial for next frame's mdf_adjust_prop
-			{
-				float n2 = w.x * w.x + w.y * w.y;
-				n2 = warp_sum(n2);
-				if (lane == 0) wpart[j * 8 + warp] = n2;
-			}
-			// background: Y += X_j * W_j
-			if (t == 0) {
-				ybg.x += xj.x * w.x;
-				ybg.y += xj.y * w.y;
-			} else {
-				ybg.x += (xj.x * w.x - xj.y * w.y);
-				ybg.y += (xj.y * w.x + xj.x * w.y);
-			}
-			xj = xj1;
+			cp_async_wait<0>();
 		}
 		__syncthreads();
-		if (t < M) {
+		if (need_wnorm && t < M) {
 			float s = 0.f;
 			for (int w8 = 0; w8 < nwarps; ++w8) s += wpart[t * 8 + w8];
 			S[ly.wnorm + t] = s;
@@ -393,7 +449,7 @@ __global__ void __launch_bounds__(256)
 		// ---- foreground error
 		specA[t] = yfg;
 		__syncthreads();
-		irfft(specA, ebuf, bufa, bufb, P, tw, spl);
+		irfft<LOG2L>(specA, ebuf, bufa, bufb, P, tw, spl);
 		{
 			const float v = input[t] - ebuf[t + F];
 			__syncthreads();
@@ -403,7 +459,7 @@ __global__ void __launch_bounds__(256)
 		// ---- background error
 		specA[t] = ybg;
 		__syncthreads();
-		irfft(specA, ybuf, bufa, bufb, P, tw, spl);
+		irfft<LOG2L>(specA, ybuf, bufa, bufb, P, tw, spl);
 		float dd = ebuf[t + F] - ybuf[t + F];
 		float Dbf = 10 + block_sum(dd * dd, red);
 		ebuf[t] = input[t] - ybuf[t + F];
@@ -422,7 +478,18 @@ __global__ void __launch_bounds__(256)
 		if (update_foreground) {
 			Davg1 = Davg2 = 0;
 			Dvar1 = Dvar2 = 0;
-			for (int j = 0; j < M; ++j) FG[(size_t)j * F + t] = W[(size_t)j * F + t];
+			{ // copy the background filter to the foreground, 4 blocks in flight per thread
+				int j = 0;
+				for (; j + 4 <= M; j += 4) {
+					const float2 a0 = W[(size_t)j * F + t], a1 = W[(size_t)(j + 1) * F + t];
+					const float2 a2 = W[(size_t)(j + 2) * F + t], a3 = W[(size_t)(j + 3) * F + t];
+					FG[(size_t)j * F + t] = a0;
+					FG[(size_t)(j + 1) * F + t] = a1;
+					FG[(size_t)(j + 2) * F + t] = a2;
+					FG[(size_t)(j + 3) * F + t] = a3;
+				}
+				for (; j < M; ++j) FG[(size_t)j * F + t] = W[(size_t)j * F + t];
+			}
 			ebuf[t + F] = P.window[t + F] * ebuf[t + F] + P.window[t] * ybuf[t + F];
 		} else {
 			int reset_background = 0;
@@ -485,10 +552,10 @@ __global__ void __launch_bounds__(256)
 		float Sey = block_sum(ebuf[t + F] * ybuf[t + F], red);
 		float Syy = block_sum(ybuf[t + F] * ybuf[t + F], red);
 		float Sdd = block_sum(input[t] * input[t], red);
-		rfft(ebuf, Eprev, bufa, bufb, P, tw, spl); // E (kept for the next frame's gradient)
+		rfft<LOG2L>(ebuf, Eprev, bufa, bufb, P, tw, spl); // E (kept for the next frame's gradient)
 		ybuf[t] = 0.f;
 		__syncthreads();
-		rfft(ybuf, specB, bufa, bufb, P, tw, spl); // Y
+		rfft<LOG2L>(ybuf, specB, bufa, bufb, P, tw, spl); // Y
 		// Rf -> vec1, Yf -> vec2, Xf -> vec3 (F+1 bins; bin F is the Nyquist term held by thread 0)
 		{
 			const float2 e = Eprev[t], y = specB[t], x0 = X[(size_t)head * F + t];
@@ -638,7 +705,7 @@ __global__ void __launch_bounds__(256)
 			tmpv[t] = P.window[t] * S[ly.last_y + t];
 			tmpv[t + F] = P.window[t + F] * S[ly.last_y + F + t];
 			__syncthreads();
-			rfft(tmpv, specB, bufa, bufb, P, tw, spl);
+			rfft<LOG2L>(tmpv, specB, bufa, bufb, P, tw, spl);
 			const float leak_now = sc[SC_LEAK];
 			const float leak2 = leak_now > .5f ? 1.f : 2 * leak_now;
 			{
@@ -664,7 +731,7 @@ __global__ void __launch_bounds__(256)
 				tmpv[F + t] = b;
 				__syncthreads();
 			}
-			rfft(tmpv, specA, bufa, bufb, P, tw, spl); // ft stays in specA (bin 0 = (ft[0], ft[2N-1]))
+			rfft<LOG2L>(tmpv, specA, bufa, bufb, P, tw, spl); // ft stays in specA (bin 0 = (ft[0], ft[2N-1]))
 			{
 				const float2 f = specA[t];
 				ps[t] = t == 0 ? f.x * f.x : f.x * f.x + f.y * f.y;
@@ -802,7 +869,7 @@ __global__ void __launch_bounds__(256)
 				specA[t] = f;
 				__syncthreads();
 			}
-			irfft(specA, tmpv, bufa, bufb, P, tw, spl);
+			irfft<LOG2L>(specA, tmpv, bufa, bufb, P, tw, spl);
 			{
 				const float a = tmpv[t] * P.pwindow[t];
 				const float b = tmpv[F + t] * P.pwindow[F + t];
@@ -847,7 +914,7 @@ static float to_bark(float n) {
 
 static size_t aec_smem_floats(int F, int M) {
 	const int N = 2 * F, L = F;
-	size_t f2 = (size_t)(L / 2) + (L + 2) + 5 * (size_t)L; // tw, spl, bufa, bufb, specA, specB, Eprev
+	size_t f2 = (size_t)(L / 2) + (L + 2) + 5 * (size_t)L + (size_t)AEC_STAGES * 3 * L; // tw, spl, bufa, bufb, specA, specB, Eprev, pipe
 	size_t fl = (size_t)N * 4 + F + (F + 1) + 5 * (size_t)(F + NB_BANDS + 1) + M + (size_t)M * 8 + 32 + SC_COUNT + IN_COUNT;
 	return f2 * 2 + fl;
 }
@@ -1018,8 +1085,12 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	int r = aec_write_init(a, 0, n_streams);
 	if (r) return r;
 	a->smem_bytes = aec_smem_floats(F, M) * sizeof(float);
-	if (a->smem_bytes > 48 * 1024)
-		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+	if (a->smem_bytes > 48 * 1024) {
+		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
+	}
 	*out = a;
 	return MSB200_OK;
 }
@@ -1062,9 +1133,17 @@ int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, 
 int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int in_stride, int in_frame0,
                        int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes) {
 	MSB200_CHECK_ARG(a && d_mic && d_ref && d_out && nframes > 0);
-	MSB200_LAUNCH(a->ctx, aec_kernel, a->n, a->P.F, a->smem_bytes, (const short *)d_mic, (const short *)d_ref,
-	              (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, a->head, in_frame0,
-	              in_ring_frames, out_stride, out_frame0, out_ring_frames);
+#define AEC_ARGS                                                                                                       \
+	(const short *)d_mic, (const short *)d_ref, (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, \
+	    a->head, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames
+	switch (a->P.F) {
+		case 256: MSB200_LAUNCH(a->ctx, aec_kernel<8>, a->n, 256, a->smem_bytes, AEC_ARGS); break;
+		case 128: MSB200_LAUNCH(a->ctx, aec_kernel<7>, a->n, 128, a->smem_bytes, AEC_ARGS); break;
+		case 64: MSB200_LAUNCH(a->ctx, aec_kernel<6>, a->n, 64, a->smem_bytes, AEC_ARGS); break;
+		case 32: MSB200_LAUNCH(a->ctx, aec_kernel<5>, a->n, 32, a->smem_bytes, AEC_ARGS); break;
+		default: msb200_set_error("unsupported AEC frame size %d", a->P.F); return MSB200_EINVAL;
+	}
+#undef AEC_ARGS
 	// advance the shared ring head exactly as the kernel did
 	for (int f = 0; f < nframes; ++f) a->head = (a->head + a->P.M) % (a->P.M + 1);
 	return MSB200_OK;

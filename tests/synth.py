@@ -18,7 +18,19 @@ def cfg2_stream(stream: int, n_samples: int, rate: int = 16000, echo_delay_ms: f
     # smooth the envelope edges (5 ms) to avoid clicks
     k = max(1, int(0.005 * rate))
     env = np.convolve(env, np.ones(k) / k, mode="same")
-    x = 6000 * np.sin(2 * np.pi * f * t) + 2500 * np.sin(2 * np.pi * (f * 1.7 + 50) * t) + 800 * rng.standard_normal(n_samples)
+    # speech-like far end: a voiced tone pair plus low-passed noise (broadband excitation lets the canceller converge)
+    w = rng.standard_normal(n_samples)
+    lp = np.empty(n_samples)
+    acc = 0.0
+    a = 0.55
+    for i in range(0, n_samples, 4096):  # one-pole low-pass, blockwise with scipy-free recursion
+        seg = w[i:i + 4096]
+        y = np.empty(len(seg))
+        for k, v in enumerate(seg):
+            acc = a * acc + (1 - a) * v
+            y[k] = acc
+        lp[i:i + 4096] = y
+    x = 2500 * np.sin(2 * np.pi * f * t) + 1200 * np.sin(2 * np.pi * (f * 1.7 + 50) * t) + 9000 * lp
     x *= env
     # echo path: exponentially decaying random FIR, delayed
     L = int(echo_tail_ms * rate / 1000)
