@@ -1,0 +1,858 @@
+// video_scale.cu — MSScaler replacement: pixel-format conversion + bilinear scaling, batched over frames.
+//
+// Replaces MSScalerDesc.context_process (/root/reference/include/mediastreamer2/msvideo.h:473-479) as used by MSPixConv
+// (/root/reference/src/videofilters/pixconv.c:62-94) and MSSizeConv (/root/reference/src/videofilters/sizeconv.c:97-184);
+// arithmetic = the swscale SWS_BILINEAR pipeline of the reference's ffmpeg back-end
+// (/root/reference/src/voip/msvideo.c:651-681), restated in oracle/oracle_video.c and pinned there bit-exactly against
+// libswscale 9.1.100. Everything is integer: this kernel is bit-exact with that restatement.
+//
+// One CTA produces a TW x TH tile of the OUTPUT image of one frame, fusing what swscale does in three passes:
+//   1. TMA (cp.async.bulk.tensor.3d, UTMALDG) pulls the source luma box and chroma box(es) the tile depends on from HBM
+//      into shared memory; out-of-image parts of a box are zero-filled by the hardware. One mbarrier, one elected thread.
+//   2. horizontal pass: hScale8To15 — 14-bit coefficients x 8-bit samples via dp2a (two taps per instruction), 15-bit
+//      intermediates kept in shared memory as int16 (never written to HBM: swscale's lumPixBuf/chrUPixBuf).
+//   3. vertical pass + colour: yuv2rgb_X / _2 / _1 templates with the ITU-601 limited-range tables evaluated in closed
+//      form (one multiply, one shift, one saturating convert per channel), or yuv2planeX for planar output.
+//   The output tile is staged in shared memory and written with 16-byte coalesced stores.
+// HBM traffic per frame is the algorithmic minimum plus the halo re-reads between neighbouring tiles (L2 hits).
+#include "msb200_internal.h"
+
+#include <cuda.h>
+
+#include <cmath>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ host: filter design
+// libswscale/utils.c initFilter(), SWS_BILINEAR, no user filters — same statement order as oracle/oracle_video.c
+struct Filter {
+	int size = 0;
+	std::vector<int32_t> pos;
+	std::vector<int16_t> coef;
+};
+
+int av_log2_i(unsigned v) {
+	int n = 0;
+	while (v >>= 1) n++;
+	return n;
+}
+int64_t rounded_div(int64_t a, int64_t b) {
+	return ((a > 0) == (b > 0)) ? (a + (b >> 1)) / b : (a - (b >> 1)) / b;
+}
+
+void init_filter(Filter &out, int xInc, int srcW, int dstW, int filterAlign, int one, int srcPos, int dstPos) {
+	int filterSize, minFilterSize;
+	std::vector<int64_t> filter;
+	std::vector<int32_t> filterPos((size_t)dstW + 3, 0);
+	const int lg = av_log2_i((unsigned)(srcW / dstW));
+	const int64_t fone = 1LL << (54 - (lg < 8 ? lg : 8));
+	if (std::abs(xInc - 0x10000) < 10 && srcPos == dstPos) {
+		filterSize = 1;
+		filter.assign((size_t)dstW, fone);
+		for (int i = 0; i < dstW; i++) filterPos[(size_t)i] = i;
+	} else {
+		const int sizeFactor = 2;
+		if (xInc <= 1 << 16) filterSize = 1 + sizeFactor;
+		else filterSize = 1 + (sizeFactor * srcW + dstW - 1) / dstW;
+		if (filterSize > srcW - 2) filterSize = srcW - 2;
+		if (filterSize < 1) filterSize = 1;
+		filter.assign((size_t)dstW * filterSize, 0);
+		int64_t xDstInSrc = ((dstPos * (int64_t)xInc) >> 7) - ((srcPos * 0x10000LL) >> 7);
+		for (int i = 0; i < dstW; i++) {
+			int xx = (int)((xDstInSrc - (filterSize - 2) * (1LL << 16)) / (1 << 17));
+			filterPos[(size_t)i] = xx;
+			for (int j = 0; j < filterSize; j++) {
+				int64_t d = std::llabs(((int64_t)xx * (1 << 17)) - xDstInSrc) << 13;
+				if (xInc > 1 << 16) d = d * dstW / srcW;
+				int64_t coeff = (1 << 30) - d;
+				if (coeff < 0) coeff = 0;
+				coeff *= fone >> 30;
+				filter[(size_t)i * filterSize + j] = coeff;
+				xx++;
+			}
+			xDstInSrc += 2 * (int64_t)xInc;
+		}
+	}
+	const int filter2Size = filterSize;
+	minFilterSize = 0;
+	for (int i = dstW - 1; i >= 0; i--) {
+		int min = filter2Size;
+		int64_t cutOff = 0;
+		for (int j = 0; j < filter2Size; j++) {
+			cutOff += std::llabs(filter[(size_t)i * filter2Size]);
+			if ((double)cutOff > 0.002 * (double)fone) break;
+			if (i < dstW - 1 && filterPos[(size_t)i] >= filterPos[(size_t)i + 1]) break;
+			for (int k = 1; k < filter2Size; k++) filter[(size_t)i * filter2Size + k - 1] = filter[(size_t)i * filter2Size + k];
+			filter[(size_t)i * filter2Size + filter2Size - 1] = 0;
+			filterPos[(size_t)i]++;
+		}
+		cutOff = 0;
+		for (int j = filter2Size - 1; j > 0; j--) {
+			cutOff += std::llabs(filter[(size_t)i * filter2Size + j]);
+			if ((double)cutOff > 0.002 * (double)fone) break;
+			min--;
+		}
+		if (min > minFilterSize) minFilterSize = min;
+	}
+	if (minFilterSize == 1 && filterAlign == 2) filterAlign = 1;
+	{
+		const int newSize = (minFilterSize + (filterAlign - 1)) & (~(filterAlign - 1));
+		std::vector<int64_t> f2((size_t)dstW * newSize, 0);
+		for (int i = 0; i < dstW; i++)
+			for (int j = 0; j < newSize; j++)
+				f2[(size_t)i * newSize + j] = j >= filter2Size ? 0 : filter[(size_t)i * filter2Size + j];
+		filter.swap(f2);
+		filterSize = newSize;
+	}
+	for (int i = 0; i < dstW; i++) { // fix borders
+		int64_t *f = &filter[(size_t)i * filterSize];
+		if (filterPos[(size_t)i] < 0) {
+			for (int j = 1; j < filterSize; j++) {
+				int left = j + filterPos[(size_t)i] > 0 ? j + filterPos[(size_t)i] : 0;
+				f[left] += f[j];
+				f[j] = 0;
+			}
+			filterPos[(size_t)i] = 0;
+		}
+		if (filterPos[(size_t)i] + filterSize > srcW) {
+			int shift = filterPos[(size_t)i] + (filterSize - srcW < 0 ? filterSize - srcW : 0);
+			int64_t acc = 0;
+			for (int j = filterSize - 1; j >= 0; j--) {
+				if (filterPos[(size_t)i] + j >= srcW) {
+					acc += f[j];
+					f[j] = 0;
+				}
+			}
+			for (int j = filterSize - 1; j >= 0; j--) {
+				if (j < shift) f[j] = 0;
+				else f[j] = f[j - shift];
+			}
+			filterPos[(size_t)i] -= shift;
+			f[srcW - 1 - filterPos[(size_t)i]] += acc;
+		}
+	}
+	out.size = filterSize;
+	out.pos.assign(filterPos.begin(), filterPos.begin() + dstW);
+	out.coef.assign((size_t)dstW * filterSize, 0);
+	for (int i = 0; i < dstW; i++) {
+		int64_t error = 0, sum = 0;
+		for (int j = 0; j < filterSize; j++) sum += filter[(size_t)i * filterSize + j];
+		sum = (sum + one / 2) / one;
+		if (!sum) sum = 1;
+		for (int j = 0; j < filterSize; j++) {
+			int64_t v = filter[(size_t)i * filterSize + j] + error;
+			int intV = (int)rounded_div(v, sum);
+			out.coef[(size_t)i * filterSize + j] = (int16_t)intV;
+			error = v - intV * sum;
+		}
+	}
+}
+
+int get_local_pos(int chr_subsample, int pos) {
+	if (pos == -1 || pos <= -513) pos = (128 << chr_subsample) - 128;
+	pos += 128;
+	return pos >> chr_subsample;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ device
+#define SC_TW 128 // output tile width (pixels)
+#define SC_TH 16  // output tile height (rows)
+#define SC_THREADS 256
+
+struct ScaleParams {
+	int src_w, src_h, dst_w, dst_h, chr_src_w, chr_src_h, chr_dst_w, chr_dst_h;
+	int src_fmt, dst_fmt;
+	int hl_size, hc_size, vl_size, vc_size; // filter sizes (hl/hc multiples of 4)
+	const int *hl_pos, *hc_pos, *vl_pos, *vc_pos;
+	const short *hl_coef, *hc_coef, *vl_coef, *vc_coef;
+	int box_lw, box_lh, box_cw, box_ch; // TMA box dims: luma (bytes x rows), chroma (bytes x rows)
+	int chroma_planes;                   // 1: interleaved CbCr plane (NV12/NV21), 2: separate U and V planes (I420)
+	// yuv2rgb closed-form constants
+	int cy, crv, cbu, cgu, cgv, yb0, yoffs;
+	size_t dst_frame_bytes;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+	return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+	unsigned ok;
+	do {
+		asm volatile("{\n"
+		             ".reg .pred p;\n"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		             "selp.u32 %0, 1, 0, p;\n"
+		             "}\n"
+		             : "=r"(ok)
+		             : "r"(smem_u32(bar)), "r"(parity)
+		             : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+	                 smem_u32(smem_dst)),
+	             "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+	             : "memory");
+}
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (a: two signed 16-bit coefficients, b: unsigned bytes)
+__device__ __forceinline__ int dp2a_lo(int a, unsigned b, int c) {
+	int d;
+	asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+__device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c) { // bytes 2 and 3 of b
+	int d;
+	asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+__device__ __forceinline__ unsigned sat_u8(int v) {
+	unsigned r;
+	asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v));
+	return r;
+}
+// 4 consecutive bytes starting at byte offset `off` of a 4-byte aligned shared array
+__device__ __forceinline__ unsigned load4_unaligned(const unsigned char *base, int off) {
+	const unsigned *w = reinterpret_cast<const unsigned *>(base) + (off >> 2);
+	return __funnelshift_r(w[0], w[1], (off & 3) * 8);
+}
+
+// horizontal pass over `rows` rows of a source box (pitch bytes) -> int16 out[rows][out_pitch] for `count` outputs.
+// MODE 0: plain plane (luma, or a planar chroma plane); MODE 1/2: Cb / Cr of an interleaved CbCr box
+template <int MODE, int COUNT>
+__device__ __forceinline__ void hpass(const unsigned char *box, int pitch, int rows, short *out, int out_pitch,
+                                      const int *pos, const short *coef, int fsize, int x0, int box_x0, int limit) {
+	for (int idx = threadIdx.x; idx < COUNT * rows; idx += SC_THREADS) {
+		const int r = idx / COUNT, x = idx - r * COUNT;
+		const int gx = x0 + x;
+		int val = 0;
+		if (gx < limit) {
+			const int p = pos[gx] - box_x0;
+			const unsigned char *row = box + (size_t)r * pitch;
+			const int *cf = reinterpret_cast<const int *>(coef + (size_t)gx * fsize); // fsize % 4 == 0 -> 8-byte aligned
+			for (int j = 0; j < fsize; j += 4) {
+				unsigned q;
+				if (MODE == 0) {
+					q = load4_unaligned(row, p + j);
+				} else {
+					const unsigned a = load4_unaligned(row, 2 * (p + j)), b = load4_unaligned(row, 2 * (p + j) + 4);
+					q = __byte_perm(a, b, MODE == 1 ? 0x6420 : 0x7531);
+				}
+				val = dp2a_lo(cf[j / 2], q, val);
+				val = dp2a_hi(cf[j / 2 + 1], q, val);
+			}
+			val >>= 7;
+			val = val < 32767 ? val : 32767;
+		}
+		out[(size_t)r * out_pitch + x] = (short)val;
+	}
+}
+
+// ---- fused scale + colour kernel, tuned for instruction count (this kernel is issue-bound, not HBM-bound: ~60 integer
+// instructions per output pixel are inherent to the bit-exact swscale arithmetic):
+//  * every thread owns one output column in the horizontal pass (filter position and coefficients live in registers,
+//    the loop runs over the rows of the source box) and one pixel-pair column in the vertical pass;
+//  * the 15-bit intermediates are kept as int32 in shared memory (no unpacking in the vertical pass);
+//  * per-row vertical filter data is staged once per tile in shared memory.
+struct RowInfo {
+	int lp, cp;     // first luma / chroma intermediate row (relative to the tile's boxes)
+	int lf[4];      // luma vertical taps (vl_size <= 4 on this path)
+	int cf[4];      // chroma vertical taps
+};
+
+template <int VL, int VC> // vertical filter sizes; VL == 0: generic (any size, taps read from global memory)
+__global__ void __launch_bounds__(SC_THREADS)
+    scale_rgb_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c0,
+                     const __grid_constant__ CUtensorMap map_c1, unsigned char *__restrict__ dst, ScaleParams P) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+	const int x0 = blockIdx.x * SC_TW, y0 = blockIdx.y * SC_TH, frame = blockIdx.z;
+	const int cx0 = x0 >> 1;
+	const int tw = min(SC_TW, P.dst_w - x0), th = min(SC_TH, P.dst_h - y0);
+	const int t = threadIdx.x;
+	auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+	size_t off = 0;
+	unsigned char *box_l = smem + off; off = align128(off + (size_t)P.box_lw * P.box_lh);
+	unsigned char *box_c0 = smem + off; off = align128(off + (size_t)P.box_cw * P.box_ch);
+	unsigned char *box_c1 = smem + off; off = align128(off + (P.chroma_planes == 2 ? (size_t)P.box_cw * P.box_ch : 0));
+	int *lum_h = reinterpret_cast<int *>(smem + off); off = align128(off + sizeof(int) * (size_t)P.box_lh * SC_TW);
+	int2 *chr_h = reinterpret_cast<int2 *>(smem + off); off = align128(off + sizeof(int2) * (size_t)P.box_ch * (SC_TW / 2));
+	unsigned char *out_s = smem + off; off = align128(off + (size_t)SC_TH * SC_TW * 3);
+	RowInfo *rows = reinterpret_cast<RowInfo *>(smem + off); off = align128(off + sizeof(RowInfo) * SC_TH);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + off);
+
+	// TMA box origins: the innermost coordinate must land on a 16-byte boundary (unaligned starts fault), so the box
+	// starts at the aligned-down byte and is 15 bytes wider than the span the filters need
+	const int lx0 = P.hl_pos[x0] & ~15, ly0 = P.vl_pos[y0];
+	const int ccx0 = P.chroma_planes == 1 ? ((2 * P.hc_pos[cx0]) & ~15) / 2 : (P.hc_pos[cx0] & ~15), ccy0 = P.vc_pos[y0];
+	if (t == 0) {
+		mbar_init(bar, 1);
+		const unsigned bytes = (unsigned)(P.box_lw * P.box_lh + P.chroma_planes * P.box_cw * P.box_ch);
+		mbar_expect_tx(bar, bytes);
+		tma_load_3d(box_l, &map_l, bar, lx0, ly0, frame);
+		if (P.chroma_planes == 1) {
+			tma_load_3d(box_c0, &map_c0, bar, 2 * ccx0, ccy0, frame);
+		} else {
+			tma_load_3d(box_c0, &map_c0, bar, ccx0, ccy0, frame);
+			tma_load_3d(box_c1, &map_c1, bar, ccx0, ccy0, frame);
+		}
+	}
+	// while the boxes are in flight: per-thread horizontal filter data and the tile's vertical filter rows
+	const int lyl = P.vl_pos[y0 + th - 1], cyl = P.vc_pos[y0 + th - 1];
+	const int l_rows = min(P.box_lh, lyl + P.vl_size - ly0);
+	const int c_rows = min(P.box_ch, cyl + P.vc_size - ccy0);
+	const int lx = t & (SC_TW - 1);
+	const int lgx = min(x0 + lx, P.dst_w - 1);
+	const int lp_off = P.hl_pos[lgx] - lx0;
+	const int cxi = t & (SC_TW / 2 - 1);
+	const int cgx = min(cx0 + cxi, P.chr_dst_w - 1);
+	const int cp_off = P.hc_pos[cgx] - ccx0;
+	if (t < SC_TH) {
+		RowInfo ri;
+		const int y = min(y0 + t, P.dst_h - 1);
+		ri.lp = P.vl_pos[y] - ly0;
+		ri.cp = P.vc_pos[y] - ccy0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			ri.lf[j] = j < P.vl_size ? P.vl_coef[(size_t)y * P.vl_size + j] : 0;
+			ri.cf[j] = j < P.vc_size ? P.vc_coef[(size_t)y * P.vc_size + j] : 0;
+		}
+		rows[t] = ri;
+	}
+	__syncthreads(); // mbarrier init + row table visible
+	mbar_wait(bar, 0);
+
+	// ---- horizontal pass, luma (hScale8To15): thread = output column, loop over box rows (two row phases per CTA)
+	{
+		const int *cf = reinterpret_cast<const int *>(P.hl_coef + (size_t)lgx * P.hl_size);
+		if (P.hl_size == 4) {
+			const int c01 = cf[0], c23 = cf[1];
+			const int wofs = lp_off >> 2, sh = (lp_off & 3) * 8;
+			const unsigned *w = reinterpret_cast<const unsigned *>(box_l) + wofs;
+			const int pitch_w = P.box_lw >> 2;
+			for (int r = t >> 7; r < l_rows; r += SC_THREADS / SC_TW) {
+				const unsigned *wr = w + (size_t)r * pitch_w;
+				const unsigned q = __funnelshift_r(wr[0], wr[1], sh);
+				int val = dp2a_hi(c23, q, dp2a_lo(c01, q, 0)) >> 7;
+				lum_h[r * SC_TW + lx] = val < 32767 ? val : 32767;
+			}
+		} else {
+			for (int r = t >> 7; r < l_rows; r += SC_THREADS / SC_TW) {
+				const unsigned char *row = box_l + (size_t)r * P.box_lw;
+				int val = 0;
+				for (int j = 0; j < P.hl_size; j += 4) {
+					const unsigned q = load4_unaligned(row, lp_off + j);
+					val = dp2a_hi(cf[j / 2 + 1], q, dp2a_lo(cf[j / 2], q, val));
+				}
+				val >>= 7;
+				lum_h[r * SC_TW + lx] = val < 32767 ? val : 32767;
+			}
+		}
+	}
+	// ---- horizontal pass, chroma: both planes per thread (they share positions and coefficients)
+	{
+		const int *cf = reinterpret_cast<const int *>(P.hc_coef + (size_t)cgx * P.hc_size);
+		const bool swap_uv = P.src_fmt == MSB200_PIX_NV21;
+		for (int r = t >> 6; r < c_rows; r += SC_THREADS / (SC_TW / 2)) {
+			int u = 0, v = 0;
+			for (int j = 0; j < P.hc_size; j += 4) {
+				unsigned qu, qv;
+				if (P.chroma_planes == 1) {
+					const unsigned char *row = box_c0 + (size_t)r * P.box_cw;
+					const unsigned a = load4_unaligned(row, 2 * (cp_off + j)), b = load4_unaligned(row, 2 * (cp_off + j) + 4);
+					qu = __byte_perm(a, b, 0x6420);
+					qv = __byte_perm(a, b, 0x7531);
+				} else {
+					qu = load4_unaligned(box_c0 + (size_t)r * P.box_cw, cp_off + j);
+					qv = load4_unaligned(box_c1 + (size_t)r * P.box_cw, cp_off + j);
+				}
+				u = dp2a_hi(cf[j / 2 + 1], qu, dp2a_lo(cf[j / 2], qu, u));
+				v = dp2a_hi(cf[j / 2 + 1], qv, dp2a_lo(cf[j / 2], qv, v));
+			}
+			u >>= 7;
+			v >>= 7;
+			u = u < 32767 ? u : 32767;
+			v = v < 32767 ? v : 32767;
+			chr_h[r * (SC_TW / 2) + cxi] = swap_uv ? make_int2(v, u) : make_int2(u, v);
+		}
+	}
+	__syncthreads();
+
+	// ---- vertical pass + colour: thread = pixel-pair column, four row phases (yuv2rgb_X / _2 / _1 templates)
+	const bool bgr = P.dst_fmt == MSB200_PIX_RGB24_REV;
+	const int ctw = (tw + 1) >> 1;
+	const int i = t & (SC_TW / 2 - 1);
+	const int2 *lcol = reinterpret_cast<const int2 *>(lum_h) + i; // (Y1, Y2) of this pair, row pitch SC_TW/2 int2
+	const int2 *ccol = chr_h + i;
+	const int c_cy = P.cy;
+	const int base_r = P.yoffs - (P.crv >> 9), base_g = P.yoffs - (P.cgu >> 9) - (P.cgv >> 9), base_b = P.yoffs - (P.cbu >> 9);
+	const int c_off = P.yb0 + 0x8000;
+	if (i < ctw) {
+		for (int ry = t >> 6; ry < th; ry += SC_THREADS / (SC_TW / 2)) {
+			const RowInfo &ri = rows[ry];
+			int Y1, Y2, U, V;
+			if (VL == 1) { // yuv2rgb_1: vertically unscaled luma
+				const int2 l0 = lcol[ri.lp * (SC_TW / 2)];
+				Y1 = (l0.x + 64) >> 7;
+				Y2 = (l0.y + 64) >> 7;
+				const int2 c0 = ccol[ri.cp * (SC_TW / 2)];
+				const int uvalpha = VC == 1 ? 0 : ri.cf[1];
+				if (uvalpha == 0) {
+					U = (c0.x + 64) >> 7;
+					V = (c0.y + 64) >> 7;
+				} else {
+					const int2 c1 = ccol[(ri.cp + 1) * (SC_TW / 2)];
+					const int uvalpha1 = 4096 - uvalpha;
+					U = (c0.x * uvalpha1 + c1.x * uvalpha + (128 << 11)) >> 19;
+					V = (c0.y * uvalpha1 + c1.y * uvalpha + (128 << 11)) >> 19;
+				}
+			} else if (VL == 2 && VC == 2) { // yuv2rgb_2: bilinear upscale
+				const int2 l0 = lcol[ri.lp * (SC_TW / 2)], l1 = lcol[(ri.lp + 1) * (SC_TW / 2)];
+				const int2 c0 = ccol[ri.cp * (SC_TW / 2)], c1 = ccol[(ri.cp + 1) * (SC_TW / 2)];
+				const int yalpha = ri.lf[1], uvalpha = ri.cf[1], yalpha1 = 4096 - yalpha, uvalpha1 = 4096 - uvalpha;
+				Y1 = (l0.x * yalpha1 + l1.x * yalpha) >> 19;
+				Y2 = (l0.y * yalpha1 + l1.y * yalpha) >> 19;
+				U = (c0.x * uvalpha1 + c1.x * uvalpha) >> 19;
+				V = (c0.y * uvalpha1 + c1.y * uvalpha) >> 19;
+			} else if (VL > 0) { // yuv2rgb_X with compile-time sizes
+				Y1 = Y2 = U = V = 1 << 18;
+#pragma unroll
+				for (int j = 0; j < VL; ++j) {
+					const int2 l = lcol[(ri.lp + j) * (SC_TW / 2)];
+					Y1 += l.x * ri.lf[j];
+					Y2 += l.y * ri.lf[j];
+				}
+#pragma unroll
+				for (int j = 0; j < VC; ++j) {
+					const int2 c = ccol[(ri.cp + j) * (SC_TW / 2)];
+					U += c.x * ri.cf[j];
+					V += c.y * ri.cf[j];
+				}
+				Y1 >>= 19; Y2 >>= 19; U >>= 19; V >>= 19;
+			} else { // generic sizes: taps from global memory
+				const int y = y0 + ry;
+				const short *lf = P.vl_coef + (size_t)y * P.vl_size, *cf = P.vc_coef + (size_t)y * P.vc_size;
+				Y1 = Y2 = U = V = 1 << 18;
+				for (int j = 0; j < P.vl_size; ++j) {
+					const int2 l = lcol[(ri.lp + j) * (SC_TW / 2)];
+					Y1 += l.x * lf[j];
+					Y2 += l.y * lf[j];
+				}
+				for (int j = 0; j < P.vc_size; ++j) {
+					const int2 c = ccol[(ri.cp + j) * (SC_TW / 2)];
+					U += c.x * cf[j];
+					V += c.y * cf[j];
+				}
+				Y1 >>= 19; Y2 >>= 19; U >>= 19; V >>= 19;
+			}
+			// ff_yuv2rgb_c_init_tables() tables in closed form: value = clip8((yb0 + (K + Y) * cy + 0x8000) >> 16)
+			const int Uc = (int)sat_u8(U), Vc = (int)sat_u8(V);
+			const int ar = c_off + (base_r + ((Vc * P.crv) >> 16)) * c_cy;
+			const int ag = c_off + (base_g + ((Uc * P.cgu) >> 16) + ((Vc * P.cgv) >> 16)) * c_cy;
+			const int ab = c_off + (base_b + ((Uc * P.cbu) >> 16)) * c_cy;
+			const int y1c = Y1 * c_cy, y2c = Y2 * c_cy;
+			const unsigned r1 = sat_u8((ar + y1c) >> 16), g1 = sat_u8((ag + y1c) >> 16), b1 = sat_u8((ab + y1c) >> 16);
+			const unsigned r2 = sat_u8((ar + y2c) >> 16), g2 = sat_u8((ag + y2c) >> 16), b2 = sat_u8((ab + y2c) >> 16);
+			unsigned short *o = reinterpret_cast<unsigned short *>(out_s + (size_t)ry * SC_TW * 3 + (size_t)i * 6);
+			const unsigned c0 = bgr ? b1 : r1, c2 = bgr ? r1 : b1, c3 = bgr ? b2 : r2, c5 = bgr ? r2 : b2;
+			o[0] = (unsigned short)(c0 | (g1 << 8));
+			o[1] = (unsigned short)(c2 | (c3 << 8));
+			o[2] = (unsigned short)(g2 | (c5 << 8));
+		}
+	}
+	__syncthreads();
+
+	// ---- coalesced write-out of the tile
+	unsigned char *fd = dst + (size_t)frame * P.dst_frame_bytes;
+	const size_t row_bytes = (size_t)P.dst_w * 3;
+	const int tile_bytes = tw * 3;
+	const bool vec = (row_bytes % 16 == 0) && (tile_bytes % 16 == 0) && (((uintptr_t)fd) % 16 == 0);
+	if (vec) {
+		const int vpr = tile_bytes / 16;
+		for (int idx = t; idx < vpr * th; idx += SC_THREADS) {
+			const int ry = idx / vpr, v = idx - ry * vpr;
+			const uint4 val = reinterpret_cast<const uint4 *>(out_s + (size_t)ry * SC_TW * 3)[v];
+			reinterpret_cast<uint4 *>(fd + (size_t)(y0 + ry) * row_bytes + (size_t)x0 * 3)[v] = val;
+		}
+	} else {
+		for (int idx = t; idx < tile_bytes * th; idx += SC_THREADS) {
+			const int ry = idx / tile_bytes, bb = idx - ry * tile_bytes;
+			fd[(size_t)(y0 + ry) * row_bytes + (size_t)x0 * 3 + bb] = out_s[(size_t)ry * SC_TW * 3 + bb];
+		}
+	}
+}
+
+// planar (YUV420P) output: yuv2planeX_8 / yuv2plane1_8 with the constant-64 dither. One launch per plane kind: the
+// tile is TW x TH of the destination PLANE (luma plane, or the U and V planes together).
+template <int TWP> // tile width in destination-plane samples (64 for interleaved-chroma sources: the CbCr box is 2 bytes/sample)
+__global__ void __launch_bounds__(SC_THREADS)
+    scale_plane_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                       unsigned char *__restrict__ dst, ScaleParams P, int is_chroma) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+	const int x0 = blockIdx.x * TWP, y0 = blockIdx.y * SC_TH, frame = blockIdx.z;
+	const int W = is_chroma ? P.chr_dst_w : P.dst_w, H = is_chroma ? P.chr_dst_h : P.dst_h;
+	const int tw = min(TWP, W - x0), th = min(SC_TH, H - y0);
+	const int *hpos = is_chroma ? P.hc_pos : P.hl_pos, *vpos = is_chroma ? P.vc_pos : P.vl_pos;
+	const short *hcoef = is_chroma ? P.hc_coef : P.hl_coef, *vcoef = is_chroma ? P.vc_coef : P.vl_coef;
+	const int hsize = is_chroma ? P.hc_size : P.hl_size, vsize = is_chroma ? P.vc_size : P.vl_size;
+	const int bw = is_chroma ? P.box_cw : P.box_lw, bh = is_chroma ? P.box_ch : P.box_lh;
+	const int nplanes = is_chroma ? 2 : 1;
+	const bool interleaved = is_chroma && P.chroma_planes == 1;
+	auto align128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+	size_t off = 0;
+	unsigned char *box0 = smem + off; off = align128(off + (size_t)bw * bh);
+	unsigned char *box1 = smem + off; off = align128(off + ((is_chroma && !interleaved) ? (size_t)bw * bh : 0));
+	short *h0 = reinterpret_cast<short *>(smem + off); off = align128(off + sizeof(short) * (size_t)bh * TWP);
+	short *h1 = reinterpret_cast<short *>(smem + off); off = align128(off + (is_chroma ? sizeof(short) * (size_t)bh * TWP : 0));
+	unsigned char *out_s = smem + off; off = align128(off + (size_t)nplanes * SC_TH * TWP);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + off);
+	const int bx0 = interleaved ? ((2 * hpos[x0]) & ~15) / 2 : (hpos[x0] & ~15), by0 = vpos[y0];
+	const int rows = min(bh, vpos[y0 + th - 1] + vsize - by0);
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		const int nboxes = (is_chroma && !interleaved) ? 2 : 1;
+		mbar_expect_tx(bar, (unsigned)(nboxes * bw * bh));
+		tma_load_3d(box0, &map0, bar, interleaved ? 2 * bx0 : bx0, by0, frame);
+		if (nboxes == 2) tma_load_3d(box1, &map1, bar, bx0, by0, frame);
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+	if (!is_chroma) {
+		hpass<0, TWP>(box0, bw, rows, h0, TWP, hpos, hcoef, hsize, x0, bx0, W);
+	} else if (interleaved) {
+		const bool nv21 = P.src_fmt == MSB200_PIX_NV21;
+		if (!nv21) {
+			hpass<1, TWP>(box0, bw, rows, h0, TWP, hpos, hcoef, hsize, x0, bx0, W);
+			hpass<2, TWP>(box0, bw, rows, h1, TWP, hpos, hcoef, hsize, x0, bx0, W);
+		} else {
+			hpass<2, TWP>(box0, bw, rows, h0, TWP, hpos, hcoef, hsize, x0, bx0, W);
+			hpass<1, TWP>(box0, bw, rows, h1, TWP, hpos, hcoef, hsize, x0, bx0, W);
+		}
+	} else {
+		hpass<0, TWP>(box0, bw, rows, h0, TWP, hpos, hcoef, hsize, x0, bx0, W);
+		hpass<0, TWP>(box1, bw, rows, h1, TWP, hpos, hcoef, hsize, x0, bx0, W);
+	}
+	__syncthreads();
+	for (int idx = threadIdx.x; idx < nplanes * TWP * th; idx += SC_THREADS) {
+		const int pl = idx / (TWP * th), rem = idx - pl * (TWP * th);
+		const int ry = rem / TWP, x = rem - ry * TWP;
+		const short *hbuf = pl ? h1 : h0;
+		const int y = y0 + ry, p = vpos[y] - by0;
+		int val;
+		if (vsize == 1) {
+			val = (hbuf[(size_t)p * TWP + x] + 64) >> 7;
+		} else {
+			val = 64 << 12;
+			const short *cf = vcoef + (size_t)y * vsize;
+			for (int j = 0; j < vsize; ++j) val += hbuf[(size_t)(p + j) * TWP + x] * cf[j];
+			val >>= 19;
+		}
+		out_s[(size_t)pl * SC_TH * TWP + (size_t)ry * TWP + x] = (unsigned char)sat_u8(val);
+	}
+	__syncthreads();
+	unsigned char *fd = dst + (size_t)frame * P.dst_frame_bytes;
+	for (int pl = 0; pl < nplanes; ++pl) {
+		unsigned char *plane = fd + (is_chroma ? (size_t)P.dst_w * P.dst_h + (size_t)pl * P.chr_dst_w * P.chr_dst_h : 0);
+		const bool vec = (W % 16 == 0) && (tw % 16 == 0) && (((uintptr_t)plane) % 16 == 0);
+		if (vec) {
+			const int vpr = tw / 16;
+			for (int idx = threadIdx.x; idx < vpr * th; idx += SC_THREADS) {
+				const int ry = idx / vpr, v = idx - ry * vpr;
+				reinterpret_cast<uint4 *>(plane + (size_t)(y0 + ry) * W + x0)[v] =
+				    reinterpret_cast<const uint4 *>(out_s + (size_t)pl * SC_TH * TWP + (size_t)ry * TWP)[v];
+			}
+		} else {
+			for (int idx = threadIdx.x; idx < tw * th; idx += SC_THREADS) {
+				const int ry = idx / tw, x = idx - ry * tw;
+				plane[(size_t)(y0 + ry) * W + x0 + x] = out_s[(size_t)pl * SC_TH * TWP + (size_t)ry * TWP + x];
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ host
+struct msb200_scaler {
+	msb200_ctx *ctx;
+	ScaleParams P;
+	Filter hl, hc, vl, vc;
+	void *d_tables;
+	size_t src_bytes, dst_bytes;
+	size_t smem_rgb, smem_luma, smem_chroma;
+	// chroma plane geometry of the source for the tensor maps
+	int cached_frames;
+	const void *cached_src;
+	CUtensorMap map_l, map_c0, map_c1;
+	msb200_devbuf src, dst;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+	static PFN_encodeTiled fn = nullptr;
+	if (fn) return fn;
+	void *p = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+		return nullptr;
+	fn = (PFN_encodeTiled)p;
+	return fn;
+}
+
+// 3-D byte tensor (width bytes, rows, frames) with a (box_w, box_h, 1) box; out-of-bounds elements read as zero
+static int make_map(CUtensorMap *m, const void *base, uint64_t width, uint64_t rows, uint64_t frames, uint64_t row_pitch,
+                    uint64_t frame_pitch, uint32_t box_w, uint32_t box_h) {
+	PFN_encodeTiled enc = get_encode();
+	if (!enc) {
+		msb200_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+		return MSB200_ECUDA;
+	}
+	cuuint64_t dims[3] = {width, rows, frames};
+	cuuint64_t strides[2] = {row_pitch, frame_pitch};
+	cuuint32_t box[3] = {box_w, box_h, 1};
+	cuuint32_t estr[3] = {1, 1, 1};
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+	                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		msb200_set_error("cuTensorMapEncodeTiled failed (%d): base %p width %llu rows %llu pitch %llu box %ux%u", (int)r, base,
+		                 (unsigned long long)width, (unsigned long long)rows, (unsigned long long)row_pitch, box_w, box_h);
+		return MSB200_ECUDA;
+	}
+	return MSB200_OK;
+}
+
+static size_t fmt_bytes(int fmt, int w, int h) {
+	if (fmt == MSB200_PIX_RGB24 || fmt == MSB200_PIX_RGB24_REV) return (size_t)w * h * 3;
+	return (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2);
+}
+
+// largest span of source samples any tile needs: max over tiles of pos[last]+size-pos[first]
+static int max_span(const Filter &f, int n, int tile) {
+	int best = 0;
+	for (int t0 = 0; t0 < n; t0 += tile) {
+		int t1 = t0 + tile - 1 < n - 1 ? t0 + tile - 1 : n - 1;
+		int span = f.pos[(size_t)t1] + f.size - f.pos[(size_t)t0];
+		if (span > best) best = span;
+	}
+	return best;
+}
+
+static int scaler_build_maps(msb200_scaler *s, const void *d_src, int n_frames) {
+	if (s->cached_src == d_src && s->cached_frames == n_frames) return MSB200_OK;
+	const ScaleParams &P = s->P;
+	const char *base = (const char *)d_src;
+	const uint64_t fp = s->src_bytes;
+	int r;
+	if ((r = make_map(&s->map_l, base, (uint64_t)P.src_w, (uint64_t)P.src_h, (uint64_t)n_frames, (uint64_t)P.src_w, fp,
+	                  (uint32_t)P.box_lw, (uint32_t)P.box_lh))) return r;
+	const char *cb = base + (size_t)P.src_w * P.src_h;
+	if (P.chroma_planes == 1) {
+		if ((r = make_map(&s->map_c0, cb, (uint64_t)P.chr_src_w * 2, (uint64_t)P.chr_src_h, (uint64_t)n_frames,
+		                  (uint64_t)P.chr_src_w * 2, fp, (uint32_t)P.box_cw, (uint32_t)P.box_ch))) return r;
+		s->map_c1 = s->map_c0;
+	} else {
+		if ((r = make_map(&s->map_c0, cb, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h, (uint64_t)n_frames,
+		                  (uint64_t)P.chr_src_w, fp, (uint32_t)P.box_cw, (uint32_t)P.box_ch))) return r;
+		if ((r = make_map(&s->map_c1, cb + (size_t)P.chr_src_w * P.chr_src_h, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h,
+		                  (uint64_t)n_frames, (uint64_t)P.chr_src_w, fp, (uint32_t)P.box_cw, (uint32_t)P.box_ch))) return r;
+	}
+	s->cached_src = d_src;
+	s->cached_frames = n_frames;
+	return MSB200_OK;
+}
+
+extern "C" {
+
+int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int dst_w, int dst_h, int dst_fmt,
+                         msb200_scaler **out) {
+	MSB200_CHECK_ARG(ctx && out);
+	const bool src_ok = src_fmt == MSB200_PIX_YUV420P || src_fmt == MSB200_PIX_NV12 || src_fmt == MSB200_PIX_NV21;
+	const bool dst_ok = dst_fmt == MSB200_PIX_YUV420P || dst_fmt == MSB200_PIX_RGB24 || dst_fmt == MSB200_PIX_RGB24_REV;
+	if (!src_ok || !dst_ok) {
+		msb200_set_error("scaler: unsupported format pair %d -> %d (sources: YUV420P/NV12/NV21; destinations: YUV420P/RGB24/BGR24)", src_fmt, dst_fmt);
+		return MSB200_EINVAL;
+	}
+	MSB200_CHECK_ARG(src_w >= 16 && src_h >= 16 && dst_w >= 16 && dst_h >= 16);
+	// TMA tensor maps need 16-byte row pitches: luma width % 16 == 0, chroma plane pitch % 16 == 0
+	MSB200_CHECK_ARG(src_w % 16 == 0 && (src_fmt != MSB200_PIX_YUV420P || (src_w / 2) % 16 == 0) && src_h % 2 == 0);
+	msb200_scaler *s = new msb200_scaler();
+	s->ctx = ctx;
+	s->cached_src = nullptr;
+	s->cached_frames = 0;
+	ScaleParams &P = s->P;
+	memset(&P, 0, sizeof(P));
+	P.src_w = src_w; P.src_h = src_h; P.dst_w = dst_w; P.dst_h = dst_h; P.src_fmt = src_fmt; P.dst_fmt = dst_fmt;
+	const bool dst_rgb = dst_fmt != MSB200_PIX_YUV420P;
+	const int chrDstH = 1, chrDstV = dst_rgb ? 0 : 1;
+	P.chr_src_w = (src_w + 1) >> 1;
+	P.chr_src_h = (src_h + 1) >> 1;
+	P.chr_dst_w = (dst_w + 1) >> chrDstH;
+	P.chr_dst_h = (dst_h + (1 << chrDstV) - 1) >> chrDstV;
+	const int lumXInc = (int)((((int64_t)src_w << 16) + (dst_w >> 1)) / dst_w);
+	const int lumYInc = (int)((((int64_t)src_h << 16) + (dst_h >> 1)) / dst_h);
+	const int chrXInc = (int)((((int64_t)P.chr_src_w << 16) + (P.chr_dst_w >> 1)) / P.chr_dst_w);
+	const int chrYInc = (int)((((int64_t)P.chr_src_h << 16) + (P.chr_dst_h >> 1)) / P.chr_dst_h);
+	init_filter(s->hl, lumXInc, src_w, dst_w, 4, 1 << 14, get_local_pos(0, 0), get_local_pos(0, 0));
+	init_filter(s->hc, chrXInc, P.chr_src_w, P.chr_dst_w, 4, 1 << 14, get_local_pos(1, -513), get_local_pos(chrDstH, -513));
+	init_filter(s->vl, lumYInc, src_h, dst_h, 2, 1 << 12, get_local_pos(0, 0), get_local_pos(0, 0));
+	init_filter(s->vc, chrYInc, P.chr_src_h, P.chr_dst_h, 2, 1 << 12, get_local_pos(1, -513), get_local_pos(chrDstV, -513));
+	// the horizontal pass consumes taps four at a time: pad the coefficient rows with zeros
+	auto pad4 = [](Filter &f) {
+		const int ns = (f.size + 3) & ~3;
+		if (ns == f.size) return;
+		const size_t n = f.pos.size();
+		std::vector<int16_t> c(n * ns, 0);
+		for (size_t i = 0; i < n; ++i)
+			for (int j = 0; j < f.size; ++j) c[i * ns + j] = f.coef[i * f.size + j];
+		f.coef.swap(c);
+		f.size = ns;
+	};
+	pad4(s->hl);
+	pad4(s->hc);
+	P.hl_size = s->hl.size; P.hc_size = s->hc.size; P.vl_size = s->vl.size; P.vc_size = s->vc.size;
+	P.chroma_planes = src_fmt == MSB200_PIX_YUV420P ? 2 : 1;
+	// TMA boxes: widest / tallest source window any tile needs (+3 bytes: the unaligned 4-byte fetch), 16-byte multiples
+	const int ctile_w = dst_rgb ? SC_TW / 2 : (src_fmt == MSB200_PIX_YUV420P ? SC_TW : SC_TW / 2), ctile_h = SC_TH;
+	int lw = max_span(s->hl, dst_w, SC_TW) + 4, cw = max_span(s->hc, P.chr_dst_w, ctile_w) + 4;
+	P.box_lw = (lw + 15 + 15) & ~15; // +15: the box origin is aligned down to 16 bytes
+	P.box_cw = P.chroma_planes == 1 ? ((2 * cw + 15 + 15) & ~15) : ((cw + 15 + 15) & ~15);
+	P.box_lh = max_span(s->vl, dst_h, SC_TH);
+	P.box_ch = max_span(s->vc, P.chr_dst_h, ctile_h);
+	if (P.box_lw > 256 || P.box_cw > 256 || P.box_lh > 256 || P.box_ch > 256) {
+		msb200_set_error("scaler: down-scaling factor too large for one TMA box per tile (%dx%d luma, %dx%d chroma)", P.box_lw,
+		                 P.box_lh, P.box_cw, P.box_ch);
+		delete s;
+		return MSB200_EINVAL;
+	}
+	{ // ff_yuv2rgb_c_init_tables(): ITU-601, limited-range source
+		int64_t crv = 104597, cbu = 132201, cgu = -25675, cgv = -53279, cy = 1 << 16, oy;
+		cy = (cy * 255) / 219;
+		oy = 16 << 16;
+		crv = ((crv * (1 << 16)) + 0x8000) / cy;
+		cbu = ((cbu * (1 << 16)) + 0x8000) / cy;
+		cgu = ((cgu * (1 << 16)) + 0x8000) / cy;
+		cgv = ((cgv * (1 << 16)) + 0x8000) / cy;
+		P.cy = (int)cy; P.crv = (int)crv; P.cbu = (int)cbu; P.cgu = (int)cgu; P.cgv = (int)cgv;
+		P.yb0 = (int)(-(384LL << 16) - 512 * cy - oy);
+		P.yoffs = 326 + 512;
+	}
+	s->src_bytes = fmt_bytes(src_fmt, src_w, src_h);
+	s->dst_bytes = fmt_bytes(dst_fmt, dst_w, dst_h);
+	P.dst_frame_bytes = s->dst_bytes;
+	// upload filter tables
+	size_t off = 0;
+	auto place = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+	const Filter *fs[4] = {&s->hl, &s->hc, &s->vl, &s->vc};
+	size_t opos[4], ocoef[4];
+	for (int i = 0; i < 4; ++i) {
+		opos[i] = place(sizeof(int32_t) * (fs[i]->pos.size() + 4));
+		ocoef[i] = place(sizeof(int16_t) * (fs[i]->coef.size() + 16));
+	}
+	MSB200_CUDA(cudaMalloc(&s->d_tables, off));
+	MSB200_CUDA(cudaMemset(s->d_tables, 0, off));
+	char *base = (char *)s->d_tables;
+	for (int i = 0; i < 4; ++i) {
+		MSB200_CUDA(cudaMemcpy(base + opos[i], fs[i]->pos.data(), sizeof(int32_t) * fs[i]->pos.size(), cudaMemcpyHostToDevice));
+		MSB200_CUDA(cudaMemcpy(base + ocoef[i], fs[i]->coef.data(), sizeof(int16_t) * fs[i]->coef.size(), cudaMemcpyHostToDevice));
+	}
+	P.hl_pos = (const int *)(base + opos[0]); P.hl_coef = (const short *)(base + ocoef[0]);
+	P.hc_pos = (const int *)(base + opos[1]); P.hc_coef = (const short *)(base + ocoef[1]);
+	P.vl_pos = (const int *)(base + opos[2]); P.vl_coef = (const short *)(base + ocoef[2]);
+	P.vc_pos = (const int *)(base + opos[3]); P.vc_coef = (const short *)(base + ocoef[3]);
+	auto a128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+	s->smem_rgb = a128((size_t)P.box_lw * P.box_lh) + a128((size_t)P.box_cw * P.box_ch) +
+	              a128(P.chroma_planes == 2 ? (size_t)P.box_cw * P.box_ch : 0) + a128(4 * (size_t)P.box_lh * SC_TW) +
+	              a128(8 * (size_t)P.box_ch * (SC_TW / 2)) + a128((size_t)SC_TH * SC_TW * 3) + a128(sizeof(RowInfo) * SC_TH) + 256;
+	s->smem_luma = a128((size_t)P.box_lw * P.box_lh) + a128(2 * (size_t)P.box_lh * SC_TW) + a128((size_t)SC_TH * SC_TW) + 256;
+	s->smem_chroma = 2 * a128((size_t)P.box_cw * P.box_ch) + 2 * a128(2 * (size_t)P.box_ch * SC_TW) + a128(2 * (size_t)SC_TH * SC_TW) + 256;
+	const size_t mx = s->smem_rgb > s->smem_chroma ? s->smem_rgb : s->smem_chroma;
+	if (mx > 200 * 1024) {
+		msb200_set_error("scaler: tile working set %zu B exceeds shared memory", mx);
+		cudaFree(s->d_tables);
+		delete s;
+		return MSB200_EINVAL;
+	}
+	if (s->smem_rgb > 48 * 1024) {
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_rgb));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_rgb));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_rgb));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_rgb));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_rgb));
+	}
+	if (s->smem_chroma > 48 * 1024 || s->smem_luma > 48 * 1024) {
+		const int mxs = (int)(s->smem_chroma > s->smem_luma ? s->smem_chroma : s->smem_luma);
+		MSB200_CUDA(cudaFuncSetAttribute(scale_plane_kernel<SC_TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, mxs));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_plane_kernel<SC_TW / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mxs));
+	}
+	*out = s;
+	return MSB200_OK;
+}
+
+void msb200_scaler_destroy(msb200_scaler *s) {
+	if (!s) return;
+	cudaStreamSynchronize(s->ctx->stream);
+	cudaFree(s->d_tables);
+	s->src.release();
+	s->dst.release();
+	delete s;
+}
+size_t msb200_scaler_src_frame_bytes(msb200_scaler *s) {
+	return s ? s->src_bytes : 0;
+}
+size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s) {
+	return s ? s->dst_bytes : 0;
+}
+
+int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst) {
+	MSB200_CHECK_ARG(s && d_src && d_dst && n_frames > 0 && n_frames <= 65535);
+	MSB200_CHECK_ARG(((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0);
+	int r = scaler_build_maps(s, d_src, n_frames);
+	if (r) return r;
+	const ScaleParams &P = s->P;
+	if (P.dst_fmt != MSB200_PIX_YUV420P) {
+		dim3 grid((unsigned)msb200_div_up(P.dst_w, SC_TW), (unsigned)msb200_div_up(P.dst_h, SC_TH), (unsigned)n_frames);
+#define RGB_ARGS s->map_l, s->map_c0, s->map_c1, (unsigned char *)d_dst, P
+		if (P.vl_size == 4 && P.vc_size == 2) MSB200_LAUNCH(s->ctx, (scale_rgb_kernel<4, 2>), grid, SC_THREADS, s->smem_rgb, RGB_ARGS);
+		else if (P.vl_size == 2 && P.vc_size == 2) MSB200_LAUNCH(s->ctx, (scale_rgb_kernel<2, 2>), grid, SC_THREADS, s->smem_rgb, RGB_ARGS);
+		else if (P.vl_size == 1 && P.vc_size == 2) MSB200_LAUNCH(s->ctx, (scale_rgb_kernel<1, 2>), grid, SC_THREADS, s->smem_rgb, RGB_ARGS);
+		else if (P.vl_size == 1 && P.vc_size == 1) MSB200_LAUNCH(s->ctx, (scale_rgb_kernel<1, 1>), grid, SC_THREADS, s->smem_rgb, RGB_ARGS);
+		else MSB200_LAUNCH(s->ctx, (scale_rgb_kernel<0, 0>), grid, SC_THREADS, s->smem_rgb, RGB_ARGS);
+#undef RGB_ARGS
+	} else {
+		dim3 gl((unsigned)msb200_div_up(P.dst_w, SC_TW), (unsigned)msb200_div_up(P.dst_h, SC_TH), (unsigned)n_frames);
+		MSB200_LAUNCH(s->ctx, scale_plane_kernel<SC_TW>, gl, SC_THREADS, s->smem_luma, s->map_l, s->map_l, (unsigned char *)d_dst, P, 0);
+		if (P.chroma_planes == 2) {
+			dim3 gc((unsigned)msb200_div_up(P.chr_dst_w, SC_TW), (unsigned)msb200_div_up(P.chr_dst_h, SC_TH), (unsigned)n_frames);
+			MSB200_LAUNCH(s->ctx, scale_plane_kernel<SC_TW>, gc, SC_THREADS, s->smem_chroma, s->map_c0, s->map_c1, (unsigned char *)d_dst, P, 1);
+		} else {
+			dim3 gc((unsigned)msb200_div_up(P.chr_dst_w, SC_TW / 2), (unsigned)msb200_div_up(P.chr_dst_h, SC_TH), (unsigned)n_frames);
+			MSB200_LAUNCH(s->ctx, scale_plane_kernel<SC_TW / 2>, gc, SC_THREADS, s->smem_chroma, s->map_c0, s->map_c1, (unsigned char *)d_dst, P, 1);
+		}
+	}
+	return MSB200_OK;
+}
+
+int msb200_scaler_process(msb200_scaler *s, int n_frames, const uint8_t *src, uint8_t *dst) {
+	MSB200_CHECK_ARG(s && src && dst && n_frames > 0);
+	int r;
+	if ((r = s->src.reserve(s->src_bytes * (size_t)n_frames + 256)) || (r = s->dst.reserve(s->dst_bytes * (size_t)n_frames + 256))) return r;
+	cudaStream_t st = s->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(s->src.p, src, s->src_bytes * (size_t)n_frames, cudaMemcpyHostToDevice, st));
+	if ((r = msb200_scaler_process_dev(s, n_frames, s->src.p, s->dst.p))) return r;
+	MSB200_CUDA(cudaMemcpyAsync(dst, s->dst.p, s->dst_bytes * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+	MSB200_CUDA(cudaStreamSynchronize(st));
+	return MSB200_OK;
+}
+
+} // extern "C"

@@ -47,3 +47,92 @@ def test_nv12_reference_test_pattern_1080p(ctx):
     exp = np.zeros(w * h * 3 // 2, np.uint8)
     L.orc_nv12_to_i420(ptr(y), ptr(c), 0, w, h, w, w, 1, 0, ptr(exp))
     assert np.array_equal(got[0], exp)
+
+
+# ------------------------------------------------------------------------------------------------ scaler (MSPixConv / MSSizeConv arithmetic)
+from pathlib import Path
+
+from mediastreamer2_b200 import _lib
+
+GOLD = Path(__file__).resolve().parent / "golden" / "swscale_bilinear.npz"
+
+
+def _rand_frames(fmt, w, h, n, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    out = []
+    for t in range(n):
+        Y = ((xx + 2 * yy + 3 * t) % 256 + rng.integers(-3, 4, size=(h, w))).clip(0, 255).astype(np.uint8)
+        ch, cw = h // 2, w // 2
+        cy, cx = np.mgrid[0:ch, 0:cw]
+        U = ((cx + t) % 256 + rng.integers(-3, 4, size=(ch, cw))).clip(0, 255).astype(np.uint8)
+        V = rng.integers(0, 256, size=(ch, cw), dtype=np.uint8) if t % 2 else ((cy + 2 * t) % 256).astype(np.uint8)
+        if fmt == _lib.PIX_YUV420P:
+            out.append(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]))
+        else:
+            a, b = (U, V) if fmt == _lib.PIX_NV12 else (V, U)
+            out.append(np.concatenate([Y.ravel(), np.stack([a, b], axis=-1).ravel()]))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("sf,sw,sh,df,dw,dh", [
+    (_lib.PIX_NV12, 192, 108, _lib.PIX_RGB24, 128, 72),        # cfg4 shape at 1/10 scale
+    (_lib.PIX_NV12, 1920, 1080, _lib.PIX_RGB24, 1280, 720),    # cfg4 full size
+    (_lib.PIX_NV12, 160, 120, _lib.PIX_RGB24, 64, 48),         # 2.5x down
+    (_lib.PIX_NV12, 64, 48, _lib.PIX_RGB24, 96, 72),           # 1.5x up (yuv2rgb_2 path)
+    (_lib.PIX_NV21, 96, 64, _lib.PIX_RGB24_REV, 64, 48),       # NV21 -> BGR24
+    (_lib.PIX_NV12, 128, 72, _lib.PIX_RGB24, 128, 72),         # same size (yuv2rgb_1 path)
+    (_lib.PIX_YUV420P, 192, 108, _lib.PIX_RGB24, 128, 72),     # planar source
+    (_lib.PIX_YUV420P, 192, 108, _lib.PIX_YUV420P, 128, 72),   # MSSizeConv: I420 -> I420 down
+    (_lib.PIX_YUV420P, 64, 48, _lib.PIX_YUV420P, 160, 120),    # MSSizeConv: I420 -> I420 up
+    (_lib.PIX_NV12, 320, 240, _lib.PIX_YUV420P, 320, 240),     # MSPixConv-like: NV12 -> I420 same size through the scaler
+    (_lib.PIX_NV12, 208, 112, _lib.PIX_RGB24, 150, 90),        # ragged tiles (150 % 128, 90 % 16 != 0)
+])
+def test_scaler_bit_exact_vs_oracle(ctx, sf, sw, sh, df, dw, dh):
+    L = O.oracle()
+    n = 3 if sw < 1000 else 2
+    frames = _rand_frames(sf, sw, sh, n, seed=sw * 7 + dh)
+    sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
+    got = sc.process(frames)
+    o = L.orc_scaler_new(sw, sh, sf, dw, dh, df)
+    assert L.orc_scaler_src_bytes(o) == sc.src_bytes and L.orc_scaler_dst_bytes(o) == sc.dst_bytes
+    for i in range(n):
+        exp = np.zeros(sc.dst_bytes + 64, np.uint8)
+        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+        assert np.array_equal(got[i], exp[:-64]), (i, np.abs(got[i].astype(int) - exp[:-64].astype(int)).max())
+    L.orc_scaler_free(o)
+    sc.close()
+
+
+def test_scaler_full_size_cfg4_matches_real_libswscale_digest(ctx):
+    """NV12 1080p -> RGB24 720p: SHA-256 of the GPU output == SHA-256 of the real libswscale 9.1.100 output."""
+    import hashlib
+
+    from test_oracle_video import cfg4_frame
+
+    g = np.load(GOLD)
+    sc = F.Scaler(ctx, 1920, 1080, _lib.PIX_NV12, 1280, 720, _lib.PIX_RGB24)
+    out = sc.process(cfg4_frame()[None, :])
+    sc.close()
+    assert hashlib.sha256(out[0].tobytes()).digest() == g["cfg4_sha256"].tobytes()
+
+
+def test_scaler_golden_frames_from_real_libswscale(ctx):
+    """the committed small golden frames (real library, default build): RGB24 cases bit-exact."""
+    g = np.load(GOLD)
+    av2ms = {0: 0, 2: 2, 3: 3, 23: 100, 24: 101}
+    checked = 0
+    k = 0
+    while f"case{k}_src" in g:
+        sf, sw, sh, df, dw, dh = [int(v) for v in g[f"case{k}_meta"]]
+        k += 1
+        if sw % 16 or (sf == 0 and (sw // 2) % 16):
+            continue  # TMA row-pitch constraint of the product (documented in DESIGN.md)
+        sc = F.Scaler(ctx, sw, sh, av2ms[sf], dw, dh, av2ms[df])
+        out = sc.process(g[f"case{k - 1}_src"][None, :])
+        sc.close()
+        assert np.array_equal(out[0], g[f"case{k - 1}_dst_bitexact"])
+        if df == 2:
+            assert np.array_equal(out[0], g[f"case{k - 1}_dst"])
+        checked += 1
+    assert checked >= 5
