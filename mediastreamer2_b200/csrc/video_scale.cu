@@ -490,6 +490,246 @@ __global__ void __launch_bounds__(SC_THREADS)
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ fast path
+// Persistent, double-buffered variant for the common geometry (interleaved CbCr source, 4-tap horizontal filters,
+// destination rows that TMA can store: dst_w*3 % 16 == 0, dst_w % 128 == 0): BASELINE cfg4 runs here.
+//   * grid = a few CTAs per SM; each CTA walks tiles (x fastest, then y, then frame) so that co-resident CTAs share halos
+//     in L2; all loop-invariant set-up is hoisted out of the tile loop;
+//   * the source boxes of tile k+1 are fetched by TMA while tile k is computed (two smem stages, one mbarrier each);
+//   * the vertical/colour pass works on groups of 4 pixels (one 16-byte luma load per tap, 12 output bytes as three
+//     32-bit shared stores), colour clamp = one multiply-add + one min/relu per channel, bytes packed with PRMT;
+//   * the finished tile leaves through TMA stores (UTMASTG) from shared memory.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"((uint64_t)map),
+	             "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+	asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+	asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+	asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+// clamp a Q16 value to [0, 255.99998]: byte 2 of the result is clip_uint8(v >> 16)
+__device__ __forceinline__ unsigned clampq16(int v) {
+	return (unsigned)__vimin_s32_relu(v, 0x00ffffff);
+}
+
+#define SCF_HALF (SC_TW * 3 / 2) // 192 bytes: one TMA store box row (box dims are limited to 256)
+
+template <int VL, int VC>
+__global__ void __launch_bounds__(SC_THREADS)
+    scale_rgb_fast_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c,
+                          const __grid_constant__ CUtensorMap map_o, ScaleParams P, int tiles_x, int tiles_y, int n_tiles) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+	const int t = threadIdx.x;
+	// ---- loop-invariant carve-up (32-bit arithmetic)
+	const unsigned lbox_bytes = (unsigned)(P.box_lw * P.box_lh), cbox_bytes = (unsigned)(P.box_cw * P.box_ch);
+	const unsigned lbox_al = (lbox_bytes + 127u) & ~127u, cbox_al = (cbox_bytes + 127u) & ~127u;
+	unsigned off = 0;
+	// stage s: luma box at smem + s*stage_bytes, CbCr box right after it
+	const unsigned stage_bytes = lbox_al + cbox_al;
+	off += 2 * stage_bytes;
+	int *lum_h = reinterpret_cast<int *>(smem + off); off += ((unsigned)(4 * P.box_lh * SC_TW) + 127u) & ~127u;
+	int2 *chr_h = reinterpret_cast<int2 *>(smem + off); off += ((unsigned)(8 * P.box_ch * (SC_TW / 2)) + 127u) & ~127u;
+	unsigned char *out_s = smem + off; off += (unsigned)(SC_TH * SC_TW * 3); // two [SC_TH][192] halves
+	RowInfo *rows = reinterpret_cast<RowInfo *>(smem + off); off += (unsigned)((sizeof(RowInfo) * SC_TH + 127) & ~127u);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + off); // [2]
+	const unsigned tx_bytes = lbox_bytes + cbox_bytes;
+	const int pitch_lw = P.box_lw >> 2, pitch_cw = P.box_cw >> 2; // in 32-bit words
+	const bool swap_uv = P.src_fmt == MSB200_PIX_NV21, bgr = P.dst_fmt == MSB200_PIX_RGB24_REV;
+	const int c_cy = P.cy, c_off = P.yb0 + 0x8000;
+	const int base_r = P.yoffs - (P.crv >> 9), base_g = P.yoffs - (P.cgu >> 9) - (P.cgv >> 9), base_b = P.yoffs - (P.cbu >> 9);
+	const int crv = P.crv, cgu = P.cgu, cgv = P.cgv, cbu = P.cbu;
+
+	auto tile_coords = [&](int tile, int &x0, int &y0, int &frame) {
+		const int tx = tile % tiles_x, r = tile / tiles_x;
+		x0 = tx * SC_TW;
+		y0 = (r % tiles_y) * SC_TH;
+		frame = r / tiles_y;
+	};
+	auto issue_load = [&](int tile, int stage) { // thread 0 only
+		int x0, y0, frame;
+		tile_coords(tile, x0, y0, frame);
+		const int lx0 = P.hl_pos[x0] & ~15, ly0 = P.vl_pos[y0];
+		const int cb0 = (2 * P.hc_pos[x0 >> 1]) & ~15, cy0 = P.vc_pos[y0];
+		mbar_expect_tx(&bar[stage], tx_bytes);
+		tma_load_3d(smem + stage * stage_bytes, &map_l, &bar[stage], lx0, ly0, frame);
+		tma_load_3d(smem + stage * stage_bytes + lbox_al, &map_c, &bar[stage], cb0, cy0, frame);
+	};
+
+	if (t == 0) {
+		mbar_init(&bar[0], 1);
+		mbar_init(&bar[1], 1);
+	}
+	__syncthreads();
+	int tile = blockIdx.x;
+	if (t == 0 && tile < n_tiles) issue_load(tile, 0);
+
+	for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+		const int stage = it & 1;
+		int x0, y0, frame;
+		tile_coords(tile, x0, y0, frame);
+		const int th = min(SC_TH, P.dst_h - y0);
+		const int lx0 = P.hl_pos[x0] & ~15, ly0 = P.vl_pos[y0];
+		const int cb0 = (2 * P.hc_pos[x0 >> 1]) & ~15, cy0 = P.vc_pos[y0];
+		// ---- A: prefetch the next tile, publish this tile's vertical filter rows
+		if (t == 0) {
+			tma_store_wait_read(); // the previous tile's TMA stores no longer read out_s
+			const int next = tile + gridDim.x;
+			if (next < n_tiles) issue_load(next, stage ^ 1);
+		}
+		if (t < SC_TH) {
+			RowInfo ri;
+			const int y = min(y0 + t, P.dst_h - 1);
+			ri.lp = (P.vl_pos[y] - ly0) * SC_TW;          // element offsets into lum_h / chr_h
+			ri.cp = (P.vc_pos[y] - cy0) * (SC_TW / 2);
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				ri.lf[j] = j < VL ? P.vl_coef[y * VL + j] : 0;
+				ri.cf[j] = j < VC ? P.vc_coef[y * VC + j] : 0;
+			}
+			rows[t] = ri;
+		}
+		const int l_rows = min(P.box_lh, P.vl_pos[y0 + th - 1] + VL - ly0);
+		const int c_rows = min(P.box_ch, P.vc_pos[y0 + th - 1] + VC - cy0);
+		// per-thread horizontal filter data (registers)
+		const int lx = t & (SC_TW - 1);
+		const int lp_off = P.hl_pos[x0 + lx] - lx0;
+		const int2 lc = reinterpret_cast<const int2 *>(P.hl_coef)[x0 + lx]; // 4 taps
+		const int cxi = t & (SC_TW / 2 - 1);
+		const int cgx = (x0 >> 1) + cxi;
+		const int cp_off = 2 * P.hc_pos[cgx] - cb0; // byte offset inside the CbCr box
+		const int2 cc = reinterpret_cast<const int2 *>(P.hc_coef)[cgx];
+		mbar_wait(&bar[stage], (unsigned)((it >> 1) & 1));
+
+		// ---- horizontal pass, luma: thread = output column; rows r = (t>>7), +2, ...
+		{
+			const unsigned *w = reinterpret_cast<const unsigned *>(smem + stage * stage_bytes) + (lp_off >> 2);
+			const int sh = (lp_off & 3) * 8;
+			int *o = lum_h + lx;
+			int r = t >> 7;
+			for (; r + 2 < l_rows; r += 4) { // two rows per iteration
+				const unsigned *w0 = w + r * pitch_lw, *w1 = w0 + 2 * pitch_lw;
+				const unsigned q0 = __funnelshift_r(w0[0], w0[1], sh), q1 = __funnelshift_r(w1[0], w1[1], sh);
+				const int v0 = dp2a_hi(lc.y, q0, dp2a_lo(lc.x, q0, 0)) >> 7, v1 = dp2a_hi(lc.y, q1, dp2a_lo(lc.x, q1, 0)) >> 7;
+				o[r * SC_TW] = min(v0, 32767);
+				o[(r + 2) * SC_TW] = min(v1, 32767);
+			}
+			for (; r < l_rows; r += 2) {
+				const unsigned *w0 = w + r * pitch_lw;
+				const unsigned q0 = __funnelshift_r(w0[0], w0[1], sh);
+				o[r * SC_TW] = min(dp2a_hi(lc.y, q0, dp2a_lo(lc.x, q0, 0)) >> 7, 32767);
+			}
+		}
+		// ---- horizontal pass, chroma: both planes per thread; rows r = (t>>6), +4, ...
+		{
+			const unsigned *w = reinterpret_cast<const unsigned *>(smem + stage * stage_bytes + lbox_al) + (cp_off >> 2);
+			const int sh = (cp_off & 3) * 8; // 0 or 16
+			for (int r = t >> 6; r < c_rows; r += 4) {
+				const unsigned *w0 = w + r * pitch_cw;
+				const unsigned a0 = w0[0], a1 = w0[1], a2 = w0[2];
+				const unsigned lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+				const unsigned qu = __byte_perm(lo, hi, 0x6420), qv = __byte_perm(lo, hi, 0x7531);
+				const int u = min(dp2a_hi(cc.y, qu, dp2a_lo(cc.x, qu, 0)) >> 7, 32767);
+				const int v = min(dp2a_hi(cc.y, qv, dp2a_lo(cc.x, qv, 0)) >> 7, 32767);
+				chr_h[r * (SC_TW / 2) + cxi] = swap_uv ? make_int2(v, u) : make_int2(u, v);
+			}
+		}
+		__syncthreads(); // B: intermediates + row table complete; previous store has released out_s (thread 0 waited)
+
+		// ---- vertical pass + colour: thread = 4-pixel column group (32 per tile) x 8 row phases
+		{
+			const int g = t & 31;
+			const int4 *lcol = reinterpret_cast<const int4 *>(lum_h) + g; // row pitch SC_TW/4 int4
+			const int4 *ccol = reinterpret_cast<const int4 *>(chr_h) + g; // (U0,V0,U1,V1), row pitch SC_TW/4 int4
+			unsigned *og = reinterpret_cast<unsigned *>(out_s + (g >= 16 ? SC_TH * SCF_HALF : 0)) + (g & 15) * 3;
+			for (int ry = t >> 5; ry < th; ry += SC_THREADS / 32) {
+				const RowInfo ri = rows[ry];
+				const int4 *lr = lcol + (ri.lp >> 2);
+				const int4 *cr = ccol + (ri.cp >> 1);
+				int Y[4], U[2], V[2];
+				if (VL == 1) {
+					const int4 l = lr[0];
+					Y[0] = (l.x + 64) >> 7; Y[1] = (l.y + 64) >> 7; Y[2] = (l.z + 64) >> 7; Y[3] = (l.w + 64) >> 7;
+					const int4 c0 = cr[0];
+					const int uvalpha = VC == 1 ? 0 : ri.cf[1];
+					if (uvalpha == 0) {
+						U[0] = (c0.x + 64) >> 7; V[0] = (c0.y + 64) >> 7; U[1] = (c0.z + 64) >> 7; V[1] = (c0.w + 64) >> 7;
+					} else {
+						const int4 c1 = cr[SC_TW / 4];
+						const int a1 = 4096 - uvalpha;
+						U[0] = (c0.x * a1 + c1.x * uvalpha + (128 << 11)) >> 19; V[0] = (c0.y * a1 + c1.y * uvalpha + (128 << 11)) >> 19;
+						U[1] = (c0.z * a1 + c1.z * uvalpha + (128 << 11)) >> 19; V[1] = (c0.w * a1 + c1.w * uvalpha + (128 << 11)) >> 19;
+					}
+				} else if (VL == 2 && VC == 2) {
+					const int4 l0 = lr[0], l1 = lr[SC_TW / 4], c0 = cr[0], c1 = cr[SC_TW / 4];
+					const int ya = ri.lf[1], ua = ri.cf[1], ya1 = 4096 - ya, ua1 = 4096 - ua;
+					Y[0] = (l0.x * ya1 + l1.x * ya) >> 19; Y[1] = (l0.y * ya1 + l1.y * ya) >> 19;
+					Y[2] = (l0.z * ya1 + l1.z * ya) >> 19; Y[3] = (l0.w * ya1 + l1.w * ya) >> 19;
+					U[0] = (c0.x * ua1 + c1.x * ua) >> 19; V[0] = (c0.y * ua1 + c1.y * ua) >> 19;
+					U[1] = (c0.z * ua1 + c1.z * ua) >> 19; V[1] = (c0.w * ua1 + c1.w * ua) >> 19;
+				} else {
+					Y[0] = Y[1] = Y[2] = Y[3] = U[0] = U[1] = V[0] = V[1] = 1 << 18;
+#pragma unroll
+					for (int j = 0; j < VL; ++j) {
+						const int4 l = lr[j * (SC_TW / 4)];
+						const int c = ri.lf[j];
+						Y[0] += l.x * c; Y[1] += l.y * c; Y[2] += l.z * c; Y[3] += l.w * c;
+					}
+#pragma unroll
+					for (int j = 0; j < VC; ++j) {
+						const int4 c4 = cr[j * (SC_TW / 4)];
+						const int c = ri.cf[j];
+						U[0] += c4.x * c; V[0] += c4.y * c; U[1] += c4.z * c; V[1] += c4.w * c;
+					}
+#pragma unroll
+					for (int k = 0; k < 4; ++k) Y[k] >>= 19;
+					U[0] >>= 19; U[1] >>= 19; V[0] >>= 19; V[1] >>= 19;
+				}
+				unsigned px[4][3]; // clamped Q16 values, byte 2 is the 8-bit channel; order (first, G, last) = (R,G,B) or (B,G,R)
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					const int Uc = (int)sat_u8(U[h]), Vc = (int)sat_u8(V[h]);
+					const int ar = c_off + (base_r + ((Vc * crv) >> 16)) * c_cy;
+					const int ag = c_off + (base_g + ((Uc * cgu) >> 16) + ((Vc * cgv) >> 16)) * c_cy;
+					const int ab = c_off + (base_b + ((Uc * cbu) >> 16)) * c_cy;
+#pragma unroll
+					for (int k = 0; k < 2; ++k) {
+						const int yc = Y[2 * h + k];
+						const unsigned r = clampq16(yc * c_cy + ar), gq = clampq16(yc * c_cy + ag), b = clampq16(yc * c_cy + ab);
+						px[2 * h + k][0] = bgr ? b : r;
+						px[2 * h + k][1] = gq;
+						px[2 * h + k][2] = bgr ? r : b;
+					}
+				}
+				// 12 bytes = c0 g0 d0 c1 | g1 d1 c2 g2 | d2 c3 g3 d3  (byte 2 of each clamped value)
+				const unsigned w0 = __byte_perm(__byte_perm(px[0][0], px[0][1], 0x0062), __byte_perm(px[0][2], px[1][0], 0x0062), 0x5410);
+				const unsigned w1 = __byte_perm(__byte_perm(px[1][1], px[1][2], 0x0062), __byte_perm(px[2][0], px[2][1], 0x0062), 0x5410);
+				const unsigned w2 = __byte_perm(__byte_perm(px[2][2], px[3][0], 0x0062), __byte_perm(px[3][1], px[3][2], 0x0062), 0x5410);
+				unsigned *o = og + ry * (SCF_HALF / 4);
+				o[0] = w0;
+				o[1] = w1;
+				o[2] = w2;
+			}
+		}
+		fence_proxy_async(); // make the generic-proxy writes to out_s visible to the TMA engine
+		__syncthreads();     // C
+		if (t == 0) {
+			tma_store_3d(&map_o, out_s, x0 * 3, y0, frame);
+			tma_store_3d(&map_o, out_s + SC_TH * SCF_HALF, x0 * 3 + SCF_HALF, y0, frame);
+			tma_store_commit();
+		}
+	}
+	if (t == 0) {
+		asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); // stores fully performed before the CTA exits
+	}
+}
+
 // planar (YUV420P) output: yuv2planeX_8 / yuv2plane1_8 with the constant-64 dither. One launch per plane kind: the
 // tile is TW x TH of the destination PLANE (luma plane, or the U and V planes together).
 template <int TWP> // tile width in destination-plane samples (64 for interleaved-chroma sources: the CbCr box is 2 bytes/sample)
@@ -590,7 +830,10 @@ struct msb200_scaler {
 	// chroma plane geometry of the source for the tensor maps
 	int cached_frames;
 	const void *cached_src;
-	CUtensorMap map_l, map_c0, map_c1;
+	CUtensorMap map_l, map_c0, map_c1, map_o;
+	const void *cached_dst;
+	bool fast_ok;
+	size_t smem_fast;
 	msb200_devbuf src, dst;
 };
 
@@ -648,6 +891,16 @@ static int max_span(const Filter &f, int n, int tile) {
 	return best;
 }
 
+static int scaler_build_out_map(msb200_scaler *s, const void *d_dst, int n_frames) {
+	if (s->cached_dst == d_dst && s->cached_frames == n_frames) return MSB200_OK;
+	const ScaleParams &P = s->P;
+	int r = make_map(&s->map_o, d_dst, (uint64_t)P.dst_w * 3, (uint64_t)P.dst_h, (uint64_t)n_frames, (uint64_t)P.dst_w * 3,
+	                 (uint64_t)s->dst_bytes, (uint32_t)SCF_HALF, (uint32_t)SC_TH);
+	if (r) return r;
+	s->cached_dst = d_dst;
+	return MSB200_OK;
+}
+
 static int scaler_build_maps(msb200_scaler *s, const void *d_src, int n_frames) {
 	if (s->cached_src == d_src && s->cached_frames == n_frames) return MSB200_OK;
 	const ScaleParams &P = s->P;
@@ -689,7 +942,10 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	msb200_scaler *s = new msb200_scaler();
 	s->ctx = ctx;
 	s->cached_src = nullptr;
+	s->cached_dst = nullptr;
 	s->cached_frames = 0;
+	s->fast_ok = false;
+	s->smem_fast = 0;
 	ScaleParams &P = s->P;
 	memset(&P, 0, sizeof(P));
 	P.src_w = src_w; P.src_h = src_h; P.dst_w = dst_w; P.dst_h = dst_h; P.src_fmt = src_fmt; P.dst_fmt = dst_fmt;
@@ -776,6 +1032,16 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	              a128(8 * (size_t)P.box_ch * (SC_TW / 2)) + a128((size_t)SC_TH * SC_TW * 3) + a128(sizeof(RowInfo) * SC_TH) + 256;
 	s->smem_luma = a128((size_t)P.box_lw * P.box_lh) + a128(2 * (size_t)P.box_lh * SC_TW) + a128((size_t)SC_TH * SC_TW) + 256;
 	s->smem_chroma = 2 * a128((size_t)P.box_cw * P.box_ch) + 2 * a128(2 * (size_t)P.box_ch * SC_TW) + a128(2 * (size_t)SC_TH * SC_TW) + 256;
+	s->fast_ok = dst_rgb && P.chroma_planes == 1 && P.hl_size == 4 && P.hc_size == 4 && (dst_w % SC_TW) == 0 &&
+	             ((P.vl_size == 4 && P.vc_size == 2) || (P.vl_size == 2 && P.vc_size == 2) || (P.vl_size == 1 && P.vc_size <= 2));
+	s->smem_fast = 2 * (a128((size_t)P.box_lw * P.box_lh) + a128((size_t)P.box_cw * P.box_ch)) + a128(4 * (size_t)P.box_lh * SC_TW) +
+	               a128(8 * (size_t)P.box_ch * (SC_TW / 2)) + (size_t)SC_TH * SC_TW * 3 + a128(sizeof(RowInfo) * SC_TH) + 16 + 256;
+	if (s->fast_ok && s->smem_fast > 48 * 1024) {
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
+		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
+	}
 	const size_t mx = s->smem_rgb > s->smem_chroma ? s->smem_rgb : s->smem_chroma;
 	if (mx > 200 * 1024) {
 		msb200_set_error("scaler: tile working set %zu B exceeds shared memory", mx);
@@ -820,6 +1086,31 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 	int r = scaler_build_maps(s, d_src, n_frames);
 	if (r) return r;
 	const ScaleParams &P = s->P;
+	if (s->fast_ok && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0) {
+		// persistent fast path: a few CTAs per SM walk the tiles, TMA in (double-buffered) and TMA out
+		if ((r = scaler_build_out_map(s, d_dst, n_frames))) return r;
+		s->cached_frames = n_frames;
+		const int tiles_x = P.dst_w / SC_TW, tiles_y = msb200_div_up(P.dst_h, SC_TH);
+		const long n_tiles_l = (long)tiles_x * tiles_y * n_frames;
+		MSB200_CHECK_ARG(n_tiles_l < (1L << 31));
+		const int n_tiles = (int)n_tiles_l;
+		int per_sm = 0;
+#define FAST_LAUNCH(VL, VC)                                                                                            \
+	do {                                                                                                               \
+		MSB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scale_rgb_fast_kernel<VL, VC>, SC_THREADS, s->smem_fast)); \
+		if (per_sm < 1) per_sm = 1;                                                                                    \
+		long g = (long)per_sm * s->ctx->sm_count;                                                                      \
+		if (g > n_tiles) g = n_tiles;                                                                                  \
+		MSB200_LAUNCH(s->ctx, (scale_rgb_fast_kernel<VL, VC>), (unsigned)g, SC_THREADS, s->smem_fast, s->map_l, s->map_c0, \
+		              s->map_o, P, tiles_x, tiles_y, n_tiles);                                                         \
+	} while (0)
+		if (P.vl_size == 4) FAST_LAUNCH(4, 2);
+		else if (P.vl_size == 2) FAST_LAUNCH(2, 2);
+		else if (P.vc_size == 2) FAST_LAUNCH(1, 2);
+		else FAST_LAUNCH(1, 1);
+#undef FAST_LAUNCH
+		return MSB200_OK;
+	}
 	if (P.dst_fmt != MSB200_PIX_YUV420P) {
 		dim3 grid((unsigned)msb200_div_up(P.dst_w, SC_TW), (unsigned)msb200_div_up(P.dst_h, SC_TH), (unsigned)n_frames);
 #define RGB_ARGS s->map_l, s->map_c0, s->map_c1, (unsigned char *)d_dst, P
