@@ -16,6 +16,7 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_SO = ROOT / "oracle" / "libmsb200oracle.so"
 REF_SO = ROOT / "oracle" / "_ref" / "libms2ref.so"
+PLUGIN_DIR = ROOT / "plugin" / "lib"
 
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 
@@ -101,7 +102,8 @@ def ref() -> C.CDLL:
         return _ref
     if not REF_SO.exists():
         pytest.skip("oracle/_ref/libms2ref.so not built (needs /root/reference)")
-    L = C.CDLL(str(REF_SO))
+    # RTLD_GLOBAL: plugins dlopen'ed by the reference's loader resolve ms_*/ortp symbols against this library
+    L = C.CDLL(str(REF_SO), mode=C.RTLD_GLOBAL)
     sig = {
         "ref_factory_new": (_P, [C.c_char_p]),
         "ref_factory_destroy": (None, [_P]),
