@@ -46,6 +46,10 @@ MSB200_API int msb200_version(void);
 MSB200_API const char *msb200_last_error(void);
 /* One context per (process, GPU): owns a CUDA stream, timing events and a pinned staging arena. */
 MSB200_API int msb200_ctx_create(int device_ordinal, msb200_ctx **out);
+/* Same, but every launch goes to a stream owned by the caller (a cudaStream_t passed as void*; NULL = the legacy default
+ * stream). Lets a host order our kernels with its own work on that stream — e.g. NCCL collectives issued by
+ * torch.distributed between msb200_mixer_partial_dev and msb200_mixer_finish_dev — without host synchronisation. */
+MSB200_API int msb200_ctx_create_on_stream(int device_ordinal, void *cuda_stream, msb200_ctx **out);
 MSB200_API void msb200_ctx_destroy(msb200_ctx *ctx);
 MSB200_API int msb200_ctx_sync(msb200_ctx *ctx);
 /* Kernel launches issued through this context since creation (bench.py reports it as gpu_launches). */

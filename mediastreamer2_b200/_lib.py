@@ -59,6 +59,7 @@ _SIGS = {
     "msb200_version": (C.c_int, []),
     "msb200_last_error": (C.c_char_p, []),
     "msb200_ctx_create": (_I, [_I, _PP]),
+    "msb200_ctx_create_on_stream": (_I, [_I, _P, _PP]),
     "msb200_ctx_destroy": (None, [_P]),
     "msb200_ctx_sync": (_I, [_P]),
     "msb200_ctx_launch_count": (C.c_uint64, [_P]),

@@ -20,7 +20,7 @@ const char *msb200_last_error(void) {
 	return g_err;
 }
 
-int msb200_ctx_create(int device_ordinal, msb200_ctx **out) {
+static int ctx_create_impl(int device_ordinal, bool own, cudaStream_t ext, msb200_ctx **out) {
 	MSB200_CHECK_ARG(out != nullptr);
 	*out = nullptr;
 	int n = 0;
@@ -43,21 +43,30 @@ int msb200_ctx_create(int device_ordinal, msb200_ctx **out) {
 	msb200_ctx *c = new msb200_ctx();
 	c->device = device_ordinal;
 	c->sm_count = prop.multiProcessorCount;
-	MSB200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	c->owns_stream = own;
+	if (own) MSB200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	else c->stream = ext;
 	MSB200_CUDA(cudaEventCreate(&c->ev_start));
 	MSB200_CUDA(cudaEventCreate(&c->ev_stop));
 	*out = c;
 	return MSB200_OK;
 }
 
+int msb200_ctx_create(int device_ordinal, msb200_ctx **out) {
+	return ctx_create_impl(device_ordinal, true, nullptr, out);
+}
+int msb200_ctx_create_on_stream(int device_ordinal, void *cuda_stream, msb200_ctx **out) {
+	return ctx_create_impl(device_ordinal, false, (cudaStream_t)cuda_stream, out);
+}
+
 void msb200_ctx_destroy(msb200_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
-	if (c->stream) cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->stream);
 	if (c->flush_buf) cudaFree(c->flush_buf);
 	if (c->ev_start) cudaEventDestroy(c->ev_start);
 	if (c->ev_stop) cudaEventDestroy(c->ev_stop);
-	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->stream && c->owns_stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
 

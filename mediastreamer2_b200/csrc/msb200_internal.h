@@ -14,6 +14,7 @@ struct msb200_ctx {
 	int device = 0;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
+	bool owns_stream = true;
 	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 	uint64_t launches = 0;
 	void *flush_buf = nullptr; // > L2, written by msb200_flush_l2

@@ -26,10 +26,13 @@ def _req(a, dtype) -> np.ndarray:
 class Context:
     """msb200_ctx: one per (process, GPU)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
         self.lib = _lib.load()
         h = C.c_void_p()
-        check(self.lib.msb200_ctx_create(device, C.byref(h)))
+        if cuda_stream is None:
+            check(self.lib.msb200_ctx_create(device, C.byref(h)))
+        else:  # launch on a stream owned by the caller (e.g. torch.cuda.current_stream().cuda_stream)
+            check(self.lib.msb200_ctx_create_on_stream(device, C.c_void_p(cuda_stream), C.byref(h)))
         self.h = h
 
     def close(self):
