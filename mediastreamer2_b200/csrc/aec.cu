@@ -52,7 +52,7 @@ struct AecParams {
 };
 
 // ------------------------------------------------------------------------------------------------ cp.async (LDGSTS)
-#define AEC_STAGES 4
+#define AEC_STAGES 3
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -215,7 +215,7 @@ __device__ __forceinline__ float qcurve(float x) {
 // ------------------------------------------------------------------------------------------------ the kernel
 // dynamic shared memory map (floats): see carve-up at the top of the kernel body
 template <int LOG2L>
-__global__ void __launch_bounds__(1 << LOG2L, (768 >> LOG2L))
+__global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
                float *__restrict__ gS, AecParams P, int head0, int in_frame0, int in_ring, int out_stride, int out_frame0,
