@@ -518,6 +518,9 @@ __device__ __forceinline__ unsigned clampq16(int v) {
 	return (unsigned)__vimin_s32_relu(v, 0x00ffffff);
 }
 
+__device__ __forceinline__ int4 unpack_uv(uint2 p) { // (U0|V0<<16, U1|V1<<16) -> (U0, V0, U1, V1)
+	return make_int4((int)(p.x & 0xffffu), (int)(p.x >> 16), (int)(p.y & 0xffffu), (int)(p.y >> 16));
+}
 #define SCF_HALF (SC_TW * 3 / 2) // 192 bytes: one TMA store box row (box dims are limited to 256)
 
 template <int VL, int VC>
@@ -535,10 +538,11 @@ __global__ void __launch_bounds__(SC_THREADS)
 	const unsigned stage_bytes = lbox_al + cbox_al;
 	off += 2 * stage_bytes;
 	int *lum_h = reinterpret_cast<int *>(smem + off); off += ((unsigned)(4 * P.box_lh * SC_TW) + 127u) & ~127u;
-	int2 *chr_h = reinterpret_cast<int2 *>(smem + off); off += ((unsigned)(8 * P.box_ch * (SC_TW / 2)) + 127u) & ~127u;
+	unsigned *chr_h = reinterpret_cast<unsigned *>(smem + off); off += ((unsigned)(4 * P.box_ch * (SC_TW / 2)) + 127u) & ~127u;
 	unsigned char *out_s = smem + off; off += (unsigned)(SC_TH * SC_TW * 3); // two [SC_TH][192] halves
 	RowInfo *rows = reinterpret_cast<RowInfo *>(smem + off); off += (unsigned)((sizeof(RowInfo) * SC_TH + 127) & ~127u);
-	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + off); // [2]
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + off); off += 16; // [2]
+	int4 *tinfo = reinterpret_cast<int4 *>(smem + off);               // [2] (x0, y0, frame, -) of the tile in each stage
 	const unsigned tx_bytes = lbox_bytes + cbox_bytes;
 	const int pitch_lw = P.box_lw >> 2, pitch_cw = P.box_cw >> 2; // in 32-bit words
 	const bool swap_uv = P.src_fmt == MSB200_PIX_NV21, bgr = P.dst_fmt == MSB200_PIX_RGB24_REV;
@@ -555,6 +559,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 	auto issue_load = [&](int tile, int stage) { // thread 0 only
 		int x0, y0, frame;
 		tile_coords(tile, x0, y0, frame);
+		tinfo[stage] = make_int4(x0, y0, frame, 0);
 		const int lx0 = P.hl_pos[x0] & ~15, ly0 = P.vl_pos[y0];
 		const int cb0 = (2 * P.hc_pos[x0 >> 1]) & ~15, cy0 = P.vc_pos[y0];
 		mbar_expect_tx(&bar[stage], tx_bytes);
@@ -562,18 +567,18 @@ __global__ void __launch_bounds__(SC_THREADS)
 		tma_load_3d(smem + stage * stage_bytes + lbox_al, &map_c, &bar[stage], cb0, cy0, frame);
 	};
 
+	int tile = blockIdx.x;
 	if (t == 0) {
 		mbar_init(&bar[0], 1);
 		mbar_init(&bar[1], 1);
+		if (tile < n_tiles) issue_load(tile, 0);
 	}
 	__syncthreads();
-	int tile = blockIdx.x;
-	if (t == 0 && tile < n_tiles) issue_load(tile, 0);
 
 	for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
 		const int stage = it & 1;
-		int x0, y0, frame;
-		tile_coords(tile, x0, y0, frame);
+		const int4 ti = tinfo[stage]; // written by thread 0 before the barrier that ended the previous iteration
+		const int x0 = ti.x, y0 = ti.y, frame = ti.z;
 		const int th = min(SC_TH, P.dst_h - y0);
 		const int lx0 = P.hl_pos[x0] & ~15, ly0 = P.vl_pos[y0];
 		const int cb0 = (2 * P.hc_pos[x0 >> 1]) & ~15, cy0 = P.vc_pos[y0];
@@ -598,32 +603,32 @@ __global__ void __launch_bounds__(SC_THREADS)
 		const int l_rows = min(P.box_lh, P.vl_pos[y0 + th - 1] + VL - ly0);
 		const int c_rows = min(P.box_ch, P.vc_pos[y0 + th - 1] + VC - cy0);
 		// per-thread horizontal filter data (registers)
-		const int lx = t & (SC_TW - 1);
-		const int lp_off = P.hl_pos[x0 + lx] - lx0;
-		const int2 lc = reinterpret_cast<const int2 *>(P.hl_coef)[x0 + lx]; // 4 taps
+		const int pi = t & (SC_TW / 2 - 1);                       // output column pair owned in the luma pass
+		const int2 lpp = reinterpret_cast<const int2 *>(P.hl_pos)[(x0 >> 1) + pi];
+		const int lp_a = lpp.x - lx0, lp_b = lpp.y - lx0;
+		const int4 lcc = reinterpret_cast<const int4 *>(P.hl_coef)[(x0 >> 1) + pi]; // 4 taps x 2 columns
+		const int2 lca = make_int2(lcc.x, lcc.y), lcb = make_int2(lcc.z, lcc.w);
 		const int cxi = t & (SC_TW / 2 - 1);
 		const int cgx = (x0 >> 1) + cxi;
 		const int cp_off = 2 * P.hc_pos[cgx] - cb0; // byte offset inside the CbCr box
 		const int2 cc = reinterpret_cast<const int2 *>(P.hc_coef)[cgx];
 		mbar_wait(&bar[stage], (unsigned)((it >> 1) & 1));
 
-		// ---- horizontal pass, luma: thread = output column; rows r = (t>>7), +2, ...
+		// ---- horizontal pass, luma: thread = output column pair (2i, 2i+1), rows r = (t>>6), +4, ...
+		// the two 4-byte source windows start at most 2 bytes apart: three aligned words cover both
 		{
-			const unsigned *w = reinterpret_cast<const unsigned *>(smem + stage * stage_bytes) + (lp_off >> 2);
-			const int sh = (lp_off & 3) * 8;
-			int *o = lum_h + lx;
-			int r = t >> 7;
-			for (; r + 2 < l_rows; r += 4) { // two rows per iteration
-				const unsigned *w0 = w + r * pitch_lw, *w1 = w0 + 2 * pitch_lw;
-				const unsigned q0 = __funnelshift_r(w0[0], w0[1], sh), q1 = __funnelshift_r(w1[0], w1[1], sh);
-				const int v0 = dp2a_hi(lc.y, q0, dp2a_lo(lc.x, q0, 0)) >> 7, v1 = dp2a_hi(lc.y, q1, dp2a_lo(lc.x, q1, 0)) >> 7;
-				o[r * SC_TW] = min(v0, 32767);
-				o[(r + 2) * SC_TW] = min(v1, 32767);
-			}
-			for (; r < l_rows; r += 2) {
-				const unsigned *w0 = w + r * pitch_lw;
-				const unsigned q0 = __funnelshift_r(w0[0], w0[1], sh);
-				o[r * SC_TW] = min(dp2a_hi(lc.y, q0, dp2a_lo(lc.x, q0, 0)) >> 7, 32767);
+			const int w0i = lp_a >> 2;
+			const unsigned *w = reinterpret_cast<const unsigned *>(smem + stage * stage_bytes) + w0i + (t >> 6) * pitch_lw;
+			const int sha = (lp_a & 3) * 8;
+			const int kb = (lp_b >> 2) - w0i;      // 0 or 1: which word the second window starts in
+			const int shb = (lp_b & 3) * 8;
+			int2 *o = reinterpret_cast<int2 *>(lum_h) + (t >> 6) * (SC_TW / 2) + pi;
+			const int step_w = 4 * pitch_lw;
+			for (int r = t >> 6; r < l_rows; r += 4, w += step_w, o += 4 * (SC_TW / 2)) {
+				const unsigned a0 = w[0], a1 = w[1], a2 = w[2];
+				const unsigned qa = __funnelshift_r(a0, a1, sha);
+				const unsigned qb = kb ? __funnelshift_r(a1, a2, shb) : __funnelshift_r(a0, a1, shb);
+				*o = make_int2(dp2a_hi(lca.y, qa, dp2a_lo(lca.x, qa, 0)) >> 7, dp2a_hi(lcb.y, qb, dp2a_lo(lcb.x, qb, 0)) >> 7);
 			}
 		}
 		// ---- horizontal pass, chroma: both planes per thread; rows r = (t>>6), +4, ...
@@ -635,9 +640,9 @@ __global__ void __launch_bounds__(SC_THREADS)
 				const unsigned a0 = w0[0], a1 = w0[1], a2 = w0[2];
 				const unsigned lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
 				const unsigned qu = __byte_perm(lo, hi, 0x6420), qv = __byte_perm(lo, hi, 0x7531);
-				const int u = min(dp2a_hi(cc.y, qu, dp2a_lo(cc.x, qu, 0)) >> 7, 32767);
-				const int v = min(dp2a_hi(cc.y, qv, dp2a_lo(cc.x, qv, 0)) >> 7, 32767);
-				chr_h[r * (SC_TW / 2) + cxi] = swap_uv ? make_int2(v, u) : make_int2(u, v);
+				const int u = dp2a_hi(cc.y, qu, dp2a_lo(cc.x, qu, 0)) >> 7;
+				const int v = dp2a_hi(cc.y, qv, dp2a_lo(cc.x, qv, 0)) >> 7;
+				chr_h[r * (SC_TW / 2) + cxi] = swap_uv ? (v | (u << 16)) : (u | (v << 16)); // 15-bit values, packed
 			}
 		}
 		__syncthreads(); // B: intermediates + row table complete; previous store has released out_s (thread 0 waited)
@@ -646,28 +651,28 @@ __global__ void __launch_bounds__(SC_THREADS)
 		{
 			const int g = t & 31;
 			const int4 *lcol = reinterpret_cast<const int4 *>(lum_h) + g; // row pitch SC_TW/4 int4
-			const int4 *ccol = reinterpret_cast<const int4 *>(chr_h) + g; // (U0,V0,U1,V1), row pitch SC_TW/4 int4
+			const uint2 *ccol = reinterpret_cast<const uint2 *>(chr_h) + g; // (U0|V0<<16, U1|V1<<16), row pitch SC_TW/4
 			unsigned *og = reinterpret_cast<unsigned *>(out_s + (g >= 16 ? SC_TH * SCF_HALF : 0)) + (g & 15) * 3;
 			for (int ry = t >> 5; ry < th; ry += SC_THREADS / 32) {
 				const RowInfo ri = rows[ry];
 				const int4 *lr = lcol + (ri.lp >> 2);
-				const int4 *cr = ccol + (ri.cp >> 1);
+				const uint2 *cr = ccol + (ri.cp >> 1);
 				int Y[4], U[2], V[2];
 				if (VL == 1) {
 					const int4 l = lr[0];
 					Y[0] = (l.x + 64) >> 7; Y[1] = (l.y + 64) >> 7; Y[2] = (l.z + 64) >> 7; Y[3] = (l.w + 64) >> 7;
-					const int4 c0 = cr[0];
+					const int4 c0 = unpack_uv(cr[0]);
 					const int uvalpha = VC == 1 ? 0 : ri.cf[1];
 					if (uvalpha == 0) {
 						U[0] = (c0.x + 64) >> 7; V[0] = (c0.y + 64) >> 7; U[1] = (c0.z + 64) >> 7; V[1] = (c0.w + 64) >> 7;
 					} else {
-						const int4 c1 = cr[SC_TW / 4];
+						const int4 c1 = unpack_uv(cr[SC_TW / 4]);
 						const int a1 = 4096 - uvalpha;
 						U[0] = (c0.x * a1 + c1.x * uvalpha + (128 << 11)) >> 19; V[0] = (c0.y * a1 + c1.y * uvalpha + (128 << 11)) >> 19;
 						U[1] = (c0.z * a1 + c1.z * uvalpha + (128 << 11)) >> 19; V[1] = (c0.w * a1 + c1.w * uvalpha + (128 << 11)) >> 19;
 					}
 				} else if (VL == 2 && VC == 2) {
-					const int4 l0 = lr[0], l1 = lr[SC_TW / 4], c0 = cr[0], c1 = cr[SC_TW / 4];
+					const int4 l0 = lr[0], l1 = lr[SC_TW / 4], c0 = unpack_uv(cr[0]), c1 = unpack_uv(cr[SC_TW / 4]);
 					const int ya = ri.lf[1], ua = ri.cf[1], ya1 = 4096 - ya, ua1 = 4096 - ua;
 					Y[0] = (l0.x * ya1 + l1.x * ya) >> 19; Y[1] = (l0.y * ya1 + l1.y * ya) >> 19;
 					Y[2] = (l0.z * ya1 + l1.z * ya) >> 19; Y[3] = (l0.w * ya1 + l1.w * ya) >> 19;
@@ -683,7 +688,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 					}
 #pragma unroll
 					for (int j = 0; j < VC; ++j) {
-						const int4 c4 = cr[j * (SC_TW / 4)];
+						const int4 c4 = unpack_uv(cr[j * (SC_TW / 4)]);
 						const int c = ri.cf[j];
 						U[0] += c4.x * c; V[0] += c4.y * c; U[1] += c4.z * c; V[1] += c4.w * c;
 					}
@@ -1032,10 +1037,15 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	              a128(8 * (size_t)P.box_ch * (SC_TW / 2)) + a128((size_t)SC_TH * SC_TW * 3) + a128(sizeof(RowInfo) * SC_TH) + 256;
 	s->smem_luma = a128((size_t)P.box_lw * P.box_lh) + a128(2 * (size_t)P.box_lh * SC_TW) + a128((size_t)SC_TH * SC_TW) + 256;
 	s->smem_chroma = 2 * a128((size_t)P.box_cw * P.box_ch) + 2 * a128(2 * (size_t)P.box_ch * SC_TW) + a128(2 * (size_t)SC_TH * SC_TW) + 256;
-	s->fast_ok = dst_rgb && P.chroma_planes == 1 && P.hl_size == 4 && P.hc_size == 4 && (dst_w % SC_TW) == 0 &&
+	// the fast path skips hScale8To15's FFMIN(val >> 7, 32767): it cannot bind when all taps are non-negative (they sum
+	// to 16384, samples are <= 255)
+	bool taps_nonneg = true;
+	for (int16_t c : s->hl.coef) taps_nonneg = taps_nonneg && c >= 0;
+	for (int16_t c : s->hc.coef) taps_nonneg = taps_nonneg && c >= 0;
+	s->fast_ok = taps_nonneg && dst_rgb && P.chroma_planes == 1 && P.hl_size == 4 && P.hc_size == 4 && (dst_w % SC_TW) == 0 &&
 	             ((P.vl_size == 4 && P.vc_size == 2) || (P.vl_size == 2 && P.vc_size == 2) || (P.vl_size == 1 && P.vc_size <= 2));
 	s->smem_fast = 2 * (a128((size_t)P.box_lw * P.box_lh) + a128((size_t)P.box_cw * P.box_ch)) + a128(4 * (size_t)P.box_lh * SC_TW) +
-	               a128(8 * (size_t)P.box_ch * (SC_TW / 2)) + (size_t)SC_TH * SC_TW * 3 + a128(sizeof(RowInfo) * SC_TH) + 16 + 256;
+	               a128(4 * (size_t)P.box_ch * (SC_TW / 2)) + (size_t)SC_TH * SC_TW * 3 + a128(sizeof(RowInfo) * SC_TH) + 16 + 32 + 256;
 	if (s->fast_ok && s->smem_fast > 48 * 1024) {
 		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
 		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
