@@ -101,6 +101,45 @@ __global__ void __launch_bounds__(256) nv12_fast_kernel(const uint8_t *__restric
 	reinterpret_cast<int4 *>(pv + (size_t)row * uw)[col] = v;
 }
 
+// ------------------------------------------------------------------------------------------------ packed 4:2:2 -> I420
+// MSPixConv's YUYV / UYVY / YUY2 inputs (src/videofilters/pixconv.c:62-94 -> ms_scaler_process at the same size): luma
+// copied, chroma = rounded average of the two source lines (what libswscale's unscaled yuyv/uyvy -> yuv420p converters
+// produce; pinned in tests/golden). One thread: 8 luma pixels x 2 rows (two 16-byte loads) -> 2 x 8 Y bytes, 4 U, 4 V.
+__global__ void __launch_bounds__(256) packed422_to_i420_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                                int w, int h, int uyvy) {
+	const int groups = w / 8, rows2 = h / 2;
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long)groups * rows2) return;
+	const int cy = (int)(t / groups), gx = (int)(t % groups);
+	const size_t frame = blockIdx.y;
+	const uint8_t *fs = src + frame * ((size_t)w * h * 2);
+	uint8_t *fd = dst + frame * ((size_t)w * h * 3 / 2);
+	const uint4 a = __ldg(reinterpret_cast<const uint4 *>(fs + (size_t)(2 * cy) * w * 2) + gx);
+	const uint4 b = __ldg(reinterpret_cast<const uint4 *>(fs + (size_t)(2 * cy + 1) * w * 2) + gx);
+	// bytes of a word: YUYV = Y0 U Y1 V, UYVY = U Y0 V Y1
+	const unsigned ysel = uyvy ? 0x7531 : 0x6420, csel = uyvy ? 0x6420 : 0x7531;
+	const unsigned ya0 = __byte_perm(a.x, a.y, ysel), ya1 = __byte_perm(a.z, a.w, ysel);
+	const unsigned yb0 = __byte_perm(b.x, b.y, ysel), yb1 = __byte_perm(b.z, b.w, ysel);
+	const unsigned ca0 = __byte_perm(a.x, a.y, csel), ca1 = __byte_perm(a.z, a.w, csel); // U V U V
+	const unsigned cb0 = __byte_perm(b.x, b.y, csel), cb1 = __byte_perm(b.z, b.w, csel);
+	const unsigned m0 = __vavgu4(ca0, cb0), m1 = __vavgu4(ca1, cb1); // per-byte (x + y + 1) >> 1
+	const unsigned u4 = __byte_perm(m0, m1, 0x6420), v4 = __byte_perm(m0, m1, 0x7531);
+	*reinterpret_cast<uint2 *>(fd + (size_t)(2 * cy) * w + (size_t)gx * 8) = make_uint2(ya0, ya1);
+	*reinterpret_cast<uint2 *>(fd + (size_t)(2 * cy + 1) * w + (size_t)gx * 8) = make_uint2(yb0, yb1);
+	uint8_t *pu = fd + (size_t)w * h, *pv = pu + (size_t)(w / 2) * (h / 2);
+	*reinterpret_cast<unsigned *>(pu + (size_t)cy * (w / 2) + (size_t)gx * 4) = u4;
+	*reinterpret_cast<unsigned *>(pv + (size_t)cy * (w / 2) + (size_t)gx * 4) = v4;
+}
+
+int msb200i_packed422_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int uyvy, void *d_dst) {
+	MSB200_CHECK_ARG(ctx && d_src && d_dst && n_frames > 0 && n_frames <= 65535 && w > 0 && h > 0 && (w % 8) == 0 && (h % 2) == 0);
+	MSB200_CHECK_ARG(((uintptr_t)d_src % 16) == 0 && ((uintptr_t)d_dst % 8) == 0);
+	const long threads = (long)(w / 8) * (h / 2);
+	dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
+	MSB200_LAUNCH(ctx, packed422_to_i420_kernel, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h, uyvy);
+	return MSB200_OK;
+}
+
 extern "C" {
 
 int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void *d_src, size_t src_frame_bytes, size_t cbcr_offset,

@@ -837,6 +837,7 @@ struct msb200_scaler {
 	const void *cached_src;
 	CUtensorMap map_l, map_c0, map_c1, map_o;
 	const void *cached_dst;
+	int packed422; // 0: no; 1: YUYV/YUY2; 2: UYVY  (MSPixConv same-size conversion, no scaling)
 	bool fast_ok;
 	size_t smem_fast;
 	msb200_devbuf src, dst;
@@ -935,6 +936,26 @@ extern "C" {
 int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int dst_w, int dst_h, int dst_fmt,
                          msb200_scaler **out) {
 	MSB200_CHECK_ARG(ctx && out);
+	if (src_fmt == MSB200_PIX_YUYV || src_fmt == MSB200_PIX_YUY2 || src_fmt == MSB200_PIX_UYVY) {
+		// MSPixConv: packed 4:2:2 -> YUV420P at the same size (pixconv.c:42-43: the output format is always YUV420P)
+		if (dst_fmt != MSB200_PIX_YUV420P || src_w != dst_w || src_h != dst_h || (src_w % 8) || (src_h % 2)) {
+			msb200_set_error("scaler: packed 4:2:2 sources convert to YUV420P at the same size only (w %% 8 == 0, h even)");
+			return MSB200_EINVAL;
+		}
+		msb200_scaler *s = new msb200_scaler();
+		s->ctx = ctx;
+		memset(&s->P, 0, sizeof(s->P));
+		s->P.src_w = src_w; s->P.src_h = src_h; s->P.dst_w = dst_w; s->P.dst_h = dst_h; s->P.src_fmt = src_fmt; s->P.dst_fmt = dst_fmt;
+		s->packed422 = src_fmt == MSB200_PIX_UYVY ? 2 : 1;
+		s->d_tables = nullptr;
+		s->cached_src = s->cached_dst = nullptr;
+		s->cached_frames = 0;
+		s->fast_ok = false;
+		s->src_bytes = (size_t)src_w * src_h * 2;
+		s->dst_bytes = (size_t)dst_w * dst_h * 3 / 2;
+		*out = s;
+		return MSB200_OK;
+	}
 	const bool src_ok = src_fmt == MSB200_PIX_YUV420P || src_fmt == MSB200_PIX_NV12 || src_fmt == MSB200_PIX_NV21;
 	const bool dst_ok = dst_fmt == MSB200_PIX_YUV420P || dst_fmt == MSB200_PIX_RGB24 || dst_fmt == MSB200_PIX_RGB24_REV;
 	if (!src_ok || !dst_ok) {
@@ -946,6 +967,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	MSB200_CHECK_ARG(src_w % 16 == 0 && (src_fmt != MSB200_PIX_YUV420P || (src_w / 2) % 16 == 0) && src_h % 2 == 0);
 	msb200_scaler *s = new msb200_scaler();
 	s->ctx = ctx;
+	s->packed422 = 0;
 	s->cached_src = nullptr;
 	s->cached_dst = nullptr;
 	s->cached_frames = 0;
@@ -1092,6 +1114,7 @@ size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s) {
 
 int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst) {
 	MSB200_CHECK_ARG(s && d_src && d_dst && n_frames > 0 && n_frames <= 65535);
+	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
 	MSB200_CHECK_ARG(((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0);
 	int r = scaler_build_maps(s, d_src, n_frames);
 	if (r) return r;

@@ -96,6 +96,9 @@ int orc_nv12_to_i420(const uint8_t *y, const uint8_t *cbcr, int rotation, int w,
 #define PIX_YUV420P 0
 #define PIX_RGB24 2
 #define PIX_BGR24 3
+#define PIX_YUYV 1
+#define PIX_UYVY 5
+#define PIX_YUY2 6
 #define PIX_NV12 100
 #define PIX_NV21 101
 
@@ -249,8 +252,22 @@ static int get_local_pos(int chr_subsample, int pos) {
 	return pos >> chr_subsample;
 }
 
+static int is_packed422(int fmt) {
+	return fmt == PIX_YUYV || fmt == PIX_UYVY || fmt == PIX_YUY2;
+}
+
 orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst_h, int dst_fmt) {
 	orc_scaler *s;
+	if (is_packed422(src_fmt)) {
+		/* MSPixConv's job (pixconv.c:62-94): packed 4:2:2 -> YUV420P at the SAME size. libswscale takes its unscaled
+		 * special converter for this (yuyvToYuv420Wrapper / uyvyToYuv420Wrapper): luma copied, chroma = rounded average of
+		 * the two source lines. Pinned against the real library in tests/golden (cases yuyv422 / uyvy422). */
+		if (dst_fmt != PIX_YUV420P || src_w != dst_w || src_h != dst_h || (src_w & 1) || (src_h & 1)) return NULL;
+		s = (orc_scaler *)calloc(1, sizeof(*s));
+		s->src_w = src_w; s->src_h = src_h; s->src_fmt = src_fmt;
+		s->dst_w = dst_w; s->dst_h = dst_h; s->dst_fmt = dst_fmt;
+		return s;
+	}
 	const int src_ok = src_fmt == PIX_YUV420P || src_fmt == PIX_NV12 || src_fmt == PIX_NV21;
 	const int dst_ok = dst_fmt == PIX_YUV420P || dst_fmt == PIX_RGB24 || dst_fmt == PIX_BGR24;
 	if (!src_ok || !dst_ok || src_w < 8 || src_h < 8 || dst_w < 8 || dst_h < 8) return NULL;
@@ -290,6 +307,10 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 }
 void orc_scaler_free(orc_scaler *s) {
 	if (!s) return;
+	if (is_packed422(s->src_fmt)) {
+		free(s);
+		return;
+	}
 	sws_filter *f[4] = {&s->hLum, &s->hChr, &s->vLum, &s->vChr};
 	for (int i = 0; i < 4; ++i) {
 		free(f[i]->pos);
@@ -299,6 +320,7 @@ void orc_scaler_free(orc_scaler *s) {
 }
 static size_t fmt_bytes(int fmt, int w, int h) {
 	if (fmt == PIX_RGB24 || fmt == PIX_BGR24) return (size_t)w * h * 3;
+	if (fmt == PIX_YUYV || fmt == PIX_UYVY || fmt == PIX_YUY2) return (size_t)w * h * 2;
 	return (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2);
 }
 size_t orc_scaler_src_bytes(orc_scaler *s) { return fmt_bytes(s->src_fmt, s->src_w, s->src_h); }
@@ -342,6 +364,21 @@ static void hscale(int16_t *dst, int dstW, const uint8_t *src, const sws_filter 
 
 int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst) {
 	const int sw = s->src_w, sh = s->src_h, dw = s->dst_w, dh = s->dst_h;
+	if (is_packed422(s->src_fmt)) {
+		const int yo = s->src_fmt == PIX_UYVY ? 1 : 0, uo = s->src_fmt == PIX_UYVY ? 0 : 1, vo = uo + 2;
+		uint8_t *dy = dst, *du = dst + (size_t)sw * sh, *dv = du + (size_t)(sw / 2) * (sh / 2);
+		for (int y = 0; y < sh; ++y)
+			for (int x = 0; x < sw; ++x)
+				dy[(size_t)y * sw + x] = src[(size_t)y * sw * 2 + 2 * x + yo];
+		for (int y = 0; y < sh / 2; ++y) {
+			const uint8_t *r0 = src + (size_t)(2 * y) * sw * 2, *r1 = r0 + (size_t)sw * 2;
+			for (int x = 0; x < sw / 2; ++x) {
+				du[(size_t)y * (sw / 2) + x] = (uint8_t)((r0[4 * x + uo] + r1[4 * x + uo] + 1) >> 1);
+				dv[(size_t)y * (sw / 2) + x] = (uint8_t)((r0[4 * x + vo] + r1[4 * x + vo] + 1) >> 1);
+			}
+		}
+		return 0;
+	}
 	const int csw = s->chr_src_w, csh = s->chr_src_h, cdw = s->chr_dst_w, cdh = s->chr_dst_h;
 	/* +16 bytes of padding after each source row copy: the aligned filter may read (zero-weighted) past the row end */
 	int16_t *lum = (int16_t *)malloc(sizeof(int16_t) * (size_t)sh * dw);

@@ -1161,6 +1161,9 @@ typedef struct B200ScalerCtx {
 static int pixfmt_to_b200(MSPixFmt fmt) {
 	switch (fmt) {
 		case MS_YUV420P: return MSB200_PIX_YUV420P;
+		case MS_YUYV: return MSB200_PIX_YUYV;
+		case MS_YUY2: return MSB200_PIX_YUY2;
+		case MS_UYVY: return MSB200_PIX_UYVY;
 		case MS_RGB24: return MSB200_PIX_RGB24;
 		case MS_RGB24_REV: return MSB200_PIX_RGB24_REV;
 		default: return -1;
@@ -1170,7 +1173,7 @@ static MSScalerContext *b200_scaler_create(int src_w, int src_h, MSPixFmt src_fm
 	B200ScalerCtx *c;
 	int sf = pixfmt_to_b200(src_fmt), df = pixfmt_to_b200(dst_fmt);
 	(void)flags;
-	if (sf != MSB200_PIX_YUV420P || df < 0) {
+	if ((sf != MSB200_PIX_YUV420P && sf != MSB200_PIX_YUYV && sf != MSB200_PIX_YUY2 && sf != MSB200_PIX_UYVY) || df < 0) {
 		ms_error("msb200 scaler: unsupported conversion %s -> %s", ms_pix_fmt_to_string(src_fmt), ms_pix_fmt_to_string(dst_fmt));
 		return NULL;
 	}
@@ -1196,11 +1199,15 @@ static int b200_scaler_process(MSScalerContext *ctx, uint8_t *src[], int src_str
 	B200ScalerCtx *c = (B200ScalerCtx *)ctx;
 	int rc, cw = (c->src_w + 1) / 2, ch = (c->src_h + 1) / 2, y;
 	uint8_t *p = c->src_pack;
-	pack_plane(p, src[0], src_strides[0], c->src_w, c->src_h);
-	p += (size_t)c->src_w * c->src_h;
-	pack_plane(p, src[1], src_strides[1], cw, ch);
-	p += (size_t)cw * ch;
-	pack_plane(p, src[2], src_strides[2], cw, ch);
+	if (c->src_fmt != MSB200_PIX_YUV420P) { /* packed 4:2:2: one plane of 2 bytes per pixel (msvideo.c:120-156) */
+		pack_plane(p, src[0], src_strides[0], c->src_w * 2, c->src_h);
+	} else {
+		pack_plane(p, src[0], src_strides[0], c->src_w, c->src_h);
+		p += (size_t)c->src_w * c->src_h;
+		pack_plane(p, src[1], src_strides[1], cw, ch);
+		p += (size_t)cw * ch;
+		pack_plane(p, src[2], src_strides[2], cw, ch);
+	}
 	DSP_LOCK();
 	rc = msb200_scaler_process(c->sc, 1, c->src_pack, c->dst_pack);
 	DSP_UNLOCK();

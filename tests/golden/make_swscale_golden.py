@@ -16,7 +16,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-AV_PIX = {"yuv420p": 0, "rgb24": 2, "bgr24": 3, "nv12": 23, "nv21": 24}
+AV_PIX = {"yuv420p": 0, "yuyv422": 1, "rgb24": 2, "bgr24": 3, "uyvy422": 15, "nv12": 23, "nv21": 24}
 SWS_BILINEAR = 2
 SWS_BITEXACT = 0x80000  # same algorithm, the library's C reference functions instead of its approximate x86 SIMD ones
 
@@ -50,6 +50,8 @@ def planes(fmt: str, w: int, h: int, buf: np.ndarray):
     cw, ch = (w + 1) // 2, (h + 1) // 2
     if fmt in ("rgb24", "bgr24"):
         return [base, 0, 0, 0], [w * 3, 0, 0, 0]
+    if fmt in ("yuyv422", "uyvy422"):
+        return [base, 0, 0, 0], [w * 2, 0, 0, 0]
     if fmt in ("nv12", "nv21"):
         return [base, base + w * h, 0, 0], [w, cw * 2, 0, 0]
     return [base, base + w * h, base + w * h + cw * ch, 0], [w, cw, cw, 0]
@@ -58,6 +60,8 @@ def planes(fmt: str, w: int, h: int, buf: np.ndarray):
 def nbytes(fmt: str, w: int, h: int) -> int:
     if fmt in ("rgb24", "bgr24"):
         return w * h * 3
+    if fmt in ("yuyv422", "uyvy422"):
+        return w * h * 2
     return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
 
 
@@ -84,6 +88,15 @@ def test_frame(fmt: str, w: int, h: int, t: int, seed: int) -> np.ndarray:
     V = ((cy + 2 * t) % 256 + rng.integers(-3, 4, size=(ch, cw))).clip(0, 255).astype(np.uint8)
     if fmt == "yuv420p":
         return np.concatenate([Y.ravel(), U.ravel(), V.ravel()])
+    if fmt in ("yuyv422", "uyvy422"):  # 4:2:2 packed: chroma at full vertical resolution
+        U2 = rng.integers(0, 256, size=(h, cw), dtype=np.uint8)
+        V2 = rng.integers(0, 256, size=(h, cw), dtype=np.uint8)
+        out = np.zeros((h, w * 2), np.uint8)
+        yo, uo = (0, 1) if fmt == "yuyv422" else (1, 0)
+        out[:, yo::2] = Y
+        out[:, uo::4] = U2
+        out[:, uo + 2::4] = V2
+        return out.ravel()
     a, b = (U, V) if fmt == "nv12" else (V, U)
     return np.concatenate([Y.ravel(), np.stack([a, b], axis=-1).ravel()])
 
@@ -99,6 +112,8 @@ CASES = [
     ("yuv420p", 176, 144, "rgb24", 128, 96),
     ("nv12", 128, 72, "rgb24", 128, 72),       # same size through the generic (unscaled) path
     ("nv12", 130, 74, "rgb24", 86, 50),        # odd chroma geometry
+    ("yuyv422", 96, 64, "yuv420p", 96, 64),    # MSPixConv: packed 4:2:2 -> I420, same size
+    ("uyvy422", 64, 48, "yuv420p", 64, 48),
 ]
 
 

@@ -120,13 +120,13 @@ def test_scaler_full_size_cfg4_matches_real_libswscale_digest(ctx):
 def test_scaler_golden_frames_from_real_libswscale(ctx):
     """the committed small golden frames (real library, default build): RGB24 cases bit-exact."""
     g = np.load(GOLD)
-    av2ms = {0: 0, 2: 2, 3: 3, 23: 100, 24: 101}
+    av2ms = {0: 0, 1: 1, 2: 2, 3: 3, 15: 5, 23: 100, 24: 101}
     checked = 0
     k = 0
     while f"case{k}_src" in g:
         sf, sw, sh, df, dw, dh = [int(v) for v in g[f"case{k}_meta"]]
         k += 1
-        if sw % 16 or (sf == 0 and (sw // 2) % 16):
+        if sf not in (1, 15) and (sw % 16 or (sf == 0 and (sw // 2) % 16)):
             continue  # TMA row-pitch constraint of the product (documented in DESIGN.md)
         sc = F.Scaler(ctx, sw, sh, av2ms[sf], dw, dh, av2ms[df])
         out = sc.process(g[f"case{k - 1}_src"][None, :])
@@ -136,3 +136,29 @@ def test_scaler_golden_frames_from_real_libswscale(ctx):
             assert np.array_equal(out[0], g[f"case{k - 1}_dst"])
         checked += 1
     assert checked >= 5
+
+
+@pytest.mark.parametrize("fmt,w,h", [(_lib.PIX_YUYV, 96, 64), (_lib.PIX_UYVY, 64, 48), (_lib.PIX_YUY2, 1280, 720)])
+def test_pixconv_packed422_to_i420_bit_exact(ctx, fmt, w, h):
+    """MSPixConv's packed inputs: GPU == oracle (itself bit-exact vs real libswscale, tests/test_oracle_video.py)."""
+    L = O.oracle()
+    rng = np.random.default_rng(w + h)
+    frames = rng.integers(0, 256, size=(3, w * h * 2), dtype=np.uint8)
+    sc = F.Scaler(ctx, w, h, fmt, w, h, _lib.PIX_YUV420P)
+    got = sc.process(frames)
+    o = L.orc_scaler_new(w, h, fmt, w, h, _lib.PIX_YUV420P)
+    for i in range(3):
+        exp = np.zeros(w * h * 3 // 2 + 64, np.uint8)
+        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+        assert np.array_equal(got[i], exp[:-64]), i
+    L.orc_scaler_free(o)
+    sc.close()
+    g = np.load(GOLD)
+    for k in range(20):
+        if f"case{k}_meta" not in g:
+            break
+        sf, sw, sh, df, dw, dh = [int(v) for v in g[f"case{k}_meta"]]
+        if (sf == 1 and fmt == _lib.PIX_YUYV) or (sf == 15 and fmt == _lib.PIX_UYVY):
+            sc2 = F.Scaler(ctx, sw, sh, fmt, dw, dh, _lib.PIX_YUV420P)
+            assert np.array_equal(sc2.process(g[f"case{k}_src"][None, :])[0], g[f"case{k}_dst"])  # the real library's output
+            sc2.close()
