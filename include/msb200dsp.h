@@ -102,6 +102,9 @@ typedef struct msb200_volume msb200_volume;
 typedef struct msb200_volume_state {
 	float energy, level_pk, instant_energy, gain, static_gain, target_gain, ng_gain, ng_threshold, ng_floorgain;
 	int32_t dc_offset, ng_noise_dur, noise_gate_enabled, remove_dc, sample_rate, fast_upramp;
+	/* chunked mode (AGC and/or echo-limiter peer, msvolume.c:480-502) */
+	float lt_speaker_en, ea_thres, ea_transmit_thres, force, vol_upramp;
+	int32_t sustain_time, sustain_dur, agc_enabled, peer; /* peer: stream index in the peer bank, -1 = none */
 } msb200_volume_state;
 MSB200_API int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_volume **out);
 MSB200_API void msb200_volume_destroy(msb200_volume *v);
@@ -111,6 +114,17 @@ MSB200_API int msb200_volume_enable_noise_gate(msb200_volume *v, int stream, int
 MSB200_API int msb200_volume_set_noise_gate_threshold(msb200_volume *v, int stream, float thr);
 MSB200_API int msb200_volume_set_noise_gate_floorgain(msb200_volume *v, int stream, float g);
 MSB200_API int msb200_volume_remove_dc(msb200_volume *v, int stream, int enabled);
+/* Chunked mode (msvolume.c:480-502): with AGC or an echo-limiter peer the reference re-frames its input to 10 ms chunks
+ * and, per chunk, runs update_energy, volume_echo_avoider_process (:201-238, reads the PEER filter's smoothed energy),
+ * volume_agc_process (:172-184), the noise gate and apply_gain. The peer is a stream of another (or the same) bank whose
+ * state is read when this bank is processed: process the peer bank first, as the ticker does for volrecv -> volsend. */
+MSB200_API int msb200_volume_enable_agc(msb200_volume *v, int stream, int enabled);                       /* MS_VOLUME_ENABLE_AGC */
+MSB200_API int msb200_volume_set_peer(msb200_volume *v, int stream, msb200_volume *peer_bank, int peer_stream); /* MS_VOLUME_SET_PEER */
+MSB200_API int msb200_volume_set_ea_threshold(msb200_volume *v, int stream, float thr);                   /* :305-314 */
+MSB200_API int msb200_volume_set_ea_speed(msb200_volume *v, int stream, float speed);                     /* :324-333 */
+MSB200_API int msb200_volume_set_ea_force(msb200_volume *v, int stream, float force);
+MSB200_API int msb200_volume_set_ea_sustain(msb200_volume *v, int stream, int ms);
+MSB200_API int msb200_volume_set_ea_transmit_threshold(msb200_volume *v, int stream, float thr);
 MSB200_API int msb200_volume_get_state(msb200_volume *v, int stream, msb200_volume_state *st);
 /* io: [stream][nsamples] s16, processed in place */
 MSB200_API int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples);

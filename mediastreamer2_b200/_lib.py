@@ -31,7 +31,9 @@ class VolumeState(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("energy", "level_pk", "instant_energy", "gain", "static_gain", "target_gain",
                                          "ng_gain", "ng_threshold", "ng_floorgain")] + \
                [(n, C.c_int32) for n in ("dc_offset", "ng_noise_dur", "noise_gate_enabled", "remove_dc", "sample_rate",
-                                         "fast_upramp")]
+                                         "fast_upramp")] + \
+               [(n, C.c_float) for n in ("lt_speaker_en", "ea_thres", "ea_transmit_thres", "force", "vol_upramp")] + \
+               [(n, C.c_int32) for n in ("sustain_time", "sustain_dur", "agc_enabled", "peer")]
 
 
 class AecInfo(C.Structure):
@@ -89,6 +91,13 @@ _SIGS = {
     "msb200_volume_set_noise_gate_threshold": (_I, [_P, _I, _F]),
     "msb200_volume_set_noise_gate_floorgain": (_I, [_P, _I, _F]),
     "msb200_volume_remove_dc": (_I, [_P, _I, _I]),
+    "msb200_volume_enable_agc": (_I, [_P, _I, _I]),
+    "msb200_volume_set_peer": (_I, [_P, _I, _P, _I]),
+    "msb200_volume_set_ea_threshold": (_I, [_P, _I, _F]),
+    "msb200_volume_set_ea_speed": (_I, [_P, _I, _F]),
+    "msb200_volume_set_ea_force": (_I, [_P, _I, _F]),
+    "msb200_volume_set_ea_sustain": (_I, [_P, _I, _I]),
+    "msb200_volume_set_ea_transmit_threshold": (_I, [_P, _I, _F]),
     "msb200_volume_get_state": (_I, [_P, _I, C.POINTER(VolumeState)]),
     "msb200_volume_process": (_I, [_P, _P, _I]),
     "msb200_volume_process_dev": (_I, [_P, _P, _I, _I]),

@@ -253,6 +253,7 @@ int msb200i_mixer_launch(msb200_mixer *m, const void *d_in, long in_pin_stride, 
 struct msb200_volume {
 	msb200_ctx *ctx;
 	int n, rate, max_block;
+	msb200_volume *peer_bank; // bank whose states the echo limiter reads (may be this one)
 	msb200_volume_state *d_state;
 	msb200_devbuf io;
 };
@@ -266,7 +267,7 @@ __device__ __forceinline__ int vol_sat(int v) { // :382-384
 // reduced across the warp; then all lanes apply the Q12 gain and store.
 __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st,
                                                      int n_streams, int nsamples, int stride, int nblocks, int block0,
-                                                     int ring_blocks) {
+                                                     int ring_blocks, const msb200_volume_state *__restrict__ peer_states) {
 	extern __shared__ short vsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int stream = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -309,6 +310,28 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 		v.level_pk = __fdiv_rn((float)pk, max_e);
 		v.instant_energy = en;
 		float tgain = v.static_gain;
+		if (v.peer >= 0 && peer_states) { // volume_echo_avoider_process :201-238
+			const float peer_e = peer_states[v.peer].energy;
+			if (peer_e > v.lt_speaker_en) v.lt_speaker_en = peer_e;
+			else v.lt_speaker_en = __fadd_rn(__fmul_rn(0.005f, peer_e), __fmul_rn(0.995f, v.lt_speaker_en));
+			const float mic_spk_ratio = __fdiv_rn(v.energy, __fadd_rn(v.lt_speaker_en, v.ea_thres));
+			if (peer_e > v.ea_thres) {
+				if (mic_spk_ratio > v.ea_transmit_thres) {
+					v.target_gain = v.static_gain;
+					v.fast_upramp = 1;
+				} else {
+					v.target_gain = __fdiv_rn(v.static_gain, __fadd_rn(1.f, __fmul_rn(peer_e, v.force))); // compute_gain :186-189
+					v.sustain_dur = v.sustain_time;
+				}
+			} else if (v.sustain_dur > 0) {
+				v.sustain_dur -= (nsamples * 1000) / v.sample_rate;
+			} else {
+				v.target_gain = v.static_gain;
+				v.fast_upramp = 1;
+			}
+			tgain = v.target_gain;
+		}
+		if (v.agc_enabled) tgain = __fdiv_rn(tgain, __fdiv_rn(__fadd_rn(0.5f, v.level_pk), 1.f)); // volume_agc_process :172-184
 		if (v.noise_gate_enabled) {
 			float t = v.ng_floorgain;
 			if (v.instant_energy > v.ng_threshold) {
@@ -322,7 +345,7 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 		}
 		if (v.gain < tgain) {
 			if (v.gain < v.ng_floorgain) v.gain = v.ng_floorgain;
-			v.gain = __fmul_rn(v.gain, v.fast_upramp ? (1 + 0.4f * 3) : (1 + 0.4f));
+			v.gain = __fmul_rn(v.gain, v.fast_upramp ? (1 + 0.4f * 3) : __fadd_rn(1.f, v.vol_upramp));
 			if (v.gain > tgain) v.gain = tgain;
 		} else if (v.gain > tgain) {
 			v.gain = __fmul_rn(v.gain, 1 - 0.4f);
@@ -381,7 +404,14 @@ int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int ma
 		s.ng_floorgain = 0.005f;
 		s.ng_gain = 1.f;
 		s.sample_rate = sample_rate;
+		s.ea_thres = 0.1f;          // noise_thres :42
+		s.ea_transmit_thres = 4.f;  // transmit_thres :43
+		s.force = 4.f;              // en_weight :41
+		s.vol_upramp = 0.4f;
+		s.sustain_time = 200;
+		s.peer = -1;
 	}
+	v->peer_bank = nullptr;
 	MSB200_CUDA(cudaMalloc(&v->d_state, sizeof(msb200_volume_state) * (size_t)n_streams));
 	MSB200_CUDA(cudaMemcpy(v->d_state, init.data(), sizeof(msb200_volume_state) * (size_t)n_streams, cudaMemcpyHostToDevice));
 	*out = v;
@@ -418,6 +448,32 @@ int msb200_volume_set_noise_gate_floorgain(msb200_volume *v, int stream, float g
 int msb200_volume_remove_dc(msb200_volume *v, int stream, int enabled) {
 	return volume_update_state(v, stream, [](msb200_volume_state *s, float, int e) { s->remove_dc = e; }, 0.f, enabled);
 }
+int msb200_volume_enable_agc(msb200_volume *v, int stream, int enabled) {
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float, int e) { s->agc_enabled = e ? 1 : 0; }, 0.f, enabled);
+}
+int msb200_volume_set_peer(msb200_volume *v, int stream, msb200_volume *peer_bank, int peer_stream) {
+	MSB200_CHECK_ARG(v && (peer_bank == nullptr || (peer_stream >= 0 && peer_stream < peer_bank->n)));
+	MSB200_CHECK_ARG(v->peer_bank == nullptr || peer_bank == nullptr || v->peer_bank == peer_bank); // one peer bank per bank
+	if (peer_bank) v->peer_bank = peer_bank;
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float, int p) { s->peer = p; }, 0.f, peer_bank ? peer_stream : -1);
+}
+int msb200_volume_set_ea_threshold(msb200_volume *v, int stream, float thr) {
+	MSB200_CHECK_ARG(thr >= 0 && thr <= 1); // "threshold must be in range [0..1]" :308-311
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) { s->ea_thres = f; }, thr, 0);
+}
+int msb200_volume_set_ea_speed(msb200_volume *v, int stream, float speed) {
+	MSB200_CHECK_ARG(speed >= 0 && speed <= .5f); // :327-330
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) { s->vol_upramp = f; }, speed, 0);
+}
+int msb200_volume_set_ea_force(msb200_volume *v, int stream, float force) {
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) { s->force = f; }, force, 0);
+}
+int msb200_volume_set_ea_sustain(msb200_volume *v, int stream, int ms) {
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float, int i) { s->sustain_time = i; }, 0.f, ms);
+}
+int msb200_volume_set_ea_transmit_threshold(msb200_volume *v, int stream, float thr) {
+	return volume_update_state(v, stream, [](msb200_volume_state *s, float f, int) { s->ea_transmit_thres = f; }, thr, 0);
+}
 int msb200_volume_get_state(msb200_volume *v, int stream, msb200_volume_state *st) {
 	MSB200_CHECK_ARG(v && st && stream >= 0 && stream < v->n);
 	MSB200_CUDA(cudaMemcpyAsync(st, v->d_state + stream, sizeof(*st), cudaMemcpyDeviceToHost, v->ctx->stream));
@@ -448,7 +504,8 @@ int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride
 	const int warps = 8;
 	size_t smem = (size_t)warps * ((nsamples + 1) & ~1) * sizeof(short);
 	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->n, warps), warps * 32, smem, (short *)d_io, v->d_state, v->n,
-	              nsamples, stride, nblocks, block0, ring_blocks);
+	              nsamples, stride, nblocks, block0, ring_blocks,
+	              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr));
 	return MSB200_OK;
 }
 

@@ -146,6 +146,24 @@ class Volume:
     def remove_dc(self, stream: int, enabled: bool):
         check(self.lib.msb200_volume_remove_dc(self.h, stream, int(enabled)))
 
+    def enable_agc(self, stream: int, enabled: bool):
+        check(self.lib.msb200_volume_enable_agc(self.h, stream, int(enabled)))
+
+    def set_peer(self, stream: int, peer_bank: "Volume", peer_stream: int):
+        check(self.lib.msb200_volume_set_peer(self.h, stream, peer_bank.h, peer_stream))
+
+    def set_ea(self, stream: int, threshold=None, speed=None, force=None, sustain=None, transmit_threshold=None):
+        if threshold is not None:
+            check(self.lib.msb200_volume_set_ea_threshold(self.h, stream, threshold))
+        if speed is not None:
+            check(self.lib.msb200_volume_set_ea_speed(self.h, stream, speed))
+        if force is not None:
+            check(self.lib.msb200_volume_set_ea_force(self.h, stream, force))
+        if sustain is not None:
+            check(self.lib.msb200_volume_set_ea_sustain(self.h, stream, sustain))
+        if transmit_threshold is not None:
+            check(self.lib.msb200_volume_set_ea_transmit_threshold(self.h, stream, transmit_threshold))
+
     def state(self, stream: int) -> _lib.VolumeState:
         st = _lib.VolumeState()
         check(self.lib.msb200_volume_get_state(self.h, stream, C.byref(st)))

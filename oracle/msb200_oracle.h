@@ -30,9 +30,13 @@ void orc_mixer_partial(int n_rooms, int n_pins, int nwords, const float *gain, c
 typedef struct orc_volume_state {
 	float energy, level_pk, instant_energy, gain, static_gain, target_gain, ng_gain, ng_threshold, ng_floorgain;
 	int32_t dc_offset, ng_noise_dur, noise_gate_enabled, remove_dc, sample_rate, fast_upramp;
+	float lt_speaker_en, ea_thres, ea_transmit_thres, force, vol_upramp;
+	int32_t sustain_time, sustain_dur, agc_enabled, peer;
 } orc_volume_state;
 void orc_volume_init(orc_volume_state *v, int sample_rate);
 void orc_volume_process(orc_volume_state *v, int16_t *io, int nsamples);
+/* chunked mode (msvolume.c:480-502): peer_energy = the peer MSVolume's smoothed energy, or NULL when there is no peer */
+void orc_volume_process_chunk(orc_volume_state *v, const float *peer_energy, int16_t *io, int nsamples);
 
 /* ---- channel adapter (chanadapt.c:68-131) */
 void orc_chanadapt(int mode, int n_streams, int frames, const int16_t *in, const int16_t *in2, int16_t *out);

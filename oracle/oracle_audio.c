@@ -80,6 +80,12 @@ void orc_volume_init(orc_volume_state *v, int sample_rate) { /* volume_init :86-
 	v->ng_floorgain = 0.005f;
 	v->ng_gain = 1;
 	v->sample_rate = sample_rate;
+	v->ea_thres = 0.1f;
+	v->ea_transmit_thres = 4;
+	v->force = 4.0f;
+	v->vol_upramp = 0.4f;
+	v->sustain_time = 200;
+	v->peer = -1;
 }
 
 static inline int16_t vol_saturate(int val) { /* :382-384 */
@@ -87,6 +93,10 @@ static inline int16_t vol_saturate(int val) { /* :382-384 */
 }
 
 void orc_volume_process(orc_volume_state *v, int16_t *io, int n) {
+	orc_volume_process_chunk(v, NULL, io, n);
+}
+
+void orc_volume_process_chunk(orc_volume_state *v, const float *peer_energy, int16_t *io, int n) {
 	/* update_energy :388-407 */
 	float acc = 0;
 	int pk = 0;
@@ -100,7 +110,30 @@ void orc_volume_process(orc_volume_state *v, int16_t *io, int n) {
 	v->energy = (en * vol_coef) + v->energy * (1.0f - vol_coef);
 	v->level_pk = (float)pk / vol_max_e;
 	v->instant_energy = en;
-	float tgain = v->static_gain; /* volume_process :507 */
+	float tgain = v->static_gain; /* volume_process :507 / :489 */
+	if (peer_energy) {            /* volume_echo_avoider_process :201-238 (peer_e and peer_pk are both the peer's energy) */
+		float peer_e = *peer_energy, peer_pk = *peer_energy, mic_spk_ratio;
+		if (peer_pk > v->lt_speaker_en) v->lt_speaker_en = peer_pk;
+		else v->lt_speaker_en = (0.005f * peer_pk) + (0.995f * v->lt_speaker_en);
+		mic_spk_ratio = (v->energy / (v->lt_speaker_en + v->ea_thres));
+		if (peer_e > v->ea_thres) {
+			if (mic_spk_ratio > v->ea_transmit_thres) {
+				v->target_gain = v->static_gain;
+				v->fast_upramp = 1;
+			} else {
+				v->target_gain = v->static_gain / (1 + (peer_e * v->force)); /* compute_gain :186-189 */
+				v->sustain_dur = v->sustain_time;
+			}
+		} else {
+			if (v->sustain_dur > 0) v->sustain_dur -= (n * 1000) / v->sample_rate;
+			else {
+				v->target_gain = v->static_gain;
+				v->fast_upramp = 1;
+			}
+		}
+		tgain = v->target_gain;
+	}
+	if (v->agc_enabled) tgain /= (0.5f + v->level_pk) / 1; /* volume_agc_process :172-184 (non-speex build) */
 	if (v->noise_gate_enabled) {  /* volume_noise_gate_process :240-260, called with instant_energy */
 		float t = v->ng_floorgain;
 		if (v->instant_energy > v->ng_threshold) {
@@ -115,7 +148,7 @@ void orc_volume_process(orc_volume_state *v, int16_t *io, int n) {
 	/* apply_gain :409-445 (vol_upramp .4, fast = 1.2, downramp .4) */
 	if (v->gain < tgain) {
 		if (v->gain < v->ng_floorgain) v->gain = v->ng_floorgain;
-		v->gain *= 1 + (v->fast_upramp ? 0.4f * 3 : 0.4f);
+		v->gain *= 1 + (v->fast_upramp ? 0.4f * 3 : v->vol_upramp);
 		if (v->gain > tgain) v->gain = tgain;
 	} else if (v->gain > tgain) {
 		v->gain *= 1 - 0.4f;

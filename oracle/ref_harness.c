@@ -297,6 +297,11 @@ unsigned int ref_method_id(const char *name) {
 	MID(MS_VOLUME_REMOVE_DC);
 	MID(MS_VOLUME_ENABLE_AGC);
 	MID(MS_VOLUME_SET_PEER);
+	MID(MS_VOLUME_SET_EA_THRESHOLD);
+	MID(MS_VOLUME_SET_EA_SPEED);
+	MID(MS_VOLUME_SET_EA_FORCE);
+	MID(MS_VOLUME_SET_EA_SUSTAIN);
+	MID(MS_VOLUME_SET_EA_TRANSMIT_THRESHOLD);
 	MID(MS_VOLUME_GET_MIN);
 	MID(MS_VOLUME_GET_MAX);
 	MID(MS_EQUALIZER_SET_GAIN);

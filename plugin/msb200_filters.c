@@ -362,9 +362,10 @@ static MSFilterDesc b200_audio_mixer_desc = {.id = MS_AUDIO_MIXER_ID,
                                              .methods = mixer_methods,
                                              .flags = MS_FILTER_IS_PUMP};
 
-/* ================================================================================================ MSVolume (light path)
- * /root/reference/src/audiofilters/msvolume.c:503-513; AGC and the echo-limiter peer (:480-502) are host-side policies
- * that are not ported in this round: enabling them is accepted and logged, the light path keeps running. */
+/* ================================================================================================ MSVolume
+ * /root/reference/src/audiofilters/msvolume.c:471-514: light path (:503-513) works in place per mblk; with AGC or an
+ * echo-limiter peer (:480-502) the input is re-framed to 10 ms chunks (MSBufferizer) and the kernel additionally runs the
+ * echo avoider against the peer filter's energy and the AGC gain reduction. */
 typedef struct VolState {
 	int rate;
 	float static_gain;
@@ -373,19 +374,37 @@ typedef struct VolState {
 	MSFilter *peer;
 	msb200_volume *bank;
 	int bank_rate;
-	bool_t dirty;
+	bool_t dirty, gain_dirty, peer_linked;
+	MSBufferizer *buffer;
+	float ea_thres, ea_speed, ea_force, ea_transmit;
+	int ea_sustain;
 } VolState;
+static MSFilterDesc b200_volume_desc;
 #define VOL_MAX_BLOCK 8192
 
 static void vol_sync_config(VolState *v) { /* DSP lock held */
-	if (!v->bank || !v->dirty) return;
-	msb200_volume_set_gain(v->bank, 0, v->static_gain);
+	if (!v->bank) return;
+	if (v->peer && !v->peer_linked && v->peer->desc == &b200_volume_desc && ((VolState *)v->peer->data)->bank) {
+		msb200_volume_set_peer(v->bank, 0, ((VolState *)v->peer->data)->bank, 0);
+		v->peer_linked = TRUE;
+	}
+	if (v->gain_dirty) { /* MS_VOLUME_SET_GAIN resets the ramp (gain = target = static, msvolume.c:270-276): apply it once */
+		msb200_volume_set_gain(v->bank, 0, v->static_gain);
+		v->gain_dirty = FALSE;
+	}
+	if (!v->dirty) return;
 	if (v->noise_gate) {
 		msb200_volume_enable_noise_gate(v->bank, 0, 1);
 		msb200_volume_set_noise_gate_threshold(v->bank, 0, v->ng_threshold);
 		msb200_volume_set_noise_gate_floorgain(v->bank, 0, v->ng_floorgain);
 	}
 	msb200_volume_remove_dc(v->bank, 0, v->remove_dc);
+	msb200_volume_enable_agc(v->bank, 0, v->agc);
+	msb200_volume_set_ea_threshold(v->bank, 0, v->ea_thres);
+	msb200_volume_set_ea_speed(v->bank, 0, v->ea_speed);
+	msb200_volume_set_ea_force(v->bank, 0, v->ea_force);
+	msb200_volume_set_ea_sustain(v->bank, 0, v->ea_sustain);
+	msb200_volume_set_ea_transmit_threshold(v->bank, 0, v->ea_transmit);
 	v->dirty = FALSE;
 }
 static void vol_init(MSFilter *f) {
@@ -394,7 +413,14 @@ static void vol_init(MSFilter *f) {
 	v->static_gain = 1.0f;
 	v->ng_threshold = 0.1f;
 	v->ng_floorgain = 0.005f;
+	v->ea_thres = 0.1f;
+	v->ea_speed = 0.4f;
+	v->ea_force = 4.0f;
+	v->ea_transmit = 4.0f;
+	v->ea_sustain = 200;
+	v->buffer = ms_bufferizer_new();
 	v->dirty = TRUE;
+	v->gain_dirty = FALSE; /* the bank starts at gain 1 like volume_init */
 	f->data = v;
 }
 static void vol_uninit(MSFilter *f) {
@@ -402,6 +428,7 @@ static void vol_uninit(MSFilter *f) {
 	DSP_LOCK();
 	msb200_volume_destroy(v->bank);
 	DSP_UNLOCK();
+	ms_bufferizer_destroy(v->buffer);
 	ms_free(v);
 }
 static void vol_preprocess(MSFilter *f) {
@@ -413,14 +440,33 @@ static void vol_preprocess(MSFilter *f) {
 		DSP_CHECK(msb200_volume_create(g_ctx, 1, v->rate, VOL_MAX_BLOCK, &v->bank), "volume_create");
 		v->bank_rate = v->rate;
 		v->dirty = TRUE;
+		v->gain_dirty = v->static_gain != 1.0f;
+		v->peer_linked = FALSE;
 	}
 	vol_sync_config(v);
 	DSP_UNLOCK();
-	if (v->agc || v->peer) ms_warning("MSVolume(b200): AGC / echo-limiter peer are not ported; running the light path");
+	if (v->peer && v->peer->desc != &b200_volume_desc) ms_warning("MSVolume(b200): the echo-limiter peer is not a B200 MSVolume; ignored");
 }
 static void vol_process(MSFilter *f) {
 	VolState *v = (VolState *)f->data;
 	mblk_t *m;
+	if (v->agc || v->peer != NULL) { /* chunked mode :480-502 */
+		int nsamples = (int)(0.01 * (float)v->rate);
+		size_t nbytes = (size_t)nsamples * 2;
+		ms_bufferizer_put_from_queue(v->buffer, f->inputs[0]);
+		while (ms_bufferizer_get_avail(v->buffer) >= nbytes) {
+			m = allocb(nbytes, 0);
+			ms_bufferizer_read(v->buffer, m->b_wptr, nbytes);
+			m->b_wptr += nbytes;
+			DSP_LOCK();
+			vol_sync_config(v);
+			if (v->bank) DSP_CHECK(msb200_volume_process(v->bank, (int16_t *)m->b_rptr, nsamples), "volume_process");
+			DSP_UNLOCK();
+			if (v->bank) ms_queue_put(f->outputs[0], m);
+			else freemsg(m);
+		}
+		return;
+	}
 	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
 		int n = (int)((m->b_wptr - m->b_rptr) / 2);
 		if (v->bank && n > 0 && n <= VOL_MAX_BLOCK) {
@@ -457,13 +503,13 @@ static int vol_get_linear(MSFilter *f, void *arg) {
 static int vol_set_gain(MSFilter *f, void *arg) {
 	VolState *v = (VolState *)f->data;
 	v->static_gain = *(float *)arg;
-	v->dirty = TRUE;
+	v->gain_dirty = TRUE;
 	return 0;
 }
 static int vol_set_db_gain(MSFilter *f, void *arg) { /* pow(10, db/10), sic: msvolume.c:262-268 */
 	VolState *v = (VolState *)f->data;
 	v->static_gain = (float)pow(10, (*(float *)arg) / 10);
-	v->dirty = TRUE;
+	v->gain_dirty = TRUE;
 	return 0;
 }
 static int vol_get_gain(MSFilter *f, void *arg) {
@@ -480,11 +526,15 @@ static int vol_set_rate(MSFilter *f, void *arg) {
 	return 0;
 }
 static int vol_set_peer(MSFilter *f, void *arg) {
-	((VolState *)f->data)->peer = (MSFilter *)arg;
+	VolState *v = (VolState *)f->data;
+	v->peer = (MSFilter *)arg;
+	v->peer_linked = FALSE;
 	return 0;
 }
 static int vol_set_agc(MSFilter *f, void *arg) {
-	((VolState *)f->data)->agc = *(int *)arg;
+	VolState *v = (VolState *)f->data;
+	v->agc = *(int *)arg;
+	v->dirty = TRUE;
 	return 0;
 }
 static int vol_enable_ng(MSFilter *f, void *arg) {
@@ -511,20 +561,55 @@ static int vol_remove_dc(MSFilter *f, void *arg) {
 	v->dirty = TRUE;
 	return 0;
 }
-static int vol_ignore_float(MSFilter *f, void *arg) {
-	(void)f;
-	(void)arg;
+static int vol_set_ea_threshold(MSFilter *f, void *arg) {
+	VolState *v = (VolState *)f->data;
+	float val = *(float *)arg;
+	if (val < 0 || val > 1) {
+		ms_error("Error: threshold must be in range [0..1]");
+		return -1;
+	}
+	v->ea_thres = val;
+	v->dirty = TRUE;
+	return 0;
+}
+static int vol_set_ea_speed(MSFilter *f, void *arg) {
+	VolState *v = (VolState *)f->data;
+	float val = *(float *)arg;
+	if (val < 0 || val > .5) {
+		ms_error("Error: speed must be in range [0..0.5]");
+		return -1;
+	}
+	v->ea_speed = val;
+	v->dirty = TRUE;
+	return 0;
+}
+static int vol_set_ea_force(MSFilter *f, void *arg) {
+	VolState *v = (VolState *)f->data;
+	v->ea_force = *(float *)arg;
+	v->dirty = TRUE;
+	return 0;
+}
+static int vol_set_ea_sustain(MSFilter *f, void *arg) {
+	VolState *v = (VolState *)f->data;
+	v->ea_sustain = *(int *)arg;
+	v->dirty = TRUE;
+	return 0;
+}
+static int vol_set_ea_transmit(MSFilter *f, void *arg) {
+	VolState *v = (VolState *)f->data;
+	v->ea_transmit = *(float *)arg;
+	v->dirty = TRUE;
 	return 0;
 }
 static MSFilterMethod vol_methods[] = {{MS_VOLUME_GET, vol_get},
                                        {MS_VOLUME_GET_LINEAR, vol_get_linear},
                                        {MS_VOLUME_SET_GAIN, vol_set_gain},
                                        {MS_VOLUME_SET_PEER, vol_set_peer},
-                                       {MS_VOLUME_SET_EA_THRESHOLD, vol_ignore_float},
-                                       {MS_VOLUME_SET_EA_SPEED, vol_ignore_float},
-                                       {MS_VOLUME_SET_EA_FORCE, vol_ignore_float},
-                                       {MS_VOLUME_SET_EA_SUSTAIN, vol_ignore_float},
-                                       {MS_VOLUME_SET_EA_TRANSMIT_THRESHOLD, vol_ignore_float},
+                                       {MS_VOLUME_SET_EA_THRESHOLD, vol_set_ea_threshold},
+                                       {MS_VOLUME_SET_EA_SPEED, vol_set_ea_speed},
+                                       {MS_VOLUME_SET_EA_FORCE, vol_set_ea_force},
+                                       {MS_VOLUME_SET_EA_SUSTAIN, vol_set_ea_sustain},
+                                       {MS_VOLUME_SET_EA_TRANSMIT_THRESHOLD, vol_set_ea_transmit},
                                        {MS_FILTER_SET_SAMPLE_RATE, vol_set_rate},
                                        {MS_VOLUME_ENABLE_AGC, vol_set_agc},
                                        {MS_VOLUME_ENABLE_NOISE_GATE, vol_enable_ng},

@@ -25,7 +25,9 @@ class OrcVolumeState(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("energy", "level_pk", "instant_energy", "gain", "static_gain", "target_gain",
                                          "ng_gain", "ng_threshold", "ng_floorgain")] + \
                [(n, C.c_int32) for n in ("dc_offset", "ng_noise_dur", "noise_gate_enabled", "remove_dc", "sample_rate",
-                                         "fast_upramp")]
+                                         "fast_upramp")] + \
+               [(n, C.c_float) for n in ("lt_speaker_en", "ea_thres", "ea_transmit_thres", "force", "vol_upramp")] + \
+               [(n, C.c_int32) for n in ("sustain_time", "sustain_dur", "agc_enabled", "peer")]
 
 
 _oracle = None
@@ -49,6 +51,7 @@ def oracle() -> C.CDLL:
         "orc_mixer_partial": (None, [_I, _I, _I, _P, _P, _P, _P, _P]),
         "orc_volume_init": (None, [C.POINTER(OrcVolumeState), _I]),
         "orc_volume_process": (None, [C.POINTER(OrcVolumeState), _P, _I]),
+        "orc_volume_process_chunk": (None, [C.POINTER(OrcVolumeState), C.POINTER(C.c_float), _P, _I]),
         "orc_chanadapt": (None, [_I, _I, _I, _P, _P, _P]),
         "orc_equalizer_new": (_P, [_I]),
         "orc_equalizer_free": (None, [_P]),
@@ -174,6 +177,12 @@ class RefGraph:
         assert mid != 0, method
         return self.L.ref_filter_call(f, mid, C.byref(arg) if arg is not None else None)
 
+    def call_ptr(self, f, method: str, ptr_value) -> int:
+        """methods whose argument IS a pointer (e.g. MS_VOLUME_SET_PEER takes the peer MSFilter*)"""
+        mid = self.L.ref_method_id(method.encode())
+        assert mid != 0, method
+        return self.L.ref_filter_call(f, mid, ptr_value)
+
     def call_int(self, f, method: str, value: int) -> int:
         return self.call(f, method, C.c_int(value))
 
@@ -210,11 +219,13 @@ class RefGraph:
         return buf.view(dtype), tri
 
     def run(self, attach_to, nticks: int):
+        """attach_to: one source filter, or a list of sources of disconnected graphs (executed in this order)"""
         if self.ticker is None:
             self.ticker = self.L.ref_ticker_new()
-        if attach_to not in self.attached:
-            assert self.L.ref_ticker_attach(self.ticker, attach_to) == 0
-            self.attached.append(attach_to)
+        for src in (attach_to if isinstance(attach_to, (list, tuple)) else [attach_to]):
+            if src not in self.attached:
+                assert self.L.ref_ticker_attach(self.ticker, src) == 0
+                self.attached.append(src)
         self.L.ref_ticker_run(self.ticker, nticks)
 
     def close(self):

@@ -236,3 +236,53 @@ def test_resample_cfg1_hello_like_stream_matches_oracle(ctx):
         assert np.array_equal(got[0], out[:480])
     L.orc_resampler_free(o)
     r.close()
+
+
+@pytest.mark.parametrize("agc,peer", [(True, False), (False, True), (True, True)])
+def test_volume_chunked_mode_bit_exact(ctx, agc, peer):
+    """AGC / echo-limiter peer (msvolume.c:480-502) on 10 ms chunks: speaker bank first, then the microphone bank whose
+    streams read their peer's energy; GPU == oracle (pinned vs the reference in test_oracle_vs_reference.py)."""
+    L = O.oracle()
+    n_streams, T, rate = 9, 40, 16000
+    n = rate // 100
+    spk_bank, mic_bank = F.Volume(ctx, n_streams, rate), F.Volume(ctx, n_streams, rate)
+    st_spk, st_mic = [], []
+    for s in range(n_streams):
+        a, b = OrcVolumeState(), OrcVolumeState()
+        L.orc_volume_init(C.byref(a), rate)
+        L.orc_volume_init(C.byref(b), rate)
+        b.gain = b.target_gain = b.static_gain = 1.5
+        mic_bank.set_gain(s, 1.5)
+        if agc:
+            b.agc_enabled = 1
+            mic_bank.enable_agc(s, True)
+        if peer:
+            ps = (s + 1) % n_streams  # peer = another stream of the speaker bank
+            b.peer = ps
+            b.ea_thres, b.vol_upramp, b.force, b.sustain_time = 0.05, 0.3, 6.0, 100
+            mic_bank.set_peer(s, spk_bank, ps)
+            mic_bank.set_ea(s, threshold=0.05, speed=0.3, force=6.0, sustain=100)
+        st_spk.append(a)
+        st_mic.append(b)
+    rng = np.random.default_rng(3)
+    for k in range(T):
+        env = 9000 if (k // 6) % 2 == 0 else 40
+        spk = (rng.standard_normal((n_streams, n)) * env).astype(np.int16)
+        mic = (rng.standard_normal((n_streams, n)) * 3000).astype(np.int16)
+        got_spk = spk_bank.process(spk)
+        got_mic = mic_bank.process(mic)
+        exp_spk, exp_mic = spk.copy(), mic.copy()
+        for s in range(n_streams):
+            L.orc_volume_process(C.byref(st_spk[s]), ptr(exp_spk[s]), n)
+        for s in range(n_streams):
+            pe = C.c_float(st_spk[st_mic[s].peer].energy) if peer else None
+            L.orc_volume_process_chunk(C.byref(st_mic[s]), C.byref(pe) if peer else None, ptr(exp_mic[s]), n)
+        assert np.array_equal(got_spk, exp_spk), k
+        assert np.array_equal(got_mic, exp_mic), k
+    for s in range(n_streams):
+        st = mic_bank.state(s)
+        for f in ("energy", "gain", "target_gain", "lt_speaker_en"):
+            assert np.float32(getattr(st, f)).tobytes() == np.float32(getattr(st_mic[s], f)).tobytes(), (s, f)
+        assert st.sustain_dur == st_mic[s].sustain_dur
+    spk_bank.close()
+    mic_bank.close()

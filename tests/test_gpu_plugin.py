@@ -236,3 +236,34 @@ def _oracle_tick_with_ec_start(oc, ref_in, mic_in, drop_ref):
         L.orc_volume_process(C.byref(oc.vol[0]), ptr(out), F)
         outs.append(out)
     return np.concatenate(outs) if outs else np.zeros(0, np.int16)
+
+
+def test_volume_plugin_chunked_mode_with_peer_bit_exact_vs_reference():
+    """echo-limiter peer + AGC (msvolume.c:480-502) through the plugin in the unmodified ticker vs the reference filters."""
+    rate, T = 16000, 50
+    n = rate // 100
+    rng = np.random.default_rng(5)
+    spk = np.concatenate([(rng.standard_normal(n) * (9000 if (k // 6) % 2 == 0 else 40)).astype(np.int16) for k in range(T)])
+    mic = (rng.standard_normal(T * n) * 3000).astype(np.int16)
+    res = []
+    for g in _graphs():
+        vspk, vmic = g.new("MSVolume"), g.new("MSVolume")
+        for v in (vspk, vmic):
+            g.call_int(v, "MS_FILTER_SET_SAMPLE_RATE", rate)
+        g.call_float(vmic, "MS_VOLUME_SET_GAIN", 1.5)
+        g.call_int(vmic, "MS_VOLUME_ENABLE_AGC", 1)
+        g.call_ptr(vmic, "MS_VOLUME_SET_PEER", vspk)
+        g.call_float(vmic, "MS_VOLUME_SET_EA_THRESHOLD", 0.05)
+        g.call_float(vmic, "MS_VOLUME_SET_EA_FORCE", 6.0)
+        s_spk, k_spk = g.source(spk, n * 2), g.sink()
+        s_mic, k_mic = g.source(mic, 2 * n * 2 // 2), g.sink()
+        g.link(s_spk, 0, vspk, 0)
+        g.link(vspk, 0, k_spk, 0)
+        g.link(s_mic, 0, vmic, 0)
+        g.link(vmic, 0, k_mic, 0)
+        g.run([s_spk, s_mic], T)
+        res.append((g.read(k_spk)[0], g.read(k_mic)[0]))
+        g.close()
+    assert len(res[0][1]) == T * n
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])

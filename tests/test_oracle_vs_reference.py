@@ -280,3 +280,89 @@ def test_nv12_oracle_bit_exact_vs_reference(rotation, down_scale):
         nb = R.ref_nv12_to_i420(ptr(ybuf), ptr(cbuf), rotation, w, h, y_stride, c_stride, u_first, down_scale, ptr(b))
         assert na == nb == w * h * 3 // 2
         assert np.array_equal(a, b)
+
+
+def _speechy(seed, n, rate, amp):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    env = (np.sin(2 * np.pi * 1.3 * t / rate + seed) > 0).astype(np.float64)
+    return (env * amp * np.sin(2 * np.pi * (200 + 37 * seed) * t / rate) + 60 * rng.standard_normal(n)).astype(np.int16)
+
+
+@pytest.mark.parametrize("agc,peer", [(True, False), (False, True), (True, True)])
+def test_volume_chunked_mode_oracle_bit_exact_vs_reference(agc, peer):
+    """msvolume.c:480-502: AGC and/or echo-limiter peer -> 10 ms chunks, echo avoider reads the peer's energy.
+    Two MSVolume filters in one ticker (speaker path first, then microphone path with the speaker filter as peer)."""
+    L = O.oracle()
+    rate, T = 16000, 60
+    n = rate // 100
+    spk = _speechy(1, T * n, rate, 9000)
+    mic = _speechy(2, T * n, rate, 5000)
+    g = RefGraph()
+    vspk, vmic = g.new("MSVolume"), g.new("MSVolume")
+    for v in (vspk, vmic):
+        g.call_int(v, "MS_FILTER_SET_SAMPLE_RATE", rate)
+    g.call_float(vmic, "MS_VOLUME_SET_GAIN", 1.5)
+    if agc:
+        g.call_int(vmic, "MS_VOLUME_ENABLE_AGC", 1)
+    if peer:
+        g.call_ptr(vmic, "MS_VOLUME_SET_PEER", vspk)
+        g.call_float(vmic, "MS_VOLUME_SET_EA_THRESHOLD", 0.05)
+        g.call_float(vmic, "MS_VOLUME_SET_EA_SPEED", 0.3)
+        g.call_float(vmic, "MS_VOLUME_SET_EA_FORCE", 6.0)
+        g.call_int(vmic, "MS_VOLUME_SET_EA_SUSTAIN", 100)
+    # odd block sizes on the microphone path: the chunked mode re-frames them to 10 ms
+    s_spk, k_spk = g.source(spk, n * 2), g.sink()
+    s_mic, k_mic = g.source(), g.sink()
+    blk = 2 * n // 3
+    pos = 0
+    tick = 0
+    while pos < len(mic):
+        g.push(s_mic, tick, mic[pos:pos + blk])
+        pos += blk
+        tick += 1 if (tick % 3) else 0
+        tick += 1 if pos % (3 * blk) == 0 else 0
+    g.link(s_spk, 0, vspk, 0)
+    g.link(vspk, 0, k_spk, 0)
+    g.link(s_mic, 0, vmic, 0)
+    g.link(vmic, 0, k_mic, 0)
+    g.run([s_spk, s_mic], T + 40)
+    y_spk, _ = g.read(k_spk)
+    y_mic, tri = g.read(k_mic)
+    g.close()
+    assert set(tri[:, 1]) == {n * 2}  # every output block is one 10 ms chunk
+    # oracle: replay tick by tick with the same arrival pattern (chunks are cut as soon as 10 ms are buffered)
+    st_spk, st_mic = OrcVolumeState(), OrcVolumeState()
+    L.orc_volume_init(C.byref(st_spk), rate)
+    L.orc_volume_init(C.byref(st_mic), rate)
+    st_mic.gain = st_mic.target_gain = st_mic.static_gain = 1.5
+    st_mic.agc_enabled = int(agc)
+    if peer:
+        st_mic.ea_thres, st_mic.vol_upramp, st_mic.force, st_mic.sustain_time = 0.05, 0.3, 6.0, 100
+    # arrival schedule of microphone samples per tick, mirrored from the pushes above
+    sched = {}
+    pos = 0
+    tick = 0
+    while pos < len(mic):
+        sched.setdefault(tick, []).append((pos, min(pos + blk, len(mic))))
+        pos += blk
+        tick += 1 if (tick % 3) else 0
+        tick += 1 if pos % (3 * blk) == 0 else 0
+    buf = np.zeros(0, np.int16)
+    out_mic = []
+    exp_spk = spk.copy()
+    for t in range(T + 40):
+        if t < T:
+            L.orc_volume_process(C.byref(st_spk), ptr(exp_spk[t * n:(t + 1) * n]), n)
+        for (a, b) in sched.get(t, []):
+            buf = np.concatenate([buf, mic[a:b]])
+        while len(buf) >= n:
+            chunk = np.ascontiguousarray(buf[:n])
+            buf = buf[n:]
+            pe = C.c_float(st_spk.energy)
+            L.orc_volume_process_chunk(C.byref(st_mic), C.byref(pe) if peer else None, ptr(chunk), n)
+            out_mic.append(chunk)
+    out_mic = np.concatenate(out_mic)
+    assert np.array_equal(y_spk, exp_spk)
+    assert len(y_mic) == len(out_mic)
+    assert np.array_equal(y_mic, out_mic)
