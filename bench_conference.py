@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--check-ticks", type=int, default=3)
+    ap.add_argument("--exchange", choices=["nccl", "peer"], default="nccl",
+                    help="nccl: partial -> ncclAllReduce -> finish; peer: one fused kernel loading the peers' partial sums over NVLink")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -67,7 +69,47 @@ def main():
     d_sum = torch.empty((ROOMS, NWORDS), dtype=torch.int32, device=dev)
     d_out = torch.empty((ROOMS, nl, NWORDS), dtype=torch.int16, device=dev)
 
+    # ---- peer-memory exchange set-up: two alternating partial-sum buffers + an epoch flag per rank, mapped everywhere
+    peer = {}
+    if args.exchange == "peer" and world > 1:
+        nbytes = ROOMS * NWORDS * 4
+        own = {"sum0": ctx.dev_alloc(nbytes), "sum1": ctx.dev_alloc(nbytes), "flag": ctx.dev_alloc(256)}
+        err = ctx.dev_alloc(256)
+        _lib.check(lib.msb200_memset_dev(ctx.h, own["flag"], 0, 256))
+        _lib.check(lib.msb200_memset_dev(ctx.h, err, 0, 256))
+        ctx.sync()
+        handles = {}
+        for k, p in own.items():
+            h = (C.c_uint8 * 64)()
+            _lib.check(lib.msb200_ipc_export(ctx.h, C.c_void_p(p), h))
+            handles[k] = bytes(h)
+        allh = [None] * world
+        dist.all_gather_object(allh, handles)
+        mapped = []
+        for r2 in range(world):
+            if r2 == rank:
+                mapped.append(own)
+                continue
+            m = {}
+            for k, hb in allh[r2].items():
+                q = C.c_void_p()
+                _lib.check(lib.msb200_ipc_import(ctx.h, (C.c_uint8 * 64).from_buffer_copy(hb), C.byref(q)))
+                m[k] = q.value
+            mapped.append(m)
+        peer = {"own": own, "err": err, "mapped": mapped, "epoch": 0,
+                "sums": [(C.c_void_p * world)(*[m["sum0"] for m in mapped]), (C.c_void_p * world)(*[m["sum1"] for m in mapped])],
+                "flags": (C.c_void_p * world)(*[m["flag"] for m in mapped])}
+        dist.barrier()
+
     def tick():
+        if peer:
+            b = peer["epoch"] & 1
+            peer["epoch"] += 1
+            _lib.check(lib.msb200_mixer_partial_dev(mixer.h, d_in.data_ptr(), d_pr.data_ptr(), peer["own"][f"sum{b}"]))
+            _lib.check(lib.msb200_signal_dev(ctx.h, peer["own"]["flag"], peer["epoch"]))
+            _lib.check(lib.msb200_mixer_finish_peers_dev(mixer.h, d_in.data_ptr(), d_pr.data_ptr(), peer["sums"][b], peer["flags"],
+                                                         world, peer["epoch"], d_out.data_ptr(), peer["err"]))
+            return
         if world == 1:
             _lib.check(lib.msb200_mixer_process_dev(mixer.h, d_in.data_ptr(), d_pr.data_ptr(), d_out.data_ptr()))
             return
@@ -116,6 +158,16 @@ def main():
         tms = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
+    if peer:
+        e = np.zeros(1, np.uint32)
+        ctx.d2h(e, peer["err"])
+        if e[0]:
+            raise RuntimeError("peer-memory exchange: a peer's epoch flag never arrived")
+        dist.barrier()  # nobody unmaps while a peer may still be reading
+        for r2, m in enumerate(peer["mapped"]):
+            if r2 != rank:
+                for q in m.values():
+                    lib.msb200_ipc_close(ctx.h, C.c_void_p(q))
     if rank == 0:
         room_ticks = ROOMS * args.steps
         line = {
@@ -124,7 +176,10 @@ def main():
             "ms_per_step": ms / args.steps, "scaling": "strong", "higher_is_better": True, "dtype": "s16/int32",
             "config": {"workload": f"{ROOMS} rooms x {PINS} pins x {NWORDS} samples, pins striped gpu = pin mod N",
                        "exchange": "none (single-pass kernel)" if world == 1 else
-                       f"ncclAllReduce int32 SUM of {ROOMS * NWORDS * 4} B per tick between partial and finish kernels"},
+                       (f"ncclAllReduce int32 SUM of {ROOMS * NWORDS * 4} B per tick between partial and finish kernels"
+                        if not peer else
+                        f"fused: finish kernel loads the {world} partial-sum buffers ({ROOMS * NWORDS * 4} B each) through "
+                        f"NVLink peer mappings after an epoch-flag handshake; no NCCL on the data path")},
             "bit_exact_vs_oracle": parity, "gpu_launches": int(launches),
             "stream_ticks_per_s": room_ticks * PINS / (ms / 1000.0),
         }

@@ -92,6 +92,22 @@ MSB200_API int msb200_mixer_process_dev(msb200_mixer *m, const void *d_in, const
 MSB200_API int msb200_mixer_partial_dev(msb200_mixer *m, const void *d_in, const void *d_present, void *d_sum_i32);
 MSB200_API int msb200_mixer_finish_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *d_sum_i32,
                                         void *d_out);
+/* Fused exchange + finish over NVLink peer memory (one process per GPU): every rank exports its partial-sum buffer and a
+ * 32-bit epoch flag with msb200_ipc_export(), imports the peers' with msb200_ipc_import(). Per tick: partial_dev into
+ * the local buffer, msb200_signal_dev(flag, epoch) (stream-ordered release), then ONE kernel that waits for every peer's
+ * flag to reach `epoch`, loads the peers' partial sums directly through their mapped pointers, adds them (integer:
+ * order-independent, bit-exact) and emits sat(total - own) for the local pins — no NCCL call, no separate reduction pass.
+ * Use two alternating sum buffers (tick parity) so a fast rank never overwrites a buffer a slow peer still reads.
+ * d_peer_sums / d_peer_flags: host arrays of n_peers device pointers (own rank included, any order). */
+#define MSB200_IPC_HANDLE_BYTES 64
+#define MSB200_MAX_PEERS 8
+MSB200_API int msb200_ipc_export(msb200_ctx *ctx, void *dev_ptr, uint8_t handle[MSB200_IPC_HANDLE_BYTES]);
+MSB200_API int msb200_ipc_import(msb200_ctx *ctx, const uint8_t handle[MSB200_IPC_HANDLE_BYTES], void **dev_ptr);
+MSB200_API int msb200_ipc_close(msb200_ctx *ctx, void *dev_ptr);
+MSB200_API int msb200_signal_dev(msb200_ctx *ctx, void *d_flag_u32, uint32_t value);
+MSB200_API int msb200_mixer_finish_peers_dev(msb200_mixer *m, const void *d_in, const void *d_present,
+                                              const void *const *d_peer_sums, const void *const *d_peer_flags, int n_peers,
+                                              uint32_t epoch, void *d_out, void *d_error_flag_u32);
 
 /* ---------------------------------------------------------------------------------------------------- MSVolume
  * Replaces the light path of volume_process() /root/reference/src/audiofilters/msvolume.c:503-513:

@@ -83,6 +83,11 @@ _SIGS = {
     "msb200_mixer_process_dev": (_I, [_P, _P, _P, _P]),
     "msb200_mixer_partial_dev": (_I, [_P, _P, _P, _P]),
     "msb200_mixer_finish_dev": (_I, [_P, _P, _P, _P, _P]),
+    "msb200_ipc_export": (_I, [_P, _P, _P]),
+    "msb200_ipc_import": (_I, [_P, _P, _PP]),
+    "msb200_ipc_close": (_I, [_P, _P]),
+    "msb200_signal_dev": (_I, [_P, _P, C.c_uint32]),
+    "msb200_mixer_finish_peers_dev": (_I, [_P, _P, _P, _P, _P, _I, C.c_uint32, _P, _P]),
     "msb200_volume_create": (_I, [_P, _I, _I, _I, _PP]),
     "msb200_volume_destroy": (None, [_P]),
     "msb200_volume_set_gain": (_I, [_P, _I, _F]),

@@ -72,15 +72,45 @@ template <> __device__ __forceinline__ short pack_s16<1>(const int (&s)[1]) {
 	return (short)s[0];
 }
 
-// mode 0: full (sum + outputs); mode 1: partial sums only -> d_sum; mode 2: outputs from given d_sum
+struct MixPeers { // peer-memory exchange (mode 3): mapped pointers of every rank's partial sums and epoch flag
+	const int *sum[MSB200_MAX_PEERS];
+	const unsigned *flag[MSB200_MAX_PEERS];
+	int n;
+	unsigned epoch;
+	unsigned *error; // set to 1 if a peer's flag never arrives (bounded spin instead of a hang)
+};
+__device__ __forceinline__ int4 ld_sys_v4(const int *p) { // peer data is read once, straight from its home memory
+	int4 v;
+	asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+// mode 0: full (sum + outputs); mode 1: partial sums only -> d_sum; mode 2: outputs from given d_sum;
+// mode 3: wait for the peers' flags, total = sum over peers' partial buffers (NVLink loads), outputs
 template <int VEC>
 __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in, const uint8_t *__restrict__ present,
                                                     const float *__restrict__ gain, const uint8_t *__restrict__ active,
                                                     short *__restrict__ out, int *__restrict__ sum_io, int n_rooms,
-                                                    int n_pins, int nwords, int conf_mode, int mode, long in_pin_vecs) {
+                                                    int n_pins, int nwords, int conf_mode, int mode, long in_pin_vecs,
+                                                    MixPeers peers) {
 	typedef typename s16vec<VEC>::type V;
 	const int nvec = nwords / VEC;
 	const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (mode == 3) { // acquire: every peer has published its partial sums for this epoch
+		if (threadIdx.x == 0) {
+			for (int g = 0; g < peers.n; ++g) {
+				const volatile unsigned *f = peers.flag[g];
+				long spins = 0;
+				while ((int)(*f - peers.epoch) < 0) {
+					if (++spins > 400000000L) {
+						*peers.error = 1u;
+						break;
+					}
+				}
+			}
+			__threadfence_system();
+		}
+		__syncthreads();
+	}
 	if (gid >= (long)n_rooms * nvec) return;
 	const int room = (int)(gid / nvec), col = (int)(gid % nvec);
 	const size_t chan0 = (size_t)room * n_pins;
@@ -89,7 +119,7 @@ __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in
 	int sum[VEC];
 #pragma unroll
 	for (int k = 0; k < VEC; ++k) sum[k] = 0;
-	if (mode != 2) {
+	if (mode == 0 || mode == 1) {
 #pragma unroll 4
 		for (int p = 0; p < n_pins; ++p) {
 			if (!present[chan0 + p] || !active[chan0 + p]) continue;
@@ -99,9 +129,16 @@ __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in
 #pragma unroll
 			for (int k = 0; k < VEC; ++k) sum[k] += mix_contrib(s[k], g);
 		}
-	} else {
+	} else if (mode == 2) {
 #pragma unroll
 		for (int k = 0; k < VEC; ++k) sum[k] = sum_io[(size_t)room * nwords + col * VEC + k];
+	} else { // mode 3: VEC == 4 (one 16-byte load per peer)
+		for (int g = 0; g < peers.n; ++g) {
+			const int4 v = ld_sys_v4(peers.sum[g] + (size_t)room * nwords + col * VEC);
+			if (VEC >= 4) {
+				sum[0] += v.x; sum[1 % VEC] += v.y; sum[2 % VEC] += v.z; sum[3 % VEC] += v.w;
+			}
+		}
 	}
 	if (mode == 1) {
 #pragma unroll
@@ -145,7 +182,7 @@ static int mixer_upload(msb200_mixer *m) {
 }
 
 static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out, void *d_sum, int mode,
-                        long in_pin_stride = 0) {
+                        long in_pin_stride = 0, const MixPeers *peers_in = nullptr) {
 	int r = mixer_upload(m);
 	if (r) return r;
 	const int nw = m->nwords;
@@ -153,13 +190,23 @@ static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present
 	if (in_pin_stride <= 0) in_pin_stride = nw;
 	int vec = (nw % 8 == 0 && al16) ? 8 : (nw % 4 == 0 && al16) ? 4 : (nw % 2 == 0 && al16) ? 2 : 1;
 	while (vec > 1 && in_pin_stride % vec) vec /= 2;
+	MixPeers peers;
+	memset(&peers, 0, sizeof(peers));
+	if (mode == 3) {
+		peers = *peers_in;
+		if (nw % 4 || !al16) {
+			msb200_set_error("mixer: the peer-memory path needs nwords %% 4 == 0 and 16-byte aligned buffers");
+			return MSB200_EINVAL;
+		}
+		vec = 4;
+	}
 	// prefer more, narrower threads when the grid would not cover the chip (148 SMs x >=4 CTAs of 128)
-	while (vec > 2 && (long)m->n_rooms * (nw / vec) < 148L * 4 * 128) vec /= 2;
+	while (mode != 3 && vec > 2 && (long)m->n_rooms * (nw / vec) < 148L * 4 * 128) vec /= 2;
 	const long nthreads = (long)m->n_rooms * (nw / vec);
 	const int block = 128, grid = (int)((nthreads + block - 1) / block);
 #define MIX_ARGS                                                                                                       \
 	(const short *)d_in, (const uint8_t *)d_present, m->d_gain, m->d_active, (short *)d_out, (int *)d_sum, m->n_rooms, \
-	    m->n_pins, nw, m->conf_mode, mode, in_pin_stride / vec
+	    m->n_pins, nw, m->conf_mode, mode, in_pin_stride / vec, peers
 	switch (vec) {
 		case 8: MSB200_LAUNCH(m->ctx, mixer_kernel<8>, grid, block, 0, MIX_ARGS); break;
 		case 4: MSB200_LAUNCH(m->ctx, mixer_kernel<4>, grid, block, 0, MIX_ARGS); break;
@@ -222,6 +269,22 @@ int msb200_mixer_partial_dev(msb200_mixer *m, const void *d_in, const void *d_pr
 int msb200_mixer_finish_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *d_sum, void *d_out) {
 	MSB200_CHECK_ARG(m && d_in && d_present && d_sum && d_out);
 	return mixer_launch(m, d_in, d_present, d_out, (void *)d_sum, 2);
+}
+int msb200_mixer_finish_peers_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *const *d_peer_sums,
+                                  const void *const *d_peer_flags, int n_peers, uint32_t epoch, void *d_out, void *d_error) {
+	MSB200_CHECK_ARG(m && d_in && d_present && d_out && d_peer_sums && d_peer_flags && d_error);
+	MSB200_CHECK_ARG(n_peers >= 1 && n_peers <= MSB200_MAX_PEERS && m->conf_mode);
+	MixPeers p;
+	memset(&p, 0, sizeof(p));
+	for (int g = 0; g < n_peers; ++g) {
+		MSB200_CHECK_ARG(d_peer_sums[g] && d_peer_flags[g] && ((uintptr_t)d_peer_sums[g] % 16) == 0);
+		p.sum[g] = (const int *)d_peer_sums[g];
+		p.flag[g] = (const unsigned *)d_peer_flags[g];
+	}
+	p.n = n_peers;
+	p.epoch = epoch;
+	p.error = (unsigned *)d_error;
+	return mixer_launch(m, d_in, d_present, d_out, nullptr, 3, 0, &p);
 }
 int msb200_mixer_process(msb200_mixer *m, const int16_t *in, const uint8_t *present, int16_t *out) {
 	MSB200_CHECK_ARG(m && in && present && out);

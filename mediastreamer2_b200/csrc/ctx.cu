@@ -3,6 +3,11 @@
 
 static thread_local char g_err[512] = "";
 
+__global__ void signal_kernel(unsigned *flag, unsigned value) {
+	__threadfence_system(); // everything this stream wrote before is visible system-wide before the flag moves
+	*reinterpret_cast<volatile unsigned *>(flag) = value;
+}
+
 void msb200_set_error(const char *fmt, ...) {
 	va_list ap;
 	va_start(ap, fmt);
@@ -129,6 +134,33 @@ int msb200_timer_stop_ms(msb200_ctx *c, float *ms) {
 	MSB200_CUDA(cudaEventRecord(c->ev_stop, c->stream));
 	MSB200_CUDA(cudaEventSynchronize(c->ev_stop));
 	MSB200_CUDA(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
+	return MSB200_OK;
+}
+int msb200_ipc_export(msb200_ctx *c, void *dev_ptr, uint8_t handle[MSB200_IPC_HANDLE_BYTES]) {
+	MSB200_CHECK_ARG(c && dev_ptr && handle);
+	static_assert(sizeof(cudaIpcMemHandle_t) <= MSB200_IPC_HANDLE_BYTES, "handle size");
+	cudaIpcMemHandle_t h;
+	MSB200_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+	memset(handle, 0, MSB200_IPC_HANDLE_BYTES);
+	memcpy(handle, &h, sizeof(h));
+	return MSB200_OK;
+}
+int msb200_ipc_import(msb200_ctx *c, const uint8_t handle[MSB200_IPC_HANDLE_BYTES], void **dev_ptr) {
+	MSB200_CHECK_ARG(c && handle && dev_ptr);
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof(h));
+	MSB200_CUDA(cudaSetDevice(c->device));
+	MSB200_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return MSB200_OK;
+}
+int msb200_ipc_close(msb200_ctx *c, void *dev_ptr) {
+	MSB200_CHECK_ARG(c && dev_ptr);
+	MSB200_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+	return MSB200_OK;
+}
+int msb200_signal_dev(msb200_ctx *c, void *d_flag, uint32_t value) {
+	MSB200_CHECK_ARG(c && d_flag);
+	MSB200_LAUNCH(c, signal_kernel, 1, 1, 0, (unsigned *)d_flag, (unsigned)value);
 	return MSB200_OK;
 }
 int msb200_flush_l2(msb200_ctx *c) {
