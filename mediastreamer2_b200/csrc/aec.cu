@@ -32,7 +32,7 @@ enum { // scal[] indices
 	SC_DAVG1, SC_DAVG2, SC_DVAR1, SC_DVAR2, SC_PEY, SC_PYY, SC_SUM_ADAPT, SC_LEAK, SC_MEMX, SC_MEMD, SC_MEME,
 	SC_NOTCH0, SC_NOTCH1, SC_COUNT = 16
 };
-enum { IN_ADAPTED, IN_SATURATED, IN_SCREWED, IN_CANCEL_COUNT, IN_NB_ADAPT, IN_MIN_COUNT, IN_COUNT = 8 };
+enum { IN_ADAPTED, IN_SATURATED, IN_SCREWED, IN_CANCEL_COUNT, IN_NB_ADAPT, IN_MIN_COUNT, IN_FG_PENDING, IN_COUNT = 8 };
 
 struct AecParams {
 	int F, N, M, L, log2L, rate;
@@ -170,6 +170,106 @@ __device__ void irfft(const float2 *spec, float *out, float2 *bufa, float2 *bufb
 	__syncthreads();
 	out[2 * k] = v.x;
 	out[2 * k + 1] = v.y;
+	__syncthreads();
+}
+
+// ---- paired transforms: two independent FFTs share every stage's index math, twiddle load and barrier
+template <int LOG2L>
+__device__ __forceinline__ void cfft_pair(float2 *&xa, float2 *&ya, float2 *&xb, float2 *&yb, const float2 *tw, int sign) {
+	const int o = threadIdx.x;
+#pragma unroll
+	for (int st = 0; st < LOG2L; ++st) {
+		const int s = 1 << st, m = 1 << (LOG2L - 1 - st);
+		const int q = o & (s - 1), tmp = o >> st, r = tmp & 1, p = tmp >> 1;
+		const int i0 = q + s * p, i1 = q + s * (p + m);
+		const float2 a = xa[i0], b = xa[i1], c = xb[i0], d = xb[i1];
+		float2 oa, ob;
+		if (!r) {
+			oa.x = a.x + b.x; oa.y = a.y + b.y;
+			ob.x = c.x + d.x; ob.y = c.y + d.y;
+		} else {
+			const float2 w = tw[p << st];
+			const float wr = w.x, wi = sign < 0 ? -w.y : w.y;
+			const float dr = a.x - b.x, di = a.y - b.y, er = c.x - d.x, ei = c.y - d.y;
+			oa.x = dr * wr - di * wi; oa.y = dr * wi + di * wr;
+			ob.x = er * wr - ei * wi; ob.y = er * wi + ei * wr;
+		}
+		ya[o] = oa;
+		yb[o] = ob;
+		__syncthreads();
+		float2 *sw = xa; xa = ya; ya = sw;
+		sw = xb; xb = yb; yb = sw;
+	}
+}
+// two real forward FFTs (same arithmetic as rfft<> per transform); scratch: a0,a1 for the first, b0,b1 for the second
+template <int LOG2L>
+__device__ void rfft_pair(const float *in_a, float2 *spec_a, const float *in_b, float2 *spec_b, float2 *a0, float2 *a1,
+                          float2 *b0, float2 *b1, const AecParams &P, const float2 *tw, const float2 *spl) {
+	const int k = threadIdx.x, L = 1 << LOG2L;
+	const float scale = (float)(1. / P.N);
+	a0[k] = make_float2(scale * in_a[2 * k], scale * in_a[2 * k + 1]);
+	b0[k] = make_float2(scale * in_b[2 * k], scale * in_b[2 * k + 1]);
+	__syncthreads();
+	float2 *xa = a0, *ya = a1, *xb = b0, *yb = b1;
+	cfft_pair<LOG2L>(xa, ya, xb, yb, tw, -1);
+	float2 oa, ob;
+	if (k == 0) {
+		oa.x = xa[0].x + xa[0].y; oa.y = xa[0].x - xa[0].y;
+		ob.x = xb[0].x + xb[0].y; ob.y = xb[0].x - xb[0].y;
+	} else {
+		const float c = spl[k].x, sn = spl[k].y;
+		{
+			const float zr = xa[k].x, zi = xa[k].y, yr = xa[L - k].x, yi = -xa[L - k].y;
+			const float er = 0.5f * (zr + yr), ei = 0.5f * (zi + yi), dr = 0.5f * (zr - yr), di = 0.5f * (zi - yi);
+			oa.x = er + (c * di - sn * dr);
+			oa.y = ei - (sn * di + c * dr);
+		}
+		{
+			const float zr = xb[k].x, zi = xb[k].y, yr = xb[L - k].x, yi = -xb[L - k].y;
+			const float er = 0.5f * (zr + yr), ei = 0.5f * (zi + yi), dr = 0.5f * (zr - yr), di = 0.5f * (zi - yi);
+			ob.x = er + (c * di - sn * dr);
+			ob.y = ei - (sn * di + c * dr);
+		}
+	}
+	__syncthreads();
+	spec_a[k] = oa;
+	spec_b[k] = ob;
+	__syncthreads();
+}
+// two real inverse FFTs
+template <int LOG2L>
+__device__ void irfft_pair(const float2 *spec_a, float *out_a, const float2 *spec_b, float *out_b, float2 *a0, float2 *a1,
+                           float2 *b0, float2 *b1, const AecParams &P, const float2 *tw, const float2 *spl) {
+	const int k = threadIdx.x, L = 1 << LOG2L;
+	float2 za, zb;
+	if (k == 0) {
+		za.x = spec_a[0].x + spec_a[0].y; za.y = spec_a[0].x - spec_a[0].y;
+		zb.x = spec_b[0].x + spec_b[0].y; zb.y = spec_b[0].x - spec_b[0].y;
+	} else {
+		const float c = spl[k].x, sn = spl[k].y;
+		{
+			const float xr = spec_a[k].x, xi = spec_a[k].y, yr = spec_a[L - k].x, yi = -spec_a[L - k].y;
+			const float er = xr + yr, ei = xi + yi, dr = xr - yr, di = xi - yi;
+			const float orr = dr * c - di * sn, oi = dr * sn + di * c;
+			za.x = er - oi; za.y = ei + orr;
+		}
+		{
+			const float xr = spec_b[k].x, xi = spec_b[k].y, yr = spec_b[L - k].x, yi = -spec_b[L - k].y;
+			const float er = xr + yr, ei = xi + yi, dr = xr - yr, di = xi - yi;
+			const float orr = dr * c - di * sn, oi = dr * sn + di * c;
+			zb.x = er - oi; zb.y = ei + orr;
+		}
+	}
+	__syncthreads();
+	a0[k] = za;
+	b0[k] = zb;
+	__syncthreads();
+	float2 *xa = a0, *ya = a1, *xb = b0, *yb = b1;
+	cfft_pair<LOG2L>(xa, ya, xb, yb, tw, +1);
+	const float2 va = xa[k], vb = xb[k];
+	__syncthreads();
+	out_a[2 * k] = va.x; out_a[2 * k + 1] = va.y;
+	out_b[2 * k] = vb.x; out_b[2 * k + 1] = vb.y;
 	__syncthreads();
 }
 
@@ -343,10 +443,14 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		}
 
 		// ---- the pass over the M blocks: foreground output, weight update (+AUMDF constraint), background output.
-		// X_{j+1}, FG_j and W_j are streamed HBM -> shared memory with cp.async, AEC_STAGES blocks ahead of their use;
+		// X_{j+1}, FG_j and W_j are streamed HBM -> shared memory with cp.async, AEC_STAGES-1 blocks ahead of their use;
 		// every thread copies and later reads only its own bin, so the pipeline needs no block barrier, only
-		// cp.async.wait_group.
+		// cp.async.wait_group. The stage loop is unrolled so that all shared-memory offsets are immediates.
+		// Deferred foreground refresh: when the previous frame decided "foreground := background" (IN_FG_PENDING), the
+		// copy is not done as a separate pass; here the W_j just loaded (still the previous frame's final value) IS the
+		// foreground block: it is used as such and written to FG_j on the way (no FG read, no extra W read).
 		const bool do_update = si[IN_SATURATED] == 0;
+		const bool fg_pending = si[IN_FG_PENDING] != 0;
 		const int cc = si[IN_CANCEL_COUNT] + 1; // st->cancel_count++ at the top of the frame
 		const int constr_j = cc % (M - 1) + 1;
 		// |W_j|^2 is only consumed by mdf_adjust_prop once the filter counts as adapted (or is about to)
@@ -356,85 +460,97 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		const float p1 = power_1[t], p1n = power_1[F]; // p1n only meaningful for thread 0 (Nyquist)
 		float2 xj = specA[t];                          // X_0 (just computed)
 		{
-			const float2 *gXt = X + t;
-			const float2 *gFt = FG + t;
-			float2 *gWt = W + t;
-			int slot_pf = head + 1; // ring slot of X_{j+1} for the block being prefetched
-			if (slot_pf > M) slot_pf = 0;
-			auto prefetch = [&](int jj, int stage) {
-				float2 *dst = pipe + (size_t)stage * 3 * F + t;
-				cp_async8(dst, gXt + (size_t)slot_pf * F);
-				cp_async8(dst + F, gFt + (size_t)jj * F);
-				cp_async8(dst + 2 * F, gWt + (size_t)jj * F);
-				slot_pf = slot_pf + 1 > M ? 0 : slot_pf + 1;
+			const float2 *gX_pf = X + (size_t)(head + 1 > M ? 0 : head + 1) * F + t; // X_{j+1} of the block being prefetched
+			const float2 *gX_end = X + (size_t)(M + 1) * F + t;                       // ring wrap
+			const float2 *gF_pf = FG + t;
+			const float2 *gW_pf = W + t;
+			float2 *gW_st = W + t, *gF_st = FG + t;
+			float2 *pipe_t = pipe + t;
+			auto prefetch = [&](int stage) {
+				float2 *dst = pipe_t + stage * 3 * F;
+				cp_async8(dst, gX_pf);
+				if (!fg_pending) cp_async8(dst + F, gF_pf);
+				cp_async8(dst + 2 * F, gW_pf);
+				gX_pf += F;
+				if (gX_pf == gX_end) gX_pf = X + t;
+				gF_pf += F;
+				gW_pf += F;
 			};
 #pragma unroll
 			for (int pj = 0; pj < AEC_STAGES - 1; ++pj) {
-				if (pj < M) prefetch(pj, pj);
+				if (pj < M) prefetch(pj);
 				cp_async_commit();
 			}
-			int stage = 0;
-			for (int j = 0; j < M; ++j) {
-				{ // keep AEC_STAGES-1 blocks in flight
-					const int jn = j + AEC_STAGES - 1;
-					int st_n = stage + AEC_STAGES - 1;
-					if (st_n >= AEC_STAGES) st_n -= AEC_STAGES;
-					if (jn < M) prefetch(jn, st_n);
-					cp_async_commit();
-				}
-				cp_async_wait<AEC_STAGES - 1>();
-				const float2 *src = pipe + (size_t)stage * 3 * F + t;
-				const float2 xj1 = src[0];
-				const float2 fg = src[F];
-				float2 w = src[2 * F];
-				stage = stage + 1 == AEC_STAGES ? 0 : stage + 1;
-				// foreground: Y += X_j * FG_j (spectral_mul_accum; bin 0 carries two real products)
-				if (t == 0) {
-					yfg.x += xj.x * fg.x;
-					yfg.y += xj.y * fg.y;
-				} else {
-					yfg.x += (xj.x * fg.x - xj.y * fg.y);
-					yfg.y += (xj.y * fg.x + xj.x * fg.y);
-				}
-				// gradient: W_j += prop_j * power_1 * conj(X_{j+1}) * E  (weighted_spectral_mul_conj)
-				if (do_update) {
-					const float pj = prop[j];
-					if (t == 0) {
-						w.x += (pj * p1) * (xj1.x * Ep.x);
-						w.y += (pj * p1n) * (xj1.y * Ep.y);
-					} else {
-						const float Wg = pj * p1;
-						w.x += Wg * (xj1.x * Ep.x + xj1.y * Ep.y);
-						w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
+			for (int j0 = 0; j0 < M; j0 += AEC_STAGES) {
+#pragma unroll
+				for (int sidx = 0; sidx < AEC_STAGES; ++sidx) {
+					const int j = j0 + sidx;
+					if (j < M) {
+						// keep AEC_STAGES-1 blocks in flight: the slot freed by block j-1 receives block j+STAGES-1
+						if (j + AEC_STAGES - 1 < M) prefetch((sidx + AEC_STAGES - 1) % AEC_STAGES);
+						cp_async_commit();
+						cp_async_wait<AEC_STAGES - 1>();
+						const float2 *src = pipe_t + sidx * 3 * F;
+						const float2 xj1 = src[0];
+						float2 w = src[2 * F];
+						float2 fg;
+						if (fg_pending) {
+							fg = w;
+							*gF_st = w;
+						} else {
+							fg = src[F];
+						}
+						// foreground: Y += X_j * FG_j (spectral_mul_accum; bin 0 carries two real products)
+						if (t == 0) {
+							yfg.x += xj.x * fg.x;
+							yfg.y += xj.y * fg.y;
+						} else {
+							yfg.x += (xj.x * fg.x - xj.y * fg.y);
+							yfg.y += (xj.y * fg.x + xj.x * fg.y);
+						}
+						// gradient: W_j += prop_j * power_1 * conj(X_{j+1}) * E  (weighted_spectral_mul_conj)
+						if (do_update) {
+							const float pj = prop[j];
+							if (t == 0) {
+								w.x += (pj * p1) * (xj1.x * Ep.x);
+								w.y += (pj * p1n) * (xj1.y * Ep.y);
+							} else {
+								const float Wg = pj * p1;
+								w.x += Wg * (xj1.x * Ep.x + xj1.y * Ep.y);
+								w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
+							}
+						}
+						// AUMDF: constrain block 0 and one rotating block (IFFT, zero second half, FFT)
+						const bool constrained = j == 0 || j == constr_j;
+						if (constrained) {
+							specB[t] = w;
+							__syncthreads();
+							irfft<LOG2L>(specB, tmpv, bufa, bufb, P, tw, spl);
+							tmpv[F + t] = 0.f;
+							__syncthreads();
+							rfft<LOG2L>(tmpv, specB, bufa, bufb, P, tw, spl);
+							w = specB[t];
+						}
+						if (do_update || constrained) *gW_st = w;
+						gW_st += F;
+						gF_st += F;
+						// |W_j|^2 partial for next frame's mdf_adjust_prop
+						if (need_wnorm) {
+							float n2 = w.x * w.x + w.y * w.y;
+							n2 = warp_sum(n2);
+							if (lane == 0) wpart[j * 8 + warp] = n2;
+						}
+						// background: Y += X_j * W_j
+						if (t == 0) {
+							ybg.x += xj.x * w.x;
+							ybg.y += xj.y * w.y;
+						} else {
+							ybg.x += (xj.x * w.x - xj.y * w.y);
+							ybg.y += (xj.y * w.x + xj.x * w.y);
+						}
+						xj = xj1;
 					}
 				}
-				// AUMDF: constrain block 0 and one rotating block (IFFT, zero second half, FFT)
-				const bool constrained = j == 0 || j == constr_j;
-				if (constrained) {
-					specB[t] = w;
-					__syncthreads();
-					irfft<LOG2L>(specB, tmpv, bufa, bufb, P, tw, spl);
-					tmpv[F + t] = 0.f;
-					__syncthreads();
-					rfft<LOG2L>(tmpv, specB, bufa, bufb, P, tw, spl);
-					w = specB[t];
-				}
-				if (do_update || constrained) gWt[(size_t)j * F] = w;
-				// |W_j|^2 partial for next frame's mdf_adjust_prop
-				if (need_wnorm) {
-					float n2 = w.x * w.x + w.y * w.y;
-					n2 = warp_sum(n2);
-					if (lane == 0) wpart[j * 8 + warp] = n2;
-				}
-				// background: Y += X_j * W_j
-				if (t == 0) {
-					ybg.x += xj.x * w.x;
-					ybg.y += xj.y * w.y;
-				} else {
-					ybg.x += (xj.x * w.x - xj.y * w.y);
-					ybg.y += (xj.y * w.x + xj.x * w.y);
-				}
-				xj = xj1;
 			}
 			cp_async_wait<0>();
 		}
@@ -444,22 +560,23 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			for (int w8 = 0; w8 < nwarps; ++w8) s += wpart[t * 8 + w8];
 			S[ly.wnorm + t] = s;
 		}
-		if (!do_update && t == 0) si[IN_SATURATED]--;
+		if (t == 0) {
+			if (!do_update) si[IN_SATURATED]--;
+			si[IN_FG_PENDING] = 0; // the foreground array is materialised again
+		}
 
-		// ---- foreground error
+		// ---- foreground and background filter outputs (one paired inverse transform)
+		float2 *pc0 = pipe, *pc1 = pipe + L; // the cp.async ring is idle outside the block pass: scratch for the pair
 		specA[t] = yfg;
+		specB[t] = ybg;
 		__syncthreads();
-		irfft<LOG2L>(specA, ebuf, bufa, bufb, P, tw, spl);
+		irfft_pair<LOG2L>(specA, ebuf, specB, ybuf, bufa, bufb, pc0, pc1, P, tw, spl);
 		{
 			const float v = input[t] - ebuf[t + F];
 			__syncthreads();
 			ebuf[t] = v;
 		}
 		float Sff = block_sum(ebuf[t] * ebuf[t], red);
-		// ---- background error
-		specA[t] = ybg;
-		__syncthreads();
-		irfft<LOG2L>(specA, ybuf, bufa, bufb, P, tw, spl);
 		float dd = ebuf[t + F] - ybuf[t + F];
 		float Dbf = 10 + block_sum(dd * dd, red);
 		ebuf[t] = input[t] - ybuf[t + F];
@@ -470,7 +587,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		float Davg2 = .85f * sc[SC_DAVG2] + .15f * (Sff - See);
 		float Dvar1 = .36f * sc[SC_DVAR1] + .16f * Sff * Dbf;
 		float Dvar2 = .7225f * sc[SC_DVAR2] + .0225f * Sff * Dbf;
-		int update_foreground = 0;
+		int update_foreground = 0, fg_refresh = 0;
 		if ((Sff - See) * fabsf(Sff - See) > (Sff * Dbf)) update_foreground = 1;
 		else if ((Davg1 * fabsf(Davg1)) > (.5f * Dvar1)) update_foreground = 1;
 		else if ((Davg2 * fabsf(Davg2)) > (.25f * Dvar2)) update_foreground = 1;
@@ -478,18 +595,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		if (update_foreground) {
 			Davg1 = Davg2 = 0;
 			Dvar1 = Dvar2 = 0;
-			{ // copy the background filter to the foreground, 4 blocks in flight per thread
-				int j = 0;
-				for (; j + 4 <= M; j += 4) {
-					const float2 a0 = W[(size_t)j * F + t], a1 = W[(size_t)(j + 1) * F + t];
-					const float2 a2 = W[(size_t)(j + 2) * F + t], a3 = W[(size_t)(j + 3) * F + t];
-					FG[(size_t)j * F + t] = a0;
-					FG[(size_t)(j + 1) * F + t] = a1;
-					FG[(size_t)(j + 2) * F + t] = a2;
-					FG[(size_t)(j + 3) * F + t] = a3;
-				}
-				for (; j < M; ++j) FG[(size_t)j * F + t] = W[(size_t)j * F + t];
-			}
+			fg_refresh = 1; // foreground := background, materialised lazily by the next frame's block pass
 			ebuf[t + F] = P.window[t + F] * ebuf[t + F] + P.window[t] * ybuf[t + F];
 		} else {
 			int reset_background = 0;
@@ -517,6 +623,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			}
 		}
 		if (t == 0) {
+			if (fg_refresh) si[IN_FG_PENDING] = 1;
 			sc[SC_DAVG1] = Davg1;
 			sc[SC_DAVG2] = Davg2;
 			sc[SC_DVAR1] = Dvar1;
@@ -552,10 +659,10 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		float Sey = block_sum(ebuf[t + F] * ybuf[t + F], red);
 		float Syy = block_sum(ybuf[t + F] * ybuf[t + F], red);
 		float Sdd = block_sum(input[t] * input[t], red);
-		rfft<LOG2L>(ebuf, Eprev, bufa, bufb, P, tw, spl); // E (kept for the next frame's gradient)
 		ybuf[t] = 0.f;
 		__syncthreads();
-		rfft<LOG2L>(ybuf, specB, bufa, bufb, P, tw, spl); // Y
+		// E (kept for the next frame's gradient) and Y in one paired transform
+		rfft_pair<LOG2L>(ebuf, Eprev, ybuf, specB, bufa, bufb, pc0, pc1, P, tw, spl);
 		// Rf -> vec1, Yf -> vec2, Xf -> vec3 (F+1 bins; bin F is the Nyquist term held by thread 0)
 		{
 			const float2 e = Eprev[t], y = specB[t], x0 = X[(size_t)head * F + t];
@@ -608,6 +715,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 				si[IN_SCREWED] = 0;
 				si[IN_SATURATED] = 0;
 				si[IN_ADAPTED] = 0;
+				si[IN_FG_PENDING] = 0;
 				sc[SC_NOTCH0] = sc[SC_NOTCH1] = 0;
 				sc[SC_MEMD] = sc[SC_MEME] = sc[SC_MEMX] = 0;
 				sc[SC_SUM_ADAPT] = 0;
@@ -1164,6 +1272,20 @@ int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, in
 	return MSB200_OK;
 }
 
+// the foreground array lags by one frame when a refresh is pending (see the block pass): logically FG == W then
+static int aec_fg_pending(msb200_aec *a, int stream, int *pending, int clear) {
+	int *d = reinterpret_cast<int *>(a->dS + (size_t)stream * a->P.lay.total + a->P.lay.ints) + IN_FG_PENDING;
+	cudaStream_t s = a->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(pending, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	if (clear && *pending) {
+		int zero = 0;
+		MSB200_CUDA(cudaMemcpyAsync(d, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
+		MSB200_CUDA(cudaStreamSynchronize(s));
+	}
+	return MSB200_OK;
+}
+
 // blob = {magic, F, M, rate} + W [M][F] float2 + FG [M][F] float2
 size_t msb200_aec_state_blob_size(msb200_aec *a) {
 	return a ? 16 + 2 * sizeof(float2) * a->P.w_stride : 0;
@@ -1175,7 +1297,9 @@ int msb200_aec_get_state_blob(msb200_aec *a, int stream, void *blob, size_t size
 	size_t wb = sizeof(float2) * a->P.w_stride;
 	cudaStream_t s = a->ctx->stream;
 	MSB200_CUDA(cudaMemcpyAsync((char *)blob + 16, a->dW + (size_t)stream * a->P.w_stride, wb, cudaMemcpyDeviceToHost, s));
-	MSB200_CUDA(cudaMemcpyAsync((char *)blob + 16 + wb, a->dFG + (size_t)stream * a->P.w_stride, wb, cudaMemcpyDeviceToHost, s));
+	int pending = 0, r = aec_fg_pending(a, stream, &pending, 0);
+	if (r) return r;
+	MSB200_CUDA(cudaMemcpyAsync((char *)blob + 16 + wb, (pending ? a->dW : a->dFG) + (size_t)stream * a->P.w_stride, wb, cudaMemcpyDeviceToHost, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));
 	return MSB200_OK;
 }
@@ -1192,7 +1316,8 @@ int msb200_aec_set_state_blob(msb200_aec *a, int stream, const void *blob, size_
 	MSB200_CUDA(cudaMemcpyAsync(a->dW + (size_t)stream * a->P.w_stride, (const char *)blob + 16, wb, cudaMemcpyHostToDevice, s));
 	MSB200_CUDA(cudaMemcpyAsync(a->dFG + (size_t)stream * a->P.w_stride, (const char *)blob + 16 + wb, wb, cudaMemcpyHostToDevice, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));
-	return MSB200_OK;
+	int pending = 0;
+	return aec_fg_pending(a, stream, &pending, 1);
 }
 
 // probes return data in the ORACLE's layout (speex packed spectra, X ordered newest block first)
@@ -1220,7 +1345,11 @@ int msb200_aec_probe(msb200_aec *a, int stream, const char *what, float *out, in
 		return n;
 	};
 	if (!strcmp(what, "W")) return unpack_blocks(a->dW + (size_t)stream * P.w_stride, M, -1);
-	if (!strcmp(what, "foreground")) return unpack_blocks(a->dFG + (size_t)stream * P.w_stride, M, -1);
+	if (!strcmp(what, "foreground")) {
+		int pending = 0, r = aec_fg_pending(a, stream, &pending, 0);
+		if (r) return r;
+		return unpack_blocks((pending ? a->dW : a->dFG) + (size_t)stream * P.w_stride, M, -1);
+	}
 	if (!strcmp(what, "X")) return unpack_blocks(a->dX + (size_t)stream * P.x_stride, M + 1, a->head);
 	std::vector<float> page((size_t)P.lay.total);
 	MSB200_CUDA(cudaMemcpyAsync(page.data(), a->dS + (size_t)stream * P.lay.total, sizeof(float) * page.size(), cudaMemcpyDeviceToHost, s));
