@@ -60,6 +60,10 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
 __device__ __forceinline__ void cp_async_commit() {
 	asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() {
 	asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
@@ -82,6 +86,29 @@ __device__ float block_sum(float v, float *red) {
 	float s = 0.f;
 	for (int w = 0; w < nw; ++w) s += red[w];
 	return s;
+}
+// three block sums sharing one pair of barriers; each sum has exactly block_sum()'s order. blockDim.x <= 256
+__device__ void block_sum3(float &a, float &b, float &c, float *red) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	a = warp_sum(a);
+	b = warp_sum(b);
+	c = warp_sum(c);
+	__syncthreads();
+	if (lane == 0) {
+		red[warp] = a;
+		red[8 + warp] = b;
+		red[16 + warp] = c;
+	}
+	__syncthreads();
+	float sa = 0.f, sb = 0.f, sc3 = 0.f;
+	for (int w = 0; w < nw; ++w) {
+		sa += red[w];
+		sb += red[8 + w];
+		sc3 += red[16 + w];
+	}
+	a = sa;
+	b = sb;
+	c = sc3;
 }
 __device__ int block_any(int pred) {
 	return __syncthreads_or(pred);
@@ -382,6 +409,39 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		head = (head + M) % (M + 1); // head - 1 mod (M+1): newest block goes to slot `head`
 		const float ss = .35f / (float)M, ss_1 = 1 - ss;
 
+		// ---- frame constants + the block pass's cp.async prologue, issued before the serial input filters so that the
+		// first blocks of X / FG / W are already in shared memory when the pass starts (they do not depend on this frame's
+		// input: X_{j+1} are older ring slots, FG and W the previous frame's filters).
+		// Deferred foreground refresh: when the previous frame decided "foreground := background" (IN_FG_PENDING), the
+		// copy is not a separate pass; the W_j streamed in (still the previous frame's final value) IS the foreground
+		// block: it is used as such and written to FG_j on the way (no FG read, no extra W read).
+		const bool do_update = si[IN_SATURATED] == 0;
+		const bool fg_pending = si[IN_FG_PENDING] != 0;
+		const int cc = si[IN_CANCEL_COUNT] + 1; // st->cancel_count++ at the top of the frame
+		const int constr_j = M > 1 ? cc % (M - 1) + 1 : 0;
+		// |W_j|^2 is only consumed by mdf_adjust_prop once the filter counts as adapted (or is about to)
+		const bool need_wnorm = si[IN_ADAPTED] || sc[SC_SUM_ADAPT] > (float)M - 1.f;
+		const float2 *gX_pf = X + (size_t)(head + 1 > M ? 0 : head + 1) * F + t; // X_{j+1} of the block being prefetched
+		const float2 *const gX_end = X + (size_t)(M + 1) * F + t;                  // ring wrap
+		const float2 *gF_pf = FG + t;
+		const float2 *gW_pf = W + t;
+		float2 *const pipe_t = pipe + t;
+		auto prefetch = [&](int stage) {
+			float2 *dst = pipe_t + stage * 3 * F;
+			cp_async8(dst, gX_pf);
+			if (!fg_pending) cp_async8(dst + F, gF_pf);
+			cp_async8(dst + 2 * F, gW_pf);
+			gX_pf += F;
+			if (gX_pf == gX_end) gX_pf = X + t;
+			gF_pf += F;
+			gW_pf += F;
+		};
+#pragma unroll
+		for (int pj = 0; pj < AEC_STAGES - 1; ++pj) {
+			if (pj < M) prefetch(pj);
+			cp_async_commit();
+		}
+
 		// ---- DC notch (serial IIR, filter_dc_notch16) then pre-emphasis on the microphone
 		tmpv[t] = (float)mic_i;
 		__syncthreads();
@@ -442,45 +502,53 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			__syncthreads();
 		}
 
-		// ---- the pass over the M blocks: foreground output, weight update (+AUMDF constraint), background output.
-		// X_{j+1}, FG_j and W_j are streamed HBM -> shared memory with cp.async, AEC_STAGES-1 blocks ahead of their use;
-		// every thread copies and later reads only its own bin, so the pipeline needs no block barrier, only
-		// cp.async.wait_group. The stage loop is unrolled so that all shared-memory offsets are immediates.
-		// Deferred foreground refresh: when the previous frame decided "foreground := background" (IN_FG_PENDING), the
-		// copy is not done as a separate pass; here the W_j just loaded (still the previous frame's final value) IS the
-		// foreground block: it is used as such and written to FG_j on the way (no FG read, no extra W read).
-		const bool do_update = si[IN_SATURATED] == 0;
-		const bool fg_pending = si[IN_FG_PENDING] != 0;
-		const int cc = si[IN_CANCEL_COUNT] + 1; // st->cancel_count++ at the top of the frame
-		const int constr_j = cc % (M - 1) + 1;
-		// |W_j|^2 is only consumed by mdf_adjust_prop once the filter counts as adapted (or is about to)
-		const bool need_wnorm = si[IN_ADAPTED] || sc[SC_SUM_ADAPT] > (float)M - 1.f;
-		float2 yfg = make_float2(0.f, 0.f), ybg = make_float2(0.f, 0.f);
+		// ---- AUMDF constraint pre-pass. Block 0 and one rotating block get their weight update followed by
+		// IFFT -> zero the second half -> FFT. Their gradient only needs X_{j+1}, E and prop_j, all known here, so both are
+		// updated and constrained now as ONE paired transform; the block pass below then runs without any barrier.
+		// Results stay in shared memory: block 0 in specB, block constr_j in tmpv (viewed as float2[L]).
 		const float2 Ep = Eprev[t];
 		const float p1 = power_1[t], p1n = power_1[F]; // p1n only meaningful for thread 0 (Nyquist)
 		float2 xj = specA[t];                          // X_0 (just computed)
+		float2 *cspec = reinterpret_cast<float2 *>(tmpv);
 		{
-			const float2 *gX_pf = X + (size_t)(head + 1 > M ? 0 : head + 1) * F + t; // X_{j+1} of the block being prefetched
-			const float2 *gX_end = X + (size_t)(M + 1) * F + t;                       // ring wrap
-			const float2 *gF_pf = FG + t;
-			const float2 *gW_pf = W + t;
-			float2 *gW_st = W + t, *gF_st = FG + t;
-			float2 *pipe_t = pipe + t;
-			auto prefetch = [&](int stage) {
-				float2 *dst = pipe_t + stage * 3 * F;
-				cp_async8(dst, gX_pf);
-				if (!fg_pending) cp_async8(dst + F, gF_pf);
-				cp_async8(dst + 2 * F, gW_pf);
-				gX_pf += F;
-				if (gX_pf == gX_end) gX_pf = X + t;
-				gF_pf += F;
-				gW_pf += F;
-			};
-#pragma unroll
-			for (int pj = 0; pj < AEC_STAGES - 1; ++pj) {
-				if (pj < M) prefetch(pj);
-				cp_async_commit();
+			const int s0 = head + 1 > M ? head - M : head + 1; // ring slot of X_1
+			int sj = head + constr_j + 1;                      // ring slot of X_{constr_j+1}
+			if (sj > M) sj -= M + 1;
+			float2 w0 = W[t], w1 = W[(size_t)constr_j * F + t];
+			if (do_update) {
+				const float2 xa = X[(size_t)s0 * F + t], xb = X[(size_t)sj * F + t];
+				const float pj0 = prop[0], pj1 = prop[constr_j];
+				if (t == 0) {
+					w0.x += (pj0 * p1) * (xa.x * Ep.x);
+					w0.y += (pj0 * p1n) * (xa.y * Ep.y);
+					w1.x += (pj1 * p1) * (xb.x * Ep.x);
+					w1.y += (pj1 * p1n) * (xb.y * Ep.y);
+				} else {
+					const float Wg0 = pj0 * p1, Wg1 = pj1 * p1;
+					w0.x += Wg0 * (xa.x * Ep.x + xa.y * Ep.y);
+					w0.y += Wg0 * (-xa.y * Ep.x + xa.x * Ep.y);
+					w1.x += Wg1 * (xb.x * Ep.x + xb.y * Ep.y);
+					w1.y += Wg1 * (-xb.y * Ep.x + xb.x * Ep.y);
+				}
 			}
+			specB[t] = w0;
+			cspec[t] = w1;
+			__syncthreads();
+			float2 *sa = reinterpret_cast<float2 *>(ebuf), *sb = reinterpret_cast<float2 *>(ybuf);
+			irfft_pair<LOG2L>(specB, reinterpret_cast<float *>(specB), cspec, tmpv, bufa, bufb, sa, sb, P, tw, spl);
+			reinterpret_cast<float *>(specB)[F + t] = 0.f;
+			tmpv[F + t] = 0.f;
+			__syncthreads();
+			rfft_pair<LOG2L>(reinterpret_cast<float *>(specB), specB, tmpv, cspec, bufa, bufb, sa, sb, P, tw, spl);
+		}
+
+		// ---- the pass over the M blocks: foreground output, weight update, background output.
+		// X_{j+1}, FG_j and W_j are streamed HBM -> shared memory with cp.async, AEC_STAGES-1 blocks ahead of their use;
+		// every thread copies and later reads only its own bin, so the pipeline needs no block barrier, only
+		// cp.async.wait_group. The stage loop is unrolled so that all shared-memory offsets are immediates.
+		float2 yfg = make_float2(0.f, 0.f), ybg = make_float2(0.f, 0.f);
+		{
+			float2 *gW_st = W + t, *gF_st = FG + t;
 			for (int j0 = 0; j0 < M; j0 += AEC_STAGES) {
 #pragma unroll
 				for (int sidx = 0; sidx < AEC_STAGES; ++sidx) {
@@ -508,8 +576,11 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 							yfg.x += (xj.x * fg.x - xj.y * fg.y);
 							yfg.y += (xj.y * fg.x + xj.x * fg.y);
 						}
-						// gradient: W_j += prop_j * power_1 * conj(X_{j+1}) * E  (weighted_spectral_mul_conj)
-						if (do_update) {
+						const bool constrained = j == 0 || j == constr_j;
+						if (constrained) {
+							w = j == 0 ? specB[t] : cspec[t]; // updated + constrained by the pre-pass
+						} else if (do_update) {
+							// gradient: W_j += prop_j * power_1 * conj(X_{j+1}) * E  (weighted_spectral_mul_conj)
 							const float pj = prop[j];
 							if (t == 0) {
 								w.x += (pj * p1) * (xj1.x * Ep.x);
@@ -519,17 +590,6 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 								w.x += Wg * (xj1.x * Ep.x + xj1.y * Ep.y);
 								w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
 							}
-						}
-						// AUMDF: constrain block 0 and one rotating block (IFFT, zero second half, FFT)
-						const bool constrained = j == 0 || j == constr_j;
-						if (constrained) {
-							specB[t] = w;
-							__syncthreads();
-							irfft<LOG2L>(specB, tmpv, bufa, bufb, P, tw, spl);
-							tmpv[F + t] = 0.f;
-							__syncthreads();
-							rfft<LOG2L>(tmpv, specB, bufa, bufb, P, tw, spl);
-							w = specB[t];
 						}
 						if (do_update || constrained) *gW_st = w;
 						gW_st += F;
@@ -565,22 +625,46 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			si[IN_FG_PENDING] = 0; // the foreground array is materialised again
 		}
 
+		// ---- per-stream state for the statistics and the preprocessor: HBM -> the idle cp.async ring, consumed much
+		// later by the thread that copied it (no barrier needed, only wait_group). Slot k holds F floats at stg[k*F].
+		float *stg = reinterpret_cast<float *>(pipe + 2 * L);
+		enum { SG_POWER, SG_EH, SG_YH, SG_LASTY1, SG_ECHO, SG_INBUF, SG_S, SG_SMIN, SG_STMP, SG_NOISE, SG_OLDPS, SG_ZETA,
+		       SG_OUTBUF, SG_BANDS };
+		cp_async4(stg + SG_POWER * F + t, S + ly.power + t);
+		cp_async4(stg + SG_EH * F + t, S + ly.Eh + t);
+		cp_async4(stg + SG_YH * F + t, S + ly.Yh + t);
+		cp_async4(stg + SG_LASTY1 * F + t, S + ly.last_y + F + t);
+		cp_async4(stg + SG_ECHO * F + t, S + ly.echo_noise + t);
+		cp_async4(stg + SG_INBUF * F + t, S + ly.inbuf + t);
+		cp_async4(stg + SG_S * F + t, S + ly.S + t);
+		cp_async4(stg + SG_SMIN * F + t, S + ly.Smin + t);
+		cp_async4(stg + SG_STMP * F + t, S + ly.Stmp + t);
+		cp_async4(stg + SG_NOISE * F + t, S + ly.noise + t);
+		cp_async4(stg + SG_OLDPS * F + t, S + ly.old_ps + t);
+		cp_async4(stg + SG_ZETA * F + t, S + ly.zeta + t);
+		cp_async4(stg + SG_OUTBUF * F + t, S + ly.outbuf + t);
+		if (t < NB_BANDS) {
+			cp_async4(stg + SG_BANDS * F + t, S + ly.old_ps + F + t);
+			cp_async4(stg + SG_BANDS * F + NB_BANDS + t, S + ly.zeta + F + t);
+		}
+		cp_async_commit();
+
 		// ---- foreground and background filter outputs (one paired inverse transform)
 		float2 *pc0 = pipe, *pc1 = pipe + L; // the cp.async ring is idle outside the block pass: scratch for the pair
 		specA[t] = yfg;
 		specB[t] = ybg;
 		__syncthreads();
 		irfft_pair<LOG2L>(specA, ebuf, specB, ybuf, bufa, bufb, pc0, pc1, P, tw, spl);
+		float Sff, Dbf, See;
 		{
-			const float v = input[t] - ebuf[t + F];
-			__syncthreads();
-			ebuf[t] = v;
+			const float ef = input[t] - ebuf[t + F], dd = ebuf[t + F] - ybuf[t + F], eb = input[t] - ybuf[t + F];
+			Sff = ef * ef;
+			Dbf = dd * dd;
+			See = eb * eb;
+			ebuf[t] = eb;
+			block_sum3(Sff, Dbf, See, red);
+			Dbf = 10 + Dbf;
 		}
-		float Sff = block_sum(ebuf[t] * ebuf[t], red);
-		float dd = ebuf[t + F] - ybuf[t + F];
-		float Dbf = 10 + block_sum(dd * dd, red);
-		ebuf[t] = input[t] - ybuf[t + F];
-		float See = block_sum(ebuf[t] * ebuf[t], red);
 
 		// ---- two-path logic (every thread evaluates the same scalars)
 		float Davg1 = .6f * sc[SC_DAVG1] + .4f * (Sff - See);
@@ -656,9 +740,8 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			ebuf[t] = 0.f;
 			__syncthreads();
 		}
-		float Sey = block_sum(ebuf[t + F] * ybuf[t + F], red);
-		float Syy = block_sum(ybuf[t + F] * ybuf[t + F], red);
-		float Sdd = block_sum(input[t] * input[t], red);
+		float Sey = ebuf[t + F] * ybuf[t + F], Syy = ybuf[t + F] * ybuf[t + F], Sdd = input[t] * input[t];
+		block_sum3(Sey, Syy, Sdd, red);
 		ybuf[t] = 0.f;
 		__syncthreads();
 		// E (kept for the next frame's gradient) and Y in one paired transform
@@ -679,6 +762,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		__syncthreads();
 
 		// ---- sanity checks
+		float lasty0, lasty1; // st->last_y halves as the preprocessor's residual-echo estimate will see them
 		int screwed = si[IN_SCREWED];
 		bool zero_out = false;
 		if (!(Syy >= 0 && Sxx >= 0 && See >= 0) || !(Sff < N * 1e9 && Syy < N * 1e9 && Sxx < N * 1e9)) {
@@ -705,6 +789,9 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 				S[ly.Yh + i] = 0;
 			}
 			S[ly.last_y + t] = 0; // first half only, as the library does
+			cp_async_wait<0>();
+			lasty0 = 0.f;
+			lasty1 = stg[SG_LASTY1 * F + t];
 			Eprev[t] = make_float2(0.f, 0.f);
 			xw[t] = 0;
 			xw[F + t] = 0;
@@ -733,19 +820,24 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			Sxx += Sxx; // the library accumulates the far-end energy a second time at this point
 			// ---- smoothed far-end power, filtered spectra, leak estimate
 			float pey_part = 0.f, pyy_part = 0.f;
+			cp_async_wait<0>(); // the staged state (own column only)
 			for (int j = t; j <= F; j += F) {
-				const float pw = ss_1 * S[ly.power + j] + 1 + ss * vec3[j];
+				const bool nyq = j == F; // thread 0's second trip: the Nyquist entries are not staged
+				const float pw = ss_1 * (nyq ? S[ly.power + j] : stg[SG_POWER * F + j]) + 1 + ss * vec3[j];
 				S[ly.power + j] = pw;
 				vec4[j] = pw;
-				const float Eh_old = S[ly.Eh + j], Yh_old = S[ly.Yh + j];
+				const float Eh_old = nyq ? S[ly.Eh + j] : stg[SG_EH * F + j];
+				const float Yh_old = nyq ? S[ly.Yh + j] : stg[SG_YH * F + j];
 				const float Eh = vec1[j] - Eh_old, Yh = vec2[j] - Yh_old;
 				pey_part += Eh * Yh;
 				pyy_part += Yh * Yh;
 				S[ly.Eh + j] = (1 - P.spec_average) * Eh_old + P.spec_average * vec1[j];
 				S[ly.Yh + j] = (1 - P.spec_average) * Yh_old + P.spec_average * vec2[j];
 			}
-			float Pey = 1.f + block_sum(pey_part, red);
-			float Pyy = 1.f + block_sum(pyy_part, red);
+			float unused3 = 0.f;
+			block_sum3(pey_part, pyy_part, unused3, red);
+			float Pey = 1.f + pey_part;
+			float Pyy = 1.f + pyy_part;
 			Pyy = (float)sqrt((double)Pyy);
 			Pey = Pey / Pyy;
 			float tmp32 = P.beta0 * Syy;
@@ -791,10 +883,11 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 				si[IN_ADAPTED] = adapted;
 			}
 			// ---- last_y (residual echo input for the preprocessor)
-			{
-				const float second = S[ly.last_y + F + t];
-				S[ly.last_y + t] = second;
-				if (adapted) S[ly.last_y + F + t] = (float)(mic_i - out_i);
+			lasty0 = lasty1 = stg[SG_LASTY1 * F + t];
+			S[ly.last_y + t] = lasty0;
+			if (adapted) {
+				lasty1 = (float)(mic_i - out_i);
+				S[ly.last_y + F + t] = lasty1;
 			}
 			__syncthreads();
 		}
@@ -809,53 +902,59 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			if (beta < .03f) beta = .03f;
 			const float beta_1 = 1.f - beta;
 			float *ps = vec1, *echo_noise = vec2, *noise = vec3, *prior = vec4, *gains = vec5;
-			// ---- speex_echo_get_residual: |FFT(window * last_y)|^2 * leak2, truncated to integers
-			tmpv[t] = P.window[t] * S[ly.last_y + t];
-			tmpv[t + F] = P.window[t + F] * S[ly.last_y + F + t];
+			// filterbank weights of this bin, and (threads < 3*Mb) the bin range of the band this thread will sum
+			const float fl = P.filter_left[t], fr = P.filter_right[t];
+			const int bl = P.bank_left[t];
+			const int fb_which = t / Mb, fb_b = t - fb_which * Mb;
+			int bs0 = 0, bs1 = 0, bs2 = 0;
+			if (t < 3 * Mb) {
+				bs0 = fb_b > 0 ? P.band_start[fb_b - 1] : 0;
+				bs1 = P.band_start[fb_b];
+				bs2 = P.band_start[fb_b + 1];
+			}
+			// ---- speex_echo_get_residual's frame (window * last_y) and preprocess_analysis' frame (inbuf | out, windowed):
+			// one paired forward transform -> specB (residual), specA (ft; bin 0 = (ft[0], ft[2N-1]))
+			tmpv[t] = P.window[t] * lasty0;
+			tmpv[t + F] = P.window[t + F] * lasty1;
+			ebuf[t] = stg[SG_INBUF * F + t] * P.pwindow[t];
+			ebuf[F + t] = (float)out_i * P.pwindow[F + t];
+			S[ly.inbuf + t] = (float)out_i;
 			__syncthreads();
-			rfft<LOG2L>(tmpv, specB, bufa, bufb, P, tw, spl);
+			rfft_pair<LOG2L>(tmpv, specB, ebuf, specA, bufa, bufb, pc0, pc1, P, tw, spl);
+			// weighted copies for the three filterbank_compute_bank32() calls: the per-band sums below then only add
+			float *eR = reinterpret_cast<float *>(pc0), *eL = eR + F, *pR = reinterpret_cast<float *>(pc1), *pL = pR + F;
+			float *nR = reinterpret_cast<float *>(bufa), *nL = nR + F;
 			const float leak_now = sc[SC_LEAK];
 			const float leak2 = leak_now > .5f ? 1.f : 2 * leak_now;
 			{
-				const float2 y = specB[t];
+				// residual echo |Y|^2 * leak2, truncated to integers; NaN / absurd-value guard on the DC term
+				const float2 y = specB[t], y0 = specB[0];
 				float re = t == 0 ? y.x * y.x : y.x * y.x + y.y * y.y;
 				re = (float)(int)(leak2 * re);
-				// NaN / absurd-value guard on the DC term (residual_echo[0])
-				if (t == 0) red[0] = re;
-				__syncthreads();
-				const float r0 = red[0];
+				const float r0 = (float)(int)(leak2 * (y0.x * y0.x));
 				if (!(r0 >= 0 && r0 < F * 1e9f)) re = 0;
-				const float a = .6f * S[ly.echo_noise + t];
-				echo_noise[t] = a > re ? a : re;
-				__syncthreads();
-			}
-			filterbank_bank32(echo_noise, echo_noise + F, P);
-			// ---- preprocess_analysis
-			{
-				const float a = S[ly.inbuf + t] * P.pwindow[t];
-				const float b = (float)out_i * P.pwindow[F + t];
-				S[ly.inbuf + t] = (float)out_i;
-				tmpv[t] = a;
-				tmpv[F + t] = b;
-				__syncthreads();
-			}
-			rfft<LOG2L>(tmpv, specA, bufa, bufb, P, tw, spl); // ft stays in specA (bin 0 = (ft[0], ft[2N-1]))
-			{
+				const float a = .6f * stg[SG_ECHO * F + t];
+				const float en = a > re ? a : re;
+				echo_noise[t] = en;
+				eR[t] = fr * en;
+				eL[t] = fl * en;
 				const float2 f = specA[t];
-				ps[t] = t == 0 ? f.x * f.x : f.x * f.x + f.y * f.y;
-				__syncthreads();
+				const float pv = t == 0 ? f.x * f.x : f.x * f.x + f.y * f.y;
+				ps[t] = pv;
+				pR[t] = fr * pv;
+				pL[t] = fl * pv;
 			}
-			filterbank_bank32(ps, ps + F, P);
+			__syncthreads();
 			// ---- update_noise_prob
-			float Sv;
 			const int min_range = nb_adapt < 100 ? 15 : (nb_adapt < 1000 ? 50 : (nb_adapt < 10000 ? 150 : 300));
 			{
-				const float Sold = S[ly.S + t];
+				float Sv;
+				const float Sold = stg[SG_S * F + t];
 				if (t == 0) Sv = .8f * Sold + .2f * ps[0];
 				else if (t == F - 1) Sv = .8f * Sold + .2f * ps[F - 1];
 				else Sv = .8f * Sold + .05f * ps[t - 1] + .1f * ps[t] + .05f * ps[t + 1];
 				S[ly.S + t] = Sv;
-				float smin = S[ly.Smin + t], stmp = S[ly.Stmp + t];
+				float smin = stg[SG_SMIN * F + t], stmp = stg[SG_STMP * F + t];
 				if (nb_adapt == 1) smin = stmp = 0;
 				if (min_count > min_range) {
 					smin = stmp < Sv ? stmp : Sv;
@@ -867,23 +966,43 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 				S[ly.Smin + t] = smin;
 				S[ly.Stmp + t] = stmp;
 				const int update_prob = (.4f * Sv > smin) ? 1 : 0;
-				float nz = S[ly.noise + t];
+				float nz = stg[SG_NOISE * F + t];
 				if (!update_prob || ps[t] < nz) {
 					const float v = beta_1 * nz + beta * ps[t];
 					nz = v > 0 ? v : 0;
 				}
 				noise[t] = nz;
+				nR[t] = fr * nz;
+				nL[t] = fl * nz;
 				S[ly.noise + t] = nz;
-				__syncthreads();
 			}
 			if (min_count > min_range) min_count = 0;
-			filterbank_bank32(noise, noise + F, P);
+			__syncthreads();
+			// ---- the three Bark filterbanks at once (3 * Mb threads; filterbank_compute_bank32's accumulation order)
+			for (int u = t; u < 3 * Mb; u += F) { // one trip unless F < 3 * Mb (8 kHz)
+				const int which = u / Mb, b = u - which * Mb;
+				int c0 = bs0, c1 = bs1, c2 = bs2;
+				if (u != t) {
+					c0 = b > 0 ? P.band_start[b - 1] : 0;
+					c1 = P.band_start[b];
+					c2 = P.band_start[b + 1];
+				}
+				const float *R = which == 0 ? eR : (which == 1 ? pR : nR);
+				const float *Lw = which == 0 ? eL : (which == 1 ? pL : nL);
+				float *dst = which == 0 ? echo_noise : (which == 1 ? ps : noise);
+				float acc = 0.f;
+				if (b > 0)
+					for (int i = c0; i < c1; ++i) acc += R[i];
+				for (int i = c1; i < c2; ++i) acc += Lw[i];
+				dst[F + b] = acc;
+			}
+			__syncthreads();
 			// ---- SNRs over F + Mb entries (thread t: bin t; threads < Mb also band F + t)
 			float post_me[2], old_ps_me[2];
 			for (int r = 0; r < 2; ++r) {
 				const int i = r == 0 ? t : F + t;
 				if (r == 1 && t >= Mb) break;
-				float old_ps = S[ly.old_ps + i];
+				float old_ps = r == 0 ? stg[SG_OLDPS * F + t] : stg[SG_BANDS * F + t];
 				if (nb_adapt == 1) old_ps = ps[i];
 				const float tot_noise = 1.f + noise[i] + echo_noise[i] + 0.f;
 				float post = ps[i] / tot_noise - 1.f;
@@ -899,29 +1018,25 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			__syncthreads();
 			// ---- zeta
 			{
-				float z = S[ly.zeta + t];
+				float z = stg[SG_ZETA * F + t];
 				if (t == 0) z = .7f * z + .3f * prior[0];
 				else if (t < F - 1) z = .7f * z + .15f * prior[t] + .075f * prior[t - 1] + .075f * prior[t + 1];
 				else z = .7f * z + .3f * prior[t];
 				S[ly.zeta + t] = z;
 				if (t < Mb) {
-					float zb = .7f * S[ly.zeta + F + t] + .3f * prior[F + t];
+					float zb = .7f * stg[SG_BANDS * F + Mb + t] + .3f * prior[F + t];
 					S[ly.zeta + F + t] = zb;
 					gains[F + t] = zb; // stash band zeta for Zframe
 				}
 				__syncthreads();
 			}
-			if (t == 0) {
-				float Zframe = 0;
-				for (int i = 0; i < Mb; ++i) Zframe = Zframe + gains[F + i];
-				red[1] = .1f + .899f * qcurve(Zframe / (float)Mb);
-			}
-			__syncthreads();
-			const float Pframe = red[1];
+			// every thread sums the Mb band zetas itself (same order): no broadcast barrier
+			float Zframe = 0;
+			for (int i = 0; i < Mb; ++i) Zframe = Zframe + gains[F + i];
+			const float Pframe = .1f + .899f * qcurve(Zframe / (float)Mb);
 			const float effective_echo_suppress =
 			    (1.f - Pframe) * (float)P.echo_suppress + Pframe * (float)P.echo_suppress_active;
 			// ---- Bark-band gains: gain -> tmpv[0..Mb), gain2 -> tmpv[Mb..2Mb), gain_floor -> tmpv[2Mb..3Mb)
-			__syncthreads();
 			if (t < Mb) {
 				const int i = F + t;
 				const float noise_floor = (float)exp((double)(.2302585f * (float)P.noise_suppress));
@@ -946,9 +1061,9 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			__syncthreads();
 			// ---- linear-frequency gains
 			{
-				const float gain_b = filterbank_psd16(tmpv, t, P);
-				const float p = filterbank_psd16(tmpv + Mb, t, P);
-				const float gfl = filterbank_psd16(tmpv + 2 * Mb, t, P);
+				const float gain_b = tmpv[bl] * fl + tmpv[bl + 1] * fr;
+				const float p = tmpv[Mb + bl] * fl + tmpv[Mb + bl + 1] * fr;
+				const float gfl = tmpv[2 * Mb + bl] * fl + tmpv[2 * Mb + bl + 1] * fr;
 				const float prior_ratio = prior[t] / (prior[t] + 1.f);
 				const float theta = prior_ratio * (1.f + post_me[0]);
 				const float MM = hypergeom_gain(theta);
@@ -973,7 +1088,6 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 					f.x = gains[t] * f.x;
 					f.y = gains[t] * f.y;
 				}
-				__syncthreads();
 				specA[t] = f;
 				__syncthreads();
 			}
@@ -981,7 +1095,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			{
 				const float a = tmpv[t] * P.pwindow[t];
 				const float b = tmpv[F + t] * P.pwindow[F + t];
-				o16[t] = word2int(S[ly.outbuf + t] + a);
+				o16[t] = word2int(stg[SG_OUTBUF * F + t] + a);
 				S[ly.outbuf + t] = b;
 			}
 			if (t == 0) {
