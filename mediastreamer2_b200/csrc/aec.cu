@@ -114,34 +114,43 @@ __device__ int block_any(int pred) {
 	return __syncthreads_or(pred);
 }
 
-// complex radix-2 Stockham FFT of length L = 1 << LOG2L over shared memory, one output element per thread per stage.
-// Mirrors oracle/oracle_aec.c:cfft() operation for operation (stage loop fully unrolled: all index math is shifts and
-// masks with compile-time constants). Returns the buffer holding the result.
-template <int LOG2L> __device__ __forceinline__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int sign) {
-	const int o = threadIdx.x;
+// complex radix-2 Stockham FFT of length L = 1 << LOG2L over shared memory. Thread b < L/2 of a group computes one
+// whole butterfly per stage: inputs x[b], x[b + L/2] (autosort: the same two slots at every stage), outputs
+// y[q + 2sp] = a + c and y[q + 2sp + s] = (a - c) * w^p with q = b mod s, p = b div s. Arithmetic per output is
+// oracle/oracle_aec.c:cfft()'s, operation for operation. Half the CTA works per transform, so a pair of transforms
+// (cfft_pair) costs the same instructions and barriers as one.
+template <int LOG2L>
+__device__ __forceinline__ void cfft_bfly(float2 *x, float2 *y, const float2 *tw, int sign, bool active) {
+	constexpr int H = 1 << (LOG2L - 1);
+	const int b = threadIdx.x & (H - 1);
 #pragma unroll
 	for (int st = 0; st < LOG2L; ++st) {
-		const int s = 1 << st, m = 1 << (LOG2L - 1 - st);
-		const int q = o & (s - 1), tmp = o >> st, r = tmp & 1, p = tmp >> 1;
-		const float2 a = x[q + s * p], b = x[q + s * (p + m)];
-		float2 out;
-		if (!r) {
-			out.x = a.x + b.x;
-			out.y = a.y + b.y;
-		} else {
-			const float2 w = tw[p << st];
+		if (active) {
+			const int s = 1 << st;
+			const int ps = b & ~(s - 1); // p << st
+			const float2 a = x[b], c = x[b + H];
+			const float2 w = tw[ps];
 			const float wr = w.x, wi = sign < 0 ? -w.y : w.y;
-			const float dr = a.x - b.x, di = a.y - b.y;
-			out.x = dr * wr - di * wi;
-			out.y = dr * wi + di * wr;
+			float2 o0, o1;
+			o0.x = a.x + c.x;
+			o0.y = a.y + c.y;
+			const float dr = a.x - c.x, di = a.y - c.y;
+			o1.x = dr * wr - di * wi;
+			o1.y = dr * wi + di * wr;
+			const int oi = b + ps; // q + 2 * s * p
+			y[oi] = o0;
+			y[oi + s] = o1;
 		}
-		y[o] = out;
 		__syncthreads();
 		float2 *sw = x;
 		x = y;
 		y = sw;
 	}
-	return x;
+}
+// single transform: threads < L/2 work. Returns the buffer holding the result.
+template <int LOG2L> __device__ __forceinline__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int sign) {
+	cfft_bfly<LOG2L>(x, y, tw, sign, threadIdx.x < (1 << (LOG2L - 1)));
+	return (LOG2L & 1) ? y : x;
 }
 
 // real forward FFT (spx_fft semantics: input scaled by 1/N): in[N] real (smem) -> spec[L] float2 (smem, bin0=(DC,Nyq))
@@ -200,30 +209,12 @@ __device__ void irfft(const float2 *spec, float *out, float2 *bufa, float2 *bufb
 	__syncthreads();
 }
 
-// ---- paired transforms: two independent FFTs share every stage's index math, twiddle load and barrier
+// ---- paired transforms: two independent FFTs, one per half of the CTA, sharing every stage's barrier
 template <int LOG2L>
 __device__ __forceinline__ void cfft_pair(float2 *&xa, float2 *&ya, float2 *&xb, float2 *&yb, const float2 *tw, int sign) {
-	const int o = threadIdx.x;
-#pragma unroll
-	for (int st = 0; st < LOG2L; ++st) {
-		const int s = 1 << st, m = 1 << (LOG2L - 1 - st);
-		const int q = o & (s - 1), tmp = o >> st, r = tmp & 1, p = tmp >> 1;
-		const int i0 = q + s * p, i1 = q + s * (p + m);
-		const float2 a = xa[i0], b = xa[i1], c = xb[i0], d = xb[i1];
-		float2 oa, ob;
-		if (!r) {
-			oa.x = a.x + b.x; oa.y = a.y + b.y;
-			ob.x = c.x + d.x; ob.y = c.y + d.y;
-		} else {
-			const float2 w = tw[p << st];
-			const float wr = w.x, wi = sign < 0 ? -w.y : w.y;
-			const float dr = a.x - b.x, di = a.y - b.y, er = c.x - d.x, ei = c.y - d.y;
-			oa.x = dr * wr - di * wi; oa.y = dr * wi + di * wr;
-			ob.x = er * wr - ei * wi; ob.y = er * wi + ei * wr;
-		}
-		ya[o] = oa;
-		yb[o] = ob;
-		__syncthreads();
+	const bool second = threadIdx.x >= (1 << (LOG2L - 1)); // lower half of the CTA: transform a, upper half: transform b
+	cfft_bfly<LOG2L>(second ? xb : xa, second ? yb : ya, tw, sign, true);
+	if (LOG2L & 1) {
 		float2 *sw = xa; xa = ya; ya = sw;
 		sw = xb; xb = yb; yb = sw;
 	}
@@ -449,12 +440,21 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			const float radius = P.notch_radius;
 			const float den2 = radius * radius + .7f * (1 - radius) * (1 - radius);
 			float m0 = sc[SC_NOTCH0], m1 = sc[SC_NOTCH1];
-			for (int i = 0; i < F; ++i) {
-				const float vin = tmpv[i];
-				const float vout = m0 + vin;
-				m0 = m1 + 2 * (-vin + radius * vout);
-				m1 = vin - den2 * vout;
-				input[i] = radius * vout;
+			// the recurrence m0 -> vout -> m0 is the critical path: keep it at add, mul, add, fma. 2*a is exact, so
+			// fma(2, a, m1) rounds exactly like m1 + 2*a; samples move through registers four at a time
+#pragma unroll 2
+			for (int i = 0; i < F; i += 4) {
+				const float4 vin4 = *reinterpret_cast<const float4 *>(tmpv + i);
+				const float vin[4] = {vin4.x, vin4.y, vin4.z, vin4.w};
+				float r[4];
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					const float vout = m0 + vin[k];
+					r[k] = radius * vout;
+					m0 = __fmaf_rn(2.f, r[k] - vin[k], m1);
+					m1 = vin[k] - den2 * vout;
+				}
+				*reinterpret_cast<float4 *>(input + i) = make_float4(r[0], r[1], r[2], r[3]);
 			}
 			sc[SC_NOTCH0] = m0;
 			sc[SC_NOTCH1] = m1;
@@ -721,10 +721,16 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		__syncthreads();
 		if (t == 0) {
 			float memE = sc[SC_MEME];
-			for (int i = 0; i < F; ++i) {
-				float tmp_out = tmpv[i] + P.preemph * memE;
-				tmpv[i] = tmp_out;
-				memE = tmp_out;
+			const float pre = P.preemph;
+#pragma unroll 2
+			for (int i = 0; i < F; i += 4) {
+				float4 v = *reinterpret_cast<const float4 *>(tmpv + i);
+				v.x = v.x + pre * memE;
+				v.y = v.y + pre * v.x;
+				v.z = v.z + pre * v.y;
+				v.w = v.w + pre * v.z;
+				memE = v.w;
+				*reinterpret_cast<float4 *>(tmpv + i) = v;
 			}
 			sc[SC_MEME] = memE;
 			if (sat && si[IN_SATURATED] == 0) si[IN_SATURATED] = 1;
