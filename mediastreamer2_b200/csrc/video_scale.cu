@@ -735,6 +735,238 @@ __global__ void __launch_bounds__(SC_THREADS)
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ strip path
+// Register-window variant of the fast path: the 15-bit intermediates of swscale's horizontal pass never touch shared
+// memory. One WARP owns a strip of 128 output columns x R output rows; every lane owns 4 adjacent output columns (two
+// luma pairs, two chroma samples) and walks DOWN the source rows of the strip:
+//   * each source luma row is filtered horizontally (dp2a) straight into a VL-deep register window (slot = source row
+//     mod VL, selected by a warp-uniform switch so that every window access has a static register index); the chroma
+//     rows likewise into a VC-deep window;
+//   * an output row is emitted as soon as its last source row is in the window: vertical taps, pre-rotated on the host
+//     to slot order (StripRow, L1-resident), colour closed form, 12 output bytes per lane as three conflict-free STS.32
+//     into the warp's staging strip;
+//   * the finished strip leaves through one TMA store issued by lane 0; the CTA's only barrier is the mbarrier of the
+//     TMA loads that brought the source boxes in.
+// Compared with scale_rgb_fast_kernel this removes the shared-memory round trip of the intermediates, the per-tile row
+// table, two of the three CTA barriers per tile and all unpacking in the vertical pass (92 -> ~45 instructions/pixel).
+#define ST_WARPS 4
+#define ST_THREADS (32 * ST_WARPS)
+#define ST_TW 128 // output columns per strip (4 per lane)
+#define ST_MAXR 16
+struct StripRow { // per output row, absolute source rows
+	int l_last, c_last; // last luma / chroma source row this output row needs
+	int cc[2];          // chroma vertical taps, rotated: cc[s] multiplies the window slot s (= source row mod VC)
+	int cl[4];          // luma vertical taps, rotated likewise (source row mod VL)
+};
+struct StripParams {
+	const StripRow *rows;
+	int R;                       // output rows per strip (per warp); a tile is ST_WARPS * R rows tall
+	int box_lw, box_lh, box_cw, box_ch;
+	unsigned stage_bytes;        // per-warp staging: R rows x 384 B
+};
+
+template <int OFF>
+__device__ __forceinline__ unsigned lds32(unsigned addr) { // explicit shared-window load (no generic LD)
+	unsigned v;
+	asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+	return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts32(unsigned addr, unsigned v) {
+	asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory");
+}
+
+template <int VL, int VC, bool BGR>
+__global__ void __launch_bounds__(ST_THREADS)
+    scale_rgb_strip_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c,
+                           const __grid_constant__ CUtensorMap map_o, const ScaleParams P, const StripParams S) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const unsigned lbox_bytes = (unsigned)(S.box_lw * S.box_lh), cbox_bytes = (unsigned)(S.box_cw * S.box_ch);
+	const unsigned lbox_al = (lbox_bytes + 127u) & ~127u, cbox_al = (cbox_bytes + 127u) & ~127u;
+	const unsigned char *lbox = smem, *cbox = smem + lbox_al;
+	unsigned char *stage = smem + lbox_al + cbox_al + warp * S.stage_bytes;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + lbox_al + cbox_al + ST_WARPS * S.stage_bytes);
+	const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * (ST_WARPS * S.R), frame = blockIdx.z;
+	const int lx0 = P.hl_pos[x0] & ~15, ly0 = P.vl_pos[y0];
+	const int cb0 = (2 * P.hc_pos[x0 >> 1]) & ~15, cy0 = P.vc_pos[y0];
+	if (t == 0) {
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, lbox_bytes + cbox_bytes);
+		tma_load_3d(smem, &map_l, bar, lx0, ly0, frame);
+		tma_load_3d(smem + lbox_al, &map_c, bar, cb0, cy0, frame);
+	}
+	// ---- per-lane horizontal filter data, fetched while the boxes are in flight
+	const int xq = (x0 >> 1) + 2 * lane; // first of the lane's two column pairs == first of its two chroma samples
+	const int4 lpos = reinterpret_cast<const int4 *>(P.hl_pos)[xq >> 1];
+	const int4 lcA = reinterpret_cast<const int4 *>(P.hl_coef)[xq], lcB = reinterpret_cast<const int4 *>(P.hl_coef)[xq + 1];
+	const int2 cpos = reinterpret_cast<const int2 *>(P.hc_pos)[xq >> 1];
+	const int4 ccf = reinterpret_cast<const int4 *>(P.hc_coef)[xq >> 1]; // 4 taps x 2 chroma samples
+	const int pA = lpos.x - lx0, pB = lpos.z - lx0;
+	const unsigned shA = (unsigned)(pA & 3) * 8, shB = (unsigned)(pB & 3) * 8;
+	const unsigned dA = (unsigned)(lpos.y - lpos.x) * 8, dB = (unsigned)(lpos.w - lpos.z) * 8; // < 32 (host-checked)
+	const unsigned lwA = smem_u32(lbox) + (unsigned)(pA & ~3), lwB = smem_u32(lbox) + (unsigned)(pB & ~3);
+	const unsigned pitch_l = (unsigned)S.box_lw, pitch_c = (unsigned)S.box_cw;
+	const int q0 = 2 * cpos.x - cb0, q1 = 2 * cpos.y - cb0;
+	const unsigned shc0 = (unsigned)(q0 & 3) * 8, shc1 = (unsigned)(q1 & 3) * 8;
+	const unsigned cw0 = smem_u32(cbox) + (unsigned)(q0 & ~3), cw1 = smem_u32(cbox) + (unsigned)(q1 & ~3);
+	// NV21 stores Cr first: the byte-lane selectors of the de-interleave swap, nothing else changes
+	const unsigned sel_u = P.src_fmt == MSB200_PIX_NV21 ? 0x7531u : 0x6420u, sel_v = P.src_fmt == MSB200_PIX_NV21 ? 0x6420u : 0x7531u;
+	const int c_cy = P.cy, c_off = P.yb0 + 0x8000;
+	const int base_r = P.yoffs - (P.crv >> 9), base_g = P.yoffs - (P.cgu >> 9) - (P.cgv >> 9), base_b = P.yoffs - (P.cbu >> 9);
+	const int crv = P.crv, cgu = P.cgu, cgv = P.cgv, cbu = P.cbu;
+
+	const int ys = y0 + warp * S.R, ye = min(ys + S.R, P.dst_h);
+	int WL[VL][4]; // luma window: [slot][column]
+	int WU[VC][2], WV[VC][2];
+#pragma unroll
+	for (int s = 0; s < VL; ++s)
+#pragma unroll
+		for (int k = 0; k < 4; ++k) WL[s][k] = 0;
+#pragma unroll
+	for (int s = 0; s < VC; ++s) WU[s][0] = WU[s][1] = WV[s][0] = WV[s][1] = 0;
+
+	__syncthreads(); // mbarrier initialised
+	mbar_wait(bar, 0);
+	if (ys < ye) {
+		int lrow = P.vl_pos[ys], crow = P.vc_pos[ys];
+		int lslot = lrow % VL, cslot = crow % VC;
+		unsigned la = lwA + (unsigned)(lrow - ly0) * pitch_l, lb = lwB + (unsigned)(lrow - ly0) * pitch_l;
+		unsigned ca = cw0 + (unsigned)(crow - cy0) * pitch_c, cb = cw1 + (unsigned)(crow - cy0) * pitch_c;
+		unsigned og = smem_u32(stage) + (unsigned)lane * 12;
+		const int4 *rtab = reinterpret_cast<const int4 *>(S.rows + ys);
+		int4 ra = __ldg(rtab), rb = __ldg(rtab + 1);
+
+		auto hluma = [&](int(&w)[4]) {
+			const unsigned a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+			const unsigned A0 = __funnelshift_r(a0, a1, shA), A1 = __funnelshift_r(a1, a2, shA);
+			const unsigned B0 = __funnelshift_r(b0, b1, shB), B1 = __funnelshift_r(b1, b2, shB);
+			const unsigned A0b = __funnelshift_r(A0, A1, dA), B0b = __funnelshift_r(B0, B1, dB);
+			w[0] = dp2a_hi(lcA.y, A0, dp2a_lo(lcA.x, A0, 0)) >> 7;
+			w[1] = dp2a_hi(lcA.w, A0b, dp2a_lo(lcA.z, A0b, 0)) >> 7;
+			w[2] = dp2a_hi(lcB.y, B0, dp2a_lo(lcB.x, B0, 0)) >> 7;
+			w[3] = dp2a_hi(lcB.w, B0b, dp2a_lo(lcB.z, B0b, 0)) >> 7;
+			la += pitch_l;
+			lb += pitch_l;
+		};
+		auto hchroma = [&](int(&wu)[2], int(&wv)[2]) {
+			const unsigned a0 = lds32<0>(ca), a1 = lds32<4>(ca), a2 = lds32<8>(ca), b0 = lds32<0>(cb), b1 = lds32<4>(cb), b2 = lds32<8>(cb);
+			const unsigned alo = __funnelshift_r(a0, a1, shc0), ahi = __funnelshift_r(a1, a2, shc0);
+			const unsigned blo = __funnelshift_r(b0, b1, shc1), bhi = __funnelshift_r(b1, b2, shc1);
+			const unsigned e0 = __byte_perm(alo, ahi, sel_u), o0 = __byte_perm(alo, ahi, sel_v);
+			const unsigned e1 = __byte_perm(blo, bhi, sel_u), o1 = __byte_perm(blo, bhi, sel_v);
+			wu[0] = dp2a_hi(ccf.y, e0, dp2a_lo(ccf.x, e0, 0)) >> 7;
+			wv[0] = dp2a_hi(ccf.y, o0, dp2a_lo(ccf.x, o0, 0)) >> 7;
+			wu[1] = dp2a_hi(ccf.w, e1, dp2a_lo(ccf.z, e1, 0)) >> 7;
+			wv[1] = dp2a_hi(ccf.w, o1, dp2a_lo(ccf.z, o1, 0)) >> 7;
+			ca += pitch_c;
+			cb += pitch_c;
+		};
+
+#pragma unroll 1
+		for (int y = ys; y < ye; ++y) {
+			const int l_last = ra.x, c_last = ra.y;
+			const int cc0 = ra.z, cc1 = ra.w;
+			const int4 cl = rb;
+			if (y + 1 < ye) { // next row's table entry: the load overlaps this row's arithmetic
+				ra = __ldg(rtab + 2 * (y + 1 - ys));
+				rb = __ldg(rtab + 2 * (y + 1 - ys) + 1);
+			}
+			// ---- bring the windows up to date (warp-uniform control flow)
+			while (lrow <= l_last) {
+				if (VL == 1) hluma(WL[0]);
+				else if (VL == 2) { if (lslot == 0) hluma(WL[0]); else hluma(WL[VL > 1 ? 1 : 0]); }
+				else {
+					switch (lslot) {
+					case 0: hluma(WL[0]); break;
+					case 1: hluma(WL[VL > 1 ? 1 : 0]); break;
+					case 2: hluma(WL[VL > 2 ? 2 : 0]); break;
+					default: hluma(WL[VL > 3 ? 3 : 0]); break;
+					}
+				}
+				++lrow;
+				lslot = lslot + 1 == VL ? 0 : lslot + 1;
+			}
+			while (crow <= c_last) {
+				if (VC == 1 || cslot == 0) hchroma(WU[0], WV[0]);
+				else hchroma(WU[VC > 1 ? 1 : 0], WV[VC > 1 ? 1 : 0]);
+				++crow;
+				cslot = cslot + 1 == VC ? 0 : cslot + 1;
+			}
+			// ---- vertical taps (yuv2rgb_1 / _2 / _X rounding rules, see scale_rgb_kernel) on the rotated windows
+			int Y[4], U[2], V[2];
+			if (VL == 1) {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) Y[k] = (WL[0][k] + 64) >> 7;
+				if (VC == 1) {
+#pragma unroll
+					for (int h = 0; h < 2; ++h) { U[h] = (WU[0][h] + 64) >> 7; V[h] = (WV[0][h] + 64) >> 7; }
+				} else {
+#pragma unroll
+					for (int h = 0; h < 2; ++h) {
+						U[h] = (WU[0][h] * cc0 + WU[VC - 1][h] * cc1 + (128 << 11)) >> 19;
+						V[h] = (WV[0][h] * cc0 + WV[VC - 1][h] * cc1 + (128 << 11)) >> 19;
+					}
+				}
+			} else if (VL == 2 && VC == 2) {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) Y[k] = (WL[0][k] * cl.x + WL[VL - 1][k] * cl.y) >> 19;
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					U[h] = (WU[0][h] * cc0 + WU[VC - 1][h] * cc1) >> 19;
+					V[h] = (WV[0][h] * cc0 + WV[VC - 1][h] * cc1) >> 19;
+				}
+			} else {
+				const int clv[4] = {cl.x, cl.y, cl.z, cl.w};
+				const int ccv[2] = {cc0, cc1};
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					int a = 1 << 18;
+#pragma unroll
+					for (int s = 0; s < VL; ++s) a += WL[s][k] * clv[s];
+					Y[k] = a >> 19;
+				}
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					int a = 1 << 18, b = 1 << 18;
+#pragma unroll
+					for (int s = 0; s < VC; ++s) { a += WU[s][h] * ccv[s]; b += WV[s][h] * ccv[s]; }
+					U[h] = a >> 19;
+					V[h] = b >> 19;
+				}
+			}
+			unsigned px[4][3];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int Uc = (int)sat_u8(U[h]), Vc = (int)sat_u8(V[h]);
+				const int ar = c_off + (base_r + ((Vc * crv) >> 16)) * c_cy;
+				const int ag = c_off + (base_g + ((Uc * cgu) >> 16) + ((Vc * cgv) >> 16)) * c_cy;
+				const int ab = c_off + (base_b + ((Uc * cbu) >> 16)) * c_cy;
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					const int yc = Y[2 * h + k];
+					const unsigned r = clampq16(yc * c_cy + ar), gq = clampq16(yc * c_cy + ag), b = clampq16(yc * c_cy + ab);
+					px[2 * h + k][0] = BGR ? b : r;
+					px[2 * h + k][1] = gq;
+					px[2 * h + k][2] = BGR ? r : b;
+				}
+			}
+			sts32<0>(og, __byte_perm(__byte_perm(px[0][0], px[0][1], 0x0062), __byte_perm(px[0][2], px[1][0], 0x0062), 0x5410));
+			sts32<4>(og, __byte_perm(__byte_perm(px[1][1], px[1][2], 0x0062), __byte_perm(px[2][0], px[2][1], 0x0062), 0x5410));
+			sts32<8>(og, __byte_perm(__byte_perm(px[2][2], px[3][0], 0x0062), __byte_perm(px[3][1], px[3][2], 0x0062), 0x5410));
+			og += ST_TW * 3;
+		}
+		fence_proxy_async(); // the strip's generic-proxy writes become visible to the TMA engine
+		__syncwarp();
+		if (lane == 0) {
+			tma_store_3d(&map_o, stage, (x0 * 3) >> 2, ys, frame); // rows past dst_h are clipped by the tensor map
+			tma_store_commit();
+			asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+		}
+	}
+}
+
 // planar (YUV420P) output: yuv2planeX_8 / yuv2plane1_8 with the constant-64 dither. One launch per plane kind: the
 // tile is TW x TH of the destination PLANE (luma plane, or the U and V planes together).
 template <int TWP> // tile width in destination-plane samples (64 for interleaved-chroma sources: the CbCr box is 2 bytes/sample)
@@ -840,6 +1072,11 @@ struct msb200_scaler {
 	int packed422; // 0: no; 1: YUYV/YUY2; 2: UYVY  (MSPixConv same-size conversion, no scaling)
 	bool fast_ok;
 	size_t smem_fast;
+	bool strip_ok;      // register-window strip kernel (scale_rgb_strip_kernel) applies
+	int force_path;     // tests/profiling: 0 = best available, 1 = skip the strip kernel, 2 = generic tile kernel only
+	StripParams S;
+	size_t smem_strip;
+	CUtensorMap map_ls, map_cs, map_os; // strip-kernel boxes (taller tiles), output as 32-bit elements
 	msb200_devbuf src, dst;
 };
 
@@ -860,7 +1097,7 @@ static PFN_encodeTiled get_encode() {
 
 // 3-D byte tensor (width bytes, rows, frames) with a (box_w, box_h, 1) box; out-of-bounds elements read as zero
 static int make_map(CUtensorMap *m, const void *base, uint64_t width, uint64_t rows, uint64_t frames, uint64_t row_pitch,
-                    uint64_t frame_pitch, uint32_t box_w, uint32_t box_h) {
+                    uint64_t frame_pitch, uint32_t box_w, uint32_t box_h, bool u32 = false) {
 	PFN_encodeTiled enc = get_encode();
 	if (!enc) {
 		msb200_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -870,7 +1107,7 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t width, uint64_t r
 	cuuint64_t strides[2] = {row_pitch, frame_pitch};
 	cuuint32_t box[3] = {box_w, box_h, 1};
 	cuuint32_t estr[3] = {1, 1, 1};
-	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+	CUresult r = enc(m, u32 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
 	                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
 	                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
@@ -904,6 +1141,28 @@ static int scaler_build_out_map(msb200_scaler *s, const void *d_dst, int n_frame
 	                 (uint64_t)s->dst_bytes, (uint32_t)SCF_HALF, (uint32_t)SC_TH);
 	if (r) return r;
 	s->cached_dst = d_dst;
+	return MSB200_OK;
+}
+
+// strip kernel: source boxes of its taller tiles, destination as rows of 32-bit words (96 per strip row)
+static int scaler_build_strip_maps(msb200_scaler *s, const void *d_src, const void *d_dst, int n_frames) {
+	const ScaleParams &P = s->P;
+	const StripParams &S = s->S;
+	int r;
+	if (!(s->cached_src == d_src && s->cached_frames == n_frames)) {
+		const char *base = (const char *)d_src;
+		if ((r = make_map(&s->map_ls, base, (uint64_t)P.src_w, (uint64_t)P.src_h, (uint64_t)n_frames, (uint64_t)P.src_w,
+		                  s->src_bytes, (uint32_t)S.box_lw, (uint32_t)S.box_lh))) return r;
+		if ((r = make_map(&s->map_cs, base + (size_t)P.src_w * P.src_h, (uint64_t)P.chr_src_w * 2, (uint64_t)P.chr_src_h,
+		                  (uint64_t)n_frames, (uint64_t)P.chr_src_w * 2, s->src_bytes, (uint32_t)S.box_cw, (uint32_t)S.box_ch))) return r;
+		s->cached_src = d_src;
+	}
+	if (!(s->cached_dst == d_dst && s->cached_frames == n_frames)) {
+		if ((r = make_map(&s->map_os, d_dst, (uint64_t)P.dst_w * 3 / 4, (uint64_t)P.dst_h, (uint64_t)n_frames, (uint64_t)P.dst_w * 3,
+		                  (uint64_t)s->dst_bytes, (uint32_t)(ST_TW * 3 / 4), (uint32_t)S.R, true))) return r;
+		s->cached_dst = d_dst;
+	}
+	s->cached_frames = n_frames;
 	return MSB200_OK;
 }
 
@@ -951,6 +1210,9 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		s->cached_src = s->cached_dst = nullptr;
 		s->cached_frames = 0;
 		s->fast_ok = false;
+		s->strip_ok = false;
+		s->force_path = 0;
+		memset(&s->S, 0, sizeof(s->S));
 		s->src_bytes = (size_t)src_w * src_h * 2;
 		s->dst_bytes = (size_t)dst_w * dst_h * 3 / 2;
 		*out = s;
@@ -973,6 +1235,9 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	s->cached_frames = 0;
 	s->fast_ok = false;
 	s->smem_fast = 0;
+	s->strip_ok = false;
+	s->force_path = 0;
+	memset(&s->S, 0, sizeof(s->S));
 	ScaleParams &P = s->P;
 	memset(&P, 0, sizeof(P));
 	P.src_w = src_w; P.src_h = src_h; P.dst_w = dst_w; P.dst_h = dst_h; P.src_fmt = src_fmt; P.dst_fmt = dst_fmt;
@@ -1074,6 +1339,58 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
 		MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_fast_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
 	}
+	// ---- strip kernel set-up: strip height, rotated vertical taps per output row, boxes of the taller tile
+	s->strip_ok = false;
+	if (s->fast_ok) {
+		bool ok = true;
+		for (int x = 0; x + 1 < dst_w && ok; x += 2) { // the second column of a pair is reached by a < 32-bit funnel shift
+			const int d = s->hl.pos[(size_t)x + 1] - s->hl.pos[(size_t)x];
+			ok = d >= 0 && d <= 3;
+		}
+		int best_r = 0, best_waste = 1 << 30;
+		for (int R = ST_MAXR; R >= 8; --R) { // least padding rows in the last tile row; ties -> the taller strip
+			const int th = ST_WARPS * R, waste = msb200_div_up(dst_h, th) * th - dst_h;
+			if (waste < best_waste) { best_waste = waste; best_r = R; }
+		}
+		StripParams &S = s->S;
+		S.R = best_r;
+		const int th = ST_WARPS * S.R;
+		S.box_lw = P.box_lw;
+		S.box_cw = P.box_cw;
+		S.box_lh = max_span(s->vl, dst_h, th);
+		S.box_ch = max_span(s->vc, P.chr_dst_h, th);
+		S.stage_bytes = (unsigned)(S.R * ST_TW * 3);
+		ok = ok && S.box_lh <= 256 && S.box_ch <= 256 && (dst_w * 3) % 16 == 0;
+		s->smem_strip = a128((size_t)S.box_lw * S.box_lh) + a128((size_t)S.box_cw * S.box_ch) + (size_t)ST_WARPS * S.stage_bytes + 16 + 128;
+		ok = ok && s->smem_strip <= 100 * 1024;
+		if (ok) {
+			std::vector<StripRow> rows((size_t)dst_h + 1);
+			for (int y = 0; y < dst_h; ++y) {
+				StripRow &r = rows[(size_t)y];
+				memset(&r, 0, sizeof(r));
+				const int lp = s->vl.pos[(size_t)y], cp = s->vc.pos[(size_t)y];
+				r.l_last = lp + P.vl_size - 1;
+				r.c_last = cp + P.vc_size - 1;
+				for (int j = 0; j < P.vl_size; ++j) r.cl[(lp + j) % P.vl_size] = s->vl.coef[(size_t)y * P.vl_size + j];
+				for (int j = 0; j < P.vc_size; ++j) r.cc[(cp + j) % P.vc_size] = s->vc.coef[(size_t)y * P.vc_size + j];
+			}
+			void *d_rows = nullptr;
+			MSB200_CUDA(cudaMalloc(&d_rows, rows.size() * sizeof(StripRow)));
+			MSB200_CUDA(cudaMemcpy(d_rows, rows.data(), rows.size() * sizeof(StripRow), cudaMemcpyHostToDevice));
+			S.rows = (const StripRow *)d_rows;
+			if (s->smem_strip > 48 * 1024) {
+#define STRIP_ATTR(VL, VC)                                                                                             \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_strip)); \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_strip))
+				STRIP_ATTR(4, 2);
+				STRIP_ATTR(2, 2);
+				STRIP_ATTR(1, 2);
+				STRIP_ATTR(1, 1);
+#undef STRIP_ATTR
+			}
+			s->strip_ok = true;
+		}
+	}
 	const size_t mx = s->smem_rgb > s->smem_chroma ? s->smem_rgb : s->smem_chroma;
 	if (mx > 200 * 1024) {
 		msb200_set_error("scaler: tile working set %zu B exceeds shared memory", mx);
@@ -1101,6 +1418,7 @@ void msb200_scaler_destroy(msb200_scaler *s) {
 	if (!s) return;
 	cudaStreamSynchronize(s->ctx->stream);
 	cudaFree(s->d_tables);
+	cudaFree((void *)s->S.rows);
 	s->src.release();
 	s->dst.release();
 	delete s;
@@ -1112,14 +1430,46 @@ size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s) {
 	return s ? s->dst_bytes : 0;
 }
 
+int msb200_scaler_set_path(msb200_scaler *s, int path) {
+	MSB200_CHECK_ARG(s && path >= 0 && path <= 2);
+	s->force_path = path;
+	s->cached_src = s->cached_dst = nullptr; // the paths use different tensor maps
+	return MSB200_OK;
+}
+int msb200_scaler_get_path(msb200_scaler *s) {
+	if (!s || s->packed422 || s->P.dst_fmt == MSB200_PIX_YUV420P) return 0;
+	if (s->strip_ok && s->force_path == 0) return 3;
+	if (s->fast_ok && s->force_path < 2) return 2;
+	return 1;
+}
+
 int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst) {
 	MSB200_CHECK_ARG(s && d_src && d_dst && n_frames > 0 && n_frames <= 65535);
 	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
 	MSB200_CHECK_ARG(((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0);
-	int r = scaler_build_maps(s, d_src, n_frames);
-	if (r) return r;
 	const ScaleParams &P = s->P;
-	if (s->fast_ok && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0) {
+	int r;
+	if (s->strip_ok && !s->force_path && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0) {
+		// register-window strip kernel: one tile (128 columns x ST_WARPS strips) per CTA, x fastest so that neighbouring
+		// tiles share their halos in L2
+		if ((r = scaler_build_strip_maps(s, d_src, d_dst, n_frames))) return r;
+		dim3 grid((unsigned)(P.dst_w / ST_TW), (unsigned)msb200_div_up(P.dst_h, ST_WARPS * s->S.R), (unsigned)n_frames);
+#define STRIP_LAUNCH(VL, VC)                                                                                           \
+	do {                                                                                                               \
+		if (P.dst_fmt == MSB200_PIX_RGB24_REV)                                                                         \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, true>), grid, ST_THREADS, s->smem_strip, s->map_ls, s->map_cs, s->map_os, P, s->S); \
+		else                                                                                                           \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, false>), grid, ST_THREADS, s->smem_strip, s->map_ls, s->map_cs, s->map_os, P, s->S); \
+	} while (0)
+		if (P.vl_size == 4) STRIP_LAUNCH(4, 2);
+		else if (P.vl_size == 2) STRIP_LAUNCH(2, 2);
+		else if (P.vc_size == 2) STRIP_LAUNCH(1, 2);
+		else STRIP_LAUNCH(1, 1);
+#undef STRIP_LAUNCH
+		return MSB200_OK;
+	}
+	if ((r = scaler_build_maps(s, d_src, n_frames))) return r;
+	if (s->fast_ok && s->force_path < 2 && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0) {
 		// persistent fast path: a few CTAs per SM walk the tiles, TMA in (double-buffered) and TMA out
 		if ((r = scaler_build_out_map(s, d_dst, n_frames))) return r;
 		s->cached_frames = n_frames;

@@ -378,6 +378,15 @@ class Scaler:
     def process_dev(self, n_frames: int, d_src: int, d_dst: int):
         check(self.lib.msb200_scaler_process_dev(self.h, n_frames, C.c_void_p(d_src), C.c_void_p(d_dst)))
 
+    def set_path(self, path: int):
+        """tests/profiling: 0 best available, 1 skip the strip kernel, 2 generic tile kernel only (all bit-exact)"""
+        check(self.lib.msb200_scaler_set_path(self.h, path))
+
+    @property
+    def path(self) -> int:
+        """3 strip kernel, 2 persistent tile kernel, 1 generic tile kernel, 0 plane / packed kernels"""
+        return self.lib.msb200_scaler_get_path(self.h)
+
 
 def nv12_to_i420(ctx: Context, frames: np.ndarray, w: int, h: int, rotation: int = 0, y_stride: int | None = None,
                  cbcr_stride: int | None = None, u_first: bool = True, down_scale: bool = False,

@@ -104,6 +104,37 @@ def test_scaler_bit_exact_vs_oracle(ctx, sf, sw, sh, df, dw, dh):
     sc.close()
 
 
+@pytest.mark.parametrize("sf,sw,sh,df,dw,dh", [
+    (_lib.PIX_NV12, 1920, 1080, _lib.PIX_RGB24, 1280, 720),     # cfg4: <4,2> taps, strips of 15 rows
+    (_lib.PIX_NV12, 192, 108, _lib.PIX_RGB24, 128, 72),         # one tile column, strips of 9 rows
+    (_lib.PIX_NV21, 384, 216, _lib.PIX_RGB24_REV, 256, 136),    # NV21 -> BGR24, ragged last tile row (136 = 2*64 + 8)
+    (_lib.PIX_NV12, 256, 144, _lib.PIX_RGB24, 384, 216),        # 1.5x up: <2,2> taps (yuv2rgb_2 rounding)
+    (_lib.PIX_NV21, 256, 144, _lib.PIX_RGB24, 256, 144),        # same size: <1,2> taps (yuv2rgb_1 rounding)
+    (_lib.PIX_NV12, 640, 368, _lib.PIX_RGB24_REV, 512, 288),    # 1.25x down
+])
+def test_scaler_strip_kernel_bit_exact(ctx, sf, sw, sh, df, dw, dh):
+    """the register-window strip kernel (path 3) == oracle == the tile kernels (paths 2 and 1) on the same frames"""
+    L = O.oracle()
+    n = 2
+    frames = _rand_frames(sf, sw, sh, n, seed=sw + dh)
+    frames[1] = np.random.default_rng(dw).integers(0, 256, size=frames.shape[1], dtype=np.uint8)  # full-range noise
+    sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
+    assert sc.path == 3, "geometry should select the strip kernel"
+    got = sc.process(frames)
+    o = L.orc_scaler_new(sw, sh, sf, dw, dh, df)
+    for i in range(n):
+        exp = np.zeros(sc.dst_bytes + 64, np.uint8)
+        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+        bad = np.flatnonzero(got[i] != exp[:-64])
+        assert bad.size == 0, (i, bad.size, bad[:8] // 3 % dw, bad[:8] // 3 // dw)
+    L.orc_scaler_free(o)
+    for path, kind in ((1, 2), (2, 1)):
+        sc.set_path(path)
+        assert sc.path == kind
+        assert np.array_equal(sc.process(frames), got)
+    sc.close()
+
+
 def test_scaler_full_size_cfg4_matches_real_libswscale_digest(ctx):
     """NV12 1080p -> RGB24 720p: SHA-256 of the GPU output == SHA-256 of the real libswscale 9.1.100 output."""
     import hashlib
