@@ -739,30 +739,39 @@ __global__ void __launch_bounds__(SC_THREADS)
 // Register-window variant of the fast path: the 15-bit intermediates of swscale's horizontal pass never touch shared
 // memory. One WARP owns a strip of 128 output columns x R output rows; every lane owns 4 adjacent output columns (two
 // luma pairs, two chroma samples) and walks DOWN the source rows of the strip:
-//   * each source luma row is filtered horizontally (dp2a) straight into a VL-deep register window (slot = source row
-//     mod VL, selected by a warp-uniform switch so that every window access has a static register index); the chroma
-//     rows likewise into a VC-deep window;
-//   * an output row is emitted as soon as its last source row is in the window: vertical taps, pre-rotated on the host
-//     to slot order (StripRow, L1-resident), colour closed form, 12 output bytes per lane as three conflict-free STS.32
-//     into the warp's staging strip;
+//   * the source-row loop is unrolled VL times, so that source row r is filtered horizontally (dp2a) straight into
+//     window slot r mod VL with a static register index; chroma rows go into a VC-deep window the same way;
+//   * an output row is emitted as soon as its last source row is in the window: vertical taps pre-rotated on the host
+//     to slot order and pre-scaled by 32 (StripRow, L1-resident) so that the 8-bit value lands in the top byte of the
+//     32-bit sum — no shift, no clamp (taps are non-negative: the sum cannot leave [0, 2^32)); colour in closed form
+//     with mul.hi on the byte-aligned chroma; channels clamped two at a time (s16x2 min/relu); 12 output bytes per
+//     lane as three conflict-free STS.32 into the warp's staging strip;
 //   * the finished strip leaves through one TMA store issued by lane 0; the CTA's only barrier is the mbarrier of the
 //     TMA loads that brought the source boxes in.
 // Compared with scale_rgb_fast_kernel this removes the shared-memory round trip of the intermediates, the per-tile row
-// table, two of the three CTA barriers per tile and all unpacking in the vertical pass (92 -> ~45 instructions/pixel).
-#define ST_WARPS 4
+// table, two of the three CTA barriers per tile and all unpacking in the vertical pass.
+#define ST_WARPS 6
+#define ST_MIN_CTAS 4 // register budget: 4 x 192 threads x 85 registers fit the file
 #define ST_THREADS (32 * ST_WARPS)
 #define ST_TW 128 // output columns per strip (4 per lane)
 #define ST_MAXR 16
+#define ST_MAX_TX 32 // dst_w <= 4096
+#define ST_MAX_TY 64
 struct StripRow { // per output row, absolute source rows
 	int l_last, c_last; // last luma / chroma source row this output row needs
-	int cc[2];          // chroma vertical taps, rotated: cc[s] multiplies the window slot s (= source row mod VC)
-	int cl[4];          // luma vertical taps, rotated likewise (source row mod VL)
+	int cc[2];          // chroma vertical taps x 32, rotated: cc[s] multiplies window slot s (= source row mod VC)
+	int cl[4];          // luma vertical taps x 32, rotated likewise (source row mod VL)
 };
 struct StripParams {
 	const StripRow *rows;
 	int R;                       // output rows per strip (per warp); a tile is ST_WARPS * R rows tall
 	int box_lw, box_lh, box_cw, box_ch;
 	unsigned stage_bytes;        // per-warp staging: R rows x 384 B
+	unsigned rnd;                // rounding term of the vertical sums, x 32: 1 << 23 (yuv2rgb_X / _1) or 0 (yuv2rgb_2)
+	int k_r, k_g, k_b;           // c_off + base_x * cy: constant part of the per-chroma colour offsets
+	unsigned sel_u, sel_v;       // byte-lane selectors de-interleaving the CbCr (NV12) or CrCb (NV21) samples
+	// box origins per tile column / tile row, in the constant bank: the TMA loads are issued without a global round trip
+	short lx0[ST_MAX_TX], cb0[ST_MAX_TX], ly0[ST_MAX_TY], cy0[ST_MAX_TY];
 };
 
 template <int OFF>
@@ -776,26 +785,35 @@ __device__ __forceinline__ void sts32(unsigned addr, unsigned v) {
 	asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) { // no selector masking, unlike __byte_perm
+	unsigned d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
+
 template <int VL, int VC, bool BGR>
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
     scale_rgb_strip_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c,
                            const __grid_constant__ CUtensorMap map_o, const ScaleParams P, const StripParams S) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	const unsigned lbox_bytes = (unsigned)(S.box_lw * S.box_lh), cbox_bytes = (unsigned)(S.box_cw * S.box_ch);
-	const unsigned lbox_al = (lbox_bytes + 127u) & ~127u, cbox_al = (cbox_bytes + 127u) & ~127u;
-	const unsigned char *lbox = smem, *cbox = smem + lbox_al;
-	unsigned char *stage = smem + lbox_al + cbox_al + warp * S.stage_bytes;
-	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + lbox_al + cbox_al + ST_WARPS * S.stage_bytes);
+	const unsigned cbox_al = (cbox_bytes + 127u) & ~127u, lbox_al = (lbox_bytes + 127u) & ~127u;
+	// layout: [staging x ST_WARPS][chroma box][luma box][mbarrier]; the luma walk may start up to VL-1 rows above its box
+	// (those window slots are overwritten before any output row reads them): that lands in the chroma box, still ours
+	unsigned char *stage = smem + warp * S.stage_bytes;
+	unsigned char *cbox = smem + ST_WARPS * S.stage_bytes;
+	unsigned char *lbox = cbox + cbox_al;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(lbox + lbox_al);
 	const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * (ST_WARPS * S.R), frame = blockIdx.z;
-	const int lx0 = P.hl_pos[x0] & ~15, ly0 = P.vl_pos[y0];
-	const int cb0 = (2 * P.hc_pos[x0 >> 1]) & ~15, cy0 = P.vc_pos[y0];
+	const int lx0 = S.lx0[blockIdx.x], ly0 = S.ly0[blockIdx.y];
+	const int cb0 = S.cb0[blockIdx.x], cy0 = S.cy0[blockIdx.y];
 	if (t == 0) {
 		mbar_init(bar, 1);
 		mbar_expect_tx(bar, lbox_bytes + cbox_bytes);
-		tma_load_3d(smem, &map_l, bar, lx0, ly0, frame);
-		tma_load_3d(smem + lbox_al, &map_c, bar, cb0, cy0, frame);
+		tma_load_3d(lbox, &map_l, bar, lx0, ly0, frame);
+		tma_load_3d(cbox, &map_c, bar, cb0, cy0, frame);
 	}
 	// ---- per-lane horizontal filter data, fetched while the boxes are in flight
 	const int xq = (x0 >> 1) + 2 * lane; // first of the lane's two column pairs == first of its two chroma samples
@@ -803,21 +821,21 @@ __global__ void __launch_bounds__(ST_THREADS)
 	const int4 lcA = reinterpret_cast<const int4 *>(P.hl_coef)[xq], lcB = reinterpret_cast<const int4 *>(P.hl_coef)[xq + 1];
 	const int2 cpos = reinterpret_cast<const int2 *>(P.hc_pos)[xq >> 1];
 	const int4 ccf = reinterpret_cast<const int4 *>(P.hc_coef)[xq >> 1]; // 4 taps x 2 chroma samples
+	const int ys = y0 + warp * S.R, ye = min(ys + S.R, P.dst_h);
+	const int4 *rtab = reinterpret_cast<const int4 *>(S.rows + min(ys, P.dst_h));
+	int4 ra = __ldg(rtab), rb = __ldg(rtab + 1);
 	const int pA = lpos.x - lx0, pB = lpos.z - lx0;
 	const unsigned shA = (unsigned)(pA & 3) * 8, shB = (unsigned)(pB & 3) * 8;
 	const unsigned dA = (unsigned)(lpos.y - lpos.x) * 8, dB = (unsigned)(lpos.w - lpos.z) * 8; // < 32 (host-checked)
-	const unsigned lwA = smem_u32(lbox) + (unsigned)(pA & ~3), lwB = smem_u32(lbox) + (unsigned)(pB & ~3);
 	const unsigned pitch_l = (unsigned)S.box_lw, pitch_c = (unsigned)S.box_cw;
 	const int q0 = 2 * cpos.x - cb0, q1 = 2 * cpos.y - cb0;
 	const unsigned shc0 = (unsigned)(q0 & 3) * 8, shc1 = (unsigned)(q1 & 3) * 8;
-	const unsigned cw0 = smem_u32(cbox) + (unsigned)(q0 & ~3), cw1 = smem_u32(cbox) + (unsigned)(q1 & ~3);
 	// NV21 stores Cr first: the byte-lane selectors of the de-interleave swap, nothing else changes
-	const unsigned sel_u = P.src_fmt == MSB200_PIX_NV21 ? 0x7531u : 0x6420u, sel_v = P.src_fmt == MSB200_PIX_NV21 ? 0x6420u : 0x7531u;
-	const int c_cy = P.cy, c_off = P.yb0 + 0x8000;
-	const int base_r = P.yoffs - (P.crv >> 9), base_g = P.yoffs - (P.cgu >> 9) - (P.cgv >> 9), base_b = P.yoffs - (P.cbu >> 9);
-	const int crv = P.crv, cgu = P.cgu, cgv = P.cgv, cbu = P.cbu;
+	const unsigned sel_u = S.sel_u, sel_v = S.sel_v;
+	const int c_cy = P.cy, crv = P.crv, cgu = P.cgu, cgv = P.cgv, cbu = P.cbu;
+	const int k_r = S.k_r, k_g = S.k_g, k_b = S.k_b;
+	const unsigned rnd = S.rnd;
 
-	const int ys = y0 + warp * S.R, ye = min(ys + S.R, P.dst_h);
 	int WL[VL][4]; // luma window: [slot][column]
 	int WU[VC][2], WV[VC][2];
 #pragma unroll
@@ -829,14 +847,18 @@ __global__ void __launch_bounds__(ST_THREADS)
 
 	__syncthreads(); // mbarrier initialised
 	mbar_wait(bar, 0);
-	if (ys < ye) {
-		int lrow = P.vl_pos[ys], crow = P.vc_pos[ys];
-		int lslot = lrow % VL, cslot = crow % VC;
-		unsigned la = lwA + (unsigned)(lrow - ly0) * pitch_l, lb = lwB + (unsigned)(lrow - ly0) * pitch_l;
-		unsigned ca = cw0 + (unsigned)(crow - cy0) * pitch_c, cb = cw1 + (unsigned)(crow - cy0) * pitch_c;
+	if (ys >= ye) return;
+	{
+		const int lrow0 = ra.x - (VL - 1);           // first luma source row of the strip
+		int row = lrow0 - lrow0 % VL;                // the unrolled walk starts on a multiple of VL: slot == unroll index
+		int crow = ra.y - (VC - 1);
+		int cslot = crow % VC;
+		unsigned la = smem_u32(lbox) + (unsigned)(pA & ~3) + (unsigned)(row - ly0) * pitch_l; // (row - ly0) may be -1..-(VL-1)
+		unsigned lb = smem_u32(lbox) + (unsigned)(pB & ~3) + (unsigned)(row - ly0) * pitch_l;
+		unsigned ca = smem_u32(cbox) + (unsigned)(q0 & ~3) + (unsigned)(crow - cy0) * pitch_c;
+		unsigned cb = smem_u32(cbox) + (unsigned)(q1 & ~3) + (unsigned)(crow - cy0) * pitch_c;
 		unsigned og = smem_u32(stage) + (unsigned)lane * 12;
-		const int4 *rtab = reinterpret_cast<const int4 *>(S.rows + ys);
-		int4 ra = __ldg(rtab), rb = __ldg(rtab + 1);
+		int y = ys;
 
 		auto hluma = [&](int(&w)[4]) {
 			const unsigned a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
@@ -854,8 +876,8 @@ __global__ void __launch_bounds__(ST_THREADS)
 			const unsigned a0 = lds32<0>(ca), a1 = lds32<4>(ca), a2 = lds32<8>(ca), b0 = lds32<0>(cb), b1 = lds32<4>(cb), b2 = lds32<8>(cb);
 			const unsigned alo = __funnelshift_r(a0, a1, shc0), ahi = __funnelshift_r(a1, a2, shc0);
 			const unsigned blo = __funnelshift_r(b0, b1, shc1), bhi = __funnelshift_r(b1, b2, shc1);
-			const unsigned e0 = __byte_perm(alo, ahi, sel_u), o0 = __byte_perm(alo, ahi, sel_v);
-			const unsigned e1 = __byte_perm(blo, bhi, sel_u), o1 = __byte_perm(blo, bhi, sel_v);
+			const unsigned e0 = prmt(alo, ahi, sel_u), o0 = prmt(alo, ahi, sel_v);
+			const unsigned e1 = prmt(blo, bhi, sel_u), o1 = prmt(blo, bhi, sel_v);
 			wu[0] = dp2a_hi(ccf.y, e0, dp2a_lo(ccf.x, e0, 0)) >> 7;
 			wv[0] = dp2a_hi(ccf.y, o0, dp2a_lo(ccf.x, o0, 0)) >> 7;
 			wu[1] = dp2a_hi(ccf.w, e1, dp2a_lo(ccf.z, e1, 0)) >> 7;
@@ -863,99 +885,88 @@ __global__ void __launch_bounds__(ST_THREADS)
 			ca += pitch_c;
 			cb += pitch_c;
 		};
-
+		// one output row from the windows; returns true when the strip is complete
+		auto emit = [&]() -> bool {
+			const int c_last = ra.y;
+			const unsigned cc0 = (unsigned)ra.z, cc1 = (unsigned)ra.w;
+			const unsigned clv[4] = {(unsigned)rb.x, (unsigned)rb.y, (unsigned)rb.z, (unsigned)rb.w};
+			++y;
 #pragma unroll 1
-		for (int y = ys; y < ye; ++y) {
-			const int l_last = ra.x, c_last = ra.y;
-			const int cc0 = ra.z, cc1 = ra.w;
-			const int4 cl = rb;
-			if (y + 1 < ye) { // next row's table entry: the load overlaps this row's arithmetic
-				ra = __ldg(rtab + 2 * (y + 1 - ys));
-				rb = __ldg(rtab + 2 * (y + 1 - ys) + 1);
-			}
-			// ---- bring the windows up to date (warp-uniform control flow)
-			while (lrow <= l_last) {
-				if (VL == 1) hluma(WL[0]);
-				else if (VL == 2) { if (lslot == 0) hluma(WL[0]); else hluma(WL[VL > 1 ? 1 : 0]); }
-				else {
-					switch (lslot) {
-					case 0: hluma(WL[0]); break;
-					case 1: hluma(WL[VL > 1 ? 1 : 0]); break;
-					case 2: hluma(WL[VL > 2 ? 2 : 0]); break;
-					default: hluma(WL[VL > 3 ? 3 : 0]); break;
-					}
-				}
-				++lrow;
-				lslot = lslot + 1 == VL ? 0 : lslot + 1;
-			}
-			while (crow <= c_last) {
+			while (crow <= c_last) { // warp-uniform; at most VC iterations, usually 0 or 1
 				if (VC == 1 || cslot == 0) hchroma(WU[0], WV[0]);
-				else hchroma(WU[VC > 1 ? 1 : 0], WV[VC > 1 ? 1 : 0]);
+				else hchroma(WU[VC - 1], WV[VC - 1]);
 				++crow;
 				cslot = cslot + 1 == VC ? 0 : cslot + 1;
 			}
-			// ---- vertical taps (yuv2rgb_1 / _2 / _X rounding rules, see scale_rgb_kernel) on the rotated windows
-			int Y[4], U[2], V[2];
-			if (VL == 1) {
+			// vertical taps: sum of window x (tap x 32) + rounding x 32; bits 24..31 are the 8-bit sample
+			unsigned Yq[4], U16[2], V16[2];
 #pragma unroll
-				for (int k = 0; k < 4; ++k) Y[k] = (WL[0][k] + 64) >> 7;
-				if (VC == 1) {
+			for (int k = 0; k < 4; ++k) {
+				unsigned a = rnd;
 #pragma unroll
-					for (int h = 0; h < 2; ++h) { U[h] = (WU[0][h] + 64) >> 7; V[h] = (WV[0][h] + 64) >> 7; }
-				} else {
-#pragma unroll
-					for (int h = 0; h < 2; ++h) {
-						U[h] = (WU[0][h] * cc0 + WU[VC - 1][h] * cc1 + (128 << 11)) >> 19;
-						V[h] = (WV[0][h] * cc0 + WV[VC - 1][h] * cc1 + (128 << 11)) >> 19;
-					}
-				}
-			} else if (VL == 2 && VC == 2) {
-#pragma unroll
-				for (int k = 0; k < 4; ++k) Y[k] = (WL[0][k] * cl.x + WL[VL - 1][k] * cl.y) >> 19;
-#pragma unroll
-				for (int h = 0; h < 2; ++h) {
-					U[h] = (WU[0][h] * cc0 + WU[VC - 1][h] * cc1) >> 19;
-					V[h] = (WV[0][h] * cc0 + WV[VC - 1][h] * cc1) >> 19;
-				}
-			} else {
-				const int clv[4] = {cl.x, cl.y, cl.z, cl.w};
-				const int ccv[2] = {cc0, cc1};
-#pragma unroll
-				for (int k = 0; k < 4; ++k) {
-					int a = 1 << 18;
-#pragma unroll
-					for (int s = 0; s < VL; ++s) a += WL[s][k] * clv[s];
-					Y[k] = a >> 19;
-				}
-#pragma unroll
-				for (int h = 0; h < 2; ++h) {
-					int a = 1 << 18, b = 1 << 18;
-#pragma unroll
-					for (int s = 0; s < VC; ++s) { a += WU[s][h] * ccv[s]; b += WV[s][h] * ccv[s]; }
-					U[h] = a >> 19;
-					V[h] = b >> 19;
-				}
+				for (int s = 0; s < VL; ++s) a += (unsigned)WL[s][k] * clv[s];
+				Yq[k] = a >> 24;
 			}
-			unsigned px[4][3];
 #pragma unroll
 			for (int h = 0; h < 2; ++h) {
-				const int Uc = (int)sat_u8(U[h]), Vc = (int)sat_u8(V[h]);
-				const int ar = c_off + (base_r + ((Vc * crv) >> 16)) * c_cy;
-				const int ag = c_off + (base_g + ((Uc * cgu) >> 16) + ((Vc * cgv) >> 16)) * c_cy;
-				const int ab = c_off + (base_b + ((Uc * cbu) >> 16)) * c_cy;
+				unsigned a = rnd, b = rnd;
+				if (VC == 1) {
+					a += (unsigned)WU[0][h] << 17;
+					b += (unsigned)WV[0][h] << 17;
+				} else {
+					a += (unsigned)WU[0][h] * cc0 + (unsigned)WU[VC - 1][h] * cc1;
+					b += (unsigned)WV[0][h] * cc0 + (unsigned)WV[VC - 1][h] * cc1;
+				}
+				U16[h] = __byte_perm(a, 0u, 0x4344); // sample << 16
+				V16[h] = __byte_perm(b, 0u, 0x4344);
+			}
+			// the taps are dead: fetch the next row's entry (the table is padded) under the colour arithmetic
+			rtab += 2;
+			ra = __ldg(rtab);
+			rb = __ldg(rtab + 1);
+			unsigned pk[6]; // clamped channel pairs in output byte order: (c0 g0)(d0 c1)(g1 d1)(c2 g2)(d2 c3)(g3 d3)
+			int q[4][3];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				// table offsets of yuv2rgb in closed form: ((chroma * coef) >> 16) == mul.hi(chroma << 16, coef)
+				const int ar = __mulhi((int)V16[h], crv) * c_cy + k_r;
+				const int ag = (__mulhi((int)U16[h], cgu) + __mulhi((int)V16[h], cgv)) * c_cy + k_g;
+				const int ab = __mulhi((int)U16[h], cbu) * c_cy + k_b;
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
-					const int yc = Y[2 * h + k];
-					const unsigned r = clampq16(yc * c_cy + ar), gq = clampq16(yc * c_cy + ag), b = clampq16(yc * c_cy + ab);
-					px[2 * h + k][0] = BGR ? b : r;
-					px[2 * h + k][1] = gq;
-					px[2 * h + k][2] = BGR ? r : b;
+					const int yc = (int)Yq[2 * h + k];
+					q[2 * h + k][0] = yc * c_cy + (BGR ? ab : ar);
+					q[2 * h + k][1] = yc * c_cy + ag;
+					q[2 * h + k][2] = yc * c_cy + (BGR ? ar : ab);
 				}
 			}
-			sts32<0>(og, __byte_perm(__byte_perm(px[0][0], px[0][1], 0x0062), __byte_perm(px[0][2], px[1][0], 0x0062), 0x5410));
-			sts32<4>(og, __byte_perm(__byte_perm(px[1][1], px[1][2], 0x0062), __byte_perm(px[2][0], px[2][1], 0x0062), 0x5410));
-			sts32<8>(og, __byte_perm(__byte_perm(px[2][2], px[3][0], 0x0062), __byte_perm(px[3][1], px[3][2], 0x0062), 0x5410));
+			// Q16 -> clip_uint8: high halves of two channels side by side, one s16x2 min + relu for both
+			const unsigned lim = 0x00ff00ffu;
+			pk[0] = __vimin_s16x2_relu(__byte_perm((unsigned)q[0][0], (unsigned)q[0][1], 0x7632), lim);
+			pk[1] = __vimin_s16x2_relu(__byte_perm((unsigned)q[0][2], (unsigned)q[1][0], 0x7632), lim);
+			pk[2] = __vimin_s16x2_relu(__byte_perm((unsigned)q[1][1], (unsigned)q[1][2], 0x7632), lim);
+			pk[3] = __vimin_s16x2_relu(__byte_perm((unsigned)q[2][0], (unsigned)q[2][1], 0x7632), lim);
+			pk[4] = __vimin_s16x2_relu(__byte_perm((unsigned)q[2][2], (unsigned)q[3][0], 0x7632), lim);
+			pk[5] = __vimin_s16x2_relu(__byte_perm((unsigned)q[3][1], (unsigned)q[3][2], 0x7632), lim);
+			sts32<0>(og, __byte_perm(pk[0], pk[1], 0x6420));
+			sts32<4>(og, __byte_perm(pk[2], pk[3], 0x6420));
+			sts32<8>(og, __byte_perm(pk[4], pk[5], 0x6420));
 			og += ST_TW * 3;
+			return y == ye;
+		};
+
+		bool done = false;
+#pragma unroll 1
+		while (!done) {
+#pragma unroll
+			for (int s = 0; s < VL; ++s) {
+				if (!done) {
+					hluma(WL[s]);
+#pragma unroll 1
+					while (!done && row == ra.x) done = emit(); // every output row whose last source row this is
+					++row;
+				}
+			}
 		}
 		fence_proxy_async(); // the strip's generic-proxy writes become visible to the TMA engine
 		__syncwarp();
@@ -1343,36 +1354,65 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	s->strip_ok = false;
 	if (s->fast_ok) {
 		bool ok = true;
+		// vertical sums stay inside [0, 2^32) after the x32 pre-scale only with non-negative taps (bilinear: always)
+		for (int16_t c : s->vl.coef) ok = ok && c >= 0;
+		for (int16_t c : s->vc.coef) ok = ok && c >= 0;
 		for (int x = 0; x + 1 < dst_w && ok; x += 2) { // the second column of a pair is reached by a < 32-bit funnel shift
 			const int d = s->hl.pos[(size_t)x + 1] - s->hl.pos[(size_t)x];
 			ok = d >= 0 && d <= 3;
 		}
-		int best_r = 0, best_waste = 1 << 30;
-		for (int R = ST_MAXR; R >= 8; --R) { // least padding rows in the last tile row; ties -> the taller strip
-			const int th = ST_WARPS * R, waste = msb200_div_up(dst_h, th) * th - dst_h;
-			if (waste < best_waste) { best_waste = waste; best_r = R; }
-		}
+		// strip height: the tallest strips (least halo rows recomputed per output row, least padding in the last tile row)
+		// whose tile still lets ST_MIN_CTAS CTAs share an SM's shared memory
 		StripParams &S = s->S;
-		S.R = best_r;
+		long best_cost = -1;
+		for (int R = 4; R <= ST_MAXR; ++R) {
+			const int th = ST_WARPS * R;
+			const size_t sm = a128((size_t)P.box_lw * max_span(s->vl, dst_h, th)) + a128((size_t)P.box_cw * max_span(s->vc, P.chr_dst_h, th)) +
+			                  (size_t)ST_WARPS * R * ST_TW * 3 + 16 + 128;
+			if ((sm + 1024) * ST_MIN_CTAS > 227 * 1024 && R > 4) continue;
+			const long cost = (long)msb200_div_up(dst_h, th) * ST_WARPS * ((long)R * src_h / dst_h + P.vl_size); // luma rows filtered
+			if (best_cost < 0 || cost <= best_cost) { best_cost = cost; S.R = R; }
+		}
 		const int th = ST_WARPS * S.R;
 		S.box_lw = P.box_lw;
 		S.box_cw = P.box_cw;
 		S.box_lh = max_span(s->vl, dst_h, th);
 		S.box_ch = max_span(s->vc, P.chr_dst_h, th);
 		S.stage_bytes = (unsigned)(S.R * ST_TW * 3);
-		ok = ok && S.box_lh <= 256 && S.box_ch <= 256 && (dst_w * 3) % 16 == 0;
+		ok = ok && S.box_lh <= 256 && S.box_ch <= 256 && (dst_w * 3) % 16 == 0 && dst_w / ST_TW <= ST_MAX_TX &&
+		     msb200_div_up(dst_h, th) <= ST_MAX_TY && src_w < 32768 && src_h < 32768;
 		s->smem_strip = a128((size_t)S.box_lw * S.box_lh) + a128((size_t)S.box_cw * S.box_ch) + (size_t)ST_WARPS * S.stage_bytes + 16 + 128;
 		ok = ok && s->smem_strip <= 100 * 1024;
 		if (ok) {
-			std::vector<StripRow> rows((size_t)dst_h + 1);
+			std::vector<StripRow> rows((size_t)dst_h + 2);
 			for (int y = 0; y < dst_h; ++y) {
 				StripRow &r = rows[(size_t)y];
 				memset(&r, 0, sizeof(r));
 				const int lp = s->vl.pos[(size_t)y], cp = s->vc.pos[(size_t)y];
 				r.l_last = lp + P.vl_size - 1;
 				r.c_last = cp + P.vc_size - 1;
-				for (int j = 0; j < P.vl_size; ++j) r.cl[(lp + j) % P.vl_size] = s->vl.coef[(size_t)y * P.vl_size + j];
-				for (int j = 0; j < P.vc_size; ++j) r.cc[(cp + j) % P.vc_size] = s->vc.coef[(size_t)y * P.vc_size + j];
+				for (int j = 0; j < P.vl_size; ++j) r.cl[(lp + j) % P.vl_size] = 32 * s->vl.coef[(size_t)y * P.vl_size + j];
+				for (int j = 0; j < P.vc_size; ++j) r.cc[(cp + j) % P.vc_size] = 32 * s->vc.coef[(size_t)y * P.vc_size + j];
+			}
+			rows[(size_t)dst_h] = rows[(size_t)dst_h - 1]; // padding entries: read (never used) after the last row
+			rows[(size_t)dst_h].l_last = 1 << 30;
+			rows[(size_t)dst_h + 1] = rows[(size_t)dst_h];
+			for (int tx = 0; tx < dst_w / ST_TW; ++tx) {
+				S.lx0[tx] = (short)(s->hl.pos[(size_t)tx * ST_TW] & ~15);
+				S.cb0[tx] = (short)((2 * s->hc.pos[(size_t)tx * ST_TW / 2]) & ~15);
+			}
+			for (int ty = 0; ty * th < dst_h; ++ty) {
+				S.ly0[ty] = (short)s->vl.pos[(size_t)ty * th];
+				S.cy0[ty] = (short)s->vc.pos[(size_t)ty * th];
+			}
+			S.rnd = (P.vl_size == 2 && P.vc_size == 2) ? 0u : 1u << 23;
+			S.sel_u = src_fmt == MSB200_PIX_NV21 ? 0x7531u : 0x6420u;
+			S.sel_v = src_fmt == MSB200_PIX_NV21 ? 0x6420u : 0x7531u;
+			{ // constant parts of the colour offsets, 32-bit wrap-around arithmetic like the kernels
+				const unsigned cy = (unsigned)P.cy, coff = (unsigned)(P.yb0 + 0x8000);
+				S.k_r = (int)(coff + (unsigned)(P.yoffs - (P.crv >> 9)) * cy);
+				S.k_g = (int)(coff + (unsigned)(P.yoffs - (P.cgu >> 9) - (P.cgv >> 9)) * cy);
+				S.k_b = (int)(coff + (unsigned)(P.yoffs - (P.cbu >> 9)) * cy);
 			}
 			void *d_rows = nullptr;
 			MSB200_CUDA(cudaMalloc(&d_rows, rows.size() * sizeof(StripRow)));
