@@ -308,8 +308,10 @@ MSB200_API size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s);
 MSB200_API int msb200_scaler_process(msb200_scaler *s, int n_frames, const uint8_t *src, uint8_t *dst);
 MSB200_API int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst);
 /* Kernel selection, for tests and profiling only (every path is bit-exact with the others): path 0 = best available,
- * 1 = skip the register-window strip kernel, 2 = generic tile kernel only. get_path reports what process() will launch:
- * 3 = strip kernel, 2 = persistent tile kernel, 1 = generic tile kernel, 0 = plane / packed-4:2:2 kernels. */
+ * 1 = persistent tile kernel, 2 = generic tile kernel, 3 = register-window strip kernel (the default where it applies),
+ * 4 = per-warp streaming variant of the strip kernel (experimental: no vertical halo, but slower on B200 today).
+ * get_path reports what process() will launch: 4 = streaming kernel, 3 = strip kernel, 2 = persistent tile kernel,
+ * 1 = generic tile kernel, 0 = plane / packed-4:2:2 kernels. */
 MSB200_API int msb200_scaler_set_path(msb200_scaler *s, int path);
 MSB200_API int msb200_scaler_get_path(msb200_scaler *s);
 

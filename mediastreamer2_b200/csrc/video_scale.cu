@@ -774,6 +774,14 @@ struct StripParams {
 	short lx0[ST_MAX_TX], cb0[ST_MAX_TX], ly0[ST_MAX_TY], cy0[ST_MAX_TY];
 };
 
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ int4 lds128(unsigned addr) {
+	int4 v;
+	asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
 template <int OFF>
 __device__ __forceinline__ unsigned lds32(unsigned addr) { // explicit shared-window load (no generic LD)
 	unsigned v;
@@ -806,6 +814,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 	unsigned char *cbox = smem + ST_WARPS * S.stage_bytes;
 	unsigned char *lbox = cbox + cbox_al;
 	uint64_t *bar = reinterpret_cast<uint64_t *>(lbox + lbox_al);
+	const unsigned s_tab = smem_u32(lbox + lbox_al) + 16; // the tile's rows of the vertical-tap table (+1), 32 B each
 	const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * (ST_WARPS * S.R), frame = blockIdx.z;
 	const int lx0 = S.lx0[blockIdx.x], ly0 = S.ly0[blockIdx.y];
 	const int cb0 = S.cb0[blockIdx.x], cy0 = S.cy0[blockIdx.y];
@@ -822,8 +831,9 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 	const int2 cpos = reinterpret_cast<const int2 *>(P.hc_pos)[xq >> 1];
 	const int4 ccf = reinterpret_cast<const int4 *>(P.hc_coef)[xq >> 1]; // 4 taps x 2 chroma samples
 	const int ys = y0 + warp * S.R, ye = min(ys + S.R, P.dst_h);
-	const int4 *rtab = reinterpret_cast<const int4 *>(S.rows + min(ys, P.dst_h));
-	int4 ra = __ldg(rtab), rb = __ldg(rtab + 1);
+	if (t < 2 * (ST_WARPS * S.R + 1)) // the table is padded: rows past dst_h exist
+		cp_async16(s_tab + t * 16, reinterpret_cast<const char *>(S.rows + y0) + t * 16);
+	asm volatile("cp.async.commit_group;\n" ::: "memory");
 	const int pA = lpos.x - lx0, pB = lpos.z - lx0;
 	const unsigned shA = (unsigned)(pA & 3) * 8, shB = (unsigned)(pB & 3) * 8;
 	const unsigned dA = (unsigned)(lpos.y - lpos.x) * 8, dB = (unsigned)(lpos.w - lpos.z) * 8; // < 32 (host-checked)
@@ -845,10 +855,13 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 #pragma unroll
 	for (int s = 0; s < VC; ++s) WU[s][0] = WU[s][1] = WV[s][0] = WV[s][1] = 0;
 
-	__syncthreads(); // mbarrier initialised
+	asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+	__syncthreads(); // mbarrier initialised, table rows in place
 	mbar_wait(bar, 0);
 	if (ys >= ye) return;
 	{
+		unsigned rtab = s_tab + (unsigned)(warp * S.R) * 32;
+		int4 ra = lds128(rtab), rb = lds128(rtab + 16);
 		const int lrow0 = ra.x - (VL - 1);           // first luma source row of the strip
 		int row = lrow0 - lrow0 % VL;                // the unrolled walk starts on a multiple of VL: slot == unroll index
 		int crow = ra.y - (VC - 1);
@@ -921,9 +934,9 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 				V16[h] = __byte_perm(b, 0u, 0x4344);
 			}
 			// the taps are dead: fetch the next row's entry (the table is padded) under the colour arithmetic
-			rtab += 2;
-			ra = __ldg(rtab);
-			rb = __ldg(rtab + 1);
+			rtab += 32;
+			ra = lds128(rtab);
+			rb = lds128(rtab + 16);
 			unsigned pk[6]; // clamped channel pairs in output byte order: (c0 g0)(d0 c1)(g1 d1)(c2 g2)(d2 c3)(g3 d3)
 			int q[4][3];
 #pragma unroll
@@ -976,6 +989,315 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 			asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 		}
 	}
+}
+
+// ------------------------------------------------------------------------------------------------ stream path
+// The strip kernel's arithmetic with the tile structure removed: every WARP is an independent software pipeline that
+// walks one 128-column strip of a frame from the top of a segment to its bottom.
+//   * source rows arrive through per-warp TMA rings (luma: 2 stages x 8 rows, chroma: 2 stages x 4 rows, one mbarrier
+//     per stage; lane 0 refills a stage as soon as the warp has consumed it), so HBM latency is hidden by the warp's
+//     own prefetch, not by occupancy, and no source row is ever filtered twice (no vertical halo between tiles);
+//   * the per-row vertical-tap table streams through a 2 x 16-row ring with cp.async (LDGSTS);
+//   * output rows leave in groups of ST_OR rows through double-buffered TMA stores;
+//   * there is no CTA-wide barrier at all; a CTA is just a bundle of SW_WARPS warps, and the grid is persistent: warps
+//     stride over the (frame, segment, strip) tasks.
+#define SW_WARPS 5    // warps per CTA: 4 CTAs x 5 warps x 96 registers fill the register file
+#define SW_MAXREG 96
+#define SW_THREADS (32 * SW_WARPS)
+#define ST_OR 5  // output rows per TMA store
+#define ST_LCH 8 // luma source rows per ring stage
+#define ST_CCH 4 // chroma source rows per ring stage
+#define ST_TCH 16 // vertical-tap table rows per ring stage
+struct StreamParams {
+	const StripRow *rows;        // dst_h entries + padding (the table ring reads up to 2 stages ahead)
+	int tiles_x, n_seg, seg_rows, n_tasks;
+	int box_lw, box_cw;          // TMA box widths in bytes (luma, interleaved chroma); heights are ST_LCH / ST_CCH
+	unsigned l_stage, c_stage;   // ring stage strides in bytes (128-byte multiples)
+	unsigned c_off, t_off, o_off, b_off, warp_bytes; // per-warp shared-memory carve-up
+	unsigned rnd;
+	int k_r, k_g, k_b;
+	unsigned sel_u, sel_v;
+	short lx0[ST_MAX_TX], cb0[ST_MAX_TX];
+};
+
+__device__ __forceinline__ void mbar_init_a(unsigned bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
+	unsigned ok;
+	do {
+		asm volatile("{\n"
+		             ".reg .pred p;\n"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		             "selp.u32 %0, 1, 0, p;\n"
+		             "}\n"
+		             : "=r"(ok)
+		             : "r"(bar), "r"(parity)
+		             : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d_a(unsigned smem_dst, const CUtensorMap *map, unsigned bar, int c0, int c1, int c2) {
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_dst),
+	             "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_a(const CUtensorMap *map, unsigned smem_src, int c0, int c1, int c2) {
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"((uint64_t)map), "r"(smem_src),
+	             "r"(c0), "r"(c1), "r"(c2)
+	             : "memory");
+}
+
+template <int VL, int VC, bool BGR>
+__global__ void __maxnreg__(SW_MAXREG)
+    scale_rgb_stream_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c,
+                            const __grid_constant__ CUtensorMap map_o, const ScaleParams P, const StreamParams S) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned sL = ((smem_u32(smem_raw) + 127u) & ~127u) + (unsigned)warp * S.warp_bytes; // luma ring
+	unsigned sC = sL + S.c_off, sT = sL + S.t_off, sO = sL + S.o_off, sB = sL + S.b_off;   // chroma, table, out, mbarriers
+	// pin the ring bases in registers: re-deriving them from %tid and the parameter bank at every use costs more
+	asm volatile("" : "+r"(sC), "+r"(sT), "+r"(sO), "+r"(sB));
+	if (lane == 0) {
+#pragma unroll
+		for (int i = 0; i < 4; ++i) mbar_init_a(sB + 8 * i, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	}
+	__syncwarp();
+	// phase parity of ring chunk c within a task is (c >> 1) & 1, offset by the phases the stage's mbarrier completed in
+	// earlier tasks: bit s of lbase / cbase
+	unsigned lbase = 0, cbase = 0;
+	const unsigned pitch_l = (unsigned)S.box_lw, pitch_c = (unsigned)S.box_cw;
+	const unsigned sel_u = S.sel_u, sel_v = S.sel_v, rnd = S.rnd;
+	const int c_cy = P.cy, crv = P.crv, cgu = P.cgu, cgv = P.cgv, cbu = P.cbu;
+	const int k_r = S.k_r, k_g = S.k_g, k_b = S.k_b;
+	unsigned obuf = 0;         // staging buffer in use
+	int WL[VL][4], WU[VC][2], WV[VC][2];
+#pragma unroll
+	for (int s = 0; s < VL; ++s)
+#pragma unroll
+		for (int k = 0; k < 4; ++k) WL[s][k] = 0;
+#pragma unroll
+	for (int s = 0; s < VC; ++s) WU[s][0] = WU[s][1] = WV[s][0] = WV[s][1] = 0;
+
+#pragma unroll 1
+	for (int task = blockIdx.x * SW_WARPS + warp; task < S.n_tasks; task += gridDim.x * SW_WARPS) {
+		const int tx = task % S.tiles_x, tr = task / S.tiles_x;
+		const int seg = tr % S.n_seg, frame = tr / S.n_seg;
+		const int x0 = tx * ST_TW, lx0 = S.lx0[tx], cb0 = S.cb0[tx];
+		const int ys = seg * S.seg_rows, ye = min(ys + S.seg_rows, P.dst_h);
+		// ---- vertical-tap table: stages 0 and 1 of the ring
+		const char *tsrc = reinterpret_cast<const char *>(S.rows + ys) + lane * 16;
+		cp_async16(sT + lane * 16, tsrc);
+		asm volatile("cp.async.commit_group;\n" ::: "memory");
+		cp_async16(sT + ST_TCH * 32 + lane * 16, tsrc + ST_TCH * 32);
+		asm volatile("cp.async.commit_group;\n" ::: "memory");
+		// ---- first and last source rows of the segment; start the rings
+		const int2 first = __ldg(reinterpret_cast<const int2 *>(S.rows + ys));
+		const int2 last = __ldg(reinterpret_cast<const int2 *>(S.rows + ye - 1));
+		const int row0 = (first.x - (VL - 1)) & ~3; // multiple of 4: window slot == unroll index, ring stages end on body ends
+		const int crow0 = first.y - (VC - 1);
+		const int last_lchunk = (last.x - row0) / ST_LCH, last_cchunk = (last.y - crow0) / ST_CCH;
+		if (lane == 0) {
+#pragma unroll
+			for (int c = 0; c < 2; ++c) {
+				if (c <= last_lchunk) {
+					mbar_expect_tx_a(sB + 8 * c, ST_LCH * pitch_l);
+					tma_load_3d_a(sL + c * S.l_stage, &map_l, sB + 8 * c, lx0, row0 + ST_LCH * c, frame);
+				}
+				if (c <= last_cchunk) {
+					mbar_expect_tx_a(sB + 16 + 8 * c, ST_CCH * pitch_c);
+					tma_load_3d_a(sC + c * S.c_stage, &map_c, sB + 16 + 8 * c, cb0, crow0 + ST_CCH * c, frame);
+				}
+			}
+		}
+		// ---- per-lane horizontal filter data
+		const int xq = (x0 >> 1) + 2 * lane; // first of the lane's two column pairs == first of its two chroma samples
+		const int4 lpos = reinterpret_cast<const int4 *>(P.hl_pos)[xq >> 1];
+		const int4 lcA = reinterpret_cast<const int4 *>(P.hl_coef)[xq], lcB = reinterpret_cast<const int4 *>(P.hl_coef)[xq + 1];
+		const int2 cpos = reinterpret_cast<const int2 *>(P.hc_pos)[xq >> 1];
+		const int4 ccf = reinterpret_cast<const int4 *>(P.hc_coef)[xq >> 1];
+		const int pA = lpos.x - lx0, pB = lpos.z - lx0;
+		const unsigned shA = (unsigned)(pA & 3) * 8, shB = (unsigned)(pB & 3) * 8;
+		const unsigned dA = (unsigned)(lpos.y - lpos.x) * 8, dB = (unsigned)(lpos.w - lpos.z) * 8;
+		const int q0 = 2 * cpos.x - cb0, q1 = 2 * cpos.y - cb0;
+		const unsigned shc0 = (unsigned)(q0 & 3) * 8, shc1 = (unsigned)(q1 & 3) * 8;
+		unsigned la = sL + (unsigned)(pA & ~3), lb = sL + (unsigned)(pB & ~3);
+		unsigned ca = sC + (unsigned)(q0 & ~3), cb = sC + (unsigned)(q1 & ~3);
+		unsigned og = sO + obuf * (ST_OR * ST_TW * 3) + (unsigned)lane * 12;
+		int row = row0, lrel = 0, crow = crow0, crel = 0, cslot = crow0 % VC;
+		int yrel = 0, oy = ys, ocnt = 0;
+		const int nrows = ye - ys;
+		asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+		__syncwarp();
+		int4 ra = lds128(sT), rb = lds128(sT + 16);
+
+		auto hluma = [&](int(&w)[4]) {
+			const unsigned a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+			const unsigned A0 = __funnelshift_r(a0, a1, shA), A1 = __funnelshift_r(a1, a2, shA);
+			const unsigned B0 = __funnelshift_r(b0, b1, shB), B1 = __funnelshift_r(b1, b2, shB);
+			const unsigned A0b = __funnelshift_r(A0, A1, dA), B0b = __funnelshift_r(B0, B1, dB);
+			w[0] = dp2a_hi(lcA.y, A0, dp2a_lo(lcA.x, A0, 0)) >> 7;
+			w[1] = dp2a_hi(lcA.w, A0b, dp2a_lo(lcA.z, A0b, 0)) >> 7;
+			w[2] = dp2a_hi(lcB.y, B0, dp2a_lo(lcB.x, B0, 0)) >> 7;
+			w[3] = dp2a_hi(lcB.w, B0b, dp2a_lo(lcB.z, B0b, 0)) >> 7;
+			la += pitch_l;
+			lb += pitch_l;
+		};
+		auto hchroma = [&](int(&wu)[2], int(&wv)[2]) {
+			const unsigned a0 = lds32<0>(ca), a1 = lds32<4>(ca), a2 = lds32<8>(ca), b0 = lds32<0>(cb), b1 = lds32<4>(cb), b2 = lds32<8>(cb);
+			const unsigned alo = __funnelshift_r(a0, a1, shc0), ahi = __funnelshift_r(a1, a2, shc0);
+			const unsigned blo = __funnelshift_r(b0, b1, shc1), bhi = __funnelshift_r(b1, b2, shc1);
+			const unsigned e0 = prmt(alo, ahi, sel_u), o0 = prmt(alo, ahi, sel_v);
+			const unsigned e1 = prmt(blo, bhi, sel_u), o1 = prmt(blo, bhi, sel_v);
+			wu[0] = dp2a_hi(ccf.y, e0, dp2a_lo(ccf.x, e0, 0)) >> 7;
+			wv[0] = dp2a_hi(ccf.y, o0, dp2a_lo(ccf.x, o0, 0)) >> 7;
+			wu[1] = dp2a_hi(ccf.w, e1, dp2a_lo(ccf.z, e1, 0)) >> 7;
+			wv[1] = dp2a_hi(ccf.w, o1, dp2a_lo(ccf.z, o1, 0)) >> 7;
+			ca += pitch_c;
+			cb += pitch_c;
+		};
+		// one output row from the windows; returns true when the segment is complete
+		auto emit = [&]() -> bool {
+			const int c_last = ra.y;
+			const unsigned cc0 = (unsigned)ra.z, cc1 = (unsigned)ra.w;
+			const unsigned clv[4] = {(unsigned)rb.x, (unsigned)rb.y, (unsigned)rb.z, (unsigned)rb.w};
+			++yrel;
+#pragma unroll 1
+			while (crow <= c_last) { // warp-uniform; at most VC iterations, usually 0 or 1
+				if ((crel & (ST_CCH - 1)) == 0) // first row of ring chunk c = crel / 4: stage c & 1, parity (c >> 1) & 1
+					mbar_wait_a(sB + 16 + ((unsigned)(crel & ST_CCH) << 1), ((unsigned)(crel >> 3) ^ (cbase >> ((crel >> 2) & 1))) & 1u);
+				if (VC == 1 || cslot == 0) hchroma(WU[0], WV[0]);
+				else hchroma(WU[VC - 1], WV[VC - 1]);
+				++crow;
+				++crel;
+				cslot = cslot + 1 == VC ? 0 : cslot + 1;
+				if ((crel & (ST_CCH - 1)) == 0) { // stage consumed: refill it with the chunk after next, move to the other stage
+					__syncwarp();
+					const int cn = crel / ST_CCH + 1, st = (cn & 1);
+					if (lane == 0 && cn <= last_cchunk) {
+						mbar_expect_tx_a(sB + 16 + 8 * st, ST_CCH * pitch_c);
+						tma_load_3d_a(sC + st * S.c_stage, &map_c, sB + 16 + 8 * st, cb0, crow0 + ST_CCH * cn, frame);
+					}
+					const unsigned adj = S.c_stage - ST_CCH * pitch_c - (st ? 2 * S.c_stage : 0); // st == 1: stage 1 just ended
+					ca += adj;
+					cb += adj;
+				}
+			}
+			unsigned Yq[4], U16[2], V16[2];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				unsigned a = rnd;
+#pragma unroll
+				for (int s = 0; s < VL; ++s) a += (unsigned)WL[s][k] * clv[s];
+				Yq[k] = a >> 24;
+			}
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				unsigned a = rnd, b = rnd;
+				if (VC == 1) {
+					a += (unsigned)WU[0][h] << 17;
+					b += (unsigned)WV[0][h] << 17;
+				} else {
+					a += (unsigned)WU[0][h] * cc0 + (unsigned)WU[VC - 1][h] * cc1;
+					b += (unsigned)WV[0][h] * cc0 + (unsigned)WV[VC - 1][h] * cc1;
+				}
+				U16[h] = __byte_perm(a, 0u, 0x4344); // sample << 16
+				V16[h] = __byte_perm(b, 0u, 0x4344);
+			}
+			// the taps are dead: fetch the next row's entry under the colour arithmetic
+			{
+				if ((yrel & (ST_TCH - 1)) == 0) { // entering the next table stage: it has landed; refill the one just left
+					asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+					__syncwarp();
+					cp_async16(sT + (unsigned)((yrel / ST_TCH + 1) & 1) * (ST_TCH * 32) + lane * 16, tsrc + (yrel + ST_TCH) * 32);
+					asm volatile("cp.async.commit_group;\n" ::: "memory");
+				}
+				const unsigned ta = sT + (unsigned)(yrel & (2 * ST_TCH - 1)) * 32;
+				ra = lds128(ta);
+				rb = lds128(ta + 16);
+			}
+			int q[4][3];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int ar = __mulhi((int)V16[h], crv) * c_cy + k_r;
+				const int ag = (__mulhi((int)U16[h], cgu) + __mulhi((int)V16[h], cgv)) * c_cy + k_g;
+				const int ab = __mulhi((int)U16[h], cbu) * c_cy + k_b;
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					const int yc = (int)Yq[2 * h + k];
+					q[2 * h + k][0] = yc * c_cy + (BGR ? ab : ar);
+					q[2 * h + k][1] = yc * c_cy + ag;
+					q[2 * h + k][2] = yc * c_cy + (BGR ? ar : ab);
+				}
+			}
+			const unsigned lim = 0x00ff00ffu;
+			unsigned pk[6];
+			pk[0] = __vimin_s16x2_relu(__byte_perm((unsigned)q[0][0], (unsigned)q[0][1], 0x7632), lim);
+			pk[1] = __vimin_s16x2_relu(__byte_perm((unsigned)q[0][2], (unsigned)q[1][0], 0x7632), lim);
+			pk[2] = __vimin_s16x2_relu(__byte_perm((unsigned)q[1][1], (unsigned)q[1][2], 0x7632), lim);
+			pk[3] = __vimin_s16x2_relu(__byte_perm((unsigned)q[2][0], (unsigned)q[2][1], 0x7632), lim);
+			pk[4] = __vimin_s16x2_relu(__byte_perm((unsigned)q[2][2], (unsigned)q[3][0], 0x7632), lim);
+			pk[5] = __vimin_s16x2_relu(__byte_perm((unsigned)q[3][1], (unsigned)q[3][2], 0x7632), lim);
+			sts32<0>(og, __byte_perm(pk[0], pk[1], 0x6420));
+			sts32<4>(og, __byte_perm(pk[2], pk[3], 0x6420));
+			sts32<8>(og, __byte_perm(pk[4], pk[5], 0x6420));
+			og += ST_TW * 3;
+			const bool fin = yrel == nrows;
+			if (++ocnt == ST_OR || fin) { // hand the staged rows to the TMA engine, continue in the other buffer
+				fence_proxy_async();
+				__syncwarp();
+				if (lane == 0) {
+					tma_store_3d_a(&map_o, sO + obuf * (ST_OR * ST_TW * 3), (x0 * 3) >> 2, oy, frame); // rows past dst_h are clipped
+					tma_store_commit();
+					asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); // the other buffer's store has been read out
+				}
+				__syncwarp();
+				obuf ^= 1u;
+				oy += ST_OR;
+				ocnt = 0;
+				og = sO + obuf * (ST_OR * ST_TW * 3) + (unsigned)lane * 12;
+			}
+			return fin;
+		};
+
+		bool done = false;
+#pragma unroll 1
+		while (!done) {
+			if ((lrel & (ST_LCH - 1)) == 0) // first row of ring chunk c = lrel / 8: stage c & 1, parity (c >> 1) & 1
+				mbar_wait_a(sB + (unsigned)(lrel & ST_LCH), ((unsigned)(lrel >> 4) ^ (lbase >> ((lrel >> 3) & 1))) & 1u);
+#pragma unroll
+			for (int s = 0; s < VL; ++s) {
+				if (!done) {
+					hluma(WL[s]);
+#pragma unroll 1
+					while (!done && row == ra.x) done = emit(); // every output row whose last source row this is
+					++row;
+				}
+			}
+			lrel += VL;
+			if ((lrel & (ST_LCH - 1)) == 0 && !done) { // stage consumed: refill it with the chunk after next
+				__syncwarp();
+				const int cn = lrel / ST_LCH + 1, st = cn & 1;
+				if (lane == 0 && cn <= last_lchunk) {
+					mbar_expect_tx_a(sB + 8 * st, ST_LCH * pitch_l);
+					tma_load_3d_a(sL + st * S.l_stage, &map_l, sB + 8 * st, lx0, row0 + ST_LCH * cn, frame);
+				}
+				if (st) { // stage 1 just ended: wrap (stage stride == ST_LCH rows exactly)
+					la -= 2 * S.l_stage;
+					lb -= 2 * S.l_stage;
+				}
+			}
+		}
+		asm volatile("cp.async.wait_group 0;\n" ::: "memory"); // table prefetches past the segment end
+		__syncwarp();
+		// chunks 0..last went through the rings: stage 0 completed (last + 2) / 2 phases, stage 1 (last + 1) / 2
+		lbase ^= (unsigned)(((last_lchunk + 2) >> 1) & 1) | ((unsigned)(((last_lchunk + 1) >> 1) & 1) << 1);
+		cbase ^= (unsigned)(((last_cchunk + 2) >> 1) & 1) | ((unsigned)(((last_cchunk + 1) >> 1) & 1) << 1);
+	}
+	if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 }
 
 // planar (YUV420P) output: yuv2planeX_8 / yuv2plane1_8 with the constant-64 dither. One launch per plane kind: the
@@ -1084,7 +1406,12 @@ struct msb200_scaler {
 	bool fast_ok;
 	size_t smem_fast;
 	bool strip_ok;      // register-window strip kernel (scale_rgb_strip_kernel) applies
-	int force_path;     // tests/profiling: 0 = best available, 1 = skip the strip kernel, 2 = generic tile kernel only
+	int force_path;     // tests/profiling: 0 = best available, 1 = persistent tile kernel, 2 = generic tile kernel, 3 = strip kernel, 4 = streaming kernel
+	bool stream_ok;     // per-warp streaming kernel (scale_rgb_stream_kernel) applies
+	StreamParams T;
+	size_t smem_stream;
+	int stream_ctas_per_sm;
+	CUtensorMap map_lt, map_ct, map_ot;
 	StripParams S;
 	size_t smem_strip;
 	CUtensorMap map_ls, map_cs, map_os; // strip-kernel boxes (taller tiles), output as 32-bit elements
@@ -1177,6 +1504,28 @@ static int scaler_build_strip_maps(msb200_scaler *s, const void *d_src, const vo
 	return MSB200_OK;
 }
 
+// streaming kernel: ring-stage boxes (ST_LCH / ST_CCH source rows), destination as rows of 32-bit words, ST_OR rows per store
+static int scaler_build_stream_maps(msb200_scaler *s, const void *d_src, const void *d_dst, int n_frames) {
+	const ScaleParams &P = s->P;
+	const StreamParams &T = s->T;
+	int r;
+	if (!(s->cached_src == d_src && s->cached_frames == n_frames)) {
+		const char *base = (const char *)d_src;
+		if ((r = make_map(&s->map_lt, base, (uint64_t)P.src_w, (uint64_t)P.src_h, (uint64_t)n_frames, (uint64_t)P.src_w,
+		                  s->src_bytes, (uint32_t)T.box_lw, ST_LCH))) return r;
+		if ((r = make_map(&s->map_ct, base + (size_t)P.src_w * P.src_h, (uint64_t)P.chr_src_w * 2, (uint64_t)P.chr_src_h,
+		                  (uint64_t)n_frames, (uint64_t)P.chr_src_w * 2, s->src_bytes, (uint32_t)T.box_cw, ST_CCH))) return r;
+		s->cached_src = d_src;
+	}
+	if (!(s->cached_dst == d_dst && s->cached_frames == n_frames)) {
+		if ((r = make_map(&s->map_ot, d_dst, (uint64_t)P.dst_w * 3 / 4, (uint64_t)P.dst_h, (uint64_t)n_frames, (uint64_t)P.dst_w * 3,
+		                  (uint64_t)s->dst_bytes, (uint32_t)(ST_TW * 3 / 4), ST_OR, true))) return r;
+		s->cached_dst = d_dst;
+	}
+	s->cached_frames = n_frames;
+	return MSB200_OK;
+}
+
 static int scaler_build_maps(msb200_scaler *s, const void *d_src, int n_frames) {
 	if (s->cached_src == d_src && s->cached_frames == n_frames) return MSB200_OK;
 	const ScaleParams &P = s->P;
@@ -1222,8 +1571,10 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		s->cached_frames = 0;
 		s->fast_ok = false;
 		s->strip_ok = false;
+		s->stream_ok = false;
 		s->force_path = 0;
 		memset(&s->S, 0, sizeof(s->S));
+		memset(&s->T, 0, sizeof(s->T));
 		s->src_bytes = (size_t)src_w * src_h * 2;
 		s->dst_bytes = (size_t)dst_w * dst_h * 3 / 2;
 		*out = s;
@@ -1247,8 +1598,10 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	s->fast_ok = false;
 	s->smem_fast = 0;
 	s->strip_ok = false;
+	s->stream_ok = false;
 	s->force_path = 0;
 	memset(&s->S, 0, sizeof(s->S));
+	memset(&s->T, 0, sizeof(s->T));
 	ScaleParams &P = s->P;
 	memset(&P, 0, sizeof(P));
 	P.src_w = src_w; P.src_h = src_h; P.dst_w = dst_w; P.dst_h = dst_h; P.src_fmt = src_fmt; P.dst_fmt = dst_fmt;
@@ -1368,7 +1721,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		for (int R = 4; R <= ST_MAXR; ++R) {
 			const int th = ST_WARPS * R;
 			const size_t sm = a128((size_t)P.box_lw * max_span(s->vl, dst_h, th)) + a128((size_t)P.box_cw * max_span(s->vc, P.chr_dst_h, th)) +
-			                  (size_t)ST_WARPS * R * ST_TW * 3 + 16 + 128;
+			                  (size_t)ST_WARPS * R * ST_TW * 3 + 16 + 32 * (size_t)(th + 1) + 128;
 			if ((sm + 1024) * ST_MIN_CTAS > 227 * 1024 && R > 4) continue;
 			const long cost = (long)msb200_div_up(dst_h, th) * ST_WARPS * ((long)R * src_h / dst_h + P.vl_size); // luma rows filtered
 			if (best_cost < 0 || cost <= best_cost) { best_cost = cost; S.R = R; }
@@ -1381,10 +1734,11 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		S.stage_bytes = (unsigned)(S.R * ST_TW * 3);
 		ok = ok && S.box_lh <= 256 && S.box_ch <= 256 && (dst_w * 3) % 16 == 0 && dst_w / ST_TW <= ST_MAX_TX &&
 		     msb200_div_up(dst_h, th) <= ST_MAX_TY && src_w < 32768 && src_h < 32768;
-		s->smem_strip = a128((size_t)S.box_lw * S.box_lh) + a128((size_t)S.box_cw * S.box_ch) + (size_t)ST_WARPS * S.stage_bytes + 16 + 128;
+		s->smem_strip = a128((size_t)S.box_lw * S.box_lh) + a128((size_t)S.box_cw * S.box_ch) + (size_t)ST_WARPS * S.stage_bytes + 16 +
+		                32 * (size_t)(th + 1) + 128;
 		ok = ok && s->smem_strip <= 100 * 1024;
 		if (ok) {
-			std::vector<StripRow> rows((size_t)dst_h + 2);
+			std::vector<StripRow> rows((size_t)dst_h + 3 * ST_TCH);
 			for (int y = 0; y < dst_h; ++y) {
 				StripRow &r = rows[(size_t)y];
 				memset(&r, 0, sizeof(r));
@@ -1396,7 +1750,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			}
 			rows[(size_t)dst_h] = rows[(size_t)dst_h - 1]; // padding entries: read (never used) after the last row
 			rows[(size_t)dst_h].l_last = 1 << 30;
-			rows[(size_t)dst_h + 1] = rows[(size_t)dst_h];
+			for (size_t i = (size_t)dst_h + 1; i < rows.size(); ++i) rows[i] = rows[(size_t)dst_h];
 			for (int tx = 0; tx < dst_w / ST_TW; ++tx) {
 				S.lx0[tx] = (short)(s->hl.pos[(size_t)tx * ST_TW] & ~15);
 				S.cb0[tx] = (short)((2 * s->hc.pos[(size_t)tx * ST_TW / 2]) & ~15);
@@ -1429,6 +1783,46 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 #undef STRIP_ATTR
 			}
 			s->strip_ok = true;
+			// ---- streaming kernel: same tables, per-warp rings instead of per-CTA boxes
+			StreamParams &T = s->T;
+			T.rows = S.rows;
+			T.tiles_x = dst_w / ST_TW;
+			T.box_lw = S.box_lw;
+			T.box_cw = S.box_cw;
+			T.l_stage = (unsigned)(ST_LCH * T.box_lw);                      // box widths are 16-byte multiples: 128-aligned
+			T.c_stage = (unsigned)((ST_CCH * T.box_cw + 127) & ~127);
+			T.c_off = 2 * T.l_stage;
+			T.t_off = T.c_off + 2 * T.c_stage;
+			T.o_off = T.t_off + 2 * ST_TCH * (unsigned)sizeof(StripRow);
+			T.b_off = T.o_off + 2 * ST_OR * ST_TW * 3;
+			T.warp_bytes = (T.b_off + 32 + 127) & ~127u;
+			T.rnd = S.rnd; T.k_r = S.k_r; T.k_g = S.k_g; T.k_b = S.k_b; T.sel_u = S.sel_u; T.sel_v = S.sel_v;
+			memcpy(T.lx0, S.lx0, sizeof(T.lx0));
+			memcpy(T.cb0, S.cb0, sizeof(T.cb0));
+			s->smem_stream = (size_t)SW_WARPS * T.warp_bytes + 128;
+			// segments: whole multiples of ST_OR rows (a TMA store always writes ST_OR rows), about 2 per frame so that the
+			// re-filtered rows at a segment top (VL - 1 + up to 3 alignment rows) stay below 2 %
+			T.n_seg = dst_h >= 512 ? 2 : 1;
+			T.seg_rows = msb200_div_up(msb200_div_up(dst_h, T.n_seg), ST_OR) * ST_OR;
+			T.n_seg = msb200_div_up(dst_h, T.seg_rows);
+			bool sok = sizeof(StripRow) == 32 && s->smem_stream <= 100 * 1024;
+			// every ring refill must stay ahead of the reader: a chunk is consumed only after the previous one
+			for (int y = 1; y < dst_h && sok; ++y) // source rows advance monotonically
+				sok = s->vl.pos[(size_t)y] >= s->vl.pos[(size_t)y - 1] && s->vc.pos[(size_t)y] >= s->vc.pos[(size_t)y - 1];
+			if (sok) {
+#define STREAM_ATTR(VL, VC)                                                                                            \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_stream_kernel<VL, VC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_stream)); \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_stream_kernel<VL, VC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_stream))
+				STREAM_ATTR(4, 2);
+				STREAM_ATTR(2, 2);
+				STREAM_ATTR(1, 2);
+				STREAM_ATTR(1, 1);
+#undef STREAM_ATTR
+				int per_sm = 0;
+				MSB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scale_rgb_stream_kernel<4, 2, false>, SW_THREADS, s->smem_stream));
+				s->stream_ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+				s->stream_ok = true;
+			}
 		}
 	}
 	const size_t mx = s->smem_rgb > s->smem_chroma ? s->smem_rgb : s->smem_chroma;
@@ -1471,15 +1865,16 @@ size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s) {
 }
 
 int msb200_scaler_set_path(msb200_scaler *s, int path) {
-	MSB200_CHECK_ARG(s && path >= 0 && path <= 2);
+	MSB200_CHECK_ARG(s && path >= 0 && path <= 4);
 	s->force_path = path;
 	s->cached_src = s->cached_dst = nullptr; // the paths use different tensor maps
 	return MSB200_OK;
 }
 int msb200_scaler_get_path(msb200_scaler *s) {
 	if (!s || s->packed422 || s->P.dst_fmt == MSB200_PIX_YUV420P) return 0;
-	if (s->strip_ok && s->force_path == 0) return 3;
-	if (s->fast_ok && s->force_path < 2) return 2;
+	if (s->stream_ok && s->force_path == 4) return 4;
+	if (s->strip_ok && (s->force_path == 0 || s->force_path >= 3)) return 3;
+	if (s->fast_ok && s->force_path != 2) return 2;
 	return 1;
 }
 
@@ -1489,7 +1884,44 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 	MSB200_CHECK_ARG(((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0);
 	const ScaleParams &P = s->P;
 	int r;
-	if (s->strip_ok && !s->force_path && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0) {
+	const bool dst16 = ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0;
+	if (s->stream_ok && s->force_path == 4 && dst16) {
+		// per-warp streaming pipelines, persistent grid: warps stride over (frame, segment, strip) tasks
+		if ((r = scaler_build_stream_maps(s, d_src, d_dst, n_frames))) return r;
+		StreamParams T = s->T;
+		long g = (long)s->stream_ctas_per_sm * s->ctx->sm_count;
+		{ // segments per frame: the warps stride statically over the tasks, so pick the split whose last round is fullest
+			// (cost = rounds x rows per segment, plus the ~6 source rows a segment re-filters at its top)
+			const long warps = g * SW_WARPS;
+			long best = -1;
+			const char *force = getenv("MSB200_STREAM_NSEG"); // debugging aid
+			for (int ns = force ? atoi(force) : 1; ns <= (force ? atoi(force) : 8); ++ns) {
+				const int seg_rows = msb200_div_up(msb200_div_up(P.dst_h, ns), ST_OR) * ST_OR;
+				const int nse = msb200_div_up(P.dst_h, seg_rows);
+				const long tasks = (long)n_frames * nse * T.tiles_x;
+				const long cost = ((tasks + warps - 1) / warps) * (seg_rows + 6);
+				if (best < 0 || cost < best) { best = cost; T.n_seg = nse; T.seg_rows = seg_rows; }
+			}
+		}
+		const long n_tasks = (long)n_frames * T.n_seg * T.tiles_x;
+		MSB200_CHECK_ARG(n_tasks < (1L << 31));
+		T.n_tasks = (int)n_tasks;
+		if (g > msb200_div_up(T.n_tasks, SW_WARPS)) g = msb200_div_up(T.n_tasks, SW_WARPS);
+#define STREAM_LAUNCH(VL, VC)                                                                                          \
+	do {                                                                                                               \
+		if (P.dst_fmt == MSB200_PIX_RGB24_REV)                                                                         \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_stream_kernel<VL, VC, true>), (unsigned)g, SW_THREADS, s->smem_stream, s->map_lt, s->map_ct, s->map_ot, P, T); \
+		else                                                                                                           \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_stream_kernel<VL, VC, false>), (unsigned)g, SW_THREADS, s->smem_stream, s->map_lt, s->map_ct, s->map_ot, P, T); \
+	} while (0)
+		if (P.vl_size == 4) STREAM_LAUNCH(4, 2);
+		else if (P.vl_size == 2) STREAM_LAUNCH(2, 2);
+		else if (P.vc_size == 2) STREAM_LAUNCH(1, 2);
+		else STREAM_LAUNCH(1, 1);
+#undef STREAM_LAUNCH
+		return MSB200_OK;
+	}
+	if (s->strip_ok && (s->force_path == 0 || s->force_path >= 3) && dst16) {
 		// register-window strip kernel: one tile (128 columns x ST_WARPS strips) per CTA, x fastest so that neighbouring
 		// tiles share their halos in L2
 		if ((r = scaler_build_strip_maps(s, d_src, d_dst, n_frames))) return r;
@@ -1509,7 +1941,7 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 		return MSB200_OK;
 	}
 	if ((r = scaler_build_maps(s, d_src, n_frames))) return r;
-	if (s->fast_ok && s->force_path < 2 && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0) {
+	if (s->fast_ok && s->force_path != 2 && dst16) {
 		// persistent fast path: a few CTAs per SM walk the tiles, TMA in (double-buffered) and TMA out
 		if ((r = scaler_build_out_map(s, d_dst, n_frames))) return r;
 		s->cached_frames = n_frames;

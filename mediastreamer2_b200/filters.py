@@ -379,12 +379,12 @@ class Scaler:
         check(self.lib.msb200_scaler_process_dev(self.h, n_frames, C.c_void_p(d_src), C.c_void_p(d_dst)))
 
     def set_path(self, path: int):
-        """tests/profiling: 0 best available, 1 skip the strip kernel, 2 generic tile kernel only (all bit-exact)"""
+        """tests/profiling: 0 best available, 1 persistent tile kernel, 2 generic tile kernel, 3 strip kernel, 4 streaming kernel (all bit-exact)"""
         check(self.lib.msb200_scaler_set_path(self.h, path))
 
     @property
     def path(self) -> int:
-        """3 strip kernel, 2 persistent tile kernel, 1 generic tile kernel, 0 plane / packed kernels"""
+        """4 streaming kernel, 3 strip kernel, 2 persistent tile kernel, 1 generic tile kernel, 0 plane / packed kernels"""
         return self.lib.msb200_scaler_get_path(self.h)
 
 

@@ -113,7 +113,7 @@ def test_scaler_bit_exact_vs_oracle(ctx, sf, sw, sh, df, dw, dh):
     (_lib.PIX_NV12, 640, 368, _lib.PIX_RGB24_REV, 512, 288),    # 1.25x down
 ])
 def test_scaler_strip_kernel_bit_exact(ctx, sf, sw, sh, df, dw, dh):
-    """the register-window strip kernel (path 3) == oracle == the tile kernels (paths 2 and 1) on the same frames"""
+    """the register-window strip kernel (default) == oracle == its streaming variant (4) == the tile kernels (2, 1)"""
     L = O.oracle()
     n = 2
     frames = _rand_frames(sf, sw, sh, n, seed=sw + dh)
@@ -128,7 +128,7 @@ def test_scaler_strip_kernel_bit_exact(ctx, sf, sw, sh, df, dw, dh):
         bad = np.flatnonzero(got[i] != exp[:-64])
         assert bad.size == 0, (i, bad.size, bad[:8] // 3 % dw, bad[:8] // 3 // dw)
     L.orc_scaler_free(o)
-    for path, kind in ((1, 2), (2, 1)):
+    for path, kind in ((4, 4), (1, 2), (2, 1)):
         sc.set_path(path)
         assert sc.path == kind
         assert np.array_equal(sc.process(frames), got)
