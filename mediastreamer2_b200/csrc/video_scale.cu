@@ -808,8 +808,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	const unsigned lbox_bytes = (unsigned)(S.box_lw * S.box_lh), cbox_bytes = (unsigned)(S.box_cw * S.box_ch);
 	const unsigned cbox_al = (cbox_bytes + 127u) & ~127u, lbox_al = (lbox_bytes + 127u) & ~127u;
-	// layout: [staging x ST_WARPS][chroma box][luma box][mbarrier]; the luma walk may start up to VL-1 rows above its box
-	// (those window slots are overwritten before any output row reads them): that lands in the chroma box, still ours
+	// layout: [staging x ST_WARPS][chroma box][luma box][mbarrier][table rows]
 	unsigned char *stage = smem + warp * S.stage_bytes;
 	unsigned char *cbox = smem + ST_WARPS * S.stage_bytes;
 	unsigned char *lbox = cbox + cbox_al;
@@ -863,10 +862,11 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 		unsigned rtab = s_tab + (unsigned)(warp * S.R) * 32;
 		int4 ra = lds128(rtab), rb = lds128(rtab + 16);
 		const int lrow0 = ra.x - (VL - 1);           // first luma source row of the strip
-		int row = lrow0 - lrow0 % VL;                // the unrolled walk starts on a multiple of VL: slot == unroll index
+		const int s0 = lrow0 % VL;                   // its window slot; the unrolled walk below starts on a multiple of VL
+		int row = lrow0;
 		int crow = ra.y - (VC - 1);
 		int cslot = crow % VC;
-		unsigned la = smem_u32(lbox) + (unsigned)(pA & ~3) + (unsigned)(row - ly0) * pitch_l; // (row - ly0) may be -1..-(VL-1)
+		unsigned la = smem_u32(lbox) + (unsigned)(pA & ~3) + (unsigned)(row - ly0) * pitch_l;
 		unsigned lb = smem_u32(lbox) + (unsigned)(pB & ~3) + (unsigned)(row - ly0) * pitch_l;
 		unsigned ca = smem_u32(cbox) + (unsigned)(q0 & ~3) + (unsigned)(crow - cy0) * pitch_c;
 		unsigned cb = smem_u32(cbox) + (unsigned)(q1 & ~3) + (unsigned)(crow - cy0) * pitch_c;
@@ -969,6 +969,15 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 		};
 
 		bool done = false;
+		if (s0 > 0) { // lead-in: rows lrow0 .. next multiple of VL go to slots s0 .. VL-1 (no output row can complete yet)
+#pragma unroll
+			for (int s = 1; s < VL; ++s) {
+				if (s >= s0) {
+					hluma(WL[s]);
+					++row;
+				}
+			}
+		}
 #pragma unroll 1
 		while (!done) {
 #pragma unroll
@@ -1717,18 +1726,19 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		// strip height: the tallest strips (least halo rows recomputed per output row, least padding in the last tile row)
 		// whose tile still lets ST_MIN_CTAS CTAs share an SM's shared memory
 		StripParams &S = s->S;
+		// box origins are aligned down to 16 bytes (TMA faults on unaligned byte coordinates): widest window + 15, rounded up
+		S.box_lw = (max_span(s->hl, dst_w, ST_TW) + 15 + 15) & ~15;
+		S.box_cw = (2 * max_span(s->hc, P.chr_dst_w, ST_TW / 2) + 15 + 15) & ~15;
 		long best_cost = -1;
 		for (int R = 4; R <= ST_MAXR; ++R) {
 			const int th = ST_WARPS * R;
-			const size_t sm = a128((size_t)P.box_lw * max_span(s->vl, dst_h, th)) + a128((size_t)P.box_cw * max_span(s->vc, P.chr_dst_h, th)) +
+			const size_t sm = a128((size_t)S.box_lw * max_span(s->vl, dst_h, th)) + a128((size_t)S.box_cw * max_span(s->vc, P.chr_dst_h, th)) +
 			                  (size_t)ST_WARPS * R * ST_TW * 3 + 16 + 32 * (size_t)(th + 1) + 128;
 			if ((sm + 1024) * ST_MIN_CTAS > 227 * 1024 && R > 4) continue;
 			const long cost = (long)msb200_div_up(dst_h, th) * ST_WARPS * ((long)R * src_h / dst_h + P.vl_size); // luma rows filtered
 			if (best_cost < 0 || cost <= best_cost) { best_cost = cost; S.R = R; }
 		}
 		const int th = ST_WARPS * S.R;
-		S.box_lw = P.box_lw;
-		S.box_cw = P.box_cw;
 		S.box_lh = max_span(s->vl, dst_h, th);
 		S.box_ch = max_span(s->vc, P.chr_dst_h, th);
 		S.stage_bytes = (unsigned)(S.R * ST_TW * 3);
