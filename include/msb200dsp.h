@@ -124,6 +124,7 @@ typedef struct msb200_volume_state {
 } msb200_volume_state;
 MSB200_API int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_volume **out);
 MSB200_API void msb200_volume_destroy(msb200_volume *v);
+MSB200_API int msb200_volume_reset_stream(msb200_volume *v, int stream); /* volume_init state, one stream */
 MSB200_API int msb200_volume_set_gain(msb200_volume *v, int stream, float gain);           /* MS_VOLUME_SET_GAIN :270-276 */
 MSB200_API int msb200_volume_set_db_gain(msb200_volume *v, int stream, float db);          /* MS_VOLUME_SET_DB_GAIN :262-268 */
 MSB200_API int msb200_volume_enable_noise_gate(msb200_volume *v, int stream, int enabled); /* :352-359 */
@@ -193,6 +194,8 @@ MSB200_API int msb200_resample_create(msb200_ctx *ctx, int n_streams, int in_rat
 MSB200_API void msb200_resample_destroy(msb200_resample *r);
 MSB200_API int msb200_resample_max_out(msb200_resample *r, int in_frames); /* inlen*out/in + 1, msresample.c:151-152 */
 MSB200_API int msb200_resample_reset(msb200_resample *r);
+/* one stream's filter memory only (a stream joining a running lockstep bank; the resampling phase stays bank-wide) */
+MSB200_API int msb200_resample_reset_stream(msb200_resample *r, int stream);
 MSB200_API int msb200_resample_process(msb200_resample *r, const int16_t *in, int in_frames, int16_t *out,
                                        int out_stride_frames, int *out_frames);
 MSB200_API int msb200_resample_process_dev(msb200_resample *r, const void *d_in, int in_frames, int in_stride_frames,
@@ -221,6 +224,10 @@ MSB200_API int msb200_aec_reset(msb200_aec *a, int stream); /* stream < 0: all *
 MSB200_API int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes);
 MSB200_API int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes,
                                       int stride_samples);
+/* as msb200_aec_process, with host buffers laid out [stream][stride_samples] (a fixed staging arena whose frame count
+ * varies from tick to tick: the plugin's lockstep batch mode) */
+MSB200_API int msb200_aec_process_strided(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out,
+                                          int nframes, int stride_samples);
 /* MS_ECHO_CANCELLER_GET/SET_STATE_STRING (speexec.c:119-167, 361-374): the adaptive-filter weights of one stream as
  * an opaque blob (our format: header + W[M][N] float). */
 MSB200_API size_t msb200_aec_state_blob_size(msb200_aec *a);

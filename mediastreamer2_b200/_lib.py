@@ -90,6 +90,7 @@ _SIGS = {
     "msb200_mixer_finish_peers_dev": (_I, [_P, _P, _P, _P, _P, _I, C.c_uint32, _P, _P]),
     "msb200_volume_create": (_I, [_P, _I, _I, _I, _PP]),
     "msb200_volume_destroy": (None, [_P]),
+    "msb200_volume_reset_stream": (_I, [_P, _I]),
     "msb200_volume_set_gain": (_I, [_P, _I, _F]),
     "msb200_volume_set_db_gain": (_I, [_P, _I, _F]),
     "msb200_volume_enable_noise_gate": (_I, [_P, _I, _I]),
@@ -122,6 +123,7 @@ _SIGS = {
     "msb200_resample_destroy": (None, [_P]),
     "msb200_resample_max_out": (_I, [_P, _I]),
     "msb200_resample_reset": (_I, [_P]),
+    "msb200_resample_reset_stream": (_I, [_P, _I]),
     "msb200_resample_process": (_I, [_P, _P, _I, _P, _I, _PI]),
     "msb200_resample_process_dev": (_I, [_P, _P, _I, _I, _P, _I, _PI]),
     "msb200_aec_frame_size_for_rate": (_I, [_I, _I]),
@@ -131,6 +133,7 @@ _SIGS = {
     "msb200_aec_reset": (_I, [_P, _I]),
     "msb200_aec_process": (_I, [_P, _P, _P, _P, _I]),
     "msb200_aec_process_dev": (_I, [_P, _P, _P, _P, _I, _I]),
+    "msb200_aec_process_strided": (_I, [_P, _P, _P, _P, _I, _I]),
     "msb200_aec_state_blob_size": (_SZ, [_P]),
     "msb200_aec_get_state_blob": (_I, [_P, _I, _P, _SZ]),
     "msb200_aec_set_state_blob": (_I, [_P, _I, _P, _SZ]),

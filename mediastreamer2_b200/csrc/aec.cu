@@ -1392,6 +1392,23 @@ int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, in
 	return MSB200_OK;
 }
 
+// host buffers laid out [stream][stride_samples] of which the first nframes * frame_size samples are this call's frames
+// (a fixed-size staging arena whose frame count varies from tick to tick)
+int msb200_aec_process_strided(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes,
+                               int stride_samples) {
+	MSB200_CHECK_ARG(a && mic && ref && out && nframes > 0 && stride_samples >= nframes * a->P.F);
+	size_t bytes = (size_t)a->n * stride_samples * 2;
+	int r;
+	if ((r = a->mic.reserve(bytes)) || (r = a->ref.reserve(bytes)) || (r = a->out.reserve(bytes))) return r;
+	cudaStream_t s = a->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(a->mic.p, mic, bytes, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaMemcpyAsync(a->ref.p, ref, bytes, cudaMemcpyHostToDevice, s));
+	if ((r = msb200_aec_process_dev(a, a->mic.p, a->ref.p, a->out.p, nframes, stride_samples))) return r;
+	MSB200_CUDA(cudaMemcpyAsync(out, a->out.p, bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
 // the foreground array lags by one frame when a refresh is pending (see the block pass): logically FG == W then
 static int aec_fg_pending(msb200_aec *a, int stream, int *pending, int clear) {
 	int *d = reinterpret_cast<int *>(a->dS + (size_t)stream * a->P.lay.total + a->P.lay.ints) + IN_FG_PENDING;

@@ -452,6 +452,28 @@ static int volume_update_state(msb200_volume *v, int stream, void (*fn)(msb200_v
 
 extern "C" {
 
+static void volume_state_init(msb200_volume_state *s, int sample_rate) { // volume_init :86-120
+	memset(s, 0, sizeof(*s));
+	s->static_gain = s->gain = s->target_gain = 1.f;
+	s->ng_threshold = 0.1f;
+	s->ng_floorgain = 0.005f;
+	s->ng_gain = 1.f;
+	s->sample_rate = sample_rate;
+	s->ea_thres = 0.1f;          // noise_thres :42
+	s->ea_transmit_thres = 4.f;  // transmit_thres :43
+	s->force = 4.f;              // en_weight :41
+	s->vol_upramp = 0.4f;
+	s->sustain_time = 200;
+	s->peer = -1;
+}
+int msb200_volume_reset_stream(msb200_volume *v, int stream) { // a fresh MSVolume in this slot (a stream joining a running bank)
+	MSB200_CHECK_ARG(v && stream >= 0 && stream < v->n);
+	msb200_volume_state s;
+	volume_state_init(&s, v->rate);
+	MSB200_CUDA(cudaStreamSynchronize(v->ctx->stream));
+	MSB200_CUDA(cudaMemcpy(v->d_state + stream, &s, sizeof(s), cudaMemcpyHostToDevice));
+	return MSB200_OK;
+}
 int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_volume **out) {
 	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && sample_rate > 0 && max_block > 0 && max_block <= 8192);
 	msb200_volume *v = new msb200_volume();
@@ -460,20 +482,7 @@ int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int ma
 	v->rate = sample_rate;
 	v->max_block = max_block;
 	std::vector<msb200_volume_state> init((size_t)n_streams);
-	for (auto &s : init) { // volume_init :86-120
-		memset(&s, 0, sizeof(s));
-		s.static_gain = s.gain = s.target_gain = 1.f;
-		s.ng_threshold = 0.1f;
-		s.ng_floorgain = 0.005f;
-		s.ng_gain = 1.f;
-		s.sample_rate = sample_rate;
-		s.ea_thres = 0.1f;          // noise_thres :42
-		s.ea_transmit_thres = 4.f;  // transmit_thres :43
-		s.force = 4.f;              // en_weight :41
-		s.vol_upramp = 0.4f;
-		s.sustain_time = 200;
-		s.peer = -1;
-	}
+	for (auto &s : init) volume_state_init(&s, sample_rate);
 	v->peer_bank = nullptr;
 	MSB200_CUDA(cudaMalloc(&v->d_state, sizeof(msb200_volume_state) * (size_t)n_streams));
 	MSB200_CUDA(cudaMemcpy(v->d_state, init.data(), sizeof(msb200_volume_state) * (size_t)n_streams, cudaMemcpyHostToDevice));

@@ -252,6 +252,13 @@ int msb200_resample_reset(msb200_resample *r) {
 	MSB200_CUDA(cudaMemsetAsync(r->d_hist, 0, sizeof(short) * (size_t)r->n * r->nch * (r->d.filt_len - 1), r->ctx->stream));
 	return MSB200_OK;
 }
+int msb200_resample_reset_stream(msb200_resample *r, int stream) {
+	MSB200_CHECK_ARG(r && stream >= 0 && stream < r->n);
+	// the phase is bank-wide (lockstep streams); a stream that (re)joins starts from an empty history like a new handle
+	const size_t per = sizeof(short) * (size_t)r->nch * (r->d.filt_len - 1);
+	MSB200_CUDA(cudaMemsetAsync((char *)r->d_hist + per * (size_t)stream, 0, per, r->ctx->stream));
+	return MSB200_OK;
+}
 int msb200_resample_process_dev(msb200_resample *r, const void *d_in, int in_frames, int in_stride, void *d_out,
                                 int out_stride, int *out_frames) {
 	return msb200i_resample_launch(r, d_in, in_frames, in_stride, d_out, out_stride, 0, 0, out_frames);

@@ -11,9 +11,15 @@
  * libmsb200dsp.so's CUDA kernels through the C ABI of include/msb200dsp.h. There is no CPU fallback: if no GPU context
  * can be created the filters log an error and drop their input.
  *
- * Execution mode: synchronous — each process() call makes one bank call for its own stream (exact reference
- * semantics, one tick latency-free). The batched path (thousands of streams per launch) is the msb200_chain / bank API
- * itself; DESIGN.md §7 describes the deferred-batch mode that connects the two.
+ * Execution modes:
+ *   synchronous (default) — each process() call makes one bank call for its own stream: exact reference semantics, no
+ *     added latency, launch-bound (a few hundred streams per ticker thread at best);
+ *   lockstep batch (MSB200_BATCH=<slots>) — the MSResample / MSSpeexEC / MSVolume / MSAudioMixer instances attached to
+ *     one MSTicker with the same configuration share ONE bank ("batch group"). process() at tick T stages the
+ *     filter's block into the group's pinned arena and emits the result of the block it staged at tick T-1; the first
+ *     member called in a tick runs the whole group's previous tick in one H2D + one launch + one D2H. Every batched
+ *     stage therefore adds one ticker interval (10 ms) of latency and nothing else: the samples are bit-identical to
+ *     the synchronous mode's. See the "batch groups" section below and DESIGN.md §7.
  *
  * Compiled against the host's mediastreamer2 / oRTP / bctoolbox headers (here: /root/reference/include + compat/).
  */
@@ -56,6 +62,205 @@ static msb200_ctx *dsp_ctx(void) {
 		if ((expr) != MSB200_OK) ms_error("msb200: %s failed: %s", what, msb200_last_error());                         \
 	} while (0)
 
+
+/* ------------------------------------------------------------------------------------------------ batch groups
+ * MSB200_BATCH=<slots> turns on the lockstep batch mode: filters of one kind, on one MSTicker, with one configuration
+ * key share a bank of <slots> streams (rooms for the mixer). All member process() calls of a ticker come from that
+ * ticker's thread (src/base/msticker.c:244-282), so a group is touched by one thread at a time; joining and leaving
+ * (preprocess / postprocess, on the attaching thread) take g_batch_mu, and so does the flush.
+ *
+ *   tick T, member i:  batch_tick()   -> first caller of the tick: run the bank over everything staged during T-1
+ *                      emit           -> the member's results of T-1 go to its output queue
+ *                      stage          -> the member's block(s) of T are copied into its arena slot
+ *
+ * A slot that staged fewer units than the group's maximum in a tick (a starving stream) is fed zeros for the missing
+ * units and its outputs for those units are discarded: the stream's audio is untouched, only its filter memory sees
+ * a silent unit. Streams that deliver the same block sizes every tick (a media server's RTP streams) never hit this.
+ */
+enum { BK_RESAMPLE, BK_EC, BK_VOLUME, BK_MIXER };
+#define BATCH_MAX_SLOTS 4096
+typedef struct Batch {
+	struct Batch *next;
+	int kind;
+	MSTicker *ticker;
+	int key[4];
+	int cap, n_members;
+	void **owner;      /* [cap] filter state owning the slot, NULL when free */
+	uint64_t seen_tick; /* ticker->ticks of the last flush */
+	void *bank;
+	int unit_in, unit_out, max_units; /* samples per unit per slot in / out; units a slot may stage per tick */
+	int16_t *in[2], *out;             /* pinned arenas [cap][max_units * unit_*] */
+	uint8_t *present;                 /* mixer: [cap][MIXER pins] */
+	int *staged, *ready;              /* units per slot: staged this tick / ready from the last flush */
+	int out_len;                      /* samples per unit the last run produced (resampler: frames out x channels) */
+	uint64_t flushes, units_run;
+} Batch;
+static Batch *g_batches = NULL;
+static pthread_mutex_t g_batch_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_batch_cap = -1;
+
+static int batch_capacity(void) {
+	if (g_batch_cap < 0) {
+		const char *e = getenv("MSB200_BATCH");
+		int v = e ? atoi(e) : 0;
+		g_batch_cap = v < 0 ? 0 : (v > BATCH_MAX_SLOTS ? BATCH_MAX_SLOTS : v);
+	}
+	return g_batch_cap;
+}
+static void *batch_pinned(size_t bytes) {
+	void *p = NULL;
+	if (msb200_host_alloc_pinned(g_ctx, bytes ? bytes : 16, &p) != MSB200_OK) return NULL;
+	memset(p, 0, bytes);
+	return p;
+}
+static void batch_free(Batch *b) { /* g_batch_mu held, no members left */
+	DSP_LOCK();
+	switch (b->kind) {
+		case BK_RESAMPLE: msb200_resample_destroy((msb200_resample *)b->bank); break;
+		case BK_EC: msb200_aec_destroy((msb200_aec *)b->bank); break;
+		case BK_VOLUME: msb200_volume_destroy((msb200_volume *)b->bank); break;
+		case BK_MIXER: msb200_mixer_destroy((msb200_mixer *)b->bank); break;
+	}
+	if (b->in[0]) msb200_host_free_pinned(g_ctx, b->in[0]);
+	if (b->in[1]) msb200_host_free_pinned(g_ctx, b->in[1]);
+	if (b->out) msb200_host_free_pinned(g_ctx, b->out);
+	DSP_UNLOCK();
+	ms_free(b->present);
+	ms_free(b->owner);
+	ms_free(b->staged);
+	ms_free(b->ready);
+	ms_free(b);
+}
+/* find (or create) the group for (kind, ticker, key) and take a slot in it; NULL when batching is off or impossible */
+static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_in, int unit_out, int max_units, void *owner,
+                         int *slot) {
+	Batch *b;
+	int i, cap = batch_capacity();
+	if (cap <= 0 || ticker == NULL) return NULL;
+	pthread_mutex_lock(&g_batch_mu);
+	for (b = g_batches; b; b = b->next)
+		if (b->kind == kind && b->ticker == ticker && memcmp(b->key, key, sizeof(b->key)) == 0 && b->n_members < b->cap) break;
+	if (!b) {
+		int rc = MSB200_OK;
+		DSP_LOCK();
+		if (!dsp_ctx()) {
+			DSP_UNLOCK();
+			pthread_mutex_unlock(&g_batch_mu);
+			return NULL;
+		}
+		b = ms_new0(Batch, 1);
+		b->kind = kind;
+		b->ticker = ticker;
+		memcpy(b->key, key, sizeof(b->key));
+		b->cap = cap;
+		b->unit_in = unit_in;
+		b->unit_out = unit_out;
+		b->max_units = max_units;
+		b->seen_tick = (uint64_t)-1;
+		switch (kind) {
+			case BK_RESAMPLE: rc = msb200_resample_create(g_ctx, cap, key[0], key[1], key[2], key[3], (msb200_resample **)&b->bank); break;
+			case BK_EC: rc = msb200_aec_create(g_ctx, cap, key[0], key[1], key[2], (msb200_aec **)&b->bank); break;
+			case BK_VOLUME: rc = msb200_volume_create(g_ctx, cap, key[0], key[1], (msb200_volume **)&b->bank); break;
+			case BK_MIXER: rc = msb200_mixer_create(g_ctx, cap, key[2], key[0], key[1], (msb200_mixer **)&b->bank); break;
+		}
+		if (rc == MSB200_OK) {
+			const size_t n_in = (size_t)cap * max_units * unit_in * sizeof(int16_t), n_out = (size_t)cap * max_units * unit_out * sizeof(int16_t);
+			b->in[0] = (int16_t *)batch_pinned(n_in);
+			if (kind == BK_EC) b->in[1] = (int16_t *)batch_pinned(n_in);
+			b->out = kind == BK_VOLUME ? NULL : (int16_t *)batch_pinned(n_out);
+			if (!b->in[0] || (kind == BK_EC && !b->in[1]) || (kind != BK_VOLUME && !b->out)) rc = MSB200_ENOMEM;
+		}
+		DSP_UNLOCK();
+		if (rc != MSB200_OK) {
+			ms_error("msb200: cannot create a batch group (%s); the filter stays synchronous", msb200_last_error());
+			b->owner = NULL;
+			batch_free(b);
+			pthread_mutex_unlock(&g_batch_mu);
+			return NULL;
+		}
+		b->owner = (void **)ms_new0(void *, cap);
+		b->staged = ms_new0(int, cap);
+		b->ready = ms_new0(int, cap);
+		if (kind == BK_MIXER) b->present = (uint8_t *)ms_malloc0((size_t)cap * key[2]);
+		b->next = g_batches;
+		g_batches = b;
+		ms_message("msb200: batch group %p: kind %d, %d slots, key {%d,%d,%d,%d} on ticker %p", b, kind, cap, key[0], key[1], key[2], key[3], ticker);
+	}
+	for (i = 0; i < b->cap && b->owner[i]; ++i) {
+	}
+	b->owner[i] = owner;
+	b->staged[i] = b->ready[i] = 0;
+	b->n_members++;
+	*slot = i;
+	pthread_mutex_unlock(&g_batch_mu);
+	return b;
+}
+static void batch_leave(Batch *b, int slot) {
+	Batch **pp;
+	if (!b) return;
+	pthread_mutex_lock(&g_batch_mu);
+	b->owner[slot] = NULL;
+	b->staged[slot] = b->ready[slot] = 0;
+	if (b->present) memset(b->present + (size_t)slot * b->key[2], 0, (size_t)b->key[2]);
+	if (--b->n_members == 0) {
+		for (pp = &g_batches; *pp && *pp != b; pp = &(*pp)->next) {
+		}
+		if (*pp) *pp = b->next;
+		batch_free(b);
+	}
+	pthread_mutex_unlock(&g_batch_mu);
+}
+/* called first thing in every member's process(): the first caller of a tick runs the group's previous tick */
+static void batch_tick(Batch *b, uint64_t ticks) {
+	int i, units = 0, rc = MSB200_OK;
+	if (b->seen_tick == ticks) return;
+	pthread_mutex_lock(&g_batch_mu);
+	b->seen_tick = ticks;
+	for (i = 0; i < b->cap; ++i)
+		if (b->staged[i] > units) units = b->staged[i];
+	if (units > 0) {
+		/* slots that staged less than the group's maximum are fed zeros for the missing units */
+		for (i = 0; i < b->cap; ++i) {
+			if (b->staged[i] < units && b->kind != BK_MIXER) {
+				const size_t off = ((size_t)i * b->max_units + b->staged[i]) * b->unit_in, n = (size_t)(units - b->staged[i]) * b->unit_in;
+				memset(b->in[0] + off, 0, n * sizeof(int16_t));
+				if (b->in[1]) memset(b->in[1] + off, 0, n * sizeof(int16_t));
+			}
+		}
+		DSP_LOCK();
+		switch (b->kind) {
+			case BK_RESAMPLE: {
+				int outlen = 0;
+				rc = msb200_resample_process((msb200_resample *)b->bank, b->in[0], b->key[3], b->out, b->unit_out / b->key[2], &outlen);
+				b->out_len = outlen * b->key[2];
+				break;
+			}
+			case BK_EC:
+				rc = msb200_aec_process_strided((msb200_aec *)b->bank, b->in[0], b->in[1], b->out, units, b->max_units * b->unit_in);
+				b->out_len = b->unit_out;
+				break;
+			case BK_VOLUME:
+				rc = msb200_volume_process((msb200_volume *)b->bank, b->in[0], b->unit_in);
+				b->out_len = b->unit_in;
+				break;
+			case BK_MIXER:
+				rc = msb200_mixer_process((msb200_mixer *)b->bank, b->in[0], b->present, b->out);
+				b->out_len = b->unit_out;
+				break;
+		}
+		DSP_UNLOCK();
+		if (rc != MSB200_OK) ms_error("msb200: batch group %p (kind %d) failed: %s", b, b->kind, msb200_last_error());
+		b->flushes++;
+		b->units_run += (uint64_t)units;
+	}
+	for (i = 0; i < b->cap; ++i) {
+		b->ready[i] = rc == MSB200_OK ? b->staged[i] : 0;
+		b->staged[i] = 0;
+	}
+	if (b->present) memset(b->present, 0, (size_t)b->cap * b->key[2]);
+	pthread_mutex_unlock(&g_batch_mu);
+}
+
 /* ================================================================================================ MSAudioMixer
  * host logic restated from /root/reference/src/audiofilters/audiomixer.c: channel bufferizers :78-90, flow control
  * :92-111, bypass mode :219-286, output dispatch :288-346, methods :348-431 */
@@ -76,10 +281,12 @@ typedef struct MixerState {
 	int nchannels, rate, bytespertick, conf_mode, skip_threshold, master_channel;
 	MixChannel channels[MIXER_MAX_CHANNELS];
 	bool_t bypass_mode, single_output;
-	msb200_mixer *bank; /* 1 room x 50 pins x nwords */
+	msb200_mixer *bank; /* 1 room x 50 pins x nwords; batch mode: the group's bank, this mixer is room `room` */
 	int16_t *in;        /* [50][nwords] */
 	uint8_t *present;   /* [50] */
 	int16_t *out;       /* [50][nwords] (conference) or [nwords] */
+	Batch *batch;       /* lockstep batch group (MSB200_BATCH), NULL in synchronous mode */
+	int room;
 } MixerState;
 
 static void mixer_init(MSFilter *f) {
@@ -122,6 +329,25 @@ static void mixer_preprocess(MSFilter *f) {
 	s->skip_threshold = s->bytespertick * 2;
 	s->bypass_mode = FALSE;
 	s->single_output = mixer_has_single_output(f, s);
+	s->room = 0;
+	if (batch_capacity() > 0) {
+		const int key[4] = {nwords, s->conf_mode, MIXER_MAX_CHANNELS, 0};
+		s->batch = batch_join(BK_MIXER, f->ticker, key, MIXER_MAX_CHANNELS * nwords, s->conf_mode ? MIXER_MAX_CHANNELS * nwords : nwords, 1,
+		                      s, &s->room);
+	}
+	if (s->batch) { /* this mixer is one room of the group's bank; its arenas are slices of the group's pinned arenas */
+		s->bank = (msb200_mixer *)s->batch->bank;
+		s->in = s->batch->in[0] + (size_t)s->room * s->batch->unit_in;
+		s->out = s->batch->out + (size_t)s->room * s->batch->unit_out;
+		s->present = s->batch->present + (size_t)s->room * MIXER_MAX_CHANNELS;
+		DSP_LOCK();
+		for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
+			msb200_mixer_set_input_gain(s->bank, s->room, i, s->channels[i].gain);
+			msb200_mixer_set_active(s->bank, s->room, i, s->channels[i].active);
+		}
+		DSP_UNLOCK();
+		return;
+	}
 	s->in = (int16_t *)ms_malloc0(sizeof(int16_t) * MIXER_MAX_CHANNELS * (size_t)nwords);
 	s->out = (int16_t *)ms_malloc0(sizeof(int16_t) * MIXER_MAX_CHANNELS * (size_t)nwords);
 	s->present = (uint8_t *)ms_malloc0(MIXER_MAX_CHANNELS);
@@ -137,6 +363,14 @@ static void mixer_preprocess(MSFilter *f) {
 }
 static void mixer_postprocess(MSFilter *f) {
 	MixerState *s = (MixerState *)f->data;
+	if (s->batch) {
+		batch_leave(s->batch, s->room);
+		s->batch = NULL;
+		s->bank = NULL;
+		s->in = s->out = NULL;
+		s->present = NULL;
+		return;
+	}
 	DSP_LOCK();
 	msb200_mixer_destroy(s->bank);
 	DSP_UNLOCK();
@@ -146,6 +380,36 @@ static void mixer_postprocess(MSFilter *f) {
 	ms_free(s->present);
 	s->in = s->out = NULL;
 	s->present = NULL;
+}
+/* one tick of results (s->out) to the output pins: channel_process_out :113-130 */
+static void mixer_emit(MSFilter *f, MixerState *s, int nwords) {
+	int i;
+	if (s->conf_mode == 0) {
+		mblk_t *om = NULL;
+		for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
+			MSQueue *q = f->outputs[i];
+			if (q && s->channels[i].output_enabled) {
+				if (om == NULL) {
+					om = allocb((size_t)nwords * 2, 0);
+					memcpy(om->b_wptr, s->out, (size_t)nwords * 2);
+					om->b_wptr += nwords * 2;
+				} else {
+					om = dupb(om);
+				}
+				ms_queue_put(q, om);
+			}
+		}
+	} else {
+		for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
+			MSQueue *q = f->outputs[i];
+			if (q && s->channels[i].output_enabled) {
+				mblk_t *om = allocb((size_t)nwords * 2, 0);
+				memcpy(om->b_wptr, s->out + (size_t)i * nwords, (size_t)nwords * 2);
+				om->b_wptr += nwords * 2;
+				ms_queue_put(q, om);
+			}
+		}
+	}
 }
 static void mixer_dispatch_output(MSFilter *f, MixerState *s, MSQueue *inq, int active_input) {
 	int i;
@@ -205,6 +469,13 @@ static void mixer_process(MSFilter *f) {
 	MixerState *s = (MixerState *)f->data;
 	int i, nwords = s->bytespertick / 2;
 	ms_filter_lock(f);
+	if (s->batch) { /* the group's previous tick is computed by the first mixer called in this tick; emit this room's share */
+		batch_tick(s->batch, f->ticker->ticks);
+		if (s->batch->ready[s->room]) {
+			s->batch->ready[s->room] = 0;
+			mixer_emit(f, s, nwords);
+		}
+	}
 	if (mixer_check_bypass(f, s)) {
 		ms_filter_unlock(f);
 		return;
@@ -237,38 +508,16 @@ static void mixer_process(MSFilter *f) {
 		if (skip > 0)
 			ms_warning("Too much data in channel %i, %i ms in excess dropped", i, (skip * 1000) / (2 * s->nchannels * s->rate));
 	}
+	if (s->batch) { /* staged: the group's launch at the start of the next tick mixes every room at once */
+		s->batch->staged[s->room] = 1;
+		ms_filter_unlock(f);
+		return;
+	}
 	/* the arithmetic: one launch for the whole mixer (sum, gains, minus-own, saturation) */
 	DSP_LOCK();
 	if (s->bank) DSP_CHECK(msb200_mixer_process(s->bank, s->in, s->present, s->out), "mixer_process");
 	DSP_UNLOCK();
-	if (s->bank) {
-		if (s->conf_mode == 0) {
-			mblk_t *om = NULL;
-			for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
-				MSQueue *q = f->outputs[i];
-				if (q && s->channels[i].output_enabled) {
-					if (om == NULL) {
-						om = allocb((size_t)nwords * 2, 0);
-						memcpy(om->b_wptr, s->out, (size_t)nwords * 2);
-						om->b_wptr += nwords * 2;
-					} else {
-						om = dupb(om);
-					}
-					ms_queue_put(q, om);
-				}
-			}
-		} else {
-			for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
-				MSQueue *q = f->outputs[i];
-				if (q && s->channels[i].output_enabled) {
-					mblk_t *om = allocb((size_t)nwords * 2, 0);
-					memcpy(om->b_wptr, s->out + (size_t)i * nwords, (size_t)nwords * 2);
-					om->b_wptr += nwords * 2;
-					ms_queue_put(q, om);
-				}
-			}
-		}
-	}
+	if (s->bank) mixer_emit(f, s, nwords);
 	ms_filter_unlock(f);
 }
 static int mixer_set_rate(MSFilter *f, void *data) {
@@ -297,7 +546,7 @@ static int mixer_set_input_gain(MSFilter *f, void *data) {
 	s->channels[ctl->pin].gain = ctl->param.gain;
 	if (s->bank) {
 		DSP_LOCK();
-		msb200_mixer_set_input_gain(s->bank, 0, ctl->pin, ctl->param.gain);
+		msb200_mixer_set_input_gain(s->bank, s->room, ctl->pin, ctl->param.gain);
 		DSP_UNLOCK();
 	}
 	return 0;
@@ -312,7 +561,7 @@ static int mixer_set_active(MSFilter *f, void *data) {
 	s->channels[ctl->pin].active = (bool_t)ctl->param.active;
 	if (s->bank) {
 		DSP_LOCK();
-		msb200_mixer_set_active(s->bank, 0, ctl->pin, ctl->param.active);
+		msb200_mixer_set_active(s->bank, s->room, ctl->pin, ctl->param.active);
 		DSP_UNLOCK();
 	}
 	return 0;
@@ -378,34 +627,47 @@ typedef struct VolState {
 	MSBufferizer *buffer;
 	float ea_thres, ea_speed, ea_force, ea_transmit;
 	int ea_sustain;
+	Batch *batch;     /* lockstep batch group (MSB200_BATCH), light path only; joined at the first block */
+	int slot;
+	mblk_t *held;     /* the block staged in the current tick: processed in the arena, copied back and forwarded next tick */
+	bool_t batch_off;
 } VolState;
 static MSFilterDesc b200_volume_desc;
 #define VOL_MAX_BLOCK 8192
 
-static void vol_sync_config(VolState *v) { /* DSP lock held */
-	if (!v->bank) return;
-	if (v->peer && !v->peer_linked && v->peer->desc == &b200_volume_desc && ((VolState *)v->peer->data)->bank) {
+static void vol_sync_config_to(VolState *v, msb200_volume *bank, int st) { /* DSP lock held */
+	if (!bank) return;
+	if (v->peer && !v->peer_linked && bank == v->bank && v->peer->desc == &b200_volume_desc && ((VolState *)v->peer->data)->bank) {
 		msb200_volume_set_peer(v->bank, 0, ((VolState *)v->peer->data)->bank, 0);
 		v->peer_linked = TRUE;
 	}
 	if (v->gain_dirty) { /* MS_VOLUME_SET_GAIN resets the ramp (gain = target = static, msvolume.c:270-276): apply it once */
-		msb200_volume_set_gain(v->bank, 0, v->static_gain);
+		msb200_volume_set_gain(bank, st, v->static_gain);
 		v->gain_dirty = FALSE;
 	}
 	if (!v->dirty) return;
 	if (v->noise_gate) {
-		msb200_volume_enable_noise_gate(v->bank, 0, 1);
-		msb200_volume_set_noise_gate_threshold(v->bank, 0, v->ng_threshold);
-		msb200_volume_set_noise_gate_floorgain(v->bank, 0, v->ng_floorgain);
+		msb200_volume_enable_noise_gate(bank, st, 1);
+		msb200_volume_set_noise_gate_threshold(bank, st, v->ng_threshold);
+		msb200_volume_set_noise_gate_floorgain(bank, st, v->ng_floorgain);
 	}
-	msb200_volume_remove_dc(v->bank, 0, v->remove_dc);
-	msb200_volume_enable_agc(v->bank, 0, v->agc);
-	msb200_volume_set_ea_threshold(v->bank, 0, v->ea_thres);
-	msb200_volume_set_ea_speed(v->bank, 0, v->ea_speed);
-	msb200_volume_set_ea_force(v->bank, 0, v->ea_force);
-	msb200_volume_set_ea_sustain(v->bank, 0, v->ea_sustain);
-	msb200_volume_set_ea_transmit_threshold(v->bank, 0, v->ea_transmit);
+	msb200_volume_remove_dc(bank, st, v->remove_dc);
+	msb200_volume_enable_agc(bank, st, v->agc);
+	msb200_volume_set_ea_threshold(bank, st, v->ea_thres);
+	msb200_volume_set_ea_speed(bank, st, v->ea_speed);
+	msb200_volume_set_ea_force(bank, st, v->ea_force);
+	msb200_volume_set_ea_sustain(bank, st, v->ea_sustain);
+	msb200_volume_set_ea_transmit_threshold(bank, st, v->ea_transmit);
 	v->dirty = FALSE;
+}
+static void vol_sync_config(VolState *v) { /* DSP lock held */
+	vol_sync_config_to(v, v->bank, 0);
+}
+static void vol_leave_batch(VolState *v) {
+	if (v->batch) batch_leave(v->batch, v->slot);
+	v->batch = NULL;
+	if (v->held) freemsg(v->held);
+	v->held = NULL;
 }
 static void vol_init(MSFilter *f) {
 	VolState *v = ms_new0(VolState, 1);
@@ -425,6 +687,7 @@ static void vol_init(MSFilter *f) {
 }
 static void vol_uninit(MSFilter *f) {
 	VolState *v = (VolState *)f->data;
+	vol_leave_batch(v);
 	DSP_LOCK();
 	msb200_volume_destroy(v->bank);
 	DSP_UNLOCK();
@@ -447,10 +710,14 @@ static void vol_preprocess(MSFilter *f) {
 	DSP_UNLOCK();
 	if (v->peer && v->peer->desc != &b200_volume_desc) ms_warning("MSVolume(b200): the echo-limiter peer is not a B200 MSVolume; ignored");
 }
+static void vol_postprocess(MSFilter *f) {
+	vol_leave_batch((VolState *)f->data);
+}
 static void vol_process(MSFilter *f) {
 	VolState *v = (VolState *)f->data;
 	mblk_t *m;
 	if (v->agc || v->peer != NULL) { /* chunked mode :480-502 */
+		if (v->batch) vol_leave_batch(v);
 		int nsamples = (int)(0.01 * (float)v->rate);
 		size_t nbytes = (size_t)nsamples * 2;
 		ms_bufferizer_put_from_queue(v->buffer, f->inputs[0]);
@@ -467,8 +734,49 @@ static void vol_process(MSFilter *f) {
 		}
 		return;
 	}
+	if (v->batch && v->batch->key[0] != v->rate) vol_leave_batch(v);
+	if (v->batch) { /* the block staged in the previous tick has been processed in the arena: copy it back and forward it */
+		Batch *b = v->batch;
+		batch_tick(b, f->ticker->ticks);
+		if (b->ready[v->slot] && v->held) {
+			b->ready[v->slot] = 0;
+			memcpy(v->held->b_rptr, b->in[0] + (size_t)v->slot * b->unit_in, (size_t)b->unit_in * 2);
+			ms_queue_put(f->outputs[0], v->held);
+			v->held = NULL;
+		}
+	}
 	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
 		int n = (int)((m->b_wptr - m->b_rptr) / 2);
+		if (!v->batch && !v->batch_off && batch_capacity() > 0 && n > 0 && n <= VOL_MAX_BLOCK) {
+			const int key[4] = {v->rate, n, 0, 0};
+			v->batch = batch_join(BK_VOLUME, f->ticker, key, n, n, 1, v, &v->slot);
+			if (v->batch) {
+				DSP_LOCK();
+				msb200_volume_reset_stream((msb200_volume *)v->batch->bank, v->slot);
+				v->dirty = TRUE;
+				v->gain_dirty = v->static_gain != 1.0f;
+				DSP_UNLOCK();
+			} else {
+				v->batch_off = TRUE;
+			}
+		}
+		if (v->batch) {
+			Batch *b = v->batch;
+			if (n == b->key[1] && b->staged[v->slot] == 0 && v->held == NULL) {
+				DSP_LOCK();
+				vol_sync_config_to(v, (msb200_volume *)b->bank, v->slot);
+				DSP_UNLOCK();
+				memcpy(b->in[0] + (size_t)v->slot * b->unit_in, m->b_rptr, (size_t)n * 2);
+				b->staged[v->slot] = 1;
+				v->held = m;
+				continue;
+			}
+			ms_warning("MSVolume(b200): irregular block (%d samples, group block %d): leaving the batch group", n, b->key[1]);
+			vol_leave_batch(v);
+			v->batch_off = TRUE;
+			v->dirty = TRUE;
+			v->gain_dirty = v->static_gain != 1.0f;
+		}
 		if (v->bank && n > 0 && n <= VOL_MAX_BLOCK) {
 			DSP_LOCK();
 			vol_sync_config(v);
@@ -482,6 +790,12 @@ static void vol_process(MSFilter *f) {
 }
 static int vol_get_state(VolState *v, msb200_volume_state *st) {
 	int rc = -1;
+	if (v->batch) { /* the slot of the group's bank holds this stream's state */
+		DSP_LOCK();
+		rc = msb200_volume_get_state((msb200_volume *)v->batch->bank, v->slot, st) == MSB200_OK ? 0 : -1;
+		DSP_UNLOCK();
+		return rc;
+	}
 	if (!v->bank) return -1;
 	DSP_LOCK();
 	rc = msb200_volume_get_state(v->bank, 0, st) == MSB200_OK ? 0 : -1;
@@ -629,6 +943,7 @@ static MSFilterDesc b200_volume_desc = {.id = MS_VOLUME_ID,
                                         .init = vol_init,
                                         .preprocess = vol_preprocess,
                                         .process = vol_process,
+                                        .postprocess = vol_postprocess,
                                         .uninit = vol_uninit,
                                         .methods = vol_methods};
 
@@ -906,6 +1221,10 @@ typedef struct RsState {
 	msb200_resample *bank;
 	uint32_t bank_in, bank_out;
 	int bank_ch;
+	Batch *batch;    /* lockstep batch group (MSB200_BATCH); joined at the first block, keyed by rates, channels, block size */
+	int slot;
+	mblk_t *held;    /* the input block staged in the current tick: its meta data travel to the output block */
+	bool_t batch_off; /* irregular block sizes: this instance stays synchronous */
 } RsState;
 #define RS_MAX_FRAMES 8192
 static void rs_init(MSFilter *f) {
@@ -915,8 +1234,15 @@ static void rs_init(MSFilter *f) {
 	s->in_nchannels = s->out_nchannels = 1;
 	f->data = s;
 }
+static void rs_leave_batch(RsState *s) {
+	if (s->batch) batch_leave(s->batch, s->slot);
+	s->batch = NULL;
+	if (s->held) freemsg(s->held);
+	s->held = NULL;
+}
 static void rs_uninit(MSFilter *f) {
 	RsState *s = (RsState *)f->data;
+	rs_leave_batch(s);
 	DSP_LOCK();
 	msb200_resample_destroy(s->bank);
 	DSP_UNLOCK();
@@ -959,11 +1285,59 @@ static void rs_process(MSFilter *f) {
 		return;
 	}
 	ms_filter_lock(f);
+	if (s->batch && (s->batch->key[0] != (int)s->input_rate || s->batch->key[1] != (int)s->output_rate || s->batch->key[2] != s->in_nchannels))
+		rs_leave_batch(s); /* rates changed under us (:138-148): a new group is joined at the next block */
+	if (s->batch) { /* the group's previous tick is computed by its first member called in this tick; emit our share */
+		Batch *b = s->batch;
+		batch_tick(b, f->ticker->ticks);
+		if (b->ready[s->slot] && s->held) {
+			const int outlen = b->out_len / s->in_nchannels;
+			mblk_t *om = allocb((size_t)b->out_len * 2, 0);
+			b->ready[s->slot] = 0;
+			memcpy(om->b_wptr, b->out + (size_t)s->slot * b->unit_out, (size_t)b->out_len * 2);
+			om->b_wptr += (size_t)b->out_len * 2;
+			mblk_meta_copy(s->held, om);
+			mblk_set_timestamp_info(om, s->ts);
+			s->ts += (uint32_t)outlen;
+			if (s->out_nchannels != s->in_nchannels) {
+				ms_queue_put(f->outputs[0], rs_channel_adapt(s->in_nchannels, s->out_nchannels, om));
+				freemsg(om);
+			} else {
+				ms_queue_put(f->outputs[0], om);
+			}
+			freemsg(s->held);
+			s->held = NULL;
+		}
+	}
 	while ((im = ms_queue_get(f->inputs[0])) != NULL) {
 		int inlen = (int)((im->b_wptr - im->b_rptr) / (2 * s->in_nchannels));
 		int outcap = (int)(((uint32_t)inlen * s->output_rate) / s->input_rate) + 1;
 		int outlen = 0;
-		mblk_t *om = allocb((size_t)outcap * 2 * (size_t)s->in_nchannels, 0);
+		mblk_t *om;
+		if (!s->batch && !s->batch_off && batch_capacity() > 0 && inlen > 0 && inlen <= RS_MAX_FRAMES) {
+			const int key[4] = {(int)s->input_rate, (int)s->output_rate, s->in_nchannels, inlen};
+			s->batch = batch_join(BK_RESAMPLE, f->ticker, key, inlen * s->in_nchannels, outcap * s->in_nchannels, 1, s, &s->slot);
+			if (s->batch) {
+				DSP_LOCK();
+				msb200_resample_reset_stream((msb200_resample *)s->batch->bank, s->slot);
+				DSP_UNLOCK();
+			} else {
+				s->batch_off = TRUE;
+			}
+		}
+		if (s->batch) {
+			Batch *b = s->batch;
+			if (inlen == b->key[3] && b->staged[s->slot] == 0 && s->held == NULL) {
+				memcpy(b->in[0] + (size_t)s->slot * b->unit_in, im->b_rptr, (size_t)b->unit_in * 2);
+				b->staged[s->slot] = 1;
+				s->held = im;
+				continue;
+			}
+			ms_warning("MSResample(b200): irregular block (%d frames, group block %d): leaving the batch group", inlen, b->key[3]);
+			rs_leave_batch(s);
+			s->batch_off = TRUE;
+		}
+		om = allocb((size_t)outcap * 2 * (size_t)s->in_nchannels, 0);
 		mblk_meta_copy(im, om);
 		DSP_LOCK();
 		rs_ensure_bank(s);
@@ -988,6 +1362,9 @@ static void rs_process(MSFilter *f) {
 		freemsg(im);
 	}
 	ms_filter_unlock(f);
+}
+static void rs_postprocess(MSFilter *f) {
+	rs_leave_batch((RsState *)f->data);
 }
 static void rs_preprocess(MSFilter *f) {
 	DSP_LOCK();
@@ -1032,6 +1409,7 @@ static MSFilterDesc b200_resample_desc = {.id = MS_RESAMPLE_ID,
                                           .init = rs_init,
                                           .preprocess = rs_preprocess,
                                           .process = rs_process,
+                                          .postprocess = rs_postprocess,
                                           .uninit = rs_uninit,
                                           .methods = rs_methods};
 
@@ -1046,7 +1424,10 @@ typedef struct EcState {
 	int framesize, framesize_at_8000, samplerate, delay_ms, tail_length_ms, nominal_ref_samples;
 	char *state_str;
 	bool_t echostarted, bypass_mode, using_zeroes;
+	Batch *batch; /* lockstep batch group (MSB200_BATCH): frames are staged here and cancelled one tick later */
+	int slot;
 } EcState;
+#define EC_BATCH_MAX_FRAMES 4 /* frames one stream may stage per tick (10 ms at 48 kHz = 1.875 frames of 256) */
 static void ec_configure_fcb(EcState *s) {
 	ms_flow_controlled_bufferizer_set_samplerate(&s->ref, s->samplerate);
 	ms_flow_controlled_bufferizer_set_max_size_ms(&s->ref, s->delay_ms);
@@ -1081,8 +1462,18 @@ static void ec_preprocess(MSFilter *f) {
 	delay_samples = s->delay_ms * s->samplerate / 1000;
 	ms_message("Initializing B200 echo canceler with framesize=%i, filterlength=%i, delay_samples=%i", s->framesize,
 	           (s->tail_length_ms * s->samplerate) / 1000, delay_samples);
+	if (batch_capacity() > 0) {
+		const int key[4] = {s->samplerate, s->tail_length_ms, s->framesize_at_8000, 0};
+		s->batch = batch_join(BK_EC, f->ticker, key, s->framesize, s->framesize, EC_BATCH_MAX_FRAMES, s, &s->slot);
+		if (s->batch) {
+			DSP_LOCK();
+			msb200_aec_reset((msb200_aec *)s->batch->bank, s->slot);
+			DSP_UNLOCK();
+		}
+	}
 	DSP_LOCK();
-	if (dsp_ctx()) DSP_CHECK(msb200_aec_create(g_ctx, 1, s->samplerate, s->tail_length_ms, s->framesize_at_8000, &s->bank), "aec_create");
+	if (!s->batch && dsp_ctx())
+		DSP_CHECK(msb200_aec_create(g_ctx, 1, s->samplerate, s->tail_length_ms, s->framesize_at_8000, &s->bank), "aec_create");
 	DSP_UNLOCK();
 	m = allocb((size_t)delay_samples * 2, 0);
 	m->b_wptr += delay_samples * 2;
@@ -1095,6 +1486,8 @@ static void ec_postprocess(MSFilter *f) {
 	ms_bufferizer_flush(&s->delayed_ref);
 	ms_bufferizer_flush(&s->echo);
 	ms_flow_controlled_bufferizer_flush(&s->ref);
+	if (s->batch) batch_leave(s->batch, s->slot);
+	s->batch = NULL;
 	DSP_LOCK();
 	msb200_aec_destroy(s->bank);
 	DSP_UNLOCK();
@@ -1105,6 +1498,18 @@ static void ec_process(MSFilter *f) {
 	int nbytes = s->framesize * 2;
 	mblk_t *refm;
 	uint8_t *ref, *echo;
+	if (s->batch) { /* frames staged during the previous tick were cancelled by the group's launch: emit ours */
+		Batch *b = s->batch;
+		int u;
+		batch_tick(b, f->ticker->ticks);
+		for (u = 0; u < b->ready[s->slot]; ++u) {
+			mblk_t *oecho = allocb((size_t)nbytes, 0);
+			memcpy(oecho->b_wptr, b->out + ((size_t)s->slot * b->max_units + u) * b->unit_out, (size_t)nbytes);
+			oecho->b_wptr += nbytes;
+			ms_queue_put(f->outputs[1], oecho);
+		}
+		b->ready[s->slot] = 0;
+	}
 	if (s->bypass_mode) {
 		while ((refm = ms_queue_get(f->inputs[0])) != NULL)
 			ms_queue_put(f->outputs[0], refm);
@@ -1151,6 +1556,20 @@ static void ec_process(MSFilter *f) {
 			ms_queue_put(f->outputs[0], refm);
 		}
 		if (ms_bufferizer_read(&s->delayed_ref, ref, (size_t)nbytes) == 0) ms_fatal("Should never happen");
+		if (s->batch) { /* stage the (mic, delayed reference) frame pair; it is cancelled at the start of the next tick */
+			Batch *b = s->batch;
+			const int u = b->staged[s->slot];
+			freemsg(oecho);
+			if (u < b->max_units) {
+				const size_t off = ((size_t)s->slot * b->max_units + u) * b->unit_in;
+				memcpy(b->in[0] + off, echo, (size_t)nbytes);
+				memcpy(b->in[1] + off, ref, (size_t)nbytes);
+				b->staged[s->slot] = u + 1;
+			} else {
+				ms_warning("MSSpeexEC(b200): more than %d frames in one tick, frame dropped", b->max_units);
+			}
+			continue;
+		}
 		/* speex_echo_cancellation + speex_preprocess_run for this frame, on the GPU */
 		DSP_LOCK();
 		if (s->bank) DSP_CHECK(msb200_aec_process(s->bank, (int16_t *)echo, (int16_t *)ref, (int16_t *)oecho->b_wptr, 1), "aec_process");
@@ -1326,6 +1745,14 @@ static MSScalerDesc b200_scaler_desc = {b200_scaler_create, b200_scaler_process,
 
 /* ================================================================================================ entry point */
 __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *factory) {
+	if (batch_capacity() > 0) {
+		/* lockstep batch mode: a filter must be called every tick to emit the result of the block it staged one tick
+		 * earlier, whether or not new input arrived (MSAudioMixer and MSChannelAdapter are pumps already) */
+		b200_volume_desc.flags |= MS_FILTER_IS_PUMP;
+		b200_resample_desc.flags |= MS_FILTER_IS_PUMP;
+		b200_speex_ec_desc.flags |= MS_FILTER_IS_PUMP;
+		ms_message("libmsb200filters: lockstep batch mode, %d slots per group (MSB200_BATCH)", batch_capacity());
+	}
 	ms_factory_register_filter(factory, &b200_audio_mixer_desc);
 	ms_factory_register_filter(factory, &b200_volume_desc);
 	ms_factory_register_filter(factory, &b200_channel_adapter_desc);
@@ -1335,6 +1762,22 @@ __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *fac
 	if (getenv("MSB200_INSTALL_SCALER")) ms_video_set_scaler_impl(&b200_scaler_desc);
 	ms_message("libmsb200filters: B200 DSP filters registered (MSAudioMixer, MSVolume, MSChannelAdapter, MSEqualizer, "
 	           "MSResample, MSSpeexEC%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
+}
+/* batch-group statistics for benchmarks: groups, launches (flushes) and units run so far, summed over all groups */
+__attribute__((visibility("default"))) void msb200_filters_batch_stats(int *groups, unsigned long long *flushes, unsigned long long *units) {
+	Batch *b;
+	int g = 0;
+	unsigned long long fl = 0, un = 0;
+	pthread_mutex_lock(&g_batch_mu);
+	for (b = g_batches; b; b = b->next) {
+		g++;
+		fl += b->flushes;
+		un += b->units_run;
+	}
+	pthread_mutex_unlock(&g_batch_mu);
+	if (groups) *groups = g;
+	if (flushes) *flushes = fl;
+	if (units) *units = un;
 }
 /* also exported so that a host can install the scaler explicitly */
 __attribute__((visibility("default"))) MSScalerDesc *msb200_ms_scaler_desc(void) {

@@ -1,0 +1,45 @@
+"""Lockstep batch mode of the plugin (MSB200_BATCH): the BASELINE cfg5 graph in the unmodified reference MSTicker gives
+bit-identical sample streams in batch mode and in synchronous mode — batch mode only delivers them later (one ticker
+interval per batched stage). The plugin's mode is fixed per process, hence the subprocesses."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _run(tmp_path, batch, tag, streams, pins, ticks, timing=False):
+    env = dict(os.environ, MSB200_BATCH=str(batch))
+    out = tmp_path / f"{tag}.npz"
+    cmd = [sys.executable, str(ROOT / "tests" / "graph_runner.py"), "--streams", str(streams), "--pins", str(pins),
+           "--ticks", str(ticks), "--dump", str(out)] + (["--timing"] if timing else [])
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    stats = json.loads(r.stdout.strip().splitlines()[-1]) if timing else None
+    return np.load(out), stats
+
+
+@pytest.mark.parametrize("streams,pins", [(8, 4), (6, 3)])
+def test_batch_mode_is_synchronous_mode_delayed(tmp_path, streams, pins):
+    ticks = 70
+    sync, _ = _run(tmp_path, 0, "sync", streams, pins, ticks)
+    batch, stats = _run(tmp_path, 16, "batch", streams, pins, ticks, timing=True)
+    n48 = 480
+    for i in range(streams):
+        # speaker path: far end -> MSResample -> MSSpeexEC pass-through: one batched stage (the resampler)
+        a, b = sync[f"spk{i}"], batch[f"spk{i}"]
+        assert len(b) >= len(a) - 2 * n48 and len(b) > 40 * n48, (i, len(a), len(b))
+        assert np.array_equal(b, a[:len(b)]), f"speaker path of stream {i}"
+        # send path: resampler, echo canceller, volume, mixer: four batched stages
+        a, b = sync[f"out{i}"], batch[f"out{i}"]
+        assert len(b) >= len(a) - 6 * n48 and len(b) > 40 * n48, (i, len(a), len(b))
+        assert np.array_equal(b, a[:len(b)]), f"send path of stream {i}"
+    # one launch per group per tick, not per stream: 4 kinds of groups (2 resamplers per stream share one)
+    assert stats["mode"] == "batch" and stats["batch_groups"] == 4
+    assert stats["batch_launches"] <= 4 * ticks
