@@ -52,6 +52,9 @@ MSB200_API int msb200_ctx_create(int device_ordinal, msb200_ctx **out);
 MSB200_API int msb200_ctx_create_on_stream(int device_ordinal, void *cuda_stream, msb200_ctx **out);
 MSB200_API void msb200_ctx_destroy(msb200_ctx *ctx);
 MSB200_API int msb200_ctx_sync(msb200_ctx *ctx);
+/* cudaSetDevice(ctx's device) for the calling thread: call it first on every thread that uses ctx (or its banks) when
+ * the process drives more than one GPU; a no-op cost otherwise */
+MSB200_API int msb200_ctx_make_current(msb200_ctx *ctx);
 /* Kernel launches issued through this context since creation (bench.py reports it as gpu_launches). */
 MSB200_API uint64_t msb200_ctx_launch_count(msb200_ctx *ctx);
 /* Raw device memory helpers so that a plain-C (or ctypes) caller can keep buffers resident in HBM. */
@@ -84,6 +87,7 @@ MSB200_API int msb200_mixer_create(msb200_ctx *ctx, int n_rooms, int n_pins, int
 MSB200_API void msb200_mixer_destroy(msb200_mixer *m);
 MSB200_API int msb200_mixer_set_input_gain(msb200_mixer *m, int room, int pin, float gain); /* MS_AUDIO_MIXER_SET_INPUT_GAIN */
 MSB200_API int msb200_mixer_set_active(msb200_mixer *m, int room, int pin, int active);     /* MS_AUDIO_MIXER_SET_ACTIVE */
+MSB200_API int msb200_mixer_set_live(msb200_mixer *m, int n_live_rooms); /* see msb200_volume_set_live */
 MSB200_API int msb200_mixer_process(msb200_mixer *m, const int16_t *in, const uint8_t *present, int16_t *out);
 MSB200_API int msb200_mixer_process_dev(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out);
 /* Cross-GPU conference: phase 1 writes each room's int32 partial sum of the LOCAL pins to d_sum
@@ -125,6 +129,9 @@ typedef struct msb200_volume_state {
 MSB200_API int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_volume **out);
 MSB200_API void msb200_volume_destroy(msb200_volume *v);
 MSB200_API int msb200_volume_reset_stream(msb200_volume *v, int stream); /* volume_init state, one stream */
+/* Partially occupied banks (all four audio banks have this call): only streams (rooms) [0, n_live) are copied and
+ * processed by the next process calls; the others keep their state and their host rows are not touched. */
+MSB200_API int msb200_volume_set_live(msb200_volume *v, int n_live);
 MSB200_API int msb200_volume_set_gain(msb200_volume *v, int stream, float gain);           /* MS_VOLUME_SET_GAIN :270-276 */
 MSB200_API int msb200_volume_set_db_gain(msb200_volume *v, int stream, float db);          /* MS_VOLUME_SET_DB_GAIN :262-268 */
 MSB200_API int msb200_volume_enable_noise_gate(msb200_volume *v, int stream, int enabled); /* :352-359 */
@@ -146,6 +153,11 @@ MSB200_API int msb200_volume_get_state(msb200_volume *v, int stream, msb200_volu
 /* io: [stream][nsamples] s16, processed in place */
 MSB200_API int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples);
 MSB200_API int msb200_volume_process_dev(msb200_volume *v, void *d_io, int nsamples, int stride_samples);
+/* up to `nblocks` consecutive blocks of `nsamples` per stream in one launch (the reference's per-mblk loop :505-512),
+ * io laid out [stream][stride_samples]; counts (NULL = nblocks for all) gives each stream's own block count: a stream
+ * that staged fewer blocks in this tick is left untouched beyond its count (the plugin's lockstep batch mode) */
+MSB200_API int msb200_volume_process_blocks(msb200_volume *v, int16_t *io, int nsamples, int stride_samples, int nblocks,
+                                            const int32_t *counts);
 
 /* ---------------------------------------------------------------------------------------------------- MSChannelAdapter
  * Replaces adapter_process() /root/reference/src/audiofilters/chanadapt.c:99-132 (mono->stereo duplicate,
@@ -194,6 +206,7 @@ MSB200_API int msb200_resample_create(msb200_ctx *ctx, int n_streams, int in_rat
 MSB200_API void msb200_resample_destroy(msb200_resample *r);
 MSB200_API int msb200_resample_max_out(msb200_resample *r, int in_frames); /* inlen*out/in + 1, msresample.c:151-152 */
 MSB200_API int msb200_resample_reset(msb200_resample *r);
+MSB200_API int msb200_resample_set_live(msb200_resample *r, int n_live); /* see msb200_volume_set_live */
 /* one stream's filter memory only (a stream joining a running lockstep bank; the resampling phase stays bank-wide) */
 MSB200_API int msb200_resample_reset_stream(msb200_resample *r, int stream);
 MSB200_API int msb200_resample_process(msb200_resample *r, const int16_t *in, int in_frames, int16_t *out,
@@ -221,6 +234,7 @@ MSB200_API int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate
 MSB200_API void msb200_aec_destroy(msb200_aec *a);
 MSB200_API int msb200_aec_get_info(msb200_aec *a, msb200_aec_info *info);
 MSB200_API int msb200_aec_reset(msb200_aec *a, int stream); /* stream < 0: all */
+MSB200_API int msb200_aec_set_live(msb200_aec *a, int n_live); /* see msb200_volume_set_live */
 MSB200_API int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes);
 MSB200_API int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes,
                                       int stride_samples);

@@ -90,7 +90,12 @@ _SIGS = {
     "msb200_mixer_finish_peers_dev": (_I, [_P, _P, _P, _P, _P, _I, C.c_uint32, _P, _P]),
     "msb200_volume_create": (_I, [_P, _I, _I, _I, _PP]),
     "msb200_volume_destroy": (None, [_P]),
+    "msb200_ctx_make_current": (_I, [_P]),
     "msb200_volume_reset_stream": (_I, [_P, _I]),
+    "msb200_volume_set_live": (_I, [_P, _I]),
+    "msb200_mixer_set_live": (_I, [_P, _I]),
+    "msb200_resample_set_live": (_I, [_P, _I]),
+    "msb200_aec_set_live": (_I, [_P, _I]),
     "msb200_volume_set_gain": (_I, [_P, _I, _F]),
     "msb200_volume_set_db_gain": (_I, [_P, _I, _F]),
     "msb200_volume_enable_noise_gate": (_I, [_P, _I, _I]),
@@ -106,6 +111,7 @@ _SIGS = {
     "msb200_volume_set_ea_transmit_threshold": (_I, [_P, _I, _F]),
     "msb200_volume_get_state": (_I, [_P, _I, C.POINTER(VolumeState)]),
     "msb200_volume_process": (_I, [_P, _P, _I]),
+    "msb200_volume_process_blocks": (_I, [_P, _P, _I, _I, _I, _P]),
     "msb200_volume_process_dev": (_I, [_P, _P, _I, _I]),
     "msb200_chanadapt_process": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "msb200_chanadapt_process_dev": (_I, [_P, _I, _I, _I, _P, _P, _P]),

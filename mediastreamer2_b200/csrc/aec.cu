@@ -1125,6 +1125,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 struct msb200_aec {
 	msb200_ctx *ctx;
 	int n;
+	int live; // streams [0, live) are processed (msb200_aec_set_live); == n by default
 	AecParams P;
 	int head; // ring head shared by all streams
 	size_t smem_bytes;
@@ -1179,7 +1180,7 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	MSB200_CHECK_ARG(M >= 2 && M <= 512);
 	msb200_aec *a = new msb200_aec();
 	a->ctx = ctx;
-	a->n = n_streams;
+	a->n = a->live = n_streams;
 	a->tail_ms = tail_length_ms;
 	a->filter_length = filter_length;
 	a->head = 0;
@@ -1364,11 +1365,11 @@ int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int 
 #define AEC_ARGS                                                                                                       \
 	(const short *)d_mic, (const short *)d_ref, (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, \
 	    a->head, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames
-	switch (a->P.F) {
-		case 256: MSB200_LAUNCH(a->ctx, aec_kernel<8>, a->n, 256, a->smem_bytes, AEC_ARGS); break;
-		case 128: MSB200_LAUNCH(a->ctx, aec_kernel<7>, a->n, 128, a->smem_bytes, AEC_ARGS); break;
-		case 64: MSB200_LAUNCH(a->ctx, aec_kernel<6>, a->n, 64, a->smem_bytes, AEC_ARGS); break;
-		case 32: MSB200_LAUNCH(a->ctx, aec_kernel<5>, a->n, 32, a->smem_bytes, AEC_ARGS); break;
+	if (a->live > 0) switch (a->P.F) {
+		case 256: MSB200_LAUNCH(a->ctx, aec_kernel<8>, a->live, 256, a->smem_bytes, AEC_ARGS); break;
+		case 128: MSB200_LAUNCH(a->ctx, aec_kernel<7>, a->live, 128, a->smem_bytes, AEC_ARGS); break;
+		case 64: MSB200_LAUNCH(a->ctx, aec_kernel<6>, a->live, 64, a->smem_bytes, AEC_ARGS); break;
+		case 32: MSB200_LAUNCH(a->ctx, aec_kernel<5>, a->live, 32, a->smem_bytes, AEC_ARGS); break;
 		default: msb200_set_error("unsupported AEC frame size %d", a->P.F); return MSB200_EINVAL;
 	}
 #undef AEC_ARGS
@@ -1380,7 +1381,8 @@ extern "C" {
 
 int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes) {
 	MSB200_CHECK_ARG(a && mic && ref && out && nframes > 0);
-	size_t bytes = (size_t)a->n * nframes * a->P.F * 2;
+	if (a->live == 0) return MSB200_OK;
+	size_t bytes = (size_t)a->live * nframes * a->P.F * 2;
 	int r;
 	if ((r = a->mic.reserve(bytes)) || (r = a->ref.reserve(bytes)) || (r = a->out.reserve(bytes))) return r;
 	cudaStream_t s = a->ctx->stream;
@@ -1397,15 +1399,24 @@ int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, in
 int msb200_aec_process_strided(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes,
                                int stride_samples) {
 	MSB200_CHECK_ARG(a && mic && ref && out && nframes > 0 && stride_samples >= nframes * a->P.F);
-	size_t bytes = (size_t)a->n * stride_samples * 2;
+	// only the staged frames of every row cross PCIe: rows of nframes*F out of stride_samples
+	const size_t pitch = (size_t)stride_samples * 2, row = (size_t)nframes * a->P.F * 2;
+	size_t bytes = (size_t)a->live * pitch + 16;
 	int r;
 	if ((r = a->mic.reserve(bytes)) || (r = a->ref.reserve(bytes)) || (r = a->out.reserve(bytes))) return r;
 	cudaStream_t s = a->ctx->stream;
-	MSB200_CUDA(cudaMemcpyAsync(a->mic.p, mic, bytes, cudaMemcpyHostToDevice, s));
-	MSB200_CUDA(cudaMemcpyAsync(a->ref.p, ref, bytes, cudaMemcpyHostToDevice, s));
+	if (a->live > 0) {
+		MSB200_CUDA(cudaMemcpy2DAsync(a->mic.p, pitch, mic, pitch, row, (size_t)a->live, cudaMemcpyHostToDevice, s));
+		MSB200_CUDA(cudaMemcpy2DAsync(a->ref.p, pitch, ref, pitch, row, (size_t)a->live, cudaMemcpyHostToDevice, s));
+	}
 	if ((r = msb200_aec_process_dev(a, a->mic.p, a->ref.p, a->out.p, nframes, stride_samples))) return r;
-	MSB200_CUDA(cudaMemcpyAsync(out, a->out.p, bytes, cudaMemcpyDeviceToHost, s));
+	if (a->live > 0) MSB200_CUDA(cudaMemcpy2DAsync(out, pitch, a->out.p, pitch, row, (size_t)a->live, cudaMemcpyDeviceToHost, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+int msb200_aec_set_live(msb200_aec *a, int n_live) {
+	MSB200_CHECK_ARG(a && n_live >= 0 && n_live <= a->n);
+	a->live = n_live;
 	return MSB200_OK;
 }
 

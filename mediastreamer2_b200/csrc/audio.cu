@@ -24,6 +24,7 @@ __device__ __forceinline__ int mix_contrib(int s, float gain) { // :46-51, only 
 struct msb200_mixer {
 	msb200_ctx *ctx;
 	int n_rooms, n_pins, nwords, conf_mode;
+	int live;          // rooms [0, live) are processed (msb200_mixer_set_live); == n_rooms by default
 	float *d_gain;     // [room][pin]
 	uint8_t *d_active; // [room][pin]
 	std::vector<float> h_gain;
@@ -201,11 +202,11 @@ static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present
 		vec = 4;
 	}
 	// prefer more, narrower threads when the grid would not cover the chip (148 SMs x >=4 CTAs of 128)
-	while (mode != 3 && vec > 2 && (long)m->n_rooms * (nw / vec) < 148L * 4 * 128) vec /= 2;
-	const long nthreads = (long)m->n_rooms * (nw / vec);
+	while (mode != 3 && vec > 2 && (long)m->live * (nw / vec) < 148L * 4 * 128) vec /= 2;
+	const long nthreads = (long)m->live * (nw / vec);
 	const int block = 128, grid = (int)((nthreads + block - 1) / block);
 #define MIX_ARGS                                                                                                       \
-	(const short *)d_in, (const uint8_t *)d_present, m->d_gain, m->d_active, (short *)d_out, (int *)d_sum, m->n_rooms, \
+	(const short *)d_in, (const uint8_t *)d_present, m->d_gain, m->d_active, (short *)d_out, (int *)d_sum, m->live, \
 	    m->n_pins, nw, m->conf_mode, mode, in_pin_stride / vec, peers
 	switch (vec) {
 		case 8: MSB200_LAUNCH(m->ctx, mixer_kernel<8>, grid, block, 0, MIX_ARGS); break;
@@ -223,7 +224,7 @@ int msb200_mixer_create(msb200_ctx *ctx, int n_rooms, int n_pins, int nwords, in
 	MSB200_CHECK_ARG(ctx && out && n_rooms > 0 && n_pins > 0 && n_pins <= 50 /* MIXER_MAX_CHANNELS :29 */ && nwords > 0);
 	msb200_mixer *m = new msb200_mixer();
 	m->ctx = ctx;
-	m->n_rooms = n_rooms;
+	m->n_rooms = m->live = n_rooms;
 	m->n_pins = n_pins;
 	m->nwords = nwords;
 	m->conf_mode = conf_mode;
@@ -286,11 +287,17 @@ int msb200_mixer_finish_peers_dev(msb200_mixer *m, const void *d_in, const void 
 	p.error = (unsigned *)d_error;
 	return mixer_launch(m, d_in, d_present, d_out, nullptr, 3, 0, &p);
 }
+int msb200_mixer_set_live(msb200_mixer *m, int n_live) {
+	MSB200_CHECK_ARG(m && n_live >= 0 && n_live <= m->n_rooms);
+	m->live = n_live;
+	return MSB200_OK;
+}
 int msb200_mixer_process(msb200_mixer *m, const int16_t *in, const uint8_t *present, int16_t *out) {
 	MSB200_CHECK_ARG(m && in && present && out);
-	size_t nch = (size_t)m->n_rooms * m->n_pins;
+	if (m->live == 0) return MSB200_OK;
+	size_t nch = (size_t)m->live * m->n_pins;
 	size_t in_bytes = nch * m->nwords * 2;
-	size_t out_bytes = m->conf_mode ? in_bytes : (size_t)m->n_rooms * m->nwords * 2;
+	size_t out_bytes = m->conf_mode ? in_bytes : (size_t)m->live * m->nwords * 2;
 	int r;
 	if ((r = m->in.reserve(in_bytes)) || (r = m->present.reserve(nch)) || (r = m->out.reserve(out_bytes))) return r;
 	cudaStream_t s = m->ctx->stream;
@@ -316,6 +323,7 @@ int msb200i_mixer_launch(msb200_mixer *m, const void *d_in, long in_pin_stride, 
 struct msb200_volume {
 	msb200_ctx *ctx;
 	int n, rate, max_block;
+	int live; // streams [0, live) are processed (msb200_volume_set_live); == n by default
 	msb200_volume *peer_bank; // bank whose states the echo limiter reads (may be this one)
 	msb200_volume_state *d_state;
 	msb200_devbuf io;
@@ -330,12 +338,14 @@ __device__ __forceinline__ int vol_sat(int v) { // :382-384
 // reduced across the warp; then all lanes apply the Q12 gain and store.
 __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st,
                                                      int n_streams, int nsamples, int stride, int nblocks, int block0,
-                                                     int ring_blocks, const msb200_volume_state *__restrict__ peer_states) {
+                                                     int ring_blocks, const msb200_volume_state *__restrict__ peer_states,
+                                                     const int *__restrict__ counts) {
 	extern __shared__ short vsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int stream = blockIdx.x * (blockDim.x >> 5) + warp;
 	if (stream >= n_streams) return;
 	short *buf = vsm + (size_t)warp * ((nsamples + 1) & ~1);
+	if (counts) nblocks = min(nblocks, counts[stream]); // ragged batches: this stream staged fewer blocks than the bank's maximum
 	// nblocks consecutive blocks (the reference processes one mblk at a time, msvolume.c:505-512), optionally laid out
 	// in a block-aligned circular buffer
 	for (int blk = 0; blk < nblocks; ++blk) {
@@ -478,7 +488,7 @@ int msb200_volume_create(msb200_ctx *ctx, int n_streams, int sample_rate, int ma
 	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && sample_rate > 0 && max_block > 0 && max_block <= 8192);
 	msb200_volume *v = new msb200_volume();
 	v->ctx = ctx;
-	v->n = n_streams;
+	v->n = v->live = n_streams;
 	v->rate = sample_rate;
 	v->max_block = max_block;
 	std::vector<msb200_volume_state> init((size_t)n_streams);
@@ -556,9 +566,32 @@ int msb200_volume_process_dev(msb200_volume *v, void *d_io, int nsamples, int st
 	MSB200_CHECK_ARG(stride >= nsamples);
 	return msb200i_volume_launch(v, d_io, nsamples, stride, 1, 0, 0);
 }
+int msb200_volume_process_blocks(msb200_volume *v, int16_t *io, int nsamples, int stride_samples, int nblocks, const int32_t *counts) {
+	MSB200_CHECK_ARG(v && io && nblocks > 0 && stride_samples >= nsamples * nblocks);
+	if (v->live == 0) return MSB200_OK;
+	// only the staged part of every row crosses PCIe: rows of nblocks*nsamples out of stride_samples
+	const size_t pitch = (size_t)stride_samples * 2, row = (size_t)nblocks * nsamples * 2;
+	const size_t bytes = ((size_t)v->live * pitch + 15) & ~(size_t)15, cbytes = counts ? sizeof(int32_t) * (size_t)v->live : 0;
+	int r = v->io.reserve(bytes + cbytes);
+	if (r) return r;
+	cudaStream_t s = v->ctx->stream;
+	int *d_counts = counts ? (int *)((char *)v->io.p + bytes) : nullptr;
+	MSB200_CUDA(cudaMemcpy2DAsync(v->io.p, pitch, io, pitch, row, (size_t)v->live, cudaMemcpyHostToDevice, s));
+	if (counts) MSB200_CUDA(cudaMemcpyAsync(d_counts, counts, cbytes, cudaMemcpyHostToDevice, s));
+	if ((r = msb200i_volume_launch(v, v->io.p, nsamples, stride_samples, nblocks, 0, 0, d_counts))) return r;
+	MSB200_CUDA(cudaMemcpy2DAsync(io, pitch, v->io.p, pitch, row, (size_t)v->live, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+int msb200_volume_set_live(msb200_volume *v, int n_live) {
+	MSB200_CHECK_ARG(v && n_live >= 0 && n_live <= v->n);
+	v->live = n_live;
+	return MSB200_OK;
+}
 int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples) {
 	MSB200_CHECK_ARG(v && io);
-	size_t bytes = (size_t)v->n * nsamples * 2;
+	if (v->live == 0) return MSB200_OK;
+	size_t bytes = (size_t)v->live * nsamples * 2;
 	int r = v->io.reserve(bytes);
 	if (r) return r;
 	cudaStream_t s = v->ctx->stream;
@@ -571,13 +604,15 @@ int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples) {
 
 } // extern "C"
 
-int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride, int nblocks, int block0, int ring_blocks) {
+int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride, int nblocks, int block0, int ring_blocks,
+                          const int *d_counts) {
 	MSB200_CHECK_ARG(v && d_io && nsamples > 0 && nsamples <= v->max_block && nblocks > 0);
 	const int warps = 8;
 	size_t smem = (size_t)warps * ((nsamples + 1) & ~1) * sizeof(short);
-	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->n, warps), warps * 32, smem, (short *)d_io, v->d_state, v->n,
+	if (v->live == 0) return MSB200_OK;
+	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->live, warps), warps * 32, smem, (short *)d_io, v->d_state, v->live,
 	              nsamples, stride, nblocks, block0, ring_blocks,
-	              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr));
+	              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr), d_counts);
 	return MSB200_OK;
 }
 

@@ -57,6 +57,12 @@ static int ctx_create_impl(int device_ordinal, bool own, cudaStream_t ext, msb20
 	return MSB200_OK;
 }
 
+int msb200_ctx_make_current(msb200_ctx *c) {
+	MSB200_CHECK_ARG(c != nullptr);
+	MSB200_CUDA(cudaSetDevice(c->device));
+	return MSB200_OK;
+}
+
 int msb200_ctx_create(int device_ordinal, msb200_ctx **out) {
 	return ctx_create_impl(device_ordinal, true, nullptr, out);
 }

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256)
 struct msb200_resample {
 	msb200_ctx *ctx;
 	int n, in_rate, out_rate, nch, max_in;
+	int live; // streams [0, live) are processed (msb200_resample_set_live); == n by default
 	ResampleDesign d;
 	ResampleParams p;
 	float *d_table;
@@ -201,7 +202,7 @@ int msb200_resample_create(msb200_ctx *ctx, int n_streams, int in_rate, int out_
 	MSB200_CHECK_ARG(nchannels >= 1 && nchannels <= 8 && max_in_frames > 0 && max_in_frames <= 16384);
 	msb200_resample *r = new msb200_resample();
 	r->ctx = ctx;
-	r->n = n_streams;
+	r->n = r->live = n_streams;
 	r->in_rate = in_rate;
 	r->out_rate = out_rate;
 	r->nch = nchannels;
@@ -275,7 +276,7 @@ int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames,
 	size_t smem = sizeof(float) * ((size_t)r->p.table_len + r->d.filt_len - 1 + (size_t)in_frames);
 	int block = n_out >= 256 ? 256 : ((n_out + 31) & ~31);
 	if (block < 32) block = 32;
-	MSB200_LAUNCH(r->ctx, resample_kernel, r->n * r->nch, block, smem, (const short *)d_in, in_frames, in_stride,
+	if (r->live > 0) MSB200_LAUNCH(r->ctx, resample_kernel, r->live * r->nch, block, smem, (const short *)d_in, in_frames, in_stride,
 	              (short *)d_out, n_out, out_stride, r->d_hist, r->d_table, r->p, last0, frac0, ring_off, ring_cap);
 	return MSB200_OK;
 }
@@ -285,14 +286,19 @@ int msb200_resample_process(msb200_resample *r, const int16_t *in, int in_frames
 	MSB200_CHECK_ARG(r && in && out && in_frames > 0);
 	int cap = msb200_resample_max_out(r, in_frames);
 	MSB200_CHECK_ARG(out_stride >= cap);
-	size_t in_bytes = (size_t)r->n * in_frames * r->nch * 2, out_bytes = (size_t)r->n * out_stride * r->nch * 2;
+	size_t in_bytes = (size_t)r->live * in_frames * r->nch * 2, out_bytes = (size_t)r->live * out_stride * r->nch * 2;
 	int rc;
-	if ((rc = r->in.reserve(in_bytes)) || (rc = r->out.reserve(out_bytes))) return rc;
+	if ((rc = r->in.reserve(in_bytes + 16)) || (rc = r->out.reserve(out_bytes + 16))) return rc;
 	cudaStream_t s = r->ctx->stream;
-	MSB200_CUDA(cudaMemcpyAsync(r->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+	if (in_bytes) MSB200_CUDA(cudaMemcpyAsync(r->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
 	if ((rc = msb200_resample_process_dev(r, r->in.p, in_frames, in_frames, r->out.p, out_stride, out_frames))) return rc;
-	MSB200_CUDA(cudaMemcpyAsync(out, r->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+	if (out_bytes) MSB200_CUDA(cudaMemcpyAsync(out, r->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+int msb200_resample_set_live(msb200_resample *r, int n_live) {
+	MSB200_CHECK_ARG(r && n_live >= 0 && n_live <= r->n);
+	r->live = n_live;
 	return MSB200_OK;
 }
 

@@ -250,6 +250,17 @@ void ref_ticker_run(void *ht, int n) {
 	pthread_mutex_unlock(&h->mu);
 	hticker_wait_parked(h);
 }
+/* the same in two halves, so that several tickers can run their ticks concurrently: release all, then wait for all */
+void ref_ticker_release(void *ht, int n) {
+	HTicker *h = (HTicker *)ht;
+	pthread_mutex_lock(&h->mu);
+	h->allowed += n;
+	pthread_cond_broadcast(&h->cv);
+	pthread_mutex_unlock(&h->mu);
+}
+void ref_ticker_wait(void *ht) {
+	hticker_wait_parked((HTicker *)ht);
+}
 unsigned long long ref_ticker_time(void *ht) {
 	return (unsigned long long)((HTicker *)ht)->ticker->time;
 }

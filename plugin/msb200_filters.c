@@ -66,16 +66,23 @@ static msb200_ctx *dsp_ctx(void) {
 /* ------------------------------------------------------------------------------------------------ batch groups
  * MSB200_BATCH=<slots> turns on the lockstep batch mode: filters of one kind, on one MSTicker, with one configuration
  * key share a bank of <slots> streams (rooms for the mixer). All member process() calls of a ticker come from that
- * ticker's thread (src/base/msticker.c:244-282), so a group is touched by one thread at a time; joining and leaving
- * (preprocess / postprocess, on the attaching thread) take g_batch_mu, and so does the flush.
+ * ticker's thread (src/base/msticker.c:244-282), so a group's arenas and slot tables are touched by one thread at a
+ * time; joining / leaving (preprocess / postprocess, on the attaching thread), control-thread methods that reach the
+ * group's bank and the flush serialise on the GROUP's mutex. Every group owns its device context (its own CUDA
+ * stream), so the groups of different tickers run concurrently on the GPU and never wait for each other on the host.
  *
  *   tick T, member i:  batch_tick()   -> first caller of the tick: run the bank over everything staged during T-1
  *                      emit           -> the member's results of T-1 go to its output queue
  *                      stage          -> the member's block(s) of T are copied into its arena slot
  *
- * A slot that staged fewer units than the group's maximum in a tick (a starving stream) is fed zeros for the missing
- * units and its outputs for those units are discarded: the stream's audio is untouched, only its filter memory sees
- * a silent unit. Streams that deliver the same block sizes every tick (a media server's RTP streams) never hit this.
+ * Only slots [0, highest occupied + 1) are copied and processed (msb200_*_set_live). A slot that staged fewer units
+ * than the group's maximum in a tick (a starving stream) is fed zeros for the missing units and its outputs for those
+ * units are discarded (MSVolume: skipped exactly, the kernel takes per-slot counts). Streams that deliver the same
+ * block sizes every tick (a media server's RTP streams) never hit this.
+ *
+ * Several GPUs in one process: MSB200_DEVICES=<n> spreads the TICKERS over devices 0..n-1 in order of first use
+ * (BASELINE cfg5: rooms are pinned to a GPU by giving their streams a ticker of that GPU); MSB200_DEVICE=<d> (default 0)
+ * is the device of the synchronous filters and of every ticker when MSB200_DEVICES is unset.
  */
 enum { BK_RESAMPLE, BK_EC, BK_VOLUME, BK_MIXER };
 #define BATCH_MAX_SLOTS 4096
@@ -84,20 +91,27 @@ typedef struct Batch {
 	int kind;
 	MSTicker *ticker;
 	int key[4];
-	int cap, n_members;
+	int cap, n_members, hi, live; /* hi: highest occupied slot + 1; live: what the bank was last told */
 	void **owner;      /* [cap] filter state owning the slot, NULL when free */
 	uint64_t seen_tick; /* ticker->ticks of the last flush */
+	msb200_ctx *ctx;   /* the group's own device context (stream) */
+	pthread_mutex_t mu; /* bank, slot tables */
 	void *bank;
 	int unit_in, unit_out, max_units; /* samples per unit per slot in / out; units a slot may stage per tick */
 	int16_t *in[2], *out;             /* pinned arenas [cap][max_units * unit_*] */
-	uint8_t *present;                 /* mixer: [cap][MIXER pins] */
+	uint8_t *present;                 /* mixer: [cap][pins] */
 	int *staged, *ready;              /* units per slot: staged this tick / ready from the last flush */
 	int out_len;                      /* samples per unit the last run produced (resampler: frames out x channels) */
+	/* moves a slot's ready results out of the arenas into mblks kept by the owner; the flush calls it for every member
+	 * that has not been scheduled since the previous flush, so a skipped tick delays a stream's output but never loses it */
+	void (*collect)(void *owner, struct Batch *b);
 	uint64_t flushes, units_run;
 } Batch;
 static Batch *g_batches = NULL;
-static pthread_mutex_t g_batch_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_batch_mu = PTHREAD_MUTEX_INITIALIZER; /* the list of groups and the ticker -> device table */
 static int g_batch_cap = -1;
+#define GRP_LOCK(b) pthread_mutex_lock(&(b)->mu)
+#define GRP_UNLOCK(b) pthread_mutex_unlock(&(b)->mu)
 
 static int batch_capacity(void) {
 	if (g_batch_cap < 0) {
@@ -107,24 +121,41 @@ static int batch_capacity(void) {
 	}
 	return g_batch_cap;
 }
-static void *batch_pinned(size_t bytes) {
+/* device of a ticker's groups (g_batch_mu held) */
+#define BATCH_MAX_TICKERS 256
+static MSTicker *g_dev_tickers[BATCH_MAX_TICKERS];
+static int g_n_dev_tickers = 0;
+static int batch_device_of(MSTicker *t) {
+	const char *e = getenv("MSB200_DEVICES"), *d = getenv("MSB200_DEVICE");
+	const int ndev = e ? atoi(e) : 0;
+	int i;
+	if (ndev <= 1) return d ? atoi(d) : 0;
+	for (i = 0; i < g_n_dev_tickers; ++i)
+		if (g_dev_tickers[i] == t) return i % ndev;
+	if (g_n_dev_tickers < BATCH_MAX_TICKERS) g_dev_tickers[g_n_dev_tickers++] = t;
+	return (g_n_dev_tickers - 1) % ndev;
+}
+static void *batch_pinned(Batch *b, size_t bytes) {
 	void *p = NULL;
-	if (msb200_host_alloc_pinned(g_ctx, bytes ? bytes : 16, &p) != MSB200_OK) return NULL;
+	if (msb200_host_alloc_pinned(b->ctx, bytes ? bytes : 16, &p) != MSB200_OK) return NULL;
 	memset(p, 0, bytes);
 	return p;
 }
-static void batch_free(Batch *b) { /* g_batch_mu held, no members left */
-	DSP_LOCK();
-	switch (b->kind) {
-		case BK_RESAMPLE: msb200_resample_destroy((msb200_resample *)b->bank); break;
-		case BK_EC: msb200_aec_destroy((msb200_aec *)b->bank); break;
-		case BK_VOLUME: msb200_volume_destroy((msb200_volume *)b->bank); break;
-		case BK_MIXER: msb200_mixer_destroy((msb200_mixer *)b->bank); break;
+static void batch_free(Batch *b) { /* unlinked, no members left */
+	if (b->ctx) {
+		msb200_ctx_make_current(b->ctx);
+		switch (b->kind) {
+			case BK_RESAMPLE: msb200_resample_destroy((msb200_resample *)b->bank); break;
+			case BK_EC: msb200_aec_destroy((msb200_aec *)b->bank); break;
+			case BK_VOLUME: msb200_volume_destroy((msb200_volume *)b->bank); break;
+			case BK_MIXER: msb200_mixer_destroy((msb200_mixer *)b->bank); break;
+		}
+		if (b->in[0]) msb200_host_free_pinned(b->ctx, b->in[0]);
+		if (b->in[1]) msb200_host_free_pinned(b->ctx, b->in[1]);
+		if (b->out) msb200_host_free_pinned(b->ctx, b->out);
+		msb200_ctx_destroy(b->ctx);
 	}
-	if (b->in[0]) msb200_host_free_pinned(g_ctx, b->in[0]);
-	if (b->in[1]) msb200_host_free_pinned(g_ctx, b->in[1]);
-	if (b->out) msb200_host_free_pinned(g_ctx, b->out);
-	DSP_UNLOCK();
+	pthread_mutex_destroy(&b->mu);
 	ms_free(b->present);
 	ms_free(b->owner);
 	ms_free(b->staged);
@@ -133,7 +164,7 @@ static void batch_free(Batch *b) { /* g_batch_mu held, no members left */
 }
 /* find (or create) the group for (kind, ticker, key) and take a slot in it; NULL when batching is off or impossible */
 static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_in, int unit_out, int max_units, void *owner,
-                         int *slot) {
+                         void (*collect)(void *, Batch *), int *slot) {
 	Batch *b;
 	int i, cap = batch_capacity();
 	if (cap <= 0 || ticker == NULL) return NULL;
@@ -141,39 +172,39 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 	for (b = g_batches; b; b = b->next)
 		if (b->kind == kind && b->ticker == ticker && memcmp(b->key, key, sizeof(b->key)) == 0 && b->n_members < b->cap) break;
 	if (!b) {
-		int rc = MSB200_OK;
-		DSP_LOCK();
-		if (!dsp_ctx()) {
-			DSP_UNLOCK();
-			pthread_mutex_unlock(&g_batch_mu);
-			return NULL;
-		}
+		int rc;
 		b = ms_new0(Batch, 1);
+		pthread_mutex_init(&b->mu, NULL);
 		b->kind = kind;
 		b->ticker = ticker;
 		memcpy(b->key, key, sizeof(b->key));
 		b->cap = cap;
+		b->live = cap;
 		b->unit_in = unit_in;
 		b->unit_out = unit_out;
 		b->max_units = max_units;
+		b->collect = collect;
 		b->seen_tick = (uint64_t)-1;
-		switch (kind) {
-			case BK_RESAMPLE: rc = msb200_resample_create(g_ctx, cap, key[0], key[1], key[2], key[3], (msb200_resample **)&b->bank); break;
-			case BK_EC: rc = msb200_aec_create(g_ctx, cap, key[0], key[1], key[2], (msb200_aec **)&b->bank); break;
-			case BK_VOLUME: rc = msb200_volume_create(g_ctx, cap, key[0], key[1], (msb200_volume **)&b->bank); break;
-			case BK_MIXER: rc = msb200_mixer_create(g_ctx, cap, key[2], key[0], key[1], (msb200_mixer **)&b->bank); break;
+		rc = msb200_ctx_create(batch_device_of(ticker), &b->ctx);
+		if (rc == MSB200_OK) {
+			switch (kind) {
+				case BK_RESAMPLE: rc = msb200_resample_create(b->ctx, cap, key[0], key[1], key[2], key[3], (msb200_resample **)&b->bank); break;
+				case BK_EC: rc = msb200_aec_create(b->ctx, cap, key[0], key[1], key[2], (msb200_aec **)&b->bank); break;
+				case BK_VOLUME: rc = msb200_volume_create(b->ctx, cap, key[0], key[1], (msb200_volume **)&b->bank); break;
+				case BK_MIXER: rc = msb200_mixer_create(b->ctx, cap, key[2], key[0], key[1], (msb200_mixer **)&b->bank); break;
+			}
+		} else {
+			b->ctx = NULL;
 		}
 		if (rc == MSB200_OK) {
 			const size_t n_in = (size_t)cap * max_units * unit_in * sizeof(int16_t), n_out = (size_t)cap * max_units * unit_out * sizeof(int16_t);
-			b->in[0] = (int16_t *)batch_pinned(n_in);
-			if (kind == BK_EC) b->in[1] = (int16_t *)batch_pinned(n_in);
-			b->out = kind == BK_VOLUME ? NULL : (int16_t *)batch_pinned(n_out);
+			b->in[0] = (int16_t *)batch_pinned(b, n_in);
+			if (kind == BK_EC) b->in[1] = (int16_t *)batch_pinned(b, n_in);
+			b->out = kind == BK_VOLUME ? NULL : (int16_t *)batch_pinned(b, n_out);
 			if (!b->in[0] || (kind == BK_EC && !b->in[1]) || (kind != BK_VOLUME && !b->out)) rc = MSB200_ENOMEM;
 		}
-		DSP_UNLOCK();
 		if (rc != MSB200_OK) {
 			ms_error("msb200: cannot create a batch group (%s); the filter stays synchronous", msb200_last_error());
-			b->owner = NULL;
 			batch_free(b);
 			pthread_mutex_unlock(&g_batch_mu);
 			return NULL;
@@ -186,48 +217,68 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 		g_batches = b;
 		ms_message("msb200: batch group %p: kind %d, %d slots, key {%d,%d,%d,%d} on ticker %p", b, kind, cap, key[0], key[1], key[2], key[3], ticker);
 	}
+	GRP_LOCK(b);
 	for (i = 0; i < b->cap && b->owner[i]; ++i) {
 	}
 	b->owner[i] = owner;
 	b->staged[i] = b->ready[i] = 0;
 	b->n_members++;
+	if (i + 1 > b->hi) b->hi = i + 1;
 	*slot = i;
+	GRP_UNLOCK(b);
 	pthread_mutex_unlock(&g_batch_mu);
 	return b;
 }
 static void batch_leave(Batch *b, int slot) {
 	Batch **pp;
+	int last;
 	if (!b) return;
 	pthread_mutex_lock(&g_batch_mu);
+	GRP_LOCK(b);
 	b->owner[slot] = NULL;
 	b->staged[slot] = b->ready[slot] = 0;
 	if (b->present) memset(b->present + (size_t)slot * b->key[2], 0, (size_t)b->key[2]);
-	if (--b->n_members == 0) {
+	while (b->hi > 0 && b->owner[b->hi - 1] == NULL)
+		b->hi--;
+	last = --b->n_members == 0;
+	if (last) {
 		for (pp = &g_batches; *pp && *pp != b; pp = &(*pp)->next) {
 		}
 		if (*pp) *pp = b->next;
-		batch_free(b);
 	}
+	GRP_UNLOCK(b);
+	if (last) batch_free(b);
 	pthread_mutex_unlock(&g_batch_mu);
 }
 /* called first thing in every member's process(): the first caller of a tick runs the group's previous tick */
 static void batch_tick(Batch *b, uint64_t ticks) {
 	int i, units = 0, rc = MSB200_OK;
 	if (b->seen_tick == ticks) return;
-	pthread_mutex_lock(&g_batch_mu);
+	GRP_LOCK(b);
 	b->seen_tick = ticks;
-	for (i = 0; i < b->cap; ++i)
+	for (i = 0; i < b->hi; ++i) {
+		if (b->ready[i] > 0 && b->owner[i] && b->collect) b->collect(b->owner[i], b); /* not scheduled since the last flush */
 		if (b->staged[i] > units) units = b->staged[i];
+	}
 	if (units > 0) {
+		msb200_ctx_make_current(b->ctx);
+		if (b->live != b->hi) {
+			switch (b->kind) {
+				case BK_RESAMPLE: msb200_resample_set_live((msb200_resample *)b->bank, b->hi); break;
+				case BK_EC: msb200_aec_set_live((msb200_aec *)b->bank, b->hi); break;
+				case BK_VOLUME: msb200_volume_set_live((msb200_volume *)b->bank, b->hi); break;
+				case BK_MIXER: msb200_mixer_set_live((msb200_mixer *)b->bank, b->hi); break;
+			}
+			b->live = b->hi;
+		}
 		/* slots that staged less than the group's maximum are fed zeros for the missing units */
-		for (i = 0; i < b->cap; ++i) {
-			if (b->staged[i] < units && b->kind != BK_MIXER) {
+		for (i = 0; i < b->hi; ++i) {
+			if (b->staged[i] < units && b->kind != BK_MIXER && b->kind != BK_VOLUME) { /* the volume kernel takes per-slot counts */
 				const size_t off = ((size_t)i * b->max_units + b->staged[i]) * b->unit_in, n = (size_t)(units - b->staged[i]) * b->unit_in;
 				memset(b->in[0] + off, 0, n * sizeof(int16_t));
 				if (b->in[1]) memset(b->in[1] + off, 0, n * sizeof(int16_t));
 			}
 		}
-		DSP_LOCK();
 		switch (b->kind) {
 			case BK_RESAMPLE: {
 				int outlen = 0;
@@ -240,7 +291,7 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 				b->out_len = b->unit_out;
 				break;
 			case BK_VOLUME:
-				rc = msb200_volume_process((msb200_volume *)b->bank, b->in[0], b->unit_in);
+				rc = msb200_volume_process_blocks((msb200_volume *)b->bank, b->in[0], b->unit_in, b->max_units * b->unit_in, units, b->staged);
 				b->out_len = b->unit_in;
 				break;
 			case BK_MIXER:
@@ -248,17 +299,16 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 				b->out_len = b->unit_out;
 				break;
 		}
-		DSP_UNLOCK();
 		if (rc != MSB200_OK) ms_error("msb200: batch group %p (kind %d) failed: %s", b, b->kind, msb200_last_error());
 		b->flushes++;
 		b->units_run += (uint64_t)units;
 	}
-	for (i = 0; i < b->cap; ++i) {
+	for (i = 0; i < b->hi; ++i) {
 		b->ready[i] = rc == MSB200_OK ? b->staged[i] : 0;
 		b->staged[i] = 0;
 	}
-	if (b->present) memset(b->present, 0, (size_t)b->cap * b->key[2]);
-	pthread_mutex_unlock(&g_batch_mu);
+	if (b->present) memset(b->present, 0, (size_t)b->hi * b->key[2]);
+	GRP_UNLOCK(b);
 }
 
 /* ================================================================================================ MSAudioMixer
@@ -287,7 +337,11 @@ typedef struct MixerState {
 	int16_t *out;       /* [50][nwords] (conference) or [nwords] */
 	Batch *batch;       /* lockstep batch group (MSB200_BATCH), NULL in synchronous mode */
 	int room;
+	int pins;           /* pins of the bank: the highest connected pin + 1, rounded up to a multiple of 4 */
 } MixerState;
+/* the bank is shared with the group's flush in batch mode, with the other synchronous filters otherwise */
+#define MIX_LOCK(s) do { if ((s)->batch) GRP_LOCK((s)->batch); else DSP_LOCK(); } while (0)
+#define MIX_UNLOCK(s) do { if ((s)->batch) GRP_UNLOCK((s)->batch); else DSP_UNLOCK(); } while (0)
 
 static void mixer_init(MSFilter *f) {
 	MixerState *s = ms_new0(MixerState, 1);
@@ -330,31 +384,37 @@ static void mixer_preprocess(MSFilter *f) {
 	s->bypass_mode = FALSE;
 	s->single_output = mixer_has_single_output(f, s);
 	s->room = 0;
+	/* the graph is fixed while attached: only the connected pins travel to the GPU (a 16-party room moves 16 rows, not 50) */
+	s->pins = 0;
+	for (i = 0; i < MIXER_MAX_CHANNELS; ++i)
+		if (f->inputs[i] || f->outputs[i]) s->pins = i + 1;
+	s->pins = (s->pins + 3) & ~3;
+	if (s->pins < 4) s->pins = 4;
+	if (s->pins > MIXER_MAX_CHANNELS) s->pins = MIXER_MAX_CHANNELS;
 	if (batch_capacity() > 0) {
-		const int key[4] = {nwords, s->conf_mode, MIXER_MAX_CHANNELS, 0};
-		s->batch = batch_join(BK_MIXER, f->ticker, key, MIXER_MAX_CHANNELS * nwords, s->conf_mode ? MIXER_MAX_CHANNELS * nwords : nwords, 1,
-		                      s, &s->room);
+		const int key[4] = {nwords, s->conf_mode, s->pins, 0};
+		s->batch = batch_join(BK_MIXER, f->ticker, key, s->pins * nwords, s->conf_mode ? s->pins * nwords : nwords, 1, s, NULL, &s->room);
 	}
 	if (s->batch) { /* this mixer is one room of the group's bank; its arenas are slices of the group's pinned arenas */
 		s->bank = (msb200_mixer *)s->batch->bank;
 		s->in = s->batch->in[0] + (size_t)s->room * s->batch->unit_in;
 		s->out = s->batch->out + (size_t)s->room * s->batch->unit_out;
-		s->present = s->batch->present + (size_t)s->room * MIXER_MAX_CHANNELS;
-		DSP_LOCK();
-		for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
+		s->present = s->batch->present + (size_t)s->room * s->pins;
+		GRP_LOCK(s->batch);
+		for (i = 0; i < s->pins; ++i) {
 			msb200_mixer_set_input_gain(s->bank, s->room, i, s->channels[i].gain);
 			msb200_mixer_set_active(s->bank, s->room, i, s->channels[i].active);
 		}
-		DSP_UNLOCK();
+		GRP_UNLOCK(s->batch);
 		return;
 	}
-	s->in = (int16_t *)ms_malloc0(sizeof(int16_t) * MIXER_MAX_CHANNELS * (size_t)nwords);
-	s->out = (int16_t *)ms_malloc0(sizeof(int16_t) * MIXER_MAX_CHANNELS * (size_t)nwords);
-	s->present = (uint8_t *)ms_malloc0(MIXER_MAX_CHANNELS);
+	s->in = (int16_t *)ms_malloc0(sizeof(int16_t) * (size_t)s->pins * (size_t)nwords);
+	s->out = (int16_t *)ms_malloc0(sizeof(int16_t) * (size_t)s->pins * (size_t)nwords);
+	s->present = (uint8_t *)ms_malloc0((size_t)s->pins);
 	DSP_LOCK();
 	if (dsp_ctx()) {
-		DSP_CHECK(msb200_mixer_create(g_ctx, 1, MIXER_MAX_CHANNELS, nwords, s->conf_mode, &s->bank), "mixer_create");
-		for (i = 0; s->bank && i < MIXER_MAX_CHANNELS; ++i) {
+		DSP_CHECK(msb200_mixer_create(g_ctx, 1, s->pins, nwords, s->conf_mode, &s->bank), "mixer_create");
+		for (i = 0; s->bank && i < s->pins; ++i) {
 			msb200_mixer_set_input_gain(s->bank, 0, i, s->channels[i].gain);
 			msb200_mixer_set_active(s->bank, 0, i, s->channels[i].active);
 		}
@@ -386,7 +446,7 @@ static void mixer_emit(MSFilter *f, MixerState *s, int nwords) {
 	int i;
 	if (s->conf_mode == 0) {
 		mblk_t *om = NULL;
-		for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
+		for (i = 0; i < s->pins; ++i) {
 			MSQueue *q = f->outputs[i];
 			if (q && s->channels[i].output_enabled) {
 				if (om == NULL) {
@@ -400,7 +460,7 @@ static void mixer_emit(MSFilter *f, MixerState *s, int nwords) {
 			}
 		}
 	} else {
-		for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
+		for (i = 0; i < s->pins; ++i) {
 			MSQueue *q = f->outputs[i];
 			if (q && s->channels[i].output_enabled) {
 				mblk_t *om = allocb((size_t)nwords * 2, 0);
@@ -480,8 +540,8 @@ static void mixer_process(MSFilter *f) {
 		ms_filter_unlock(f);
 		return;
 	}
-	memset(s->present, 0, MIXER_MAX_CHANNELS);
-	for (i = 0; i < f->desc->ninputs; ++i) {
+	memset(s->present, 0, (size_t)s->pins);
+	for (i = 0; i < s->pins; ++i) {
 		MSQueue *q = f->inputs[i];
 		MixChannel *chan = &s->channels[i];
 		int size, skip = 0;
@@ -544,10 +604,10 @@ static int mixer_set_input_gain(MSFilter *f, void *data) {
 		return -1;
 	}
 	s->channels[ctl->pin].gain = ctl->param.gain;
-	if (s->bank) {
-		DSP_LOCK();
+	if (s->bank && ctl->pin < s->pins) {
+		MIX_LOCK(s);
 		msb200_mixer_set_input_gain(s->bank, s->room, ctl->pin, ctl->param.gain);
-		DSP_UNLOCK();
+		MIX_UNLOCK(s);
 	}
 	return 0;
 }
@@ -559,10 +619,10 @@ static int mixer_set_active(MSFilter *f, void *data) {
 		return -1;
 	}
 	s->channels[ctl->pin].active = (bool_t)ctl->param.active;
-	if (s->bank) {
-		DSP_LOCK();
+	if (s->bank && ctl->pin < s->pins) {
+		MIX_LOCK(s);
 		msb200_mixer_set_active(s->bank, s->room, ctl->pin, ctl->param.active);
-		DSP_UNLOCK();
+		MIX_UNLOCK(s);
 	}
 	return 0;
 }
@@ -629,11 +689,14 @@ typedef struct VolState {
 	int ea_sustain;
 	Batch *batch;     /* lockstep batch group (MSB200_BATCH), light path only; joined at the first block */
 	int slot;
-	mblk_t *held;     /* the block staged in the current tick: processed in the arena, copied back and forwarded next tick */
+	mblk_t *held[8];  /* the blocks staged in the current tick: processed in the arena, copied back and forwarded next tick */
+	int n_held;
+	MSQueue pend;     /* processed blocks waiting for this filter's next process() */
 	bool_t batch_off;
 } VolState;
 static MSFilterDesc b200_volume_desc;
 #define VOL_MAX_BLOCK 8192
+#define VOL_BATCH_UNITS 8 /* blocks one stream may stage per tick (an upstream MSSpeexEC emits 1-2 frames per 10 ms) */
 
 static void vol_sync_config_to(VolState *v, msb200_volume *bank, int st) { /* DSP lock held */
 	if (!bank) return;
@@ -664,13 +727,29 @@ static void vol_sync_config(VolState *v) { /* DSP lock held */
 	vol_sync_config_to(v, v->bank, 0);
 }
 static void vol_leave_batch(VolState *v) {
+	int i;
 	if (v->batch) batch_leave(v->batch, v->slot);
 	v->batch = NULL;
-	if (v->held) freemsg(v->held);
-	v->held = NULL;
+	for (i = 0; i < v->n_held; ++i) freemsg(v->held[i]);
+	v->n_held = 0;
+}
+static void vol_collect(void *owner, Batch *b) { /* processed in place in the arena: copy back into the held blocks */
+	VolState *v = (VolState *)owner;
+	int u;
+	for (u = 0; u < v->n_held; ++u) {
+		if (b->ready[v->slot] == v->n_held) {
+			memcpy(v->held[u]->b_rptr, b->in[0] + ((size_t)v->slot * b->max_units + u) * b->unit_in, (size_t)b->unit_in * 2);
+			ms_queue_put(&v->pend, v->held[u]);
+		} else { /* the group's launch failed (logged there): never forward unprocessed audio */
+			freemsg(v->held[u]);
+		}
+	}
+	b->ready[v->slot] = 0;
+	v->n_held = 0;
 }
 static void vol_init(MSFilter *f) {
 	VolState *v = ms_new0(VolState, 1);
+	ms_queue_init(&v->pend);
 	v->rate = 8000;
 	v->static_gain = 1.0f;
 	v->ng_threshold = 0.1f;
@@ -688,6 +767,7 @@ static void vol_init(MSFilter *f) {
 static void vol_uninit(MSFilter *f) {
 	VolState *v = (VolState *)f->data;
 	vol_leave_batch(v);
+	ms_queue_flush(&v->pend);
 	DSP_LOCK();
 	msb200_volume_destroy(v->bank);
 	DSP_UNLOCK();
@@ -735,40 +815,40 @@ static void vol_process(MSFilter *f) {
 		return;
 	}
 	if (v->batch && v->batch->key[0] != v->rate) vol_leave_batch(v);
-	if (v->batch) { /* the block staged in the previous tick has been processed in the arena: copy it back and forward it */
-		Batch *b = v->batch;
-		batch_tick(b, f->ticker->ticks);
-		if (b->ready[v->slot] && v->held) {
-			b->ready[v->slot] = 0;
-			memcpy(v->held->b_rptr, b->in[0] + (size_t)v->slot * b->unit_in, (size_t)b->unit_in * 2);
-			ms_queue_put(f->outputs[0], v->held);
-			v->held = NULL;
-		}
+	if (v->batch) { /* the blocks staged in the previous tick have been processed in the arena by the group's launch */
+		batch_tick(v->batch, f->ticker->ticks);
+		if (v->n_held && v->batch->staged[v->slot] == 0) vol_collect(v, v->batch);
 	}
+	while ((m = ms_queue_get(&v->pend)) != NULL)
+		ms_queue_put(f->outputs[0], m);
 	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
 		int n = (int)((m->b_wptr - m->b_rptr) / 2);
 		if (!v->batch && !v->batch_off && batch_capacity() > 0 && n > 0 && n <= VOL_MAX_BLOCK) {
 			const int key[4] = {v->rate, n, 0, 0};
-			v->batch = batch_join(BK_VOLUME, f->ticker, key, n, n, 1, v, &v->slot);
+			v->batch = batch_join(BK_VOLUME, f->ticker, key, n, n, VOL_BATCH_UNITS, v, vol_collect, &v->slot);
 			if (v->batch) {
-				DSP_LOCK();
+				GRP_LOCK(v->batch);
+				msb200_ctx_make_current(v->batch->ctx);
 				msb200_volume_reset_stream((msb200_volume *)v->batch->bank, v->slot);
 				v->dirty = TRUE;
 				v->gain_dirty = v->static_gain != 1.0f;
-				DSP_UNLOCK();
+				GRP_UNLOCK(v->batch);
 			} else {
 				v->batch_off = TRUE;
 			}
 		}
 		if (v->batch) {
 			Batch *b = v->batch;
-			if (n == b->key[1] && b->staged[v->slot] == 0 && v->held == NULL) {
-				DSP_LOCK();
-				vol_sync_config_to(v, (msb200_volume *)b->bank, v->slot);
-				DSP_UNLOCK();
-				memcpy(b->in[0] + (size_t)v->slot * b->unit_in, m->b_rptr, (size_t)n * 2);
-				b->staged[v->slot] = 1;
-				v->held = m;
+			if (n == b->key[1] && b->staged[v->slot] < b->max_units && v->n_held == b->staged[v->slot]) {
+				if (v->dirty || v->gain_dirty) {
+					GRP_LOCK(b);
+					msb200_ctx_make_current(b->ctx);
+					vol_sync_config_to(v, (msb200_volume *)b->bank, v->slot);
+					GRP_UNLOCK(b);
+				}
+				memcpy(b->in[0] + ((size_t)v->slot * b->max_units + b->staged[v->slot]) * b->unit_in, m->b_rptr, (size_t)n * 2);
+				b->staged[v->slot]++;
+				v->held[v->n_held++] = m;
 				continue;
 			}
 			ms_warning("MSVolume(b200): irregular block (%d samples, group block %d): leaving the batch group", n, b->key[1]);
@@ -791,9 +871,10 @@ static void vol_process(MSFilter *f) {
 static int vol_get_state(VolState *v, msb200_volume_state *st) {
 	int rc = -1;
 	if (v->batch) { /* the slot of the group's bank holds this stream's state */
-		DSP_LOCK();
+		GRP_LOCK(v->batch);
+		msb200_ctx_make_current(v->batch->ctx);
 		rc = msb200_volume_get_state((msb200_volume *)v->batch->bank, v->slot, st) == MSB200_OK ? 0 : -1;
-		DSP_UNLOCK();
+		GRP_UNLOCK(v->batch);
 		return rc;
 	}
 	if (!v->bank) return -1;
@@ -1224,6 +1305,7 @@ typedef struct RsState {
 	Batch *batch;    /* lockstep batch group (MSB200_BATCH); joined at the first block, keyed by rates, channels, block size */
 	int slot;
 	mblk_t *held;    /* the input block staged in the current tick: its meta data travel to the output block */
+	MSQueue pend;    /* resampled blocks waiting for this filter's next process() */
 	bool_t batch_off; /* irregular block sizes: this instance stays synchronous */
 } RsState;
 #define RS_MAX_FRAMES 8192
@@ -1232,6 +1314,7 @@ static void rs_init(MSFilter *f) {
 	s->input_rate = 8000;
 	s->output_rate = 16000;
 	s->in_nchannels = s->out_nchannels = 1;
+	ms_queue_init(&s->pend);
 	f->data = s;
 }
 static void rs_leave_batch(RsState *s) {
@@ -1243,6 +1326,7 @@ static void rs_leave_batch(RsState *s) {
 static void rs_uninit(MSFilter *f) {
 	RsState *s = (RsState *)f->data;
 	rs_leave_batch(s);
+	ms_queue_flush(&s->pend);
 	DSP_LOCK();
 	msb200_resample_destroy(s->bank);
 	DSP_UNLOCK();
@@ -1270,6 +1354,27 @@ static mblk_t *rs_channel_adapt(int in_ch, int out_ch, mblk_t *im) { /* resample
 	mblk_meta_copy(im, om);
 	return om;
 }
+static void rs_collect(void *owner, Batch *b) { /* the slot's resampled block: arena -> mblk (meta data of the input block) */
+	RsState *s = (RsState *)owner;
+	if (s->held && b->ready[s->slot]) {
+		const int outlen = b->out_len / s->in_nchannels;
+		mblk_t *om = allocb((size_t)b->out_len * 2, 0);
+		memcpy(om->b_wptr, b->out + (size_t)s->slot * b->unit_out, (size_t)b->out_len * 2);
+		om->b_wptr += (size_t)b->out_len * 2;
+		mblk_meta_copy(s->held, om);
+		mblk_set_timestamp_info(om, s->ts);
+		s->ts += (uint32_t)outlen;
+		if (s->out_nchannels != s->in_nchannels) {
+			ms_queue_put(&s->pend, rs_channel_adapt(s->in_nchannels, s->out_nchannels, om));
+			freemsg(om);
+		} else {
+			ms_queue_put(&s->pend, om);
+		}
+	}
+	if (s->held) freemsg(s->held);
+	s->held = NULL;
+	b->ready[s->slot] = 0;
+}
 static void rs_process(MSFilter *f) {
 	RsState *s = (RsState *)f->data;
 	mblk_t *im;
@@ -1288,27 +1393,11 @@ static void rs_process(MSFilter *f) {
 	if (s->batch && (s->batch->key[0] != (int)s->input_rate || s->batch->key[1] != (int)s->output_rate || s->batch->key[2] != s->in_nchannels))
 		rs_leave_batch(s); /* rates changed under us (:138-148): a new group is joined at the next block */
 	if (s->batch) { /* the group's previous tick is computed by its first member called in this tick; emit our share */
-		Batch *b = s->batch;
-		batch_tick(b, f->ticker->ticks);
-		if (b->ready[s->slot] && s->held) {
-			const int outlen = b->out_len / s->in_nchannels;
-			mblk_t *om = allocb((size_t)b->out_len * 2, 0);
-			b->ready[s->slot] = 0;
-			memcpy(om->b_wptr, b->out + (size_t)s->slot * b->unit_out, (size_t)b->out_len * 2);
-			om->b_wptr += (size_t)b->out_len * 2;
-			mblk_meta_copy(s->held, om);
-			mblk_set_timestamp_info(om, s->ts);
-			s->ts += (uint32_t)outlen;
-			if (s->out_nchannels != s->in_nchannels) {
-				ms_queue_put(f->outputs[0], rs_channel_adapt(s->in_nchannels, s->out_nchannels, om));
-				freemsg(om);
-			} else {
-				ms_queue_put(f->outputs[0], om);
-			}
-			freemsg(s->held);
-			s->held = NULL;
-		}
+		batch_tick(s->batch, f->ticker->ticks);
+		if (s->held && s->batch->staged[s->slot] == 0) rs_collect(s, s->batch);
 	}
+	while ((im = ms_queue_get(&s->pend)) != NULL)
+		ms_queue_put(f->outputs[0], im);
 	while ((im = ms_queue_get(f->inputs[0])) != NULL) {
 		int inlen = (int)((im->b_wptr - im->b_rptr) / (2 * s->in_nchannels));
 		int outcap = (int)(((uint32_t)inlen * s->output_rate) / s->input_rate) + 1;
@@ -1316,11 +1405,12 @@ static void rs_process(MSFilter *f) {
 		mblk_t *om;
 		if (!s->batch && !s->batch_off && batch_capacity() > 0 && inlen > 0 && inlen <= RS_MAX_FRAMES) {
 			const int key[4] = {(int)s->input_rate, (int)s->output_rate, s->in_nchannels, inlen};
-			s->batch = batch_join(BK_RESAMPLE, f->ticker, key, inlen * s->in_nchannels, outcap * s->in_nchannels, 1, s, &s->slot);
+			s->batch = batch_join(BK_RESAMPLE, f->ticker, key, inlen * s->in_nchannels, outcap * s->in_nchannels, 1, s, rs_collect, &s->slot);
 			if (s->batch) {
-				DSP_LOCK();
+				GRP_LOCK(s->batch);
+				msb200_ctx_make_current(s->batch->ctx);
 				msb200_resample_reset_stream((msb200_resample *)s->batch->bank, s->slot);
-				DSP_UNLOCK();
+				GRP_UNLOCK(s->batch);
 			} else {
 				s->batch_off = TRUE;
 			}
@@ -1426,6 +1516,7 @@ typedef struct EcState {
 	bool_t echostarted, bypass_mode, using_zeroes;
 	Batch *batch; /* lockstep batch group (MSB200_BATCH): frames are staged here and cancelled one tick later */
 	int slot;
+	MSQueue pend; /* cancelled frames waiting for this filter's next process() */
 } EcState;
 #define EC_BATCH_MAX_FRAMES 4 /* frames one stream may stage per tick (10 ms at 48 kHz = 1.875 frames of 256) */
 static void ec_configure_fcb(EcState *s) {
@@ -1443,10 +1534,24 @@ static void ec_init(MSFilter *f) {
 	s->tail_length_ms = 250;
 	s->framesize_at_8000 = 64;
 	s->framesize = 64;
+	ms_queue_init(&s->pend);
 	f->data = s;
+}
+static void ec_collect(void *owner, Batch *b) { /* the slot's cancelled frames: arena -> one mblk per frame */
+	EcState *s = (EcState *)owner;
+	const int nbytes = s->framesize * 2;
+	int u;
+	for (u = 0; u < b->ready[s->slot]; ++u) {
+		mblk_t *oecho = allocb((size_t)nbytes, 0);
+		memcpy(oecho->b_wptr, b->out + ((size_t)s->slot * b->max_units + u) * b->unit_out, (size_t)nbytes);
+		oecho->b_wptr += nbytes;
+		ms_queue_put(&s->pend, oecho);
+	}
+	b->ready[s->slot] = 0;
 }
 static void ec_uninit(MSFilter *f) {
 	EcState *s = (EcState *)f->data;
+	ms_queue_flush(&s->pend);
 	if (s->state_str) ms_free(s->state_str);
 	ms_bufferizer_uninit(&s->delayed_ref);
 	ms_bufferizer_uninit(&s->echo);
@@ -1464,11 +1569,12 @@ static void ec_preprocess(MSFilter *f) {
 	           (s->tail_length_ms * s->samplerate) / 1000, delay_samples);
 	if (batch_capacity() > 0) {
 		const int key[4] = {s->samplerate, s->tail_length_ms, s->framesize_at_8000, 0};
-		s->batch = batch_join(BK_EC, f->ticker, key, s->framesize, s->framesize, EC_BATCH_MAX_FRAMES, s, &s->slot);
+		s->batch = batch_join(BK_EC, f->ticker, key, s->framesize, s->framesize, EC_BATCH_MAX_FRAMES, s, ec_collect, &s->slot);
 		if (s->batch) {
-			DSP_LOCK();
+			GRP_LOCK(s->batch);
+			msb200_ctx_make_current(s->batch->ctx);
 			msb200_aec_reset((msb200_aec *)s->batch->bank, s->slot);
-			DSP_UNLOCK();
+			GRP_UNLOCK(s->batch);
 		}
 	}
 	DSP_LOCK();
@@ -1499,17 +1605,11 @@ static void ec_process(MSFilter *f) {
 	mblk_t *refm;
 	uint8_t *ref, *echo;
 	if (s->batch) { /* frames staged during the previous tick were cancelled by the group's launch: emit ours */
-		Batch *b = s->batch;
-		int u;
-		batch_tick(b, f->ticker->ticks);
-		for (u = 0; u < b->ready[s->slot]; ++u) {
-			mblk_t *oecho = allocb((size_t)nbytes, 0);
-			memcpy(oecho->b_wptr, b->out + ((size_t)s->slot * b->max_units + u) * b->unit_out, (size_t)nbytes);
-			oecho->b_wptr += nbytes;
-			ms_queue_put(f->outputs[1], oecho);
-		}
-		b->ready[s->slot] = 0;
+		batch_tick(s->batch, f->ticker->ticks);
+		if (s->batch->staged[s->slot] == 0) ec_collect(s, s->batch);
 	}
+	while ((refm = ms_queue_get(&s->pend)) != NULL)
+		ms_queue_put(f->outputs[1], refm);
 	if (s->bypass_mode) {
 		while ((refm = ms_queue_get(f->inputs[0])) != NULL)
 			ms_queue_put(f->outputs[0], refm);

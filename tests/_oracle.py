@@ -125,6 +125,8 @@ def ref() -> C.CDLL:
         "ref_ticker_attach": (_I, [_P, _P]),
         "ref_ticker_detach": (_I, [_P, _P]),
         "ref_ticker_run": (None, [_P, _I]),
+        "ref_ticker_release": (None, [_P, _I]),
+        "ref_ticker_wait": (None, [_P]),
         "ref_ticker_time": (C.c_ulonglong, [_P]),
         "ref_ticker_destroy": (None, [_P]),
         "ref_method_id": (C.c_uint, [C.c_char_p]),

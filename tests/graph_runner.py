@@ -7,6 +7,8 @@
 Run as a script (the plugin's execution mode is fixed per process by MSB200_BATCH, so tests and the bench spawn it):
 
     MSB200_BATCH=0|<slots> python tests/graph_runner.py --streams 8 --pins 4 --ticks 60 --dump out.npz [--timing]
+                                                        [--tickers K]   rooms are dealt round-robin to K MSTickers
+                                                        (K threads; SURVEY.md cfg5: one ticker per 256 streams)
 
 --dump  writes every sink's sample stream (parity: batch mode == synchronous mode, one ticker interval later per stage)
 --timing prints one JSON line: wall time per tick of the free-running (gated, never sleeping) ticker, p50/p99, launches.
@@ -82,20 +84,30 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--dump", default="")
     ap.add_argument("--timing", action="store_true")
+    ap.add_argument("--tickers", type=int, default=1)
     a = ap.parse_args()
     g = RefGraph(plugins_dir=str(O.PLUGIN_DIR))
     sources, spk_sinks, out_sinks = build(g, a.streams, a.pins, a.ticks)
-    # one ticker for all rooms (a room's streams are one connected graph through its mixer)
-    g.run(sources, 0)
+    # a room's streams are one connected graph through its mixer: whole rooms are dealt to the tickers
+    tickers = [g.L.ref_ticker_new() for _ in range(max(1, a.tickers))]
+    for r, src in enumerate(sources):
+        assert g.L.ref_ticker_attach(tickers[r % len(tickers)], src) == 0
+
+    def run(n):  # every ticker advances n ticks, concurrently
+        for t in tickers:
+            g.L.ref_ticker_release(t, n)
+        for t in tickers:
+            g.L.ref_ticker_wait(t)
+
     per_tick = []
     if a.timing:
-        g.L.ref_ticker_run(g.ticker, a.warmup)
+        run(a.warmup)
         for _ in range(a.ticks - a.warmup):
             t0 = time.perf_counter()
-            g.L.ref_ticker_run(g.ticker, 1)
+            run(1)
             per_tick.append(time.perf_counter() - t0)
     else:
-        g.L.ref_ticker_run(g.ticker, a.ticks)
+        run(a.ticks)
     if a.dump:
         np.savez(a.dump, **{f"out{i}": g.read(k)[0] for i, k in enumerate(out_sinks)},
                  **{f"spk{i}": g.read(k)[0] for i, k in enumerate(spk_sinks)})
@@ -103,6 +115,7 @@ def main():
         ms = np.array(per_tick) * 1000.0
         stats = {"mode": "batch" if int(os.environ.get("MSB200_BATCH", "0") or 0) > 0 else "sync",
                  "batch_slots": int(os.environ.get("MSB200_BATCH", "0") or 0), "streams": a.streams, "pins": a.pins,
+                 "tickers": len(tickers),
                  "ticks_timed": len(ms), "tick_ms_mean": float(ms.mean()), "tick_ms_p50": float(np.percentile(ms, 50)),
                  "tick_ms_p99": float(np.percentile(ms, 99)), "tick_ms_max": float(ms.max()),
                  "late_ticks_10ms": int((ms > 10.0).sum()),
@@ -115,6 +128,10 @@ def main():
         except (OSError, AttributeError):
             pass
         print(json.dumps(stats), flush=True)
+    for r, src in enumerate(sources):
+        g.L.ref_ticker_detach(tickers[r % len(tickers)], src)
+    for t in tickers:
+        g.L.ref_ticker_destroy(t)
     g.close()
 
 
