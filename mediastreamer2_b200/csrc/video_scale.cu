@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 //     TMA loads that brought the source boxes in.
 // Compared with scale_rgb_fast_kernel this removes the shared-memory round trip of the intermediates, the per-tile row
 // table, two of the three CTA barriers per tile and all unpacking in the vertical pass.
-#define ST_WARPS 6
+#define ST_WARPS 5
 #define ST_MIN_CTAS 4 // register budget: 4 x 192 threads x 85 registers fit the file
 #define ST_THREADS (32 * ST_WARPS)
 #define ST_TW 128 // output columns per strip (4 per lane)
@@ -873,8 +873,15 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 		unsigned og = smem_u32(stage) + (unsigned)lane * 12;
 		int y = ys;
 
+		// software pipeline: the six words of the NEXT luma row (and of the next chroma row) are fetched right after the
+		// current row has been filtered, so their shared-memory latency hides under the colour arithmetic of emit()
+		unsigned a0, a1, a2, b0, b1, b2;
+		auto lload = [&]() {
+			a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+			la += pitch_l;
+			lb += pitch_l;
+		};
 		auto hluma = [&](int(&w)[4]) {
-			const unsigned a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
 			const unsigned A0 = __funnelshift_r(a0, a1, shA), A1 = __funnelshift_r(a1, a2, shA);
 			const unsigned B0 = __funnelshift_r(b0, b1, shB), B1 = __funnelshift_r(b1, b2, shB);
 			const unsigned A0b = __funnelshift_r(A0, A1, dA), B0b = __funnelshift_r(B0, B1, dB);
@@ -882,21 +889,24 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 			w[1] = dp2a_hi(lcA.w, A0b, dp2a_lo(lcA.z, A0b, 0)) >> 7;
 			w[2] = dp2a_hi(lcB.y, B0, dp2a_lo(lcB.x, B0, 0)) >> 7;
 			w[3] = dp2a_hi(lcB.w, B0b, dp2a_lo(lcB.z, B0b, 0)) >> 7;
-			la += pitch_l;
-			lb += pitch_l;
+			lload();
+		};
+		unsigned c0, c1, c2, d0, d1, d2;
+		auto cload = [&]() {
+			c0 = lds32<0>(ca), c1 = lds32<4>(ca), c2 = lds32<8>(ca), d0 = lds32<0>(cb), d1 = lds32<4>(cb), d2 = lds32<8>(cb);
+			ca += pitch_c;
+			cb += pitch_c;
 		};
 		auto hchroma = [&](int(&wu)[2], int(&wv)[2]) {
-			const unsigned a0 = lds32<0>(ca), a1 = lds32<4>(ca), a2 = lds32<8>(ca), b0 = lds32<0>(cb), b1 = lds32<4>(cb), b2 = lds32<8>(cb);
-			const unsigned alo = __funnelshift_r(a0, a1, shc0), ahi = __funnelshift_r(a1, a2, shc0);
-			const unsigned blo = __funnelshift_r(b0, b1, shc1), bhi = __funnelshift_r(b1, b2, shc1);
+			const unsigned alo = __funnelshift_r(c0, c1, shc0), ahi = __funnelshift_r(c1, c2, shc0);
+			const unsigned blo = __funnelshift_r(d0, d1, shc1), bhi = __funnelshift_r(d1, d2, shc1);
 			const unsigned e0 = prmt(alo, ahi, sel_u), o0 = prmt(alo, ahi, sel_v);
 			const unsigned e1 = prmt(blo, bhi, sel_u), o1 = prmt(blo, bhi, sel_v);
 			wu[0] = dp2a_hi(ccf.y, e0, dp2a_lo(ccf.x, e0, 0)) >> 7;
 			wv[0] = dp2a_hi(ccf.y, o0, dp2a_lo(ccf.x, o0, 0)) >> 7;
 			wu[1] = dp2a_hi(ccf.w, e1, dp2a_lo(ccf.z, e1, 0)) >> 7;
 			wv[1] = dp2a_hi(ccf.w, o1, dp2a_lo(ccf.z, o1, 0)) >> 7;
-			ca += pitch_c;
-			cb += pitch_c;
+			cload();
 		};
 		// one output row from the windows; returns true when the strip is complete
 		auto emit = [&]() -> bool {
@@ -969,6 +979,8 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 		};
 
 		bool done = false;
+		lload(); // rows one past the boxes are read (never used) at the very end: they lie inside the CTA's shared memory
+		cload();
 		if (s0 > 0) { // lead-in: rows lrow0 .. next multiple of VL go to slots s0 .. VL-1 (no output row can complete yet)
 #pragma unroll
 			for (int s = 1; s < VL; ++s) {
