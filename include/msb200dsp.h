@@ -335,6 +335,11 @@ MSB200_API int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const v
  * 1 = generic tile kernel, 0 = plane / packed-4:2:2 kernels. */
 MSB200_API int msb200_scaler_set_path(msb200_scaler *s, int path);
 MSB200_API int msb200_scaler_get_path(msb200_scaler *s);
+/* Strip kernel only: index of the static row schedule its straight-line instantiation runs (0 = 3:2 down-scale,
+ * 1 = 1:1), or -1 when the general loop handles every strip. *regular_strips / *strips (may be
+ * NULL) receive how many strips of a frame column follow the schedule. Environment MSB200_SCALER_NO_SCHED=1 at create
+ * time forces the general loop (A/B runs). */
+MSB200_API int msb200_scaler_get_schedule(msb200_scaler *s, int *regular_strips, int *strips);
 
 #ifdef __cplusplus
 }

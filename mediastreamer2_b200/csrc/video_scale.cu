@@ -750,8 +750,9 @@ __global__ void __launch_bounds__(SC_THREADS)
 //     TMA loads that brought the source boxes in.
 // Compared with scale_rgb_fast_kernel this removes the shared-memory round trip of the intermediates, the per-tile row
 // table, two of the three CTA barriers per tile and all unpacking in the vertical pass.
-#define ST_WARPS 5
-#define ST_MIN_CTAS 4 // register budget: 4 x 192 threads x 85 registers fit the file
+#define ST_WARPS 4
+#define ST_MIN_CTAS 5   // general loop: 5 x 128 threads x 96 registers
+#define ST_SCHED_CTAS 7 // static schedule: 7 x 128 threads x 72 registers
 #define ST_THREADS (32 * ST_WARPS)
 #define ST_TW 128 // output columns per strip (4 per lane)
 #define ST_MAXR 16
@@ -772,6 +773,12 @@ struct StripParams {
 	unsigned sel_u, sel_v;       // byte-lane selectors de-interleaving the CbCr (NV12) or CrCb (NV21) samples
 	// box origins per tile column / tile row, in the constant bank: the TMA loads are issued without a global round trip
 	short lx0[ST_MAX_TX], cb0[ST_MAX_TX], ly0[ST_MAX_TY], cy0[ST_MAX_TY];
+	unsigned regular[16];        // static-schedule variant: bit (tile row * ST_WARPS + warp) set = the strip follows the schedule
+	short ty_list[ST_MAX_TY];    // general loop: tile rows to process (all of them, or those holding strips off the schedule)
+	int n_ty;
+	// static schedule: the vertical taps of the PR rows of a strip (identical in every strip on the schedule), x 32 and
+	// rotated like StripRow's: [row][0..1] chroma, [row][2..5] luma. Constant-bank operands of the IMADs: no loads.
+	int staps[16][6];
 };
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
@@ -799,8 +806,15 @@ __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
 	return d;
 }
 
-template <int VL, int VC, bool BGR>
-__global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
+// PR > 0 selects the STATIC-SCHEDULE variant for strips of exactly PR output rows: with a rational scale factor the
+// number of new source rows each output row needs repeats with a short period (1080 -> 720: luma 2,1,2,1,..., chroma
+// 1,1,1,0,...), so the whole strip is one straight-line instruction stream: NLPAT / NCPAT hold, one nibble per output row
+// of the strip (row 0 excluded: it always fills the whole window), how many luma / chroma rows to filter before that
+// row is emitted; SL0 / SC0 are the window slots of the strip's first source rows. No row counters, no loops, no
+// branches, static shared-memory offsets. The host marks the strips that follow the schedule (S.regular; the first and
+// the last strip of a frame do not: swscale clamps its filter positions at the borders) and those run the general loop.
+template <int VL, int VC, bool BGR, int PR = 0, unsigned NLPAT = 0, unsigned NCPAT = 0, int SL0 = 0, int SC0 = 0>
+__global__ void __launch_bounds__(ST_THREADS, PR > 0 ? ST_SCHED_CTAS : ST_MIN_CTAS)
     scale_rgb_strip_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c,
                            const __grid_constant__ CUtensorMap map_o, const ScaleParams P, const StripParams S) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -814,9 +828,11 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 	unsigned char *lbox = cbox + cbox_al;
 	uint64_t *bar = reinterpret_cast<uint64_t *>(lbox + lbox_al);
 	const unsigned s_tab = smem_u32(lbox + lbox_al) + 16; // the tile's rows of the vertical-tap table (+1), 32 B each
-	const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * (ST_WARPS * S.R), frame = blockIdx.z;
-	const int lx0 = S.lx0[blockIdx.x], ly0 = S.ly0[blockIdx.y];
-	const int cb0 = S.cb0[blockIdx.x], cy0 = S.cy0[blockIdx.y];
+	// the general loop may be launched over a subset of the tile rows (second launch of a scheduled frame)
+	const int ty = PR > 0 ? (int)blockIdx.y : (int)S.ty_list[blockIdx.y];
+	const int x0 = blockIdx.x * ST_TW, y0 = ty * (ST_WARPS * S.R), frame = blockIdx.z;
+	const int lx0 = S.lx0[blockIdx.x], ly0 = S.ly0[ty];
+	const int cb0 = S.cb0[blockIdx.x], cy0 = S.cy0[ty];
 	if (t == 0) {
 		mbar_init(bar, 1);
 		mbar_expect_tx(bar, lbox_bytes + cbox_bytes);
@@ -875,13 +891,28 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 
 		// software pipeline: the six words of the NEXT luma row (and of the next chroma row) are fetched right after the
 		// current row has been filtered, so their shared-memory latency hides under the colour arithmetic of emit()
+		// The static instantiation (host-checked: the second pair's window starts in the same or in the next 32-bit word)
+		// fetches the four distinct words once and picks the second pair's three by a lane-constant predicate: 4 LDS
+		// instead of 6 — the shared-memory pipe, at two wavefronts per LDS here (a warp's row spans 48 words), is the
+		// busiest unit of this kernel.
+		constexpr bool NARROW = PR > 0;
+		const bool nextA = NARROW && ((pB & ~3) != (pA & ~3)), nextC = NARROW && ((q1 & ~3) != (q0 & ~3));
 		unsigned a0, a1, a2, b0, b1, b2;
 		auto lload = [&]() {
-			a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+			if (NARROW) {
+				a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b2 = lds32<12>(la);
+			} else {
+				a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+				lb += pitch_l;
+			}
 			la += pitch_l;
-			lb += pitch_l;
 		};
 		auto hluma = [&](int(&w)[4]) {
+			if (NARROW) {
+				b0 = nextA ? a1 : a0;
+				b1 = nextA ? a2 : a1;
+				b2 = nextA ? b2 : a2;
+			}
 			const unsigned A0 = __funnelshift_r(a0, a1, shA), A1 = __funnelshift_r(a1, a2, shA);
 			const unsigned B0 = __funnelshift_r(b0, b1, shB), B1 = __funnelshift_r(b1, b2, shB);
 			const unsigned A0b = __funnelshift_r(A0, A1, dA), B0b = __funnelshift_r(B0, B1, dB);
@@ -893,11 +924,20 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 		};
 		unsigned c0, c1, c2, d0, d1, d2;
 		auto cload = [&]() {
-			c0 = lds32<0>(ca), c1 = lds32<4>(ca), c2 = lds32<8>(ca), d0 = lds32<0>(cb), d1 = lds32<4>(cb), d2 = lds32<8>(cb);
+			if (NARROW) {
+				c0 = lds32<0>(ca), c1 = lds32<4>(ca), c2 = lds32<8>(ca), d2 = lds32<12>(ca);
+			} else {
+				c0 = lds32<0>(ca), c1 = lds32<4>(ca), c2 = lds32<8>(ca), d0 = lds32<0>(cb), d1 = lds32<4>(cb), d2 = lds32<8>(cb);
+				cb += pitch_c;
+			}
 			ca += pitch_c;
-			cb += pitch_c;
 		};
 		auto hchroma = [&](int(&wu)[2], int(&wv)[2]) {
+			if (NARROW) {
+				d0 = nextC ? c1 : c0;
+				d1 = nextC ? c2 : c1;
+				d2 = nextC ? d2 : c2;
+			}
 			const unsigned alo = __funnelshift_r(c0, c1, shc0), ahi = __funnelshift_r(c1, c2, shc0);
 			const unsigned blo = __funnelshift_r(d0, d1, shc1), bhi = __funnelshift_r(d1, d2, shc1);
 			const unsigned e0 = prmt(alo, ahi, sel_u), o0 = prmt(alo, ahi, sel_v);
@@ -908,19 +948,8 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 			wv[1] = dp2a_hi(ccf.w, o1, dp2a_lo(ccf.z, o1, 0)) >> 7;
 			cload();
 		};
-		// one output row from the windows; returns true when the strip is complete
-		auto emit = [&]() -> bool {
-			const int c_last = ra.y;
-			const unsigned cc0 = (unsigned)ra.z, cc1 = (unsigned)ra.w;
-			const unsigned clv[4] = {(unsigned)rb.x, (unsigned)rb.y, (unsigned)rb.z, (unsigned)rb.w};
-			++y;
-#pragma unroll 1
-			while (crow <= c_last) { // warp-uniform; at most VC iterations, usually 0 or 1
-				if (VC == 1 || cslot == 0) hchroma(WU[0], WV[0]);
-				else hchroma(WU[VC - 1], WV[VC - 1]);
-				++crow;
-				cslot = cslot + 1 == VC ? 0 : cslot + 1;
-			}
+		// the arithmetic of one output row: vertical taps over the windows, colour, clamp, 12 bytes to the staging strip
+		auto emit_math = [&](const unsigned cc0, const unsigned cc1, const unsigned(&clv)[4], auto store) {
 			// vertical taps: sum of window x (tap x 32) + rounding x 32; bits 24..31 are the 8-bit sample
 			unsigned Yq[4], U16[2], V16[2];
 #pragma unroll
@@ -943,10 +972,6 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 				U16[h] = __byte_perm(a, 0u, 0x4344); // sample << 16
 				V16[h] = __byte_perm(b, 0u, 0x4344);
 			}
-			// the taps are dead: fetch the next row's entry (the table is padded) under the colour arithmetic
-			rtab += 32;
-			ra = lds128(rtab);
-			rb = lds128(rtab + 16);
 			unsigned pk[6]; // clamped channel pairs in output byte order: (c0 g0)(d0 c1)(g1 d1)(c2 g2)(d2 c3)(g3 d3)
 			int q[4][3];
 #pragma unroll
@@ -971,9 +996,68 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 			pk[3] = __vimin_s16x2_relu(__byte_perm((unsigned)q[2][0], (unsigned)q[2][1], 0x7632), lim);
 			pk[4] = __vimin_s16x2_relu(__byte_perm((unsigned)q[2][2], (unsigned)q[3][0], 0x7632), lim);
 			pk[5] = __vimin_s16x2_relu(__byte_perm((unsigned)q[3][1], (unsigned)q[3][2], 0x7632), lim);
-			sts32<0>(og, __byte_perm(pk[0], pk[1], 0x6420));
-			sts32<4>(og, __byte_perm(pk[2], pk[3], 0x6420));
-			sts32<8>(og, __byte_perm(pk[4], pk[5], 0x6420));
+			store(__byte_perm(pk[0], pk[1], 0x6420), __byte_perm(pk[2], pk[3], 0x6420), __byte_perm(pk[4], pk[5], 0x6420));
+		};
+		const bool regular = (S.regular[(ty * ST_WARPS + warp) >> 5] >> ((ty * ST_WARPS + warp) & 31)) & 1u;
+		if (PR == 0 && regular) return; // second launch of a scheduled frame: only the strips off the schedule are left
+		if (PR > 0 && !regular) return; // (they run the general loop in that second launch)
+		if (PR > 0) {
+			// ---- static schedule (see the kernel's header comment): everything below unrolls to straight-line code
+			lload();
+			cload();
+			int sl = SL0, sc = SC0;
+#pragma unroll
+			for (int j = 0; j < (PR > 0 ? PR : 1); ++j) {
+				const int nl = j == 0 ? VL : (int)((NLPAT >> (4 * j)) & 15u), nc = j == 0 ? VC : (int)((NCPAT >> (4 * j)) & 15u);
+#pragma unroll
+				for (int i = 0; i < VL; ++i) {
+					if (i < nl) {
+						hluma(WL[sl]);
+						sl = sl + 1 == VL ? 0 : sl + 1;
+					}
+				}
+#pragma unroll
+				for (int i = 0; i < VC; ++i) {
+					if (i < nc) {
+						if (VC == 1 || sc == 0) hchroma(WU[0], WV[0]);
+						else hchroma(WU[VC - 1], WV[VC - 1]);
+						sc = sc + 1 == VC ? 0 : sc + 1;
+					}
+				}
+				const unsigned clv[4] = {(unsigned)S.staps[j][2], (unsigned)S.staps[j][3], (unsigned)S.staps[j][4], (unsigned)S.staps[j][5]};
+				emit_math((unsigned)S.staps[j][0], (unsigned)S.staps[j][1], clv, [&](unsigned w0, unsigned w1, unsigned w2) {
+					switch (j) { // j is a constant after unrolling: static store offsets
+#define ST_ROW(J) case J: sts32<(J) * ST_TW * 3>(og, w0); sts32<(J) * ST_TW * 3 + 4>(og, w1); sts32<(J) * ST_TW * 3 + 8>(og, w2); break;
+						ST_ROW(0) ST_ROW(1) ST_ROW(2) ST_ROW(3) ST_ROW(4) ST_ROW(5) ST_ROW(6) ST_ROW(7)
+						ST_ROW(8) ST_ROW(9) ST_ROW(10) ST_ROW(11) ST_ROW(12) ST_ROW(13) ST_ROW(14) ST_ROW(15)
+#undef ST_ROW
+					}
+				});
+			}
+		} else {
+		// ---- general loop
+		// one output row from the windows; returns true when the strip is complete
+		auto emit = [&]() -> bool {
+			const int c_last = ra.y;
+			const unsigned cc0 = (unsigned)ra.z, cc1 = (unsigned)ra.w;
+			const unsigned clv[4] = {(unsigned)rb.x, (unsigned)rb.y, (unsigned)rb.z, (unsigned)rb.w};
+			++y;
+#pragma unroll 1
+			while (crow <= c_last) { // warp-uniform; at most VC iterations, usually 0 or 1
+				if (VC == 1 || cslot == 0) hchroma(WU[0], WV[0]);
+				else hchroma(WU[VC - 1], WV[VC - 1]);
+				++crow;
+				cslot = cslot + 1 == VC ? 0 : cslot + 1;
+			}
+			// fetch the next row's entry (the table is padded) ahead of the arithmetic
+			rtab += 32;
+			ra = lds128(rtab);
+			rb = lds128(rtab + 16);
+			emit_math(cc0, cc1, clv, [&](unsigned w0, unsigned w1, unsigned w2) {
+				sts32<0>(og, w0);
+				sts32<4>(og, w1);
+				sts32<8>(og, w2);
+			});
 			og += ST_TW * 3;
 			return y == ye;
 		};
@@ -1002,6 +1086,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 				}
 			}
 		}
+		} // general loop
 		fence_proxy_async(); // the strip's generic-proxy writes become visible to the TMA engine
 		__syncwarp();
 		if (lane == 0) {
@@ -1411,6 +1496,23 @@ __global__ void __launch_bounds__(SC_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------ host
+// row schedules with an instantiated straight-line strip kernel (see scale_rgb_strip_kernel): strips of ST_SCHED_ROWS rows
+#define ST_SCHED_ROWS 8
+struct StripSched {
+	int vl, vc;
+	unsigned nlpat, ncpat;
+	int sl0, sc0;
+};
+#define ST_N_SCHED 2
+static const StripSched kStripSched[ST_N_SCHED] = {
+    {4, 2, 0x21212120u, 0x11101110u, 3, 1}, // 3:2 down-scale (1080p -> 720p, 720p -> 480p)
+    {1, 2, 0x11111110u, 0x10101010u, 0, 1}, // 1:1 (MSPixConv: colour conversion only)
+};
+// X(index, VL, VC, NLPAT, NCPAT, SL0, SC0): one line per instantiation, same order as kStripSched
+#define ST_SCHED_LIST(X)                                                                                               \
+	X(0, 4, 2, 0x21212120u, 0x11101110u, 3, 1)                                                                         \
+	X(1, 1, 2, 0x11111110u, 0x10101010u, 0, 1)
+
 struct msb200_scaler {
 	msb200_ctx *ctx;
 	ScaleParams P;
@@ -1427,6 +1529,8 @@ struct msb200_scaler {
 	bool fast_ok;
 	size_t smem_fast;
 	bool strip_ok;      // register-window strip kernel (scale_rgb_strip_kernel) applies
+	int sched;          // index into kStripSched when the static-schedule instantiation applies, else -1
+	int force_sched_off; // tests/profiling: 1 = always run the general loop
 	int force_path;     // tests/profiling: 0 = best available, 1 = persistent tile kernel, 2 = generic tile kernel, 3 = strip kernel, 4 = streaming kernel
 	bool stream_ok;     // per-warp streaming kernel (scale_rgb_stream_kernel) applies
 	StreamParams T;
@@ -1741,12 +1845,69 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		// box origins are aligned down to 16 bytes (TMA faults on unaligned byte coordinates): widest window + 15, rounded up
 		S.box_lw = (max_span(s->hl, dst_w, ST_TW) + 15 + 15) & ~15;
 		S.box_cw = (2 * max_span(s->hc, P.chr_dst_w, ST_TW / 2) + 15 + 15) & ~15;
+		// static-schedule variant: does the interior of the frame follow one of the instantiated row schedules?
+		s->sched = -1;
+		memset(S.regular, 0, sizeof(S.regular));
+		s->force_sched_off = getenv("MSB200_SCALER_NO_SCHED") != nullptr; // A/B runs and tests of the general loop
+		if (s->force_sched_off == 0) {
+			const int PR = ST_SCHED_ROWS, n_strips = dst_h / PR;
+			auto l_last = [&](int y) { return s->vl.pos[(size_t)y] + P.vl_size - 1; };
+			auto c_last = [&](int y) { return s->vc.pos[(size_t)y] + P.vc_size - 1; };
+			// the instantiation's narrow fetch: a lane's second column pair (chroma sample) must start in the same 32-bit
+			// word as its first, or in the next one
+			bool narrow = ok;
+			for (int x = 0; x + 3 < dst_w && narrow; x += 4) {
+				const int d = (s->hl.pos[(size_t)x + 2] & ~3) - (s->hl.pos[(size_t)x] & ~3);
+				narrow = d == 0 || d == 4;
+			}
+			for (int c = 0; c + 1 < P.chr_dst_w && narrow; c += 2) {
+				const int d = ((2 * s->hc.pos[(size_t)c + 1]) & ~3) - ((2 * s->hc.pos[(size_t)c]) & ~3);
+				narrow = d == 0 || d == 4;
+			}
+			// rotated x32 taps of output row y, in the layout of StripParams::staps
+			auto taps_of = [&](int y, int(&t)[6]) {
+				memset(t, 0, sizeof(t));
+				const int lp = s->vl.pos[(size_t)y], cp = s->vc.pos[(size_t)y];
+				for (int j = 0; j < P.vc_size; ++j) t[(cp + j) % P.vc_size] = 32 * s->vc.coef[(size_t)y * P.vc_size + j];
+				for (int j = 0; j < P.vl_size; ++j) t[2 + (lp + j) % P.vl_size] = 32 * s->vl.coef[(size_t)y * P.vl_size + j];
+			};
+			for (int k = 0; k < ST_N_SCHED && s->sched < 0 && n_strips <= 32 * 16 && narrow; ++k) {
+				const StripSched &d = kStripSched[k];
+				if (d.vl != P.vl_size || d.vc != P.vc_size) continue;
+				unsigned mask[16] = {0};
+				int n_reg = 0, staps[16][6];
+				for (int st = 0; st < n_strips; ++st) {
+					const int ys = st * PR;
+					bool reg = (l_last(ys) - (d.vl - 1)) >= 0 && (l_last(ys) - (d.vl - 1)) % d.vl == d.sl0 &&
+					           (c_last(ys) - (d.vc - 1)) >= 0 && (c_last(ys) - (d.vc - 1)) % d.vc == d.sc0;
+					for (int j = 1; j < PR && reg; ++j)
+						reg = l_last(ys + j) - l_last(ys + j - 1) == (int)((d.nlpat >> (4 * j)) & 15u) &&
+						      c_last(ys + j) - c_last(ys + j - 1) == (int)((d.ncpat >> (4 * j)) & 15u);
+					for (int j = 0; j < PR && reg; ++j) { // and the same taps as the first strip on the schedule
+						int t[6];
+						taps_of(ys + j, t);
+						if (n_reg == 0) memcpy(staps[j], t, sizeof(t));
+						else reg = memcmp(staps[j], t, sizeof(t)) == 0;
+					}
+					if (reg) {
+						mask[st >> 5] |= 1u << (st & 31);
+						++n_reg;
+					}
+				}
+				if (n_reg * 4 >= n_strips * 3) { // worth it when at least 3/4 of the strips run the straight-line code
+					s->sched = k;
+					memcpy(S.regular, mask, sizeof(mask));
+					memcpy(S.staps, staps, sizeof(staps));
+				}
+			}
+		}
 		long best_cost = -1;
 		for (int R = 4; R <= ST_MAXR; ++R) {
+			if (s->sched >= 0 && R != ST_SCHED_ROWS) continue;
 			const int th = ST_WARPS * R;
 			const size_t sm = a128((size_t)S.box_lw * max_span(s->vl, dst_h, th)) + a128((size_t)S.box_cw * max_span(s->vc, P.chr_dst_h, th)) +
 			                  (size_t)ST_WARPS * R * ST_TW * 3 + 16 + 32 * (size_t)(th + 1) + 128;
-			if ((sm + 1024) * ST_MIN_CTAS > 227 * 1024 && R > 4) continue;
+			if ((sm + 1024) * (s->sched >= 0 ? ST_SCHED_CTAS : ST_MIN_CTAS) > 227 * 1024 && R > 4) continue;
 			const long cost = (long)msb200_div_up(dst_h, th) * ST_WARPS * ((long)R * src_h / dst_h + P.vl_size); // luma rows filtered
 			if (best_cost < 0 || cost <= best_cost) { best_cost = cost; S.R = R; }
 		}
@@ -1781,6 +1942,15 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 				S.ly0[ty] = (short)s->vl.pos[(size_t)ty * th];
 				S.cy0[ty] = (short)s->vc.pos[(size_t)ty * th];
 			}
+			S.n_ty = 0; // tile rows of the general loop: all, or (scheduled frame) those with a strip off the schedule
+			for (int ty = 0; ty * th < dst_h; ++ty) {
+				bool need = s->sched < 0;
+				for (int w = 0; w < ST_WARPS && !need; ++w) {
+					const int st = ty * ST_WARPS + w;
+					need = st * S.R < dst_h && !((S.regular[st >> 5] >> (st & 31)) & 1u);
+				}
+				if (need) S.ty_list[S.n_ty++] = (short)ty;
+			}
 			S.rnd = (P.vl_size == 2 && P.vc_size == 2) ? 0u : 1u << 23;
 			S.sel_u = src_fmt == MSB200_PIX_NV21 ? 0x7531u : 0x6420u;
 			S.sel_v = src_fmt == MSB200_PIX_NV21 ? 0x6420u : 0x7531u;
@@ -1803,6 +1973,13 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 				STRIP_ATTR(1, 2);
 				STRIP_ATTR(1, 1);
 #undef STRIP_ATTR
+#define SCHED_ATTR(K, VL, VC, NL, NC, SL, SC)                                                                          \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, false, ST_SCHED_ROWS, NL, NC, SL, SC>,             \
+	                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_strip));                \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, true, ST_SCHED_ROWS, NL, NC, SL, SC>,              \
+	                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_strip));
+				ST_SCHED_LIST(SCHED_ATTR)
+#undef SCHED_ATTR
 			}
 			s->strip_ok = true;
 			// ---- streaming kernel: same tables, per-warp rings instead of per-CTA boxes
@@ -1900,6 +2077,17 @@ int msb200_scaler_get_path(msb200_scaler *s) {
 	return 1;
 }
 
+int msb200_scaler_get_schedule(msb200_scaler *s, int *regular_strips, int *strips) {
+	if (regular_strips) *regular_strips = 0;
+	if (strips) *strips = 0;
+	if (!s || !s->strip_ok || s->sched < 0) return -1;
+	int n = 0;
+	for (unsigned w : s->S.regular) n += __builtin_popcount(w);
+	if (regular_strips) *regular_strips = n;
+	if (strips) *strips = msb200_div_up(s->P.dst_h, s->S.R);
+	return s->sched;
+}
+
 int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst) {
 	MSB200_CHECK_ARG(s && d_src && d_dst && n_frames > 0 && n_frames <= 65535);
 	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
@@ -1948,13 +2136,26 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 		// tiles share their halos in L2
 		if ((r = scaler_build_strip_maps(s, d_src, d_dst, n_frames))) return r;
 		dim3 grid((unsigned)(P.dst_w / ST_TW), (unsigned)msb200_div_up(P.dst_h, ST_WARPS * s->S.R), (unsigned)n_frames);
+		dim3 grid_g((unsigned)(P.dst_w / ST_TW), (unsigned)s->S.n_ty, (unsigned)n_frames); // general loop
 #define STRIP_LAUNCH(VL, VC)                                                                                           \
 	do {                                                                                                               \
 		if (P.dst_fmt == MSB200_PIX_RGB24_REV)                                                                         \
-			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, true>), grid, ST_THREADS, s->smem_strip, s->map_ls, s->map_cs, s->map_os, P, s->S); \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, true>), grid_g, ST_THREADS, s->smem_strip, s->map_ls, s->map_cs, s->map_os, P, s->S); \
 		else                                                                                                           \
-			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, false>), grid, ST_THREADS, s->smem_strip, s->map_ls, s->map_cs, s->map_os, P, s->S); \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, false>), grid_g, ST_THREADS, s->smem_strip, s->map_ls, s->map_cs, s->map_os, P, s->S); \
 	} while (0)
+#define SCHED_LAUNCH(K, VL, VC, NL, NC, SL, SC)                                                                        \
+	if (s->sched == K) {                                                                                               \
+		if (P.dst_fmt == MSB200_PIX_RGB24_REV)                                                                         \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, true, ST_SCHED_ROWS, NL, NC, SL, SC>), grid, ST_THREADS, s->smem_strip, \
+			              s->map_ls, s->map_cs, s->map_os, P, s->S);                                                   \
+		else                                                                                                           \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, false, ST_SCHED_ROWS, NL, NC, SL, SC>), grid, ST_THREADS, s->smem_strip, \
+			              s->map_ls, s->map_cs, s->map_os, P, s->S);                                                   \
+	}
+		ST_SCHED_LIST(SCHED_LAUNCH) // straight-line instantiation for this frame's row schedule, when there is one
+#undef SCHED_LAUNCH
+		if (s->S.n_ty == 0) return MSB200_OK; // every strip was on the schedule
 		if (P.vl_size == 4) STRIP_LAUNCH(4, 2);
 		else if (P.vl_size == 2) STRIP_LAUNCH(2, 2);
 		else if (P.vc_size == 2) STRIP_LAUNCH(1, 2);

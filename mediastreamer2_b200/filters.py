@@ -388,6 +388,14 @@ class Scaler:
         return self.lib.msb200_scaler_get_path(self.h)
 
 
+    @property
+    def schedule(self) -> tuple[int, int, int]:
+        """(static row schedule index or -1, strips on the schedule, strips per frame column) of the strip kernel"""
+        a, b = C.c_int(), C.c_int()
+        k = self.lib.msb200_scaler_get_schedule(self.h, C.byref(a), C.byref(b))
+        return k, a.value, b.value
+
+
 def nv12_to_i420(ctx: Context, frames: np.ndarray, w: int, h: int, rotation: int = 0, y_stride: int | None = None,
                  cbcr_stride: int | None = None, u_first: bool = True, down_scale: bool = False,
                  cbcr_offset: int | None = None) -> np.ndarray:

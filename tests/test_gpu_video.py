@@ -135,6 +135,40 @@ def test_scaler_strip_kernel_bit_exact(ctx, sf, sw, sh, df, dw, dh):
     sc.close()
 
 
+@pytest.mark.parametrize("sf,sw,sh,df,dw,dh,sched", [
+    (_lib.PIX_NV12, 1920, 1080, _lib.PIX_RGB24, 1280, 720, 0),      # cfg4: 3:2, 88 of 90 strips on the schedule
+    (_lib.PIX_NV21, 384, 216, _lib.PIX_RGB24_REV, 256, 144, 0),     # 3:2, NV21 -> BGR24
+    (_lib.PIX_NV12, 1280, 720, _lib.PIX_RGB24, 1280, 720, 1),       # 1:1 (MSPixConv): <1,2> taps
+    (_lib.PIX_NV21, 256, 144, _lib.PIX_RGB24_REV, 256, 144, 1),
+    (_lib.PIX_NV12, 640, 368, _lib.PIX_RGB24, 512, 288, -1),        # 5:4: no instantiated schedule -> general loop only
+])
+def test_scaler_static_schedule_bit_exact(ctx, monkeypatch, sf, sw, sh, df, dw, dh, sched):
+    """the straight-line (static row schedule) instantiation of the strip kernel == oracle == the general loop"""
+    L = O.oracle()
+    n = 3
+    frames = _rand_frames(sf, sw, sh, n, seed=sw + dh)
+    frames[1] = np.random.default_rng(dw).integers(0, 256, size=frames.shape[1], dtype=np.uint8)  # full-range noise
+    sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
+    k, regular, strips = sc.schedule
+    assert sc.path == 3 and k == sched, (sc.path, k, regular, strips)
+    if sched >= 0:
+        assert regular >= strips - 3 and regular * 4 >= strips * 3, (regular, strips)
+    got = sc.process(frames)
+    sc.close()
+    o = L.orc_scaler_new(sw, sh, sf, dw, dh, df)
+    for i in range(n):
+        exp = np.zeros(got.shape[1] + 64, np.uint8)
+        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+        bad = np.flatnonzero(got[i] != exp[:-64])
+        assert bad.size == 0, (i, bad.size, bad[:8] // 3 % dw, bad[:8] // 3 // dw)
+    L.orc_scaler_free(o)
+    monkeypatch.setenv("MSB200_SCALER_NO_SCHED", "1")
+    sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
+    assert sc.schedule[0] == -1
+    assert np.array_equal(sc.process(frames), got)
+    sc.close()
+
+
 def test_scaler_full_size_cfg4_matches_real_libswscale_digest(ctx):
     """NV12 1080p -> RGB24 720p: SHA-256 of the GPU output == SHA-256 of the real libswscale 9.1.100 output."""
     import hashlib
