@@ -969,17 +969,18 @@ __global__ void __launch_bounds__(ST_THREADS, PR > 0 ? ST_SCHED_CTAS : ST_MIN_CT
 					a += (unsigned)WU[0][h] * cc0 + (unsigned)WU[VC - 1][h] * cc1;
 					b += (unsigned)WV[0][h] * cc0 + (unsigned)WV[VC - 1][h] * cc1;
 				}
-				U16[h] = __byte_perm(a, 0u, 0x4344); // sample << 16
-				V16[h] = __byte_perm(b, 0u, 0x4344);
+				U16[h] = a >> 24; // the 8-bit sample
+				V16[h] = b >> 24;
 			}
 			unsigned pk[6]; // clamped channel pairs in output byte order: (c0 g0)(d0 c1)(g1 d1)(c2 g2)(d2 c3)(g3 d3)
 			int q[4][3];
 #pragma unroll
 			for (int h = 0; h < 2; ++h) {
-				// table offsets of yuv2rgb in closed form: ((chroma * coef) >> 16) == mul.hi(chroma << 16, coef)
-				const int ar = __mulhi((int)V16[h], crv) * c_cy + k_r;
-				const int ag = (__mulhi((int)U16[h], cgu) + __mulhi((int)V16[h], cgv)) * c_cy + k_g;
-				const int ab = __mulhi((int)U16[h], cbu) * c_cy + k_b;
+				// table offsets of yuv2rgb in closed form: (chroma * coef) >> 16. IMAD + shift, not mul.hi: IMAD.HI issues at
+				// a quarter of the IMAD rate on sm_100 (measured: a mul.hi costs ~3.5 issue slots)
+				const int ar = (((int)V16[h] * crv) >> 16) * c_cy + k_r;
+				const int ag = ((((int)U16[h] * cgu) >> 16) + (((int)V16[h] * cgv) >> 16)) * c_cy + k_g;
+				const int ab = (((int)U16[h] * cbu) >> 16) * c_cy + k_b;
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
 					const int yc = (int)Yq[2 * h + k];
@@ -1092,7 +1093,8 @@ __global__ void __launch_bounds__(ST_THREADS, PR > 0 ? ST_SCHED_CTAS : ST_MIN_CT
 		if (lane == 0) {
 			tma_store_3d(&map_o, stage, (x0 * 3) >> 2, ys, frame); // rows past dst_h are clipped by the tensor map
 			tma_store_commit();
-			asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+			// the staging strip must outlive the TMA engine's READ of it, not the global writes (kernel completion orders those)
+			asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 		}
 	}
 }
