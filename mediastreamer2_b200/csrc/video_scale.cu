@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <type_traits>
 
 namespace {
 
@@ -758,6 +759,7 @@ __global__ void __launch_bounds__(SC_THREADS)
 #define ST_MAXR 16
 #define ST_MAX_TX 32 // dst_w <= 4096
 #define ST_MAX_TY 64
+#define ST_SCHED_ROWS 8 // rows per strip of the static-schedule instantiations
 struct StripRow { // per output row, absolute source rows
 	int l_last, c_last; // last luma / chroma source row this output row needs
 	int cc[2];          // chroma vertical taps x 32, rotated: cc[s] multiplies window slot s (= source row mod VC)
@@ -778,7 +780,9 @@ struct StripParams {
 	int n_ty;
 	// static schedule: the vertical taps of the PR rows of a strip (identical in every strip on the schedule), x 32 and
 	// rotated like StripRow's: [row][0..1] chroma, [row][2..5] luma. Constant-bank operands of the IMADs: no loads.
-	int staps[16][6];
+	int staps[ST_SCHED_ROWS][6];
+	int b_first, b_last;         // strips (index) that run the first-strip / last-strip border schedules, or -1
+	int staps_f[ST_SCHED_ROWS][6], staps_l[ST_SCHED_ROWS][6];
 };
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
@@ -813,7 +817,10 @@ __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
 // row is emitted; SL0 / SC0 are the window slots of the strip's first source rows. No row counters, no loops, no
 // branches, static shared-memory offsets. The host marks the strips that follow the schedule (S.regular; the first and
 // the last strip of a frame do not: swscale clamps its filter positions at the borders) and those run the general loop.
-template <int VL, int VC, bool BGR, int PR = 0, unsigned NLPAT = 0, unsigned NCPAT = 0, int SL0 = 0, int SC0 = 0>
+// The first and the last strip of a frame have schedules of their own (NLF/NCF/SLF/SCF and NLL/NCL): three straight-line
+// bodies in one kernel, picked per warp; whatever fits none of them is left to the general loop's launch.
+template <int VL, int VC, bool BGR, int PR = 0, unsigned NLPAT = 0, unsigned NCPAT = 0, int SL0 = 0, int SC0 = 0,
+          unsigned NLF = 0, unsigned NCF = 0, int SLF = 0, int SCF = 0, unsigned NLL = 0, unsigned NCL = 0>
 __global__ void __launch_bounds__(ST_THREADS, PR > 0 ? ST_SCHED_CTAS : ST_MIN_CTAS)
     scale_rgb_strip_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c,
                            const __grid_constant__ CUtensorMap map_o, const ScaleParams P, const StripParams S) {
@@ -999,42 +1006,54 @@ __global__ void __launch_bounds__(ST_THREADS, PR > 0 ? ST_SCHED_CTAS : ST_MIN_CT
 			pk[5] = __vimin_s16x2_relu(__byte_perm((unsigned)q[3][1], (unsigned)q[3][2], 0x7632), lim);
 			store(__byte_perm(pk[0], pk[1], 0x6420), __byte_perm(pk[2], pk[3], 0x6420), __byte_perm(pk[4], pk[5], 0x6420));
 		};
-		const bool regular = (S.regular[(ty * ST_WARPS + warp) >> 5] >> ((ty * ST_WARPS + warp) & 31)) & 1u;
-		if (PR == 0 && regular) return; // second launch of a scheduled frame: only the strips off the schedule are left
-		if (PR > 0 && !regular) return; // (they run the general loop in that second launch)
+		const int sidx = ty * ST_WARPS + warp;
+		// 1 = on the frame's schedule, 2 / 3 = first / last strip on their border schedules, 0 = general loop
+		const int kind = ((S.regular[sidx >> 5] >> (sidx & 31)) & 1u) ? 1 : (sidx == S.b_first ? 2 : (sidx == S.b_last ? 3 : 0));
+		if (PR == 0 && kind) return;  // second launch of a scheduled frame: only the strips off every schedule are left
+		if (PR > 0 && !kind) return;  // (they run the general loop in that second launch)
 		if (PR > 0) {
 			// ---- static schedule (see the kernel's header comment): everything below unrolls to straight-line code
-			lload();
-			cload();
-			int sl = SL0, sc = SC0;
+			auto run_static = [&](auto nlp_c, auto ncp_c, auto sl_c, auto sc_c, const int(&taps)[ST_SCHED_ROWS][6]) {
+				constexpr unsigned NLP = decltype(nlp_c)::value, NCP = decltype(ncp_c)::value;
+				lload();
+				cload();
+				int sl = decltype(sl_c)::value, sc = decltype(sc_c)::value;
 #pragma unroll
-			for (int j = 0; j < (PR > 0 ? PR : 1); ++j) {
-				const int nl = j == 0 ? VL : (int)((NLPAT >> (4 * j)) & 15u), nc = j == 0 ? VC : (int)((NCPAT >> (4 * j)) & 15u);
+				for (int j = 0; j < (PR > 0 ? PR : 1); ++j) {
+					const int nl = j == 0 ? VL : (int)((NLP >> (4 * j)) & 15u), nc = j == 0 ? VC : (int)((NCP >> (4 * j)) & 15u);
 #pragma unroll
-				for (int i = 0; i < VL; ++i) {
-					if (i < nl) {
-						hluma(WL[sl]);
-						sl = sl + 1 == VL ? 0 : sl + 1;
+					for (int i = 0; i < VL; ++i) {
+						if (i < nl) {
+							hluma(WL[sl]);
+							sl = sl + 1 == VL ? 0 : sl + 1;
+						}
 					}
-				}
 #pragma unroll
-				for (int i = 0; i < VC; ++i) {
-					if (i < nc) {
-						if (VC == 1 || sc == 0) hchroma(WU[0], WV[0]);
-						else hchroma(WU[VC - 1], WV[VC - 1]);
-						sc = sc + 1 == VC ? 0 : sc + 1;
+					for (int i = 0; i < VC; ++i) {
+						if (i < nc) {
+							if (VC == 1 || sc == 0) hchroma(WU[0], WV[0]);
+							else hchroma(WU[VC - 1], WV[VC - 1]);
+							sc = sc + 1 == VC ? 0 : sc + 1;
+						}
 					}
-				}
-				const unsigned clv[4] = {(unsigned)S.staps[j][2], (unsigned)S.staps[j][3], (unsigned)S.staps[j][4], (unsigned)S.staps[j][5]};
-				emit_math((unsigned)S.staps[j][0], (unsigned)S.staps[j][1], clv, [&](unsigned w0, unsigned w1, unsigned w2) {
-					switch (j) { // j is a constant after unrolling: static store offsets
+					const unsigned clv[4] = {(unsigned)taps[j][2], (unsigned)taps[j][3], (unsigned)taps[j][4], (unsigned)taps[j][5]};
+					emit_math((unsigned)taps[j][0], (unsigned)taps[j][1], clv, [&](unsigned w0, unsigned w1, unsigned w2) {
+						switch (j) { // j is a constant after unrolling: static store offsets
 #define ST_ROW(J) case J: sts32<(J) * ST_TW * 3>(og, w0); sts32<(J) * ST_TW * 3 + 4>(og, w1); sts32<(J) * ST_TW * 3 + 8>(og, w2); break;
-						ST_ROW(0) ST_ROW(1) ST_ROW(2) ST_ROW(3) ST_ROW(4) ST_ROW(5) ST_ROW(6) ST_ROW(7)
-						ST_ROW(8) ST_ROW(9) ST_ROW(10) ST_ROW(11) ST_ROW(12) ST_ROW(13) ST_ROW(14) ST_ROW(15)
+							ST_ROW(0) ST_ROW(1) ST_ROW(2) ST_ROW(3) ST_ROW(4) ST_ROW(5) ST_ROW(6) ST_ROW(7)
 #undef ST_ROW
-					}
-				});
-			}
+						}
+					});
+				}
+			};
+			typedef std::integral_constant<unsigned, NLPAT> c_nl; typedef std::integral_constant<unsigned, NCPAT> c_nc;
+			typedef std::integral_constant<unsigned, NLF> c_nlf; typedef std::integral_constant<unsigned, NCF> c_ncf;
+			typedef std::integral_constant<unsigned, NLL> c_nll; typedef std::integral_constant<unsigned, NCL> c_ncl;
+			typedef std::integral_constant<int, SL0> c_sl; typedef std::integral_constant<int, SC0> c_sc;
+			typedef std::integral_constant<int, SLF> c_slf; typedef std::integral_constant<int, SCF> c_scf;
+			if (kind == 1) run_static(c_nl{}, c_nc{}, c_sl{}, c_sc{}, S.staps);
+			else if (kind == 2) run_static(c_nlf{}, c_ncf{}, c_slf{}, c_scf{}, S.staps_f);
+			else run_static(c_nll{}, c_ncl{}, c_sl{}, c_sc{}, S.staps_l);
 		} else {
 		// ---- general loop
 		// one output row from the windows; returns true when the strip is complete
@@ -1499,21 +1518,23 @@ __global__ void __launch_bounds__(SC_THREADS)
 
 // ------------------------------------------------------------------------------------------------ host
 // row schedules with an instantiated straight-line strip kernel (see scale_rgb_strip_kernel): strips of ST_SCHED_ROWS rows
-#define ST_SCHED_ROWS 8
 struct StripSched {
 	int vl, vc;
 	unsigned nlpat, ncpat;
 	int sl0, sc0;
+	unsigned nlf, ncf; // first strip of a frame
+	int slf, scf;
+	unsigned nll, ncl; // last strip (same slots as the interior)
 };
 #define ST_N_SCHED 2
 static const StripSched kStripSched[ST_N_SCHED] = {
-    {4, 2, 0x21212120u, 0x11101110u, 3, 1}, // 3:2 down-scale (1080p -> 720p, 720p -> 480p)
-    {1, 2, 0x11111110u, 0x10101010u, 0, 1}, // 1:1 (MSPixConv: colour conversion only)
+    {4, 2, 0x21212120u, 0x11101110u, 3, 1, 0x21212110u, 0x11101100u, 0, 0, 0x01212120u, 0x01101110u}, // 3:2 down-scale (1080p -> 720p)
+    {1, 2, 0x11111110u, 0x10101010u, 0, 1, 0x11111110u, 0x10101000u, 0, 0, 0x11111110u, 0x00101010u}, // 1:1 (MSPixConv)
 };
-// X(index, VL, VC, NLPAT, NCPAT, SL0, SC0): one line per instantiation, same order as kStripSched
+// X(index, VL, VC, NLPAT, NCPAT, SL0, SC0, NLF, NCF, SLF, SCF, NLL, NCL): one line per instantiation, same order as kStripSched
 #define ST_SCHED_LIST(X)                                                                                               \
-	X(0, 4, 2, 0x21212120u, 0x11101110u, 3, 1)                                                                         \
-	X(1, 1, 2, 0x11111110u, 0x10101010u, 0, 1)
+	X(0, 4, 2, 0x21212120u, 0x11101110u, 3, 1, 0x21212110u, 0x11101100u, 0, 0, 0x01212120u, 0x01101110u)               \
+	X(1, 1, 2, 0x11111110u, 0x10101010u, 0, 1, 0x11111110u, 0x10101000u, 0, 0, 0x11111110u, 0x00101010u)
 
 struct msb200_scaler {
 	msb200_ctx *ctx;
@@ -1850,6 +1871,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		// static-schedule variant: does the interior of the frame follow one of the instantiated row schedules?
 		s->sched = -1;
 		memset(S.regular, 0, sizeof(S.regular));
+		S.b_first = S.b_last = -1;
 		s->force_sched_off = getenv("MSB200_SCALER_NO_SCHED") != nullptr; // A/B runs and tests of the general loop
 		if (s->force_sched_off == 0) {
 			const int PR = ST_SCHED_ROWS, n_strips = dst_h / PR;
@@ -1873,24 +1895,26 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 				for (int j = 0; j < P.vc_size; ++j) t[(cp + j) % P.vc_size] = 32 * s->vc.coef[(size_t)y * P.vc_size + j];
 				for (int j = 0; j < P.vl_size; ++j) t[2 + (lp + j) % P.vl_size] = 32 * s->vl.coef[(size_t)y * P.vl_size + j];
 			};
+			// does strip `st` follow (nlpat, ncpat, sl0, sc0)? its rotated taps go to `taps`
+			auto follows = [&](int st, unsigned nlpat, unsigned ncpat, int sl0, int sc0, int vl, int vc, int(&taps)[ST_SCHED_ROWS][6]) {
+				const int ys = st * PR;
+				bool reg = ys + PR <= dst_h && (l_last(ys) - (vl - 1)) >= 0 && (l_last(ys) - (vl - 1)) % vl == sl0 &&
+				           (c_last(ys) - (vc - 1)) >= 0 && (c_last(ys) - (vc - 1)) % vc == sc0;
+				for (int j = 1; j < PR && reg; ++j)
+					reg = l_last(ys + j) - l_last(ys + j - 1) == (int)((nlpat >> (4 * j)) & 15u) &&
+					      c_last(ys + j) - c_last(ys + j - 1) == (int)((ncpat >> (4 * j)) & 15u);
+				for (int j = 0; j < PR && reg; ++j) taps_of(ys + j, taps[j]);
+				return reg;
+			};
 			for (int k = 0; k < ST_N_SCHED && s->sched < 0 && n_strips <= 32 * 16 && narrow; ++k) {
 				const StripSched &d = kStripSched[k];
 				if (d.vl != P.vl_size || d.vc != P.vc_size) continue;
 				unsigned mask[16] = {0};
-				int n_reg = 0, staps[16][6];
+				int n_reg = 0, staps[ST_SCHED_ROWS][6], t[ST_SCHED_ROWS][6];
 				for (int st = 0; st < n_strips; ++st) {
-					const int ys = st * PR;
-					bool reg = (l_last(ys) - (d.vl - 1)) >= 0 && (l_last(ys) - (d.vl - 1)) % d.vl == d.sl0 &&
-					           (c_last(ys) - (d.vc - 1)) >= 0 && (c_last(ys) - (d.vc - 1)) % d.vc == d.sc0;
-					for (int j = 1; j < PR && reg; ++j)
-						reg = l_last(ys + j) - l_last(ys + j - 1) == (int)((d.nlpat >> (4 * j)) & 15u) &&
-						      c_last(ys + j) - c_last(ys + j - 1) == (int)((d.ncpat >> (4 * j)) & 15u);
-					for (int j = 0; j < PR && reg; ++j) { // and the same taps as the first strip on the schedule
-						int t[6];
-						taps_of(ys + j, t);
-						if (n_reg == 0) memcpy(staps[j], t, sizeof(t));
-						else reg = memcmp(staps[j], t, sizeof(t)) == 0;
-					}
+					bool reg = follows(st, d.nlpat, d.ncpat, d.sl0, d.sc0, d.vl, d.vc, t);
+					if (reg && n_reg == 0) memcpy(staps, t, sizeof(t));
+					reg = reg && memcmp(staps, t, sizeof(t)) == 0; // and the same taps as the first strip on the schedule
 					if (reg) {
 						mask[st >> 5] |= 1u << (st & 31);
 						++n_reg;
@@ -1900,6 +1924,11 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 					s->sched = k;
 					memcpy(S.regular, mask, sizeof(mask));
 					memcpy(S.staps, staps, sizeof(staps));
+					// the frame's first and last strips: their own (border) schedules, when they fit
+					if (!(mask[0] & 1u) && follows(0, d.nlf, d.ncf, d.slf, d.scf, d.vl, d.vc, S.staps_f)) S.b_first = 0;
+					const int ls = n_strips - 1;
+					if (ls > 0 && dst_h % PR == 0 && !((mask[ls >> 5] >> (ls & 31)) & 1u) &&
+					    follows(ls, d.nll, d.ncl, d.sl0, d.sc0, d.vl, d.vc, S.staps_l)) S.b_last = ls;
 				}
 			}
 		}
@@ -1949,7 +1978,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 				bool need = s->sched < 0;
 				for (int w = 0; w < ST_WARPS && !need; ++w) {
 					const int st = ty * ST_WARPS + w;
-					need = st * S.R < dst_h && !((S.regular[st >> 5] >> (st & 31)) & 1u);
+					need = st * S.R < dst_h && !((S.regular[st >> 5] >> (st & 31)) & 1u) && st != S.b_first && st != S.b_last;
 				}
 				if (need) S.ty_list[S.n_ty++] = (short)ty;
 			}
@@ -1975,10 +2004,10 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 				STRIP_ATTR(1, 2);
 				STRIP_ATTR(1, 1);
 #undef STRIP_ATTR
-#define SCHED_ATTR(K, VL, VC, NL, NC, SL, SC)                                                                          \
-	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, false, ST_SCHED_ROWS, NL, NC, SL, SC>,             \
+#define SCHED_ATTR(K, VL, VC, NL, NC, SL, SC, NLF, NCF, SLF, SCF, NLL, NCL)                                             \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, false, ST_SCHED_ROWS, NL, NC, SL, SC, NLF, NCF, SLF, SCF, NLL, NCL>, \
 	                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_strip));                \
-	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, true, ST_SCHED_ROWS, NL, NC, SL, SC>,              \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_rgb_strip_kernel<VL, VC, true, ST_SCHED_ROWS, NL, NC, SL, SC, NLF, NCF, SLF, SCF, NLL, NCL>, \
 	                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_strip));
 				ST_SCHED_LIST(SCHED_ATTR)
 #undef SCHED_ATTR
@@ -2146,13 +2175,13 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 		else                                                                                                           \
 			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, false>), grid_g, ST_THREADS, s->smem_strip, s->map_ls, s->map_cs, s->map_os, P, s->S); \
 	} while (0)
-#define SCHED_LAUNCH(K, VL, VC, NL, NC, SL, SC)                                                                        \
+#define SCHED_LAUNCH(K, VL, VC, NL, NC, SL, SC, NLF, NCF, SLF, SCF, NLL, NCL)                                           \
 	if (s->sched == K) {                                                                                               \
 		if (P.dst_fmt == MSB200_PIX_RGB24_REV)                                                                         \
-			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, true, ST_SCHED_ROWS, NL, NC, SL, SC>), grid, ST_THREADS, s->smem_strip, \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, true, ST_SCHED_ROWS, NL, NC, SL, SC, NLF, NCF, SLF, SCF, NLL, NCL>), grid, ST_THREADS, s->smem_strip, \
 			              s->map_ls, s->map_cs, s->map_os, P, s->S);                                                   \
 		else                                                                                                           \
-			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, false, ST_SCHED_ROWS, NL, NC, SL, SC>), grid, ST_THREADS, s->smem_strip, \
+			MSB200_LAUNCH(s->ctx, (scale_rgb_strip_kernel<VL, VC, false, ST_SCHED_ROWS, NL, NC, SL, SC, NLF, NCF, SLF, SCF, NLL, NCL>), grid, ST_THREADS, s->smem_strip, \
 			              s->map_ls, s->map_cs, s->map_os, P, s->S);                                                   \
 	}
 		ST_SCHED_LIST(SCHED_LAUNCH) // straight-line instantiation for this frame's row schedule, when there is one
