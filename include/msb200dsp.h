@@ -319,7 +319,10 @@ MSB200_API int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void
  * (include/mediastreamer2/msvideo.h:473-479; backends src/voip/msvideo.c:517-691), used by MSPixConv
  * (src/videofilters/pixconv.c:62-94) and MSSizeConv (src/videofilters/sizeconv.c:97-184), batched over n_frames.
  * Arithmetic: the swscale SWS_BILINEAR pipeline the reference's ffmpeg back-end runs (msvideo.c:651-681) restated in
- * oracle/oracle_video.c and pinned against libswscale 9.1.100 golden frames (tests/golden/). */
+ * oracle/oracle_video.c and pinned against libswscale 9.1.100 golden frames (tests/golden/).
+ * Format pairs: YUV420P / NV12 / NV21 -> YUV420P / RGB24 / RGB24_REV(BGR byte order) with bilinear scaling (source
+ * width % 16 == 0; down-scale factor < 2); MSPixConv's same-size conversions YUYV / YUY2 / UYVY / RGB24 / RGB24_REV ->
+ * YUV420P (w % 8 == 0 for 4:2:2, w % 4 == 0 for RGB; h even). Frames are tight (no row padding), back to back. */
 typedef struct msb200_scaler msb200_scaler;
 MSB200_API int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int dst_w, int dst_h,
                                     int dst_fmt, msb200_scaler **out);

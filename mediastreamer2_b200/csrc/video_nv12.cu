@@ -140,6 +140,111 @@ int msb200i_packed422_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, 
 	return MSB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ packed RGB -> I420
+// MSPixConv's MS_RGB24 / MS_RGB24_REV inputs (src/videofilters/pixconv.c:62-94 -> ms_scaler_process at the same size)
+// as libswscale 9.1 converts them (arithmetic and its pinning: oracle/oracle_video.c rgb_to_i420()):
+//   RGB24: generic scaler path — Y through rgb24ToY / hScale16To15 / yuv2plane1, chroma from horizontal pixel pairs at
+//          full height, then the 2:1 vertical bilinear filter {512,1536,1536,512}/4096 over rows 2y-1..2y+2 (clamped);
+//   BGR24: the unscaled special converter (ff_rgb24toyv12): truncating Q15 luma, chroma from the 2x2 component means.
+// One thread: 4 pixels x 2 rows of luma (two chroma samples); rows are read as three aligned 32-bit words (w % 4 == 0).
+// HBM-bound: 3 B/pixel in + 1.5 B/pixel out; the two halo rows of the RGB24 path come from L1/L2 (neighbour threads).
+#define RGB_RY 8414
+#define RGB_GY 16519
+#define RGB_BY 3208
+#define RGB_RU (-4865)
+#define RGB_GU (-9528)
+#define RGB_BU 14392
+#define RGB_RV 14392
+#define RGB_GV (-12061)
+#define RGB_BV (-2332)
+__device__ __forceinline__ void rgb_unpack4(const uint8_t *row, int c[4][3]) { // 12 bytes = 4 pixels x 3 components
+	const uint3 wd = *reinterpret_cast<const uint3 *>(row);
+	const unsigned w3[3] = {wd.x, wd.y, wd.z};
+#pragma unroll
+	for (int i = 0; i < 12; ++i) c[i / 3][i % 3] = (int)((w3[i >> 2] >> (8 * (i & 3))) & 255u);
+}
+template <bool BGR>
+__global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h) {
+	const int groups = w / 4, rows2 = h / 2;
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long)groups * rows2) return;
+	const int cy = (int)(t / groups), gx = (int)(t % groups);
+	const size_t frame = blockIdx.y, pitch = (size_t)w * 3;
+	const uint8_t *fs = src + frame * (pitch * h) + (size_t)gx * 12;
+	uint8_t *fd = dst + frame * ((size_t)w * h * 3 / 2);
+	uint8_t *pu = fd + (size_t)w * h, *pv = pu + (size_t)(w / 2) * (h / 2);
+	int a[4][3], b[4][3]; // the block's two rows
+	rgb_unpack4(fs + (size_t)(2 * cy) * pitch, a);
+	rgb_unpack4(fs + (size_t)(2 * cy + 1) * pitch, b);
+	unsigned ya = 0, yb = 0;
+	if (BGR) {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			ya |= (unsigned)(((RGB_RY * a[k][2] + RGB_GY * a[k][1] + RGB_BY * a[k][0]) >> 15) + 16) << (8 * k);
+			yb |= (unsigned)(((RGB_RY * b[k][2] + RGB_GY * b[k][1] + RGB_BY * b[k][0]) >> 15) + 16) << (8 * k);
+		}
+		unsigned u2 = 0, v2 = 0;
+#pragma unroll
+		for (int s = 0; s < 2; ++s) {
+			int m[3];
+#pragma unroll
+			for (int k = 0; k < 3; ++k) m[k] = (a[2 * s][k] + a[2 * s + 1][k] + b[2 * s][k] + b[2 * s + 1][k]) >> 2;
+			u2 |= (unsigned)((((RGB_RU * m[2] + RGB_GU * m[1] + RGB_BU * m[0]) >> 15) + 128) & 255) << (8 * s);
+			v2 |= (unsigned)((((RGB_RV * m[2] + RGB_GV * m[1] + RGB_BV * m[0]) >> 15) + 128) & 255) << (8 * s);
+		}
+		*reinterpret_cast<unsigned short *>(pu + (size_t)cy * (w / 2) + (size_t)gx * 2) = (unsigned short)u2;
+		*reinterpret_cast<unsigned short *>(pv + (size_t)cy * (w / 2) + (size_t)gx * 2) = (unsigned short)v2;
+	} else {
+		auto luma = [](const int(&c)[3]) {
+			int v = (RGB_RY * c[0] + RGB_GY * c[1] + RGB_BY * c[2] + (32 << 14) + (1 << 8)) >> 9;
+			v = min(v * 2, 32767); // hScale16To15 with its single 1 << 14 tap: (v * 16384) >> 13
+			v = (v + 64) >> 7;
+			return (unsigned)min(max(v, 0), 255);
+		};
+		// 15-bit chroma of a pixel pair
+		auto chroma = [](const int(&p)[3], const int(&q)[3], int &u, int &v) {
+			const int r = p[0] + q[0], g = p[1] + q[1], bl = p[2] + q[2];
+			u = min(((RGB_RU * r + RGB_GU * g + RGB_BU * bl + (256 << 15) + (1 << 9)) >> 10) * 2, 32767);
+			v = min(((RGB_RV * r + RGB_GV * g + RGB_BV * bl + (256 << 15) + (1 << 9)) >> 10) * 2, 32767);
+		};
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			ya |= luma(a[k]) << (8 * k);
+			yb |= luma(b[k]) << (8 * k);
+		}
+		int above[4][3], below[4][3]; // rows 2cy-1 and 2cy+2, folded onto the picture's border rows
+		rgb_unpack4(fs + (size_t)max(2 * cy - 1, 0) * pitch, above);
+		rgb_unpack4(fs + (size_t)min(2 * cy + 2, h - 1) * pitch, below);
+		unsigned u2 = 0, v2 = 0;
+#pragma unroll
+		for (int s = 0; s < 2; ++s) {
+			int u[4], v[4];
+			chroma(above[2 * s], above[2 * s + 1], u[0], v[0]);
+			chroma(a[2 * s], a[2 * s + 1], u[1], v[1]);
+			chroma(b[2 * s], b[2 * s + 1], u[2], v[2]);
+			chroma(below[2 * s], below[2 * s + 1], u[3], v[3]);
+			const int su = ((64 << 12) + 512 * (u[0] + u[3]) + 1536 * (u[1] + u[2])) >> 19;
+			const int sv = ((64 << 12) + 512 * (v[0] + v[3]) + 1536 * (v[1] + v[2])) >> 19;
+			u2 |= (unsigned)min(max(su, 0), 255) << (8 * s);
+			v2 |= (unsigned)min(max(sv, 0), 255) << (8 * s);
+		}
+		*reinterpret_cast<unsigned short *>(pu + (size_t)cy * (w / 2) + (size_t)gx * 2) = (unsigned short)u2;
+		*reinterpret_cast<unsigned short *>(pv + (size_t)cy * (w / 2) + (size_t)gx * 2) = (unsigned short)v2;
+	}
+	*reinterpret_cast<unsigned *>(fd + (size_t)(2 * cy) * w + (size_t)gx * 4) = ya;
+	*reinterpret_cast<unsigned *>(fd + (size_t)(2 * cy + 1) * w + (size_t)gx * 4) = yb;
+}
+
+int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int bgr, void *d_dst) {
+	MSB200_CHECK_ARG(ctx && d_src && d_dst && n_frames > 0 && n_frames <= 65535 && w > 0 && h > 0 && (w % 4) == 0 && (h % 2) == 0);
+	MSB200_CHECK_ARG(((uintptr_t)d_src % 4) == 0 && ((uintptr_t)d_dst % 4) == 0);
+	const long threads = (long)(w / 4) * (h / 2);
+	dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
+	if (bgr) MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<true>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h);
+	else MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<false>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h);
+	return MSB200_OK;
+}
+
 extern "C" {
 
 int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void *d_src, size_t src_frame_bytes, size_t cbcr_offset,

@@ -268,6 +268,15 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 		s->dst_w = dst_w; s->dst_h = dst_h; s->dst_fmt = dst_fmt;
 		return s;
 	}
+	if (src_fmt == PIX_RGB24 || src_fmt == PIX_BGR24) {
+		/* MSPixConv's RGB inputs (pixconv.c:62-94, MS_RGB24 -> AV_PIX_FMT_RGB24, MS_RGB24_REV -> AV_PIX_FMT_BGR24 read bottom-up
+		 * through a negative stride, :78-81): packed RGB -> YUV420P at the SAME size. See rgb_to_i420() below. */
+		if (dst_fmt != PIX_YUV420P || src_w != dst_w || src_h != dst_h || (src_w & 1) || (src_h & 1)) return NULL;
+		s = (orc_scaler *)calloc(1, sizeof(*s));
+		s->src_w = src_w; s->src_h = src_h; s->src_fmt = src_fmt;
+		s->dst_w = dst_w; s->dst_h = dst_h; s->dst_fmt = dst_fmt;
+		return s;
+	}
 	const int src_ok = src_fmt == PIX_YUV420P || src_fmt == PIX_NV12 || src_fmt == PIX_NV21;
 	const int dst_ok = dst_fmt == PIX_YUV420P || dst_fmt == PIX_RGB24 || dst_fmt == PIX_BGR24;
 	if (!src_ok || !dst_ok || src_w < 8 || src_h < 8 || dst_w < 8 || dst_h < 8) return NULL;
@@ -307,7 +316,7 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 }
 void orc_scaler_free(orc_scaler *s) {
 	if (!s) return;
-	if (is_packed422(s->src_fmt)) {
+	if (is_packed422(s->src_fmt) || s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24) {
 		free(s);
 		return;
 	}
@@ -362,8 +371,91 @@ static void hscale(int16_t *dst, int dstW, const uint8_t *src, const sws_filter 
 	}
 }
 
+/* Packed RGB -> YUV420P at the same size, as libswscale 9.1 (FFmpeg 8; the reference's ffmpeg back-end calls
+ * sws_getContext(..., SWS_BILINEAR), /root/reference/src/voip/msvideo.c:651-670) does it. libswscale is not under
+ * /root/reference: the arithmetic below restates its published C code and is pinned against the real library
+ * (tests/golden cases rgb24 / bgr24; tests/test_oracle_video.py).
+ *
+ * ITU-601 limited-range coefficients in Q15 (libswscale's input_rgb2yuv_table).
+ *
+ * RGB24 takes the GENERIC scaler path with an RGB input stage:
+ *   luma   rgb24ToY_c:        y14 = (RY r + GY g + BY b + (32 << 14) + (1 << 8)) >> 9
+ *          hScale16To15_c:    y15 = min((y14 * 16384) >> 13, 32767)          (unscaled: one tap of 1 << 14, sh = 13)
+ *          yuv2plane1_c:      Y   = clip_u8((y15 + 64) >> 7)
+ *   chroma rgb24ToUV_half_c:  sums of two horizontally adjacent pixels, u14 = (RU r2 + GU g2 + BU b2 + (256 << 15) + (1 << 9)) >> 10
+ *          hScale16To15_c     as above; the chroma plane keeps the full source height (chrSrcVSubSample = 0)
+ *          vertical 2:1 bilinear filter of initFilter: taps {512, 1536, 1536, 512} / 4096 on rows 2y-1 .. 2y+2, rows
+ *          outside the picture folded onto the border row; yuv2planeX_8_c: clip_u8(((64 << 12) + sum) >> 19)
+ * BGR24 takes the unscaled special converter bgr24ToYv12Wrapper -> ff_rgb24toyv12_c:
+ *   Y = ((RY r + GY g + BY b) >> 15) + 16 per pixel; U/V from the 2x2 block's component means ((sum of 4) >> 2):
+ *   U = ((RU r + GU g + BU b) >> 15) + 128 (arithmetic shifts). */
+static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, uint8_t *dst) {
+	enum { RY = 8414, GY = 16519, BY = 3208, RU = -4865, GU = -9528, BU = 14392, RV = 14392, GV = -12061, BV = -2332 };
+	uint8_t *dy = dst, *du = dst + (size_t)w * h, *dv = du + (size_t)(w / 2) * (h / 2);
+	const int cw = w / 2;
+	if (bgr) {
+		for (int y = 0; y < h; ++y)
+			for (int x = 0; x < w; ++x) {
+				const uint8_t *p = src + ((size_t)y * w + x) * 3;
+				dy[(size_t)y * w + x] = (uint8_t)(((RY * p[2] + GY * p[1] + BY * p[0]) >> 15) + 16);
+			}
+		for (int y = 0; y < h / 2; ++y)
+			for (int x = 0; x < cw; ++x) {
+				int c[3];
+				for (int k = 0; k < 3; ++k) {
+					const uint8_t *p = src + ((size_t)(2 * y) * w + 2 * x) * 3 + k;
+					c[k] = (p[0] + p[3] + p[(size_t)w * 3] + p[(size_t)w * 3 + 3]) >> 2;
+				}
+				du[(size_t)y * cw + x] = (uint8_t)(((RU * c[2] + GU * c[1] + BU * c[0]) >> 15) + 128);
+				dv[(size_t)y * cw + x] = (uint8_t)(((RV * c[2] + GV * c[1] + BV * c[0]) >> 15) + 128);
+			}
+		return;
+	}
+	for (int y = 0; y < h; ++y)
+		for (int x = 0; x < w; ++x) {
+			const uint8_t *p = src + ((size_t)y * w + x) * 3;
+			int v = (RY * p[0] + GY * p[1] + BY * p[2] + (32 << 14) + (1 << 8)) >> 9;
+			v = (v * 16384) >> 13;
+			if (v > 32767) v = 32767;
+			v = (v + 64) >> 7;
+			dy[(size_t)y * w + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+		}
+	int16_t *u15 = (int16_t *)malloc(sizeof(int16_t) * (size_t)h * cw), *v15 = (int16_t *)malloc(sizeof(int16_t) * (size_t)h * cw);
+	for (int y = 0; y < h; ++y)
+		for (int x = 0; x < cw; ++x) {
+			const uint8_t *p = src + ((size_t)y * w + 2 * x) * 3;
+			const int r = p[0] + p[3], g = p[1] + p[4], b = p[2] + p[5];
+			int u = (RU * r + GU * g + BU * b + (256 << 15) + (1 << 9)) >> 10, v = (RV * r + GV * g + BV * b + (256 << 15) + (1 << 9)) >> 10;
+			u = (u * 16384) >> 13;
+			v = (v * 16384) >> 13;
+			u15[(size_t)y * cw + x] = (int16_t)(u > 32767 ? 32767 : u);
+			v15[(size_t)y * cw + x] = (int16_t)(v > 32767 ? 32767 : v);
+		}
+	static const int tap[4] = {512, 1536, 1536, 512};
+	for (int y = 0; y < h / 2; ++y)
+		for (int x = 0; x < cw; ++x) {
+			int au = 64 << 12, av = 64 << 12;
+			for (int j = 0; j < 4; ++j) {
+				int row = 2 * y - 1 + j;
+				row = row < 0 ? 0 : (row > h - 1 ? h - 1 : row);
+				au += tap[j] * u15[(size_t)row * cw + x];
+				av += tap[j] * v15[(size_t)row * cw + x];
+			}
+			au >>= 19;
+			av >>= 19;
+			du[(size_t)y * cw + x] = (uint8_t)(au < 0 ? 0 : (au > 255 ? 255 : au));
+			dv[(size_t)y * cw + x] = (uint8_t)(av < 0 ? 0 : (av > 255 ? 255 : av));
+		}
+	free(u15);
+	free(v15);
+}
+
 int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst) {
 	const int sw = s->src_w, sh = s->src_h, dw = s->dst_w, dh = s->dst_h;
+	if (s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24) {
+		rgb_to_i420(src, sw, sh, s->src_fmt == PIX_BGR24, dst);
+		return 0;
+	}
 	if (is_packed422(s->src_fmt)) {
 		const int yo = s->src_fmt == PIX_UYVY ? 1 : 0, uo = s->src_fmt == PIX_UYVY ? 0 : 1, vo = uo + 2;
 		uint8_t *dy = dst, *du = dst + (size_t)sw * sh, *dv = du + (size_t)(sw / 2) * (sh / 2);

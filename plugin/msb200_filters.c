@@ -1777,7 +1777,8 @@ static MSScalerContext *b200_scaler_create(int src_w, int src_h, MSPixFmt src_fm
 	B200ScalerCtx *c;
 	int sf = pixfmt_to_b200(src_fmt), df = pixfmt_to_b200(dst_fmt);
 	(void)flags;
-	if ((sf != MSB200_PIX_YUV420P && sf != MSB200_PIX_YUYV && sf != MSB200_PIX_YUY2 && sf != MSB200_PIX_UYVY) || df < 0) {
+	if ((sf != MSB200_PIX_YUV420P && sf != MSB200_PIX_YUYV && sf != MSB200_PIX_YUY2 && sf != MSB200_PIX_UYVY && sf != MSB200_PIX_RGB24 &&
+	     sf != MSB200_PIX_RGB24_REV) || df < 0) {
 		ms_error("msb200 scaler: unsupported conversion %s -> %s", ms_pix_fmt_to_string(src_fmt), ms_pix_fmt_to_string(dst_fmt));
 		return NULL;
 	}
@@ -1794,16 +1795,20 @@ static MSScalerContext *b200_scaler_create(int src_w, int src_h, MSPixFmt src_fm
 	c->dst_pack = (uint8_t *)ms_malloc(msb200_scaler_dst_frame_bytes(c->sc));
 	return (MSScalerContext *)c;
 }
-static void pack_plane(uint8_t *dst, const uint8_t *src, int stride, int w, int h) {
+static void pack_plane(uint8_t *dst, const uint8_t *src, int stride, int w, int h) { /* stride may be negative (bottom-up DIBs) */
 	int y;
 	for (y = 0; y < h; ++y)
-		memcpy(dst + (size_t)y * w, src + (size_t)y * stride, (size_t)w);
+		memcpy(dst + (size_t)y * w, src + (ptrdiff_t)y * (ptrdiff_t)stride, (size_t)w);
 }
 static int b200_scaler_process(MSScalerContext *ctx, uint8_t *src[], int src_strides[], uint8_t *dst[], int dst_strides[]) {
 	B200ScalerCtx *c = (B200ScalerCtx *)ctx;
 	int rc, cw = (c->src_w + 1) / 2, ch = (c->src_h + 1) / 2, y;
 	uint8_t *p = c->src_pack;
-	if (c->src_fmt != MSB200_PIX_YUV420P) { /* packed 4:2:2: one plane of 2 bytes per pixel (msvideo.c:120-156) */
+	if (c->src_fmt == MSB200_PIX_RGB24 || c->src_fmt == MSB200_PIX_RGB24_REV) {
+		/* packed RGB: one plane of 3 bytes per pixel; MSPixConv hands MS_RGB24_REV over with a negative stride, starting
+		 * at the last stored row (pixconv.c:78-81): the rows are packed in display order */
+		pack_plane(p, src[0], src_strides[0], c->src_w * 3, c->src_h);
+	} else if (c->src_fmt != MSB200_PIX_YUV420P) { /* packed 4:2:2: one plane of 2 bytes per pixel (msvideo.c:120-156) */
 		pack_plane(p, src[0], src_strides[0], c->src_w * 2, c->src_h);
 	} else {
 		pack_plane(p, src[0], src_strides[0], c->src_w, c->src_h);

@@ -86,6 +86,10 @@ def test_frame(fmt: str, w: int, h: int, t: int, seed: int) -> np.ndarray:
     cy, cx = np.mgrid[0:ch, 0:cw]
     U = ((cx + t) % 256 + rng.integers(-3, 4, size=(ch, cw))).clip(0, 255).astype(np.uint8)
     V = ((cy + 2 * t) % 256 + rng.integers(-3, 4, size=(ch, cw))).clip(0, 255).astype(np.uint8)
+    if fmt in ("rgb24", "bgr24"):  # MSPixConv's RGB inputs: a colour ramp plus full-range noise in one quadrant
+        rgb = np.stack([(3 * xx + t) % 256, (2 * yy + 5 * t) % 256, (xx + yy) % 256], axis=-1).astype(np.uint8)
+        rgb[: h // 2, : w // 2] = rng.integers(0, 256, size=(h // 2, w // 2, 3), dtype=np.uint8)
+        return rgb.ravel()
     if fmt == "yuv420p":
         return np.concatenate([Y.ravel(), U.ravel(), V.ravel()])
     if fmt in ("yuyv422", "uyvy422"):  # 4:2:2 packed: chroma at full vertical resolution
@@ -114,6 +118,9 @@ CASES = [
     ("nv12", 130, 74, "rgb24", 86, 50),        # odd chroma geometry
     ("yuyv422", 96, 64, "yuv420p", 96, 64),    # MSPixConv: packed 4:2:2 -> I420, same size
     ("uyvy422", 64, 48, "yuv420p", 64, 48),
+    ("rgb24", 96, 64, "yuv420p", 96, 64),      # MSPixConv: MS_RGB24 -> I420 (generic scaler path with the RGB input stage)
+    ("bgr24", 64, 48, "yuv420p", 64, 48),      # MSPixConv: MS_RGB24_REV -> I420 (unscaled special converter rgb24toyv12)
+    ("rgb24", 132, 70, "yuv420p", 132, 70),    # width % 8 != 0
 ]
 
 
