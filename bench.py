@@ -310,6 +310,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["pixconv"] = pixconv_bench(ctx, peak)
     except ImportError:
         pass
+    try:
+        from bench_g711 import g711_bench  # noqa: WPS433
+
+        if rank == 0:
+            line["g711"] = g711_bench(ctx, peak, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    except ImportError:
+        pass
     if rank == 0:
         print(json.dumps(line), flush=True)
     chain.close()

@@ -18,4 +18,6 @@ typedef struct _PayloadType {
 } PayloadType;
 typedef PayloadType OrtpPayloadType;
 typedef struct _RtpProfile RtpProfile;
+/* "a=fmtp" parameter lookup (oRTP payloadtype.c): value of `param_name` in a "k1=v1; k2=v2" list */
+bool_t fmtp_get_value(const char *fmtp, const char *param_name, char *result, size_t result_len);
 #endif

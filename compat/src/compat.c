@@ -8,6 +8,7 @@
 #include "bctoolbox/port.h"
 #include "ortp/str_utils.h"
 #include "ortp/utils.h"
+#include "ortp/payloadtype.h"
 
 /* ------------------------------------------------------------------ memory / strings */
 void *bctbx_malloc(size_t sz) {
@@ -548,4 +549,27 @@ float ortp_extremum_get_current(OrtpExtremum *obj) {
 }
 float ortp_extremum_get_previous(OrtpExtremum *obj) {
 	return obj->last_stable;
+}
+
+/* ---------------------------------------------------------------- fmtp parameters (used by the G.711 encoders' ptime) */
+bool_t fmtp_get_value(const char *fmtp, const char *param_name, char *result, size_t result_len) {
+	const size_t klen = strlen(param_name);
+	const char *p = fmtp;
+	if (result_len == 0) return FALSE;
+	while (p && *p) {
+		const char *end = strchr(p, ';');
+		const size_t len = end ? (size_t)(end - p) : strlen(p);
+		const char *k = p;
+		size_t n = len;
+		while (n && (*k == ' ' || *k == '\t')) ++k, --n;
+		if (n > klen && strncasecmp(k, param_name, klen) == 0 && k[klen] == '=') {
+			size_t vlen = n - klen - 1;
+			if (vlen >= result_len) vlen = result_len - 1;
+			memcpy(result, k + klen + 1, vlen);
+			result[vlen] = 0;
+			return TRUE;
+		}
+		p = end ? end + 1 : NULL;
+	}
+	return FALSE;
 }

@@ -251,6 +251,18 @@ MSB200_API int msb200_aec_set_state_blob(msb200_aec *a, int stream, const void *
  * "prop","noise","echo_noise","gain2", scalar pack "scalars"). Returns number of floats written or <0. */
 MSB200_API int msb200_aec_probe(msb200_aec *a, int stream, const char *what, float *out, int max_floats);
 
+/* ---------------------------------------------------------------------------------------------------- G.711
+ * MSAlawDec / MSUlawDec (/root/reference/src/audiofilters/alaw.c:199-211, ulaw.c) and the arithmetic of MSAlawEnc /
+ * MSUlawEnc (alaw.c:84-87): Snack_Alaw2Lin / Snack_Mulaw2Lin / Snack_Lin2Alaw / Snack_Lin2Mulaw
+ * (src/audiofilters/g711.c:119-262), over a flat batch of n samples (any concatenation of RTP payloads: the codec is
+ * stateless). Bit-exact. The encoders' re-framing to ptime stays on the host (plugin/msb200_filters.c). */
+#define MSB200_G711_ALAW 0 /* PCMA */
+#define MSB200_G711_ULAW 1 /* PCMU */
+MSB200_API int msb200_g711_decode(msb200_ctx *ctx, int law, const uint8_t *code, int16_t *pcm, size_t n);
+MSB200_API int msb200_g711_encode(msb200_ctx *ctx, int law, const int16_t *pcm, uint8_t *code, size_t n);
+MSB200_API int msb200_g711_decode_dev(msb200_ctx *ctx, int law, const void *d_code, void *d_pcm, size_t n);
+MSB200_API int msb200_g711_encode_dev(msb200_ctx *ctx, int law, const void *d_pcm, void *d_code, size_t n);
+
 /* ---------------------------------------------------------------------------------------------------- audio chain
  * The BASELINE cfg2 pipeline as one resident device-side graph, one call per 10 ms tick for `n_streams` streams:
  *   ref  [in_rate] -> MSResample -> \

@@ -91,6 +91,10 @@ _SIGS = {
     "msb200_volume_create": (_I, [_P, _I, _I, _I, _PP]),
     "msb200_volume_destroy": (None, [_P]),
     "msb200_ctx_make_current": (_I, [_P]),
+    "msb200_g711_decode": (_I, [_P, _I, _P, _P, _SZ]),
+    "msb200_g711_encode": (_I, [_P, _I, _P, _P, _SZ]),
+    "msb200_g711_decode_dev": (_I, [_P, _I, _P, _P, _SZ]),
+    "msb200_g711_encode_dev": (_I, [_P, _I, _P, _P, _SZ]),
     "msb200_volume_reset_stream": (_I, [_P, _I]),
     "msb200_volume_set_live": (_I, [_P, _I]),
     "msb200_mixer_set_live": (_I, [_P, _I]),

@@ -412,3 +412,30 @@ def nv12_to_i420(ctx: Context, frames: np.ndarray, w: int, h: int, rotation: int
     check(ctx.lib.msb200_nv12_to_i420(ctx.h, n, _ptr(frames), fb, cbcr_offset, rotation, w, h, y_stride, cbcr_stride,
                                       int(u_first), int(down_scale), _ptr(out)))
     return out
+
+
+G711_ALAW, G711_ULAW = 0, 1
+
+
+def g711_decode(ctx: Context, law: int, code: np.ndarray) -> np.ndarray:
+    """MSAlawDec / MSUlawDec arithmetic (alaw.c:199-211; g711.c:152-172, 249-262) over a flat batch of code words."""
+    code = _req(code, np.uint8)
+    pcm = np.empty(code.shape, np.int16)
+    check(ctx.lib.msb200_g711_decode(ctx.h, law, _ptr(code), _ptr(pcm), code.size))
+    return pcm
+
+
+def g711_encode(ctx: Context, law: int, pcm: np.ndarray) -> np.ndarray:
+    """MSAlawEnc / MSUlawEnc arithmetic (alaw.c:84-87; g711.c:119-146, 208-238) over a flat batch of samples."""
+    pcm = _req(pcm, np.int16)
+    code = np.empty(pcm.shape, np.uint8)
+    check(ctx.lib.msb200_g711_encode(ctx.h, law, _ptr(pcm), _ptr(code), pcm.size))
+    return code
+
+
+def g711_decode_dev(ctx: Context, law: int, d_code: int, d_pcm: int, n: int):
+    check(ctx.lib.msb200_g711_decode_dev(ctx.h, law, C.c_void_p(d_code), C.c_void_p(d_pcm), n))
+
+
+def g711_encode_dev(ctx: Context, law: int, d_pcm: int, d_code: int, n: int):
+    check(ctx.lib.msb200_g711_encode_dev(ctx.h, law, C.c_void_p(d_pcm), C.c_void_p(d_code), n))

@@ -100,6 +100,10 @@ int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst);
 int orc_scaler_get_filter(orc_scaler *s, int which /*0 lumH,1 chrH,2 lumV,3 chrV*/, int32_t *pos, int16_t *coef,
                           int max_entries);
 
+/* G.711 (oracle_g711.c): law 0 = A-law, 1 = mu-law */
+void orc_g711_encode(int law, const int16_t *pcm, uint8_t *code, size_t n);
+void orc_g711_decode(int law, const uint8_t *code, int16_t *pcm, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -329,6 +329,10 @@ unsigned int ref_method_id(const char *name) {
 	MID(MS_ECHO_CANCELLER_GET_BYPASS_MODE);
 	MID(MS_ECHO_CANCELLER_GET_STATE_STRING);
 	MID(MS_ECHO_CANCELLER_SET_STATE_STRING);
+	MID(MS_FILTER_ADD_FMTP);
+	MID(MS_FILTER_ADD_ATTR);
+	MID(MS_AUDIO_ENCODER_GET_PTIME);
+	MID(MS_DECODER_HAVE_PLC);
 	return 0;
 }
 

@@ -37,6 +37,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1754,6 +1755,201 @@ static MSFilterDesc b200_speex_ec_desc = {.id = MS_SPEEX_EC_ID,
                                           .uninit = ec_uninit,
                                           .methods = ec_methods};
 
+/* ================================================================================================ G.711 codecs
+ * MSAlawEnc / MSAlawDec / MSUlawEnc / MSUlawDec (/root/reference/src/audiofilters/alaw.c, ulaw.c): the "decode stub /
+ * encode stub" either side of the audio path in a media server. Host logic restated from the
+ * reference — encoder: MSBufferizer re-framing to ptime (alaw.c:56-94), fmtp / attr parsing (:96-138), getters
+ * (:140-160); decoder: one output block per input block, meta data copied (:199-211). The companding itself runs on the
+ * GPU (msb200_g711_*): one call for everything queued in the tick. */
+typedef struct G711EncState {
+	MSBufferizer *bz;
+	int ptime, maxptime, law;
+	uint32_t ts;
+} G711EncState;
+static void g711_enc_init_law(MSFilter *f, int law) {
+	G711EncState *s = ms_new0(G711EncState, 1);
+	s->bz = ms_bufferizer_new();
+	s->ptime = 0;
+	s->maxptime = MS_DEFAULT_MAX_PTIME < 140 ? MS_DEFAULT_MAX_PTIME : 140;
+	s->law = law;
+	f->data = s;
+}
+static void alaw_enc_init(MSFilter *f) { g711_enc_init_law(f, MSB200_G711_ALAW); }
+static void ulaw_enc_init(MSFilter *f) { g711_enc_init_law(f, MSB200_G711_ULAW); }
+static void g711_enc_uninit(MSFilter *f) {
+	G711EncState *s = (G711EncState *)f->data;
+	ms_bufferizer_destroy(s->bz);
+	ms_free(s);
+}
+static void g711_enc_process(MSFilter *f) {
+	G711EncState *s = (G711EncState *)f->data;
+	int frame_per_packet = 2, npk, k;
+	size_t size_of_pcm, avail;
+	mblk_t *m;
+	uint8_t *pcm, *code;
+	if (s->ptime >= 10) frame_per_packet = s->ptime / 10;
+	if (frame_per_packet <= 0) frame_per_packet = 1;
+	if (frame_per_packet > 14) frame_per_packet = 14; /* 140 ms max */
+	size_of_pcm = (size_t)160 * frame_per_packet;       /* bytes: 80 samples per 10 ms at 8 kHz */
+	while ((m = ms_queue_get(f->inputs[0])) != NULL)
+		ms_bufferizer_put(s->bz, m);
+	avail = ms_bufferizer_get_avail(s->bz);
+	npk = (int)(avail / size_of_pcm);
+	if (npk == 0) return;
+	/* every complete packet of this tick in ONE device call; meta data are taken per packet, as the reference does */
+	pcm = (uint8_t *)ms_malloc((size_t)npk * size_of_pcm);
+	code = (uint8_t *)ms_malloc((size_t)npk * size_of_pcm / 2);
+	{
+		mblk_t **outs = (mblk_t **)ms_malloc(sizeof(mblk_t *) * (size_t)npk);
+		int rc = MSB200_ENODEV;
+		for (k = 0; k < npk; ++k) {
+			ms_bufferizer_read(s->bz, pcm + (size_t)k * size_of_pcm, size_of_pcm);
+			outs[k] = allocb(size_of_pcm / 2, 0);
+			ms_bufferizer_fill_current_metas(s->bz, outs[k]);
+		}
+		DSP_LOCK();
+		if (dsp_ctx()) {
+			rc = msb200_g711_encode(g_ctx, s->law, (const int16_t *)pcm, code, (size_t)npk * size_of_pcm / 2);
+			if (rc != MSB200_OK) ms_error("msb200: g711_encode failed: %s", msb200_last_error());
+		}
+		DSP_UNLOCK();
+		for (k = 0; k < npk; ++k) {
+			if (rc != MSB200_OK) { /* no GPU: never emit a packet that was not encoded */
+				freemsg(outs[k]);
+				continue;
+			}
+			memcpy(outs[k]->b_wptr, code + (size_t)k * size_of_pcm / 2, size_of_pcm / 2);
+			outs[k]->b_wptr += size_of_pcm / 2;
+			mblk_set_timestamp_info(outs[k], s->ts);
+			s->ts += (uint32_t)(size_of_pcm / 2);
+			ms_queue_put(f->outputs[0], outs[k]);
+		}
+		ms_free(outs);
+	}
+	ms_free(pcm);
+	ms_free(code);
+}
+static int g711_enc_add_fmtp(MSFilter *f, void *arg) { /* enc_add_fmtp alaw.c:96-110 */
+	const char *fmtp = (const char *)arg;
+	G711EncState *s = (G711EncState *)f->data;
+	char tmp[30];
+	if (fmtp_get_value(fmtp, "maxptime", tmp, sizeof(tmp))) {
+		int v = atoi(tmp);
+		s->maxptime = v < MS_DEFAULT_MAX_PTIME ? v : MS_DEFAULT_MAX_PTIME;
+	}
+	if (fmtp_get_value(fmtp, "ptime", tmp, sizeof(tmp))) {
+		int v = atoi(tmp);
+		ms_message("%s configured with ptime=%s", f->desc->name, tmp);
+		s->ptime = v < s->maxptime ? v : s->maxptime;
+		if (s->ptime == s->maxptime) ms_message("%s ptime set to maxptime=%i", f->desc->name, s->maxptime);
+	}
+	return 0;
+}
+static int g711_enc_add_attr(MSFilter *f, void *arg) { /* enc_add_attr alaw.c:112-138: "ptime:<10..140 step 10>" */
+	const char *attr = (const char *)arg;
+	G711EncState *s = (G711EncState *)f->data;
+	int p;
+	/* the reference tests the strings in ascending order with strstr and takes the FIRST hit: "ptime:100" also matches
+	 * "ptime:10" and therefore yields 10, like the original if/else chain */
+	for (p = 10; p <= 140; p += 10) {
+		char key[16];
+		snprintf(key, sizeof(key), "ptime:%d", p);
+		if (strstr(attr, key) != NULL) {
+			s->ptime = p;
+			break;
+		}
+	}
+	return 0;
+}
+static int g711_get_sample_rate(MSFilter *f, void *arg) {
+	(void)f;
+	*(int *)arg = 8000;
+	return 0;
+}
+static int g711_get_channels(MSFilter *f, void *arg) {
+	(void)f;
+	*(int *)arg = 1;
+	return 0;
+}
+static int g711_get_ptime(MSFilter *f, void *arg) {
+	*(int *)arg = ((G711EncState *)f->data)->ptime;
+	return 0;
+}
+static int g711_dec_have_plc(MSFilter *f, void *arg) {
+	(void)f;
+	*(int *)arg = 0;
+	return 0;
+}
+static MSFilterMethod g711_enc_methods[] = {{MS_FILTER_ADD_ATTR, g711_enc_add_attr},
+                                            {MS_FILTER_ADD_FMTP, g711_enc_add_fmtp},
+                                            {MS_FILTER_GET_NCHANNELS, g711_get_channels},
+                                            {MS_FILTER_GET_SAMPLE_RATE, g711_get_sample_rate},
+                                            {MS_AUDIO_ENCODER_GET_PTIME, g711_get_ptime},
+                                            {0, NULL}};
+static MSFilterMethod g711_dec_methods[] = {{MS_FILTER_GET_NCHANNELS, g711_get_channels},
+                                            {MS_FILTER_GET_SAMPLE_RATE, g711_get_sample_rate},
+                                            {MS_DECODER_HAVE_PLC, g711_dec_have_plc},
+                                            {0, NULL}};
+static void g711_dec_process_law(MSFilter *f, int law) { /* alaw_dec_process alaw.c:199-211 */
+	mblk_t *m, *list[64];
+	size_t total = 0, off = 0;
+	int n = 0, k;
+	uint8_t *code;
+	int16_t *pcm;
+	int rc = MSB200_ENODEV;
+	/* everything queued in this tick (usually one RTP payload) goes to the device in ONE call */
+	while (n < 64 && (m = ms_queue_get(f->inputs[0])) != NULL) {
+		msgpullup(m, (size_t)-1);
+		list[n++] = m;
+		total += (size_t)(m->b_wptr - m->b_rptr);
+	}
+	if (n == 0) return;
+	code = (uint8_t *)ms_malloc(total ? total : 1);
+	pcm = (int16_t *)ms_malloc(total ? total * 2 : 2);
+	for (k = 0; k < n; ++k) {
+		const size_t len = (size_t)(list[k]->b_wptr - list[k]->b_rptr);
+		memcpy(code + off, list[k]->b_rptr, len);
+		off += len;
+	}
+	DSP_LOCK();
+	if (dsp_ctx()) {
+		rc = msb200_g711_decode(g_ctx, law, code, pcm, total);
+		if (rc != MSB200_OK) ms_error("msb200: g711_decode failed: %s", msb200_last_error());
+	}
+	DSP_UNLOCK();
+	off = 0;
+	for (k = 0; k < n; ++k) {
+		const size_t len = (size_t)(list[k]->b_wptr - list[k]->b_rptr);
+		if (rc == MSB200_OK) {
+			mblk_t *o = allocb(len * 2, 0);
+			mblk_meta_copy(list[k], o);
+			memcpy(o->b_wptr, pcm + off, len * 2);
+			o->b_wptr += len * 2;
+			ms_queue_put(f->outputs[0], o);
+		}
+		off += len;
+		freemsg(list[k]);
+	}
+	ms_free(code);
+	ms_free(pcm);
+}
+static void alaw_dec_process(MSFilter *f) { g711_dec_process_law(f, MSB200_G711_ALAW); }
+static void ulaw_dec_process(MSFilter *f) { g711_dec_process_law(f, MSB200_G711_ULAW); }
+static MSFilterDesc b200_alaw_enc_desc = {.id = MS_ALAW_ENC_ID, .name = "MSAlawEnc", .text = "B200: ITU-G.711 alaw encoder (libmsb200dsp)",
+                                          .category = MS_FILTER_ENCODER, .enc_fmt = "pcma", .ninputs = 1, .noutputs = 1,
+                                          .init = alaw_enc_init, .process = g711_enc_process, .uninit = g711_enc_uninit,
+                                          .methods = g711_enc_methods};
+static MSFilterDesc b200_ulaw_enc_desc = {.id = MS_ULAW_ENC_ID, .name = "MSUlawEnc", .text = "B200: ITU-G.711 ulaw encoder (libmsb200dsp)",
+                                          .category = MS_FILTER_ENCODER, .enc_fmt = "pcmu", .ninputs = 1, .noutputs = 1,
+                                          .init = ulaw_enc_init, .process = g711_enc_process, .uninit = g711_enc_uninit,
+                                          .methods = g711_enc_methods};
+static MSFilterDesc b200_alaw_dec_desc = {.id = MS_ALAW_DEC_ID, .name = "MSAlawDec", .text = "B200: ITU-G.711 alaw decoder (libmsb200dsp)",
+                                          .category = MS_FILTER_DECODER, .enc_fmt = "pcma", .ninputs = 1, .noutputs = 1,
+                                          .process = alaw_dec_process, .methods = g711_dec_methods};
+static MSFilterDesc b200_ulaw_dec_desc = {.id = MS_ULAW_DEC_ID, .name = "MSUlawDec", .text = "B200: ITU-G.711 ulaw decoder (libmsb200dsp)",
+                                          .category = MS_FILTER_DECODER, .enc_fmt = "pcmu", .ninputs = 1, .noutputs = 1,
+                                          .process = ulaw_dec_process, .methods = g711_dec_methods};
+
 /* ================================================================================================ MSScalerDesc
  * the second drop-in boundary (/root/reference/include/mediastreamer2/msvideo.h:473-492): installed with
  * ms_video_set_scaler_impl() so that the reference's own MSPixConv / MSSizeConv / display filters scale on the GPU. */
@@ -1864,9 +2060,13 @@ __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *fac
 	ms_factory_register_filter(factory, &b200_equalizer_desc);
 	ms_factory_register_filter(factory, &b200_resample_desc);
 	ms_factory_register_filter(factory, &b200_speex_ec_desc);
+	ms_factory_register_filter(factory, &b200_alaw_enc_desc);
+	ms_factory_register_filter(factory, &b200_alaw_dec_desc);
+	ms_factory_register_filter(factory, &b200_ulaw_enc_desc);
+	ms_factory_register_filter(factory, &b200_ulaw_dec_desc);
 	if (getenv("MSB200_INSTALL_SCALER")) ms_video_set_scaler_impl(&b200_scaler_desc);
 	ms_message("libmsb200filters: B200 DSP filters registered (MSAudioMixer, MSVolume, MSChannelAdapter, MSEqualizer, "
-	           "MSResample, MSSpeexEC%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
+	           "MSResample, MSSpeexEC, MSAlawEnc/Dec, MSUlawEnc/Dec%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
 }
 /* batch-group statistics for benchmarks: groups, launches (flushes) and units run so far, summed over all groups */
 __attribute__((visibility("default"))) void msb200_filters_batch_stats(int *groups, unsigned long long *flushes, unsigned long long *units) {

@@ -83,6 +83,8 @@ def oracle() -> C.CDLL:
         "orc_scaler_dst_bytes": (C.c_size_t, [_P]),
         "orc_scaler_process": (_I, [_P, _P, _P]),
         "orc_scaler_get_filter": (_I, [_P, _I, _P, _P, _I]),
+        "orc_g711_encode": (None, [_I, _P, _P, C.c_size_t]),
+        "orc_g711_decode": (None, [_I, _P, _P, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

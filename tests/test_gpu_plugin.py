@@ -267,3 +267,35 @@ def test_volume_plugin_chunked_mode_with_peer_bit_exact_vs_reference():
     assert len(res[0][1]) == T * n
     assert np.array_equal(res[0][0], res[1][0])
     assert np.array_equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("name,ptime", [("MSAlaw", 0), ("MSUlaw", 0), ("MSAlaw", 30), ("MSUlaw", 10)])
+def test_plugin_g711_codecs_bit_exact_vs_reference_filters(name, ptime):
+    """source -> <law>Enc -> <law>Dec -> sink in the unmodified MSTicker: the plugin's filters (GPU companding, host
+    re-framing) give the same blocks — sizes, timestamps and samples — as the reference's filters"""
+    import ctypes as C
+    rng = np.random.default_rng(17 + ptime)
+    n, ticks = 80, 30
+    pcm = (rng.standard_normal(n * ticks) * 9000).clip(-32768, 32767).astype(np.int16)
+    pcm[:16] = [-32768, 32767, 0, -1, 1, -8, 8, -9, 255, 256, -256, -257, 4095, 4096, -4096, -4097]
+
+    def run(plugins_dir):
+        g = RefGraph(plugins_dir=plugins_dir)
+        src, enc, dec, sink_c, sink_p = g.source(pcm, n * 2), g.new(name + "Enc"), g.new(name + "Dec"), g.sink(), g.sink()
+        if plugins_dir:
+            assert g.text(enc).startswith("B200:") and g.text(dec).startswith("B200:")
+        if ptime:
+            assert g.call_ptr(enc, "MS_FILTER_ADD_FMTP", C.c_char_p(b"ptime=%d" % ptime)) == 0
+        g.link(src, 0, enc, 0)
+        g.link(enc, 0, dec, 0)
+        g.link(dec, 0, sink_p, 0)
+        g.run(src, ticks + 2)
+        out, tri = g.read(sink_p)
+        g.close()
+        return out, tri
+
+    ref_out, ref_tri = run(None)
+    got_out, got_tri = run(str(O.PLUGIN_DIR))
+    assert len(ref_out) > n * (ticks - 4)
+    assert np.array_equal(got_tri, ref_tri)  # (tick, bytes, timestamp) of every block
+    assert np.array_equal(got_out, ref_out)

@@ -366,3 +366,49 @@ def test_volume_chunked_mode_oracle_bit_exact_vs_reference(agc, peer):
     assert np.array_equal(y_spk, exp_spk)
     assert len(y_mic) == len(out_mic)
     assert np.array_equal(y_mic, out_mic)
+
+
+# ---------------------------------------------------------------------------------------------------- G.711
+def test_g711_oracle_exhaustive_vs_reference_functions():
+    """oracle/oracle_g711.c == the UNMODIFIED Snack_* routines (g711.c:119-262) on every 16-bit sample and every code"""
+    import ctypes as C
+    L, R = O.oracle(), O.ref()
+    pcm = np.arange(-32768, 32768, dtype=np.int16)
+    codes = np.arange(256, dtype=np.uint8)
+    for law, enc, dec in ((0, R.Snack_Lin2Alaw, R.Snack_Alaw2Lin), (1, R.Snack_Lin2Mulaw, R.Snack_Mulaw2Lin)):
+        enc.restype, enc.argtypes = C.c_ubyte, [C.c_short]
+        dec.restype, dec.argtypes = C.c_short, [C.c_ubyte]
+        got_c = np.zeros(pcm.size, np.uint8)
+        L.orc_g711_encode(law, ptr(pcm), ptr(got_c), pcm.size)
+        exp_c = np.array([enc(int(v)) for v in pcm], np.uint8)
+        assert np.array_equal(got_c, exp_c), law
+        got_p = np.zeros(256, np.int16)
+        L.orc_g711_decode(law, ptr(codes), ptr(got_p), 256)
+        exp_p = np.array([dec(int(c)) for c in codes], np.int16)
+        assert np.array_equal(got_p, exp_p), law
+
+
+@pytest.mark.parametrize("name,law", [("MSAlaw", 0), ("MSUlaw", 1)])
+def test_g711_oracle_vs_reference_filters_in_ticker(name, law):
+    """the reference's encoder (MSBufferizer re-framing to ptime, alaw.c:56-94) and decoder (:199-211) filters in the
+    unmodified MSTicker == oracle arithmetic on the same samples"""
+    L = O.oracle()
+    rng = np.random.default_rng(11 + law)
+    n, ticks = 80, 24  # 8 kHz, 10 ms blocks
+    pcm = (rng.standard_normal(n * ticks) * 9000).clip(-32768, 32767).astype(np.int16)
+    pcm[:64] = np.array([-32768, 32767, 0, -1, 1, -8, 8, -9] * 8, np.int16)
+    g = RefGraph()
+    src, enc, dec, sink_p = g.source(pcm, n * 2), g.new(name + "Enc"), g.new(name + "Dec"), g.sink()
+    g.link(src, 0, enc, 0)
+    g.link(enc, 0, dec, 0)
+    g.link(dec, 0, sink_p, 0)
+    g.run(src, ticks + 2)
+    out_p, tri = g.read(sink_p)
+    g.close()
+    # default ptime: 2 frames of 10 ms per packet (alaw.c:59-72) -> blocks of 160 samples
+    assert len(out_p) == (n * ticks // 160) * 160 and np.all(tri[:, 1] == 320)  # (tick, bytes, timestamp) per block
+    code = np.zeros(len(out_p), np.uint8)
+    L.orc_g711_encode(law, ptr(pcm), ptr(code), len(out_p))
+    exp = np.zeros(len(out_p), np.int16)
+    L.orc_g711_decode(law, ptr(code), ptr(exp), len(out_p))
+    assert np.array_equal(out_p, exp)

@@ -6,7 +6,8 @@ import pytest
 import _oracle as O
 from _oracle import RefGraph
 
-NAMES = ["MSAudioMixer", "MSVolume", "MSChannelAdapter", "MSEqualizer", "MSResample", "MSSpeexEC"]
+NAMES = ["MSAudioMixer", "MSVolume", "MSChannelAdapter", "MSEqualizer", "MSResample", "MSSpeexEC",
+         "MSAlawEnc", "MSAlawDec", "MSUlawEnc", "MSUlawDec"]
 
 
 def _need_plugin():
@@ -65,4 +66,37 @@ def test_plugin_method_tables_accept_the_reference_method_ids():
     assert g.call_int(ec, "MS_FILTER_SET_SAMPLE_RATE", 48000) == 0
     assert g.call_int(ec, "MS_ECHO_CANCELLER_SET_TAIL_LENGTH", 250) == 0
     assert g.call_int(ec, "MS_ECHO_CANCELLER_SET_DELAY", 0) == 0
+    # G.711 codecs: the same answers as alaw.c:140-160 / ulaw.c, incl. the first-match quirk of the "ptime:" attribute
+    for nm in ("MSAlawEnc", "MSUlawEnc"):
+        enc = g.new(nm)
+        v = C.c_int(-1)
+        assert g.call(enc, "MS_FILTER_GET_SAMPLE_RATE", v) == 0 and v.value == 8000
+        assert g.call(enc, "MS_FILTER_GET_NCHANNELS", v) == 0 and v.value == 1
+        assert g.call(enc, "MS_AUDIO_ENCODER_GET_PTIME", v) == 0 and v.value == 0
+        assert g.call_ptr(enc, "MS_FILTER_ADD_FMTP", C.c_char_p(b"maxptime=60; ptime=80")) == 0
+        assert g.call(enc, "MS_AUDIO_ENCODER_GET_PTIME", v) == 0 and v.value == 60
+        assert g.call_ptr(enc, "MS_FILTER_ADD_ATTR", C.c_char_p(b"ptime:30")) == 0
+        assert g.call(enc, "MS_AUDIO_ENCODER_GET_PTIME", v) == 0 and v.value == 30
+        assert g.call_ptr(enc, "MS_FILTER_ADD_ATTR", C.c_char_p(b"ptime:100")) == 0
+        assert g.call(enc, "MS_AUDIO_ENCODER_GET_PTIME", v) == 0 and v.value == 10  # strstr("ptime:10") hits first
+    for nm in ("MSAlawDec", "MSUlawDec"):
+        dec = g.new(nm)
+        v = C.c_int(-1)
+        assert g.call(dec, "MS_DECODER_HAVE_PLC", v) == 0 and v.value == 0
+        assert g.call(dec, "MS_FILTER_GET_SAMPLE_RATE", v) == 0 and v.value == 8000
+    g.close()
+
+
+def test_g711_reference_filters_answer_the_same():
+    """the unmodified reference encoders give the answers asserted above (the quirk included)"""
+    import ctypes as C
+
+    g = RefGraph()
+    for nm in ("MSAlawEnc", "MSUlawEnc"):
+        enc = g.new(nm)
+        v = C.c_int(-1)
+        assert g.call_ptr(enc, "MS_FILTER_ADD_FMTP", C.c_char_p(b"maxptime=60; ptime=80")) == 0
+        assert g.call(enc, "MS_AUDIO_ENCODER_GET_PTIME", v) == 0 and v.value == 60
+        assert g.call_ptr(enc, "MS_FILTER_ADD_ATTR", C.c_char_p(b"ptime:100")) == 0
+        assert g.call(enc, "MS_AUDIO_ENCODER_GET_PTIME", v) == 0 and v.value == 10
     g.close()
