@@ -55,9 +55,10 @@ def pixconv_bench(ctx, hbm_peak_gbs: float, n_frames: int = 512, iters: int = 10
     src_pin[...] = base[np.arange(ne) % 8]
     import time
 
-    sc.process(src_pin)
+    dst_pin = ctx.pinned((ne, DST_BYTES), np.uint8)
+    sc.process(src_pin, dst_pin)
     t0 = time.perf_counter()
-    out = sc.process(src_pin)
+    out = sc.process(src_pin, dst_pin)
     e2e_s = time.perf_counter() - t0
     ctx.dev_free(d_src)
     ctx.dev_free(d_dst)

@@ -292,6 +292,14 @@ MSB200_API int msb200_chain_max_out_samples(msb200_chain *c);
  * H2D, all kernels, D2H inside. */
 MSB200_API int msb200_chain_tick(msb200_chain *c, const int16_t *ref_in, const int16_t *mic_in, int16_t *out,
                                  int *out_samples);
+/* Pipelined host path for free-running hosts: submit() enqueues tick T (H2D of its inputs, its kernels, D2H of its
+ * output into `out`) on three streams and returns at once — *out_samples is known immediately, the samples are in `out`
+ * after the matching wait(). At most two ticks in flight: tick T's input copy and tick T-1's output copy overlap the
+ * kernels. ref_in / mic_in / out must be pinned (msb200_host_alloc_pinned) and stay untouched until that wait().
+ * Results are identical to msb200_chain_tick(); do not mix the two styles while ticks are in flight. */
+MSB200_API int msb200_chain_submit(msb200_chain *c, const int16_t *ref_in, const int16_t *mic_in, int16_t *out,
+                                   int *out_samples);
+MSB200_API int msb200_chain_wait(msb200_chain *c); /* waits for the OLDEST tick in flight (no-op when none) */
 /* Device path: inputs/outputs already resident; asynchronous. */
 MSB200_API int msb200_chain_tick_dev(msb200_chain *c, const void *d_ref_in, const void *d_mic_in, void *d_out,
                                      int *out_samples);

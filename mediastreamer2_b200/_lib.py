@@ -153,6 +153,8 @@ _SIGS = {
     "msb200_chain_next_out_samples": (_I, [_P]),
     "msb200_chain_max_out_samples": (_I, [_P]),
     "msb200_chain_tick": (_I, [_P, _P, _P, _P, _PI]),
+    "msb200_chain_submit": (_I, [_P, _P, _P, _P, _PI]),
+    "msb200_chain_wait": (_I, [_P]),
     "msb200_chain_tick_dev": (_I, [_P, _P, _P, _P, _PI]),
     "msb200_chain_launches_per_tick": (_I, [_P]),
     "msb200_chain_aec": (_P, [_P]),

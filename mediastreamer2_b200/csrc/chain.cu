@@ -32,6 +32,12 @@ struct msb200_chain {
 	short *d_in_ref, *d_in_mic, *d_stage_out;
 	int max_out;
 	int launches_last_tick;
+	// pipelined host path (msb200_chain_submit / _wait): copy streams, double buffers, events
+	cudaStream_t s_in, s_out;
+	short *pd_in_ref[2], *pd_in_mic[2], *pd_stage[2];
+	cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+	int pipe_ready;            // streams / buffers / events created
+	unsigned long long n_submitted, n_collected;
 	// optional per-launch timing of the AEC kernel (bench.py roofline)
 	bool timing;
 	std::vector<cudaEvent_t> *ev; // pairs (start, stop), reused round-robin after being drained
@@ -120,6 +126,20 @@ void msb200_chain_destroy(msb200_chain *c) {
 	cudaFree(c->d_in_ref);
 	cudaFree(c->d_in_mic);
 	cudaFree(c->d_stage_out);
+	if (c->pipe_ready) {
+		cudaStreamSynchronize(c->s_in);
+		cudaStreamSynchronize(c->s_out);
+		for (int k = 0; k < 2; ++k) {
+			cudaFree(c->pd_in_ref[k]);
+			cudaFree(c->pd_in_mic[k]);
+			cudaFree(c->pd_stage[k]);
+			cudaEventDestroy(c->ev_in[k]);
+			cudaEventDestroy(c->ev_done[k]);
+			cudaEventDestroy(c->ev_out[k]);
+		}
+		cudaStreamDestroy(c->s_in);
+		cudaStreamDestroy(c->s_out);
+	}
 	for (cudaEvent_t e : *c->ev) cudaEventDestroy(e);
 	delete c->ev;
 	delete c;
@@ -240,6 +260,68 @@ int msb200_chain_tick(msb200_chain *c, const int16_t *ref_in, const int16_t *mic
 		                              (size_t)c->S, cudaMemcpyDeviceToHost, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));
 	if (out_samples) *out_samples = n;
+	return MSB200_OK;
+}
+
+// ---- pipelined host path: tick T's input copy and tick T-1's output copy overlap tick T's kernels.
+// Three streams: s_in (H2D), the context's stream (kernels), s_out (D2H); double buffers on the device; per slot the
+// events in -> done -> out chain the three stages, and `done` / `out` of the slot's previous use gate its reuse.
+static int chain_pipe_init(msb200_chain *c) {
+	if (c->pipe_ready) return MSB200_OK;
+	MSB200_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+	MSB200_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+	for (int k = 0; k < 2; ++k) {
+		MSB200_CUDA(cudaMalloc(&c->pd_in_ref[k], (size_t)c->S * c->tick_in * sizeof(short)));
+		MSB200_CUDA(cudaMalloc(&c->pd_in_mic[k], (size_t)c->S * c->tick_in * sizeof(short)));
+		MSB200_CUDA(cudaMalloc(&c->pd_stage[k], (size_t)c->S * c->max_out * sizeof(short)));
+		MSB200_CUDA(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+		MSB200_CUDA(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+		MSB200_CUDA(cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming));
+	}
+	c->pipe_ready = 1;
+	return MSB200_OK;
+}
+
+int msb200_chain_submit(msb200_chain *c, const int16_t *ref_in, const int16_t *mic_in, int16_t *out, int *out_samples) {
+	MSB200_CHECK_ARG(c && ref_in && mic_in && out);
+	int r = chain_pipe_init(c);
+	if (r) return r;
+	if (c->n_submitted - c->n_collected >= 2) {
+		msb200_set_error("chain: two ticks are already in flight; call msb200_chain_wait() first");
+		return MSB200_ESTATE;
+	}
+	const int k = (int)(c->n_submitted & 1);
+	const bool reused = c->n_submitted >= 2; // the slot has a previous occupant whose stages must have drained
+	cudaStream_t sc = c->ctx->stream;
+	const size_t in_bytes = (size_t)c->S * c->tick_in * sizeof(short);
+	// stage 1: inputs -> device (after the kernels of tick T-2 stopped reading this slot's input buffers)
+	if (reused) MSB200_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_done[k], 0));
+	MSB200_CUDA(cudaMemcpyAsync(c->pd_in_ref[k], ref_in, in_bytes, cudaMemcpyHostToDevice, c->s_in));
+	MSB200_CUDA(cudaMemcpyAsync(c->pd_in_mic[k], mic_in, in_bytes, cudaMemcpyHostToDevice, c->s_in));
+	MSB200_CUDA(cudaEventRecord(c->ev_in[k], c->s_in));
+	// stage 2: the tick's kernels (after the inputs landed and tick T-2's output left this slot's staging buffer)
+	MSB200_CUDA(cudaStreamWaitEvent(sc, c->ev_in[k], 0));
+	if (reused) MSB200_CUDA(cudaStreamWaitEvent(sc, c->ev_out[k], 0));
+	int n = 0;
+	if ((r = msb200_chain_tick_dev(c, c->pd_in_ref[k], c->pd_in_mic[k], c->pd_stage[k], &n))) return r;
+	MSB200_CUDA(cudaEventRecord(c->ev_done[k], sc));
+	// stage 3: output -> host
+	MSB200_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
+	if (n > 0)
+		MSB200_CUDA(cudaMemcpy2DAsync(out, (size_t)c->max_out * 2, c->pd_stage[k], (size_t)c->max_out * 2, (size_t)n * 2,
+		                              (size_t)c->S, cudaMemcpyDeviceToHost, c->s_out));
+	MSB200_CUDA(cudaEventRecord(c->ev_out[k], c->s_out));
+	c->n_submitted++;
+	if (out_samples) *out_samples = n;
+	return MSB200_OK;
+}
+
+int msb200_chain_wait(msb200_chain *c) {
+	MSB200_CHECK_ARG(c);
+	if (c->n_collected >= c->n_submitted) return MSB200_OK; // nothing in flight
+	const int k = (int)(c->n_collected & 1);
+	MSB200_CUDA(cudaEventSynchronize(c->ev_out[k]));
+	c->n_collected++;
 	return MSB200_OK;
 }
 

@@ -339,6 +339,15 @@ class AudioChain:
         check(self.lib.msb200_chain_tick(self.h, _ptr(ref_in), _ptr(mic_in), _ptr(out), C.byref(got)))
         return out, got.value
 
+    def submit(self, ref_in: np.ndarray, mic_in: np.ndarray, out: np.ndarray) -> int:
+        """pipelined tick (pinned buffers; valid in `out` after the matching wait()): returns the sample count"""
+        got = C.c_int()
+        check(self.lib.msb200_chain_submit(self.h, _ptr(ref_in), _ptr(mic_in), _ptr(out), C.byref(got)))
+        return got.value
+
+    def wait(self):
+        check(self.lib.msb200_chain_wait(self.h))
+
     def enable_kernel_timing(self, enabled: bool = True):
         check(self.lib.msb200_chain_enable_kernel_timing(self.h, int(enabled)))
 
@@ -369,9 +378,11 @@ class Scaler:
             self.lib.msb200_scaler_destroy(self.h)
             self.h = None
 
-    def process(self, frames: np.ndarray) -> np.ndarray:
+    def process(self, frames: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """host frames in, host frames out (pass pinned `frames` / `out` from Context.pinned for full PCIe speed)"""
         frames = _req(frames, np.uint8).reshape(-1, self.src_bytes)
-        out = np.empty((frames.shape[0], self.dst_bytes), np.uint8)
+        if out is None:
+            out = np.empty((frames.shape[0], self.dst_bytes), np.uint8)
         check(self.lib.msb200_scaler_process(self.h, frames.shape[0], _ptr(frames), _ptr(out)))
         return out
 

@@ -39,3 +39,46 @@ def test_chain_matches_oracle_composition(ctx, in_rate, rate, pins):
         assert abs(sum(sizes) - ticks * (rate // 100)) < F_  # nothing lost, less than one frame still buffered
     ch.close()
     oc.close()
+
+
+@pytest.mark.parametrize("pins", [0, 4])
+def test_pipelined_submit_wait_equals_synchronous_tick(ctx, pins):
+    """msb200_chain_submit / _wait (copies overlapped with the neighbouring ticks' kernels, two ticks in flight) gives
+    bit-identical samples and block sizes to the synchronous msb200_chain_tick"""
+    n, ticks, in_rate, rate = 16, 30, 16000, 48000
+    ti = in_rate // 100
+    data = [cfg2_stream(300 + s, ti * ticks, in_rate) for s in range(n)]
+    ref = np.stack([d[0] for d in data]).reshape(n, ticks, ti)
+    mic = np.stack([d[1] for d in data]).reshape(n, ticks, ti)
+    a = F.AudioChain(ctx, n, in_rate, rate, 250, 0.8, pins)
+    b = F.AudioChain(ctx, n, in_rate, rate, 250, 0.8, pins)
+    ref_pin = ctx.pinned((ticks, n, ti), np.int16)
+    mic_pin = ctx.pinned((ticks, n, ti), np.int16)
+    ref_pin[...] = ref.transpose(1, 0, 2)
+    mic_pin[...] = mic.transpose(1, 0, 2)
+    outs = [ctx.pinned((n, b.max_out), np.int16) for _ in range(2)]
+    sync = [a.tick(np.ascontiguousarray(ref[:, t]), np.ascontiguousarray(mic[:, t])) for t in range(ticks)]
+    sync = [(o[:, :k].copy(), k) for o, k in sync]
+    got, pending = [], []
+    for t in range(ticks):
+        if len(pending) == 2:
+            b.wait()
+            tt, k = pending.pop(0)
+            got.append((outs[tt & 1][:, :k].copy(), k))
+        k = b.submit(ref_pin[t], mic_pin[t], outs[t & 1])
+        pending.append((t, k))
+    with pytest.raises(Exception):
+        # a third tick in flight is refused (the oldest one must be collected first)
+        if len(pending) == 2:
+            b.submit(ref_pin[0], mic_pin[0], outs[0])
+        else:
+            raise RuntimeError("pipeline not full")
+    while pending:
+        b.wait()
+        tt, k = pending.pop(0)
+        got.append((outs[tt & 1][:, :k].copy(), k))
+    assert [k for _, k in got] == [k for _, k in sync]
+    for t, ((o1, k1), (o2, _)) in enumerate(zip(got, sync)):
+        assert np.array_equal(o1, o2), t
+    a.close()
+    b.close()
