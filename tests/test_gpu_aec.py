@@ -123,3 +123,29 @@ def test_aec_white_noise_converges_and_state_blob_roundtrip(ctx):
     assert np.abs(w).max() > 0
     ec.close()
     ec2.close()
+
+
+def test_aec_on_the_reference_testers_simple_talk_material(ctx):
+    """the reference tester's own echo scenario (tests/aec_fixture.py): the GPU canceller removes the lone far-end
+    talker's echo by >= 25 dB, keeps the lone near-end talker, and tracks the oracle's ERLE within 2 dB"""
+    import aec_fixture as A
+
+    L = O.oracle()
+    far, mic, near = A.load()
+    ec = F.SpeexEC(ctx, 2, A.RATE, 250)  # two identical streams: the bank must treat them identically
+    Fs = ec.frame_size
+    nfr = len(mic) // Fs
+    got = np.zeros((2, nfr * Fs), np.int16)
+    step = 25
+    for k in range(0, nfr, step):
+        c = min(step, nfr - k)
+        sl = slice(k * Fs, (k + c) * Fs)
+        m2 = np.ascontiguousarray(np.stack([mic[sl], mic[sl]]))
+        r2 = np.ascontiguousarray(np.stack([far[sl], far[sl]]))
+        got[:, sl] = ec.process(m2, r2)
+    ec.close()
+    assert np.array_equal(got[0], got[1])
+    erle, keep, corr = A.check_behaviour(got[0], mic, near, min_erle_db=25.0)
+    _, exp = _oracle_run(L, A.RATE, 250, mic[:nfr * Fs], far[:nfr * Fs])
+    erle_o, _, _ = A.check_behaviour(exp, mic, near, min_erle_db=25.0)
+    assert max(abs(a - b) for a, b in zip(erle, erle_o)) <= 2.0, (erle, erle_o)
