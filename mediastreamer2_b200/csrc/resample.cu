@@ -160,6 +160,55 @@ __global__ void __launch_bounds__(256)
 	for (int i = threadIdx.x; i < N - 1; i += blockDim.x) h[i] = (short)x[i + in_frames];
 }
 
+// Integer-ratio up-sampling (16 kHz -> 48 kHz of BASELINE cfg2, 8 -> 16/48 kHz, ...): num = 1, den = R, 48 taps. Every
+// input position m yields the R outputs R*m .. R*m+R-1 from the SAME 48-sample window with the R rows of the sinc table.
+// One thread per input position: the window is read once into registers (48 LDS instead of 96 LDS per OUTPUT in the
+// general kernel, whose shared-memory traffic is what bounds it) and the coefficients are compile-time-indexed kernel
+// parameters, i.e. constant-bank operands of the multiplies — no loads at all. The products are accumulated in the
+// library's order (j = 0..47, separate multiply and add), R independent chains per thread: bit-exact with the general
+// kernel and the oracle. Requires phase (0, 0) at the start of the call: true for every block of a stream fed whole
+// ticks (the phase returns to (0, 0) after each block).
+#define RS_UP_TAPS 48
+template <int R> struct ResampleUpTable { float t[R * RS_UP_TAPS]; };
+template <int R>
+__global__ void __launch_bounds__(256)
+    resample_up_kernel(const short *__restrict__ in, int in_frames, int in_stride, short *__restrict__ out, int out_stride,
+                       short *__restrict__ hist, const __grid_constant__ ResampleUpTable<R> tab, int nch, int ring_off, int ring_cap) {
+	extern __shared__ float rsm[];
+	constexpr int N = RS_UP_TAPS;
+	float *x = rsm; // [N-1 + in_frames]
+	const int stream = blockIdx.x / nch, ch = blockIdx.x % nch;
+	const short *gin = in + ((size_t)stream * in_stride) * nch + ch;
+	short *gout = out + ((size_t)stream * out_stride) * nch + ch;
+	short *h = hist + ((size_t)stream * nch + ch) * (N - 1);
+	for (int i = threadIdx.x; i < N - 1; i += blockDim.x) x[i] = (float)h[i];
+	for (int i = threadIdx.x; i < in_frames; i += blockDim.x) x[N - 1 + i] = (float)gin[(size_t)i * nch];
+	__syncthreads();
+	for (int m = threadIdx.x; m < in_frames; m += blockDim.x) {
+		float acc[R];
+#pragma unroll
+		for (int f = 0; f < R; ++f) acc[f] = 0.f;
+		const float *w = x + m;
+#pragma unroll
+		for (int j = 0; j < N; ++j) {
+			const float v = w[j];
+#pragma unroll
+			for (int f = 0; f < R; ++f) acc[f] = __fadd_rn(acc[f], __fmul_rn(tab.t[f * N + j], v));
+		}
+#pragma unroll
+		for (int f = 0; f < R; ++f) {
+			int ko = R * m + f;
+			if (ring_cap > 0) {
+				ko += ring_off;
+				if (ko >= ring_cap) ko -= ring_cap;
+			}
+			gout[(size_t)ko * nch] = word2int(acc[f]);
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < N - 1; i += blockDim.x) h[i] = (short)x[i + in_frames];
+}
+
 struct msb200_resample {
 	msb200_ctx *ctx;
 	int n, in_rate, out_rate, nch, max_in;
@@ -273,6 +322,26 @@ int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames,
 	int last0 = r->last_sample, frac0 = r->samp_frac;
 	int n_out = resample_count(r->d, in_frames, cap, r->last_sample, r->samp_frac);
 	if (out_frames) *out_frames = n_out;
+	// integer-ratio up-sampling from phase (0, 0): one thread per input position, coefficients in the constant bank
+	if (r->live > 0 && r->p.use_direct && r->p.int_advance == 0 && r->p.frac_advance == 1 && r->p.filt_len == RS_UP_TAPS && last0 == 0 &&
+	    frac0 == 0 && n_out == r->p.den * in_frames && (ring_cap == 0 || (ring_off + n_out <= 2 * ring_cap && n_out <= ring_cap)) &&
+	    (r->p.den == 2 || r->p.den == 3 || r->p.den == 6)) {
+		const size_t sm = sizeof(float) * (size_t)(RS_UP_TAPS - 1 + in_frames);
+		int blk = in_frames >= 256 ? 256 : ((in_frames + 31) & ~31);
+#define RS_UP_LAUNCH(R)                                                                                                \
+	do {                                                                                                               \
+		ResampleUpTable<R> tb;                                                                                         \
+		memcpy(tb.t, r->d.table.data(), sizeof(tb.t));                                                                 \
+		if (sm > 48 * 1024) MSB200_CUDA(cudaFuncSetAttribute(resample_up_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+		MSB200_LAUNCH(r->ctx, resample_up_kernel<R>, r->live * r->nch, blk, sm, (const short *)d_in, in_frames, in_stride, (short *)d_out, \
+		              out_stride, r->d_hist, tb, r->nch, ring_off, ring_cap);                                          \
+	} while (0)
+		if (r->p.den == 2) RS_UP_LAUNCH(2);
+		else if (r->p.den == 3) RS_UP_LAUNCH(3);
+		else RS_UP_LAUNCH(6);
+#undef RS_UP_LAUNCH
+		return MSB200_OK;
+	}
 	size_t smem = sizeof(float) * ((size_t)r->p.table_len + r->d.filt_len - 1 + (size_t)in_frames);
 	int block = n_out >= 256 ? 256 : ((n_out + 31) & ~31);
 	if (block < 32) block = 32;
