@@ -340,8 +340,9 @@ MSB200_API int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void
  * (src/videofilters/pixconv.c:62-94) and MSSizeConv (src/videofilters/sizeconv.c:97-184), batched over n_frames.
  * Arithmetic: the swscale SWS_BILINEAR pipeline the reference's ffmpeg back-end runs (msvideo.c:651-681) restated in
  * oracle/oracle_video.c and pinned against libswscale 9.1.100 golden frames (tests/golden/).
- * Format pairs: YUV420P / NV12 / NV21 -> YUV420P / RGB24 / RGB24_REV(BGR byte order) with bilinear scaling (source
- * width % 16 == 0; down-scale factor < 2); MSPixConv's same-size conversions YUYV / YUY2 / UYVY / RGB24 / RGB24_REV ->
+ * Format pairs: YUV420P / NV12 / NV21 -> YUV420P / RGB24 / RGB24_REV(BGR byte order) with bilinear scaling, any sizes
+ * >= 8 (the TMA-tiled kernels take source widths % 16 == 0 and down-scale factors < 2; everything else runs the
+ * tile-free direct kernel, same arithmetic); MSPixConv's same-size conversions YUYV / YUY2 / UYVY / RGB24 / RGB24_REV ->
  * YUV420P (w % 8 == 0 for 4:2:2, w % 4 == 0 for RGB; h even). Frames are tight (no row padding), back to back. */
 typedef struct msb200_scaler msb200_scaler;
 MSB200_API int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int dst_w, int dst_h,
@@ -355,7 +356,7 @@ MSB200_API int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const v
  * 1 = persistent tile kernel, 2 = generic tile kernel, 3 = register-window strip kernel (the default where it applies),
  * 4 = per-warp streaming variant of the strip kernel (experimental: no vertical halo, but slower on B200 today).
  * get_path reports what process() will launch: 4 = streaming kernel, 3 = strip kernel, 2 = persistent tile kernel,
- * 1 = generic tile kernel, 0 = plane / packed-4:2:2 kernels. */
+ * 1 = generic tile kernel, 0 = plane / packed-4:2:2 kernels, 5 = tile-free direct kernel (geometry outside the TMA limits). */
 MSB200_API int msb200_scaler_set_path(msb200_scaler *s, int path);
 MSB200_API int msb200_scaler_get_path(msb200_scaler *s);
 /* Strip kernel only: index of the static row schedule its straight-line instantiation runs (0 = 3:2 down-scale,

@@ -371,8 +371,21 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 	if (lane == 0) {
 		msb200_volume_state v = st[stream];
 		float acc = 0.f;
-		for (int i = 0; i < nsamples; ++i) {
-			int s = buf[i];
+		// only the float additions are sequential (the reference's accumulation order): loads, squares and conversions
+		// of eight samples are issued together so that their latency is paid once per group, not once per sample
+		int i = 0;
+		for (; i + 8 <= nsamples; i += 8) {
+			float q[8];
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const int s = buf[i + k];
+				q[k] = (float)(s * s);
+			}
+#pragma unroll
+			for (int k = 0; k < 8; ++k) acc = __fadd_rn(acc, q[k]);
+		}
+		for (; i < nsamples; ++i) {
+			const int s = buf[i];
 			acc = __fadd_rn(acc, (float)(s * s));
 		}
 		const float max_e = 32768 * 0.7f;

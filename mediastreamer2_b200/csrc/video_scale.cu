@@ -1516,6 +1516,124 @@ __global__ void __launch_bounds__(SC_THREADS)
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ direct path
+// Any geometry the tile kernels cannot take — in practice down-scales by 2x and more, whose source window per 128-column
+// tile exceeds the 256-element limit of a TMA box (MSSizeConv thumbnails, 1080p -> 360p ...). No tiles, no shared memory:
+// one thread computes one planar output sample (or one RGB pixel pair) straight from global memory, re-deriving the
+// 15-bit horizontal intermediates of each vertical tap (swscale's hScale8To15 -> yuv2planeX / yuv2rgb_X, _2, _1 chain,
+// same arithmetic as the tile kernels). The filters are short relative to the reduction in pixels, the source rows of
+// neighbouring threads overlap in L1/L2; this path is about being complete and exact, not about the roofline.
+__device__ __forceinline__ int direct_h(const unsigned char *row, int limit, int step, const int *pos, const short *coef, int fsize, int x) {
+	const int p = pos[x];
+	const short *cf = coef + (size_t)x * fsize;
+	int val = 0;
+	for (int j = 0; j < fsize; ++j) {
+		const int q = min(p + j, limit - 1); // zero-weighted alignment taps may point past the row
+		val += (int)row[(size_t)q * step] * cf[j];
+	}
+	val >>= 7;
+	return val < 32767 ? val : 32767;
+}
+__global__ void __launch_bounds__(256) scale_direct_kernel(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst,
+                                                           const ScaleParams P, size_t src_frame_bytes) {
+	const size_t frame = blockIdx.y;
+	const unsigned char *fs = src + frame * src_frame_bytes;
+	unsigned char *fd = dst + frame * P.dst_frame_bytes;
+	const unsigned char *sy = fs, *sc = fs + (size_t)P.src_w * P.src_h;
+	const bool inter = P.chroma_planes == 1; // NV12 / NV21: interleaved chroma plane
+	const bool swap_uv = P.src_fmt == MSB200_PIX_NV21;
+	// chroma sample (row r, component k: 0 = U, 1 = V) horizontally filtered at output chroma column x
+	auto chroma_h = [&](int r, int k, int x) {
+		if (inter) return direct_h(sc + (size_t)r * P.chr_src_w * 2 + ((k ^ (int)swap_uv) & 1), P.chr_src_w, 2, P.hc_pos, P.hc_coef, P.hc_size, x);
+		return direct_h(sc + (size_t)k * P.chr_src_w * P.chr_src_h + (size_t)r * P.chr_src_w, P.chr_src_w, 1, P.hc_pos, P.hc_coef, P.hc_size, x);
+	};
+	auto luma_h = [&](int r, int x) { return direct_h(sy + (size_t)r * P.src_w, P.src_w, 1, P.hl_pos, P.hl_coef, P.hl_size, x); };
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (P.dst_fmt == MSB200_PIX_YUV420P) {
+		const long nl = (long)P.dst_w * P.dst_h, nc = (long)P.chr_dst_w * P.chr_dst_h;
+		if (t >= nl + 2 * nc) return;
+		int val;
+		if (t < nl) {
+			const int y = (int)(t / P.dst_w), x = (int)(t % P.dst_w), p = P.vl_pos[y];
+			if (P.vl_size == 1) {
+				val = (luma_h(p, x) + 64) >> 7;
+			} else {
+				val = 64 << 12;
+				for (int j = 0; j < P.vl_size; ++j) val += luma_h(min(p + j, P.src_h - 1), x) * P.vl_coef[(size_t)y * P.vl_size + j];
+				val >>= 19;
+			}
+		} else {
+			const long u = t - nl;
+			const int k = u >= nc, y = (int)((u - k * nc) / P.chr_dst_w), x = (int)((u - k * nc) % P.chr_dst_w), p = P.vc_pos[y];
+			if (P.vc_size == 1) {
+				val = (chroma_h(p, k, x) + 64) >> 7;
+			} else {
+				val = 64 << 12;
+				for (int j = 0; j < P.vc_size; ++j) val += chroma_h(min(p + j, P.chr_src_h - 1), k, x) * P.vc_coef[(size_t)y * P.vc_size + j];
+				val >>= 19;
+			}
+		}
+		fd[t] = (unsigned char)sat_u8(val);
+		return;
+	}
+	// RGB24 / BGR24: one pixel pair (x, x+1) sharing the chroma sample x/2
+	const int pairs = (P.dst_w + 1) >> 1;
+	if (t >= (long)pairs * P.dst_h) return;
+	const int y = (int)(t / pairs), i = (int)(t % pairs), x = 2 * i;
+	const bool two = x + 1 < P.dst_w;
+	const int lp = P.vl_pos[y], cp = P.vc_pos[y];
+	const short *lf = P.vl_coef + (size_t)y * P.vl_size, *cf = P.vc_coef + (size_t)y * P.vc_size;
+	auto lrow = [&](int j) { return min(lp + j, P.src_h - 1); };
+	auto crow = [&](int j) { return min(cp + j, P.chr_src_h - 1); };
+	int Y1, Y2, U, V;
+	if (P.vl_size == 1) { // yuv2rgb_1
+		Y1 = (luma_h(lp, x) + 64) >> 7;
+		Y2 = two ? (luma_h(lp, x + 1) + 64) >> 7 : 0;
+		const int uvalpha = P.vc_size == 1 ? 0 : cf[1];
+		if (uvalpha == 0) {
+			U = (chroma_h(cp, 0, i) + 64) >> 7;
+			V = (chroma_h(cp, 1, i) + 64) >> 7;
+		} else {
+			const int uvalpha1 = 4096 - uvalpha;
+			U = (chroma_h(cp, 0, i) * uvalpha1 + chroma_h(crow(1), 0, i) * uvalpha + (128 << 11)) >> 19;
+			V = (chroma_h(cp, 1, i) * uvalpha1 + chroma_h(crow(1), 1, i) * uvalpha + (128 << 11)) >> 19;
+		}
+	} else if (P.vl_size == 2 && P.vc_size == 2) { // yuv2rgb_2
+		const int yalpha = lf[1], uvalpha = cf[1], yalpha1 = 4096 - yalpha, uvalpha1 = 4096 - uvalpha;
+		Y1 = (luma_h(lp, x) * yalpha1 + luma_h(lrow(1), x) * yalpha) >> 19;
+		Y2 = two ? (luma_h(lp, x + 1) * yalpha1 + luma_h(lrow(1), x + 1) * yalpha) >> 19 : 0;
+		U = (chroma_h(cp, 0, i) * uvalpha1 + chroma_h(crow(1), 0, i) * uvalpha) >> 19;
+		V = (chroma_h(cp, 1, i) * uvalpha1 + chroma_h(crow(1), 1, i) * uvalpha) >> 19;
+	} else { // yuv2rgb_X
+		Y1 = Y2 = U = V = 1 << 18;
+		for (int j = 0; j < P.vl_size; ++j) {
+			Y1 += luma_h(lrow(j), x) * lf[j];
+			if (two) Y2 += luma_h(lrow(j), x + 1) * lf[j];
+		}
+		for (int j = 0; j < P.vc_size; ++j) {
+			U += chroma_h(crow(j), 0, i) * cf[j];
+			V += chroma_h(crow(j), 1, i) * cf[j];
+		}
+		Y1 >>= 19; Y2 >>= 19; U >>= 19; V >>= 19;
+	}
+	const bool bgr = P.dst_fmt == MSB200_PIX_RGB24_REV;
+	const int c_cy = P.cy;
+	const int base_r = P.yoffs - (P.crv >> 9), base_g = P.yoffs - (P.cgu >> 9) - (P.cgv >> 9), base_b = P.yoffs - (P.cbu >> 9);
+	const int c_off = P.yb0 + 0x8000;
+	const int Uc = (int)sat_u8(U), Vc = (int)sat_u8(V);
+	const int ar = c_off + (base_r + ((Vc * P.crv) >> 16)) * c_cy;
+	const int ag = c_off + (base_g + ((Uc * P.cgu) >> 16) + ((Vc * P.cgv) >> 16)) * c_cy;
+	const int ab = c_off + (base_b + ((Uc * P.cbu) >> 16)) * c_cy;
+	unsigned char *o = fd + ((size_t)y * P.dst_w + x) * 3;
+	const int y1c = Y1 * c_cy, y2c = Y2 * c_cy;
+	const unsigned r1 = sat_u8((ar + y1c) >> 16), g1 = sat_u8((ag + y1c) >> 16), b1 = sat_u8((ab + y1c) >> 16);
+	o[0] = (unsigned char)(bgr ? b1 : r1); o[1] = (unsigned char)g1; o[2] = (unsigned char)(bgr ? r1 : b1);
+	if (two) {
+		const unsigned r2 = sat_u8((ar + y2c) >> 16), g2 = sat_u8((ag + y2c) >> 16), b2 = sat_u8((ab + y2c) >> 16);
+		o[3] = (unsigned char)(bgr ? b2 : r2); o[4] = (unsigned char)g2; o[5] = (unsigned char)(bgr ? r2 : b2);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ host
 // row schedules with an instantiated straight-line strip kernel (see scale_rgb_strip_kernel): strips of ST_SCHED_ROWS rows
 struct StripSched {
@@ -1550,6 +1668,7 @@ struct msb200_scaler {
 	const void *cached_dst;
 	int packed422; // 0: no; 1: YUYV/YUY2; 2: UYVY; 3: RGB24; 4: BGR24  (MSPixConv same-size conversions to I420, no scaling)
 	bool fast_ok;
+	bool direct;        // geometry outside the tile kernels' TMA box limits: scale_direct_kernel
 	size_t smem_fast;
 	bool strip_ok;      // register-window strip kernel (scale_rgb_strip_kernel) applies
 	int sched;          // index into kStripSched when the static-schedule instantiation applies, else -1
@@ -1761,9 +1880,11 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		msb200_set_error("scaler: unsupported format pair %d -> %d (sources: YUV420P/NV12/NV21; destinations: YUV420P/RGB24/BGR24)", src_fmt, dst_fmt);
 		return MSB200_EINVAL;
 	}
-	MSB200_CHECK_ARG(src_w >= 16 && src_h >= 16 && dst_w >= 16 && dst_h >= 16);
-	// TMA tensor maps need 16-byte row pitches: luma width % 16 == 0, chroma plane pitch % 16 == 0
-	MSB200_CHECK_ARG(src_w % 16 == 0 && (src_fmt != MSB200_PIX_YUV420P || (src_w / 2) % 16 == 0) && src_h % 2 == 0);
+	MSB200_CHECK_ARG(src_w >= 8 && src_h >= 8 && dst_w >= 8 && dst_h >= 8);
+	// TMA tensor maps need 16-byte row pitches (luma width % 16 == 0, chroma plane pitch % 16 == 0); frames that do not
+	// have them, and down-scales whose per-tile source window exceeds a TMA box, take the tile-free direct kernel
+	bool direct = !(src_w >= 16 && src_h >= 16 && dst_w >= 16 && dst_h >= 16 && src_w % 16 == 0 &&
+	                (src_fmt != MSB200_PIX_YUV420P || (src_w / 2) % 16 == 0) && src_h % 2 == 0);
 	msb200_scaler *s = new msb200_scaler();
 	s->ctx = ctx;
 	s->packed422 = 0;
@@ -1816,12 +1937,8 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	P.box_cw = P.chroma_planes == 1 ? ((2 * cw + 15 + 15) & ~15) : ((cw + 15 + 15) & ~15);
 	P.box_lh = max_span(s->vl, dst_h, SC_TH);
 	P.box_ch = max_span(s->vc, P.chr_dst_h, ctile_h);
-	if (P.box_lw > 256 || P.box_cw > 256 || P.box_lh > 256 || P.box_ch > 256) {
-		msb200_set_error("scaler: down-scaling factor too large for one TMA box per tile (%dx%d luma, %dx%d chroma)", P.box_lw,
-		                 P.box_lh, P.box_cw, P.box_ch);
-		delete s;
-		return MSB200_EINVAL;
-	}
+	if (P.box_lw > 256 || P.box_cw > 256 || P.box_lh > 256 || P.box_ch > 256) direct = true; // >= 2x down-scales
+	s->direct = direct;
 	{ // ff_yuv2rgb_c_init_tables(): ITU-601, limited-range source
 		int64_t crv = 104597, cbu = 132201, cgu = -25675, cgv = -53279, cy = 1 << 16, oy;
 		cy = (cy * 255) / 219;
@@ -1868,7 +1985,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	bool taps_nonneg = true;
 	for (int16_t c : s->hl.coef) taps_nonneg = taps_nonneg && c >= 0;
 	for (int16_t c : s->hc.coef) taps_nonneg = taps_nonneg && c >= 0;
-	s->fast_ok = taps_nonneg && dst_rgb && P.chroma_planes == 1 && P.hl_size == 4 && P.hc_size == 4 && (dst_w % SC_TW) == 0 &&
+	s->fast_ok = !direct && taps_nonneg && dst_rgb && P.chroma_planes == 1 && P.hl_size == 4 && P.hc_size == 4 && (dst_w % SC_TW) == 0 &&
 	             ((P.vl_size == 4 && P.vc_size == 2) || (P.vl_size == 2 && P.vc_size == 2) || (P.vl_size == 1 && P.vc_size <= 2));
 	s->smem_fast = 2 * (a128((size_t)P.box_lw * P.box_lh) + a128((size_t)P.box_cw * P.box_ch)) + a128(4 * (size_t)P.box_lh * SC_TW) +
 	               a128(4 * (size_t)P.box_ch * (SC_TW / 2)) + (size_t)SC_TH * SC_TW * 3 + a128(sizeof(RowInfo) * SC_TH) + 16 + 32 + 256;
@@ -2082,6 +2199,11 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			}
 		}
 	}
+	if (direct) { // no tiles, no shared memory
+		s->strip_ok = s->stream_ok = false;
+		*out = s;
+		return MSB200_OK;
+	}
 	const size_t mx = s->smem_rgb > s->smem_chroma ? s->smem_rgb : s->smem_chroma;
 	if (mx > 200 * 1024) {
 		msb200_set_error("scaler: tile working set %zu B exceeds shared memory", mx);
@@ -2128,6 +2250,7 @@ int msb200_scaler_set_path(msb200_scaler *s, int path) {
 	return MSB200_OK;
 }
 int msb200_scaler_get_path(msb200_scaler *s) {
+	if (s && s->direct) return 5;
 	if (!s || s->packed422 || s->P.dst_fmt == MSB200_PIX_YUV420P) return 0;
 	if (s->stream_ok && s->force_path == 4) return 4;
 	if (s->strip_ok && (s->force_path == 0 || s->force_path >= 3)) return 3;
@@ -2150,8 +2273,15 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 	MSB200_CHECK_ARG(s && d_src && d_dst && n_frames > 0 && n_frames <= 65535);
 	if (s->packed422 >= 3) return msb200i_rgb24_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 4, d_dst);
 	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
-	MSB200_CHECK_ARG(((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0);
 	const ScaleParams &P = s->P;
+	if (s->direct) {
+		const long threads = P.dst_fmt == MSB200_PIX_YUV420P ? (long)P.dst_w * P.dst_h + 2L * P.chr_dst_w * P.chr_dst_h
+		                                                       : (long)((P.dst_w + 1) / 2) * P.dst_h;
+		dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
+		MSB200_LAUNCH(s->ctx, scale_direct_kernel, grid, 256, 0, (const unsigned char *)d_src, (unsigned char *)d_dst, P, s->src_bytes);
+		return MSB200_OK;
+	}
+	MSB200_CHECK_ARG(((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0);
 	int r;
 	const bool dst16 = ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 16) == 0;
 	if (s->stream_ok && s->force_path == 4 && dst16) {
