@@ -325,7 +325,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         from bench_video import pixconv_bench  # noqa: WPS433
 
         if rank == 0:
-            line["pixconv"] = pixconv_bench(ctx, peak)
+            line["pixconv"] = pixconv_bench(ctx, peak, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
     except ImportError:
         pass
     try:

@@ -21,7 +21,85 @@ DST_BYTES = DST_W * DST_H * 3        # 2,764,800
 ALGO_BYTES = SRC_BYTES + DST_BYTES   # 5,875,200 per frame
 
 
-def pixconv_bench(ctx, hbm_peak_gbs: float, n_frames: int = 512, iters: int = 10) -> dict:
+def _load_libswscale():
+    """The REAL libswscale (what the reference's ffmpeg scaler back-end calls, src/voip/msvideo.c:651-681) from the opencv
+    wheel of this image, with its private dependency chain loaded by absolute path. None when the wheel is absent."""
+    import ctypes as C
+    import glob
+    import os
+
+    d = None
+    for p in sys.path:
+        c = glob.glob(os.path.join(p, "opencv_python_headless.libs", "libswscale-*.so*"))
+        if c:
+            d = os.path.dirname(c[0])
+            break
+    if d is None:
+        return None
+    try:
+        for name in ("libcrypto", "libssl", "libdrm", "libavutil"):
+            for f in sorted(glob.glob(os.path.join(d, name + "-*.so*"))):
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(glob.glob(os.path.join(d, "libswscale-*.so*"))[0])
+    except OSError:
+        return None
+    L.sws_getContext.restype = C.c_void_p
+    L.sws_getContext.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3
+    L.sws_scale.restype = C.c_int
+    L.sws_scale.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                            C.POINTER(C.c_int)]
+    L.sws_freeContext.argtypes = [C.c_void_p]
+    L.swscale_version.restype = C.c_uint
+    return L
+
+
+def pixconv_cpu_baseline(frame: np.ndarray, budget_s: float = 8.0):
+    """cfg4 on the host cores through the reference's own library call (sws_getContext(..., SWS_BILINEAR) + sws_scale),
+    one context per thread, all cores, bounded to ~budget_s of wall time. Returns (dict, first output frame) or None."""
+    import ctypes as C
+    import os
+    import threading
+    import time
+
+    L = _load_libswscale()
+    if L is None:
+        return None
+    threads = os.cpu_count() or 1
+    ver = L.swscale_version()
+    outs = [None] * threads
+
+    def work(k, n):
+        ctx = L.sws_getContext(SRC_W, SRC_H, 23, DST_W, DST_H, 2, 2, None, None, None)  # NV12 -> RGB24, SWS_BILINEAR
+        dst = np.zeros(DST_BYTES + 64, np.uint8)
+        sp = (C.c_void_p * 4)(frame.ctypes.data, frame.ctypes.data + SRC_W * SRC_H, 0, 0)
+        ss = (C.c_int * 4)(SRC_W, SRC_W, 0, 0)
+        dp = (C.c_void_p * 4)(dst.ctypes.data, 0, 0, 0)
+        ds = (C.c_int * 4)(DST_W * 3, 0, 0, 0)
+        for _ in range(n):
+            L.sws_scale(ctx, sp, ss, 0, SRC_H, dp, ds)
+        L.sws_freeContext(ctx)
+        outs[k] = dst[:DST_BYTES]
+
+    def run(n):
+        th = [threading.Thread(target=work, args=(k, n)) for k in range(threads)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+
+    dt = run(2)  # calibrate
+    n = max(2, min(200, int(budget_s / max(dt / 2, 1e-3))))
+    dt = run(n)
+    fps = threads * n / dt
+    return ({"mpix_per_s_in": SRC_W * SRC_H * fps / 1e6, "frames_per_s": fps, "cores": threads,
+             "kind": f"reference: libswscale {ver >> 16}.{(ver >> 8) & 255}.{ver & 255} (the library the reference's ffmpeg scaler back-end calls)",
+             "sample": f"{threads} threads x {n} frames, one SwsContext per thread, NV12 {SRC_W}x{SRC_H} -> RGB24 {DST_W}x{DST_H}, SWS_BILINEAR"},
+            outs[0])
+
+
+def pixconv_bench(ctx, hbm_peak_gbs: float, n_frames: int = 512, iters: int = 10, cpu_baseline: bool = True) -> dict:
     from mediastreamer2_b200 import _lib
     from mediastreamer2_b200 import filters as F
 
@@ -64,7 +142,13 @@ def pixconv_bench(ctx, hbm_peak_gbs: float, n_frames: int = 512, iters: int = 10
     ctx.dev_free(d_dst)
     sc.close()
     achieved = ALGO_BYTES * n_frames / (ms / 1000.0) / 1e9
-    return {
+    cpu = None
+    if cpu_baseline:
+        got = pixconv_cpu_baseline(np.ascontiguousarray(base[0]))
+        if got is not None:
+            cpu, ref_frame = got
+            cpu["gpu_frame_equals_library_frame"] = bool(np.array_equal(out[0], ref_frame))  # same input frame: bit-exact
+    res = {
         "workload": f"cfg4: {n_frames} concurrent streams, NV12 {SRC_W}x{SRC_H} -> RGB24 {DST_W}x{DST_H}, one frame each per launch",
         "mpix_per_s_in": SRC_W * SRC_H * n_frames / (ms / 1000.0) / 1e6,
         "mpix_per_s_out": DST_W * DST_H * n_frames / (ms / 1000.0) / 1e6,
@@ -75,6 +159,9 @@ def pixconv_bench(ctx, hbm_peak_gbs: float, n_frames: int = 512, iters: int = 10
                 "h2d_bytes": ne * SRC_BYTES, "d2h_bytes": ne * DST_BYTES},
         "checksum": int(out[:2].astype(np.uint64).sum()),
     }
+    if cpu is not None:
+        res["cpu_baseline"] = cpu
+    return res
 
 
 if __name__ == "__main__":

@@ -277,3 +277,22 @@ def test_pixconv_packed422_to_i420_bit_exact(ctx, fmt, w, h):
             sc2 = F.Scaler(ctx, sw, sh, fmt, dw, dh, _lib.PIX_YUV420P)
             assert np.array_equal(sc2.process(g[f"case{k}_src"][None, :])[0], g[f"case{k}_dst"])  # the real library's output
             sc2.close()
+
+
+def test_scaler_host_batches_flow_through_the_chunk_pipeline(ctx):
+    """msb200_scaler_process with a batch large enough to be cut into >= 3 chunks (upload / kernels / download overlapped
+    on three streams, ragged last chunk): every frame equals the frame converted alone"""
+    sw, sh, dw, dh = 1920, 1080, 1280, 720
+    n = 17  # 16 MB chunks of 5 frames: 5 + 5 + 5 + 2
+    base = _rand_frames(_lib.PIX_NV12, sw, sh, 3, seed=99)
+    rng = np.random.default_rng(5)
+    frames = np.stack([np.roll(base[i % 3], int(rng.integers(0, 4096))) for i in range(n)])
+    sc = F.Scaler(ctx, sw, sh, _lib.PIX_NV12, dw, dh, _lib.PIX_RGB24)
+    src_pin = ctx.pinned(frames.shape, np.uint8)
+    src_pin[...] = frames
+    dst_pin = ctx.pinned((n, sc.dst_bytes), np.uint8)
+    got = sc.process(src_pin, dst_pin)
+    for i in range(n):
+        alone = sc.process(frames[i:i + 1])
+        assert np.array_equal(got[i], alone[0]), i
+    sc.close()
