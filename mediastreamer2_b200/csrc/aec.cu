@@ -549,6 +549,8 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		float2 yfg = make_float2(0.f, 0.f), ybg = make_float2(0.f, 0.f);
 		{
 			float2 *gW_st = W + t, *gF_st = FG + t;
+			static_assert(AEC_STAGES == 3, "the grouped |W_j|^2 reduction below folds exactly three blocks");
+			float nrm[AEC_STAGES] = {0.f, 0.f, 0.f};
 			for (int j0 = 0; j0 < M; j0 += AEC_STAGES) {
 #pragma unroll
 				for (int sidx = 0; sidx < AEC_STAGES; ++sidx) {
@@ -594,12 +596,8 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 						if (do_update || constrained) *gW_st = w;
 						gW_st += F;
 						gF_st += F;
-						// |W_j|^2 partial for next frame's mdf_adjust_prop
-						if (need_wnorm) {
-							float n2 = w.x * w.x + w.y * w.y;
-							n2 = warp_sum(n2);
-							if (lane == 0) wpart[j * 8 + warp] = n2;
-						}
+						// |W_j|^2 partial for next frame's mdf_adjust_prop: reduced three blocks at a time after the group
+						if (need_wnorm) nrm[sidx] = w.x * w.x + w.y * w.y;
 						// background: Y += X_j * W_j
 						if (t == 0) {
 							ybg.x += xj.x * w.x;
@@ -610,6 +608,22 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 						}
 						xj = xj1;
 					}
+				}
+				if (need_wnorm) {
+					// three warp sums for the price of one and a bit: after the first two folds the three quantities live
+					// in disjoint lane groups (block j0: lanes 0-7, j0+1: 16-23, j0+2: 8-15 and 24-31) and share the
+					// remaining folds. Same pairing order (xor 16, 8, 4, 2, 1) as warp_sum: identical sums, 6 SHFL not 15.
+					const bool hi16 = lane & 16, hi8 = lane & 8;
+					float a = hi16 ? nrm[1] : nrm[0];
+					a += __shfl_xor_sync(0xffffffffu, hi16 ? nrm[0] : nrm[1], 16);
+					float c2 = nrm[2] + __shfl_xor_sync(0xffffffffu, nrm[2], 16);
+					float c = hi8 ? c2 : a;
+					c += __shfl_xor_sync(0xffffffffu, hi8 ? a : c2, 8);
+					c += __shfl_xor_sync(0xffffffffu, c, 4);
+					c += __shfl_xor_sync(0xffffffffu, c, 2);
+					c += __shfl_xor_sync(0xffffffffu, c, 1);
+					const int jw = lane == 0 ? j0 : (lane == 16 ? j0 + 1 : j0 + 2);
+					if ((lane == 0 || lane == 16 || lane == 8) && jw < M) wpart[jw * 8 + warp] = c;
 				}
 			}
 			cp_async_wait<0>();
