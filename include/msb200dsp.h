@@ -320,7 +320,8 @@ MSB200_API msb200_aec *msb200_chain_aec(msb200_chain *c);
 #define MSB200_PIX_RGB24_REV 3 /* BGR24 bottom-up in the reference's world; here: BGR byte order */
 #define MSB200_PIX_UYVY 5
 #define MSB200_PIX_YUY2 6
-#define MSB200_PIX_RGBA32 7
+#define MSB200_PIX_RGBA32 7      /* R G B A bytes */
+#define MSB200_PIX_RGBA32_REV 11 /* B G R A bytes (MS_RGBA32_REV -> AV_PIX_FMT_BGRA, msvideo.c:600-601) */
 #define MSB200_PIX_NV12 100
 #define MSB200_PIX_NV21 101
 
@@ -342,8 +343,8 @@ MSB200_API int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void
  * oracle/oracle_video.c and pinned against libswscale 9.1.100 golden frames (tests/golden/).
  * Format pairs: YUV420P / NV12 / NV21 -> YUV420P / RGB24 / RGB24_REV(BGR byte order) with bilinear scaling, any sizes
  * >= 8 (the TMA-tiled kernels take source widths % 16 == 0 and down-scale factors < 2; everything else runs the
- * tile-free direct kernel, same arithmetic); MSPixConv's same-size conversions YUYV / YUY2 / UYVY / RGB24 / RGB24_REV ->
- * YUV420P (w % 8 == 0 for 4:2:2, w % 4 == 0 for RGB; h even). Frames are tight (no row padding), back to back. */
+ * tile-free direct kernel, same arithmetic); MSPixConv's same-size conversions YUYV / YUY2 / UYVY / RGB24 / RGB24_REV / RGBA32 /
+ * RGBA32_REV -> YUV420P (w % 8 == 0 for 4:2:2, w % 4 == 0 for RGB; h even). Frames are tight (no row padding), back to back. */
 typedef struct msb200_scaler msb200_scaler;
 MSB200_API int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int dst_w, int dst_h,
                                     int dst_fmt, msb200_scaler **out);

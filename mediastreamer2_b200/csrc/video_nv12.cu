@@ -163,14 +163,34 @@ __device__ __forceinline__ void rgb_unpack4(const uint8_t *row, int c[4][3]) { /
 #pragma unroll
 	for (int i = 0; i < 12; ++i) c[i / 3][i % 3] = (int)((w3[i >> 2] >> (8 * (i & 3))) & 255u);
 }
-template <bool BGR>
+// 16 bytes = 4 pixels x 4 bytes (RGBA / BGRA): components moved to (R, G, B) order, alpha dropped
+template <bool SWAP_RB>
+__device__ __forceinline__ void rgbx_unpack4(const uint8_t *row, int c[4][3]) {
+	const uint4 wd = *reinterpret_cast<const uint4 *>(row);
+	const unsigned w4[4] = {wd.x, wd.y, wd.z, wd.w};
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		c[k][SWAP_RB ? 2 : 0] = (int)(w4[k] & 255u);
+		c[k][1] = (int)((w4[k] >> 8) & 255u);
+		c[k][SWAP_RB ? 0 : 2] = (int)((w4[k] >> 16) & 255u);
+	}
+}
+// FMT: 0 = RGB24 (generic path), 1 = BGR24 (special converter), 2 = RGBA, 3 = BGRA (generic path, alpha ignored)
+template <int FMT>
 __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h) {
+	constexpr bool BGR = FMT == 1;
+	constexpr int BPP = FMT >= 2 ? 4 : 3;
 	const int groups = w / 4, rows2 = h / 2;
 	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= (long)groups * rows2) return;
 	const int cy = (int)(t / groups), gx = (int)(t % groups);
-	const size_t frame = blockIdx.y, pitch = (size_t)w * 3;
-	const uint8_t *fs = src + frame * (pitch * h) + (size_t)gx * 12;
+	const size_t frame = blockIdx.y, pitch = (size_t)w * BPP;
+	const uint8_t *fs = src + frame * (pitch * h) + (size_t)gx * 4 * BPP;
+	auto rgb_unpack4 = [](const uint8_t *row, int(&c)[4][3]) {
+		if (FMT == 2) rgbx_unpack4<false>(row, c);
+		else if (FMT == 3) rgbx_unpack4<true>(row, c);
+		else ::rgb_unpack4(row, c);
+	};
 	uint8_t *fd = dst + frame * ((size_t)w * h * 3 / 2);
 	uint8_t *pu = fd + (size_t)w * h, *pv = pu + (size_t)(w / 2) * (h / 2);
 	int a[4][3], b[4][3]; // the block's two rows
@@ -235,13 +255,18 @@ __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__res
 	*reinterpret_cast<unsigned *>(fd + (size_t)(2 * cy + 1) * w + (size_t)gx * 4) = yb;
 }
 
-int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int bgr, void *d_dst) {
+// fmt: 0 RGB24, 1 BGR24, 2 RGBA, 3 BGRA
+int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int fmt, void *d_dst) {
 	MSB200_CHECK_ARG(ctx && d_src && d_dst && n_frames > 0 && n_frames <= 65535 && w > 0 && h > 0 && (w % 4) == 0 && (h % 2) == 0);
-	MSB200_CHECK_ARG(((uintptr_t)d_src % 4) == 0 && ((uintptr_t)d_dst % 4) == 0);
+	MSB200_CHECK_ARG(fmt >= 0 && fmt <= 3 && ((uintptr_t)d_src % (fmt >= 2 ? 16 : 4)) == 0 && ((uintptr_t)d_dst % 4) == 0);
 	const long threads = (long)(w / 4) * (h / 2);
 	dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
-	if (bgr) MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<true>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h);
-	else MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<false>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h);
+	switch (fmt) {
+		case 0: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<0>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+		case 1: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<1>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+		case 2: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<2>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+		default: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<3>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+	}
 	return MSB200_OK;
 }
 

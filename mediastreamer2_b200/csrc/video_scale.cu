@@ -1666,7 +1666,7 @@ struct msb200_scaler {
 	const void *cached_src;
 	CUtensorMap map_l, map_c0, map_c1, map_o;
 	const void *cached_dst;
-	int packed422; // 0: no; 1: YUYV/YUY2; 2: UYVY; 3: RGB24; 4: BGR24  (MSPixConv same-size conversions to I420, no scaling)
+	int packed422; // 0: no; 1: YUYV/YUY2; 2: UYVY; 3: RGB24; 4: BGR24; 5: RGBA; 6: BGRA  (MSPixConv same-size conversions to I420)
 	bool fast_ok;
 	bool direct;        // geometry outside the tile kernels' TMA box limits: scale_direct_kernel
 	cudaStream_t pipe_in, pipe_out;   // host-buffer batches: upload / download streams of the chunk pipeline
@@ -1849,7 +1849,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		*out = s;
 		return MSB200_OK;
 	}
-	if (src_fmt == MSB200_PIX_RGB24 || src_fmt == MSB200_PIX_RGB24_REV) {
+	if (src_fmt == MSB200_PIX_RGB24 || src_fmt == MSB200_PIX_RGB24_REV || src_fmt == MSB200_PIX_RGBA32 || src_fmt == MSB200_PIX_RGBA32_REV) {
 		// MSPixConv: packed RGB / BGR -> YUV420P at the same size (the bottom-up order of MS_RGB24_REV is the caller's
 		// negative stride, pixconv.c:78-81: plugin/msb200_filters.c packs the rows in display order)
 		if (dst_fmt != MSB200_PIX_YUV420P || src_w != dst_w || src_h != dst_h || (src_w % 4) || (src_h % 2)) {
@@ -1860,7 +1860,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		s->ctx = ctx;
 		memset(&s->P, 0, sizeof(s->P));
 		s->P.src_w = src_w; s->P.src_h = src_h; s->P.dst_w = dst_w; s->P.dst_h = dst_h; s->P.src_fmt = src_fmt; s->P.dst_fmt = dst_fmt;
-		s->packed422 = src_fmt == MSB200_PIX_RGB24 ? 3 : 4;
+		s->packed422 = src_fmt == MSB200_PIX_RGB24 ? 3 : (src_fmt == MSB200_PIX_RGB24_REV ? 4 : (src_fmt == MSB200_PIX_RGBA32 ? 5 : 6));
 		s->d_tables = nullptr;
 		s->cached_src = s->cached_dst = nullptr;
 		s->cached_frames = 0;
@@ -1871,7 +1871,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		s->sched = -1;
 		memset(&s->S, 0, sizeof(s->S));
 		memset(&s->T, 0, sizeof(s->T));
-		s->src_bytes = (size_t)src_w * src_h * 3;
+		s->src_bytes = (size_t)src_w * src_h * (s->packed422 >= 5 ? 4 : 3);
 		s->dst_bytes = (size_t)dst_w * dst_h * 3 / 2;
 		*out = s;
 		return MSB200_OK;
@@ -2278,7 +2278,7 @@ int msb200_scaler_get_schedule(msb200_scaler *s, int *regular_strips, int *strip
 
 int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst) {
 	MSB200_CHECK_ARG(s && d_src && d_dst && n_frames > 0 && n_frames <= 65535);
-	if (s->packed422 >= 3) return msb200i_rgb24_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 4, d_dst);
+	if (s->packed422 >= 3) return msb200i_rgb24_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 - 3, d_dst);
 	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
 	const ScaleParams &P = s->P;
 	if (s->direct) {

@@ -97,6 +97,8 @@ int orc_nv12_to_i420(const uint8_t *y, const uint8_t *cbcr, int rotation, int w,
 #define PIX_RGB24 2
 #define PIX_BGR24 3
 #define PIX_YUYV 1
+#define PIX_RGBA32 7
+#define PIX_BGRA32 11
 #define PIX_UYVY 5
 #define PIX_YUY2 6
 #define PIX_NV12 100
@@ -268,7 +270,7 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 		s->dst_w = dst_w; s->dst_h = dst_h; s->dst_fmt = dst_fmt;
 		return s;
 	}
-	if (src_fmt == PIX_RGB24 || src_fmt == PIX_BGR24) {
+	if (src_fmt == PIX_RGB24 || src_fmt == PIX_BGR24 || src_fmt == PIX_RGBA32 || src_fmt == PIX_BGRA32) {
 		/* MSPixConv's RGB inputs (pixconv.c:62-94, MS_RGB24 -> AV_PIX_FMT_RGB24, MS_RGB24_REV -> AV_PIX_FMT_BGR24 read bottom-up
 		 * through a negative stride, :78-81): packed RGB -> YUV420P at the SAME size. See rgb_to_i420() below. */
 		if (dst_fmt != PIX_YUV420P || src_w != dst_w || src_h != dst_h || (src_w & 1) || (src_h & 1)) return NULL;
@@ -316,7 +318,7 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 }
 void orc_scaler_free(orc_scaler *s) {
 	if (!s) return;
-	if (is_packed422(s->src_fmt) || s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24) {
+	if (is_packed422(s->src_fmt) || s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24 || s->src_fmt == PIX_RGBA32 || s->src_fmt == PIX_BGRA32) {
 		free(s);
 		return;
 	}
@@ -329,6 +331,7 @@ void orc_scaler_free(orc_scaler *s) {
 }
 static size_t fmt_bytes(int fmt, int w, int h) {
 	if (fmt == PIX_RGB24 || fmt == PIX_BGR24) return (size_t)w * h * 3;
+	if (fmt == PIX_RGBA32 || fmt == PIX_BGRA32) return (size_t)w * h * 4;
 	if (fmt == PIX_YUYV || fmt == PIX_UYVY || fmt == PIX_YUY2) return (size_t)w * h * 2;
 	return (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2);
 }
@@ -389,7 +392,10 @@ static void hscale(int16_t *dst, int dstW, const uint8_t *src, const sws_filter 
  * BGR24 takes the unscaled special converter bgr24ToYv12Wrapper -> ff_rgb24toyv12_c:
  *   Y = ((RY r + GY g + BY b) >> 15) + 16 per pixel; U/V from the 2x2 block's component means ((sum of 4) >> 2):
  *   U = ((RU r + GU g + BU b) >> 15) + 128 (arithmetic shifts). */
-static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, uint8_t *dst) {
+/* bpp / ro / go / bo: bytes per pixel and byte offsets of R, G, B for the GENERIC path (RGB24: 3,0,1,2; RGBA: 4,0,1,2;
+ * BGRA: 4,2,1,0 — the 32-bit formats take the generic path too and give the RGB24 result for equal colours, alpha
+ * ignored: verified against the real library); bgr = 1 selects BGR24's special converter instead. */
+static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, int bpp, int ro, int go, int bo, uint8_t *dst) {
 	enum { RY = 8414, GY = 16519, BY = 3208, RU = -4865, GU = -9528, BU = 14392, RV = 14392, GV = -12061, BV = -2332 };
 	uint8_t *dy = dst, *du = dst + (size_t)w * h, *dv = du + (size_t)(w / 2) * (h / 2);
 	const int cw = w / 2;
@@ -413,8 +419,8 @@ static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, uint8_t *dst)
 	}
 	for (int y = 0; y < h; ++y)
 		for (int x = 0; x < w; ++x) {
-			const uint8_t *p = src + ((size_t)y * w + x) * 3;
-			int v = (RY * p[0] + GY * p[1] + BY * p[2] + (32 << 14) + (1 << 8)) >> 9;
+			const uint8_t *p = src + ((size_t)y * w + x) * bpp;
+			int v = (RY * p[ro] + GY * p[go] + BY * p[bo] + (32 << 14) + (1 << 8)) >> 9;
 			v = (v * 16384) >> 13;
 			if (v > 32767) v = 32767;
 			v = (v + 64) >> 7;
@@ -423,8 +429,8 @@ static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, uint8_t *dst)
 	int16_t *u15 = (int16_t *)malloc(sizeof(int16_t) * (size_t)h * cw), *v15 = (int16_t *)malloc(sizeof(int16_t) * (size_t)h * cw);
 	for (int y = 0; y < h; ++y)
 		for (int x = 0; x < cw; ++x) {
-			const uint8_t *p = src + ((size_t)y * w + 2 * x) * 3;
-			const int r = p[0] + p[3], g = p[1] + p[4], b = p[2] + p[5];
+			const uint8_t *p = src + ((size_t)y * w + 2 * x) * bpp;
+			const int r = p[ro] + p[bpp + ro], g = p[go] + p[bpp + go], b = p[bo] + p[bpp + bo];
 			int u = (RU * r + GU * g + BU * b + (256 << 15) + (1 << 9)) >> 10, v = (RV * r + GV * g + BV * b + (256 << 15) + (1 << 9)) >> 10;
 			u = (u * 16384) >> 13;
 			v = (v * 16384) >> 13;
@@ -452,8 +458,9 @@ static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, uint8_t *dst)
 
 int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst) {
 	const int sw = s->src_w, sh = s->src_h, dw = s->dst_w, dh = s->dst_h;
-	if (s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24) {
-		rgb_to_i420(src, sw, sh, s->src_fmt == PIX_BGR24, dst);
+	if (s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24 || s->src_fmt == PIX_RGBA32 || s->src_fmt == PIX_BGRA32) {
+		const int f = s->src_fmt, four = f == PIX_RGBA32 || f == PIX_BGRA32;
+		rgb_to_i420(src, sw, sh, f == PIX_BGR24, four ? 4 : 3, f == PIX_BGRA32 ? 2 : 0, 1, f == PIX_BGRA32 ? 0 : 2, dst);
 		return 0;
 	}
 	if (is_packed422(s->src_fmt)) {

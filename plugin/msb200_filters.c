@@ -1966,6 +1966,8 @@ static int pixfmt_to_b200(MSPixFmt fmt) {
 		case MS_UYVY: return MSB200_PIX_UYVY;
 		case MS_RGB24: return MSB200_PIX_RGB24;
 		case MS_RGB24_REV: return MSB200_PIX_RGB24_REV;
+		case MS_RGBA32: return MSB200_PIX_RGBA32;
+		case MS_RGBA32_REV: return MSB200_PIX_RGBA32_REV;
 		default: return -1;
 	}
 }
@@ -1974,7 +1976,8 @@ static MSScalerContext *b200_scaler_create(int src_w, int src_h, MSPixFmt src_fm
 	int sf = pixfmt_to_b200(src_fmt), df = pixfmt_to_b200(dst_fmt);
 	(void)flags;
 	if ((sf != MSB200_PIX_YUV420P && sf != MSB200_PIX_YUYV && sf != MSB200_PIX_YUY2 && sf != MSB200_PIX_UYVY && sf != MSB200_PIX_RGB24 &&
-	     sf != MSB200_PIX_RGB24_REV) || df < 0) {
+	     sf != MSB200_PIX_RGB24_REV && sf != MSB200_PIX_RGBA32 && sf != MSB200_PIX_RGBA32_REV) || df < 0 || df == MSB200_PIX_RGBA32 ||
+	    df == MSB200_PIX_RGBA32_REV) {
 		ms_error("msb200 scaler: unsupported conversion %s -> %s", ms_pix_fmt_to_string(src_fmt), ms_pix_fmt_to_string(dst_fmt));
 		return NULL;
 	}
@@ -2000,7 +2003,9 @@ static int b200_scaler_process(MSScalerContext *ctx, uint8_t *src[], int src_str
 	B200ScalerCtx *c = (B200ScalerCtx *)ctx;
 	int rc, cw = (c->src_w + 1) / 2, ch = (c->src_h + 1) / 2, y;
 	uint8_t *p = c->src_pack;
-	if (c->src_fmt == MSB200_PIX_RGB24 || c->src_fmt == MSB200_PIX_RGB24_REV) {
+	if (c->src_fmt == MSB200_PIX_RGBA32 || c->src_fmt == MSB200_PIX_RGBA32_REV) {
+		pack_plane(p, src[0], src_strides[0], c->src_w * 4, c->src_h); /* packed 32-bit RGB: msvideo.c:143-150 */
+	} else if (c->src_fmt == MSB200_PIX_RGB24 || c->src_fmt == MSB200_PIX_RGB24_REV) {
 		/* packed RGB: one plane of 3 bytes per pixel; MSPixConv hands MS_RGB24_REV over with a negative stride, starting
 		 * at the last stored row (pixconv.c:78-81): the rows are packed in display order */
 		pack_plane(p, src[0], src_strides[0], c->src_w * 3, c->src_h);

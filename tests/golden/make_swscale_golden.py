@@ -16,7 +16,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-AV_PIX = {"yuv420p": 0, "yuyv422": 1, "rgb24": 2, "bgr24": 3, "uyvy422": 15, "nv12": 23, "nv21": 24}
+AV_PIX = {"yuv420p": 0, "yuyv422": 1, "rgb24": 2, "bgr24": 3, "uyvy422": 15, "nv12": 23, "nv21": 24, "rgba": 26, "bgra": 28}
 SWS_BILINEAR = 2
 SWS_BITEXACT = 0x80000  # same algorithm, the library's C reference functions instead of its approximate x86 SIMD ones
 
@@ -50,6 +50,8 @@ def planes(fmt: str, w: int, h: int, buf: np.ndarray):
     cw, ch = (w + 1) // 2, (h + 1) // 2
     if fmt in ("rgb24", "bgr24"):
         return [base, 0, 0, 0], [w * 3, 0, 0, 0]
+    if fmt in ("rgba", "bgra"):
+        return [base, 0, 0, 0], [w * 4, 0, 0, 0]
     if fmt in ("yuyv422", "uyvy422"):
         return [base, 0, 0, 0], [w * 2, 0, 0, 0]
     if fmt in ("nv12", "nv21"):
@@ -60,6 +62,8 @@ def planes(fmt: str, w: int, h: int, buf: np.ndarray):
 def nbytes(fmt: str, w: int, h: int) -> int:
     if fmt in ("rgb24", "bgr24"):
         return w * h * 3
+    if fmt in ("rgba", "bgra"):
+        return w * h * 4
     if fmt in ("yuyv422", "uyvy422"):
         return w * h * 2
     return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
@@ -86,9 +90,10 @@ def test_frame(fmt: str, w: int, h: int, t: int, seed: int) -> np.ndarray:
     cy, cx = np.mgrid[0:ch, 0:cw]
     U = ((cx + t) % 256 + rng.integers(-3, 4, size=(ch, cw))).clip(0, 255).astype(np.uint8)
     V = ((cy + 2 * t) % 256 + rng.integers(-3, 4, size=(ch, cw))).clip(0, 255).astype(np.uint8)
-    if fmt in ("rgb24", "bgr24"):  # MSPixConv's RGB inputs: a colour ramp plus full-range noise in one quadrant
-        rgb = np.stack([(3 * xx + t) % 256, (2 * yy + 5 * t) % 256, (xx + yy) % 256], axis=-1).astype(np.uint8)
-        rgb[: h // 2, : w // 2] = rng.integers(0, 256, size=(h // 2, w // 2, 3), dtype=np.uint8)
+    if fmt in ("rgb24", "bgr24", "rgba", "bgra"):  # MSPixConv's RGB inputs: a colour ramp plus full-range noise in one quadrant
+        nc = 4 if fmt in ("rgba", "bgra") else 3
+        rgb = np.stack([(3 * xx + t) % 256, (2 * yy + 5 * t) % 256, (xx + yy) % 256, (xx * yy) % 256][:nc], axis=-1).astype(np.uint8)
+        rgb[: h // 2, : w // 2] = rng.integers(0, 256, size=(h // 2, w // 2, nc), dtype=np.uint8)
         return rgb.ravel()
     if fmt == "yuv420p":
         return np.concatenate([Y.ravel(), U.ravel(), V.ravel()])
@@ -121,6 +126,8 @@ CASES = [
     ("rgb24", 96, 64, "yuv420p", 96, 64),      # MSPixConv: MS_RGB24 -> I420 (generic scaler path with the RGB input stage)
     ("bgr24", 64, 48, "yuv420p", 64, 48),      # MSPixConv: MS_RGB24_REV -> I420 (unscaled special converter rgb24toyv12)
     ("rgb24", 132, 70, "yuv420p", 132, 70),    # width % 8 != 0
+    ("rgba", 96, 64, "yuv420p", 96, 64),       # MSPixConv: MS_RGBA32 -> I420
+    ("bgra", 64, 48, "yuv420p", 64, 48),       # MSPixConv: MS_RGBA32_REV -> I420
 ]
 
 

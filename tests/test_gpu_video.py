@@ -215,7 +215,7 @@ def test_scaler_full_size_cfg4_matches_real_libswscale_digest(ctx):
 def test_scaler_golden_frames_from_real_libswscale(ctx):
     """the committed small golden frames (real library, default build): RGB24 cases bit-exact."""
     g = np.load(GOLD)
-    av2ms = {0: 0, 1: 1, 2: 2, 3: 3, 15: 5, 23: 100, 24: 101}
+    av2ms = {0: 0, 1: 1, 2: 2, 3: 3, 15: 5, 23: 100, 24: 101, 26: 7, 28: 11}
     checked = 0
     k = 0
     while f"case{k}_src" in g:
@@ -228,18 +228,21 @@ def test_scaler_golden_frames_from_real_libswscale(ctx):
         if df == 2:
             assert np.array_equal(out[0], g[f"case{k - 1}_dst"])
         checked += 1
-    assert checked == k and checked >= 14  # every golden case, the odd-geometry ones through the direct kernel
+    assert checked == k and checked >= 16  # every golden case, the odd-geometry ones through the direct kernel
 
 
 @pytest.mark.parametrize("fmt,w,h", [(_lib.PIX_RGB24, 96, 64), (_lib.PIX_RGB24_REV, 64, 48), (_lib.PIX_RGB24, 132, 70),
-                                     (_lib.PIX_RGB24, 1280, 720), (_lib.PIX_RGB24_REV, 1920, 1080)])
+                                     (_lib.PIX_RGB24, 1280, 720), (_lib.PIX_RGB24_REV, 1920, 1080),
+                                     (_lib.PIX_RGBA32, 96, 64), (_lib.PIX_RGBA32_REV, 132, 70), (_lib.PIX_RGBA32, 1280, 720)])
 def test_pixconv_rgb24_to_i420_bit_exact(ctx, fmt, w, h):
     """MSPixConv's MS_RGB24 / MS_RGB24_REV inputs: GPU == oracle (itself bit-exact vs the real libswscale's C paths,
     tests/test_oracle_video.py); full-range noise, saturated primaries and a flat frame among the inputs."""
     L = O.oracle()
     rng = np.random.default_rng(w * 3 + h)
-    frames = rng.integers(0, 256, size=(4, w * h * 3), dtype=np.uint8)
-    frames[1] = np.tile(np.array([255, 0, 0, 0, 255, 0, 0, 0, 255, 255, 255, 255], np.uint8), w * h // 4)
+    bpp = 4 if fmt in (_lib.PIX_RGBA32, _lib.PIX_RGBA32_REV) else 3
+    frames = rng.integers(0, 256, size=(4, w * h * bpp), dtype=np.uint8)
+    prim = [255, 0, 0, 0, 255, 0, 0, 0, 255, 255, 255, 255] if bpp == 3 else [255, 0, 0, 7, 0, 255, 0, 9, 0, 0, 255, 1, 255, 255, 255, 0]
+    frames[1] = np.tile(np.array(prim, np.uint8), w * h // 4)
     frames[2] = 0
     sc = F.Scaler(ctx, w, h, fmt, w, h, _lib.PIX_YUV420P)
     got = sc.process(frames)
