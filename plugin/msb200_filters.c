@@ -85,7 +85,7 @@ static msb200_ctx *dsp_ctx(void) {
  * (BASELINE cfg5: rooms are pinned to a GPU by giving their streams a ticker of that GPU); MSB200_DEVICE=<d> (default 0)
  * is the device of the synchronous filters and of every ticker when MSB200_DEVICES is unset.
  */
-enum { BK_RESAMPLE, BK_EC, BK_VOLUME, BK_MIXER };
+enum { BK_RESAMPLE, BK_EC, BK_VOLUME, BK_MIXER, BK_G711DEC, BK_G711ENC }; /* the codecs are stateless: no bank, key[0] = law */
 #define BATCH_MAX_SLOTS 4096
 typedef struct Batch {
 	struct Batch *next;
@@ -274,7 +274,7 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 		}
 		/* slots that staged less than the group's maximum are fed zeros for the missing units */
 		for (i = 0; i < b->hi; ++i) {
-			if (b->staged[i] < units && b->kind != BK_MIXER && b->kind != BK_VOLUME) { /* the volume kernel takes per-slot counts */
+			if (b->staged[i] < units && (b->kind == BK_RESAMPLE || b->kind == BK_EC)) { /* stateful banks without per-slot counts */
 				const size_t off = ((size_t)i * b->max_units + b->staged[i]) * b->unit_in, n = (size_t)(units - b->staged[i]) * b->unit_in;
 				memset(b->in[0] + off, 0, n * sizeof(int16_t));
 				if (b->in[1]) memset(b->in[1] + off, 0, n * sizeof(int16_t));
@@ -297,6 +297,14 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 				break;
 			case BK_MIXER:
 				rc = msb200_mixer_process((msb200_mixer *)b->bank, b->in[0], b->present, b->out);
+				b->out_len = b->unit_out;
+				break;
+			case BK_G711DEC: /* arenas are contiguous over the live slots: one flat batch (unstaged units decode garbage nobody reads) */
+				rc = msb200_g711_decode(b->ctx, b->key[0], (const uint8_t *)b->in[0], b->out, (size_t)b->hi * b->max_units * b->unit_out);
+				b->out_len = b->unit_out;
+				break;
+			case BK_G711ENC:
+				rc = msb200_g711_encode(b->ctx, b->key[0], b->in[0], (uint8_t *)b->out, (size_t)b->hi * b->max_units * b->unit_in);
 				b->out_len = b->unit_out;
 				break;
 		}
@@ -1761,23 +1769,58 @@ static MSFilterDesc b200_speex_ec_desc = {.id = MS_SPEEX_EC_ID,
  * reference — encoder: MSBufferizer re-framing to ptime (alaw.c:56-94), fmtp / attr parsing (:96-138), getters
  * (:140-160); decoder: one output block per input block, meta data copied (:199-211). The companding itself runs on the
  * GPU (msb200_g711_*): one call for everything queued in the tick. */
+#define G711_BATCH_UNITS 4 /* packets one stream may stage per tick */
 typedef struct G711EncState {
 	MSBufferizer *bz;
 	int ptime, maxptime, law;
 	uint32_t ts;
+	Batch *batch; /* lockstep batch group (MSB200_BATCH), keyed by law and packet size */
+	int slot, n_held;
+	mblk_t *held[G711_BATCH_UNITS]; /* output packets staged in the current tick: meta data and timestamp set, payload pending */
+	MSQueue pend;
+	bool_t batch_off;
 } G711EncState;
+static void g711_enc_collect(void *owner, Batch *b) { /* encoded payloads: arena -> the held packets */
+	G711EncState *s = (G711EncState *)owner;
+	int u;
+	for (u = 0; u < s->n_held; ++u) {
+		if (b->ready[s->slot] == s->n_held) {
+			const size_t nb = (size_t)b->unit_out * 2;
+			memcpy(s->held[u]->b_wptr, (uint8_t *)b->out + ((size_t)s->slot * b->max_units + u) * nb, nb);
+			s->held[u]->b_wptr += nb;
+			ms_queue_put(&s->pend, s->held[u]);
+		} else {
+			freemsg(s->held[u]); /* the group's launch failed (logged there) */
+		}
+	}
+	b->ready[s->slot] = 0;
+	s->n_held = 0;
+}
+static void g711_enc_leave_batch(G711EncState *s) {
+	int u;
+	if (s->batch) batch_leave(s->batch, s->slot);
+	s->batch = NULL;
+	for (u = 0; u < s->n_held; ++u) freemsg(s->held[u]);
+	s->n_held = 0;
+}
 static void g711_enc_init_law(MSFilter *f, int law) {
 	G711EncState *s = ms_new0(G711EncState, 1);
 	s->bz = ms_bufferizer_new();
 	s->ptime = 0;
 	s->maxptime = MS_DEFAULT_MAX_PTIME < 140 ? MS_DEFAULT_MAX_PTIME : 140;
 	s->law = law;
+	ms_queue_init(&s->pend);
 	f->data = s;
 }
 static void alaw_enc_init(MSFilter *f) { g711_enc_init_law(f, MSB200_G711_ALAW); }
 static void ulaw_enc_init(MSFilter *f) { g711_enc_init_law(f, MSB200_G711_ULAW); }
+static void g711_enc_postprocess(MSFilter *f) {
+	g711_enc_leave_batch((G711EncState *)f->data);
+}
 static void g711_enc_uninit(MSFilter *f) {
 	G711EncState *s = (G711EncState *)f->data;
+	g711_enc_leave_batch(s);
+	ms_queue_flush(&s->pend);
 	ms_bufferizer_destroy(s->bz);
 	ms_free(s);
 }
@@ -1793,9 +1836,36 @@ static void g711_enc_process(MSFilter *f) {
 	size_of_pcm = (size_t)160 * frame_per_packet;       /* bytes: 80 samples per 10 ms at 8 kHz */
 	while ((m = ms_queue_get(f->inputs[0])) != NULL)
 		ms_bufferizer_put(s->bz, m);
+	if (s->batch && s->batch->key[1] != (int)size_of_pcm / 2) g711_enc_leave_batch(s); /* ptime changed under us */
+	if (s->batch) { /* the packets staged in the previous tick were encoded by the group's launch */
+		batch_tick(s->batch, f->ticker->ticks);
+		if (s->n_held && s->batch->staged[s->slot] == 0) g711_enc_collect(s, s->batch);
+	}
+	while ((m = ms_queue_get(&s->pend)) != NULL)
+		ms_queue_put(f->outputs[0], m);
 	avail = ms_bufferizer_get_avail(s->bz);
 	npk = (int)(avail / size_of_pcm);
 	if (npk == 0) return;
+	if (!s->batch && !s->batch_off && batch_capacity() > 0) {
+		const int key[4] = {s->law, (int)size_of_pcm / 2, 0, 0};
+		s->batch = batch_join(BK_G711ENC, f->ticker, key, (int)size_of_pcm / 2, (int)size_of_pcm / 4, G711_BATCH_UNITS, s, g711_enc_collect,
+		                      &s->slot);
+		if (!s->batch) s->batch_off = TRUE;
+	}
+	if (s->batch) { /* stage whole packets; their payload is filled in at the start of the next tick */
+		Batch *b = s->batch;
+		while (npk > 0 && b->staged[s->slot] < b->max_units && s->n_held == b->staged[s->slot]) {
+			mblk_t *o = allocb(size_of_pcm / 2, 0);
+			ms_bufferizer_read(s->bz, (uint8_t *)(b->in[0] + ((size_t)s->slot * b->max_units + b->staged[s->slot]) * b->unit_in), size_of_pcm);
+			ms_bufferizer_fill_current_metas(s->bz, o);
+			mblk_set_timestamp_info(o, s->ts);
+			s->ts += (uint32_t)(size_of_pcm / 2);
+			s->held[s->n_held++] = o;
+			b->staged[s->slot]++;
+			--npk;
+		}
+		return; /* packets beyond the per-tick capacity stay in the bufferizer for the next tick */
+	}
 	/* every complete packet of this tick in ONE device call; meta data are taken per packet, as the reference does */
 	pcm = (uint8_t *)ms_malloc((size_t)npk * size_of_pcm);
 	code = (uint8_t *)ms_malloc((size_t)npk * size_of_pcm / 2);
@@ -1890,16 +1960,98 @@ static MSFilterMethod g711_dec_methods[] = {{MS_FILTER_GET_NCHANNELS, g711_get_c
                                             {MS_FILTER_GET_SAMPLE_RATE, g711_get_sample_rate},
                                             {MS_DECODER_HAVE_PLC, g711_dec_have_plc},
                                             {0, NULL}};
+typedef struct G711DecState {
+	int law;
+	Batch *batch; /* lockstep batch group (MSB200_BATCH), keyed by law and payload size */
+	int slot, n_held;
+	mblk_t *held[G711_BATCH_UNITS]; /* output blocks staged in the current tick (meta data copied), samples pending */
+	MSQueue pend;
+	bool_t batch_off;
+} G711DecState;
+static void g711_dec_collect(void *owner, Batch *b) {
+	G711DecState *s = (G711DecState *)owner;
+	int u;
+	for (u = 0; u < s->n_held; ++u) {
+		if (b->ready[s->slot] == s->n_held) {
+			const size_t nb = (size_t)b->unit_out * 2;
+			memcpy(s->held[u]->b_wptr, b->out + ((size_t)s->slot * b->max_units + u) * b->unit_out, nb);
+			s->held[u]->b_wptr += nb;
+			ms_queue_put(&s->pend, s->held[u]);
+		} else {
+			freemsg(s->held[u]);
+		}
+	}
+	b->ready[s->slot] = 0;
+	s->n_held = 0;
+}
+static void g711_dec_leave_batch(G711DecState *s) {
+	int u;
+	if (s->batch) batch_leave(s->batch, s->slot);
+	s->batch = NULL;
+	for (u = 0; u < s->n_held; ++u) freemsg(s->held[u]);
+	s->n_held = 0;
+}
+static void g711_dec_init_law(MSFilter *f, int law) {
+	G711DecState *s = ms_new0(G711DecState, 1);
+	s->law = law;
+	ms_queue_init(&s->pend);
+	f->data = s;
+}
+static void alaw_dec_init(MSFilter *f) { g711_dec_init_law(f, MSB200_G711_ALAW); }
+static void ulaw_dec_init(MSFilter *f) { g711_dec_init_law(f, MSB200_G711_ULAW); }
+static void g711_dec_postprocess(MSFilter *f) {
+	g711_dec_leave_batch((G711DecState *)f->data);
+}
+static void g711_dec_uninit(MSFilter *f) {
+	G711DecState *s = (G711DecState *)f->data;
+	g711_dec_leave_batch(s);
+	ms_queue_flush(&s->pend);
+	ms_free(s);
+}
+/* batch mode: returns TRUE when the block was staged */
+static bool_t g711_dec_stage(MSFilter *f, G711DecState *s, mblk_t *m) {
+	const int n = (int)(m->b_wptr - m->b_rptr);
+	if (!s->batch && !s->batch_off && batch_capacity() > 0 && n > 0 && (n % 2) == 0 && n <= 4096) {
+		const int key[4] = {s->law, n, 0, 0};
+		s->batch = batch_join(BK_G711DEC, f->ticker, key, n / 2, n, G711_BATCH_UNITS, s, g711_dec_collect, &s->slot);
+		if (!s->batch) s->batch_off = TRUE;
+	}
+	if (!s->batch) return FALSE;
+	{
+		Batch *b = s->batch;
+		if (n == b->key[1] && b->staged[s->slot] < b->max_units && s->n_held == b->staged[s->slot]) {
+			mblk_t *o = allocb((size_t)n * 2, 0);
+			mblk_meta_copy(m, o);
+			memcpy((uint8_t *)(b->in[0] + ((size_t)s->slot * b->max_units + b->staged[s->slot]) * b->unit_in), m->b_rptr, (size_t)n);
+			s->held[s->n_held++] = o;
+			b->staged[s->slot]++;
+			freemsg(m);
+			return TRUE;
+		}
+		ms_warning("%s(b200): irregular payload (%d bytes, group payload %d): leaving the batch group", f->desc->name, n, b->key[1]);
+		g711_dec_leave_batch(s);
+		s->batch_off = TRUE;
+	}
+	return FALSE;
+}
 static void g711_dec_process_law(MSFilter *f, int law) { /* alaw_dec_process alaw.c:199-211 */
+	G711DecState *st = (G711DecState *)f->data;
 	mblk_t *m, *list[64];
 	size_t total = 0, off = 0;
 	int n = 0, k;
 	uint8_t *code;
 	int16_t *pcm;
 	int rc = MSB200_ENODEV;
+	if (st->batch) { /* the payloads staged in the previous tick were decoded by the group's launch */
+		batch_tick(st->batch, f->ticker->ticks);
+		if (st->n_held && st->batch->staged[st->slot] == 0) g711_dec_collect(st, st->batch);
+	}
+	while ((m = ms_queue_get(&st->pend)) != NULL)
+		ms_queue_put(f->outputs[0], m);
 	/* everything queued in this tick (usually one RTP payload) goes to the device in ONE call */
 	while (n < 64 && (m = ms_queue_get(f->inputs[0])) != NULL) {
 		msgpullup(m, (size_t)-1);
+		if (g711_dec_stage(f, st, m)) continue; /* lockstep batch mode: decoded by the group, emitted next tick */
 		list[n++] = m;
 		total += (size_t)(m->b_wptr - m->b_rptr);
 	}
@@ -1937,18 +2089,20 @@ static void alaw_dec_process(MSFilter *f) { g711_dec_process_law(f, MSB200_G711_
 static void ulaw_dec_process(MSFilter *f) { g711_dec_process_law(f, MSB200_G711_ULAW); }
 static MSFilterDesc b200_alaw_enc_desc = {.id = MS_ALAW_ENC_ID, .name = "MSAlawEnc", .text = "B200: ITU-G.711 alaw encoder (libmsb200dsp)",
                                           .category = MS_FILTER_ENCODER, .enc_fmt = "pcma", .ninputs = 1, .noutputs = 1,
-                                          .init = alaw_enc_init, .process = g711_enc_process, .uninit = g711_enc_uninit,
+                                          .init = alaw_enc_init, .process = g711_enc_process, .postprocess = g711_enc_postprocess, .uninit = g711_enc_uninit,
                                           .methods = g711_enc_methods};
 static MSFilterDesc b200_ulaw_enc_desc = {.id = MS_ULAW_ENC_ID, .name = "MSUlawEnc", .text = "B200: ITU-G.711 ulaw encoder (libmsb200dsp)",
                                           .category = MS_FILTER_ENCODER, .enc_fmt = "pcmu", .ninputs = 1, .noutputs = 1,
-                                          .init = ulaw_enc_init, .process = g711_enc_process, .uninit = g711_enc_uninit,
+                                          .init = ulaw_enc_init, .process = g711_enc_process, .postprocess = g711_enc_postprocess, .uninit = g711_enc_uninit,
                                           .methods = g711_enc_methods};
 static MSFilterDesc b200_alaw_dec_desc = {.id = MS_ALAW_DEC_ID, .name = "MSAlawDec", .text = "B200: ITU-G.711 alaw decoder (libmsb200dsp)",
                                           .category = MS_FILTER_DECODER, .enc_fmt = "pcma", .ninputs = 1, .noutputs = 1,
-                                          .process = alaw_dec_process, .methods = g711_dec_methods};
+                                          .init = alaw_dec_init, .process = alaw_dec_process, .postprocess = g711_dec_postprocess,
+                                          .uninit = g711_dec_uninit, .methods = g711_dec_methods};
 static MSFilterDesc b200_ulaw_dec_desc = {.id = MS_ULAW_DEC_ID, .name = "MSUlawDec", .text = "B200: ITU-G.711 ulaw decoder (libmsb200dsp)",
                                           .category = MS_FILTER_DECODER, .enc_fmt = "pcmu", .ninputs = 1, .noutputs = 1,
-                                          .process = ulaw_dec_process, .methods = g711_dec_methods};
+                                          .init = ulaw_dec_init, .process = ulaw_dec_process, .postprocess = g711_dec_postprocess,
+                                          .uninit = g711_dec_uninit, .methods = g711_dec_methods};
 
 /* ================================================================================================ MSScalerDesc
  * the second drop-in boundary (/root/reference/include/mediastreamer2/msvideo.h:473-492): installed with
@@ -2057,6 +2211,10 @@ __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *fac
 		b200_volume_desc.flags |= MS_FILTER_IS_PUMP;
 		b200_resample_desc.flags |= MS_FILTER_IS_PUMP;
 		b200_speex_ec_desc.flags |= MS_FILTER_IS_PUMP;
+		b200_alaw_enc_desc.flags |= MS_FILTER_IS_PUMP;
+		b200_alaw_dec_desc.flags |= MS_FILTER_IS_PUMP;
+		b200_ulaw_enc_desc.flags |= MS_FILTER_IS_PUMP;
+		b200_ulaw_dec_desc.flags |= MS_FILTER_IS_PUMP;
 		ms_message("libmsb200filters: lockstep batch mode, %d slots per group (MSB200_BATCH)", batch_capacity());
 	}
 	ms_factory_register_filter(factory, &b200_audio_mixer_desc);

@@ -36,9 +36,20 @@ from synth import cfg2_stream  # noqa: E402
 IN_RATE, RATE, TAIL_MS, GAIN = 16000, 48000, 250, 0.8
 
 
-def build(g: RefGraph, n_streams: int, pins: int, ticks: int, pool: int = 8):
-    ti = IN_RATE // 100
-    base = [cfg2_stream(s, ti * ticks, IN_RATE) for s in range(min(pool, n_streams))]
+def _alaw(pcm: np.ndarray) -> np.ndarray:
+    L = O.oracle()
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    code = np.zeros(pcm.size, np.uint8)
+    L.orc_g711_encode(0, O.ptr(pcm), O.ptr(code), pcm.size)
+    return code
+
+
+def build(g: RefGraph, n_streams: int, pins: int, ticks: int, pool: int = 8, codec: str = "none"):
+    """codec == "alaw": the decode / encode stubs of cfg5 made real — the sources emit 8 kHz G.711 A-law payloads (80 bytes
+    per tick) into MSAlawDec, and every mixer output goes through MSResample(48k->8k) -> MSAlawEnc (20 ms packets)"""
+    in_rate = 8000 if codec == "alaw" else IN_RATE
+    ti = in_rate // 100
+    base = [cfg2_stream(s, ti * ticks, in_rate) for s in range(min(pool, n_streams))]
     sources, spk_sinks, out_sinks, mixers = [], [], [], []  # sources: ONE per room (attaching it schedules the whole room)
     for s in range(n_streams):
         if s % pins == 0:
@@ -49,10 +60,14 @@ def build(g: RefGraph, n_streams: int, pins: int, ticks: int, pool: int = 8):
         far, mic = base[s % len(base)][0], base[s % len(base)][1]
         if s >= len(base):  # distinct streams from a small pool: rotate so that rooms do not mix identical signals
             far, mic = np.roll(far, 37 * s), np.roll(mic, 37 * s)
-        s_far, s_mic = g.source(far, ti * 2), g.source(mic, ti * 2)
+        if codec == "alaw":
+            s_far, s_mic = g.source(_alaw(far), ti), g.source(_alaw(mic), ti)
+            d_far, d_mic = g.new("MSAlawDec"), g.new("MSAlawDec")
+        else:
+            s_far, s_mic = g.source(far, ti * 2), g.source(mic, ti * 2)
         rs_far, rs_mic = g.new("MSResample"), g.new("MSResample")
         for r in (rs_far, rs_mic):
-            g.call_int(r, "MS_FILTER_SET_SAMPLE_RATE", IN_RATE)
+            g.call_int(r, "MS_FILTER_SET_SAMPLE_RATE", in_rate)
             g.call_int(r, "MS_FILTER_SET_OUTPUT_SAMPLE_RATE", RATE)
         ec = g.new("MSSpeexEC")
         g.call_int(ec, "MS_FILTER_SET_SAMPLE_RATE", RATE)
@@ -61,14 +76,28 @@ def build(g: RefGraph, n_streams: int, pins: int, ticks: int, pool: int = 8):
         g.call_int(vol, "MS_FILTER_SET_SAMPLE_RATE", RATE)
         g.call_float(vol, "MS_VOLUME_SET_GAIN", GAIN)
         spk, out = g.sink(), g.sink()
-        g.link(s_far, 0, rs_far, 0)
+        if codec == "alaw":
+            g.link(s_far, 0, d_far, 0)
+            g.link(d_far, 0, rs_far, 0)
+            g.link(s_mic, 0, d_mic, 0)
+            g.link(d_mic, 0, rs_mic, 0)
+        else:
+            g.link(s_far, 0, rs_far, 0)
+            g.link(s_mic, 0, rs_mic, 0)
         g.link(rs_far, 0, ec, 0)
         g.link(ec, 0, spk, 0)
-        g.link(s_mic, 0, rs_mic, 0)
         g.link(rs_mic, 0, ec, 1)
         g.link(ec, 1, vol, 0)
         g.link(vol, 0, mixers[-1], s % pins)
-        g.link(mixers[-1], s % pins, out, 0)
+        if codec == "alaw":
+            rs_out, enc = g.new("MSResample"), g.new("MSAlawEnc")
+            g.call_int(rs_out, "MS_FILTER_SET_SAMPLE_RATE", RATE)
+            g.call_int(rs_out, "MS_FILTER_SET_OUTPUT_SAMPLE_RATE", in_rate)
+            g.link(mixers[-1], s % pins, rs_out, 0)
+            g.link(rs_out, 0, enc, 0)
+            g.link(enc, 0, out, 0)
+        else:
+            g.link(mixers[-1], s % pins, out, 0)
         if s % pins == 0:
             sources.append(s_far)
         spk_sinks.append(spk)
@@ -85,9 +114,10 @@ def main():
     ap.add_argument("--dump", default="")
     ap.add_argument("--timing", action="store_true")
     ap.add_argument("--tickers", type=int, default=1)
+    ap.add_argument("--codec", choices=["none", "alaw"], default="none")
     a = ap.parse_args()
     g = RefGraph(plugins_dir=str(O.PLUGIN_DIR))
-    sources, spk_sinks, out_sinks = build(g, a.streams, a.pins, a.ticks)
+    sources, spk_sinks, out_sinks = build(g, a.streams, a.pins, a.ticks, codec=a.codec)
     # a room's streams are one connected graph through its mixer: whole rooms are dealt to the tickers
     tickers = [g.L.ref_ticker_new() for _ in range(max(1, a.tickers))]
     for r, src in enumerate(sources):
@@ -109,13 +139,13 @@ def main():
     else:
         run(a.ticks)
     if a.dump:
-        np.savez(a.dump, **{f"out{i}": g.read(k)[0] for i, k in enumerate(out_sinks)},
+        np.savez(a.dump, **{f"out{i}": g.read(k, np.uint8 if a.codec == "alaw" else np.int16)[0] for i, k in enumerate(out_sinks)},
                  **{f"spk{i}": g.read(k)[0] for i, k in enumerate(spk_sinks)})
     if a.timing:
         ms = np.array(per_tick) * 1000.0
         stats = {"mode": "batch" if int(os.environ.get("MSB200_BATCH", "0") or 0) > 0 else "sync",
                  "batch_slots": int(os.environ.get("MSB200_BATCH", "0") or 0), "streams": a.streams, "pins": a.pins,
-                 "tickers": len(tickers),
+                 "tickers": len(tickers), "codec": a.codec,
                  "ticks_timed": len(ms), "tick_ms_mean": float(ms.mean()), "tick_ms_p50": float(np.percentile(ms, 50)),
                  "tick_ms_p99": float(np.percentile(ms, 99)), "tick_ms_max": float(ms.max()),
                  "late_ticks_10ms": int((ms > 10.0).sum()),

@@ -14,11 +14,11 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _run(tmp_path, batch, tag, streams, pins, ticks, timing=False, tickers=1):
+def _run(tmp_path, batch, tag, streams, pins, ticks, timing=False, tickers=1, codec="none"):
     env = dict(os.environ, MSB200_BATCH=str(batch))
     out = tmp_path / f"{tag}.npz"
     cmd = [sys.executable, str(ROOT / "tests" / "graph_runner.py"), "--streams", str(streams), "--pins", str(pins),
-           "--ticks", str(ticks), "--tickers", str(tickers), "--dump", str(out)] + (["--timing"] if timing else [])
+           "--ticks", str(ticks), "--tickers", str(tickers), "--codec", codec, "--dump", str(out)] + (["--timing"] if timing else [])
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     stats = json.loads(r.stdout.strip().splitlines()[-1]) if timing else None
@@ -48,3 +48,24 @@ def test_batch_mode_is_synchronous_mode_delayed(tmp_path, streams, pins, tickers
     # (per ticker: every ticker has its own groups, each with its own CUDA stream)
     assert stats["mode"] == "batch" and stats["batch_groups"] == 4 * tickers
     assert stats["batch_launches"] <= 4 * ticks * tickers
+
+
+def test_batch_mode_with_g711_codecs_is_synchronous_mode_delayed(tmp_path):
+    """the cfg5 graph with its decode / encode stubs made real (MSAlawDec -> ... -> MSResample(48k->8k) -> MSAlawEnc): seven
+    batched stages on the send path; batch mode delivers the synchronous mode's A-law byte stream after extra leading
+    silence (A-law code 0xD5) of a whole number of ticks"""
+    streams, pins, ticks = 8, 4, 80
+    sync, _ = _run(tmp_path, 0, "sync", streams, pins, ticks, codec="alaw")
+    batch, stats = _run(tmp_path, 16, "batch", streams, pins, ticks, timing=True, codec="alaw")
+    tick_bytes = 80
+    for i in range(streams):
+        a, b = sync[f"spk{i}"], batch[f"spk{i}"]  # far end: decoder and resampler batched
+        assert len(b) > 40 * 480 and np.array_equal(b, a[:len(b)]), f"speaker path of stream {i}"
+        a, b = sync[f"out{i}"], batch[f"out{i}"]
+        assert len(b) > 40 * tick_bytes, (i, len(a), len(b))
+        shifts = [d for d in range(0, 9) if np.all(b[:d * tick_bytes] == 0xD5) and
+                  np.array_equal(b[d * tick_bytes:], a[:len(b) - d * tick_bytes])]
+        assert shifts, f"send path of stream {i}: no whole-tick shift <= 8 aligns batch mode with synchronous mode"
+        assert np.any(a[:len(b) - shifts[0] * tick_bytes] != 0xD5), "compared silence only"
+    # resampler x2 (8k->48k, 48k->8k), EC, volume, mixer, decoder, encoder groups
+    assert stats["mode"] == "batch" and stats["batch_groups"] == 7
