@@ -335,6 +335,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["g711"] = g711_bench(ctx, peak, cpu_baseline=(world == 1 and not args.no_cpu_baseline))
     except ImportError:
         pass
+    try:
+        from bench_kernels import kernels_bench  # noqa: WPS433
+
+        if rank == 0 and world == 1:
+            line["kernels"] = kernels_bench(ctx, peak)
+    except ImportError:
+        pass
     if rank == 0:
         print(json.dumps(line), flush=True)
     chain.close()

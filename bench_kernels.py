@@ -1,0 +1,131 @@
+"""Per-kernel measurements for every SURVEY.md §8 row that bench.py's two headline blocks do not cover: each bank's
+`*_process_dev` entry point on device-resident buffers LARGER than the 126 MB L2 (so the bytes really come from HBM),
+timed with CUDA events on the launching stream after warm-up. Reports ms per launch, achieved GB/s on the row's
+ALGORITHMIC bytes (SURVEY §8d / DESIGN §5) and the fraction of the measured HBM peak. Imported by bench.py ("kernels"
+block); runnable alone:
+
+    python bench_kernels.py
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def _time(ctx, fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(iters):
+        fn()
+    return ctx.timer_stop_ms() / iters
+
+
+def _fill(ctx, dev, nbytes, seed, lo=0, hi=256, dtype=np.uint8):
+    rng = np.random.default_rng(seed)
+    chunk = rng.integers(lo, hi, (4 << 20) // np.dtype(dtype).itemsize).astype(dtype)
+    for off in range(0, nbytes, chunk.nbytes):
+        n = min(chunk.nbytes, nbytes - off)
+        ctx.h2d(dev + off, chunk[: n // chunk.itemsize])
+
+
+def kernels_bench(ctx, hbm_peak_gbs: float) -> dict:
+    from mediastreamer2_b200 import _lib
+    from mediastreamer2_b200 import filters as F
+
+    lib = ctx.lib
+    P = C.c_void_p
+    rows = {}
+
+    def row(name, what, algo_bytes, ms, units, unit_name):
+        gbs = algo_bytes / (ms / 1000.0) / 1e9
+        rows[name] = {"what": what, "ms_per_launch": ms, "algorithmic_bytes": int(algo_bytes), "achieved_gbs": gbs,
+                      "frac_of_hbm_peak": gbs / hbm_peak_gbs, unit_name + "_per_s": units / (ms / 1000.0)}
+
+    # ---------------------------------------------------------------- audio banks, 48 kHz mono 10 ms blocks
+    n, w = 262144, 480  # 252 MB of s16 per buffer: twice the L2
+    d_a, d_b = ctx.dev_alloc(n * w * 2 * 2), ctx.dev_alloc(n * w * 2 * 2)
+    _fill(ctx, d_a, n * w * 2 * 2, 1, -9000, 9000, np.int16)
+    # a3 MSAudioMixer: 16-party conference rooms
+    rooms, pins = n // 16, 16
+    mix = F.AudioMixer(ctx, rooms, pins, w, True)
+    d_present = ctx.dev_alloc(rooms * pins)
+    ctx.h2d(d_present, np.ones(rooms * pins, np.uint8))
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_mixer_process_dev(mix.h, P(d_a), P(d_present), P(d_b))))
+    row("mixer_kernel", f"a3 MSAudioMixer conference mode, {rooms} rooms x {pins} pins x {w} samples", rooms * pins * w * 2 * 2, ms, rooms, "room_ticks")
+    mix.close()
+    ctx.dev_free(d_present)
+    # a4 MSVolume light path (in place)
+    vol = F.Volume(ctx, n, 48000, w)
+    vol.set_gain(-1, 0.8)
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_volume_process_dev(vol.h, P(d_a), w, w)))
+    row("volume_kernel", f"a4 MSVolume light path, {n} streams x {w} samples in place", n * w * 2 * 2, ms, n, "stream_ticks")
+    vol.close()
+    # a5 MSEqualizer (512-tap FIR at 48 kHz): compute-bound by design, reported against the same yardstick
+    ne = 16384
+    eq = F.Equalizer(ctx, ne, 48000, w)
+    eq.set_gain(0, 1000.0, 2.0, 300.0)  # every stream runs the full 512-tap FIR whatever its taps are
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_equalizer_process_dev(eq.h, P(d_a), w, w)), iters=5)
+    row("eq_fir_kernel", f"a5 MSEqualizer 512-tap FIR, {ne} streams x {w} samples in place (compute-bound: 2*512 flop/sample)", ne * w * 2 * 2, ms, ne, "stream_ticks")
+    rows["eq_fir_kernel"]["tflops"] = ne * w * 2 * 512 / (ms / 1000.0) / 1e12
+    eq.close()
+    # a6 MSChannelAdapter mono -> stereo
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_chanadapt_process_dev(ctx.h, 0, n, w, P(d_a), None, P(d_b))))
+    row("chanadapt_kernel", f"a6 MSChannelAdapter mono->stereo, {n} streams x {w} frames", n * w * 2 * 3, ms, n, "stream_ticks")
+    # a1 MSResample 16 kHz -> 48 kHz
+    rs = F.Resample(ctx, n, 16000, 48000, 1, 160)
+    got = C.c_int()
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_resample_process_dev(rs.h, P(d_a), 160, 160, P(d_b), 481, C.byref(got))))
+    row("resample_up_kernel<3>", f"a1 MSResample 16k->48k, {n} streams x 160 frames", n * (160 + 480) * 2, ms, n, "stream_ticks")
+    rs.close()
+    # a1 general kernel: 48 kHz -> 16 kHz (144-tap down-sampling filter)
+    nd = 65536
+    rs = F.Resample(ctx, nd, 48000, 16000, 1, 480)
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_resample_process_dev(rs.h, P(d_a), 480, 480, P(d_b), 161, C.byref(got))), iters=5)
+    row("resample_kernel", f"a1 MSResample 48k->16k (general kernel), {nd} streams x 480 frames", nd * (480 + 160) * 2, ms, nd, "stream_ticks")
+    rs.close()
+    ctx.dev_free(d_a)
+    ctx.dev_free(d_b)
+    # ---------------------------------------------------------------- video, 1080p, 128 frames (>= 400 MB per buffer)
+    nf, sw, sh = 128, 1920, 1080
+    src_b = sw * sh * 3  # largest source format here (RGB24)
+    d_src, d_dst = ctx.dev_alloc(nf * src_b), ctx.dev_alloc(nf * src_b)
+    _fill(ctx, d_src, nf * src_b, 2)
+    i420 = sw * sh * 3 // 2
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_nv12_to_i420_dev(ctx.h, nf, P(d_src), i420, sw * sh, 0, sw, sh, sw, sw, 1, 0, P(d_dst))))
+    row("nv12_fast_kernel", f"a9 NV12->I420, {nf} frames {sw}x{sh}", nf * i420 * 2, ms, nf, "frames")
+    ms = _time(ctx, lambda: _lib.check(lib.msb200_nv12_to_i420_dev(ctx.h, nf, P(d_src), i420, sw * sh, 90, sh, sw, sw, sw, 1, 0, P(d_dst))))
+    row("nv12_generic_kernel(rot90)", f"a9 NV12->I420 rotated 90 degrees, {nf} frames {sw}x{sh}", nf * i420 * 2, ms, nf, "frames")
+    for name, sf, df, dw, dh, sbytes, dbytes, what in (
+            ("scale_plane_kernel", _lib.PIX_YUV420P, _lib.PIX_YUV420P, 1280, 720, i420, 1280 * 720 * 3 // 2, "a8 MSSizeConv I420 1080p -> I420 720p"),
+            ("rgb24_to_i420_kernel<0>", _lib.PIX_RGB24, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv RGB24 -> I420 1080p"),
+            ("rgb24_to_i420_kernel<1>", _lib.PIX_RGB24_REV, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv BGR24 -> I420 1080p"),
+            ("packed422_to_i420_kernel", _lib.PIX_YUY2, _lib.PIX_YUV420P, sw, sh, sw * sh * 2, i420, "a7 MSPixConv YUY2 -> I420 1080p"),
+            ("scale_direct_kernel", _lib.PIX_NV12, _lib.PIX_RGB24, 640, 360, i420, 640 * 360 * 3, "a8/a11 NV12 1080p -> RGB24 360p (3:1, tile-free path)")):
+        sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
+        ms = _time(ctx, lambda: sc.process_dev(nf, d_src, d_dst), iters=5)
+        row(name, f"{what}, {nf} frames", nf * (sbytes + dbytes), ms, nf, "frames")
+        sc.close()
+    ctx.dev_free(d_src)
+    ctx.dev_free(d_dst)
+    return rows
+
+
+if __name__ == "__main__":
+    from mediastreamer2_b200 import filters as F
+
+    c = F.Context(0)
+    out = kernels_bench(c, 6455.9)
+    for k, v in out.items():
+        print(f"{k:32s} {v['ms_per_launch']:9.4f} ms  {v['achieved_gbs']:8.1f} GB/s  frac {v['frac_of_hbm_peak']:.3f}   {v['what']}")
+    print(json.dumps(out))
+    c.close()
