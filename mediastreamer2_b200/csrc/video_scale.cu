@@ -1118,6 +1118,131 @@ __global__ void __launch_bounds__(ST_THREADS, PR > 0 ? ST_SCHED_CTAS : ST_MIN_CT
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ plane strips
+// MSSizeConv's case (src/videofilters/sizeconv.c:159-169: I420 -> I420 bilinear): every plane is scaled on its own —
+// hScale8To15 with the plane's horizontal filter, then yuv2planeX / yuv2plane1 with its vertical filter and the flat
+// dither 64: byte = (sum(h15 * tap) + (64 << 12)) >> 19 (for one tap of 4096 that IS (h15 + 64) >> 7). The strip
+// kernel's machinery without the colour stage: one warp per strip of 128 output columns x R rows, the source box in by
+// TMA, the horizontal pass (dp2a) straight into a rotating register window of VT rows, vertical taps pre-rotated and
+// pre-scaled by 32 so that the byte lands in bits 24..31 of the 32-bit sum (taps are non-negative and sum to 4096:
+// no clamp can bind), 4 bytes per lane written as one coalesced 32-bit store per output row. blockIdx.z = frame * NP + plane
+// for the NP planes of equal geometry handled by one launch (Y alone; U and V together).
+struct PlaneStripParams {
+	const StripRow *rows; // per output row of the plane: l_last and the rotated x32 taps in cl[]
+	const int *hpos;
+	const short *hcoef;   // 4 taps per output column (hl_size / hc_size == 4)
+	int R, box_w, box_h, W, H, n_planes;
+	size_t dst_frame_bytes, dst_off[2]; // byte offset of each plane inside a destination frame
+	short x0[ST_MAX_TX], y0[ST_MAX_TY];
+};
+template <int VT>
+__global__ void __launch_bounds__(ST_THREADS, 8)
+    scale_plane_strip_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                             unsigned char *__restrict__ dst, const PlaneStripParams S) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const unsigned box_bytes = (unsigned)(S.box_w * S.box_h), box_al = (box_bytes + 127u) & ~127u;
+	unsigned char *box = smem;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(box + box_al);
+	const unsigned s_tab = smem_u32(box + box_al) + 16;
+	const int frame = blockIdx.z / S.n_planes, plane = blockIdx.z - frame * S.n_planes;
+	const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * (ST_WARPS * S.R);
+	const int bx0 = S.x0[blockIdx.x], by0 = S.y0[blockIdx.y];
+	if (t == 0) {
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, box_bytes);
+		tma_load_3d(box, plane ? &map_b : &map_a, bar, bx0, by0, frame);
+	}
+	const int xq = (x0 >> 1) + 2 * lane;
+	const bool col_ok = x0 + 4 * lane < S.W; // ragged last tile column: lanes past the plane neither read tables nor store
+	int4 lpos = make_int4(bx0, bx0, bx0, bx0), lcA = make_int4(0, 0, 0, 0), lcB = lcA;
+	if (col_ok) {
+		lpos = reinterpret_cast<const int4 *>(S.hpos)[xq >> 1];
+		lcA = reinterpret_cast<const int4 *>(S.hcoef)[xq];
+		lcB = reinterpret_cast<const int4 *>(S.hcoef)[xq + 1];
+	}
+	const int ys = y0 + warp * S.R, ye = min(ys + S.R, S.H);
+	if (t < 2 * (ST_WARPS * S.R + 1)) cp_async16(s_tab + t * 16, reinterpret_cast<const char *>(S.rows + y0) + t * 16);
+	asm volatile("cp.async.commit_group;\n" ::: "memory");
+	const int pA = lpos.x - bx0, pB = lpos.z - bx0;
+	const unsigned shA = (unsigned)(pA & 3) * 8, shB = (unsigned)(pB & 3) * 8;
+	const unsigned dA = (unsigned)(lpos.y - lpos.x) * 8, dB = (unsigned)(lpos.w - lpos.z) * 8;
+	const unsigned pitch = (unsigned)S.box_w;
+	int WL[VT][4];
+#pragma unroll
+	for (int s = 0; s < VT; ++s)
+#pragma unroll
+		for (int k = 0; k < 4; ++k) WL[s][k] = 0;
+	asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+	__syncthreads();
+	mbar_wait(bar, 0);
+	if (ys >= ye) return;
+	unsigned rtab = s_tab + (unsigned)(warp * S.R) * 32;
+	int4 ra = lds128(rtab), rb = lds128(rtab + 16);
+	const int lrow0 = ra.x - (VT - 1);
+	const int s0 = lrow0 % VT;
+	int row = lrow0;
+	unsigned la = smem_u32(box) + (unsigned)(pA & ~3) + (unsigned)(row - by0) * pitch;
+	unsigned lb = smem_u32(box) + (unsigned)(pB & ~3) + (unsigned)(row - by0) * pitch;
+	unsigned char *o = dst + (size_t)frame * S.dst_frame_bytes + S.dst_off[plane] + (size_t)ys * S.W + x0 + 4 * lane;
+	int y = ys;
+	auto hrow = [&](int(&w)[4]) {
+		const unsigned a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+		const unsigned A0 = __funnelshift_r(a0, a1, shA), A1 = __funnelshift_r(a1, a2, shA);
+		const unsigned B0 = __funnelshift_r(b0, b1, shB), B1 = __funnelshift_r(b1, b2, shB);
+		const unsigned A0b = __funnelshift_r(A0, A1, dA), B0b = __funnelshift_r(B0, B1, dB);
+		w[0] = dp2a_hi(lcA.y, A0, dp2a_lo(lcA.x, A0, 0)) >> 7;
+		w[1] = dp2a_hi(lcA.w, A0b, dp2a_lo(lcA.z, A0b, 0)) >> 7;
+		w[2] = dp2a_hi(lcB.y, B0, dp2a_lo(lcB.x, B0, 0)) >> 7;
+		w[3] = dp2a_hi(lcB.w, B0b, dp2a_lo(lcB.z, B0b, 0)) >> 7;
+		la += pitch;
+		lb += pitch;
+	};
+	auto emit = [&]() -> bool {
+		const unsigned clv[4] = {(unsigned)rb.x, (unsigned)rb.y, (unsigned)rb.z, (unsigned)rb.w};
+		++y;
+		unsigned q[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			unsigned a = 1u << 23; // (64 << 12) x 32
+#pragma unroll
+			for (int s = 0; s < VT; ++s) a += (unsigned)WL[s][k] * clv[s];
+			q[k] = a;
+		}
+		rtab += 32;
+		ra = lds128(rtab);
+		rb = lds128(rtab + 16);
+		// bytes 3 of the four sums, in column order
+		const unsigned v = __byte_perm(__byte_perm(q[0], q[1], 0x0073), __byte_perm(q[2], q[3], 0x0073), 0x5410);
+		if (col_ok) *reinterpret_cast<unsigned *>(o) = v;
+		o += S.W;
+		return y == ye;
+	};
+	bool done = false;
+	if (s0 > 0) {
+#pragma unroll
+		for (int s = 1; s < VT; ++s) {
+			if (s >= s0) {
+				hrow(WL[s]);
+				++row;
+			}
+		}
+	}
+#pragma unroll 1
+	while (!done) {
+#pragma unroll
+		for (int s = 0; s < VT; ++s) {
+			if (!done) {
+				hrow(WL[s]);
+#pragma unroll 1
+				while (!done && row == ra.x) done = emit();
+				++row;
+			}
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ stream path
 // The strip kernel's arithmetic with the tile structure removed: every WARP is an independent software pipeline that
 // walks one 128-column strip of a frame from the top of a segment to its bottom.
@@ -1669,6 +1794,10 @@ struct msb200_scaler {
 	int packed422; // 0: no; 1: YUYV/YUY2; 2: UYVY; 3: RGB24; 4: BGR24; 5: RGBA; 6: BGRA  (MSPixConv same-size conversions to I420)
 	bool fast_ok;
 	bool direct;        // geometry outside the tile kernels' TMA box limits: scale_direct_kernel
+	bool pstrip_ok;                   // planar I420 -> I420 (MSSizeConv): scale_plane_strip_kernel applies
+	PlaneStripParams PL, PC;          // luma plane; the two chroma planes
+	size_t smem_pl, smem_pc;
+	CUtensorMap map_py, map_pu, map_pv;
 	cudaStream_t pipe_in, pipe_out;   // host-buffer batches: upload / download streams of the chunk pipeline
 	std::vector<cudaEvent_t> pipe_ev; // (uploaded, computed) per chunk
 	size_t smem_fast;
@@ -2201,10 +2330,67 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			}
 		}
 	}
+	s->pstrip_ok = false;
 	if (direct) { // no tiles, no shared memory
 		s->strip_ok = s->stream_ok = false;
 		*out = s;
 		return MSB200_OK;
+	}
+	// ---- plane strips (MSSizeConv: planar I420 -> I420): per-plane tables, boxes and tile geometry
+	if (!dst_rgb && src_fmt == MSB200_PIX_YUV420P && P.hl_size == 4 && P.hc_size == 4 && (P.vl_size == 1 || P.vl_size == 2 || P.vl_size == 4) &&
+	    (P.vc_size == 1 || P.vc_size == 2 || P.vc_size == 4) && dst_w % 8 == 0 && dst_h % 2 == 0 && (src_w / 2) % 16 == 0 &&
+	    ((size_t)dst_w * dst_h) % 4 == 0 && ((size_t)P.chr_dst_w * P.chr_dst_h) % 4 == 0) {
+		bool ok = true;
+		auto plane_setup = [&](PlaneStripParams &Q, const Filter &hf, const Filter &vf, int vsize, int W, int H, size_t &smem) -> int {
+			for (int16_t c : hf.coef) ok = ok && c >= 0;
+			for (int16_t c : vf.coef) ok = ok && c >= 0;
+			for (int x = 0; x + 1 < W && ok; x += 2) {
+				const int d = hf.pos[(size_t)x + 1] - hf.pos[(size_t)x];
+				ok = d >= 0 && d <= 3;
+			}
+			memset(&Q, 0, sizeof(Q));
+			Q.W = W;
+			Q.H = H;
+			Q.box_w = (max_span(hf, W, ST_TW) + 15 + 15) & ~15;
+			Q.R = 0;
+			for (int R = 16; R >= 4 && !Q.R; R -= 4) // tallest strips whose source box still fits a TMA box and 8 CTAs' smem
+				if (max_span(vf, H, ST_WARPS * R) <= 256 && ((size_t)Q.box_w * max_span(vf, H, ST_WARPS * R) + 4096) * 8 <= 220 * 1024) Q.R = R;
+			ok = ok && Q.R > 0 && Q.box_w <= 256 && msb200_div_up(W, ST_TW) <= ST_MAX_TX && msb200_div_up(H, ST_WARPS * (Q.R ? Q.R : 4)) <= ST_MAX_TY;
+			if (!ok) return MSB200_OK;
+			const int th = ST_WARPS * Q.R;
+			Q.box_h = max_span(vf, H, th);
+			smem = (((size_t)Q.box_w * Q.box_h + 127) & ~(size_t)127) + 16 + 32 * (size_t)(th + 1) + 128;
+			std::vector<StripRow> rows((size_t)H + th + 2);
+			for (int y = 0; y < H; ++y) {
+				StripRow &r = rows[(size_t)y];
+				memset(&r, 0, sizeof(r));
+				const int vp = vf.pos[(size_t)y];
+				r.l_last = vp + vsize - 1;
+				for (int j = 0; j < vsize; ++j) r.cl[(vp + j) % vsize] = 32 * vf.coef[(size_t)y * vsize + j];
+			}
+			for (size_t i = (size_t)H; i < rows.size(); ++i) {
+				rows[i] = rows[(size_t)H - 1];
+				rows[i].l_last = 1 << 30; // padding entries: never reached
+			}
+			for (int tx = 0; tx * ST_TW < W; ++tx) Q.x0[tx] = (short)(hf.pos[(size_t)tx * ST_TW] & ~15);
+			for (int ty = 0; ty * th < H; ++ty) Q.y0[ty] = (short)vf.pos[(size_t)ty * th];
+			void *d_rows = nullptr;
+			MSB200_CUDA(cudaMalloc(&d_rows, rows.size() * sizeof(StripRow)));
+			MSB200_CUDA(cudaMemcpy(d_rows, rows.data(), rows.size() * sizeof(StripRow), cudaMemcpyHostToDevice));
+			Q.rows = (const StripRow *)d_rows;
+			Q.dst_frame_bytes = s->dst_bytes;
+			return MSB200_OK;
+		};
+		int rc;
+		if ((rc = plane_setup(s->PL, s->hl, s->vl, P.vl_size, dst_w, dst_h, s->smem_pl))) return rc;
+		if (ok && (rc = plane_setup(s->PC, s->hc, s->vc, P.vc_size, P.chr_dst_w, P.chr_dst_h, s->smem_pc))) return rc;
+		if (ok) {
+			s->PL.hpos = P.hl_pos; s->PL.hcoef = P.hl_coef; s->PL.n_planes = 1; s->PL.dst_off[0] = 0;
+			s->PC.hpos = P.hc_pos; s->PC.hcoef = P.hc_coef; s->PC.n_planes = 2;
+			s->PC.dst_off[0] = (size_t)dst_w * dst_h;
+			s->PC.dst_off[1] = (size_t)dst_w * dst_h + (size_t)P.chr_dst_w * P.chr_dst_h;
+			s->pstrip_ok = true;
+		}
 	}
 	const size_t mx = s->smem_rgb > s->smem_chroma ? s->smem_rgb : s->smem_chroma;
 	if (mx > 200 * 1024) {
@@ -2239,6 +2425,8 @@ void msb200_scaler_destroy(msb200_scaler *s) {
 	for (cudaEvent_t e : s->pipe_ev) cudaEventDestroy(e);
 	cudaFree(s->d_tables);
 	cudaFree((void *)s->S.rows);
+	cudaFree((void *)s->PL.rows);
+	cudaFree((void *)s->PC.rows);
 	s->src.release();
 	s->dst.release();
 	delete s;
@@ -2357,6 +2545,33 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 		else if (P.vc_size == 2) STRIP_LAUNCH(1, 2);
 		else STRIP_LAUNCH(1, 1);
 #undef STRIP_LAUNCH
+		return MSB200_OK;
+	}
+	if (s->pstrip_ok && s->force_path == 0 && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 4) == 0) {
+		// planar I420 -> I420: one warp per plane strip, Y in one launch, U and V together in a second
+		const char *base = (const char *)d_src;
+		const uint64_t fp = s->src_bytes;
+		if (!(s->cached_src == d_src && s->cached_frames == n_frames)) {
+			if ((r = make_map(&s->map_py, base, (uint64_t)P.src_w, (uint64_t)P.src_h, (uint64_t)n_frames, (uint64_t)P.src_w, fp,
+			                  (uint32_t)s->PL.box_w, (uint32_t)s->PL.box_h))) return r;
+			const char *cb = base + (size_t)P.src_w * P.src_h;
+			if ((r = make_map(&s->map_pu, cb, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h, (uint64_t)n_frames, (uint64_t)P.chr_src_w, fp,
+			                  (uint32_t)s->PC.box_w, (uint32_t)s->PC.box_h))) return r;
+			if ((r = make_map(&s->map_pv, cb + (size_t)P.chr_src_w * P.chr_src_h, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h,
+			                  (uint64_t)n_frames, (uint64_t)P.chr_src_w, fp, (uint32_t)s->PC.box_w, (uint32_t)s->PC.box_h))) return r;
+			s->cached_src = d_src;
+			s->cached_frames = n_frames;
+		}
+#define PSTRIP_LAUNCH(Q, VS, MA, MB, SM)                                                                               \
+	do {                                                                                                               \
+		dim3 g((unsigned)msb200_div_up((Q).W, ST_TW), (unsigned)msb200_div_up((Q).H, ST_WARPS * (Q).R), (unsigned)(n_frames * (Q).n_planes)); \
+		if ((VS) == 4) MSB200_LAUNCH(s->ctx, scale_plane_strip_kernel<4>, g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q); \
+		else if ((VS) == 2) MSB200_LAUNCH(s->ctx, scale_plane_strip_kernel<2>, g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q); \
+		else MSB200_LAUNCH(s->ctx, scale_plane_strip_kernel<1>, g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q);  \
+	} while (0)
+		PSTRIP_LAUNCH(s->PL, P.vl_size, s->map_py, s->map_py, s->smem_pl);
+		PSTRIP_LAUNCH(s->PC, P.vc_size, s->map_pu, s->map_pv, s->smem_pc);
+#undef PSTRIP_LAUNCH
 		return MSB200_OK;
 	}
 	if ((r = scaler_build_maps(s, d_src, n_frames))) return r;

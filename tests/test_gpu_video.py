@@ -299,3 +299,32 @@ def test_scaler_host_batches_flow_through_the_chunk_pipeline(ctx):
         alone = sc.process(frames[i:i + 1])
         assert np.array_equal(got[i], alone[0]), i
     sc.close()
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [
+    (1920, 1080, 1280, 720),   # MSSizeConv's cfg4 step: <4> luma taps, <4> chroma taps (540 -> 360 rows)
+    (1280, 720, 1920, 1080),   # up-scale: <2> taps
+    (640, 480, 640, 480),      # same size: <1> tap (yuv2plane1)
+    (704, 576, 200, 120),      # not reachable by the tiles (3.5x): direct kernel instead
+    (384, 288, 264, 200),      # ragged last tile column (264 = 2 * 128 + 8) and tile row
+    (192, 108, 128, 72),
+])
+def test_sizeconv_i420_plane_strips_bit_exact(ctx, sw, sh, dw, dh):
+    """MSSizeConv (I420 -> I420 bilinear, sizeconv.c:159-169): the plane-strip kernel == oracle == the tile kernels"""
+    L = O.oracle()
+    n = 3
+    frames = _rand_frames(_lib.PIX_YUV420P, sw, sh, n, seed=sw + dh)
+    frames[1] = np.random.default_rng(dh).integers(0, 256, size=frames.shape[1], dtype=np.uint8)
+    sc = F.Scaler(ctx, sw, sh, _lib.PIX_YUV420P, dw, dh, _lib.PIX_YUV420P)
+    got = sc.process(frames)
+    o = L.orc_scaler_new(sw, sh, _lib.PIX_YUV420P, dw, dh, _lib.PIX_YUV420P)
+    for i in range(n):
+        exp = np.zeros(got.shape[1] + 64, np.uint8)
+        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+        bad = np.flatnonzero(got[i] != exp[:-64])
+        assert bad.size == 0, (i, bad.size, bad[:8])
+    L.orc_scaler_free(o)
+    if sc.path != 5:
+        sc.set_path(2)  # the generic tile kernels (scale_plane_kernel)
+        assert np.array_equal(sc.process(frames), got)
+    sc.close()
