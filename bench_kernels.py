@@ -104,7 +104,7 @@ def kernels_bench(ctx, hbm_peak_gbs: float) -> dict:
     ms = _time(ctx, lambda: _lib.check(lib.msb200_nv12_to_i420_dev(ctx.h, nf, P(d_src), i420, sw * sh, 0, sw, sh, sw, sw, 1, 0, P(d_dst))))
     row("nv12_fast_kernel", f"a9 NV12->I420, {nf} frames {sw}x{sh}", nf * i420 * 2, ms, nf, "frames")
     ms = _time(ctx, lambda: _lib.check(lib.msb200_nv12_to_i420_dev(ctx.h, nf, P(d_src), i420, sw * sh, 90, sh, sw, sw, sw, 1, 0, P(d_dst))))
-    row("nv12_generic_kernel(rot90)", f"a9 NV12->I420 rotated 90 degrees, {nf} frames {sw}x{sh}", nf * i420 * 2, ms, nf, "frames")
+    row("nv12_rot_kernel<90>", f"a9 NV12->I420 rotated 90 degrees, {nf} frames {sw}x{sh}", nf * i420 * 2, ms, nf, "frames")
     for name, sf, df, dw, dh, sbytes, dbytes, what in (
             ("scale_plane_strip_kernel", _lib.PIX_YUV420P, _lib.PIX_YUV420P, 1280, 720, i420, 1280 * 720 * 3 // 2, "a8 MSSizeConv I420 1080p -> I420 720p"),
             ("rgb24_to_i420_kernel<0>", _lib.PIX_RGB24, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv RGB24 -> I420 1080p"),

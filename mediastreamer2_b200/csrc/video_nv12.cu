@@ -101,6 +101,96 @@ __global__ void __launch_bounds__(256) nv12_fast_kernel(const uint8_t *__restric
 	reinterpret_cast<int4 *>(pv + (size_t)row * uw)[col] = v;
 }
 
+// ------------------------------------------------------------------------------------------------ tiled rotation
+// Rotation by 90 / 270 degrees at full size (msvideo.c:734-776 with down-scale off) is a byte-matrix transpose plus a
+// flip. The destination-centric generic kernel reads one byte per source ROW per thread (32 sectors per warp load);
+// here a CTA moves a 64 x 64 tile through shared memory instead: phase 1 reads the source rows the tile needs with
+// aligned 32-bit (luma) / 64-bit (CbCr pairs, de-interleaved on the way) loads, flipped as the rotation asks, into
+// T[b][a] = dst(i0 + a, j0 + b); phase 2 gives every thread one 4 x 4 byte block, transposes it in registers (8 PRMT) and
+// writes four coalesced 32-bit words, one per destination row. Both directions of the copy are sector-coalesced.
+//   rotation  90: dst(i, j) = src(row = W - 1 - j, col = i)      rotation 270: dst(i, j) = src(row = j, col = H - 1 - i)
+// with (W, H) the destination plane size; chroma planes likewise on (W/2, H/2) with 2-byte source pixels.
+#define ROT_T 64
+#define ROT_PITCH 17 // words per tile row: 64 bytes + 4 of padding
+__device__ __forceinline__ unsigned rot_prmt(unsigned a, unsigned b, unsigned sel) {
+	unsigned d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
+// phase 2: tile words -> destination plane (tight rows of `W` bytes)
+__device__ __forceinline__ void rot_store_tile(const unsigned *T, uint8_t *plane, int W, int H, int i0, int j0) {
+	const int t = threadIdx.x, b4 = t & 15, a4 = t >> 4; // 16 x 16 blocks of 4 x 4 bytes
+	const unsigned r0 = T[(4 * b4 + 0) * ROT_PITCH + a4], r1 = T[(4 * b4 + 1) * ROT_PITCH + a4];
+	const unsigned r2 = T[(4 * b4 + 2) * ROT_PITCH + a4], r3 = T[(4 * b4 + 3) * ROT_PITCH + a4];
+	const unsigned t0 = rot_prmt(r0, r1, 0x5140), t1 = rot_prmt(r2, r3, 0x5140);
+	const unsigned t2 = rot_prmt(r0, r1, 0x7362), t3 = rot_prmt(r2, r3, 0x7362);
+	const unsigned o[4] = {rot_prmt(t0, t1, 0x5410), rot_prmt(t0, t1, 0x7632), rot_prmt(t2, t3, 0x5410), rot_prmt(t2, t3, 0x7632)};
+	const int j = j0 + 4 * b4;
+	if (j < W) { // W % 4 == 0: a block is inside or outside as a whole
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int i = i0 + 4 * a4 + k;
+			if (i < H) *reinterpret_cast<unsigned *>(plane + (size_t)i * W + j) = o[k];
+		}
+	}
+}
+template <int ROT>
+__global__ void __launch_bounds__(256) nv12_rot_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, Nv12Params p) {
+	__shared__ unsigned TU[ROT_T * ROT_PITCH], TV[ROT_T * ROT_PITCH];
+	const int W = p.w, H = p.h, uw = W / 2, uh = H / 2;
+	const int ltx = (W + ROT_T - 1) / ROT_T, lty = (H + ROT_T - 1) / ROT_T, n_lt = ltx * lty;
+	const int ctx_ = (uw + ROT_T - 1) / ROT_T;
+	const uint8_t *fs = src + (size_t)blockIdx.y * p.src_frame_bytes;
+	uint8_t *fd = dst + (size_t)blockIdx.y * p.dst_frame_bytes;
+	const int t = threadIdx.x;
+	if ((int)blockIdx.x < n_lt) { // ---- luma tile
+		const int i0 = ((int)blockIdx.x / ltx) * ROT_T, j0 = ((int)blockIdx.x % ltx) * ROT_T;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int idx = t + 256 * q, b = idx >> 4, a4 = idx & 15; // tile row b (dst column j0 + b), word a4 (dst rows i0 + 4a4 ..)
+			const int j = j0 + b, i = i0 + 4 * a4;
+			unsigned v = 0;
+			if (j < W && i < H) {
+				if (ROT == 90) v = __ldg(reinterpret_cast<const unsigned *>(fs + (size_t)(W - 1 - j) * p.ys + i));
+				else v = rot_prmt(__ldg(reinterpret_cast<const unsigned *>(fs + (size_t)j * p.ys + (H - 4 - i))), 0u, 0x0123);
+			}
+			TU[b * ROT_PITCH + a4] = v;
+		}
+		__syncthreads();
+		rot_store_tile(TU, fd, W, H, i0, j0);
+		return;
+	}
+	// ---- chroma tile: the same walk over (uw, uh) with CbCr pairs as source pixels, two destination planes
+	const int c = (int)blockIdx.x - n_lt;
+	const int i0 = (c / ctx_) * ROT_T, j0 = (c % ctx_) * ROT_T;
+	const uint8_t *cb = fs + p.cbcr_offset;
+	const size_t cpitch = (size_t)(p.cs / 2) * 2;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const int idx = t + 256 * q, b = idx >> 4, a4 = idx & 15;
+		const int j = j0 + b, i = i0 + 4 * a4;
+		unsigned u = 0, v = 0;
+		if (j < uw && i < uh) {
+			uint2 w2;
+			if (ROT == 90) w2 = __ldg(reinterpret_cast<const uint2 *>(cb + (size_t)(uw - 1 - j) * cpitch + (size_t)i * 2));
+			else w2 = __ldg(reinterpret_cast<const uint2 *>(cb + (size_t)j * cpitch + (size_t)(uh - 4 - i) * 2));
+			u = rot_prmt(w2.x, w2.y, 0x6420); // Cb of the four pixels, in address order
+			v = rot_prmt(w2.x, w2.y, 0x7531);
+			if (ROT != 90) {
+				u = rot_prmt(u, 0u, 0x0123);
+				v = rot_prmt(v, 0u, 0x0123);
+			}
+		}
+		TU[b * ROT_PITCH + a4] = u;
+		TV[b * ROT_PITCH + a4] = v;
+	}
+	__syncthreads();
+	uint8_t *pu = fd + (size_t)W * H + (p.u_first ? 0 : (size_t)uw * uh);
+	uint8_t *pv = fd + (size_t)W * H + (p.u_first ? (size_t)uw * uh : 0);
+	rot_store_tile(TU, pu, uw, uh, i0, j0);
+	rot_store_tile(TV, pv, uw, uh, i0, j0);
+}
+
 // ------------------------------------------------------------------------------------------------ packed 4:2:2 -> I420
 // MSPixConv's YUYV / UYVY / YUY2 inputs (src/videofilters/pixconv.c:62-94 -> ms_scaler_process at the same size): luma
 // copied, chroma = rounded average of the two source lines (what libswscale's unscaled yuyv/uyvy -> yuv420p converters
@@ -294,7 +384,16 @@ int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void *d_src, si
 	const bool fast = rotation == 0 && !down_scale && (w % 32) == 0 && (y_stride % 16) == 0 && (cbcr_stride % 16) == 0 &&
 	                  (cbcr_offset % 16) == 0 && (src_frame_bytes % 16) == 0 && ((uintptr_t)d_src % 16) == 0 &&
 	                  ((uintptr_t)d_dst % 16) == 0 && (((size_t)w * h / 4) % 16) == 0;
-	if (fast) {
+	const bool tiled_rot = (rotation == 90 || rotation == 270) && !down_scale && (w % 8) == 0 && (h % 8) == 0 && (y_stride % 4) == 0 &&
+	                       (cbcr_stride % 8) == 0 && (cbcr_offset % 8) == 0 && (src_frame_bytes % 8) == 0 &&
+	                       ((uintptr_t)d_src % 8) == 0 && ((uintptr_t)d_dst % 4) == 0;
+	if (tiled_rot) {
+		const int n_lt = ((w + ROT_T - 1) / ROT_T) * ((h + ROT_T - 1) / ROT_T);
+		const int n_ct = ((w / 2 + ROT_T - 1) / ROT_T) * ((h / 2 + ROT_T - 1) / ROT_T);
+		dim3 grid((unsigned)(n_lt + n_ct), (unsigned)n_frames);
+		if (rotation == 90) MSB200_LAUNCH(ctx, nv12_rot_kernel<90>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, p);
+		else MSB200_LAUNCH(ctx, nv12_rot_kernel<270>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, p);
+	} else if (fast) {
 		long threads = (long)(w / 16) * h + (long)(w / 32) * (h / 2);
 		dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
 		MSB200_LAUNCH(ctx, nv12_fast_kernel, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, p);
