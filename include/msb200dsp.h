@@ -251,6 +251,29 @@ MSB200_API int msb200_aec_set_state_blob(msb200_aec *a, int stream, const void *
  * "prop","noise","echo_noise","gain2", scalar pack "scalars"). Returns number of floats written or <0. */
 MSB200_API int msb200_aec_probe(msb200_aec *a, int stream, const char *what, float *out, int max_floats);
 
+/* ---------------------------------------------------------------------------------------------------- MSAudioFlowControl
+ * ms_audio_flow_controller_process() /root/reference/src/audiofilters/flowcontrol.c:110-150 (+ :58-108): while a drop
+ * target is armed (ms_audio_flow_controller_set_target :51-56, from MS_AUDIO_FLOW_CONTROL_DROP :196-207) a block passes,
+ * is dropped whole, or loses a few samples at the flattest three-sample runs. One block of `nsamples` per stream per
+ * call, in place; out_nsamples[stream] = samples that remain (0: block dropped). Bit-exact. */
+#define MSB200_FLOWCONTROL_BASIC 0 /* MSAudioFlowControlBasic */
+#define MSB200_FLOWCONTROL_SOFT 1  /* MSAudioFlowControlSoft */
+typedef struct msb200_flowcontrol msb200_flowcontrol;
+typedef struct msb200_flowcontrol_state { /* MSAudioFlowController, include/mediastreamer2/flowcontrol.h:37-43 */
+	int32_t strategy;
+	float silent_threshold;
+	uint32_t target_samples, total_samples, current_pos, current_dropped;
+} msb200_flowcontrol_state;
+MSB200_API int msb200_flowcontrol_create(msb200_ctx *ctx, int n_streams, int max_block, msb200_flowcontrol **out);
+MSB200_API void msb200_flowcontrol_destroy(msb200_flowcontrol *f);
+MSB200_API int msb200_flowcontrol_set_config(msb200_flowcontrol *f, int stream, int strategy, float silent_threshold);
+MSB200_API int msb200_flowcontrol_set_target(msb200_flowcontrol *f, int stream, uint32_t samples_to_drop, uint32_t total_samples);
+MSB200_API int msb200_flowcontrol_reset(msb200_flowcontrol *f, int stream);
+MSB200_API int msb200_flowcontrol_get_state(msb200_flowcontrol *f, int stream, msb200_flowcontrol_state *st);
+MSB200_API int msb200_flowcontrol_process(msb200_flowcontrol *f, int16_t *io, int nsamples, int32_t *out_nsamples);
+MSB200_API int msb200_flowcontrol_process_dev(msb200_flowcontrol *f, void *d_io, int nsamples, int stride_samples,
+                                              void *d_out_nsamples);
+
 /* ---------------------------------------------------------------------------------------------------- G.711
  * MSAlawDec / MSUlawDec (/root/reference/src/audiofilters/alaw.c:199-211, ulaw.c) and the arithmetic of MSAlawEnc /
  * MSUlawEnc (alaw.c:84-87): Snack_Alaw2Lin / Snack_Mulaw2Lin / Snack_Lin2Alaw / Snack_Lin2Mulaw

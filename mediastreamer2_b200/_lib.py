@@ -91,6 +91,14 @@ _SIGS = {
     "msb200_volume_create": (_I, [_P, _I, _I, _I, _PP]),
     "msb200_volume_destroy": (None, [_P]),
     "msb200_ctx_make_current": (_I, [_P]),
+    "msb200_flowcontrol_create": (_I, [_P, _I, _I, _PP]),
+    "msb200_flowcontrol_destroy": (None, [_P]),
+    "msb200_flowcontrol_set_config": (_I, [_P, _I, _I, _F]),
+    "msb200_flowcontrol_set_target": (_I, [_P, _I, C.c_uint32, C.c_uint32]),
+    "msb200_flowcontrol_reset": (_I, [_P, _I]),
+    "msb200_flowcontrol_get_state": (_I, [_P, _I, _P]),
+    "msb200_flowcontrol_process": (_I, [_P, _P, _I, _P]),
+    "msb200_flowcontrol_process_dev": (_I, [_P, _P, _I, _I, _P]),
     "msb200_g711_decode": (_I, [_P, _I, _P, _P, _SZ]),
     "msb200_g711_encode": (_I, [_P, _I, _P, _P, _SZ]),
     "msb200_g711_decode_dev": (_I, [_P, _I, _P, _P, _SZ]),

@@ -917,3 +917,214 @@ int msb200_equalizer_process(msb200_equalizer *e, int16_t *io, int nsamples) {
 }
 
 } // extern "C"
+
+// ======================================================================================================= flow control
+// MSAudioFlowControl: ms_audio_flow_controller_process() /root/reference/src/audiofilters/flowcontrol.c
+// :110-150 — while a drop target is armed, every block either passes, is dropped whole (basic strategy; almost silent
+// frame; too many samples to delete) or loses `todrop` samples, each taken from the middle of the flattest three-sample
+// run (discard_well_choosed_samples :58-92; ties go to the LAST position). Integer work, bit-exact; the frame power is
+// the reference's sequential float32 sum (one thread, additions in order). One CTA per stream: the block lives in
+// shared memory, every deletion is a block-wide arg-min followed by a shifted copy between two buffers.
+struct msb200_flowcontrol {
+	msb200_ctx *ctx;
+	int n, max_block;
+	msb200_flowcontrol_state *d_state;
+	int *d_out_n;
+	msb200_devbuf io;
+};
+
+__global__ void __launch_bounds__(128) flowctl_kernel(short *__restrict__ io, int stride, int nsamples,
+                                                      msb200_flowcontrol_state *__restrict__ st, int *__restrict__ out_n, int n_streams) {
+	extern __shared__ short fsm[];
+	short *cur = fsm, *nxt = fsm + ((nsamples + 1) & ~1);
+	__shared__ int sh_mode, sh_todrop, sh_val[4], sh_pos[4];
+	const int stream = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	if (stream >= n_streams) return;
+	short *g = io + (size_t)stream * stride;
+	for (int i = t; i < nsamples; i += blockDim.x) cur[i] = g[i];
+	__syncthreads();
+	if (t == 0) {
+		msb200_flowcontrol_state c = st[stream];
+		int mode = 0; // 0 pass, 1 drop the block, 2 delete sh_todrop samples
+		unsigned todrop = 0;
+		const unsigned n = (unsigned)nsamples;
+		if (c.total_samples > 0 && c.target_samples > 0) {
+			c.current_pos += n;
+			if (c.strategy == 0) {
+				if (c.current_dropped + n <= c.target_samples) {
+					c.current_dropped += n;
+					mode = 1;
+				}
+			} else {
+				const unsigned th = (unsigned)(((unsigned long long)c.target_samples * (unsigned long long)c.current_pos) /
+				                               (unsigned long long)c.total_samples);
+				todrop = th > c.current_dropped ? th - c.current_dropped : 0;
+				if (todrop > 0) {
+					bool silent = false;
+					if (n <= c.target_samples) { // compute_frame_power :100-108
+						float acc = 0.f;
+						for (unsigned i = 0; i < n; ++i) {
+							const int v = cur[i];
+							acc = __fadd_rn(acc, (float)(v * v));
+						}
+						silent = __fdiv_rn(sqrtf(__fdiv_rn(acc, (float)n)), 32768 * 0.7f) < c.silent_threshold;
+					}
+					if (silent || !(todrop * 8 < n)) {
+						todrop = n;
+						mode = 1;
+					} else {
+						mode = 2;
+					}
+					c.current_dropped += todrop;
+				}
+			}
+			if (c.current_pos >= c.total_samples) c.target_samples = 0;
+			st[stream] = c;
+		}
+		sh_mode = mode;
+		sh_todrop = (int)todrop;
+	}
+	__syncthreads();
+	const int mode = sh_mode;
+	int n = nsamples;
+	if (mode == 1) {
+		if (t == 0) out_n[stream] = 0;
+		return;
+	}
+	if (mode == 2) {
+		for (int d = 0; d < sh_todrop; ++d) {
+			// arg-min of |s[i]-s[i+1]| + |s[i+1]-s[i+2]| over i < n-2, the LAST position among equal minima
+			int best = 32768 * 4, pos = 0;
+			for (int i = t; i + 2 < n; i += blockDim.x) {
+				const int a = cur[i], b = cur[i + 1], c2 = cur[i + 2];
+				const int v = abs(a - b) + abs(b - c2);
+				if (v <= best) {
+					best = v;
+					pos = i;
+				}
+			}
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				const int ob = __shfl_xor_sync(0xffffffffu, best, o), op = __shfl_xor_sync(0xffffffffu, pos, o);
+				if (ob < best || (ob == best && op > pos)) {
+					best = ob;
+					pos = op;
+				}
+			}
+			if (lane == 0) {
+				sh_val[warp] = best;
+				sh_pos[warp] = pos;
+			}
+			__syncthreads();
+			best = sh_val[0];
+			pos = sh_pos[0];
+#pragma unroll
+			for (int w = 1; w < 4; ++w)
+				if (sh_val[w] < best || (sh_val[w] == best && sh_pos[w] > pos)) {
+					best = sh_val[w];
+					pos = sh_pos[w];
+				}
+			// the reference starts from min_diff = 32768 with `<=`: a run whose measure exceeds it is never selected and
+			// position 0 is removed instead (cannot happen for 16-bit samples: the measure is <= 2 * 65535... it can)
+			if (best > 32768) pos = 0;
+			for (int i = t; i < n - 1; i += blockDim.x) nxt[i] = cur[i <= pos ? i : i + 1];
+			--n;
+			__syncthreads();
+			short *sw = cur;
+			cur = nxt;
+			nxt = sw;
+		}
+		for (int i = t; i < n; i += blockDim.x) g[i] = cur[i];
+	}
+	if (t == 0) out_n[stream] = n;
+}
+
+extern "C" {
+
+static void flowctl_state_init(msb200_flowcontrol_state *s) { // ms_audio_flow_controller_init :37-41
+	memset(s, 0, sizeof(*s));
+	s->strategy = MSB200_FLOWCONTROL_SOFT;
+	s->silent_threshold = 0.02f;
+}
+int msb200_flowcontrol_create(msb200_ctx *ctx, int n_streams, int max_block, msb200_flowcontrol **out) {
+	MSB200_CHECK_ARG(ctx && out && n_streams > 0 && max_block >= 3 && max_block <= 8192);
+	msb200_flowcontrol *f = new msb200_flowcontrol();
+	f->ctx = ctx;
+	f->n = n_streams;
+	f->max_block = max_block;
+	std::vector<msb200_flowcontrol_state> init((size_t)n_streams);
+	for (auto &s : init) flowctl_state_init(&s);
+	MSB200_CUDA(cudaMalloc(&f->d_state, sizeof(msb200_flowcontrol_state) * (size_t)n_streams));
+	MSB200_CUDA(cudaMalloc(&f->d_out_n, sizeof(int) * (size_t)n_streams));
+	MSB200_CUDA(cudaMemcpy(f->d_state, init.data(), sizeof(msb200_flowcontrol_state) * (size_t)n_streams, cudaMemcpyHostToDevice));
+	*out = f;
+	return MSB200_OK;
+}
+void msb200_flowcontrol_destroy(msb200_flowcontrol *f) {
+	if (!f) return;
+	cudaStreamSynchronize(f->ctx->stream);
+	cudaFree(f->d_state);
+	cudaFree(f->d_out_n);
+	f->io.release();
+	delete f;
+}
+int msb200_flowcontrol_get_state(msb200_flowcontrol *f, int stream, msb200_flowcontrol_state *st) {
+	MSB200_CHECK_ARG(f && st && stream >= 0 && stream < f->n);
+	MSB200_CUDA(cudaMemcpyAsync(st, f->d_state + stream, sizeof(*st), cudaMemcpyDeviceToHost, f->ctx->stream));
+	MSB200_CUDA(cudaStreamSynchronize(f->ctx->stream));
+	return MSB200_OK;
+}
+static int flowctl_put_state(msb200_flowcontrol *f, int stream, const msb200_flowcontrol_state *st) {
+	MSB200_CUDA(cudaMemcpyAsync(f->d_state + stream, st, sizeof(*st), cudaMemcpyHostToDevice, f->ctx->stream));
+	MSB200_CUDA(cudaStreamSynchronize(f->ctx->stream));
+	return MSB200_OK;
+}
+int msb200_flowcontrol_set_config(msb200_flowcontrol *f, int stream, int strategy, float silent_threshold) {
+	MSB200_CHECK_ARG(f && stream >= 0 && stream < f->n && (strategy == MSB200_FLOWCONTROL_BASIC || strategy == MSB200_FLOWCONTROL_SOFT));
+	msb200_flowcontrol_state st;
+	int r = msb200_flowcontrol_get_state(f, stream, &st);
+	if (r) return r;
+	st.strategy = strategy;
+	st.silent_threshold = silent_threshold;
+	return flowctl_put_state(f, stream, &st);
+}
+int msb200_flowcontrol_set_target(msb200_flowcontrol *f, int stream, uint32_t samples_to_drop, uint32_t total_samples) {
+	MSB200_CHECK_ARG(f && stream >= 0 && stream < f->n);
+	msb200_flowcontrol_state st;
+	int r = msb200_flowcontrol_get_state(f, stream, &st);
+	if (r) return r;
+	st.target_samples = samples_to_drop; // ms_audio_flow_controller_set_target :51-56
+	st.total_samples = total_samples;
+	st.current_pos = 0;
+	st.current_dropped = 0;
+	return flowctl_put_state(f, stream, &st);
+}
+int msb200_flowcontrol_reset(msb200_flowcontrol *f, int stream) { // ms_audio_flow_controller_reset :30-35 (the configuration stays)
+	MSB200_CHECK_ARG(f && stream >= 0 && stream < f->n);
+	msb200_flowcontrol_state st;
+	int r = msb200_flowcontrol_get_state(f, stream, &st);
+	if (r) return r;
+	st.target_samples = st.total_samples = st.current_pos = st.current_dropped = 0;
+	return flowctl_put_state(f, stream, &st);
+}
+int msb200_flowcontrol_process_dev(msb200_flowcontrol *f, void *d_io, int nsamples, int stride, void *d_out_nsamples) {
+	MSB200_CHECK_ARG(f && d_io && d_out_nsamples && nsamples >= 3 && nsamples <= f->max_block && stride >= nsamples);
+	const size_t smem = 2 * sizeof(short) * (size_t)((nsamples + 1) & ~1);
+	MSB200_LAUNCH(f->ctx, flowctl_kernel, f->n, 128, smem, (short *)d_io, stride, nsamples, f->d_state, (int *)d_out_nsamples, f->n);
+	return MSB200_OK;
+}
+int msb200_flowcontrol_process(msb200_flowcontrol *f, int16_t *io, int nsamples, int32_t *out_nsamples) {
+	MSB200_CHECK_ARG(f && io && out_nsamples);
+	const size_t bytes = (size_t)f->n * nsamples * 2;
+	int r = f->io.reserve(bytes);
+	if (r) return r;
+	cudaStream_t s = f->ctx->stream;
+	MSB200_CUDA(cudaMemcpyAsync(f->io.p, io, bytes, cudaMemcpyHostToDevice, s));
+	if ((r = msb200_flowcontrol_process_dev(f, f->io.p, nsamples, nsamples, f->d_out_n))) return r;
+	MSB200_CUDA(cudaMemcpyAsync(io, f->io.p, bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaMemcpyAsync(out_nsamples, f->d_out_n, sizeof(int) * (size_t)f->n, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaStreamSynchronize(s));
+	return MSB200_OK;
+}
+
+} // extern "C"

@@ -450,3 +450,43 @@ def g711_decode_dev(ctx: Context, law: int, d_code: int, d_pcm: int, n: int):
 
 def g711_encode_dev(ctx: Context, law: int, d_pcm: int, d_code: int, n: int):
     check(ctx.lib.msb200_g711_encode_dev(ctx.h, law, C.c_void_p(d_pcm), C.c_void_p(d_code), n))
+
+
+class FlowControlState(C.Structure):  # msb200_flowcontrol_state
+    _fields_ = [("strategy", C.c_int32), ("silent_threshold", C.c_float), ("target_samples", C.c_uint32),
+                ("total_samples", C.c_uint32), ("current_pos", C.c_uint32), ("current_dropped", C.c_uint32)]
+
+
+class FlowControl:
+    """n x MSAudioFlowControl (flowcontrol.c:110-150): blocks pass, are dropped, or lose a few well chosen samples."""
+
+    BASIC, SOFT = 0, 1
+
+    def __init__(self, ctx: Context, n_streams: int, max_block: int = 960):
+        self.ctx, self.lib, self.n = ctx, ctx.lib, n_streams
+        h = C.c_void_p()
+        check(self.lib.msb200_flowcontrol_create(ctx.h, n_streams, max_block, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.msb200_flowcontrol_destroy(self.h)
+            self.h = None
+
+    def set_config(self, stream: int, strategy: int, silent_threshold: float = 0.02):
+        check(self.lib.msb200_flowcontrol_set_config(self.h, stream, strategy, silent_threshold))
+
+    def set_target(self, stream: int, samples_to_drop: int, total_samples: int):
+        check(self.lib.msb200_flowcontrol_set_target(self.h, stream, samples_to_drop, total_samples))
+
+    def state(self, stream: int) -> FlowControlState:
+        st = FlowControlState()
+        check(self.lib.msb200_flowcontrol_get_state(self.h, stream, C.byref(st)))
+        return st
+
+    def process(self, pcm: np.ndarray):
+        """pcm [n][nsamples] s16 -> (pcm processed in place copy, remaining sample count per stream)"""
+        io = np.array(_req(pcm, np.int16).reshape(self.n, -1), copy=True)
+        out_n = np.zeros(self.n, np.int32)
+        check(self.lib.msb200_flowcontrol_process(self.h, _ptr(io), io.shape[1], _ptr(out_n)))
+        return io, out_n

@@ -100,6 +100,16 @@ int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst);
 int orc_scaler_get_filter(orc_scaler *s, int which /*0 lumH,1 chrH,2 lumV,3 chrV*/, int32_t *pos, int16_t *coef,
                           int max_entries);
 
+/* MSAudioFlowControl (oracle_audio.c) */
+typedef struct orc_flowctl {
+	int32_t strategy; /* 0 basic, 1 soft */
+	float silent_threshold;
+	uint32_t target_samples, total_samples, current_pos, current_dropped;
+} orc_flowctl;
+void orc_flowctl_init(orc_flowctl *c);
+void orc_flowctl_set_target(orc_flowctl *c, uint32_t samples_to_drop, uint32_t total_samples);
+int orc_flowctl_process(orc_flowctl *c, int16_t *samples, int nsamples);
+
 /* G.711 (oracle_g711.c): law 0 = A-law, 1 = mu-law */
 void orc_g711_encode(int law, const int16_t *pcm, uint8_t *code, size_t n);
 void orc_g711_decode(int law, const uint8_t *code, int16_t *pcm, size_t n);

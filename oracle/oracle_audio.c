@@ -339,3 +339,70 @@ void orc_equalizer_process(orc_equalizer *s, int16_t *io, int n) { /* equalizer_
 	if (s->needs_update) eq_compute_impulse_response(s);
 	orc_fir_s16(s->fir, s->nfft, s->mem, io, n);
 }
+
+/* ---------------------------------------------------------------------------------------------------- MSAudioFlowControl
+ * ms_audio_flow_controller_process() /root/reference/src/audiofilters/flowcontrol.c:110-150 with its helpers
+ * discard_well_choosed_samples :58-92 (three-sample criterion, ties resolved towards the LAST position: `<=`) and
+ * compute_frame_power :100-108 (sequential float32 sum, sqrtf). Restated iteratively. Pinned bit-exact against the
+ * unmodified reference filter in an MSTicker (tests/test_oracle_vs_reference.py::test_flowcontrol_*). */
+void orc_flowctl_init(orc_flowctl *c) {
+	c->strategy = 1; /* MSAudioFlowControlSoft */
+	c->silent_threshold = 0.02f;
+	c->target_samples = c->total_samples = c->current_pos = c->current_dropped = 0;
+}
+void orc_flowctl_set_target(orc_flowctl *c, uint32_t samples_to_drop, uint32_t total_samples) {
+	c->target_samples = samples_to_drop;
+	c->total_samples = total_samples;
+	c->current_pos = 0;
+	c->current_dropped = 0;
+}
+/* processes one block in place; returns the number of samples that remain (0: the block is dropped) */
+int orc_flowctl_process(orc_flowctl *c, int16_t *s, int nsamples) {
+	uint32_t n = (uint32_t)nsamples;
+	if (!(c->total_samples > 0 && c->target_samples > 0)) return nsamples;
+	c->current_pos += n;
+	if (c->strategy == 0) { /* basic: whole blocks while they fit in the target */
+		if (c->current_dropped + n <= c->target_samples) {
+			c->current_dropped += n;
+			n = 0;
+		}
+	} else {
+		const uint32_t th = (uint32_t)(((uint64_t)c->target_samples * (uint64_t)c->current_pos) / (uint64_t)c->total_samples);
+		uint32_t todrop = th > c->current_dropped ? th - c->current_dropped : 0;
+		if (todrop > 0) {
+			int silent = 0;
+			if (n <= c->target_samples) {
+				float acc = 0;
+				for (uint32_t i = 0; i < n; ++i) {
+					const int v = s[i];
+					acc += (float)(v * v);
+				}
+				silent = sqrtf(acc / (float)n) / (32768 * 0.7f) < c->silent_threshold;
+			}
+			if (silent) {
+				todrop = n;
+				n = 0;
+			} else if (todrop * 8 < n) {
+				for (uint32_t d = 0; d < todrop; ++d) { /* remove the middle sample of the flattest three-sample run */
+					int best = 32768;
+					uint32_t pos = 0;
+					for (uint32_t i = 0; i + 2 < n; ++i) {
+						const int t = abs((int)s[i] - (int)s[i + 1]) + abs((int)s[i + 1] - (int)s[i + 2]);
+						if (t <= best) {
+							best = t;
+							pos = i;
+						}
+					}
+					memmove(s + pos + 1, s + pos + 2, (size_t)(n - pos - 2) * sizeof(int16_t));
+					--n;
+				}
+			} else {
+				todrop = n;
+				n = 0;
+			}
+			c->current_dropped += todrop;
+		}
+	}
+	if (c->current_pos >= c->total_samples) c->target_samples = 0;
+	return (int)n;
+}

@@ -13,6 +13,7 @@
 #include "mediastreamer2/msaudiomixer.h"
 #include "mediastreamer2/mschanadapter.h"
 #include "mediastreamer2/msequalizer.h"
+#include "mediastreamer2/flowcontrol.h"
 #include "mediastreamer2/msfactory.h"
 #include "mediastreamer2/msfilter.h"
 #include "mediastreamer2/msinterfaces.h"
@@ -333,6 +334,8 @@ unsigned int ref_method_id(const char *name) {
 	MID(MS_FILTER_ADD_ATTR);
 	MID(MS_AUDIO_ENCODER_GET_PTIME);
 	MID(MS_DECODER_HAVE_PLC);
+	MID(MS_AUDIO_FLOW_CONTROL_SET_CONFIG);
+	MID(MS_AUDIO_FLOW_CONTROL_DROP);
 	return 0;
 }
 

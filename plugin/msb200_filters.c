@@ -23,6 +23,7 @@
  *
  * Compiled against the host's mediastreamer2 / oRTP / bctoolbox headers (here: /root/reference/include + compat/).
  */
+#include "mediastreamer2/flowcontrol.h"
 #include "mediastreamer2/msaudiomixer.h"
 #include "mediastreamer2/mschanadapter.h"
 #include "mediastreamer2/msequalizer.h"
@@ -2104,6 +2105,137 @@ static MSFilterDesc b200_ulaw_dec_desc = {.id = MS_ULAW_DEC_ID, .name = "MSUlawD
                                           .init = ulaw_dec_init, .process = ulaw_dec_process, .postprocess = g711_dec_postprocess,
                                           .uninit = g711_dec_uninit, .methods = g711_dec_methods};
 
+/* ================================================================================================ MSAudioFlowControl
+ * /root/reference/src/audiofilters/flowcontrol.c:152-279: filter shell (state, methods, drop request in ms -> samples
+ * :196-207) on the host, ms_audio_flow_controller_process() :110-150 on the GPU (msb200_flowcontrol_*). Synchronous mode:
+ * the controller is only armed for a few hundred ms after a drop event; a disarmed controller forwards blocks untouched
+ * without any device call, exactly as the reference's `running` test does (:94-96). */
+typedef struct FlowCtlState {
+	msb200_flowcontrol *bank; /* 1 stream */
+	int samplerate, nchannels, max_block;
+	int strategy;
+	float silent_threshold;
+	bool_t armed; /* host mirror of ms_audio_flow_controller_running() */
+} FlowCtlState;
+#define FLOWCTL_MAX_BLOCK 8192
+static void flowctl_init(MSFilter *f) {
+	FlowCtlState *s = ms_new0(FlowCtlState, 1);
+	s->strategy = MSB200_FLOWCONTROL_SOFT;
+	s->silent_threshold = 0.02f;
+	f->data = s;
+}
+static void flowctl_ensure_bank(FlowCtlState *s) { /* DSP lock held */
+	if (s->bank || !dsp_ctx()) return;
+	DSP_CHECK(msb200_flowcontrol_create(g_ctx, 1, FLOWCTL_MAX_BLOCK, &s->bank), "flowcontrol_create");
+	if (s->bank) msb200_flowcontrol_set_config(s->bank, 0, s->strategy, s->silent_threshold);
+}
+static void flowctl_preprocess(MSFilter *f) { /* ms_audio_flow_controller_reset */
+	FlowCtlState *s = (FlowCtlState *)f->data;
+	DSP_LOCK();
+	flowctl_ensure_bank(s);
+	if (s->bank) msb200_flowcontrol_reset(s->bank, 0);
+	DSP_UNLOCK();
+	s->armed = FALSE;
+}
+static void flowctl_process(MSFilter *f) {
+	FlowCtlState *s = (FlowCtlState *)f->data;
+	mblk_t *m;
+	ms_filter_lock(f);
+	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+		const int n = (int)((m->b_wptr - m->b_rptr) / 2);
+		int32_t left = n;
+		if (s->armed && s->bank && n >= 3 && n <= FLOWCTL_MAX_BLOCK) {
+			msb200_flowcontrol_state st;
+			int rc;
+			DSP_LOCK();
+			rc = msb200_flowcontrol_process(s->bank, (int16_t *)m->b_rptr, n, &left);
+			if (rc == MSB200_OK) rc = msb200_flowcontrol_get_state(s->bank, 0, &st);
+			DSP_UNLOCK();
+			if (rc != MSB200_OK) {
+				ms_error("msb200: flowcontrol_process failed: %s", msb200_last_error());
+				left = n;
+			} else {
+				s->armed = st.total_samples > 0 && st.target_samples > 0;
+			}
+		}
+		if (left <= 0) {
+			freemsg(m);
+			continue;
+		}
+		m->b_wptr = m->b_rptr + (size_t)left * 2;
+		ms_queue_put(f->outputs[0], m);
+	}
+	ms_filter_unlock(f);
+}
+static void flowctl_uninit(MSFilter *f) {
+	FlowCtlState *s = (FlowCtlState *)f->data;
+	DSP_LOCK();
+	msb200_flowcontrol_destroy(s->bank);
+	DSP_UNLOCK();
+	ms_free(s);
+}
+static int flowctl_set_config(MSFilter *f, void *arg) {
+	FlowCtlState *s = (FlowCtlState *)f->data;
+	const MSAudioFlowControlConfig *cfg = (const MSAudioFlowControlConfig *)arg;
+	s->strategy = cfg->strategy == MSAudioFlowControlBasic ? MSB200_FLOWCONTROL_BASIC : MSB200_FLOWCONTROL_SOFT;
+	s->silent_threshold = cfg->silent_threshold;
+	ms_message("MSAudioFlowControl(b200): configured with strategy=[%i] and silent_threshold=[%f].", cfg->strategy, cfg->silent_threshold);
+	DSP_LOCK();
+	if (s->bank) msb200_flowcontrol_set_config(s->bank, 0, s->strategy, s->silent_threshold);
+	DSP_UNLOCK();
+	return 0;
+}
+static int flowctl_drop(MSFilter *f, void *arg) { /* ms_audio_flow_control_drop :196-207 */
+	FlowCtlState *s = (FlowCtlState *)f->data;
+	const MSAudioFlowControlDropEvent *ev = (const MSAudioFlowControlDropEvent *)arg;
+	ms_filter_lock(f);
+	if (!s->armed) {
+		const uint32_t drop = (ev->drop_ms * (uint32_t)s->samplerate * (uint32_t)s->nchannels) / 1000;
+		const uint32_t total = (ev->flow_control_interval_ms * (uint32_t)s->samplerate * (uint32_t)s->nchannels) / 1000;
+		ms_message("MSAudioFlowControl(b200): requested to drop %i ms ", (int)ev->drop_ms);
+		DSP_LOCK();
+		flowctl_ensure_bank(s);
+		if (s->bank && msb200_flowcontrol_set_target(s->bank, 0, drop, total) == MSB200_OK) s->armed = total > 0 && drop > 0;
+		DSP_UNLOCK();
+	}
+	ms_filter_unlock(f);
+	return 0;
+}
+static int flowctl_set_sr(MSFilter *f, void *arg) {
+	((FlowCtlState *)f->data)->samplerate = *(int *)arg;
+	return 0;
+}
+static int flowctl_get_sr(MSFilter *f, void *arg) {
+	*(int *)arg = ((FlowCtlState *)f->data)->samplerate;
+	return 0;
+}
+static int flowctl_set_nch(MSFilter *f, void *arg) {
+	((FlowCtlState *)f->data)->nchannels = *(int *)arg;
+	return 0;
+}
+static int flowctl_get_nch(MSFilter *f, void *arg) {
+	*(int *)arg = ((FlowCtlState *)f->data)->nchannels;
+	return 0;
+}
+static MSFilterMethod flowctl_methods[] = {{MS_AUDIO_FLOW_CONTROL_SET_CONFIG, flowctl_set_config},
+                                           {MS_AUDIO_FLOW_CONTROL_DROP, flowctl_drop},
+                                           {MS_FILTER_SET_SAMPLE_RATE, flowctl_set_sr},
+                                           {MS_FILTER_GET_SAMPLE_RATE, flowctl_get_sr},
+                                           {MS_FILTER_SET_NCHANNELS, flowctl_set_nch},
+                                           {MS_FILTER_GET_NCHANNELS, flowctl_get_nch},
+                                           {0, NULL}};
+static MSFilterDesc b200_flow_control_desc = {.id = MS_AUDIO_FLOW_CONTROL_ID,
+                                              .name = "MSAudioFlowControl",
+                                              .text = "B200: flow control filter dropping samples when too many are queued (libmsb200dsp)",
+                                              .category = MS_FILTER_OTHER,
+                                              .ninputs = 1,
+                                              .noutputs = 1,
+                                              .init = flowctl_init,
+                                              .preprocess = flowctl_preprocess,
+                                              .process = flowctl_process,
+                                              .uninit = flowctl_uninit,
+                                              .methods = flowctl_methods};
+
 /* ================================================================================================ MSScalerDesc
  * the second drop-in boundary (/root/reference/include/mediastreamer2/msvideo.h:473-492): installed with
  * ms_video_set_scaler_impl() so that the reference's own MSPixConv / MSSizeConv / display filters scale on the GPU. */
@@ -2227,9 +2359,10 @@ __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *fac
 	ms_factory_register_filter(factory, &b200_alaw_dec_desc);
 	ms_factory_register_filter(factory, &b200_ulaw_enc_desc);
 	ms_factory_register_filter(factory, &b200_ulaw_dec_desc);
+	ms_factory_register_filter(factory, &b200_flow_control_desc);
 	if (getenv("MSB200_INSTALL_SCALER")) ms_video_set_scaler_impl(&b200_scaler_desc);
 	ms_message("libmsb200filters: B200 DSP filters registered (MSAudioMixer, MSVolume, MSChannelAdapter, MSEqualizer, "
-	           "MSResample, MSSpeexEC, MSAlawEnc/Dec, MSUlawEnc/Dec%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
+	           "MSResample, MSSpeexEC, MSAlawEnc/Dec, MSUlawEnc/Dec, MSAudioFlowControl%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
 }
 /* batch-group statistics for benchmarks: groups, launches (flushes) and units run so far, summed over all groups */
 __attribute__((visibility("default"))) void msb200_filters_batch_stats(int *groups, unsigned long long *flushes, unsigned long long *units) {

@@ -83,6 +83,9 @@ def oracle() -> C.CDLL:
         "orc_scaler_dst_bytes": (C.c_size_t, [_P]),
         "orc_scaler_process": (_I, [_P, _P, _P]),
         "orc_scaler_get_filter": (_I, [_P, _I, _P, _P, _I]),
+        "orc_flowctl_init": (None, [_P]),
+        "orc_flowctl_set_target": (None, [_P, C.c_uint32, C.c_uint32]),
+        "orc_flowctl_process": (_I, [_P, _P, _I]),
         "orc_g711_encode": (None, [_I, _P, _P, C.c_size_t]),
         "orc_g711_decode": (None, [_I, _P, _P, C.c_size_t]),
     }
@@ -151,6 +154,19 @@ class MixerCtl(C.Structure):  # MSAudioMixerCtl, include/mediastreamer2/msaudiom
 
 class EqualizerGain(C.Structure):  # MSEqualizerGain, include/mediastreamer2/msequalizer.h:26-31
     _fields_ = [("frequency", C.c_float), ("gain", C.c_float), ("width", C.c_float)]
+
+
+class OrcFlowCtl(C.Structure):
+    _fields_ = [("strategy", C.c_int32), ("silent_threshold", C.c_float), ("target_samples", C.c_uint32),
+                ("total_samples", C.c_uint32), ("current_pos", C.c_uint32), ("current_dropped", C.c_uint32)]
+
+
+class FlowControlConfig(C.Structure):  # MSAudioFlowControlConfig
+    _fields_ = [("strategy", C.c_int), ("silent_threshold", C.c_float)]
+
+
+class FlowControlDropEvent(C.Structure):  # MSAudioFlowControlDropEvent
+    _fields_ = [("flow_control_interval_ms", C.c_uint32), ("drop_ms", C.c_uint32)]
 
 
 class RefGraph:

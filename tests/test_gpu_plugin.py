@@ -299,3 +299,35 @@ def test_plugin_g711_codecs_bit_exact_vs_reference_filters(name, ptime):
     assert len(ref_out) > n * (ticks - 4)
     assert np.array_equal(got_tri, ref_tri)  # (tick, bytes, timestamp) of every block
     assert np.array_equal(got_out, ref_out)
+
+
+@pytest.mark.parametrize("strategy,drop_ms,interval_ms", [(1, 30, 200), (0, 40, 300), (1, 120, 150)])
+def test_plugin_flowcontrol_bit_exact_vs_reference_filter(strategy, drop_ms, interval_ms):
+    """source -> MSAudioFlowControl -> sink with a drop request after two ticks: the plugin's filter forwards the same
+    blocks (sizes) and samples as the reference's"""
+    from _oracle import FlowControlConfig, FlowControlDropEvent
+    from test_oracle_vs_reference import _flowctl_signal
+    rate, n, ticks = 16000, 160, 40
+    x = _flowctl_signal(np.random.default_rng(drop_ms), n, ticks)
+
+    def run(plugins_dir):
+        g = RefGraph(plugins_dir=plugins_dir)
+        src, fc, sink = g.source(x, n * 2), g.new("MSAudioFlowControl"), g.sink()
+        assert g.text(fc).startswith("B200:") == bool(plugins_dir)
+        assert g.call_int(fc, "MS_FILTER_SET_SAMPLE_RATE", rate) == 0
+        assert g.call_int(fc, "MS_FILTER_SET_NCHANNELS", 1) == 0
+        assert g.call(fc, "MS_AUDIO_FLOW_CONTROL_SET_CONFIG", FlowControlConfig(strategy, 0.02)) == 0
+        g.link(src, 0, fc, 0)
+        g.link(fc, 0, sink, 0)
+        g.run(src, 2)
+        assert g.call(fc, "MS_AUDIO_FLOW_CONTROL_DROP", FlowControlDropEvent(interval_ms, drop_ms)) == 0
+        g.run(src, ticks)
+        out, tri = g.read(sink)
+        g.close()
+        return out, tri
+
+    ref_out, ref_tri = run(None)
+    got_out, got_tri = run(str(O.PLUGIN_DIR))
+    assert len(ref_out) < len(x)
+    assert np.array_equal(got_tri[:, 1], ref_tri[:, 1])
+    assert np.array_equal(got_out, ref_out)

@@ -412,3 +412,51 @@ def test_g711_oracle_vs_reference_filters_in_ticker(name, law):
     exp = np.zeros(len(out_p), np.int16)
     L.orc_g711_decode(law, ptr(code), ptr(exp), len(out_p))
     assert np.array_equal(out_p, exp)
+
+
+# ---------------------------------------------------------------------------------------------------- MSAudioFlowControl (§8f-3)
+def _flowctl_signal(rng, n, ticks):
+    """speech-like bursts, near-silent stretches (whole-frame drops) and flat runs (ties in the three-sample criterion)"""
+    x = (rng.standard_normal(n * ticks) * 6000).clip(-32768, 32767).astype(np.int16)
+    x[n * 6:n * 9] = rng.integers(-20, 21, n * 3)          # almost silent
+    x[n * 14:n * 14 + 40] = 1234                             # flat: many equal minima
+    x[n * 20:n * 22] = (np.arange(n * 2) % 7 - 3) * 100      # periodic: repeated minima
+    return x
+
+
+@pytest.mark.parametrize("strategy,drop_ms,interval_ms", [(1, 30, 200), (1, 8, 100), (0, 40, 300), (1, 120, 150)])
+def test_flowcontrol_oracle_bit_exact_vs_reference_filter(strategy, drop_ms, interval_ms):
+    """oracle == the unmodified MSAudioFlowControl in an MSTicker: same blocks (sizes) and samples, for both strategies,
+    silent-frame drops, zero-crossing sample deletion and the too-many-samples whole-frame drop"""
+    from _oracle import FlowControlConfig, FlowControlDropEvent, OrcFlowCtl
+    L = O.oracle()
+    rate, n, ticks = 16000, 160, 40
+    x = _flowctl_signal(np.random.default_rng(drop_ms), n, ticks)
+    g = RefGraph()
+    src, fc, sink = g.source(x, n * 2), g.new("MSAudioFlowControl"), g.sink()
+    assert g.call_int(fc, "MS_FILTER_SET_SAMPLE_RATE", rate) == 0
+    assert g.call_int(fc, "MS_FILTER_SET_NCHANNELS", 1) == 0
+    assert g.call(fc, "MS_AUDIO_FLOW_CONTROL_SET_CONFIG", FlowControlConfig(strategy, 0.02)) == 0
+    g.link(src, 0, fc, 0)
+    g.link(fc, 0, sink, 0)
+    g.run(src, 2)
+    assert g.call(fc, "MS_AUDIO_FLOW_CONTROL_DROP", FlowControlDropEvent(interval_ms, drop_ms)) == 0
+    g.run(src, ticks)
+    ref_out, tri = g.read(sink)
+    g.close()
+    c = OrcFlowCtl()
+    L.orc_flowctl_init(C.byref(c))
+    c.strategy = strategy
+    out, sizes = [], []
+    for t in range(ticks):
+        if t == 2:
+            L.orc_flowctl_set_target(C.byref(c), drop_ms * rate // 1000, interval_ms * rate // 1000)
+        blk = x[t * n:(t + 1) * n].copy()
+        k = L.orc_flowctl_process(C.byref(c), ptr(blk), n)
+        if k:
+            out.append(blk[:k])
+            sizes.append(2 * k)
+    out = np.concatenate(out)
+    assert list(tri[:, 1]) == sizes
+    assert np.array_equal(ref_out, out)
+    assert len(out) < len(x)  # something was dropped

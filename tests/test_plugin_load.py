@@ -7,7 +7,7 @@ import _oracle as O
 from _oracle import RefGraph
 
 NAMES = ["MSAudioMixer", "MSVolume", "MSChannelAdapter", "MSEqualizer", "MSResample", "MSSpeexEC",
-         "MSAlawEnc", "MSAlawDec", "MSUlawEnc", "MSUlawDec"]
+         "MSAlawEnc", "MSAlawDec", "MSUlawEnc", "MSUlawDec", "MSAudioFlowControl"]
 
 
 def _need_plugin():
