@@ -115,6 +115,8 @@ def main():
     ap.add_argument("--timing", action="store_true")
     ap.add_argument("--tickers", type=int, default=1)
     ap.add_argument("--codec", choices=["none", "alaw"], default="none")
+    ap.add_argument("--churn", default="", help="T1,T2: detach the LAST room's graph after T1 ticks and attach it again after T2 ticks "
+                    "(its filters leave and re-join their batch groups; the other rooms must not notice)")
     a = ap.parse_args()
     g = RefGraph(plugins_dir=str(O.PLUGIN_DIR))
     sources, spk_sinks, out_sinks = build(g, a.streams, a.pins, a.ticks, codec=a.codec)
@@ -130,7 +132,16 @@ def main():
             g.L.ref_ticker_wait(t)
 
     per_tick = []
-    if a.timing:
+    if a.churn:
+        t1, t2 = (int(v) for v in a.churn.split(","))
+        last = len(sources) - 1
+        tk = tickers[last % len(tickers)]
+        run(t1)
+        assert g.L.ref_ticker_detach(tk, sources[last]) == 0   # postprocess: the room's filters leave their groups
+        run(t2 - t1)
+        assert g.L.ref_ticker_attach(tk, sources[last]) == 0   # preprocess: they join again (fresh slots, reset state)
+        run(a.ticks - t2)
+    elif a.timing:
         run(a.warmup)
         for _ in range(a.ticks - a.warmup):
             t0 = time.perf_counter()

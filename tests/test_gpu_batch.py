@@ -14,11 +14,11 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _run(tmp_path, batch, tag, streams, pins, ticks, timing=False, tickers=1, codec="none"):
+def _run(tmp_path, batch, tag, streams, pins, ticks, timing=False, tickers=1, codec="none", churn=""):
     env = dict(os.environ, MSB200_BATCH=str(batch))
     out = tmp_path / f"{tag}.npz"
     cmd = [sys.executable, str(ROOT / "tests" / "graph_runner.py"), "--streams", str(streams), "--pins", str(pins),
-           "--ticks", str(ticks), "--tickers", str(tickers), "--codec", codec, "--dump", str(out)] + (["--timing"] if timing else [])
+           "--ticks", str(ticks), "--tickers", str(tickers), "--codec", codec, "--dump", str(out)] + (["--timing"] if timing else []) + (["--churn", churn] if churn else [])
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     stats = json.loads(r.stdout.strip().splitlines()[-1]) if timing else None
@@ -69,3 +69,20 @@ def test_batch_mode_with_g711_codecs_is_synchronous_mode_delayed(tmp_path):
         assert np.any(a[:len(b) - shifts[0] * tick_bytes] != 0xD5), "compared silence only"
     # resampler x2 (8k->48k, 48k->8k), EC, volume, mixer, decoder, encoder groups
     assert stats["mode"] == "batch" and stats["batch_groups"] == 7
+
+
+@pytest.mark.parametrize("tickers", [1, 2])
+def test_batch_groups_survive_rooms_leaving_and_rejoining(tmp_path, tickers):
+    """a conference room is detached from the running ticker and attached again later (its filters leave their batch
+    groups and re-join with fresh slots): the rooms that stay keep producing exactly what they produce without the churn"""
+    streams, pins, ticks = 12, 4, 90
+    calm, _ = _run(tmp_path, 16, "calm", streams, pins, ticks, tickers=tickers)
+    churn, _ = _run(tmp_path, 16, "churn", streams, pins, ticks, tickers=tickers, churn="30,55")
+    for i in range(streams - pins):  # rooms 0 and 1 stay attached throughout
+        for key in (f"spk{i}", f"out{i}"):
+            assert np.array_equal(churn[key], calm[key]), key
+    # the churned room: identical until it leaves, then a gap, then audio again
+    for i in range(streams - pins, streams):
+        a, b = calm[f"out{i}"], churn[f"out{i}"]
+        assert len(b) < len(a) and np.array_equal(b[:20 * 480], a[:20 * 480])
+        assert b[-10 * 480:].any(), "the re-joined room produces audio again"
