@@ -1795,6 +1795,8 @@ struct msb200_scaler {
 	bool fast_ok;
 	bool direct;        // geometry outside the tile kernels' TMA box limits: scale_direct_kernel
 	bool pstrip_ok;                   // planar I420 -> I420 (MSSizeConv): scale_plane_strip_kernel applies
+	msb200_devbuf deint;              // NV12 / NV21 -> I420 pre-pass output (planar scratch frames)
+	void *deint_last;
 	PlaneStripParams PL, PC;          // luma plane; the two chroma planes
 	size_t smem_pl, smem_pc;
 	CUtensorMap map_py, map_pu, map_pv;
@@ -2337,7 +2339,10 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		return MSB200_OK;
 	}
 	// ---- plane strips (MSSizeConv: planar I420 -> I420): per-plane tables, boxes and tile geometry
-	if (!dst_rgb && src_fmt == MSB200_PIX_YUV420P && P.hl_size == 4 && P.hc_size == 4 && (P.vl_size == 1 || P.vl_size == 2 || P.vl_size == 4) &&
+	// (NV12 / NV21 sources reach the same kernels through a de-interleaving pre-pass into a planar scratch frame: the
+	// chroma geometry and filters are those of the planar source, the de-interleave is exact)
+	if (!dst_rgb && (src_fmt == MSB200_PIX_YUV420P || ((src_fmt == MSB200_PIX_NV12 || src_fmt == MSB200_PIX_NV21) && src_w % 32 == 0)) &&
+	    P.hl_size == 4 && P.hc_size == 4 && (P.vl_size == 1 || P.vl_size == 2 || P.vl_size == 4) &&
 	    (P.vc_size == 1 || P.vc_size == 2 || P.vc_size == 4) && dst_w % 8 == 0 && dst_h % 2 == 0 && (src_w / 2) % 16 == 0 &&
 	    ((size_t)dst_w * dst_h) % 4 == 0 && ((size_t)P.chr_dst_w * P.chr_dst_h) % 4 == 0) {
 		bool ok = true;
@@ -2427,6 +2432,7 @@ void msb200_scaler_destroy(msb200_scaler *s) {
 	cudaFree((void *)s->S.rows);
 	cudaFree((void *)s->PL.rows);
 	cudaFree((void *)s->PC.rows);
+	s->deint.release();
 	s->src.release();
 	s->dst.release();
 	delete s;
@@ -2549,6 +2555,14 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 	}
 	if (s->pstrip_ok && s->force_path == 0 && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 4) == 0) {
 		// planar I420 -> I420: one warp per plane strip, Y in one launch, U and V together in a second
+		if (P.src_fmt != MSB200_PIX_YUV420P) { // interleaved chroma: exact de-interleave into a planar scratch frame first
+			if ((r = s->deint.reserve(s->src_bytes * (size_t)n_frames + 256))) return r;
+			if ((r = msb200_nv12_to_i420_dev(s->ctx, n_frames, d_src, s->src_bytes, (size_t)P.src_w * P.src_h, 0, P.src_w, P.src_h, P.src_w,
+			                                 P.src_w, P.src_fmt == MSB200_PIX_NV12 ? 1 : 0, 0, s->deint.p))) return r;
+			if (s->deint.p != s->deint_last) s->cached_src = nullptr; // the scratch buffer moved: tensor maps are stale
+			s->deint_last = s->deint.p;
+			d_src = s->deint.p;
+		}
 		const char *base = (const char *)d_src;
 		const uint64_t fp = s->src_bytes;
 		if (!(s->cached_src == d_src && s->cached_frames == n_frames)) {

@@ -328,3 +328,29 @@ def test_sizeconv_i420_plane_strips_bit_exact(ctx, sw, sh, dw, dh):
         sc.set_path(2)  # the generic tile kernels (scale_plane_kernel)
         assert np.array_equal(sc.process(frames), got)
     sc.close()
+
+
+@pytest.mark.parametrize("sf,sw,sh,dw,dh", [
+    (_lib.PIX_NV12, 1920, 1080, 1280, 720),   # the reference-shaped two-step of cfg4 in one call
+    (_lib.PIX_NV21, 640, 480, 320, 240 + 8),  # NV21, 2:1-ish (chroma filter of 4 taps)
+    (_lib.PIX_NV12, 640, 352, 640, 352),      # same size: plain de-interleave + yuv2plane1
+    (_lib.PIX_NV12, 320, 240, 480, 360),      # up-scale
+])
+def test_nv12_to_i420_with_scaling_bit_exact(ctx, sf, sw, sh, dw, dh):
+    """NV12 / NV21 -> I420 with bilinear scaling (exact de-interleave pre-pass + the plane-strip kernels) == oracle"""
+    L = O.oracle()
+    n = 2
+    frames = _rand_frames(sf, sw, sh, n, seed=sw + dh)
+    frames[1] = np.random.default_rng(dh).integers(0, 256, size=frames.shape[1], dtype=np.uint8)
+    sc = F.Scaler(ctx, sw, sh, sf, dw, dh, _lib.PIX_YUV420P)
+    got = sc.process(frames)
+    got2 = sc.process(frames[::-1].copy())  # a second batch through the cached tensor maps / scratch buffer
+    sc.close()
+    o = L.orc_scaler_new(sw, sh, sf, dw, dh, _lib.PIX_YUV420P)
+    assert o
+    for i in range(n):
+        exp = np.zeros(got.shape[1] + 64, np.uint8)
+        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+        assert np.array_equal(got[i], exp[:-64]), i
+        assert np.array_equal(got2[n - 1 - i], exp[:-64]), i
+    L.orc_scaler_free(o)
