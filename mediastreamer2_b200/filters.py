@@ -316,7 +316,7 @@ class AudioChain:
     """BASELINE cfg2 graph resident on the device: 2x MSResample -> MSSpeexEC -> MSVolume [-> MSAudioMixer]."""
 
     def __init__(self, ctx: Context, n_streams: int, in_rate: int = 16000, rate: int = 48000, tail_length_ms: int = 250,
-                 volume_gain: float = 0.8, mixer_pins: int = 0, use_cuda_graph: bool = True):
+                 volume_gain: float = 0.8, mixer_pins: int = 0, use_cuda_graph: bool = False):
         self.ctx, self.lib, self.n = ctx, ctx.lib, n_streams
         p = _lib.ChainParams(n_streams, in_rate, rate, tail_length_ms, 64, volume_gain, mixer_pins, int(use_cuda_graph))
         h = C.c_void_p()
