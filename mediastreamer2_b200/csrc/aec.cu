@@ -414,22 +414,22 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		const bool need_wnorm = si[IN_ADAPTED] || sc[SC_SUM_ADAPT] > (float)M - 1.f;
 		const float2 *gX_pf = X + (size_t)(head + 1 > M ? 0 : head + 1) * F + t; // X_{j+1} of the block being prefetched
 		const float2 *const gX_end = X + (size_t)(M + 1) * F + t;                  // ring wrap
-		const float2 *gF_pf = FG + t;
-		const float2 *gW_pf = W + t;
+		// W and FG are walked through ONE pointer each that moves once per unrolled group of AEC_STAGES blocks: the
+		// prefetch of block j + AEC_STAGES - 1 and the stores of block j are that pointer plus compile-time offsets
+		// (immediates in the LDGSTS / STG encodings) instead of four running 64-bit pointers bumped every block
+		float2 *gW_grp = W + t, *gF_grp = FG + t;
 		float2 *const pipe_t = pipe + t;
-		auto prefetch = [&](int stage) {
+		auto prefetch = [&](int stage, int rel) { // rel: block index relative to the group the pointers stand at
 			float2 *dst = pipe_t + stage * 3 * F;
 			cp_async8(dst, gX_pf);
-			if (!fg_pending) cp_async8(dst + F, gF_pf);
-			cp_async8(dst + 2 * F, gW_pf);
+			if (!fg_pending) cp_async8(dst + F, gF_grp + rel * F);
+			cp_async8(dst + 2 * F, gW_grp + rel * F);
 			gX_pf += F;
 			if (gX_pf == gX_end) gX_pf = X + t;
-			gF_pf += F;
-			gW_pf += F;
 		};
 #pragma unroll
 		for (int pj = 0; pj < AEC_STAGES - 1; ++pj) {
-			if (pj < M) prefetch(pj);
+			if (pj < M) prefetch(pj, pj);
 			cp_async_commit();
 		}
 
@@ -548,7 +548,6 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		// cp.async.wait_group. The stage loop is unrolled so that all shared-memory offsets are immediates.
 		float2 yfg = make_float2(0.f, 0.f), ybg = make_float2(0.f, 0.f);
 		{
-			float2 *gW_st = W + t, *gF_st = FG + t;
 			static_assert(AEC_STAGES == 3, "the grouped |W_j|^2 reduction below folds exactly three blocks");
 			float nrm[AEC_STAGES] = {0.f, 0.f, 0.f};
 			for (int j0 = 0; j0 < M; j0 += AEC_STAGES) {
@@ -557,7 +556,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 					const int j = j0 + sidx;
 					if (j < M) {
 						// keep AEC_STAGES-1 blocks in flight: the slot freed by block j-1 receives block j+STAGES-1
-						if (j + AEC_STAGES - 1 < M) prefetch((sidx + AEC_STAGES - 1) % AEC_STAGES);
+						if (j + AEC_STAGES - 1 < M) prefetch((sidx + AEC_STAGES - 1) % AEC_STAGES, sidx + AEC_STAGES - 1);
 						cp_async_commit();
 						cp_async_wait<AEC_STAGES - 1>();
 						const float2 *src = pipe_t + sidx * 3 * F;
@@ -566,7 +565,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 						float2 fg;
 						if (fg_pending) {
 							fg = w;
-							*gF_st = w;
+							gF_grp[sidx * F] = w;
 						} else {
 							fg = src[F];
 						}
@@ -593,9 +592,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 								w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
 							}
 						}
-						if (do_update || constrained) *gW_st = w;
-						gW_st += F;
-						gF_st += F;
+						if (do_update || constrained) gW_grp[sidx * F] = w;
 						// |W_j|^2 partial for next frame's mdf_adjust_prop: reduced three blocks at a time after the group
 						if (need_wnorm) nrm[sidx] = w.x * w.x + w.y * w.y;
 						// background: Y += X_j * W_j
@@ -609,6 +606,8 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 						xj = xj1;
 					}
 				}
+				gW_grp += AEC_STAGES * F;
+				gF_grp += AEC_STAGES * F;
 				if (need_wnorm) {
 					// three warp sums for the price of one and a bit: after the first two folds the three quantities live
 					// in disjoint lane groups (block j0: lanes 0-7, j0+1: 16-23, j0+2: 8-15 and 24-31) and share the
