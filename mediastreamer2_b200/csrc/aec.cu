@@ -412,8 +412,12 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		const int constr_j = M > 1 ? cc % (M - 1) + 1 : 0;
 		// |W_j|^2 is only consumed by mdf_adjust_prop once the filter counts as adapted (or is about to)
 		const bool need_wnorm = si[IN_ADAPTED] || sc[SC_SUM_ADAPT] > (float)M - 1.f;
-		const float2 *gX_pf = X + (size_t)(head + 1 > M ? 0 : head + 1) * F + t; // X_{j+1} of the block being prefetched
-		const float2 *const gX_end = X + (size_t)(M + 1) * F + t;                  // ring wrap
+		const int xs0 = head + 1 > M ? 0 : head + 1;
+		const float2 *gX_pf = X + (size_t)xs0 * F + t; // X_{j+1} of the block being prefetched
+		// ring wrap: a uniform count-down and a constant step back, instead of comparing against (and re-deriving) the
+		// ring's end and base addresses at every block
+		int x_left = M + 1 - xs0;
+		const long x_ring = (long)(M + 1) * F;
 		// W and FG are walked through ONE pointer each that moves once per unrolled group of AEC_STAGES blocks: the
 		// prefetch of block j + AEC_STAGES - 1 and the stores of block j are that pointer plus compile-time offsets
 		// (immediates in the LDGSTS / STG encodings) instead of four running 64-bit pointers bumped every block
@@ -425,7 +429,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			if (!fg_pending) cp_async8(dst + F, gF_grp + rel * F);
 			cp_async8(dst + 2 * F, gW_grp + rel * F);
 			gX_pf += F;
-			if (gX_pf == gX_end) gX_pf = X + t;
+			if (--x_left == 0) gX_pf -= x_ring;
 		};
 #pragma unroll
 		for (int pj = 0; pj < AEC_STAGES - 1; ++pj) {
