@@ -274,6 +274,27 @@ MSB200_API int msb200_flowcontrol_process(msb200_flowcontrol *f, int16_t *io, in
 MSB200_API int msb200_flowcontrol_process_dev(msb200_flowcontrol *f, void *d_io, int nsamples, int stride_samples,
                                               void *d_out_nsamples);
 
+/* ---------------------------------------------------------------------------------------------------- Generic PLC
+ * MSGenericPLC (/root/reference/src/audiofilters/msgenericplc.c:61-157 over src/audiofilters/genericplc.c:74-241):
+ * packet-loss concealment by spectral stretching of the last 50 ms (windowed N-point real FFT, packed bins moved to
+ * twice their index x 0.85, 2N-point inverse; ms_fft / ms_ifft = float kiss_fft, src/utils/dsptools.c:362-376), a 5 ms
+ * continuity delay with cross-fades in and out of the concealed stretch, fade to silence between 100 and 150 ms.
+ * One bank = n_streams mono streams at one rate (8 / 16 / 32 / 48 kHz: transform sizes must factor into 2, 3, 4, 5).
+ * The concealer clock (MSConcealerContext, src/base/mscommon.c:315-362) is the caller's: each tick it passes one mode
+ * byte per stream. Concealed samples are bit-identical to the reference's. */
+#define MSB200_PLC_IDLE 0     /* nothing for this stream in this call */
+#define MSB200_PLC_PACKET 1   /* io[stream] holds a received block: delayed / cross-faded in place (:64-117) */
+#define MSB200_PLC_CONCEAL 2  /* write nsamples concealed samples to io[stream] (:147-152) */
+#define MSB200_PLC_AFTER_CNG 4 /* OR-ed with PACKET: the filter was emitting comfort noise before this block (:77-88) */
+typedef struct msb200_plc msb200_plc;
+MSB200_API int msb200_plc_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_block, msb200_plc **out);
+MSB200_API void msb200_plc_destroy(msb200_plc *p);
+MSB200_API int msb200_plc_history_samples(const msb200_plc *p);
+MSB200_API int msb200_plc_reset_stream(msb200_plc *p, int stream);
+/* io: [n_streams][nsamples] s16 (host), mode: [n_streams] */
+MSB200_API int msb200_plc_process(msb200_plc *p, int16_t *io, int nsamples, const uint8_t *mode);
+MSB200_API int msb200_plc_process_dev(msb200_plc *p, void *d_io, int nsamples, int stride_samples, const void *d_mode);
+
 /* ---------------------------------------------------------------------------------------------------- G.711
  * MSAlawDec / MSUlawDec (/root/reference/src/audiofilters/alaw.c:199-211, ulaw.c) and the arithmetic of MSAlawEnc /
  * MSUlawEnc (alaw.c:84-87): Snack_Alaw2Lin / Snack_Mulaw2Lin / Snack_Lin2Alaw / Snack_Lin2Mulaw

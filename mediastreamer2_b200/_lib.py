@@ -99,6 +99,12 @@ _SIGS = {
     "msb200_flowcontrol_get_state": (_I, [_P, _I, _P]),
     "msb200_flowcontrol_process": (_I, [_P, _P, _I, _P]),
     "msb200_flowcontrol_process_dev": (_I, [_P, _P, _I, _I, _P]),
+    "msb200_plc_create": (_I, [_P, _I, _I, _I, _PP]),
+    "msb200_plc_destroy": (None, [_P]),
+    "msb200_plc_history_samples": (_I, [_P]),
+    "msb200_plc_reset_stream": (_I, [_P, _I]),
+    "msb200_plc_process": (_I, [_P, _P, _I, _P]),
+    "msb200_plc_process_dev": (_I, [_P, _P, _I, _I, _P]),
     "msb200_g711_decode": (_I, [_P, _I, _P, _P, _SZ]),
     "msb200_g711_encode": (_I, [_P, _I, _P, _P, _SZ]),
     "msb200_g711_decode_dev": (_I, [_P, _I, _P, _P, _SZ]),

@@ -490,3 +490,35 @@ class FlowControl:
         out_n = np.zeros(self.n, np.int32)
         check(self.lib.msb200_flowcontrol_process(self.h, _ptr(io), io.shape[1], _ptr(out_n)))
         return io, out_n
+
+
+class GenericPLC:
+    """n x MSGenericPLC (msgenericplc.c:61-157): per tick and stream either a received block (delayed by 5 ms, cross-faded
+    out of a concealed stretch) or a concealed block stretched from the last 50 ms; the concealer clock is the caller's."""
+
+    IDLE, PACKET, CONCEAL, AFTER_CNG = 0, 1, 2, 4
+
+    def __init__(self, ctx: Context, n_streams: int, sample_rate: int, max_block: int | None = None):
+        self.ctx, self.lib, self.n, self.rate = ctx, ctx.lib, n_streams, sample_rate
+        h = C.c_void_p()
+        check(self.lib.msb200_plc_create(ctx.h, n_streams, sample_rate, max_block or sample_rate // 50, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.msb200_plc_destroy(self.h)
+            self.h = None
+
+    @property
+    def history_samples(self) -> int:
+        return self.lib.msb200_plc_history_samples(self.h)
+
+    def reset_stream(self, stream: int):
+        check(self.lib.msb200_plc_reset_stream(self.h, stream))
+
+    def process(self, pcm: np.ndarray, mode) -> np.ndarray:
+        """pcm [n][nsamples] s16 (rows of streams in CONCEAL / IDLE mode are ignored on input), mode [n] -> output rows"""
+        io = np.array(_req(pcm, np.int16).reshape(self.n, -1), copy=True)
+        md = np.ascontiguousarray(np.asarray(mode, np.uint8).reshape(self.n))
+        check(self.lib.msb200_plc_process(self.h, _ptr(io), io.shape[1], _ptr(md)))
+        return io

@@ -110,6 +110,18 @@ void orc_flowctl_init(orc_flowctl *c);
 void orc_flowctl_set_target(orc_flowctl *c, uint32_t samples_to_drop, uint32_t total_samples);
 int orc_flowctl_process(orc_flowctl *c, int16_t *samples, int nsamples);
 
+/* MSGenericPLC (oracle_plc.c): signal level (packet / conceal) and filter level (concealer clock) */
+typedef struct orc_plc orc_plc;
+int orc_plc_rate_supported(int rate);
+orc_plc *orc_plc_create(int rate);
+void orc_plc_destroy(orc_plc *c);
+int orc_plc_history_len(const orc_plc *c);
+void orc_plc_packet(orc_plc *c, int16_t *data, int n, int after_cng);
+void orc_plc_conceal(orc_plc *c, int16_t *data, int n);
+void orc_plc_filter_set_cn(orc_plc *c);
+void orc_plc_filter_packet(orc_plc *c, uint64_t now_ms, int16_t *data, int n, int nchannels);
+int orc_plc_filter_tick(orc_plc *c, uint64_t now_ms, int interval_ms, int nchannels, int16_t *out, int *kind);
+
 /* G.711 (oracle_g711.c): law 0 = A-law, 1 = mu-law */
 void orc_g711_encode(int law, const int16_t *pcm, uint8_t *code, size_t n);
 void orc_g711_decode(int law, const uint8_t *code, int16_t *pcm, size_t n);

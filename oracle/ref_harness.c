@@ -14,6 +14,7 @@
 #include "mediastreamer2/mschanadapter.h"
 #include "mediastreamer2/msequalizer.h"
 #include "mediastreamer2/flowcontrol.h"
+#include "mediastreamer2/msgenericplc.h"
 #include "mediastreamer2/msfactory.h"
 #include "mediastreamer2/msfilter.h"
 #include "mediastreamer2/msinterfaces.h"
@@ -336,6 +337,7 @@ unsigned int ref_method_id(const char *name) {
 	MID(MS_DECODER_HAVE_PLC);
 	MID(MS_AUDIO_FLOW_CONTROL_SET_CONFIG);
 	MID(MS_AUDIO_FLOW_CONTROL_DROP);
+	MID(MS_GENERIC_PLC_SET_CN);
 	return 0;
 }
 

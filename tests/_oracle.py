@@ -88,6 +88,15 @@ def oracle() -> C.CDLL:
         "orc_flowctl_process": (_I, [_P, _P, _I]),
         "orc_g711_encode": (None, [_I, _P, _P, C.c_size_t]),
         "orc_g711_decode": (None, [_I, _P, _P, C.c_size_t]),
+        "orc_plc_rate_supported": (_I, [_I]),
+        "orc_plc_create": (_P, [_I]),
+        "orc_plc_destroy": (None, [_P]),
+        "orc_plc_history_len": (_I, [_P]),
+        "orc_plc_packet": (None, [_P, _P, _I, _I]),
+        "orc_plc_conceal": (None, [_P, _P, _I]),
+        "orc_plc_filter_set_cn": (None, [_P]),
+        "orc_plc_filter_packet": (None, [_P, C.c_uint64, _P, _I, _I]),
+        "orc_plc_filter_tick": (_I, [_P, C.c_uint64, _I, _I, _P, _P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

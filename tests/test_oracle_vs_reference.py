@@ -460,3 +460,120 @@ def test_flowcontrol_oracle_bit_exact_vs_reference_filter(strategy, drop_ms, int
     assert list(tri[:, 1]) == sizes
     assert np.array_equal(ref_out, out)
     assert len(out) < len(x)  # something was dropped
+
+
+# ---------------------------------------------------------------------------------------------------- MSGenericPLC
+class _CngData(C.Structure):  # MSCngData, include/mediastreamer2/mscngdtx.h:23-26
+    _fields_ = [("datasize", C.c_int), ("data", C.c_uint8 * 32)]
+
+
+def plc_signal(rate: int, nsamples: int, seed: int = 1) -> np.ndarray:
+    t = np.arange(nsamples)
+    rng = np.random.default_rng(seed)
+    x = (6000 * np.sin(2 * np.pi * 440 * t / rate) + 3000 * np.sin(2 * np.pi * 1234.5 * t / rate + 1)
+         + rng.normal(0, 300, nsamples))
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
+def plc_reference_run(rate, ticks, schedule, x, cn_at=()):
+    """the UNMODIFIED MSGenericPLC in the reference's MSTicker; schedule[tick] = list of (offset, nsamples) blocks that
+    arrive in that tick; cn_at = ticks before which MS_GENERIC_PLC_SET_CN is called. Returns samples and (tick, bytes)."""
+    g = RefGraph()
+    src, plc, sink = g.source(), g.new("MSGenericPLC"), g.sink()
+    assert g.call_int(plc, "MS_FILTER_SET_SAMPLE_RATE", rate) == 0
+    assert g.call_int(plc, "MS_FILTER_SET_NCHANNELS", 1) == 0
+    for k, blocks in schedule.items():
+        for off, n in blocks:
+            g.push(src, k, x[off:off + n])
+    g.link(src, 0, plc, 0)
+    g.link(plc, 0, sink, 0)
+    done = 0
+    for stop in sorted(set(cn_at)) + [ticks]:
+        if stop > done:
+            g.run(src, stop - done)
+            done = stop
+        if stop < ticks:
+            assert g.call(plc, "MS_GENERIC_PLC_SET_CN", _CngData()) == 0
+    out, tri = g.read(sink)
+    g.close()
+    return out, [(int(a), int(b)) for a, b, _ in tri]
+
+
+def plc_oracle_run(rate, ticks, schedule, x, cn_at=()):
+    L = O.oracle()
+    c = L.orc_plc_create(rate)
+    assert c
+    out, blocks, kind = [], [], C.c_int(0)
+    tick_n = rate // 100
+    for k in range(ticks):
+        if k in cn_at:
+            L.orc_plc_filter_set_cn(c)
+        for off, n in schedule.get(k, []):
+            b = x[off:off + n].copy()
+            L.orc_plc_filter_packet(c, k * 10, ptr(b), n, 1)
+            out.append(b)
+            blocks.append((k, 2 * n))
+        o = np.zeros(tick_n, np.int16)
+        m = L.orc_plc_filter_tick(c, k * 10, 10, 1, ptr(o), C.byref(kind))
+        if m:
+            out.append(o[:m])
+            blocks.append((k, 2 * m))
+    L.orc_plc_destroy(c)
+    return np.concatenate(out), blocks
+
+
+def plc_schedule(rate, ticks, lost, block_ms=10):
+    """one block of block_ms every block_ms, except the block indices in `lost`"""
+    n, step = rate * block_ms // 1000, block_ms // 10
+    return {k: [((k // step) * n, n)] for k in range(0, ticks, step) if (k // step) not in lost}
+
+
+@pytest.mark.parametrize("rate", [8000, 16000, 32000, 48000])
+def test_plc_oracle_bit_exact_vs_reference_filter(rate):
+    """single losses, a 4-block burst, a 220 ms hole (fade to silence, then zeros) and a back-to-back pair: every block the
+    unmodified filter emits (sizes, order, samples) equals the oracle's; transform sizes 400..4800 cover radix 2, 3, 4, 5"""
+    ticks = 70
+    lost = set(range(10, 14)) | {20} | set(range(30, 52)) | {60, 61}
+    x = plc_signal(rate, ticks * rate // 100)
+    sched = plc_schedule(rate, ticks, lost)
+    ref, ref_blocks = plc_reference_run(rate, ticks, sched, x)
+    out, blocks = plc_oracle_run(rate, ticks, sched, x)
+    assert ref_blocks == blocks
+    assert np.array_equal(ref, out)
+    n = rate // 100
+    assert np.abs(ref[10 * n:12 * n].astype(int)).max() > 1000  # the concealed stretch is not silence
+
+
+def test_plc_oracle_long_hole_wraps_the_16_bit_counters():
+    """plc_samples_used is a uint16_t in the reference (genericplc.h:46): after 65536 concealed samples it wraps and the
+    filter re-emits stale generated signal; the oracle reproduces that"""
+    rate, ticks = 48000, 260
+    x = plc_signal(rate, ticks * 480, seed=3)
+    sched = plc_schedule(rate, ticks, set(range(20, 240)))
+    ref, ref_blocks = plc_reference_run(rate, ticks, sched, x)
+    out, blocks = plc_oracle_run(rate, ticks, sched, x)
+    assert ref_blocks == blocks and np.array_equal(ref, out)
+    assert np.any(ref[160 * 480:170 * 480] != 0)  # stale signal after the wrap (would be silence with wider counters)
+
+
+@pytest.mark.parametrize("rate,block_ms", [(16000, 20), (8000, 20), (16000, 30)])
+def test_plc_oracle_longer_packets(rate, block_ms):
+    ticks = 90
+    x = plc_signal(rate, ticks * rate // 100, seed=block_ms)
+    sched = plc_schedule(rate, ticks, {5, 6, 12} | set(range(20, 31)), block_ms)
+    ref, ref_blocks = plc_reference_run(rate, ticks, sched, x)
+    out, blocks = plc_oracle_run(rate, ticks, sched, x)
+    # the recording sink counts its own invocations, which are not ticks when some ticks carry nothing: compare sizes
+    assert [b for _, b in ref_blocks] == [b for _, b in blocks] and np.array_equal(ref, out)
+
+
+def test_plc_oracle_comfort_noise_path():
+    """MS_GENERIC_PLC_SET_CN before a hole: the hole is filled with flagged silence instead of concealment and the first
+    block after it fades in from zero (msgenericplc.c:77-88, 131-141)"""
+    rate, ticks = 16000, 60
+    x = plc_signal(rate, ticks * 160, seed=9)
+    sched = plc_schedule(rate, ticks, set(range(12, 20)) | set(range(30, 34)))
+    ref, ref_blocks = plc_reference_run(rate, ticks, sched, x, cn_at=(12,))
+    out, blocks = plc_oracle_run(rate, ticks, sched, x, cn_at=(12,))
+    assert ref_blocks == blocks and np.array_equal(ref, out)
+    assert not ref[12 * 160:20 * 160].any()
