@@ -29,6 +29,7 @@
 #include "mediastreamer2/msequalizer.h"
 #include "mediastreamer2/msfactory.h"
 #include "mediastreamer2/msfilter.h"
+#include "mediastreamer2/msgenericplc.h"
 #include "mediastreamer2/msinterfaces.h"
 #include "mediastreamer2/msticker.h"
 #include "mediastreamer2/msvideo.h"
@@ -2236,6 +2237,145 @@ static MSFilterDesc b200_flow_control_desc = {.id = MS_AUDIO_FLOW_CONTROL_ID,
                                               .uninit = flowctl_uninit,
                                               .methods = flowctl_methods};
 
+/* ================================================================================================ MSGenericPLC
+ * /root/reference/src/audiofilters/msgenericplc.c:44-157: filter shell and the concealer clock (MSConcealerContext,
+ * src/base/mscommon.c:315-362, restated below: it is control logic) on the host; the signal work of every received block
+ * (history, 5 ms continuity delay, cross-fade out of a concealed stretch) and of every concealed block
+ * (genericplc.c:74-241) on the GPU (msb200_plc_*). Synchronous mode. Rates whose transform sizes need a radix above 5
+ * (44.1 kHz) are refused loudly and the stream passes untouched. */
+typedef struct PlcState {
+	msb200_plc *bank; /* 1 stream */
+	int bank_rate, bank_block;
+	int rate, nchannels;
+	int64_t sample_time, plc_start_time; /* MSConcealerContext (max_plc_time = UINT32_MAX, msgenericplc.c:44,51) */
+	unsigned long total_plc;
+	MSCngData cng_data;
+	bool_t cng_set, cng_running, refused;
+} PlcState;
+static void plc_init(MSFilter *f) {
+	PlcState *s = ms_new0(PlcState, 1);
+	s->nchannels = 1;
+	s->sample_time = -1;
+	s->plc_start_time = -1;
+	f->data = s;
+}
+static void plc_preprocess(MSFilter *f) {
+	PlcState *s = (PlcState *)f->data;
+	if (s->bank || s->refused || !dsp_ctx()) return; /* as the reference: the context is created once (:57-60) */
+	{
+		const int N = ((s->rate * 2 / 40) / 100) * 100, T = s->rate * 5 / 1000;
+		s->bank_block = 2 * N - 2 * T;
+		DSP_LOCK();
+		if (s->rate < 8000 || msb200_plc_create(g_ctx, 1, s->rate, s->bank_block, &s->bank) != MSB200_OK) {
+			ms_error("MSGenericPLC(b200): no concealment at %d Hz: %s", s->rate, msb200_last_error());
+			s->bank = NULL;
+			s->refused = TRUE;
+		}
+		DSP_UNLOCK();
+		s->bank_rate = s->rate;
+	}
+}
+static void plc_device(PlcState *s, int16_t *io, int n, uint8_t mode) {
+	int rc;
+	if (!s->bank) return;
+	if (n > s->bank_block) {
+		ms_error("MSGenericPLC(b200): block of %d samples exceeds the %d-sample concealment window", n, s->bank_block);
+		return;
+	}
+	DSP_LOCK();
+	rc = msb200_plc_process(s->bank, io, n, &mode);
+	DSP_UNLOCK();
+	if (rc != MSB200_OK) ms_error("msb200: plc_process failed: %s", msb200_last_error());
+}
+static void plc_process(MSFilter *f) {
+	PlcState *s = (PlcState *)f->data;
+	const uint64_t now = f->ticker->time;
+	mblk_t *m;
+	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+		size_t msg_size;
+		if (m->b_cont) msgpullup(m, (size_t)-1);
+		msg_size = (size_t)(m->b_wptr - m->b_rptr);
+		/* ms_concealer_inc_sample_time(concealer, now, duration, TRUE) */
+		if (s->sample_time == -1) s->sample_time = (int64_t)now;
+		s->sample_time += (unsigned int)((1000 * msg_size) / ((size_t)s->rate * sizeof(int16_t) * (size_t)s->nchannels));
+		s->plc_start_time = -1;
+		plc_device(s, (int16_t *)m->b_rptr, (int)(msg_size / 2),
+		           (uint8_t)(MSB200_PLC_PACKET | (s->cng_running ? MSB200_PLC_AFTER_CNG : 0)));
+		if (s->cng_running) {
+			s->cng_running = FALSE;
+			s->cng_set = FALSE;
+		}
+		ms_queue_put(f->outputs[0], m);
+	}
+	/* ms_concealer_context_is_concealement_required(concealer, now) */
+	if (s->sample_time != -1 && (uint64_t)s->sample_time <= now) {
+		const unsigned int buff_size = (unsigned int)(s->rate * s->nchannels * f->ticker->interval / 1000) * sizeof(int16_t);
+		if (s->plc_start_time == -1) s->plc_start_time = s->sample_time;
+		if ((uint32_t)(now - (uint64_t)s->plc_start_time) >= UINT32_MAX) {
+			s->sample_time = -1;
+			return;
+		}
+		s->total_plc++;
+		m = allocb(buff_size, 0);
+		memset(m->b_wptr, 0, buff_size);
+		if (s->cng_set) { /* comfort noise without a G.729B decoder is flagged silence (:131-141) */
+			s->cng_set = FALSE;
+			s->cng_running = TRUE;
+			mblk_set_cng_flag(m, 1);
+		} else if (s->cng_running) {
+			mblk_set_cng_flag(m, 1);
+		} else {
+			mblk_set_plc_flag(m, 1);
+			plc_device(s, (int16_t *)m->b_wptr, (int)(buff_size / sizeof(int16_t)), MSB200_PLC_CONCEAL);
+		}
+		m->b_wptr += buff_size;
+		ms_queue_put(f->outputs[0], m);
+		s->sample_time += f->ticker->interval; /* ms_concealer_inc_sample_time(..., interval, FALSE) */
+	}
+}
+static void plc_uninit(MSFilter *f) {
+	PlcState *s = (PlcState *)f->data;
+	DSP_LOCK();
+	msb200_plc_destroy(s->bank);
+	DSP_UNLOCK();
+	ms_free(s);
+}
+static int plc_get_sr(MSFilter *f, void *arg) {
+	*(int *)arg = ((PlcState *)f->data)->rate;
+	return 0;
+}
+static int plc_set_sr(MSFilter *f, void *arg) {
+	((PlcState *)f->data)->rate = *(int *)arg;
+	return 0;
+}
+static int plc_set_nch(MSFilter *f, void *arg) {
+	((PlcState *)f->data)->nchannels = *(int *)arg;
+	return 0;
+}
+static int plc_set_cn(MSFilter *f, void *arg) {
+	PlcState *s = (PlcState *)f->data;
+	memcpy(&s->cng_data, arg, sizeof(MSCngData));
+	s->cng_set = TRUE;
+	return 0;
+}
+static MSFilterMethod plc_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, plc_set_sr},
+                                       {MS_FILTER_GET_SAMPLE_RATE, plc_get_sr},
+                                       {MS_FILTER_SET_NCHANNELS, plc_set_nch},
+                                       {MS_GENERIC_PLC_SET_CN, plc_set_cn},
+                                       {0, NULL}};
+static MSFilterDesc b200_generic_plc_desc = {.id = MS_GENERIC_PLC_ID,
+                                             .name = "MSGenericPLC",
+                                             .text = "B200: generic packet-loss concealment (libmsb200dsp)",
+                                             .category = MS_FILTER_OTHER,
+                                             .ninputs = 1,
+                                             .noutputs = 1,
+                                             .init = plc_init,
+                                             .preprocess = plc_preprocess,
+                                             .process = plc_process,
+                                             .uninit = plc_uninit,
+                                             .methods = plc_methods,
+                                             .flags = MS_FILTER_IS_PUMP};
+
 /* ================================================================================================ MSScalerDesc
  * the second drop-in boundary (/root/reference/include/mediastreamer2/msvideo.h:473-492): installed with
  * ms_video_set_scaler_impl() so that the reference's own MSPixConv / MSSizeConv / display filters scale on the GPU. */
@@ -2360,9 +2500,10 @@ __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *fac
 	ms_factory_register_filter(factory, &b200_ulaw_enc_desc);
 	ms_factory_register_filter(factory, &b200_ulaw_dec_desc);
 	ms_factory_register_filter(factory, &b200_flow_control_desc);
+	ms_factory_register_filter(factory, &b200_generic_plc_desc);
 	if (getenv("MSB200_INSTALL_SCALER")) ms_video_set_scaler_impl(&b200_scaler_desc);
 	ms_message("libmsb200filters: B200 DSP filters registered (MSAudioMixer, MSVolume, MSChannelAdapter, MSEqualizer, "
-	           "MSResample, MSSpeexEC, MSAlawEnc/Dec, MSUlawEnc/Dec, MSAudioFlowControl%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
+	           "MSResample, MSSpeexEC, MSAlawEnc/Dec, MSUlawEnc/Dec, MSAudioFlowControl, MSGenericPLC%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
 }
 /* batch-group statistics for benchmarks: groups, launches (flushes) and units run so far, summed over all groups */
 __attribute__((visibility("default"))) void msb200_filters_batch_stats(int *groups, unsigned long long *flushes, unsigned long long *units) {

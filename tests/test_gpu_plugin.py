@@ -331,3 +331,20 @@ def test_plugin_flowcontrol_bit_exact_vs_reference_filter(strategy, drop_ms, int
     assert len(ref_out) < len(x)
     assert np.array_equal(got_tri[:, 1], ref_tri[:, 1])
     assert np.array_equal(got_out, ref_out)
+
+
+@pytest.mark.parametrize("rate,block_ms,cn_at", [(16000, 10, ()), (48000, 10, ()), (8000, 20, ()), (16000, 10, (12,))])
+def test_plugin_generic_plc_bit_exact_vs_reference_filter(rate, block_ms, cn_at):
+    """source (with holes) -> MSGenericPLC -> sink: the plugin's filter (host concealer clock + msb200_plc_* on the GPU)
+    emits the same blocks as the unmodified reference filter: delayed, concealed, faded, comfort-noise silence"""
+    from test_oracle_vs_reference import plc_reference_run, plc_schedule, plc_signal
+    ticks = 70
+    lost = set(range(10, 14)) | {20} | set(range(30, 52)) | {60, 61}
+    if block_ms != 10:
+        lost = {5, 6, 12} | set(range(20, 31))
+    x = plc_signal(rate, ticks * rate // 100, seed=rate // 1000)
+    sched = plc_schedule(rate, ticks, lost, block_ms)
+    ref_out, ref_blocks = plc_reference_run(rate, ticks, sched, x, cn_at)
+    got_out, got_blocks = plc_reference_run(rate, ticks, sched, x, cn_at, plugins_dir=str(O.PLUGIN_DIR))
+    assert got_blocks == ref_blocks
+    assert np.array_equal(got_out, ref_out)

@@ -475,11 +475,12 @@ def plc_signal(rate: int, nsamples: int, seed: int = 1) -> np.ndarray:
     return np.clip(np.round(x), -32768, 32767).astype(np.int16)
 
 
-def plc_reference_run(rate, ticks, schedule, x, cn_at=()):
+def plc_reference_run(rate, ticks, schedule, x, cn_at=(), plugins_dir=None):
     """the UNMODIFIED MSGenericPLC in the reference's MSTicker; schedule[tick] = list of (offset, nsamples) blocks that
     arrive in that tick; cn_at = ticks before which MS_GENERIC_PLC_SET_CN is called. Returns samples and (tick, bytes)."""
-    g = RefGraph()
+    g = RefGraph(plugins_dir=plugins_dir)
     src, plc, sink = g.source(), g.new("MSGenericPLC"), g.sink()
+    assert g.text(plc).startswith("B200:") == bool(plugins_dir)
     assert g.call_int(plc, "MS_FILTER_SET_SAMPLE_RATE", rate) == 0
     assert g.call_int(plc, "MS_FILTER_SET_NCHANNELS", 1) == 0
     for k, blocks in schedule.items():

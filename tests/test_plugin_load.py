@@ -7,7 +7,7 @@ import _oracle as O
 from _oracle import RefGraph
 
 NAMES = ["MSAudioMixer", "MSVolume", "MSChannelAdapter", "MSEqualizer", "MSResample", "MSSpeexEC",
-         "MSAlawEnc", "MSAlawDec", "MSUlawEnc", "MSUlawDec", "MSAudioFlowControl"]
+         "MSAlawEnc", "MSAlawDec", "MSUlawEnc", "MSUlawDec", "MSAudioFlowControl", "MSGenericPLC"]
 
 
 def _need_plugin():
@@ -84,6 +84,12 @@ def test_plugin_method_tables_accept_the_reference_method_ids():
         v = C.c_int(-1)
         assert g.call(dec, "MS_DECODER_HAVE_PLC", v) == 0 and v.value == 0
         assert g.call(dec, "MS_FILTER_GET_SAMPLE_RATE", v) == 0 and v.value == 8000
+    plc = g.new("MSGenericPLC")  # msgenericplc.c:185-189
+    v = C.c_int(-1)
+    assert g.call_int(plc, "MS_FILTER_SET_SAMPLE_RATE", 16000) == 0
+    assert g.call(plc, "MS_FILTER_GET_SAMPLE_RATE", v) == 0 and v.value == 16000
+    assert g.call_int(plc, "MS_FILTER_SET_NCHANNELS", 1) == 0
+    assert g.call(plc, "MS_GENERIC_PLC_SET_CN", (C.c_uint8 * 36)()) == 0
     g.close()
 
 
