@@ -93,6 +93,30 @@ def kernels_bench(ctx, hbm_peak_gbs: float) -> dict:
     ms = _time(ctx, lambda: _lib.check(lib.msb200_resample_process_dev(rs.h, P(d_a), 480, 480, P(d_b), 161, C.byref(got))), iters=5)
     row("resample_kernel", f"a1 MSResample 48k->16k (general kernel), {nd} streams x 480 frames", nd * (480 + 160) * 2, ms, nd, "stream_ticks")
     rs.close()
+    # f3 MSGenericPLC, 16 kHz: (i) every stream receives its block (history + 5 ms continuity delay), (ii) every stream
+    # lost its block right after a received one, i.e. the worst case: one 800-point + one 1600-point transform per stream
+    try:
+        ns, wn = 16384, 160
+        plc = F.GenericPLC(ctx, ns, 16000, wn)
+        N = plc.history_samples
+        d_mode_pkt, d_mode_lost = ctx.dev_alloc(ns), ctx.dev_alloc(ns)
+        ctx.h2d(d_mode_pkt, np.full(ns, 1, np.uint8))
+        ctx.h2d(d_mode_lost, np.full(ns, 2, np.uint8))
+        pkt = lambda: _lib.check(lib.msb200_plc_process_dev(plc.h, P(d_a), wn, wn, P(d_mode_pkt)))  # noqa: E731
+        ms_pkt = _time(ctx, pkt)
+
+        def pkt_then_lost():
+            pkt()
+            _lib.check(lib.msb200_plc_process_dev(plc.h, P(d_b), wn, wn, P(d_mode_lost)))
+        ms_pair = _time(ctx, pkt_then_lost, iters=5)
+        row("plc_kernel (received)", f"f3 MSGenericPLC received block, {ns} streams x {wn} samples @16 kHz", ns * (2 * wn + 2 * N + 80) * 2, ms_pkt, ns, "stream_ticks")
+        row("plc_kernel (concealed)", f"f3 MSGenericPLC first concealed block (800 + 1600-point float FFTs per stream), {ns} streams",
+            ns * (wn + 3 * N + 4 * N + 320) * 2, max(ms_pair - ms_pkt, 1e-6), ns, "concealments")
+        plc.close()
+        ctx.dev_free(d_mode_pkt)
+        ctx.dev_free(d_mode_lost)
+    except Exception as e:  # noqa: BLE001 - a side measurement must not take the headline line down with it
+        rows["plc_kernel"] = {"error": repr(e)}
     ctx.dev_free(d_a)
     ctx.dev_free(d_b)
     # ---------------------------------------------------------------- video, 1080p, 128 frames (>= 400 MB per buffer)
@@ -128,6 +152,9 @@ if __name__ == "__main__":
     c = F.Context(0)
     out = kernels_bench(c, 6455.9)
     for k, v in out.items():
+        if "error" in v:
+            print(k, v)
+            continue
         print(f"{k:32s} {v['ms_per_launch']:9.4f} ms  {v['achieved_gbs']:8.1f} GB/s  frac {v['frac_of_hbm_peak']:.3f}   {v['what']}")
     print(json.dumps(out))
     c.close()
