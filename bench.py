@@ -162,6 +162,43 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+def realtime_block(ctx, F, sizes=(4096, 16384, 32768), ticks=1000):
+    """SURVEY.md §8(d) S_rt: the number of concurrent streams whose full tick — pinned host PCM in, H2D, kernels, D2H, result
+    on the host — completes within the 10 ms ticker interval at p99 over >= 1000 ticks. Every tick is one synchronous
+    `msb200_chain_tick` (what a paced media server calls once per interval), timed on the host around the call."""
+    ti = IN_RATE // 100
+    pool = 8
+    out = {"budget_ms": 10.0, "ticks": ticks, "call": "msb200_chain_tick (synchronous: H2D + kernels + D2H)", "sizes": {}}
+    s_rt = 0
+    for n in sizes:
+        chain = None
+        try:
+            chain = F.AudioChain(ctx, n, IN_RATE, RATE, TAIL_MS, GAIN, 0)
+            ref_h, mic_h = synth_inputs(n, pool)
+            ref_pin, mic_pin = ctx.pinned((pool, n, ti), np.int16), ctx.pinned((pool, n, ti), np.int16)
+            out_pin = ctx.pinned((n, chain.max_out), np.int16)
+            ref_pin[...] = ref_h
+            mic_pin[...] = mic_h
+            for k in range(16):
+                chain.tick(ref_pin[k % pool], mic_pin[k % pool], out_pin)
+            lat = np.empty(ticks)
+            for k in range(ticks):
+                t0 = time.perf_counter()
+                chain.tick(ref_pin[k % pool], mic_pin[k % pool], out_pin)
+                lat[k] = 1000.0 * (time.perf_counter() - t0)
+            p50, p99, worst = (float(np.percentile(lat, 50)), float(np.percentile(lat, 99)), float(lat.max()))
+            out["sizes"][str(n)] = {"p50_ms": p50, "p99_ms": p99, "max_ms": worst, "within_budget": p99 < 10.0}
+            if p99 < 10.0:
+                s_rt = max(s_rt, n)
+            else:
+                break
+        finally:
+            if chain is not None:
+                chain.close()
+    out["s_rt_streams_at_least"] = s_rt
+    return out
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
 
@@ -342,6 +379,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["kernels"] = kernels_bench(ctx, peak)
     except ImportError:
         pass
+    # ---------------------------------------------------------------- SURVEY §8(d) S_rt: tick latency vs the 10 ms budget
+    if rank == 0 and world == 1 and not args.no_realtime:
+        try:
+            line["realtime"] = realtime_block(ctx, F)
+        except Exception as e:  # noqa: BLE001 - a side measurement must not take the headline line down with it
+            line["realtime"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     chain.close()
@@ -359,6 +402,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-realtime", action="store_true", help="skip the S_rt tick-latency block (SURVEY §8d)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
