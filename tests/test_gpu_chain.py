@@ -82,3 +82,26 @@ def test_pipelined_submit_wait_equals_synchronous_tick(ctx, pins):
         assert np.array_equal(o1, o2), t
     a.close()
     b.close()
+
+
+def test_chain_large_bank_crosses_the_4_gib_state_boundary(ctx):
+    """16384 streams: the echo cancellers' device state (4.7 GB) spans the 32-bit offset boundary. Eight distinct inputs
+    tiled over the bank: every stream must produce exactly what its twin in the first eight does (which the tests above
+    check against the oracle), tick after tick — any 32-bit addressing slip in a kernel or an init pass breaks this."""
+    n, base, ticks, in_rate, rate = 16384, 8, 24, 16000, 48000
+    ti = in_rate // 100
+    data = [cfg2_stream(700 + s, ti * ticks, in_rate) for s in range(base)]
+    ref = np.stack([d[0] for d in data]).reshape(base, ticks, ti)
+    mic = np.stack([d[1] for d in data]).reshape(base, ticks, ti)
+    idx = np.arange(n) % base
+    ch = F.AudioChain(ctx, n, in_rate, rate, 250, 0.8, 0)
+    produced = 0
+    for t in range(ticks):
+        out, k = ch.tick(np.ascontiguousarray(ref[idx, t]), np.ascontiguousarray(mic[idx, t]))
+        if k:
+            produced += k
+            got = out[:, :k].reshape(n // base, base, k)
+            assert np.array_equal(got, np.broadcast_to(got[0], got.shape)), f"tick {t}"
+            assert got[0].any()
+    assert produced >= (ticks - 2) * (rate // 100)
+    ch.close()
