@@ -293,6 +293,9 @@ MSB200_API int msb200_plc_history_samples(const msb200_plc *p);
 MSB200_API int msb200_plc_reset_stream(msb200_plc *p, int stream);
 /* io: [n_streams][nsamples] s16 (host), mode: [n_streams] */
 MSB200_API int msb200_plc_process(msb200_plc *p, int16_t *io, int nsamples, const uint8_t *mode);
+/* rows `stride_samples` apart (an arena with several units per stream); only streams [0, n_live) are copied and run */
+MSB200_API int msb200_plc_process_strided(msb200_plc *p, int16_t *io, int nsamples, int stride_samples, const uint8_t *mode);
+MSB200_API int msb200_plc_set_live(msb200_plc *p, int n_live);
 MSB200_API int msb200_plc_process_dev(msb200_plc *p, void *d_io, int nsamples, int stride_samples, const void *d_mode);
 
 /* ---------------------------------------------------------------------------------------------------- G.711

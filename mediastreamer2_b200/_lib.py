@@ -104,6 +104,8 @@ _SIGS = {
     "msb200_plc_history_samples": (_I, [_P]),
     "msb200_plc_reset_stream": (_I, [_P, _I]),
     "msb200_plc_process": (_I, [_P, _P, _I, _P]),
+    "msb200_plc_process_strided": (_I, [_P, _P, _I, _I, _P]),
+    "msb200_plc_set_live": (_I, [_P, _I]),
     "msb200_plc_process_dev": (_I, [_P, _P, _I, _I, _P]),
     "msb200_g711_decode": (_I, [_P, _I, _P, _P, _SZ]),
     "msb200_g711_encode": (_I, [_P, _I, _P, _P, _SZ]),

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(PLC_THREADS) plc_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------------------ host side
 struct msb200_plc {
 	msb200_ctx *ctx = nullptr;
-	int n = 0, rate = 0, max_block = 0;
+	int n = 0, live = 0, rate = 0, max_block = 0; // live: streams [0, live) are copied and run (msb200_plc_set_live)
 	PlcParams P{};
 	void *d_tables = nullptr, *d_state = nullptr;
 	msb200_devbuf io, md;
@@ -374,6 +374,7 @@ int msb200_plc_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_b
 	msb200_plc *p = new msb200_plc();
 	p->ctx = ctx;
 	p->n = n_streams;
+	p->live = n_streams;
 	p->rate = sample_rate;
 	p->max_block = max_block;
 	// tables: window | tw_f | super_f | tw_i | super_i | perm_f | perm_i
@@ -470,25 +471,37 @@ int msb200_plc_reset_stream(msb200_plc *p, int stream) {
 	return MSB200_OK;
 }
 
+int msb200_plc_set_live(msb200_plc *p, int n_live) {
+	MSB200_CHECK_ARG(p && n_live >= 0 && n_live <= p->n);
+	p->live = n_live;
+	return MSB200_OK;
+}
+
 int msb200_plc_process_dev(msb200_plc *p, void *d_io, int nsamples, int stride_samples, const void *d_mode) {
 	MSB200_CHECK_ARG(p && d_io && d_mode && nsamples > 0 && nsamples <= p->max_block && stride_samples >= nsamples);
-	MSB200_LAUNCH(p->ctx, plc_kernel, p->n, PLC_THREADS, p->smem, p->P, static_cast<short *>(d_io), nsamples, stride_samples,
+	if (p->live == 0) return MSB200_OK;
+	MSB200_LAUNCH(p->ctx, plc_kernel, p->live, PLC_THREADS, p->smem, p->P, static_cast<short *>(d_io), nsamples, stride_samples,
 	              static_cast<const uint8_t *>(d_mode));
 	return MSB200_OK;
 }
 
-int msb200_plc_process(msb200_plc *p, int16_t *io, int nsamples, const uint8_t *mode) {
-	MSB200_CHECK_ARG(p && io && mode && nsamples > 0 && nsamples <= p->max_block);
-	const size_t bytes = (size_t)p->n * nsamples * 2;
-	int r = p->io.reserve(bytes);
-	if (r || (r = p->md.reserve((size_t)p->n))) return r;
+int msb200_plc_process_strided(msb200_plc *p, int16_t *io, int nsamples, int stride_samples, const uint8_t *mode) {
+	MSB200_CHECK_ARG(p && io && mode && nsamples > 0 && nsamples <= p->max_block && stride_samples >= nsamples);
+	if (p->live == 0) return MSB200_OK;
+	const size_t row = (size_t)nsamples * 2, rows = (size_t)p->live;
+	int r = p->io.reserve(row * rows);
+	if (r || (r = p->md.reserve(rows))) return r;
 	cudaStream_t s = p->ctx->stream;
-	MSB200_CUDA(cudaMemcpyAsync(p->io.p, io, bytes, cudaMemcpyHostToDevice, s));
-	MSB200_CUDA(cudaMemcpyAsync(p->md.p, mode, (size_t)p->n, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaMemcpy2DAsync(p->io.p, row, io, (size_t)stride_samples * 2, row, rows, cudaMemcpyHostToDevice, s));
+	MSB200_CUDA(cudaMemcpyAsync(p->md.p, mode, rows, cudaMemcpyHostToDevice, s));
 	if ((r = msb200_plc_process_dev(p, p->io.p, nsamples, nsamples, p->md.p))) return r;
-	MSB200_CUDA(cudaMemcpyAsync(io, p->io.p, bytes, cudaMemcpyDeviceToHost, s));
+	MSB200_CUDA(cudaMemcpy2DAsync(io, (size_t)stride_samples * 2, p->io.p, row, row, rows, cudaMemcpyDeviceToHost, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));
 	return MSB200_OK;
+}
+
+int msb200_plc_process(msb200_plc *p, int16_t *io, int nsamples, const uint8_t *mode) {
+	return msb200_plc_process_strided(p, io, nsamples, nsamples, mode);
 }
 
 } // extern "C"

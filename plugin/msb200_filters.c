@@ -87,7 +87,7 @@ static msb200_ctx *dsp_ctx(void) {
  * (BASELINE cfg5: rooms are pinned to a GPU by giving their streams a ticker of that GPU); MSB200_DEVICE=<d> (default 0)
  * is the device of the synchronous filters and of every ticker when MSB200_DEVICES is unset.
  */
-enum { BK_RESAMPLE, BK_EC, BK_VOLUME, BK_MIXER, BK_G711DEC, BK_G711ENC }; /* the codecs are stateless: no bank, key[0] = law */
+enum { BK_RESAMPLE, BK_EC, BK_VOLUME, BK_MIXER, BK_G711DEC, BK_G711ENC, BK_PLC }; /* the codecs are stateless: no bank, key[0] = law */
 #define BATCH_MAX_SLOTS 4096
 typedef struct Batch {
 	struct Batch *next;
@@ -102,7 +102,8 @@ typedef struct Batch {
 	void *bank;
 	int unit_in, unit_out, max_units; /* samples per unit per slot in / out; units a slot may stage per tick */
 	int16_t *in[2], *out;             /* pinned arenas [cap][max_units * unit_*] */
-	uint8_t *present;                 /* mixer: [cap][pins] */
+	uint8_t *present;                 /* mixer: [cap][pins]; PLC: [cap][max_units] mode bytes (key[2] = max_units) */
+	uint8_t *modes;                   /* PLC: [cap] the mode bytes of one unit, gathered for the launch */
 	int *staged, *ready;              /* units per slot: staged this tick / ready from the last flush */
 	int out_len;                      /* samples per unit the last run produced (resampler: frames out x channels) */
 	/* moves a slot's ready results out of the arenas into mblks kept by the owner; the flush calls it for every member
@@ -152,6 +153,7 @@ static void batch_free(Batch *b) { /* unlinked, no members left */
 			case BK_EC: msb200_aec_destroy((msb200_aec *)b->bank); break;
 			case BK_VOLUME: msb200_volume_destroy((msb200_volume *)b->bank); break;
 			case BK_MIXER: msb200_mixer_destroy((msb200_mixer *)b->bank); break;
+			case BK_PLC: msb200_plc_destroy((msb200_plc *)b->bank); break;
 		}
 		if (b->in[0]) msb200_host_free_pinned(b->ctx, b->in[0]);
 		if (b->in[1]) msb200_host_free_pinned(b->ctx, b->in[1]);
@@ -160,6 +162,7 @@ static void batch_free(Batch *b) { /* unlinked, no members left */
 	}
 	pthread_mutex_destroy(&b->mu);
 	ms_free(b->present);
+	ms_free(b->modes);
 	ms_free(b->owner);
 	ms_free(b->staged);
 	ms_free(b->ready);
@@ -195,6 +198,7 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 				case BK_EC: rc = msb200_aec_create(b->ctx, cap, key[0], key[1], key[2], (msb200_aec **)&b->bank); break;
 				case BK_VOLUME: rc = msb200_volume_create(b->ctx, cap, key[0], key[1], (msb200_volume **)&b->bank); break;
 				case BK_MIXER: rc = msb200_mixer_create(b->ctx, cap, key[2], key[0], key[1], (msb200_mixer **)&b->bank); break;
+				case BK_PLC: rc = msb200_plc_create(b->ctx, cap, key[0], key[1], (msb200_plc **)&b->bank); break;
 			}
 		} else {
 			b->ctx = NULL;
@@ -203,8 +207,8 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 			const size_t n_in = (size_t)cap * max_units * unit_in * sizeof(int16_t), n_out = (size_t)cap * max_units * unit_out * sizeof(int16_t);
 			b->in[0] = (int16_t *)batch_pinned(b, n_in);
 			if (kind == BK_EC) b->in[1] = (int16_t *)batch_pinned(b, n_in);
-			b->out = kind == BK_VOLUME ? NULL : (int16_t *)batch_pinned(b, n_out);
-			if (!b->in[0] || (kind == BK_EC && !b->in[1]) || (kind != BK_VOLUME && !b->out)) rc = MSB200_ENOMEM;
+			b->out = (kind == BK_VOLUME || kind == BK_PLC) ? NULL : (int16_t *)batch_pinned(b, n_out); /* those two work in place */
+			if (!b->in[0] || (kind == BK_EC && !b->in[1]) || (kind != BK_VOLUME && kind != BK_PLC && !b->out)) rc = MSB200_ENOMEM;
 		}
 		if (rc != MSB200_OK) {
 			ms_error("msb200: cannot create a batch group (%s); the filter stays synchronous", msb200_last_error());
@@ -215,7 +219,8 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 		b->owner = (void **)ms_new0(void *, cap);
 		b->staged = ms_new0(int, cap);
 		b->ready = ms_new0(int, cap);
-		if (kind == BK_MIXER) b->present = (uint8_t *)ms_malloc0((size_t)cap * key[2]);
+		if (kind == BK_MIXER || kind == BK_PLC) b->present = (uint8_t *)ms_malloc0((size_t)cap * key[2]); /* PLC: [slot][unit] mode bytes */
+		if (kind == BK_PLC) b->modes = (uint8_t *)ms_malloc0((size_t)cap);
 		b->next = g_batches;
 		g_batches = b;
 		ms_message("msb200: batch group %p: kind %d, %d slots, key {%d,%d,%d,%d} on ticker %p", b, kind, cap, key[0], key[1], key[2], key[3], ticker);
@@ -271,6 +276,7 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 				case BK_EC: msb200_aec_set_live((msb200_aec *)b->bank, b->hi); break;
 				case BK_VOLUME: msb200_volume_set_live((msb200_volume *)b->bank, b->hi); break;
 				case BK_MIXER: msb200_mixer_set_live((msb200_mixer *)b->bank, b->hi); break;
+				case BK_PLC: msb200_plc_set_live((msb200_plc *)b->bank, b->hi); break;
 			}
 			b->live = b->hi;
 		}
@@ -301,6 +307,18 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 				rc = msb200_mixer_process((msb200_mixer *)b->bank, b->in[0], b->present, b->out);
 				b->out_len = b->unit_out;
 				break;
+			case BK_PLC: { /* one launch per unit; a unit in which no slot has device work (comfort noise only) is skipped */
+				int u;
+				for (u = 0; u < units && rc == MSB200_OK; ++u) {
+					int any = 0;
+					for (i = 0; i < b->hi; ++i) any |= (b->modes[i] = b->present[(size_t)i * b->key[2] + u]);
+					if (any)
+						rc = msb200_plc_process_strided((msb200_plc *)b->bank, b->in[0] + (size_t)u * b->unit_in, b->unit_in,
+						                                b->max_units * b->unit_in, b->modes);
+				}
+				b->out_len = b->unit_in;
+				break;
+			}
 			case BK_G711DEC: /* arenas are contiguous over the live slots: one flat batch (unstaged units decode garbage nobody reads) */
 				rc = msb200_g711_decode(b->ctx, b->key[0], (const uint8_t *)b->in[0], b->out, (size_t)b->hi * b->max_units * b->unit_out);
 				b->out_len = b->unit_out;
@@ -2243,25 +2261,33 @@ static MSFilterDesc b200_flow_control_desc = {.id = MS_AUDIO_FLOW_CONTROL_ID,
  * (history, 5 ms continuity delay, cross-fade out of a concealed stretch) and of every concealed block
  * (genericplc.c:74-241) on the GPU (msb200_plc_*). Synchronous mode. Rates whose transform sizes need a radix above 5
  * (44.1 kHz) are refused loudly and the stream passes untouched. */
+#define PLC_BATCH_UNITS 4 /* units a stream may stage per tick in a batch group: received blocks + one concealed block */
 typedef struct PlcState {
-	msb200_plc *bank; /* 1 stream */
+	msb200_plc *bank; /* 1 stream (synchronous mode) */
 	int bank_rate, bank_block;
 	int rate, nchannels;
 	int64_t sample_time, plc_start_time; /* MSConcealerContext (max_plc_time = UINT32_MAX, msgenericplc.c:44,51) */
 	unsigned long total_plc;
 	MSCngData cng_data;
 	bool_t cng_set, cng_running, refused;
+	/* lockstep batch mode (MSB200_BATCH): the stream's signal state lives in slot `slot` of the group's bank */
+	Batch *batch;
+	int slot, n_units;
+	bool_t batch_off;
+	mblk_t *unit_blk[PLC_BATCH_UNITS]; /* received block / prepared silence of each staged unit; NULL: concealed unit */
+	uint8_t unit_kind[PLC_BATCH_UNITS]; /* 1 received, 2 concealed, 3 comfort-noise silence (no device work) */
+	MSQueue pend;
 } PlcState;
 static void plc_init(MSFilter *f) {
 	PlcState *s = ms_new0(PlcState, 1);
 	s->nchannels = 1;
 	s->sample_time = -1;
 	s->plc_start_time = -1;
+	ms_queue_init(&s->pend);
 	f->data = s;
 }
-static void plc_preprocess(MSFilter *f) {
-	PlcState *s = (PlcState *)f->data;
-	if (s->bank || s->refused || !dsp_ctx()) return; /* as the reference: the context is created once (:57-60) */
+static void plc_ensure_bank(PlcState *s) { /* as the reference: the context is created once (:57-60) */
+	if (s->bank || s->refused || !dsp_ctx()) return;
 	{
 		const int N = ((s->rate * 2 / 40) / 100) * 100, T = s->rate * 5 / 1000;
 		s->bank_block = 2 * N - 2 * T;
@@ -2275,8 +2301,13 @@ static void plc_preprocess(MSFilter *f) {
 		s->bank_rate = s->rate;
 	}
 }
+static void plc_preprocess(MSFilter *f) {
+	PlcState *s = (PlcState *)f->data;
+	if (batch_capacity() <= 0) plc_ensure_bank(s); /* batch mode: the private bank is only made if the stream leaves its group */
+}
 static void plc_device(PlcState *s, int16_t *io, int n, uint8_t mode) {
 	int rc;
+	plc_ensure_bank(s);
 	if (!s->bank) return;
 	if (n > s->bank_block) {
 		ms_error("MSGenericPLC(b200): block of %d samples exceeds the %d-sample concealment window", n, s->bank_block);
@@ -2287,54 +2318,154 @@ static void plc_device(PlcState *s, int16_t *io, int n, uint8_t mode) {
 	DSP_UNLOCK();
 	if (rc != MSB200_OK) ms_error("msb200: plc_process failed: %s", msb200_last_error());
 }
+/* results of the units staged in the previous tick: received blocks get their delayed / cross-faded samples back,
+ * concealed blocks are created here, comfort-noise silence passes; everything goes to `pend` in staging order */
+static void plc_collect(void *owner, Batch *b) {
+	PlcState *s = (PlcState *)owner;
+	const bool_t ok = b->ready[s->slot] == s->n_units;
+	int u;
+	for (u = 0; u < s->n_units; ++u) {
+		const int16_t *row = b->in[0] + ((size_t)s->slot * b->max_units + u) * b->unit_in;
+		mblk_t *m = s->unit_blk[u];
+		if (s->unit_kind[u] == 1) {
+			if (ok) {
+				memcpy(m->b_rptr, row, (size_t)b->unit_in * 2);
+				ms_queue_put(&s->pend, m);
+			} else freemsg(m); /* the group's launch failed (logged there): never forward unprocessed audio */
+		} else if (s->unit_kind[u] == 2) {
+			if (ok) {
+				m = allocb((size_t)b->unit_in * 2, 0);
+				memcpy(m->b_wptr, row, (size_t)b->unit_in * 2);
+				m->b_wptr += (size_t)b->unit_in * 2;
+				mblk_set_plc_flag(m, 1);
+				ms_queue_put(&s->pend, m);
+			}
+		} else {
+			ms_queue_put(&s->pend, m);
+		}
+		s->unit_blk[u] = NULL;
+	}
+	b->ready[s->slot] = 0;
+	s->n_units = 0;
+}
+static void plc_leave_batch(PlcState *s) {
+	int u;
+	if (s->batch) batch_leave(s->batch, s->slot);
+	s->batch = NULL;
+	for (u = 0; u < s->n_units; ++u)
+		if (s->unit_blk[u]) freemsg(s->unit_blk[u]);
+	s->n_units = 0;
+}
+/* stage one unit of this tick in the group's arena; FALSE: no room left (the stream then leaves the group) */
+static bool_t plc_stage(PlcState *s, uint8_t kind, uint8_t mode, mblk_t *m) {
+	Batch *b = s->batch;
+	const int u = b->staged[s->slot];
+	if (u >= b->max_units || u != s->n_units) return FALSE;
+	if (kind == 1) memcpy(b->in[0] + ((size_t)s->slot * b->max_units + u) * b->unit_in, m->b_rptr, (size_t)b->unit_in * 2);
+	b->present[(size_t)s->slot * b->key[2] + u] = mode;
+	b->staged[s->slot] = u + 1;
+	s->unit_blk[u] = m;
+	s->unit_kind[u] = kind;
+	s->n_units = u + 1;
+	return TRUE;
+}
 static void plc_process(MSFilter *f) {
 	PlcState *s = (PlcState *)f->data;
 	const uint64_t now = f->ticker->time;
+	const int tick_samples = s->rate * s->nchannels * f->ticker->interval / 1000;
 	mblk_t *m;
+	if (s->batch && s->batch->key[0] != s->rate) plc_leave_batch(s);
+	if (s->batch) { /* the units staged in the previous tick have been processed in the arena by the group's launch */
+		batch_tick(s->batch, f->ticker->ticks);
+		if (s->n_units && s->batch->staged[s->slot] == 0) plc_collect(s, s->batch);
+	}
+	while ((m = ms_queue_get(&s->pend)) != NULL)
+		ms_queue_put(f->outputs[0], m);
 	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
 		size_t msg_size;
+		uint8_t mode;
 		if (m->b_cont) msgpullup(m, (size_t)-1);
 		msg_size = (size_t)(m->b_wptr - m->b_rptr);
 		/* ms_concealer_inc_sample_time(concealer, now, duration, TRUE) */
 		if (s->sample_time == -1) s->sample_time = (int64_t)now;
 		s->sample_time += (unsigned int)((1000 * msg_size) / ((size_t)s->rate * sizeof(int16_t) * (size_t)s->nchannels));
 		s->plc_start_time = -1;
-		plc_device(s, (int16_t *)m->b_rptr, (int)(msg_size / 2),
-		           (uint8_t)(MSB200_PLC_PACKET | (s->cng_running ? MSB200_PLC_AFTER_CNG : 0)));
+		mode = (uint8_t)(MSB200_PLC_PACKET | (s->cng_running ? MSB200_PLC_AFTER_CNG : 0));
 		if (s->cng_running) {
 			s->cng_running = FALSE;
 			s->cng_set = FALSE;
 		}
+		/* batch mode takes streams whose packets last one ticker interval (the shape of the concealed blocks) */
+		if (!s->batch && !s->batch_off && batch_capacity() > 0 && (int)(msg_size / 2) == tick_samples && tick_samples > 0) {
+			const int N = ((s->rate * 2 / 40) / 100) * 100, T = s->rate * 5 / 1000;
+			const int key[4] = {s->rate, tick_samples, PLC_BATCH_UNITS, 0};
+			if (s->rate >= 8000 && tick_samples + 2 * T <= 2 * N)
+				s->batch = batch_join(BK_PLC, f->ticker, key, tick_samples, tick_samples, PLC_BATCH_UNITS, s, plc_collect, &s->slot);
+			if (s->batch) {
+				GRP_LOCK(s->batch);
+				msb200_ctx_make_current(s->batch->ctx);
+				msb200_plc_reset_stream((msb200_plc *)s->batch->bank, s->slot);
+				GRP_UNLOCK(s->batch);
+				s->n_units = 0;
+			} else {
+				s->batch_off = TRUE;
+			}
+		}
+		if (s->batch) {
+			if ((int)(msg_size / 2) == s->batch->key[1] && plc_stage(s, 1, mode, m)) continue;
+			ms_warning("MSGenericPLC(b200): irregular input (%d samples, group block %d): leaving the batch group",
+			           (int)(msg_size / 2), s->batch->key[1]);
+			plc_leave_batch(s);
+			s->batch_off = TRUE;
+		}
+		plc_device(s, (int16_t *)m->b_rptr, (int)(msg_size / 2), mode);
 		ms_queue_put(f->outputs[0], m);
 	}
 	/* ms_concealer_context_is_concealement_required(concealer, now) */
 	if (s->sample_time != -1 && (uint64_t)s->sample_time <= now) {
-		const unsigned int buff_size = (unsigned int)(s->rate * s->nchannels * f->ticker->interval / 1000) * sizeof(int16_t);
+		const unsigned int buff_size = (unsigned int)tick_samples * sizeof(int16_t);
+		uint8_t kind;
 		if (s->plc_start_time == -1) s->plc_start_time = s->sample_time;
 		if ((uint32_t)(now - (uint64_t)s->plc_start_time) >= UINT32_MAX) {
 			s->sample_time = -1;
 			return;
 		}
 		s->total_plc++;
-		m = allocb(buff_size, 0);
-		memset(m->b_wptr, 0, buff_size);
+		s->sample_time += f->ticker->interval; /* ms_concealer_inc_sample_time(..., interval, FALSE) */
 		if (s->cng_set) { /* comfort noise without a G.729B decoder is flagged silence (:131-141) */
 			s->cng_set = FALSE;
 			s->cng_running = TRUE;
+			kind = 3;
+		} else kind = s->cng_running ? 3 : 2;
+		if (s->batch && kind == 2 && tick_samples == s->batch->key[1] && plc_stage(s, 2, MSB200_PLC_CONCEAL, NULL)) return;
+		m = allocb(buff_size, 0);
+		memset(m->b_wptr, 0, buff_size);
+		m->b_wptr += buff_size;
+		if (kind == 3) {
 			mblk_set_cng_flag(m, 1);
-		} else if (s->cng_running) {
-			mblk_set_cng_flag(m, 1);
+			if (s->batch && plc_stage(s, 3, MSB200_PLC_IDLE, m)) return; /* keeps its place behind the units in flight */
 		} else {
 			mblk_set_plc_flag(m, 1);
-			plc_device(s, (int16_t *)m->b_wptr, (int)(buff_size / sizeof(int16_t)), MSB200_PLC_CONCEAL);
 		}
-		m->b_wptr += buff_size;
+		if (s->batch) {
+			ms_warning("MSGenericPLC(b200): no room for this tick's unit: leaving the batch group");
+			plc_leave_batch(s);
+			s->batch_off = TRUE;
+		}
+		if (kind == 2) plc_device(s, (int16_t *)m->b_rptr, tick_samples, MSB200_PLC_CONCEAL);
 		ms_queue_put(f->outputs[0], m);
-		s->sample_time += f->ticker->interval; /* ms_concealer_inc_sample_time(..., interval, FALSE) */
 	}
+}
+static void plc_postprocess(MSFilter *f) { /* the group belongs to the ticker the filter is being detached from */
+	PlcState *s = (PlcState *)f->data;
+	plc_leave_batch(s);
+	ms_queue_flush(&s->pend);
+	s->batch_off = FALSE;
 }
 static void plc_uninit(MSFilter *f) {
 	PlcState *s = (PlcState *)f->data;
+	plc_leave_batch(s);
+	ms_queue_flush(&s->pend);
 	DSP_LOCK();
 	msb200_plc_destroy(s->bank);
 	DSP_UNLOCK();
@@ -2372,6 +2503,7 @@ static MSFilterDesc b200_generic_plc_desc = {.id = MS_GENERIC_PLC_ID,
                                              .init = plc_init,
                                              .preprocess = plc_preprocess,
                                              .process = plc_process,
+                                             .postprocess = plc_postprocess,
                                              .uninit = plc_uninit,
                                              .methods = plc_methods,
                                              .flags = MS_FILTER_IS_PUMP};

@@ -86,3 +86,32 @@ def test_batch_groups_survive_rooms_leaving_and_rejoining(tmp_path, tickers):
         a, b = calm[f"out{i}"], churn[f"out{i}"]
         assert len(b) < len(a) and np.array_equal(b[:20 * 480], a[:20 * 480])
         assert b[-10 * 480:].any(), "the re-joined room produces audio again"
+
+
+@pytest.mark.parametrize("rate,streams", [(16000, 12), (48000, 5)])
+def test_plc_batch_mode_is_synchronous_mode_delayed(tmp_path, rate, streams):
+    """MSGenericPLC in a lockstep batch group (one bank, one launch per unit per tick for all lossy streams of the ticker):
+    every stream's blocks equal the synchronous filter's (which test_gpu_plugin.py pins against the reference filter),
+    one ticker interval later — received, concealed, faded and comfort-noise blocks alike"""
+    ticks = 80
+
+    def run(batch, tag):
+        out = tmp_path / f"plc_{tag}.npz"
+        cmd = [sys.executable, str(ROOT / "tests" / "plc_runner.py"), "--streams", str(streams), "--ticks", str(ticks),
+               "--rate", str(rate), "--dump", str(out)]
+        r = subprocess.run(cmd, env=dict(os.environ, MSB200_BATCH=str(batch)), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return np.load(out), json.loads(r.stdout.strip().splitlines()[-1])
+
+    sync, _ = run(0, "sync")
+    batch, stats = run(16, "batch")
+    assert stats["batch_groups"] == 1 and stats["batch_launches"] >= ticks - 2
+    n = rate // 100
+    concealed_somewhere = False
+    for i in range(streams):
+        a, b = sync[f"pcm{i}"], batch[f"pcm{i}"]
+        assert len(a) - len(b) == n, (i, len(a), len(b))  # the last tick's block is still in flight
+        assert np.array_equal(a[:len(b)], b), f"stream {i}"
+        assert list(batch[f"sizes{i}"]) == list(sync[f"sizes{i}"])[:len(batch[f"sizes{i}"])]
+        concealed_somewhere |= len(a) > 0
+    assert concealed_somewhere
