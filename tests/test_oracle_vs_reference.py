@@ -475,14 +475,14 @@ def plc_signal(rate: int, nsamples: int, seed: int = 1) -> np.ndarray:
     return np.clip(np.round(x), -32768, 32767).astype(np.int16)
 
 
-def plc_reference_run(rate, ticks, schedule, x, cn_at=(), plugins_dir=None):
+def plc_reference_run(rate, ticks, schedule, x, cn_at=(), plugins_dir=None, nchannels=1):
     """the UNMODIFIED MSGenericPLC in the reference's MSTicker; schedule[tick] = list of (offset, nsamples) blocks that
     arrive in that tick; cn_at = ticks before which MS_GENERIC_PLC_SET_CN is called. Returns samples and (tick, bytes)."""
     g = RefGraph(plugins_dir=plugins_dir)
     src, plc, sink = g.source(), g.new("MSGenericPLC"), g.sink()
     assert g.text(plc).startswith("B200:") == bool(plugins_dir)
     assert g.call_int(plc, "MS_FILTER_SET_SAMPLE_RATE", rate) == 0
-    assert g.call_int(plc, "MS_FILTER_SET_NCHANNELS", 1) == 0
+    assert g.call_int(plc, "MS_FILTER_SET_NCHANNELS", nchannels) == 0
     for k, blocks in schedule.items():
         for off, n in blocks:
             g.push(src, k, x[off:off + n])
@@ -500,22 +500,22 @@ def plc_reference_run(rate, ticks, schedule, x, cn_at=(), plugins_dir=None):
     return out, [(int(a), int(b)) for a, b, _ in tri]
 
 
-def plc_oracle_run(rate, ticks, schedule, x, cn_at=()):
+def plc_oracle_run(rate, ticks, schedule, x, cn_at=(), nchannels=1):
     L = O.oracle()
     c = L.orc_plc_create(rate)
     assert c
     out, blocks, kind = [], [], C.c_int(0)
-    tick_n = rate // 100
+    tick_n = nchannels * rate // 100
     for k in range(ticks):
         if k in cn_at:
             L.orc_plc_filter_set_cn(c)
         for off, n in schedule.get(k, []):
             b = x[off:off + n].copy()
-            L.orc_plc_filter_packet(c, k * 10, ptr(b), n, 1)
+            L.orc_plc_filter_packet(c, k * 10, ptr(b), n, nchannels)
             out.append(b)
             blocks.append((k, 2 * n))
         o = np.zeros(tick_n, np.int16)
-        m = L.orc_plc_filter_tick(c, k * 10, 10, 1, ptr(o), C.byref(kind))
+        m = L.orc_plc_filter_tick(c, k * 10, 10, nchannels, ptr(o), C.byref(kind))
         if m:
             out.append(o[:m])
             blocks.append((k, 2 * m))
@@ -578,3 +578,15 @@ def test_plc_oracle_comfort_noise_path():
     out, blocks = plc_oracle_run(rate, ticks, sched, x, cn_at=(12,))
     assert ref_blocks == blocks and np.array_equal(ref, out)
     assert not ref[12 * 160:20 * 160].any()
+
+
+def test_plc_oracle_stereo_blocks():
+    """nchannels = 2: the reference treats the interleaved block as one long mono signal at `rate` (msgenericplc.c:66-68,
+    121) — twice the samples per block and per concealed tick; the oracle follows"""
+    rate, ticks, nch = 16000, 60, 2
+    n = nch * rate // 100
+    x = plc_signal(rate, ticks * n, seed=21)
+    sched = {k: [(k * n, n)] for k in range(ticks) if k not in ({7} | set(range(20, 40)))}
+    ref, ref_blocks = plc_reference_run(rate, ticks, sched, x, nchannels=nch)
+    out, blocks = plc_oracle_run(rate, ticks, sched, x, nchannels=nch)
+    assert ref_blocks == blocks and np.array_equal(ref, out)
