@@ -12,6 +12,8 @@
  * pass a flat loop over independent butterflies — the shape the CUDA kernel uses), while each butterfly keeps the
  * reference's order of float operations so that the results are bit-identical (no FMA contraction: -ffp-contract=off).
  * Supported rates are those whose transform sizes factor into 2, 3, 4 and 5 (8 / 16 / 32 / 48 kHz ...).
+ * One deliberate difference: resuming from comfort noise above 16 kHz the reference reads past its 80-sample stack buffer
+ * (msgenericplc.c:79-86, undefined behaviour); here the missing samples are the zeros the code evidently means.
  * Pinned: bit-exact against the UNMODIFIED MSGenericPLC filter run in the reference's own MSTicker
  * (oracle/_ref/libms2ref.so) — tests/test_oracle_vs_reference.py::test_plc_*. */
 #include "msb200_oracle.h"

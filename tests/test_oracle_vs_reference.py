@@ -590,3 +590,29 @@ def test_plc_oracle_stereo_blocks():
     ref, ref_blocks = plc_reference_run(rate, ticks, sched, x, nchannels=nch)
     out, blocks = plc_oracle_run(rate, ticks, sched, x, nchannels=nch)
     assert ref_blocks == blocks and np.array_equal(ref, out)
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_plc_oracle_random_schedules(seed):
+    """random rate, packet length, loss bursts (1..30 blocks) and comfort-noise requests: oracle == reference filter"""
+    rng = np.random.default_rng(1000 + seed)
+    rate = int(rng.choice([8000, 16000, 32000, 48000]))
+    block_ms = int(rng.choice([10, 10, 20]))
+    ticks = 120
+    nblocks = ticks * 10 // block_ms
+    lost, k = set(), int(rng.integers(2, 10))
+    while k < nblocks:
+        burst = int(rng.choice([1, 1, 2, 3, 5, 12, 30]))
+        lost |= set(range(k, min(k + burst, nblocks)))
+        k += burst + int(rng.integers(1, 15))
+    cn_at = tuple(sorted(int(t) for t in rng.choice(np.arange(5, ticks - 5), size=int(rng.integers(0, 3)), replace=False)))
+    if rate > 16000:
+        # above 16 kHz the reference's comfort-noise resume reads past its 80-sample stack buffer (msgenericplc.c:79-86:
+        # `int16_t continuity_buffer[80]` used for rate * 5 / 1000 samples): undefined there, all-zero in the oracle / GPU
+        cn_at = ()
+    x = plc_signal(rate, ticks * rate // 100, seed=seed)
+    sched = plc_schedule(rate, ticks, lost, block_ms)
+    ref, ref_blocks = plc_reference_run(rate, ticks, sched, x, cn_at)
+    out, blocks = plc_oracle_run(rate, ticks, sched, x, cn_at)
+    assert [b for _, b in ref_blocks] == [b for _, b in blocks]
+    assert np.array_equal(ref, out)
