@@ -616,3 +616,109 @@ def test_plc_oracle_random_schedules(seed):
     out, blocks = plc_oracle_run(rate, ticks, sched, x, cn_at)
     assert [b for _, b in ref_blocks] == [b for _, b in blocks]
     assert np.array_equal(ref, out)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_flowcontrol_oracle_random_scenarios(seed):
+    """random rate, block length, strategy, silence threshold, loudness and two drop requests at random ticks (the second one
+    is ignored while the first is still running, flowcontrol.c:196-207): oracle == reference filter, sizes and samples"""
+    from _oracle import FlowControlConfig, FlowControlDropEvent, OrcFlowCtl
+    L = O.oracle()
+    rng = np.random.default_rng(seed)
+    rate = int(rng.choice([8000, 16000, 48000]))
+    n, ticks = rate // 100 * int(rng.choice([1, 1, 2])), 50
+    strategy, thr = int(rng.integers(0, 2)), float(rng.choice([0.02, 0.0, 0.1]))
+    drop_ms, interval_ms = int(rng.choice([5, 8, 15, 30, 60, 120, 250])), int(rng.choice([50, 100, 200, 400]))
+    x = _flowctl_signal(rng, n, ticks)
+    if rng.integers(0, 2):
+        x = (x.astype(np.int32) * int(rng.integers(1, 6))).clip(-32768, 32767).astype(np.int16)
+    arm = int(rng.integers(1, 10))  # after the attach: preprocess resets the controller (:163-166)
+    arm2 = arm + int(rng.integers(3, 30))
+    g = RefGraph()
+    src, fc, sink = g.source(x, n * 2), g.new("MSAudioFlowControl"), g.sink()
+    g.call_int(fc, "MS_FILTER_SET_SAMPLE_RATE", rate)
+    g.call_int(fc, "MS_FILTER_SET_NCHANNELS", 1)
+    g.call(fc, "MS_AUDIO_FLOW_CONTROL_SET_CONFIG", FlowControlConfig(strategy, thr))
+    g.link(src, 0, fc, 0)
+    g.link(fc, 0, sink, 0)
+    done = 0
+    for stop in (arm, arm2, ticks):
+        if stop > done:
+            g.run(src, stop - done)
+            done = stop
+        if stop < ticks:
+            g.call(fc, "MS_AUDIO_FLOW_CONTROL_DROP", FlowControlDropEvent(interval_ms, drop_ms))
+    ref_out, tri = g.read(sink)
+    g.close()
+    c = OrcFlowCtl()
+    L.orc_flowctl_init(C.byref(c))
+    c.strategy, c.silent_threshold = strategy, thr
+    out, sizes = [], []
+    for t in range(ticks):
+        if t in (arm, arm2) and not (c.total_samples > 0 and c.target_samples > 0):
+            L.orc_flowctl_set_target(C.byref(c), drop_ms * rate // 1000, interval_ms * rate // 1000)
+        blk = x[t * n:(t + 1) * n].copy()
+        k = L.orc_flowctl_process(C.byref(c), ptr(blk), n)
+        if k:
+            out.append(blk[:k])
+            sizes.append(2 * k)
+    assert list(tri[:, 1]) == sizes
+    assert np.array_equal(ref_out, np.concatenate(out) if out else np.zeros(0, np.int16))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_mixer_oracle_random_rooms(seed):
+    """random rate, 2..12 pins, both modes, gains (0 and > 1 included), muted pins, a pin stuck at -32768, pins that starve
+    on random ticks: every output block of the reference filter equals the oracle's"""
+    L = O.oracle()
+    rng = np.random.default_rng(seed)
+    rate, P, T = int(rng.choice([8000, 16000, 48000])), int(rng.integers(2, 13)), 10
+    nwords, conf = rate // 100, bool(rng.integers(0, 2))
+    amp = int(rng.choice([3000, 9000, 30000]))
+    pcm = rng.integers(-amp, amp + 1, size=(P, T * nwords)).astype(np.int16)
+    if rng.integers(0, 2):
+        pcm[int(rng.integers(0, P)), 2 * nwords:3 * nwords] = -32768
+    gains = {int(p): float(rng.choice([0.5, 1.7, 0.0, 2.5, 1.0])) for p in rng.choice(P, size=int(rng.integers(0, P)), replace=False)}
+    inactive = tuple(int(p) for p in rng.choice(P, size=int(rng.integers(0, max(1, P // 2))), replace=False))
+    starve = {(int(rng.integers(0, P)), int(rng.integers(1, T))) for _ in range(int(rng.integers(0, 4)))}
+    g = RefGraph()
+    mix = g.new("MSAudioMixer")
+    g.call_int(mix, "MS_FILTER_SET_SAMPLE_RATE", rate)
+    g.call_int(mix, "MS_AUDIO_MIXER_ENABLE_CONFERENCE_MODE", int(conf))
+    for p, gn in gains.items():
+        ctl = MixerCtl(pin=p)
+        ctl.param.gain = gn
+        assert g.call(mix, "MS_AUDIO_MIXER_SET_INPUT_GAIN", ctl) == 0
+    for p in inactive:
+        ctl = MixerCtl(pin=p)
+        ctl.param.active = 0
+        assert g.call(mix, "MS_AUDIO_MIXER_SET_ACTIVE", ctl) == 0
+    srcs, sinks = [], []
+    for p in range(P):
+        s = g.source()
+        for t in range(T):
+            if (p, t) not in starve:
+                g.push(s, t, pcm[p, t * nwords:(t + 1) * nwords])
+        k = g.sink()
+        g.link(s, 0, mix, p)
+        g.link(mix, p, k, 0)
+        srcs.append(s)
+        sinks.append(k)
+    g.run(srcs[0], T)
+    outs = [g.read(k)[0] for k in sinks]
+    g.close()
+    gain = np.ones(P, np.float32)
+    for p, v in gains.items():
+        gain[p] = v
+    active = np.ones(P, np.uint8)
+    active[list(inactive)] = 0
+    for t in range(T):
+        present = np.ones(P, np.uint8)
+        for p, tt in starve:
+            if tt == t:
+                present[p] = 0
+        blk = np.ascontiguousarray(pcm[:, t * nwords:(t + 1) * nwords])
+        out = np.zeros((P, nwords) if conf else (1, nwords), np.int16)
+        L.orc_mixer_process(1, P, nwords, int(conf), ptr(gain), ptr(active), ptr(blk), ptr(present), ptr(out))
+        for p in range(P):
+            assert np.array_equal(out[p] if conf else out[0], outs[p][t * nwords:(t + 1) * nwords]), (t, p)
