@@ -722,3 +722,79 @@ def test_mixer_oracle_random_rooms(seed):
         L.orc_mixer_process(1, P, nwords, int(conf), ptr(gain), ptr(active), ptr(blk), ptr(present), ptr(out))
         for p in range(P):
             assert np.array_equal(out[p] if conf else out[0], outs[p][t * nwords:(t + 1) * nwords]), (t, p)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_volume_oracle_random_configs(seed):
+    """random rate, block length, gain (0 .. 6), noise gate threshold / floor gain (below the 0.005 minimum included), DC
+    removal, signal level, DC offset and noise: samples and the smoothed energy equal the reference filter's bit for bit"""
+    L = O.oracle()
+    rng = np.random.default_rng(seed)
+    rate, T = int(rng.choice([8000, 16000, 48000])), 40
+    n = rate // 100 * int(rng.choice([1, 1, 2]))
+    t = np.arange(T * n)
+    env = (np.sin(2 * np.pi * float(rng.uniform(0.5, 3)) * t / rate) > 0).astype(np.float64)
+    amp = float(rng.choice([300, 3000, 9000, 20000, 32000]))
+    x = (env * amp * np.sin(2 * np.pi * float(rng.uniform(100, 3000)) * t / rate)
+         + float(rng.uniform(0, 500)) * np.sin(2 * np.pi * 50 * t / rate) + float(rng.uniform(-2000, 2000))
+         + rng.normal(0, float(rng.choice([0, 30, 300])), T * n)).clip(-32768, 32767).astype(np.int16)
+    if rng.integers(0, 2):
+        x[5 * n:6 * n] = 32767
+        x[6 * n:7 * n] = -32768
+    gain = float(rng.choice([0.0, 0.1, 0.8, 1.0, 1.3, 2.5, 6.0]))
+    ng, dc = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    thr, floor = float(rng.choice([0.01, 0.05, 0.2])), float(rng.choice([0.0, 0.02, 0.3]))
+    g = RefGraph()
+    vol = g.new("MSVolume")
+    g.call_int(vol, "MS_FILTER_SET_SAMPLE_RATE", rate)
+    g.call_float(vol, "MS_VOLUME_SET_GAIN", gain)
+    if ng:
+        g.call(vol, "MS_VOLUME_ENABLE_NOISE_GATE", C.c_ubyte(1))
+        g.call_float(vol, "MS_VOLUME_SET_NOISE_GATE_THRESHOLD", thr)
+        g.call_float(vol, "MS_VOLUME_SET_NOISE_GATE_FLOORGAIN", floor)
+    if dc:
+        g.call_int(vol, "MS_VOLUME_REMOVE_DC", 1)
+    src, sink = g.source(x, n * 2), g.sink()
+    g.link(src, 0, vol, 0)
+    g.link(vol, 0, sink, 0)
+    g.run(src, T)
+    y_ref, _ = g.read(sink)
+    lin = C.c_float()
+    g.call(vol, "MS_VOLUME_GET_LINEAR", lin)
+    g.close()
+    st = OrcVolumeState()
+    L.orc_volume_init(C.byref(st), rate)
+    st.gain = st.target_gain = st.static_gain = gain
+    if ng:
+        st.noise_gate_enabled = 1
+        st.ng_threshold = thr
+        st.ng_floorgain = max(floor, 0.005)  # volume_set_noise_gate_floorgain clamps (msvolume.c:366-369)
+        st.gain = st.target_gain = st.ng_floorgain  # soft start (:352, :371)
+    if dc:
+        st.remove_dc = 1
+    y = x.copy()
+    for k in range(T):
+        L.orc_volume_process(C.byref(st), ptr(y[k * n:(k + 1) * n]), n)
+    assert np.array_equal(y, y_ref)
+    assert np.float32(lin.value) == np.float32(st.energy)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_nv12_oracle_random_geometries(seed):
+    """random frame sizes (8 .. 320 wide), paddings, rotations, decimation and plane order on random pixels"""
+    L, R = O.oracle(), O.ref()
+    rng = np.random.default_rng(seed)
+    rotation, ds = int(rng.choice([0, 90, 180, 270])), int(rng.integers(0, 2))
+    f = 2 if ds else 1
+    sw, sh = int(rng.integers(1, 40)) * 4 * f, int(rng.integers(1, 30)) * 4 * f
+    w, h = (sw // f, sh // f) if rotation % 180 == 0 else (sh // f, sw // f)
+    y_stride, c_stride = sw + int(rng.choice([0, 4, 16, 33])), sw + int(rng.choice([0, 2, 8, 64]))
+    ybuf = rng.integers(0, 256, y_stride * sh + 64).astype(np.uint8)
+    cbuf = rng.integers(0, 256, c_stride * (sh // 2) + 64).astype(np.uint8)
+    u_first = int(rng.integers(0, 2))
+    a = np.zeros(w * h * 3 // 2 + 64, np.uint8)
+    b = np.zeros_like(a)
+    na = L.orc_nv12_to_i420(ptr(ybuf), ptr(cbuf), rotation, w, h, y_stride, c_stride, u_first, ds, ptr(a))
+    nb = R.ref_nv12_to_i420(ptr(ybuf), ptr(cbuf), rotation, w, h, y_stride, c_stride, u_first, ds, ptr(b))
+    assert na == nb == w * h * 3 // 2
+    assert np.array_equal(a, b)
