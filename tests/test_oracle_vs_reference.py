@@ -798,3 +798,40 @@ def test_nv12_oracle_random_geometries(seed):
     nb = R.ref_nv12_to_i420(ptr(ybuf), ptr(cbuf), rotation, w, h, y_stride, c_stride, u_first, ds, ptr(b))
     assert na == nb == w * h * 3 // 2
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_equalizer_oracle_random_gain_tables(seed):
+    """random rate (nfft 128 / 256 / 512), up to four random gain points (0.1 .. 4, widths 50 .. 1000 Hz), random multi-tone
+    input with noise: within 1 LSB of the reference filter (float kiss_fft taps there, double-precision DFT here)"""
+    L = O.oracle()
+    rng = np.random.default_rng(seed)
+    rate, T = int(rng.choice([8000, 16000, 32000, 48000])), 12
+    n = rate // 100
+    t = np.arange(T * n)
+    x = np.zeros(T * n)
+    for _ in range(int(rng.integers(1, 5))):
+        x += float(rng.uniform(500, 6000)) * np.sin(2 * np.pi * float(rng.uniform(50, rate / 2 - 100)) * t / rate + float(rng.uniform(0, 6)))
+    x += rng.normal(0, float(rng.choice([0, 100, 1500])), T * n)
+    x = x.clip(-32768, 32767).astype(np.int16)
+    gains = [(int(rng.uniform(50, rate / 2 - 50)), float(rng.choice([0.1, 0.4, 1.0, 2.0, 4.0])), int(rng.choice([50, 200, 400, 1000])))
+             for _ in range(int(rng.integers(0, 5)))]
+    g = RefGraph()
+    eq = g.new("MSEqualizer")
+    g.call_int(eq, "MS_FILTER_SET_SAMPLE_RATE", rate)
+    for f, gn, w in gains:
+        g.call(eq, "MS_EQUALIZER_SET_GAIN", EqualizerGain(f, gn, w))
+    src, sink = g.source(x, n * 2), g.sink()
+    g.link(src, 0, eq, 0)
+    g.link(eq, 0, sink, 0)
+    g.run(src, T)
+    y_ref, _ = g.read(sink)
+    g.close()
+    e = L.orc_equalizer_new(rate)
+    for f, gn, w in gains:
+        L.orc_equalizer_set_gain(e, f, gn, w)
+    y = x.copy()
+    for k in range(T):
+        L.orc_equalizer_process(e, ptr(y[k * n:(k + 1) * n]), n)
+    L.orc_equalizer_free(e)
+    assert np.abs(y.astype(np.int32) - y_ref.astype(np.int32)).max() <= 1
