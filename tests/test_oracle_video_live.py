@@ -1,0 +1,116 @@
+"""oracle/oracle_video.c against the LIVE libswscale of this image (the library the reference's ffmpeg scaler back-end calls,
+src/voip/msvideo.c:651-681) on random geometries and formats — a wider net than the 16 committed golden frames. Skipped
+where the library is absent (the GPU box). Also pins, as known limits, the two places where the library leaves the algorithm
+the oracle restates."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+
+import _oracle as O  # noqa: E402
+from _oracle import ptr  # noqa: E402
+from bench_video import _load_libswscale  # noqa: E402
+from make_swscale_golden import AV_PIX, SWS_BILINEAR, SWS_BITEXACT, sws_convert  # noqa: E402
+from make_swscale_golden import test_frame as make_frame  # noqa: E402
+
+AV2MS = {0: 0, 1: 1, 2: 2, 3: 3, 15: 5, 23: 100, 24: 101, 26: 7, 28: 11}  # AVPixelFormat -> MSB200_PIX_*
+_SWS = None
+
+
+def _sws():
+    global _SWS
+    if _SWS is None:
+        _SWS = _load_libswscale() or False
+    if not _SWS:
+        pytest.skip("libswscale (opencv wheel) not available here")
+    return _SWS
+
+
+def _oracle_convert(src, sf, sw, sh, df, dw, dh):
+    L = O.oracle()
+    s = L.orc_scaler_new(sw, sh, AV2MS[AV_PIX[sf]], dw, dh, AV2MS[AV_PIX[df]])
+    assert s
+    out = np.zeros(L.orc_scaler_dst_bytes(s) + 64, np.uint8)
+    assert L.orc_scaler_process(s, ptr(np.ascontiguousarray(src)), ptr(out)) == 0
+    L.orc_scaler_free(s)
+    return out[:-64]
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_scaler_oracle_vs_live_libswscale_random(seed):
+    """random source sizes (16 .. 300), scale factors 0.25 .. 3 (independent per axis), all supported format pairs.
+    Bit-exact against the library's C reference functions (SWS_BITEXACT); where that flag itself changes the FILTER (it zeroes
+    the taps the alignment padding would keep, utils.c initFilter) the oracle must equal the plain-flag output the reference
+    really asks for: exactly for RGB24, within the library's approximate x86 SIMD for planar (<= 1) and BGR24 (<= 5)."""
+    sws = _sws()
+    rng = np.random.default_rng(seed)
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        sf, df = str(rng.choice(["nv12", "nv21", "yuv420p"])), str(rng.choice(["rgb24", "bgr24"]))
+    elif kind == 1:
+        sf = df = "yuv420p"
+    elif kind == 2:
+        sf, df = str(rng.choice(["nv12", "nv21"])), "yuv420p"
+    else:
+        sf, df = str(rng.choice(["yuyv422", "uyvy422", "rgb24", "bgr24", "rgba", "bgra"])), "yuv420p"
+    sw, sh = int(rng.integers(8, 150)) * 2, int(rng.integers(8, 100)) * 2
+    if kind == 3:
+        if sf in ("yuyv422", "uyvy422"):
+            sw = (sw + 15) // 16 * 16  # see test_packed422_tail_columns_known_limit
+        dw, dh = sw, sh
+    else:
+        r = float(rng.choice([0.25, 0.4, 0.5, 0.6667, 0.75, 0.9, 1.0, 1.25, 1.5, 2.0, 3.0]))
+        r2 = r if rng.integers(0, 3) else float(rng.choice([0.5, 0.75, 1.0, 1.5]))
+        dw, dh = max(8, int(sw * r) // 2 * 2), max(8, int(sh * r2) // 2 * 2)
+        if sf == "yuv420p" and df in ("rgb24", "bgr24") and (dw, dh) == (sw, sh):
+            dw += 2  # see test_yuv420p_to_rgb_same_size_known_limit
+    src = make_frame(sf, sw, sh, t=seed, seed=seed)
+    out = _oracle_convert(src, sf, sw, sh, df, dw, dh)
+    exact = sws_convert(sws, src, sf, sw, sh, df, dw, dh, SWS_BILINEAR | SWS_BITEXACT)
+    if np.array_equal(out, exact):
+        return
+    plain = sws_convert(sws, src, sf, sw, sh, df, dw, dh, SWS_BILINEAR)
+    d = np.abs(out.astype(int) - plain.astype(int))
+    tol = 0 if df == "rgb24" else (5 if df == "bgr24" else 1)
+    assert d.max() <= tol, (sf, sw, sh, df, dw, dh, int(d.max()))
+
+
+@pytest.mark.parametrize("w", [46, 90, 148, 260])
+def test_packed422_tail_columns_known_limit(w):
+    """YUYV / UYVY -> I420: the library averages the two chroma lines with a rounding SIMD average over whole 16-pixel
+    groups and a truncating scalar loop over the rest of the row (rgb2rgb, x86). The oracle (and the GPU) round everywhere:
+    exact for every width that is a multiple of 16 (all standard video sizes), within 1 in the tail chroma columns otherwise."""
+    sws = _sws()
+    h = 16
+    src = make_frame("yuyv422", w, h, t=1, seed=w)
+    out = _oracle_convert(src, "yuyv422", w, h, "yuv420p", w, h)
+    ref = sws_convert(sws, src, "yuyv422", w, h, "yuv420p", w, h, SWS_BILINEAR)
+    cw = w // 2
+    assert np.array_equal(out[:w * h], ref[:w * h])
+    for plane in range(2):
+        a = out[w * h + plane * cw * (h // 2):][:cw * (h // 2)].reshape(h // 2, cw).astype(int)
+        b = ref[w * h + plane * cw * (h // 2):][:cw * (h // 2)].reshape(h // 2, cw).astype(int)
+        assert np.array_equal(a[:, :cw & ~7], b[:, :cw & ~7])
+        assert np.abs(a - b).max() <= 1 and np.all(a >= b)
+
+
+def test_yuv420p_to_rgb_same_size_known_limit():
+    """YUV420P -> RGB24 at IDENTICAL size: the library leaves the scaler for its table-driven unscaled converter (yuv2rgb.c);
+    the oracle (and the GPU) stay on the scaler path the reference's display filters get at every other size. NV12 input has
+    no such converter and is exact at identical size too."""
+    sws = _sws()
+    w, h = 128, 72
+    src = make_frame("yuv420p", w, h, t=5, seed=5)
+    out = _oracle_convert(src, "yuv420p", w, h, "rgb24", w, h)
+    ref = sws_convert(sws, src, "yuv420p", w, h, "rgb24", w, h, SWS_BILINEAR)
+    d = np.abs(out.astype(int) - ref.astype(int))
+    assert 0 < d.max() <= 6 and d.mean() < 1.0
+    src = make_frame("nv12", w, h, t=5, seed=5)
+    assert np.array_equal(_oracle_convert(src, "nv12", w, h, "rgb24", w, h),
+                          sws_convert(sws, src, "nv12", w, h, "rgb24", w, h, SWS_BILINEAR))
