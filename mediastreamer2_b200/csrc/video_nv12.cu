@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(256) packed422_to_i420_kernel(const uint8_t *_
 	const unsigned yb0 = __byte_perm(b.x, b.y, ysel), yb1 = __byte_perm(b.z, b.w, ysel);
 	const unsigned ca0 = __byte_perm(a.x, a.y, csel), ca1 = __byte_perm(a.z, a.w, csel); // U V U V
 	const unsigned cb0 = __byte_perm(b.x, b.y, csel), cb1 = __byte_perm(b.z, b.w, csel);
-	const unsigned m0 = __vavgu4(ca0, cb0), m1 = __vavgu4(ca1, cb1); // per-byte (x + y + 1) >> 1
+	// per-byte (x + y + 1) >> 1 — except in the row's last group when w % 16 == 8: the library's x86 row function rounds over
+	// whole groups of 8 chroma samples only and truncates in its scalar tail (oracle_video.c, pinned on the live library)
+	const bool tail = gx * 4 >= ((w / 2) & ~7);
+	const unsigned m0 = tail ? __vhaddu4(ca0, cb0) : __vavgu4(ca0, cb0), m1 = tail ? __vhaddu4(ca1, cb1) : __vavgu4(ca1, cb1);
 	const unsigned u4 = __byte_perm(m0, m1, 0x6420), v4 = __byte_perm(m0, m1, 0x7531);
 	*reinterpret_cast<uint2 *>(fd + (size_t)(2 * cy) * w + (size_t)gx * 8) = make_uint2(ya0, ya1);
 	*reinterpret_cast<uint2 *>(fd + (size_t)(2 * cy + 1) * w + (size_t)gx * 8) = make_uint2(yb0, yb1);

@@ -472,8 +472,12 @@ int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst) {
 		for (int y = 0; y < sh / 2; ++y) {
 			const uint8_t *r0 = src + (size_t)(2 * y) * sw * 2, *r1 = r0 + (size_t)sw * 2;
 			for (int x = 0; x < sw / 2; ++x) {
-				du[(size_t)y * (sw / 2) + x] = (uint8_t)((r0[4 * x + uo] + r1[4 * x + uo] + 1) >> 1);
-				dv[(size_t)y * (sw / 2) + x] = (uint8_t)((r0[4 * x + vo] + r1[4 * x + vo] + 1) >> 1);
+				/* the library's x86 row function averages whole groups of 8 chroma samples with a rounding SIMD average and
+				 * the rest of the row with a truncating scalar loop (rgb2rgb extract_odd2avg): reproduced as observed on the
+				 * live library (tests/test_oracle_video_live.py) */
+				const int rnd = x < ((sw / 2) & ~7) ? 1 : 0;
+				du[(size_t)y * (sw / 2) + x] = (uint8_t)((r0[4 * x + uo] + r1[4 * x + uo] + rnd) >> 1);
+				dv[(size_t)y * (sw / 2) + x] = (uint8_t)((r0[4 * x + vo] + r1[4 * x + vo] + rnd) >> 1);
 			}
 		}
 		return 0;
