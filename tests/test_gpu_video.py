@@ -256,7 +256,8 @@ def test_pixconv_rgb24_to_i420_bit_exact(ctx, fmt, w, h):
     L.orc_scaler_free(o)
 
 
-@pytest.mark.parametrize("fmt,w,h", [(_lib.PIX_YUYV, 96, 64), (_lib.PIX_UYVY, 64, 48), (_lib.PIX_YUY2, 1280, 720)])
+@pytest.mark.parametrize("fmt,w,h", [(_lib.PIX_YUYV, 96, 64), (_lib.PIX_UYVY, 64, 48), (_lib.PIX_YUY2, 1280, 720),
+                                     (_lib.PIX_YUYV, 104, 32), (_lib.PIX_UYVY, 72, 16)])  # w % 16 == 8: the truncating tail group
 def test_pixconv_packed422_to_i420_bit_exact(ctx, fmt, w, h):
     """MSPixConv's packed inputs: GPU == oracle (itself bit-exact vs real libswscale, tests/test_oracle_video.py)."""
     L = O.oracle()
