@@ -2014,6 +2014,11 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		return MSB200_EINVAL;
 	}
 	MSB200_CHECK_ARG(src_w >= 8 && src_h >= 8 && dst_w >= 8 && dst_h >= 8);
+	if (dst_fmt != MSB200_PIX_YUV420P && (dst_w & 1)) {
+		// libswscale forces SWS_FULL_CHR_H_INT for an odd RGB output width (utils.c sws_init_context): a different algorithm
+		msb200_set_error("scaler: RGB destinations need an even width (%d)", dst_w);
+		return MSB200_EINVAL;
+	}
 	// TMA tensor maps need 16-byte row pitches (luma width % 16 == 0, chroma plane pitch % 16 == 0); frames that do not
 	// have them, and down-scales whose per-tile source window exceeds a TMA box, take the tile-free direct kernel
 	bool direct = !(src_w >= 16 && src_h >= 16 && dst_w >= 16 && dst_h >= 16 && src_w % 16 == 0 &&

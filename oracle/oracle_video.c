@@ -282,6 +282,9 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 	const int src_ok = src_fmt == PIX_YUV420P || src_fmt == PIX_NV12 || src_fmt == PIX_NV21;
 	const int dst_ok = dst_fmt == PIX_YUV420P || dst_fmt == PIX_RGB24 || dst_fmt == PIX_BGR24;
 	if (!src_ok || !dst_ok || src_w < 8 || src_h < 8 || dst_w < 8 || dst_h < 8) return NULL;
+	/* an odd RGB output width makes the library switch to full horizontal chroma interpolation (SWS_FULL_CHR_H_INT is forced,
+	 * utils.c sws_init_context): another algorithm, not restated — refused here and by msb200_scaler_create alike */
+	if (dst_fmt != PIX_YUV420P && (dst_w & 1)) return NULL;
 	s = (orc_scaler *)calloc(1, sizeof(*s));
 	s->src_w = src_w; s->src_h = src_h; s->src_fmt = src_fmt;
 	s->dst_w = dst_w; s->dst_h = dst_h; s->dst_fmt = dst_fmt;

@@ -106,3 +106,45 @@ def test_yuv420p_to_rgb_same_size_known_limit():
     src = make_frame("nv12", w, h, t=5, seed=5)
     assert np.array_equal(_oracle_convert(src, "nv12", w, h, "rgb24", w, h),
                           sws_convert(sws, src, "nv12", w, h, "rgb24", w, h, SWS_BILINEAR))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_scaler_oracle_vs_live_libswscale_extreme_ratios_and_odd_sizes(seed):
+    """scale factors 0.1 .. 6 (independent per axis), odd source / destination sizes (odd chroma geometry, last-row and
+    last-column folding of the filters): same acceptance as above. Output widths below 16 are left out: the library itself
+    writes past the end of such narrow tight planes."""
+    sws = _sws()
+    rng = np.random.default_rng(10000 + seed)
+    sf, df = str(rng.choice(["nv12", "nv21", "yuv420p"])), str(rng.choice(["rgb24", "bgr24", "yuv420p"]))
+    odd = bool(rng.integers(0, 2))
+    sw, sh = int(rng.integers(16, 400)), int(rng.integers(16, 300))
+    r = float(rng.choice([0.1, 0.15, 0.2, 0.3, 0.45, 0.55, 0.8, 1.1, 1.7, 2.5, 4.0, 6.0]))
+    r2 = float(rng.choice([r, r, 0.3, 1.0, 2.2]))
+    dw, dh = max(16, int(sw * r)), max(8, int(sh * r2))
+    if not odd:
+        sw, sh, dw, dh = sw & ~1, sh & ~1, dw & ~1, dh & ~1
+    if df != "yuv420p":
+        dw &= ~1  # odd RGB widths are refused: test_odd_rgb_width_is_refused
+    if (dw, dh) == (sw, sh):
+        dw += 2
+    if dw > 1200 or dh > 900:
+        dw, dh = min(dw, 1200) & ~1, min(dh, 900) & ~1
+    src = make_frame(sf, sw, sh, t=seed, seed=seed)
+    out = _oracle_convert(src, sf, sw, sh, df, dw, dh)
+    exact = sws_convert(sws, src, sf, sw, sh, df, dw, dh, SWS_BILINEAR | SWS_BITEXACT)
+    if np.array_equal(out, exact):
+        return
+    plain = sws_convert(sws, src, sf, sw, sh, df, dw, dh, SWS_BILINEAR)
+    d = np.abs(out.astype(int) - plain.astype(int))
+    tol = 0 if df == "rgb24" else (5 if df == "bgr24" else 1)
+    assert d.max() <= tol, (sf, sw, sh, df, dw, dh, int(d.max()))
+
+
+def test_odd_rgb_width_is_refused():
+    """for an odd RGB output width the library forces SWS_FULL_CHR_H_INT (full horizontal chroma interpolation, another
+    algorithm): the oracle refuses it, and so does msb200_scaler_create"""
+    L = O.oracle()
+    assert not L.orc_scaler_new(64, 48, 0, 33, 24, 2)
+    s = L.orc_scaler_new(64, 48, 0, 33, 24, 0)  # planar output: fine
+    assert s
+    L.orc_scaler_free(s)
