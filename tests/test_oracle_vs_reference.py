@@ -835,3 +835,75 @@ def test_equalizer_oracle_random_gain_tables(seed):
         L.orc_equalizer_process(e, ptr(y[k * n:(k + 1) * n]), n)
     L.orc_equalizer_free(e)
     assert np.abs(y.astype(np.int32) - y_ref.astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_volume_chunked_mode_oracle_random_configs(seed):
+    """AGC and / or echo limiter with random rate, gain, thresholds, speed, force, sustain, loudness, and microphone blocks
+    of random length arriving on random ticks (0 .. 2 ticks apart, several per tick): oracle == reference filters"""
+    L = O.oracle()
+    rng = np.random.default_rng(seed)
+    rate, T = int(rng.choice([8000, 16000, 48000])), 60
+    n = rate // 100
+    agc, peer = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    if not agc and not peer:
+        agc = True
+    spk = _speechy(seed * 2 + 1, T * n, rate, float(rng.choice([500, 3000, 9000, 25000])))
+    mic = _speechy(seed * 2 + 2, T * n, rate, float(rng.choice([300, 2000, 5000, 20000])))
+    gain = float(rng.choice([0.5, 1.0, 1.5, 3.0]))
+    ea = (float(rng.choice([0.01, 0.05, 0.2])), float(rng.choice([0.1, 0.3, 0.5])), float(rng.choice([2.0, 6.0, 15.0])),
+          int(rng.choice([50, 100, 400])))
+    blk = int(rng.choice([2 * n // 3, n, n // 2, 3 * n // 2]))
+    g = RefGraph()
+    vspk, vmic = g.new("MSVolume"), g.new("MSVolume")
+    for v in (vspk, vmic):
+        g.call_int(v, "MS_FILTER_SET_SAMPLE_RATE", rate)
+    g.call_float(vmic, "MS_VOLUME_SET_GAIN", gain)
+    if agc:
+        g.call_int(vmic, "MS_VOLUME_ENABLE_AGC", 1)
+    if peer:
+        g.call_ptr(vmic, "MS_VOLUME_SET_PEER", vspk)
+        assert g.call_float(vmic, "MS_VOLUME_SET_EA_THRESHOLD", ea[0]) == 0
+        assert g.call_float(vmic, "MS_VOLUME_SET_EA_SPEED", ea[1]) == 0
+        assert g.call_float(vmic, "MS_VOLUME_SET_EA_SPEED", 0.9) == -1  # out of [0, 0.5]: refused, value kept (:324-333)
+        g.call_float(vmic, "MS_VOLUME_SET_EA_FORCE", ea[2])
+        g.call_int(vmic, "MS_VOLUME_SET_EA_SUSTAIN", ea[3])
+    s_spk, k_spk = g.source(spk, n * 2), g.sink()
+    s_mic, k_mic = g.source(), g.sink()
+    sched, pos, tick = {}, 0, 0
+    while pos < len(mic):
+        g.push(s_mic, tick, mic[pos:pos + blk])
+        sched.setdefault(tick, []).append((pos, min(pos + blk, len(mic))))
+        pos += blk
+        tick += int(rng.integers(0, 3))
+    g.link(s_spk, 0, vspk, 0)
+    g.link(vspk, 0, k_spk, 0)
+    g.link(s_mic, 0, vmic, 0)
+    g.link(vmic, 0, k_mic, 0)
+    total = max(T, tick) + 5
+    g.run([s_spk, s_mic], total)
+    y_spk, _ = g.read(k_spk)
+    y_mic, _ = g.read(k_mic)
+    g.close()
+    st_spk, st_mic = OrcVolumeState(), OrcVolumeState()
+    L.orc_volume_init(C.byref(st_spk), rate)
+    L.orc_volume_init(C.byref(st_mic), rate)
+    st_mic.gain = st_mic.target_gain = st_mic.static_gain = gain
+    st_mic.agc_enabled = int(agc)
+    if peer:
+        st_mic.ea_thres, st_mic.vol_upramp, st_mic.force, st_mic.sustain_time = ea
+    buf, out_mic, exp_spk = np.zeros(0, np.int16), [], spk.copy()
+    for t in range(total):
+        if t < T:
+            L.orc_volume_process(C.byref(st_spk), ptr(exp_spk[t * n:(t + 1) * n]), n)
+        for a, b in sched.get(t, []):
+            buf = np.concatenate([buf, mic[a:b]])
+        while len(buf) >= n:
+            chunk = np.ascontiguousarray(buf[:n])
+            buf = buf[n:]
+            pe = C.c_float(st_spk.energy)
+            L.orc_volume_process_chunk(C.byref(st_mic), C.byref(pe) if peer else None, ptr(chunk), n)
+            out_mic.append(chunk)
+    out_mic = np.concatenate(out_mic) if out_mic else np.zeros(0, np.int16)
+    assert np.array_equal(y_spk, exp_spk)
+    assert len(y_mic) == len(out_mic) and np.array_equal(y_mic, out_mic)
