@@ -187,6 +187,9 @@ MSB200_API int msb200_equalizer_set_gain(msb200_equalizer *e, int stream, float 
 MSB200_API int msb200_equalizer_get_gain(msb200_equalizer *e, int stream, float frequency, float *gain);
 MSB200_API int msb200_equalizer_set_active(msb200_equalizer *e, int stream, int active);
 /* direct tap access (tests, state restore): taps [nfft] float */
+/* the design step alone (equalizer_state_compute_impulse_response, equalizer.c:215-237: ms_ifft of the packed gain table,
+ * time shift, Hamming window), on the host, no device needed: nfft in {128, 256, 512}; taps equal the reference's bit for bit */
+MSB200_API int msb200_equalizer_design(int nfft, const float *gain_table, float *taps);
 MSB200_API int msb200_equalizer_set_taps(msb200_equalizer *e, int stream, const float *taps);
 MSB200_API int msb200_equalizer_get_taps(msb200_equalizer *e, int stream, float *taps);
 MSB200_API int msb200_equalizer_process(msb200_equalizer *e, int16_t *io, int nsamples);

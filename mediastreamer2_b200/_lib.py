@@ -141,6 +141,7 @@ _SIGS = {
     "msb200_equalizer_set_gain": (_I, [_P, _I, _F, _F, _F]),
     "msb200_equalizer_get_gain": (_I, [_P, _I, _F, C.POINTER(C.c_float)]),
     "msb200_equalizer_set_active": (_I, [_P, _I, _I]),
+    "msb200_equalizer_design": (_I, [_I, _P, _P]),
     "msb200_equalizer_set_taps": (_I, [_P, _I, _P]),
     "msb200_equalizer_get_taps": (_I, [_P, _I, _P]),
     "msb200_equalizer_process": (_I, [_P, _P, _I]),

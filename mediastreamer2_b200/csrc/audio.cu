@@ -766,27 +766,94 @@ static void eq_point_set(std::vector<float> &t, int nfft, int i, float gain) { /
 	int index = 1 + ((i - 1) * 2);
 	if (index >= 0 && index < nfft) t[(size_t)index] = (t[(size_t)index] * (float)(int)(gain * 32768)) / 32768;
 }
-// gain table -> impulse response: ms_ifft (unnormalised packed-real inverse, kiss_fftr.c:261-296) + time_shift
-// (equalizer.c:184-193) + Hamming (:203-213). The inverse transform is evaluated directly in double precision.
+// ms_ifft (dsptools.c:373-376) for the equalizer's sizes (128 / 256 / 512 points): kiss_fftri2 (kiss_fftr.c:261-296) over the
+// float kiss_fft (kiss_fft.c: digit-reversal gather, then radix-2 / radix-4 passes from the innermost level out), every
+// float operation in the reference's order, twiddles from the same double-precision expressions, so that the taps - and with
+// the FIR's summation order (eq_fir_kernel) every output sample - equal the reference's bit for bit. Host code.
+namespace {
+struct EqCpx {
+	float r, i;
+};
+inline EqCpx eq_cmul(EqCpx a, EqCpx b) { return {a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }
+inline EqCpx eq_cadd(EqCpx a, EqCpx b) { return {a.r + b.r, a.i + b.i}; }
+inline EqCpx eq_csub(EqCpx a, EqCpx b) { return {a.r - b.r, a.i - b.i}; }
+bool eq_kiss_irfft(const float *spec, float *out, int nfft) {
+	const double pi = 3.14159265358979323846264338327;
+	const int n = nfft / 2;
+	std::vector<EqCpx> tw((size_t)n), super((size_t)n), tmp((size_t)n), F((size_t)n);
+	for (int i = 0; i < n; ++i) {
+		const double phase = -((-2 * pi / n) * i); // inverse transform
+		tw[(size_t)i] = {(float)cos(phase), (float)sin(phase)};
+		const double ph2 = pi * (((double)i) / n + .5);
+		super[(size_t)i] = {(float)cos(ph2), (float)sin(ph2)};
+	}
+	int p[16], m[16], st[16], nf = 0, rem = n, stride = 1, radix = 4; // kf_factor
+	do {
+		while (rem % radix) {
+			radix = radix == 4 ? 2 : (radix == 2 ? 3 : radix + 2);
+			if (radix > 32000 || radix * radix > rem) radix = rem;
+		}
+		rem /= radix;
+		if ((radix != 4 && radix != 2) || nf >= 16) return false;
+		p[nf] = radix;
+		m[nf] = rem;
+		st[nf] = stride;
+		stride *= radix;
+		++nf;
+	} while (rem > 1);
+	tmp[0] = {spec[0] + spec[2 * n - 1], spec[0] - spec[2 * n - 1]};
+	for (int k = 1; k <= n / 2; ++k) {
+		const EqCpx fk = {spec[2 * k - 1], spec[2 * k]}, fnkc = {spec[2 * (n - k) - 1], -spec[2 * (n - k)]};
+		const EqCpx fek = eq_cadd(fk, fnkc), fok = eq_cmul(eq_csub(fk, fnkc), super[(size_t)k]);
+		tmp[(size_t)k] = eq_cadd(fek, fok);
+		EqCpx r = eq_csub(fek, fok);
+		r.i *= -1;
+		tmp[(size_t)(n - k)] = r;
+	}
+	for (int o = 0; o < n; ++o) { // kf_shuffle
+		int src = 0;
+		for (int d = 0; d < nf; ++d) src += ((o / m[d]) % p[d]) * st[d];
+		F[(size_t)o] = tmp[(size_t)src];
+	}
+	for (int d = nf - 1; d >= 0; --d) {
+		const int mm = m[d], s = st[d];
+		for (int b = 0; b < s * mm; ++b) {
+			const int j = b % mm;
+			EqCpx *f = F.data() + (size_t)(b / mm) * p[d] * mm + j;
+			if (p[d] == 2) { // kf_bfly2
+				const EqCpx t = eq_cmul(f[mm], tw[(size_t)(j * s)]);
+				f[mm] = eq_csub(f[0], t);
+				f[0] = eq_cadd(f[0], t);
+			} else { // kf_bfly4, inverse
+				const EqCpx s0 = eq_cmul(f[mm], tw[(size_t)(j * s)]), s1 = eq_cmul(f[2 * mm], tw[(size_t)(2 * j * s)]),
+				            s2 = eq_cmul(f[3 * mm], tw[(size_t)(3 * j * s)]);
+				const EqCpx s5 = eq_csub(f[0], s1);
+				f[0] = eq_cadd(f[0], s1);
+				const EqCpx s3 = eq_cadd(s0, s2), s4 = eq_csub(s0, s2);
+				f[2 * mm] = eq_csub(f[0], s3);
+				f[0] = eq_cadd(f[0], s3);
+				f[mm] = {s5.r - s4.i, s5.i + s4.r};
+				f[3 * mm] = {s5.r + s4.i, s5.i - s4.r};
+			}
+		}
+	}
+	for (int o = 0; o < n; ++o) {
+		out[2 * o] = F[(size_t)o].r;
+		out[2 * o + 1] = F[(size_t)o].i;
+	}
+	return true;
+}
+} // namespace
+// gain table -> impulse response: ms_ifft + time_shift (equalizer.c:184-193) + Hamming (:203-213)
 static void eq_design(const std::vector<float> &spec, int n, std::vector<float> &fir) {
 	fir.assign((size_t)n, 0.f);
 	const int half = n / 2;
-	std::vector<double> ct((size_t)n), sn((size_t)n);
-	for (int i = 0; i < n; ++i) {
-		ct[(size_t)i] = cos(2.0 * M_PI * i / n);
-		sn[(size_t)i] = sin(2.0 * M_PI * i / n);
-	}
-	for (int t = 0; t < n; ++t) {
-		double acc = (double)spec[0] + ((t & 1) ? -(double)spec[(size_t)n - 1] : (double)spec[(size_t)n - 1]);
-		for (int k = 1; k < half; ++k) {
-			size_t a = (size_t)(((long)k * t) % n);
-			acc += 2.0 * ((double)spec[(size_t)(2 * k - 1)] * ct[a] - (double)spec[(size_t)(2 * k)] * sn[a]);
-		}
-		fir[(size_t)((t + half) % n)] = (float)acc; // time shift: swap halves
-	}
+	std::vector<float> t((size_t)n, 0.f);
+	eq_kiss_irfft(spec.data(), t.data(), n);
+	for (int i = 0; i < n; ++i) fir[(size_t)((i + half) % n)] = t[(size_t)i]; // time shift: swap halves
 	for (int i = 0; i < n; ++i) {
 		float x = (float)((float)i * 2 * M_PI / (float)n);
-		float w = (float)(0.54 - (0.46 * cos(x)));
+		float w = (float)(0.54 - (0.46 * cos((double)x))); // C's cos(): double (a bare cos(float) would be cosf in C++)
 		fir[(size_t)i] = w * fir[(size_t)i];
 	}
 }
@@ -880,6 +947,14 @@ int msb200_equalizer_set_active(msb200_equalizer *e, int stream, int active) {
 	MSB200_CUDA(cudaStreamSynchronize(e->ctx->stream));
 	return MSB200_OK;
 }
+int msb200_equalizer_design(int nfft, const float *gain_table, float *taps) { // pure host code: no device needed
+	MSB200_CHECK_ARG(gain_table && taps && (nfft == 128 || nfft == 256 || nfft == 512));
+	std::vector<float> spec(gain_table, gain_table + nfft), fir;
+	eq_design(spec, nfft, fir);
+	memcpy(taps, fir.data(), sizeof(float) * (size_t)nfft);
+	return MSB200_OK;
+}
+
 int msb200_equalizer_set_taps(msb200_equalizer *e, int stream, const float *taps) {
 	MSB200_CHECK_ARG(e && taps && stream >= 0 && stream < e->n);
 	MSB200_CUDA(cudaMemcpyAsync(e->d_taps + (size_t)stream * e->nfft, taps, sizeof(float) * (size_t)e->nfft,

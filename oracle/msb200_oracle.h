@@ -110,6 +110,10 @@ void orc_flowctl_init(orc_flowctl *c);
 void orc_flowctl_set_target(orc_flowctl *c, uint32_t samples_to_drop, uint32_t total_samples);
 int orc_flowctl_process(orc_flowctl *c, int16_t *samples, int nsamples);
 
+/* ms_ifft / ms_fft (dsptools.c:362-376 over the float kiss_fft), restated bit-exactly in oracle_plc.c; 0 on success */
+int orc_kiss_irfft(const float *spec, float *out, int nfft);
+int orc_kiss_rfft(const float *time, float *spec, int nfft);
+
 /* MSGenericPLC (oracle_plc.c): signal level (packet / conceal) and filter level (concealer clock) */
 typedef struct orc_plc orc_plc;
 int orc_plc_rate_supported(int rate);

@@ -303,17 +303,10 @@ void orc_equalizer_set_gain(orc_equalizer *s, float frequency, float gain, float
 }
 
 /* ms_ifft (dsptools.c:373-376 -> kiss_fftri2, kiss_fftr.c:261-296): unnormalised inverse of the packed real spectrum
- * [r0, r1, i1, ..., r(n/2-1), i(n/2-1), r(n/2)]. Restated as a direct inverse DFT in double precision (the reference
- * uses a float radix FFT: taps agree to ~1e-7 relative, see tests). */
+ * [r0, r1, i1, ..., r(n/2-1), i(n/2-1), r(n/2)] through the bit-exact restatement of the float kiss_fft in oracle_plc.c:
+ * the taps, and with them every output sample, equal the reference's bit for bit. */
 static void eq_packed_irfft(const float *spec, float *out, int n) {
-	for (int t = 0; t < n; ++t) {
-		double acc = (double)spec[0] + ((t & 1) ? -(double)spec[n - 1] : (double)spec[n - 1]);
-		for (int k = 1; k < n / 2; ++k) {
-			double ang = 2.0 * M_PI * (double)((long)k * t % n) / (double)n;
-			acc += 2.0 * ((double)spec[2 * k - 1] * cos(ang) - (double)spec[2 * k] * sin(ang));
-		}
-		out[t] = (float)acc;
-	}
+	if (orc_kiss_irfft(spec, out, n) != 0) memset(out, 0, sizeof(float) * (size_t)n);
 }
 static void eq_compute_impulse_response(orc_equalizer *s) { /* :215-237 */
 	int n = s->nfft, half = n / 2;

@@ -225,6 +225,30 @@ static void rfft_inverse(rfft *r, const float *freq, float *time) {
 	kfft_run(&r->sub, t, (cpx *)time);
 }
 
+/* ms_ifft for any even size whose half factors into 2, 3, 4, 5 (used by the equalizer oracle: 128 / 256 / 512 points) */
+int orc_kiss_irfft(const float *spec, float *out, int nfft) {
+	rfft r;
+	int v = nfft / 2;
+	if (nfft < 4 || (nfft & 1)) return -1;
+	while (v % 2 == 0) v /= 2;
+	while (v % 3 == 0) v /= 3;
+	while (v % 5 == 0) v /= 5;
+	if (v != 1) return -1;
+	rfft_init(&r, nfft, 1);
+	rfft_inverse(&r, spec, out);
+	rfft_free(&r);
+	return 0;
+}
+/* ms_fft (scaled by 1/N), same size rule */
+int orc_kiss_rfft(const float *time, float *spec, int nfft) {
+	rfft r;
+	if (nfft < 4 || (nfft & 1)) return -1;
+	rfft_init(&r, nfft, 0);
+	rfft_forward(&r, time, spec);
+	rfft_free(&r);
+	return 0;
+}
+
 struct orc_plc {
 	int rate, N, T;        /* history length (samples), transition length (samples) */
 	int16_t *hist;         /* [N]   plc_buffer */
