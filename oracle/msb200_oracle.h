@@ -96,6 +96,9 @@ void orc_scaler_free(orc_scaler *s);
 size_t orc_scaler_src_bytes(orc_scaler *s);
 size_t orc_scaler_dst_bytes(orc_scaler *s);
 int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst);
+/* planar output only: 1 = round like the library's x86 SIMD vertical scaler (what a plain SWS_BILINEAR call returns on x86),
+ * 0 (default) = its C reference arithmetic (SWS_BITEXACT), which is what the GPU kernels compute this round */
+void orc_scaler_set_x86_vertical(orc_scaler *s, int on);
 /* filter tables (shared verbatim with the product through tests only): returns filter size, fills pos/coef */
 int orc_scaler_get_filter(orc_scaler *s, int which /*0 lumH,1 chrH,2 lumV,3 chrV*/, int32_t *pos, int16_t *coef,
                           int max_entries);

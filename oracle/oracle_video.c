@@ -246,6 +246,7 @@ struct orc_scaler {
 	/* yuv2rgb tables in closed form */
 	int64_t cy, crv, cbu, cgu, cgv, yb0;
 	int yoffs;
+	int x86_vertical; /* orc_scaler_set_x86_vertical(): planar output as the library's x86 SIMD vertical scaler rounds it */
 };
 
 static int get_local_pos(int chr_subsample, int pos) {
@@ -318,6 +319,11 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 		s->yoffs = 326 + 512;
 	}
 	return s;
+}
+/* planar (YUV420P) output only: 0 = the library's C reference arithmetic (SWS_BITEXACT; what the GPU kernels compute),
+ * 1 = its x86 SIMD vertical scaler, i.e. what sws_scale returns for the reference's plain SWS_BILINEAR call on x86 */
+void orc_scaler_set_x86_vertical(orc_scaler *s, int on) {
+	if (s) s->x86_vertical = on;
 }
 void orc_scaler_free(orc_scaler *s) {
 	if (!s) return;
@@ -525,6 +531,14 @@ int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst) {
 					int val;
 					if (vf->size == 1) {
 						val = (plane[(size_t)vf->pos[y] * W + x] + 64) >> 7;
+					} else if (s->x86_vertical && y < (pl == 0 ? dh - 2 : cdh - 1)) { /* the last two output lines (and the chroma line that goes with them) are done by the C functions (swscale.c: "can't use MMX here without overwriting this array's tail") */
+						/* the library's x86 vertical scaler for planar output without SWS_ACCURATE_RND / SWS_BITEXACT
+						 * (x86/yuv2yuvX.asm): 16-bit accumulators, one pmulhw per tap (the fraction of every product is
+						 * dropped), a rounder that pays the expected loss back: ((64 + 8 (taps - 1)) >> 4), final >> 3 */
+						int acc = (64 + 8 * (vf->size - 1)) >> 4;
+						for (int j = 0; j < vf->size; ++j)
+							acc += (plane[(size_t)(vf->pos[y] + j) * W + x] * cf[j]) >> 16;
+						val = (int16_t)acc >> 3;
 					} else {
 						val = 64 << 12;
 						for (int j = 0; j < vf->size; ++j)

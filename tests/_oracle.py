@@ -83,6 +83,7 @@ def oracle() -> C.CDLL:
         "orc_scaler_dst_bytes": (C.c_size_t, [_P]),
         "orc_scaler_process": (_I, [_P, _P, _P]),
         "orc_scaler_get_filter": (_I, [_P, _I, _P, _P, _I]),
+        "orc_scaler_set_x86_vertical": (None, [_P, _I]),
         "orc_flowctl_init": (None, [_P]),
         "orc_flowctl_set_target": (None, [_P, C.c_uint32, C.c_uint32]),
         "orc_flowctl_process": (_I, [_P, _P, _I]),

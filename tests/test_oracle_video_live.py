@@ -148,3 +148,28 @@ def test_odd_rgb_width_is_refused():
     s = L.orc_scaler_new(64, 48, 0, 33, 24, 0)  # planar output: fine
     assert s
     L.orc_scaler_free(s)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_planar_output_x86_vertical_mode_equals_plain_flag_library_exactly(seed):
+    """what the reference's MSSizeConv really gets on x86: sws_getContext(..., SWS_BILINEAR) without SWS_BITEXACT runs the
+    library's SIMD vertical scaler for planar output (x86/yuv2yuvX.asm: 16-bit accumulators, one pmulhw per tap, rounder
+    (64 + 8 (taps - 1)) >> 4, final >> 3; the last two output lines by the C functions). The oracle's x86 mode restates it:
+    bit-exact against the live library on random geometries. The GPU kernels compute the C arithmetic (<= 1 away) this
+    round; switching them is the next step for row a8."""
+    sws = _sws()
+    L = O.oracle()
+    rng = np.random.default_rng(seed)
+    sf = str(rng.choice(["yuv420p", "nv12", "nv21"]))
+    sw, sh = int(rng.integers(8, 200)) * 2, int(rng.integers(8, 120)) * 2
+    r = float(rng.choice([0.25, 0.4, 0.5, 0.6667, 0.75, 0.9, 1.25, 1.5, 2.0, 3.0]))
+    r2 = r if rng.integers(0, 3) else float(rng.choice([0.5, 0.75, 1.5]))
+    dw, dh = max(16, int(sw * r) // 2 * 2), max(8, int(sh * r2) // 2 * 2)
+    src = make_frame(sf, sw, sh, t=seed, seed=seed)
+    s = L.orc_scaler_new(sw, sh, AV2MS[AV_PIX[sf]], dw, dh, AV2MS[AV_PIX["yuv420p"]])
+    assert s
+    L.orc_scaler_set_x86_vertical(s, 1)
+    out = np.zeros(L.orc_scaler_dst_bytes(s) + 64, np.uint8)
+    assert L.orc_scaler_process(s, ptr(np.ascontiguousarray(src)), ptr(out)) == 0
+    L.orc_scaler_free(s)
+    assert np.array_equal(out[:-64], sws_convert(sws, src, sf, sw, sh, "yuv420p", dw, dh, SWS_BILINEAR))
