@@ -404,7 +404,7 @@ static void hscale(int16_t *dst, int dstW, const uint8_t *src, const sws_filter 
 /* bpp / ro / go / bo: bytes per pixel and byte offsets of R, G, B for the GENERIC path (RGB24: 3,0,1,2; RGBA: 4,0,1,2;
  * BGRA: 4,2,1,0 — the 32-bit formats take the generic path too and give the RGB24 result for equal colours, alpha
  * ignored: verified against the real library); bgr = 1 selects BGR24's special converter instead. */
-static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, int bpp, int ro, int go, int bo, uint8_t *dst) {
+static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, int bpp, int ro, int go, int bo, uint8_t *dst, int x86_vertical) {
 	enum { RY = 8414, GY = 16519, BY = 3208, RU = -4865, GU = -9528, BU = 14392, RV = 14392, GV = -12061, BV = -2332 };
 	uint8_t *dy = dst, *du = dst + (size_t)w * h, *dv = du + (size_t)(w / 2) * (h / 2);
 	const int cw = w / 2;
@@ -447,8 +447,26 @@ static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, int bpp, int 
 			v15[(size_t)y * cw + x] = (int16_t)(v > 32767 ? 32767 : v);
 		}
 	static const int tap[4] = {512, 1536, 1536, 512};
+	sws_filter vf = {0, NULL, NULL};
+	if (x86_vertical) /* the library's own vertical chroma filter (h rows -> h / 2): border rows carry FOLDED coefficients,
+	                   * which the SIMD scaler's per-tap truncation sees differently from replicated rows */
+		init_filter(&vf, (int)((((int64_t)h << 16) + ((h / 2) >> 1)) / (h / 2)), h, h / 2, 2, 1 << 12, get_local_pos(0, -513),
+		            get_local_pos(1, -513));
 	for (int y = 0; y < h / 2; ++y)
 		for (int x = 0; x < cw; ++x) {
+			if (x86_vertical && y < h / 2 - 1) { /* x86/yuv2yuvX.asm, see orc_scaler_set_x86_vertical; last line: C functions */
+				const int16_t *cf = vf.coef + (size_t)y * vf.size;
+				int au = (64 + 8 * (vf.size - 1)) >> 4, av = au;
+				for (int j = 0; j < vf.size; ++j) {
+					au += (u15[(size_t)(vf.pos[y] + j) * cw + x] * cf[j]) >> 16;
+					av += (v15[(size_t)(vf.pos[y] + j) * cw + x] * cf[j]) >> 16;
+				}
+				au = (int16_t)au >> 3;
+				av = (int16_t)av >> 3;
+				du[(size_t)y * cw + x] = (uint8_t)(au < 0 ? 0 : (au > 255 ? 255 : au));
+				dv[(size_t)y * cw + x] = (uint8_t)(av < 0 ? 0 : (av > 255 ? 255 : av));
+				continue;
+			}
 			int au = 64 << 12, av = 64 << 12;
 			for (int j = 0; j < 4; ++j) {
 				int row = 2 * y - 1 + j;
@@ -463,13 +481,15 @@ static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, int bpp, int 
 		}
 	free(u15);
 	free(v15);
+	free(vf.pos);
+	free(vf.coef);
 }
 
 int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst) {
 	const int sw = s->src_w, sh = s->src_h, dw = s->dst_w, dh = s->dst_h;
 	if (s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24 || s->src_fmt == PIX_RGBA32 || s->src_fmt == PIX_BGRA32) {
 		const int f = s->src_fmt, four = f == PIX_RGBA32 || f == PIX_BGRA32;
-		rgb_to_i420(src, sw, sh, f == PIX_BGR24, four ? 4 : 3, f == PIX_BGRA32 ? 2 : 0, 1, f == PIX_BGRA32 ? 0 : 2, dst);
+		rgb_to_i420(src, sw, sh, f == PIX_BGR24, four ? 4 : 3, f == PIX_BGRA32 ? 2 : 0, 1, f == PIX_BGRA32 ? 0 : 2, dst, s->x86_vertical);
 		return 0;
 	}
 	if (is_packed422(s->src_fmt)) {

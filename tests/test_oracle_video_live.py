@@ -173,3 +173,23 @@ def test_planar_output_x86_vertical_mode_equals_plain_flag_library_exactly(seed)
     assert L.orc_scaler_process(s, ptr(np.ascontiguousarray(src)), ptr(out)) == 0
     L.orc_scaler_free(s)
     assert np.array_equal(out[:-64], sws_convert(sws, src, sf, sw, sh, "yuv420p", dw, dh, SWS_BILINEAR))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_rgb_sources_x86_vertical_mode_equals_plain_flag_library_exactly(seed):
+    """MSPixConv's RGB24 / RGBA / BGRA inputs go through the scaler's 2:1 vertical chroma filter, hence through the same SIMD
+    vertical scaler on x86 (border lines carry folded coefficients there, which matters once every tap is truncated);
+    BGR24 takes the library's special converter and has no such mode. x86 mode == live plain-flag library, bit for bit."""
+    sws = _sws()
+    L = O.oracle()
+    rng = np.random.default_rng(seed)
+    sf = str(rng.choice(["rgb24", "rgba", "bgra", "bgr24"]))
+    w, h = int(rng.integers(4, 100)) * 4, int(rng.integers(4, 80)) * 2
+    src = make_frame(sf, w, h, t=seed, seed=seed)
+    s = L.orc_scaler_new(w, h, AV2MS[AV_PIX[sf]], w, h, AV2MS[AV_PIX["yuv420p"]])
+    assert s
+    L.orc_scaler_set_x86_vertical(s, 1)
+    out = np.zeros(L.orc_scaler_dst_bytes(s) + 64, np.uint8)
+    assert L.orc_scaler_process(s, ptr(np.ascontiguousarray(src)), ptr(out)) == 0
+    L.orc_scaler_free(s)
+    assert np.array_equal(out[:-64], sws_convert(sws, src, sf, w, h, "yuv420p", w, h, SWS_BILINEAR))
