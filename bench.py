@@ -41,6 +41,11 @@ METRIC = "concurrent 48 kHz streams/sec through resample+AEC+mix @ 10 ms tick; p
 UNIT = "stream-ticks/s"
 WORKLOAD = ("cfg2: 4096 concurrent 48 kHz mono streams per GPU, MSResample(16k->48k) x2 -> MSSpeexEC(tail 250 ms, "
             "frame 256, M 47) -> MSVolume(0.8), one 10 ms tick per step")
+# `config` is static and identical in both arms (the driver compares them); measured values never go in it
+CONFIG = {"workload": WORKLOAD, "streams_per_gpu": STREAMS_PER_GPU,
+          "l2": "per-step working set (AEC state 1.19 GB per 4096 streams) >> 126 MB L2; no flush needed",
+          "sharding": "streams independent: 4096 per rank, no data-path collective (weak scaling); the one exchange step of the "
+                      "path (cfg3 striped conference) is reported in `conference` when N > 1"}
 # algorithmic HBM bytes of one echo-canceller frame of one stream:
 # X ring read M blocks + write 1, FG read, W read + write; blocks of F float2
 AEC_F, AEC_M = 256, 47
@@ -149,13 +154,15 @@ def run_reference(args, rank: int, world: int):
         if t_total > 150:  # bounded: the whole arm ends within a few minutes whatever K is
             break
     value = n_total / t_total
-    sample = (f"{per_step_streams} streams x {ticks_per_step} ticks per step, {threads} threads, free-running; "
-              f"restated speexdsp chain (oracle/), the library itself is not in the reference tree")
+    sample = (f"{per_step_streams} streams x {ticks_per_step} ticks per step ({steps_done} steps run), {threads} threads, "
+              f"free-running; restated speexdsp chain (oracle/), the library itself is not in the reference tree; "
+              f"{per_step_streams // threads} streams x 0.3 MB of canceller state per thread stay L2/L3-resident on the host, "
+              f"while the GPU arm streams 1.19 GB of state from HBM every step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(1, steps_done), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "steps_run": steps_done},
+        "config": CONFIG,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,6 +204,30 @@ def realtime_block(ctx, F, sizes=(4096, 16384, 32768), ticks=1000):
             if chain is not None:
                 chain.close()
     out["s_rt_streams_at_least"] = s_rt
+    return out
+
+
+def summary(line: dict) -> dict:
+    """the numbers of the side blocks in < 1.5 KB, as the LAST key of the line"""
+    out = {"realtime_streams_equiv": line["value"] / 100.0 / max(1, line["n_gpus"]), "aec_frac_of_hbm": line["roofline"]["frac"]}
+    px = line.get("pixconv") or {}
+    if "roofline" in px:
+        out["pixconv"] = {"kernel": px["roofline"].get("kernel"), "frac_of_hbm": px["roofline"].get("frac"),
+                          "mpix_s_in": px.get("value"), "e2e_mpix_s_in": (px.get("e2e") or {}).get("value"),
+                          "cpu_mpix_s_in": (px.get("cpu_baseline") or {}).get("value"),
+                          "cpu_kind": (px.get("cpu_baseline") or {}).get("kind")}
+    rt = line.get("realtime") or {}
+    if "s_rt_streams_at_least" in rt:
+        out["s_rt_streams_at_least"] = rt["s_rt_streams_at_least"]
+        out["s_rt_p99_ms"] = {k: round(v["p99_ms"], 3) for k, v in rt.get("sizes", {}).items()}
+    cf = line.get("conference") or {}
+    if "error" in cf:
+        out["conference"] = cf
+    elif cf:
+        out["conference"] = {"n_gpus": cf["n_gpus"], "bit_exact_vs_oracle": cf["bit_exact_vs_oracle"],
+                             **{k: {"ms_per_step": round(cf[k]["ms_per_step"], 5), "room_ticks_per_s": round(cf[k]["room_ticks_per_s"]),
+                                    "bit_exact": cf[k]["bit_exact_vs_oracle"]}
+                                for k in ("room_local", "nccl", "fused") if "ms_per_step" in cf.get(k, {})}}
     return out
 
 
@@ -319,11 +350,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if aec_launches and aec_ms > 0:
         bytes_per_launch = AEC_BYTES_PER_FRAME * (aec_frames / aec_launches) * S
         achieved = bytes_per_launch / (aec_ms / aec_launches / 1000.0) / 1e9
-    traffic = None
+    # DRAM traffic cannot be read without a profiler: it comes from the committed ncu capture of this kernel
+    # (profiles/aec_traffic.json names the capture and the source revision it was taken from)
+    traffic, traffic_src = None, None
     tpath = ROOT / "profiles" / "aec_traffic.json"
     if tpath.exists():
         try:
-            traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tpath.read_text())
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except ValueError:
             traffic = None
 
@@ -331,16 +365,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "streams_per_gpu": S, "realtime_streams_equiv": value / 100.0,
-                   "l2": "per-step working set (AEC state 1.19 GB per 4096 streams) >> 126 MB L2; no flush needed",
-                   "sharding": "streams independent: 4096 per rank, no data-path collective"},
+        "config": CONFIG,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * tick_bytes,
                 "d2h_bytes_per_step": int(out_samples / args.steps) * S * 2 if args.steps else 0,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "aec_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "bytes_per_frame_per_stream": AEC_BYTES_PER_FRAME,
                      "kernel_ms_per_launch": (aec_ms / aec_launches) if aec_launches else None,
                      "kernel_share_of_step": (aec_ms / ms_dev) if ms_dev else None},
@@ -357,7 +390,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             best = max(best, v)
         line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{n_streams} streams x {n_ticks} ticks, {threads} pthreads, best of {reps}; "
-                                          f"oracle chain (restated speexdsp resampler + MDF + preprocessor, in-tree volume)"}
+                                          f"oracle chain (restated speexdsp resampler + MDF + preprocessor, in-tree volume); "
+                                          f"the sample's canceller state ({n_streams} x 0.3 MB) is L2/L3-resident on the host"}
+    # ---------------------------------------------------------------- the one exchange step of the path (cfg3), N > 1
+    if world > 1 and not args.no_conference:
+        from bench_conference import conference_block
+
+        try:
+            block = conference_block(ctx, rank, world, dist, steps=max(args.steps, 100), warmup=max(args.warmup, 5), peak_gbs=peak)
+        except Exception as e:  # noqa: BLE001 - reported, the headline line still goes out
+            block = {"error": repr(e)}
+        if rank == 0:
+            line["conference"] = block
     # ---------------------------------------------------------------- second headline: pixconv (when built)
     try:
         from bench_video import pixconv_bench  # noqa: WPS433
@@ -387,6 +431,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         except Exception as e:  # noqa: BLE001 - a side measurement must not take the headline line down with it
             line["realtime"] = {"error": repr(e)}
     if rank == 0:
+        line["summary"] = summary(line)  # last key: the driver's record keeps the tail of the line
         print(json.dumps(line), flush=True)
     chain.close()
     for p in (d_ref, d_mic, d_out):
@@ -404,6 +449,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-realtime", action="store_true", help="skip the S_rt tick-latency block (SURVEY §8d)")
+    ap.add_argument("--no-conference", action="store_true", help="skip the cfg3 cross-GPU conference block (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -153,7 +153,7 @@ def pixconv_bench(ctx, hbm_peak_gbs: float, n_frames: int = 512, iters: int = 10
         "mpix_per_s_in": SRC_W * SRC_H * n_frames / (ms / 1000.0) / 1e6,
         "mpix_per_s_out": DST_W * DST_H * n_frames / (ms / 1000.0) / 1e6,
         "ms_per_batch": ms, "frames_per_s": n_frames / (ms / 1000.0),
-        "roofline": {"bound": "hbm", "kernel": "scale_rgb_kernel", "achieved": achieved, "peak": hbm_peak_gbs,
+        "roofline": {"bound": "hbm", "kernel": "scale_rgb_strip_kernel (static row schedule)", "achieved": achieved, "peak": hbm_peak_gbs,
                      "unit": "GB/s", "frac": achieved / hbm_peak_gbs, "bytes_per_frame": ALGO_BYTES},
         "e2e": {"frames": ne, "mpix_per_s_in": SRC_W * SRC_H * ne / e2e_s / 1e6,
                 "h2d_bytes": ne * SRC_BYTES, "d2h_bytes": ne * DST_BYTES},

@@ -96,22 +96,52 @@ MSB200_API int msb200_mixer_process_dev(msb200_mixer *m, const void *d_in, const
 MSB200_API int msb200_mixer_partial_dev(msb200_mixer *m, const void *d_in, const void *d_present, void *d_sum_i32);
 MSB200_API int msb200_mixer_finish_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *d_sum_i32,
                                         void *d_out);
-/* Fused exchange + finish over NVLink peer memory (one process per GPU): every rank exports its partial-sum buffer and a
- * 32-bit epoch flag with msb200_ipc_export(), imports the peers' with msb200_ipc_import(). Per tick: partial_dev into
- * the local buffer, msb200_signal_dev(flag, epoch) (stream-ordered release), then ONE kernel that waits for every peer's
- * flag to reach `epoch`, loads the peers' partial sums directly through their mapped pointers, adds them (integer:
- * order-independent, bit-exact) and emits sat(total - own) for the local pins — no NCCL call, no separate reduction pass.
- * Use two alternating sum buffers (tick parity) so a fast rank never overwrites a buffer a slow peer still reads.
- * d_peer_sums / d_peer_flags: host arrays of n_peers device pointers (own rank included, any order). */
+/* Device-memory sharing between the per-GPU processes of one node (cudaIpc): export a cudaMalloc'ed pointer as 64 opaque
+ * bytes, import it in another process of the node, close it before the exporter frees the memory. */
 #define MSB200_IPC_HANDLE_BYTES 64
 #define MSB200_MAX_PEERS 8
 MSB200_API int msb200_ipc_export(msb200_ctx *ctx, void *dev_ptr, uint8_t handle[MSB200_IPC_HANDLE_BYTES]);
 MSB200_API int msb200_ipc_import(msb200_ctx *ctx, const uint8_t handle[MSB200_IPC_HANDLE_BYTES], void **dev_ptr);
 MSB200_API int msb200_ipc_close(msb200_ctx *ctx, void *dev_ptr);
-MSB200_API int msb200_signal_dev(msb200_ctx *ctx, void *d_flag_u32, uint32_t value);
-MSB200_API int msb200_mixer_finish_peers_dev(msb200_mixer *m, const void *d_in, const void *d_present,
-                                              const void *const *d_peer_sums, const void *const *d_peer_flags, int n_peers,
-                                              uint32_t epoch, void *d_out, void *d_error_flag_u32);
+
+/* ---- the cross-GPU conference exchange behind the C ABI, two ways (csrc/mixer_xchg.cu) -------------------------------
+ * Striped layout (BASELINE cfg3): rank r of `world` owns the pins {r, r+world, ...} of EVERY room; its msb200_mixer bank is
+ * created with n_pins = the local pin count and conference mode on. The reference semantics are those of ONE mixer with
+ * all the pins: sum :288-346, out_i = sat(sum - own_i) :113-130, +-32767 :40-44 — integer, so any reduction order is
+ * bit-exact.
+ *
+ * (1) NCCL: a communicator bound to the context's stream. libnccl.so.2 is dlopen'ed on first use (search order: the
+ *     MSB200_NCCL_LIB environment variable, a copy the process already loaded, the default library path); one rank
+ *     calls msb200_comm_unique_id() and hands the 128 bytes to the others through any side channel.
+ *     msb200_mixer_process_striped_dev = partial_dev -> ncclAllReduce(int32, SUM) in place -> finish_dev: 3 launches. */
+#define MSB200_COMM_ID_BYTES 128
+typedef struct msb200_comm msb200_comm;
+MSB200_API int msb200_comm_available(void);    /* 1 when an NCCL library could be loaded */
+MSB200_API int msb200_comm_nccl_version(void); /* e.g. 22809, 0 when unavailable */
+MSB200_API int msb200_comm_unique_id(uint8_t id[MSB200_COMM_ID_BYTES]);
+MSB200_API int msb200_comm_create(msb200_ctx *ctx, const uint8_t id[MSB200_COMM_ID_BYTES], int rank, int world,
+                                  msb200_comm **out); /* collective: every rank of `world` calls it */
+MSB200_API void msb200_comm_destroy(msb200_comm *c);
+MSB200_API int msb200_comm_allreduce_sum_i32_dev(msb200_comm *c, void *d_buf_i32, size_t count);
+MSB200_API int msb200_mixer_process_striped_dev(msb200_mixer *m, msb200_comm *c, const void *d_in, const void *d_present,
+                                                 void *d_sum_i32, void *d_out);
+/* (2) Fused over NVLink peer memory: ONE kernel per tick and rank, no NCCL on the data path. Each CTA pushes its int32
+ *     partial sums into a receive slot of every rank (posted 16-byte stores), publishes a per-CTA epoch flag on every rank,
+ *     waits on its LOCAL flags for the same CTA of every peer, then adds the world's slots from local memory and emits the
+ *     local pins' outputs. Set-up: create on every rank; exchange the export() handles (ranks in different processes:
+ *     connect(handles[world][64]); ranks that are contexts of ONE process, e.g. a host driving several GPUs:
+ *     connect_local(all[world])); barrier; then process_dev once per tick on every rank, in the same order of ticks.
+ *     A peer that stays silent for MSB200_XCHG_TIMEOUT_MS (default 2000) is counted in status() instead of hanging the
+ *     GPU; that tick's outputs are then undefined. Barrier again before destroy (peers may still be reading). */
+typedef struct msb200_mixer_xchg msb200_mixer_xchg;
+MSB200_API int msb200_mixer_xchg_create(msb200_mixer *m, int rank, int world, msb200_mixer_xchg **out);
+MSB200_API int msb200_mixer_xchg_export(msb200_mixer_xchg *x, uint8_t handle[MSB200_IPC_HANDLE_BYTES]);
+MSB200_API int msb200_mixer_xchg_connect(msb200_mixer_xchg *x, const uint8_t *handles);
+MSB200_API int msb200_mixer_xchg_connect_local(msb200_mixer_xchg *x, msb200_mixer_xchg *const *all);
+MSB200_API int msb200_mixer_xchg_process_dev(msb200_mixer_xchg *x, const void *d_in, const void *d_present, void *d_out);
+MSB200_API int msb200_mixer_xchg_status(msb200_mixer_xchg *x, uint32_t *timeouts);
+MSB200_API size_t msb200_mixer_xchg_wire_bytes_per_tick(msb200_mixer_xchg *x); /* (world - 1) x rooms x nwords x 4 pushed */
+MSB200_API void msb200_mixer_xchg_destroy(msb200_mixer_xchg *x);
 
 /* ---------------------------------------------------------------------------------------------------- MSVolume
  * Replaces the light path of volume_process() /root/reference/src/audiofilters/msvolume.c:503-513:

@@ -86,8 +86,21 @@ _SIGS = {
     "msb200_ipc_export": (_I, [_P, _P, _P]),
     "msb200_ipc_import": (_I, [_P, _P, _PP]),
     "msb200_ipc_close": (_I, [_P, _P]),
-    "msb200_signal_dev": (_I, [_P, _P, C.c_uint32]),
-    "msb200_mixer_finish_peers_dev": (_I, [_P, _P, _P, _P, _P, _I, C.c_uint32, _P, _P]),
+    "msb200_comm_available": (_I, []),
+    "msb200_comm_nccl_version": (_I, []),
+    "msb200_comm_unique_id": (_I, [_P]),
+    "msb200_comm_create": (_I, [_P, _P, _I, _I, _PP]),
+    "msb200_comm_destroy": (None, [_P]),
+    "msb200_comm_allreduce_sum_i32_dev": (_I, [_P, _P, _SZ]),
+    "msb200_mixer_process_striped_dev": (_I, [_P, _P, _P, _P, _P, _P]),
+    "msb200_mixer_xchg_create": (_I, [_P, _I, _I, _PP]),
+    "msb200_mixer_xchg_export": (_I, [_P, _P]),
+    "msb200_mixer_xchg_connect": (_I, [_P, _P]),
+    "msb200_mixer_xchg_connect_local": (_I, [_P, _PP]),
+    "msb200_mixer_xchg_process_dev": (_I, [_P, _P, _P, _P]),
+    "msb200_mixer_xchg_status": (_I, [_P, C.POINTER(C.c_uint32)]),
+    "msb200_mixer_xchg_wire_bytes_per_tick": (_SZ, [_P]),
+    "msb200_mixer_xchg_destroy": (None, [_P]),
     "msb200_volume_create": (_I, [_P, _I, _I, _I, _PP]),
     "msb200_volume_destroy": (None, [_P]),
     "msb200_ctx_make_current": (_I, [_P]),

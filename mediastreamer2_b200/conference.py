@@ -51,3 +51,95 @@ def cfg3_inputs(n_rooms: int, n_pins: int, nwords: int, tick: int):
     if n_pins > 7:
         active[:, 7] = 0
     return pcm, present, gain, active
+
+
+# ------------------------------------------------------------------------------------------------ device-side driver
+# Plumbing over the C ABI (include/msb200dsp.h "cross-GPU conference exchange"); nothing below computes on the CPU.
+EXCHANGES = ("nccl", "fused")
+
+
+class StripedConference:
+    """One rank's share of `rooms` conferences of `pins` pins striped over `world` GPUs (gpu = pin mod world).
+
+    exchange = "nccl":  msb200_mixer_process_striped_dev (partial -> ncclAllReduce int32 -> finish, 3 launches per tick)
+    exchange = "fused": msb200_mixer_xchg_process_dev (ONE kernel: push partial sums over NVLink, per-CTA epoch flags, finish)
+    `allgather(obj) -> list` is the caller's side channel (torch.distributed.all_gather_object, or a list built by hand when
+    the ranks are contexts of one process); `barrier()` likewise.
+    """
+
+    def __init__(self, ctx, rank: int, world: int, rooms: int, pins: int, nwords: int, exchange: str, allgather, barrier):
+        import ctypes as C
+
+        from . import _lib
+        from . import filters as F
+
+        assert exchange in EXCHANGES
+        self.C, self._lib = C, _lib
+        self.ctx, self.lib, self.rank, self.world, self.exchange = ctx, ctx.lib, rank, world, exchange
+        self.rooms, self.pins, self.nwords = rooms, pins, nwords
+        self.lp = local_pins(rank, world, pins)
+        self.nl = len(self.lp)
+        self.mixer = F.AudioMixer(ctx, rooms, self.nl, nwords, True)
+        self.barrier = barrier
+        self.comm = self.xchg = None
+        self.d_sum = None
+        if exchange == "nccl":
+            uid = (C.c_uint8 * 128)()
+            if rank == 0:
+                _lib.check(self.lib.msb200_comm_unique_id(uid))
+            uid0 = allgather(bytes(uid))[0]
+            h = C.c_void_p()
+            _lib.check(self.lib.msb200_comm_create(ctx.h, (C.c_uint8 * 128).from_buffer_copy(uid0), rank, world, C.byref(h)))
+            self.comm = h
+            self.d_sum = ctx.dev_alloc(rooms * nwords * 4)
+        else:
+            h = C.c_void_p()
+            _lib.check(self.lib.msb200_mixer_xchg_create(self.mixer.h, rank, world, C.byref(h)))
+            self.xchg = h
+            mine = (C.c_uint8 * 64)()
+            _lib.check(self.lib.msb200_mixer_xchg_export(h, mine))
+            handles = b"".join(allgather(bytes(mine)))
+            _lib.check(self.lib.msb200_mixer_xchg_connect(h, (C.c_uint8 * len(handles)).from_buffer_copy(handles)))
+            barrier()  # every rank's flags are zeroed and mapped before the first push
+
+    def set_controls(self, gain: np.ndarray, active: np.ndarray) -> None:
+        """full [rooms][pins] tables -> this rank's pins (MS_AUDIO_MIXER_SET_INPUT_GAIN / SET_ACTIVE)"""
+        lgain, lact = shard_controls(gain, active, self.rank, self.world)
+        for r, k in zip(*np.nonzero(lgain != 1.0)):
+            self.mixer.set_input_gain(int(r), int(k), float(lgain[r, k]))
+        for r, k in zip(*np.nonzero(lact == 0)):
+            self.mixer.set_active(int(r), int(k), False)
+
+    def tick_dev(self, d_in: int, d_present: int, d_out: int) -> None:
+        C, check = self.C, self._lib.check
+        if self.comm is not None:
+            check(self.lib.msb200_mixer_process_striped_dev(self.mixer.h, self.comm, C.c_void_p(d_in), C.c_void_p(d_present),
+                                                            C.c_void_p(self.d_sum), C.c_void_p(d_out)))
+        else:
+            check(self.lib.msb200_mixer_xchg_process_dev(self.xchg, C.c_void_p(d_in), C.c_void_p(d_present), C.c_void_p(d_out)))
+
+    def timeouts(self) -> int:
+        if self.xchg is None:
+            return 0
+        n = self.C.c_uint32()
+        self._lib.check(self.lib.msb200_mixer_xchg_status(self.xchg, self.C.byref(n)))
+        return int(n.value)
+
+    def wire_bytes_per_tick(self) -> int:
+        """bytes this rank moves over NVLink per tick"""
+        if self.xchg is not None:
+            return int(self.lib.msb200_mixer_xchg_wire_bytes_per_tick(self.xchg))
+        # ring all-reduce: 2 (world-1)/world of the buffer out of every rank
+        return int(2 * (self.world - 1) / self.world * self.rooms * self.nwords * 4)
+
+    def close(self) -> None:
+        self.ctx.sync()
+        self.barrier()  # nobody unmaps / frees while a peer may still push or read
+        if self.xchg is not None:
+            self.lib.msb200_mixer_xchg_destroy(self.xchg)
+        if self.comm is not None:
+            self.lib.msb200_comm_destroy(self.comm)
+        if self.d_sum:
+            self.ctx.dev_free(self.d_sum)
+        self.mixer.close()
+        self.xchg = self.comm = self.d_sum = None

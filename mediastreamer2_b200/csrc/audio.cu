@@ -6,6 +6,7 @@
 // divisions, asymmetric +-32767 clamp); float32 state machines and dot products use __fmul_rn/__fadd_rn in the
 // reference's evaluation order so that nvcc never contracts them into FMAs.
 #include "msb200_internal.h"
+#include "mixer_internal.cuh"
 
 #include <cmath>
 
@@ -13,105 +14,16 @@
 // reference: /root/reference/src/audiofilters/audiomixer.c  (accumulate :33-38, saturate :40-44, apply_gain :46-51,
 // channel_process_in :78-90, channel_process_out :113-130, make_output :210-217)
 
-__device__ __forceinline__ int mix_sat(int s) { // audiomixer.c:40-44 — clamps to [-32767, 32767]
-	return s > 32767 ? 32767 : (s < -32767 ? -32767 : s);
-}
-__device__ __forceinline__ int mix_contrib(int s, float gain) { // :46-51, only when gain != 1.0 (:82)
-	if (gain != 1.0f) return mix_sat(__float2int_rz(__fmul_rn(gain, (float)s)));
-	return s;
-}
-
-struct msb200_mixer {
-	msb200_ctx *ctx;
-	int n_rooms, n_pins, nwords, conf_mode;
-	int live;          // rooms [0, live) are processed (msb200_mixer_set_live); == n_rooms by default
-	float *d_gain;     // [room][pin]
-	uint8_t *d_active; // [room][pin]
-	std::vector<float> h_gain;
-	std::vector<uint8_t> h_active;
-	bool dirty;
-	msb200_devbuf in, present, out;
-};
-
-// One thread owns a column of VEC consecutive samples of one room and walks the pins twice: first to build the
-// int32 sums, then to emit sat(sum - own) per pin. The second walk re-reads lines the same thread just touched
-// (L1/L2 hits), so DRAM traffic stays at the algorithmic P*2n in + P*2n out.
-template <int VEC> struct s16vec;
-template <> struct s16vec<8> { typedef int4 type; };
-template <> struct s16vec<4> { typedef int2 type; };
-template <> struct s16vec<2> { typedef int type; };
-template <> struct s16vec<1> { typedef short type; };
-
-template <int VEC> __device__ __forceinline__ void unpack_s16(const typename s16vec<VEC>::type &v, int (&s)[VEC]);
-template <> __device__ __forceinline__ void unpack_s16<8>(const int4 &v, int (&s)[8]) {
-	s[0] = (short)(v.x & 0xffff); s[1] = v.x >> 16; s[2] = (short)(v.y & 0xffff); s[3] = v.y >> 16;
-	s[4] = (short)(v.z & 0xffff); s[5] = v.z >> 16; s[6] = (short)(v.w & 0xffff); s[7] = v.w >> 16;
-}
-template <> __device__ __forceinline__ void unpack_s16<4>(const int2 &v, int (&s)[4]) {
-	s[0] = (short)(v.x & 0xffff); s[1] = v.x >> 16; s[2] = (short)(v.y & 0xffff); s[3] = v.y >> 16;
-}
-template <> __device__ __forceinline__ void unpack_s16<2>(const int &v, int (&s)[2]) {
-	s[0] = (short)(v & 0xffff); s[1] = v >> 16;
-}
-template <> __device__ __forceinline__ void unpack_s16<1>(const short &v, int (&s)[1]) {
-	s[0] = v;
-}
-__device__ __forceinline__ int pack2(int lo, int hi) {
-	return (lo & 0xffff) | (hi << 16);
-}
-template <int VEC> __device__ __forceinline__ typename s16vec<VEC>::type pack_s16(const int (&s)[VEC]);
-template <> __device__ __forceinline__ int4 pack_s16<8>(const int (&s)[8]) {
-	return make_int4(pack2(s[0], s[1]), pack2(s[2], s[3]), pack2(s[4], s[5]), pack2(s[6], s[7]));
-}
-template <> __device__ __forceinline__ int2 pack_s16<4>(const int (&s)[4]) {
-	return make_int2(pack2(s[0], s[1]), pack2(s[2], s[3]));
-}
-template <> __device__ __forceinline__ int pack_s16<2>(const int (&s)[2]) {
-	return pack2(s[0], s[1]);
-}
-template <> __device__ __forceinline__ short pack_s16<1>(const int (&s)[1]) {
-	return (short)s[0];
-}
-
-struct MixPeers { // peer-memory exchange (mode 3): mapped pointers of every rank's partial sums and epoch flag
-	const int *sum[MSB200_MAX_PEERS];
-	const unsigned *flag[MSB200_MAX_PEERS];
-	int n;
-	unsigned epoch;
-	unsigned *error; // set to 1 if a peer's flag never arrives (bounded spin instead of a hang)
-};
-__device__ __forceinline__ int4 ld_sys_v4(const int *p) { // peer data is read once, straight from its home memory
-	int4 v;
-	asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-	return v;
-}
-// mode 0: full (sum + outputs); mode 1: partial sums only -> d_sum; mode 2: outputs from given d_sum;
-// mode 3: wait for the peers' flags, total = sum over peers' partial buffers (NVLink loads), outputs
+// mode 0: full (sum + outputs); mode 1: partial sums only -> d_sum; mode 2: outputs from given d_sum
+// (the fused cross-GPU exchange is its own kernel: mixer_xchg.cu)
 template <int VEC>
 __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in, const uint8_t *__restrict__ present,
                                                     const float *__restrict__ gain, const uint8_t *__restrict__ active,
                                                     short *__restrict__ out, int *__restrict__ sum_io, int n_rooms,
-                                                    int n_pins, int nwords, int conf_mode, int mode, long in_pin_vecs,
-                                                    MixPeers peers) {
+                                                    int n_pins, int nwords, int conf_mode, int mode, long in_pin_vecs) {
 	typedef typename s16vec<VEC>::type V;
 	const int nvec = nwords / VEC;
 	const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (mode == 3) { // acquire: every peer has published its partial sums for this epoch
-		if (threadIdx.x == 0) {
-			for (int g = 0; g < peers.n; ++g) {
-				const volatile unsigned *f = peers.flag[g];
-				long spins = 0;
-				while ((int)(*f - peers.epoch) < 0) {
-					if (++spins > 400000000L) {
-						*peers.error = 1u;
-						break;
-					}
-				}
-			}
-			__threadfence_system();
-		}
-		__syncthreads();
-	}
 	if (gid >= (long)n_rooms * nvec) return;
 	const int room = (int)(gid / nvec), col = (int)(gid % nvec);
 	const size_t chan0 = (size_t)room * n_pins;
@@ -130,16 +42,9 @@ __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in
 #pragma unroll
 			for (int k = 0; k < VEC; ++k) sum[k] += mix_contrib(s[k], g);
 		}
-	} else if (mode == 2) {
+	} else {
 #pragma unroll
 		for (int k = 0; k < VEC; ++k) sum[k] = sum_io[(size_t)room * nwords + col * VEC + k];
-	} else { // mode 3: VEC == 4 (one 16-byte load per peer)
-		for (int g = 0; g < peers.n; ++g) {
-			const int4 v = ld_sys_v4(peers.sum[g] + (size_t)room * nwords + col * VEC);
-			if (VEC >= 4) {
-				sum[0] += v.x; sum[1 % VEC] += v.y; sum[2 % VEC] += v.z; sum[3 % VEC] += v.w;
-			}
-		}
 	}
 	if (mode == 1) {
 #pragma unroll
@@ -171,7 +76,7 @@ __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in
 	}
 }
 
-static int mixer_upload(msb200_mixer *m) {
+int msb200i_mixer_upload(msb200_mixer *m) {
 	if (!m->dirty) return MSB200_OK;
 	size_t n = (size_t)m->n_rooms * m->n_pins;
 	MSB200_CUDA(cudaMemcpyAsync(m->d_gain, m->h_gain.data(), n * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
@@ -183,31 +88,21 @@ static int mixer_upload(msb200_mixer *m) {
 }
 
 static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present, void *d_out, void *d_sum, int mode,
-                        long in_pin_stride = 0, const MixPeers *peers_in = nullptr) {
-	int r = mixer_upload(m);
+                        long in_pin_stride = 0) {
+	int r = msb200i_mixer_upload(m);
 	if (r) return r;
 	const int nw = m->nwords;
 	const bool al16 = ((uintptr_t)d_in % 16 == 0) && (d_out == nullptr || (uintptr_t)d_out % 16 == 0);
 	if (in_pin_stride <= 0) in_pin_stride = nw;
 	int vec = (nw % 8 == 0 && al16) ? 8 : (nw % 4 == 0 && al16) ? 4 : (nw % 2 == 0 && al16) ? 2 : 1;
 	while (vec > 1 && in_pin_stride % vec) vec /= 2;
-	MixPeers peers;
-	memset(&peers, 0, sizeof(peers));
-	if (mode == 3) {
-		peers = *peers_in;
-		if (nw % 4 || !al16) {
-			msb200_set_error("mixer: the peer-memory path needs nwords %% 4 == 0 and 16-byte aligned buffers");
-			return MSB200_EINVAL;
-		}
-		vec = 4;
-	}
 	// prefer more, narrower threads when the grid would not cover the chip (148 SMs x >=4 CTAs of 128)
-	while (mode != 3 && vec > 2 && (long)m->live * (nw / vec) < 148L * 4 * 128) vec /= 2;
+	while (vec > 2 && (long)m->live * (nw / vec) < 148L * 4 * 128) vec /= 2;
 	const long nthreads = (long)m->live * (nw / vec);
 	const int block = 128, grid = (int)((nthreads + block - 1) / block);
 #define MIX_ARGS                                                                                                       \
 	(const short *)d_in, (const uint8_t *)d_present, m->d_gain, m->d_active, (short *)d_out, (int *)d_sum, m->live, \
-	    m->n_pins, nw, m->conf_mode, mode, in_pin_stride / vec, peers
+	    m->n_pins, nw, m->conf_mode, mode, in_pin_stride / vec
 	switch (vec) {
 		case 8: MSB200_LAUNCH(m->ctx, mixer_kernel<8>, grid, block, 0, MIX_ARGS); break;
 		case 4: MSB200_LAUNCH(m->ctx, mixer_kernel<4>, grid, block, 0, MIX_ARGS); break;
@@ -270,22 +165,6 @@ int msb200_mixer_partial_dev(msb200_mixer *m, const void *d_in, const void *d_pr
 int msb200_mixer_finish_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *d_sum, void *d_out) {
 	MSB200_CHECK_ARG(m && d_in && d_present && d_sum && d_out);
 	return mixer_launch(m, d_in, d_present, d_out, (void *)d_sum, 2);
-}
-int msb200_mixer_finish_peers_dev(msb200_mixer *m, const void *d_in, const void *d_present, const void *const *d_peer_sums,
-                                  const void *const *d_peer_flags, int n_peers, uint32_t epoch, void *d_out, void *d_error) {
-	MSB200_CHECK_ARG(m && d_in && d_present && d_out && d_peer_sums && d_peer_flags && d_error);
-	MSB200_CHECK_ARG(n_peers >= 1 && n_peers <= MSB200_MAX_PEERS && m->conf_mode);
-	MixPeers p;
-	memset(&p, 0, sizeof(p));
-	for (int g = 0; g < n_peers; ++g) {
-		MSB200_CHECK_ARG(d_peer_sums[g] && d_peer_flags[g] && ((uintptr_t)d_peer_sums[g] % 16) == 0);
-		p.sum[g] = (const int *)d_peer_sums[g];
-		p.flag[g] = (const unsigned *)d_peer_flags[g];
-	}
-	p.n = n_peers;
-	p.epoch = epoch;
-	p.error = (unsigned *)d_error;
-	return mixer_launch(m, d_in, d_present, d_out, nullptr, 3, 0, &p);
 }
 int msb200_mixer_set_live(msb200_mixer *m, int n_live) {
 	MSB200_CHECK_ARG(m && n_live >= 0 && n_live <= m->n_rooms);

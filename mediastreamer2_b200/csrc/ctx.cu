@@ -3,11 +3,6 @@
 
 static thread_local char g_err[512] = "";
 
-__global__ void signal_kernel(unsigned *flag, unsigned value) {
-	__threadfence_system(); // everything this stream wrote before is visible system-wide before the flag moves
-	*reinterpret_cast<volatile unsigned *>(flag) = value;
-}
-
 void msb200_set_error(const char *fmt, ...) {
 	va_list ap;
 	va_start(ap, fmt);
@@ -162,11 +157,6 @@ int msb200_ipc_import(msb200_ctx *c, const uint8_t handle[MSB200_IPC_HANDLE_BYTE
 int msb200_ipc_close(msb200_ctx *c, void *dev_ptr) {
 	MSB200_CHECK_ARG(c && dev_ptr);
 	MSB200_CUDA(cudaIpcCloseMemHandle(dev_ptr));
-	return MSB200_OK;
-}
-int msb200_signal_dev(msb200_ctx *c, void *d_flag, uint32_t value) {
-	MSB200_CHECK_ARG(c && d_flag);
-	MSB200_LAUNCH(c, signal_kernel, 1, 1, 0, (unsigned *)d_flag, (unsigned)value);
 	return MSB200_OK;
 }
 int msb200_flush_l2(msb200_ctx *c) {

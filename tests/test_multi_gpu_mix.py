@@ -1,6 +1,16 @@
-"""N>1 path on CPU: world_size 2, gloo. Each rank owns the striped half of every room's pins, computes partial sums
-(oracle standing in for msb200_mixer_partial_dev), all-reduces int32 over gloo, finishes its local pins; the gathered
-result must equal the single-process 16-pin conference mix bit for bit (integer sums are order-independent)."""
+"""The N>1 path: a conference whose pins are striped over the ranks (BASELINE cfg3).
+
+CPU (`-m "not gpu"`): world_size 2 over gloo — the host-side sharding logic (mediastreamer2_b200/conference.py) with the
+oracle standing in for the kernels; the gathered result equals the single-process 16-pin conference mix bit for bit.
+
+GPU (`-m gpu`): the REAL entry points of include/msb200dsp.h —
+  * two ranks as two contexts of one process (msb200_mixer_xchg_connect_local): the fused push / flag / finish kernel
+  * two ranks as two PROCESSES (gloo side channel): msb200_mixer_partial_dev -> all-reduce -> msb200_mixer_finish_dev, and
+    the fused kernel over cudaIpc mappings (msb200_mixer_xchg_export / _connect); with >= 2 GPUs also the dlopen'ed NCCL
+    communicator (msb200_comm_*, msb200_mixer_process_striped_dev)
+  * msb200_comm_* at world 1 on any box (NCCL loads, a 1-rank all-reduce is the identity)
+each bit-exact against the oracle's single mixer (audiomixer.c:288-346, :113-130, :40-44)."""
+import ctypes as C
 import os
 import socket
 import sys
@@ -25,7 +35,30 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, rooms, pins, nwords, ticks, outdir):
+def _inputs(rooms, pins, nwords, t):
+    from mediastreamer2_b200 import conference as conf
+
+    pcm, present, gain, active = conf.cfg3_inputs(rooms, pins, nwords, t)
+    if t == 1:
+        present[:, 5] = 0  # a starving pin: contributes zeros, still receives the mix
+    if t == 2:
+        pcm[0, :, :7] = 32767  # saturation on both sides of the clamp
+        pcm[1, :, :7] = -32768
+    return pcm, present, gain, active
+
+
+def _expected(pcm, present, gain, active):
+    import _oracle as O
+
+    L = O.oracle()
+    exp = np.zeros_like(pcm)
+    r, p, n = pcm.shape
+    L.orc_mixer_process(r, p, n, 1, O.ptr(gain), O.ptr(active), O.ptr(pcm), O.ptr(present), O.ptr(exp))
+    return exp
+
+
+# ---------------------------------------------------------------------------------------------- CPU: host logic over gloo
+def _worker_cpu(rank, world, port, rooms, pins, nwords, ticks, outdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -36,18 +69,13 @@ def _worker(rank, world, port, rooms, pins, nwords, ticks, outdir):
     L = O.oracle()
     ok = True
     for t in range(ticks):
-        pcm, present, gain, active = conf.cfg3_inputs(rooms, pins, nwords, t)
-        if t == 1:
-            present[:, 5] = 0  # a starving pin: contributes zeros, still receives the mix
+        pcm, present, gain, active = _inputs(rooms, pins, nwords, t)
         lpcm, lpres, lp = conf.shard_inputs(pcm, present, rank, world)
         lgain, lact = conf.shard_controls(gain, active, rank, world)
-        # phase 1: local partial sums
         part = np.zeros((rooms, nwords), np.int32)
         L.orc_mixer_partial(rooms, len(lp), nwords, ptr(lgain), ptr(lact), ptr(lpcm), ptr(lpres), ptr(part))
-        # phase 2: the one exchange step
         tsum = torch.from_numpy(part)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        # phase 3: finish local pins from the reduced sum  (== msb200_mixer_finish_dev)
         total = tsum.numpy()
         lout = np.zeros_like(lpcm)
         for r in range(rooms):
@@ -58,8 +86,7 @@ def _worker(rank, world, port, rooms, pins, nwords, ticks, outdir):
                     if lgain[r, k] != 1.0:
                         x = np.clip((np.float32(lgain[r, k]) * lpcm[r, k].astype(np.float32)).astype(np.int32), -32767, 32767).astype(np.int64)
                     own = x
-                lout[r, k] = np.clip(total[r].astype(np.int64) - (own if lact[r, k] else 0), -32767, 32767).astype(np.int16)
-        # gather everybody's outputs on rank 0 and compare with the single-process mixer
+                lout[r, k] = np.clip(total[r].astype(np.int64) - own, -32767, 32767).astype(np.int16)
         lout32 = torch.from_numpy(lout.astype(np.int32))  # gloo has no int16 collectives
         gathered = [torch.zeros_like(lout32) for _ in range(world)] if rank == 0 else None
         dist.gather(lout32, gathered, dst=0)
@@ -67,9 +94,7 @@ def _worker(rank, world, port, rooms, pins, nwords, ticks, outdir):
             full = np.zeros((rooms, pins, nwords), np.int16)
             for r2 in range(world):
                 conf.scatter_outputs(full, gathered[r2].numpy().astype(np.int16), r2, world)
-            exp = np.zeros_like(full)
-            L.orc_mixer_process(rooms, pins, nwords, 1, ptr(gain), ptr(active), ptr(pcm), ptr(present), ptr(exp))
-            ok = ok and bool(np.array_equal(full, exp))
+            ok = ok and bool(np.array_equal(full, _expected(pcm, present, gain, active)))
     if rank == 0:
         Path(outdir, "ok").write_text("1" if ok else "0")
     dist.destroy_process_group()
@@ -77,7 +102,7 @@ def _worker(rank, world, port, rooms, pins, nwords, ticks, outdir):
 
 def test_striped_conference_all_reduce_is_bit_exact_world2(tmp_path):
     world, port = 2, _free_port()
-    mp.spawn(_worker, args=(world, port, 6, 16, 160, 3, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker_cpu, args=(world, port, 6, 16, 160, 3, str(tmp_path)), nprocs=world, join=True)
     assert (tmp_path / "ok").read_text() == "1"
 
 
@@ -87,3 +112,190 @@ def test_local_pin_striping_partitions_the_room():
     for world in (1, 2, 4, 8):
         seen = np.concatenate([conf.local_pins(r, world, 16) for r in range(world)])
         assert sorted(seen.tolist()) == list(range(16))
+
+
+# ---------------------------------------------------------------------------------------------- GPU: one process, N contexts
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,rooms,nwords", [(2, 64, 480), (4, 33, 160), (3, 256, 480), (2, 1024, 480)])
+def test_fused_exchange_kernel_contexts_of_one_process(world, rooms, nwords):
+    """msb200_mixer_xchg_* with the ranks as contexts (streams) of this process on cuda:0: every tick is ONE kernel per rank
+    that pushes its partial sums into the peers' slots, flags them and finishes from its own slots. 7 ticks exercise both
+    slot parities and the epoch counter; world 3 leaves ranks with unequal pin counts (6, 5, 5). (Sizes keep every rank's grid
+    co-resident on the ONE GPU the ranks share here; on the real layout each rank has a GPU to itself.)"""
+    from mediastreamer2_b200 import _lib
+    from mediastreamer2_b200 import conference as conf
+    from mediastreamer2_b200 import filters as F
+
+    pins = 16
+    ctxs = [F.Context(0) for _ in range(world)]
+    lib = ctxs[0].lib
+    mixers, xs, bufs = [], [], []
+    for r in range(world):
+        nl = len(conf.local_pins(r, world, pins))
+        m = F.AudioMixer(ctxs[r], rooms, nl, nwords, True)
+        h = C.c_void_p()
+        _lib.check(lib.msb200_mixer_xchg_create(m.h, r, world, C.byref(h)))
+        mixers.append(m)
+        xs.append(h)
+        nb = rooms * nl * nwords * 2
+        bufs.append((ctxs[r].dev_alloc(nb), ctxs[r].dev_alloc(rooms * nl), ctxs[r].dev_alloc(nb), nl))
+    arr = (C.c_void_p * world)(*[x.value for x in xs])
+    for r in range(world):
+        _lib.check(lib.msb200_mixer_xchg_connect_local(xs[r], arr))
+    _, _, gain, active = _inputs(rooms, pins, nwords, 0)
+    for r in range(world):
+        lgain, lact = conf.shard_controls(gain, active, r, world)
+        for rr, k in zip(*np.nonzero(lgain != 1.0)):
+            mixers[r].set_input_gain(int(rr), int(k), float(lgain[rr, k]))
+        for rr, k in zip(*np.nonzero(lact == 0)):
+            mixers[r].set_active(int(rr), int(k), False)
+    try:
+        for t in range(7):
+            pcm, present, gain, active = _inputs(rooms, pins, nwords, t)
+            for r in range(world):
+                lpcm, lpres, _ = conf.shard_inputs(pcm, present, r, world)
+                ctxs[r].h2d(bufs[r][0], lpcm)
+                ctxs[r].h2d(bufs[r][1], lpres)
+            order = range(world) if t % 2 == 0 else reversed(range(world))  # no rank is always first
+            for r in order:
+                _lib.check(lib.msb200_mixer_xchg_process_dev(xs[r], bufs[r][0], bufs[r][1], bufs[r][2]))
+            full = np.zeros((rooms, pins, nwords), np.int16)
+            for r in range(world):
+                lout = np.empty((rooms, bufs[r][3], nwords), np.int16)
+                ctxs[r].d2h(lout, bufs[r][2])
+                conf.scatter_outputs(full, lout, r, world)
+                n = C.c_uint32()
+                _lib.check(lib.msb200_mixer_xchg_status(xs[r], C.byref(n)))
+                assert n.value == 0, f"rank {r}: {n.value} flag waits timed out at tick {t}"
+            assert np.array_equal(full, _expected(pcm, present, gain, active)), f"tick {t}"
+    finally:
+        for r in range(world):
+            ctxs[r].sync()
+        for r in range(world):
+            lib.msb200_mixer_xchg_destroy(xs[r])
+            mixers[r].close()
+            for p in bufs[r][:3]:
+                ctxs[r].dev_free(p)
+            ctxs[r].close()
+
+
+@pytest.mark.gpu
+def test_nccl_entry_points_world1(ctx):
+    """the dlopen'ed NCCL communicator at world 1: msb200_mixer_process_striped_dev == single-pass mixer == oracle"""
+    from mediastreamer2_b200 import _lib
+    from mediastreamer2_b200 import filters as F
+
+    lib = ctx.lib
+    assert lib.msb200_comm_available() == 1, lib.msb200_last_error().decode()
+    assert lib.msb200_comm_nccl_version() >= 20000
+    uid = (C.c_uint8 * 128)()
+    _lib.check(lib.msb200_comm_unique_id(uid))
+    comm = C.c_void_p()
+    _lib.check(lib.msb200_comm_create(ctx.h, uid, 0, 1, C.byref(comm)))
+    rooms, pins, nwords = 12, 16, 480
+    pcm, present, gain, active = _inputs(rooms, pins, nwords, 2)
+    m = F.AudioMixer(ctx, rooms, pins, nwords, True)
+    for rr, k in zip(*np.nonzero(gain != 1.0)):
+        m.set_input_gain(int(rr), int(k), float(gain[rr, k]))
+    for rr, k in zip(*np.nonzero(active == 0)):
+        m.set_active(int(rr), int(k), False)
+    d_in, d_pr = ctx.dev_alloc(pcm.nbytes), ctx.dev_alloc(present.nbytes)
+    d_sum, d_out = ctx.dev_alloc(rooms * nwords * 4), ctx.dev_alloc(pcm.nbytes)
+    ctx.h2d(d_in, pcm)
+    ctx.h2d(d_pr, present)
+    _lib.check(lib.msb200_mixer_process_striped_dev(m.h, comm, d_in, d_pr, d_sum, d_out))
+    out = np.zeros_like(pcm)
+    ctx.d2h(out, d_out)
+    lib.msb200_comm_destroy(comm)
+    m.close()
+    for p in (d_in, d_pr, d_sum, d_out):
+        ctx.dev_free(p)
+    assert np.array_equal(out, _expected(pcm, present, gain, active))
+
+
+# ---------------------------------------------------------------------------------------------- GPU: two processes
+def _worker_gpu(rank, world, port, rooms, pins, nwords, ticks, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mediastreamer2_b200 import _lib
+    from mediastreamer2_b200 import conference as conf
+    from mediastreamer2_b200 import filters as F
+
+    ndev = torch.cuda.device_count()
+    ctx = F.Context(rank % ndev)
+    lib = ctx.lib
+
+    def allgather(obj):
+        got = [None] * world
+        dist.all_gather_object(got, obj)
+        return got
+
+    def barrier():
+        ctx.sync()
+        dist.barrier()
+
+    exchanges = ["gloo", "fused"] + (["nccl"] if ndev >= world and lib.msb200_comm_available() else [])
+    verdict = {}
+    for exchange in exchanges:
+        ok = True
+        sc = None
+        if exchange == "gloo":  # the two real kernels either side of an all-reduce done by the test (host, int32)
+            lp = conf.local_pins(rank, world, pins)
+            mixer = F.AudioMixer(ctx, rooms, len(lp), nwords, True)
+            nl = len(lp)
+        else:
+            sc = conf.StripedConference(ctx, rank, world, rooms, pins, nwords, exchange, allgather, barrier)
+            mixer, nl = sc.mixer, sc.nl
+        _, _, gain, active = _inputs(rooms, pins, nwords, 0)
+        lgain, lact = conf.shard_controls(gain, active, rank, world)
+        for rr, k in zip(*np.nonzero(lgain != 1.0)):
+            mixer.set_input_gain(int(rr), int(k), float(lgain[rr, k]))
+        for rr, k in zip(*np.nonzero(lact == 0)):
+            mixer.set_active(int(rr), int(k), False)
+        nb = rooms * nl * nwords * 2
+        d_in, d_pr, d_out, d_sum = ctx.dev_alloc(nb), ctx.dev_alloc(rooms * nl), ctx.dev_alloc(nb), ctx.dev_alloc(rooms * nwords * 4)
+        for t in range(ticks):
+            pcm, present, gain, active = _inputs(rooms, pins, nwords, t)
+            lpcm, lpres, _ = conf.shard_inputs(pcm, present, rank, world)
+            ctx.h2d(d_in, lpcm)
+            ctx.h2d(d_pr, lpres)
+            if sc is not None:
+                sc.tick_dev(d_in, d_pr, d_out)
+            else:
+                _lib.check(lib.msb200_mixer_partial_dev(mixer.h, d_in, d_pr, d_sum))
+                part = np.empty((rooms, nwords), np.int32)
+                ctx.d2h(part, d_sum)
+                tsum = torch.from_numpy(part)
+                dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+                ctx.h2d(d_sum, tsum.numpy())
+                _lib.check(lib.msb200_mixer_finish_dev(mixer.h, d_in, d_pr, d_sum, d_out))
+            lout = np.empty((rooms, nl, nwords), np.int16)
+            ctx.d2h(lout, d_out)
+            parts = allgather(lout)
+            if rank == 0:
+                full = np.zeros((rooms, pins, nwords), np.int16)
+                for r2 in range(world):
+                    conf.scatter_outputs(full, parts[r2], r2, world)
+                ok = ok and bool(np.array_equal(full, _expected(pcm, present, gain, active)))
+        if sc is not None:
+            ok = ok and sum(allgather(sc.timeouts())) == 0
+            sc.close()
+        else:
+            mixer.close()
+        for p in (d_in, d_pr, d_out, d_sum):
+            ctx.dev_free(p)
+        verdict[exchange] = ok
+    if rank == 0:
+        Path(outdir, "verdict").write_text(repr(verdict))
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_striped_conference_real_kernels_two_processes(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_gpu, args=(world, port, 48, 16, 480, 4, str(tmp_path)), nprocs=world, join=True)
+    verdict = eval((tmp_path / "verdict").read_text())  # noqa: S307 - our own repr of a dict of bools
+    assert verdict and all(verdict.values()), verdict
+    assert {"gloo", "fused"} <= set(verdict)
