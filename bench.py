@@ -213,9 +213,10 @@ def summary(line: dict) -> dict:
     px = line.get("pixconv") or {}
     if "roofline" in px:
         out["pixconv"] = {"kernel": px["roofline"].get("kernel"), "frac_of_hbm": px["roofline"].get("frac"),
-                          "mpix_s_in": px.get("value"), "e2e_mpix_s_in": (px.get("e2e") or {}).get("value"),
-                          "cpu_mpix_s_in": (px.get("cpu_baseline") or {}).get("value"),
-                          "cpu_kind": (px.get("cpu_baseline") or {}).get("kind")}
+                          "mpix_s_in": px.get("mpix_per_s_in"), "e2e_mpix_s_in": (px.get("e2e") or {}).get("mpix_per_s_in"),
+                          "cpu_mpix_s_in": (px.get("cpu_baseline") or {}).get("mpix_per_s_in"),
+                          "cpu_kind": (px.get("cpu_baseline") or {}).get("kind"),
+                          "cpu_cores": (px.get("cpu_baseline") or {}).get("cores")}
     rt = line.get("realtime") or {}
     if "s_rt_streams_at_least" in rt:
         out["s_rt_streams_at_least"] = rt["s_rt_streams_at_least"]

@@ -573,3 +573,75 @@ bool_t fmtp_get_value(const char *fmtp, const char *param_name, char *result, si
 	}
 	return FALSE;
 }
+
+/* ---------------------------------------------------------------- bctoolbox/vfs.h over POSIX descriptors
+ * (the reference's WAV reader msfileplayer.c:98-150 and utils/audiodiff.c read their files through it) */
+#include "bctoolbox/vfs.h"
+#include <sys/stat.h>
+#include <unistd.h>
+struct bctbx_vfs_t {
+	int unused;
+};
+static bctbx_vfs_t g_default_vfs;
+bctbx_vfs_t *bctbx_vfs_get_default(void) {
+	return &g_default_vfs;
+}
+bctbx_vfs_file_t *bctbx_file_open2(bctbx_vfs_t *vfs, const char *path, int openflags) {
+	(void)vfs;
+	int fd = open(path, openflags, 0644);
+	if (fd < 0) return NULL;
+	bctbx_vfs_file_t *f = (bctbx_vfs_file_t *)calloc(1, sizeof(*f));
+	f->fd = fd;
+	f->offset = 0;
+	return f;
+}
+bctbx_vfs_file_t *bctbx_file_open(bctbx_vfs_t *vfs, const char *path, const char *mode) {
+	int flags = O_RDONLY;
+	if (mode && strchr(mode, 'w')) flags = O_WRONLY | O_CREAT | O_TRUNC;
+	if (mode && strchr(mode, '+')) flags = O_RDWR | O_CREAT;
+	return bctbx_file_open2(vfs, path, flags);
+}
+int64_t bctbx_file_size(bctbx_vfs_file_t *f) {
+	struct stat st;
+	if (!f || fstat(f->fd, &st) != 0) return BCTBX_VFS_ERROR;
+	return (int64_t)st.st_size;
+}
+int bctbx_file_close(bctbx_vfs_file_t *f) {
+	if (!f) return BCTBX_VFS_ERROR;
+	close(f->fd);
+	free(f);
+	return BCTBX_VFS_OK;
+}
+ssize_t bctbx_file_read(bctbx_vfs_file_t *f, void *buf, size_t count, off_t offset) {
+	if (!f) return BCTBX_VFS_ERROR;
+	ssize_t r = pread(f->fd, buf, count, offset);
+	return r < 0 ? BCTBX_VFS_ERROR : r;
+}
+ssize_t bctbx_file_read2(bctbx_vfs_file_t *f, void *buf, size_t count) {
+	ssize_t r = bctbx_file_read(f, buf, count, f ? f->offset : 0);
+	if (r > 0) f->offset += r;
+	return r;
+}
+ssize_t bctbx_file_write(bctbx_vfs_file_t *f, const void *buf, size_t count, off_t offset) {
+	if (!f) return BCTBX_VFS_ERROR;
+	ssize_t r = pwrite(f->fd, buf, count, offset);
+	return r < 0 ? BCTBX_VFS_ERROR : r;
+}
+ssize_t bctbx_file_write2(bctbx_vfs_file_t *f, const void *buf, size_t count) {
+	ssize_t r = bctbx_file_write(f, buf, count, f ? f->offset : 0);
+	if (r > 0) f->offset += r;
+	return r;
+}
+off_t bctbx_file_seek(bctbx_vfs_file_t *f, off_t offset, int whence) {
+	if (!f) return BCTBX_VFS_ERROR;
+	if (whence == SEEK_SET) f->offset = offset;
+	else if (whence == SEEK_CUR) f->offset += offset;
+	else if (whence == SEEK_END) f->offset = (off_t)bctbx_file_size(f) + offset;
+	return f->offset;
+}
+int bctbx_file_truncate(bctbx_vfs_file_t *f, int64_t size) {
+	return (f && ftruncate(f->fd, size) == 0) ? BCTBX_VFS_OK : BCTBX_VFS_ERROR;
+}
+int bctbx_file_sync(bctbx_vfs_file_t *f) {
+	return (f && fsync(f->fd) == 0) ? BCTBX_VFS_OK : BCTBX_VFS_ERROR;
+}

@@ -129,6 +129,24 @@ def test_aec_white_noise_converges_and_state_blob_roundtrip(ctx):
     ec2.close()
 
 
+def _gpu_run_scenarios(ctx, sigs):
+    """every scenario as one stream of ONE bank (lockstep frames), 25 frames per call"""
+    n = min(len(m) for _, m, _ in sigs)
+    ec = F.SpeexEC(ctx, len(sigs), 16000, 250)
+    Fs = ec.frame_size
+    nfr = n // Fs
+    got = np.zeros((len(sigs), nfr * Fs), np.int16)
+    step = 25
+    for k in range(0, nfr, step):
+        c = min(step, nfr - k)
+        sl = slice(k * Fs, (k + c) * Fs)
+        mics = np.ascontiguousarray(np.stack([m[sl] for _, m, _ in sigs]))
+        refs = np.ascontiguousarray(np.stack([f[sl] for f, _, _ in sigs]))
+        got[:, sl] = ec.process(mics, refs)
+    ec.close()
+    return got
+
+
 def test_aec_on_the_reference_testers_simple_talk_material(ctx):
     """the reference tester's own echo scenario (tests/aec_fixture.py): the GPU canceller removes the lone far-end
     talker's echo by >= 25 dB, keeps the lone near-end talker, and tracks the oracle's ERLE within 2 dB"""
@@ -136,20 +154,38 @@ def test_aec_on_the_reference_testers_simple_talk_material(ctx):
 
     L = O.oracle()
     far, mic, near = A.load()
-    ec = F.SpeexEC(ctx, 2, A.RATE, 250)  # two identical streams: the bank must treat them identically
-    Fs = ec.frame_size
-    nfr = len(mic) // Fs
-    got = np.zeros((2, nfr * Fs), np.int16)
-    step = 25
-    for k in range(0, nfr, step):
-        c = min(step, nfr - k)
-        sl = slice(k * Fs, (k + c) * Fs)
-        m2 = np.ascontiguousarray(np.stack([mic[sl], mic[sl]]))
-        r2 = np.ascontiguousarray(np.stack([far[sl], far[sl]]))
-        got[:, sl] = ec.process(m2, r2)
-    ec.close()
+    got = _gpu_run_scenarios(ctx, [(far, mic, near), (far, mic, near)])  # two identical streams: treated identically
     assert np.array_equal(got[0], got[1])
+    n = got.shape[1]
     erle, keep, corr = A.check_behaviour(got[0], mic, near, min_erle_db=25.0)
-    _, exp = _oracle_run(L, A.RATE, 250, mic[:nfr * Fs], far[:nfr * Fs])
+    _, exp = _oracle_run(L, A.RATE, 250, mic[:n], far[:n])
     erle_o, _, _ = A.check_behaviour(exp, mic, near, min_erle_db=25.0)
     assert max(abs(a - b) for a, b in zip(erle, erle_o)) <= 2.0, (erle, erle_o)
+
+
+def test_aec_reference_suite_metric_gpu_vs_oracle(ctx, tmp_path):
+    """Every scenario of the reference's AEC suite that the committed material covers, through the reference's OWN metric
+    (ms_audio_compare_silence_and_speech, unmodified audiodiff.c in oracle/_ref): the GPU bank meets the same bounds as the
+    oracle (tests/test_oracle_aec_fixture.py) and lands within 0.01 similarity of it."""
+    import aec_fixture as A
+
+    L = O.oracle()
+    R = O.ref()
+    g = A.load_all()
+    names = list(A.SCENARIOS)
+    sigs = [A.scenario_signals(g, nm) for nm in names]
+    got = _gpu_run_scenarios(ctx, sigs)
+    n = got.shape[1]
+    ideal = _gpu_run_scenarios(ctx, [(np.zeros_like(nr), nr.copy(), nr) for _, _, nr in sigs])
+    for k, nm in enumerate(names):
+        far, mic, near = sigs[k]
+        sim, energy = A.silence_and_speech(R, tmp_path, near[:n], got[k], nm)
+        _, exp = _oracle_run(L, A.RATE, 250, mic[:n], far[:n])
+        sim_o, energy_o = A.silence_and_speech(R, tmp_path, near[:n], exp, nm)
+        min_sim, max_energy = A.SCENARIOS[nm][6]
+        assert min_sim <= sim < 1.0 and energy <= max_energy, (nm, sim, energy)
+        assert abs(sim - sim_o) <= 0.01, (nm, sim, sim_o)
+        assert abs(energy - energy_o) <= 0.25 * energy_o + 0.05, (nm, energy, energy_o)
+        if far.any():
+            sim_i, _ = A.silence_and_speech(R, tmp_path, ideal[k], got[k], nm)
+            assert sim_i >= A.ISOLATED_MIN[nm], (nm, sim_i)
