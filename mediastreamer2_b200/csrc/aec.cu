@@ -52,7 +52,13 @@ struct AecParams {
 };
 
 // ------------------------------------------------------------------------------------------------ cp.async (LDGSTS)
-#define AEC_STAGES 3
+// The block pass keeps AEC_STAGES - 1 blocks (X_{j+1}, FG_j, W_j: 3 rows of 8F bytes each) in flight per CTA. With 4 CTAs
+// per SM and ~1 us of loaded HBM latency, 2 blocks in flight (12 KB) cap a CTA at ~10 GB/s, so the memory system only
+// saturates while ALL four CTAs of an SM are inside their passes at once — they are not (FFTs, serial IIR sections). Five
+// blocks in flight (30 KB) let two CTAs saturate the SM's share of HBM. The two extra ring slots cost no shared memory:
+// they alias scratch that is dead during the pass (see the carve-up in the kernel).
+#define AEC_STAGES 6
+#define AEC_OWN_STAGES 4 // ring slots with storage of their own; slots [AEC_OWN_STAGES, AEC_STAGES) alias dead scratch
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -346,24 +352,28 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 	// ---- shared memory carve-up
 	float2 *tw = reinterpret_cast<float2 *>(sm);           // [L/2]
 	float2 *spl = tw + L / 2;                              // [L+1] (+1 pad)
-	float2 *bufa = spl + L + 2;                            // [L]
-	float2 *bufb = bufa + L;                               // [L]
-	float2 *specA = bufb + L;                              // [L] spectrum scratch A
-	float2 *specB = specA + L;                             // [L] spectrum scratch B
+	float2 *specB = spl + L + 2;                           // [L] spectrum scratch B
 	float2 *Eprev = specB + L;                             // [L] previous frame's error spectrum
 	float2 *pipe = Eprev + L;                              // [AEC_STAGES][3][L] cp.async ring: X_{j+1}, FG_j, W_j
-	float *xw = reinterpret_cast<float *>(pipe + AEC_STAGES * 3 * L); // [N] far-end window
-	float *ebuf = xw + N;                                  // [N]
+	// ring slots AEC_OWN_STAGES.. live on top of the seven arrays below, all dead between the constraint pre-pass and the
+	// end of the block pass: 5 * 8F + 2 * 4(F + NB_BANDS + 1) bytes >= 2 slots of 24F bytes
+	float2 *bufa = pipe + AEC_OWN_STAGES * 3 * L;          // [L]
+	float2 *bufb = bufa + L;                               // [L]
+	float2 *specA = bufb + L;                              // [L] spectrum scratch A
+	float *ebuf = reinterpret_cast<float *>(specA + L);    // [N]
 	float *ybuf = ebuf + N;                                // [N]
-	float *input = ybuf + N;                               // [F]
+	constexpr int VLEN = (F + NB_BANDS + 1 + 3) & ~3;      // F + NB_BANDS + 1 entries, rounded so that what follows stays 16-byte aligned
+	float *vec1 = ybuf + N;                                // [VLEN]
+	float *vec2 = vec1 + VLEN;                             // [VLEN]
+	static_assert(AEC_STAGES - AEC_OWN_STAGES == 2, "the aliased scratch holds exactly two ring slots");
+	float *vec3 = vec2 + VLEN;                             // [VLEN]
+	float *vec4 = vec3 + VLEN;                             // [VLEN]
+	float *vec5 = vec4 + VLEN;                             // [VLEN]
+	float *xw = vec5 + VLEN;                               // [N] far-end window
+	float *input = xw + N;                                 // [F]
 	float *tmpv = input + F;                               // [N] generic real scratch
 	float *power_1 = tmpv + N;                             // [F+1]
-	float *vec1 = power_1 + F + 1;                         // [F+NB_BANDS+1]
-	float *vec2 = vec1 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
-	float *vec3 = vec2 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
-	float *vec4 = vec3 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
-	float *vec5 = vec4 + F + NB_BANDS + 1;                 // [F+NB_BANDS+1]
-	float *prop = vec5 + F + NB_BANDS + 1;                 // [M]
+	float *prop = power_1 + F + 1;                         // [M]
 	float *wpart = prop + M;                               // [M][8] per-warp |W_j|^2 partials
 	float *red = wpart + M * 8;                            // [32]
 	float *sc = red + 32;                                  // [SC_COUNT]
@@ -431,8 +441,9 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			gX_pf += F;
 			if (--x_left == 0) gX_pf -= x_ring;
 		};
+		// early prologue: the ring slots with storage of their own (the aliased ones are still scratch until the pre-pass ends)
 #pragma unroll
-		for (int pj = 0; pj < AEC_STAGES - 1; ++pj) {
+		for (int pj = 0; pj < AEC_OWN_STAGES; ++pj) {
 			if (pj < M) prefetch(pj, pj);
 			cp_async_commit();
 		}
@@ -545,6 +556,12 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			__syncthreads();
 			rfft_pair<LOG2L>(reinterpret_cast<float *>(specB), specB, tmpv, cspec, bufa, bufb, sa, sb, P, tw, spl);
 		}
+		// late prologue: from here to the end of the pass bufa / bufb / specA / ebuf / ybuf / vec1 / vec2 are ring slots
+#pragma unroll
+		for (int pj = AEC_OWN_STAGES; pj < AEC_STAGES - 1; ++pj) {
+			if (pj < M) prefetch(pj, pj);
+			cp_async_commit();
+		}
 
 		// ---- the pass over the M blocks: foreground output, weight update, background output.
 		// X_{j+1}, FG_j and W_j are streamed HBM -> shared memory with cp.async, AEC_STAGES-1 blocks ahead of their use;
@@ -552,8 +569,8 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		// cp.async.wait_group. The stage loop is unrolled so that all shared-memory offsets are immediates.
 		float2 yfg = make_float2(0.f, 0.f), ybg = make_float2(0.f, 0.f);
 		{
-			static_assert(AEC_STAGES == 3, "the grouped |W_j|^2 reduction below folds exactly three blocks");
-			float nrm[AEC_STAGES] = {0.f, 0.f, 0.f};
+			static_assert(AEC_STAGES % 3 == 0, "the grouped |W_j|^2 reduction below folds three blocks at a time");
+			float nrm[3] = {0.f, 0.f, 0.f};
 			for (int j0 = 0; j0 < M; j0 += AEC_STAGES) {
 #pragma unroll
 				for (int sidx = 0; sidx < AEC_STAGES; ++sidx) {
@@ -598,7 +615,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 						}
 						if (do_update || constrained) gW_grp[sidx * F] = w;
 						// |W_j|^2 partial for next frame's mdf_adjust_prop: reduced three blocks at a time after the group
-						if (need_wnorm) nrm[sidx] = w.x * w.x + w.y * w.y;
+						if (need_wnorm) nrm[sidx % 3] = w.x * w.x + w.y * w.y;
 						// background: Y += X_j * W_j
 						if (t == 0) {
 							ybg.x += xj.x * w.x;
@@ -609,25 +626,26 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 						}
 						xj = xj1;
 					}
+					if (sidx % 3 == 2 && need_wnorm && j0 + sidx - 2 < M) {
+						// three warp sums for the price of one and a bit: after the first two folds the three quantities live
+						// in disjoint lane groups (block jb: lanes 0-7, jb+1: 16-23, jb+2: 8-15 and 24-31) and share the
+						// remaining folds. Same pairing order (xor 16, 8, 4, 2, 1) as warp_sum: identical sums, 6 SHFL not 15.
+						const int jb = j0 + sidx - 2;
+						const bool hi16 = lane & 16, hi8 = lane & 8;
+						float a = hi16 ? nrm[1] : nrm[0];
+						a += __shfl_xor_sync(0xffffffffu, hi16 ? nrm[0] : nrm[1], 16);
+						float c2 = nrm[2] + __shfl_xor_sync(0xffffffffu, nrm[2], 16);
+						float c = hi8 ? c2 : a;
+						c += __shfl_xor_sync(0xffffffffu, hi8 ? a : c2, 8);
+						c += __shfl_xor_sync(0xffffffffu, c, 4);
+						c += __shfl_xor_sync(0xffffffffu, c, 2);
+						c += __shfl_xor_sync(0xffffffffu, c, 1);
+						const int jw = lane == 0 ? jb : (lane == 16 ? jb + 1 : jb + 2);
+						if ((lane == 0 || lane == 16 || lane == 8) && jw < M) wpart[jw * 8 + warp] = c;
+					}
 				}
 				gW_grp += AEC_STAGES * F;
 				gF_grp += AEC_STAGES * F;
-				if (need_wnorm) {
-					// three warp sums for the price of one and a bit: after the first two folds the three quantities live
-					// in disjoint lane groups (block j0: lanes 0-7, j0+1: 16-23, j0+2: 8-15 and 24-31) and share the
-					// remaining folds. Same pairing order (xor 16, 8, 4, 2, 1) as warp_sum: identical sums, 6 SHFL not 15.
-					const bool hi16 = lane & 16, hi8 = lane & 8;
-					float a = hi16 ? nrm[1] : nrm[0];
-					a += __shfl_xor_sync(0xffffffffu, hi16 ? nrm[0] : nrm[1], 16);
-					float c2 = nrm[2] + __shfl_xor_sync(0xffffffffu, nrm[2], 16);
-					float c = hi8 ? c2 : a;
-					c += __shfl_xor_sync(0xffffffffu, hi8 ? a : c2, 8);
-					c += __shfl_xor_sync(0xffffffffu, c, 4);
-					c += __shfl_xor_sync(0xffffffffu, c, 2);
-					c += __shfl_xor_sync(0xffffffffu, c, 1);
-					const int jw = lane == 0 ? j0 : (lane == 16 ? j0 + 1 : j0 + 2);
-					if ((lane == 0 || lane == 16 || lane == 8) && jw < M) wpart[jw * 8 + warp] = c;
-				}
 			}
 			cp_async_wait<0>();
 		}
@@ -1160,8 +1178,8 @@ static float to_bark(float n) {
 
 static size_t aec_smem_floats(int F, int M) {
 	const int N = 2 * F, L = F;
-	size_t f2 = (size_t)(L / 2) + (L + 2) + 5 * (size_t)L + (size_t)AEC_STAGES * 3 * L; // tw, spl, bufa, bufb, specA, specB, Eprev, pipe
-	size_t fl = (size_t)N * 4 + F + (F + 1) + 5 * (size_t)(F + NB_BANDS + 1) + M + (size_t)M * 8 + 32 + SC_COUNT + IN_COUNT;
+	size_t f2 = (size_t)(L / 2) + (L + 2) + 5 * (size_t)L + (size_t)AEC_OWN_STAGES * 3 * L; // tw, spl, bufa, bufb, specA, specB, Eprev, pipe (own slots)
+	size_t fl = (size_t)N * 4 + F + (F + 1) + 5 * (size_t)((F + NB_BANDS + 1 + 3) & ~3) + M + (size_t)M * 8 + 32 + SC_COUNT + IN_COUNT;
 	return f2 * 2 + fl;
 }
 
@@ -1331,12 +1349,10 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	int r = aec_write_init(a, 0, n_streams);
 	if (r) return r;
 	a->smem_bytes = aec_smem_floats(F, M) * sizeof(float);
-	if (a->smem_bytes > 48 * 1024) {
-		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
-		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
-		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
-		MSB200_CUDA(cudaFuncSetAttribute(aec_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem_bytes));
-	}
+	MSB200_SMEM_OPTIN(aec_kernel<8>, ctx, a->smem_bytes);
+	MSB200_SMEM_OPTIN(aec_kernel<7>, ctx, a->smem_bytes);
+	MSB200_SMEM_OPTIN(aec_kernel<6>, ctx, a->smem_bytes);
+	MSB200_SMEM_OPTIN(aec_kernel<5>, ctx, a->smem_bytes);
 	*out = a;
 	return MSB200_OK;
 }

@@ -499,9 +499,14 @@ int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples) {
 int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride, int nblocks, int block0, int ring_blocks,
                           const int *d_counts) {
 	MSB200_CHECK_ARG(v && d_io && nsamples > 0 && nsamples <= v->max_block && nblocks > 0);
-	const int warps = 8;
-	size_t smem = (size_t)warps * ((nsamples + 1) & ~1) * sizeof(short);
+	// one warp per stream, the block staged in shared memory: 8 warps per CTA while that fits the default 48 KB, fewer for
+	// long blocks (48 kHz stereo at 40 ms is 3840 samples; max_block goes up to 8192), opting in beyond 48 KB
+	int warps = 8;
+	const size_t per_warp = (size_t)((nsamples + 1) & ~1) * sizeof(short);
+	while (warps > 1 && warps * per_warp > 48 * 1024) warps >>= 1;
+	const size_t smem = warps * per_warp;
 	if (v->live == 0) return MSB200_OK;
+	MSB200_SMEM_OPTIN(volume_kernel, v->ctx, smem);
 	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->live, warps), warps * 32, smem, (short *)d_io, v->d_state, v->live,
 	              nsamples, stride, nblocks, block0, ring_blocks,
 	              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr), d_counts);
@@ -852,7 +857,7 @@ int msb200_equalizer_process_dev(msb200_equalizer *e, void *d_io, int nsamples, 
 	MSB200_CHECK_ARG(e && d_io && nsamples > 0 && nsamples <= e->max_block && stride >= nsamples);
 	size_t smem = sizeof(float) * (size_t)(e->nfft + e->nfft - 1 + nsamples);
 	int block = nsamples >= 512 ? 512 : ((nsamples + 31) & ~31);
-	if (smem > 48 * 1024) MSB200_CUDA(cudaFuncSetAttribute(eq_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	MSB200_SMEM_OPTIN(eq_fir_kernel, e->ctx, smem);
 	MSB200_LAUNCH(e->ctx, eq_fir_kernel, e->n, block, smem, (short *)d_io, e->d_taps, e->d_hist, e->d_active, nsamples,
 	              stride, e->nfft);
 	return MSB200_OK;

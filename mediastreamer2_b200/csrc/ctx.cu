@@ -10,6 +10,20 @@ void msb200_set_error(const char *fmt, ...) {
 	va_end(ap);
 }
 
+#include <map>
+#include <mutex>
+cudaError_t msb200_smem_optin(const void *func, int device, size_t bytes) {
+	static std::mutex mu;
+	static std::map<std::pair<const void *, int>, size_t> cur;
+	if (bytes <= 48 * 1024) return cudaSuccess;
+	std::lock_guard<std::mutex> g(mu);
+	size_t &have = cur[std::make_pair(func, device)];
+	if (bytes <= have) return cudaSuccess;
+	cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+	if (e == cudaSuccess) have = bytes;
+	return e;
+}
+
 extern "C" {
 
 int msb200_version(void) {

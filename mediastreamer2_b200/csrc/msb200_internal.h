@@ -21,6 +21,11 @@ struct msb200_ctx {
 	size_t flush_bytes = 0;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION (per device), not to the bank that sets it: banks of
+// different geometry share it, so it is only ever raised. Returns a cudaError_t.
+cudaError_t msb200_smem_optin(const void *func, int device, size_t bytes);
+#define MSB200_SMEM_OPTIN(func, ctx, bytes) MSB200_CUDA(msb200_smem_optin((const void *)(func), (ctx)->device, (bytes)))
+
 void msb200_set_error(const char *fmt, ...);
 
 #define MSB200_CUDA(expr)                                                                                              \

@@ -435,8 +435,7 @@ int msb200_plc_create(msb200_ctx *ctx, int n_streams, int sample_rate, int max_b
 	P.gen = P.cont + (size_t)n_streams * 2 * T;
 	P.ctr = reinterpret_cast<unsigned short *>(P.gen + (size_t)n_streams * 2 * N);
 	p->smem = 16 * (size_t)N + 2 * ((size_t)((max_block + 7) & ~7) + (size_t)((2 * T + 7) & ~7) + (size_t)N);
-	if (p->smem > 48 * 1024 &&
-	    cudaFuncSetAttribute(plc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess) {
+	if (msb200_smem_optin((const void *)plc_kernel, ctx->device, p->smem) != cudaSuccess) {
 		msb200_set_error("msb200_plc_create: %zu bytes of shared memory per stream not available", p->smem);
 		msb200_plc_destroy(p);
 		return MSB200_ECUDA;

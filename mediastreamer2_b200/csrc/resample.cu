@@ -273,8 +273,7 @@ int msb200_resample_create(msb200_ctx *ctx, int n_streams, int in_rate, int out_
 		delete r;
 		return MSB200_EINVAL;
 	}
-	if (smem > 48 * 1024)
-		MSB200_CUDA(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	MSB200_SMEM_OPTIN(resample_kernel, ctx, smem);
 	size_t hist = (size_t)n_streams * nchannels * (r->d.filt_len - 1);
 	MSB200_CUDA(cudaMalloc(&r->d_table, sizeof(float) * r->d.table.size()));
 	MSB200_CUDA(cudaMalloc(&r->d_hist, sizeof(short) * hist));
@@ -332,7 +331,7 @@ int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames,
 	do {                                                                                                               \
 		ResampleUpTable<R> tb;                                                                                         \
 		memcpy(tb.t, r->d.table.data(), sizeof(tb.t));                                                                 \
-		if (sm > 48 * 1024) MSB200_CUDA(cudaFuncSetAttribute(resample_up_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+		MSB200_SMEM_OPTIN(resample_up_kernel<R>, r->ctx, sm);                                                          \
 		MSB200_LAUNCH(r->ctx, resample_up_kernel<R>, r->live * r->nch, blk, sm, (const short *)d_in, in_frames, in_stride, (short *)d_out, \
 		              out_stride, r->d_hist, tb, r->nch, ring_off, ring_cap);                                          \
 	} while (0)

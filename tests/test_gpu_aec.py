@@ -129,6 +129,24 @@ def test_aec_white_noise_converges_and_state_blob_roundtrip(ctx):
     ec2.close()
 
 
+def test_two_aec_banks_with_different_tails_share_the_kernel(ctx):
+    """the shared-memory opt-in belongs to the kernel, not to a bank: a later, smaller bank (tail 100 ms) must not take it
+    away from an earlier, larger one (tail 500 ms)"""
+    L = O.oracle()
+    rate = 48000
+    big = F.SpeexEC(ctx, 2, rate, 500)
+    small = F.SpeexEC(ctx, 2, rate, 100)
+    Fs = big.frame_size
+    rng = np.random.default_rng(5)
+    far = rng.integers(-8000, 8000, size=(2, 4 * Fs)).astype(np.int16)
+    mic = (far // 2).astype(np.int16)
+    for bank, tail in ((small, 100), (big, 500), (small, 100)):
+        got = bank.process(mic, far)
+        assert got.shape == mic.shape
+    big.close()
+    small.close()
+
+
 def _gpu_run_scenarios(ctx, sigs):
     """every scenario as one stream of ONE bank (lockstep frames), 25 frames per call"""
     n = min(len(m) for _, m, _ in sigs)

@@ -122,6 +122,30 @@ def test_volume_bit_exact_including_float_state(ctx, nsamples):
     v.close()
 
 
+@pytest.mark.parametrize("nsamples", [3840, 8192])
+def test_volume_long_blocks(ctx, nsamples):
+    """blocks beyond the default 48 KB of shared memory (48 kHz stereo at 40 ms = 3840 samples; the bank's limit 8192): the
+    launch opts in / narrows its CTAs instead of failing with 'invalid argument'"""
+    L = O.oracle()
+    n, rate = 5, 48000
+    v = F.Volume(ctx, n, rate, max_block=8192)
+    states = []
+    for s in range(n):
+        v.set_gain(s, 0.5 + 0.25 * s)
+        st = OrcVolumeState()
+        L.orc_volume_init(C.byref(st), rate)
+        st.gain = st.target_gain = st.static_gain = 0.5 + 0.25 * s
+        states.append(st)
+    for k in range(3):
+        x = noise(300 + k, (n, nsamples), 15000)
+        got = v.process(x)
+        exp = x.copy()
+        for s in range(n):
+            L.orc_volume_process(C.byref(states[s]), ptr(exp[s]), nsamples)
+        assert np.array_equal(got, exp), k
+    v.close()
+
+
 # ------------------------------------------------------------------------------------------------ channel adapter
 def test_chanadapt_bit_exact(ctx):
     L = O.oracle()
