@@ -275,6 +275,14 @@ MSB200_API int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const vo
  * varies from tick to tick: the plugin's lockstep batch mode) */
 MSB200_API int msb200_aec_process_strided(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out,
                                           int nframes, int stride_samples);
+/* ragged batches: counts[stream] (NULL = nframes for all) is the number of frames stream `stream` really staged in this
+ * call; a stream with fewer frames than `nframes` runs only its own — its far-end history and adaptive filter never see
+ * padding — and its output rows are left untouched beyond its count. Every stream keeps its own position in the far-end
+ * ring, so streams whose 10 ms ticks fall differently against the frame grid can share a bank. */
+MSB200_API int msb200_aec_process_counts(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes,
+                                         int stride_samples, const int32_t *counts);
+MSB200_API int msb200_aec_process_counts_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes,
+                                             int stride_samples, const void *d_counts_i32);
 /* MS_ECHO_CANCELLER_GET/SET_STATE_STRING (speexec.c:119-167, 361-374): the adaptive-filter weights of one stream as
  * an opaque blob (our format: header + W[M][N] float). */
 MSB200_API size_t msb200_aec_state_blob_size(msb200_aec *a);
@@ -433,6 +441,12 @@ MSB200_API size_t msb200_scaler_src_frame_bytes(msb200_scaler *s);
 MSB200_API size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s);
 MSB200_API int msb200_scaler_process(msb200_scaler *s, int n_frames, const uint8_t *src, uint8_t *dst);
 MSB200_API int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst);
+/* as msb200_scaler_process for frames that do NOT lie back to back on the host: src_frames / dst_frames are arrays of
+ * n_frames host pointers (tight frames; pinned memory makes the copies asynchronous). Runs of adjacent frames are copied
+ * in one piece; the kernels run once over the whole batch. What the plugin's MSPixConv / MSSizeConv use: a ticker's worth
+ * of frames staged in a pinned arena in, pinned arena slots lent to the output mblks out. */
+MSB200_API int msb200_scaler_process_frames(msb200_scaler *s, int n_frames, const uint8_t *const *src_frames,
+                                            uint8_t *const *dst_frames);
 /* Kernel selection, for tests and profiling only (every path is bit-exact with the others): path 0 = best available,
  * 1 = persistent tile kernel, 2 = generic tile kernel, 3 = register-window strip kernel (the default where it applies),
  * 4 = per-warp streaming variant of the strip kernel (experimental: no vertical halo, but slower on B200 today).

@@ -174,6 +174,8 @@ _SIGS = {
     "msb200_aec_process": (_I, [_P, _P, _P, _P, _I]),
     "msb200_aec_process_dev": (_I, [_P, _P, _P, _P, _I, _I]),
     "msb200_aec_process_strided": (_I, [_P, _P, _P, _P, _I, _I]),
+    "msb200_aec_process_counts": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "msb200_aec_process_counts_dev": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "msb200_aec_state_blob_size": (_SZ, [_P]),
     "msb200_aec_get_state_blob": (_I, [_P, _I, _P, _SZ]),
     "msb200_aec_set_state_blob": (_I, [_P, _I, _P, _SZ]),
@@ -198,6 +200,7 @@ _SIGS = {
     "msb200_scaler_dst_frame_bytes": (_SZ, [_P]),
     "msb200_scaler_process": (_I, [_P, _I, _P, _P]),
     "msb200_scaler_process_dev": (_I, [_P, _I, _P, _P]),
+    "msb200_scaler_process_frames": (_I, [_P, _I, _P, _P]),
     "msb200_scaler_set_path": (_I, [_P, _I]),
     "msb200_scaler_get_schedule": (_I, [_P, _PI, _PI]),
     "msb200_scaler_get_path": (_I, [_P]),

@@ -10,8 +10,9 @@
 // |W_j|^2), which sum in tree order instead of sequentially.
 //
 // Data layout in HBM (per stream, contiguous "page" so one CTA streams it linearly; SURVEY §8d: ~0.39 MB/frame):
-//   X   [(M+1)][F] float2   far-end spectra, ring buffer over blocks (slot = (head + j) % (M+1), head shared by the
-//                           bank because all streams advance in lockstep) — replaces speex's per-frame memmove
+//   X   [(M+1)][F] float2   far-end spectra, ring buffer over blocks (slot = (head + j) % (M+1); every stream keeps its
+//                           own head in its state page, so streams may run different numbers of frames per launch) —
+//                           replaces speex's per-frame memmove
 //   W   [M][F] float2       background (adaptive) filter
 //   FG  [M][F] float2       foreground filter
 //   small state             window halves, previous error spectrum, power spectra, preprocessor state (~20 KB)
@@ -32,7 +33,7 @@ enum { // scal[] indices
 	SC_DAVG1, SC_DAVG2, SC_DVAR1, SC_DVAR2, SC_PEY, SC_PYY, SC_SUM_ADAPT, SC_LEAK, SC_MEMX, SC_MEMD, SC_MEME,
 	SC_NOTCH0, SC_NOTCH1, SC_COUNT = 16
 };
-enum { IN_ADAPTED, IN_SATURATED, IN_SCREWED, IN_CANCEL_COUNT, IN_NB_ADAPT, IN_MIN_COUNT, IN_FG_PENDING, IN_COUNT = 8 };
+enum { IN_ADAPTED, IN_SATURATED, IN_SCREWED, IN_CANCEL_COUNT, IN_NB_ADAPT, IN_MIN_COUNT, IN_FG_PENDING, IN_HEAD, IN_COUNT = 8 };
 
 struct AecParams {
 	int F, N, M, L, log2L, rate;
@@ -52,13 +53,16 @@ struct AecParams {
 };
 
 // ------------------------------------------------------------------------------------------------ cp.async (LDGSTS)
-// The block pass keeps AEC_STAGES - 1 blocks (X_{j+1}, FG_j, W_j: 3 rows of 8F bytes each) in flight per CTA. With 4 CTAs
-// per SM and ~1 us of loaded HBM latency, 2 blocks in flight (12 KB) cap a CTA at ~10 GB/s, so the memory system only
-// saturates while ALL four CTAs of an SM are inside their passes at once — they are not (FFTs, serial IIR sections). Five
-// blocks in flight (30 KB) let two CTAs saturate the SM's share of HBM. The two extra ring slots cost no shared memory:
-// they alias scratch that is dead during the pass (see the carve-up in the kernel).
-#define AEC_STAGES 6
-#define AEC_OWN_STAGES 4 // ring slots with storage of their own; slots [AEC_OWN_STAGES, AEC_STAGES) alias dead scratch
+// The block pass keeps AEC_STAGES - 1 blocks (X_{j+1}, FG_j, W_j: 3 rows of 8F bytes each) in flight per CTA.
+// Measured on B200 (profiles/r2c_aec_kernel_deep_pipe.*): going from 2 to 5 blocks in flight (-DAEC_STAGES=6
+// -DAEC_OWN_STAGES=4: two extra ring slots aliased onto scratch that is dead during the pass, still 4 CTAs per SM) changes
+// nothing — 851 vs 832 us, long-scoreboard stalls are 9 % of the warp latency either way. The pass is not latency bound;
+// the kernel sits on the L1 / shared-memory pipe (65 %), on CTA barriers (28 % of warp latency) and on issue slots (59 %).
+// The shallow ring stays the default (less shared memory); the deep one remains a build option for other shapes.
+#ifndef AEC_STAGES
+#define AEC_STAGES 3
+#define AEC_OWN_STAGES 3 // ring slots with storage of their own; slots [AEC_OWN_STAGES, AEC_STAGES) alias dead scratch
+#endif
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -342,13 +346,17 @@ template <int LOG2L>
 __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
-               float *__restrict__ gS, AecParams P, int head0, int in_frame0, int in_ring, int out_stride, int out_frame0,
+               float *__restrict__ gS, AecParams P, const int *__restrict__ counts, int in_frame0, int in_ring, int out_stride, int out_frame0,
                int out_ring) {
 	extern __shared__ float sm[];
 	constexpr int F = 1 << LOG2L, N = 2 * F, L = F;
 	const int M = P.M;
 	const int t = threadIdx.x;
 	const int stream = blockIdx.x;
+	// ragged batches: this stream's own frame count (a stream that staged fewer frames than the bank's maximum in this
+	// tick must NOT be fed padding: a made-up frame would enter its far-end history and its adaptive filter)
+	if (counts) nframes = min(nframes, counts[stream]);
+	if (nframes <= 0) return;
 	// ---- shared memory carve-up
 	float2 *tw = reinterpret_cast<float2 *>(sm);           // [L/2]
 	float2 *spl = tw + L / 2;                              // [L+1] (+1 pad)
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 	constexpr int VLEN = (F + NB_BANDS + 1 + 3) & ~3;      // F + NB_BANDS + 1 entries, rounded so that what follows stays 16-byte aligned
 	float *vec1 = ybuf + N;                                // [VLEN]
 	float *vec2 = vec1 + VLEN;                             // [VLEN]
-	static_assert(AEC_STAGES - AEC_OWN_STAGES == 2, "the aliased scratch holds exactly two ring slots");
+	static_assert(AEC_STAGES - AEC_OWN_STAGES >= 0 && AEC_STAGES - AEC_OWN_STAGES <= 2, "the aliased scratch holds at most two ring slots");
 	float *vec3 = vec2 + VLEN;                             // [VLEN]
 	float *vec4 = vec3 + VLEN;                             // [VLEN]
 	float *vec5 = vec4 + VLEN;                             // [VLEN]
@@ -397,7 +405,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 	if (t < IN_COUNT) si[t] = reinterpret_cast<int *>(S + ly.ints)[t];
 	__syncthreads();
 
-	int head = head0;
+	int head = si[IN_HEAD];
 	for (int fr = 0; fr < nframes; ++fr) {
 		// frame addressing: linear, or frame-aligned circular buffers (chain re-framing between 10 ms ticks and frames)
 		const int fin = in_ring > 0 ? (in_frame0 + fr) % in_ring : fr;
@@ -1153,7 +1161,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 	for (int i = t; i <= F; i += F) S[ly.power_1 + i] = power_1[i];
 	for (int i = t; i < M; i += F) S[ly.prop + i] = prop[i];
 	if (t < SC_COUNT) S[ly.scal + t] = sc[t];
-	if (t < IN_COUNT) reinterpret_cast<int *>(S + ly.ints)[t] = si[t];
+	if (t < IN_COUNT) reinterpret_cast<int *>(S + ly.ints)[t] = t == IN_HEAD ? head : si[t];
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1162,7 +1170,7 @@ struct msb200_aec {
 	int n;
 	int live; // streams [0, live) are processed (msb200_aec_set_live); == n by default
 	AecParams P;
-	int head; // ring head shared by all streams
+	msb200_devbuf counts; // per-stream frame counts of a ragged host call
 	size_t smem_bytes;
 	float2 *dX, *dW, *dFG;
 	float *dS;
@@ -1218,7 +1226,6 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	a->n = a->live = n_streams;
 	a->tail_ms = tail_length_ms;
 	a->filter_length = filter_length;
-	a->head = 0;
 	AecParams &P = a->P;
 	P.F = F; P.N = N; P.M = M; P.L = L; P.rate = sample_rate;
 	P.log2L = 0;
@@ -1365,6 +1372,7 @@ void msb200_aec_destroy(msb200_aec *a) {
 	cudaFree(a->dFG);
 	cudaFree(a->dS);
 	cudaFree(a->d_tables);
+	a->counts.release();
 	a->mic.release();
 	a->ref.release();
 	a->out.release();
@@ -1389,15 +1397,21 @@ int msb200_aec_reset(msb200_aec *a, int stream) {
 
 int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes, int stride) {
 	MSB200_CHECK_ARG(a && nframes > 0 && stride >= nframes * a->P.F);
-	return msb200i_aec_launch(a, d_mic, d_ref, stride, 0, 0, d_out, stride, 0, 0, nframes);
+	return msb200i_aec_launch(a, d_mic, d_ref, stride, 0, 0, d_out, stride, 0, 0, nframes, nullptr);
+}
+int msb200_aec_process_counts_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes, int stride,
+                                  const void *d_counts) {
+	MSB200_CHECK_ARG(a && nframes > 0 && stride >= nframes * a->P.F);
+	return msb200i_aec_launch(a, d_mic, d_ref, stride, 0, 0, d_out, stride, 0, 0, nframes, (const int *)d_counts);
 }
 } // extern "C"
 int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int in_stride, int in_frame0,
-                       int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes) {
+                       int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes,
+                       const int *d_counts) {
 	MSB200_CHECK_ARG(a && d_mic && d_ref && d_out && nframes > 0);
 #define AEC_ARGS                                                                                                       \
 	(const short *)d_mic, (const short *)d_ref, (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, \
-	    a->head, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames
+	    d_counts, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames
 	if (a->live > 0) switch (a->P.F) {
 		case 256: MSB200_LAUNCH(a->ctx, aec_kernel<8>, a->live, 256, a->smem_bytes, AEC_ARGS); break;
 		case 128: MSB200_LAUNCH(a->ctx, aec_kernel<7>, a->live, 128, a->smem_bytes, AEC_ARGS); break;
@@ -1406,8 +1420,6 @@ int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int 
 		default: msb200_set_error("unsupported AEC frame size %d", a->P.F); return MSB200_EINVAL;
 	}
 #undef AEC_ARGS
-	// advance the shared ring head exactly as the kernel did
-	for (int f = 0; f < nframes; ++f) a->head = (a->head + a->P.M) % (a->P.M + 1);
 	return MSB200_OK;
 }
 extern "C" {
@@ -1431,6 +1443,10 @@ int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, in
 // (a fixed-size staging arena whose frame count varies from tick to tick)
 int msb200_aec_process_strided(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes,
                                int stride_samples) {
+	return msb200_aec_process_counts(a, mic, ref, out, nframes, stride_samples, nullptr);
+}
+int msb200_aec_process_counts(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes,
+                              int stride_samples, const int32_t *counts) {
 	MSB200_CHECK_ARG(a && mic && ref && out && nframes > 0 && stride_samples >= nframes * a->P.F);
 	// only the staged frames of every row cross PCIe: rows of nframes*F out of stride_samples
 	const size_t pitch = (size_t)stride_samples * 2, row = (size_t)nframes * a->P.F * 2;
@@ -1442,7 +1458,12 @@ int msb200_aec_process_strided(msb200_aec *a, const int16_t *mic, const int16_t 
 		MSB200_CUDA(cudaMemcpy2DAsync(a->mic.p, pitch, mic, pitch, row, (size_t)a->live, cudaMemcpyHostToDevice, s));
 		MSB200_CUDA(cudaMemcpy2DAsync(a->ref.p, pitch, ref, pitch, row, (size_t)a->live, cudaMemcpyHostToDevice, s));
 	}
-	if ((r = msb200_aec_process_dev(a, a->mic.p, a->ref.p, a->out.p, nframes, stride_samples))) return r;
+	if (counts && a->live > 0) {
+		if ((r = a->counts.reserve(sizeof(int32_t) * (size_t)a->n))) return r;
+		MSB200_CUDA(cudaMemcpyAsync(a->counts.p, counts, sizeof(int32_t) * (size_t)a->live, cudaMemcpyHostToDevice, s));
+	}
+	if ((r = msb200_aec_process_counts_dev(a, a->mic.p, a->ref.p, a->out.p, nframes, stride_samples, counts ? a->counts.p : nullptr)))
+		return r;
 	if (a->live > 0) MSB200_CUDA(cudaMemcpy2DAsync(out, pitch, a->out.p, pitch, row, (size_t)a->live, cudaMemcpyDeviceToHost, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));
 	return MSB200_OK;
@@ -1531,7 +1552,12 @@ int msb200_aec_probe(msb200_aec *a, int stream, const char *what, float *out, in
 		if (r) return r;
 		return unpack_blocks((pending ? a->dW : a->dFG) + (size_t)stream * P.w_stride, M, -1);
 	}
-	if (!strcmp(what, "X")) return unpack_blocks(a->dX + (size_t)stream * P.x_stride, M + 1, a->head);
+	if (!strcmp(what, "X")) { // every stream keeps its own ring head in its state page
+		int head = 0;
+		MSB200_CUDA(cudaMemcpy(&head, reinterpret_cast<int *>(a->dS + (size_t)stream * P.lay.total + P.lay.ints) + IN_HEAD, sizeof(int),
+		                       cudaMemcpyDeviceToHost));
+		return unpack_blocks(a->dX + (size_t)stream * P.x_stride, M + 1, head);
+	}
 	std::vector<float> page((size_t)P.lay.total);
 	MSB200_CUDA(cudaMemcpyAsync(page.data(), a->dS + (size_t)stream * P.lay.total, sizeof(float) * page.size(), cudaMemcpyDeviceToHost, s));
 	MSB200_CUDA(cudaStreamSynchronize(s));

@@ -89,7 +89,8 @@ struct msb200_devbuf {
 int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames, int in_stride, void *d_out,
                             int out_stride, int ring_off, int ring_cap, int *out_frames);
 int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int in_stride, int in_frame0,
-                       int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes);
+                       int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes,
+                       const int *d_counts = nullptr);
 int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride, int nblocks, int block0, int ring_blocks,
                           const int *d_counts = nullptr);
 int msb200i_mixer_launch(msb200_mixer *m, const void *d_in, long in_pin_stride, const void *d_present, void *d_out);

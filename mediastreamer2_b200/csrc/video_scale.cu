@@ -2690,4 +2690,35 @@ int msb200_scaler_process(msb200_scaler *s, int n_frames, const uint8_t *src, ui
 	return MSB200_OK;
 }
 
+// Frames that do not lie back to back on the host (a ticker's worth of mblk payloads, or pinned arena slots lent to
+// mblks): one copy per run of adjacent frames in, ONE launch sequence over the whole batch, one copy per run out.
+int msb200_scaler_process_frames(msb200_scaler *s, int n_frames, const uint8_t *const *src_frames, uint8_t *const *dst_frames) {
+	MSB200_CHECK_ARG(s && src_frames && dst_frames && n_frames > 0);
+	int r;
+	if ((r = s->src.reserve(s->src_bytes * (size_t)n_frames + 256)) || (r = s->dst.reserve(s->dst_bytes * (size_t)n_frames + 256))) return r;
+	cudaStream_t st = s->ctx->stream;
+	for (int i = 0; i < n_frames;) {
+		int j = i + 1;
+		while (j < n_frames && src_frames[j] == src_frames[j - 1] + s->src_bytes) ++j;
+		MSB200_CHECK_ARG(src_frames[i] != nullptr);
+		MSB200_CUDA(cudaMemcpyAsync((char *)s->src.p + (size_t)i * s->src_bytes, src_frames[i], s->src_bytes * (size_t)(j - i),
+		                            cudaMemcpyHostToDevice, st));
+		i = j;
+	}
+	if ((r = msb200_scaler_process_dev(s, n_frames, s->src.p, s->dst.p))) {
+		cudaStreamSynchronize(st);
+		return r;
+	}
+	for (int i = 0; i < n_frames;) {
+		int j = i + 1;
+		while (j < n_frames && dst_frames[j] == dst_frames[j - 1] + s->dst_bytes) ++j;
+		MSB200_CHECK_ARG(dst_frames[i] != nullptr);
+		MSB200_CUDA(cudaMemcpyAsync(dst_frames[i], (const char *)s->dst.p + (size_t)i * s->dst_bytes, s->dst_bytes * (size_t)(j - i),
+		                            cudaMemcpyDeviceToHost, st));
+		i = j;
+	}
+	MSB200_CUDA(cudaStreamSynchronize(st));
+	return MSB200_OK;
+}
+
 } // extern "C"

@@ -21,6 +21,7 @@
 #include "mediastreamer2/msticker.h"
 #include "mediastreamer2/msvideo.h"
 #include "mediastreamer2/msvolume.h"
+#include "msb200_ms2.h" /* the plugin's extension methods (include/), so that tests can name them */
 
 #include <pthread.h>
 #include <string.h>
@@ -30,6 +31,9 @@ typedef struct HBlock {
 	struct HBlock *next;
 	int tick;
 	int nbytes;
+	int w, h;       /* > 0: an I420 frame, delivered the way cameras / decoders do: ms_yuv_buf_alloc (16-byte header + planes) */
+	int has_ts;     /* set the mblk's timestamp */
+	uint32_t ts;
 	uint8_t data[1];
 } HBlock;
 
@@ -48,9 +52,17 @@ static void hsrc_process(MSFilter *f) {
 	HSource *s = (HSource *)f->data;
 	while (s->head && s->head->tick <= s->tick) {
 		HBlock *b = s->head;
-		mblk_t *m = allocb((size_t)b->nbytes, 0);
-		memcpy(m->b_wptr, b->data, (size_t)b->nbytes);
-		m->b_wptr += b->nbytes;
+		mblk_t *m;
+		if (b->w > 0) {
+			YuvBuf yb;
+			m = ms_yuv_buf_alloc(&yb, b->w, b->h); /* src/voip/msvideo.c:158-172 */
+			memcpy(yb.planes[0], b->data, (size_t)b->nbytes);
+		} else {
+			m = allocb((size_t)b->nbytes, 0);
+			memcpy(m->b_wptr, b->data, (size_t)b->nbytes);
+			m->b_wptr += b->nbytes;
+		}
+		if (b->has_ts) mblk_set_timestamp_info(m, b->ts);
 		if (f->outputs[0]) ms_queue_put(f->outputs[0], m);
 		else freemsg(m);
 		s->head = b->next;
@@ -83,6 +95,7 @@ typedef struct HSink {
 	uint8_t *buf;
 	size_t len, cap;
 	int *sizes; /* (tick, nbytes, timestamp) triples */
+	int *dims;  /* (w, h) of the 16-byte video header below b_rptr (msvideo.c:79-83), (0, 0) when the block has none */
 	int nblocks, blocks_cap;
 	int tick;
 } HSink;
@@ -111,6 +124,13 @@ static void hsink_process(MSFilter *f) {
 		if (s->nblocks == s->blocks_cap) {
 			s->blocks_cap = s->blocks_cap * 2 + 64;
 			s->sizes = (int *)ms_realloc(s->sizes, sizeof(int) * 3 * (size_t)s->blocks_cap);
+			s->dims = (int *)ms_realloc(s->dims, sizeof(int) * 2 * (size_t)s->blocks_cap);
+		}
+		s->dims[2 * s->nblocks] = s->dims[2 * s->nblocks + 1] = 0;
+		if (m->b_rptr - dblk_base(m->b_datap) >= 16) {
+			const uint16_t *hdr = (const uint16_t *)dblk_base(m->b_datap);
+			s->dims[2 * s->nblocks] = hdr[0];
+			s->dims[2 * s->nblocks + 1] = hdr[1];
 		}
 		s->sizes[3 * s->nblocks] = s->tick;
 		s->sizes[3 * s->nblocks + 1] = (int)n;
@@ -124,6 +144,7 @@ static void hsink_uninit(MSFilter *f) {
 	HSink *s = (HSink *)f->data;
 	ms_free(s->buf);
 	ms_free(s->sizes);
+	ms_free(s->dims);
 	ms_free(s);
 }
 static MSFilterDesc harness_sink_desc = {.id = MS_FILTER_PLUGIN_ID,
@@ -179,6 +200,31 @@ void ref_source_push(void *f, int tick, const void *data, int nbytes) {
 	if (s->tail) s->tail->next = b;
 	else s->head = b;
 	s->tail = b;
+}
+/* an I420 frame of w x h (tight planes, w * h * 3 / 2 bytes) or, with w == 0, a raw packed frame; timestamp set */
+void ref_source_push_video(void *f, int tick, const void *data, int nbytes, int w, int h, unsigned int ts) {
+	HSource *s = (HSource *)((MSFilter *)f)->data;
+	ref_source_push(f, tick, data, nbytes);
+	s->tail->w = w;
+	s->tail->h = h;
+	s->tail->has_ts = 1;
+	s->tail->ts = ts;
+}
+void ref_sink_read_dims(void *f, int *pairs) {
+	HSink *s = (HSink *)((MSFilter *)f)->data;
+	memcpy(pairs, s->dims, sizeof(int) * 2 * (size_t)s->nblocks);
+}
+/* ms_video_set_scaler_impl (src/voip/msvideo.c:719-721) with a desc built from three callbacks (the test's oracle scaler)
+ * or with a ready MSScalerDesc (the plugin's msb200_ms_scaler_desc()); NULL restores "no scaler" */
+static MSScalerDesc g_cb_scaler;
+void ref_set_scaler_callbacks(void *create, void *process, void *ctx_free) {
+	g_cb_scaler.create_context = (MSScalerContext * (*)(int, int, MSPixFmt, int, int, MSPixFmt, int)) create;
+	g_cb_scaler.context_process = (int (*)(MSScalerContext *, uint8_t *[], int[], uint8_t *[], int[]))process;
+	g_cb_scaler.context_free = (void (*)(MSScalerContext *))ctx_free;
+	ms_video_set_scaler_impl(&g_cb_scaler);
+}
+void ref_set_scaler_desc(void *desc) {
+	ms_video_set_scaler_impl((MSScalerDesc *)desc);
 }
 /* push `nblocks` consecutive blocks of `block_bytes`, one per tick starting at tick0 */
 void ref_source_push_stream(void *f, int tick0, const void *data, int block_bytes, int nblocks) {
@@ -293,6 +339,8 @@ unsigned int ref_method_id(const char *name) {
 	MID(MS_FILTER_GET_VIDEO_SIZE);
 	MID(MS_FILTER_SET_PIX_FMT);
 	MID(MS_FILTER_SET_FPS);
+	MID(MSB200_PIX_CONV_SET_OUTPUT_FMT);
+	MID(MSB200_PIX_CONV_SET_OUTPUT_SIZE);
 	MID(MS_AUDIO_MIXER_SET_INPUT_GAIN);
 	MID(MS_AUDIO_MIXER_SET_ACTIVE);
 	MID(MS_AUDIO_MIXER_ENABLE_CONFERENCE_MODE);

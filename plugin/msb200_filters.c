@@ -36,6 +36,7 @@
 #include "mediastreamer2/msvolume.h"
 
 #include "msb200dsp.h"
+#include "msb200_plugin.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -58,7 +59,13 @@ static msb200_ctx *dsp_ctx(void) {
 	}
 	return g_ctx;
 }
-#define DSP_LOCK() pthread_mutex_lock(&g_mu)
+/* taking the lock also makes the context's device current for the calling thread: process() runs on ticker threads that
+ * never called cudaSetDevice (with MSB200_DEVICE != 0 their launches would otherwise target device 0) */
+#define DSP_LOCK()                                                                                                     \
+	do {                                                                                                               \
+		pthread_mutex_lock(&g_mu);                                                                                     \
+		if (g_ctx) msb200_ctx_make_current(g_ctx);                                                                     \
+	} while (0)
 #define DSP_UNLOCK() pthread_mutex_unlock(&g_mu)
 #define DSP_CHECK(expr, what)                                                                                          \
 	do {                                                                                                               \
@@ -79,9 +86,9 @@ static msb200_ctx *dsp_ctx(void) {
  *                      stage          -> the member's block(s) of T are copied into its arena slot
  *
  * Only slots [0, highest occupied + 1) are copied and processed (msb200_*_set_live). A slot that staged fewer units
- * than the group's maximum in a tick (a starving stream) is fed zeros for the missing units and its outputs for those
- * units are discarded (MSVolume: skipped exactly, the kernel takes per-slot counts). Streams that deliver the same
- * block sizes every tick (a media server's RTP streams) never hit this.
+ * than the group's maximum in a tick runs only its own units: MSVolume and MSSpeexEC take per-slot counts (streams
+ * that joined at different ticks stage their 1-or-2 frames of 256 per 480-sample tick in different ticks). Only the
+ * resampler bank is fed zeros for a starving stream's missing block, and that block's output is discarded.
  *
  * Several GPUs in one process: MSB200_DEVICES=<n> spreads the TICKERS over devices 0..n-1 in order of first use
  * (BASELINE cfg5: rooms are pinned to a GPU by giving their streams a ticker of that GPU); MSB200_DEVICE=<d> (default 0)
@@ -282,7 +289,7 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 		}
 		/* slots that staged less than the group's maximum are fed zeros for the missing units */
 		for (i = 0; i < b->hi; ++i) {
-			if (b->staged[i] < units && (b->kind == BK_RESAMPLE || b->kind == BK_EC)) { /* stateful banks without per-slot counts */
+			if (b->staged[i] < units && b->kind == BK_RESAMPLE) { /* the one stateful bank without per-slot counts */
 				const size_t off = ((size_t)i * b->max_units + b->staged[i]) * b->unit_in, n = (size_t)(units - b->staged[i]) * b->unit_in;
 				memset(b->in[0] + off, 0, n * sizeof(int16_t));
 				if (b->in[1]) memset(b->in[1] + off, 0, n * sizeof(int16_t));
@@ -296,7 +303,9 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 				break;
 			}
 			case BK_EC:
-				rc = msb200_aec_process_strided((msb200_aec *)b->bank, b->in[0], b->in[1], b->out, units, b->max_units * b->unit_in);
+				/* per-slot frame counts: streams whose ticks fall differently against the frame grid stage 1 or 2 frames in
+				 * different ticks; none of them is ever fed a made-up frame */
+				rc = msb200_aec_process_counts((msb200_aec *)b->bank, b->in[0], b->in[1], b->out, units, b->max_units * b->unit_in, b->staged);
 				b->out_len = b->unit_out;
 				break;
 			case BK_VOLUME:
@@ -2287,11 +2296,15 @@ static void plc_init(MSFilter *f) {
 	f->data = s;
 }
 static void plc_ensure_bank(PlcState *s) { /* as the reference: the context is created once (:57-60) */
-	if (s->bank || s->refused || !dsp_ctx()) return;
+	if (s->bank || s->refused) return;
 	{
 		const int N = ((s->rate * 2 / 40) / 100) * 100, T = s->rate * 5 / 1000;
 		s->bank_block = 2 * N - 2 * T;
-		DSP_LOCK();
+		DSP_LOCK(); /* the context is created under the lock too: two filters may get here at once */
+		if (!dsp_ctx()) {
+			DSP_UNLOCK();
+			return;
+		}
 		if (s->rate < 8000 || msb200_plc_create(g_ctx, 1, s->rate, s->bank_block, &s->bank) != MSB200_OK) {
 			ms_error("MSGenericPLC(b200): no concealment at %d Hz: %s", s->rate, msb200_last_error());
 			s->bank = NULL;
@@ -2508,105 +2521,6 @@ static MSFilterDesc b200_generic_plc_desc = {.id = MS_GENERIC_PLC_ID,
                                              .methods = plc_methods,
                                              .flags = MS_FILTER_IS_PUMP};
 
-/* ================================================================================================ MSScalerDesc
- * the second drop-in boundary (/root/reference/include/mediastreamer2/msvideo.h:473-492): installed with
- * ms_video_set_scaler_impl() so that the reference's own MSPixConv / MSSizeConv / display filters scale on the GPU. */
-typedef struct B200ScalerCtx {
-	msb200_scaler *sc;
-	int src_w, src_h, dst_w, dst_h, src_fmt, dst_fmt;
-	uint8_t *src_pack, *dst_pack;
-} B200ScalerCtx;
-static int pixfmt_to_b200(MSPixFmt fmt) {
-	switch (fmt) {
-		case MS_YUV420P: return MSB200_PIX_YUV420P;
-		case MS_YUYV: return MSB200_PIX_YUYV;
-		case MS_YUY2: return MSB200_PIX_YUY2;
-		case MS_UYVY: return MSB200_PIX_UYVY;
-		case MS_RGB24: return MSB200_PIX_RGB24;
-		case MS_RGB24_REV: return MSB200_PIX_RGB24_REV;
-		case MS_RGBA32: return MSB200_PIX_RGBA32;
-		case MS_RGBA32_REV: return MSB200_PIX_RGBA32_REV;
-		default: return -1;
-	}
-}
-static MSScalerContext *b200_scaler_create(int src_w, int src_h, MSPixFmt src_fmt, int dst_w, int dst_h, MSPixFmt dst_fmt, int flags) {
-	B200ScalerCtx *c;
-	int sf = pixfmt_to_b200(src_fmt), df = pixfmt_to_b200(dst_fmt);
-	(void)flags;
-	if ((sf != MSB200_PIX_YUV420P && sf != MSB200_PIX_YUYV && sf != MSB200_PIX_YUY2 && sf != MSB200_PIX_UYVY && sf != MSB200_PIX_RGB24 &&
-	     sf != MSB200_PIX_RGB24_REV && sf != MSB200_PIX_RGBA32 && sf != MSB200_PIX_RGBA32_REV) || df < 0 || df == MSB200_PIX_RGBA32 ||
-	    df == MSB200_PIX_RGBA32_REV) {
-		ms_error("msb200 scaler: unsupported conversion %s -> %s", ms_pix_fmt_to_string(src_fmt), ms_pix_fmt_to_string(dst_fmt));
-		return NULL;
-	}
-	c = ms_new0(B200ScalerCtx, 1);
-	c->src_w = src_w; c->src_h = src_h; c->dst_w = dst_w; c->dst_h = dst_h; c->src_fmt = sf; c->dst_fmt = df;
-	DSP_LOCK();
-	if (dsp_ctx()) DSP_CHECK(msb200_scaler_create(g_ctx, src_w, src_h, sf, dst_w, dst_h, df, &c->sc), "scaler_create");
-	DSP_UNLOCK();
-	if (!c->sc) {
-		ms_free(c);
-		return NULL;
-	}
-	c->src_pack = (uint8_t *)ms_malloc(msb200_scaler_src_frame_bytes(c->sc));
-	c->dst_pack = (uint8_t *)ms_malloc(msb200_scaler_dst_frame_bytes(c->sc));
-	return (MSScalerContext *)c;
-}
-static void pack_plane(uint8_t *dst, const uint8_t *src, int stride, int w, int h) { /* stride may be negative (bottom-up DIBs) */
-	int y;
-	for (y = 0; y < h; ++y)
-		memcpy(dst + (size_t)y * w, src + (ptrdiff_t)y * (ptrdiff_t)stride, (size_t)w);
-}
-static int b200_scaler_process(MSScalerContext *ctx, uint8_t *src[], int src_strides[], uint8_t *dst[], int dst_strides[]) {
-	B200ScalerCtx *c = (B200ScalerCtx *)ctx;
-	int rc, cw = (c->src_w + 1) / 2, ch = (c->src_h + 1) / 2, y;
-	uint8_t *p = c->src_pack;
-	if (c->src_fmt == MSB200_PIX_RGBA32 || c->src_fmt == MSB200_PIX_RGBA32_REV) {
-		pack_plane(p, src[0], src_strides[0], c->src_w * 4, c->src_h); /* packed 32-bit RGB: msvideo.c:143-150 */
-	} else if (c->src_fmt == MSB200_PIX_RGB24 || c->src_fmt == MSB200_PIX_RGB24_REV) {
-		/* packed RGB: one plane of 3 bytes per pixel; MSPixConv hands MS_RGB24_REV over with a negative stride, starting
-		 * at the last stored row (pixconv.c:78-81): the rows are packed in display order */
-		pack_plane(p, src[0], src_strides[0], c->src_w * 3, c->src_h);
-	} else if (c->src_fmt != MSB200_PIX_YUV420P) { /* packed 4:2:2: one plane of 2 bytes per pixel (msvideo.c:120-156) */
-		pack_plane(p, src[0], src_strides[0], c->src_w * 2, c->src_h);
-	} else {
-		pack_plane(p, src[0], src_strides[0], c->src_w, c->src_h);
-		p += (size_t)c->src_w * c->src_h;
-		pack_plane(p, src[1], src_strides[1], cw, ch);
-		p += (size_t)cw * ch;
-		pack_plane(p, src[2], src_strides[2], cw, ch);
-	}
-	DSP_LOCK();
-	rc = msb200_scaler_process(c->sc, 1, c->src_pack, c->dst_pack);
-	DSP_UNLOCK();
-	if (rc != MSB200_OK) {
-		ms_error("msb200 scaler: %s", msb200_last_error());
-		return -1;
-	}
-	p = c->dst_pack;
-	if (c->dst_fmt == MSB200_PIX_YUV420P) {
-		int dcw = (c->dst_w + 1) / 2, dch = (c->dst_h + 1) / 2;
-		for (y = 0; y < c->dst_h; ++y) memcpy(dst[0] + (size_t)y * dst_strides[0], p + (size_t)y * c->dst_w, (size_t)c->dst_w);
-		p += (size_t)c->dst_w * c->dst_h;
-		for (y = 0; y < dch; ++y) memcpy(dst[1] + (size_t)y * dst_strides[1], p + (size_t)y * dcw, (size_t)dcw);
-		p += (size_t)dcw * dch;
-		for (y = 0; y < dch; ++y) memcpy(dst[2] + (size_t)y * dst_strides[2], p + (size_t)y * dcw, (size_t)dcw);
-	} else {
-		for (y = 0; y < c->dst_h; ++y) memcpy(dst[0] + (size_t)y * dst_strides[0], p + (size_t)y * c->dst_w * 3, (size_t)c->dst_w * 3);
-	}
-	return 0;
-}
-static void b200_scaler_free(MSScalerContext *ctx) {
-	B200ScalerCtx *c = (B200ScalerCtx *)ctx;
-	DSP_LOCK();
-	msb200_scaler_destroy(c->sc);
-	DSP_UNLOCK();
-	ms_free(c->src_pack);
-	ms_free(c->dst_pack);
-	ms_free(c);
-}
-static MSScalerDesc b200_scaler_desc = {b200_scaler_create, b200_scaler_process, b200_scaler_free};
-
 /* ================================================================================================ entry point */
 __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *factory) {
 	if (batch_capacity() > 0) {
@@ -2633,9 +2547,11 @@ __attribute__((visibility("default"))) void libmsb200filters_init(MSFactory *fac
 	ms_factory_register_filter(factory, &b200_ulaw_dec_desc);
 	ms_factory_register_filter(factory, &b200_flow_control_desc);
 	ms_factory_register_filter(factory, &b200_generic_plc_desc);
-	if (getenv("MSB200_INSTALL_SCALER")) ms_video_set_scaler_impl(&b200_scaler_desc);
+	msb200p_register_video_filters(factory);
+	if (getenv("MSB200_INSTALL_SCALER")) ms_video_set_scaler_impl(msb200p_scaler_desc());
 	ms_message("libmsb200filters: B200 DSP filters registered (MSAudioMixer, MSVolume, MSChannelAdapter, MSEqualizer, "
-	           "MSResample, MSSpeexEC, MSAlawEnc/Dec, MSUlawEnc/Dec, MSAudioFlowControl, MSGenericPLC%s)", getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
+	           "MSResample, MSSpeexEC, MSAlawEnc/Dec, MSUlawEnc/Dec, MSAudioFlowControl, MSGenericPLC, MSPixConv, MSSizeConv%s)",
+	           getenv("MSB200_INSTALL_SCALER") ? ", MSScaler" : "");
 }
 /* batch-group statistics for benchmarks: groups, launches (flushes) and units run so far, summed over all groups */
 __attribute__((visibility("default"))) void msb200_filters_batch_stats(int *groups, unsigned long long *flushes, unsigned long long *units) {
@@ -2655,5 +2571,31 @@ __attribute__((visibility("default"))) void msb200_filters_batch_stats(int *grou
 }
 /* also exported so that a host can install the scaler explicitly */
 __attribute__((visibility("default"))) MSScalerDesc *msb200_ms_scaler_desc(void) {
-	return &b200_scaler_desc;
+	return msb200p_scaler_desc();
+}
+/* ---- shared with the other translation units of the plugin (msb200_plugin.h) */
+msb200_ctx *msb200p_sync_ctx(void) {
+	msb200_ctx *c;
+	DSP_LOCK();
+	c = dsp_ctx();
+	if (c) msb200_ctx_make_current(c); /* the calling thread may be a ticker that never touched this device (MSB200_DEVICE != 0) */
+	DSP_UNLOCK();
+	return c;
+}
+void msb200p_sync_lock(void) {
+	DSP_LOCK();
+	if (g_ctx) msb200_ctx_make_current(g_ctx);
+}
+void msb200p_sync_unlock(void) {
+	DSP_UNLOCK();
+}
+int msb200p_batch_capacity(void) {
+	return batch_capacity();
+}
+int msb200p_device_of_ticker(MSTicker *t) {
+	int d;
+	pthread_mutex_lock(&g_batch_mu);
+	d = batch_device_of(t);
+	pthread_mutex_unlock(&g_batch_mu);
+	return d;
 }

@@ -133,6 +133,10 @@ def ref() -> C.CDLL:
         "ref_unlink": (_I, [_P, _I, _P, _I]),
         "ref_source_push": (None, [_P, _I, _P, _I]),
         "ref_source_push_stream": (None, [_P, _I, _P, _I, _I]),
+        "ref_source_push_video": (None, [_P, _I, _P, _I, _I, _I, C.c_uint]),
+        "ref_sink_read_dims": (None, [_P, _P]),
+        "ref_set_scaler_callbacks": (None, [_P, _P, _P]),
+        "ref_set_scaler_desc": (None, [_P]),
         "ref_sink_size": (C.c_long, [_P]),
         "ref_sink_nblocks": (_I, [_P]),
         "ref_sink_read": (None, [_P, _P, _P]),
@@ -236,6 +240,18 @@ class RefGraph:
     def push(self, s, tick: int, data: np.ndarray):
         data = np.ascontiguousarray(data)
         self.L.ref_source_push(s, tick, data.ctypes.data_as(C.c_void_p), data.nbytes)
+
+    def push_video(self, s, tick: int, frame: np.ndarray, w: int, h: int, ts: int):
+        """w > 0: an I420 frame in a header-carrying video mblk (ms_yuv_buf_alloc); w == 0: a raw packed frame"""
+        frame = np.ascontiguousarray(frame)
+        self.L.ref_source_push_video(s, tick, frame.ctypes.data_as(C.c_void_p), frame.nbytes, w, h, ts)
+
+    def read_dims(self, sink) -> np.ndarray:
+        nb = self.L.ref_sink_nblocks(sink)
+        d = np.zeros((nb, 2), np.int32)
+        if nb:
+            self.L.ref_sink_read_dims(sink, d.ctypes.data_as(C.c_void_p))
+        return d
 
     def sink(self):
         return self.new("HarnessSink")

@@ -147,9 +147,66 @@ def test_two_aec_banks_with_different_tails_share_the_kernel(ctx):
     small.close()
 
 
+def test_aec_ragged_frame_counts_keep_streams_independent(ctx):
+    """Streams whose 10 ms ticks fall differently against the 256-sample frame grid stage 1 or 2 frames in DIFFERENT ticks
+    (the plugin's lockstep batch mode). With per-stream counts each stream must produce exactly what it produces alone:
+    no padding frame ever enters its far-end history or its adaptive filter."""
+    from mediastreamer2_b200 import _lib
+
+    rate, n, ticks = 48000, 3, 40
+    lib = ctx.lib
+    rng = np.random.default_rng(11)
+    bank = F.SpeexEC(ctx, n, rate, 250)
+    Fs = bank.frame_size
+    # frames staged per tick: 480 samples per tick against frames of 256, each stream starting at another phase
+    counts = np.zeros((ticks, n), np.int32)
+    have = np.array([0, 130, 250])
+    for k in range(ticks):
+        have += 480
+        counts[k] = have // Fs
+        have %= Fs
+    total = counts.sum(0)
+    far = rng.integers(-9000, 9000, size=(n, total.max() * Fs)).astype(np.int16)
+    mic = (far // 3 + rng.integers(-300, 300, size=far.shape)).astype(np.int16)
+    got = [np.zeros(total[s] * Fs, np.int16) for s in range(n)]
+    pos = np.zeros(n, np.int64)
+    maxu = 4
+    arena_m = np.zeros((n, maxu * Fs), np.int16)
+    arena_r = np.zeros_like(arena_m)
+    arena_o = np.zeros_like(arena_m)
+    for k in range(ticks):
+        for s in range(n):
+            c = counts[k, s]
+            arena_m[s, :c * Fs] = mic[s, pos[s] * Fs:(pos[s] + c) * Fs]
+            arena_r[s, :c * Fs] = far[s, pos[s] * Fs:(pos[s] + c) * Fs]
+            arena_m[s, c * Fs:] = 12345  # garbage beyond the count must never be read
+            arena_r[s, c * Fs:] = -12345
+        units = int(counts[k].max())
+        if units == 0:
+            continue
+        ck = np.ascontiguousarray(counts[k])
+        _lib.check(lib.msb200_aec_process_counts(bank.h, O.ptr(arena_m), O.ptr(arena_r), O.ptr(arena_o), units, maxu * Fs, O.ptr(ck)))
+        for s in range(n):
+            c = counts[k, s]
+            got[s][pos[s] * Fs:(pos[s] + c) * Fs] = arena_o[s, :c * Fs]
+            pos[s] += c
+    bank.close()
+    for s in range(n):
+        solo = F.SpeexEC(ctx, 1, rate, 250)
+        exp = np.zeros(total[s] * Fs, np.int16)
+        for k in range(0, total[s], 2):
+            c = min(2, total[s] - k)
+            exp[k * Fs:(k + c) * Fs] = solo.process(mic[s:s + 1, k * Fs:(k + c) * Fs], far[s:s + 1, k * Fs:(k + c) * Fs])[0]
+        solo.close()
+        assert np.array_equal(got[s], exp), f"stream {s} differs from its solo run"
+        assert exp[20 * Fs:].any()
+
+
 def _gpu_run_scenarios(ctx, sigs):
-    """every scenario as one stream of ONE bank (lockstep frames), 25 frames per call"""
-    n = min(len(m) for _, m, _ in sigs)
+    """every scenario as one stream of ONE bank (lockstep frames), 25 frames per call; shorter scenarios are padded with
+    silence (the caller cuts each stream back to its own length)"""
+    n = max(len(m) for _, m, _ in sigs)
+    sigs = [(np.pad(f, (0, n - len(f))), np.pad(m, (0, n - len(m))), nr) for f, m, nr in sigs]
     ec = F.SpeexEC(ctx, len(sigs), 16000, 250)
     Fs = ec.frame_size
     nfr = n // Fs
@@ -175,6 +232,7 @@ def test_aec_on_the_reference_testers_simple_talk_material(ctx):
     got = _gpu_run_scenarios(ctx, [(far, mic, near), (far, mic, near)])  # two identical streams: treated identically
     assert np.array_equal(got[0], got[1])
     n = got.shape[1]
+    mic, far = mic[:n], far[:n]
     erle, keep, corr = A.check_behaviour(got[0], mic, near, min_erle_db=25.0)
     _, exp = _oracle_run(L, A.RATE, 250, mic[:n], far[:n])
     erle_o, _, _ = A.check_behaviour(exp, mic, near, min_erle_db=25.0)
@@ -193,11 +251,12 @@ def test_aec_reference_suite_metric_gpu_vs_oracle(ctx, tmp_path):
     names = list(A.SCENARIOS)
     sigs = [A.scenario_signals(g, nm) for nm in names]
     got = _gpu_run_scenarios(ctx, sigs)
-    n = got.shape[1]
     ideal = _gpu_run_scenarios(ctx, [(np.zeros_like(nr), nr.copy(), nr) for _, _, nr in sigs])
+    Fs = 128
     for k, nm in enumerate(names):
         far, mic, near = sigs[k]
-        sim, energy = A.silence_and_speech(R, tmp_path, near[:n], got[k], nm)
+        n = len(mic) // Fs * Fs  # each scenario at its OWN length: the metric's windows reach to 14.5 s of the 15 s cuts
+        sim, energy = A.silence_and_speech(R, tmp_path, near[:n], got[k][:n], nm)
         _, exp = _oracle_run(L, A.RATE, 250, mic[:n], far[:n])
         sim_o, energy_o = A.silence_and_speech(R, tmp_path, near[:n], exp, nm)
         min_sim, max_energy = A.SCENARIOS[nm][6]
@@ -205,5 +264,5 @@ def test_aec_reference_suite_metric_gpu_vs_oracle(ctx, tmp_path):
         assert abs(sim - sim_o) <= 0.01, (nm, sim, sim_o)
         assert abs(energy - energy_o) <= 0.25 * energy_o + 0.05, (nm, energy, energy_o)
         if far.any():
-            sim_i, _ = A.silence_and_speech(R, tmp_path, ideal[k], got[k], nm)
+            sim_i, _ = A.silence_and_speech(R, tmp_path, ideal[k][:n], got[k][:n], nm)
             assert sim_i >= A.ISOLATED_MIN[nm], (nm, sim_i)
