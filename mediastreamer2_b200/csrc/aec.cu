@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		};
 		// early prologue: the ring slots with storage of their own (the aliased ones are still scratch until the pre-pass ends)
 #pragma unroll
-		for (int pj = 0; pj < AEC_OWN_STAGES; ++pj) {
+		for (int pj = 0; pj < (AEC_OWN_STAGES < AEC_STAGES - 1 ? AEC_OWN_STAGES : AEC_STAGES - 1); ++pj) {
 			if (pj < M) prefetch(pj, pj);
 			cp_async_commit();
 		}
