@@ -424,6 +424,30 @@ MSB200_API int msb200_nv12_to_i420_dev(msb200_ctx *ctx, int n_frames, const void
                                        size_t cbcr_offset, int rotation, int w, int h, int y_stride, int cbcr_stride,
                                        int u_first, int down_scale, void *d_dst);
 
+/* ms_yuv_buf_copy_with_pix_strides() /root/reference/src/voip/msvideo.c:245-270 (plane_copy :204-227, row_copy :188-202),
+ * batched over n_frames frames laid out frame_bytes apart: copies the region src_roi of a three-plane YUV picture to
+ * dst_roi of another, every plane with its own row stride and PIXEL stride — the reference's way of converting between
+ * planar I420 and semi-planar NV12 / NV21 (pixel stride 2 on the chroma planes, plane 2 one byte after plane 1) and of
+ * placing a picture inside a larger one (a compositor's tile). For planes 1 and 2 every field of both rectangles is
+ * halved. Bytes outside the destination region are left as they are. Bit-exact, including plane_copy's one-memcpy
+ * shortcut for equal strides and rectangles. Pinned by the reference's own eight test patterns
+ * (tester/mediastreamer2_framework_tester.c:393-500). */
+typedef struct msb200_rect { /* MSRect, include/mediastreamer2/msvideo.h */
+	int32_t x, y, w, h;
+} msb200_rect;
+typedef struct msb200_yuv_layout {
+	size_t plane_offset[3]; /* first byte of each plane inside a frame */
+	int32_t row_stride[3];
+	int32_t pix_stride[3];
+	size_t frame_bytes;     /* distance between consecutive frames of the batch */
+} msb200_yuv_layout;
+MSB200_API int msb200_yuv_copy_strided(msb200_ctx *ctx, int n_frames, const uint8_t *src, const msb200_yuv_layout *src_layout,
+                                       msb200_rect src_roi, uint8_t *dst, const msb200_yuv_layout *dst_layout,
+                                       msb200_rect dst_roi);
+MSB200_API int msb200_yuv_copy_strided_dev(msb200_ctx *ctx, int n_frames, const void *d_src,
+                                           const msb200_yuv_layout *src_layout, msb200_rect src_roi, void *d_dst,
+                                           const msb200_yuv_layout *dst_layout, msb200_rect dst_roi);
+
 /* MSScaler replacement: create_context / context_process / context_free of MSScalerDesc
  * (include/mediastreamer2/msvideo.h:473-479; backends src/voip/msvideo.c:517-691), used by MSPixConv
  * (src/videofilters/pixconv.c:62-94) and MSSizeConv (src/videofilters/sizeconv.c:97-184), batched over n_frames.

@@ -41,6 +41,15 @@ class AecInfo(C.Structure):
                 ("filter_length", C.c_int32), ("state_bytes_per_stream", C.c_size_t)]
 
 
+class Rect(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32)]
+
+
+class YuvLayout(C.Structure):
+    _fields_ = [("plane_offset", C.c_size_t * 3), ("row_stride", C.c_int32 * 3), ("pix_stride", C.c_int32 * 3),
+                ("frame_bytes", C.c_size_t)]
+
+
 class ChainParams(C.Structure):
     _fields_ = [("n_streams", C.c_int32), ("in_rate", C.c_int32), ("rate", C.c_int32), ("tail_length_ms", C.c_int32),
                 ("framesize_at_8000", C.c_int32), ("volume_gain", C.c_float), ("mixer_pins", C.c_int32),
@@ -194,6 +203,8 @@ _SIGS = {
     "msb200_chain_get_kernel_timing": (_I, [_P, C.POINTER(C.c_float), _PI, _PI]),
     "msb200_nv12_to_i420": (_I, [_P, _I, _P, _SZ, _SZ, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msb200_nv12_to_i420_dev": (_I, [_P, _I, _P, _SZ, _SZ, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "msb200_yuv_copy_strided": (_I, [_P, _I, _P, C.POINTER(YuvLayout), Rect, _P, C.POINTER(YuvLayout), Rect]),
+    "msb200_yuv_copy_strided_dev": (_I, [_P, _I, _P, C.POINTER(YuvLayout), Rect, _P, C.POINTER(YuvLayout), Rect]),
     "msb200_scaler_create": (_I, [_P, _I, _I, _I, _I, _I, _I, _PP]),
     "msb200_scaler_destroy": (None, [_P]),
     "msb200_scaler_src_frame_bytes": (_SZ, [_P]),

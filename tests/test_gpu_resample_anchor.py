@@ -35,8 +35,9 @@ def test_gpu_sine_fit(ctx, in_rate, out_rate):
         got.setdefault("x", []).append(x)
         return np.zeros(len(x) * out_rate // in_rate + 4096)
 
-    for fr in fracs:
-        RA.sine_fit(run, in_rate, out_rate, fl, fr)
+    with np.errstate(divide="ignore"):  # this pass only collects the inputs: the fit of an all-zero "output" is discarded
+        for fr in fracs:
+            RA.sine_fit(run, in_rate, out_rate, fl, fr)
     ys = gpu_resample(ctx, np.stack(got["x"]), in_rate, out_rate)
     for k, fr in enumerate(fracs):
         gain_db, delay_err, resid = RA.sine_fit(lambda x, k=k: ys[k], in_rate, out_rate, fl, fr)

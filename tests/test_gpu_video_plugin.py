@@ -38,8 +38,10 @@ def _same(a, b):
     assert np.array_equal(da, db)
 
 
-CASES = [(V.MS_YUY2, 64, 48, (32, 24)), (V.MS_UYVY, 80, 48, (48, 32)), (V.MS_RGB24, 64, 48, (96, 72)), (V.MS_RGB24_REV, 64, 48, None),
-         (V.MS_RGBA32, 48, 32, (32, 24)), (V.MS_YUV420P, 96, 64, (64, 48)), (V.MS_YUYV, 640, 480, (320, 240))]
+# targets keep the input's aspect ratio (MSSizeConv corrects any other target and then waits for the host: the dedicated
+# test below covers that path)
+CASES = [(V.MS_YUY2, 64, 48, (32, 24)), (V.MS_UYVY, 80, 48, (40, 24)), (V.MS_RGB24, 64, 48, (96, 72)), (V.MS_RGB24_REV, 64, 48, None),
+         (V.MS_RGBA32, 48, 32, (24, 16)), (V.MS_YUV420P, 96, 64, (48, 32)), (V.MS_YUYV, 640, 480, (320, 240))]
 
 
 @pytest.mark.parametrize("fmt,w,h,target", CASES)
