@@ -141,6 +141,28 @@ def kernels_bench(ctx, hbm_peak_gbs: float) -> dict:
         ms = _time(ctx, lambda: sc.process_dev(nf, d_src, d_dst), iters=5)
         row(name, f"{what}, {nf} frames", nf * (sbytes + dbytes), ms, nf, "frames")
         sc.close()
+    # f4: 16-tile mosaic — sixteen 480x270 participants scaled to 320x180 and composed into 1280x720 canvases by the
+    # scaler's own launches (set_canvas); 64 canvases per launch = 1024 source frames (199 MB in, 88 MB out)
+    try:
+        tw, th, cw, ch, tiles, ncanv = 320, 180, 1280, 720, 16, 64
+        msw, msh = 480, 270
+        sc = F.Scaler(ctx, msw, msh, _lib.PIX_YUV420P, tw, th, _lib.PIX_YUV420P)
+        rects = (_lib.Rect * tiles)(*[_lib.Rect((k % 4) * tw, (k // 4) * th, tw, th) for k in range(tiles)])
+        _lib.check(lib.msb200_scaler_set_canvas(sc.h, cw, ch, tiles, rects))
+        n_src = tiles * ncanv
+        sbytes, cbytes = msw * msh * 3 // 2, cw * ch * 3 // 2
+        ms = _time(ctx, lambda: sc.process_dev(n_src, d_src, d_dst), iters=5)
+        row("scale_plane_strip_kernel (mosaic)", f"f4 16-tile 720p mosaic: 16 x I420 {msw}x{msh} -> 320x180 tiles of one 1280x720 canvas, {ncanv} canvases",
+            n_src * sbytes + ncanv * cbytes, ms, ncanv, "canvases")
+        sc.close()
+        # f4: ms_yuv_buf_copy_with_pix_strides, 1080p I420 -> NV12 (planar to semi-planar), 128 frames
+        lay_p = _lib.YuvLayout((C.c_size_t * 3)(0, sw * sh, sw * sh * 5 // 4), (C.c_int32 * 3)(sw, sw // 2, sw // 2), (C.c_int32 * 3)(1, 1, 1), i420)
+        lay_s = _lib.YuvLayout((C.c_size_t * 3)(0, sw * sh, sw * sh + 1), (C.c_int32 * 3)(sw, sw, sw), (C.c_int32 * 3)(1, 2, 2), i420)
+        roi = _lib.Rect(0, 0, sw, sh)
+        ms = _time(ctx, lambda: _lib.check(lib.msb200_yuv_copy_strided_dev(ctx.h, nf, P(d_src), C.byref(lay_p), roi, P(d_dst), C.byref(lay_s), roi)))
+        row("yuv_copy_rows+chroma_kernel", f"f4 ms_yuv_buf_copy_with_pix_strides I420 -> NV12, {nf} frames {sw}x{sh}", nf * i420 * 2, ms, nf, "frames")
+    except Exception as e:  # noqa: BLE001
+        rows["mosaic"] = {"error": repr(e)}
     ctx.dev_free(d_src)
     ctx.dev_free(d_dst)
     return rows

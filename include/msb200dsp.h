@@ -471,6 +471,16 @@ MSB200_API int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const v
  * of frames staged in a pinned arena in, pinned arena slots lent to the output mblks out. */
 MSB200_API int msb200_scaler_process_frames(msb200_scaler *s, int n_frames, const uint8_t *const *src_frames,
                                             uint8_t *const *dst_frames);
+/* Mosaic / compositor (the reference's building blocks: ms_yuv_buf_copy_with_pix_strides src/voip/msvideo.c:
+ * 245-270 places a picture in a region of a larger one, src/voip/layouts.c computes the rectangles): after set_canvas the
+ * scaler writes frame k of a batch straight into rectangle tiles[k % n_tiles] of canvas k / n_tiles (I420, canvas_w x
+ * canvas_h, tight planes) — N participants scaled AND composed in the same launches, with the scaler's bit-exact
+ * arithmetic; bytes outside the tiles are not touched. Planar-output scalers only (YUV420P / NV12 / NV21 -> YUV420P);
+ * every tile is dst_w x dst_h, tile x % 8 == 0, tile y % 2 == 0, canvas_w % 8 == 0. n_tiles == 0 restores tight frames.
+ * process_dev: n_frames must be a multiple of n_tiles; d_dst holds n_frames / n_tiles canvases. */
+MSB200_API int msb200_scaler_set_canvas(msb200_scaler *s, int canvas_w, int canvas_h, int n_tiles, const msb200_rect *tiles);
+MSB200_API size_t msb200_scaler_canvas_bytes(msb200_scaler *s);
+
 /* Kernel selection, for tests and profiling only (every path is bit-exact with the others): path 0 = best available,
  * 1 = persistent tile kernel, 2 = generic tile kernel, 3 = register-window strip kernel (the default where it applies),
  * 4 = per-warp streaming variant of the strip kernel (experimental: no vertical halo, but slower on B200 today).

@@ -1133,6 +1133,10 @@ struct PlaneStripParams {
 	const short *hcoef;   // 4 taps per output column (hl_size / hc_size == 4)
 	int R, box_w, box_h, W, H, n_planes;
 	size_t dst_frame_bytes, dst_off[2]; // byte offset of each plane inside a destination frame
+	// mosaic (msb200_scaler_set_canvas): `group` consecutive frames are the tiles of ONE destination canvas whose rows are
+	// dst_pitch bytes apart; tile k starts at (tile_xy[k].x, tile_xy[k].y) >> tile_shift of this plane. Defaults: 1, W, null.
+	int group, dst_pitch, tile_shift;
+	const short2 *tile_xy;
 	short x0[ST_MAX_TX], y0[ST_MAX_TY];
 };
 template <int VT>
@@ -1185,7 +1189,11 @@ __global__ void __launch_bounds__(ST_THREADS, 8)
 	int row = lrow0;
 	unsigned la = smem_u32(box) + (unsigned)(pA & ~3) + (unsigned)(row - by0) * pitch;
 	unsigned lb = smem_u32(box) + (unsigned)(pB & ~3) + (unsigned)(row - by0) * pitch;
-	unsigned char *o = dst + (size_t)frame * S.dst_frame_bytes + S.dst_off[plane] + (size_t)ys * S.W + x0 + 4 * lane;
+	unsigned char *o = dst + (size_t)(frame / S.group) * S.dst_frame_bytes + S.dst_off[plane] + (size_t)ys * S.dst_pitch + x0 + 4 * lane;
+	if (S.tile_xy) {
+		const short2 txy = S.tile_xy[frame % S.group];
+		o += (size_t)(txy.y >> S.tile_shift) * S.dst_pitch + (txy.x >> S.tile_shift);
+	}
 	int y = ys;
 	auto hrow = [&](int(&w)[4]) {
 		const unsigned a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
@@ -1216,7 +1224,7 @@ __global__ void __launch_bounds__(ST_THREADS, 8)
 		// bytes 3 of the four sums, in column order
 		const unsigned v = __byte_perm(__byte_perm(q[0], q[1], 0x0073), __byte_perm(q[2], q[3], 0x0073), 0x5410);
 		if (col_ok) *reinterpret_cast<unsigned *>(o) = v;
-		o += S.W;
+		o += S.dst_pitch;
 		return y == ye;
 	};
 	bool done = false;
@@ -1798,6 +1806,8 @@ struct msb200_scaler {
 	msb200_devbuf deint;              // NV12 / NV21 -> I420 pre-pass output (planar scratch frames)
 	void *deint_last;
 	PlaneStripParams PL, PC;          // luma plane; the two chroma planes
+	int canvas_w, canvas_h, canvas_tiles; // mosaic destination (msb200_scaler_set_canvas), 0 = tight frames
+	void *d_tile_xy;
 	size_t smem_pl, smem_pc;
 	CUtensorMap map_py, map_pu, map_pv;
 	cudaStream_t pipe_in, pipe_out;   // host-buffer batches: upload / download streams of the chunk pipeline
@@ -2389,6 +2399,10 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			MSB200_CUDA(cudaMemcpy(d_rows, rows.data(), rows.size() * sizeof(StripRow), cudaMemcpyHostToDevice));
 			Q.rows = (const StripRow *)d_rows;
 			Q.dst_frame_bytes = s->dst_bytes;
+			Q.group = 1;
+			Q.dst_pitch = W;
+			Q.tile_shift = 0;
+			Q.tile_xy = nullptr;
 			return MSB200_OK;
 		};
 		int rc;
@@ -2437,6 +2451,7 @@ void msb200_scaler_destroy(msb200_scaler *s) {
 	cudaFree((void *)s->S.rows);
 	cudaFree((void *)s->PL.rows);
 	cudaFree((void *)s->PC.rows);
+	cudaFree(s->d_tile_xy);
 	s->deint.release();
 	s->src.release();
 	s->dst.release();
@@ -2447,6 +2462,61 @@ size_t msb200_scaler_src_frame_bytes(msb200_scaler *s) {
 }
 size_t msb200_scaler_dst_frame_bytes(msb200_scaler *s) {
 	return s ? s->dst_bytes : 0;
+}
+
+// Mosaic destination: the scaled frames are written straight into rectangles of a larger I420 canvas — the strip kernel's
+// stores get the canvas pitch and a per-tile origin, nothing else changes (same arithmetic, same launches).
+int msb200_scaler_set_canvas(msb200_scaler *s, int canvas_w, int canvas_h, int n_tiles, const msb200_rect *tiles) {
+	MSB200_CHECK_ARG(s);
+	if (n_tiles == 0) { // back to tight frames
+		s->canvas_tiles = 0;
+		s->PL.group = s->PC.group = 1;
+		s->PL.dst_pitch = s->PL.W;
+		s->PC.dst_pitch = s->PC.W;
+		s->PL.tile_xy = s->PC.tile_xy = nullptr;
+		s->PL.dst_frame_bytes = s->PC.dst_frame_bytes = s->dst_bytes;
+		s->PL.dst_off[0] = 0;
+		s->PC.dst_off[0] = (size_t)s->P.dst_w * s->P.dst_h;
+		s->PC.dst_off[1] = s->PC.dst_off[0] + (size_t)s->P.chr_dst_w * s->P.chr_dst_h;
+		return MSB200_OK;
+	}
+	MSB200_CHECK_ARG(tiles && n_tiles > 0 && n_tiles <= 4096 && canvas_w > 0 && canvas_h > 0);
+	if (!s->pstrip_ok || s->P.dst_fmt != MSB200_PIX_YUV420P) {
+		msb200_set_error("scaler: a canvas needs the planar strip path (YUV420P / NV12 / NV21 -> YUV420P, TMA-able geometry)");
+		return MSB200_EINVAL;
+	}
+	// 32-bit stores per lane: every plane's tile origin and pitch must keep 4-byte alignment
+	MSB200_CHECK_ARG(canvas_w % 8 == 0 && canvas_h % 2 == 0 && s->P.dst_w % 2 == 0 && s->P.dst_h % 2 == 0);
+	std::vector<short2> xy((size_t)n_tiles);
+	for (int k = 0; k < n_tiles; ++k) {
+		const msb200_rect &t = tiles[k];
+		MSB200_CHECK_ARG(t.w == s->P.dst_w && t.h == s->P.dst_h && t.x >= 0 && t.y >= 0 && t.x % 8 == 0 && t.y % 2 == 0 &&
+		                 t.x + t.w <= canvas_w && t.y + t.h <= canvas_h);
+		xy[(size_t)k] = make_short2((short)t.x, (short)t.y);
+	}
+	cudaStreamSynchronize(s->ctx->stream);
+	cudaFree(s->d_tile_xy);
+	s->d_tile_xy = nullptr;
+	MSB200_CUDA(cudaMalloc(&s->d_tile_xy, sizeof(short2) * (size_t)n_tiles));
+	MSB200_CUDA(cudaMemcpy(s->d_tile_xy, xy.data(), sizeof(short2) * (size_t)n_tiles, cudaMemcpyHostToDevice));
+	const size_t ysz = (size_t)canvas_w * canvas_h, csz = (size_t)(canvas_w / 2) * (canvas_h / 2);
+	s->canvas_w = canvas_w;
+	s->canvas_h = canvas_h;
+	s->canvas_tiles = n_tiles;
+	s->PL.group = s->PC.group = n_tiles;
+	s->PL.tile_xy = s->PC.tile_xy = (const short2 *)s->d_tile_xy;
+	s->PL.tile_shift = 0;
+	s->PC.tile_shift = 1;
+	s->PL.dst_pitch = canvas_w;
+	s->PC.dst_pitch = canvas_w / 2;
+	s->PL.dst_frame_bytes = s->PC.dst_frame_bytes = ysz + 2 * csz;
+	s->PL.dst_off[0] = 0;
+	s->PC.dst_off[0] = ysz;
+	s->PC.dst_off[1] = ysz + csz;
+	return MSB200_OK;
+}
+size_t msb200_scaler_canvas_bytes(msb200_scaler *s) {
+	return s && s->canvas_tiles > 0 ? (size_t)s->canvas_w * s->canvas_h * 3 / 2 : 0;
 }
 
 int msb200_scaler_set_path(msb200_scaler *s, int path) {
@@ -2558,7 +2628,8 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 #undef STRIP_LAUNCH
 		return MSB200_OK;
 	}
-	if (s->pstrip_ok && s->force_path == 0 && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 4) == 0) {
+	if (s->canvas_tiles > 0) MSB200_CHECK_ARG(n_frames % s->canvas_tiles == 0 && ((uintptr_t)d_dst % 16) == 0);
+	if (s->pstrip_ok && (s->canvas_tiles > 0 || (s->force_path == 0 && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 4) == 0))) {
 		// planar I420 -> I420: one warp per plane strip, Y in one launch, U and V together in a second
 		if (P.src_fmt != MSB200_PIX_YUV420P) { // interleaved chroma: exact de-interleave into a planar scratch frame first
 			if ((r = s->deint.reserve(s->src_bytes * (size_t)n_frames + 256))) return r;

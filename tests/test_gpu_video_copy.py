@@ -55,3 +55,51 @@ def test_random_regions_equal_the_unmodified_reference_function(ctx):
         Y.reference_copy(R, src, sl, sroi, exp, dl, droi)
         gpu_copy(ctx, 1, src, sl, sroi, got, dl, droi, size)
         assert np.array_equal(got, exp), (case, bw, bh, src_semi, dst_semi, sroi, droi)
+
+
+@pytest.mark.parametrize("src_fmt", [_lib.PIX_YUV420P, _lib.PIX_NV12])
+def test_mosaic_canvas_equals_oracle_tiles_placed_by_hand(ctx, src_fmt):
+    """msb200_scaler_set_canvas: N scaled participants land in their rectangles of one canvas in the scaler's own launches;
+    every tile equals the oracle's scaled frame, every byte outside the tiles keeps the background"""
+    L = O.oracle()
+    lib = ctx.lib
+    sw, sh, tw, th = 96, 64, 64, 48
+    cw, ch = 144, 100
+    tiles = [(0, 0), (72, 0), (0, 50), (80, 52)]
+    n_canvas = 3
+    n = len(tiles) * n_canvas
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, size=(n, sw * sh * 3 // 2)).astype(np.uint8)
+    h = C.c_void_p()
+    _lib.check(lib.msb200_scaler_create(ctx.h, sw, sh, src_fmt, tw, th, _lib.PIX_YUV420P, C.byref(h)))
+    rects = (_lib.Rect * len(tiles))(*[_lib.Rect(x, y, tw, th) for x, y in tiles])
+    _lib.check(lib.msb200_scaler_set_canvas(h, cw, ch, len(tiles), rects))
+    cbytes = lib.msb200_scaler_canvas_bytes(h)
+    assert cbytes == cw * ch * 3 // 2
+    d_src, d_dst = ctx.dev_alloc(src.nbytes), ctx.dev_alloc(cbytes * n_canvas)
+    background = np.full(cbytes * n_canvas, 0x5A, np.uint8)
+    ctx.h2d(d_src, src)
+    ctx.h2d(d_dst, background)
+    _lib.check(lib.msb200_scaler_process_dev(h, n, d_src, d_dst))
+    got = np.empty_like(background)
+    ctx.d2h(got, d_dst)
+    # a rectangle that would need unaligned 32-bit stores is refused, not mis-written
+    bad = (_lib.Rect * 1)(_lib.Rect(4, 0, tw, th))
+    assert lib.msb200_scaler_set_canvas(h, cw, ch, 1, bad) == _lib.EINVAL
+    lib.msb200_scaler_destroy(h)
+    ctx.dev_free(d_src)
+    ctx.dev_free(d_dst)
+    o = L.orc_scaler_new(sw, sh, src_fmt, tw, th, _lib.PIX_YUV420P)
+    exp = background.copy().reshape(n_canvas, cbytes)
+    for k in range(n):
+        tile = np.zeros(tw * th * 3 // 2, np.uint8)
+        L.orc_scaler_process(o, O.ptr(src[k]), O.ptr(tile))
+        c, (x, y) = k // len(tiles), tiles[k % len(tiles)]
+        Y_ = exp[c][:cw * ch].reshape(ch, cw)
+        U_ = exp[c][cw * ch:cw * ch + cw * ch // 4].reshape(ch // 2, cw // 2)
+        V_ = exp[c][cw * ch + cw * ch // 4:].reshape(ch // 2, cw // 2)
+        Y_[y:y + th, x:x + tw] = tile[:tw * th].reshape(th, tw)
+        U_[y // 2:y // 2 + th // 2, x // 2:x // 2 + tw // 2] = tile[tw * th:tw * th + tw * th // 4].reshape(th // 2, tw // 2)
+        V_[y // 2:y // 2 + th // 2, x // 2:x // 2 + tw // 2] = tile[tw * th + tw * th // 4:].reshape(th // 2, tw // 2)
+    L.orc_scaler_free(o)
+    assert np.array_equal(got.reshape(n_canvas, cbytes), exp)
