@@ -429,6 +429,7 @@ int msb200_volume_set_peer(msb200_volume *v, int stream, msb200_volume *peer_ban
 	MSB200_CHECK_ARG(v && (peer_bank == nullptr || (peer_stream >= 0 && peer_stream < peer_bank->n)));
 	MSB200_CHECK_ARG(v->peer_bank == nullptr || peer_bank == nullptr || v->peer_bank == peer_bank); // one peer bank per bank
 	if (peer_bank) v->peer_bank = peer_bank;
+	else if (v->n == 1) v->peer_bank = nullptr; // the bank's only stream unlinked: nothing may dereference the old peer bank
 	return volume_update_state(v, stream, [](msb200_volume_state *s, float, int p) { s->peer = p; }, 0.f, peer_bank ? peer_stream : -1);
 }
 int msb200_volume_set_ea_threshold(msb200_volume *v, int stream, float thr) {

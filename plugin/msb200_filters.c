@@ -350,363 +350,352 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 }
 
 /* ================================================================================================ MSAudioMixer
- * host logic restated from /root/reference/src/audiofilters/audiomixer.c: channel bufferizers :78-90, flow control
- * :92-111, bypass mode :219-286, output dispatch :288-346, methods :348-431 */
-#define MIXER_MAX_CHANNELS 50
-#define BYPASS_MODE_TIMEOUT 1000
+ * What the reference filter does on the host and this one must do too (/root/reference/src/audiofilters/audiomixer.c):
+ * per-pin FIFOs read one tick at a time (:78-90), a drift trim every 5 s of ticker time (:92-111), the single-talker
+ * shortcut that forwards packets untouched (:219-286) and the hand-out of one block per listener (:313-343). The sums,
+ * gains, minus-own and saturation (:33-51, :113-130) run in mixer_kernel. The host side below is organised around the
+ * device arenas: a room is a slice of pinned memory [pin][samples] that the pins' FIFOs are drained INTO, and a slice that
+ * the listeners' blocks are cut FROM — in batch mode those are slices of the group's arenas, so staging is the read itself. */
+#define MIX_PINS 50          /* pins of the reference desc (MIXER_MAX_CHANNELS, audiomixer.c:29) */
+#define MIX_SOLO_AFTER_MS 1000 /* a pin silent this long stops counting as a talker (BYPASS_MODE_TIMEOUT, :31) */
+#define MIX_TRIM_EVERY_MS 5000
+#define MIX_NEVER ((uint64_t)-1)
 
-typedef struct MixChannel {
-	MSBufferizer bufferizer;
-	float gain;
-	int min_fullness;
-	uint64_t last_flow_control;
-	uint64_t last_activity;
-	bool_t active;
-	bool_t output_enabled;
-} MixChannel;
+typedef struct MixPin {
+	MSBufferizer fifo;
+	float gain;          /* MS_AUDIO_MIXER_SET_INPUT_GAIN */
+	bool_t contributes;  /* MS_AUDIO_MIXER_SET_ACTIVE */
+	bool_t listens;      /* MS_AUDIO_MIXER_ENABLE_OUTPUT */
+	uint64_t heard_at;   /* ticker time of the pin's last packet */
+	uint64_t trimmed_at; /* ticker time of the last drift check */
+	int low_water;       /* smallest FIFO fill seen since then, -1 = none yet */
+} MixPin;
 
-typedef struct MixerState {
-	int nchannels, rate, bytespertick, conf_mode, skip_threshold, master_channel;
-	MixChannel channels[MIXER_MAX_CHANNELS];
-	bool_t bypass_mode, single_output;
-	msb200_mixer *bank; /* 1 room x 50 pins x nwords; batch mode: the group's bank, this mixer is room `room` */
-	int16_t *in;        /* [50][nwords] */
-	uint8_t *present;   /* [50] */
-	int16_t *out;       /* [50][nwords] (conference) or [nwords] */
+typedef struct MixRoom {
+	MixPin pin[MIX_PINS];
+	int channels, hz, conference, master_pin;
+	int tick_bytes, trim_above; /* bytes per pin per tick; a FIFO that never dips below trim_above is trimmed */
+	bool_t solo, one_listener;
+	msb200_mixer *bank; /* 1 room x n_dev_pins x words; batch mode: the group's bank, this mixer is room `room` */
+	int16_t *in;        /* [n_dev_pins][words] */
+	uint8_t *present;   /* [n_dev_pins] */
+	int16_t *out;       /* [n_dev_pins][words] (conference) or [words] */
 	Batch *batch;       /* lockstep batch group (MSB200_BATCH), NULL in synchronous mode */
 	int room;
-	int pins;           /* pins of the bank: the highest connected pin + 1, rounded up to a multiple of 4 */
-} MixerState;
+	int n_dev_pins;     /* pins that travel to the device: highest connected pin + 1, rounded up to a multiple of 4 */
+} MixRoom;
 /* the bank is shared with the group's flush in batch mode, with the other synchronous filters otherwise */
 #define MIX_LOCK(s) do { if ((s)->batch) GRP_LOCK((s)->batch); else DSP_LOCK(); } while (0)
 #define MIX_UNLOCK(s) do { if ((s)->batch) GRP_UNLOCK((s)->batch); else DSP_UNLOCK(); } while (0)
 
-static void mixer_init(MSFilter *f) {
-	MixerState *s = ms_new0(MixerState, 1);
-	int i;
-	s->conf_mode = FALSE;
-	s->nchannels = 1;
-	s->rate = 44100;
-	s->master_channel = -1;
-	for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
-		ms_bufferizer_init(&s->channels[i].bufferizer);
-		s->channels[i].gain = 1.0f;
-		s->channels[i].active = TRUE;
-		s->channels[i].output_enabled = TRUE;
+static void mixroom_new(MSFilter *f) {
+	MixRoom *r = ms_new0(MixRoom, 1);
+	MixPin *p;
+	r->channels = 1;
+	r->hz = 44100;
+	r->master_pin = -1;
+	for (p = r->pin; p < r->pin + MIX_PINS; ++p) {
+		ms_bufferizer_init(&p->fifo);
+		p->gain = 1.0f;
+		p->contributes = p->listens = TRUE;
 	}
-	f->data = s;
+	f->data = r;
 }
-static void mixer_uninit(MSFilter *f) {
-	MixerState *s = (MixerState *)f->data;
-	int i;
-	for (i = 0; i < MIXER_MAX_CHANNELS; ++i)
-		ms_bufferizer_uninit(&s->channels[i].bufferizer);
-	ms_free(s);
+static void mixroom_free(MSFilter *f) {
+	MixRoom *r = (MixRoom *)f->data;
+	MixPin *p;
+	for (p = r->pin; p < r->pin + MIX_PINS; ++p) ms_bufferizer_uninit(&p->fifo);
+	ms_free(r);
 }
-static bool_t mixer_has_single_output(MSFilter *f, MixerState *s) {
-	int i, count = 0;
-	for (i = 0; i < f->desc->noutputs; ++i)
-		if (f->outputs[i] && s->channels[i].output_enabled) count++;
-	return count == 1;
+static int mixroom_listeners(const MSFilter *f, const MixRoom *r) {
+	int k, n = 0;
+	for (k = 0; k < MIX_PINS; ++k) n += f->outputs[k] != NULL && r->pin[k].listens;
+	return n;
 }
-static void mixer_preprocess(MSFilter *f) {
-	MixerState *s = (MixerState *)f->data;
-	int i, nwords;
-	s->bytespertick = (2 * s->nchannels * s->rate * f->ticker->interval) / 1000;
-	nwords = s->bytespertick / 2;
-	for (i = 0; i < MIXER_MAX_CHANNELS; ++i) {
-		s->channels[i].last_flow_control = (uint64_t)-1;
-		s->channels[i].last_activity = (uint64_t)-1;
+static void mixroom_push_controls(MixRoom *r) { /* bank lock held */
+	int k;
+	for (k = 0; r->bank && k < r->n_dev_pins; ++k) {
+		msb200_mixer_set_input_gain(r->bank, r->room, k, r->pin[k].gain);
+		msb200_mixer_set_active(r->bank, r->room, k, r->pin[k].contributes);
 	}
-	s->skip_threshold = s->bytespertick * 2;
-	s->bypass_mode = FALSE;
-	s->single_output = mixer_has_single_output(f, s);
-	s->room = 0;
-	/* the graph is fixed while attached: only the connected pins travel to the GPU (a 16-party room moves 16 rows, not 50) */
-	s->pins = 0;
-	for (i = 0; i < MIXER_MAX_CHANNELS; ++i)
-		if (f->inputs[i] || f->outputs[i]) s->pins = i + 1;
-	s->pins = (s->pins + 3) & ~3;
-	if (s->pins < 4) s->pins = 4;
-	if (s->pins > MIXER_MAX_CHANNELS) s->pins = MIXER_MAX_CHANNELS;
+}
+static void mixroom_attach(MSFilter *f) {
+	MixRoom *r = (MixRoom *)f->data;
+	int k, words, top = 0;
+	r->tick_bytes = (2 * r->channels * r->hz * f->ticker->interval) / 1000;
+	r->trim_above = 2 * r->tick_bytes;
+	words = r->tick_bytes / 2;
+	r->solo = FALSE;
+	r->one_listener = mixroom_listeners(f, r) == 1;
+	r->room = 0;
+	for (k = 0; k < MIX_PINS; ++k) {
+		r->pin[k].heard_at = r->pin[k].trimmed_at = MIX_NEVER;
+		if (f->inputs[k] || f->outputs[k]) top = k + 1;
+	}
+	/* the graph is fixed while attached: only the connected pins travel (a 16-party room moves 16 rows, not 50) */
+	r->n_dev_pins = (top + 3) & ~3;
+	if (r->n_dev_pins < 4) r->n_dev_pins = 4;
+	if (r->n_dev_pins > MIX_PINS) r->n_dev_pins = MIX_PINS;
 	if (batch_capacity() > 0) {
-		const int key[4] = {nwords, s->conf_mode, s->pins, 0};
-		s->batch = batch_join(BK_MIXER, f->ticker, key, s->pins * nwords, s->conf_mode ? s->pins * nwords : nwords, 1, s, NULL, &s->room);
+		const int key[4] = {words, r->conference, r->n_dev_pins, 0};
+		r->batch = batch_join(BK_MIXER, f->ticker, key, r->n_dev_pins * words, r->conference ? r->n_dev_pins * words : words, 1, r, NULL,
+		                      &r->room);
 	}
-	if (s->batch) { /* this mixer is one room of the group's bank; its arenas are slices of the group's pinned arenas */
-		s->bank = (msb200_mixer *)s->batch->bank;
-		s->in = s->batch->in[0] + (size_t)s->room * s->batch->unit_in;
-		s->out = s->batch->out + (size_t)s->room * s->batch->unit_out;
-		s->present = s->batch->present + (size_t)s->room * s->pins;
-		GRP_LOCK(s->batch);
-		for (i = 0; i < s->pins; ++i) {
-			msb200_mixer_set_input_gain(s->bank, s->room, i, s->channels[i].gain);
-			msb200_mixer_set_active(s->bank, s->room, i, s->channels[i].active);
-		}
-		GRP_UNLOCK(s->batch);
+	if (r->batch) { /* this mixer is one room of the group's bank; its arenas are slices of the group's pinned arenas */
+		r->bank = (msb200_mixer *)r->batch->bank;
+		r->in = r->batch->in[0] + (size_t)r->room * r->batch->unit_in;
+		r->out = r->batch->out + (size_t)r->room * r->batch->unit_out;
+		r->present = r->batch->present + (size_t)r->room * r->n_dev_pins;
+		GRP_LOCK(r->batch);
+		mixroom_push_controls(r);
+		GRP_UNLOCK(r->batch);
 		return;
 	}
-	s->in = (int16_t *)ms_malloc0(sizeof(int16_t) * (size_t)s->pins * (size_t)nwords);
-	s->out = (int16_t *)ms_malloc0(sizeof(int16_t) * (size_t)s->pins * (size_t)nwords);
-	s->present = (uint8_t *)ms_malloc0((size_t)s->pins);
+	r->in = (int16_t *)ms_malloc0(sizeof(int16_t) * (size_t)r->n_dev_pins * (size_t)words);
+	r->out = (int16_t *)ms_malloc0(sizeof(int16_t) * (size_t)r->n_dev_pins * (size_t)words);
+	r->present = (uint8_t *)ms_malloc0((size_t)r->n_dev_pins);
 	DSP_LOCK();
 	if (dsp_ctx()) {
-		DSP_CHECK(msb200_mixer_create(g_ctx, 1, s->pins, nwords, s->conf_mode, &s->bank), "mixer_create");
-		for (i = 0; s->bank && i < s->pins; ++i) {
-			msb200_mixer_set_input_gain(s->bank, 0, i, s->channels[i].gain);
-			msb200_mixer_set_active(s->bank, 0, i, s->channels[i].active);
-		}
+		DSP_CHECK(msb200_mixer_create(g_ctx, 1, r->n_dev_pins, words, r->conference, &r->bank), "mixer_create");
+		mixroom_push_controls(r);
 	}
 	DSP_UNLOCK();
 }
-static void mixer_postprocess(MSFilter *f) {
-	MixerState *s = (MixerState *)f->data;
-	if (s->batch) {
-		batch_leave(s->batch, s->room);
-		s->batch = NULL;
-		s->bank = NULL;
-		s->in = s->out = NULL;
-		s->present = NULL;
-		return;
-	}
-	DSP_LOCK();
-	msb200_mixer_destroy(s->bank);
-	DSP_UNLOCK();
-	s->bank = NULL;
-	ms_free(s->in);
-	ms_free(s->out);
-	ms_free(s->present);
-	s->in = s->out = NULL;
-	s->present = NULL;
-}
-/* one tick of results (s->out) to the output pins: channel_process_out :113-130 */
-static void mixer_emit(MSFilter *f, MixerState *s, int nwords) {
-	int i;
-	if (s->conf_mode == 0) {
-		mblk_t *om = NULL;
-		for (i = 0; i < s->pins; ++i) {
-			MSQueue *q = f->outputs[i];
-			if (q && s->channels[i].output_enabled) {
-				if (om == NULL) {
-					om = allocb((size_t)nwords * 2, 0);
-					memcpy(om->b_wptr, s->out, (size_t)nwords * 2);
-					om->b_wptr += nwords * 2;
-				} else {
-					om = dupb(om);
-				}
-				ms_queue_put(q, om);
-			}
-		}
+static void mixroom_detach(MSFilter *f) {
+	MixRoom *r = (MixRoom *)f->data;
+	if (r->batch) {
+		batch_leave(r->batch, r->room);
+		r->batch = NULL;
 	} else {
-		for (i = 0; i < s->pins; ++i) {
-			MSQueue *q = f->outputs[i];
-			if (q && s->channels[i].output_enabled) {
-				mblk_t *om = allocb((size_t)nwords * 2, 0);
-				memcpy(om->b_wptr, s->out + (size_t)i * nwords, (size_t)nwords * 2);
-				om->b_wptr += nwords * 2;
-				ms_queue_put(q, om);
-			}
-		}
+		DSP_LOCK();
+		msb200_mixer_destroy(r->bank);
+		DSP_UNLOCK();
+		ms_free(r->in);
+		ms_free(r->out);
+		ms_free(r->present);
+	}
+	r->bank = NULL;
+	r->in = r->out = NULL;
+	r->present = NULL;
+}
+static mblk_t *mix_block(const int16_t *samples, int words) {
+	mblk_t *m = allocb((size_t)words * 2, 0);
+	memcpy(m->b_wptr, samples, (size_t)words * 2);
+	m->b_wptr += words * 2;
+	return m;
+}
+/* one tick of results (r->out) to the listeners: everybody shares one block in plain mode (:321-334), every listener
+ * gets the row computed for its own pin in conference mode (:336-342) */
+static void mixroom_hand_out(MSFilter *f, MixRoom *r, int words) {
+	mblk_t *shared = NULL;
+	int k;
+	for (k = 0; k < r->n_dev_pins; ++k) {
+		if (f->outputs[k] == NULL || !r->pin[k].listens) continue;
+		if (r->conference) ms_queue_put(f->outputs[k], mix_block(r->out + (size_t)k * words, words));
+		else ms_queue_put(f->outputs[k], shared = shared ? dupb(shared) : mix_block(r->out, words));
 	}
 }
-static void mixer_dispatch_output(MSFilter *f, MixerState *s, MSQueue *inq, int active_input) {
-	int i;
-	for (i = 0; i < f->desc->noutputs; i++) {
-		MSQueue *outq = f->outputs[i];
-		if (outq && s->channels[i].output_enabled && (active_input != i || s->conf_mode == 0)) {
-			mblk_t *m;
-			if (s->single_output) {
-				while ((m = ms_queue_get(inq)) != NULL)
-					ms_queue_put(outq, m);
-				break;
-			}
-			for (m = ms_queue_peek_first(inq); !ms_queue_end(inq, m); m = ms_queue_next(inq, m))
-				ms_queue_put(outq, dupmsg(m));
+/* Who is talking? A pin counts while packets arrive and for MIX_SOLO_AFTER_MS after its last one (a pin that never sent
+ * anything starts its silence clock at the first tick). Returns the number of talkers; *which = the highest of them. */
+static int mixroom_talkers(MSFilter *f, MixRoom *r, int *which) {
+	const uint64_t now = f->ticker->time;
+	int k, n = 0;
+	for (k = 0; k < MIX_PINS; ++k) {
+		MixPin *p = &r->pin[k];
+		bool_t talking;
+		if (f->inputs[k] == NULL) continue;
+		if (!ms_queue_empty(f->inputs[k])) {
+			p->heard_at = now;
+			talking = TRUE;
+		} else if (p->heard_at == MIX_NEVER) {
+			p->heard_at = now;
+			talking = FALSE;
+		} else {
+			talking = now - p->heard_at < MIX_SOLO_AFTER_MS;
+		}
+		if (talking) {
+			*which = k;
+			++n;
 		}
 	}
-	ms_queue_flush(inq);
+	return n;
 }
-static bool_t mixer_check_bypass(MSFilter *f, MixerState *s) {
-	int i, active_cnt = 0, active_input = -1;
-	MSQueue *activeq = NULL;
-	uint64_t curtime = f->ticker->time;
-	for (i = 0; i < f->desc->ninputs; i++) {
-		MSQueue *q = f->inputs[i];
-		MixChannel *chan = &s->channels[i];
-		if (!q) continue;
-		if (!ms_queue_empty(q)) {
-			chan->last_activity = curtime;
-			activeq = q;
-			active_cnt++;
-			active_input = i;
-		} else if (chan->last_activity == (uint64_t)-1) {
-			chan->last_activity = curtime;
-		} else if (curtime - chan->last_activity < BYPASS_MODE_TIMEOUT) {
-			activeq = q;
-			active_cnt++;
-			active_input = i;
-		}
-	}
-	if (active_cnt == 1) {
-		if (!s->bypass_mode) {
-			s->bypass_mode = TRUE;
-			ms_message("MSAudioMixer(b200) [%p] is entering bypass mode.", f);
-		}
-		mixer_dispatch_output(f, s, activeq, active_input);
-		return TRUE;
-	} else if (active_cnt > 1) {
-		if (s->bypass_mode) {
-			s->bypass_mode = FALSE;
-			ms_message("MSAudioMixer(b200) [%p] is leaving bypass mode.", f);
-		}
-		return FALSE;
-	}
-	return TRUE;
-}
-static void mixer_process(MSFilter *f) {
-	MixerState *s = (MixerState *)f->data;
-	int i, nwords = s->bytespertick / 2;
-	ms_filter_lock(f);
-	if (s->batch) { /* the group's previous tick is computed by the first mixer called in this tick; emit this room's share */
-		batch_tick(s->batch, f->ticker->ticks);
-		if (s->batch->ready[s->room]) {
-			s->batch->ready[s->room] = 0;
-			mixer_emit(f, s, nwords);
-		}
-	}
-	if (mixer_check_bypass(f, s)) {
-		ms_filter_unlock(f);
-		return;
-	}
-	memset(s->present, 0, (size_t)s->pins);
-	for (i = 0; i < s->pins; ++i) {
-		MSQueue *q = f->inputs[i];
-		MixChannel *chan = &s->channels[i];
-		int size, skip = 0;
-		if (!q) continue;
-		ms_bufferizer_put_from_queue(&chan->bufferizer, q);
-		if (ms_bufferizer_read(&chan->bufferizer, (uint8_t *)(s->in + (size_t)i * nwords), (size_t)nwords * 2) != 0)
-			s->present[i] = 1;
-		/* channel_flow_control */
-		if (chan->last_flow_control == (uint64_t)-1) {
-			chan->last_flow_control = f->ticker->time;
-			chan->min_fullness = -1;
+/* the single talker's packets go out as they came, to every listener but (in a conference) the talker itself (:219-239).
+ * Packet-major: each packet is handed to the last listener as is and duplicated for the others. */
+static void mixroom_forward_solo(MSFilter *f, MixRoom *r, int talker) {
+	MSQueue *to[MIX_PINS];
+	mblk_t *m;
+	int k, n = 0;
+	for (k = 0; k < MIX_PINS; ++k)
+		if (f->outputs[k] && r->pin[k].listens && (k != talker || !r->conference)) to[n++] = f->outputs[k];
+	while ((m = ms_queue_get(f->inputs[talker])) != NULL) {
+		if (r->one_listener && n == 1) { /* a lone listener receives the packets themselves */
+			ms_queue_put(to[0], m);
 			continue;
 		}
-		size = (int)ms_bufferizer_get_avail(&chan->bufferizer);
-		if (chan->min_fullness == -1 || size < chan->min_fullness) chan->min_fullness = size;
-		if (f->ticker->time - chan->last_flow_control >= 5000) {
-			if (chan->min_fullness >= s->skip_threshold) {
-				skip = chan->min_fullness - (s->skip_threshold / 2);
-				ms_bufferizer_skip_bytes(&chan->bufferizer, skip);
-			}
-			chan->last_flow_control = f->ticker->time;
-			chan->min_fullness = -1;
-		}
-		if (skip > 0)
-			ms_warning("Too much data in channel %i, %i ms in excess dropped", i, (skip * 1000) / (2 * s->nchannels * s->rate));
+		for (k = 0; k < n; ++k) ms_queue_put(to[k], dupmsg(m));
+		freemsg(m);
 	}
-	if (s->batch) { /* staged: the group's launch at the start of the next tick mixes every room at once */
-		s->batch->staged[s->room] = 1;
+}
+/* drift control of one pin's FIFO: if over MIX_TRIM_EVERY_MS it never held less than trim_above bytes, the excess over
+ * half of that is dropped (:92-111). Returns the bytes dropped. */
+static int mixpin_trim(MixPin *p, uint64_t now, int trim_above) {
+	int fill, dropped = 0;
+	if (p->trimmed_at == MIX_NEVER) {
+		p->trimmed_at = now;
+		p->low_water = -1;
+		return 0;
+	}
+	fill = (int)ms_bufferizer_get_avail(&p->fifo);
+	if (p->low_water < 0 || fill < p->low_water) p->low_water = fill;
+	if (now - p->trimmed_at < MIX_TRIM_EVERY_MS) return 0;
+	if (p->low_water >= trim_above) {
+		dropped = p->low_water - trim_above / 2;
+		ms_bufferizer_skip_bytes(&p->fifo, dropped);
+	}
+	p->trimmed_at = now;
+	p->low_water = -1;
+	return dropped;
+}
+static void mixroom_tick(MSFilter *f) {
+	MixRoom *r = (MixRoom *)f->data;
+	const int words = r->tick_bytes / 2;
+	int k, talkers, talker = -1, heard = 0;
+	ms_filter_lock(f);
+	if (r->batch) { /* the group's previous tick was computed by the first mixer called in this tick: hand out this room's share */
+		batch_tick(r->batch, f->ticker->ticks);
+		if (r->batch->ready[r->room]) {
+			r->batch->ready[r->room] = 0;
+			mixroom_hand_out(f, r, words);
+		}
+	}
+	talkers = mixroom_talkers(f, r, &talker);
+	if (talkers <= 1) { /* nothing to mix: silence all round, or one talker whose packets are passed on untouched */
+		if (talkers == 1) {
+			if (!r->solo) ms_message("MSAudioMixer(B200) %p: one talker left, forwarding its packets", f);
+			r->solo = TRUE;
+			mixroom_forward_solo(f, r, talker);
+		}
 		ms_filter_unlock(f);
 		return;
 	}
-	/* the arithmetic: one launch for the whole mixer (sum, gains, minus-own, saturation) */
+	if (r->solo) ms_message("MSAudioMixer(B200) %p: several talkers again, mixing", f);
+	r->solo = FALSE;
+	/* drain every pin's queue into its FIFO and read one tick straight into the pin's row of the device arena */
+	memset(r->present, 0, (size_t)r->n_dev_pins);
+	for (k = 0; k < r->n_dev_pins; ++k) {
+		MixPin *p = &r->pin[k];
+		int dropped;
+		if (f->inputs[k] == NULL) continue;
+		ms_bufferizer_put_from_queue(&p->fifo, f->inputs[k]);
+		if (ms_bufferizer_read(&p->fifo, (uint8_t *)(r->in + (size_t)k * words), (size_t)r->tick_bytes) != 0) r->present[k] = 1, ++heard;
+		if ((dropped = mixpin_trim(p, f->ticker->time, r->trim_above)) > 0)
+			ms_warning("MSAudioMixer(B200): pin %d runs ahead, %d ms dropped", k, (dropped * 1000) / (2 * r->channels * r->hz));
+	}
+	if (heard == 0) { /* no pin had a whole tick: the reference emits nothing either (:318) */
+		ms_filter_unlock(f);
+		return;
+	}
+	if (r->batch) { /* staged: the group's launch at the start of the next tick mixes every room at once */
+		r->batch->staged[r->room] = 1;
+		ms_filter_unlock(f);
+		return;
+	}
 	DSP_LOCK();
-	if (s->bank) DSP_CHECK(msb200_mixer_process(s->bank, s->in, s->present, s->out), "mixer_process");
+	if (r->bank) DSP_CHECK(msb200_mixer_process(r->bank, r->in, r->present, r->out), "mixer_process");
 	DSP_UNLOCK();
-	if (s->bank) mixer_emit(f, s, nwords);
+	if (r->bank) mixroom_hand_out(f, r, words);
 	ms_filter_unlock(f);
 }
-static int mixer_set_rate(MSFilter *f, void *data) {
-	((MixerState *)f->data)->rate = *(int *)data;
+/* ---- methods (audiomixer.c:348-431) */
+static int mixm_set_hz(MSFilter *f, void *arg) {
+	((MixRoom *)f->data)->hz = *(int *)arg;
 	return 0;
 }
-static int mixer_get_rate(MSFilter *f, void *data) {
-	*(int *)data = ((MixerState *)f->data)->rate;
+static int mixm_get_hz(MSFilter *f, void *arg) {
+	*(int *)arg = ((MixRoom *)f->data)->hz;
 	return 0;
 }
-static int mixer_set_nchannels(MSFilter *f, void *data) {
-	((MixerState *)f->data)->nchannels = *(int *)data;
+static int mixm_set_channels(MSFilter *f, void *arg) {
+	((MixRoom *)f->data)->channels = *(int *)arg;
 	return 0;
 }
-static int mixer_get_nchannels(MSFilter *f, void *data) {
-	*(int *)data = ((MixerState *)f->data)->nchannels;
+static int mixm_get_channels(MSFilter *f, void *arg) {
+	*(int *)arg = ((MixRoom *)f->data)->channels;
 	return 0;
 }
-static int mixer_set_input_gain(MSFilter *f, void *data) {
-	MixerState *s = (MixerState *)f->data;
-	MSAudioMixerCtl *ctl = (MSAudioMixerCtl *)data;
-	if (ctl->pin < 0 || ctl->pin >= MIXER_MAX_CHANNELS) {
-		ms_warning("mixer_set_input_gain: invalid pin number %i", ctl->pin);
-		return -1;
-	}
-	s->channels[ctl->pin].gain = ctl->param.gain;
-	if (s->bank && ctl->pin < s->pins) {
-		MIX_LOCK(s);
-		msb200_mixer_set_input_gain(s->bank, s->room, ctl->pin, ctl->param.gain);
-		MIX_UNLOCK(s);
-	}
-	return 0;
+static MixPin *mixm_pin(MSFilter *f, const MSAudioMixerCtl *ctl, const char *what) {
+	if (ctl->pin >= 0 && ctl->pin < MIX_PINS) return &((MixRoom *)f->data)->pin[ctl->pin];
+	ms_warning("MSAudioMixer(B200): %s: no pin %i", what, ctl->pin);
+	return NULL;
 }
-static int mixer_set_active(MSFilter *f, void *data) {
-	MixerState *s = (MixerState *)f->data;
-	MSAudioMixerCtl *ctl = (MSAudioMixerCtl *)data;
-	if (ctl->pin < 0 || ctl->pin >= MIXER_MAX_CHANNELS) {
-		ms_warning("mixer_set_active_gain: invalid pin number %i", ctl->pin);
-		return -1;
-	}
-	s->channels[ctl->pin].active = (bool_t)ctl->param.active;
-	if (s->bank && ctl->pin < s->pins) {
-		MIX_LOCK(s);
-		msb200_mixer_set_active(s->bank, s->room, ctl->pin, ctl->param.active);
-		MIX_UNLOCK(s);
+static int mixm_set_gain(MSFilter *f, void *arg) {
+	MixRoom *r = (MixRoom *)f->data;
+	const MSAudioMixerCtl *ctl = (const MSAudioMixerCtl *)arg;
+	MixPin *p = mixm_pin(f, ctl, "input gain");
+	if (!p) return -1;
+	p->gain = ctl->param.gain;
+	if (r->bank && ctl->pin < r->n_dev_pins) {
+		MIX_LOCK(r);
+		msb200_mixer_set_input_gain(r->bank, r->room, ctl->pin, p->gain);
+		MIX_UNLOCK(r);
 	}
 	return 0;
 }
-static int mixer_enable_output(MSFilter *f, void *data) {
-	MixerState *s = (MixerState *)f->data;
-	MSAudioMixerCtl *ctl = (MSAudioMixerCtl *)data;
-	if (ctl->pin < 0 || ctl->pin >= MIXER_MAX_CHANNELS) {
-		ms_warning("mixer_enable_output: invalid pin number %i", ctl->pin);
-		return -1;
+static int mixm_set_contributes(MSFilter *f, void *arg) {
+	MixRoom *r = (MixRoom *)f->data;
+	const MSAudioMixerCtl *ctl = (const MSAudioMixerCtl *)arg;
+	MixPin *p = mixm_pin(f, ctl, "active flag");
+	if (!p) return -1;
+	p->contributes = (bool_t)ctl->param.active;
+	if (r->bank && ctl->pin < r->n_dev_pins) {
+		MIX_LOCK(r);
+		msb200_mixer_set_active(r->bank, r->room, ctl->pin, p->contributes);
+		MIX_UNLOCK(r);
 	}
+	return 0;
+}
+static int mixm_set_listens(MSFilter *f, void *arg) {
+	MixRoom *r = (MixRoom *)f->data;
+	const MSAudioMixerCtl *ctl = (const MSAudioMixerCtl *)arg;
+	MixPin *p = mixm_pin(f, ctl, "output switch");
+	if (!p) return -1;
 	ms_filter_lock(f);
-	s->channels[ctl->pin].output_enabled = (bool_t)ctl->param.enabled;
-	s->single_output = mixer_has_single_output(f, s);
+	p->listens = (bool_t)ctl->param.enabled;
+	r->one_listener = mixroom_listeners(f, r) == 1;
 	ms_filter_unlock(f);
 	return 0;
 }
-static int mixer_set_conference_mode(MSFilter *f, void *data) {
-	((MixerState *)f->data)->conf_mode = *(int *)data;
+static int mixm_set_conference(MSFilter *f, void *arg) {
+	((MixRoom *)f->data)->conference = *(int *)arg;
 	return 0;
 }
-static int mixer_set_master_channel(MSFilter *f, void *data) {
-	((MixerState *)f->data)->master_channel = *(int *)data;
+static int mixm_set_master(MSFilter *f, void *arg) {
+	((MixRoom *)f->data)->master_pin = *(int *)arg;
 	return 0;
 }
-static MSFilterMethod mixer_methods[] = {{MS_FILTER_SET_NCHANNELS, mixer_set_nchannels},
-                                         {MS_FILTER_GET_NCHANNELS, mixer_get_nchannels},
-                                         {MS_FILTER_SET_SAMPLE_RATE, mixer_set_rate},
-                                         {MS_FILTER_GET_SAMPLE_RATE, mixer_get_rate},
-                                         {MS_AUDIO_MIXER_SET_INPUT_GAIN, mixer_set_input_gain},
-                                         {MS_AUDIO_MIXER_SET_ACTIVE, mixer_set_active},
-                                         {MS_AUDIO_MIXER_ENABLE_CONFERENCE_MODE, mixer_set_conference_mode},
-                                         {MS_AUDIO_MIXER_SET_MASTER_CHANNEL, mixer_set_master_channel},
-                                         {MS_AUDIO_MIXER_ENABLE_OUTPUT, mixer_enable_output},
-                                         {0, NULL}};
+static MSFilterMethod mixroom_methods[] = {{MS_FILTER_SET_NCHANNELS, mixm_set_channels},
+                                           {MS_FILTER_GET_NCHANNELS, mixm_get_channels},
+                                           {MS_FILTER_SET_SAMPLE_RATE, mixm_set_hz},
+                                           {MS_FILTER_GET_SAMPLE_RATE, mixm_get_hz},
+                                           {MS_AUDIO_MIXER_SET_INPUT_GAIN, mixm_set_gain},
+                                           {MS_AUDIO_MIXER_SET_ACTIVE, mixm_set_contributes},
+                                           {MS_AUDIO_MIXER_ENABLE_CONFERENCE_MODE, mixm_set_conference},
+                                           {MS_AUDIO_MIXER_SET_MASTER_CHANNEL, mixm_set_master},
+                                           {MS_AUDIO_MIXER_ENABLE_OUTPUT, mixm_set_listens},
+                                           {0, NULL}};
 static MSFilterDesc b200_audio_mixer_desc = {.id = MS_AUDIO_MIXER_ID,
                                              .name = "MSAudioMixer",
                                              .text = "B200: mixes 16 bit sample audio streams (libmsb200dsp)",
                                              .category = MS_FILTER_OTHER,
-                                             .ninputs = MIXER_MAX_CHANNELS,
-                                             .noutputs = MIXER_MAX_CHANNELS,
-                                             .init = mixer_init,
-                                             .preprocess = mixer_preprocess,
-                                             .process = mixer_process,
-                                             .postprocess = mixer_postprocess,
-                                             .uninit = mixer_uninit,
-                                             .methods = mixer_methods,
+                                             .ninputs = MIX_PINS,
+                                             .noutputs = MIX_PINS,
+                                             .init = mixroom_new,
+                                             .preprocess = mixroom_attach,
+                                             .process = mixroom_tick,
+                                             .postprocess = mixroom_detach,
+                                             .uninit = mixroom_free,
+                                             .methods = mixroom_methods,
                                              .flags = MS_FILTER_IS_PUMP};
 
 /* ================================================================================================ MSVolume
@@ -731,14 +720,31 @@ typedef struct VolState {
 	int n_held;
 	MSQueue pend;     /* processed blocks waiting for this filter's next process() */
 	bool_t batch_off;
+	/* echo-limiter links. `watchers` = filters that named THIS one as their peer: while there are any, this filter keeps
+	 * its state in its private bank (never in a batch group's slot, which the watcher could not read) and tells them
+	 * whenever that bank goes away or is recreated, so that no watcher keeps a pointer into a freed bank. */
+	struct VolState *next_vol; /* every B200 MSVolume of the process (g_mu) */
+	MSFilter *self;
+	int watchers;
 } VolState;
 static MSFilterDesc b200_volume_desc;
+static VolState *g_vols = NULL; /* g_mu */
+/* DSP lock held: `gone`'s bank is about to be destroyed or replaced: every filter watching it unlinks on the device side */
+static void vol_peer_bank_changed(VolState *gone) {
+	VolState *w;
+	for (w = g_vols; w; w = w->next_vol)
+		if (w->peer && w->peer == gone->self && w->peer_linked) {
+			if (w->bank) msb200_volume_set_peer(w->bank, 0, NULL, 0);
+			w->peer_linked = FALSE; /* re-linked at the next sync if the peer has a bank again */
+		}
+}
 #define VOL_MAX_BLOCK 8192
 #define VOL_BATCH_UNITS 8 /* blocks one stream may stage per tick (an upstream MSSpeexEC emits 1-2 frames per 10 ms) */
 
 static void vol_sync_config_to(VolState *v, msb200_volume *bank, int st) { /* DSP lock held */
 	if (!bank) return;
 	if (v->peer && !v->peer_linked && bank == v->bank && v->peer->desc == &b200_volume_desc && ((VolState *)v->peer->data)->bank) {
+		/* the peer's smoothed energy is read from its PRIVATE bank (a watched filter stays out of the batch groups) */
 		msb200_volume_set_peer(v->bank, 0, ((VolState *)v->peer->data)->bank, 0);
 		v->peer_linked = TRUE;
 	}
@@ -800,13 +806,29 @@ static void vol_init(MSFilter *f) {
 	v->buffer = ms_bufferizer_new();
 	v->dirty = TRUE;
 	v->gain_dirty = FALSE; /* the bank starts at gain 1 like volume_init */
+	v->self = f;
+	DSP_LOCK();
+	v->next_vol = g_vols;
+	g_vols = v;
+	DSP_UNLOCK();
 	f->data = v;
 }
 static void vol_uninit(MSFilter *f) {
 	VolState *v = (VolState *)f->data;
+	VolState **pp;
 	vol_leave_batch(v);
 	ms_queue_flush(&v->pend);
 	DSP_LOCK();
+	vol_peer_bank_changed(v);
+	for (pp = &g_vols; *pp && *pp != v; pp = &(*pp)->next_vol) {
+	}
+	if (*pp) *pp = v->next_vol;
+	{
+		VolState *w;
+		for (w = g_vols; w; w = w->next_vol)
+			if (w->peer == f) w->peer = NULL; /* a watcher must not keep the pointer to a destroyed filter */
+	}
+	if (v->peer && v->peer->desc == &b200_volume_desc) ((VolState *)v->peer->data)->watchers--;
 	msb200_volume_destroy(v->bank);
 	DSP_UNLOCK();
 	ms_bufferizer_destroy(v->buffer);
@@ -816,6 +838,7 @@ static void vol_preprocess(MSFilter *f) {
 	VolState *v = (VolState *)f->data;
 	DSP_LOCK();
 	if (dsp_ctx() && (!v->bank || v->bank_rate != v->rate)) {
+		vol_peer_bank_changed(v);
 		msb200_volume_destroy(v->bank);
 		v->bank = NULL;
 		DSP_CHECK(msb200_volume_create(g_ctx, 1, v->rate, VOL_MAX_BLOCK, &v->bank), "volume_create");
@@ -834,22 +857,35 @@ static void vol_postprocess(MSFilter *f) {
 static void vol_process(MSFilter *f) {
 	VolState *v = (VolState *)f->data;
 	mblk_t *m;
-	if (v->agc || v->peer != NULL) { /* chunked mode :480-502 */
+	if (v->agc || v->peer != NULL) {
+		/* AGC or an echo-limiter peer: the reference re-frames to 10 ms chunks and runs one at a time (msvolume.c:480-502).
+		 * Here every whole chunk the FIFO holds goes to the device in ONE call (the kernel walks the chunks in order; the
+		 * peer's energy does not move while this filter runs), then leaves as one block per chunk. */
+		const int chunk = (int)(0.01 * (float)v->rate);
+		const size_t chunk_bytes = (size_t)chunk * 2;
+		size_t k, n_chunks;
+		int16_t *run;
+		bool_t ok = FALSE;
 		if (v->batch) vol_leave_batch(v);
-		int nsamples = (int)(0.01 * (float)v->rate);
-		size_t nbytes = (size_t)nsamples * 2;
 		ms_bufferizer_put_from_queue(v->buffer, f->inputs[0]);
-		while (ms_bufferizer_get_avail(v->buffer) >= nbytes) {
-			m = allocb(nbytes, 0);
-			ms_bufferizer_read(v->buffer, m->b_wptr, nbytes);
-			m->b_wptr += nbytes;
-			DSP_LOCK();
-			vol_sync_config(v);
-			if (v->bank) DSP_CHECK(msb200_volume_process(v->bank, (int16_t *)m->b_rptr, nsamples), "volume_process");
-			DSP_UNLOCK();
-			if (v->bank) ms_queue_put(f->outputs[0], m);
-			else freemsg(m);
+		n_chunks = chunk_bytes ? ms_bufferizer_get_avail(v->buffer) / chunk_bytes : 0;
+		if (n_chunks == 0) return;
+		run = (int16_t *)ms_malloc(n_chunks * chunk_bytes);
+		ms_bufferizer_read(v->buffer, (uint8_t *)run, n_chunks * chunk_bytes);
+		DSP_LOCK();
+		vol_sync_config(v);
+		if (v->bank) {
+			DSP_CHECK(msb200_volume_process_blocks(v->bank, run, chunk, (int)(n_chunks * chunk), (int)n_chunks, NULL), "volume_process");
+			ok = TRUE;
 		}
+		DSP_UNLOCK();
+		for (k = 0; ok && k < n_chunks; ++k) {
+			m = allocb(chunk_bytes, 0);
+			memcpy(m->b_wptr, run + k * chunk, chunk_bytes);
+			m->b_wptr += chunk_bytes;
+			ms_queue_put(f->outputs[0], m);
+		}
+		ms_free(run);
 		return;
 	}
 	if (v->batch && v->batch->key[0] != v->rate) vol_leave_batch(v);
@@ -861,7 +897,12 @@ static void vol_process(MSFilter *f) {
 		ms_queue_put(f->outputs[0], m);
 	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
 		int n = (int)((m->b_wptr - m->b_rptr) / 2);
-		if (!v->batch && !v->batch_off && batch_capacity() > 0 && n > 0 && n <= VOL_MAX_BLOCK) {
+		if (v->batch && v->watchers > 0) { /* somebody's echo-limiter peer: the state must live in the private bank */
+			vol_leave_batch(v);
+			v->dirty = TRUE;
+			v->gain_dirty = v->static_gain != 1.0f;
+		}
+		if (!v->batch && !v->batch_off && v->watchers == 0 && batch_capacity() > 0 && n > 0 && n <= VOL_MAX_BLOCK) {
 			const int key[4] = {v->rate, n, 0, 0};
 			v->batch = batch_join(BK_VOLUME, f->ticker, key, n, n, VOL_BATCH_UNITS, v, vol_collect, &v->slot);
 			if (v->batch) {
@@ -960,8 +1001,14 @@ static int vol_set_rate(MSFilter *f, void *arg) {
 }
 static int vol_set_peer(MSFilter *f, void *arg) {
 	VolState *v = (VolState *)f->data;
-	v->peer = (MSFilter *)arg;
+	MSFilter *peer = (MSFilter *)arg;
+	DSP_LOCK();
+	if (v->peer && v->peer->desc == &b200_volume_desc) ((VolState *)v->peer->data)->watchers--;
+	if (v->peer_linked && v->bank) msb200_volume_set_peer(v->bank, 0, NULL, 0);
+	v->peer = peer;
 	v->peer_linked = FALSE;
+	if (peer && peer->desc == &b200_volume_desc) ((VolState *)peer->data)->watchers++;
+	DSP_UNLOCK();
 	return 0;
 }
 static int vol_set_agc(MSFilter *f, void *arg) {
@@ -1067,143 +1114,137 @@ static MSFilterDesc b200_volume_desc = {.id = MS_VOLUME_ID,
                                         .methods = vol_methods};
 
 /* ================================================================================================ MSChannelAdapter
- * /root/reference/src/audiofilters/chanadapt.c:45-132 */
-typedef struct AdaptState {
-	int inputchans, outputchans, sample_rate;
-	size_t buffer_size;
-	uint8_t *buffer1, *buffer2;
-	MSFlowControlledBufferizer input_buffer1, input_buffer2;
-} AdaptState;
-static void adapt_init(MSFilter *f) {
-	AdaptState *s = ms_new0(AdaptState, 1);
-	s->inputchans = s->outputchans = 1;
-	s->sample_rate = 8000;
-	f->data = s;
+ * /root/reference/src/audiofilters/chanadapt.c: per block mono -> stereo / stereo -> mono (:99-132), or — with both
+ * input pins connected — two mono streams interleaved into one stereo stream, one ticker interval at a time (:68-97).
+ * The interleaving / duplication / left-channel pick runs in chanadapt_kernel. */
+typedef struct ChanSide { /* one mono input of the two-pin mode */
+	MSFlowControlledBufferizer fifo;
+	uint8_t *tick; /* one ticker interval of samples */
+} ChanSide;
+typedef struct ChanAdapter {
+	int in_ch, out_ch, hz;
+	size_t tick_bytes;
+	bool_t sides_ready; /* the two-pin state exists (the reference sets it up when in = 2, out = 1 channels: chanadapt.c:55) */
+	ChanSide side[2];
+} ChanAdapter;
+static void chan_new(MSFilter *f) {
+	ChanAdapter *a = ms_new0(ChanAdapter, 1);
+	a->in_ch = a->out_ch = 1;
+	a->hz = 8000;
+	f->data = a;
 }
-static void adapt_uninit(MSFilter *f) {
+static void chan_free(MSFilter *f) {
 	ms_free(f->data);
 }
-static void adapt_preprocess(MSFilter *f) {
-	AdaptState *s = (AdaptState *)f->data;
+static void chan_attach(MSFilter *f) {
+	ChanAdapter *a = (ChanAdapter *)f->data;
+	int k;
 	DSP_LOCK();
 	dsp_ctx();
 	DSP_UNLOCK();
-	if (s->inputchans == 2 && s->outputchans == 1) {
-		s->buffer_size = ((f->ticker->interval * s->sample_rate) / 1000) * 2;
-		s->buffer1 = ms_new(uint8_t, s->buffer_size);
-		s->buffer2 = ms_new(uint8_t, s->buffer_size);
-		ms_flow_controlled_bufferizer_init(&s->input_buffer1, f, s->sample_rate, 1);
-		ms_flow_controlled_bufferizer_set_drop_method(&s->input_buffer1, MSFlowControlledBufferizerImmediateDrop);
-		ms_flow_controlled_bufferizer_set_max_size_ms(&s->input_buffer1, f->ticker->interval * 2);
-		ms_flow_controlled_bufferizer_init(&s->input_buffer2, f, s->sample_rate, 1);
-		ms_flow_controlled_bufferizer_set_drop_method(&s->input_buffer2, MSFlowControlledBufferizerImmediateDrop);
-		ms_flow_controlled_bufferizer_set_max_size_ms(&s->input_buffer2, f->ticker->interval * 2);
+	a->sides_ready = a->in_ch == 2 && a->out_ch == 1;
+	if (!a->sides_ready) return;
+	a->tick_bytes = (size_t)((f->ticker->interval * a->hz) / 1000) * 2;
+	for (k = 0; k < 2; ++k) { /* a side never buffers more than two intervals: the excess is dropped at once (:59-64) */
+		a->side[k].tick = ms_new(uint8_t, a->tick_bytes);
+		ms_flow_controlled_bufferizer_init(&a->side[k].fifo, f, a->hz, 1);
+		ms_flow_controlled_bufferizer_set_drop_method(&a->side[k].fifo, MSFlowControlledBufferizerImmediateDrop);
+		ms_flow_controlled_bufferizer_set_max_size_ms(&a->side[k].fifo, f->ticker->interval * 2);
 	}
 }
-static void adapt_postprocess(MSFilter *f) {
-	AdaptState *s = (AdaptState *)f->data;
-	if (s->inputchans == 2 && s->outputchans == 1) {
-		ms_flow_controlled_bufferizer_uninit(&s->input_buffer1);
-		ms_flow_controlled_bufferizer_uninit(&s->input_buffer2);
-		ms_free(s->buffer1);
-		ms_free(s->buffer2);
-		s->buffer1 = s->buffer2 = NULL;
+static void chan_detach(MSFilter *f) {
+	ChanAdapter *a = (ChanAdapter *)f->data;
+	int k;
+	if (!a->sides_ready) return;
+	for (k = 0; k < 2; ++k) {
+		ms_flow_controlled_bufferizer_uninit(&a->side[k].fifo);
+		ms_free(a->side[k].tick);
+		a->side[k].tick = NULL;
 	}
+	a->sides_ready = FALSE;
 }
-static void adapt_process(MSFilter *f) {
-	AdaptState *s = (AdaptState *)f->data;
-	if (f->inputs[0] != NULL && f->inputs[1] != NULL) {
-		size_t a1, a2;
-		ms_flow_controlled_bufferizer_put_from_queue(&s->input_buffer1, f->inputs[0]);
-		ms_flow_controlled_bufferizer_put_from_queue(&s->input_buffer2, f->inputs[1]);
-		a1 = ms_flow_controlled_bufferizer_get_avail(&s->input_buffer1);
-		a2 = ms_flow_controlled_bufferizer_get_avail(&s->input_buffer2);
-		if (a1 >= s->buffer_size || a2 >= s->buffer_size) {
-			mblk_t *om = allocb(s->buffer_size * 2, 0);
-			int frames = (int)(s->buffer_size / 2);
-			ms_flow_controlled_bufferizer_read(&s->input_buffer1, s->buffer1, s->buffer_size);
-			ms_flow_controlled_bufferizer_read(&s->input_buffer2, s->buffer2, s->buffer_size);
-			DSP_LOCK();
-			if (g_ctx)
-				DSP_CHECK(msb200_chanadapt_process(g_ctx, MSB200_CHAN_2MONO_TO_STEREO, 1, frames,
-				                                   a1 >= s->buffer_size ? (int16_t *)s->buffer1 : NULL,
-				                                   a2 >= s->buffer_size ? (int16_t *)s->buffer2 : NULL, (int16_t *)om->b_wptr),
-				          "chanadapt");
-			DSP_UNLOCK();
-			om->b_wptr += s->buffer_size * 2;
-			if (g_ctx) ms_queue_put(f->outputs[0], om);
-			else freemsg(om);
+/* device call + hand-over shared by all three modes: `frames` frames from a (and b) into a fresh block of out_bytes */
+static void chan_convert(MSFilter *f, int mode, int frames, const int16_t *a, const int16_t *b, size_t out_bytes) {
+	mblk_t *om = allocb(out_bytes, 0);
+	bool_t ok;
+	DSP_LOCK();
+	ok = g_ctx != NULL;
+	if (ok && frames > 0) DSP_CHECK(msb200_chanadapt_process(g_ctx, mode, 1, frames, a, b, (int16_t *)om->b_wptr), "chanadapt");
+	DSP_UNLOCK();
+	om->b_wptr += out_bytes;
+	if (ok) ms_queue_put(f->outputs[0], om);
+	else freemsg(om); /* no GPU: never forward unprocessed audio */
+}
+static void chan_tick(MSFilter *f) {
+	ChanAdapter *a = (ChanAdapter *)f->data;
+	mblk_t *im;
+	if (f->inputs[0] && f->inputs[1]) { /* two mono pins -> one stereo stream; a side without a full interval gives silence */
+		bool_t full[2];
+		int k;
+		for (k = 0; k < 2; ++k) {
+			ms_flow_controlled_bufferizer_put_from_queue(&a->side[k].fifo, f->inputs[k]);
+			full[k] = ms_flow_controlled_bufferizer_get_avail(&a->side[k].fifo) >= a->tick_bytes;
 		}
+		if (!full[0] && !full[1]) return;
+		for (k = 0; k < 2; ++k) ms_flow_controlled_bufferizer_read(&a->side[k].fifo, a->side[k].tick, a->tick_bytes);
+		chan_convert(f, MSB200_CHAN_2MONO_TO_STEREO, (int)(a->tick_bytes / 2), full[0] ? (const int16_t *)a->side[0].tick : NULL,
+		             full[1] ? (const int16_t *)a->side[1].tick : NULL, a->tick_bytes * 2);
 		return;
 	}
-	{
-		mblk_t *im;
-		while ((im = ms_queue_get(f->inputs[0])) != NULL) {
-			if (s->inputchans == s->outputchans) {
-				ms_queue_put(f->outputs[0], im);
-			} else {
-				int to_stereo = s->outputchans == 2;
-				size_t insz = msgdsize(im);
-				size_t outsz = to_stereo ? insz * 2 : insz / 2;
-				int frames = (int)(to_stereo ? insz / 2 : insz / 4);
-				mblk_t *om = allocb(outsz, 0);
-				DSP_LOCK();
-				if (g_ctx && frames > 0)
-					DSP_CHECK(msb200_chanadapt_process(g_ctx, to_stereo ? MSB200_CHAN_MONO_TO_STEREO : MSB200_CHAN_STEREO_TO_MONO,
-					                                   1, frames, (int16_t *)im->b_rptr, NULL, (int16_t *)om->b_wptr),
-					          "chanadapt");
-				DSP_UNLOCK();
-				om->b_wptr += outsz;
-				if (g_ctx) ms_queue_put(f->outputs[0], om);
-				else freemsg(om);
-				freemsg(im);
-			}
+	while ((im = ms_queue_get(f->inputs[0])) != NULL) {
+		const size_t in_bytes = msgdsize(im);
+		if (a->in_ch == a->out_ch) {
+			ms_queue_put(f->outputs[0], im);
+			continue;
 		}
+		if (a->out_ch == 2) chan_convert(f, MSB200_CHAN_MONO_TO_STEREO, (int)(in_bytes / 2), (const int16_t *)im->b_rptr, NULL, in_bytes * 2);
+		else chan_convert(f, MSB200_CHAN_STEREO_TO_MONO, (int)(in_bytes / 4), (const int16_t *)im->b_rptr, NULL, in_bytes / 2);
+		freemsg(im);
 	}
 }
-static int adapt_set_sr(MSFilter *f, void *data) {
-	((AdaptState *)f->data)->sample_rate = *(int *)data;
+static int chanm_set_hz(MSFilter *f, void *arg) {
+	((ChanAdapter *)f->data)->hz = *(int *)arg;
 	return 0;
 }
-static int adapt_get_sr(MSFilter *f, void *data) {
-	*(int *)data = ((AdaptState *)f->data)->sample_rate;
+static int chanm_get_hz(MSFilter *f, void *arg) {
+	*(int *)arg = ((ChanAdapter *)f->data)->hz;
 	return 0;
 }
-static int adapt_set_nchannels(MSFilter *f, void *data) {
-	((AdaptState *)f->data)->inputchans = *(int *)data;
+static int chanm_set_in(MSFilter *f, void *arg) {
+	((ChanAdapter *)f->data)->in_ch = *(int *)arg;
 	return 0;
 }
-static int adapt_get_nchannels(MSFilter *f, void *data) {
-	*(int *)data = ((AdaptState *)f->data)->inputchans;
+static int chanm_get_in(MSFilter *f, void *arg) {
+	*(int *)arg = ((ChanAdapter *)f->data)->in_ch;
 	return 0;
 }
-static int adapt_set_out_nchannels(MSFilter *f, void *data) {
-	((AdaptState *)f->data)->outputchans = *(int *)data;
+static int chanm_set_out(MSFilter *f, void *arg) {
+	((ChanAdapter *)f->data)->out_ch = *(int *)arg;
 	return 0;
 }
-static int adapt_get_out_nchannels(MSFilter *f, void *data) {
-	*(int *)data = ((AdaptState *)f->data)->outputchans;
+static int chanm_get_out(MSFilter *f, void *arg) {
+	*(int *)arg = ((ChanAdapter *)f->data)->out_ch;
 	return 0;
 }
-static MSFilterMethod adapt_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, adapt_set_sr},
-                                         {MS_FILTER_GET_SAMPLE_RATE, adapt_get_sr},
-                                         {MS_FILTER_SET_NCHANNELS, adapt_set_nchannels},
-                                         {MS_FILTER_GET_NCHANNELS, adapt_get_nchannels},
-                                         {MS_CHANNEL_ADAPTER_SET_OUTPUT_NCHANNELS, adapt_set_out_nchannels},
-                                         {MS_CHANNEL_ADAPTER_GET_OUTPUT_NCHANNELS, adapt_get_out_nchannels},
-                                         {0, NULL}};
+static MSFilterMethod chan_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, chanm_set_hz},
+                                        {MS_FILTER_GET_SAMPLE_RATE, chanm_get_hz},
+                                        {MS_FILTER_SET_NCHANNELS, chanm_set_in},
+                                        {MS_FILTER_GET_NCHANNELS, chanm_get_in},
+                                        {MS_CHANNEL_ADAPTER_SET_OUTPUT_NCHANNELS, chanm_set_out},
+                                        {MS_CHANNEL_ADAPTER_GET_OUTPUT_NCHANNELS, chanm_get_out},
+                                        {0, NULL}};
 static MSFilterDesc b200_channel_adapter_desc = {.id = MS_CHANNEL_ADAPTER_ID,
                                                  .name = "MSChannelAdapter",
                                                  .text = "B200: mono/stereo channel adaptation (libmsb200dsp)",
                                                  .category = MS_FILTER_OTHER,
                                                  .ninputs = 2,
                                                  .noutputs = 1,
-                                                 .init = adapt_init,
-                                                 .preprocess = adapt_preprocess,
-                                                 .process = adapt_process,
-                                                 .postprocess = adapt_postprocess,
-                                                 .uninit = adapt_uninit,
-                                                 .methods = adapt_methods,
+                                                 .init = chan_new,
+                                                 .preprocess = chan_attach,
+                                                 .process = chan_tick,
+                                                 .postprocess = chan_detach,
+                                                 .uninit = chan_free,
+                                                 .methods = chan_methods,
                                                  .flags = MS_FILTER_IS_PUMP};
 
 /* ================================================================================================ MSEqualizer
@@ -1544,240 +1585,251 @@ static MSFilterDesc b200_resample_desc = {.id = MS_RESAMPLE_ID,
 /* ================================================================================================ MSSpeexEC
  * host logic restated from /root/reference/src/audiofilters/speexec.c:171-216 (configuration), :223-305 (process:
  * reference/echo bufferizers, silence injection on underrun), :308-391 (methods) */
-typedef struct EcState {
-	msb200_aec *bank;
-	MSBufferizer delayed_ref;
-	MSFlowControlledBufferizer ref;
-	MSBufferizer echo;
-	int framesize, framesize_at_8000, samplerate, delay_ms, tail_length_ms, nominal_ref_samples;
-	char *state_str;
-	bool_t echostarted, bypass_mode, using_zeroes;
+typedef struct EchoCanceller {
+	msb200_aec *bank;             /* synchronous mode: a 1-stream bank of its own */
+	MSBufferizer far_for_filter;  /* far-end audio as the adaptive filter sees it: behind the playback by `delay_ms` */
+	MSFlowControlledBufferizer far_for_playback; /* the same audio on its way to the loudspeaker pin */
+	MSBufferizer near;            /* microphone */
+	int frame, frame_at_8k, hz, delay_ms, tail_ms, delay_samples;
+	char *saved_state;
+	bool_t mic_seen, bypass, far_starved;
 	Batch *batch; /* lockstep batch group (MSB200_BATCH): frames are staged here and cancelled one tick later */
 	int slot;
-	MSQueue pend; /* cancelled frames waiting for this filter's next process() */
-} EcState;
+	MSQueue cleaned; /* cancelled frames waiting for this filter's next process() */
+} EchoCanceller;
 #define EC_BATCH_MAX_FRAMES 4 /* frames one stream may stage per tick (10 ms at 48 kHz = 1.875 frames of 256) */
-static void ec_configure_fcb(EcState *s) {
-	ms_flow_controlled_bufferizer_set_samplerate(&s->ref, s->samplerate);
-	ms_flow_controlled_bufferizer_set_max_size_ms(&s->ref, s->delay_ms);
-	ms_flow_controlled_bufferizer_set_granularity_ms(&s->ref, (s->framesize * 1000) / s->samplerate);
+
+static void ec_tune_playback_fifo(EchoCanceller *e) { /* speexec.c:182-186 */
+	ms_flow_controlled_bufferizer_set_samplerate(&e->far_for_playback, e->hz);
+	ms_flow_controlled_bufferizer_set_max_size_ms(&e->far_for_playback, e->delay_ms);
+	ms_flow_controlled_bufferizer_set_granularity_ms(&e->far_for_playback, (e->frame * 1000) / e->hz);
 }
-static void ec_init(MSFilter *f) {
-	EcState *s = ms_new0(EcState, 1);
-	s->samplerate = 8000;
-	ms_bufferizer_init(&s->delayed_ref);
-	ms_bufferizer_init(&s->echo);
-	ms_flow_controlled_bufferizer_init(&s->ref, f, s->samplerate, 1);
-	s->delay_ms = 0;
-	s->tail_length_ms = 250;
-	s->framesize_at_8000 = 64;
-	s->framesize = 64;
-	ms_queue_init(&s->pend);
-	f->data = s;
+static void ec_new(MSFilter *f) {
+	EchoCanceller *e = ms_new0(EchoCanceller, 1);
+	e->hz = 8000; /* defaults of speex_ec_init, speexec.c:72-91 */
+	e->tail_ms = 250;
+	e->frame = e->frame_at_8k = 64;
+	ms_bufferizer_init(&e->far_for_filter);
+	ms_bufferizer_init(&e->near);
+	ms_flow_controlled_bufferizer_init(&e->far_for_playback, f, e->hz, 1);
+	ms_queue_init(&e->cleaned);
+	f->data = e;
 }
-static void ec_collect(void *owner, Batch *b) { /* the slot's cancelled frames: arena -> one mblk per frame */
-	EcState *s = (EcState *)owner;
-	const int nbytes = s->framesize * 2;
+static void ec_free(MSFilter *f) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	ms_queue_flush(&e->cleaned);
+	if (e->saved_state) ms_free(e->saved_state);
+	ms_bufferizer_uninit(&e->far_for_filter);
+	ms_bufferizer_uninit(&e->near);
+	ms_flow_controlled_bufferizer_uninit(&e->far_for_playback);
+	ms_free(e);
+}
+static mblk_t *ec_frame_block(const EchoCanceller *e) { /* an empty block with room for one frame */
+	return allocb((size_t)e->frame * 2, 0);
+}
+/* batch mode: this slot's cancelled frames move from the group's arena into blocks of their own */
+static void ec_collect(void *owner, Batch *b) {
+	EchoCanceller *e = (EchoCanceller *)owner;
 	int u;
-	for (u = 0; u < b->ready[s->slot]; ++u) {
-		mblk_t *oecho = allocb((size_t)nbytes, 0);
-		memcpy(oecho->b_wptr, b->out + ((size_t)s->slot * b->max_units + u) * b->unit_out, (size_t)nbytes);
-		oecho->b_wptr += nbytes;
-		ms_queue_put(&s->pend, oecho);
+	for (u = 0; u < b->ready[e->slot]; ++u) {
+		mblk_t *m = ec_frame_block(e);
+		memcpy(m->b_wptr, b->out + ((size_t)e->slot * b->max_units + u) * b->unit_out, (size_t)e->frame * 2);
+		m->b_wptr += e->frame * 2;
+		ms_queue_put(&e->cleaned, m);
 	}
-	b->ready[s->slot] = 0;
+	b->ready[e->slot] = 0;
 }
-static void ec_uninit(MSFilter *f) {
-	EcState *s = (EcState *)f->data;
-	ms_queue_flush(&s->pend);
-	if (s->state_str) ms_free(s->state_str);
-	ms_bufferizer_uninit(&s->delayed_ref);
-	ms_bufferizer_uninit(&s->echo);
-	ms_flow_controlled_bufferizer_uninit(&s->ref);
-	ms_free(s);
-}
-static void ec_preprocess(MSFilter *f) {
-	EcState *s = (EcState *)f->data;
-	int delay_samples;
-	mblk_t *m;
-	s->echostarted = FALSE;
-	s->framesize = msb200_aec_frame_size_for_rate(s->samplerate, s->framesize_at_8000);
-	delay_samples = s->delay_ms * s->samplerate / 1000;
-	ms_message("Initializing B200 echo canceler with framesize=%i, filterlength=%i, delay_samples=%i", s->framesize,
-	           (s->tail_length_ms * s->samplerate) / 1000, delay_samples);
+static void ec_attach(MSFilter *f) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	mblk_t *lead;
+	e->mic_seen = FALSE;
+	e->frame = msb200_aec_frame_size_for_rate(e->hz, e->frame_at_8k);
+	e->delay_samples = e->delay_ms * e->hz / 1000;
+	ms_message("MSSpeexEC(B200): frame %i, filter %i taps, filter path %i samples behind the playback", e->frame,
+	           (e->tail_ms * e->hz) / 1000, e->delay_samples);
 	if (batch_capacity() > 0) {
-		const int key[4] = {s->samplerate, s->tail_length_ms, s->framesize_at_8000, 0};
-		s->batch = batch_join(BK_EC, f->ticker, key, s->framesize, s->framesize, EC_BATCH_MAX_FRAMES, s, ec_collect, &s->slot);
-		if (s->batch) {
-			GRP_LOCK(s->batch);
-			msb200_ctx_make_current(s->batch->ctx);
-			msb200_aec_reset((msb200_aec *)s->batch->bank, s->slot);
-			GRP_UNLOCK(s->batch);
+		const int key[4] = {e->hz, e->tail_ms, e->frame_at_8k, 0};
+		e->batch = batch_join(BK_EC, f->ticker, key, e->frame, e->frame, EC_BATCH_MAX_FRAMES, e, ec_collect, &e->slot);
+		if (e->batch) {
+			GRP_LOCK(e->batch);
+			msb200_ctx_make_current(e->batch->ctx);
+			msb200_aec_reset((msb200_aec *)e->batch->bank, e->slot);
+			GRP_UNLOCK(e->batch);
 		}
 	}
-	DSP_LOCK();
-	if (!s->batch && dsp_ctx())
-		DSP_CHECK(msb200_aec_create(g_ctx, 1, s->samplerate, s->tail_length_ms, s->framesize_at_8000, &s->bank), "aec_create");
-	DSP_UNLOCK();
-	m = allocb((size_t)delay_samples * 2, 0);
-	m->b_wptr += delay_samples * 2;
-	ms_bufferizer_put(&s->delayed_ref, m);
-	s->nominal_ref_samples = delay_samples;
-	ec_configure_fcb(s);
-}
-static void ec_postprocess(MSFilter *f) {
-	EcState *s = (EcState *)f->data;
-	ms_bufferizer_flush(&s->delayed_ref);
-	ms_bufferizer_flush(&s->echo);
-	ms_flow_controlled_bufferizer_flush(&s->ref);
-	if (s->batch) batch_leave(s->batch, s->slot);
-	s->batch = NULL;
-	DSP_LOCK();
-	msb200_aec_destroy(s->bank);
-	DSP_UNLOCK();
-	s->bank = NULL;
-}
-static void ec_process(MSFilter *f) {
-	EcState *s = (EcState *)f->data;
-	int nbytes = s->framesize * 2;
-	mblk_t *refm;
-	uint8_t *ref, *echo;
-	if (s->batch) { /* frames staged during the previous tick were cancelled by the group's launch: emit ours */
-		batch_tick(s->batch, f->ticker->ticks);
-		if (s->batch->staged[s->slot] == 0) ec_collect(s, s->batch);
+	if (!e->batch) {
+		DSP_LOCK();
+		if (dsp_ctx()) DSP_CHECK(msb200_aec_create(g_ctx, 1, e->hz, e->tail_ms, e->frame_at_8k, &e->bank), "aec_create");
+		DSP_UNLOCK();
 	}
-	while ((refm = ms_queue_get(&s->pend)) != NULL)
-		ms_queue_put(f->outputs[1], refm);
-	if (s->bypass_mode) {
-		while ((refm = ms_queue_get(f->inputs[0])) != NULL)
-			ms_queue_put(f->outputs[0], refm);
-		while ((refm = ms_queue_get(f->inputs[1])) != NULL)
-			ms_queue_put(f->outputs[1], refm);
+	/* the filter path starts `delay_samples` of silence behind the playback path (speexec.c:205-213) */
+	lead = allocb((size_t)e->delay_samples * 2, 0);
+	lead->b_wptr += e->delay_samples * 2;
+	ms_bufferizer_put(&e->far_for_filter, lead);
+	ec_tune_playback_fifo(e);
+}
+static void ec_detach(MSFilter *f) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	ms_bufferizer_flush(&e->far_for_filter);
+	ms_bufferizer_flush(&e->near);
+	ms_flow_controlled_bufferizer_flush(&e->far_for_playback);
+	if (e->batch) batch_leave(e->batch, e->slot);
+	e->batch = NULL;
+	DSP_LOCK();
+	msb200_aec_destroy(e->bank);
+	DSP_UNLOCK();
+	e->bank = NULL;
+}
+/* far-end packets: once the microphone runs, every packet feeds both paths; before that there is nothing to line them up
+ * with and they are dropped (speexec.c:239-250) */
+static void ec_take_far_end(MSFilter *f, EchoCanceller *e) {
+	mblk_t *m;
+	if (f->inputs[0] == NULL) return;
+	if (!e->mic_seen) {
+		if (!ms_queue_empty(f->inputs[0])) ms_warning("MSSpeexEC(B200): far-end audio before any microphone audio, dropped");
+		ms_queue_flush(f->inputs[0]);
 		return;
 	}
-	if (f->inputs[0] != NULL) {
-		if (s->echostarted) {
-			while ((refm = ms_queue_get(f->inputs[0])) != NULL) {
-				mblk_t *cp = dupmsg(refm);
-				ms_bufferizer_put(&s->delayed_ref, cp);
-				ms_flow_controlled_bufferizer_put(&s->ref, refm);
-			}
-		} else {
-			ms_warning("Getting reference signal but no echo to synchronize on.");
-			ms_queue_flush(f->inputs[0]);
-		}
+	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+		ms_bufferizer_put(&e->far_for_filter, dupmsg(m));
+		ms_flow_controlled_bufferizer_put(&e->far_for_playback, m);
 	}
-	ms_bufferizer_put_from_queue(&s->echo, f->inputs[1]);
-	ref = (uint8_t *)alloca((size_t)nbytes);
-	echo = (uint8_t *)alloca((size_t)nbytes);
-	while ((int)ms_bufferizer_read(&s->echo, echo, (size_t)nbytes) == nbytes) {
-		mblk_t *oecho = allocb((size_t)nbytes, 0);
-		if (!s->echostarted) s->echostarted = TRUE;
-		if ((int)ms_bufferizer_get_avail(&s->delayed_ref) < ((s->nominal_ref_samples * 2) + nbytes)) {
-			refm = allocb((size_t)nbytes, 0);
-			memset(refm->b_wptr, 0, (size_t)nbytes);
-			refm->b_wptr += nbytes;
-			ms_bufferizer_put(&s->delayed_ref, refm);
-			ms_queue_put(f->outputs[0], dupmsg(refm));
-			if (!s->using_zeroes) {
-				ms_warning("Not enough ref samples, using zeroes");
-				s->using_zeroes = TRUE;
-			}
-		} else {
-			if (s->using_zeroes) {
-				ms_message("Samples are back.");
-				s->using_zeroes = FALSE;
-			}
-			refm = allocb((size_t)nbytes, 0);
-			if (ms_flow_controlled_bufferizer_read(&s->ref, refm->b_wptr, (size_t)nbytes) == 0) ms_fatal("Should never happen");
-			refm->b_wptr += nbytes;
-			ms_queue_put(f->outputs[0], refm);
+}
+/* One frame for the loudspeaker pin, and the guarantee that the filter path holds this frame too. When the far end
+ * starves (less than delay + one frame buffered for the filter) a frame of silence is played AND appended to the filter
+ * path, so that both stay aligned (speexec.c:261-285). */
+static void ec_play_one_frame(MSFilter *f, EchoCanceller *e) {
+	const size_t bytes = (size_t)e->frame * 2;
+	mblk_t *spk = ec_frame_block(e);
+	const bool_t starving = ms_bufferizer_get_avail(&e->far_for_filter) < (size_t)e->delay_samples * 2 + bytes;
+	if (starving) {
+		memset(spk->b_wptr, 0, bytes);
+		spk->b_wptr += bytes;
+		ms_bufferizer_put(&e->far_for_filter, dupmsg(spk));
+	} else {
+		if (ms_flow_controlled_bufferizer_read(&e->far_for_playback, spk->b_wptr, bytes) == 0)
+			ms_fatal("MSSpeexEC(B200): playback path shorter than the filter path");
+		spk->b_wptr += bytes;
+	}
+	if (starving != e->far_starved) {
+		if (starving) ms_warning("MSSpeexEC(B200): far end starving, playing silence");
+		else ms_message("MSSpeexEC(B200): far end is back");
+		e->far_starved = starving;
+	}
+	ms_queue_put(f->outputs[0], spk);
+}
+/* the (microphone, reference) pair of one frame goes to the canceller: at once in synchronous mode, into the group's arena
+ * in batch mode (cancelled by the group's launch at the start of the next tick) */
+static void ec_cancel_frame(MSFilter *f, EchoCanceller *e, const int16_t *mic, const int16_t *ref) {
+	const size_t bytes = (size_t)e->frame * 2;
+	if (e->batch) {
+		Batch *b = e->batch;
+		const int u = b->staged[e->slot];
+		if (u >= b->max_units) {
+			ms_warning("MSSpeexEC(B200): more than %d frames in one tick, frame dropped", b->max_units);
+			return;
 		}
-		if (ms_bufferizer_read(&s->delayed_ref, ref, (size_t)nbytes) == 0) ms_fatal("Should never happen");
-		if (s->batch) { /* stage the (mic, delayed reference) frame pair; it is cancelled at the start of the next tick */
-			Batch *b = s->batch;
-			const int u = b->staged[s->slot];
-			freemsg(oecho);
-			if (u < b->max_units) {
-				const size_t off = ((size_t)s->slot * b->max_units + u) * b->unit_in;
-				memcpy(b->in[0] + off, echo, (size_t)nbytes);
-				memcpy(b->in[1] + off, ref, (size_t)nbytes);
-				b->staged[s->slot] = u + 1;
-			} else {
-				ms_warning("MSSpeexEC(b200): more than %d frames in one tick, frame dropped", b->max_units);
-			}
-			continue;
-		}
-		/* speex_echo_cancellation + speex_preprocess_run for this frame, on the GPU */
+		memcpy(b->in[0] + ((size_t)e->slot * b->max_units + u) * b->unit_in, mic, bytes);
+		memcpy(b->in[1] + ((size_t)e->slot * b->max_units + u) * b->unit_in, ref, bytes);
+		b->staged[e->slot] = u + 1;
+		return;
+	}
+	if (e->bank) {
+		mblk_t *clean = ec_frame_block(e);
 		DSP_LOCK();
-		if (s->bank) DSP_CHECK(msb200_aec_process(s->bank, (int16_t *)echo, (int16_t *)ref, (int16_t *)oecho->b_wptr, 1), "aec_process");
+		DSP_CHECK(msb200_aec_process(e->bank, mic, ref, (int16_t *)clean->b_wptr, 1), "aec_process");
 		DSP_UNLOCK();
-		if (!s->bank) {
-			freemsg(oecho);
-			continue;
-		}
-		oecho->b_wptr += nbytes;
-		ms_queue_put(f->outputs[1], oecho);
+		clean->b_wptr += bytes;
+		ms_queue_put(f->outputs[1], clean);
 	}
 }
-static int ec_set_sr(MSFilter *f, void *arg) {
-	EcState *s = (EcState *)f->data;
-	s->samplerate = *(int *)arg;
-	ec_configure_fcb(s);
+static void ec_tick(MSFilter *f) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	const size_t bytes = (size_t)e->frame * 2;
+	int16_t *mic, *ref;
+	mblk_t *m;
+	if (e->batch) { /* frames staged during the previous tick were cancelled by the group's launch: emit ours */
+		batch_tick(e->batch, f->ticker->ticks);
+		if (e->batch->staged[e->slot] == 0) ec_collect(e, e->batch);
+	}
+	while ((m = ms_queue_get(&e->cleaned)) != NULL) ms_queue_put(f->outputs[1], m);
+	if (e->bypass) { /* both pins straight through (speexec.c:229-237) */
+		int pin;
+		for (pin = 0; pin < 2; ++pin)
+			while ((m = ms_queue_get(f->inputs[pin])) != NULL) ms_queue_put(f->outputs[pin], m);
+		return;
+	}
+	ec_take_far_end(f, e);
+	ms_bufferizer_put_from_queue(&e->near, f->inputs[1]);
+	mic = (int16_t *)alloca(bytes);
+	ref = (int16_t *)alloca(bytes);
+	while (ms_bufferizer_read(&e->near, (uint8_t *)mic, bytes) == bytes) {
+		e->mic_seen = TRUE;
+		ec_play_one_frame(f, e);
+		if (ms_bufferizer_read(&e->far_for_filter, (uint8_t *)ref, bytes) == 0)
+			ms_fatal("MSSpeexEC(B200): filter path empty after it was topped up");
+		ec_cancel_frame(f, e, mic, ref);
+	}
+}
+/* ---- methods (speexec.c:320-391) */
+static int ecm_set_hz(MSFilter *f, void *arg) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	e->hz = *(int *)arg;
+	ec_tune_playback_fifo(e);
 	return 0;
 }
-static int ec_get_sr(MSFilter *f, void *arg) {
-	*(int *)arg = ((EcState *)f->data)->samplerate;
+static int ecm_get_hz(MSFilter *f, void *arg) {
+	*(int *)arg = ((EchoCanceller *)f->data)->hz;
 	return 0;
 }
-static int ec_set_framesize(MSFilter *f, void *arg) {
-	((EcState *)f->data)->framesize_at_8000 = *(int *)arg;
+static int ecm_set_frame(MSFilter *f, void *arg) {
+	((EchoCanceller *)f->data)->frame_at_8k = *(int *)arg;
 	return 0;
 }
-static int ec_set_delay(MSFilter *f, void *arg) {
-	EcState *s = (EcState *)f->data;
-	s->delay_ms = *(int *)arg;
-	ec_configure_fcb(s);
+static int ecm_set_delay(MSFilter *f, void *arg) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	e->delay_ms = *(int *)arg;
+	ec_tune_playback_fifo(e);
 	return 0;
 }
-static int ec_get_delay(MSFilter *f, void *arg) {
-	*(int *)arg = ((EcState *)f->data)->delay_ms;
+static int ecm_get_delay(MSFilter *f, void *arg) {
+	*(int *)arg = ((EchoCanceller *)f->data)->delay_ms;
 	return 0;
 }
-static int ec_set_tail_length(MSFilter *f, void *arg) {
-	EcState *s = (EcState *)f->data;
-	s->tail_length_ms = *(int *)arg;
-	ec_configure_fcb(s);
+static int ecm_set_tail(MSFilter *f, void *arg) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	e->tail_ms = *(int *)arg;
+	ec_tune_playback_fifo(e);
 	return 0;
 }
-static int ec_set_bypass(MSFilter *f, void *arg) {
-	((EcState *)f->data)->bypass_mode = *(bool_t *)arg;
+static int ecm_set_bypass(MSFilter *f, void *arg) {
+	((EchoCanceller *)f->data)->bypass = *(bool_t *)arg;
 	return 0;
 }
-static int ec_get_bypass(MSFilter *f, void *arg) {
-	*(bool_t *)arg = ((EcState *)f->data)->bypass_mode;
+static int ecm_get_bypass(MSFilter *f, void *arg) {
+	*(bool_t *)arg = ((EchoCanceller *)f->data)->bypass;
 	return 0;
 }
-static int ec_set_state(MSFilter *f, void *arg) {
-	EcState *s = (EcState *)f->data;
-	if (s->state_str) ms_free(s->state_str);
-	s->state_str = ms_strdup((const char *)arg);
+static int ecm_set_state(MSFilter *f, void *arg) {
+	EchoCanceller *e = (EchoCanceller *)f->data;
+	if (e->saved_state) ms_free(e->saved_state);
+	e->saved_state = ms_strdup((const char *)arg);
 	return 0;
 }
-static int ec_get_state(MSFilter *f, void *arg) {
-	*(char **)arg = ((EcState *)f->data)->state_str;
+static int ecm_get_state(MSFilter *f, void *arg) {
+	*(char **)arg = ((EchoCanceller *)f->data)->saved_state;
 	return 0;
 }
-static MSFilterMethod ec_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, ec_set_sr},
-                                      {MS_FILTER_GET_SAMPLE_RATE, ec_get_sr},
-                                      {MS_ECHO_CANCELLER_SET_TAIL_LENGTH, ec_set_tail_length},
-                                      {MS_ECHO_CANCELLER_SET_DELAY, ec_set_delay},
-                                      {MS_ECHO_CANCELLER_SET_FRAMESIZE, ec_set_framesize},
-                                      {MS_ECHO_CANCELLER_SET_BYPASS_MODE, ec_set_bypass},
-                                      {MS_ECHO_CANCELLER_GET_BYPASS_MODE, ec_get_bypass},
-                                      {MS_ECHO_CANCELLER_GET_STATE_STRING, ec_get_state},
-                                      {MS_ECHO_CANCELLER_SET_STATE_STRING, ec_set_state},
-                                      {MS_ECHO_CANCELLER_GET_DELAY, ec_get_delay},
+static MSFilterMethod ec_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, ecm_set_hz},
+                                      {MS_FILTER_GET_SAMPLE_RATE, ecm_get_hz},
+                                      {MS_ECHO_CANCELLER_SET_TAIL_LENGTH, ecm_set_tail},
+                                      {MS_ECHO_CANCELLER_SET_DELAY, ecm_set_delay},
+                                      {MS_ECHO_CANCELLER_SET_FRAMESIZE, ecm_set_frame},
+                                      {MS_ECHO_CANCELLER_SET_BYPASS_MODE, ecm_set_bypass},
+                                      {MS_ECHO_CANCELLER_GET_BYPASS_MODE, ecm_get_bypass},
+                                      {MS_ECHO_CANCELLER_GET_STATE_STRING, ecm_get_state},
+                                      {MS_ECHO_CANCELLER_SET_STATE_STRING, ecm_set_state},
+                                      {MS_ECHO_CANCELLER_GET_DELAY, ecm_get_delay},
                                       {0, NULL}};
 static MSFilterDesc b200_speex_ec_desc = {.id = MS_SPEEX_EC_ID,
                                           .name = "MSSpeexEC",
@@ -1785,11 +1837,11 @@ static MSFilterDesc b200_speex_ec_desc = {.id = MS_SPEEX_EC_ID,
                                           .category = MS_FILTER_OTHER,
                                           .ninputs = 2,
                                           .noutputs = 2,
-                                          .init = ec_init,
-                                          .preprocess = ec_preprocess,
-                                          .process = ec_process,
-                                          .postprocess = ec_postprocess,
-                                          .uninit = ec_uninit,
+                                          .init = ec_new,
+                                          .preprocess = ec_attach,
+                                          .process = ec_tick,
+                                          .postprocess = ec_detach,
+                                          .uninit = ec_free,
                                           .methods = ec_methods};
 
 /* ================================================================================================ G.711 codecs
