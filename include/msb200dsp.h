@@ -351,6 +351,48 @@ MSB200_API int msb200_g711_encode(msb200_ctx *ctx, int law, const int16_t *pcm, 
 MSB200_API int msb200_g711_decode_dev(msb200_ctx *ctx, int law, const void *d_code, void *d_pcm, size_t n);
 MSB200_API int msb200_g711_encode_dev(msb200_ctx *ctx, int law, const void *d_pcm, void *d_code, size_t n);
 
+/* ---------------------------------------------------------------------------------------------------- RTP payload hand-off
+ * The caller side of the audio path in a media server: what MSRtpRecv does to every received packet before
+ * the decoder sees it — header fields into the block's meta data, b_rptr advanced to the payload
+ * (/root/reference/src/otherfilters/msrtp.c:1050-1092) — and what MSRtpSend does to every block the encoder emits — a
+ * header in front (:617-705) — for ALL streams of a ticker at once, fused with the G.711 banks: packets in, PCM out (or
+ * left in HBM for the next bank), and PCM in, packets out. One payload copy per packet (into / out of a pinned arena),
+ * one launch per direction per tick. Sockets, jitter buffer, RTCP, SRTP stay the host's (oRTP's). RFC 3550 §5.1 / §5.3.1. */
+typedef struct msb200_rtp_meta { /* what receiver_process copies from the RTP header into the mblk_t (:1078-1080) */
+	uint32_t timestamp;  /* mblk_set_timestamp_info(m, rtp_get_timestamp(m)) */
+	uint32_t ssrc;
+	int32_t payload_len; /* bytes; 0 = nothing for this stream in this tick */
+	uint16_t seq;        /* mblk_set_cseq(m, rtp_get_seqnumber(m)) */
+	uint8_t marker;      /* mblk_set_marker_info(m, rtp_get_markbit(m)) */
+	uint8_t payload_type;
+} msb200_rtp_meta;
+/* header of one packet: fills *meta, *payload_offset = first payload byte (rtp_get_payload); CSRC list, header extension
+ * and padding are skipped; MSB200_EINVAL for anything that is not a well-formed version 2 packet. Host only. */
+MSB200_API int msb200_rtp_parse(const uint8_t *packet, size_t len, msb200_rtp_meta *meta, size_t *payload_offset);
+typedef struct msb200_rtp_rx msb200_rtp_rx;
+MSB200_API int msb200_rtp_rx_create(msb200_ctx *ctx, int n_streams, int law, int max_payload, msb200_rtp_rx **out);
+MSB200_API void msb200_rtp_rx_destroy(msb200_rtp_rx *r);
+MSB200_API int msb200_rtp_rx_row_samples(const msb200_rtp_rx *r); /* samples per stream row of the PCM output (>= max_payload) */
+MSB200_API int msb200_rtp_rx_begin_tick(msb200_rtp_rx *r);
+/* returns the payload length taken (0: empty payload or another payload type than expected_pt >= 0), < 0 on error */
+MSB200_API int msb200_rtp_rx_push(msb200_rtp_rx *r, int stream, const uint8_t *packet, size_t len, int expected_pt);
+MSB200_API int msb200_rtp_rx_push_payload(msb200_rtp_rx *r, int stream, const uint8_t *payload, int len, const msb200_rtp_meta *meta);
+/* pcm: host [n_streams][row_samples] s16, the first meta[s].payload_len samples of a row are stream s's decoded packet */
+MSB200_API int msb200_rtp_rx_decode(msb200_rtp_rx *r, int16_t *pcm, msb200_rtp_meta *meta);
+MSB200_API int msb200_rtp_rx_decode_dev(msb200_rtp_rx *r, void **d_pcm, const msb200_rtp_meta **meta);
+typedef struct msb200_rtp_tx msb200_rtp_tx;
+MSB200_API int msb200_rtp_tx_create(msb200_ctx *ctx, int n_streams, int law, int samples_per_packet, msb200_rtp_tx **out);
+MSB200_API void msb200_rtp_tx_destroy(msb200_rtp_tx *t);
+MSB200_API int msb200_rtp_tx_set_stream(msb200_rtp_tx *t, int stream, uint32_t ssrc, int payload_type, uint16_t next_seq,
+                                        uint32_t next_ts);
+MSB200_API size_t msb200_rtp_tx_packet_bytes(const msb200_rtp_tx *t); /* 12 + samples_per_packet */
+/* pcm [n_streams][samples_per_packet] -> *packets = pinned arena [n_streams][packet_bytes], valid until the next call.
+ * marker / send: NULL or [n_streams] flags; a stream with send[s] == 0 keeps its sequence number and timestamp. */
+MSB200_API int msb200_rtp_tx_encode(msb200_rtp_tx *t, const int16_t *pcm, const uint8_t *marker, const uint8_t *send,
+                                    const uint8_t **packets);
+MSB200_API int msb200_rtp_tx_encode_dev(msb200_rtp_tx *t, const void *d_pcm, const uint8_t *marker, const uint8_t *send,
+                                        const uint8_t **packets);
+
 /* ---------------------------------------------------------------------------------------------------- audio chain
  * The BASELINE cfg2 pipeline as one resident device-side graph, one call per 10 ms tick for `n_streams` streams:
  *   ref  [in_rate] -> MSResample -> \

@@ -50,6 +50,11 @@ class YuvLayout(C.Structure):
                 ("frame_bytes", C.c_size_t)]
 
 
+class RtpMeta(C.Structure):
+    _fields_ = [("timestamp", C.c_uint32), ("ssrc", C.c_uint32), ("payload_len", C.c_int32), ("seq", C.c_uint16),
+                ("marker", C.c_uint8), ("payload_type", C.c_uint8)]
+
+
 class ChainParams(C.Structure):
     _fields_ = [("n_streams", C.c_int32), ("in_rate", C.c_int32), ("rate", C.c_int32), ("tail_length_ms", C.c_int32),
                 ("framesize_at_8000", C.c_int32), ("volume_gain", C.c_float), ("mixer_pins", C.c_int32),
@@ -189,6 +194,21 @@ _SIGS = {
     "msb200_aec_get_state_blob": (_I, [_P, _I, _P, _SZ]),
     "msb200_aec_set_state_blob": (_I, [_P, _I, _P, _SZ]),
     "msb200_aec_probe": (_I, [_P, _I, C.c_char_p, _P, _I]),
+    "msb200_rtp_parse": (_I, [_P, _SZ, C.POINTER(RtpMeta), C.POINTER(C.c_size_t)]),
+    "msb200_rtp_rx_create": (_I, [_P, _I, _I, _I, _PP]),
+    "msb200_rtp_rx_destroy": (None, [_P]),
+    "msb200_rtp_rx_row_samples": (_I, [_P]),
+    "msb200_rtp_rx_begin_tick": (_I, [_P]),
+    "msb200_rtp_rx_push": (_I, [_P, _I, _P, _SZ, _I]),
+    "msb200_rtp_rx_push_payload": (_I, [_P, _I, _P, _I, C.POINTER(RtpMeta)]),
+    "msb200_rtp_rx_decode": (_I, [_P, _P, _P]),
+    "msb200_rtp_rx_decode_dev": (_I, [_P, _PP, _PP]),
+    "msb200_rtp_tx_create": (_I, [_P, _I, _I, _I, _PP]),
+    "msb200_rtp_tx_destroy": (None, [_P]),
+    "msb200_rtp_tx_set_stream": (_I, [_P, _I, C.c_uint32, _I, C.c_uint16, C.c_uint32]),
+    "msb200_rtp_tx_packet_bytes": (_SZ, [_P]),
+    "msb200_rtp_tx_encode": (_I, [_P, _P, _P, _P, _PP]),
+    "msb200_rtp_tx_encode_dev": (_I, [_P, _P, _P, _P, _PP]),
     "msb200_chain_create": (_I, [_P, C.POINTER(ChainParams), _PP]),
     "msb200_chain_destroy": (None, [_P]),
     "msb200_chain_next_out_samples": (_I, [_P]),
