@@ -560,7 +560,7 @@ static int mixpin_trim(MixPin *p, uint64_t now, int trim_above) {
 static void mixroom_tick(MSFilter *f) {
 	MixRoom *r = (MixRoom *)f->data;
 	const int words = r->tick_bytes / 2;
-	int k, talkers, talker = -1, heard = 0;
+	int k, talkers, talker = -1;
 	ms_filter_lock(f);
 	if (r->batch) { /* the group's previous tick was computed by the first mixer called in this tick: hand out this room's share */
 		batch_tick(r->batch, f->ticker->ticks);
@@ -588,14 +588,12 @@ static void mixroom_tick(MSFilter *f) {
 		int dropped;
 		if (f->inputs[k] == NULL) continue;
 		ms_bufferizer_put_from_queue(&p->fifo, f->inputs[k]);
-		if (ms_bufferizer_read(&p->fifo, (uint8_t *)(r->in + (size_t)k * words), (size_t)r->tick_bytes) != 0) r->present[k] = 1, ++heard;
+		if (ms_bufferizer_read(&p->fifo, (uint8_t *)(r->in + (size_t)k * words), (size_t)r->tick_bytes) != 0) r->present[k] = 1;
 		if ((dropped = mixpin_trim(p, f->ticker->time, r->trim_above)) > 0)
 			ms_warning("MSAudioMixer(B200): pin %d runs ahead, %d ms dropped", k, (dropped * 1000) / (2 * r->channels * r->hz));
 	}
-	if (heard == 0) { /* no pin had a whole tick: the reference emits nothing either (:318) */
-		ms_filter_unlock(f);
-		return;
-	}
+	/* a block goes out every tick while several pins count as talkers, even when none of them had a whole tick of samples
+	 * (silence then): the reference is built with ALWAYS_STREAMOUT (audiomixer.c:30, :315-317) */
 	if (r->batch) { /* staged: the group's launch at the start of the next tick mixes every room at once */
 		r->batch->staged[r->room] = 1;
 		ms_filter_unlock(f);
