@@ -513,6 +513,13 @@ MSB200_API int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const v
  * of frames staged in a pinned arena in, pinned arena slots lent to the output mblks out. */
 MSB200_API int msb200_scaler_process_frames(msb200_scaler *s, int n_frames, const uint8_t *const *src_frames,
                                             uint8_t *const *dst_frames);
+/* Vertical rounding of the scaled PLANAR output (MSSizeConv's I420 -> I420, row a8). libswscale has two: its C functions
+ * (what SWS_BITEXACT selects; the default here) and, on x86, the SIMD vertical scaler a plain SWS_BILINEAR call — the call
+ * the reference makes, src/voip/msvideo.c:660 — really runs, which differs by at most 1 (per-tap truncation in 16-bit
+ * lanes, a compensating rounder, the last two luma rows and the last chroma row by the C functions). on = 1 reproduces the
+ * x86 result bit for bit (pinned: the oracle's same mode equals the live library on random geometries). */
+MSB200_API int msb200_scaler_set_x86_vertical(msb200_scaler *s, int on);
+
 /* Mosaic / compositor (the reference's building blocks: ms_yuv_buf_copy_with_pix_strides src/voip/msvideo.c:
  * 245-270 places a picture in a region of a larger one, src/voip/layouts.c computes the rectangles): after set_canvas the
  * scaler writes frame k of a batch straight into rectangle tiles[k % n_tiles] of canvas k / n_tiles (I420, canvas_w x

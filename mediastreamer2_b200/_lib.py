@@ -233,6 +233,7 @@ _SIGS = {
     "msb200_scaler_process_dev": (_I, [_P, _I, _P, _P]),
     "msb200_scaler_process_frames": (_I, [_P, _I, _P, _P]),
     "msb200_scaler_set_canvas": (_I, [_P, _I, _I, _I, _P]),
+    "msb200_scaler_set_x86_vertical": (_I, [_P, _I]),
     "msb200_scaler_canvas_bytes": (_SZ, [_P]),
     "msb200_scaler_set_path": (_I, [_P, _I]),
     "msb200_scaler_get_schedule": (_I, [_P, _PI, _PI]),

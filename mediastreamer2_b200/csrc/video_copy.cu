@@ -100,6 +100,33 @@ __global__ void __launch_bounds__(256) yuv_copy_chroma_kernel(const CopyChroma P
 	}
 }
 
+// eight (a, b) pairs per thread: 8 + 8 planar bytes <-> 16 interleaved bytes, every access one aligned vector. The host
+// takes this path when exactly one side is interleaved, w % 8 == 0 and all pointers / strides keep the alignment.
+__global__ void __launch_bounds__(256) yuv_copy_chroma_vec_kernel(const CopyChroma P, int n_frames) {
+	const int wv = P.w >> 3;
+	const long per_frame = (long)wv * P.h, total = per_frame * n_frames;
+	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+		const int f = (int)(i / per_frame);
+		const int r = (int)(i - (long)f * per_frame);
+		const int y = r / wv, x = (r - y * wv) << 3;
+		const long so = (long)f * P.src_frame + (long)y * P.src_row, dof = (long)f * P.dst_frame + (long)y * P.dst_row;
+		if (P.semi_src) { // 16 interleaved bytes -> 8 + 8
+			const uint4 v = *reinterpret_cast<const uint4 *>(P.src_a + so + 2 * x);
+			uint2 a, b;
+			a.x = __byte_perm(v.x, v.y, 0x6420); b.x = __byte_perm(v.x, v.y, 0x7531);
+			a.y = __byte_perm(v.z, v.w, 0x6420); b.y = __byte_perm(v.z, v.w, 0x7531);
+			*reinterpret_cast<uint2 *>(P.dst_a + dof + x) = a;
+			*reinterpret_cast<uint2 *>(P.dst_b + dof + x) = b;
+		} else { // 8 + 8 -> 16 interleaved bytes
+			const uint2 a = *reinterpret_cast<const uint2 *>(P.src_a + so + x), b = *reinterpret_cast<const uint2 *>(P.src_b + so + x);
+			uint4 v;
+			v.x = __byte_perm(a.x, b.x, 0x5140); v.y = __byte_perm(a.x, b.x, 0x7362);
+			v.z = __byte_perm(a.y, b.y, 0x5140); v.w = __byte_perm(a.y, b.y, 0x7362);
+			*reinterpret_cast<uint4 *>(P.dst_a + dof + 2 * x) = v;
+		}
+	}
+}
+
 static int grid_for(msb200_ctx *ctx, long items) {
 	long g = (items + 255) / 256;
 	const long cap = (long)ctx->sm_count * 8;
@@ -168,7 +195,14 @@ static int copy_launch(msb200_ctx *ctx, int n_frames, const unsigned char *src, 
 				if (s_semi && (((uintptr_t)q.src_a | (uintptr_t)q.src_row | (uintptr_t)q.src_frame) & 1)) ok = false;
 				if (d_semi && (((uintptr_t)q.dst_a | (uintptr_t)q.dst_row | (uintptr_t)q.dst_frame) & 1)) ok = false;
 				if (ok) {
-					MSB200_LAUNCH(ctx, yuv_copy_chroma_kernel, grid_for(ctx, (long)q.w * q.h * n_frames), 256, 0, q, n_frames);
+					auto al = [](const void *p, long a, long b, int m) { return (((uintptr_t)p | (uintptr_t)a | (uintptr_t)b) & (uintptr_t)(m - 1)) == 0; };
+					const bool vec = s_semi != d_semi && q.w % 8 == 0 &&
+					                 (s_semi ? al(q.src_a, q.src_row, q.src_frame, 16) && al(q.dst_a, q.dst_row, q.dst_frame, 8) &&
+					                               al(q.dst_b, 0, 0, 8)
+					                         : al(q.dst_a, q.dst_row, q.dst_frame, 16) && al(q.src_a, q.src_row, q.src_frame, 8) &&
+					                               al(q.src_b, 0, 0, 8));
+					if (vec) MSB200_LAUNCH(ctx, yuv_copy_chroma_vec_kernel, grid_for(ctx, (long)(q.w / 8) * q.h * n_frames), 256, 0, q, n_frames);
+					else MSB200_LAUNCH(ctx, yuv_copy_chroma_kernel, grid_for(ctx, (long)q.w * q.h * n_frames), 256, 0, q, n_frames);
 					break; // planes 1 and 2 done
 				}
 			}

@@ -173,6 +173,11 @@ struct ScaleParams {
 	// yuv2rgb closed-form constants
 	int cy, crv, cbu, cgu, cgv, yb0, yoffs;
 	size_t dst_frame_bytes;
+	// planar output only (msb200_scaler_set_x86_vertical): 1 = round the vertical filter like libswscale's x86 SIMD scaler
+	// (x86/yuv2yuvX.asm: per-tap (h15 * coef) >> 16 in 16-bit lanes, rounder (64 + 8 (taps - 1)) >> 4, final >> 3) — what a
+	// plain SWS_BILINEAR call, the one the reference makes (msvideo.c:660), returns on an x86 host; the last two luma rows
+	// and the last chroma row keep the C arithmetic, as in the library. 0 = its C arithmetic (SWS_BITEXACT) on every row.
+	int x86_vertical;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
@@ -1137,6 +1142,7 @@ struct PlaneStripParams {
 	// dst_pitch bytes apart; tile k starts at (tile_xy[k].x, tile_xy[k].y) >> tile_shift of this plane. Defaults: 1, W, null.
 	int group, dst_pitch, tile_shift;
 	const short2 *tile_xy;
+	int x86_rows; // output rows [0, x86_rows) round like the library's x86 SIMD vertical scaler (ScaleParams::x86_vertical)
 	short x0[ST_MAX_TX], y0[ST_MAX_TY];
 };
 template <int VT>
@@ -1211,12 +1217,24 @@ __global__ void __launch_bounds__(ST_THREADS, 8)
 		const unsigned clv[4] = {(unsigned)rb.x, (unsigned)rb.y, (unsigned)rb.z, (unsigned)rb.w};
 		++y;
 		unsigned q[4];
+		if (VT > 1 && y <= S.x86_rows) { // (y was advanced already: this is output row y - 1)
+			// x86/yuv2yuvX.asm: every product loses its low 16 bits before the sum; the rounder pays the expected loss back.
+			// The taps come pre-scaled by 32 (exactly: they are 12-bit); h15 and the taps are non-negative, so is the sum.
 #pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			unsigned a = 1u << 23; // (64 << 12) x 32
+			for (int k = 0; k < 4; ++k) {
+				unsigned a = (64u + 8u * (VT - 1)) >> 4;
 #pragma unroll
-			for (int s = 0; s < VT; ++s) a += (unsigned)WL[s][k] * clv[s];
-			q[k] = a;
+				for (int s = 0; s < VT; ++s) a += ((unsigned)WL[s][k] * (clv[s] >> 5)) >> 16;
+				q[k] = min(a >> 3, 255u) << 24;
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				unsigned a = 1u << 23; // (64 << 12) x 32
+#pragma unroll
+				for (int s = 0; s < VT; ++s) a += (unsigned)WL[s][k] * clv[s];
+				q[k] = a;
+			}
 		}
 		rtab += 32;
 		ra = lds128(rtab);
@@ -1690,6 +1708,10 @@ __global__ void __launch_bounds__(256) scale_direct_kernel(const unsigned char *
 			const int y = (int)(t / P.dst_w), x = (int)(t % P.dst_w), p = P.vl_pos[y];
 			if (P.vl_size == 1) {
 				val = (luma_h(p, x) + 64) >> 7;
+			} else if (P.x86_vertical && y < P.dst_h - 2) {
+				val = (64 + 8 * (P.vl_size - 1)) >> 4;
+				for (int j = 0; j < P.vl_size; ++j) val += (luma_h(min(p + j, P.src_h - 1), x) * P.vl_coef[(size_t)y * P.vl_size + j]) >> 16;
+				val >>= 3;
 			} else {
 				val = 64 << 12;
 				for (int j = 0; j < P.vl_size; ++j) val += luma_h(min(p + j, P.src_h - 1), x) * P.vl_coef[(size_t)y * P.vl_size + j];
@@ -1700,6 +1722,11 @@ __global__ void __launch_bounds__(256) scale_direct_kernel(const unsigned char *
 			const int k = u >= nc, y = (int)((u - k * nc) / P.chr_dst_w), x = (int)((u - k * nc) % P.chr_dst_w), p = P.vc_pos[y];
 			if (P.vc_size == 1) {
 				val = (chroma_h(p, k, x) + 64) >> 7;
+			} else if (P.x86_vertical && y < P.chr_dst_h - 1) {
+				val = (64 + 8 * (P.vc_size - 1)) >> 4;
+				for (int j = 0; j < P.vc_size; ++j)
+					val += (chroma_h(min(p + j, P.chr_src_h - 1), k, x) * P.vc_coef[(size_t)y * P.vc_size + j]) >> 16;
+				val >>= 3;
 			} else {
 				val = 64 << 12;
 				for (int j = 0; j < P.vc_size; ++j) val += chroma_h(min(p + j, P.chr_src_h - 1), k, x) * P.vc_coef[(size_t)y * P.vc_size + j];
@@ -2403,6 +2430,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			Q.dst_pitch = W;
 			Q.tile_shift = 0;
 			Q.tile_xy = nullptr;
+			Q.x86_rows = 0;
 			return MSB200_OK;
 		};
 		int rc;
@@ -2515,6 +2543,19 @@ int msb200_scaler_set_canvas(msb200_scaler *s, int canvas_w, int canvas_h, int n
 	s->PC.dst_off[1] = ysz + csz;
 	return MSB200_OK;
 }
+// planar output rounded like libswscale's x86 SIMD vertical scaler (see ScaleParams::x86_vertical)
+int msb200_scaler_set_x86_vertical(msb200_scaler *s, int on) {
+	MSB200_CHECK_ARG(s);
+	if (s->P.dst_fmt != MSB200_PIX_YUV420P || s->packed422) {
+		if (!on) return MSB200_OK;
+		msb200_set_error("scaler: the x86 vertical rounding only exists for the scaled planar output (YUV420P / NV12 / NV21 -> YUV420P)");
+		return MSB200_EINVAL;
+	}
+	s->P.x86_vertical = on ? 1 : 0;
+	s->PL.x86_rows = on ? s->P.dst_h - 2 : 0;
+	s->PC.x86_rows = on ? s->P.chr_dst_h - 1 : 0;
+	return MSB200_OK;
+}
 size_t msb200_scaler_canvas_bytes(msb200_scaler *s) {
 	return s && s->canvas_tiles > 0 ? (size_t)s->canvas_w * s->canvas_h * 3 / 2 : 0;
 }
@@ -2550,7 +2591,7 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 	if (s->packed422 >= 3) return msb200i_rgb24_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 - 3, d_dst);
 	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
 	const ScaleParams &P = s->P;
-	if (s->direct) {
+	if (s->direct || (P.x86_vertical && !s->pstrip_ok)) { // (the tile kernels implement the C rounding only)
 		const long threads = P.dst_fmt == MSB200_PIX_YUV420P ? (long)P.dst_w * P.dst_h + 2L * P.chr_dst_w * P.chr_dst_h
 		                                                       : (long)((P.dst_w + 1) / 2) * P.dst_h;
 		dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);

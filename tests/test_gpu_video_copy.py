@@ -103,3 +103,39 @@ def test_mosaic_canvas_equals_oracle_tiles_placed_by_hand(ctx, src_fmt):
         V_[y // 2:y // 2 + th // 2, x // 2:x // 2 + tw // 2] = tile[tw * th + tw * th // 4:].reshape(th // 2, tw // 2)
     L.orc_scaler_free(o)
     assert np.array_equal(got.reshape(n_canvas, cbytes), exp)
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh,src_fmt", [(1920, 1080, 1280, 720, _lib.PIX_YUV420P), (640, 480, 352, 288, _lib.PIX_YUV420P),
+                                                 (320, 240, 480, 360, _lib.PIX_NV12), (1280, 720, 320, 180, _lib.PIX_YUV420P),
+                                                 (176, 144, 352, 288, _lib.PIX_NV21), (650, 366, 322, 182, _lib.PIX_YUV420P)])
+def test_planar_scaler_x86_vertical_rounding_equals_oracle_x86_mode(ctx, sw, sh, dw, dh, src_fmt):
+    """msb200_scaler_set_x86_vertical(1): MSSizeConv's output as a plain SWS_BILINEAR call returns it on x86 — the oracle's
+    x86 mode is pinned bit-exact against the live library (tests/test_oracle_video_live.py); the strip kernel (TMA-able
+    geometries) and the tile-free kernel (4:1 down-scale, odd pitch) must both equal it, and differ from the C rounding"""
+    L = O.oracle()
+    lib = ctx.lib
+    rng = np.random.default_rng(sw + dh)
+    n = 2
+    sbytes = sw * sh * 3 // 2
+    src = rng.integers(0, 256, size=(n, sbytes)).astype(np.uint8)
+    h = C.c_void_p()
+    _lib.check(lib.msb200_scaler_create(ctx.h, sw, sh, src_fmt, dw, dh, _lib.PIX_YUV420P, C.byref(h)))
+    dbytes = lib.msb200_scaler_dst_frame_bytes(h)
+    outs = {}
+    for mode in (0, 1):
+        _lib.check(lib.msb200_scaler_set_x86_vertical(h, mode))
+        got = np.zeros((n, dbytes), np.uint8)
+        _lib.check(lib.msb200_scaler_process(h, n, O.ptr(src), O.ptr(got)))
+        outs[mode] = got
+    lib.msb200_scaler_destroy(h)
+    o = L.orc_scaler_new(sw, sh, src_fmt, dw, dh, _lib.PIX_YUV420P)
+    for mode in (0, 1):
+        L.orc_scaler_set_x86_vertical(o, mode)
+        for k in range(n):
+            exp = np.zeros(dbytes, np.uint8)
+            L.orc_scaler_process(o, O.ptr(src[k]), O.ptr(exp))
+            assert np.array_equal(outs[mode][k], exp), (mode, k)
+    L.orc_scaler_free(o)
+    if dh != sh:
+        d = np.abs(outs[0].astype(np.int16) - outs[1].astype(np.int16))
+        assert d.max() == 1  # the two roundings really differ, by one at most
