@@ -451,6 +451,7 @@ MSB200_API msb200_aec *msb200_chain_aec(msb200_chain *c);
 #define MSB200_PIX_UYVY 5
 #define MSB200_PIX_YUY2 6
 #define MSB200_PIX_RGBA32 7      /* R G B A bytes */
+#define MSB200_PIX_RGB565 8      /* MS_RGB565 -> AV_PIX_FMT_RGB565 little endian (msvideo.c:610-611): 16 bits per pixel, r5 g6 b5 */
 #define MSB200_PIX_RGBA32_REV 11 /* B G R A bytes (MS_RGBA32_REV -> AV_PIX_FMT_BGRA, msvideo.c:600-601) */
 #define MSB200_PIX_NV12 100
 #define MSB200_PIX_NV21 101
@@ -498,7 +499,7 @@ MSB200_API int msb200_yuv_copy_strided_dev(msb200_ctx *ctx, int n_frames, const 
  * Format pairs: YUV420P / NV12 / NV21 -> YUV420P / RGB24 / RGB24_REV(BGR byte order) with bilinear scaling, any sizes
  * >= 8 (the TMA-tiled kernels take source widths % 16 == 0 and down-scale factors < 2; everything else runs the
  * tile-free direct kernel, same arithmetic); MSPixConv's same-size conversions YUYV / YUY2 / UYVY / RGB24 / RGB24_REV / RGBA32 /
- * RGBA32_REV -> YUV420P (w % 8 == 0 for 4:2:2, w % 4 == 0 for RGB; h even). Frames are tight (no row padding), back to back. */
+ * RGBA32_REV / RGB565 -> YUV420P (w % 8 == 0 for 4:2:2, w % 4 == 0 for RGB; h even). Frames are tight (no row padding), back to back. */
 typedef struct msb200_scaler msb200_scaler;
 MSB200_API int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int dst_w, int dst_h,
                                     int dst_fmt, msb200_scaler **out);

@@ -19,6 +19,7 @@ OK, EINVAL, ENODEV, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 CHAN_MONO_TO_STEREO, CHAN_STEREO_TO_MONO, CHAN_2MONO_TO_STEREO = 0, 1, 2
 PIX_YUV420P, PIX_YUYV, PIX_RGB24, PIX_RGB24_REV, PIX_UYVY, PIX_YUY2, PIX_RGBA32, PIX_RGBA32_REV = 0, 1, 2, 3, 5, 6, 7, 11
 PIX_NV12, PIX_NV21 = 100, 101
+PIX_RGB565 = 8
 
 
 class Msb200Error(RuntimeError):

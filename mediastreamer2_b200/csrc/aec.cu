@@ -61,8 +61,14 @@ struct AecParams {
 // The shallow ring stays the default (less shared memory); the deep one remains a build option for other shapes.
 #ifndef AEC_STAGES
 #define AEC_STAGES 3
-#define AEC_OWN_STAGES 3 // ring slots with storage of their own; slots [AEC_OWN_STAGES, AEC_STAGES) alias dead scratch
+#define AEC_OWN_STAGES 2 // ring slots with storage of their own; slots [AEC_OWN_STAGES, AEC_STAGES) alias dead scratch
 #endif
+// Occupancy, measured A/B in one session on B200 (MSB200_AEC_CTAS, 200 ticks of 4096 streams each): 4 CTAs of 256 threads
+// per SM at 64 registers: 0.784 ms per launch; 5 CTAs at 48 registers (ptxas spills 20 bytes; shared memory cut to 43 KB by
+// aliasing the third ring slot onto FFT scratch and loading the late state vectors into registers): 0.801 ms — the extra
+// warps do not pay for the coarser wave quantisation (4096 CTAs = 5.5 waves of 740 instead of 6.9 of 592); 40 registers:
+// 0.839 ms. The default stays 4.
+#define AEC_CTAS_PER_SM_256 4
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -342,8 +348,8 @@ __device__ __forceinline__ float qcurve(float x) {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 // dynamic shared memory map (floats): see carve-up at the top of the kernel body
-template <int LOG2L>
-__global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
+template <int LOG2L, int CTAS = AEC_CTAS_PER_SM_256>
+__global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 : ((256 * CTAS) >> LOG2L))
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
                float *__restrict__ gS, AecParams P, const int *__restrict__ counts, int in_frame0, int in_ring, int out_stride, int out_frame0,
@@ -671,8 +677,8 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		// ---- per-stream state for the statistics and the preprocessor: HBM -> the idle cp.async ring, consumed much
 		// later by the thread that copied it (no barrier needed, only wait_group). Slot k holds F floats at stg[k*F].
 		float *stg = reinterpret_cast<float *>(pipe + 2 * L);
-		enum { SG_POWER, SG_EH, SG_YH, SG_LASTY1, SG_ECHO, SG_INBUF, SG_S, SG_SMIN, SG_STMP, SG_NOISE, SG_OLDPS, SG_ZETA,
-		       SG_OUTBUF, SG_BANDS };
+		enum { SG_POWER, SG_EH, SG_YH, SG_LASTY1, SG_ECHO, SG_INBUF, SG_S, SG_SMIN, SG_SLOTS };
+		static_assert((2 + SG_SLOTS / 2) * 1 <= AEC_OWN_STAGES * 3, "pc0, pc1 and the staged state fit the ring's own slots");
 		cp_async4(stg + SG_POWER * F + t, S + ly.power + t);
 		cp_async4(stg + SG_EH * F + t, S + ly.Eh + t);
 		cp_async4(stg + SG_YH * F + t, S + ly.Yh + t);
@@ -681,15 +687,6 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		cp_async4(stg + SG_INBUF * F + t, S + ly.inbuf + t);
 		cp_async4(stg + SG_S * F + t, S + ly.S + t);
 		cp_async4(stg + SG_SMIN * F + t, S + ly.Smin + t);
-		cp_async4(stg + SG_STMP * F + t, S + ly.Stmp + t);
-		cp_async4(stg + SG_NOISE * F + t, S + ly.noise + t);
-		cp_async4(stg + SG_OLDPS * F + t, S + ly.old_ps + t);
-		cp_async4(stg + SG_ZETA * F + t, S + ly.zeta + t);
-		cp_async4(stg + SG_OUTBUF * F + t, S + ly.outbuf + t);
-		if (t < NB_BANDS) {
-			cp_async4(stg + SG_BANDS * F + t, S + ly.old_ps + F + t);
-			cp_async4(stg + SG_BANDS * F + NB_BANDS + t, S + ly.zeta + F + t);
-		}
 		cp_async_commit();
 
 		// ---- foreground and background filter outputs (one paired inverse transform)
@@ -944,6 +941,11 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 		// ========================================================================= speex_preprocess_run
 		{
 			const int Mb = NB_BANDS;
+			// state vectors consumed late in the preprocessor: loaded into registers now, their latency hides behind the
+			// paired transform below (the same thread reads and later rewrites each element: no hazard)
+			const float r_stmp = S[ly.Stmp + t], r_noise = S[ly.noise + t], r_oldps = S[ly.old_ps + t], r_zeta = S[ly.zeta + t];
+			const float r_outbuf = S[ly.outbuf + t];
+			const float r_band_oldps = t < NB_BANDS ? S[ly.old_ps + F + t] : 0.f, r_band_zeta = t < NB_BANDS ? S[ly.zeta + F + t] : 0.f;
 			int nb_adapt = si[IN_NB_ADAPT] + 1;
 			if (nb_adapt > 20000) nb_adapt = 20000;
 			int min_count = si[IN_MIN_COUNT] + 1;
@@ -1003,7 +1005,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 				else if (t == F - 1) Sv = .8f * Sold + .2f * ps[F - 1];
 				else Sv = .8f * Sold + .05f * ps[t - 1] + .1f * ps[t] + .05f * ps[t + 1];
 				S[ly.S + t] = Sv;
-				float smin = stg[SG_SMIN * F + t], stmp = stg[SG_STMP * F + t];
+				float smin = stg[SG_SMIN * F + t], stmp = r_stmp;
 				if (nb_adapt == 1) smin = stmp = 0;
 				if (min_count > min_range) {
 					smin = stmp < Sv ? stmp : Sv;
@@ -1015,7 +1017,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 				S[ly.Smin + t] = smin;
 				S[ly.Stmp + t] = stmp;
 				const int update_prob = (.4f * Sv > smin) ? 1 : 0;
-				float nz = stg[SG_NOISE * F + t];
+				float nz = r_noise;
 				if (!update_prob || ps[t] < nz) {
 					const float v = beta_1 * nz + beta * ps[t];
 					nz = v > 0 ? v : 0;
@@ -1051,7 +1053,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			for (int r = 0; r < 2; ++r) {
 				const int i = r == 0 ? t : F + t;
 				if (r == 1 && t >= Mb) break;
-				float old_ps = r == 0 ? stg[SG_OLDPS * F + t] : stg[SG_BANDS * F + t];
+				float old_ps = r == 0 ? r_oldps : r_band_oldps;
 				if (nb_adapt == 1) old_ps = ps[i];
 				const float tot_noise = 1.f + noise[i] + echo_noise[i] + 0.f;
 				float post = ps[i] / tot_noise - 1.f;
@@ -1067,13 +1069,13 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			__syncthreads();
 			// ---- zeta
 			{
-				float z = stg[SG_ZETA * F + t];
+				float z = r_zeta;
 				if (t == 0) z = .7f * z + .3f * prior[0];
 				else if (t < F - 1) z = .7f * z + .15f * prior[t] + .075f * prior[t - 1] + .075f * prior[t + 1];
 				else z = .7f * z + .3f * prior[t];
 				S[ly.zeta + t] = z;
 				if (t < Mb) {
-					float zb = .7f * stg[SG_BANDS * F + Mb + t] + .3f * prior[F + t];
+					float zb = .7f * r_band_zeta + .3f * prior[F + t];
 					S[ly.zeta + F + t] = zb;
 					gains[F + t] = zb; // stash band zeta for Zframe
 				}
@@ -1144,7 +1146,7 @@ __global__ void __launch_bounds__(1 << LOG2L, (1024 >> LOG2L))
 			{
 				const float a = tmpv[t] * P.pwindow[t];
 				const float b = tmpv[F + t] * P.pwindow[F + t];
-				o16[t] = word2int(stg[SG_OUTBUF * F + t] + a);
+				o16[t] = word2int(r_outbuf + a);
 				S[ly.outbuf + t] = b;
 			}
 			if (t == 0) {
@@ -1356,7 +1358,9 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	int r = aec_write_init(a, 0, n_streams);
 	if (r) return r;
 	a->smem_bytes = aec_smem_floats(F, M) * sizeof(float);
-	MSB200_SMEM_OPTIN(aec_kernel<8>, ctx, a->smem_bytes);
+	MSB200_SMEM_OPTIN((aec_kernel<8, AEC_CTAS_PER_SM_256>), ctx, a->smem_bytes);
+	MSB200_SMEM_OPTIN((aec_kernel<8, 5>), ctx, a->smem_bytes);
+	MSB200_SMEM_OPTIN((aec_kernel<8, 6>), ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN(aec_kernel<7>, ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN(aec_kernel<6>, ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN(aec_kernel<5>, ctx, a->smem_bytes);
@@ -1413,7 +1417,14 @@ int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int 
 	(const short *)d_mic, (const short *)d_ref, (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, \
 	    d_counts, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames
 	if (a->live > 0) switch (a->P.F) {
-		case 256: MSB200_LAUNCH(a->ctx, aec_kernel<8>, a->live, 256, a->smem_bytes, AEC_ARGS); break;
+		case 256: {
+			// occupancy A/B (profiling): MSB200_AEC_CTAS=5 selects the 48-register build (5 CTAs per SM), 6 the 40-register one
+			static const int ctas = getenv("MSB200_AEC_CTAS") ? atoi(getenv("MSB200_AEC_CTAS")) : AEC_CTAS_PER_SM_256;
+			if (ctas == 5) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 5>), a->live, 256, a->smem_bytes, AEC_ARGS);
+			else if (ctas == 6) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 6>), a->live, 256, a->smem_bytes, AEC_ARGS);
+			else MSB200_LAUNCH(a->ctx, (aec_kernel<8, AEC_CTAS_PER_SM_256>), a->live, 256, a->smem_bytes, AEC_ARGS);
+			break;
+		}
 		case 128: MSB200_LAUNCH(a->ctx, aec_kernel<7>, a->live, 128, a->smem_bytes, AEC_ARGS); break;
 		case 64: MSB200_LAUNCH(a->ctx, aec_kernel<6>, a->live, 64, a->smem_bytes, AEC_ARGS); break;
 		case 32: MSB200_LAUNCH(a->ctx, aec_kernel<5>, a->live, 32, a->smem_bytes, AEC_ARGS); break;

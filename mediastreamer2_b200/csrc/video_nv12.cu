@@ -268,11 +268,24 @@ __device__ __forceinline__ void rgbx_unpack4(const uint8_t *row, int c[4][3]) {
 		c[k][SWAP_RB ? 0 : 2] = (int)((w4[k] >> 16) & 255u);
 	}
 }
-// FMT: 0 = RGB24 (generic path), 1 = BGR24 (special converter), 2 = RGBA, 3 = BGRA (generic path, alpha ignored)
+// 8 bytes = 4 pixels of RGB565 (little endian): the fields widened by plain shifts (r5 << 3, g6 << 2, b5 << 3), which is
+// what libswscale's 16-bit reader amounts to (oracle/oracle_video.c, pinned against the live library)
+__device__ __forceinline__ void rgb565_unpack4(const uint8_t *row, int c[4][3]) {
+	const uint2 wd = *reinterpret_cast<const uint2 *>(row);
+	const unsigned px[4] = {wd.x & 0xffffu, wd.x >> 16, wd.y & 0xffffu, wd.y >> 16};
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		c[k][0] = (int)((px[k] >> 11) << 3);
+		c[k][1] = (int)(((px[k] >> 5) & 63u) << 2);
+		c[k][2] = (int)((px[k] & 31u) << 3);
+	}
+}
+// FMT: 0 = RGB24 (generic path), 1 = BGR24 (special converter), 2 = RGBA, 3 = BGRA (generic path, alpha ignored),
+// 4 = RGB565 (generic path)
 template <int FMT>
 __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h) {
 	constexpr bool BGR = FMT == 1;
-	constexpr int BPP = FMT >= 2 ? 4 : 3;
+	constexpr int BPP = FMT == 4 ? 2 : (FMT >= 2 ? 4 : 3);
 	const int groups = w / 4, rows2 = h / 2;
 	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= (long)groups * rows2) return;
@@ -282,6 +295,7 @@ __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__res
 	auto rgb_unpack4 = [](const uint8_t *row, int(&c)[4][3]) {
 		if (FMT == 2) rgbx_unpack4<false>(row, c);
 		else if (FMT == 3) rgbx_unpack4<true>(row, c);
+		else if (FMT == 4) rgb565_unpack4(row, c);
 		else ::rgb_unpack4(row, c);
 	};
 	uint8_t *fd = dst + frame * ((size_t)w * h * 3 / 2);
@@ -358,7 +372,8 @@ int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int 
 		case 0: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<0>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
 		case 1: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<1>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
 		case 2: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<2>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
-		default: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<3>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+		case 3: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<3>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+		default: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<4>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
 	}
 	return MSB200_OK;
 }

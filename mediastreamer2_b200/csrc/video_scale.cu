@@ -2017,7 +2017,8 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		*out = s;
 		return MSB200_OK;
 	}
-	if (src_fmt == MSB200_PIX_RGB24 || src_fmt == MSB200_PIX_RGB24_REV || src_fmt == MSB200_PIX_RGBA32 || src_fmt == MSB200_PIX_RGBA32_REV) {
+	if (src_fmt == MSB200_PIX_RGB24 || src_fmt == MSB200_PIX_RGB24_REV || src_fmt == MSB200_PIX_RGBA32 || src_fmt == MSB200_PIX_RGBA32_REV ||
+	    src_fmt == MSB200_PIX_RGB565) {
 		// MSPixConv: packed RGB / BGR -> YUV420P at the same size (the bottom-up order of MS_RGB24_REV is the caller's
 		// negative stride, pixconv.c:78-81: plugin/msb200_filters.c packs the rows in display order)
 		if (dst_fmt != MSB200_PIX_YUV420P || src_w != dst_w || src_h != dst_h || (src_w % 4) || (src_h % 2)) {
@@ -2028,7 +2029,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		s->ctx = ctx;
 		memset(&s->P, 0, sizeof(s->P));
 		s->P.src_w = src_w; s->P.src_h = src_h; s->P.dst_w = dst_w; s->P.dst_h = dst_h; s->P.src_fmt = src_fmt; s->P.dst_fmt = dst_fmt;
-		s->packed422 = src_fmt == MSB200_PIX_RGB24 ? 3 : (src_fmt == MSB200_PIX_RGB24_REV ? 4 : (src_fmt == MSB200_PIX_RGBA32 ? 5 : 6));
+		s->packed422 = src_fmt == MSB200_PIX_RGB24 ? 3 : (src_fmt == MSB200_PIX_RGB24_REV ? 4 : (src_fmt == MSB200_PIX_RGBA32 ? 5 : (src_fmt == MSB200_PIX_RGBA32_REV ? 6 : 7)));
 		s->d_tables = nullptr;
 		s->cached_src = s->cached_dst = nullptr;
 		s->cached_frames = 0;
@@ -2039,7 +2040,7 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		s->sched = -1;
 		memset(&s->S, 0, sizeof(s->S));
 		memset(&s->T, 0, sizeof(s->T));
-		s->src_bytes = (size_t)src_w * src_h * (s->packed422 >= 5 ? 4 : 3);
+		s->src_bytes = (size_t)src_w * src_h * (s->packed422 == 7 ? 2 : (s->packed422 >= 5 ? 4 : 3));
 		s->dst_bytes = (size_t)dst_w * dst_h * 3 / 2;
 		*out = s;
 		return MSB200_OK;

@@ -99,6 +99,7 @@ int orc_nv12_to_i420(const uint8_t *y, const uint8_t *cbcr, int rotation, int w,
 #define PIX_YUYV 1
 #define PIX_RGBA32 7
 #define PIX_BGRA32 11
+#define PIX_RGB565 8 /* MS_RGB565 -> AV_PIX_FMT_RGB565 (little endian), src/voip/msvideo.c:610-611 */
 #define PIX_UYVY 5
 #define PIX_YUY2 6
 #define PIX_NV12 100
@@ -271,7 +272,7 @@ orc_scaler *orc_scaler_new(int src_w, int src_h, int src_fmt, int dst_w, int dst
 		s->dst_w = dst_w; s->dst_h = dst_h; s->dst_fmt = dst_fmt;
 		return s;
 	}
-	if (src_fmt == PIX_RGB24 || src_fmt == PIX_BGR24 || src_fmt == PIX_RGBA32 || src_fmt == PIX_BGRA32) {
+	if (src_fmt == PIX_RGB24 || src_fmt == PIX_BGR24 || src_fmt == PIX_RGBA32 || src_fmt == PIX_BGRA32 || src_fmt == PIX_RGB565) {
 		/* MSPixConv's RGB inputs (pixconv.c:62-94, MS_RGB24 -> AV_PIX_FMT_RGB24, MS_RGB24_REV -> AV_PIX_FMT_BGR24 read bottom-up
 		 * through a negative stride, :78-81): packed RGB -> YUV420P at the SAME size. See rgb_to_i420() below. */
 		if (dst_fmt != PIX_YUV420P || src_w != dst_w || src_h != dst_h || (src_w & 1) || (src_h & 1)) return NULL;
@@ -327,7 +328,7 @@ void orc_scaler_set_x86_vertical(orc_scaler *s, int on) {
 }
 void orc_scaler_free(orc_scaler *s) {
 	if (!s) return;
-	if (is_packed422(s->src_fmt) || s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24 || s->src_fmt == PIX_RGBA32 || s->src_fmt == PIX_BGRA32) {
+	if (is_packed422(s->src_fmt) || s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24 || s->src_fmt == PIX_RGBA32 || s->src_fmt == PIX_BGRA32 || s->src_fmt == PIX_RGB565) {
 		free(s);
 		return;
 	}
@@ -341,7 +342,7 @@ void orc_scaler_free(orc_scaler *s) {
 static size_t fmt_bytes(int fmt, int w, int h) {
 	if (fmt == PIX_RGB24 || fmt == PIX_BGR24) return (size_t)w * h * 3;
 	if (fmt == PIX_RGBA32 || fmt == PIX_BGRA32) return (size_t)w * h * 4;
-	if (fmt == PIX_YUYV || fmt == PIX_UYVY || fmt == PIX_YUY2) return (size_t)w * h * 2;
+	if (fmt == PIX_YUYV || fmt == PIX_UYVY || fmt == PIX_YUY2 || fmt == PIX_RGB565) return (size_t)w * h * 2;
 	return (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2);
 }
 size_t orc_scaler_src_bytes(orc_scaler *s) { return fmt_bytes(s->src_fmt, s->src_w, s->src_h); }
@@ -487,6 +488,23 @@ static void rgb_to_i420(const uint8_t *src, int w, int h, int bgr, int bpp, int 
 
 int orc_scaler_process(orc_scaler *s, const uint8_t *src, uint8_t *dst) {
 	const int sw = s->src_w, sh = s->src_h, dw = s->dst_w, dh = s->dst_h;
+	if (s->src_fmt == PIX_RGB565) {
+		/* libswscale's 16-bit RGB readers (input.c rgb16_32ToY_c_template / rgb16_32ToUV_half_c_template, instantiated for
+		 * rgb16le with masks 0xF800 / 0x07E0 / 0x001F, coefficient shifts 0 / 5 / 11 and S = RGB2YUV_SHIFT + 8) multiply the
+		 * masked fields where they stand; term by term that is the RGB24 reader's arithmetic scaled by 2^8 on
+		 * r = r5 << 3, g = g6 << 2, b = b5 << 3 (plain shifts, no bit replication) — so: expand, then the RGB24 path.
+		 * Pinned against the live library (tests/test_oracle_video_live.py). */
+		uint8_t *tmp = (uint8_t *)malloc((size_t)sw * sh * 3);
+		for (size_t i = 0; i < (size_t)sw * sh; ++i) {
+			const unsigned px = src[2 * i] | ((unsigned)src[2 * i + 1] << 8);
+			tmp[3 * i] = (uint8_t)((px >> 11) << 3);
+			tmp[3 * i + 1] = (uint8_t)(((px >> 5) & 63) << 2);
+			tmp[3 * i + 2] = (uint8_t)((px & 31) << 3);
+		}
+		rgb_to_i420(tmp, sw, sh, 0, 3, 0, 1, 2, dst, s->x86_vertical);
+		free(tmp);
+		return 0;
+	}
 	if (s->src_fmt == PIX_RGB24 || s->src_fmt == PIX_BGR24 || s->src_fmt == PIX_RGBA32 || s->src_fmt == PIX_BGRA32) {
 		const int f = s->src_fmt, four = f == PIX_RGBA32 || f == PIX_BGRA32;
 		rgb_to_i420(src, sw, sh, f == PIX_BGR24, four ? 4 : 3, f == PIX_BGRA32 ? 2 : 0, 1, f == PIX_BGRA32 ? 0 : 2, dst, s->x86_vertical);

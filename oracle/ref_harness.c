@@ -98,6 +98,7 @@ typedef struct HSink {
 	int *dims;  /* (w, h) of the 16-byte video header below b_rptr (msvideo.c:79-83), (0, 0) when the block has none */
 	int nblocks, blocks_cap;
 	int tick;
+	int discard; /* timing runs: count the blocks and bytes, keep nothing (no growing buffer inside the timed ticks) */
 } HSink;
 
 static void hsink_init(MSFilter *f) {
@@ -112,6 +113,12 @@ static void hsink_process(MSFilter *f) {
 	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
 		mblk_t *it;
 		size_t n = msgdsize(m);
+		if (s->discard) {
+			s->len += n;
+			s->nblocks++;
+			freemsg(m);
+			continue;
+		}
 		if (s->len + n > s->cap) {
 			s->cap = (s->len + n) * 2 + 4096;
 			s->buf = (uint8_t *)ms_realloc(s->buf, s->cap);
@@ -209,6 +216,9 @@ void ref_source_push_video(void *f, int tick, const void *data, int nbytes, int 
 	s->tail->h = h;
 	s->tail->has_ts = 1;
 	s->tail->ts = ts;
+}
+void ref_sink_set_discard(void *f, int on) {
+	((HSink *)((MSFilter *)f)->data)->discard = on;
 }
 void ref_sink_read_dims(void *f, int *pairs) {
 	HSink *s = (HSink *)((MSFilter *)f)->data;

@@ -42,6 +42,7 @@ int msb200p_pixfmt_to_b200(MSPixFmt fmt) {
 		case MS_RGB24_REV: return MSB200_PIX_RGB24_REV;
 		case MS_RGBA32: return MSB200_PIX_RGBA32;
 		case MS_RGBA32_REV: return MSB200_PIX_RGBA32_REV;
+		case MS_RGB565: return MSB200_PIX_RGB565;
 		default: return -1;
 	}
 }
@@ -51,7 +52,7 @@ static size_t frame_bytes(int b200_fmt, int w, int h, int *packed_row) {
 	int row = 0;
 	size_t n;
 	switch (b200_fmt) {
-		case MSB200_PIX_YUYV: case MSB200_PIX_YUY2: case MSB200_PIX_UYVY: row = w * 2; break;
+		case MSB200_PIX_YUYV: case MSB200_PIX_YUY2: case MSB200_PIX_UYVY: case MSB200_PIX_RGB565: row = w * 2; break;
 		case MSB200_PIX_RGB24: case MSB200_PIX_RGB24_REV: row = w * 3; break;
 		case MSB200_PIX_RGBA32: case MSB200_PIX_RGBA32_REV: row = w * 4; break;
 		default: break;

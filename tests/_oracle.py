@@ -135,6 +135,7 @@ def ref() -> C.CDLL:
         "ref_source_push_stream": (None, [_P, _I, _P, _I, _I]),
         "ref_source_push_video": (None, [_P, _I, _P, _I, _I, _I, C.c_uint]),
         "ref_sink_read_dims": (None, [_P, _P]),
+        "ref_sink_set_discard": (None, [_P, _I]),
         "ref_set_scaler_callbacks": (None, [_P, _P, _P]),
         "ref_set_scaler_desc": (None, [_P]),
         "ref_sink_size": (C.c_long, [_P]),

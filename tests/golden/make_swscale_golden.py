@@ -16,7 +16,8 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-AV_PIX = {"yuv420p": 0, "yuyv422": 1, "rgb24": 2, "bgr24": 3, "uyvy422": 15, "nv12": 23, "nv21": 24, "rgba": 26, "bgra": 28}
+AV_PIX = {"yuv420p": 0, "yuyv422": 1, "rgb24": 2, "bgr24": 3, "uyvy422": 15, "nv12": 23, "nv21": 24, "rgba": 26, "bgra": 28,
+          "rgb565le": 37}
 SWS_BILINEAR = 2
 SWS_BITEXACT = 0x80000  # same algorithm, the library's C reference functions instead of its approximate x86 SIMD ones
 
@@ -52,7 +53,7 @@ def planes(fmt: str, w: int, h: int, buf: np.ndarray):
         return [base, 0, 0, 0], [w * 3, 0, 0, 0]
     if fmt in ("rgba", "bgra"):
         return [base, 0, 0, 0], [w * 4, 0, 0, 0]
-    if fmt in ("yuyv422", "uyvy422"):
+    if fmt in ("yuyv422", "uyvy422", "rgb565le"):
         return [base, 0, 0, 0], [w * 2, 0, 0, 0]
     if fmt in ("nv12", "nv21"):
         return [base, base + w * h, 0, 0], [w, cw * 2, 0, 0]
@@ -64,7 +65,7 @@ def nbytes(fmt: str, w: int, h: int) -> int:
         return w * h * 3
     if fmt in ("rgba", "bgra"):
         return w * h * 4
-    if fmt in ("yuyv422", "uyvy422"):
+    if fmt in ("yuyv422", "uyvy422", "rgb565le"):
         return w * h * 2
     return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
 

@@ -120,6 +120,9 @@ def main():
     a = ap.parse_args()
     g = RefGraph(plugins_dir=str(O.PLUGIN_DIR))
     sources, spk_sinks, out_sinks = build(g, a.streams, a.pins, a.ticks, codec=a.codec)
+    if a.timing and not a.dump:  # timing runs: the recording sinks only count (no growing buffers inside the timed ticks)
+        for k in spk_sinks + out_sinks:
+            g.L.ref_sink_set_discard(k, 1)
     # a room's streams are one connected graph through its mixer: whole rooms are dealt to the tickers
     tickers = [g.L.ref_ticker_new() for _ in range(max(1, a.tickers))]
     for r, src in enumerate(sources):

@@ -233,15 +233,17 @@ def test_scaler_golden_frames_from_real_libswscale(ctx):
 
 @pytest.mark.parametrize("fmt,w,h", [(_lib.PIX_RGB24, 96, 64), (_lib.PIX_RGB24_REV, 64, 48), (_lib.PIX_RGB24, 132, 70),
                                      (_lib.PIX_RGB24, 1280, 720), (_lib.PIX_RGB24_REV, 1920, 1080),
-                                     (_lib.PIX_RGBA32, 96, 64), (_lib.PIX_RGBA32_REV, 132, 70), (_lib.PIX_RGBA32, 1280, 720)])
+                                     (_lib.PIX_RGBA32, 96, 64), (_lib.PIX_RGBA32_REV, 132, 70), (_lib.PIX_RGBA32, 1280, 720),
+                                     (_lib.PIX_RGB565, 96, 64), (_lib.PIX_RGB565, 132, 70), (_lib.PIX_RGB565, 1920, 1080)])
 def test_pixconv_rgb24_to_i420_bit_exact(ctx, fmt, w, h):
     """MSPixConv's MS_RGB24 / MS_RGB24_REV inputs: GPU == oracle (itself bit-exact vs the real libswscale's C paths,
     tests/test_oracle_video.py); full-range noise, saturated primaries and a flat frame among the inputs."""
     L = O.oracle()
     rng = np.random.default_rng(w * 3 + h)
-    bpp = 4 if fmt in (_lib.PIX_RGBA32, _lib.PIX_RGBA32_REV) else 3
+    bpp = 4 if fmt in (_lib.PIX_RGBA32, _lib.PIX_RGBA32_REV) else (2 if fmt == _lib.PIX_RGB565 else 3)
     frames = rng.integers(0, 256, size=(4, w * h * bpp), dtype=np.uint8)
-    prim = [255, 0, 0, 0, 255, 0, 0, 0, 255, 255, 255, 255] if bpp == 3 else [255, 0, 0, 7, 0, 255, 0, 9, 0, 0, 255, 1, 255, 255, 255, 0]
+    prim = {3: [255, 0, 0, 0, 255, 0, 0, 0, 255, 255, 255, 255], 4: [255, 0, 0, 7, 0, 255, 0, 9, 0, 0, 255, 1, 255, 255, 255, 0],
+            2: [0x00, 0xF8, 0xE0, 0x07, 0x1F, 0x00, 0xFF, 0xFF]}[bpp]  # RGB565 little endian: red, green, blue, white
     frames[1] = np.tile(np.array(prim, np.uint8), w * h // 4)
     frames[2] = 0
     sc = F.Scaler(ctx, w, h, fmt, w, h, _lib.PIX_YUV420P)

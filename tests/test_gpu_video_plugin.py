@@ -102,3 +102,22 @@ def test_b200_video_batch_lane_is_the_synchronous_mode_one_tick_later(monkeypatc
     subprocess.run([sys.executable, "-c", code.replace("\\n", "\n"), out], check=True, env=env, cwd=str(O.ROOT))
     z = np.load(out)
     _same(exp, (z["d"], z["t"], z["m"]))
+
+
+def test_b200_pixconv_takes_rgb565_which_the_reference_filter_drops():
+    """MS_RGB565 is a member of MSPixFmt and libswscale reads it (msvideo.c:610-611), but the reference's MSPixConv cannot
+    wrap such a frame (ms_picture_init_from_mblk_with_size has no case for it, msvideo.c:120-156) and drops it. The plugin's
+    MSPixConv converts it; expected = the oracle's RGB565 reader, itself pinned against the live libswscale."""
+    w, h = 64, 48
+    frames = [V.synth_frame(V.MS_RGB565, w, h, t) for t in range(3)]
+    ref = _expected(frames, V.MS_RGB565, w, h)
+    assert len(ref[1]) == 0
+    data, tri, dims = V.run_pixconv_sizeconv(_plugin_graph(), frames, V.MS_RGB565, w, h, want_b200=True)
+    assert len(tri) == 3 and (dims == (w, h)).all()
+    L = O.oracle()
+    o = L.orc_scaler_new(w, h, 8, w, h, 0)
+    for k, fr in enumerate(frames):
+        exp = np.zeros(w * h * 3 // 2, np.uint8)
+        L.orc_scaler_process(o, O.ptr(fr), O.ptr(exp))
+        assert np.array_equal(data[k * exp.size:(k + 1) * exp.size], exp), k
+    L.orc_scaler_free(o)

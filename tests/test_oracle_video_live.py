@@ -19,7 +19,7 @@ from bench_video import _load_libswscale  # noqa: E402
 from make_swscale_golden import AV_PIX, SWS_BILINEAR, SWS_BITEXACT, sws_convert  # noqa: E402
 from make_swscale_golden import test_frame as make_frame  # noqa: E402
 
-AV2MS = {0: 0, 1: 1, 2: 2, 3: 3, 15: 5, 23: 100, 24: 101, 26: 7, 28: 11}  # AVPixelFormat -> MSB200_PIX_*
+AV2MS = {0: 0, 1: 1, 2: 2, 3: 3, 15: 5, 23: 100, 24: 101, 26: 7, 28: 11, 37: 8}  # AVPixelFormat -> MSB200_PIX_*
 _SWS = None
 
 
@@ -193,3 +193,28 @@ def test_rgb_sources_x86_vertical_mode_equals_plain_flag_library_exactly(seed):
     assert L.orc_scaler_process(s, ptr(np.ascontiguousarray(src)), ptr(out)) == 0
     L.orc_scaler_free(s)
     assert np.array_equal(out[:-64], sws_convert(sws, src, sf, w, h, "yuv420p", w, h, SWS_BILINEAR))
+
+
+@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("flags_x86", [(SWS_BILINEAR | SWS_BITEXACT, 0), (SWS_BILINEAR, 1)])
+def test_rgb565_source_equals_the_library_exactly(seed, flags_x86):
+    """MS_RGB565 (AV_PIX_FMT_RGB565LE) -> YUV420P at the same size, MSPixConv's remaining RGB input: the library's 16-bit
+    reader is the RGB24 reader on r5 << 3, g6 << 2, b5 << 3; both roundings of the vertical chroma filter"""
+    sws = _sws()
+    L = O.oracle()
+    flags, x86 = flags_x86
+    rng = np.random.default_rng(100 + seed)
+    w, h = int(rng.integers(4, 100)) * 4, int(rng.integers(4, 80)) * 2
+    src = rng.integers(0, 256, w * h * 2).astype(np.uint8)
+    if seed % 3 == 0:  # saturated colours and pure ramps as well as noise
+        px = (np.arange(w * h, dtype=np.uint32) * 2654435761 >> 7).astype(np.uint16)
+        px[: w * h // 3] = 0xFFFF
+        px[w * h // 3: w * h // 2] = 0x0000
+        src = px.view(np.uint8).copy()
+    s = L.orc_scaler_new(w, h, 8, w, h, 0)
+    assert s
+    L.orc_scaler_set_x86_vertical(s, x86)
+    out = np.zeros(L.orc_scaler_dst_bytes(s) + 64, np.uint8)
+    assert L.orc_scaler_process(s, ptr(np.ascontiguousarray(src)), ptr(out)) == 0
+    L.orc_scaler_free(s)
+    assert np.array_equal(out[:-64], sws_convert(sws, src, "rgb565le", w, h, "yuv420p", w, h, flags))

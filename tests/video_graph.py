@@ -16,8 +16,9 @@ from _oracle import RefGraph
 
 # MSPixFmt (include/mediastreamer2/msvideo.h:267-280) -> oracle / MSB200_PIX_* constants
 MS_YUV420P, MS_YUYV, MS_RGB24, MS_RGB24_REV, MS_UYVY, MS_YUY2, MS_RGBA32, MS_RGBA32_REV = 1, 2, 3, 4, 6, 7, 8, 11
+MS_RGB565 = 9
 MS_NV12, MS_NV21 = 12, 13  # include/msb200_ms2.h
-_TO_ORC = {MS_YUV420P: 0, MS_YUYV: 1, MS_RGB24: 2, MS_RGB24_REV: 3, MS_UYVY: 5, MS_YUY2: 6, MS_RGBA32: 7, MS_RGBA32_REV: 11,
+_TO_ORC = {MS_RGB565: 8, MS_YUV420P: 0, MS_YUYV: 1, MS_RGB24: 2, MS_RGB24_REV: 3, MS_UYVY: 5, MS_YUY2: 6, MS_RGBA32: 7, MS_RGBA32_REV: 11,
            MS_NV12: 100, MS_NV21: 101}
 
 
@@ -62,7 +63,7 @@ class OracleScalerDesc:
                 cw, ch = (sw + 1) // 2, (sh + 1) // 2
                 frame = np.concatenate([rows(src[0], sstr[0], sw, sh), rows(src[1], sstr[1], cw, ch), rows(src[2], sstr[2], cw, ch)])
             else:
-                bpp = {MS_YUYV: 2, MS_YUY2: 2, MS_UYVY: 2, MS_RGB24: 3, MS_RGB24_REV: 3, MS_RGBA32: 4, MS_RGBA32_REV: 4}[sf]
+                bpp = {MS_YUYV: 2, MS_YUY2: 2, MS_UYVY: 2, MS_RGB565: 2, MS_RGB24: 3, MS_RGB24_REV: 3, MS_RGBA32: 4, MS_RGBA32_REV: 4}[sf]
                 frame = rows(src[0], sstr[0], sw * bpp, sh)
             assert frame.nbytes == self.L.orc_scaler_src_bytes(o)
             out = np.zeros(self.L.orc_scaler_dst_bytes(o), np.uint8)
@@ -133,7 +134,7 @@ def synth_frame(fmt: int, w: int, h: int, t: int, seed: int = 0) -> np.ndarray:
         out[..., 0 if fmt != MS_UYVY else 1] = y
         out[..., 1 if fmt != MS_UYVY else 0] = c
         return out.reshape(-1)
-    bpp = 3 if fmt in (MS_RGB24, MS_RGB24_REV) else 4
+    bpp = 3 if fmt in (MS_RGB24, MS_RGB24_REV) else (2 if fmt == MS_RGB565 else 4)
     out = rng.integers(0, 256, (h, w, bpp)).astype(np.uint8)
     out[..., 0] = (xx * 2 + t * 9) % 256
     out[..., 1] = (yy * 3 + t) % 256

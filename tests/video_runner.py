@@ -53,6 +53,7 @@ def main():
         g.link(sz, 0, sink, 0)
         for k, t in enumerate(range(s % a.period, a.ticks, a.period)):  # cameras are not in phase
             g.push_video(src, t, frames[(s + k) % len(frames)], 0, 0, 90 * t)
+        g.L.ref_sink_set_discard(sink, 1)
         sources.append(src)
         sinks.append(sink)
     tickers = [g.L.ref_ticker_new() for _ in range(max(1, a.tickers))]
