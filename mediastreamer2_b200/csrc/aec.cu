@@ -69,6 +69,7 @@ struct AecParams {
 // warps do not pay for the coarser wave quantisation (4096 CTAs = 5.5 waves of 740 instead of 6.9 of 592); 40 registers:
 // 0.839 ms. The default stays 4.
 #define AEC_CTAS_PER_SM_256 4
+#define AEC_DEFAULT_SKEW_US 0
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -135,25 +136,58 @@ __device__ int block_any(int pred) {
 // y[q + 2sp] = a + c and y[q + 2sp + s] = (a - c) * w^p with q = b mod s, p = b div s. Arithmetic per output is
 // oracle/oracle_aec.c:cfft()'s, operation for operation. Half the CTA works per transform, so a pair of transforms
 // (cfft_pair) costs the same instructions and barriers as one.
+// One thread carries FOUR points through TWO consecutive stages in registers: the pair of stage-st butterflies (u, u + H/2)
+// feeds exactly the pair of stage-(st+1) butterflies (u + ps, u + ps + s), so the intermediate values never touch shared
+// memory and every other CTA barrier disappears — while each value is still produced by the very same operations on the very
+// same operands as in the stage-by-stage form (bit-identical spectra: test_aec_first_frames_match_oracle, probe "X").
+// Thread u < H/2 of a group works; outputs land at u + 3 ps + {0, s, 2s, 3s}. An odd stage count ends with one plain stage.
 template <int LOG2L>
 __device__ __forceinline__ void cfft_bfly(float2 *x, float2 *y, const float2 *tw, int sign, bool active) {
-	constexpr int H = 1 << (LOG2L - 1);
+	constexpr int H = 1 << (LOG2L - 1), Q = H >> 1;
 	const int b = threadIdx.x & (H - 1);
+	auto bfly = [&](const float2 a, const float2 c, const float2 w, float2 &o0, float2 &o1) {
+		const float wr = w.x, wi = sign < 0 ? -w.y : w.y;
+		o0.x = a.x + c.x;
+		o0.y = a.y + c.y;
+		const float dr = a.x - c.x, di = a.y - c.y;
+		o1.x = dr * wr - di * wi;
+		o1.y = dr * wi + di * wr;
+	};
+#ifdef AEC_FFT_PLAIN // A/B build: one stage per barrier, as in round 1
+	constexpr int DOUBLE_END = 0;
+#else
+	constexpr int DOUBLE_END = LOG2L & ~1;
+#endif
 #pragma unroll
-	for (int st = 0; st < LOG2L; ++st) {
-		if (active) {
+	for (int st = 0; st < DOUBLE_END; st += 2) {
+		if (active && b < Q) {
 			const int s = 1 << st;
 			const int ps = b & ~(s - 1); // p << st
-			const float2 a = x[b], c = x[b + H];
-			const float2 w = tw[ps];
-			const float wr = w.x, wi = sign < 0 ? -w.y : w.y;
+			float2 y0, y1, y0b, y1b, z0, z1, z2, z3;
+			bfly(x[b], x[b + H], tw[ps], y0, y1);               // stage st, butterfly b
+			bfly(x[b + Q], x[b + Q + H], tw[ps + Q], y0b, y1b); // stage st, butterfly b + H/2
+			const float2 w2 = tw[2 * ps];
+			bfly(y0, y0b, w2, z0, z2);                          // stage st + 1, butterfly b + ps
+			bfly(y1, y1b, w2, z1, z3);                          // stage st + 1, butterfly b + ps + s
+			const int o = b + 3 * ps;
+			y[o] = z0;
+			y[o + s] = z1;
+			y[o + 2 * s] = z2;
+			y[o + 3 * s] = z3;
+		}
+		__syncthreads();
+		float2 *sw = x;
+		x = y;
+		y = sw;
+	}
+#pragma unroll
+	for (int st = DOUBLE_END; st < LOG2L; ++st) {
+		if (active) {
+			const int s = 1 << st;
+			const int ps = b & ~(s - 1);
 			float2 o0, o1;
-			o0.x = a.x + c.x;
-			o0.y = a.y + c.y;
-			const float dr = a.x - c.x, di = a.y - c.y;
-			o1.x = dr * wr - di * wi;
-			o1.y = dr * wi + di * wr;
-			const int oi = b + ps; // q + 2 * s * p
+			bfly(x[b], x[b + H], tw[ps], o0, o1);
+			const int oi = b + ps;
 			y[oi] = o0;
 			y[oi + s] = o1;
 		}
@@ -163,10 +197,16 @@ __device__ __forceinline__ void cfft_bfly(float2 *x, float2 *y, const float2 *tw
 		y = sw;
 	}
 }
+// number of buffer swaps of cfft_bfly: one per (double or single) pass
+#ifdef AEC_FFT_PLAIN
+template <int LOG2L> struct CfftSwaps { static constexpr int value = LOG2L; };
+#else
+template <int LOG2L> struct CfftSwaps { static constexpr int value = (LOG2L + 1) / 2; };
+#endif
 // single transform: threads < L/2 work. Returns the buffer holding the result.
 template <int LOG2L> __device__ __forceinline__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int sign) {
 	cfft_bfly<LOG2L>(x, y, tw, sign, threadIdx.x < (1 << (LOG2L - 1)));
-	return (LOG2L & 1) ? y : x;
+	return (CfftSwaps<LOG2L>::value & 1) ? y : x;
 }
 
 // real forward FFT (spx_fft semantics: input scaled by 1/N): in[N] real (smem) -> spec[L] float2 (smem, bin0=(DC,Nyq))
@@ -230,7 +270,7 @@ template <int LOG2L>
 __device__ __forceinline__ void cfft_pair(float2 *&xa, float2 *&ya, float2 *&xb, float2 *&yb, const float2 *tw, int sign) {
 	const bool second = threadIdx.x >= (1 << (LOG2L - 1)); // lower half of the CTA: transform a, upper half: transform b
 	cfft_bfly<LOG2L>(second ? xb : xa, second ? yb : ya, tw, sign, true);
-	if (LOG2L & 1) {
+	if (CfftSwaps<LOG2L>::value & 1) {
 		float2 *sw = xa; xa = ya; ya = sw;
 		sw = xb; xb = yb; yb = sw;
 	}
@@ -353,7 +393,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
                float *__restrict__ gS, AecParams P, const int *__restrict__ counts, int in_frame0, int in_ring, int out_stride, int out_frame0,
-               int out_ring) {
+               int out_ring, int skew_ns, int skew_ctas) {
 	extern __shared__ float sm[];
 	constexpr int F = 1 << LOG2L, N = 2 * F, L = F;
 	const int M = P.M;
@@ -363,6 +403,22 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 	// tick must NOT be fed padding: a made-up frame would enter its far-end history and its adaptive filter)
 	if (counts) nframes = min(nframes, counts[stream]);
 	if (nframes <= 0) return;
+	// Phase skew. All CTAs of the first wave start together and would walk through a frame in lock step: everybody in the
+	// transforms and serial sections (no HBM traffic at all), then everybody in the block pass (HBM saturated) — the memory
+	// system idles while the SMs compute and the SMs idle while it streams. Delaying the k-th CTA of every SM by k x skew
+	// spreads the passes over the frame time; later waves inherit the spread (a CTA starts when a slot frees).
+	if (skew_ns > 0 && (int)blockIdx.x < 4 * skew_ctas && (int)blockIdx.x >= skew_ctas) {
+		if (threadIdx.x == 0) {
+			const unsigned long long wait = (unsigned long long)(blockIdx.x / skew_ctas) * (unsigned long long)skew_ns;
+			unsigned long long t0, t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+			do {
+				__nanosleep(500);
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			} while (t1 - t0 < wait);
+		}
+		__syncthreads();
+	}
 	// ---- shared memory carve-up
 	float2 *tw = reinterpret_cast<float2 *>(sm);           // [L/2]
 	float2 *spl = tw + L / 2;                              // [L+1] (+1 pad)
@@ -455,12 +511,14 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			gX_pf += F;
 			if (--x_left == 0) gX_pf -= x_ring;
 		};
+#ifndef AEC_PASS_DIRECT
 		// early prologue: the ring slots with storage of their own (the aliased ones are still scratch until the pre-pass ends)
 #pragma unroll
 		for (int pj = 0; pj < (AEC_OWN_STAGES < AEC_STAGES - 1 ? AEC_OWN_STAGES : AEC_STAGES - 1); ++pj) {
 			if (pj < M) prefetch(pj, pj);
 			cp_async_commit();
 		}
+#endif
 
 		// ---- DC notch (serial IIR, filter_dc_notch16) then pre-emphasis on the microphone
 		tmpv[t] = (float)mic_i;
@@ -570,12 +628,14 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			__syncthreads();
 			rfft_pair<LOG2L>(reinterpret_cast<float *>(specB), specB, tmpv, cspec, bufa, bufb, sa, sb, P, tw, spl);
 		}
+#ifndef AEC_PASS_DIRECT
 		// late prologue: from here to the end of the pass bufa / bufb / specA / ebuf / ybuf / vec1 / vec2 are ring slots
 #pragma unroll
 		for (int pj = AEC_OWN_STAGES; pj < AEC_STAGES - 1; ++pj) {
 			if (pj < M) prefetch(pj, pj);
 			cp_async_commit();
 		}
+#endif
 
 		// ---- the pass over the M blocks: foreground output, weight update, background output.
 		// X_{j+1}, FG_j and W_j are streamed HBM -> shared memory with cp.async, AEC_STAGES-1 blocks ahead of their use;
@@ -585,11 +645,35 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 		{
 			static_assert(AEC_STAGES % 3 == 0, "the grouped |W_j|^2 reduction below folds three blocks at a time");
 			float nrm[3] = {0.f, 0.f, 0.f};
-			for (int j0 = 0; j0 < M; j0 += AEC_STAGES) {
+#ifdef AEC_PASS_DIRECT
+			// A/B build: X_{j+1}, FG_j, W_j go HBM -> REGISTERS (two blocks ahead, a ring of two register sets) instead of
+			// HBM -> shared memory -> registers: no LDGSTS, no LDS in the pass (the shared-memory pipe is the busiest unit)
+			constexpr int GROUP = 6;
+			float2 rX[2], rF[2], rW[2];
+			auto fetch = [&](int slot, int rel) {
+				rX[slot] = *gX_pf;
+				rW[slot] = gW_grp[rel * F];
+				if (!fg_pending) rF[slot] = gF_grp[rel * F];
+				gX_pf += F;
+				if (--x_left == 0) gX_pf -= x_ring;
+			};
+			if (0 < M) fetch(0, 0);
+			if (1 < M) fetch(1, 1);
+#else
+			constexpr int GROUP = AEC_STAGES;
+#endif
+			for (int j0 = 0; j0 < M; j0 += GROUP) {
 #pragma unroll
-				for (int sidx = 0; sidx < AEC_STAGES; ++sidx) {
+				for (int sidx = 0; sidx < GROUP; ++sidx) {
 					const int j = j0 + sidx;
 					if (j < M) {
+#ifdef AEC_PASS_DIRECT
+						const float2 xj1 = rX[sidx & 1];
+						float2 w = rW[sidx & 1];
+						float2 fg = fg_pending ? w : rF[sidx & 1];
+						if (fg_pending) gF_grp[sidx * F] = w;
+						if (j + 2 < M) fetch(sidx & 1, sidx + 2);
+#else
 						// keep AEC_STAGES-1 blocks in flight: the slot freed by block j-1 receives block j+STAGES-1
 						if (j + AEC_STAGES - 1 < M) prefetch((sidx + AEC_STAGES - 1) % AEC_STAGES, sidx + AEC_STAGES - 1);
 						cp_async_commit();
@@ -604,6 +688,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 						} else {
 							fg = src[F];
 						}
+#endif
 						// foreground: Y += X_j * FG_j (spectral_mul_accum; bin 0 carries two real products)
 						if (t == 0) {
 							yfg.x += xj.x * fg.x;
@@ -658,8 +743,8 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 						if ((lane == 0 || lane == 16 || lane == 8) && jw < M) wpart[jw * 8 + warp] = c;
 					}
 				}
-				gW_grp += AEC_STAGES * F;
-				gF_grp += AEC_STAGES * F;
+				gW_grp += GROUP * F;
+				gF_grp += GROUP * F;
 			}
 			cp_async_wait<0>();
 		}
@@ -1413,9 +1498,12 @@ int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int 
                        int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes,
                        const int *d_counts) {
 	MSB200_CHECK_ARG(a && d_mic && d_ref && d_out && nframes > 0);
+	// phase skew between the CTAs that share an SM (see the kernel): only worth it when the grid fills the chip
+	static const int skew_env = getenv("MSB200_AEC_SKEW_US") ? atoi(getenv("MSB200_AEC_SKEW_US")) : AEC_DEFAULT_SKEW_US;
+	const int skew_ns = a->live >= 4 * a->ctx->sm_count ? skew_env * 1000 : 0;
 #define AEC_ARGS                                                                                                       \
 	(const short *)d_mic, (const short *)d_ref, (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, \
-	    d_counts, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames
+	    d_counts, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames, skew_ns, a->ctx->sm_count
 	if (a->live > 0) switch (a->P.F) {
 		case 256: {
 			// occupancy A/B (profiling): MSB200_AEC_CTAS=5 selects the 48-register build (5 CTAs per SM), 6 the 40-register one
