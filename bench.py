@@ -167,7 +167,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def realtime_block(ctx, F, sizes=(4096, 16384, 32768), ticks=1000):
@@ -433,7 +433,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["realtime"] = {"error": repr(e)}
     if rank == 0:
         line["summary"] = summary(line)  # last key: the driver's record keeps the tail of the line
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     chain.close()
     for p in (d_ref, d_mic, d_out):
         ctx.dev_free(p)
@@ -442,7 +442,34 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+class _OneLineStdout:
+    """The contract is ONE JSON line on stdout. Libraries loaded along the way (NCCL prints its version banner with printf
+    when a communicator is created, CUDA / torch may warn) must not add to it: while this is active, file descriptor 1 points
+    at stderr; emit() writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+_OUT = None
+
+
+def emit_line(obj: dict):
+    if _OUT is not None:
+        _OUT.emit(json.dumps(obj))
+    else:
+        print(json.dumps(obj), flush=True)
+
+
 def main():
+    global _OUT
+    _OUT = _OneLineStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

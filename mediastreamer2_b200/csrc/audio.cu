@@ -76,6 +76,65 @@ __global__ void __launch_bounds__(128) mixer_kernel(const short *__restrict__ in
 	}
 }
 
+// Conference rooms of up to 16 pins (BASELINE cfg3's shape): every pin's column is loaded ONCE and stays in registers
+// between the sum and the per-listener outputs — as packed post-gain contributions, which fit 16 bits (apply_gain saturates,
+// audiomixer.c:46-51) — so the DRAM / L2 traffic is exactly the algorithmic P*2n in + P*2n out. Same arithmetic as
+// mixer_kernel mode 0.
+#define MIX_REG_PINS 16
+template <int VEC>
+__global__ void __launch_bounds__(128) mixer_conf_regs_kernel(const short *__restrict__ in, const uint8_t *__restrict__ present,
+                                                              const float *__restrict__ gain, const uint8_t *__restrict__ active,
+                                                              short *__restrict__ out, int n_rooms, int n_pins, int nwords,
+                                                              long in_pin_vecs) {
+	typedef typename s16vec<VEC>::type V;
+	const int nvec = nwords / VEC;
+	const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long)n_rooms * nvec) return;
+	const int room = (int)(gid / nvec), col = (int)(gid % nvec);
+	const size_t chan0 = (size_t)room * n_pins;
+	const V *inv = reinterpret_cast<const V *>(in) + chan0 * in_pin_vecs + col;
+	V c[MIX_REG_PINS];
+	unsigned live = 0;
+#pragma unroll
+	for (int p = 0; p < MIX_REG_PINS; ++p)
+		if (p < n_pins && present[chan0 + p] && active[chan0 + p]) {
+			live |= 1u << p;
+			c[p] = inv[(size_t)p * in_pin_vecs]; // all loads issued before the first use
+		}
+	int sum[VEC];
+#pragma unroll
+	for (int k = 0; k < VEC; ++k) sum[k] = 0;
+#pragma unroll
+	for (int p = 0; p < MIX_REG_PINS; ++p)
+		if (live >> p & 1u) {
+			const float g = gain[chan0 + p];
+			int s[VEC];
+			unpack_s16<VEC>(c[p], s);
+#pragma unroll
+			for (int k = 0; k < VEC; ++k) {
+				s[k] = mix_contrib(s[k], g);
+				sum[k] += s[k];
+			}
+			c[p] = pack_s16<VEC>(s);
+		}
+	V *outv = reinterpret_cast<V *>(out) + chan0 * nvec + col;
+#pragma unroll
+	for (int p = 0; p < MIX_REG_PINS; ++p)
+		if (p < n_pins) { // channel_process_out :113-130
+			int o[VEC];
+			if (live >> p & 1u) {
+				int s[VEC];
+				unpack_s16<VEC>(c[p], s);
+#pragma unroll
+				for (int k = 0; k < VEC; ++k) o[k] = mix_sat(sum[k] - s[k]);
+			} else {
+#pragma unroll
+				for (int k = 0; k < VEC; ++k) o[k] = mix_sat(sum[k]);
+			}
+			outv[(size_t)p * nvec] = pack_s16<VEC>(o);
+		}
+}
+
 int msb200i_mixer_upload(msb200_mixer *m) {
 	if (!m->dirty) return MSB200_OK;
 	size_t n = (size_t)m->n_rooms * m->n_pins;
@@ -98,6 +157,18 @@ static int mixer_launch(msb200_mixer *m, const void *d_in, const void *d_present
 	while (vec > 1 && in_pin_stride % vec) vec /= 2;
 	// prefer more, narrower threads when the grid would not cover the chip (148 SMs x >=4 CTAs of 128)
 	while (vec > 2 && (long)m->live * (nw / vec) < 148L * 4 * 128) vec /= 2;
+	if (mode == 0 && m->conf_mode && m->n_pins <= MIX_REG_PINS && vec >= 4) { // register-resident rooms
+		if (vec == 8 && (long)m->live * (nw / 8) < 148L * 8 * 128) vec = 4; // cover the chip before widening the vectors
+		const long nth = (long)m->live * (nw / vec);
+		const int g = (int)((nth + 127) / 128);
+		if (vec == 8)
+			MSB200_LAUNCH(m->ctx, mixer_conf_regs_kernel<8>, g, 128, 0, (const short *)d_in, (const uint8_t *)d_present, m->d_gain,
+			              m->d_active, (short *)d_out, m->live, m->n_pins, nw, in_pin_stride / vec);
+		else
+			MSB200_LAUNCH(m->ctx, mixer_conf_regs_kernel<4>, g, 128, 0, (const short *)d_in, (const uint8_t *)d_present, m->d_gain,
+			              m->d_active, (short *)d_out, m->live, m->n_pins, nw, in_pin_stride / vec);
+		return MSB200_OK;
+	}
 	const long nthreads = (long)m->live * (nw / vec);
 	const int block = 128, grid = (int)((nthreads + block - 1) / block);
 #define MIX_ARGS                                                                                                       \
