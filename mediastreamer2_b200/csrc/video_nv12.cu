@@ -362,10 +362,10 @@ __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__res
 	*reinterpret_cast<unsigned *>(fd + (size_t)(2 * cy + 1) * w + (size_t)gx * 4) = yb;
 }
 
-// fmt: 0 RGB24, 1 BGR24, 2 RGBA, 3 BGRA
+// fmt: 0 RGB24, 1 BGR24, 2 RGBA, 3 BGRA, 4 RGB565
 int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int fmt, void *d_dst) {
 	MSB200_CHECK_ARG(ctx && d_src && d_dst && n_frames > 0 && n_frames <= 65535 && w > 0 && h > 0 && (w % 4) == 0 && (h % 2) == 0);
-	MSB200_CHECK_ARG(fmt >= 0 && fmt <= 3 && ((uintptr_t)d_src % (fmt >= 2 ? 16 : 4)) == 0 && ((uintptr_t)d_dst % 4) == 0);
+	MSB200_CHECK_ARG(fmt >= 0 && fmt <= 4 && ((uintptr_t)d_src % (fmt == 2 || fmt == 3 ? 16 : fmt == 4 ? 8 : 4)) == 0 && ((uintptr_t)d_dst % 4) == 0);
 	const long threads = (long)(w / 4) * (h / 2);
 	dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
 	switch (fmt) {

@@ -1143,20 +1143,27 @@ struct PlaneStripParams {
 	int group, dst_pitch, tile_shift;
 	const short2 *tile_xy;
 	int x86_rows; // output rows [0, x86_rows) round like the library's x86 SIMD vertical scaler (ScaleParams::x86_vertical)
+	int inter_v_first; // INTER kernels (NV12 / NV21 chroma read in place): 1 = the V sample is the pair's first byte (NV21)
 	short x0[ST_MAX_TX], y0[ST_MAX_TY];
 };
-template <int VT>
+// INTER: the source is the interleaved CbCr plane of an NV12 / NV21 frame, read IN PLACE through a tensor map of 16-bit
+// (Cb, Cr) pairs — no de-interleaving pre-pass, no planar scratch frame (cfg4's reference-shaped NV12 -> I420 + scale
+// otherwise moves 2.4 x the bytes). The box holds pairs; each of the two planes of the launch picks its byte of every pair
+// with one PRMT per word pair on the way into the horizontal pass. Everything downstream is the planar kernel.
+template <int VT, bool INTER = false>
 __global__ void __launch_bounds__(ST_THREADS, 8)
     scale_plane_strip_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                              unsigned char *__restrict__ dst, const PlaneStripParams S) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	const unsigned box_bytes = (unsigned)(S.box_w * S.box_h), box_al = (box_bytes + 127u) & ~127u;
+	constexpr unsigned EB = INTER ? 2u : 1u; // bytes per box element
+	const unsigned box_bytes = (unsigned)(S.box_w * S.box_h) * EB, box_al = (box_bytes + 127u) & ~127u;
 	unsigned char *box = smem;
 	uint64_t *bar = reinterpret_cast<uint64_t *>(box + box_al);
 	const unsigned s_tab = smem_u32(box + box_al) + 16;
 	const int frame = blockIdx.z / S.n_planes, plane = blockIdx.z - frame * S.n_planes;
+	const unsigned pick = (plane ^ S.inter_v_first) & 1 ? 0x7531u : 0x6420u; // INTER: second / first byte of every pair
 	const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * (ST_WARPS * S.R);
 	const int bx0 = S.x0[blockIdx.x], by0 = S.y0[blockIdx.y];
 	if (t == 0) {
@@ -1178,7 +1185,7 @@ __global__ void __launch_bounds__(ST_THREADS, 8)
 	const int pA = lpos.x - bx0, pB = lpos.z - bx0;
 	const unsigned shA = (unsigned)(pA & 3) * 8, shB = (unsigned)(pB & 3) * 8;
 	const unsigned dA = (unsigned)(lpos.y - lpos.x) * 8, dB = (unsigned)(lpos.w - lpos.z) * 8;
-	const unsigned pitch = (unsigned)S.box_w;
+	const unsigned pitch = (unsigned)S.box_w * EB;
 	int WL[VT][4];
 #pragma unroll
 	for (int s = 0; s < VT; ++s)
@@ -1193,8 +1200,8 @@ __global__ void __launch_bounds__(ST_THREADS, 8)
 	const int lrow0 = ra.x - (VT - 1);
 	const int s0 = lrow0 % VT;
 	int row = lrow0;
-	unsigned la = smem_u32(box) + (unsigned)(pA & ~3) + (unsigned)(row - by0) * pitch;
-	unsigned lb = smem_u32(box) + (unsigned)(pB & ~3) + (unsigned)(row - by0) * pitch;
+	unsigned la = smem_u32(box) + (unsigned)(pA & ~3) * EB + (unsigned)(row - by0) * pitch;
+	unsigned lb = smem_u32(box) + (unsigned)(pB & ~3) * EB + (unsigned)(row - by0) * pitch;
 	unsigned char *o = dst + (size_t)(frame / S.group) * S.dst_frame_bytes + S.dst_off[plane] + (size_t)ys * S.dst_pitch + x0 + 4 * lane;
 	if (S.tile_xy) {
 		const short2 txy = S.tile_xy[frame % S.group];
@@ -1202,7 +1209,17 @@ __global__ void __launch_bounds__(ST_THREADS, 8)
 	}
 	int y = ys;
 	auto hrow = [&](int(&w)[4]) {
-		const unsigned a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+		unsigned a0, a1, a2, b0, b1, b2;
+		if (INTER) { // 24 bytes of pairs -> this plane's 12 samples
+			a0 = __byte_perm(lds32<0>(la), lds32<4>(la), pick);
+			a1 = __byte_perm(lds32<8>(la), lds32<12>(la), pick);
+			a2 = __byte_perm(lds32<16>(la), lds32<20>(la), pick);
+			b0 = __byte_perm(lds32<0>(lb), lds32<4>(lb), pick);
+			b1 = __byte_perm(lds32<8>(lb), lds32<12>(lb), pick);
+			b2 = __byte_perm(lds32<16>(lb), lds32<20>(lb), pick);
+		} else {
+			a0 = lds32<0>(la), a1 = lds32<4>(la), a2 = lds32<8>(la), b0 = lds32<0>(lb), b1 = lds32<4>(lb), b2 = lds32<8>(lb);
+		}
 		const unsigned A0 = __funnelshift_r(a0, a1, shA), A1 = __funnelshift_r(a1, a2, shA);
 		const unsigned B0 = __funnelshift_r(b0, b1, shB), B1 = __funnelshift_r(b1, b2, shB);
 		const unsigned A0b = __funnelshift_r(A0, A1, dA), B0b = __funnelshift_r(B0, B1, dB);
@@ -1830,8 +1847,6 @@ struct msb200_scaler {
 	bool fast_ok;
 	bool direct;        // geometry outside the tile kernels' TMA box limits: scale_direct_kernel
 	bool pstrip_ok;                   // planar I420 -> I420 (MSSizeConv): scale_plane_strip_kernel applies
-	msb200_devbuf deint;              // NV12 / NV21 -> I420 pre-pass output (planar scratch frames)
-	void *deint_last;
 	PlaneStripParams PL, PC;          // luma plane; the two chroma planes
 	int canvas_w, canvas_h, canvas_tiles; // mosaic destination (msb200_scaler_set_canvas), 0 = tight frames
 	void *d_tile_xy;
@@ -1872,7 +1887,7 @@ static PFN_encodeTiled get_encode() {
 
 // 3-D byte tensor (width bytes, rows, frames) with a (box_w, box_h, 1) box; out-of-bounds elements read as zero
 static int make_map(CUtensorMap *m, const void *base, uint64_t width, uint64_t rows, uint64_t frames, uint64_t row_pitch,
-                    uint64_t frame_pitch, uint32_t box_w, uint32_t box_h, bool u32 = false) {
+                    uint64_t frame_pitch, uint32_t box_w, uint32_t box_h, bool u32 = false, bool u16 = false) {
 	PFN_encodeTiled enc = get_encode();
 	if (!enc) {
 		msb200_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -1882,7 +1897,7 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t width, uint64_t r
 	cuuint64_t strides[2] = {row_pitch, frame_pitch};
 	cuuint32_t box[3] = {box_w, box_h, 1};
 	cuuint32_t estr[3] = {1, 1, 1};
-	CUresult r = enc(m, u32 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+	CUresult r = enc(m, u32 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : (u16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8), 3, const_cast<void *>(base), dims, strides, box, estr,
 	                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
 	                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
@@ -2382,14 +2397,14 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 		return MSB200_OK;
 	}
 	// ---- plane strips (MSSizeConv: planar I420 -> I420): per-plane tables, boxes and tile geometry
-	// (NV12 / NV21 sources reach the same kernels through a de-interleaving pre-pass into a planar scratch frame: the
-	// chroma geometry and filters are those of the planar source, the de-interleave is exact)
+	// (NV12 / NV21 sources reach the same kernels in place: the chroma geometry and filters are those of the planar source,
+	// the chroma box holds 16-bit (Cb, Cr) pairs and each plane's warp picks its byte of every pair)
 	if (!dst_rgb && (src_fmt == MSB200_PIX_YUV420P || ((src_fmt == MSB200_PIX_NV12 || src_fmt == MSB200_PIX_NV21) && src_w % 32 == 0)) &&
 	    P.hl_size == 4 && P.hc_size == 4 && (P.vl_size == 1 || P.vl_size == 2 || P.vl_size == 4) &&
 	    (P.vc_size == 1 || P.vc_size == 2 || P.vc_size == 4) && dst_w % 8 == 0 && dst_h % 2 == 0 && (src_w / 2) % 16 == 0 &&
 	    ((size_t)dst_w * dst_h) % 4 == 0 && ((size_t)P.chr_dst_w * P.chr_dst_h) % 4 == 0) {
 		bool ok = true;
-		auto plane_setup = [&](PlaneStripParams &Q, const Filter &hf, const Filter &vf, int vsize, int W, int H, size_t &smem) -> int {
+		auto plane_setup = [&](PlaneStripParams &Q, const Filter &hf, const Filter &vf, int vsize, int W, int H, size_t &smem, int eb) -> int {
 			for (int16_t c : hf.coef) ok = ok && c >= 0;
 			for (int16_t c : vf.coef) ok = ok && c >= 0;
 			for (int x = 0; x + 1 < W && ok; x += 2) {
@@ -2402,12 +2417,12 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			Q.box_w = (max_span(hf, W, ST_TW) + 15 + 15) & ~15;
 			Q.R = 0;
 			for (int R = 16; R >= 4 && !Q.R; R -= 4) // tallest strips whose source box still fits a TMA box and 8 CTAs' smem
-				if (max_span(vf, H, ST_WARPS * R) <= 256 && ((size_t)Q.box_w * max_span(vf, H, ST_WARPS * R) + 4096) * 8 <= 220 * 1024) Q.R = R;
+				if (max_span(vf, H, ST_WARPS * R) <= 256 && ((size_t)Q.box_w * eb * max_span(vf, H, ST_WARPS * R) + 4096) * 8 <= 220 * 1024) Q.R = R;
 			ok = ok && Q.R > 0 && Q.box_w <= 256 && msb200_div_up(W, ST_TW) <= ST_MAX_TX && msb200_div_up(H, ST_WARPS * (Q.R ? Q.R : 4)) <= ST_MAX_TY;
 			if (!ok) return MSB200_OK;
 			const int th = ST_WARPS * Q.R;
 			Q.box_h = max_span(vf, H, th);
-			smem = (((size_t)Q.box_w * Q.box_h + 127) & ~(size_t)127) + 16 + 32 * (size_t)(th + 1) + 128;
+			smem = (((size_t)Q.box_w * eb * Q.box_h + 127) & ~(size_t)127) + 16 + 32 * (size_t)(th + 1) + 128;
 			std::vector<StripRow> rows((size_t)H + th + 2);
 			for (int y = 0; y < H; ++y) {
 				StripRow &r = rows[(size_t)y];
@@ -2435,13 +2450,15 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			return MSB200_OK;
 		};
 		int rc;
-		if ((rc = plane_setup(s->PL, s->hl, s->vl, P.vl_size, dst_w, dst_h, s->smem_pl))) return rc;
-		if (ok && (rc = plane_setup(s->PC, s->hc, s->vc, P.vc_size, P.chr_dst_w, P.chr_dst_h, s->smem_pc))) return rc;
+		const int chroma_eb = src_fmt == MSB200_PIX_YUV420P ? 1 : 2; // NV12 / NV21: the chroma box holds (Cb, Cr) pairs
+		if ((rc = plane_setup(s->PL, s->hl, s->vl, P.vl_size, dst_w, dst_h, s->smem_pl, 1))) return rc;
+		if (ok && (rc = plane_setup(s->PC, s->hc, s->vc, P.vc_size, P.chr_dst_w, P.chr_dst_h, s->smem_pc, chroma_eb))) return rc;
 		if (ok) {
 			s->PL.hpos = P.hl_pos; s->PL.hcoef = P.hl_coef; s->PL.n_planes = 1; s->PL.dst_off[0] = 0;
 			s->PC.hpos = P.hc_pos; s->PC.hcoef = P.hc_coef; s->PC.n_planes = 2;
 			s->PC.dst_off[0] = (size_t)dst_w * dst_h;
 			s->PC.dst_off[1] = (size_t)dst_w * dst_h + (size_t)P.chr_dst_w * P.chr_dst_h;
+			s->PC.inter_v_first = src_fmt == MSB200_PIX_NV21 ? 1 : 0;
 			s->pstrip_ok = true;
 		}
 	}
@@ -2481,7 +2498,6 @@ void msb200_scaler_destroy(msb200_scaler *s) {
 	cudaFree((void *)s->PL.rows);
 	cudaFree((void *)s->PC.rows);
 	cudaFree(s->d_tile_xy);
-	s->deint.release();
 	s->src.release();
 	s->dst.release();
 	delete s;
@@ -2672,25 +2688,25 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 	}
 	if (s->canvas_tiles > 0) MSB200_CHECK_ARG(n_frames % s->canvas_tiles == 0 && ((uintptr_t)d_dst % 16) == 0);
 	if (s->pstrip_ok && (s->canvas_tiles > 0 || (s->force_path == 0 && ((uintptr_t)d_dst % 16) == 0 && (s->dst_bytes % 4) == 0))) {
-		// planar I420 -> I420: one warp per plane strip, Y in one launch, U and V together in a second
-		if (P.src_fmt != MSB200_PIX_YUV420P) { // interleaved chroma: exact de-interleave into a planar scratch frame first
-			if ((r = s->deint.reserve(s->src_bytes * (size_t)n_frames + 256))) return r;
-			if ((r = msb200_nv12_to_i420_dev(s->ctx, n_frames, d_src, s->src_bytes, (size_t)P.src_w * P.src_h, 0, P.src_w, P.src_h, P.src_w,
-			                                 P.src_w, P.src_fmt == MSB200_PIX_NV12 ? 1 : 0, 0, s->deint.p))) return r;
-			if (s->deint.p != s->deint_last) s->cached_src = nullptr; // the scratch buffer moved: tensor maps are stale
-			s->deint_last = s->deint.p;
-			d_src = s->deint.p;
-		}
+		// planar output: one warp per plane strip, Y in one launch, U and V together in a second. NV12 / NV21 sources are read
+		// in place: their Y plane IS a planar Y plane, their chroma plane goes through a tensor map of 16-bit (Cb, Cr) pairs
+		const bool inter = P.src_fmt != MSB200_PIX_YUV420P;
 		const char *base = (const char *)d_src;
 		const uint64_t fp = s->src_bytes;
 		if (!(s->cached_src == d_src && s->cached_frames == n_frames)) {
 			if ((r = make_map(&s->map_py, base, (uint64_t)P.src_w, (uint64_t)P.src_h, (uint64_t)n_frames, (uint64_t)P.src_w, fp,
 			                  (uint32_t)s->PL.box_w, (uint32_t)s->PL.box_h))) return r;
 			const char *cb = base + (size_t)P.src_w * P.src_h;
-			if ((r = make_map(&s->map_pu, cb, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h, (uint64_t)n_frames, (uint64_t)P.chr_src_w, fp,
-			                  (uint32_t)s->PC.box_w, (uint32_t)s->PC.box_h))) return r;
-			if ((r = make_map(&s->map_pv, cb + (size_t)P.chr_src_w * P.chr_src_h, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h,
-			                  (uint64_t)n_frames, (uint64_t)P.chr_src_w, fp, (uint32_t)s->PC.box_w, (uint32_t)s->PC.box_h))) return r;
+			if (inter) {
+				if ((r = make_map(&s->map_pu, cb, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h, (uint64_t)n_frames, (uint64_t)P.chr_src_w * 2,
+				                  fp, (uint32_t)s->PC.box_w, (uint32_t)s->PC.box_h, false, true))) return r;
+				s->map_pv = s->map_pu;
+			} else {
+				if ((r = make_map(&s->map_pu, cb, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h, (uint64_t)n_frames, (uint64_t)P.chr_src_w, fp,
+				                  (uint32_t)s->PC.box_w, (uint32_t)s->PC.box_h))) return r;
+				if ((r = make_map(&s->map_pv, cb + (size_t)P.chr_src_w * P.chr_src_h, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h,
+				                  (uint64_t)n_frames, (uint64_t)P.chr_src_w, fp, (uint32_t)s->PC.box_w, (uint32_t)s->PC.box_h))) return r;
+			}
 			s->cached_src = d_src;
 			s->cached_frames = n_frames;
 		}
@@ -2701,8 +2717,17 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 		else if ((VS) == 2) MSB200_LAUNCH(s->ctx, scale_plane_strip_kernel<2>, g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q); \
 		else MSB200_LAUNCH(s->ctx, scale_plane_strip_kernel<1>, g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q);  \
 	} while (0)
+#define PSTRIP_LAUNCH_INTER(Q, VS, MA, MB, SM)                                                                         \
+	do {                                                                                                               \
+		dim3 g((unsigned)msb200_div_up((Q).W, ST_TW), (unsigned)msb200_div_up((Q).H, ST_WARPS * (Q).R), (unsigned)(n_frames * (Q).n_planes)); \
+		if ((VS) == 4) MSB200_LAUNCH(s->ctx, (scale_plane_strip_kernel<4, true>), g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q); \
+		else if ((VS) == 2) MSB200_LAUNCH(s->ctx, (scale_plane_strip_kernel<2, true>), g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q); \
+		else MSB200_LAUNCH(s->ctx, (scale_plane_strip_kernel<1, true>), g, ST_THREADS, SM, MA, MB, (unsigned char *)d_dst, Q); \
+	} while (0)
 		PSTRIP_LAUNCH(s->PL, P.vl_size, s->map_py, s->map_py, s->smem_pl);
-		PSTRIP_LAUNCH(s->PC, P.vc_size, s->map_pu, s->map_pv, s->smem_pc);
+		if (inter) PSTRIP_LAUNCH_INTER(s->PC, P.vc_size, s->map_pu, s->map_pv, s->smem_pc);
+		else PSTRIP_LAUNCH(s->PC, P.vc_size, s->map_pu, s->map_pv, s->smem_pc);
+#undef PSTRIP_LAUNCH_INTER
 #undef PSTRIP_LAUNCH
 		return MSB200_OK;
 	}

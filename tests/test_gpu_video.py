@@ -87,6 +87,12 @@ def _rand_frames(fmt, w, h, n, seed):
     (_lib.PIX_YUV420P, 64, 48, _lib.PIX_YUV420P, 160, 120),    # MSSizeConv: I420 -> I420 up
     (_lib.PIX_NV12, 320, 240, _lib.PIX_YUV420P, 320, 240),     # MSPixConv-like: NV12 -> I420 same size through the scaler
     (_lib.PIX_NV12, 208, 112, _lib.PIX_RGB24, 150, 90),        # ragged tiles (150 % 128, 90 % 16 != 0)
+    (_lib.PIX_NV12, 192, 108, _lib.PIX_YUV420P, 128, 72),      # NV12 -> I420 down: CbCr plane read in place (pair map)
+    (_lib.PIX_NV21, 192, 108, _lib.PIX_YUV420P, 128, 72),      # ... and with Cr first
+    (_lib.PIX_NV12, 1920, 1080, _lib.PIX_YUV420P, 1280, 720),  # cfg4's reference-shaped two-step as one pass, full size
+    (_lib.PIX_NV21, 64, 48, _lib.PIX_YUV420P, 160, 120),       # 2.5x up from an interleaved chroma plane
+    (_lib.PIX_NV12, 208, 112, _lib.PIX_YUV420P, 150, 90),      # ragged tiles, odd chroma width (75)
+    (_lib.PIX_NV12, 1280, 720, _lib.PIX_YUV420P, 640, 360),    # 2:1 down
 ])
 def test_scaler_bit_exact_vs_oracle(ctx, sf, sw, sh, df, dw, dh):
     L = O.oracle()
