@@ -1811,6 +1811,364 @@ __global__ void __launch_bounds__(256) scale_direct_kernel(const unsigned char *
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ down-scale tiles
+// Down-scales by 2x and more (MSSizeConv thumbnails, mosaic tiles, 1080p -> 360p previews): the 128-column tiles of the
+// kernels above would need source windows wider than a TMA box (256 elements), and the filters grow with the ratio
+// (8 taps at 3:1, 24 at 12:1). Here the tile narrows instead — TW = 64, 32 or 16 output columns x D.th rows, so that the
+// window fits one box per plane — and the two passes go through shared memory:
+//   H  thread = output column, loop over the rows of the box: the column's taps live in registers as dp2a pairs (HG
+//      groups of four; HG == 0: any size, taps re-read through L1), the window comes out of three to seven 32-bit shared
+//      loads and one funnel shift per group; the 15-bit result is kept as int32 (no unpacking later). Interleaved CbCr
+//      boxes hold 16-bit pairs and are split with PRMT on the way in.
+//   V  RGB: thread = pixel pair, vertical taps from a per-tile table, colour stage as in the kernels above, rows staged
+//      and written with 16-byte stores.  Planar: thread = four samples of a row, one 32-bit store each; the placement
+//      is the plane strips' (canvas pitch + per-tile origin), so a mosaic of >= 2x thumbnails takes this path too.
+// Source bytes dominate here (9 per output pixel at 3:1): per source byte the H pass costs ~4 instructions, the V pass 2 - 3.
+#define DN_THREADS 256
+struct DownParams {
+	int th;                     // luma output rows per tile (even)
+	int box_lw, box_lh;         // luma box: bytes x rows
+	int box_cw, box_ch;         // chroma box: elements (pairs when interleaved) x rows
+	int lt_pitch, ct_pitch;     // ints per output row of the tile's vertical-tap table: [first row, taps...], multiples of 4
+	int vt_ints;                // ints per tile row of the table in global memory (luma rows, then chroma rows)
+	unsigned o_c0, o_c1, o_lh, o_ch, o_vt, o_bar; // shared-memory layout (bytes from the 128-byte aligned base)
+	const int2 *tile_x;         // per tile column: box origins {luma x, chroma x}
+	const int4 *tile_y;         // per tile row: {luma y, chroma y, luma rows to filter, chroma rows to filter}
+	const int *vtab;            // per tile row: the vertical-tap tables, positions relative to the box
+	size_t dst_frame_bytes, off_u, off_v;
+	int pitch_y, pitch_c, group; // planar placement (msb200_scaler_set_canvas); tight frames: dst_w, chr_dst_w, 1
+	const short2 *tile_xy;
+};
+__device__ __forceinline__ uint2 lds64(unsigned addr) {
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, int a, int b) {
+	asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// a[0..3] += taps x four adjacent columns of int32 intermediates: rows `pitch` bytes apart starting at addr, the taps at
+// ktab + 4 (ktab is 16-byte aligned: [first row, tap 0, tap 1, ...]). N > 0: compile-time tap count, N == 0: n at run time.
+// X86: libswscale's SIMD vertical scaler drops the low 16 bits of every product (ScaleParams::x86_vertical)
+template <int N, bool X86>
+__device__ __forceinline__ void vacc4(unsigned addr, unsigned pitch, unsigned ktab, int n, int (&a)[4]) {
+	if (N > 0) {
+		int kk[(N + 4) & ~3];
+#pragma unroll
+		for (int q = 0; q < (N + 4) / 4; ++q) {
+			const int4 v = lds128(ktab + 16 * q);
+			kk[4 * q] = v.x; kk[4 * q + 1] = v.y; kk[4 * q + 2] = v.z; kk[4 * q + 3] = v.w;
+		}
+#pragma unroll
+		for (int j = 0; j < N; ++j) {
+			const int4 l = lds128(addr);
+			addr += pitch;
+			const int k = kk[1 + j];
+			if (X86) { a[0] += (l.x * k) >> 16; a[1] += (l.y * k) >> 16; a[2] += (l.z * k) >> 16; a[3] += (l.w * k) >> 16; }
+			else { a[0] += l.x * k; a[1] += l.y * k; a[2] += l.z * k; a[3] += l.w * k; }
+		}
+	} else {
+#pragma unroll 2
+		for (int j = 0; j < n; ++j) {
+			const int4 l = lds128(addr);
+			addr += pitch;
+			ktab += 4;
+			const int k = (int)lds32<0>(ktab);
+			if (X86) { a[0] += (l.x * k) >> 16; a[1] += (l.y * k) >> 16; a[2] += (l.z * k) >> 16; a[3] += (l.w * k) >> 16; }
+			else { a[0] += l.x * k; a[1] += l.y * k; a[2] += l.z * k; a[3] += l.w * k; }
+		}
+	}
+}
+template <bool X86>
+__device__ __forceinline__ void vacc4_any(unsigned addr, unsigned pitch, unsigned ktab, int n, int (&a)[4]) {
+	switch (n) {
+		case 4: vacc4<4, X86>(addr, pitch, ktab, n, a); break;
+		case 6: vacc4<6, X86>(addr, pitch, ktab, n, a); break;
+		case 8: vacc4<8, X86>(addr, pitch, ktab, n, a); break;
+		default: vacc4<0, X86>(addr, pitch, ktab, n, a); break;
+	}
+}
+__device__ __forceinline__ unsigned pack4_u8(const int (&a)[4]) {
+	return sat_u8(a[0]) | (sat_u8(a[1]) << 8) | (sat_u8(a[2]) << 16) | (sat_u8(a[3]) << 24);
+}
+template <int TW, int HG, bool RGB>
+__global__ void __launch_bounds__(DN_THREADS, 4)
+    scale_down_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c0,
+                      const __grid_constant__ CUtensorMap map_c1, unsigned char *__restrict__ dst, const ScaleParams P, const DownParams D) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	constexpr int CW = TW / 2; // chroma columns (and luma column pairs) per tile
+	const unsigned sb = (smem_u32(smem_raw) + 127u) & ~127u;
+	unsigned char *smem = smem_raw + (sb - smem_u32(smem_raw));
+	const int t = threadIdx.x;
+	const int x0 = blockIdx.x * TW, y0 = blockIdx.y * D.th, frame = blockIdx.z;
+	const int cx0 = x0 >> 1, cy0 = RGB ? y0 : y0 >> 1;
+	const int th = min(D.th, P.dst_h - y0);
+	const int cth = RGB ? th : min(D.th >> 1, P.chr_dst_h - cy0);
+	const bool inter = P.chroma_planes == 1;
+	const unsigned s_box_l = sb, s_c0 = sb + D.o_c0, s_c1 = sb + D.o_c1, s_lh = sb + D.o_lh, s_ch = sb + D.o_ch, s_vt = sb + D.o_vt;
+	const unsigned s_ct = s_vt + 4u * (unsigned)(D.th * D.lt_pitch);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + D.o_bar);
+	const int2 ox = D.tile_x[blockIdx.x];
+	const int4 oy = D.tile_y[blockIdx.y];
+	if (t == 0) {
+		const unsigned cbox_bytes = (unsigned)(D.box_cw * D.box_ch) * (inter ? 2u : 1u);
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, (unsigned)(D.box_lw * D.box_lh) + (inter ? 1u : 2u) * cbox_bytes);
+		tma_load_3d(smem, &map_l, bar, ox.x, oy.x, frame);
+		tma_load_3d(smem + D.o_c0, &map_c0, bar, ox.y, oy.y, frame);
+		if (!inter) tma_load_3d(smem + D.o_c1, &map_c1, bar, ox.y, oy.y, frame);
+	}
+	// while the boxes are in flight: the tile row's vertical taps, and this thread's horizontal filters
+	for (int i = t; 4 * i < D.vt_ints; i += DN_THREADS) cp_async16(s_vt + 16 * i, D.vtab + (size_t)blockIdx.y * D.vt_ints + 4 * i);
+	asm volatile("cp.async.commit_group;\n" ::: "memory");
+	const int l_rows = oy.z, c_rows = oy.w;
+	const int cxi = t % CW, cgx = min(cx0 + cxi, P.chr_dst_w - 1), cp_off = P.hc_pos[cgx] - ox.y;
+	const int *ccf = reinterpret_cast<const int *>(P.hc_coef + (size_t)cgx * P.hc_size);
+	constexpr int NG = HG > 0 ? HG : 1;
+	int ck[2 * NG];
+#pragma unroll
+	for (int g = 0; g < 2 * NG; ++g) ck[g] = HG > 0 ? ccf[g] : 0;
+
+	if (HG > 0) {
+		// ---- H, luma: thread = two adjacent output columns (their windows overlap: the second one's is the first one's,
+		// funnel-shifted by the distance of the filter positions — at most four source samples here), loop over box rows
+		const int gxa = min(x0 + 2 * cxi, P.dst_w - 1), gxb = min(gxa + 1, P.dst_w - 1);
+		const int pa = P.hl_pos[gxa] - ox.x;
+		const unsigned sh = (unsigned)(pa & 3) * 8, dsh = (unsigned)(P.hl_pos[gxb] - ox.x - pa) * 8;
+		const int *fa = reinterpret_cast<const int *>(P.hl_coef + (size_t)gxa * P.hl_size);
+		const int *fb = reinterpret_cast<const int *>(P.hl_coef + (size_t)gxb * P.hl_size);
+		int ka[2 * NG], kb[2 * NG];
+#pragma unroll
+		for (int g = 0; g < 2 * NG; ++g) {
+			ka[g] = fa[g];
+			kb[g] = fb[g];
+		}
+		const int rg = t / CW;
+		unsigned la = s_box_l + (unsigned)(pa & ~3) + (unsigned)(rg * D.box_lw);
+		unsigned lo = s_lh + 4u * (unsigned)(rg * TW + 2 * cxi);
+		const unsigned lstep = (unsigned)D.box_lw * (DN_THREADS / CW);
+		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+		__syncthreads(); // barrier initialised, tables in place
+		mbar_wait(bar, 0);
+		for (int r = rg; r < l_rows; r += DN_THREADS / CW) {
+			unsigned w[NG + 2], A[NG + 1];
+			w[0] = lds32<0>(la);
+			w[1] = lds32<4>(la);
+			w[2] = lds32<8>(la);
+			if (NG > 1) w[NG + 1] = lds32<4 * (NG + 1)>(la);
+#pragma unroll
+			for (int g = 0; g <= NG; ++g) A[g] = __funnelshift_r(w[g], w[g + 1], sh);
+			int va = 0, vb = 0;
+#pragma unroll
+			for (int g = 0; g < NG; ++g) {
+				const unsigned qb = __funnelshift_rc(A[g], A[g + 1], dsh);
+				va = dp2a_hi(ka[2 * g + 1], A[g], dp2a_lo(ka[2 * g], A[g], va));
+				vb = dp2a_hi(kb[2 * g + 1], qb, dp2a_lo(kb[2 * g], qb, vb));
+			}
+			sts64(lo, min(va >> 7, 32767), min(vb >> 7, 32767));
+			la += lstep;
+			lo += 4u * TW * (DN_THREADS / CW);
+		}
+	} else {
+		// ---- H, luma, any filter size: thread = one output column, taps re-read through L1
+		const int lx = t % TW, lgx = min(x0 + lx, P.dst_w - 1), lp_off = P.hl_pos[lgx] - ox.x;
+		const int *lcf = reinterpret_cast<const int *>(P.hl_coef + (size_t)lgx * P.hl_size);
+		const unsigned sh = (unsigned)(lp_off & 3) * 8;
+		const int rg = t / TW, groups = P.hl_size >> 2;
+		unsigned la = s_box_l + (unsigned)(lp_off & ~3) + (unsigned)(rg * D.box_lw);
+		unsigned lo = s_lh + 4u * (unsigned)(rg * TW + lx);
+		const unsigned lstep = (unsigned)D.box_lw * (DN_THREADS / TW);
+		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+		__syncthreads();
+		mbar_wait(bar, 0);
+		for (int r = rg; r < l_rows; r += DN_THREADS / TW) {
+			int val = 0;
+			unsigned a = lds32<0>(la);
+			for (int g = 0; g < groups; ++g) {
+				const unsigned b = lds32<4>(la + 4u * g), q = __funnelshift_r(a, b, sh);
+				val = dp2a_hi(lcf[2 * g + 1], q, dp2a_lo(lcf[2 * g], q, val));
+				a = b;
+			}
+			sts32<0>(lo, (unsigned)min(val >> 7, 32767));
+			la += lstep;
+			lo += 4u * TW * (DN_THREADS / TW);
+		}
+	}
+	// ---- H, chroma: thread = one output column, both components (same positions and taps)
+	{
+		const int rg = t / CW, groups = HG > 0 ? NG : P.hc_size >> 2;
+		unsigned co = s_ch + 8u * (unsigned)(rg * CW + cxi);
+		if (inter) {
+			const bool swap_uv = P.src_fmt == MSB200_PIX_NV21;
+			const unsigned sh = (unsigned)(cp_off & 1) * 16;
+			unsigned ca = s_c0 + 4u * (unsigned)(cp_off >> 1) + (unsigned)(rg * D.box_cw * 2);
+			const unsigned cstep = (unsigned)D.box_cw * 2u * (DN_THREADS / CW);
+			for (int r = rg; r < c_rows; r += DN_THREADS / CW) {
+				int u = 0, v = 0;
+				unsigned a = lds32<0>(ca);
+				auto group = [&](unsigned b, unsigned c, int k0, int k1) {
+					const unsigned p0 = __funnelshift_r(a, b, sh), p1 = __funnelshift_r(b, c, sh); // four (Cb, Cr) pairs
+					const unsigned qu = __byte_perm(p0, p1, 0x6420), qv = __byte_perm(p0, p1, 0x7531);
+					u = dp2a_hi(k1, qu, dp2a_lo(k0, qu, u));
+					v = dp2a_hi(k1, qv, dp2a_lo(k0, qv, v));
+					a = c;
+				};
+				if (HG > 0) {
+					group(lds32<4>(ca), lds32<8>(ca), ck[0], ck[1]);
+					if (NG > 1) group(lds32<12>(ca), lds32<16>(ca), ck[2 * (NG - 1)], ck[2 * (NG - 1) + 1]);
+				} else {
+					for (int g = 0; g < groups; ++g) group(lds32<4>(ca + 8u * g), lds32<8>(ca + 8u * g), ccf[2 * g], ccf[2 * g + 1]);
+				}
+				u = min(u >> 7, 32767);
+				v = min(v >> 7, 32767);
+				sts64(co, swap_uv ? v : u, swap_uv ? u : v);
+				ca += cstep;
+				co += 8u * CW * (DN_THREADS / CW);
+			}
+		} else {
+			const unsigned sh = (unsigned)(cp_off & 3) * 8;
+			unsigned ca = (unsigned)(cp_off & ~3) + (unsigned)(rg * D.box_cw);
+			const unsigned cstep = (unsigned)D.box_cw * (DN_THREADS / CW);
+			for (int r = rg; r < c_rows; r += DN_THREADS / CW) {
+				int u = 0, v = 0;
+				unsigned au = lds32<0>(s_c0 + ca), av = lds32<0>(s_c1 + ca);
+				auto group = [&](unsigned bu, unsigned bv, int k0, int k1) {
+					const unsigned qu = __funnelshift_r(au, bu, sh), qv = __funnelshift_r(av, bv, sh);
+					u = dp2a_hi(k1, qu, dp2a_lo(k0, qu, u));
+					v = dp2a_hi(k1, qv, dp2a_lo(k0, qv, v));
+					au = bu;
+					av = bv;
+				};
+				if (HG > 0) {
+					group(lds32<4>(s_c0 + ca), lds32<4>(s_c1 + ca), ck[0], ck[1]);
+					if (NG > 1) group(lds32<8>(s_c0 + ca), lds32<8>(s_c1 + ca), ck[2 * (NG - 1)], ck[2 * (NG - 1) + 1]);
+				} else {
+					for (int g = 0; g < groups; ++g) group(lds32<4>(s_c0 + ca + 4u * g), lds32<4>(s_c1 + ca + 4u * g), ccf[2 * g], ccf[2 * g + 1]);
+				}
+				sts64(co, min(u >> 7, 32767), min(v >> 7, 32767));
+				ca += cstep;
+				co += 8u * CW * (DN_THREADS / CW);
+			}
+		}
+	}
+	__syncthreads();
+
+	if (RGB) {
+		// ---- V + colour (yuv2rgb_X: the host sends vertically unscaled and two-tap geometries elsewhere): thread = four
+		// pixels of one row (two chroma samples); rows are staged over the luma box (dead by now) and leave as 16-byte stores
+		constexpr int QW = TW / 4;
+		const int q = t % QW, ry = t / QW;
+		const int tw = min(TW, P.dst_w - x0);
+		if (ry < th && 4 * q < tw) {
+			const unsigned lt = s_vt + 4u * (unsigned)(ry * D.lt_pitch), ct = s_ct + 4u * (unsigned)(ry * D.ct_pitch);
+			int Y[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18}, C[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18}; // C: U0 V0 U1 V1
+			vacc4_any<false>(s_lh + 16u * (unsigned)((int)lds32<0>(lt) * QW + q), 16u * QW, lt, P.vl_size, Y);
+			vacc4_any<false>(s_ch + 16u * (unsigned)((int)lds32<0>(ct) * QW + q), 16u * QW, ct, P.vc_size, C);
+			const bool bgr = P.dst_fmt == MSB200_PIX_RGB24_REV;
+			const int c_cy = P.cy, c_off = P.yb0 + 0x8000;
+			const int base_r = P.yoffs - (P.crv >> 9), base_g = P.yoffs - (P.cgu >> 9) - (P.cgv >> 9), base_b = P.yoffs - (P.cbu >> 9);
+			unsigned px[4]; // c0 | g << 8 | c2 << 16 per pixel
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int Uc = (int)sat_u8(C[2 * h] >> 19), Vc = (int)sat_u8(C[2 * h + 1] >> 19);
+				const int ar = c_off + (base_r + ((Vc * P.crv) >> 16)) * c_cy;
+				const int ag = c_off + (base_g + ((Uc * P.cgu) >> 16) + ((Vc * P.cgv) >> 16)) * c_cy;
+				const int ab = c_off + (base_b + ((Uc * P.cbu) >> 16)) * c_cy;
+#pragma unroll
+				for (int e = 0; e < 2; ++e) {
+					const int yc = (Y[2 * h + e] >> 19) * c_cy;
+					const unsigned r = sat_u8((ar + yc) >> 16), g = sat_u8((ag + yc) >> 16), b = sat_u8((ab + yc) >> 16);
+					px[2 * h + e] = (bgr ? b : r) | (g << 8) | ((bgr ? r : b) << 16);
+				}
+			}
+			const unsigned os = s_box_l + (unsigned)(ry * TW * 3 + q * 12);
+			sts32<0>(os, px[0] | (px[1] << 24));
+			sts32<4>(os, (px[1] >> 8) | (px[2] << 16));
+			sts32<8>(os, (px[2] >> 16) | (px[3] << 8));
+		}
+		__syncthreads();
+		unsigned char *fd = dst + (size_t)frame * P.dst_frame_bytes;
+		const size_t row_bytes = (size_t)P.dst_w * 3;
+		const int tile_bytes = tw * 3;
+		if ((row_bytes % 16 == 0) && (tile_bytes % 16 == 0) && (((uintptr_t)fd) % 16 == 0)) {
+			const int vpr = tile_bytes / 16;
+			for (int idx = t; idx < vpr * th; idx += DN_THREADS) {
+				const int oy_ = idx / vpr, v = idx - oy_ * vpr;
+				const int4 val = lds128(s_box_l + (unsigned)(oy_ * TW * 3 + v * 16));
+				reinterpret_cast<int4 *>(fd + (size_t)(y0 + oy_) * row_bytes + (size_t)x0 * 3)[v] = val;
+			}
+		} else {
+			for (int idx = t; idx < tile_bytes * th; idx += DN_THREADS) {
+				const int oy_ = idx / tile_bytes, bb = idx - oy_ * tile_bytes;
+				fd[(size_t)(y0 + oy_) * row_bytes + (size_t)x0 * 3 + bb] = smem[(size_t)oy_ * TW * 3 + bb];
+			}
+		}
+		return;
+	}
+	// ---- V, planar (yuv2planeX / yuv2plane1, flat dither 64): four samples per thread, one 32-bit store per plane row
+	unsigned char *fd = dst + (size_t)(frame / D.group) * D.dst_frame_bytes;
+	int tx = 0, ty = 0;
+	if (D.tile_xy) {
+		const short2 xy = D.tile_xy[frame % D.group];
+		tx = xy.x;
+		ty = xy.y;
+	}
+	{
+		constexpr int GW = TW / 4;
+		const int g = t % GW, ry = t / GW;
+		if (ry < th && x0 + 4 * g < P.dst_w) {
+			const unsigned lt = s_vt + 4u * (unsigned)(ry * D.lt_pitch);
+			const unsigned la = s_lh + 16u * (unsigned)((int)lds32<0>(lt) * GW + g);
+			int a[4];
+			if (P.vl_size == 1) {
+				const int4 l = lds128(la);
+				a[0] = (l.x + 64) >> 7; a[1] = (l.y + 64) >> 7; a[2] = (l.z + 64) >> 7; a[3] = (l.w + 64) >> 7;
+			} else if (P.x86_vertical && y0 + ry < P.dst_h - 2) {
+				a[0] = a[1] = a[2] = a[3] = (64 + 8 * (P.vl_size - 1)) >> 4;
+				vacc4_any<true>(la, 16u * GW, lt, P.vl_size, a);
+				a[0] >>= 3; a[1] >>= 3; a[2] >>= 3; a[3] >>= 3;
+			} else {
+				a[0] = a[1] = a[2] = a[3] = 64 << 12;
+				vacc4_any<false>(la, 16u * GW, lt, P.vl_size, a);
+				a[0] >>= 19; a[1] >>= 19; a[2] >>= 19; a[3] >>= 19;
+			}
+			*reinterpret_cast<unsigned *>(fd + (size_t)(ty + y0 + ry) * D.pitch_y + tx + x0 + 4 * g) = pack4_u8(a);
+		}
+	}
+	{
+		constexpr int GW = CW / 4; // groups of four chroma columns: two int4 of (U, V) pairs per intermediate row
+		const int g = t % GW, ry = t / GW;
+		if (ry < cth && cx0 + 4 * g < P.chr_dst_w) {
+			const unsigned ct = s_ct + 4u * (unsigned)(ry * D.ct_pitch);
+			const unsigned ca = s_ch + 32u * (unsigned)((int)lds32<0>(ct) * GW + g);
+			int a[4], b[4]; // U0 V0 U1 V1, U2 V2 U3 V3
+			if (P.vc_size == 1) {
+				const int4 c0 = lds128(ca), c1 = lds128(ca + 16);
+				a[0] = (c0.x + 64) >> 7; a[1] = (c0.y + 64) >> 7; a[2] = (c0.z + 64) >> 7; a[3] = (c0.w + 64) >> 7;
+				b[0] = (c1.x + 64) >> 7; b[1] = (c1.y + 64) >> 7; b[2] = (c1.z + 64) >> 7; b[3] = (c1.w + 64) >> 7;
+			} else if (P.x86_vertical && cy0 + ry < P.chr_dst_h - 1) {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) a[k] = b[k] = (64 + 8 * (P.vc_size - 1)) >> 4;
+				vacc4_any<true>(ca, 32u * GW, ct, P.vc_size, a);
+				vacc4_any<true>(ca + 16, 32u * GW, ct, P.vc_size, b);
+#pragma unroll
+				for (int k = 0; k < 4; ++k) { a[k] >>= 3; b[k] >>= 3; }
+			} else {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) a[k] = b[k] = 64 << 12;
+				vacc4_any<false>(ca, 32u * GW, ct, P.vc_size, a);
+				vacc4_any<false>(ca + 16, 32u * GW, ct, P.vc_size, b);
+#pragma unroll
+				for (int k = 0; k < 4; ++k) { a[k] >>= 19; b[k] >>= 19; }
+			}
+			const size_t o = (size_t)((ty >> 1) + cy0 + ry) * D.pitch_c + (tx >> 1) + cx0 + 4 * g;
+			const int u[4] = {a[0], a[2], b[0], b[2]}, v[4] = {a[1], a[3], b[1], b[3]};
+			*reinterpret_cast<unsigned *>(fd + D.off_u + o) = pack4_u8(u);
+			*reinterpret_cast<unsigned *>(fd + D.off_v + o) = pack4_u8(v);
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ host
 // row schedules with an instantiated straight-line strip kernel (see scale_rgb_strip_kernel): strips of ST_SCHED_ROWS rows
 struct StripSched {
@@ -1846,6 +2204,11 @@ struct msb200_scaler {
 	int packed422; // 0: no; 1: YUYV/YUY2; 2: UYVY; 3: RGB24; 4: BGR24; 5: RGBA; 6: BGRA  (MSPixConv same-size conversions to I420)
 	bool fast_ok;
 	bool direct;        // geometry outside the tile kernels' TMA box limits: scale_direct_kernel
+	bool down_ok;       // ... of which the >= 2x down-scales with TMA-able pitches run scale_down_kernel<down_tw, down_hg>
+	int down_tw, down_hg;
+	DownParams D;
+	size_t smem_down;
+	void *d_down_tab; // tile_x, tile_y, vtab of D
 	bool pstrip_ok;                   // planar I420 -> I420 (MSSizeConv): scale_plane_strip_kernel applies
 	PlaneStripParams PL, PC;          // luma plane; the two chroma planes
 	int canvas_w, canvas_h, canvas_tiles; // mosaic destination (msb200_scaler_set_canvas), 0 = tight frames
@@ -2074,8 +2437,9 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	}
 	// TMA tensor maps need 16-byte row pitches (luma width % 16 == 0, chroma plane pitch % 16 == 0); frames that do not
 	// have them, and down-scales whose per-tile source window exceeds a TMA box, take the tile-free direct kernel
-	bool direct = !(src_w >= 16 && src_h >= 16 && dst_w >= 16 && dst_h >= 16 && src_w % 16 == 0 &&
-	                (src_fmt != MSB200_PIX_YUV420P || (src_w / 2) % 16 == 0) && src_h % 2 == 0);
+	const bool tma_ok = src_w >= 16 && src_h >= 16 && dst_w >= 16 && dst_h >= 16 && src_w % 16 == 0 &&
+	                    (src_fmt != MSB200_PIX_YUV420P || (src_w / 2) % 16 == 0) && src_h % 2 == 0;
+	bool direct = !tma_ok;
 	msb200_scaler *s = new msb200_scaler();
 	s->ctx = ctx;
 	s->packed422 = 0;
@@ -2130,6 +2494,99 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	P.box_ch = max_span(s->vc, P.chr_dst_h, ctile_h);
 	if (P.box_lw > 256 || P.box_cw > 256 || P.box_lh > 256 || P.box_ch > 256) direct = true; // >= 2x down-scales
 	s->direct = direct;
+	s->down_ok = false;
+	memset(&s->D, 0, sizeof(s->D));
+	if (direct && tma_ok && (dst_rgb ? !(P.vl_size == 1 || (P.vl_size == 2 && P.vc_size == 2)) : (dst_w % 8 == 0 && dst_h % 2 == 0))) {
+		// narrower tiles whose source windows fit one TMA box per plane: scale_down_kernel
+		const bool inter = P.chroma_planes == 1;
+		int hg_all = P.hl_size != P.hc_size ? 0 : (P.hl_size == 4 ? 1 : (P.hl_size == 8 ? 2 : 0));
+		for (int x = 0; x + 1 < dst_w && hg_all; x += 2) { // the paired-column horizontal pass funnel-shifts by pos[x+1] - pos[x]
+			const int d = s->hl.pos[(size_t)x + 1] - s->hl.pos[(size_t)x];
+			if (d < 0 || d > 4) hg_all = 0;
+		}
+		auto a128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+		for (int TW = 64; TW >= 16 && !s->down_ok; TW >>= 1) {
+			int hg = hg_all;
+			if (hg == 0 && TW == 64) continue;            // (instantiated: <64,1> <64,2> <32,2> <32,0> <16,0>)
+			if ((hg == 1 && TW < 64) || (hg == 2 && TW == 16)) hg = 0;
+			const int blw = (max_span(s->hl, dst_w, TW) + 8 + 15 + 15) & ~15;
+			const int cel = max_span(s->hc, P.chr_dst_w, TW / 2) + 4;
+			const int bcw = inter ? ((cel + 7 + 7) & ~7) : ((cel + 15 + 15) & ~15);
+			if (blw > 256 || bcw > 256) continue;
+			for (int th = 16; th >= 2 && !s->down_ok; th >>= 1) {
+				const int cth = dst_rgb ? th : th / 2;
+				const int blh = max_span(s->vl, dst_h, th), bch = max_span(s->vc, P.chr_dst_h, cth);
+				if (blh > 256 || bch > 256 || (size_t)th * TW * 3 > (size_t)blw * blh) continue;
+				DownParams D;
+				memset(&D, 0, sizeof(D));
+				D.th = th;
+				D.box_lw = blw; D.box_lh = blh; D.box_cw = bcw; D.box_ch = bch;
+				D.lt_pitch = (1 + P.vl_size + 3) & ~3;
+				D.ct_pitch = (1 + P.vc_size + 3) & ~3;
+				D.vt_ints = th * D.lt_pitch + cth * D.ct_pitch;
+				const size_t cbox = (size_t)bcw * bch * (inter ? 2 : 1);
+				size_t off = a128((size_t)blw * blh);
+				D.o_c0 = (unsigned)off; off = a128(off + cbox);
+				D.o_c1 = (unsigned)off; off = a128(off + (inter ? 0 : cbox));
+				D.o_lh = (unsigned)off; off = a128(off + sizeof(int) * (size_t)blh * TW);
+				D.o_ch = (unsigned)off; off = a128(off + sizeof(int2) * (size_t)bch * (TW / 2));
+				D.o_vt = (unsigned)off; off = a128(off + sizeof(int) * (size_t)D.vt_ints);
+				D.o_bar = (unsigned)off; off += 16;
+				const size_t sm = off + 128;
+				if (sm > 56 * 1024 && th > 2) continue; // four CTAs per SM at least
+				if (sm > 200 * 1024) continue;
+				s->D = D;
+				s->down_tw = TW;
+				s->down_hg = hg;
+				s->smem_down = sm;
+				s->down_ok = true;
+			}
+		}
+		if (s->down_ok) { // per-tile tables: box origins, rows to filter, vertical taps relative to the box
+			DownParams &D = s->D;
+			const int TW = s->down_tw, th = D.th, cth = dst_rgb ? th : th / 2;
+			const int ntx = msb200_div_up(dst_w, TW), nty = msb200_div_up(dst_h, th);
+			std::vector<int> tab((size_t)2 * ntx + (size_t)4 * nty + (size_t)nty * D.vt_ints + 8, 0);
+			int *tx = tab.data(), *ty = tx + 2 * ntx + ((2 * ntx) & 3 ? 4 - ((2 * ntx) & 3) : 0), *vt = ty + 4 * nty;
+			for (int i = 0; i < ntx; ++i) {
+				tx[2 * i] = s->hl.pos[(size_t)i * TW] & ~15;
+				tx[2 * i + 1] = s->hc.pos[(size_t)i * (TW / 2)] & (inter ? ~7 : ~15);
+			}
+			for (int i = 0; i < nty; ++i) {
+				const int y0 = i * th, cy0 = dst_rgb ? y0 : y0 / 2;
+				const int rows = std::min(th, dst_h - y0), crows = dst_rgb ? rows : std::min(cth, P.chr_dst_h - cy0);
+				const int ly0 = s->vl.pos[(size_t)y0], ccy0 = s->vc.pos[(size_t)cy0];
+				ty[4 * i] = ly0;
+				ty[4 * i + 1] = ccy0;
+				ty[4 * i + 2] = std::min(D.box_lh, s->vl.pos[(size_t)(y0 + rows - 1)] + P.vl_size - ly0);
+				ty[4 * i + 3] = std::min(D.box_ch, s->vc.pos[(size_t)(cy0 + crows - 1)] + P.vc_size - ccy0);
+				int *l = vt + (size_t)i * D.vt_ints, *c = l + th * D.lt_pitch;
+				for (int r = 0; r < th; ++r) {
+					const int y = std::min(y0 + r, dst_h - 1);
+					l[r * D.lt_pitch] = s->vl.pos[(size_t)y] - ly0;
+					for (int j = 0; j < P.vl_size; ++j) l[r * D.lt_pitch + 1 + j] = s->vl.coef[(size_t)y * P.vl_size + j];
+				}
+				for (int r = 0; r < cth; ++r) {
+					const int y = std::min(cy0 + r, P.chr_dst_h - 1);
+					c[r * D.ct_pitch] = s->vc.pos[(size_t)y] - ccy0;
+					for (int j = 0; j < P.vc_size; ++j) c[r * D.ct_pitch + 1 + j] = s->vc.coef[(size_t)y * P.vc_size + j];
+				}
+			}
+			MSB200_CUDA(cudaMalloc(&s->d_down_tab, tab.size() * sizeof(int)));
+			MSB200_CUDA(cudaMemcpy(s->d_down_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+			const int *base = (const int *)s->d_down_tab;
+			D.tile_x = (const int2 *)base;
+			D.tile_y = (const int4 *)(base + (ty - tx));
+			D.vtab = base + (vt - tx);
+		}
+		if (s->down_ok && s->smem_down > 48 * 1024) {
+#define DOWN_ATTR(TW, HG)                                                                                              \
+	MSB200_SMEM_OPTIN((scale_down_kernel<TW, HG, true>), ctx, s->smem_down);                                           \
+	MSB200_SMEM_OPTIN((scale_down_kernel<TW, HG, false>), ctx, s->smem_down)
+			DOWN_ATTR(64, 1); DOWN_ATTR(64, 2); DOWN_ATTR(32, 2); DOWN_ATTR(32, 0); DOWN_ATTR(16, 0);
+#undef DOWN_ATTR
+		}
+	}
 	{ // ff_yuv2rgb_c_init_tables(): ITU-601, limited-range source
 		int64_t crv = 104597, cbu = 132201, cgu = -25675, cgv = -53279, cy = 1 << 16, oy;
 		cy = (cy * 255) / 219;
@@ -2145,6 +2602,13 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 	s->src_bytes = fmt_bytes(src_fmt, src_w, src_h);
 	s->dst_bytes = fmt_bytes(dst_fmt, dst_w, dst_h);
 	P.dst_frame_bytes = s->dst_bytes;
+	s->D.dst_frame_bytes = s->dst_bytes;
+	s->D.off_u = (size_t)dst_w * dst_h;
+	s->D.off_v = s->D.off_u + (size_t)P.chr_dst_w * P.chr_dst_h;
+	s->D.pitch_y = dst_w;
+	s->D.pitch_c = P.chr_dst_w;
+	s->D.group = 1;
+	s->D.tile_xy = nullptr;
 	// upload filter tables
 	size_t off = 0;
 	auto place = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
@@ -2498,6 +2962,7 @@ void msb200_scaler_destroy(msb200_scaler *s) {
 	cudaFree((void *)s->PL.rows);
 	cudaFree((void *)s->PC.rows);
 	cudaFree(s->d_tile_xy);
+	cudaFree(s->d_down_tab);
 	s->src.release();
 	s->dst.release();
 	delete s;
@@ -2523,11 +2988,18 @@ int msb200_scaler_set_canvas(msb200_scaler *s, int canvas_w, int canvas_h, int n
 		s->PL.dst_off[0] = 0;
 		s->PC.dst_off[0] = (size_t)s->P.dst_w * s->P.dst_h;
 		s->PC.dst_off[1] = s->PC.dst_off[0] + (size_t)s->P.chr_dst_w * s->P.chr_dst_h;
+		s->D.group = 1;
+		s->D.pitch_y = s->P.dst_w;
+		s->D.pitch_c = s->P.chr_dst_w;
+		s->D.tile_xy = nullptr;
+		s->D.dst_frame_bytes = s->dst_bytes;
+		s->D.off_u = s->PC.dst_off[0];
+		s->D.off_v = s->PC.dst_off[1];
 		return MSB200_OK;
 	}
 	MSB200_CHECK_ARG(tiles && n_tiles > 0 && n_tiles <= 4096 && canvas_w > 0 && canvas_h > 0);
-	if (!s->pstrip_ok || s->P.dst_fmt != MSB200_PIX_YUV420P) {
-		msb200_set_error("scaler: a canvas needs the planar strip path (YUV420P / NV12 / NV21 -> YUV420P, TMA-able geometry)");
+	if (!(s->pstrip_ok || s->down_ok) || s->P.dst_fmt != MSB200_PIX_YUV420P) {
+		msb200_set_error("scaler: a canvas needs a planar tile path (YUV420P / NV12 / NV21 -> YUV420P, TMA-able geometry)");
 		return MSB200_EINVAL;
 	}
 	// 32-bit stores per lane: every plane's tile origin and pitch must keep 4-byte alignment
@@ -2558,6 +3030,13 @@ int msb200_scaler_set_canvas(msb200_scaler *s, int canvas_w, int canvas_h, int n
 	s->PL.dst_off[0] = 0;
 	s->PC.dst_off[0] = ysz;
 	s->PC.dst_off[1] = ysz + csz;
+	s->D.group = n_tiles;
+	s->D.tile_xy = (const short2 *)s->d_tile_xy;
+	s->D.pitch_y = canvas_w;
+	s->D.pitch_c = canvas_w / 2;
+	s->D.dst_frame_bytes = ysz + 2 * csz;
+	s->D.off_u = ysz;
+	s->D.off_v = ysz + csz;
 	return MSB200_OK;
 }
 // planar output rounded like libswscale's x86 SIMD vertical scaler (see ScaleParams::x86_vertical)
@@ -2578,12 +3057,13 @@ size_t msb200_scaler_canvas_bytes(msb200_scaler *s) {
 }
 
 int msb200_scaler_set_path(msb200_scaler *s, int path) {
-	MSB200_CHECK_ARG(s && path >= 0 && path <= 4);
+	MSB200_CHECK_ARG(s && path >= 0 && path <= 5); // 5: the tile-free direct kernel where scale_down_kernel would run (cross-checks)
 	s->force_path = path;
 	s->cached_src = s->cached_dst = nullptr; // the paths use different tensor maps
 	return MSB200_OK;
 }
 int msb200_scaler_get_path(msb200_scaler *s) {
+	if (s && s->down_ok && s->force_path != 5) return 6;
 	if (s && s->direct) return 5;
 	if (!s || s->packed422 || s->P.dst_fmt == MSB200_PIX_YUV420P) return 0;
 	if (s->stream_ok && s->force_path == 4) return 4;
@@ -2608,6 +3088,44 @@ int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src,
 	if (s->packed422 >= 3) return msb200i_rgb24_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 - 3, d_dst);
 	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
 	const ScaleParams &P = s->P;
+	if (s->down_ok && s->force_path != 5 && ((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0 &&
+	    (P.dst_fmt != MSB200_PIX_YUV420P || ((uintptr_t)d_dst % 4) == 0)) {
+		if (s->canvas_tiles > 0) MSB200_CHECK_ARG(n_frames % s->canvas_tiles == 0);
+		const DownParams &D = s->D;
+		if (!(s->cached_src == d_src && s->cached_frames == n_frames)) {
+			const char *base = (const char *)d_src;
+			const char *cb = base + (size_t)P.src_w * P.src_h;
+			int r;
+			if ((r = make_map(&s->map_l, base, (uint64_t)P.src_w, (uint64_t)P.src_h, (uint64_t)n_frames, (uint64_t)P.src_w, s->src_bytes,
+			                  (uint32_t)D.box_lw, (uint32_t)D.box_lh))) return r;
+			if (P.chroma_planes == 1) {
+				if ((r = make_map(&s->map_c0, cb, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h, (uint64_t)n_frames, (uint64_t)P.chr_src_w * 2,
+				                  s->src_bytes, (uint32_t)D.box_cw, (uint32_t)D.box_ch, false, true))) return r;
+				s->map_c1 = s->map_c0;
+			} else {
+				if ((r = make_map(&s->map_c0, cb, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h, (uint64_t)n_frames, (uint64_t)P.chr_src_w,
+				                  s->src_bytes, (uint32_t)D.box_cw, (uint32_t)D.box_ch))) return r;
+				if ((r = make_map(&s->map_c1, cb + (size_t)P.chr_src_w * P.chr_src_h, (uint64_t)P.chr_src_w, (uint64_t)P.chr_src_h,
+				                  (uint64_t)n_frames, (uint64_t)P.chr_src_w, s->src_bytes, (uint32_t)D.box_cw, (uint32_t)D.box_ch))) return r;
+			}
+			s->cached_src = d_src;
+			s->cached_frames = n_frames;
+		}
+		const dim3 g((unsigned)msb200_div_up(P.dst_w, s->down_tw), (unsigned)msb200_div_up(P.dst_h, D.th), (unsigned)n_frames);
+		const bool rgb = P.dst_fmt != MSB200_PIX_YUV420P;
+#define DOWN_LAUNCH(TW, HG)                                                                                            \
+	do {                                                                                                               \
+		if (rgb) MSB200_LAUNCH(s->ctx, (scale_down_kernel<TW, HG, true>), g, DN_THREADS, s->smem_down, s->map_l, s->map_c0, s->map_c1, (unsigned char *)d_dst, P, D); \
+		else MSB200_LAUNCH(s->ctx, (scale_down_kernel<TW, HG, false>), g, DN_THREADS, s->smem_down, s->map_l, s->map_c0, s->map_c1, (unsigned char *)d_dst, P, D); \
+	} while (0)
+		if (s->down_tw == 64 && s->down_hg == 1) DOWN_LAUNCH(64, 1);
+		else if (s->down_tw == 64) DOWN_LAUNCH(64, 2);
+		else if (s->down_tw == 32 && s->down_hg == 2) DOWN_LAUNCH(32, 2);
+		else if (s->down_tw == 32) DOWN_LAUNCH(32, 0);
+		else DOWN_LAUNCH(16, 0);
+#undef DOWN_LAUNCH
+		return MSB200_OK;
+	}
 	if (s->direct || (P.x86_vertical && !s->pstrip_ok)) { // (the tile kernels implement the C rounding only)
 		const long threads = P.dst_fmt == MSB200_PIX_YUV420P ? (long)P.dst_w * P.dst_h + 2L * P.chr_dst_w * P.chr_dst_h
 		                                                       : (long)((P.dst_w + 1) / 2) * P.dst_h;

@@ -1909,9 +1909,7 @@ static void g711_enc_process(MSFilter *f) {
 	size_t size_of_pcm, avail;
 	mblk_t *m;
 	uint8_t *pcm, *code;
-	if (s->ptime >= 10) frame_per_packet = s->ptime / 10;
-	if (frame_per_packet <= 0) frame_per_packet = 1;
-	if (frame_per_packet > 14) frame_per_packet = 14; /* 140 ms max */
+	if (s->ptime >= 10) frame_per_packet = s->ptime / 10 < 14 ? s->ptime / 10 : 14; /* packets of 10 .. 140 ms */
 	size_of_pcm = (size_t)160 * frame_per_packet;       /* bytes: 80 samples per 10 ms at 8 kHz */
 	while ((m = ms_queue_get(f->inputs[0])) != NULL)
 		ms_bufferizer_put(s->bz, m);
@@ -1978,19 +1976,20 @@ static void g711_enc_process(MSFilter *f) {
 	ms_free(pcm);
 	ms_free(code);
 }
-static int g711_enc_add_fmtp(MSFilter *f, void *arg) { /* enc_add_fmtp alaw.c:96-110 */
-	const char *fmtp = (const char *)arg;
+/* one integer parameter of an SDP fmtp line; 0 when the key is absent */
+static int g711_fmtp_int(const char *line, const char *key, int *out) {
+	char text[32];
+	if (!fmtp_get_value(line, key, text, sizeof(text))) return 0;
+	*out = atoi(text);
+	return 1;
+}
+static int g711_enc_add_fmtp(MSFilter *f, void *arg) { /* same meaning as enc_add_fmtp, alaw.c:96-110: maxptime caps ptime */
 	G711EncState *s = (G711EncState *)f->data;
-	char tmp[30];
-	if (fmtp_get_value(fmtp, "maxptime", tmp, sizeof(tmp))) {
-		int v = atoi(tmp);
-		s->maxptime = v < MS_DEFAULT_MAX_PTIME ? v : MS_DEFAULT_MAX_PTIME;
-	}
-	if (fmtp_get_value(fmtp, "ptime", tmp, sizeof(tmp))) {
-		int v = atoi(tmp);
-		ms_message("%s configured with ptime=%s", f->desc->name, tmp);
-		s->ptime = v < s->maxptime ? v : s->maxptime;
-		if (s->ptime == s->maxptime) ms_message("%s ptime set to maxptime=%i", f->desc->name, s->maxptime);
+	int ms = 0;
+	if (g711_fmtp_int((const char *)arg, "maxptime", &ms)) s->maxptime = ms < MS_DEFAULT_MAX_PTIME ? ms : MS_DEFAULT_MAX_PTIME;
+	if (g711_fmtp_int((const char *)arg, "ptime", &ms)) {
+		s->ptime = ms < s->maxptime ? ms : s->maxptime;
+		ms_message("%s: ptime %d ms asked, %d ms used (maxptime %d)", f->desc->name, ms, s->ptime, s->maxptime);
 	}
 	return 0;
 }

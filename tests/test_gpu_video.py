@@ -110,6 +110,39 @@ def test_scaler_bit_exact_vs_oracle(ctx, sf, sw, sh, df, dw, dh):
     sc.close()
 
 
+@pytest.mark.parametrize("sf,sw,sh,df,dw,dh,tile", [
+    (_lib.PIX_NV12, 1920, 1080, _lib.PIX_RGB24, 640, 360, "<64,2>"),       # 3:1 preview: 8 horizontal taps, 6 / 4 vertical
+    (_lib.PIX_NV12, 1920, 1080, _lib.PIX_YUV420P, 960, 540, "<64,1>"),     # 2:1: 4-tap filters, windows too wide for 128-column tiles
+    (_lib.PIX_YUV420P, 1280, 720, _lib.PIX_YUV420P, 320, 180, "<32,2>"),   # 4:1 thumbnail (MSSizeConv), planar chroma boxes
+    (_lib.PIX_NV21, 1920, 1080, _lib.PIX_RGB24_REV, 160, 90, "<16,0>"),    # 12:1: 24 taps each way, Cr first, BGR
+    (_lib.PIX_YUV420P, 640, 480, _lib.PIX_RGB24, 128, 96, "<32,0>"),       # 5:1: 12 taps (no register specialisation)
+    (_lib.PIX_NV12, 320, 240, _lib.PIX_RGB24, 100, 74, "<64,2>"),          # ragged tiles, rows that are not 16-byte multiples
+    (_lib.PIX_NV12, 1920, 1080, _lib.PIX_YUV420P, 480, 270, "<32,2>"),     # 4:1, interleaved chroma, last tile row of 14
+    (_lib.PIX_YUV420P, 1920, 1088, _lib.PIX_YUV420P, 704, 400, "<64,2>"),  # 2.7:1 planar
+])
+def test_scaler_down_tiles_bit_exact(ctx, sf, sw, sh, df, dw, dh, tile):
+    """down-scales by 2x and more (scale_down_kernel: narrow tiles, both passes through shared memory) == oracle == the
+    tile-free kernel they used to run (path 5)"""
+    L = O.oracle()
+    n = 2
+    frames = _rand_frames(sf, sw, sh, n, seed=sw + dh)
+    frames[1] = np.random.default_rng(dw).integers(0, 256, size=frames.shape[1], dtype=np.uint8)  # full-range noise
+    sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
+    assert sc.path == 6, "geometry should select the down-scale tile kernel"
+    got = sc.process(frames)
+    o = L.orc_scaler_new(sw, sh, sf, dw, dh, df)
+    for i in range(n):
+        exp = np.zeros(sc.dst_bytes + 64, np.uint8)
+        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+        bad = np.flatnonzero(got[i] != exp[:-64])
+        assert bad.size == 0, (i, bad.size, bad[:8])
+    L.orc_scaler_free(o)
+    sc.set_path(5)
+    assert sc.path == 5
+    assert np.array_equal(sc.process(frames), got)
+    sc.close()
+
+
 @pytest.mark.parametrize("sf,sw,sh,df,dw,dh", [
     (_lib.PIX_NV12, 1920, 1080, _lib.PIX_RGB24, 1280, 720),     # cfg4: <4,2> taps, strips of 15 rows
     (_lib.PIX_NV12, 192, 108, _lib.PIX_RGB24, 128, 72),         # one tile column, strips of 9 rows
@@ -185,13 +218,15 @@ def test_scaler_static_schedule_bit_exact(ctx, monkeypatch, sf, sw, sh, df, dw, 
     (_lib.PIX_NV12, 1920, 1080, _lib.PIX_YUV420P, 640, 360),       # 3:1 NV12 -> I420
 ])
 def test_scaler_direct_kernel_bit_exact(ctx, sf, sw, sh, df, dw, dh):
-    """geometries outside the TMA-tiled kernels (>= 2x down-scales, row pitches that are not multiples of 16) run the
-    tile-free direct kernel: same swscale arithmetic, bit-exact vs the oracle"""
+    """the tile-free direct kernel (row pitches that are not multiples of 16; >= 2x down-scales when asked for with
+    set_path(5)): same swscale arithmetic, bit-exact vs the oracle"""
     L = O.oracle()
     n = 2
     frames = _rand_frames(sf, sw, sh, n, seed=sw + dh)
     frames[1] = np.random.default_rng(dw).integers(0, 256, size=frames.shape[1], dtype=np.uint8)
     sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
+    if sc.path == 6:  # a >= 2x down-scale with TMA-able pitches: the down-scale tile kernel by default, this one on request
+        sc.set_path(5)
     assert sc.path == 5
     got = sc.process(frames)
     sc.close()

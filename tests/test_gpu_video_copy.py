@@ -57,13 +57,14 @@ def test_random_regions_equal_the_unmodified_reference_function(ctx):
         assert np.array_equal(got, exp), (case, bw, bh, src_semi, dst_semi, sroi, droi)
 
 
+@pytest.mark.parametrize("sw,sh", [(96, 64), (256, 192), (320, 144)])  # 1.5:1 (plane strips), 4:1 and 5:1 x 3:1 (down-scale tiles)
 @pytest.mark.parametrize("src_fmt", [_lib.PIX_YUV420P, _lib.PIX_NV12])
-def test_mosaic_canvas_equals_oracle_tiles_placed_by_hand(ctx, src_fmt):
+def test_mosaic_canvas_equals_oracle_tiles_placed_by_hand(ctx, src_fmt, sw, sh):
     """msb200_scaler_set_canvas: N scaled participants land in their rectangles of one canvas in the scaler's own launches;
     every tile equals the oracle's scaled frame, every byte outside the tiles keeps the background"""
     L = O.oracle()
     lib = ctx.lib
-    sw, sh, tw, th = 96, 64, 64, 48
+    tw, th = 64, 48
     cw, ch = 144, 100
     tiles = [(0, 0), (72, 0), (0, 50), (80, 52)]
     n_canvas = 3
@@ -107,11 +108,12 @@ def test_mosaic_canvas_equals_oracle_tiles_placed_by_hand(ctx, src_fmt):
 
 @pytest.mark.parametrize("sw,sh,dw,dh,src_fmt", [(1920, 1080, 1280, 720, _lib.PIX_YUV420P), (640, 480, 352, 288, _lib.PIX_YUV420P),
                                                  (320, 240, 480, 360, _lib.PIX_NV12), (1280, 720, 320, 180, _lib.PIX_YUV420P),
-                                                 (176, 144, 352, 288, _lib.PIX_NV21), (650, 366, 322, 182, _lib.PIX_YUV420P)])
+                                                 (176, 144, 352, 288, _lib.PIX_NV21), (650, 366, 322, 182, _lib.PIX_YUV420P),
+                                                 (1920, 1080, 960, 540, _lib.PIX_NV12), (640, 480, 128, 96, _lib.PIX_NV21)])
 def test_planar_scaler_x86_vertical_rounding_equals_oracle_x86_mode(ctx, sw, sh, dw, dh, src_fmt):
     """msb200_scaler_set_x86_vertical(1): MSSizeConv's output as a plain SWS_BILINEAR call returns it on x86 — the oracle's
     x86 mode is pinned bit-exact against the live library (tests/test_oracle_video_live.py); the strip kernel (TMA-able
-    geometries) and the tile-free kernel (4:1 down-scale, odd pitch) must both equal it, and differ from the C rounding"""
+    geometries), the down-scale tile kernel (2:1, 4:1, 5:1) and the tile-free kernel (odd pitch) must all equal it, and differ from the C rounding"""
     L = O.oracle()
     lib = ctx.lib
     rng = np.random.default_rng(sw + dh)
