@@ -136,7 +136,9 @@ def kernels_bench(ctx, hbm_peak_gbs: float) -> dict:
             ("rgb24_to_i420_kernel<0>", _lib.PIX_RGB24, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv RGB24 -> I420 1080p"),
             ("rgb24_to_i420_kernel<1>", _lib.PIX_RGB24_REV, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv BGR24 -> I420 1080p"),
             ("packed422_to_i420_kernel", _lib.PIX_YUY2, _lib.PIX_YUV420P, sw, sh, sw * sh * 2, i420, "a7 MSPixConv YUY2 -> I420 1080p"),
-            ("scale_direct_kernel", _lib.PIX_NV12, _lib.PIX_RGB24, 640, 360, i420, 640 * 360 * 3, "a8/a11 NV12 1080p -> RGB24 360p (3:1, tile-free path)")):
+            ("scale_down_kernel<64,2,rgb>", _lib.PIX_NV12, _lib.PIX_RGB24, 640, 360, i420, 640 * 360 * 3, "a8/a11 NV12 1080p -> RGB24 360p (3:1 down-scale tiles)"),
+            ("scale_down_kernel<64,1,planar>", _lib.PIX_NV12, _lib.PIX_YUV420P, 960, 540, i420, 960 * 540 * 3 // 2, "a8 NV12 1080p -> I420 540p (2:1 down-scale tiles)"),
+            ("scale_down_kernel<32,2,planar>", _lib.PIX_YUV420P, _lib.PIX_YUV420P, 480, 270, i420, 480 * 270 * 3 // 2, "a8 MSSizeConv I420 1080p -> I420 270p thumbnail (4:1 down-scale tiles)")):
         sc = F.Scaler(ctx, sw, sh, sf, dw, dh, df)
         ms = _time(ctx, lambda: sc.process_dev(nf, d_src, d_dst), iters=5)
         row(name, f"{what}, {nf} frames", nf * (sbytes + dbytes), ms, nf, "frames")
@@ -153,6 +155,15 @@ def kernels_bench(ctx, hbm_peak_gbs: float) -> dict:
         sbytes, cbytes = msw * msh * 3 // 2, cw * ch * 3 // 2
         ms = _time(ctx, lambda: sc.process_dev(n_src, d_src, d_dst), iters=5)
         row("scale_plane_strip_kernel (mosaic)", f"f4 16-tile 720p mosaic: 16 x I420 {msw}x{msh} -> 320x180 tiles of one 1280x720 canvas, {ncanv} canvases",
+            n_src * sbytes + ncanv * cbytes, ms, ncanv, "canvases")
+        sc.close()
+        # the same mosaic from sixteen 720p participants (4:1 thumbnails): 16 canvases per launch = 256 source frames (354 MB in)
+        msw, msh, ncanv = 1280, 720, 16
+        sc = F.Scaler(ctx, msw, msh, _lib.PIX_YUV420P, tw, th, _lib.PIX_YUV420P)
+        _lib.check(lib.msb200_scaler_set_canvas(sc.h, cw, ch, tiles, rects))
+        n_src, sbytes = tiles * ncanv, msw * msh * 3 // 2
+        ms = _time(ctx, lambda: sc.process_dev(n_src, d_src, d_dst), iters=5)
+        row("scale_down_kernel (mosaic)", f"f4 16-tile 720p mosaic from 720p participants: 16 x I420 {msw}x{msh} -> 320x180 tiles of one 1280x720 canvas, {ncanv} canvases",
             n_src * sbytes + ncanv * cbytes, ms, ncanv, "canvases")
         sc.close()
         # f4: ms_yuv_buf_copy_with_pix_strides, 1080p I420 -> NV12 (planar to semi-planar), 128 frames

@@ -1818,7 +1818,7 @@ __global__ void __launch_bounds__(256) scale_direct_kernel(const unsigned char *
 // window fits one box per plane — and the two passes go through shared memory:
 //   H  thread = output column, loop over the rows of the box: the column's taps live in registers as dp2a pairs (HG
 //      groups of four; HG == 0: any size, taps re-read through L1), the window comes out of three to seven 32-bit shared
-//      loads and one funnel shift per group; the 15-bit result is kept as int32 (no unpacking later). Interleaved CbCr
+//      loads and one funnel shift per group; the 15-bit results are kept as packed 16-bit pairs (the shared-memory pipe is this kernel's bound). Interleaved CbCr
 //      boxes hold 16-bit pairs and are split with PRMT on the way in.
 //   V  RGB: thread = pixel pair, vertical taps from a per-tile table, colour stage as in the kernels above, rows staged
 //      and written with 16-byte stores.  Planar: thread = four samples of a row, one 32-bit store each; the placement
@@ -1844,14 +1844,23 @@ __device__ __forceinline__ uint2 lds64(unsigned addr) {
 	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
 	return v;
 }
+__device__ __forceinline__ void sts16(unsigned addr, unsigned v) {
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
 __device__ __forceinline__ void sts64(unsigned addr, int a, int b) {
 	asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
-// a[0..3] += taps x four adjacent columns of int32 intermediates: rows `pitch` bytes apart starting at addr, the taps at
-// ktab + 4 (ktab is 16-byte aligned: [first row, tap 0, tap 1, ...]). N > 0: compile-time tap count, N == 0: n at run time.
-// X86: libswscale's SIMD vertical scaler drops the low 16 bits of every product (ScaleParams::x86_vertical)
+// a[0..3] += taps x four adjacent 15-bit intermediates (two 32-bit words of packed pairs per row): rows `pitch` bytes
+// apart starting at addr, the taps at ktab + 4 (ktab is 16-byte aligned: [first row, tap 0, tap 1, ...]). N > 0:
+// compile-time tap count, N == 0: n at run time. X86: libswscale's SIMD vertical scaler drops the low 16 bits of every
+// product (ScaleParams::x86_vertical)
 template <int N, bool X86>
 __device__ __forceinline__ void vacc4(unsigned addr, unsigned pitch, unsigned ktab, int n, int (&a)[4]) {
+	auto tap = [&](uint2 w, int k) {
+		const int l0 = (int)(w.x & 0xffffu), l1 = (int)(w.x >> 16), l2 = (int)(w.y & 0xffffu), l3 = (int)(w.y >> 16);
+		if (X86) { a[0] += (l0 * k) >> 16; a[1] += (l1 * k) >> 16; a[2] += (l2 * k) >> 16; a[3] += (l3 * k) >> 16; }
+		else { a[0] += l0 * k; a[1] += l1 * k; a[2] += l2 * k; a[3] += l3 * k; }
+	};
 	if (N > 0) {
 		int kk[(N + 4) & ~3];
 #pragma unroll
@@ -1861,21 +1870,15 @@ __device__ __forceinline__ void vacc4(unsigned addr, unsigned pitch, unsigned kt
 		}
 #pragma unroll
 		for (int j = 0; j < N; ++j) {
-			const int4 l = lds128(addr);
+			tap(lds64(addr), kk[1 + j]);
 			addr += pitch;
-			const int k = kk[1 + j];
-			if (X86) { a[0] += (l.x * k) >> 16; a[1] += (l.y * k) >> 16; a[2] += (l.z * k) >> 16; a[3] += (l.w * k) >> 16; }
-			else { a[0] += l.x * k; a[1] += l.y * k; a[2] += l.z * k; a[3] += l.w * k; }
 		}
 	} else {
 #pragma unroll 2
 		for (int j = 0; j < n; ++j) {
-			const int4 l = lds128(addr);
-			addr += pitch;
 			ktab += 4;
-			const int k = (int)lds32<0>(ktab);
-			if (X86) { a[0] += (l.x * k) >> 16; a[1] += (l.y * k) >> 16; a[2] += (l.z * k) >> 16; a[3] += (l.w * k) >> 16; }
-			else { a[0] += l.x * k; a[1] += l.y * k; a[2] += l.z * k; a[3] += l.w * k; }
+			tap(lds64(addr), (int)lds32<0>(ktab));
+			addr += pitch;
 		}
 	}
 }
@@ -1892,7 +1895,7 @@ __device__ __forceinline__ unsigned pack4_u8(const int (&a)[4]) {
 	return sat_u8(a[0]) | (sat_u8(a[1]) << 8) | (sat_u8(a[2]) << 16) | (sat_u8(a[3]) << 24);
 }
 template <int TW, int HG, bool RGB>
-__global__ void __launch_bounds__(DN_THREADS, 4)
+__global__ void __launch_bounds__(DN_THREADS, 5)
     scale_down_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_c0,
                       const __grid_constant__ CUtensorMap map_c1, unsigned char *__restrict__ dst, const ScaleParams P, const DownParams D) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1945,7 +1948,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 		}
 		const int rg = t / CW;
 		unsigned la = s_box_l + (unsigned)(pa & ~3) + (unsigned)(rg * D.box_lw);
-		unsigned lo = s_lh + 4u * (unsigned)(rg * TW + 2 * cxi);
+		unsigned lo = s_lh + 2u * (unsigned)(rg * TW + 2 * cxi);
 		const unsigned lstep = (unsigned)D.box_lw * (DN_THREADS / CW);
 		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 		__syncthreads(); // barrier initialised, tables in place
@@ -1965,9 +1968,9 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 				va = dp2a_hi(ka[2 * g + 1], A[g], dp2a_lo(ka[2 * g], A[g], va));
 				vb = dp2a_hi(kb[2 * g + 1], qb, dp2a_lo(kb[2 * g], qb, vb));
 			}
-			sts64(lo, min(va >> 7, 32767), min(vb >> 7, 32767));
+			sts32<0>(lo, (unsigned)min(va >> 7, 32767) | ((unsigned)min(vb >> 7, 32767) << 16));
 			la += lstep;
-			lo += 4u * TW * (DN_THREADS / CW);
+			lo += 2u * TW * (DN_THREADS / CW);
 		}
 	} else {
 		// ---- H, luma, any filter size: thread = one output column, taps re-read through L1
@@ -1976,7 +1979,7 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 		const unsigned sh = (unsigned)(lp_off & 3) * 8;
 		const int rg = t / TW, groups = P.hl_size >> 2;
 		unsigned la = s_box_l + (unsigned)(lp_off & ~3) + (unsigned)(rg * D.box_lw);
-		unsigned lo = s_lh + 4u * (unsigned)(rg * TW + lx);
+		unsigned lo = s_lh + 2u * (unsigned)(rg * TW + lx);
 		const unsigned lstep = (unsigned)D.box_lw * (DN_THREADS / TW);
 		asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 		__syncthreads();
@@ -1989,15 +1992,15 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 				val = dp2a_hi(lcf[2 * g + 1], q, dp2a_lo(lcf[2 * g], q, val));
 				a = b;
 			}
-			sts32<0>(lo, (unsigned)min(val >> 7, 32767));
+			sts16(lo, (unsigned)min(val >> 7, 32767));
 			la += lstep;
-			lo += 4u * TW * (DN_THREADS / TW);
+			lo += 2u * TW * (DN_THREADS / TW);
 		}
 	}
 	// ---- H, chroma: thread = one output column, both components (same positions and taps)
 	{
 		const int rg = t / CW, groups = HG > 0 ? NG : P.hc_size >> 2;
-		unsigned co = s_ch + 8u * (unsigned)(rg * CW + cxi);
+		unsigned co = s_ch + 4u * (unsigned)(rg * CW + cxi);
 		if (inter) {
 			const bool swap_uv = P.src_fmt == MSB200_PIX_NV21;
 			const unsigned sh = (unsigned)(cp_off & 1) * 16;
@@ -2021,9 +2024,9 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 				}
 				u = min(u >> 7, 32767);
 				v = min(v >> 7, 32767);
-				sts64(co, swap_uv ? v : u, swap_uv ? u : v);
+				sts32<0>(co, swap_uv ? (unsigned)v | ((unsigned)u << 16) : (unsigned)u | ((unsigned)v << 16));
 				ca += cstep;
-				co += 8u * CW * (DN_THREADS / CW);
+				co += 4u * CW * (DN_THREADS / CW);
 			}
 		} else {
 			const unsigned sh = (unsigned)(cp_off & 3) * 8;
@@ -2045,9 +2048,9 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 				} else {
 					for (int g = 0; g < groups; ++g) group(lds32<4>(s_c0 + ca + 4u * g), lds32<4>(s_c1 + ca + 4u * g), ccf[2 * g], ccf[2 * g + 1]);
 				}
-				sts64(co, min(u >> 7, 32767), min(v >> 7, 32767));
+				sts32<0>(co, (unsigned)min(u >> 7, 32767) | ((unsigned)min(v >> 7, 32767) << 16));
 				ca += cstep;
-				co += 8u * CW * (DN_THREADS / CW);
+				co += 4u * CW * (DN_THREADS / CW);
 			}
 		}
 	}
@@ -2059,11 +2062,14 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 		constexpr int QW = TW / 4;
 		const int q = t % QW, ry = t / QW;
 		const int tw = min(TW, P.dst_w - x0);
+		unsigned char *fd = dst + (size_t)frame * P.dst_frame_bytes;
+		const size_t row_bytes = (size_t)P.dst_w * 3;
+		const bool direct_out = (P.dst_w & 3) == 0 && ((uintptr_t)dst & 3) == 0;
 		if (ry < th && 4 * q < tw) {
 			const unsigned lt = s_vt + 4u * (unsigned)(ry * D.lt_pitch), ct = s_ct + 4u * (unsigned)(ry * D.ct_pitch);
 			int Y[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18}, C[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18}; // C: U0 V0 U1 V1
-			vacc4_any<false>(s_lh + 16u * (unsigned)((int)lds32<0>(lt) * QW + q), 16u * QW, lt, P.vl_size, Y);
-			vacc4_any<false>(s_ch + 16u * (unsigned)((int)lds32<0>(ct) * QW + q), 16u * QW, ct, P.vc_size, C);
+			vacc4_any<false>(s_lh + 8u * (unsigned)((int)lds32<0>(lt) * QW + q), 8u * QW, lt, P.vl_size, Y);
+			vacc4_any<false>(s_ch + 8u * (unsigned)((int)lds32<0>(ct) * QW + q), 8u * QW, ct, P.vc_size, C);
 			const bool bgr = P.dst_fmt == MSB200_PIX_RGB24_REV;
 			const int c_cy = P.cy, c_off = P.yb0 + 0x8000;
 			const int base_r = P.yoffs - (P.crv >> 9), base_g = P.yoffs - (P.cgu >> 9) - (P.cgv >> 9), base_b = P.yoffs - (P.cbu >> 9);
@@ -2081,23 +2087,23 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 					px[2 * h + e] = (bgr ? b : r) | (g << 8) | ((bgr ? r : b) << 16);
 				}
 			}
-			const unsigned os = s_box_l + (unsigned)(ry * TW * 3 + q * 12);
-			sts32<0>(os, px[0] | (px[1] << 24));
-			sts32<4>(os, (px[1] >> 8) | (px[2] << 16));
-			sts32<8>(os, (px[2] >> 16) | (px[3] << 8));
-		}
-		__syncthreads();
-		unsigned char *fd = dst + (size_t)frame * P.dst_frame_bytes;
-		const size_t row_bytes = (size_t)P.dst_w * 3;
-		const int tile_bytes = tw * 3;
-		if ((row_bytes % 16 == 0) && (tile_bytes % 16 == 0) && (((uintptr_t)fd) % 16 == 0)) {
-			const int vpr = tile_bytes / 16;
-			for (int idx = t; idx < vpr * th; idx += DN_THREADS) {
-				const int oy_ = idx / vpr, v = idx - oy_ * vpr;
-				const int4 val = lds128(s_box_l + (unsigned)(oy_ * TW * 3 + v * 16));
-				reinterpret_cast<int4 *>(fd + (size_t)(y0 + oy_) * row_bytes + (size_t)x0 * 3)[v] = val;
+			const unsigned w0 = px[0] | (px[1] << 24), w1 = (px[1] >> 8) | (px[2] << 16), w2 = (px[2] >> 16) | (px[3] << 8);
+			if (direct_out) { // 12 bytes per lane, the lanes of a row adjacent: the three stores of a warp fill whole sectors in L2
+				unsigned *o = reinterpret_cast<unsigned *>(fd + (size_t)(y0 + ry) * row_bytes + (size_t)(x0 + 4 * q) * 3);
+				o[0] = w0;
+				o[1] = w1;
+				o[2] = w2;
+			} else {
+				const unsigned os = s_box_l + (unsigned)(ry * TW * 3 + q * 12);
+				sts32<0>(os, w0);
+				sts32<4>(os, w1);
+				sts32<8>(os, w2);
 			}
-		} else {
+		}
+		if (direct_out) return;
+		__syncthreads();
+		const int tile_bytes = tw * 3;
+		{ // (widths that are not multiples of four: byte stores from the staged rows)
 			for (int idx = t; idx < tile_bytes * th; idx += DN_THREADS) {
 				const int oy_ = idx / tile_bytes, bb = idx - oy_ * tile_bytes;
 				fd[(size_t)(y0 + oy_) * row_bytes + (size_t)x0 * 3 + bb] = smem[(size_t)oy_ * TW * 3 + bb];
@@ -2118,46 +2124,50 @@ __global__ void __launch_bounds__(DN_THREADS, 4)
 		const int g = t % GW, ry = t / GW;
 		if (ry < th && x0 + 4 * g < P.dst_w) {
 			const unsigned lt = s_vt + 4u * (unsigned)(ry * D.lt_pitch);
-			const unsigned la = s_lh + 16u * (unsigned)((int)lds32<0>(lt) * GW + g);
+			const unsigned la = s_lh + 8u * (unsigned)((int)lds32<0>(lt) * GW + g);
 			int a[4];
 			if (P.vl_size == 1) {
-				const int4 l = lds128(la);
-				a[0] = (l.x + 64) >> 7; a[1] = (l.y + 64) >> 7; a[2] = (l.z + 64) >> 7; a[3] = (l.w + 64) >> 7;
+				const uint2 l = lds64(la);
+				a[0] = (int)((l.x & 0xffffu) + 64) >> 7; a[1] = (int)((l.x >> 16) + 64) >> 7; a[2] = (int)((l.y & 0xffffu) + 64) >> 7; a[3] = (int)((l.y >> 16) + 64) >> 7;
 			} else if (P.x86_vertical && y0 + ry < P.dst_h - 2) {
 				a[0] = a[1] = a[2] = a[3] = (64 + 8 * (P.vl_size - 1)) >> 4;
-				vacc4_any<true>(la, 16u * GW, lt, P.vl_size, a);
+				vacc4_any<true>(la, 8u * GW, lt, P.vl_size, a);
 				a[0] >>= 3; a[1] >>= 3; a[2] >>= 3; a[3] >>= 3;
 			} else {
 				a[0] = a[1] = a[2] = a[3] = 64 << 12;
-				vacc4_any<false>(la, 16u * GW, lt, P.vl_size, a);
+				vacc4_any<false>(la, 8u * GW, lt, P.vl_size, a);
 				a[0] >>= 19; a[1] >>= 19; a[2] >>= 19; a[3] >>= 19;
 			}
 			*reinterpret_cast<unsigned *>(fd + (size_t)(ty + y0 + ry) * D.pitch_y + tx + x0 + 4 * g) = pack4_u8(a);
 		}
 	}
 	{
-		constexpr int GW = CW / 4; // groups of four chroma columns: two int4 of (U, V) pairs per intermediate row
+		constexpr int GW = CW / 4; // groups of four chroma columns: four packed (U, V) words per intermediate row
 		const int g = t % GW, ry = t / GW;
 		if (ry < cth && cx0 + 4 * g < P.chr_dst_w) {
 			const unsigned ct = s_ct + 4u * (unsigned)(ry * D.ct_pitch);
-			const unsigned ca = s_ch + 32u * (unsigned)((int)lds32<0>(ct) * GW + g);
+			const unsigned ca = s_ch + 16u * (unsigned)((int)lds32<0>(ct) * GW + g);
 			int a[4], b[4]; // U0 V0 U1 V1, U2 V2 U3 V3
 			if (P.vc_size == 1) {
-				const int4 c0 = lds128(ca), c1 = lds128(ca + 16);
-				a[0] = (c0.x + 64) >> 7; a[1] = (c0.y + 64) >> 7; a[2] = (c0.z + 64) >> 7; a[3] = (c0.w + 64) >> 7;
-				b[0] = (c1.x + 64) >> 7; b[1] = (c1.y + 64) >> 7; b[2] = (c1.z + 64) >> 7; b[3] = (c1.w + 64) >> 7;
+				const int4 c = lds128(ca);
+				const unsigned w[4] = {(unsigned)c.x, (unsigned)c.y, (unsigned)c.z, (unsigned)c.w};
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					a[2 * k] = (int)((w[k] & 0xffffu) + 64) >> 7; a[2 * k + 1] = (int)((w[k] >> 16) + 64) >> 7;
+					b[2 * k] = (int)((w[2 + k] & 0xffffu) + 64) >> 7; b[2 * k + 1] = (int)((w[2 + k] >> 16) + 64) >> 7;
+				}
 			} else if (P.x86_vertical && cy0 + ry < P.chr_dst_h - 1) {
 #pragma unroll
 				for (int k = 0; k < 4; ++k) a[k] = b[k] = (64 + 8 * (P.vc_size - 1)) >> 4;
-				vacc4_any<true>(ca, 32u * GW, ct, P.vc_size, a);
-				vacc4_any<true>(ca + 16, 32u * GW, ct, P.vc_size, b);
+				vacc4_any<true>(ca, 16u * GW, ct, P.vc_size, a);
+				vacc4_any<true>(ca + 8, 16u * GW, ct, P.vc_size, b);
 #pragma unroll
 				for (int k = 0; k < 4; ++k) { a[k] >>= 3; b[k] >>= 3; }
 			} else {
 #pragma unroll
 				for (int k = 0; k < 4; ++k) a[k] = b[k] = 64 << 12;
-				vacc4_any<false>(ca, 32u * GW, ct, P.vc_size, a);
-				vacc4_any<false>(ca + 16, 32u * GW, ct, P.vc_size, b);
+				vacc4_any<false>(ca, 16u * GW, ct, P.vc_size, a);
+				vacc4_any<false>(ca + 8, 16u * GW, ct, P.vc_size, b);
 #pragma unroll
 				for (int k = 0; k < 4; ++k) { a[k] >>= 19; b[k] >>= 19; }
 			}
@@ -2528,8 +2538,8 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 				size_t off = a128((size_t)blw * blh);
 				D.o_c0 = (unsigned)off; off = a128(off + cbox);
 				D.o_c1 = (unsigned)off; off = a128(off + (inter ? 0 : cbox));
-				D.o_lh = (unsigned)off; off = a128(off + sizeof(int) * (size_t)blh * TW);
-				D.o_ch = (unsigned)off; off = a128(off + sizeof(int2) * (size_t)bch * (TW / 2));
+				D.o_lh = (unsigned)off; off = a128(off + sizeof(short) * (size_t)blh * TW);
+				D.o_ch = (unsigned)off; off = a128(off + sizeof(short2) * (size_t)bch * (TW / 2));
 				D.o_vt = (unsigned)off; off = a128(off + sizeof(int) * (size_t)D.vt_ints);
 				D.o_bar = (unsigned)off; off += 16;
 				const size_t sm = off + 128;
@@ -2579,10 +2589,12 @@ int msb200_scaler_create(msb200_ctx *ctx, int src_w, int src_h, int src_fmt, int
 			D.tile_y = (const int4 *)(base + (ty - tx));
 			D.vtab = base + (vt - tx);
 		}
-		if (s->down_ok && s->smem_down > 48 * 1024) {
+		if (s->down_ok) { // five CTAs per SM need the large shared-memory carve-out
 #define DOWN_ATTR(TW, HG)                                                                                              \
 	MSB200_SMEM_OPTIN((scale_down_kernel<TW, HG, true>), ctx, s->smem_down);                                           \
-	MSB200_SMEM_OPTIN((scale_down_kernel<TW, HG, false>), ctx, s->smem_down)
+	MSB200_SMEM_OPTIN((scale_down_kernel<TW, HG, false>), ctx, s->smem_down);                                          \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_down_kernel<TW, HG, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+	MSB200_CUDA(cudaFuncSetAttribute(scale_down_kernel<TW, HG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
 			DOWN_ATTR(64, 1); DOWN_ATTR(64, 2); DOWN_ATTR(32, 2); DOWN_ATTR(32, 0); DOWN_ATTR(16, 0);
 #undef DOWN_ATTR
 		}
