@@ -52,6 +52,12 @@ MSB200_API int msb200_ctx_create(int device_ordinal, msb200_ctx **out);
 MSB200_API int msb200_ctx_create_on_stream(int device_ordinal, void *cuda_stream, msb200_ctx **out);
 MSB200_API void msb200_ctx_destroy(msb200_ctx *ctx);
 MSB200_API int msb200_ctx_sync(msb200_ctx *ctx);
+/* Deferred synchronisation for hosts that flush several banks per tick (the plugin's lockstep groups of one MSTicker): while
+ * on, the host-buffer entry points msb200_resample_process, msb200_aec_process_counts, msb200_volume_process_blocks,
+ * msb200_mixer_process, msb200_plc_process_strided and msb200_g711_decode / _encode return as soon as their copies and
+ * kernels are enqueued on the context's stream; their outputs are valid after the next msb200_ctx_sync(). The buffers must
+ * be pinned (msb200_host_alloc_pinned) and stay untouched until then. Turning it off synchronises. */
+MSB200_API int msb200_ctx_set_deferred_sync(msb200_ctx *ctx, int on);
 /* cudaSetDevice(ctx's device) for the calling thread: call it first on every thread that uses ctx (or its banks) when
  * the process drives more than one GPU; a no-op cost otherwise */
 MSB200_API int msb200_ctx_make_current(msb200_ctx *ctx);

@@ -79,6 +79,7 @@ _SIGS = {
     "msb200_ctx_create_on_stream": (_I, [_I, _P, _PP]),
     "msb200_ctx_destroy": (None, [_P]),
     "msb200_ctx_sync": (_I, [_P]),
+    "msb200_ctx_set_deferred_sync": (_I, [_P, _I]),
     "msb200_ctx_launch_count": (C.c_uint64, [_P]),
     "msb200_dev_alloc": (_I, [_P, _SZ, _PP]),
     "msb200_dev_free": (_I, [_P, _P]),

@@ -1564,7 +1564,7 @@ int msb200_aec_process_counts(msb200_aec *a, const int16_t *mic, const int16_t *
 	if ((r = msb200_aec_process_counts_dev(a, a->mic.p, a->ref.p, a->out.p, nframes, stride_samples, counts ? a->counts.p : nullptr)))
 		return r;
 	if (a->live > 0) MSB200_CUDA(cudaMemcpy2DAsync(out, pitch, a->out.p, pitch, row, (size_t)a->live, cudaMemcpyDeviceToHost, s));
-	MSB200_CUDA(cudaStreamSynchronize(s));
+	MSB200_HOST_DONE(a->ctx);
 	return MSB200_OK;
 }
 int msb200_aec_set_live(msb200_aec *a, int n_live) {

@@ -255,7 +255,7 @@ int msb200_mixer_process(msb200_mixer *m, const int16_t *in, const uint8_t *pres
 	MSB200_CUDA(cudaMemcpyAsync(m->present.p, present, nch, cudaMemcpyHostToDevice, s));
 	if ((r = mixer_launch(m, m->in.p, m->present.p, m->out.p, nullptr, 0))) return r;
 	MSB200_CUDA(cudaMemcpyAsync(out, m->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
-	MSB200_CUDA(cudaStreamSynchronize(s));
+	MSB200_HOST_DONE(m->ctx);
 	return MSB200_OK;
 }
 
@@ -544,7 +544,7 @@ int msb200_volume_process_blocks(msb200_volume *v, int16_t *io, int nsamples, in
 	if (counts) MSB200_CUDA(cudaMemcpyAsync(d_counts, counts, cbytes, cudaMemcpyHostToDevice, s));
 	if ((r = msb200i_volume_launch(v, v->io.p, nsamples, stride_samples, nblocks, 0, 0, d_counts))) return r;
 	MSB200_CUDA(cudaMemcpy2DAsync(io, pitch, v->io.p, pitch, row, (size_t)v->live, cudaMemcpyDeviceToHost, s));
-	MSB200_CUDA(cudaStreamSynchronize(s));
+	MSB200_HOST_DONE(v->ctx);
 	return MSB200_OK;
 }
 int msb200_volume_set_live(msb200_volume *v, int n_live) {

@@ -96,6 +96,13 @@ int msb200_ctx_sync(msb200_ctx *c) {
 	return MSB200_OK;
 }
 
+int msb200_ctx_set_deferred_sync(msb200_ctx *c, int on) {
+	MSB200_CHECK_ARG(c);
+	if (!on && c->defer_sync) MSB200_CUDA(cudaStreamSynchronize(c->stream));
+	c->defer_sync = on != 0;
+	return MSB200_OK;
+}
+
 uint64_t msb200_ctx_launch_count(msb200_ctx *c) {
 	return c ? c->launches : 0;
 }

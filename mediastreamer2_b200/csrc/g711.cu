@@ -152,7 +152,7 @@ static int g711_host(msb200_ctx *ctx, int law, int encode, const void *in, void 
 	}
 	cudaFreeAsync(d_in, s);
 	cudaFreeAsync(d_out, s);
-	MSB200_CUDA(cudaStreamSynchronize(s));
+	MSB200_HOST_DONE(ctx);
 	return r;
 }
 int msb200_g711_decode(msb200_ctx *ctx, int law, const uint8_t *code, int16_t *pcm, size_t n) {

@@ -19,7 +19,15 @@ struct msb200_ctx {
 	uint64_t launches = 0;
 	void *flush_buf = nullptr; // > L2, written by msb200_flush_l2
 	size_t flush_bytes = 0;
+	bool defer_sync = false; // msb200_ctx_set_deferred_sync: host-buffer entry points return after enqueueing
 };
+
+// what a host-buffer entry point ends with: wait for the stream, unless the caller collects several calls under one
+// msb200_ctx_sync()
+#define MSB200_HOST_DONE(ctx)                                                                                          \
+	do {                                                                                                               \
+		if (!(ctx)->defer_sync) MSB200_CUDA(cudaStreamSynchronize((ctx)->stream));                                     \
+	} while (0)
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION (per device), not to the bank that sets it: banks of
 // different geometry share it, so it is only ever raised. Returns a cudaError_t.

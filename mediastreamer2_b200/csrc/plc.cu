@@ -495,7 +495,7 @@ int msb200_plc_process_strided(msb200_plc *p, int16_t *io, int nsamples, int str
 	MSB200_CUDA(cudaMemcpyAsync(p->md.p, mode, rows, cudaMemcpyHostToDevice, s));
 	if ((r = msb200_plc_process_dev(p, p->io.p, nsamples, nsamples, p->md.p))) return r;
 	MSB200_CUDA(cudaMemcpy2DAsync(io, (size_t)stride_samples * 2, p->io.p, row, row, rows, cudaMemcpyDeviceToHost, s));
-	MSB200_CUDA(cudaStreamSynchronize(s));
+	MSB200_HOST_DONE(p->ctx);
 	return MSB200_OK;
 }
 

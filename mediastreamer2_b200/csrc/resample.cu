@@ -361,7 +361,7 @@ int msb200_resample_process(msb200_resample *r, const int16_t *in, int in_frames
 	if (in_bytes) MSB200_CUDA(cudaMemcpyAsync(r->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
 	if ((rc = msb200_resample_process_dev(r, r->in.p, in_frames, in_frames, r->out.p, out_stride, out_frames))) return rc;
 	if (out_bytes) MSB200_CUDA(cudaMemcpyAsync(out, r->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
-	MSB200_CUDA(cudaStreamSynchronize(s));
+	MSB200_HOST_DONE(r->ctx);
 	return MSB200_OK;
 }
 int msb200_resample_set_live(msb200_resample *r, int n_live) {

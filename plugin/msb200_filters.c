@@ -78,11 +78,13 @@ static msb200_ctx *dsp_ctx(void) {
  * key share a bank of <slots> streams (rooms for the mixer). All member process() calls of a ticker come from that
  * ticker's thread (src/base/msticker.c:244-282), so a group's arenas and slot tables are touched by one thread at a
  * time; joining / leaving (preprocess / postprocess, on the attaching thread), control-thread methods that reach the
- * group's bank and the flush serialise on the GROUP's mutex. Every group owns its device context (its own CUDA
- * stream), so the groups of different tickers run concurrently on the GPU and never wait for each other on the host.
+ * group's bank and the flush serialise on the GROUP's mutex. Every TICKER owns one device context (one CUDA stream)
+ * shared by all its groups, so the tickers run concurrently on the GPU and never wait for each other on the host, and a
+ * ticker waits for the device ONCE per tick: the first member called in tick T enqueues the work of ALL the ticker's groups
+ * back to back (copies in, kernels, copies out: msb200_ctx_set_deferred_sync) and synchronises once.
  *
- *   tick T, member i:  batch_tick()   -> first caller of the tick: run the bank over everything staged during T-1
- *                      emit           -> the member's results of T-1 go to its output queue
+ *   tick T, first member of the ticker:  flush -> every group's bank runs over everything staged during T-1
+ *   tick T, member i:  emit           -> the member's results of T-1 go to its output queue
  *                      stage          -> the member's block(s) of T are copied into its arena slot
  *
  * Only slots [0, highest occupied + 1) are copied and processed (msb200_*_set_live). A slot that staged fewer units
@@ -96,15 +98,27 @@ static msb200_ctx *dsp_ctx(void) {
  */
 enum { BK_RESAMPLE, BK_EC, BK_VOLUME, BK_MIXER, BK_G711DEC, BK_G711ENC, BK_PLC }; /* the codecs are stateless: no bank, key[0] = law */
 #define BATCH_MAX_SLOTS 4096
+struct Batch;
+typedef struct TickerDev { /* a ticker's device context and its groups */
+	struct TickerDev *next;
+	MSTicker *ticker;
+	msb200_ctx *ctx;
+	pthread_mutex_t mu;    /* the group list and the joint flush */
+	struct Batch *groups;  /* through Batch.tnext */
+	int n_groups;
+	uint64_t seen_tick;    /* ticker->ticks of the last flush */
+	uint64_t flushes;
+} TickerDev;
 typedef struct Batch {
-	struct Batch *next;
+	struct Batch *next, *tnext;
+	TickerDev *td;
 	int kind;
 	MSTicker *ticker;
 	int key[4];
 	int cap, n_members, hi, live; /* hi: highest occupied slot + 1; live: what the bank was last told */
 	void **owner;      /* [cap] filter state owning the slot, NULL when free */
-	uint64_t seen_tick; /* ticker->ticks of the last flush */
-	msb200_ctx *ctx;   /* the group's own device context (stream) */
+	msb200_ctx *ctx;   /* the ticker's device context (td->ctx) */
+	int run_units, run_rc; /* of the flush in progress */
 	pthread_mutex_t mu; /* bank, slot tables */
 	void *bank;
 	int unit_in, unit_out, max_units; /* samples per unit per slot in / out; units a slot may stage per tick */
@@ -119,6 +133,7 @@ typedef struct Batch {
 	uint64_t flushes, units_run;
 } Batch;
 static Batch *g_batches = NULL;
+static TickerDev *g_ticker_devs = NULL; /* g_batch_mu */
 static pthread_mutex_t g_batch_mu = PTHREAD_MUTEX_INITIALIZER; /* the list of groups and the ticker -> device table */
 static int g_batch_cap = -1;
 #define GRP_LOCK(b) pthread_mutex_lock(&(b)->mu)
@@ -152,7 +167,46 @@ static void *batch_pinned(Batch *b, size_t bytes) {
 	memset(p, 0, bytes);
 	return p;
 }
-static void batch_free(Batch *b) { /* unlinked, no members left */
+/* the ticker's device context (g_batch_mu held); created with the ticker's first group, destroyed with its last */
+static TickerDev *ticker_dev(MSTicker *ticker) {
+	TickerDev *td;
+	for (td = g_ticker_devs; td; td = td->next)
+		if (td->ticker == ticker) return td;
+	td = ms_new0(TickerDev, 1);
+	td->ticker = ticker;
+	td->seen_tick = (uint64_t)-1;
+	if (msb200_ctx_create(batch_device_of(ticker), &td->ctx) != MSB200_OK) {
+		ms_free(td);
+		return NULL;
+	}
+	pthread_mutex_init(&td->mu, NULL);
+	td->next = g_ticker_devs;
+	g_ticker_devs = td;
+	return td;
+}
+static void ticker_dev_release(TickerDev *td) { /* g_batch_mu held */
+	TickerDev **tp;
+	if (td->n_groups > 0) return;
+	for (tp = &g_ticker_devs; *tp && *tp != td; tp = &(*tp)->next) {
+	}
+	if (*tp) *tp = td->next;
+	msb200_ctx_destroy(td->ctx);
+	pthread_mutex_destroy(&td->mu);
+	ms_free(td);
+}
+static void batch_free(Batch *b) { /* g_batch_mu held; unlinked from g_batches, no members left */
+	TickerDev *td = b->td;
+	if (td) { /* out of the ticker's flush first (a flush in progress finishes under td->mu) */
+		Batch **gp;
+		pthread_mutex_lock(&td->mu);
+		for (gp = &td->groups; *gp && *gp != b; gp = &(*gp)->tnext) {
+		}
+		if (*gp) {
+			*gp = b->tnext;
+			td->n_groups--;
+		}
+		pthread_mutex_unlock(&td->mu);
+	}
 	if (b->ctx) {
 		msb200_ctx_make_current(b->ctx);
 		switch (b->kind) {
@@ -165,8 +219,8 @@ static void batch_free(Batch *b) { /* unlinked, no members left */
 		if (b->in[0]) msb200_host_free_pinned(b->ctx, b->in[0]);
 		if (b->in[1]) msb200_host_free_pinned(b->ctx, b->in[1]);
 		if (b->out) msb200_host_free_pinned(b->ctx, b->out);
-		msb200_ctx_destroy(b->ctx);
 	}
+	if (td) ticker_dev_release(td); /* the last group takes the context with it */
 	pthread_mutex_destroy(&b->mu);
 	ms_free(b->present);
 	ms_free(b->modes);
@@ -185,7 +239,8 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 	for (b = g_batches; b; b = b->next)
 		if (b->kind == kind && b->ticker == ticker && memcmp(b->key, key, sizeof(b->key)) == 0 && b->n_members < b->cap) break;
 	if (!b) {
-		int rc;
+		int rc = MSB200_ECUDA;
+		TickerDev *td = ticker_dev(ticker);
 		b = ms_new0(Batch, 1);
 		pthread_mutex_init(&b->mu, NULL);
 		b->kind = kind;
@@ -197,9 +252,10 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 		b->unit_out = unit_out;
 		b->max_units = max_units;
 		b->collect = collect;
-		b->seen_tick = (uint64_t)-1;
-		rc = msb200_ctx_create(batch_device_of(ticker), &b->ctx);
-		if (rc == MSB200_OK) {
+		if (td) {
+			b->ctx = td->ctx;
+			msb200_ctx_make_current(b->ctx);
+			rc = MSB200_OK;
 			switch (kind) {
 				case BK_RESAMPLE: rc = msb200_resample_create(b->ctx, cap, key[0], key[1], key[2], key[3], (msb200_resample **)&b->bank); break;
 				case BK_EC: rc = msb200_aec_create(b->ctx, cap, key[0], key[1], key[2], (msb200_aec **)&b->bank); break;
@@ -207,8 +263,6 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 				case BK_MIXER: rc = msb200_mixer_create(b->ctx, cap, key[2], key[0], key[1], (msb200_mixer **)&b->bank); break;
 				case BK_PLC: rc = msb200_plc_create(b->ctx, cap, key[0], key[1], (msb200_plc **)&b->bank); break;
 			}
-		} else {
-			b->ctx = NULL;
 		}
 		if (rc == MSB200_OK) {
 			const size_t n_in = (size_t)cap * max_units * unit_in * sizeof(int16_t), n_out = (size_t)cap * max_units * unit_out * sizeof(int16_t);
@@ -220,6 +274,7 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 		if (rc != MSB200_OK) {
 			ms_error("msb200: cannot create a batch group (%s); the filter stays synchronous", msb200_last_error());
 			batch_free(b);
+			if (td) ticker_dev_release(td);
 			pthread_mutex_unlock(&g_batch_mu);
 			return NULL;
 		}
@@ -230,6 +285,12 @@ static Batch *batch_join(int kind, MSTicker *ticker, const int key[4], int unit_
 		if (kind == BK_PLC) b->modes = (uint8_t *)ms_malloc0((size_t)cap);
 		b->next = g_batches;
 		g_batches = b;
+		pthread_mutex_lock(&td->mu); /* from now on the ticker's flush runs this group too */
+		b->td = td;
+		b->tnext = td->groups;
+		td->groups = b;
+		td->n_groups++;
+		pthread_mutex_unlock(&td->mu);
 		ms_message("msb200: batch group %p: kind %d, %d slots, key {%d,%d,%d,%d} on ticker %p", b, kind, cap, key[0], key[1], key[2], key[3], ticker);
 	}
 	GRP_LOCK(b);
@@ -265,18 +326,15 @@ static void batch_leave(Batch *b, int slot) {
 	if (last) batch_free(b);
 	pthread_mutex_unlock(&g_batch_mu);
 }
-/* called first thing in every member's process(): the first caller of a tick runs the group's previous tick */
-static void batch_tick(Batch *b, uint64_t ticks) {
+/* one group's share of the ticker's flush (group lock held, deferred synchronisation on): everything staged since the
+ * last flush is enqueued on the ticker's stream — copies in, kernels, copies out */
+static void batch_enqueue(Batch *b) {
 	int i, units = 0, rc = MSB200_OK;
-	if (b->seen_tick == ticks) return;
-	GRP_LOCK(b);
-	b->seen_tick = ticks;
 	for (i = 0; i < b->hi; ++i) {
 		if (b->ready[i] > 0 && b->owner[i] && b->collect) b->collect(b->owner[i], b); /* not scheduled since the last flush */
 		if (b->staged[i] > units) units = b->staged[i];
 	}
 	if (units > 0) {
-		msb200_ctx_make_current(b->ctx);
 		if (b->live != b->hi) {
 			switch (b->kind) {
 				case BK_RESAMPLE: msb200_resample_set_live((msb200_resample *)b->bank, b->hi); break;
@@ -341,13 +399,46 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 		b->flushes++;
 		b->units_run += (uint64_t)units;
 	}
+	b->run_units = units;
+	b->run_rc = rc;
+}
+/* after the ticker's one synchronisation: the staged units are now results */
+static void batch_finish(Batch *b, int sync_rc) {
+	int i;
+	const int ok = b->run_rc == MSB200_OK && sync_rc == MSB200_OK;
 	for (i = 0; i < b->hi; ++i) {
-		b->ready[i] = rc == MSB200_OK ? b->staged[i] : 0;
+		b->ready[i] = ok ? b->staged[i] : 0;
 		b->staged[i] = 0;
 	}
 	if (b->present) memset(b->present, 0, (size_t)b->hi * b->key[2]);
-	GRP_UNLOCK(b);
 }
+/* called first thing in every member's process(), and by a filter that joins a group from its process() BEFORE it stages
+ * its first block (a block staged ahead of the tick's flush would run a tick early and leave the slot empty — for the
+ * resampler: zero-fed — at the next one): the first caller of a tick, whatever its group, runs the previous tick of ALL
+ * the ticker's groups — their device work goes out back to back on the ticker's stream and the thread waits once */
+static void batch_tick(Batch *b, uint64_t ticks) {
+	TickerDev *td = b->td;
+	Batch *g;
+	int rc;
+	if (td->seen_tick == ticks) return; /* (only the ticker's own thread writes it) */
+	pthread_mutex_lock(&td->mu);
+	td->seen_tick = ticks;
+	td->flushes++;
+	msb200_ctx_make_current(td->ctx);
+	msb200_ctx_set_deferred_sync(td->ctx, 1);
+	for (g = td->groups; g; g = g->tnext) {
+		GRP_LOCK(g);
+		batch_enqueue(g);
+	}
+	rc = msb200_ctx_set_deferred_sync(td->ctx, 0); /* synchronises */
+	if (rc != MSB200_OK) ms_error("msb200: flush of ticker %p failed: %s", td->ticker, msb200_last_error());
+	for (g = td->groups; g; g = g->tnext) {
+		batch_finish(g, rc);
+		GRP_UNLOCK(g);
+	}
+	pthread_mutex_unlock(&td->mu);
+}
+
 
 /* ================================================================================================ MSAudioMixer
  * What the reference filter does on the host and this one must do too (/root/reference/src/audiofilters/audiomixer.c):
@@ -910,6 +1001,7 @@ static void vol_process(MSFilter *f) {
 				v->dirty = TRUE;
 				v->gain_dirty = v->static_gain != 1.0f;
 				GRP_UNLOCK(v->batch);
+				batch_tick(v->batch, f->ticker->ticks); /* (nothing of ours is staged yet: see batch_tick) */
 			} else {
 				v->batch_off = TRUE;
 			}
@@ -1488,6 +1580,7 @@ static void rs_process(MSFilter *f) {
 				msb200_ctx_make_current(s->batch->ctx);
 				msb200_resample_reset_stream((msb200_resample *)s->batch->bank, s->slot);
 				GRP_UNLOCK(s->batch);
+				batch_tick(s->batch, f->ticker->ticks);
 			} else {
 				s->batch_off = TRUE;
 			}
@@ -1928,6 +2021,7 @@ static void g711_enc_process(MSFilter *f) {
 		s->batch = batch_join(BK_G711ENC, f->ticker, key, (int)size_of_pcm / 2, (int)size_of_pcm / 4, G711_BATCH_UNITS, s, g711_enc_collect,
 		                      &s->slot);
 		if (!s->batch) s->batch_off = TRUE;
+		else batch_tick(s->batch, f->ticker->ticks);
 	}
 	if (s->batch) { /* stage whole packets; their payload is filled in at the start of the next tick */
 		Batch *b = s->batch;
@@ -2093,6 +2187,7 @@ static bool_t g711_dec_stage(MSFilter *f, G711DecState *s, mblk_t *m) {
 		const int key[4] = {s->law, n, 0, 0};
 		s->batch = batch_join(BK_G711DEC, f->ticker, key, n / 2, n, G711_BATCH_UNITS, s, g711_dec_collect, &s->slot);
 		if (!s->batch) s->batch_off = TRUE;
+		else batch_tick(s->batch, f->ticker->ticks);
 	}
 	if (!s->batch) return FALSE;
 	{
@@ -2468,6 +2563,7 @@ static void plc_process(MSFilter *f) {
 				msb200_ctx_make_current(s->batch->ctx);
 				msb200_plc_reset_stream((msb200_plc *)s->batch->bank, s->slot);
 				GRP_UNLOCK(s->batch);
+				batch_tick(s->batch, f->ticker->ticks);
 				s->n_units = 0;
 			} else {
 				s->batch_off = TRUE;
