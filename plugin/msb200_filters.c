@@ -43,6 +43,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ------------------------------------------------------------------------------------------------ device context */
 static msb200_ctx *g_ctx = NULL;
@@ -72,6 +73,52 @@ static msb200_ctx *dsp_ctx(void) {
 		if ((expr) != MSB200_OK) ms_error("msb200: %s failed: %s", what, msb200_last_error());                         \
 	} while (0)
 
+
+/* ------------------------------------------------------------------------------------------------ host profile
+ * MSB200_PROFILE=1: where a ticker thread's time goes, per filter kind — nanoseconds inside process() (the flush a first
+ * caller runs is counted apart: enqueue and wait). Striped counters, read by msb200_filters_host_profile(). */
+enum { PF_MIXER, PF_VOLUME, PF_CHAN, PF_EQ, PF_RESAMPLE, PF_EC, PF_G711ENC, PF_G711DEC, PF_FLOWCTL, PF_PLC, PF_FLUSH_ENQUEUE, PF_FLUSH_WAIT, PF_N };
+static const char *const g_prof_names[PF_N] = {"MSAudioMixer", "MSVolume", "MSChannelAdapter", "MSEqualizer", "MSResample", "MSSpeexEC",
+                                               "G711Enc", "G711Dec", "MSAudioFlowControl", "MSGenericPLC", "flush_enqueue", "flush_wait"};
+#define PROF_STRIPES 64
+typedef struct ProfStripe {
+	uint64_t ns[PF_N], calls[PF_N];
+	char pad[64];
+} ProfStripe;
+static ProfStripe g_prof[PROF_STRIPES];
+static int g_prof_on = -1;
+static __thread uint64_t t_flush_ns = 0; /* flush time inside the process() call in progress */
+static __thread int t_stripe = -1;
+static inline int prof_on(void) {
+	if (g_prof_on < 0) {
+		const char *e = getenv("MSB200_PROFILE");
+		g_prof_on = e && atoi(e) > 0;
+	}
+	return g_prof_on;
+}
+static inline uint64_t prof_now(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+static void prof_add(int kind, uint64_t ns) {
+	static int next_stripe = 0;
+	if (t_stripe < 0) t_stripe = __atomic_fetch_add(&next_stripe, 1, __ATOMIC_RELAXED) % PROF_STRIPES;
+	__atomic_fetch_add(&g_prof[t_stripe].ns[kind], ns, __ATOMIC_RELAXED);
+	__atomic_fetch_add(&g_prof[t_stripe].calls[kind], 1, __ATOMIC_RELAXED);
+}
+#define PROF_WRAP(kind, fn)                                                                                            \
+	static void fn##_timed(MSFilter *f) {                                                                              \
+		uint64_t t0, fl0;                                                                                              \
+		if (!prof_on()) {                                                                                              \
+			fn(f);                                                                                                     \
+			return;                                                                                                    \
+		}                                                                                                              \
+		t0 = prof_now();                                                                                               \
+		fl0 = t_flush_ns;                                                                                              \
+		fn(f);                                                                                                         \
+		prof_add(kind, prof_now() - t0 - (t_flush_ns - fl0));                                                          \
+	}
 
 /* ------------------------------------------------------------------------------------------------ batch groups
  * MSB200_BATCH=<slots> turns on the lockstep batch mode: filters of one kind, on one MSTicker, with one configuration
@@ -420,17 +467,26 @@ static void batch_tick(Batch *b, uint64_t ticks) {
 	TickerDev *td = b->td;
 	Batch *g;
 	int rc;
+	uint64_t t0 = 0, t1 = 0;
 	if (td->seen_tick == ticks) return; /* (only the ticker's own thread writes it) */
 	pthread_mutex_lock(&td->mu);
 	td->seen_tick = ticks;
 	td->flushes++;
+	if (prof_on()) t0 = prof_now();
 	msb200_ctx_make_current(td->ctx);
 	msb200_ctx_set_deferred_sync(td->ctx, 1);
 	for (g = td->groups; g; g = g->tnext) {
 		GRP_LOCK(g);
 		batch_enqueue(g);
 	}
+	if (prof_on()) t1 = prof_now();
 	rc = msb200_ctx_set_deferred_sync(td->ctx, 0); /* synchronises */
+	if (prof_on()) {
+		const uint64_t t2 = prof_now();
+		prof_add(PF_FLUSH_ENQUEUE, t1 - t0);
+		prof_add(PF_FLUSH_WAIT, t2 - t1);
+		t_flush_ns += t2 - t0;
+	}
 	if (rc != MSB200_OK) ms_error("msb200: flush of ticker %p failed: %s", td->ticker, msb200_last_error());
 	for (g = td->groups; g; g = g->tnext) {
 		batch_finish(g, rc);
@@ -773,6 +829,7 @@ static MSFilterMethod mixroom_methods[] = {{MS_FILTER_SET_NCHANNELS, mixm_set_ch
                                            {MS_AUDIO_MIXER_SET_MASTER_CHANNEL, mixm_set_master},
                                            {MS_AUDIO_MIXER_ENABLE_OUTPUT, mixm_set_listens},
                                            {0, NULL}};
+PROF_WRAP(PF_MIXER, mixroom_tick)
 static MSFilterDesc b200_audio_mixer_desc = {.id = MS_AUDIO_MIXER_ID,
                                              .name = "MSAudioMixer",
                                              .text = "B200: mixes 16 bit sample audio streams (libmsb200dsp)",
@@ -781,7 +838,7 @@ static MSFilterDesc b200_audio_mixer_desc = {.id = MS_AUDIO_MIXER_ID,
                                              .noutputs = MIX_PINS,
                                              .init = mixroom_new,
                                              .preprocess = mixroom_attach,
-                                             .process = mixroom_tick,
+                                             .process = mixroom_tick_timed,
                                              .postprocess = mixroom_detach,
                                              .uninit = mixroom_free,
                                              .methods = mixroom_methods,
@@ -1190,6 +1247,7 @@ static MSFilterMethod vol_methods[] = {{MS_VOLUME_GET, vol_get},
                                        {MS_VOLUME_GET_GAIN_DB, vol_get_gain_db},
                                        {MS_VOLUME_REMOVE_DC, vol_remove_dc},
                                        {0, NULL}};
+PROF_WRAP(PF_VOLUME, vol_process)
 static MSFilterDesc b200_volume_desc = {.id = MS_VOLUME_ID,
                                         .name = "MSVolume",
                                         .text = "B200: controls and measures sound volume (libmsb200dsp)",
@@ -1198,7 +1256,7 @@ static MSFilterDesc b200_volume_desc = {.id = MS_VOLUME_ID,
                                         .noutputs = 1,
                                         .init = vol_init,
                                         .preprocess = vol_preprocess,
-                                        .process = vol_process,
+                                        .process = vol_process_timed,
                                         .postprocess = vol_postprocess,
                                         .uninit = vol_uninit,
                                         .methods = vol_methods};
@@ -1323,6 +1381,7 @@ static MSFilterMethod chan_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, chanm_set_hz
                                         {MS_CHANNEL_ADAPTER_SET_OUTPUT_NCHANNELS, chanm_set_out},
                                         {MS_CHANNEL_ADAPTER_GET_OUTPUT_NCHANNELS, chanm_get_out},
                                         {0, NULL}};
+PROF_WRAP(PF_CHAN, chan_tick)
 static MSFilterDesc b200_channel_adapter_desc = {.id = MS_CHANNEL_ADAPTER_ID,
                                                  .name = "MSChannelAdapter",
                                                  .text = "B200: mono/stereo channel adaptation (libmsb200dsp)",
@@ -1331,7 +1390,7 @@ static MSFilterDesc b200_channel_adapter_desc = {.id = MS_CHANNEL_ADAPTER_ID,
                                                  .noutputs = 1,
                                                  .init = chan_new,
                                                  .preprocess = chan_attach,
-                                                 .process = chan_tick,
+                                                 .process = chan_tick_timed,
                                                  .postprocess = chan_detach,
                                                  .uninit = chan_free,
                                                  .methods = chan_methods,
@@ -1451,6 +1510,7 @@ static MSFilterMethod eq_methods[] = {{MS_EQUALIZER_SET_GAIN, eq_set_gain},
                                       {MS_FILTER_SET_SAMPLE_RATE, eq_set_rate},
                                       {MS_EQUALIZER_GET_NUM_FREQUENCIES, eq_get_nfreqs},
                                       {0, NULL}};
+PROF_WRAP(PF_EQ, eq_process)
 static MSFilterDesc b200_equalizer_desc = {.id = MS_EQUALIZER_ID,
                                            .name = "MSEqualizer",
                                            .text = "B200: parametric sound equalizer (libmsb200dsp)",
@@ -1459,7 +1519,7 @@ static MSFilterDesc b200_equalizer_desc = {.id = MS_EQUALIZER_ID,
                                            .noutputs = 1,
                                            .init = eq_init,
                                            .preprocess = eq_preprocess,
-                                           .process = eq_process,
+                                           .process = eq_process_timed,
                                            .uninit = eq_uninit,
                                            .methods = eq_methods};
 
@@ -1660,6 +1720,7 @@ static MSFilterMethod rs_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, rs_set_sr},
                                       {MS_FILTER_SET_NCHANNELS, rs_set_in_nch},
                                       {MS_FILTER_SET_OUTPUT_NCHANNELS, rs_set_out_nch},
                                       {0, NULL}};
+PROF_WRAP(PF_RESAMPLE, rs_process)
 static MSFilterDesc b200_resample_desc = {.id = MS_RESAMPLE_ID,
                                           .name = "MSResample",
                                           .text = "B200: audio resampler (libmsb200dsp)",
@@ -1668,7 +1729,7 @@ static MSFilterDesc b200_resample_desc = {.id = MS_RESAMPLE_ID,
                                           .noutputs = 1,
                                           .init = rs_init,
                                           .preprocess = rs_preprocess,
-                                          .process = rs_process,
+                                          .process = rs_process_timed,
                                           .postprocess = rs_postprocess,
                                           .uninit = rs_uninit,
                                           .methods = rs_methods};
@@ -1922,6 +1983,7 @@ static MSFilterMethod ec_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, ecm_set_hz},
                                       {MS_ECHO_CANCELLER_SET_STATE_STRING, ecm_set_state},
                                       {MS_ECHO_CANCELLER_GET_DELAY, ecm_get_delay},
                                       {0, NULL}};
+PROF_WRAP(PF_EC, ec_tick)
 static MSFilterDesc b200_speex_ec_desc = {.id = MS_SPEEX_EC_ID,
                                           .name = "MSSpeexEC",
                                           .text = "B200: MDF echo canceller + preprocessor (libmsb200dsp)",
@@ -1930,7 +1992,7 @@ static MSFilterDesc b200_speex_ec_desc = {.id = MS_SPEEX_EC_ID,
                                           .noutputs = 2,
                                           .init = ec_new,
                                           .preprocess = ec_attach,
-                                          .process = ec_tick,
+                                          .process = ec_tick_timed,
                                           .postprocess = ec_detach,
                                           .uninit = ec_free,
                                           .methods = ec_methods};
@@ -2260,21 +2322,24 @@ static void g711_dec_process_law(MSFilter *f, int law) { /* alaw_dec_process ala
 }
 static void alaw_dec_process(MSFilter *f) { g711_dec_process_law(f, MSB200_G711_ALAW); }
 static void ulaw_dec_process(MSFilter *f) { g711_dec_process_law(f, MSB200_G711_ULAW); }
+PROF_WRAP(PF_G711ENC, g711_enc_process)
 static MSFilterDesc b200_alaw_enc_desc = {.id = MS_ALAW_ENC_ID, .name = "MSAlawEnc", .text = "B200: ITU-G.711 alaw encoder (libmsb200dsp)",
                                           .category = MS_FILTER_ENCODER, .enc_fmt = "pcma", .ninputs = 1, .noutputs = 1,
-                                          .init = alaw_enc_init, .process = g711_enc_process, .postprocess = g711_enc_postprocess, .uninit = g711_enc_uninit,
+                                          .init = alaw_enc_init, .process = g711_enc_process_timed, .postprocess = g711_enc_postprocess, .uninit = g711_enc_uninit,
                                           .methods = g711_enc_methods};
 static MSFilterDesc b200_ulaw_enc_desc = {.id = MS_ULAW_ENC_ID, .name = "MSUlawEnc", .text = "B200: ITU-G.711 ulaw encoder (libmsb200dsp)",
                                           .category = MS_FILTER_ENCODER, .enc_fmt = "pcmu", .ninputs = 1, .noutputs = 1,
-                                          .init = ulaw_enc_init, .process = g711_enc_process, .postprocess = g711_enc_postprocess, .uninit = g711_enc_uninit,
+                                          .init = ulaw_enc_init, .process = g711_enc_process_timed, .postprocess = g711_enc_postprocess, .uninit = g711_enc_uninit,
                                           .methods = g711_enc_methods};
+PROF_WRAP(PF_G711DEC, alaw_dec_process)
 static MSFilterDesc b200_alaw_dec_desc = {.id = MS_ALAW_DEC_ID, .name = "MSAlawDec", .text = "B200: ITU-G.711 alaw decoder (libmsb200dsp)",
                                           .category = MS_FILTER_DECODER, .enc_fmt = "pcma", .ninputs = 1, .noutputs = 1,
-                                          .init = alaw_dec_init, .process = alaw_dec_process, .postprocess = g711_dec_postprocess,
+                                          .init = alaw_dec_init, .process = alaw_dec_process_timed, .postprocess = g711_dec_postprocess,
                                           .uninit = g711_dec_uninit, .methods = g711_dec_methods};
+PROF_WRAP(PF_G711DEC, ulaw_dec_process)
 static MSFilterDesc b200_ulaw_dec_desc = {.id = MS_ULAW_DEC_ID, .name = "MSUlawDec", .text = "B200: ITU-G.711 ulaw decoder (libmsb200dsp)",
                                           .category = MS_FILTER_DECODER, .enc_fmt = "pcmu", .ninputs = 1, .noutputs = 1,
-                                          .init = ulaw_dec_init, .process = ulaw_dec_process, .postprocess = g711_dec_postprocess,
+                                          .init = ulaw_dec_init, .process = ulaw_dec_process_timed, .postprocess = g711_dec_postprocess,
                                           .uninit = g711_dec_uninit, .methods = g711_dec_methods};
 
 /* ================================================================================================ MSAudioFlowControl
@@ -2396,6 +2461,7 @@ static MSFilterMethod flowctl_methods[] = {{MS_AUDIO_FLOW_CONTROL_SET_CONFIG, fl
                                            {MS_FILTER_SET_NCHANNELS, flowctl_set_nch},
                                            {MS_FILTER_GET_NCHANNELS, flowctl_get_nch},
                                            {0, NULL}};
+PROF_WRAP(PF_FLOWCTL, flowctl_process)
 static MSFilterDesc b200_flow_control_desc = {.id = MS_AUDIO_FLOW_CONTROL_ID,
                                               .name = "MSAudioFlowControl",
                                               .text = "B200: flow control filter dropping samples when too many are queued (libmsb200dsp)",
@@ -2404,7 +2470,7 @@ static MSFilterDesc b200_flow_control_desc = {.id = MS_AUDIO_FLOW_CONTROL_ID,
                                               .noutputs = 1,
                                               .init = flowctl_init,
                                               .preprocess = flowctl_preprocess,
-                                              .process = flowctl_process,
+                                              .process = flowctl_process_timed,
                                               .uninit = flowctl_uninit,
                                               .methods = flowctl_methods};
 
@@ -2652,6 +2718,7 @@ static MSFilterMethod plc_methods[] = {{MS_FILTER_SET_SAMPLE_RATE, plc_set_sr},
                                        {MS_FILTER_SET_NCHANNELS, plc_set_nch},
                                        {MS_GENERIC_PLC_SET_CN, plc_set_cn},
                                        {0, NULL}};
+PROF_WRAP(PF_PLC, plc_process)
 static MSFilterDesc b200_generic_plc_desc = {.id = MS_GENERIC_PLC_ID,
                                              .name = "MSGenericPLC",
                                              .text = "B200: generic packet-loss concealment (libmsb200dsp)",
@@ -2660,7 +2727,7 @@ static MSFilterDesc b200_generic_plc_desc = {.id = MS_GENERIC_PLC_ID,
                                              .noutputs = 1,
                                              .init = plc_init,
                                              .preprocess = plc_preprocess,
-                                             .process = plc_process,
+                                             .process = plc_process_timed,
                                              .postprocess = plc_postprocess,
                                              .uninit = plc_uninit,
                                              .methods = plc_methods,
@@ -2713,6 +2780,27 @@ __attribute__((visibility("default"))) void msb200_filters_batch_stats(int *grou
 	if (groups) *groups = g;
 	if (flushes) *flushes = fl;
 	if (units) *units = un;
+}
+__attribute__((visibility("default"))) void msb200_filters_host_profile_reset(void) { /* e.g. after the warm-up ticks (joins, set-up) */
+	memset(g_prof, 0, sizeof(g_prof));
+}
+/* MSB200_PROFILE=1: one line of JSON, {"<kind>": {"ms": total milliseconds inside process(), "calls": n}, ...} */
+__attribute__((visibility("default"))) int msb200_filters_host_profile(char *buf, int size) {
+	int k, i, n = 0;
+	if (!buf || size < 2) return 0;
+	n += snprintf(buf + n, (size_t)(size - n), "{");
+	for (k = 0; k < PF_N && n < size; ++k) {
+		uint64_t ns = 0, calls = 0;
+		for (i = 0; i < PROF_STRIPES; ++i) {
+			ns += __atomic_load_n(&g_prof[i].ns[k], __ATOMIC_RELAXED);
+			calls += __atomic_load_n(&g_prof[i].calls[k], __ATOMIC_RELAXED);
+		}
+		if (calls == 0) continue;
+		n += snprintf(buf + n, (size_t)(size - n), "%s\"%s\": {\"ms\": %.3f, \"calls\": %llu}", n > 1 ? ", " : "", g_prof_names[k],
+		              (double)ns / 1e6, (unsigned long long)calls);
+	}
+	if (n < size) n += snprintf(buf + n, (size_t)(size - n), "}");
+	return n;
 }
 /* also exported so that a host can install the scaler explicitly */
 __attribute__((visibility("default"))) MSScalerDesc *msb200_ms_scaler_desc(void) {

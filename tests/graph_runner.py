@@ -146,6 +146,8 @@ def main():
         run(a.ticks - t2)
     elif a.timing:
         run(a.warmup)
+        if int(os.environ.get("MSB200_PROFILE", "0") or 0) > 0:  # the profile covers the timed ticks only (no joins, no set-up)
+            C.CDLL(str(O.PLUGIN_DIR / "libmsb200filters.so")).msb200_filters_host_profile_reset()
         for _ in range(a.ticks - a.warmup):
             t0 = time.perf_counter()
             run(1)
@@ -169,6 +171,11 @@ def main():
             gr, fl, un = C.c_int(), C.c_ulonglong(), C.c_ulonglong()
             plug.msb200_filters_batch_stats(C.byref(gr), C.byref(fl), C.byref(un))
             stats.update({"batch_groups": gr.value, "batch_launches": fl.value})
+            if int(os.environ.get("MSB200_PROFILE", "0") or 0) > 0:  # thread-milliseconds inside our process() calls, per kind,
+                buf = C.create_string_buffer(4096)                    # over the timed ticks; the rest of a ticker thread's
+                plug.msb200_filters_host_profile(buf, 4096)           # time is the reference's own runtime (and the harness)
+                stats["host_profile_ms"] = {k: v["ms"] for k, v in json.loads(buf.value.decode()).items()}
+                stats["thread_ms_total"] = float(ms.sum() * len(tickers))
         except (OSError, AttributeError):
             pass
         print(json.dumps(stats), flush=True)
