@@ -133,7 +133,7 @@ def kernels_bench(ctx, hbm_peak_gbs: float) -> dict:
             ("scale_plane_strip_kernel", _lib.PIX_YUV420P, _lib.PIX_YUV420P, 1280, 720, i420, 1280 * 720 * 3 // 2, "a8 MSSizeConv I420 1080p -> I420 720p"),
             ("scale_plane_strip_kernel<INTER>", _lib.PIX_NV12, _lib.PIX_YUV420P, 1280, 720, i420, 1280 * 720 * 3 // 2,
              "cfg4 reference-shaped two-step as ONE pass: NV12 1080p -> I420 720p, CbCr plane read in place"),
-            ("rgb24_to_i420_kernel<0>", _lib.PIX_RGB24, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv RGB24 -> I420 1080p"),
+            ("rgb_to_i420_march_kernel<0>", _lib.PIX_RGB24, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv RGB24 -> I420 1080p"),
             ("rgb24_to_i420_kernel<1>", _lib.PIX_RGB24_REV, _lib.PIX_YUV420P, sw, sh, sw * sh * 3, i420, "a7 MSPixConv BGR24 -> I420 1080p"),
             ("packed422_to_i420_kernel", _lib.PIX_YUY2, _lib.PIX_YUV420P, sw, sh, sw * sh * 2, i420, "a7 MSPixConv YUY2 -> I420 1080p"),
             ("scale_down_kernel<64,2,rgb>", _lib.PIX_NV12, _lib.PIX_RGB24, 640, 360, i420, 640 * 360 * 3, "a8/a11 NV12 1080p -> RGB24 360p (3:1 down-scale tiles)"),

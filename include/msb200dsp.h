@@ -524,7 +524,9 @@ MSB200_API int msb200_scaler_process_frames(msb200_scaler *s, int n_frames, cons
  * (what SWS_BITEXACT selects; the default here) and, on x86, the SIMD vertical scaler a plain SWS_BILINEAR call — the call
  * the reference makes, src/voip/msvideo.c:660 — really runs, which differs by at most 1 (per-tap truncation in 16-bit
  * lanes, a compensating rounder, the last two luma rows and the last chroma row by the C functions). on = 1 reproduces the
- * x86 result bit for bit (pinned: the oracle's same mode equals the live library on random geometries). */
+ * x86 result bit for bit (pinned: the oracle's same mode equals the live library on random geometries). Also accepted by
+ * MSPixConv's RGB inputs (RGB24 / RGBA / BGRA / RGB565 -> YUV420P), whose chroma rows the library filters 2:1 with the same
+ * vertical scaler (folded taps on the top row); BGR24's special converter has no vertical filter and is unaffected. */
 MSB200_API int msb200_scaler_set_x86_vertical(msb200_scaler *s, int on);
 
 /* Mosaic / compositor (the reference's building blocks: ms_yuv_buf_copy_with_pix_strides src/voip/msvideo.c:

@@ -103,4 +103,4 @@ int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride
                           const int *d_counts = nullptr);
 int msb200i_mixer_launch(msb200_mixer *m, const void *d_in, long in_pin_stride, const void *d_present, void *d_out);
 int msb200i_packed422_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int uyvy, void *d_dst);
-int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int fmt, void *d_dst);
+int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int fmt, void *d_dst, int x86_vertical = 0);

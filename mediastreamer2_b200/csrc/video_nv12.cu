@@ -282,7 +282,7 @@ __device__ __forceinline__ void rgb565_unpack4(const uint8_t *row, int c[4][3]) 
 }
 // FMT: 0 = RGB24 (generic path), 1 = BGR24 (special converter), 2 = RGBA, 3 = BGRA (generic path, alpha ignored),
 // 4 = RGB565 (generic path)
-template <int FMT>
+template <int FMT, bool X86 = false>
 __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h) {
 	constexpr bool BGR = FMT == 1;
 	constexpr int BPP = FMT == 4 ? 2 : (FMT >= 2 ? 4 : 3);
@@ -350,8 +350,22 @@ __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__res
 			chroma(a[2 * s], a[2 * s + 1], u[1], v[1]);
 			chroma(b[2 * s], b[2 * s + 1], u[2], v[2]);
 			chroma(below[2 * s], below[2 * s + 1], u[3], v[3]);
-			const int su = ((64 << 12) + 512 * (u[0] + u[3]) + 1536 * (u[1] + u[2])) >> 19;
-			const int sv = ((64 << 12) + 512 * (v[0] + v[3]) + 1536 * (v[1] + v[2])) >> 19;
+			int su, sv;
+			if (X86 && cy < h / 2 - 1) {
+				// libswscale's x86 SIMD vertical scaler (what a plain SWS_BILINEAR call runs): every product loses its low 16
+				// bits before the sum, rounder (64 + 8 * 3) >> 4, final >> 3; the last chroma row is done by the C function.
+				// At the top border the library's filter is FOLDED (taps 2048, 1536, 512 on rows 0, 1, 2), not replicated rows
+				if (cy == 0) {
+					su = (5 + ((u[1] * 2048) >> 16) + ((u[2] * 1536) >> 16) + ((u[3] * 512) >> 16)) >> 3;
+					sv = (5 + ((v[1] * 2048) >> 16) + ((v[2] * 1536) >> 16) + ((v[3] * 512) >> 16)) >> 3;
+				} else {
+					su = (5 + ((u[0] * 512) >> 16) + ((u[1] * 1536) >> 16) + ((u[2] * 1536) >> 16) + ((u[3] * 512) >> 16)) >> 3;
+					sv = (5 + ((v[0] * 512) >> 16) + ((v[1] * 1536) >> 16) + ((v[2] * 1536) >> 16) + ((v[3] * 512) >> 16)) >> 3;
+				}
+			} else {
+				su = ((64 << 12) + 512 * (u[0] + u[3]) + 1536 * (u[1] + u[2])) >> 19;
+				sv = ((64 << 12) + 512 * (v[0] + v[3]) + 1536 * (v[1] + v[2])) >> 19;
+			}
 			u2 |= (unsigned)min(max(su, 0), 255) << (8 * s);
 			v2 |= (unsigned)min(max(sv, 0), 255) << (8 * s);
 		}
@@ -362,19 +376,114 @@ __global__ void __launch_bounds__(256) rgb24_to_i420_kernel(const uint8_t *__res
 	*reinterpret_cast<unsigned *>(fd + (size_t)(2 * cy + 1) * w + (size_t)gx * 4) = yb;
 }
 
+// The generic path again, marching: one thread walks RGB_MARCH row pairs of its 4-pixel column group and carries the
+// 15-bit chroma of the two rows it shares with the next pair in registers, so every source row is unpacked (and its chroma
+// computed) once — plus one halo row at each end of the walk — instead of twice (the kernel above reads rows 2cy-1 .. 2cy+2
+// for every cy: 4 rows per 2). Same arithmetic, same bytes.
+#define RGB_MARCH 4
+template <int FMT, bool X86>
+__global__ void __launch_bounds__(256) rgb_to_i420_march_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int w, int h) {
+	constexpr int BPP = FMT == 4 ? 2 : (FMT >= 2 ? 4 : 3);
+	const int groups = w / 4, rows2 = h / 2, walks = (rows2 + RGB_MARCH - 1) / RGB_MARCH;
+	const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long)groups * walks) return;
+	const int cy0 = (int)(t / groups) * RGB_MARCH, gx = (int)(t % groups), cy1 = min(cy0 + RGB_MARCH, rows2);
+	const size_t frame = blockIdx.y, pitch = (size_t)w * BPP;
+	const uint8_t *fs = src + frame * (pitch * h) + (size_t)gx * 4 * BPP;
+	uint8_t *fd = dst + frame * ((size_t)w * h * 3 / 2);
+	uint8_t *py = fd + (size_t)gx * 4, *pu = fd + (size_t)w * h + (size_t)gx * 2, *pv = pu + (size_t)(w / 2) * (h / 2);
+	auto unpack = [&](int row, int(&c)[4][3]) {
+		const uint8_t *p = fs + (size_t)row * pitch;
+		if (FMT == 2) rgbx_unpack4<false>(p, c);
+		else if (FMT == 3) rgbx_unpack4<true>(p, c);
+		else if (FMT == 4) rgb565_unpack4(p, c);
+		else rgb_unpack4(p, c);
+	};
+	auto luma4 = [](const int(&c)[4][3]) {
+		unsigned y = 0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			int v = (RGB_RY * c[k][0] + RGB_GY * c[k][1] + RGB_BY * c[k][2] + (32 << 14) + (1 << 8)) >> 9;
+			v = (min(v * 2, 32767) + 64) >> 7; // hScale16To15 with its single 1 << 14 tap, then yuv2plane1
+			y |= (unsigned)min(max(v, 0), 255) << (8 * k);
+		}
+		return y;
+	};
+	auto chroma2 = [](const int(&c)[4][3], int(&u)[2], int(&v)[2]) { // 15-bit chroma of the two pixel pairs
+#pragma unroll
+		for (int s = 0; s < 2; ++s) {
+			const int r = c[2 * s][0] + c[2 * s + 1][0], g = c[2 * s][1] + c[2 * s + 1][1], bl = c[2 * s][2] + c[2 * s + 1][2];
+			u[s] = min(((RGB_RU * r + RGB_GU * g + RGB_BU * bl + (256 << 15) + (1 << 9)) >> 10) * 2, 32767);
+			v[s] = min(((RGB_RV * r + RGB_GV * g + RGB_BV * bl + (256 << 15) + (1 << 9)) >> 10) * 2, 32767);
+		}
+	};
+	int px[4][3], up[2], vp[2], ua[2], va[2], ub[2], vb[2], un[2], vn[2];
+	unpack(max(2 * cy0 - 1, 0), px);
+	chroma2(px, up, vp);
+	unpack(2 * cy0, px);
+	chroma2(px, ua, va);
+	*reinterpret_cast<unsigned *>(py + (size_t)(2 * cy0) * w) = luma4(px);
+#pragma unroll
+	for (int k = 0; k < RGB_MARCH; ++k) {
+		const int cy = cy0 + k;
+		if (cy >= cy1) break;
+		unpack(2 * cy + 1, px);
+		chroma2(px, ub, vb);
+		*reinterpret_cast<unsigned *>(py + (size_t)(2 * cy + 1) * w) = luma4(px);
+		unpack(min(2 * cy + 2, h - 1), px);
+		chroma2(px, un, vn);
+		if (cy + 1 < cy1) *reinterpret_cast<unsigned *>(py + (size_t)(2 * cy + 2) * w) = luma4(px);
+		unsigned u2 = 0, v2 = 0;
+#pragma unroll
+		for (int s = 0; s < 2; ++s) {
+			int su, sv;
+			if (X86 && cy < rows2 - 1) { // see rgb24_to_i420_kernel
+				if (cy == 0) {
+					su = (5 + ((ua[s] * 2048) >> 16) + ((ub[s] * 1536) >> 16) + ((un[s] * 512) >> 16)) >> 3;
+					sv = (5 + ((va[s] * 2048) >> 16) + ((vb[s] * 1536) >> 16) + ((vn[s] * 512) >> 16)) >> 3;
+				} else {
+					su = (5 + ((up[s] * 512) >> 16) + ((ua[s] * 1536) >> 16) + ((ub[s] * 1536) >> 16) + ((un[s] * 512) >> 16)) >> 3;
+					sv = (5 + ((vp[s] * 512) >> 16) + ((va[s] * 1536) >> 16) + ((vb[s] * 1536) >> 16) + ((vn[s] * 512) >> 16)) >> 3;
+				}
+			} else {
+				su = ((64 << 12) + 512 * (up[s] + un[s]) + 1536 * (ua[s] + ub[s])) >> 19;
+				sv = ((64 << 12) + 512 * (vp[s] + vn[s]) + 1536 * (va[s] + vb[s])) >> 19;
+			}
+			u2 |= (unsigned)min(max(su, 0), 255) << (8 * s);
+			v2 |= (unsigned)min(max(sv, 0), 255) << (8 * s);
+			up[s] = ub[s]; vp[s] = vb[s];
+			ua[s] = un[s]; va[s] = vn[s];
+		}
+		*reinterpret_cast<unsigned short *>(pu + (size_t)cy * (w / 2)) = (unsigned short)u2;
+		*reinterpret_cast<unsigned short *>(pv + (size_t)cy * (w / 2)) = (unsigned short)v2;
+	}
+}
+
 // fmt: 0 RGB24, 1 BGR24, 2 RGBA, 3 BGRA, 4 RGB565
-int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int fmt, void *d_dst) {
+int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int fmt, void *d_dst, int x86_vertical) {
 	MSB200_CHECK_ARG(ctx && d_src && d_dst && n_frames > 0 && n_frames <= 65535 && w > 0 && h > 0 && (w % 4) == 0 && (h % 2) == 0);
 	MSB200_CHECK_ARG(fmt >= 0 && fmt <= 4 && ((uintptr_t)d_src % (fmt == 2 || fmt == 3 ? 16 : fmt == 4 ? 8 : 4)) == 0 && ((uintptr_t)d_dst % 4) == 0);
 	const long threads = (long)(w / 4) * (h / 2);
 	dim3 grid((unsigned)((threads + 255) / 256), (unsigned)n_frames);
+	static const bool block_kernel = getenv("MSB200_RGB_BLOCK_KERNEL") != nullptr;
+#define RGB_LAUNCH(F)                                                                                                  \
+	do {                                                                                                               \
+		const long walks = (long)(w / 4) * ((h / 2 + RGB_MARCH - 1) / RGB_MARCH);                                      \
+		const dim3 gm((unsigned)((walks + 255) / 256), (unsigned)n_frames);                                            \
+		if (block_kernel) { /* A/B: the one-block-per-thread kernel */                                                 \
+			if (x86_vertical) MSB200_LAUNCH(ctx, (rgb24_to_i420_kernel<F, true>), grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); \
+			else MSB200_LAUNCH(ctx, (rgb24_to_i420_kernel<F, false>), grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); \
+		} else if (x86_vertical) MSB200_LAUNCH(ctx, (rgb_to_i420_march_kernel<F, true>), gm, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); \
+		else MSB200_LAUNCH(ctx, (rgb_to_i420_march_kernel<F, false>), gm, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); \
+	} while (0)
 	switch (fmt) {
-		case 0: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<0>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
-		case 1: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<1>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
-		case 2: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<2>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
-		case 3: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<3>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
-		default: MSB200_LAUNCH(ctx, rgb24_to_i420_kernel<4>, grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+		case 0: RGB_LAUNCH(0); break;
+		case 1: MSB200_LAUNCH(ctx, (rgb24_to_i420_kernel<1, false>), grid, 256, 0, (const uint8_t *)d_src, (uint8_t *)d_dst, w, h); break;
+		case 2: RGB_LAUNCH(2); break;
+		case 3: RGB_LAUNCH(3); break;
+		default: RGB_LAUNCH(4); break;
 	}
+#undef RGB_LAUNCH
 	return MSB200_OK;
 }
 

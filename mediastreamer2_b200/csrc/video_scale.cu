@@ -3054,9 +3054,14 @@ int msb200_scaler_set_canvas(msb200_scaler *s, int canvas_w, int canvas_h, int n
 // planar output rounded like libswscale's x86 SIMD vertical scaler (see ScaleParams::x86_vertical)
 int msb200_scaler_set_x86_vertical(msb200_scaler *s, int on) {
 	MSB200_CHECK_ARG(s);
+	if (s->packed422 >= 3) { // MSPixConv's RGB inputs: the library filters their chroma rows 2:1 with the same vertical scaler
+		s->P.x86_vertical = on ? 1 : 0; // (BGR24's special converter has no vertical filter: same bytes either way)
+		return MSB200_OK;
+	}
 	if (s->P.dst_fmt != MSB200_PIX_YUV420P || s->packed422) {
 		if (!on) return MSB200_OK;
-		msb200_set_error("scaler: the x86 vertical rounding only exists for the scaled planar output (YUV420P / NV12 / NV21 -> YUV420P)");
+		msb200_set_error("scaler: the x86 vertical rounding only exists where the library runs its vertical scaler on planar output "
+		                 "(YUV420P / NV12 / NV21 -> YUV420P, RGB inputs -> YUV420P)");
 		return MSB200_EINVAL;
 	}
 	s->P.x86_vertical = on ? 1 : 0;
@@ -3097,7 +3102,7 @@ int msb200_scaler_get_schedule(msb200_scaler *s, int *regular_strips, int *strip
 
 int msb200_scaler_process_dev(msb200_scaler *s, int n_frames, const void *d_src, void *d_dst) {
 	MSB200_CHECK_ARG(s && d_src && d_dst && n_frames > 0 && n_frames <= 65535);
-	if (s->packed422 >= 3) return msb200i_rgb24_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 - 3, d_dst);
+	if (s->packed422 >= 3) return msb200i_rgb24_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 - 3, d_dst, s->P.x86_vertical);
 	if (s->packed422) return msb200i_packed422_to_i420(s->ctx, n_frames, d_src, s->P.src_w, s->P.src_h, s->packed422 == 2, d_dst);
 	const ScaleParams &P = s->P;
 	if (s->down_ok && s->force_path != 5 && ((uintptr_t)d_src % 16) == 0 && (s->src_bytes % 16) == 0 &&

@@ -47,6 +47,14 @@ int msb200p_pixfmt_to_b200(MSPixFmt fmt) {
 	}
 }
 /* bytes of one tight frame and of one of its rows when it is a single packed plane (0: planar) */
+/* MSB200_SWS_X86=1: planar outputs rounded like libswscale's x86 SIMD vertical scaler — what the reference's plain
+ * SWS_BILINEAR call (src/voip/msvideo.c:660) returns on an x86 host; default: the library's C arithmetic (differs by <= 1).
+ * Formats without that stage (RGB outputs, YUY2 / UYVY / BGR24 inputs) refuse the switch and stay as they are. */
+static void sws_rounding(msb200_scaler *sc) {
+	const char *e = getenv("MSB200_SWS_X86");
+	if (e && atoi(e) > 0) (void)msb200_scaler_set_x86_vertical(sc, 1);
+}
+
 static size_t frame_bytes(int b200_fmt, int w, int h, int *packed_row) {
 	const int he = h & 1 ? h + 1 : h; /* the reference rounds odd heights up when it sizes a frame (msvideo.c:158) */
 	int row = 0;
@@ -163,6 +171,7 @@ static VLane *lane_join(MSTicker *ticker, const int key[6]) {
 	}
 	if (rc == MSB200_OK) rc = msb200_scaler_create(l->ctx, key[0], key[1], key[2], key[3], key[4], key[5], &l->sc);
 	if (rc == MSB200_OK) {
+		sws_rounding(l->sc);
 		l->src_bytes = msb200_scaler_src_frame_bytes(l->sc);
 		l->dst_bytes = msb200_scaler_dst_frame_bytes(l->sc);
 		l->dst_stride = (VSLOT_PREFIX + VHDR + l->dst_bytes + 16 + 255) & ~(size_t)255;
@@ -597,6 +606,7 @@ static MSScalerContext *b200_scaler_create(int src_w, int src_h, MSPixFmt src_fm
 	msb200p_sync_lock();
 	rc = msb200_scaler_create(ctx, src_w, src_h, sf, dst_w, dst_h, df, &c->sc);
 	if (rc == MSB200_OK) {
+		sws_rounding(c->sc);
 		c->src_bytes = msb200_scaler_src_frame_bytes(c->sc);
 		c->dst_bytes = msb200_scaler_dst_frame_bytes(c->sc);
 		rc = msb200_host_alloc_pinned(ctx, c->src_bytes, (void **)&c->src_pack);

@@ -288,15 +288,25 @@ def test_pixconv_rgb24_to_i420_bit_exact(ctx, fmt, w, h):
     frames[1] = np.tile(np.array(prim, np.uint8), w * h // 4)
     frames[2] = 0
     sc = F.Scaler(ctx, w, h, fmt, w, h, _lib.PIX_YUV420P)
-    got = sc.process(frames)
+    got = {0: sc.process(frames)}
+    # ... and as a plain SWS_BILINEAR call returns them on x86 (the library's SIMD vertical scaler on the chroma rows, folded
+    # taps on the top row): the oracle's x86 mode is pinned against the live plain-flag library (test_oracle_video_live.py)
+    _lib.check(ctx.lib.msb200_scaler_set_x86_vertical(sc.h, 1))
+    got[1] = sc.process(frames)
     sc.close()
     o = L.orc_scaler_new(w, h, fmt, w, h, _lib.PIX_YUV420P)
     assert o
-    for i in range(frames.shape[0]):
-        exp = np.zeros(w * h * 3 // 2 + 64, np.uint8)
-        L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
-        assert np.array_equal(got[i], exp[:-64]), (i, int(np.abs(got[i].astype(int) - exp[:-64].astype(int)).max()))
+    for mode in (0, 1):
+        L.orc_scaler_set_x86_vertical(o, mode)
+        for i in range(frames.shape[0]):
+            exp = np.zeros(w * h * 3 // 2 + 64, np.uint8)
+            L.orc_scaler_process(o, ptr(np.ascontiguousarray(frames[i])), ptr(exp))
+            assert np.array_equal(got[mode][i], exp[:-64]), (mode, i, int(np.abs(got[mode][i].astype(int) - exp[:-64].astype(int)).max()))
     L.orc_scaler_free(o)
+    d = np.abs(got[0].astype(np.int16) - got[1].astype(np.int16))
+    assert d.max() <= 1 and np.array_equal(got[0][:, :w * h], got[1][:, :w * h])  # luma untouched, chroma within one
+    if fmt != _lib.PIX_RGB24_REV:
+        assert d.max() == 1  # the two roundings really differ (BGR24's special converter has no vertical filter)
 
 
 @pytest.mark.parametrize("fmt,w,h", [(_lib.PIX_YUYV, 96, 64), (_lib.PIX_UYVY, 64, 48), (_lib.PIX_YUY2, 1280, 720),
