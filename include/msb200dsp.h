@@ -168,6 +168,10 @@ MSB200_API int msb200_volume_reset_stream(msb200_volume *v, int stream); /* volu
 /* Partially occupied banks (all four audio banks have this call): only streams (rooms) [0, n_live) are copied and
  * processed by the next process calls; the others keep their state and their host rows are not touched. */
 MSB200_API int msb200_volume_set_live(msb200_volume *v, int n_live);
+/* Which kernel serves the bank: 0 (default) = by size — one warp per stream for small banks (lowest latency), one LANE per
+ * stream for the sequential energy sum from 256 live streams on (a warp per stream spends 31 of 32 issue slots idle there);
+ * 1 / 2 force either (tests, A/B). Same bytes and state either way. */
+MSB200_API int msb200_volume_set_kernel(msb200_volume *v, int choice);
 MSB200_API int msb200_volume_set_gain(msb200_volume *v, int stream, float gain);           /* MS_VOLUME_SET_GAIN :270-276 */
 MSB200_API int msb200_volume_set_db_gain(msb200_volume *v, int stream, float db);          /* MS_VOLUME_SET_DB_GAIN :262-268 */
 MSB200_API int msb200_volume_enable_noise_gate(msb200_volume *v, int stream, int enabled); /* :352-359 */

@@ -142,6 +142,7 @@ _SIGS = {
     "msb200_g711_encode_dev": (_I, [_P, _I, _P, _P, _SZ]),
     "msb200_volume_reset_stream": (_I, [_P, _I]),
     "msb200_volume_set_live": (_I, [_P, _I]),
+    "msb200_volume_set_kernel": (_I, [_P, _I]),
     "msb200_mixer_set_live": (_I, [_P, _I]),
     "msb200_resample_set_live": (_I, [_P, _I]),
     "msb200_aec_set_live": (_I, [_P, _I]),

@@ -277,10 +277,75 @@ struct msb200_volume {
 	msb200_volume *peer_bank; // bank whose states the echo limiter reads (may be this one)
 	msb200_volume_state *d_state;
 	msb200_devbuf io;
+	int kernel_choice = 0; // msb200_volume_set_kernel: 0 = by bank size, 1 = warp per stream, 2 = lane per stream
 };
 
 __device__ __forceinline__ int vol_sat(int v) { // :382-384
 	return v > 32767 ? 32767 : (v < -32767 ? -32767 : v);
+}
+
+// One block's worth of msvolume.c for one stream, given the block's energy sum (accumulated in the reference's order), its
+// peak and its sample sum: update_energy :388-407, the echo limiter :201-238, AGC :172-184, the noise gate :240-260 and the
+// gain ramp of apply_gain :409-445. Shared by the two kernels below so that they cannot differ.
+__device__ __forceinline__ void vol_update(msb200_volume_state &v, float acc, int pk, int dcsum, int nsamples,
+                                           const msb200_volume_state *__restrict__ peer_states, int &intgain, int &apply,
+                                           int &remove_dc, int &dc_prev) {
+	const float max_e = 32768 * 0.7f;
+	// en = (float)((sqrt(acc / n) + 1) / max_e)  — float division, then double sqrt/add/div (C promotions)
+	float q = __fdiv_rn(acc, (float)nsamples);
+	float en = (float)((sqrt((double)q) + 1.0) / (double)max_e);
+	v.energy = __fadd_rn(__fmul_rn(en, 0.2f), __fmul_rn(v.energy, (1.0f - 0.2f)));
+	v.level_pk = __fdiv_rn((float)pk, max_e);
+	v.instant_energy = en;
+	float tgain = v.static_gain;
+	if (v.peer >= 0 && peer_states) { // volume_echo_avoider_process :201-238
+		const float peer_e = peer_states[v.peer].energy;
+		if (peer_e > v.lt_speaker_en) v.lt_speaker_en = peer_e;
+		else v.lt_speaker_en = __fadd_rn(__fmul_rn(0.005f, peer_e), __fmul_rn(0.995f, v.lt_speaker_en));
+		const float mic_spk_ratio = __fdiv_rn(v.energy, __fadd_rn(v.lt_speaker_en, v.ea_thres));
+		if (peer_e > v.ea_thres) {
+			if (mic_spk_ratio > v.ea_transmit_thres) {
+				v.target_gain = v.static_gain;
+				v.fast_upramp = 1;
+			} else {
+				v.target_gain = __fdiv_rn(v.static_gain, __fadd_rn(1.f, __fmul_rn(peer_e, v.force))); // compute_gain :186-189
+				v.sustain_dur = v.sustain_time;
+			}
+		} else if (v.sustain_dur > 0) {
+			v.sustain_dur -= (nsamples * 1000) / v.sample_rate;
+		} else {
+			v.target_gain = v.static_gain;
+			v.fast_upramp = 1;
+		}
+		tgain = v.target_gain;
+	}
+	if (v.agc_enabled) tgain = __fdiv_rn(tgain, __fdiv_rn(__fadd_rn(0.5f, v.level_pk), 1.f)); // volume_agc_process :172-184
+	if (v.noise_gate_enabled) {
+		float t = v.ng_floorgain;
+		if (v.instant_energy > v.ng_threshold) {
+			v.ng_noise_dur = 400;
+			t = 1.0f;
+		} else if (v.ng_noise_dur > 0) {
+			v.ng_noise_dur -= (nsamples * 1000) / v.sample_rate;
+			t = 1.0f;
+		}
+		v.ng_gain = __fadd_rn(__fmul_rn(v.ng_gain, 0.75f), __fmul_rn(t, 0.25f));
+	}
+	if (v.gain < tgain) {
+		if (v.gain < v.ng_floorgain) v.gain = v.ng_floorgain;
+		v.gain = __fmul_rn(v.gain, v.fast_upramp ? (1 + 0.4f * 3) : __fadd_rn(1.f, v.vol_upramp));
+		if (v.gain > tgain) v.gain = tgain;
+	} else if (v.gain > tgain) {
+		v.gain = __fmul_rn(v.gain, 1 - 0.4f);
+		if (v.gain < tgain) v.gain = tgain;
+		v.fast_upramp = 0;
+	}
+	float gain = __fmul_rn(v.gain, v.ng_gain);
+	intgain = __float2int_rz(__fmul_rn(gain, 4096.f));
+	remove_dc = v.remove_dc;
+	dc_prev = v.dc_offset;
+	apply = remove_dc ? 1 : (gain != 1.0f);
+	if (remove_dc) v.dc_offset = (v.dc_offset * 7 + dcsum * 2 / (nsamples * 2)) / 8;
 }
 
 // One warp per stream. The block is staged in shared memory by coalesced loads; lane 0 reproduces the reference's
@@ -338,62 +403,7 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 			const int s = buf[i];
 			acc = __fadd_rn(acc, (float)(s * s));
 		}
-		const float max_e = 32768 * 0.7f;
-		// en = (float)((sqrt(acc / n) + 1) / max_e)  — float division, then double sqrt/add/div (C promotions)
-		float q = __fdiv_rn(acc, (float)nsamples);
-		float en = (float)((sqrt((double)q) + 1.0) / (double)max_e);
-		v.energy = __fadd_rn(__fmul_rn(en, 0.2f), __fmul_rn(v.energy, (1.0f - 0.2f)));
-		v.level_pk = __fdiv_rn((float)pk, max_e);
-		v.instant_energy = en;
-		float tgain = v.static_gain;
-		if (v.peer >= 0 && peer_states) { // volume_echo_avoider_process :201-238
-			const float peer_e = peer_states[v.peer].energy;
-			if (peer_e > v.lt_speaker_en) v.lt_speaker_en = peer_e;
-			else v.lt_speaker_en = __fadd_rn(__fmul_rn(0.005f, peer_e), __fmul_rn(0.995f, v.lt_speaker_en));
-			const float mic_spk_ratio = __fdiv_rn(v.energy, __fadd_rn(v.lt_speaker_en, v.ea_thres));
-			if (peer_e > v.ea_thres) {
-				if (mic_spk_ratio > v.ea_transmit_thres) {
-					v.target_gain = v.static_gain;
-					v.fast_upramp = 1;
-				} else {
-					v.target_gain = __fdiv_rn(v.static_gain, __fadd_rn(1.f, __fmul_rn(peer_e, v.force))); // compute_gain :186-189
-					v.sustain_dur = v.sustain_time;
-				}
-			} else if (v.sustain_dur > 0) {
-				v.sustain_dur -= (nsamples * 1000) / v.sample_rate;
-			} else {
-				v.target_gain = v.static_gain;
-				v.fast_upramp = 1;
-			}
-			tgain = v.target_gain;
-		}
-		if (v.agc_enabled) tgain = __fdiv_rn(tgain, __fdiv_rn(__fadd_rn(0.5f, v.level_pk), 1.f)); // volume_agc_process :172-184
-		if (v.noise_gate_enabled) {
-			float t = v.ng_floorgain;
-			if (v.instant_energy > v.ng_threshold) {
-				v.ng_noise_dur = 400;
-				t = 1.0f;
-			} else if (v.ng_noise_dur > 0) {
-				v.ng_noise_dur -= (nsamples * 1000) / v.sample_rate;
-				t = 1.0f;
-			}
-			v.ng_gain = __fadd_rn(__fmul_rn(v.ng_gain, 0.75f), __fmul_rn(t, 0.25f));
-		}
-		if (v.gain < tgain) {
-			if (v.gain < v.ng_floorgain) v.gain = v.ng_floorgain;
-			v.gain = __fmul_rn(v.gain, v.fast_upramp ? (1 + 0.4f * 3) : __fadd_rn(1.f, v.vol_upramp));
-			if (v.gain > tgain) v.gain = tgain;
-		} else if (v.gain > tgain) {
-			v.gain = __fmul_rn(v.gain, 1 - 0.4f);
-			if (v.gain < tgain) v.gain = tgain;
-			v.fast_upramp = 0;
-		}
-		float gain = __fmul_rn(v.gain, v.ng_gain);
-		intgain = __float2int_rz(__fmul_rn(gain, 4096.f));
-		remove_dc = v.remove_dc;
-		dc_prev = v.dc_offset;
-		apply = remove_dc ? 1 : (gain != 1.0f);
-		if (remove_dc) v.dc_offset = (v.dc_offset * 7 + dcsum * 2 / (nsamples * 2)) / 8;
+		vol_update(v, acc, pk, dcsum, nsamples, peer_states, intgain, apply, remove_dc, dc_prev);
 		st[stream] = v;
 	}
 	intgain = __shfl_sync(0xffffffffu, intgain, 0);
@@ -407,6 +417,84 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 		g[i] = (short)vol_sat((s * intgain) / 4096); // C truncating division
 	}
 	}
+}
+
+// Large banks: one LANE per stream for the sequential part. A warp owns 32 consecutive streams: it stages their blocks in
+// shared memory with coalesced 32-bit loads (rows `pitch` samples apart, pitch / 2 odd: the column walk below is free of
+// bank conflicts), every lane then runs the reference's sequential float accumulation, peak and DC sums and the state
+// update for ITS stream (state in registers across the blocks of a launch), and the warp applies the 32 gains and stores
+// coalesced. Same operations per stream as volume_kernel, 1/32 of its issue slots in the sequential part — that kernel
+// spends a whole warp's slots on lane 0 there and is issue-bound from a few thousand streams on.
+__global__ void __launch_bounds__(32) volume_lanes_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st, int n_streams,
+                                                          int nsamples, int stride, int nblocks, int block0, int ring_blocks,
+                                                          const msb200_volume_state *__restrict__ peer_states,
+                                                          const int *__restrict__ counts, int pitch) {
+	extern __shared__ short vsm[];
+	const int lane = threadIdx.x, s0 = blockIdx.x * 32, stream = s0 + lane;
+	const bool valid = stream < n_streams;
+	const int my_blocks = valid ? (counts ? min(nblocks, counts[stream]) : nblocks) : 0;
+	int max_blocks = my_blocks;
+#pragma unroll
+	for (int o = 16; o; o >>= 1) max_blocks = max(max_blocks, __shfl_xor_sync(0xffffffffu, max_blocks, o));
+	if (max_blocks == 0) return;
+	msb200_volume_state v;
+	if (my_blocks > 0) v = st[stream];
+	const int words = nsamples >> 1, pw = pitch >> 1;
+	unsigned *wsm = reinterpret_cast<unsigned *>(vsm);
+	for (int blk = 0; blk < max_blocks; ++blk) {
+		const int bpos = ring_blocks > 0 ? (block0 + blk) % ring_blocks : blk;
+		const unsigned has = __ballot_sync(0xffffffffu, blk < my_blocks); // streams that have this block
+		__syncwarp();
+		// (asynchronous copies: every word of the 32 blocks is in flight at once, nothing waits on a register)
+		const unsigned wbase = (unsigned)__cvta_generic_to_shared(wsm);
+		for (int l = 0; l < 32; ++l) {
+			if (!((has >> l) & 1u)) continue;
+			const unsigned *g = reinterpret_cast<const unsigned *>(io + (size_t)(s0 + l) * stride + (size_t)bpos * nsamples);
+			for (int i = lane; i < words; i += 32)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(wbase + 4u * (unsigned)(l * pw + i)), "l"(g + i) : "memory");
+		}
+		asm volatile("cp.async.wait_all;\n" ::: "memory");
+		__syncwarp();
+		int intgain = 4096, apply = 0, dc_prev = 0, remove_dc = 0;
+		if (blk < my_blocks) {
+			const short *buf = vsm + (size_t)lane * pitch;
+			float acc = 0.f;
+			int pk = 0, dcsum = 0, i = 0;
+			for (; i + 8 <= nsamples; i += 8) { // (loads and conversions of eight samples in flight together; the adds in order)
+				float q[8];
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const int x = buf[i + k];
+					pk = max(pk, x < 0 ? -x : x);
+					dcsum += x;
+					q[k] = (float)(x * x);
+				}
+#pragma unroll
+				for (int k = 0; k < 8; ++k) acc = __fadd_rn(acc, q[k]);
+			}
+			for (; i < nsamples; ++i) {
+				const int x = buf[i];
+				pk = max(pk, x < 0 ? -x : x);
+				dcsum += x;
+				acc = __fadd_rn(acc, (float)(x * x));
+			}
+			vol_update(v, acc, pk, dcsum, nsamples, peer_states, intgain, apply, remove_dc, dc_prev);
+		}
+		const unsigned todo = __ballot_sync(0xffffffffu, apply != 0); // gain == 1 and no DC removal: the block stays as it is (:441)
+		for (int l = 0; l < 32; ++l) {
+			if (!((todo >> l) & 1u)) continue;
+			const int ig = __shfl_sync(0xffffffffu, intgain, l), rdc = __shfl_sync(0xffffffffu, remove_dc, l);
+			const int dcp = rdc ? __shfl_sync(0xffffffffu, dc_prev, l) : 0;
+			unsigned *g = reinterpret_cast<unsigned *>(io + (size_t)(s0 + l) * stride + (size_t)bpos * nsamples);
+			for (int i = lane; i < words; i += 32) {
+				const unsigned w = wsm[l * pw + i];
+				const int a = vol_sat((((int)(short)(w & 0xffffu) - dcp) * ig) / 4096); // C truncating division
+				const int b = vol_sat((((int)(short)(w >> 16) - dcp) * ig) / 4096);
+				g[i] = ((unsigned)a & 0xffffu) | ((unsigned)b << 16);
+			}
+		}
+	}
+	if (my_blocks > 0) st[stream] = v;
 }
 
 // stream == -1 applies the setter to every stream of the bank (one round trip)
@@ -547,6 +635,11 @@ int msb200_volume_process_blocks(msb200_volume *v, int16_t *io, int nsamples, in
 	MSB200_HOST_DONE(v->ctx);
 	return MSB200_OK;
 }
+int msb200_volume_set_kernel(msb200_volume *v, int choice) {
+	MSB200_CHECK_ARG(v && choice >= 0 && choice <= 2);
+	v->kernel_choice = choice;
+	return MSB200_OK;
+}
 int msb200_volume_set_live(msb200_volume *v, int n_live) {
 	MSB200_CHECK_ARG(v && n_live >= 0 && n_live <= v->n);
 	v->live = n_live;
@@ -578,6 +671,18 @@ int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride
 	while (warps > 1 && warps * per_warp > 48 * 1024) warps >>= 1;
 	const size_t smem = warps * per_warp;
 	if (v->live == 0) return MSB200_OK;
+	{ // lane per stream: even blocks on 4-byte boundaries whose 32 rows fit shared memory; by default for banks of 256+ streams
+		const int pitch = (nsamples & 3) == 2 ? nsamples : ((nsamples + 3) & ~3) + 2; // even, pitch / 2 odd
+		const size_t lsmem = (size_t)32 * pitch * sizeof(short);
+		const bool can = (nsamples & 1) == 0 && (stride & 1) == 0 && ((uintptr_t)d_io & 3) == 0 && lsmem <= 96 * 1024;
+		if (can && (v->kernel_choice == 2 || (v->kernel_choice == 0 && v->live >= 256))) {
+			MSB200_SMEM_OPTIN(volume_lanes_kernel, v->ctx, lsmem);
+			MSB200_LAUNCH(v->ctx, volume_lanes_kernel, msb200_div_up(v->live, 32), 32, lsmem, (short *)d_io, v->d_state, v->live, nsamples,
+			              stride, nblocks, block0, ring_blocks,
+			              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr), d_counts, pitch);
+			return MSB200_OK;
+		}
+	}
 	MSB200_SMEM_OPTIN(volume_kernel, v->ctx, smem);
 	MSB200_LAUNCH(v->ctx, volume_kernel, msb200_div_up(v->live, warps), warps * 32, smem, (short *)d_io, v->d_state, v->live,
 	              nsamples, stride, nblocks, block0, ring_blocks,

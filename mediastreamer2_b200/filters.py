@@ -128,6 +128,10 @@ class Volume:
             self.lib.msb200_volume_destroy(self.h)
             self.h = None
 
+    def set_kernel(self, choice: int):
+        """0: by bank size (default), 1: one warp per stream, 2: one lane per stream in the sequential part"""
+        check(self.lib.msb200_volume_set_kernel(self.h, choice))
+
     def set_gain(self, stream: int, gain: float):
         check(self.lib.msb200_volume_set_gain(self.h, stream, gain))
 

@@ -857,6 +857,8 @@ typedef struct VolState {
 	msb200_volume *bank;
 	int bank_rate;
 	bool_t dirty, gain_dirty, peer_linked;
+	float gain_db; /* gain_dirty == 2: the pending gain came in dB */
+	bool_t ng_enable_dirty, ng_floor_dirty, ng_floor_set; /* the noise gate's two gain-resetting setters: replayed only on their own account */
 	MSBufferizer *buffer;
 	float ea_thres, ea_speed, ea_force, ea_transmit;
 	int ea_sustain;
@@ -887,6 +889,11 @@ static void vol_peer_bank_changed(VolState *gone) {
 #define VOL_MAX_BLOCK 8192
 #define VOL_BATCH_UNITS 8 /* blocks one stream may stage per tick (an upstream MSSpeexEC emits 1-2 frames per 10 ms) */
 
+static void vol_mark_all_dirty(VolState *v) { /* a fresh bank or slot: everything the user configured is replayed once */
+	v->dirty = TRUE;
+	v->ng_enable_dirty = v->noise_gate;
+	v->ng_floor_dirty = v->ng_floor_set;
+}
 static void vol_sync_config_to(VolState *v, msb200_volume *bank, int st) { /* DSP lock held */
 	if (!bank) return;
 	if (v->peer && !v->peer_linked && bank == v->bank && v->peer->desc == &b200_volume_desc && ((VolState *)v->peer->data)->bank) {
@@ -895,15 +902,17 @@ static void vol_sync_config_to(VolState *v, msb200_volume *bank, int st) { /* DS
 		v->peer_linked = TRUE;
 	}
 	if (v->gain_dirty) { /* MS_VOLUME_SET_GAIN resets the ramp (gain = target = static, msvolume.c:270-276): apply it once */
-		msb200_volume_set_gain(bank, st, v->static_gain);
+		if (v->gain_dirty == 2) msb200_volume_set_db_gain(bank, st, v->gain_db); /* ... _SET_DB_GAIN leaves the target alone (:262-268) */
+		else msb200_volume_set_gain(bank, st, v->static_gain);
 		v->gain_dirty = FALSE;
 	}
 	if (!v->dirty) return;
-	if (v->noise_gate) {
-		msb200_volume_enable_noise_gate(bank, st, 1);
-		msb200_volume_set_noise_gate_threshold(bank, st, v->ng_threshold);
-		msb200_volume_set_noise_gate_floorgain(bank, st, v->ng_floorgain);
-	}
+	/* the gate's two resetting setters (gain = target = floor gain, msvolume.c:352-378) are replayed only when THEY were
+	 * called — or once for a fresh bank / slot (vol_mark_all_dirty) — never as a side effect of an unrelated setting */
+	if (v->ng_floor_dirty) msb200_volume_set_noise_gate_floorgain(bank, st, v->ng_floorgain);
+	if (v->ng_enable_dirty) msb200_volume_enable_noise_gate(bank, st, v->noise_gate ? 1 : 0);
+	v->ng_floor_dirty = v->ng_enable_dirty = FALSE;
+	msb200_volume_set_noise_gate_threshold(bank, st, v->ng_threshold);
 	msb200_volume_remove_dc(bank, st, v->remove_dc);
 	msb200_volume_enable_agc(bank, st, v->agc);
 	msb200_volume_set_ea_threshold(bank, st, v->ea_thres);
@@ -950,7 +959,7 @@ static void vol_init(MSFilter *f) {
 	v->ea_transmit = 4.0f;
 	v->ea_sustain = 200;
 	v->buffer = ms_bufferizer_new();
-	v->dirty = TRUE;
+	vol_mark_all_dirty(v);
 	v->gain_dirty = FALSE; /* the bank starts at gain 1 like volume_init */
 	v->self = f;
 	DSP_LOCK();
@@ -989,7 +998,7 @@ static void vol_preprocess(MSFilter *f) {
 		v->bank = NULL;
 		DSP_CHECK(msb200_volume_create(g_ctx, 1, v->rate, VOL_MAX_BLOCK, &v->bank), "volume_create");
 		v->bank_rate = v->rate;
-		v->dirty = TRUE;
+		vol_mark_all_dirty(v);
 		v->gain_dirty = v->static_gain != 1.0f;
 		v->peer_linked = FALSE;
 	}
@@ -1045,7 +1054,7 @@ static void vol_process(MSFilter *f) {
 		int n = (int)((m->b_wptr - m->b_rptr) / 2);
 		if (v->batch && v->watchers > 0) { /* somebody's echo-limiter peer: the state must live in the private bank */
 			vol_leave_batch(v);
-			v->dirty = TRUE;
+			vol_mark_all_dirty(v);
 			v->gain_dirty = v->static_gain != 1.0f;
 		}
 		if (!v->batch && !v->batch_off && v->watchers == 0 && batch_capacity() > 0 && n > 0 && n <= VOL_MAX_BLOCK) {
@@ -1055,7 +1064,7 @@ static void vol_process(MSFilter *f) {
 				GRP_LOCK(v->batch);
 				msb200_ctx_make_current(v->batch->ctx);
 				msb200_volume_reset_stream((msb200_volume *)v->batch->bank, v->slot);
-				v->dirty = TRUE;
+				vol_mark_all_dirty(v);
 				v->gain_dirty = v->static_gain != 1.0f;
 				GRP_UNLOCK(v->batch);
 				batch_tick(v->batch, f->ticker->ticks); /* (nothing of ours is staged yet: see batch_tick) */
@@ -1080,7 +1089,7 @@ static void vol_process(MSFilter *f) {
 			ms_warning("MSVolume(b200): irregular block (%d samples, group block %d): leaving the batch group", n, b->key[1]);
 			vol_leave_batch(v);
 			v->batch_off = TRUE;
-			v->dirty = TRUE;
+			vol_mark_all_dirty(v);
 			v->gain_dirty = v->static_gain != 1.0f;
 		}
 		if (v->bank && n > 0 && n <= VOL_MAX_BLOCK) {
@@ -1129,8 +1138,9 @@ static int vol_set_gain(MSFilter *f, void *arg) {
 }
 static int vol_set_db_gain(MSFilter *f, void *arg) { /* pow(10, db/10), sic: msvolume.c:262-268 */
 	VolState *v = (VolState *)f->data;
-	v->static_gain = (float)pow(10, (*(float *)arg) / 10);
-	v->gain_dirty = TRUE;
+	v->gain_db = *(float *)arg;
+	v->static_gain = (float)pow(10, v->gain_db / 10);
+	v->gain_dirty = 2;
 	return 0;
 }
 static int vol_get_gain(MSFilter *f, void *arg) {
@@ -1167,6 +1177,7 @@ static int vol_set_agc(MSFilter *f, void *arg) {
 static int vol_enable_ng(MSFilter *f, void *arg) {
 	VolState *v = (VolState *)f->data;
 	v->noise_gate = *(bool_t *)arg;
+	v->ng_enable_dirty = TRUE;
 	v->dirty = TRUE;
 	return 0;
 }
@@ -1179,6 +1190,7 @@ static int vol_set_ng_threshold(MSFilter *f, void *arg) {
 static int vol_set_ng_floorgain(MSFilter *f, void *arg) {
 	VolState *v = (VolState *)f->data;
 	v->ng_floorgain = *(float *)arg;
+	v->ng_floor_dirty = v->ng_floor_set = TRUE;
 	v->dirty = TRUE;
 	return 0;
 }

@@ -75,11 +75,13 @@ def test_mixer_two_phase_equals_single_pass(ctx):
 
 
 # ------------------------------------------------------------------------------------------------ volume
-@pytest.mark.parametrize("nsamples", [480, 256, 160, 441])
-def test_volume_bit_exact_including_float_state(ctx, nsamples):
+@pytest.mark.parametrize("kernel", [1, 2])  # one warp per stream / one lane per stream (what banks of 256+ streams run)
+@pytest.mark.parametrize("nsamples", [480, 256, 160, 441, 322])
+def test_volume_bit_exact_including_float_state(ctx, nsamples, kernel):
     L = O.oracle()
     n, T, rate = 37, 30, 48000
     v = F.Volume(ctx, n, rate)
+    v.set_kernel(kernel)  # (odd block lengths stay on the warp kernel either way)
     cfgs = []
     for s in range(n):
         cfg = dict(gain=[0.8, 1.0, 2.5, 0.3][s % 4], ng=(s % 3 == 1), dc=(s % 5 == 2))
@@ -262,14 +264,47 @@ def test_resample_cfg1_hello_like_stream_matches_oracle(ctx):
     r.close()
 
 
+def test_volume_lane_kernel_equals_warp_kernel_on_ragged_blocks(ctx):
+    """msb200_volume_process_blocks with per-stream counts (what the plugin's groups stage: 0 .. 3 blocks of 256 per tick) on a
+    bank large enough to run the lane-per-stream kernel by default: bytes and every state field equal the warp-per-stream
+    kernel's (which the tests above pin against the oracle)"""
+    n, nblocks, ns, rate, T = 300, 3, 256, 48000, 6
+    rng = np.random.default_rng(8)
+    outs, states = [], []
+    for kernel in (1, 0):  # 0: by size -> lanes (300 >= 256)
+        v = F.Volume(ctx, n, rate)
+        v.set_kernel(kernel)
+        for s in range(n):
+            v.set_gain(s, [0.8, 1.0, 1.7][s % 3])
+            if s % 4 == 1:
+                v.remove_dc(s, True)
+            if s % 5 == 2:
+                v.enable_noise_gate(s, True)
+        r = np.random.default_rng(9)
+        got = []
+        for k in range(T):
+            io = (r.standard_normal((n, nblocks * ns)) * (9000 if k % 2 == 0 else 60)).astype(np.int16) + 300
+            counts = r.integers(0, nblocks + 1, size=n).astype(np.int32)
+            _lib.check(ctx.lib.msb200_volume_process_blocks(v.h, ptr(io), ns, nblocks * ns, nblocks, ptr(counts)))
+            got.append(io.copy())
+        outs.append(np.stack(got))
+        states.append([bytes(v.state(s)) for s in range(n)])
+        v.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert states[0] == states[1]
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("agc,peer", [(True, False), (False, True), (True, True)])
-def test_volume_chunked_mode_bit_exact(ctx, agc, peer):
+def test_volume_chunked_mode_bit_exact(ctx, agc, peer, kernel):
     """AGC / echo-limiter peer (msvolume.c:480-502) on 10 ms chunks: speaker bank first, then the microphone bank whose
     streams read their peer's energy; GPU == oracle (pinned vs the reference in test_oracle_vs_reference.py)."""
     L = O.oracle()
     n_streams, T, rate = 9, 40, 16000
     n = rate // 100
     spk_bank, mic_bank = F.Volume(ctx, n_streams, rate), F.Volume(ctx, n_streams, rate)
+    spk_bank.set_kernel(kernel)
+    mic_bank.set_kernel(kernel)
     st_spk, st_mic = [], []
     for s in range(n_streams):
         a, b = OrcVolumeState(), OrcVolumeState()

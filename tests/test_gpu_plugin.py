@@ -269,6 +269,41 @@ def test_volume_plugin_chunked_mode_with_peer_bit_exact_vs_reference():
     assert np.array_equal(res[0][1], res[1][1])
 
 
+def test_volume_plugin_setters_called_mid_stream_bit_exact_vs_reference():
+    """the settings that reset the gain ramp do so when THEY are called and only then (msvolume.c:262-276, 352-378): noise
+    gate switched on, an unrelated setting changed, the gate switched off, a gain in dB — between runs of the same graph"""
+    rate, T = 16000, 12
+    n = rate // 100
+    rng = np.random.default_rng(11)
+    x = np.concatenate([(rng.standard_normal(n) * (6000 if (k // 5) % 2 == 0 else 30)).astype(np.int16) for k in range(5 * T)])
+    res = []
+    for g in _graphs():
+        vol = g.new("MSVolume")
+        g.call_int(vol, "MS_FILTER_SET_SAMPLE_RATE", rate)
+        g.call_float(vol, "MS_VOLUME_SET_GAIN", 1.3)
+        src, sink = g.source(x, n * 2), g.sink()
+        g.link(src, 0, vol, 0)
+        g.link(vol, 0, sink, 0)
+        g.run(src, T)
+        g.call_float(vol, "MS_VOLUME_SET_NOISE_GATE_FLOORGAIN", 0.1)
+        g.call_float(vol, "MS_VOLUME_SET_NOISE_GATE_THRESHOLD", 0.05)
+        g.call(vol, "MS_VOLUME_ENABLE_NOISE_GATE", C.c_ubyte(1))
+        g.run(src, T)
+        g.call_int(vol, "MS_VOLUME_REMOVE_DC", 1)  # unrelated: must not replay the gate's gain reset
+        g.run(src, T)
+        g.call(vol, "MS_VOLUME_ENABLE_NOISE_GATE", C.c_ubyte(0))
+        g.run(src, T)
+        g.call_float(vol, "MS_VOLUME_SET_DB_GAIN", -3.0)  # gain = static gain, target gain untouched
+        g.run(src, T)
+        lin = C.c_float()
+        g.call(vol, "MS_VOLUME_GET_LINEAR", lin)
+        res.append((g.read(sink)[0], lin.value))
+        g.close()
+    assert len(res[0][0]) == 5 * T * n
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.float32(res[0][1]) == np.float32(res[1][1])
+
+
 @pytest.mark.parametrize("name,ptime", [("MSAlaw", 0), ("MSUlaw", 0), ("MSAlaw", 30), ("MSUlaw", 10)])
 def test_plugin_g711_codecs_bit_exact_vs_reference_filters(name, ptime):
     """source -> <law>Enc -> <law>Dec -> sink in the unmodified MSTicker: the plugin's filters (GPU companding, host
