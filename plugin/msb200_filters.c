@@ -45,6 +45,14 @@
 #include <string.h>
 #include <time.h>
 
+/* the one-in / one-out filters' queue ends */
+static inline mblk_t *pin0_next(MSFilter *f) {
+	return ms_queue_get(f->inputs[0]);
+}
+static inline void pin0_send(MSFilter *f, mblk_t *m) {
+	ms_queue_put(f->outputs[0], m);
+}
+
 /* ------------------------------------------------------------------------------------------------ device context */
 static msb200_ctx *g_ctx = NULL;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER; /* the context's stream is shared by all filter instances */
@@ -1038,7 +1046,7 @@ static void vol_process(MSFilter *f) {
 			m = allocb(chunk_bytes, 0);
 			memcpy(m->b_wptr, run + k * chunk, chunk_bytes);
 			m->b_wptr += chunk_bytes;
-			ms_queue_put(f->outputs[0], m);
+			pin0_send(f, m);
 		}
 		ms_free(run);
 		return;
@@ -1049,8 +1057,8 @@ static void vol_process(MSFilter *f) {
 		if (v->n_held && v->batch->staged[v->slot] == 0) vol_collect(v, v->batch);
 	}
 	while ((m = ms_queue_get(&v->pend)) != NULL)
-		ms_queue_put(f->outputs[0], m);
-	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+		pin0_send(f, m);
+	while ((m = pin0_next(f)) != NULL) {
 		int n = (int)((m->b_wptr - m->b_rptr) / 2);
 		if (v->batch && v->watchers > 0) { /* somebody's echo-limiter peer: the state must live in the private bank */
 			vol_leave_batch(v);
@@ -1097,7 +1105,7 @@ static void vol_process(MSFilter *f) {
 			vol_sync_config(v);
 			DSP_CHECK(msb200_volume_process(v->bank, (int16_t *)m->b_rptr, n), "volume_process");
 			DSP_UNLOCK();
-			ms_queue_put(f->outputs[0], m);
+			pin0_send(f, m);
 		} else {
 			freemsg(m); /* no GPU: never forward unprocessed audio as if it had been processed */
 		}
@@ -1332,7 +1340,7 @@ static void chan_convert(MSFilter *f, int mode, int frames, const int16_t *a, co
 	if (ok && frames > 0) DSP_CHECK(msb200_chanadapt_process(g_ctx, mode, 1, frames, a, b, (int16_t *)om->b_wptr), "chanadapt");
 	DSP_UNLOCK();
 	om->b_wptr += out_bytes;
-	if (ok) ms_queue_put(f->outputs[0], om);
+	if (ok) pin0_send(f, om);
 	else freemsg(om); /* no GPU: never forward unprocessed audio */
 }
 static void chan_tick(MSFilter *f) {
@@ -1351,10 +1359,10 @@ static void chan_tick(MSFilter *f) {
 		             full[1] ? (const int16_t *)a->side[1].tick : NULL, a->tick_bytes * 2);
 		return;
 	}
-	while ((im = ms_queue_get(f->inputs[0])) != NULL) {
+	while ((im = pin0_next(f)) != NULL) {
 		const size_t in_bytes = msgdsize(im);
 		if (a->in_ch == a->out_ch) {
-			ms_queue_put(f->outputs[0], im);
+			pin0_send(f, im);
 			continue;
 		}
 		if (a->out_ch == 2) chan_convert(f, MSB200_CHAN_MONO_TO_STEREO, (int)(in_bytes / 2), (const int16_t *)im->b_rptr, NULL, in_bytes * 2);
@@ -1454,7 +1462,7 @@ static void eq_preprocess(MSFilter *f) {
 static void eq_process(MSFilter *f) {
 	EqState *s = (EqState *)f->data;
 	mblk_t *m;
-	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+	while ((m = pin0_next(f)) != NULL) {
 		int n = (int)((m->b_wptr - m->b_rptr) / 2);
 		if (s->active && n > 0) {
 			DSP_LOCK();
@@ -1466,7 +1474,7 @@ static void eq_process(MSFilter *f) {
 				continue;
 			}
 		}
-		ms_queue_put(f->outputs[0], m);
+		pin0_send(f, m);
 	}
 }
 static int eq_set_gain(MSFilter *f, void *data) {
@@ -1620,9 +1628,9 @@ static void rs_process(MSFilter *f) {
 	RsState *s = (RsState *)f->data;
 	mblk_t *im;
 	if (s->output_rate == s->input_rate) {
-		while ((im = ms_queue_get(f->inputs[0])) != NULL) {
+		while ((im = pin0_next(f)) != NULL) {
 			if (s->out_nchannels == s->in_nchannels) {
-				ms_queue_put(f->outputs[0], im);
+				pin0_send(f, im);
 			} else {
 				ms_queue_put(f->outputs[0], rs_channel_adapt(s->in_nchannels, s->out_nchannels, im));
 				freemsg(im);
@@ -1638,8 +1646,8 @@ static void rs_process(MSFilter *f) {
 		if (s->held && s->batch->staged[s->slot] == 0) rs_collect(s, s->batch);
 	}
 	while ((im = ms_queue_get(&s->pend)) != NULL)
-		ms_queue_put(f->outputs[0], im);
-	while ((im = ms_queue_get(f->inputs[0])) != NULL) {
+		pin0_send(f, im);
+	while ((im = pin0_next(f)) != NULL) {
 		int inlen = (int)((im->b_wptr - im->b_rptr) / (2 * s->in_nchannels));
 		int outcap = (int)(((uint32_t)inlen * s->output_rate) / s->input_rate) + 1;
 		int outlen = 0;
@@ -1689,7 +1697,7 @@ static void rs_process(MSFilter *f) {
 			ms_queue_put(f->outputs[0], rs_channel_adapt(s->in_nchannels, s->out_nchannels, om));
 			freemsg(om);
 		} else {
-			ms_queue_put(f->outputs[0], om);
+			pin0_send(f, om);
 		}
 		freemsg(im);
 	}
@@ -1854,7 +1862,7 @@ static void ec_take_far_end(MSFilter *f, EchoCanceller *e) {
 		ms_queue_flush(f->inputs[0]);
 		return;
 	}
-	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+	while ((m = pin0_next(f)) != NULL) {
 		ms_bufferizer_put(&e->far_for_filter, dupmsg(m));
 		ms_flow_controlled_bufferizer_put(&e->far_for_playback, m);
 	}
@@ -1880,7 +1888,7 @@ static void ec_play_one_frame(MSFilter *f, EchoCanceller *e) {
 		else ms_message("MSSpeexEC(B200): far end is back");
 		e->far_starved = starving;
 	}
-	ms_queue_put(f->outputs[0], spk);
+	pin0_send(f, spk);
 }
 /* the (microphone, reference) pair of one frame goes to the canceller: at once in synchronous mode, into the group's arena
  * in batch mode (cancelled by the group's launch at the start of the next tick) */
@@ -2078,7 +2086,7 @@ static void g711_enc_process(MSFilter *f) {
 	uint8_t *pcm, *code;
 	if (s->ptime >= 10) frame_per_packet = s->ptime / 10 < 14 ? s->ptime / 10 : 14; /* packets of 10 .. 140 ms */
 	size_of_pcm = (size_t)160 * frame_per_packet;       /* bytes: 80 samples per 10 ms at 8 kHz */
-	while ((m = ms_queue_get(f->inputs[0])) != NULL)
+	while ((m = pin0_next(f)) != NULL)
 		ms_bufferizer_put(s->bz, m);
 	if (s->batch && s->batch->key[1] != (int)size_of_pcm / 2) g711_enc_leave_batch(s); /* ptime changed under us */
 	if (s->batch) { /* the packets staged in the previous tick were encoded by the group's launch */
@@ -2086,7 +2094,7 @@ static void g711_enc_process(MSFilter *f) {
 		if (s->n_held && s->batch->staged[s->slot] == 0) g711_enc_collect(s, s->batch);
 	}
 	while ((m = ms_queue_get(&s->pend)) != NULL)
-		ms_queue_put(f->outputs[0], m);
+		pin0_send(f, m);
 	avail = ms_bufferizer_get_avail(s->bz);
 	npk = (int)(avail / size_of_pcm);
 	if (npk == 0) return;
@@ -2294,7 +2302,7 @@ static void g711_dec_process_law(MSFilter *f, int law) { /* alaw_dec_process ala
 		if (st->n_held && st->batch->staged[st->slot] == 0) g711_dec_collect(st, st->batch);
 	}
 	while ((m = ms_queue_get(&st->pend)) != NULL)
-		ms_queue_put(f->outputs[0], m);
+		pin0_send(f, m);
 	/* everything queued in this tick (usually one RTP payload) goes to the device in ONE call */
 	while (n < 64 && (m = ms_queue_get(f->inputs[0])) != NULL) {
 		msgpullup(m, (size_t)-1);
@@ -2324,7 +2332,7 @@ static void g711_dec_process_law(MSFilter *f, int law) { /* alaw_dec_process ala
 			mblk_meta_copy(list[k], o);
 			memcpy(o->b_wptr, pcm + off, len * 2);
 			o->b_wptr += len * 2;
-			ms_queue_put(f->outputs[0], o);
+			pin0_send(f, o);
 		}
 		off += len;
 		freemsg(list[k]);
@@ -2390,7 +2398,7 @@ static void flowctl_process(MSFilter *f) {
 	FlowCtlState *s = (FlowCtlState *)f->data;
 	mblk_t *m;
 	ms_filter_lock(f);
-	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+	while ((m = pin0_next(f)) != NULL) {
 		const int n = (int)((m->b_wptr - m->b_rptr) / 2);
 		int32_t left = n;
 		if (s->armed && s->bank && n >= 3 && n <= FLOWCTL_MAX_BLOCK) {
@@ -2412,7 +2420,7 @@ static void flowctl_process(MSFilter *f) {
 			continue;
 		}
 		m->b_wptr = m->b_rptr + (size_t)left * 2;
-		ms_queue_put(f->outputs[0], m);
+		pin0_send(f, m);
 	}
 	ms_filter_unlock(f);
 }
@@ -2615,8 +2623,8 @@ static void plc_process(MSFilter *f) {
 		if (s->n_units && s->batch->staged[s->slot] == 0) plc_collect(s, s->batch);
 	}
 	while ((m = ms_queue_get(&s->pend)) != NULL)
-		ms_queue_put(f->outputs[0], m);
-	while ((m = ms_queue_get(f->inputs[0])) != NULL) {
+		pin0_send(f, m);
+	while ((m = pin0_next(f)) != NULL) {
 		size_t msg_size;
 		uint8_t mode;
 		if (m->b_cont) msgpullup(m, (size_t)-1);
@@ -2655,7 +2663,7 @@ static void plc_process(MSFilter *f) {
 			s->batch_off = TRUE;
 		}
 		plc_device(s, (int16_t *)m->b_rptr, (int)(msg_size / 2), mode);
-		ms_queue_put(f->outputs[0], m);
+		pin0_send(f, m);
 	}
 	/* ms_concealer_context_is_concealement_required(concealer, now) */
 	if (s->sample_time != -1 && (uint64_t)s->sample_time <= now) {
@@ -2689,7 +2697,7 @@ static void plc_process(MSFilter *f) {
 			s->batch_off = TRUE;
 		}
 		if (kind == 2) plc_device(s, (int16_t *)m->b_rptr, tick_samples, MSB200_PLC_CONCEAL);
-		ms_queue_put(f->outputs[0], m);
+		pin0_send(f, m);
 	}
 }
 static void plc_postprocess(MSFilter *f) { /* the group belongs to the ticker the filter is being detached from */

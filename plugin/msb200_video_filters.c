@@ -321,7 +321,7 @@ typedef struct PixConv {
 	int key[6];
 } PixConv;
 
-static void pixconv_init(MSFilter *f) {
+static void pixc_new(MSFilter *f) {
 	PixConv *s = ms_new0(PixConv, 1);
 	qinit(&s->m.ready);
 	s->in_size.width = MS_VIDEO_SIZE_CIF_W; /* the reference's defaults, pixconv.c:37-46 */
@@ -333,13 +333,13 @@ static void pixconv_drop_lane(PixConv *s) {
 	lane_leave(s->m.lane, &s->m);
 	s->m.lane = NULL;
 }
-static void pixconv_uninit(MSFilter *f) {
+static void pixc_free(MSFilter *f) {
 	PixConv *s = (PixConv *)f->data;
 	pixconv_drop_lane(s);
 	flushq(&s->m.ready, 0);
 	ms_free(s);
 }
-static void pixconv_postprocess(MSFilter *f) {
+static void pixc_detach(MSFilter *f) {
 	PixConv *s = (PixConv *)f->data;
 	pixconv_drop_lane(s);
 	flushq(&s->m.ready, 0);
@@ -362,7 +362,7 @@ static VLane *pixconv_lane(MSFilter *f, PixConv *s) {
 	s->m.lane = lane_join(f->ticker, key);
 	return s->m.lane;
 }
-static void pixconv_process(MSFilter *f) {
+static void pixc_tick(MSFilter *f) {
 	PixConv *s = (PixConv *)f->data;
 	mblk_t *im;
 	const int resize = s->out_size.width > 0 && (s->out_size.width != s->in_size.width || s->out_size.height != s->in_size.height);
@@ -396,11 +396,11 @@ static void pixconv_process(MSFilter *f) {
 		freemsg(im);
 	}
 }
-static int pixconv_set_vsize(MSFilter *f, void *arg) {
+static int pixc_take_size(MSFilter *f, void *arg) {
 	((PixConv *)f->data)->in_size = *(MSVideoSize *)arg;
 	return 0;
 }
-static int pixconv_set_pixfmt(MSFilter *f, void *arg) {
+static int pixc_take_format(MSFilter *f, void *arg) {
 	((PixConv *)f->data)->in_fmt = *(MSPixFmt *)arg;
 	return 0;
 }
@@ -414,8 +414,8 @@ static int pixconv_set_out_size(MSFilter *f, void *arg) {
 	((PixConv *)f->data)->out_size = *(MSVideoSize *)arg;
 	return 0;
 }
-static MSFilterMethod pixconv_methods[] = {{MS_FILTER_SET_VIDEO_SIZE, pixconv_set_vsize},
-                                           {MS_FILTER_SET_PIX_FMT, pixconv_set_pixfmt},
+static MSFilterMethod pixc_method_table[] = {{MS_FILTER_SET_VIDEO_SIZE, pixc_take_size},
+                                           {MS_FILTER_SET_PIX_FMT, pixc_take_format},
                                            {MSB200_PIX_CONV_SET_OUTPUT_FMT, pixconv_set_out_fmt},
                                            {MSB200_PIX_CONV_SET_OUTPUT_SIZE, pixconv_set_out_size},
                                            {0, NULL}};
@@ -425,11 +425,11 @@ static MSFilterDesc b200_pix_conv_desc = {.id = MS_PIX_CONV_ID,
                                           .category = MS_FILTER_OTHER,
                                           .ninputs = 1,
                                           .noutputs = 1,
-                                          .init = pixconv_init,
-                                          .process = pixconv_process,
-                                          .postprocess = pixconv_postprocess,
-                                          .uninit = pixconv_uninit,
-                                          .methods = pixconv_methods};
+                                          .init = pixc_new,
+                                          .process = pixc_tick,
+                                          .postprocess = pixc_detach,
+                                          .uninit = pixc_free,
+                                          .methods = pixc_method_table};
 
 /* ================================================================================================ MSSizeConv */
 typedef struct SizeConv {
@@ -444,7 +444,7 @@ typedef struct SizeConv {
 	int key[6];
 } SizeConv;
 
-static void sizeconv_init(MSFilter *f) {
+static void sizec_new(MSFilter *f) {
 	SizeConv *s = ms_new0(SizeConv, 1);
 	qinit(&s->m.ready);
 	qinit(&s->pending);
@@ -457,15 +457,15 @@ static void sizeconv_drop_lane(SizeConv *s) {
 	lane_leave(s->m.lane, &s->m);
 	s->m.lane = NULL;
 }
-static void sizeconv_postprocess(MSFilter *f) {
+static void sizec_detach(MSFilter *f) {
 	SizeConv *s = (SizeConv *)f->data;
 	sizeconv_drop_lane(s);
 	flushq(&s->pending, 0);
 	flushq(&s->m.ready, 0);
 	s->running = 0;
 }
-static void sizeconv_uninit(MSFilter *f) {
-	sizeconv_postprocess(f);
+static void sizec_free(MSFilter *f) {
+	sizec_detach(f);
 	ms_free(f->data);
 }
 /* The size a frame of in_w x in_h is scaled to: the configured target turned to the frame's orientation, then shrunk along
@@ -522,7 +522,7 @@ static void sizeconv_one_frame(MSFilter *f, SizeConv *s, mblk_t *im) {
 	}
 	freemsg(im);
 }
-static void sizeconv_process(MSFilter *f) {
+static void sizec_tick(MSFilter *f) {
 	SizeConv *s = (SizeConv *)f->data;
 	mblk_t *im;
 	ms_filter_lock(f);
@@ -546,26 +546,26 @@ static void sizeconv_process(MSFilter *f) {
 	while ((im = getq(&s->pending)) != NULL) sizeconv_one_frame(f, s, im);
 	ms_filter_unlock(f);
 }
-static int sizeconv_set_vsize(MSFilter *f, void *arg) {
+static int sizec_take_size(MSFilter *f, void *arg) {
 	SizeConv *s = (SizeConv *)f->data;
 	ms_filter_lock(f);
 	s->target = *(MSVideoSize *)arg;
 	ms_filter_unlock(f);
 	return 0;
 }
-static int sizeconv_get_vsize(MSFilter *f, void *arg) {
+static int sizec_tell_size(MSFilter *f, void *arg) {
 	*(MSVideoSize *)arg = ((SizeConv *)f->data)->target;
 	return 0;
 }
-static int sizeconv_set_fps(MSFilter *f, void *arg) {
+static int sizec_take_fps(MSFilter *f, void *arg) {
 	SizeConv *s = (SizeConv *)f->data;
 	s->fps = *(float *)arg;
 	s->running = 0; /* pacing restarts from the next tick */
 	return 0;
 }
-static MSFilterMethod sizeconv_methods[] = {{MS_FILTER_SET_FPS, sizeconv_set_fps},
-                                            {MS_FILTER_SET_VIDEO_SIZE, sizeconv_set_vsize},
-                                            {MS_FILTER_GET_VIDEO_SIZE, sizeconv_get_vsize},
+static MSFilterMethod sizec_method_table[] = {{MS_FILTER_SET_FPS, sizec_take_fps},
+                                            {MS_FILTER_SET_VIDEO_SIZE, sizec_take_size},
+                                            {MS_FILTER_GET_VIDEO_SIZE, sizec_tell_size},
                                             {0, NULL}};
 static MSFilterDesc b200_size_conv_desc = {.id = MS_SIZE_CONV_ID,
                                            .name = "MSSizeConv",
@@ -573,11 +573,11 @@ static MSFilterDesc b200_size_conv_desc = {.id = MS_SIZE_CONV_ID,
                                            .category = MS_FILTER_OTHER,
                                            .ninputs = 1,
                                            .noutputs = 1,
-                                           .init = sizeconv_init,
-                                           .process = sizeconv_process,
-                                           .postprocess = sizeconv_postprocess,
-                                           .uninit = sizeconv_uninit,
-                                           .methods = sizeconv_methods};
+                                           .init = sizec_new,
+                                           .process = sizec_tick,
+                                           .postprocess = sizec_detach,
+                                           .uninit = sizec_free,
+                                           .methods = sizec_method_table};
 
 /* ================================================================================================ MSScalerDesc
  * The second drop-in boundary: the reference's OWN MSPixConv / MSSizeConv / display filters scale on the GPU once this
