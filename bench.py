@@ -405,6 +405,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["conference"] = block
     # ---------------------------------------------------------------- second headline: pixconv (when built)
     try:
+        if args.headline_only:
+            raise ImportError
         from bench_video import pixconv_bench  # noqa: WPS433
 
         if rank == 0:
@@ -412,6 +414,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     except ImportError:
         pass
     try:
+        if args.headline_only:
+            raise ImportError
         from bench_g711 import g711_bench  # noqa: WPS433
 
         if rank == 0:
@@ -419,6 +423,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     except ImportError:
         pass
     try:
+        if args.headline_only:
+            raise ImportError
         from bench_kernels import kernels_bench  # noqa: WPS433
 
         if rank == 0 and world == 1:
@@ -478,6 +484,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-realtime", action="store_true", help="skip the S_rt tick-latency block (SURVEY §8d)")
     ap.add_argument("--no-conference", action="store_true", help="skip the cfg3 cross-GPU conference block (N > 1)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the pixconv / g711 / kernels side blocks (A/B runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -278,6 +278,10 @@ MSB200_API void msb200_aec_destroy(msb200_aec *a);
 MSB200_API int msb200_aec_get_info(msb200_aec *a, msb200_aec_info *info);
 MSB200_API int msb200_aec_reset(msb200_aec *a, int stream); /* stream < 0: all */
 MSB200_API int msb200_aec_set_live(msb200_aec *a, int n_live); /* see msb200_volume_set_live */
+/* Cross-check switch for the 48 kHz kernel builds (results are bit-identical, the tests assert it): 0 = default (a ninth
+ * "serial" warp runs the DC notch / pre-emphasis / de-emphasis IIRs beside the 256 per-bin threads), 1 = the 256-thread
+ * build (one of the per-bin threads runs them, the others wait), 3 = the serial-warp build at 3 CTAs per SM. */
+MSB200_API int msb200_aec_set_path(msb200_aec *a, int path);
 MSB200_API int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes);
 MSB200_API int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes,
                                       int stride_samples);

@@ -146,6 +146,7 @@ _SIGS = {
     "msb200_mixer_set_live": (_I, [_P, _I]),
     "msb200_resample_set_live": (_I, [_P, _I]),
     "msb200_aec_set_live": (_I, [_P, _I]),
+    "msb200_aec_set_path": (_I, [_P, _I]),
     "msb200_volume_set_gain": (_I, [_P, _I, _F]),
     "msb200_volume_set_db_gain": (_I, [_P, _I, _F]),
     "msb200_volume_enable_noise_gate": (_I, [_P, _I, _I]),

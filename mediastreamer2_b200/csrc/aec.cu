@@ -85,8 +85,33 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 	asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ barriers
+// The F "main" threads (one per bin) synchronise on named barrier 1, never on barrier 0: the 48 kHz kernel carries a
+// NINTH warp (the serial warp, see the kernel) that must not take part in their barriers. Barriers 2 - 4 are the
+// producer / consumer hand-offs between that warp and the main threads (arrive on one side, sync on the other).
+template <int NT> __device__ __forceinline__ void bar_main() {
+	asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+template <int NT> __device__ __forceinline__ int bar_main_or(int pred) {
+	int r;
+	asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.or.pred q, 1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+	             : "=r"(r)
+	             : "r"(pred), "n"(NT)
+	             : "memory");
+	return r;
+}
+template <int ID, int NT> __device__ __forceinline__ void bar_arrive() { // prior shared-memory writes first
+	__threadfence_block();
+	asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NT) : "memory");
+}
+template <int ID, int NT> __device__ __forceinline__ void bar_wait() {
+	asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory");
+}
+#define MAIN_SYNC() bar_main<(1 << LOG2L)>()
+enum { BAR_INPUT = 2, BAR_DEEMPH_IN = 3, BAR_DEEMPH_OUT = 4 };
+
 // ------------------------------------------------------------------------------------------------ block helpers
-// All helpers are called by every thread of the CTA (blockDim.x == F).
+// All helpers are called by every main thread of the CTA (threadIdx.x < F).
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -94,29 +119,31 @@ __device__ __forceinline__ float warp_sum(float v) {
 	return v;
 }
 // deterministic block sum: shuffle tree inside each warp, then warp partials added in warp order. `red` = smem[32]
-__device__ float block_sum(float v, float *red) {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+template <int LOG2L> __device__ float block_sum(float v, float *red) {
+	constexpr int nw = ((1 << LOG2L) + 31) >> 5;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	v = warp_sum(v);
-	__syncthreads(); // protect `red` from the previous use
+	MAIN_SYNC(); // protect `red` from the previous use
 	if (lane == 0) red[warp] = v;
-	__syncthreads();
+	MAIN_SYNC();
 	float s = 0.f;
 	for (int w = 0; w < nw; ++w) s += red[w];
 	return s;
 }
 // three block sums sharing one pair of barriers; each sum has exactly block_sum()'s order. blockDim.x <= 256
-__device__ void block_sum3(float &a, float &b, float &c, float *red) {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+template <int LOG2L> __device__ void block_sum3(float &a, float &b, float &c, float *red) {
+	constexpr int nw = ((1 << LOG2L) + 31) >> 5;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	a = warp_sum(a);
 	b = warp_sum(b);
 	c = warp_sum(c);
-	__syncthreads();
+	MAIN_SYNC();
 	if (lane == 0) {
 		red[warp] = a;
 		red[8 + warp] = b;
 		red[16 + warp] = c;
 	}
-	__syncthreads();
+	MAIN_SYNC();
 	float sa = 0.f, sb = 0.f, sc3 = 0.f;
 	for (int w = 0; w < nw; ++w) {
 		sa += red[w];
@@ -127,8 +154,8 @@ __device__ void block_sum3(float &a, float &b, float &c, float *red) {
 	b = sb;
 	c = sc3;
 }
-__device__ int block_any(int pred) {
-	return __syncthreads_or(pred);
+template <int LOG2L> __device__ int block_any(int pred) {
+	return bar_main_or<(1 << LOG2L)>(pred);
 }
 
 // complex radix-2 Stockham FFT of length L = 1 << LOG2L over shared memory. Thread b < L/2 of a group computes one
@@ -175,7 +202,7 @@ __device__ __forceinline__ void cfft_bfly(float2 *x, float2 *y, const float2 *tw
 			y[o + 2 * s] = z2;
 			y[o + 3 * s] = z3;
 		}
-		__syncthreads();
+		MAIN_SYNC();
 		float2 *sw = x;
 		x = y;
 		y = sw;
@@ -191,7 +218,7 @@ __device__ __forceinline__ void cfft_bfly(float2 *x, float2 *y, const float2 *tw
 			y[oi] = o0;
 			y[oi + s] = o1;
 		}
-		__syncthreads();
+		MAIN_SYNC();
 		float2 *sw = x;
 		x = y;
 		y = sw;
@@ -217,7 +244,7 @@ __device__ void rfft(const float *in, float2 *spec, float2 *bufa, float2 *bufb, 
 	const int k = threadIdx.x, L = 1 << LOG2L;
 	const float scale = (float)(1. / P.N);
 	bufa[k] = make_float2(scale * in[2 * k], scale * in[2 * k + 1]);
-	__syncthreads();
+	MAIN_SYNC();
 	const float2 *Z = cfft<LOG2L>(bufa, bufb, tw, -1);
 	float2 out;
 	if (k == 0) {
@@ -231,9 +258,9 @@ __device__ void rfft(const float *in, float2 *spec, float2 *bufa, float2 *bufb, 
 		out.x = er + (c * di - s * dr);
 		out.y = ei - (s * di + c * dr);
 	}
-	__syncthreads(); // all reads of Z done before spec (which may be reused scratch by the caller later) is written
+	MAIN_SYNC(); // all reads of Z done before spec (which may be reused scratch by the caller later) is written
 	spec[k] = out;
-	__syncthreads();
+	MAIN_SYNC();
 }
 
 // real inverse FFT (spx_ifft, unscaled): spec[L] float2 (bin0=(DC,Nyq)) -> out[N] real (smem)
@@ -254,15 +281,15 @@ __device__ void irfft(const float2 *spec, float *out, float2 *bufa, float2 *bufb
 		z.x = er - oi;
 		z.y = ei + orr;
 	}
-	__syncthreads();
+	MAIN_SYNC();
 	bufa[k] = z;
-	__syncthreads();
+	MAIN_SYNC();
 	const float2 *r = cfft<LOG2L>(bufa, bufb, tw, +1);
 	const float2 v = r[k];
-	__syncthreads();
+	MAIN_SYNC();
 	out[2 * k] = v.x;
 	out[2 * k + 1] = v.y;
-	__syncthreads();
+	MAIN_SYNC();
 }
 
 // ---- paired transforms: two independent FFTs, one per half of the CTA, sharing every stage's barrier
@@ -283,7 +310,7 @@ __device__ void rfft_pair(const float *in_a, float2 *spec_a, const float *in_b, 
 	const float scale = (float)(1. / P.N);
 	a0[k] = make_float2(scale * in_a[2 * k], scale * in_a[2 * k + 1]);
 	b0[k] = make_float2(scale * in_b[2 * k], scale * in_b[2 * k + 1]);
-	__syncthreads();
+	MAIN_SYNC();
 	float2 *xa = a0, *ya = a1, *xb = b0, *yb = b1;
 	cfft_pair<LOG2L>(xa, ya, xb, yb, tw, -1);
 	float2 oa, ob;
@@ -305,10 +332,10 @@ __device__ void rfft_pair(const float *in_a, float2 *spec_a, const float *in_b, 
 			ob.y = ei - (sn * di + c * dr);
 		}
 	}
-	__syncthreads();
+	MAIN_SYNC();
 	spec_a[k] = oa;
 	spec_b[k] = ob;
-	__syncthreads();
+	MAIN_SYNC();
 }
 // two real inverse FFTs
 template <int LOG2L>
@@ -334,40 +361,21 @@ __device__ void irfft_pair(const float2 *spec_a, float *out_a, const float2 *spe
 			zb.x = er - oi; zb.y = ei + orr;
 		}
 	}
-	__syncthreads();
+	MAIN_SYNC();
 	a0[k] = za;
 	b0[k] = zb;
-	__syncthreads();
+	MAIN_SYNC();
 	float2 *xa = a0, *ya = a1, *xb = b0, *yb = b1;
 	cfft_pair<LOG2L>(xa, ya, xb, yb, tw, +1);
 	const float2 va = xa[k], vb = xb[k];
-	__syncthreads();
+	MAIN_SYNC();
 	out_a[2 * k] = va.x; out_a[2 * k + 1] = va.y;
 	out_b[2 * k] = vb.x; out_b[2 * k + 1] = vb.y;
-	__syncthreads();
+	MAIN_SYNC();
 }
 
 __device__ __forceinline__ short word2int(float x) {
 	return (short)(x < -32767.5f ? -32768 : (x > 32766.5f ? 32767 : (int)floor(.5 + (double)x)));
-}
-
-// per-band sum in the oracle's accumulation order (filterbank_compute_bank32): thread b < NB_BANDS
-__device__ void filterbank_bank32(const float *ps, float *mel, const AecParams &P) {
-	const int b = threadIdx.x;
-	if (b < NB_BANDS) {
-		float acc = 0.f;
-		if (b > 0)
-			for (int i = P.band_start[b - 1]; i < P.band_start[b]; ++i) acc += P.filter_right[i] * ps[i];
-		for (int i = P.band_start[b]; i < P.band_start[b + 1]; ++i) acc += P.filter_left[i] * ps[i];
-		mel[b] = acc;
-	}
-	__syncthreads();
-}
-__device__ __forceinline__ float filterbank_psd16(const float *mel, int i, const AecParams &P) {
-	const int l = P.bank_left[i];
-	float tmp = mel[l] * P.filter_left[i];
-	tmp += mel[l + 1] * P.filter_right[i];
-	return tmp;
 }
 
 __device__ float hypergeom_gain(float xx) {
@@ -388,8 +396,14 @@ __device__ __forceinline__ float qcurve(float x) {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 // dynamic shared memory map (floats): see carve-up at the top of the kernel body
-template <int LOG2L, int CTAS = AEC_CTAS_PER_SM_256>
-__global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 : ((256 * CTAS) >> LOG2L))
+// SW (48 kHz only): the CTA has a ninth warp, the SERIAL warp. Lane 0 of it runs the two sequential IIR filters of the
+// frame — DC notch + pre-emphasis of the microphone, de-emphasis of the output — that a main thread used to run while
+// the other 255 waited at a barrier (ncu, profiles/r2c_aec_kernel_deep_pipe.hotlines.txt: 18 % of all warp stall samples
+// sat on those two barriers). The notch of frame k+1 now runs under the tail of frame k and the far-end transforms /
+// block pass of frame k+1 (none of them needs the microphone), the de-emphasis under the E / Y transforms and the
+// adaptation statistics. Same operations on the same operands in the same order: results are bit-identical.
+template <int LOG2L, int CTAS = AEC_CTAS_PER_SM_256, bool SW = false>
+__global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >> LOG2L) > 32 ? 32 : ((256 * CTAS) >> LOG2L))
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
                float *__restrict__ gS, AecParams P, const int *__restrict__ counts, int in_frame0, int in_ring, int out_stride, int out_frame0,
@@ -417,7 +431,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
 			} while (t1 - t0 < wait);
 		}
-		__syncthreads();
+		__syncthreads(); // every thread of the CTA, the serial warp included
 	}
 	// ---- shared memory carve-up
 	float2 *tw = reinterpret_cast<float2 *>(sm);           // [L/2]
@@ -440,14 +454,19 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 	float *vec4 = vec3 + VLEN;                             // [VLEN]
 	float *vec5 = vec4 + VLEN;                             // [VLEN]
 	float *xw = vec5 + VLEN;                               // [N] far-end window
-	float *input = xw + N;                                 // [F]
-	float *tmpv = input + F;                               // [N] generic real scratch
+	float *input_own = xw + N;                             // [F] (builds without the serial warp)
+	float *tmpv = input_own + F;                               // [N] generic real scratch
 	float *power_1 = tmpv + N;                             // [F+1]
 	float *prop = power_1 + F + 1;                         // [M]
 	float *wpart = prop + M;                               // [M][8] per-warp |W_j|^2 partials
 	float *red = wpart + M * 8;                            // [32]
 	float *sc = red + 32;                                  // [SC_COUNT]
 	int *si = reinterpret_cast<int *>(sc + SC_COUNT);      // [IN_COUNT]
+	// serial-warp hand-off (SW only): reset flag, the microphone frame as floats, two filtered input frames (frame parity)
+	int *sw_reset = si + IN_COUNT;                                                                  // [4]
+	float *micf = reinterpret_cast<float *>((reinterpret_cast<size_t>(sw_reset + 4) + 15) & ~(size_t)15); // [F]
+	float *inq = micf + F;                                                                          // [2][F]
+	constexpr int NT_ALL = F + 32;
 
 	float2 *X = gX + (size_t)stream * P.x_stride;
 	float2 *W = gW + (size_t)stream * P.w_stride;
@@ -455,6 +474,69 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 	float *S = gS + (size_t)stream * P.lay.total;
 	const AecLayout &ly = P.lay;
 	const int nwarps = (F + 31) >> 5, lane = t & 31, warp = t >> 5;
+
+	if (SW && t >= F) {
+		// ================================================================================ the serial warp
+		// Filter memories live in registers for the whole launch (read from and written back to the state page here:
+		// the main threads leave these four scalars alone in SW builds).
+		float m0 = S[ly.scal + SC_NOTCH0], m1 = S[ly.scal + SC_NOTCH1], memD = S[ly.scal + SC_MEMD], memE = S[ly.scal + SC_MEME];
+		const float radius = P.notch_radius, pre = P.preemph;
+		const float den2 = radius * radius + .7f * (1 - radius) * (1 - radius);
+		for (int fr = 0; fr < nframes; ++fr) {
+			const int fin = in_ring > 0 ? (in_frame0 + fr) % in_ring : fr;
+			const short *in_mic = mic + (size_t)stream * io_stride + (size_t)fin * F;
+#pragma unroll
+			for (int k = 0; k < F / 32; ++k) micf[lane + 32 * k] = (float)in_mic[lane + 32 * k];
+			__syncwarp();
+			if (lane == 0) {
+				// DC notch (filter_dc_notch16) then pre-emphasis; the recurrence m0 -> vout -> m0 is the critical path: add,
+				// mul, add, fma (2*a is exact, so fma(2, a, m1) rounds exactly like m1 + 2*a)
+				float *dst = inq + (fr & 1) * F;
+#pragma unroll 2
+				for (int i = 0; i < F; i += 4) {
+					const float4 vin4 = *reinterpret_cast<const float4 *>(micf + i);
+					const float vin[4] = {vin4.x, vin4.y, vin4.z, vin4.w};
+					float r[4], o[4];
+#pragma unroll
+					for (int k = 0; k < 4; ++k) {
+						const float vout = m0 + vin[k];
+						r[k] = radius * vout;
+						m0 = __fmaf_rn(2.f, r[k] - vin[k], m1);
+						m1 = vin[k] - den2 * vout;
+						o[k] = r[k] - pre * memD;
+						memD = r[k];
+					}
+					*reinterpret_cast<float4 *>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+				}
+			}
+			__syncwarp();
+			bar_arrive<BAR_INPUT, NT_ALL>();
+			bar_wait<BAR_DEEMPH_IN, NT_ALL>(); // tmpv = this frame's error signal, sw_reset = its verdict
+			const int reset = sw_reset[0];
+			if (lane == 0) {
+#pragma unroll 2
+				for (int i = 0; i < F; i += 4) {
+					float4 v = *reinterpret_cast<const float4 *>(tmpv + i);
+					v.x = v.x + pre * memE;
+					v.y = v.y + pre * v.x;
+					v.z = v.z + pre * v.y;
+					v.w = v.w + pre * v.z;
+					memE = v.w;
+					*reinterpret_cast<float4 *>(tmpv + i) = v;
+				}
+			}
+			__syncwarp();
+			bar_arrive<BAR_DEEMPH_OUT, NT_ALL>();
+			if (reset) m0 = m1 = memD = memE = 0.f; // speex_echo_state_reset() of this frame, before the next frame's notch
+		}
+		if (lane == 0) {
+			S[ly.scal + SC_NOTCH0] = m0;
+			S[ly.scal + SC_NOTCH1] = m1;
+			S[ly.scal + SC_MEMD] = memD;
+			S[ly.scal + SC_MEME] = memE;
+		}
+		return;
+	}
 
 	// ---- load constants and per-stream small state
 	for (int i = t; i < L / 2; i += F) tw[i] = P.tw[i];
@@ -465,7 +547,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 	for (int i = t; i < M; i += F) prop[i] = S[ly.prop + i];
 	if (t < SC_COUNT) sc[t] = S[ly.scal + t];
 	if (t < IN_COUNT) si[t] = reinterpret_cast<int *>(S + ly.ints)[t];
-	__syncthreads();
+	MAIN_SYNC();
 
 	int head = si[IN_HEAD];
 	for (int fr = 0; fr < nframes; ++fr) {
@@ -520,9 +602,12 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 		}
 #endif
 
-		// ---- DC notch (serial IIR, filter_dc_notch16) then pre-emphasis on the microphone
+		// ---- DC notch (serial IIR, filter_dc_notch16) then pre-emphasis on the microphone: the serial warp's job in SW
+		// builds (the filtered frame arrives in inq[frame parity], first needed after the block pass)
+		float *const input = SW ? inq + (fr & 1) * F : input_own;
+		if (!SW) {
 		tmpv[t] = (float)mic_i;
-		__syncthreads();
+		MAIN_SYNC();
 		if (t == 0) {
 			const float radius = P.notch_radius;
 			const float den2 = radius * radius + .7f * (1 - radius) * (1 - radius);
@@ -546,36 +631,37 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			sc[SC_NOTCH0] = m0;
 			sc[SC_NOTCH1] = m1;
 		}
-		__syncthreads();
+		MAIN_SYNC();
 		{
 			const float prev = t == 0 ? sc[SC_MEMD] : input[t - 1];
 			const float v = input[t] - P.preemph * prev;
 			const float lastv = input[F - 1];
-			__syncthreads();
+			MAIN_SYNC();
 			input[t] = v;
 			if (t == 0) sc[SC_MEMD] = lastv;
+		}
 		}
 		// ---- far-end window shift + pre-emphasis
 		{
 			const float old = xw[F + t];
 			tmpv[t] = (float)ref_i;
-			__syncthreads();
+			MAIN_SYNC();
 			const float prev = t == 0 ? sc[SC_MEMX] : tmpv[t - 1];
 			xw[t] = old;
 			xw[F + t] = (float)ref_i - P.preemph * prev;
-			__syncthreads();
+			MAIN_SYNC();
 			if (t == 0) sc[SC_MEMX] = tmpv[F - 1];
 		}
 		// ---- X_0 = FFT(x) into the ring
 		rfft<LOG2L>(xw, specA, bufa, bufb, P, tw, spl);
 		X[(size_t)head * F + t] = specA[t];
-		float Sxx = block_sum(xw[F + t] * xw[F + t], red);
+		float Sxx = block_sum<LOG2L>(xw[F + t] * xw[F + t], red);
 
 		// ---- adjust proportional adaptation rate (uses |W_j|^2 of the previous frame's final W)
 		if (si[IN_ADAPTED]) {
 			// mdf_adjust_prop: prop_j = sqrt(1 + |W_j|^2); += .1*max; normalise to .99
 			if (t < M) prop[t] = (float)sqrt((double)(1.f + S[ly.wnorm + t]));
-			__syncthreads();
+			MAIN_SYNC();
 			if (t == 0) {
 				float max_sum = 1, prop_sum = 1;
 				for (int i = 0; i < M; ++i)
@@ -586,7 +672,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				}
 				for (int i = 0; i < M; ++i) prop[i] = (.99f * prop[i]) / prop_sum;
 			}
-			__syncthreads();
+			MAIN_SYNC();
 		}
 
 		// ---- AUMDF constraint pre-pass. Block 0 and one rotating block get their weight update followed by
@@ -620,12 +706,12 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			}
 			specB[t] = w0;
 			cspec[t] = w1;
-			__syncthreads();
+			MAIN_SYNC();
 			float2 *sa = reinterpret_cast<float2 *>(ebuf), *sb = reinterpret_cast<float2 *>(ybuf);
 			irfft_pair<LOG2L>(specB, reinterpret_cast<float *>(specB), cspec, tmpv, bufa, bufb, sa, sb, P, tw, spl);
 			reinterpret_cast<float *>(specB)[F + t] = 0.f;
 			tmpv[F + t] = 0.f;
-			__syncthreads();
+			MAIN_SYNC();
 			rfft_pair<LOG2L>(reinterpret_cast<float *>(specB), specB, tmpv, cspec, bufa, bufb, sa, sb, P, tw, spl);
 		}
 #ifndef AEC_PASS_DIRECT
@@ -748,7 +834,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			}
 			cp_async_wait<0>();
 		}
-		__syncthreads();
+		MAIN_SYNC();
 		if (need_wnorm && t < M) {
 			float s = 0.f;
 			for (int w8 = 0; w8 < nwarps; ++w8) s += wpart[t * 8 + w8];
@@ -778,8 +864,9 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 		float2 *pc0 = pipe, *pc1 = pipe + L; // the cp.async ring is idle outside the block pass: scratch for the pair
 		specA[t] = yfg;
 		specB[t] = ybg;
-		__syncthreads();
+		MAIN_SYNC();
 		irfft_pair<LOG2L>(specA, ebuf, specB, ybuf, bufa, bufb, pc0, pc1, P, tw, spl);
+		if (SW) bar_wait<BAR_INPUT, NT_ALL>(); // the serial warp's filtered microphone frame
 		float Sff, Dbf, See;
 		{
 			const float ef = input[t] - ebuf[t + F], dd = ebuf[t + F] - ybuf[t + F], eb = input[t] - ybuf[t + F];
@@ -787,7 +874,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			Dbf = dd * dd;
 			See = eb * eb;
 			ebuf[t] = eb;
-			block_sum3(Sff, Dbf, See, red);
+			block_sum3<LOG2L>(Sff, Dbf, See, red);
 			Dbf = 10 + Dbf;
 		}
 
@@ -800,7 +887,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 		if ((Sff - See) * fabsf(Sff - See) > (Sff * Dbf)) update_foreground = 1;
 		else if ((Davg1 * fabsf(Davg1)) > (.5f * Dvar1)) update_foreground = 1;
 		else if ((Davg2 * fabsf(Davg2)) > (.25f * Dvar2)) update_foreground = 1;
-		__syncthreads(); // everyone has read sc[] before it is rewritten
+		MAIN_SYNC(); // everyone has read sc[] before it is rewritten
 		if (update_foreground) {
 			Davg1 = Davg2 = 0;
 			Dvar1 = Dvar2 = 0;
@@ -818,7 +905,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 					float n2 = warp_sum(w.x * w.x + w.y * w.y);
 					if (lane == 0) wpart[j * 8 + warp] = n2;
 				}
-				__syncthreads();
+				MAIN_SYNC();
 				if (t < M) {
 					float s = 0.f;
 					for (int w8 = 0; w8 < nwarps; ++w8) s += wpart[t * 8 + w8];
@@ -838,43 +925,58 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			sc[SC_DVAR1] = Dvar1;
 			sc[SC_DVAR2] = Dvar2;
 		}
-		__syncthreads();
+		MAIN_SYNC();
 
-		// ---- output with de-emphasis (serial IIR) and saturation test
-		const int sat = block_any(mic_i <= -32000 || mic_i >= 32000);
-		tmpv[t] = input[t] - ebuf[t + F];
-		__syncthreads();
-		if (t == 0) {
-			float memE = sc[SC_MEME];
-			const float pre = P.preemph;
-#pragma unroll 2
-			for (int i = 0; i < F; i += 4) {
-				float4 v = *reinterpret_cast<const float4 *>(tmpv + i);
-				v.x = v.x + pre * memE;
-				v.y = v.y + pre * v.x;
-				v.z = v.z + pre * v.y;
-				v.w = v.w + pre * v.z;
-				memE = v.w;
-				*reinterpret_cast<float4 *>(tmpv + i) = v;
-			}
-			sc[SC_MEME] = memE;
-			if (sat && si[IN_SATURATED] == 0) si[IN_SATURATED] = 1;
-		}
-		__syncthreads();
-		int out_i = word2int(tmpv[t]);
-
-		// ---- error / echo-estimate spectra for the next update
+		// ---- output signal and saturation test. The error / echo-estimate signals and their energies are settled first
+		// (every thread touches its own elements only), so that the frame's sanity verdict is known BEFORE the serial
+		// de-emphasis is handed over: a reset also clears that filter's memory.
+		const int sat = block_any<LOG2L>(mic_i <= -32000 || mic_i >= 32000);
+		const float de_in = input[t] - ebuf[t + F];
 		{
 			const float ev = ebuf[t];
-			__syncthreads();
 			ebuf[t + F] = ev;
 			ebuf[t] = 0.f;
-			__syncthreads();
 		}
 		float Sey = ebuf[t + F] * ybuf[t + F], Syy = ybuf[t + F] * ybuf[t + F], Sdd = input[t] * input[t];
-		block_sum3(Sey, Syy, Sdd, red);
+		block_sum3<LOG2L>(Sey, Syy, Sdd, red);
+		// ---- sanity checks
+		float lasty0, lasty1; // st->last_y halves as the preprocessor's residual-echo estimate will see them
+		int screwed = si[IN_SCREWED];
+		bool zero_out = false;
+		if (!(Syy >= 0 && Sxx >= 0 && See >= 0) || !(Sff < N * 1e9 && Syy < N * 1e9 && Sxx < N * 1e9)) {
+			screwed += 50;
+			zero_out = true;
+		} else if (Sff > Sdd + (float)(N * 10000)) {
+			screwed++;
+		} else {
+			screwed = 0;
+		}
+		// ---- de-emphasis (serial IIR) of the output, in place in tmpv
+		tmpv[t] = de_in;
 		ybuf[t] = 0.f;
-		__syncthreads();
+		if (t == 0 && sat && si[IN_SATURATED] == 0) si[IN_SATURATED] = 1;
+		if (SW) {
+			if (t == 0) sw_reset[0] = screwed >= 50;
+			bar_arrive<BAR_DEEMPH_IN, NT_ALL>(); // the serial warp filters while the transforms and statistics below run
+		} else {
+			MAIN_SYNC();
+			if (t == 0) {
+				float memE = sc[SC_MEME];
+				const float pre = P.preemph;
+#pragma unroll 2
+				for (int i = 0; i < F; i += 4) {
+					float4 v = *reinterpret_cast<const float4 *>(tmpv + i);
+					v.x = v.x + pre * memE;
+					v.y = v.y + pre * v.x;
+					v.z = v.z + pre * v.y;
+					v.w = v.w + pre * v.z;
+					memE = v.w;
+					*reinterpret_cast<float4 *>(tmpv + i) = v;
+				}
+				sc[SC_MEME] = memE;
+			}
+		}
+		MAIN_SYNC();
 		// E (kept for the next frame's gradient) and Y in one paired transform
 		rfft_pair<LOG2L>(ebuf, Eprev, ybuf, specB, bufa, bufb, pc0, pc1, P, tw, spl);
 		// Rf -> vec1, Yf -> vec2, Xf -> vec3 (F+1 bins; bin F is the Nyquist term held by thread 0)
@@ -890,22 +992,8 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				vec3[t] = x0.x * x0.x + x0.y * x0.y;
 			}
 		}
-		__syncthreads();
-
-		// ---- sanity checks
-		float lasty0, lasty1; // st->last_y halves as the preprocessor's residual-echo estimate will see them
-		int screwed = si[IN_SCREWED];
-		bool zero_out = false;
-		if (!(Syy >= 0 && Sxx >= 0 && See >= 0) || !(Sff < N * 1e9 && Syy < N * 1e9 && Sxx < N * 1e9)) {
-			screwed += 50;
-			zero_out = true;
-		} else if (Sff > Sdd + (float)(N * 10000)) {
-			screwed++;
-		} else {
-			screwed = 0;
-		}
-		if (zero_out) out_i = 0;
-		__syncthreads();
+		MAIN_SYNC();
+		int adapted_now = 0;
 		if (screwed >= 50) {
 			// speex_echo_state_reset(): filters, history and statistics back to their initial values
 			for (int j = 0; j < M; ++j) {
@@ -927,7 +1015,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			xw[t] = 0;
 			xw[F + t] = 0;
 			if (t < M) S[ly.wnorm + t] = 0;
-			__syncthreads();
+			MAIN_SYNC();
 			if (t == 0) {
 				si[IN_CANCEL_COUNT] = 0;
 				si[IN_SCREWED] = 0;
@@ -940,7 +1028,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				sc[SC_PEY] = sc[SC_PYY] = 1.f;
 				sc[SC_DAVG1] = sc[SC_DAVG2] = sc[SC_DVAR1] = sc[SC_DVAR2] = 0;
 			}
-			__syncthreads();
+			MAIN_SYNC();
 			// the library returns before the adaptation statistics; the preprocessor still runs on `out`
 		} else {
 			if (t == 0) {
@@ -966,7 +1054,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				S[ly.Yh + j] = (1 - P.spec_average) * Yh_old + P.spec_average * vec2[j];
 			}
 			float unused3 = 0.f;
-			block_sum3(pey_part, pyy_part, unused3, red);
+			block_sum3<LOG2L>(pey_part, pyy_part, unused3, red);
 			float Pey = 1.f + pey_part;
 			float Pyy = 1.f + pyy_part;
 			Pyy = (float)sqrt((double)Pyy);
@@ -987,7 +1075,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			int adapted = si[IN_ADAPTED];
 			float sum_adapt = sc[SC_SUM_ADAPT];
 			if (!adapted && sum_adapt > (float)M && leak * Syy > .03f * Syy) adapted = 1;
-			__syncthreads();
+			MAIN_SYNC();
 			if (adapted) {
 				for (int i = t; i <= F; i += F) {
 					float r = leak * vec2[i];
@@ -1013,15 +1101,20 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				sc[SC_SUM_ADAPT] = sum_adapt;
 				si[IN_ADAPTED] = adapted;
 			}
-			// ---- last_y (residual echo input for the preprocessor)
+			adapted_now = adapted;
+		}
+		// ---- the output frame (the de-emphasis is done by now), then last_y (residual echo input for the preprocessor)
+		if (SW) bar_wait<BAR_DEEMPH_OUT, NT_ALL>();
+		const int out_i = zero_out ? 0 : word2int(tmpv[t]);
+		if (screwed < 50) {
 			lasty0 = lasty1 = stg[SG_LASTY1 * F + t];
 			S[ly.last_y + t] = lasty0;
-			if (adapted) {
+			if (adapted_now) {
 				lasty1 = (float)(mic_i - out_i);
 				S[ly.last_y + F + t] = lasty1;
 			}
-			__syncthreads();
 		}
+		MAIN_SYNC();
 
 		// ========================================================================= speex_preprocess_run
 		{
@@ -1055,7 +1148,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 			ebuf[t] = stg[SG_INBUF * F + t] * P.pwindow[t];
 			ebuf[F + t] = (float)out_i * P.pwindow[F + t];
 			S[ly.inbuf + t] = (float)out_i;
-			__syncthreads();
+			MAIN_SYNC();
 			rfft_pair<LOG2L>(tmpv, specB, ebuf, specA, bufa, bufb, pc0, pc1, P, tw, spl);
 			// weighted copies for the three filterbank_compute_bank32() calls: the per-band sums below then only add
 			float *eR = reinterpret_cast<float *>(pc0), *eL = eR + F, *pR = reinterpret_cast<float *>(pc1), *pL = pR + F;
@@ -1080,7 +1173,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				pR[t] = fr * pv;
 				pL[t] = fl * pv;
 			}
-			__syncthreads();
+			MAIN_SYNC();
 			// ---- update_noise_prob
 			const int min_range = nb_adapt < 100 ? 15 : (nb_adapt < 1000 ? 50 : (nb_adapt < 10000 ? 150 : 300));
 			{
@@ -1113,7 +1206,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				S[ly.noise + t] = nz;
 			}
 			if (min_count > min_range) min_count = 0;
-			__syncthreads();
+			MAIN_SYNC();
 			// ---- the three Bark filterbanks at once (3 * Mb threads; filterbank_compute_bank32's accumulation order)
 			for (int u = t; u < 3 * Mb; u += F) { // one trip unless F < 3 * Mb (8 kHz)
 				const int which = u / Mb, b = u - which * Mb;
@@ -1132,7 +1225,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				for (int i = c1; i < c2; ++i) acc += Lw[i];
 				dst[F + b] = acc;
 			}
-			__syncthreads();
+			MAIN_SYNC();
 			// ---- SNRs over F + Mb entries (thread t: bin t; threads < Mb also band F + t)
 			float post_me[2], old_ps_me[2];
 			for (int r = 0; r < 2; ++r) {
@@ -1151,7 +1244,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				post_me[r] = post;
 				old_ps_me[r] = old_ps;
 			}
-			__syncthreads();
+			MAIN_SYNC();
 			// ---- zeta
 			{
 				float z = r_zeta;
@@ -1164,7 +1257,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 					S[ly.zeta + F + t] = zb;
 					gains[F + t] = zb; // stash band zeta for Zframe
 				}
-				__syncthreads();
+				MAIN_SYNC();
 			}
 			// every thread sums the Mb band zetas itself (same order): no broadcast barrier
 			float Zframe = 0;
@@ -1194,7 +1287,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				tmpv[Mb + t] = gain2b;
 				tmpv[2 * Mb + t] = gfl;
 			}
-			__syncthreads();
+			MAIN_SYNC();
 			// ---- linear-frequency gains
 			{
 				const float gain_b = tmpv[bl] * fl + tmpv[bl + 1] * fr;
@@ -1212,7 +1305,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				gains[t] = tq * tq;
 				S[ly.echo_noise + t] = echo_noise[t];
 				if (t < Mb) S[ly.echo_noise + F + t] = echo_noise[F + t]; // band part is recomputed each frame
-				__syncthreads();
+				MAIN_SYNC();
 			}
 			// ---- apply gain, inverse FFT, synthesis window, overlap-add
 			{
@@ -1225,7 +1318,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 					f.y = gains[t] * f.y;
 				}
 				specA[t] = f;
-				__syncthreads();
+				MAIN_SYNC();
 			}
 			irfft<LOG2L>(specA, tmpv, bufa, bufb, P, tw, spl);
 			{
@@ -1238,7 +1331,7 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 				si[IN_NB_ADAPT] = nb_adapt;
 				si[IN_MIN_COUNT] = min_count;
 			}
-			__syncthreads();
+			MAIN_SYNC();
 		}
 	}
 
@@ -1247,7 +1340,8 @@ __global__ void __launch_bounds__(1 << LOG2L, ((256 * CTAS) >> LOG2L) > 32 ? 32 
 	S[ly.xprev + t] = xw[F + t];
 	for (int i = t; i <= F; i += F) S[ly.power_1 + i] = power_1[i];
 	for (int i = t; i < M; i += F) S[ly.prop + i] = prop[i];
-	if (t < SC_COUNT) S[ly.scal + t] = sc[t];
+	// (the two input filters' memories belong to the serial warp in SW builds)
+	if (t < SC_COUNT && !(SW && (t == SC_NOTCH0 || t == SC_NOTCH1 || t == SC_MEMD || t == SC_MEME))) S[ly.scal + t] = sc[t];
 	if (t < IN_COUNT) reinterpret_cast<int *>(S + ly.ints)[t] = t == IN_HEAD ? head : si[t];
 }
 
@@ -1259,6 +1353,8 @@ struct msb200_aec {
 	AecParams P;
 	msb200_devbuf counts; // per-stream frame counts of a ragged host call
 	size_t smem_bytes;
+	size_t smem_bytes_sw; // the build with the serial warp (48 kHz)
+	int path;             // msb200_aec_set_path: 0 serial warp (default), 1 the 256-thread build, 3 serial warp at 3 CTAs per SM
 	float2 *dX, *dW, *dFG;
 	float *dS;
 	void *d_tables;
@@ -1271,10 +1367,11 @@ static float to_bark(float n) {
 	return 13.1f * (float)atan(.00074f * n) + 2.24f * (float)atan(n * n * 1.85e-8f) + 1e-4f * n;
 }
 
-static size_t aec_smem_floats(int F, int M) {
+static size_t aec_smem_floats(int F, int M, bool sw = false) {
 	const int N = 2 * F, L = F;
 	size_t f2 = (size_t)(L / 2) + (L + 2) + 5 * (size_t)L + (size_t)AEC_OWN_STAGES * 3 * L; // tw, spl, bufa, bufb, specA, specB, Eprev, pipe (own slots)
 	size_t fl = (size_t)N * 4 + F + (F + 1) + 5 * (size_t)((F + NB_BANDS + 1 + 3) & ~3) + M + (size_t)M * 8 + 32 + SC_COUNT + IN_COUNT;
+	if (sw) fl += 4 + 4 + 3 * (size_t)F; // reset flag, alignment slack, micf[F], inq[2][F]
 	return f2 * 2 + fl;
 }
 
@@ -1312,6 +1409,8 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	a->ctx = ctx;
 	a->n = a->live = n_streams;
 	a->tail_ms = tail_length_ms;
+	a->path = getenv("MSB200_AEC_PATH") ? atoi(getenv("MSB200_AEC_PATH")) : 0;
+	if (a->path != 1 && a->path != 3) a->path = 0;
 	a->filter_length = filter_length;
 	AecParams &P = a->P;
 	P.F = F; P.N = N; P.M = M; P.L = L; P.rate = sample_rate;
@@ -1443,7 +1542,10 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	int r = aec_write_init(a, 0, n_streams);
 	if (r) return r;
 	a->smem_bytes = aec_smem_floats(F, M) * sizeof(float);
+	a->smem_bytes_sw = aec_smem_floats(F, M, true) * sizeof(float);
 	MSB200_SMEM_OPTIN((aec_kernel<8, AEC_CTAS_PER_SM_256>), ctx, a->smem_bytes);
+	MSB200_SMEM_OPTIN((aec_kernel<8, AEC_CTAS_PER_SM_256, true>), ctx, a->smem_bytes_sw);
+	MSB200_SMEM_OPTIN((aec_kernel<8, 3, true>), ctx, a->smem_bytes_sw);
 	MSB200_SMEM_OPTIN((aec_kernel<8, 5>), ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN((aec_kernel<8, 6>), ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN(aec_kernel<7>, ctx, a->smem_bytes);
@@ -1508,7 +1610,13 @@ int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int 
 		case 256: {
 			// occupancy A/B (profiling): MSB200_AEC_CTAS=5 selects the 48-register build (5 CTAs per SM), 6 the 40-register one
 			static const int ctas = getenv("MSB200_AEC_CTAS") ? atoi(getenv("MSB200_AEC_CTAS")) : AEC_CTAS_PER_SM_256;
-			if (ctas == 5) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 5>), a->live, 256, a->smem_bytes, AEC_ARGS);
+			// serial warp (default): 288 threads per CTA; msb200_aec_set_path / MSB200_AEC_PATH select the 256-thread build
+			// (1) or the serial-warp build at 3 CTAs per SM (3: 72 registers instead of 56) for A/B runs and cross-checks
+			const int sw = a->path == 0 ? 1 : (a->path == 1 ? 0 : 3);
+			if (sw == 3) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 3, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
+			else if (sw && ctas == AEC_CTAS_PER_SM_256)
+				MSB200_LAUNCH(a->ctx, (aec_kernel<8, AEC_CTAS_PER_SM_256, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
+			else if (ctas == 5) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 5>), a->live, 256, a->smem_bytes, AEC_ARGS);
 			else if (ctas == 6) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 6>), a->live, 256, a->smem_bytes, AEC_ARGS);
 			else MSB200_LAUNCH(a->ctx, (aec_kernel<8, AEC_CTAS_PER_SM_256>), a->live, 256, a->smem_bytes, AEC_ARGS);
 			break;
@@ -1565,6 +1673,11 @@ int msb200_aec_process_counts(msb200_aec *a, const int16_t *mic, const int16_t *
 		return r;
 	if (a->live > 0) MSB200_CUDA(cudaMemcpy2DAsync(out, pitch, a->out.p, pitch, row, (size_t)a->live, cudaMemcpyDeviceToHost, s));
 	MSB200_HOST_DONE(a->ctx);
+	return MSB200_OK;
+}
+int msb200_aec_set_path(msb200_aec *a, int path) {
+	MSB200_CHECK_ARG(a && (path == 0 || path == 1 || path == 3));
+	a->path = path;
 	return MSB200_OK;
 }
 int msb200_aec_set_live(msb200_aec *a, int n_live) {

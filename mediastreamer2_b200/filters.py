@@ -298,6 +298,9 @@ class SpeexEC:
         check(self.lib.msb200_aec_process(self.h, _ptr(mic), _ptr(ref), _ptr(out), mic.shape[1] // self.frame_size))
         return out
 
+    def set_path(self, path: int):
+        check(self.lib.msb200_aec_set_path(self.h, path))
+
     def probe(self, stream: int, what: str, max_floats: int) -> np.ndarray:
         buf = np.zeros(max_floats, np.float32)
         n = self.lib.msb200_aec_probe(self.h, stream, what.encode(), _ptr(buf), max_floats)

@@ -67,6 +67,80 @@ def test_aec_first_frames_match_oracle(ctx, rate, tail):
     ec.close()
 
 
+def test_aec_serial_warp_build_is_bit_identical_to_the_plain_build(ctx):
+    """48 kHz: the default kernel hands the frame's sequential IIR filters (DC notch, pre-emphasis, de-emphasis) to a ninth
+    warp that runs beside the per-bin threads; same operations in the same order, so samples AND state must equal the
+    256-thread build's bit for bit — including saturated microphone frames, ragged frame counts (1, 2, 3 frames per call)
+    and a stream driven into speex_echo_state_reset (the reset also clears the filters' memories)."""
+    rate, tail, n_streams, nframes = 48000, 250, 5, 90
+    banks = {p: F.SpeexEC(ctx, n_streams, rate, tail) for p in (0, 1, 3)}
+    for p, ec in banks.items():
+        ec.set_path(p)
+    Fs = banks[0].frame_size
+    n = Fs * nframes
+    mics, refs = [], []
+    for s in range(n_streams):
+        x, mic, _, _ = cfg2_stream(70 + s, n, rate)
+        mics.append(mic.copy())
+        refs.append(x.copy())
+    mics, refs = np.stack(mics), np.stack(refs)
+    mics[1, 20 * Fs:23 * Fs] = 32767  # saturation: the adaptation freezes for a frame
+    outs = {}
+    for p, ec in banks.items():
+        got = np.zeros_like(mics)
+        k, step = 0, 1
+        while k < nframes:
+            if k == 30:
+                # stream 4: an absurd foreground filter -> the frame's sanity checks trip -> speex_echo_state_reset
+                blob = bytearray(ec.get_state_blob(4))
+                w = np.frombuffer(blob, np.float32, offset=16)
+                w[w.size // 2:] = 1e18
+                ec.set_state_blob(4, bytes(blob))
+            c = min(step, nframes - k)
+            sl = slice(k * Fs, (k + c) * Fs)
+            got[:, sl] = ec.process(np.ascontiguousarray(mics[:, sl]), np.ascontiguousarray(refs[:, sl]))
+            k += c
+            step = step % 3 + 1
+        outs[p] = got
+        assert ec.probe(4, "scalars", 16)[11] < 60  # cancel_count restarted: the reset did happen
+    M, N = banks[0].info.M, banks[0].info.window_size
+    for p in (0, 3):
+        assert np.array_equal(outs[p], outs[1]), (p, np.abs(outs[p].astype(int) - outs[1].astype(int)).max())
+        for s in range(n_streams):
+            for what, size in (("W", M * N), ("foreground", M * N), ("X", (M + 1) * N), ("E", N), ("power_1", Fs + 1),
+                               ("noise", Fs), ("scalars", 16)):
+                a, b = banks[p].probe(s, what, size), banks[1].probe(s, what, size)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (p, s, what)
+    for ec in banks.values():
+        ec.close()
+
+
+def test_aec_serial_warp_build_at_full_occupancy(ctx):
+    """the same identity on a grid that fills the chip several times over (four CTAs per SM, every hand-off between the
+    serial warp and the per-bin threads contended): 2048 streams x 8 frames in calls of 2 frames"""
+    rate, n_streams, nframes = 48000, 2048, 8
+    Fs = 256
+    rng = np.random.default_rng(11)
+    base = np.stack([np.stack(cfg2_stream(500 + s, Fs * nframes, rate)[:2]) for s in range(16)])  # [16][2][n]
+    pick = rng.integers(0, 16, n_streams)
+    gain = rng.uniform(0.3, 1.0, (n_streams, 1))
+    refs = (base[pick, 0] * gain).astype(np.int16)
+    mics = (base[pick, 1] * gain).astype(np.int16)
+    outs = {}
+    for p in (0, 1):
+        ec = F.SpeexEC(ctx, n_streams, rate, 250)
+        ec.set_path(p)
+        got = np.zeros_like(mics)
+        for k in range(0, nframes, 2):
+            sl = slice(k * Fs, (k + 2) * Fs)
+            got[:, sl] = ec.process(np.ascontiguousarray(mics[:, sl]), np.ascontiguousarray(refs[:, sl]))
+        outs[p] = (got, np.stack([ec.probe(s, "E", 2 * Fs) for s in range(0, n_streams, 97)]))
+        ec.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    assert np.abs(outs[0][0]).max() > 0
+
+
 def _erle(mic, out, near, rate, lo, hi):
     seg = slice(int(lo * rate), int(hi * rate))
     m = np.abs(near[seg]) < 1
