@@ -278,9 +278,10 @@ MSB200_API void msb200_aec_destroy(msb200_aec *a);
 MSB200_API int msb200_aec_get_info(msb200_aec *a, msb200_aec_info *info);
 MSB200_API int msb200_aec_reset(msb200_aec *a, int stream); /* stream < 0: all */
 MSB200_API int msb200_aec_set_live(msb200_aec *a, int n_live); /* see msb200_volume_set_live */
-/* Cross-check switch for the 48 kHz kernel builds (results are bit-identical, the tests assert it): 0 = default (a ninth
- * "serial" warp runs the DC notch / pre-emphasis / de-emphasis IIRs beside the 256 per-bin threads), 1 = the 256-thread
- * build (one of the per-bin threads runs them, the others wait), 3 = the serial-warp build at 3 CTAs per SM. */
+/* Cross-check switch for the 48 kHz kernel builds (results are bit-identical, the tests assert it): 0 = default, 1 = the
+ * 256-thread build (one of the per-bin threads runs the frame's sequential IIR filters, the others wait), 3 / 4 = builds
+ * with a ninth "serial" warp that runs those filters beside the per-bin threads (3: at 3 CTAs per SM; 4: the serial warp
+ * also feeds the block pass with cp.async.bulk row copies instead of per-thread cp.async). */
 MSB200_API int msb200_aec_set_path(msb200_aec *a, int path);
 MSB200_API int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes);
 MSB200_API int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes,
@@ -447,6 +448,13 @@ MSB200_API int msb200_chain_wait(msb200_chain *c); /* waits for the OLDEST tick 
 /* Device path: inputs/outputs already resident; asynchronous. */
 MSB200_API int msb200_chain_tick_dev(msb200_chain *c, const void *d_ref_in, const void *d_mic_in, void *d_out,
                                      int *out_samples);
+/* Overlap mode of msb200_chain_tick_dev (msb200_chain_submit: with MSB200_CHAIN_OVERLAP=1): the resamplers of tick T+1 and the
+ * volume / hand-out of tick T-1 run on side streams beside the echo canceller of tick T, so the cancellers of consecutive
+ * ticks run back to back. Same samples. What changes for the caller: d_ref_in / d_mic_in must be COMPLETE when the call is
+ * made (not merely ordered on the context's stream), and d_out is complete in the context's stream order only after
+ * msb200_chain_join(). Ignored for conference chains (mixer_pins > 0). */
+MSB200_API int msb200_chain_set_overlap(msb200_chain *c, int enabled);
+MSB200_API int msb200_chain_join(msb200_chain *c);
 MSB200_API int msb200_chain_launches_per_tick(msb200_chain *c);
 /* Per-kernel device timing of the dominant kernel (the echo canceller) with CUDA events recorded on the launching
  * stream around every AEC launch while enabled; get_ returns the accumulated milliseconds, launches and frames since

@@ -221,6 +221,8 @@ _SIGS = {
     "msb200_chain_submit": (_I, [_P, _P, _P, _P, _PI]),
     "msb200_chain_wait": (_I, [_P]),
     "msb200_chain_tick_dev": (_I, [_P, _P, _P, _P, _PI]),
+    "msb200_chain_set_overlap": (_I, [_P, _I]),
+    "msb200_chain_join": (_I, [_P]),
     "msb200_chain_launches_per_tick": (_I, [_P]),
     "msb200_chain_aec": (_P, [_P]),
     "msb200_chain_enable_kernel_timing": (_I, [_P, _I]),

@@ -39,6 +39,7 @@ struct AecParams {
 	int F, N, M, L, log2L, rate;
 	float spec_average, beta0, beta_max, notch_radius, preemph;
 	int noise_suppress, echo_suppress, echo_suppress_active;
+	float noise_floor; // (float)exp(.2302585f * noise_suppress)
 	AecLayout lay;
 	size_t x_stride, w_stride; // float2 per stream for X and for W / FG
 	// bank-wide constant tables (device pointers)
@@ -108,7 +109,40 @@ template <int ID, int NT> __device__ __forceinline__ void bar_wait() {
 	asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory");
 }
 #define MAIN_SYNC() bar_main<(1 << LOG2L)>()
-enum { BAR_INPUT = 2, BAR_DEEMPH_IN = 3, BAR_DEEMPH_OUT = 4 };
+enum { BAR_INPUT = 2, BAR_DEEMPH_IN = 3, BAR_DEEMPH_OUT = 4, BAR_RING_OWN = 5, BAR_RING_ALIAS = 6 };
+
+// ------------------------------------------------------------------------------------------------ bulk copies (TMA)
+// TMA builds: the serial warp's lane 0 is also the PRODUCER of the block pass. It moves every 2 KB row X_{j+1}, FG_j, W_j
+// with one cp.async.bulk (UBLKCP) into the ring and the per-bin threads wait on the slot's "full" mbarrier, instead of
+// every thread copying its own 8 bytes with LDGSTS (3 LDGSTS per thread and block were 2/3 of the pass's load on the
+// shared-memory pipe, the busiest unit of the kernel, plus the address bookkeeping). A slot goes back to the producer
+// through its "empty" mbarrier (one arrival per warp of per-bin threads).
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+	return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(bar),
+	             "r"(parity)
+	             : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+	             "r"(bytes), "r"(bar)
+	             : "memory");
+}
+// generic-proxy accesses (plain loads / stores, LDGSTS) before, async-proxy accesses (the bulk copies) after
+__device__ __forceinline__ void fence_proxy_async_all() {
+	asm volatile("fence.proxy.async;" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------------------------ block helpers
 // All helpers are called by every main thread of the CTA (threadIdx.x < F).
@@ -402,7 +436,7 @@ __device__ __forceinline__ float qcurve(float x) {
 // sat on those two barriers). The notch of frame k+1 now runs under the tail of frame k and the far-end transforms /
 // block pass of frame k+1 (none of them needs the microphone), the de-emphasis under the E / Y transforms and the
 // adaptation statistics. Same operations on the same operands in the same order: results are bit-identical.
-template <int LOG2L, int CTAS = AEC_CTAS_PER_SM_256, bool SW = false>
+template <int LOG2L, int CTAS = AEC_CTAS_PER_SM_256, bool SW = false, bool TMA = false>
 __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >> LOG2L) > 32 ? 32 : ((256 * CTAS) >> LOG2L))
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
@@ -466,7 +500,20 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 	int *sw_reset = si + IN_COUNT;                                                                  // [4]
 	float *micf = reinterpret_cast<float *>((reinterpret_cast<size_t>(sw_reset + 4) + 15) & ~(size_t)15); // [F]
 	float *inq = micf + F;                                                                          // [2][F]
+	unsigned long long *mbars = reinterpret_cast<unsigned long long *>(inq + 2 * F);                // [AEC_STAGES] full, [AEC_STAGES] empty (TMA)
 	constexpr int NT_ALL = F + 32;
+	static_assert(!TMA || SW, "the bulk-copy producer is the serial warp");
+	const unsigned pipe_s = smem_addr(pipe), full_s = smem_addr(mbars), empty_s = full_s + 8 * AEC_STAGES;
+	if (TMA) {
+		if (t == 0) {
+			for (int i = 0; i < AEC_STAGES; ++i) {
+				mbar_init(full_s + 8 * i, 1);               // the producer's arrive.expect_tx
+				mbar_init(empty_s + 8 * i, (F + 31) >> 5);  // lane 0 of every warp of per-bin threads
+			}
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads(); // every thread of the CTA: producer and consumers see the initialised barriers
+	}
 
 	float2 *X = gX + (size_t)stream * P.x_stride;
 	float2 *W = gW + (size_t)stream * P.w_stride;
@@ -482,6 +529,11 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 		float m0 = S[ly.scal + SC_NOTCH0], m1 = S[ly.scal + SC_NOTCH1], memD = S[ly.scal + SC_MEMD], memE = S[ly.scal + SC_MEME];
 		const float radius = P.notch_radius, pre = P.preemph;
 		const float den2 = radius * radius + .7f * (1 - radius) * (1 - radius);
+		// producer state (TMA builds): this stream's far-end ring head, whether the foreground array is stale (then W_j
+		// doubles as FG_j and no FG row is fetched), and the phase parity of every slot's "empty" barrier
+		int p_head = reinterpret_cast<const int *>(S + ly.ints)[IN_HEAD];
+		int p_fg_pending = reinterpret_cast<const int *>(S + ly.ints)[IN_FG_PENDING];
+		unsigned p_empty_par = (1u << AEC_STAGES) - 1; // a fresh barrier passes a wait for parity 1: every slot starts free
 		for (int fr = 0; fr < nframes; ++fr) {
 			const int fin = in_ring > 0 ? (in_frame0 + fr) % in_ring : fr;
 			const short *in_mic = mic + (size_t)stream * io_stride + (size_t)fin * F;
@@ -511,8 +563,43 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			}
 			__syncwarp();
 			bar_arrive<BAR_INPUT, NT_ALL>();
+			if (TMA) {
+				// ---- the block pass's producer: rows X_{j+1}, FG_j, W_j of block j into ring slot j % AEC_STAGES
+				p_head = (p_head + M) % (M + 1);
+				int xslot = p_head + 1 > M ? 0 : p_head + 1;
+				const float2 *srcW = W, *srcF = FG;
+				const unsigned row_bytes = F * sizeof(float2);
+				const unsigned tx = p_fg_pending ? 2 * row_bytes : 3 * row_bytes;
+				for (int j0 = 0; j0 < M; j0 += AEC_STAGES) {
+#pragma unroll
+					for (int sidx = 0; sidx < AEC_STAGES; ++sidx) {
+						const int j = j0 + sidx;
+						if (j < M) {
+							// the ring's memory is the per-bin threads' scratch outside the pass: the slots with storage of
+							// their own are handed over at the top of the frame, the aliased ones when the pre-pass is over
+							if (j == 0) bar_wait<BAR_RING_OWN, NT_ALL>();
+							if (j == AEC_OWN_STAGES) bar_wait<BAR_RING_ALIAS, NT_ALL>();
+							if (lane == 0) {
+								mbar_wait(empty_s + 8 * sidx, (p_empty_par >> sidx) & 1);
+								const unsigned dst = pipe_s + sidx * 3 * row_bytes, bar = full_s + 8 * sidx;
+								mbar_expect_tx(bar, tx);
+								bulk_g2s(dst, X + (size_t)xslot * F, row_bytes, bar);
+								if (!p_fg_pending) bulk_g2s(dst + row_bytes, srcF, row_bytes, bar);
+								bulk_g2s(dst + 2 * row_bytes, srcW, row_bytes, bar);
+							}
+							p_empty_par ^= 1u << sidx;
+							xslot = xslot == M ? 0 : xslot + 1;
+							srcW += F;
+							srcF += F;
+							__syncwarp();
+						}
+					}
+				}
+				if (M <= AEC_OWN_STAGES) bar_wait<BAR_RING_ALIAS, NT_ALL>(); // keep the hand-off counts in step
+			}
 			bar_wait<BAR_DEEMPH_IN, NT_ALL>(); // tmpv = this frame's error signal, sw_reset = its verdict
 			const int reset = sw_reset[0];
+			if (TMA) p_fg_pending = reset ? 0 : si[IN_FG_PENDING]; // as the next frame's pass will find it
 			if (lane == 0) {
 #pragma unroll 2
 				for (int i = 0; i < F; i += 4) {
@@ -550,6 +637,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 	MAIN_SYNC();
 
 	int head = si[IN_HEAD];
+	unsigned full_par = 0; // phase parity of every ring slot's "full" barrier (TMA builds)
 	for (int fr = 0; fr < nframes; ++fr) {
 		// frame addressing: linear, or frame-aligned circular buffers (chain re-framing between 10 ms ticks and frames)
 		const int fin = in_ring > 0 ? (in_frame0 + fr) % in_ring : fr;
@@ -594,11 +682,18 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			if (--x_left == 0) gX_pf -= x_ring;
 		};
 #ifndef AEC_PASS_DIRECT
+		if (TMA) {
+			// the producer may fill the ring's own slots from here on. Everything it will read (last frame's W / FG / X
+			// stores) and overwrite (the slots, last frame's scratch) was accessed through the generic proxy: fence first
+			fence_proxy_async_all();
+			bar_arrive<BAR_RING_OWN, NT_ALL>();
+		} else {
 		// early prologue: the ring slots with storage of their own (the aliased ones are still scratch until the pre-pass ends)
 #pragma unroll
 		for (int pj = 0; pj < (AEC_OWN_STAGES < AEC_STAGES - 1 ? AEC_OWN_STAGES : AEC_STAGES - 1); ++pj) {
 			if (pj < M) prefetch(pj, pj);
 			cp_async_commit();
+		}
 		}
 #endif
 
@@ -659,18 +754,24 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 
 		// ---- adjust proportional adaptation rate (uses |W_j|^2 of the previous frame's final W)
 		if (si[IN_ADAPTED]) {
-			// mdf_adjust_prop: prop_j = sqrt(1 + |W_j|^2); += .1*max; normalise to .99
-			if (t < M) prop[t] = (float)sqrt((double)(1.f + S[ly.wnorm + t]));
+			// mdf_adjust_prop: prop_j = sqrt(1 + |W_j|^2); += .1*max; normalise to .99. One warp does it: the maximum by
+			// shuffles (exact in any order), the sum of the M terms in the library's sequential order by every lane at once
+			// (M dependent adds; one thread walking all three loops alone cost 4.5 % of the kernel's warp time in the
+			// adapted regime, everybody else at the barrier), the rest per element. (float)sqrt((double)x) is the correctly
+			// rounded float square root (53 >= 2 * 24 + 2 bits: no double rounding), i.e. __fsqrt_rn.
+			for (int i = t; i < M; i += F) prop[i] = __fsqrt_rn(1.f + S[ly.wnorm + i]);
 			MAIN_SYNC();
-			if (t == 0) {
-				float max_sum = 1, prop_sum = 1;
-				for (int i = 0; i < M; ++i)
-					if (prop[i] > max_sum) max_sum = prop[i];
-				for (int i = 0; i < M; ++i) {
-					prop[i] += .1f * max_sum;
-					prop_sum += prop[i];
-				}
-				for (int i = 0; i < M; ++i) prop[i] = (.99f * prop[i]) / prop_sum;
+			if (warp == 0) {
+				float mx = 1.f;
+				for (int i = lane; i < M; i += 32) mx = fmaxf(mx, prop[i]);
+#pragma unroll
+				for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+				for (int i = lane; i < M; i += 32) prop[i] += .1f * mx;
+				__syncwarp();
+				float prop_sum = 1.f;
+				for (int i = 0; i < M; ++i) prop_sum += prop[i];
+				__syncwarp();
+				for (int i = lane; i < M; i += 32) prop[i] = (.99f * prop[i]) / prop_sum;
 			}
 			MAIN_SYNC();
 		}
@@ -716,10 +817,15 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 		}
 #ifndef AEC_PASS_DIRECT
 		// late prologue: from here to the end of the pass bufa / bufb / specA / ebuf / ybuf / vec1 / vec2 are ring slots
+		if (TMA) {
+			fence_proxy_async_all();
+			bar_arrive<BAR_RING_ALIAS, NT_ALL>();
+		} else {
 #pragma unroll
 		for (int pj = AEC_OWN_STAGES; pj < AEC_STAGES - 1; ++pj) {
 			if (pj < M) prefetch(pj, pj);
 			cp_async_commit();
+		}
 		}
 #endif
 
@@ -760,10 +866,15 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 						if (fg_pending) gF_grp[sidx * F] = w;
 						if (j + 2 < M) fetch(sidx & 1, sidx + 2);
 #else
-						// keep AEC_STAGES-1 blocks in flight: the slot freed by block j-1 receives block j+STAGES-1
-						if (j + AEC_STAGES - 1 < M) prefetch((sidx + AEC_STAGES - 1) % AEC_STAGES, sidx + AEC_STAGES - 1);
-						cp_async_commit();
-						cp_async_wait<AEC_STAGES - 1>();
+						if (TMA) {
+							mbar_wait(full_s + 8 * sidx, (full_par >> sidx) & 1);
+							full_par ^= 1u << sidx;
+						} else {
+							// keep AEC_STAGES-1 blocks in flight: the slot freed by block j-1 receives block j+STAGES-1
+							if (j + AEC_STAGES - 1 < M) prefetch((sidx + AEC_STAGES - 1) % AEC_STAGES, sidx + AEC_STAGES - 1);
+							cp_async_commit();
+							cp_async_wait<AEC_STAGES - 1>();
+						}
 						const float2 *src = pipe_t + sidx * 3 * F;
 						const float2 xj1 = src[0];
 						float2 w = src[2 * F];
@@ -810,6 +921,11 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 							ybg.y += (xj.y * w.x + xj.x * w.y);
 						}
 						xj = xj1;
+						if (TMA) {
+							// the slot goes back to the producer once the whole warp has read its three rows
+							__syncwarp();
+							if (lane == 0) mbar_arrive(empty_s + 8 * sidx);
+						}
 					}
 					if (sidx % 3 == 2 && need_wnorm && j0 + sidx - 2 < M) {
 						// three warp sums for the price of one and a bit: after the first two folds the three quantities live
@@ -1057,7 +1173,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			block_sum3<LOG2L>(pey_part, pyy_part, unused3, red);
 			float Pey = 1.f + pey_part;
 			float Pyy = 1.f + pyy_part;
-			Pyy = (float)sqrt((double)Pyy);
+			Pyy = __fsqrt_rn(Pyy); // == (float)sqrt((double)Pyy), see mdf_adjust_prop above
 			Pey = Pey / Pyy;
 			float tmp32 = P.beta0 * Syy;
 			if (tmp32 > P.beta_max * See) tmp32 = P.beta_max * See;
@@ -1268,7 +1384,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			// ---- Bark-band gains: gain -> tmpv[0..Mb), gain2 -> tmpv[Mb..2Mb), gain_floor -> tmpv[2Mb..3Mb)
 			if (t < Mb) {
 				const int i = F + t;
-				const float noise_floor = (float)exp((double)(.2302585f * (float)P.noise_suppress));
+				const float noise_floor = P.noise_floor; // exp(.2302585 * noise_suppress): a constant of the bank (host)
 				const float echo_floor = (float)exp((double)(.2302585f * effective_echo_suppress));
 				const float gfl = (float)(sqrt((double)(noise_floor * noise[i] + echo_floor * echo_noise[i])) /
 				                          sqrt((double)(1 + noise[i] + echo_noise[i])));
@@ -1301,7 +1417,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 				if (.333f * g > gain_b) g = 3.f * gain_b;
 				S[ly.old_ps + t] = .2f * old_ps_me[0] + (.8f * (g * g)) * ps[t];
 				if (g < gfl) g = gfl;
-				const float tq = p * (float)sqrt((double)g) + (1.f - p) * (float)sqrt((double)gfl);
+				const float tq = p * __fsqrt_rn(g) + (1.f - p) * __fsqrt_rn(gfl); // correctly rounded, as the double detour is
 				gains[t] = tq * tq;
 				S[ly.echo_noise + t] = echo_noise[t];
 				if (t < Mb) S[ly.echo_noise + F + t] = echo_noise[F + t]; // band part is recomputed each frame
@@ -1371,7 +1487,7 @@ static size_t aec_smem_floats(int F, int M, bool sw = false) {
 	const int N = 2 * F, L = F;
 	size_t f2 = (size_t)(L / 2) + (L + 2) + 5 * (size_t)L + (size_t)AEC_OWN_STAGES * 3 * L; // tw, spl, bufa, bufb, specA, specB, Eprev, pipe (own slots)
 	size_t fl = (size_t)N * 4 + F + (F + 1) + 5 * (size_t)((F + NB_BANDS + 1 + 3) & ~3) + M + (size_t)M * 8 + 32 + SC_COUNT + IN_COUNT;
-	if (sw) fl += 4 + 4 + 3 * (size_t)F; // reset flag, alignment slack, micf[F], inq[2][F]
+	if (sw) fl += 4 + 4 + 3 * (size_t)F + 4 * AEC_STAGES; // reset flag, alignment slack, micf[F], inq[2][F], mbarriers
 	return f2 * 2 + fl;
 }
 
@@ -1410,7 +1526,7 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	a->n = a->live = n_streams;
 	a->tail_ms = tail_length_ms;
 	a->path = getenv("MSB200_AEC_PATH") ? atoi(getenv("MSB200_AEC_PATH")) : 0;
-	if (a->path != 1 && a->path != 3) a->path = 0;
+	if (a->path != 1 && a->path != 3 && a->path != 4) a->path = 0;
 	a->filter_length = filter_length;
 	AecParams &P = a->P;
 	P.F = F; P.N = N; P.M = M; P.L = L; P.rate = sample_rate;
@@ -1422,6 +1538,7 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	P.notch_radius = sample_rate < 12000 ? .9f : (sample_rate < 24000 ? .982f : .992f);
 	P.preemph = .9f;
 	P.noise_suppress = -15; P.echo_suppress = -40; P.echo_suppress_active = -15;
+	P.noise_floor = (float)exp((double)(.2302585f * (float)P.noise_suppress));
 	// small-state layout
 	AecLayout &ly = P.lay;
 	int o = 0;
@@ -1546,6 +1663,7 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	MSB200_SMEM_OPTIN((aec_kernel<8, AEC_CTAS_PER_SM_256>), ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN((aec_kernel<8, AEC_CTAS_PER_SM_256, true>), ctx, a->smem_bytes_sw);
 	MSB200_SMEM_OPTIN((aec_kernel<8, 3, true>), ctx, a->smem_bytes_sw);
+	MSB200_SMEM_OPTIN((aec_kernel<8, AEC_CTAS_PER_SM_256, true, true>), ctx, a->smem_bytes_sw);
 	MSB200_SMEM_OPTIN((aec_kernel<8, 5>), ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN((aec_kernel<8, 6>), ctx, a->smem_bytes);
 	MSB200_SMEM_OPTIN(aec_kernel<7>, ctx, a->smem_bytes);
@@ -1612,8 +1730,10 @@ int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int 
 			static const int ctas = getenv("MSB200_AEC_CTAS") ? atoi(getenv("MSB200_AEC_CTAS")) : AEC_CTAS_PER_SM_256;
 			// serial warp (default): 288 threads per CTA; msb200_aec_set_path / MSB200_AEC_PATH select the 256-thread build
 			// (1) or the serial-warp build at 3 CTAs per SM (3: 72 registers instead of 56) for A/B runs and cross-checks
-			const int sw = a->path == 0 ? 1 : (a->path == 1 ? 0 : 3);
-			if (sw == 3) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 3, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
+			const int sw = a->path == 0 ? 1 : (a->path == 1 ? 0 : a->path);
+			if (sw == 4)
+				MSB200_LAUNCH(a->ctx, (aec_kernel<8, AEC_CTAS_PER_SM_256, true, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
+			else if (sw == 3) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 3, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
 			else if (sw && ctas == AEC_CTAS_PER_SM_256)
 				MSB200_LAUNCH(a->ctx, (aec_kernel<8, AEC_CTAS_PER_SM_256, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
 			else if (ctas == 5) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 5>), a->live, 256, a->smem_bytes, AEC_ARGS);
@@ -1676,7 +1796,7 @@ int msb200_aec_process_counts(msb200_aec *a, const int16_t *mic, const int16_t *
 	return MSB200_OK;
 }
 int msb200_aec_set_path(msb200_aec *a, int path) {
-	MSB200_CHECK_ARG(a && (path == 0 || path == 1 || path == 3));
+	MSB200_CHECK_ARG(a && (path == 0 || path == 1 || path == 3 || path == 4));
 	a->path = path;
 	return MSB200_OK;
 }

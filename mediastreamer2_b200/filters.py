@@ -363,6 +363,12 @@ class AudioChain:
         check(self.lib.msb200_chain_get_kernel_timing(self.h, C.byref(ms), C.byref(nl), C.byref(nf)))
         return float(ms.value), nl.value, nf.value
 
+    def set_overlap(self, enabled: bool):
+        check(self.lib.msb200_chain_set_overlap(self.h, int(enabled)))
+
+    def join(self):
+        check(self.lib.msb200_chain_join(self.h))
+
     def tick_dev(self, d_ref: int, d_mic: int, d_out: int) -> int:
         got = C.c_int()
         check(self.lib.msb200_chain_tick_dev(self.h, C.c_void_p(d_ref), C.c_void_p(d_mic), C.c_void_p(d_out), C.byref(got)))

@@ -105,3 +105,42 @@ def test_chain_large_bank_crosses_the_4_gib_state_boundary(ctx):
             assert got[0].any()
     assert produced >= (ticks - 2) * (rate // 100)
     ch.close()
+
+
+@pytest.mark.parametrize("in_rate,rate,n", [(16000, 48000, 600), (8000, 16000, 64)])
+def test_overlap_mode_of_tick_dev_equals_the_serial_order(ctx, in_rate, rate, n):
+    """msb200_chain_set_overlap: the resamplers of tick T+1 and the volume / hand-out of tick T-1 on side streams beside
+    the canceller of tick T. Same samples as the one-stream order, tick by tick, with a grid that fills the chip (the side
+    streams really run beside the canceller) and a rate pair whose rings are as tight as the overlap's run-ahead allows;
+    switching the mode on and off in mid-stream included."""
+    ticks = 36
+    ti = in_rate // 100
+    base = [cfg2_stream(700 + s, ti * ticks, in_rate) for s in range(8)]
+    rng = np.random.default_rng(2)
+    pick, gain = rng.integers(0, 8, n), rng.uniform(0.4, 1.0, (n, 1))
+    ref = (np.stack([base[p][0] for p in pick]) * gain).astype(np.int16).reshape(n, ticks, ti)
+    mic = (np.stack([base[p][1] for p in pick]) * gain).astype(np.int16).reshape(n, ticks, ti)
+    d_ref, d_mic = ctx.dev_alloc(ticks * n * ti * 2), ctx.dev_alloc(ticks * n * ti * 2)
+    ctx.h2d(d_ref, np.ascontiguousarray(ref.transpose(1, 0, 2)))
+    ctx.h2d(d_mic, np.ascontiguousarray(mic.transpose(1, 0, 2)))
+    ctx.sync()
+    outs = []
+    for overlap in (False, True):
+        ch = F.AudioChain(ctx, n, in_rate, rate, 250, 0.8, 0)
+        d_out = ctx.dev_alloc(ticks * n * ch.max_out * 2)  # one output block per tick: nothing is overwritten in flight
+        got, sizes = np.zeros((ticks, n, ch.max_out), np.int16), []
+        for t in range(ticks):
+            ch.set_overlap(overlap and not 20 <= t < 24)  # a stretch of serial ticks in the middle of the overlapped run
+            sizes.append(ch.tick_dev(d_ref + t * n * ti * 2, d_mic + t * n * ti * 2, d_out + t * n * ch.max_out * 2))
+        ch.join()
+        ctx.d2h(got, d_out)
+        ctx.sync()
+        outs.append((got, sizes))
+        ch.close()
+        ctx.dev_free(d_out)
+    ctx.dev_free(d_ref)
+    ctx.dev_free(d_mic)
+    assert outs[0][1] == outs[1][1] and sum(outs[0][1]) > 0
+    for t, k in enumerate(outs[0][1]):
+        assert np.array_equal(outs[0][0][t, :, :k], outs[1][0][t, :, :k]), t
+    assert np.abs(outs[0][0]).max() > 0
