@@ -407,7 +407,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if tpath.exists():
         try:
             tj = json.loads(tpath.read_text())
-            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("capture")
+            if traffic and aec_launches and tj.get("frames_in_captured_launch"):  # per launch of THIS run's average frame count
+                traffic = traffic / tj["frames_in_captured_launch"] * (aec_frames / aec_launches)
         except ValueError:
             traffic = None
 

@@ -59,6 +59,24 @@ struct msb200_chain {
 	float t_ms;
 };
 
+// hand-out of a tick's EC / volume blocks: ring frames [wframe0, wframe0 + nframes) of every stream -> dst[stream][max_out],
+// 16 bytes per thread. A kernel, not cudaMemcpy2DAsync: a device-to-device copy is served by a copy engine, and in the
+// pipelined host path the copy engines are busy with the neighbouring ticks' PCIe transfers — the kernel stream then waited
+// for them between one tick's volume and the next tick's resamplers.
+__global__ void chain_handout_kernel(const short *__restrict__ ring, short *__restrict__ dst, int S, int F, int cap, int K, int max_out,
+                                     int wframe0, int nframes) {
+	const int vec_per_frame = F >> 3, vec_per_stream = nframes * vec_per_frame;
+	const long total = (long)S * vec_per_stream;
+	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+		const int stream = (int)(i / vec_per_stream), rem = (int)(i - (long)stream * vec_per_stream);
+		const int f = rem / vec_per_frame, v = rem - f * vec_per_frame;
+		int pos = wframe0 + f;
+		if (pos >= K) pos -= K;
+		const int4 *src = reinterpret_cast<const int4 *>(ring + (size_t)stream * cap + (size_t)pos * F) + v;
+		reinterpret_cast<int4 *>(dst + (size_t)stream * max_out + (size_t)f * F)[v] = *src;
+	}
+}
+
 static int chain_drain_events(msb200_chain *c) {
 	for (int i = 0; i + 1 < c->ev_used; i += 2) {
 		float ms = 0.f;
@@ -327,6 +345,14 @@ static int chain_tick_impl(msb200_chain *c, const void *d_ref_in, const void *d_
 	}
 	if (!c->mix) {
 		// 3a. hand the EC/volume output blocks to the caller: [stream][max_out], first nframes*F valid
+		if (nframes > 0 && nframes <= K && (c->F & 7) == 0 && ((uintptr_t)d_out & 15) == 0) {
+			const long vecs = (long)c->S * nframes * (c->F >> 3);
+			const long want = (vecs + 255) / 256;
+			c->ctx->stream = s;
+			MSB200_LAUNCH(c->ctx, chain_handout_kernel, (int)(want < (long)c->ctx->sm_count * 8 ? want : (long)c->ctx->sm_count * 8), 256, 0,
+			              (const short *)c->d_out_ring, (short *)d_out, c->S, c->F, c->cap, K, c->max_out, wframe0, nframes);
+			c->ctx->stream = sA;
+		} else
 		for (int f = 0; f < nframes; ++f) {
 			const int pos = (wframe0 + f) % K;
 			MSB200_CUDA(cudaMemcpy2DAsync((short *)d_out + (size_t)f * c->F, (size_t)c->max_out * 2,
