@@ -258,6 +258,76 @@ __device__ __forceinline__ void cfft_bfly(float2 *x, float2 *y, const float2 *tw
 		y = sw;
 	}
 }
+// The same transform as ONE out-of-line function for all seven call sites of a frame (AEC_FFT_INLINE builds keep the inlined
+// copies): the inlined butterflies were 1846 of the 48 kHz kernel's 7776 instructions (29 of 124 KB) — with four CTAs of an
+// SM in four different phases of the frame the kernel ran at 69 % of the instruction cache hierarchy's request rate and
+// 7.5 % of the warp stall samples were instruction fetches. Operands are shared-memory addresses (ld / st.shared, no generic
+// pointers across the call); the inverse transform's conjugated twiddle is a sign-bit flip, as `-w.y` is.
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_f2(unsigned a, float2 v) {
+	asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+template <int LOG2L> __device__ __noinline__ void cfft_core(unsigned x, unsigned y, unsigned tw, unsigned conj_mask, int active) {
+	constexpr int H = 1 << (LOG2L - 1), Q = H >> 1;
+	const int b = threadIdx.x & (H - 1);
+	auto bfly = [&](const float2 a, const float2 c, const float2 w, float2 &o0, float2 &o1) {
+		const float wr = w.x, wi = __int_as_float(__float_as_int(w.y) ^ (int)conj_mask);
+		o0.x = a.x + c.x;
+		o0.y = a.y + c.y;
+		const float dr = a.x - c.x, di = a.y - c.y;
+		o1.x = dr * wr - di * wi;
+		o1.y = dr * wi + di * wr;
+	};
+	constexpr int DOUBLE_END = LOG2L & ~1;
+#pragma unroll
+	for (int st = 0; st < DOUBLE_END; st += 2) {
+		if (active && b < Q) {
+			const int s = 1 << st;
+			const int ps = b & ~(s - 1);
+			float2 y0, y1, y0b, y1b, z0, z1, z2, z3;
+			bfly(lds_f2(x + 8 * b), lds_f2(x + 8 * (b + H)), lds_f2(tw + 8 * ps), y0, y1);
+			bfly(lds_f2(x + 8 * (b + Q)), lds_f2(x + 8 * (b + Q + H)), lds_f2(tw + 8 * (ps + Q)), y0b, y1b);
+			const float2 w2 = lds_f2(tw + 16 * ps);
+			bfly(y0, y0b, w2, z0, z2);
+			bfly(y1, y1b, w2, z1, z3);
+			const unsigned o = y + 8 * (b + 3 * ps);
+			sts_f2(o, z0);
+			sts_f2(o + 8 * s, z1);
+			sts_f2(o + 16 * s, z2);
+			sts_f2(o + 24 * s, z3);
+		}
+		MAIN_SYNC();
+		const unsigned sw = x;
+		x = y;
+		y = sw;
+	}
+#pragma unroll
+	for (int st = DOUBLE_END; st < LOG2L; ++st) {
+		if (active) {
+			const int s = 1 << st;
+			const int ps = b & ~(s - 1);
+			float2 o0, o1;
+			bfly(lds_f2(x + 8 * b), lds_f2(x + 8 * (b + H)), lds_f2(tw + 8 * ps), o0, o1);
+			const unsigned oi = y + 8 * (b + ps);
+			sts_f2(oi, o0);
+			sts_f2(oi + 8 * s, o1);
+		}
+		MAIN_SYNC();
+		const unsigned sw = x;
+		x = y;
+		y = sw;
+	}
+}
+#if defined(AEC_FFT_INLINE) || defined(AEC_FFT_PLAIN)
+#define CFFT_RUN(LOG2L, x, y, tw, sign, active) cfft_bfly<LOG2L>(x, y, tw, sign, active)
+#else
+#define CFFT_RUN(LOG2L, x, y, tw, sign, active) \
+	cfft_core<LOG2L>(smem_addr(x), smem_addr(y), smem_addr(tw), (sign) < 0 ? 0x80000000u : 0u, (active) ? 1 : 0)
+#endif
 // number of buffer swaps of cfft_bfly: one per (double or single) pass
 #ifdef AEC_FFT_PLAIN
 template <int LOG2L> struct CfftSwaps { static constexpr int value = LOG2L; };
@@ -266,7 +336,7 @@ template <int LOG2L> struct CfftSwaps { static constexpr int value = (LOG2L + 1)
 #endif
 // single transform: threads < L/2 work. Returns the buffer holding the result.
 template <int LOG2L> __device__ __forceinline__ float2 *cfft(float2 *x, float2 *y, const float2 *tw, int sign) {
-	cfft_bfly<LOG2L>(x, y, tw, sign, threadIdx.x < (1 << (LOG2L - 1)));
+	CFFT_RUN(LOG2L, x, y, tw, sign, threadIdx.x < (1 << (LOG2L - 1)));
 	return (CfftSwaps<LOG2L>::value & 1) ? y : x;
 }
 
@@ -330,7 +400,7 @@ __device__ void irfft(const float2 *spec, float *out, float2 *bufa, float2 *bufb
 template <int LOG2L>
 __device__ __forceinline__ void cfft_pair(float2 *&xa, float2 *&ya, float2 *&xb, float2 *&yb, const float2 *tw, int sign) {
 	const bool second = threadIdx.x >= (1 << (LOG2L - 1)); // lower half of the CTA: transform a, upper half: transform b
-	cfft_bfly<LOG2L>(second ? xb : xa, second ? yb : ya, tw, sign, true);
+	CFFT_RUN(LOG2L, second ? xb : xa, second ? yb : ya, tw, sign, true);
 	if (CfftSwaps<LOG2L>::value & 1) {
 		float2 *sw = xa; xa = ya; ya = sw;
 		sw = xb; xb = yb; yb = sw;
@@ -412,7 +482,14 @@ __device__ __forceinline__ short word2int(float x) {
 	return (short)(x < -32767.5f ? -32768 : (x > 32766.5f ? 32767 : (int)floor(.5 + (double)x)));
 }
 
-__device__ float hypergeom_gain(float xx) {
+// double-precision library routines as ONE out-of-line copy each (code size: see cfft_core)
+__device__ __noinline__ double exp_d(double x) {
+	return exp(x);
+}
+__device__ __noinline__ double sqrt_d(double x) {
+	return sqrt(x);
+}
+__device__ __noinline__ float hypergeom_gain(float xx) {
 	const float table[21] = {0.82157f, 1.02017f, 1.20461f, 1.37534f, 1.53363f, 1.68092f, 1.81865f,
 	                         1.94811f, 2.07038f, 2.18638f, 2.29688f, 2.40255f, 2.50391f, 2.60144f,
 	                         2.69551f, 2.78647f, 2.87458f, 2.96015f, 3.04333f, 3.12431f, 3.20326f};
@@ -422,7 +499,7 @@ __device__ float hypergeom_gain(float xx) {
 	if (ind < 0) return 1.f;
 	if (ind > 19) return (float)(1 + .1296 / (double)x);
 	float frac = 2 * x - integer;
-	return (float)((double)((1 - frac) * table[ind] + frac * table[ind + 1]) / sqrt((double)(x + .0001f)));
+	return (float)((double)((1 - frac) * table[ind] + frac * table[ind + 1]) / sqrt_d((double)(x + .0001f)));
 }
 __device__ __forceinline__ float qcurve(float x) {
 	return 1.f / (1.f + .15f / x);
@@ -544,7 +621,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 				// DC notch (filter_dc_notch16) then pre-emphasis; the recurrence m0 -> vout -> m0 is the critical path: add,
 				// mul, add, fma (2*a is exact, so fma(2, a, m1) rounds exactly like m1 + 2*a)
 				float *dst = inq + (fr & 1) * F;
-#pragma unroll 2
+#pragma unroll 1
 				for (int i = 0; i < F; i += 4) {
 					const float4 vin4 = *reinterpret_cast<const float4 *>(micf + i);
 					const float vin[4] = {vin4.x, vin4.y, vin4.z, vin4.w};
@@ -601,7 +678,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			const int reset = sw_reset[0];
 			if (TMA) p_fg_pending = reset ? 0 : si[IN_FG_PENDING]; // as the next frame's pass will find it
 			if (lane == 0) {
-#pragma unroll 2
+#pragma unroll 1
 				for (int i = 0; i < F; i += 4) {
 					float4 v = *reinterpret_cast<const float4 *>(tmpv + i);
 					v.x = v.x + pre * memE;
@@ -626,11 +703,15 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 	}
 
 	// ---- load constants and per-stream small state
+#pragma unroll 1
 	for (int i = t; i < L / 2; i += F) tw[i] = P.tw[i];
+#pragma unroll 1
 	for (int i = t; i <= L; i += F) spl[i] = P.spl[i];
 	Eprev[t] = reinterpret_cast<float2 *>(S + ly.E)[t];
 	xw[F + t] = S[ly.xprev + t];
+#pragma unroll 1
 	for (int i = t; i <= F; i += F) power_1[i] = S[ly.power_1 + i];
+#pragma unroll 1
 	for (int i = t; i < M; i += F) prop[i] = S[ly.prop + i];
 	if (t < SC_COUNT) sc[t] = S[ly.scal + t];
 	if (t < IN_COUNT) si[t] = reinterpret_cast<int *>(S + ly.ints)[t];
@@ -759,18 +840,23 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			// (M dependent adds; one thread walking all three loops alone cost 4.5 % of the kernel's warp time in the
 			// adapted regime, everybody else at the barrier), the rest per element. (float)sqrt((double)x) is the correctly
 			// rounded float square root (53 >= 2 * 24 + 2 bits: no double rounding), i.e. __fsqrt_rn.
+#pragma unroll 1
 			for (int i = t; i < M; i += F) prop[i] = __fsqrt_rn(1.f + S[ly.wnorm + i]);
 			MAIN_SYNC();
 			if (warp == 0) {
 				float mx = 1.f;
+#pragma unroll 1
 				for (int i = lane; i < M; i += 32) mx = fmaxf(mx, prop[i]);
 #pragma unroll
 				for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll 1
 				for (int i = lane; i < M; i += 32) prop[i] += .1f * mx;
 				__syncwarp();
 				float prop_sum = 1.f;
+#pragma unroll 4
 				for (int i = 0; i < M; ++i) prop_sum += prop[i];
 				__syncwarp();
+#pragma unroll 1
 				for (int i = lane; i < M; i += 32) prop[i] = (.99f * prop[i]) / prop_sum;
 			}
 			MAIN_SYNC();
@@ -1117,6 +1203,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 				FG[(size_t)j * F + t] = make_float2(0.f, 0.f);
 			}
 			for (int j = 0; j <= M; ++j) X[(size_t)j * F + t] = make_float2(0.f, 0.f);
+#pragma unroll 1
 			for (int i = t; i <= F; i += F) {
 				S[ly.power + i] = 0;
 				power_1[i] = 1.f;
@@ -1156,6 +1243,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			// ---- smoothed far-end power, filtered spectra, leak estimate
 			float pey_part = 0.f, pyy_part = 0.f;
 			cp_async_wait<0>(); // the staged state (own column only)
+#pragma unroll 1
 			for (int j = t; j <= F; j += F) {
 				const bool nyq = j == F; // thread 0's second trip: the Nyquist entries are not staged
 				const float pw = ss_1 * (nyq ? S[ly.power + j] : stg[SG_POWER * F + j]) + 1 + ss * vec3[j];
@@ -1193,6 +1281,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			if (!adapted && sum_adapt > (float)M && leak * Syy > .03f * Syy) adapted = 1;
 			MAIN_SYNC();
 			if (adapted) {
+#pragma unroll 1
 				for (int i = t; i <= F; i += F) {
 					float r = leak * vec2[i];
 					const float e = vec1[i] + 1;
@@ -1207,6 +1296,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 					if (tq > .25f * See) tq = .25f * See;
 					adapt_rate = tq / See;
 				}
+#pragma unroll 1
 				for (int i = t; i <= F; i += F) power_1[i] = adapt_rate / (vec4[i] + 10);
 				sum_adapt = sum_adapt + adapt_rate;
 			}
@@ -1324,6 +1414,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			if (min_count > min_range) min_count = 0;
 			MAIN_SYNC();
 			// ---- the three Bark filterbanks at once (3 * Mb threads; filterbank_compute_bank32's accumulation order)
+#pragma unroll 1
 			for (int u = t; u < 3 * Mb; u += F) { // one trip unless F < 3 * Mb (8 kHz)
 				const int which = u / Mb, b = u - which * Mb;
 				int c0 = bs0, c1 = bs1, c2 = bs2;
@@ -1385,9 +1476,9 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 			if (t < Mb) {
 				const int i = F + t;
 				const float noise_floor = P.noise_floor; // exp(.2302585 * noise_suppress): a constant of the bank (host)
-				const float echo_floor = (float)exp((double)(.2302585f * effective_echo_suppress));
-				const float gfl = (float)(sqrt((double)(noise_floor * noise[i] + echo_floor * echo_noise[i])) /
-				                          sqrt((double)(1 + noise[i] + echo_noise[i])));
+				const float echo_floor = (float)exp_d((double)(.2302585f * effective_echo_suppress));
+				const float gfl = (float)(sqrt_d((double)(noise_floor * noise[i] + echo_floor * echo_noise[i])) /
+				                          sqrt_d((double)(1 + noise[i] + echo_noise[i])));
 				const float prior_ratio = prior[i] / (prior[i] + 1.f);
 				const float theta = prior_ratio * (1.f + post_me[1]);
 				const float MM = hypergeom_gain(theta);
@@ -1397,7 +1488,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 				const float zb = gains[F + t];
 				const float P1 = .199f + .8f * qcurve(zb);
 				const float q = 1.f - Pframe * P1;
-				const double ee = exp((double)(-theta));
+				const double ee = exp_d((double)(-theta));
 				const float gain2b = (float)(1 / (1.f + (double)((q / (1.f - q)) * (1 + prior[i])) * ee));
 				tmpv[t] = g;
 				tmpv[Mb + t] = gain2b;
@@ -1454,7 +1545,9 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 	// ---- store per-stream small state kept in shared memory
 	reinterpret_cast<float2 *>(S + ly.E)[t] = Eprev[t];
 	S[ly.xprev + t] = xw[F + t];
+#pragma unroll 1
 	for (int i = t; i <= F; i += F) S[ly.power_1 + i] = power_1[i];
+#pragma unroll 1
 	for (int i = t; i < M; i += F) S[ly.prop + i] = prop[i];
 	// (the two input filters' memories belong to the serial warp in SW builds)
 	if (t < SC_COUNT && !(SW && (t == SC_NOTCH0 || t == SC_NOTCH1 || t == SC_MEMD || t == SC_MEME))) S[ly.scal + t] = sc[t];
