@@ -230,6 +230,7 @@ static void lane_leave(VLane *l, VMember *m) {
 /* run everything staged: one upload, one kernel sequence, downloads into ring slots, results queued on their members */
 static void lane_flush(VLane *l) {
 	int k, n, rc;
+	mblk_t *drop;
 	if (l->n_staged == 0) return;
 	n = l->n_staged;
 	pthread_mutex_lock(&g_vmu);
@@ -260,6 +261,11 @@ static void lane_flush(VLane *l) {
 		if (!l->owns_ctx) msb200p_sync_unlock();
 		if (rc != MSB200_OK) ms_error("msb200 video: lane %p: %s", l, msb200_last_error());
 	}
+	/* delivery under the lane lock: a member that is leaving on another thread (postprocess) either still gets its frame
+	 * here, before lane_leave() clears its entries and its queue is flushed, or is no longer seen at all; frames nobody
+	 * takes are freed after the lock is dropped (freeing one takes the lock again to return its slot) */
+	drop = NULL;
+	pthread_mutex_lock(&g_vmu);
 	for (k = 0; k < n; ++k) {
 		uint8_t *base = l->dst + (size_t)l->slotv[k] * l->dst_stride + VSLOT_PREFIX;
 		mblk_t *m = esballoc(base, VHDR + l->dst_bytes + 16, 0, vslot_release);
@@ -271,7 +277,17 @@ static void lane_flush(VLane *l) {
 		m->b_wptr = m->b_rptr + l->dst_bytes;
 		mblk_set_timestamp_info(m, l->ts[k]);
 		if (rc == MSB200_OK && l->who[k]) putq(&l->who[k]->ready, m);
-		else freemsg(m); /* gives the slot back */
+		else {
+			m->b_next = drop;
+			drop = m;
+		}
+	}
+	pthread_mutex_unlock(&g_vmu);
+	while (drop) { /* gives the slots back */
+		mblk_t *m = drop;
+		drop = m->b_next;
+		m->b_next = NULL;
+		freemsg(m);
 	}
 	l->flushes++;
 	l->frames += (uint64_t)n;
