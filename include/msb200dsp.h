@@ -281,7 +281,9 @@ MSB200_API int msb200_aec_set_live(msb200_aec *a, int n_live); /* see msb200_vol
 /* Cross-check switch for the 48 kHz kernel builds (results are bit-identical, the tests assert it): 0 = default, 1 = the
  * 256-thread build (one of the per-bin threads runs the frame's sequential IIR filters, the others wait), 3 / 4 = builds
  * with a ninth "serial" warp that runs those filters beside the per-bin threads (3: at 3 CTAs per SM; 4: the serial warp
- * also feeds the block pass with cp.async.bulk row copies instead of per-thread cp.async). */
+ * also feeds the block pass with cp.async.bulk row copies instead of per-thread cp.async); 5 = the default build with the
+ * generic loop of the block pass for every frame (the default runs the common frame through a tighter form of that loop;
+ * any frame size). */
 MSB200_API int msb200_aec_set_path(msb200_aec *a, int path);
 MSB200_API int msb200_aec_process(msb200_aec *a, const int16_t *mic, const int16_t *ref, int16_t *out, int nframes);
 MSB200_API int msb200_aec_process_dev(msb200_aec *a, const void *d_mic, const void *d_ref, void *d_out, int nframes,

@@ -21,6 +21,7 @@
 #include "msb200_internal.h"
 
 #include <cmath>
+#include <type_traits>
 
 #define NB_BANDS 24
 
@@ -70,7 +71,7 @@ struct AecParams {
 // warps do not pay for the coarser wave quantisation (4096 CTAs = 5.5 waves of 740 instead of 6.9 of 592); 40 registers:
 // 0.839 ms. The default stays 4.
 #define AEC_CTAS_PER_SM_256 4
-#define AEC_DEFAULT_SKEW_US 0
+#define AEC_DEFAULT_SKEW_US 6 // measured after the tight pass went in (one box, 4096 streams, steady state): 0 -> 0.7678 ms per launch, 4 / 5 / 6 / 8 / 10 us -> 0.7617 / 0.7601 / 0.7593 / 0.7600 / 0.7611
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -518,10 +519,15 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
     aec_kernel(const short *__restrict__ mic, const short *__restrict__ ref, short *__restrict__ out, int nframes,
                int io_stride, float2 *__restrict__ gX, float2 *__restrict__ gW, float2 *__restrict__ gFG,
                float *__restrict__ gS, AecParams P, const int *__restrict__ counts, int in_frame0, int in_ring, int out_stride, int out_frame0,
-               int out_ring, int skew_ns, int skew_ctas) {
+               int out_ring, int skew_ns, int skew_ctas, int pass_generic) {
 	extern __shared__ float sm[];
 	constexpr int F = 1 << LOG2L, N = 2 * F, L = F;
 	const int M = P.M;
+#ifdef AEC_DIAG_NO_PASS // timing experiment only (results are meaningless): the frame without its block pass
+	const int M_PASS = 0;
+#else
+	const int M_PASS = M;
+#endif
 	const int t = threadIdx.x;
 	const int stream = blockIdx.x;
 	// ragged batches: this stream's own frame count (a stream that staged fewer frames than the bank's maximum in this
@@ -744,23 +750,31 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 		// |W_j|^2 is only consumed by mdf_adjust_prop once the filter counts as adapted (or is about to)
 		const bool need_wnorm = si[IN_ADAPTED] || sc[SC_SUM_ADAPT] > (float)M - 1.f;
 		const int xs0 = head + 1 > M ? 0 : head + 1;
+#ifdef AEC_PASS_DIRECT
 		const float2 *gX_pf = X + (size_t)xs0 * F + t; // X_{j+1} of the block being prefetched
 		// ring wrap: a uniform count-down and a constant step back, instead of comparing against (and re-deriving) the
 		// ring's end and base addresses at every block
 		int x_left = M + 1 - xs0;
 		const long x_ring = (long)(M + 1) * F;
+#endif
 		// W and FG are walked through ONE pointer each that moves once per unrolled group of AEC_STAGES blocks: the
 		// prefetch of block j + AEC_STAGES - 1 and the stores of block j are that pointer plus compile-time offsets
 		// (immediates in the LDGSTS / STG encodings) instead of four running 64-bit pointers bumped every block
 		float2 *gW_grp = W + t, *gF_grp = FG + t;
 		float2 *const pipe_t = pipe + t;
+		// The far-end ring is walked with a 32-bit BYTE offset from this thread's column (add a row, back to 0 at the ring's
+		// end): an add, a compare and a select per block instead of a 64-bit pointer stepped back by the ring's length
+		const char *const xg = reinterpret_cast<const char *>(X + t);
+		constexpr unsigned ROW_BYTES = F * (unsigned)sizeof(float2);
+		unsigned xoff = (unsigned)xs0 * ROW_BYTES;
+		const unsigned x_ring_bytes = (unsigned)(M + 1) * ROW_BYTES;
 		auto prefetch = [&](int stage, int rel) { // rel: block index relative to the group the pointers stand at
 			float2 *dst = pipe_t + stage * 3 * F;
-			cp_async8(dst, gX_pf);
+			cp_async8(dst, xg + xoff);
 			if (!fg_pending) cp_async8(dst + F, gF_grp + rel * F);
 			cp_async8(dst + 2 * F, gW_grp + rel * F);
-			gX_pf += F;
-			if (--x_left == 0) gX_pf -= x_ring;
+			xoff += ROW_BYTES;
+			if (xoff == x_ring_bytes) xoff = 0;
 		};
 #ifndef AEC_PASS_DIRECT
 		if (TMA) {
@@ -772,7 +786,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 		// early prologue: the ring slots with storage of their own (the aliased ones are still scratch until the pre-pass ends)
 #pragma unroll
 		for (int pj = 0; pj < (AEC_OWN_STAGES < AEC_STAGES - 1 ? AEC_OWN_STAGES : AEC_STAGES - 1); ++pj) {
-			if (pj < M) prefetch(pj, pj);
+			if (pj < M_PASS) prefetch(pj, pj);
 			cp_async_commit();
 		}
 		}
@@ -909,7 +923,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 		} else {
 #pragma unroll
 		for (int pj = AEC_OWN_STAGES; pj < AEC_STAGES - 1; ++pj) {
-			if (pj < M) prefetch(pj, pj);
+			if (pj < M_PASS) prefetch(pj, pj);
 			cp_async_commit();
 		}
 		}
@@ -923,6 +937,23 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 		{
 			static_assert(AEC_STAGES % 3 == 0, "the grouped |W_j|^2 reduction below folds three blocks at a time");
 			float nrm[3] = {0.f, 0.f, 0.f};
+			// |W_j|^2 of blocks jb .. jb + 2 (nrm[0 .. 2]) summed over the warp: three warp sums for the price of one and a
+			// bit: after the first two folds the three quantities live in disjoint lane groups (block jb: lanes 0-7, jb+1:
+			// 16-23, jb+2: 8-15 and 24-31) and share the remaining folds. Same pairing order (xor 16, 8, 4, 2, 1) as warp_sum:
+			// identical sums, 6 SHFL not 15.
+			auto wnorm_fold = [&](const int jb) {
+				const bool hi16 = lane & 16, hi8 = lane & 8;
+				float a = hi16 ? nrm[1] : nrm[0];
+				a += __shfl_xor_sync(0xffffffffu, hi16 ? nrm[0] : nrm[1], 16);
+				float c2 = nrm[2] + __shfl_xor_sync(0xffffffffu, nrm[2], 16);
+				float c = hi8 ? c2 : a;
+				c += __shfl_xor_sync(0xffffffffu, hi8 ? a : c2, 8);
+				c += __shfl_xor_sync(0xffffffffu, c, 4);
+				c += __shfl_xor_sync(0xffffffffu, c, 2);
+				c += __shfl_xor_sync(0xffffffffu, c, 1);
+				const int jw = lane == 0 ? jb : (lane == 16 ? jb + 1 : jb + 2);
+				if ((lane == 0 || lane == 16 || lane == 8) && jw < M) wpart[jw * 8 + warp] = c;
+			};
 #ifdef AEC_PASS_DIRECT
 			// A/B build: X_{j+1}, FG_j, W_j go HBM -> REGISTERS (two blocks ahead, a ring of two register sets) instead of
 			// HBM -> shared memory -> registers: no LDGSTS, no LDS in the pass (the shared-memory pipe is the busiest unit)
@@ -940,7 +971,88 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 #else
 			constexpr int GROUP = AEC_STAGES;
 #endif
-			for (int j0 = 0; j0 < M; j0 += GROUP) {
+			int j0_first = 0;
+#if !defined(AEC_PASS_DIRECT) && !defined(AEC_NO_TIGHT) && AEC_STAGES == 3
+			// ---- the tight form of the pass for the common frame: no foreground refresh pending, adaptation on, and only the
+			// groups whose three blocks AND their prefetches (two blocks ahead) all exist — 15 of the 16 groups at 48 kHz; the
+			// generic loop below finishes the rest (and runs every other kind of frame). Same operations on the same operands in
+			// the same order as the generic loop (bit-identical: test_aec_pass_forms_are_bit_identical); what it drops are the
+			// per-block tests for the end of the filter, the end of the prefetches, a pending refresh and adaptation being off.
+			// Measured (B200, 4096 streams, steady state, one box, A/B interleaved): 0.7818 ms per launch before, 0.7752 with the
+			// 32-bit ring offset alone, 0.7676 with this loop — although it executes a third fewer instructions per block (ncu
+			// on the generic loop, profiles/r2z_aec_kernel.*: 95 per block and warp, 30 of them arithmetic): the pass is paced
+			// by its loads, not by its instructions. Variants that cost MORE than they saved: a second copy of the loop without
+			// the bin-0 code for warps 1-7 (0.8126: every change of the kernel's size or register allocation moves the
+			// non-pass code by a few per cent at the 56-register cap), the whole pass as an out-of-line function with the
+			// register file to itself (0.8054).
+			if (!TMA && !pass_generic && !fg_pending && do_update && M_PASS >= 5) {
+				char *wg = reinterpret_cast<char *>(gW_grp);
+				const char *fgp = reinterpret_cast<const char *>(gF_grp);
+				const int n_fast = (M - 5) / 3 + 1; // groups j0 = 0, 3, ... with j0 + 4 < M
+				auto block = [&](auto sidx_c, const int j0) {
+					constexpr int SIDX = decltype(sidx_c)::value;
+					const int j = j0 + SIDX;
+					{ // block j + 2 into the slot block j - 1 left
+						float2 *dst = pipe_t + ((SIDX + 2) % 3) * 3 * F;
+						cp_async8(dst, xg + xoff);
+						cp_async8(dst + F, fgp + (SIDX + 2) * ROW_BYTES);
+						cp_async8(dst + 2 * F, wg + (SIDX + 2) * ROW_BYTES);
+					}
+					xoff += ROW_BYTES;
+					if (xoff == x_ring_bytes) xoff = 0;
+					cp_async_commit();
+					cp_async_wait<AEC_STAGES - 1>();
+					const float2 *src = pipe_t + SIDX * 3 * F;
+					const float2 xj1 = src[0];
+					float2 w = src[2 * F];
+					const float2 fg = src[F];
+					if (t == 0) {
+						yfg.x += xj.x * fg.x;
+						yfg.y += xj.y * fg.y;
+					} else {
+						yfg.x += (xj.x * fg.x - xj.y * fg.y);
+						yfg.y += (xj.y * fg.x + xj.x * fg.y);
+					}
+					if (j == 0 || j == constr_j) {
+						w = j == 0 ? specB[t] : cspec[t];
+					} else {
+						const float pj = prop[j];
+						if (t == 0) {
+							w.x += (pj * p1) * (xj1.x * Ep.x);
+							w.y += (pj * p1n) * (xj1.y * Ep.y);
+						} else {
+							const float Wg = pj * p1;
+							w.x += Wg * (xj1.x * Ep.x + xj1.y * Ep.y);
+							w.y += Wg * (-xj1.y * Ep.x + xj1.x * Ep.y);
+						}
+					}
+					*reinterpret_cast<float2 *>(wg + SIDX * ROW_BYTES) = w;
+					if (need_wnorm) nrm[SIDX] = w.x * w.x + w.y * w.y;
+					if (t == 0) {
+						ybg.x += xj.x * w.x;
+						ybg.y += xj.y * w.y;
+					} else {
+						ybg.x += (xj.x * w.x - xj.y * w.y);
+						ybg.y += (xj.y * w.x + xj.x * w.y);
+					}
+					xj = xj1;
+				};
+#pragma unroll 1
+				for (int g = 0; g < n_fast; ++g) {
+					const int j0 = 3 * g;
+					block(std::integral_constant<int, 0>{}, j0);
+					block(std::integral_constant<int, 1>{}, j0);
+					block(std::integral_constant<int, 2>{}, j0);
+					if (need_wnorm) wnorm_fold(j0);
+					wg += 3 * ROW_BYTES;
+					fgp += 3 * ROW_BYTES;
+				}
+				gW_grp = reinterpret_cast<float2 *>(wg);
+				gF_grp += (size_t)n_fast * 3 * F;
+				j0_first = 3 * n_fast;
+			}
+#endif
+			for (int j0 = j0_first; j0 < M_PASS; j0 += GROUP) {
 #pragma unroll
 				for (int sidx = 0; sidx < GROUP; ++sidx) {
 					const int j = j0 + sidx;
@@ -1013,23 +1125,7 @@ __global__ void __launch_bounds__((1 << LOG2L) + (SW ? 32 : 0), ((256 * CTAS) >>
 							if (lane == 0) mbar_arrive(empty_s + 8 * sidx);
 						}
 					}
-					if (sidx % 3 == 2 && need_wnorm && j0 + sidx - 2 < M) {
-						// three warp sums for the price of one and a bit: after the first two folds the three quantities live
-						// in disjoint lane groups (block jb: lanes 0-7, jb+1: 16-23, jb+2: 8-15 and 24-31) and share the
-						// remaining folds. Same pairing order (xor 16, 8, 4, 2, 1) as warp_sum: identical sums, 6 SHFL not 15.
-						const int jb = j0 + sidx - 2;
-						const bool hi16 = lane & 16, hi8 = lane & 8;
-						float a = hi16 ? nrm[1] : nrm[0];
-						a += __shfl_xor_sync(0xffffffffu, hi16 ? nrm[0] : nrm[1], 16);
-						float c2 = nrm[2] + __shfl_xor_sync(0xffffffffu, nrm[2], 16);
-						float c = hi8 ? c2 : a;
-						c += __shfl_xor_sync(0xffffffffu, hi8 ? a : c2, 8);
-						c += __shfl_xor_sync(0xffffffffu, c, 4);
-						c += __shfl_xor_sync(0xffffffffu, c, 2);
-						c += __shfl_xor_sync(0xffffffffu, c, 1);
-						const int jw = lane == 0 ? jb : (lane == 16 ? jb + 1 : jb + 2);
-						if ((lane == 0 || lane == 16 || lane == 8) && jw < M) wpart[jw * 8 + warp] = c;
-					}
+					if (sidx % 3 == 2 && need_wnorm && j0 + sidx - 2 < M) wnorm_fold(j0 + sidx - 2);
 				}
 				gW_grp += GROUP * F;
 				gF_grp += GROUP * F;
@@ -1619,7 +1715,7 @@ int msb200_aec_create(msb200_ctx *ctx, int n_streams, int sample_rate, int tail_
 	a->n = a->live = n_streams;
 	a->tail_ms = tail_length_ms;
 	a->path = getenv("MSB200_AEC_PATH") ? atoi(getenv("MSB200_AEC_PATH")) : 0;
-	if (a->path != 1 && a->path != 3 && a->path != 4) a->path = 0;
+	if (a->path != 1 && a->path != 3 && a->path != 4 && a->path != 5) a->path = 0;
 	a->filter_length = filter_length;
 	AecParams &P = a->P;
 	P.F = F; P.N = N; P.M = M; P.L = L; P.rate = sample_rate;
@@ -1813,17 +1909,21 @@ int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int 
 	MSB200_CHECK_ARG(a && d_mic && d_ref && d_out && nframes > 0);
 	// phase skew between the CTAs that share an SM (see the kernel): only worth it when the grid fills the chip
 	static const int skew_env = getenv("MSB200_AEC_SKEW_US") ? atoi(getenv("MSB200_AEC_SKEW_US")) : AEC_DEFAULT_SKEW_US;
-	const int skew_ns = a->live >= 4 * a->ctx->sm_count ? skew_env * 1000 : 0;
+	// (three waves and more: on a grid of one or two waves the late starters of the first wave would end the launch late)
+	const int skew_ns = a->live >= 12 * a->ctx->sm_count ? skew_env * 1000 : 0;
+	// path 5 (cross-checks, A/B runs): the default build with the generic loop of the block pass for every frame
+	static const int generic_env = getenv("MSB200_AEC_PASS_GENERIC") ? atoi(getenv("MSB200_AEC_PASS_GENERIC")) : 0;
+	const int pass_generic = a->path == 5 || generic_env != 0;
 #define AEC_ARGS                                                                                                       \
 	(const short *)d_mic, (const short *)d_ref, (short *)d_out, nframes, in_stride, a->dX, a->dW, a->dFG, a->dS, a->P, \
-	    d_counts, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames, skew_ns, a->ctx->sm_count
+	    d_counts, in_frame0, in_ring_frames, out_stride, out_frame0, out_ring_frames, skew_ns, a->ctx->sm_count, pass_generic
 	if (a->live > 0) switch (a->P.F) {
 		case 256: {
 			// occupancy A/B (profiling): MSB200_AEC_CTAS=5 selects the 48-register build (5 CTAs per SM), 6 the 40-register one
 			static const int ctas = getenv("MSB200_AEC_CTAS") ? atoi(getenv("MSB200_AEC_CTAS")) : AEC_CTAS_PER_SM_256;
 			// serial warp (default): 288 threads per CTA; msb200_aec_set_path / MSB200_AEC_PATH select the 256-thread build
 			// (1) or the serial-warp build at 3 CTAs per SM (3: 72 registers instead of 56) for A/B runs and cross-checks
-			const int sw = a->path == 0 ? 1 : (a->path == 1 ? 0 : a->path);
+			const int sw = (a->path == 0 || a->path == 5) ? 1 : (a->path == 1 ? 0 : a->path);
 			if (sw == 4)
 				MSB200_LAUNCH(a->ctx, (aec_kernel<8, AEC_CTAS_PER_SM_256, true, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
 			else if (sw == 3) MSB200_LAUNCH(a->ctx, (aec_kernel<8, 3, true>), a->live, 288, a->smem_bytes_sw, AEC_ARGS);
@@ -1889,7 +1989,7 @@ int msb200_aec_process_counts(msb200_aec *a, const int16_t *mic, const int16_t *
 	return MSB200_OK;
 }
 int msb200_aec_set_path(msb200_aec *a, int path) {
-	MSB200_CHECK_ARG(a && (path == 0 || path == 1 || path == 3 || path == 4));
+	MSB200_CHECK_ARG(a && (path == 0 || path == 1 || path == 3 || path == 4 || path == 5));
 	a->path = path;
 	return MSB200_OK;
 }

@@ -73,7 +73,7 @@ def test_aec_serial_warp_build_is_bit_identical_to_the_plain_build(ctx):
     256-thread build's bit for bit — including saturated microphone frames, ragged frame counts (1, 2, 3 frames per call)
     and a stream driven into speex_echo_state_reset (the reset also clears the filters' memories)."""
     rate, tail, n_streams, nframes = 48000, 250, 5, 240
-    banks = {p: F.SpeexEC(ctx, n_streams, rate, tail) for p in (0, 1, 3, 4)}
+    banks = {p: F.SpeexEC(ctx, n_streams, rate, tail) for p in (0, 1, 3, 4, 5)}
     for p, ec in banks.items():
         ec.set_path(p)
     Fs = banks[0].frame_size
@@ -104,7 +104,7 @@ def test_aec_serial_warp_build_is_bit_identical_to_the_plain_build(ctx):
         outs[p] = got
         assert ec.probe(4, "scalars", 16)[11] < nframes - 30 + 1  # cancel_count restarted: the reset did happen
     M, N = banks[0].info.M, banks[0].info.window_size
-    for p in (0, 3, 4):
+    for p in (0, 3, 4, 5):  # 4 and 5 run the generic loop of the block pass, the others its tight form
         assert np.array_equal(outs[p], outs[1]), (p, np.abs(outs[p].astype(int) - outs[1].astype(int)).max())
         for s in range(n_streams):
             for what, size in (("W", M * N), ("foreground", M * N), ("X", (M + 1) * N), ("E", N), ("power_1", Fs + 1),
@@ -113,6 +113,38 @@ def test_aec_serial_warp_build_is_bit_identical_to_the_plain_build(ctx):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (p, s, what)
     for ec in banks.values():
         ec.close()
+
+
+@pytest.mark.parametrize("rate,tail", [(8000, 250), (16000, 250), (16000, 100), (48000, 250)])
+def test_aec_pass_forms_are_bit_identical(ctx, rate, tail):
+    """the block pass has a tight form for the common frame (no foreground refresh pending, adaptation on, whole groups of
+    three blocks) and a generic loop for everything else; set_path(5) runs every frame through the generic loop. Samples and
+    state must be equal bit for bit at every frame size, through the start-up, the adapted regime (|W_j|^2 bookkeeping), a
+    saturated stretch (adaptation off: generic loop in both) and the foreground refreshes on the way."""
+    n_streams, seconds = 3, 2.6
+    a, b = F.SpeexEC(ctx, n_streams, rate, tail), F.SpeexEC(ctx, n_streams, rate, tail)
+    b.set_path(5)
+    Fs = a.frame_size
+    nframes = int(seconds * rate) // Fs
+    mics, refs = [], []
+    for s in range(n_streams):
+        x, mic, _, _ = cfg2_stream(900 + s, Fs * nframes, rate)
+        mics.append(mic.copy())
+        refs.append(x.copy())
+    mics, refs = np.stack(mics), np.stack(refs)
+    mics[2, 40 * Fs:42 * Fs] = -32768
+    for k in range(0, nframes, 2):
+        sl = slice(k * Fs, min(k + 2, nframes) * Fs)
+        ya = a.process(np.ascontiguousarray(mics[:, sl]), np.ascontiguousarray(refs[:, sl]))
+        yb = b.process(np.ascontiguousarray(mics[:, sl]), np.ascontiguousarray(refs[:, sl]))
+        assert np.array_equal(ya, yb), (rate, k)
+    M, N = a.info.M, a.info.window_size
+    for s in range(n_streams):
+        for what, size in (("W", M * N), ("foreground", M * N), ("X", (M + 1) * N), ("E", N), ("scalars", 16)):
+            assert np.array_equal(a.probe(s, what, size).view(np.uint32), b.probe(s, what, size).view(np.uint32)), (s, what)
+    assert a.probe(0, "scalars", 16)[0] == 1  # the adapted regime was reached
+    a.close()
+    b.close()
 
 
 def test_aec_serial_warp_build_at_full_occupancy(ctx):
@@ -127,7 +159,7 @@ def test_aec_serial_warp_build_at_full_occupancy(ctx):
     refs = (base[pick, 0] * gain).astype(np.int16)
     mics = (base[pick, 1] * gain).astype(np.int16)
     outs = {}
-    for p in (0, 1, 4):
+    for p in (0, 1, 4, 5):
         ec = F.SpeexEC(ctx, n_streams, rate, 250)
         ec.set_path(p)
         got = np.zeros_like(mics)
@@ -136,7 +168,7 @@ def test_aec_serial_warp_build_at_full_occupancy(ctx):
             got[:, sl] = ec.process(np.ascontiguousarray(mics[:, sl]), np.ascontiguousarray(refs[:, sl]))
         outs[p] = (got, np.stack([ec.probe(s, "E", 2 * Fs) for s in range(0, n_streams, 97)]))
         ec.close()
-    for p in (0, 4):
+    for p in (0, 4, 5):
         assert np.array_equal(outs[p][0], outs[1][0]), p
         assert np.array_equal(outs[p][1].view(np.uint32), outs[1][1].view(np.uint32)), p
     assert np.abs(outs[0][0]).max() > 0
