@@ -425,66 +425,79 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 // update for ITS stream (state in registers across the blocks of a launch), and the warp applies the 32 gains and stores
 // coalesced. Same operations per stream as volume_kernel, 1/32 of its issue slots in the sequential part — that kernel
 // spends a whole warp's slots on lane 0 there and is issue-bound from a few thousand streams on.
-__global__ void __launch_bounds__(32) volume_lanes_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st, int n_streams,
+// VW warps per CTA share the two parallel parts — staging the 32 rows and applying the 32 gains (rows l = warp, warp + VW,
+// ...) — around the sequential part, which stays with the lanes of warp 0. With one warp per CTA (the first form of this
+// kernel) a 4096-stream bank was 128 lone warps walking ~3500 instructions per block on their own: 21 us per tick of two
+// blocks, nearly all of it staging and gain arithmetic that four warps now do side by side.
+#define VOL_LANES_WARPS 4
+__global__ void __launch_bounds__(32 * VOL_LANES_WARPS) volume_lanes_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st, int n_streams,
                                                           int nsamples, int stride, int nblocks, int block0, int ring_blocks,
                                                           const msb200_volume_state *__restrict__ peer_states,
                                                           const int *__restrict__ counts, int pitch) {
 	extern __shared__ short vsm[];
-	const int lane = threadIdx.x, s0 = blockIdx.x * 32, stream = s0 + lane;
+	__shared__ int sh_gain[32], sh_dc[32]; // per stream of the CTA: intgain (0 = leave the block as it is), DC to remove
+	__shared__ unsigned sh_has;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, s0 = blockIdx.x * 32, stream = s0 + lane;
 	const bool valid = stream < n_streams;
-	const int my_blocks = valid ? (counts ? min(nblocks, counts[stream]) : nblocks) : 0;
+	const int my_blocks = valid ? (counts ? min(nblocks, counts[stream]) : nblocks) : 0; // (the same in every warp)
 	int max_blocks = my_blocks;
 #pragma unroll
 	for (int o = 16; o; o >>= 1) max_blocks = max(max_blocks, __shfl_xor_sync(0xffffffffu, max_blocks, o));
-	if (max_blocks == 0) return;
+	if (max_blocks == 0) return; // uniform over the CTA
 	msb200_volume_state v;
-	if (my_blocks > 0) v = st[stream];
+	if (warp == 0 && my_blocks > 0) v = st[stream];
 	const int words = nsamples >> 1, pw = pitch >> 1;
 	unsigned *wsm = reinterpret_cast<unsigned *>(vsm);
+	const unsigned wbase = (unsigned)__cvta_generic_to_shared(wsm);
 	for (int blk = 0; blk < max_blocks; ++blk) {
 		const int bpos = ring_blocks > 0 ? (block0 + blk) % ring_blocks : blk;
 		const unsigned has = __ballot_sync(0xffffffffu, blk < my_blocks); // streams that have this block
-		__syncwarp();
-		// (asynchronous copies: every word of the 32 blocks is in flight at once, nothing waits on a register)
-		const unsigned wbase = (unsigned)__cvta_generic_to_shared(wsm);
-		for (int l = 0; l < 32; ++l) {
+		__syncthreads(); // the previous block's gain pass has read its rows
+		// (asynchronous copies: every word of the rows is in flight at once, nothing waits on a register)
+		for (int l = warp; l < 32; l += VOL_LANES_WARPS) {
 			if (!((has >> l) & 1u)) continue;
 			const unsigned *g = reinterpret_cast<const unsigned *>(io + (size_t)(s0 + l) * stride + (size_t)bpos * nsamples);
 			for (int i = lane; i < words; i += 32)
 				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(wbase + 4u * (unsigned)(l * pw + i)), "l"(g + i) : "memory");
 		}
 		asm volatile("cp.async.wait_all;\n" ::: "memory");
-		__syncwarp();
-		int intgain = 4096, apply = 0, dc_prev = 0, remove_dc = 0;
-		if (blk < my_blocks) {
-			const short *buf = vsm + (size_t)lane * pitch;
-			float acc = 0.f;
-			int pk = 0, dcsum = 0, i = 0;
-			for (; i + 8 <= nsamples; i += 8) { // (loads and conversions of eight samples in flight together; the adds in order)
-				float q[8];
+		__syncthreads();
+		if (warp == 0) {
+			int intgain = 4096, apply = 0, dc_prev = 0, remove_dc = 0;
+			if (blk < my_blocks) {
+				const short *buf = vsm + (size_t)lane * pitch;
+				float acc = 0.f;
+				int pk = 0, dcsum = 0, i = 0;
+				for (; i + 8 <= nsamples; i += 8) { // (loads and conversions of eight samples in flight together; the adds in order)
+					float q[8];
 #pragma unroll
-				for (int k = 0; k < 8; ++k) {
-					const int x = buf[i + k];
+					for (int k = 0; k < 8; ++k) {
+						const int x = buf[i + k];
+						pk = max(pk, x < 0 ? -x : x);
+						dcsum += x;
+						q[k] = (float)(x * x);
+					}
+#pragma unroll
+					for (int k = 0; k < 8; ++k) acc = __fadd_rn(acc, q[k]);
+				}
+				for (; i < nsamples; ++i) {
+					const int x = buf[i];
 					pk = max(pk, x < 0 ? -x : x);
 					dcsum += x;
-					q[k] = (float)(x * x);
+					acc = __fadd_rn(acc, (float)(x * x));
 				}
-#pragma unroll
-				for (int k = 0; k < 8; ++k) acc = __fadd_rn(acc, q[k]);
+				vol_update(v, acc, pk, dcsum, nsamples, peer_states, intgain, apply, remove_dc, dc_prev);
 			}
-			for (; i < nsamples; ++i) {
-				const int x = buf[i];
-				pk = max(pk, x < 0 ? -x : x);
-				dcsum += x;
-				acc = __fadd_rn(acc, (float)(x * x));
-			}
-			vol_update(v, acc, pk, dcsum, nsamples, peer_states, intgain, apply, remove_dc, dc_prev);
+			sh_gain[lane] = apply ? intgain : 0; // gain == 1 and no DC removal: the block stays as it is (:441)
+			sh_dc[lane] = remove_dc ? dc_prev : 0;
+			const unsigned todo = __ballot_sync(0xffffffffu, apply != 0);
+			if (lane == 0) sh_has = todo;
 		}
-		const unsigned todo = __ballot_sync(0xffffffffu, apply != 0); // gain == 1 and no DC removal: the block stays as it is (:441)
-		for (int l = 0; l < 32; ++l) {
+		__syncthreads();
+		const unsigned todo = sh_has;
+		for (int l = warp; l < 32; l += VOL_LANES_WARPS) {
 			if (!((todo >> l) & 1u)) continue;
-			const int ig = __shfl_sync(0xffffffffu, intgain, l), rdc = __shfl_sync(0xffffffffu, remove_dc, l);
-			const int dcp = rdc ? __shfl_sync(0xffffffffu, dc_prev, l) : 0;
+			const int ig = sh_gain[l], dcp = sh_dc[l];
 			unsigned *g = reinterpret_cast<unsigned *>(io + (size_t)(s0 + l) * stride + (size_t)bpos * nsamples);
 			for (int i = lane; i < words; i += 32) {
 				const unsigned w = wsm[l * pw + i];
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(32) volume_lanes_kernel(short *__restrict__ io
 			}
 		}
 	}
-	if (my_blocks > 0) st[stream] = v;
+	if (warp == 0 && my_blocks > 0) st[stream] = v;
 }
 
 // stream == -1 applies the setter to every stream of the bank (one round trip)
@@ -677,7 +690,7 @@ int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride
 		const bool can = (nsamples & 1) == 0 && (stride & 1) == 0 && ((uintptr_t)d_io & 3) == 0 && lsmem <= 96 * 1024;
 		if (can && (v->kernel_choice == 2 || (v->kernel_choice == 0 && v->live >= 256))) {
 			MSB200_SMEM_OPTIN(volume_lanes_kernel, v->ctx, lsmem);
-			MSB200_LAUNCH(v->ctx, volume_lanes_kernel, msb200_div_up(v->live, 32), 32, lsmem, (short *)d_io, v->d_state, v->live, nsamples,
+			MSB200_LAUNCH(v->ctx, volume_lanes_kernel, msb200_div_up(v->live, 32), 32 * VOL_LANES_WARPS, lsmem, (short *)d_io, v->d_state, v->live, nsamples,
 			              stride, nblocks, block0, ring_blocks,
 			              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr), d_counts, pitch);
 			return MSB200_OK;

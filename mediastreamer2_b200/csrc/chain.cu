@@ -10,7 +10,8 @@
 //   resampler 10 ms blocks -> EC frames      speexec.c:252-259 (ms_bufferizer_read(&s->echo, ..., framesize*2))
 //   EC frames -> mixer 10 ms blocks          audiomixer.c:78-90  (ms_bufferizer_read(..., bytespertick))
 // Ring capacities are lcm(tick, frame) samples so that neither a tick-sized nor a frame-sized block ever wraps.
-// Per tick: 2 resample launches, 1 AEC launch (0..2 frames inside), 1 volume launch, optionally 1 mixer launch.
+// Per tick: 1 resample launch for both resamplers (2 when they are not integer-ratio up-samplers), 1 AEC launch (0..2 frames
+// inside), 1 volume launch, 1 hand-out or mixer launch.
 //
 // Overlap mode (msb200_chain_set_overlap; inside msb200_chain_submit with MSB200_CHAIN_OVERLAP=1): the echo canceller is 90 % of a tick and
 // the only kernel that fills the chip; the resamplers (before it) and the volume + hand-out copies (after it) are small,
@@ -282,12 +283,13 @@ static int chain_tick_impl(msb200_chain *c, const void *d_ref_in, const void *d_
 	}
 	// 1. both resamplers write their 10 ms block straight into the EC input rings
 	c->ctx->stream = sB;
-	r = msb200i_resample_launch(c->rs_ref, d_ref_in, c->tick_in, c->tick_in, c->d_ref_ring, c->cap, c->wpos_in, c->cap, &got);
+	// (one launch for both when they are integer-ratio up-samplers in phase, else two: msb200i_resample_launch_pair)
+	r = msb200i_resample_launch_pair(c->rs_ref, c->rs_mic, d_ref_in, d_mic_in, c->tick_in, c->tick_in, c->d_ref_ring, c->d_mic_ring, c->cap,
+	                                 c->wpos_in, c->cap, &got);
 	if (r == MSB200_OK && got != c->tick) {
 		msb200_set_error("chain: resampler produced %d samples for a %d-sample tick (non-integer rate ratio?)", got, c->tick);
 		r = MSB200_ESTATE;
 	}
-	if (r == MSB200_OK) r = msb200i_resample_launch(c->rs_mic, d_mic_in, c->tick_in, c->tick_in, c->d_mic_ring, c->cap, c->wpos_in, c->cap, &got);
 	c->ctx->stream = sA;
 	if (r) return r;
 	if (overlap) {

@@ -96,6 +96,8 @@ struct msb200_devbuf {
 // ---- internal launchers used by chain.cu (ring-buffer addressing for the re-framing between stages); ring == 0: linear
 int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames, int in_stride, void *d_out,
                             int out_stride, int ring_off, int ring_cap, int *out_frames);
+int msb200i_resample_launch_pair(msb200_resample *a, msb200_resample *b, const void *d_in_a, const void *d_in_b, int in_frames,
+                                 int in_stride, void *d_out_a, void *d_out_b, int out_stride, int ring_off, int ring_cap, int *out_frames);
 int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int in_stride, int in_frame0,
                        int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes,
                        const int *d_counts = nullptr);

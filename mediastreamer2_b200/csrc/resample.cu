@@ -173,10 +173,18 @@ template <int R> struct ResampleUpTable { float t[R * RS_UP_TAPS]; };
 template <int R>
 __global__ void __launch_bounds__(256)
     resample_up_kernel(const short *__restrict__ in, int in_frames, int in_stride, short *__restrict__ out, int out_stride,
-                       short *__restrict__ hist, const __grid_constant__ ResampleUpTable<R> tab, int nch, int ring_off, int ring_cap) {
+                       short *__restrict__ hist, const __grid_constant__ ResampleUpTable<R> tab, int nch, int ring_off, int ring_cap,
+                       const short *__restrict__ in_b, short *__restrict__ out_b, short *__restrict__ hist_b) {
 	extern __shared__ float rsm[];
 	constexpr int N = RS_UP_TAPS;
 	float *x = rsm; // [N-1 + in_frames]
+	// gridDim.y == 2: two banks of one geometry and phase in ONE launch (the far-end and microphone resamplers of a chain
+	// tick: two grids of small CTAs back to back left the chip half empty twice)
+	if (blockIdx.y) {
+		in = in_b;
+		out = out_b;
+		hist = hist_b;
+	}
 	const int stream = blockIdx.x / nch, ch = blockIdx.x % nch;
 	const short *gin = in + ((size_t)stream * in_stride) * nch + ch;
 	short *gout = out + ((size_t)stream * out_stride) * nch + ch;
@@ -333,7 +341,7 @@ int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames,
 		memcpy(tb.t, r->d.table.data(), sizeof(tb.t));                                                                 \
 		MSB200_SMEM_OPTIN(resample_up_kernel<R>, r->ctx, sm);                                                          \
 		MSB200_LAUNCH(r->ctx, resample_up_kernel<R>, r->live * r->nch, blk, sm, (const short *)d_in, in_frames, in_stride, (short *)d_out, \
-		              out_stride, r->d_hist, tb, r->nch, ring_off, ring_cap);                                          \
+		              out_stride, r->d_hist, tb, r->nch, ring_off, ring_cap, (const short *)nullptr, (short *)nullptr, (short *)nullptr); \
 	} while (0)
 		if (r->p.den == 2) RS_UP_LAUNCH(2);
 		else if (r->p.den == 3) RS_UP_LAUNCH(3);
@@ -346,6 +354,50 @@ int msb200i_resample_launch(msb200_resample *r, const void *d_in, int in_frames,
 	if (block < 32) block = 32;
 	if (r->live > 0) MSB200_LAUNCH(r->ctx, resample_kernel, r->live * r->nch, block, smem, (const short *)d_in, in_frames, in_stride,
 	              (short *)d_out, n_out, out_stride, r->d_hist, r->d_table, r->p, last0, frac0, ring_off, ring_cap);
+	return MSB200_OK;
+}
+// Two banks of the same design, channel count, live range and phase in one launch (integer-ratio up-sampling from phase
+// (0, 0), what a chain tick is); anything else: two launches. Same kernel, same arithmetic.
+int msb200i_resample_launch_pair(msb200_resample *a, msb200_resample *b, const void *d_in_a, const void *d_in_b, int in_frames,
+                                 int in_stride, void *d_out_a, void *d_out_b, int out_stride, int ring_off, int ring_cap, int *out_frames) {
+	MSB200_CHECK_ARG(a && b && d_in_a && d_in_b && d_out_a && d_out_b);
+	const ResampleParams &p = a->p;
+	const int n_out_expected = (int)p.den * in_frames;
+	const bool same = a->ctx == b->ctx && a->in_rate == b->in_rate && a->out_rate == b->out_rate && a->nch == b->nch && a->live == b->live &&
+	                  a->last_sample == 0 && a->samp_frac == 0 && b->last_sample == 0 && b->samp_frac == 0;
+	const bool up = a->live > 0 && p.use_direct && p.int_advance == 0 && p.frac_advance == 1 && p.filt_len == RS_UP_TAPS &&
+	                (p.den == 2 || p.den == 3 || p.den == 6) && in_frames > 0 && in_frames <= a->max_in && in_frames <= b->max_in &&
+	                in_stride >= in_frames && (ring_cap > 0 ? (out_stride >= ring_cap && ring_off + n_out_expected <= 2 * ring_cap && n_out_expected <= ring_cap)
+	                                                        : out_stride >= n_out_expected);
+	if (!(same && up)) {
+		int r = msb200i_resample_launch(a, d_in_a, in_frames, in_stride, d_out_a, out_stride, ring_off, ring_cap, out_frames);
+		if (r) return r;
+		return msb200i_resample_launch(b, d_in_b, in_frames, in_stride, d_out_b, out_stride, ring_off, ring_cap, out_frames);
+	}
+	// the phase bookkeeping of both banks, as msb200i_resample_launch does it
+	const int cap = msb200_resample_max_out(a, in_frames);
+	const int n_out = resample_count(a->d, in_frames, cap, a->last_sample, a->samp_frac);
+	const int n_out_b = resample_count(b->d, in_frames, cap, b->last_sample, b->samp_frac);
+	if (n_out != n_out_expected || n_out_b != n_out_expected) {
+		msb200_set_error("resample pair: %d / %d outputs for %d expected", n_out, n_out_b, n_out_expected);
+		return MSB200_ESTATE;
+	}
+	if (out_frames) *out_frames = n_out;
+	const size_t sm = sizeof(float) * (size_t)(RS_UP_TAPS - 1 + in_frames);
+	const int blk = in_frames >= 256 ? 256 : ((in_frames + 31) & ~31);
+	const dim3 grid((unsigned)(a->live * a->nch), 2, 1);
+#define RS_UP_PAIR(R)                                                                                                  \
+	do {                                                                                                               \
+		ResampleUpTable<R> tb;                                                                                         \
+		memcpy(tb.t, a->d.table.data(), sizeof(tb.t));                                                                 \
+		MSB200_SMEM_OPTIN(resample_up_kernel<R>, a->ctx, sm);                                                          \
+		MSB200_LAUNCH(a->ctx, resample_up_kernel<R>, grid, blk, sm, (const short *)d_in_a, in_frames, in_stride, (short *)d_out_a, out_stride, \
+		              a->d_hist, tb, a->nch, ring_off, ring_cap, (const short *)d_in_b, (short *)d_out_b, b->d_hist); \
+	} while (0)
+	if (p.den == 2) RS_UP_PAIR(2);
+	else if (p.den == 3) RS_UP_PAIR(3);
+	else RS_UP_PAIR(6);
+#undef RS_UP_PAIR
 	return MSB200_OK;
 }
 extern "C" {
