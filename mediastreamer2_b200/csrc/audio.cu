@@ -433,7 +433,10 @@ __global__ void __launch_bounds__(256) volume_kernel(short *__restrict__ io, msb
 __global__ void __launch_bounds__(32 * VOL_LANES_WARPS) volume_lanes_kernel(short *__restrict__ io, msb200_volume_state *__restrict__ st, int n_streams,
                                                           int nsamples, int stride, int nblocks, int block0, int ring_blocks,
                                                           const msb200_volume_state *__restrict__ peer_states,
-                                                          const int *__restrict__ counts, int pitch) {
+                                                          const int *__restrict__ counts, int pitch, short *__restrict__ copy_out,
+                                                          int copy_stride) {
+	// copy_out (optional): every processed block ALSO goes to copy_out[stream][blk * nsamples ...], rows copy_stride samples
+	// apart — the chain's hand-out of a tick's blocks, which was a launch of its own
 	extern __shared__ short vsm[];
 	__shared__ int sh_gain[32], sh_dc[32]; // per stream of the CTA: intgain (0 = leave the block as it is), DC to remove
 	__shared__ unsigned sh_has;
@@ -496,14 +499,20 @@ __global__ void __launch_bounds__(32 * VOL_LANES_WARPS) volume_lanes_kernel(shor
 		__syncthreads();
 		const unsigned todo = sh_has;
 		for (int l = warp; l < 32; l += VOL_LANES_WARPS) {
-			if (!((todo >> l) & 1u)) continue;
+			const bool ap = (todo >> l) & 1u;
+			if (!((has >> l) & 1u) || (!ap && !copy_out)) continue;
 			const int ig = sh_gain[l], dcp = sh_dc[l];
 			unsigned *g = reinterpret_cast<unsigned *>(io + (size_t)(s0 + l) * stride + (size_t)bpos * nsamples);
+			unsigned *c = copy_out ? reinterpret_cast<unsigned *>(copy_out + (size_t)(s0 + l) * copy_stride + (size_t)blk * nsamples) : nullptr;
 			for (int i = lane; i < words; i += 32) {
-				const unsigned w = wsm[l * pw + i];
-				const int a = vol_sat((((int)(short)(w & 0xffffu) - dcp) * ig) / 4096); // C truncating division
-				const int b = vol_sat((((int)(short)(w >> 16) - dcp) * ig) / 4096);
-				g[i] = ((unsigned)a & 0xffffu) | ((unsigned)b << 16);
+				unsigned w = wsm[l * pw + i];
+				if (ap) {
+					const int a = vol_sat((((int)(short)(w & 0xffffu) - dcp) * ig) / 4096); // C truncating division
+					const int b = vol_sat((((int)(short)(w >> 16) - dcp) * ig) / 4096);
+					w = ((unsigned)a & 0xffffu) | ((unsigned)b << 16);
+					g[i] = w;
+				}
+				if (c) c[i] = w;
 			}
 		}
 	}
@@ -629,7 +638,7 @@ int msb200_volume_get_state(msb200_volume *v, int stream, msb200_volume_state *s
 }
 int msb200_volume_process_dev(msb200_volume *v, void *d_io, int nsamples, int stride) {
 	MSB200_CHECK_ARG(stride >= nsamples);
-	return msb200i_volume_launch(v, d_io, nsamples, stride, 1, 0, 0);
+	return msb200i_volume_launch(v, d_io, nsamples, stride, 1, 0, 0, nullptr, nullptr, 0, nullptr);
 }
 int msb200_volume_process_blocks(msb200_volume *v, int16_t *io, int nsamples, int stride_samples, int nblocks, const int32_t *counts) {
 	MSB200_CHECK_ARG(v && io && nblocks > 0 && stride_samples >= nsamples * nblocks);
@@ -643,7 +652,7 @@ int msb200_volume_process_blocks(msb200_volume *v, int16_t *io, int nsamples, in
 	int *d_counts = counts ? (int *)((char *)v->io.p + bytes) : nullptr;
 	MSB200_CUDA(cudaMemcpy2DAsync(v->io.p, pitch, io, pitch, row, (size_t)v->live, cudaMemcpyHostToDevice, s));
 	if (counts) MSB200_CUDA(cudaMemcpyAsync(d_counts, counts, cbytes, cudaMemcpyHostToDevice, s));
-	if ((r = msb200i_volume_launch(v, v->io.p, nsamples, stride_samples, nblocks, 0, 0, d_counts))) return r;
+	if ((r = msb200i_volume_launch(v, v->io.p, nsamples, stride_samples, nblocks, 0, 0, d_counts, nullptr, 0, nullptr))) return r;
 	MSB200_CUDA(cudaMemcpy2DAsync(io, pitch, v->io.p, pitch, row, (size_t)v->live, cudaMemcpyDeviceToHost, s));
 	MSB200_HOST_DONE(v->ctx);
 	return MSB200_OK;
@@ -675,8 +684,9 @@ int msb200_volume_process(msb200_volume *v, int16_t *io, int nsamples) {
 } // extern "C"
 
 int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride, int nblocks, int block0, int ring_blocks,
-                          const int *d_counts) {
+                          const int *d_counts, void *d_copy_out, int copy_stride, int *copied) {
 	MSB200_CHECK_ARG(v && d_io && nsamples > 0 && nsamples <= v->max_block && nblocks > 0);
+	if (copied) *copied = 0;
 	// one warp per stream, the block staged in shared memory: 8 warps per CTA while that fits the default 48 KB, fewer for
 	// long blocks (48 kHz stereo at 40 ms is 3840 samples; max_block goes up to 8192), opting in beyond 48 KB
 	int warps = 8;
@@ -690,9 +700,12 @@ int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride
 		const bool can = (nsamples & 1) == 0 && (stride & 1) == 0 && ((uintptr_t)d_io & 3) == 0 && lsmem <= 96 * 1024;
 		if (can && (v->kernel_choice == 2 || (v->kernel_choice == 0 && v->live >= 256))) {
 			MSB200_SMEM_OPTIN(volume_lanes_kernel, v->ctx, lsmem);
+			const bool cp = d_copy_out && copied && ((uintptr_t)d_copy_out & 3) == 0 && (copy_stride & 1) == 0 && copy_stride >= nblocks * nsamples;
 			MSB200_LAUNCH(v->ctx, volume_lanes_kernel, msb200_div_up(v->live, 32), 32 * VOL_LANES_WARPS, lsmem, (short *)d_io, v->d_state, v->live, nsamples,
 			              stride, nblocks, block0, ring_blocks,
-			              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr), d_counts, pitch);
+			              (const msb200_volume_state *)(v->peer_bank ? v->peer_bank->d_state : nullptr), d_counts, pitch,
+			              cp ? (short *)d_copy_out : (short *)nullptr, copy_stride);
+			if (cp) *copied = 1;
 			return MSB200_OK;
 		}
 	}

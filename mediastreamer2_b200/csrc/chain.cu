@@ -261,7 +261,7 @@ static int chain_tick_impl(msb200_chain *c, const void *d_ref_in, const void *d_
 	const uint64_t l0 = c->ctx->launches;
 	cudaStream_t const sA = c->ctx->stream;
 	cudaStream_t s = sA, sB = sA, sC = sA;
-	int r, got = 0;
+	int r, got = 0, handed_out = 0;
 	if (overlap) {
 		if ((r = chain_overlap_init(c))) return r;
 		sB = c->s_pre;
@@ -340,14 +340,17 @@ static int chain_tick_impl(msb200_chain *c, const void *d_ref_in, const void *d_
 	}
 	if (nframes > 0) {
 		c->ctx->stream = sC;
-		r = msb200i_volume_launch(c->vol, c->d_out_ring, c->F, c->cap, nframes, c->wframe_out, K);
+		// (without a mixer the lane kernel also writes the tick's blocks to the caller's buffer: no hand-out launch)
+		r = msb200i_volume_launch(c->vol, c->d_out_ring, c->F, c->cap, nframes, c->wframe_out, K, nullptr, c->mix ? nullptr : d_out, c->max_out,
+		                          &handed_out);
 		c->ctx->stream = sA;
 		if (r) return r;
 		c->wframe_out = (c->wframe_out + nframes) % K;
 	}
 	if (!c->mix) {
 		// 3a. hand the EC/volume output blocks to the caller: [stream][max_out], first nframes*F valid
-		if (nframes > 0 && nframes <= K && (c->F & 7) == 0 && ((uintptr_t)d_out & 15) == 0) {
+		if (handed_out) {
+		} else if (nframes > 0 && nframes <= K && (c->F & 7) == 0 && ((uintptr_t)d_out & 15) == 0) {
 			const long vecs = (long)c->S * nframes * (c->F >> 3);
 			const long want = (vecs + 255) / 256;
 			c->ctx->stream = s;

@@ -101,8 +101,10 @@ int msb200i_resample_launch_pair(msb200_resample *a, msb200_resample *b, const v
 int msb200i_aec_launch(msb200_aec *a, const void *d_mic, const void *d_ref, int in_stride, int in_frame0,
                        int in_ring_frames, void *d_out, int out_stride, int out_frame0, int out_ring_frames, int nframes,
                        const int *d_counts = nullptr);
+// d_copy_out (optional, with `copied`): the processed blocks also go to d_copy_out[stream][blk * nsamples ...] (rows copy_stride
+// samples apart) when the lane kernel runs; *copied tells whether it did
 int msb200i_volume_launch(msb200_volume *v, void *d_io, int nsamples, int stride, int nblocks, int block0, int ring_blocks,
-                          const int *d_counts = nullptr);
+                          const int *d_counts = nullptr, void *d_copy_out = nullptr, int copy_stride = 0, int *copied = nullptr);
 int msb200i_mixer_launch(msb200_mixer *m, const void *d_in, long in_pin_stride, const void *d_present, void *d_out);
 int msb200i_packed422_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int uyvy, void *d_dst);
 int msb200i_rgb24_to_i420(msb200_ctx *ctx, int n_frames, const void *d_src, int w, int h, int fmt, void *d_dst, int x86_vertical = 0);
