@@ -428,7 +428,7 @@ typedef struct msb200_chain_params {
 	int32_t framesize_at_8000; /* 64 */
 	float volume_gain;       /* 0.8 */
 	int32_t mixer_pins;      /* 0 = no mixer stage; else streams are grouped in rooms of this many pins (conference mode) */
-	int32_t use_cuda_graph;  /* reserved, ignored: a tick is 5 launches on a GPU-bound ~0.9 ms step, there is no launch gap to remove */
+	int32_t use_cuda_graph;  /* reserved, ignored: a tick is 3 launches on a GPU-bound ~0.8 ms step, there is no launch gap to remove */
 } msb200_chain_params;
 MSB200_API int msb200_chain_create(msb200_ctx *ctx, const msb200_chain_params *p, msb200_chain **out);
 MSB200_API void msb200_chain_destroy(msb200_chain *c);
