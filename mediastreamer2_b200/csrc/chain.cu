@@ -11,7 +11,8 @@
 //   EC frames -> mixer 10 ms blocks          audiomixer.c:78-90  (ms_bufferizer_read(..., bytespertick))
 // Ring capacities are lcm(tick, frame) samples so that neither a tick-sized nor a frame-sized block ever wraps.
 // Per tick: 1 resample launch for both resamplers (2 when they are not integer-ratio up-samplers), 1 AEC launch (0..2 frames
-// inside), 1 volume launch, 1 hand-out or mixer launch.
+// inside), 1 volume launch that also hands the tick's blocks to the caller (banks of 256+ streams; else a small hand-out
+// launch), or volume + 1 mixer launch for conference chains.
 //
 // Overlap mode (msb200_chain_set_overlap; inside msb200_chain_submit with MSB200_CHAIN_OVERLAP=1): the echo canceller is 90 % of a tick and
 // the only kernel that fills the chip; the resamplers (before it) and the volume + hand-out copies (after it) are small,
