@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(32 * VOL_LANES_WARPS) volume_lanes_kernel(shor
 	// copy_out (optional): every processed block ALSO goes to copy_out[stream][blk * nsamples ...], rows copy_stride samples
 	// apart — the chain's hand-out of a tick's blocks, which was a launch of its own
 	extern __shared__ short vsm[];
-	__shared__ int sh_gain[32], sh_dc[32]; // per stream of the CTA: intgain (0 = leave the block as it is), DC to remove
-	__shared__ unsigned sh_has;
+	__shared__ int sh_gain[32], sh_dc[32]; // per stream of the CTA: the block's integer gain, the DC to remove first
+	__shared__ unsigned sh_has;            // streams whose block gets a gain pass at all (bit per stream)
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, s0 = blockIdx.x * 32, stream = s0 + lane;
 	const bool valid = stream < n_streams;
 	const int my_blocks = valid ? (counts ? min(nblocks, counts[stream]) : nblocks) : 0; // (the same in every warp)
@@ -491,9 +491,9 @@ __global__ void __launch_bounds__(32 * VOL_LANES_WARPS) volume_lanes_kernel(shor
 				}
 				vol_update(v, acc, pk, dcsum, nsamples, peer_states, intgain, apply, remove_dc, dc_prev);
 			}
-			sh_gain[lane] = apply ? intgain : 0; // gain == 1 and no DC removal: the block stays as it is (:441)
+			sh_gain[lane] = intgain;
 			sh_dc[lane] = remove_dc ? dc_prev : 0;
-			const unsigned todo = __ballot_sync(0xffffffffu, apply != 0);
+			const unsigned todo = __ballot_sync(0xffffffffu, apply != 0); // gain == 1 and no DC removal: the block stays as it is (:441)
 			if (lane == 0) sh_has = todo;
 		}
 		__syncthreads();
