@@ -2230,8 +2230,8 @@ struct msb200_scaler {
 	size_t smem_fast;
 	bool strip_ok;      // register-window strip kernel (scale_rgb_strip_kernel) applies
 	int sched;          // index into kStripSched when the static-schedule instantiation applies, else -1
-	int force_sched_off; // tests/profiling: 1 = always run the general loop
-	int force_path;     // tests/profiling: 0 = best available, 1 = persistent tile kernel, 2 = generic tile kernel, 3 = strip kernel, 4 = streaming kernel
+	int force_sched_off; // tests and profiling: 1 = always run the general loop
+	int force_path;     // tests and profiling: 0 = best available, 1 = persistent tile kernel, 2 = generic tile kernel, 3 = strip kernel, 4 = streaming kernel
 	bool stream_ok;     // per-warp streaming kernel (scale_rgb_stream_kernel) applies
 	StreamParams T;
 	size_t smem_stream;
